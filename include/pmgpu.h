@@ -1,0 +1,188 @@
+/*
+ * pmgpu.h — C ABI of the B200-native ICP hot path (libpmgpu.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Each entry point
+ * names the libpointmatcher (v1.3.1) interface it replaces; paths are relative to the reference
+ * tree.  The C++ module classes in libpointmatcher_b200/host/ (same names, parameters and
+ * exceptions as the reference's) and the ctypes binding in libpointmatcher_b200/capi.py are thin
+ * marshalling layers over these functions.  INTEGRATION.md shows the binding a libpointmatcher
+ * maintainer would add to Registry.cpp.
+ *
+ * Conventions
+ *  - clouds are `rows x n` column-major float matrices exactly as `DataPoints::features`
+ *    (pointmatcher/PointMatcher.h:169,331): rows == 4 (x, y, z, w) for 3-D.  Only float / 3-D
+ *    is implemented on the GPU; anything else returns PMGPU_ERR_UNSUPPORTED (there is no CPU
+ *    fallback by design).
+ *  - match results are `k x n` column-major (`Matches::ids/dists`, PointMatcher.h:373-374):
+ *    ids int32 (-1 = Matches::InvalidId), dists float SQUARED distances (+inf = InvalidDist).
+ *  - 4x4 transforms are column-major float[16] (Eigen default).
+ *  - every pointer argument may be a host pointer (pageable or pinned) or a device pointer
+ *    (copies use cudaMemcpyDefault); NULL for an optional output skips that download.
+ *  - all functions return a PMGPU_* status; pmgpu_last_error(ctx) gives the message.  The
+ *    status -> reference exception mapping is listed beside each code.
+ *  - a context owns one CUDA stream and all device buffers; one context per thread / per
+ *    concurrent registration (the reference's ICP object is not re-entrant either,
+ *    evaluations/eval_solution.cpp:628-630).
+ */
+#ifndef PMGPU_H
+#define PMGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pmgpu_ctx pmgpu_ctx;
+
+enum pmgpu_status {
+    PMGPU_OK = 0,
+    PMGPU_ERR_CUDA = 1,                 /* std::runtime_error (CUDA failure) */
+    PMGPU_ERR_BAD_ARG = 2,              /* std::runtime_error / InvalidParameter */
+    PMGPU_ERR_UNSUPPORTED = 3,          /* ConfigurationError("GPU module: only float/3-D ...") */
+    PMGPU_ERR_NO_REFERENCE = 4,         /* std::runtime_error: init() was not called */
+    PMGPU_ERR_NO_READING = 5,
+    PMGPU_ERR_NO_MATCHES = 6,           /* weights/minimize called before knn */
+    PMGPU_ERR_NO_OUTLIER_TO_FILTER = 7, /* ConvergenceError("no outlier to filter")       Matches.cpp:76-77 */
+    PMGPU_ERR_BAD_QUANTILE = 8,         /* ConvergenceError("quantile must be ...")       Matches.cpp:79-80 */
+    PMGPU_ERR_NO_POINT_TO_MINIMIZE = 9, /* ConvergenceError("ErrorMnimizer: no point ...") ErrorMinimizer.cpp:76-77 */
+    PMGPU_ERR_NO_NORMALS = 10,          /* InvalidField("Field normals not found")        DataPoints.cpp:941 */
+    PMGPU_ERR_NOT_ORTHOGONAL = 11,      /* TransformationError                            TransformationsImpl.cpp:62-63 */
+    PMGPU_ERR_KNN_TOO_LARGE = 12,       /* libnabo: "knn larger than the number of points" */
+    PMGPU_ERR_NAN = 13,                 /* ConvergenceError("abs rotation norm not a number") TransformationCheckersImpl.cpp:154-157 */
+    PMGPU_ERR_COMM = 14                 /* NCCL failure */
+};
+
+/* OutlierFiltersImpl.h: the three filters on the hot path */
+enum pmgpu_filter_type {
+    PMGPU_FILTER_MAXDIST = 0,    /* MaxDistOutlierFilter     param = maxDist (un-squared)  OutlierFiltersImpl.cpp:66-81   */
+    PMGPU_FILTER_MEDIANDIST = 1, /* MedianDistOutlierFilter  param = factor                OutlierFiltersImpl.cpp:109-125 */
+    PMGPU_FILTER_TRIMMEDDIST = 2 /* TrimmedDistOutlierFilter param = ratio                 OutlierFiltersImpl.cpp:132-147 */
+};
+
+enum pmgpu_minimizer {
+    PMGPU_MIN_P2POINT = 0,     /* PointToPointErrorMinimizer          ErrorMinimizers/PointToPoint.cpp:61-101 */
+    PMGPU_MIN_P2PLANE = 1,     /* PointToPlaneErrorMinimizer          ErrorMinimizers/PointToPlane.cpp:171-312 */
+    PMGPU_MIN_P2POINT_COV = 2, /* PointToPointWithCovErrorMinimizer   ErrorMinimizers/PointToPointWithCov.cpp:49-145 */
+    PMGPU_MIN_P2PLANE_COV = 3  /* PointToPlaneWithCovErrorMinimizer   ErrorMinimizers/PointToPlaneWithCov.cpp:60-162 */
+};
+
+/* SurfaceNormalDataPointsFilter keep* flags (DataPointsFilters/SurfaceNormal.h:65-80) */
+enum pmgpu_normals_flags {
+    PMGPU_NORMALS_SORT_EIGEN = 1,
+    PMGPU_NORMALS_SMOOTH = 2
+};
+
+/* ---- context ------------------------------------------------------------------------- */
+int pmgpu_ctx_create(int device, pmgpu_ctx** ctx_out);
+void pmgpu_ctx_destroy(pmgpu_ctx* ctx);
+const char* pmgpu_last_error(const pmgpu_ctx* ctx);
+const char* pmgpu_status_string(int status);
+/* CUDA stream of the context as an opaque pointer (cudaStream_t), for event timing */
+void* pmgpu_ctx_stream(pmgpu_ctx* ctx);
+int pmgpu_sync(pmgpu_ctx* ctx);
+/* number of kernel launches issued by this context since creation (bench `gpu_launches`) */
+uint64_t pmgpu_launch_count(const pmgpu_ctx* ctx);
+
+/* ---- K1: KDTreeMatcher::init (MatchersImpl.cpp:77-83) ----------------------------------
+ * Uploads the reference features and builds the search structure over the first rows-1
+ * coordinates.  `normals`: optional 3 x n block with column stride `normals_ld` floats
+ * (the "normals" descriptor rows inside DataPoints::descriptors, DataPoints.cpp:917-942);
+ * needed by the point-to-plane minimizers.  Replaces any previous reference. */
+int pmgpu_ref_set(pmgpu_ctx* ctx, const float* features, int rows, int n, const float* normals, int normals_ld);
+/* (re)attach normals to the current reference without rebuilding the tree */
+int pmgpu_ref_set_normals(pmgpu_ctx* ctx, const float* normals, int normals_ld);
+
+/* ---- reading (the `filteredReading` argument of findClosests / compute) ---------------- */
+int pmgpu_reading_set(pmgpu_ctx* ctx, const float* features, int rows, int n);
+
+/* RigidTransformation::compute on the resident reading, in place (TransformationsImpl.cpp:49-87;
+ * the `transformations.apply(reading, T_refMean_dataIn)` of ICP.cpp:345-347).  Returns
+ * PMGPU_ERR_NOT_ORTHOGONAL if |1 - det R| > 1e-3. */
+int pmgpu_reading_apply_transform(pmgpu_ctx* ctx, const float* T);
+/* optional download of the resident reading (4 x n) */
+int pmgpu_reading_get(pmgpu_ctx* ctx, float* features_out);
+
+/* ---- K2: RigidTransformation::compute + KDTreeMatcher::findClosests ---------------------
+ * (TransformationsImpl.cpp:49-87, MatchersImpl.cpp:85-101).  Applies T (NULL = identity) to
+ * the resident reading and finds, for every transformed point, the k nearest reference
+ * points: exact search, squared float distances accumulated x,y,z each op rounded once,
+ * candidates kept iff dist <= maxDist^2, result ascending in (dist, index) — the result
+ * libnabo's brute-force search returns.  epsilon > 0 is accepted and answered exactly.
+ * Returns PMGPU_ERR_NOT_ORTHOGONAL if |1 - det R| > 1e-3 (TransformationsImpl.cpp:90-105).
+ * ids_out / dists_out: optional k x n downloads; visit_out: optional number of reference
+ * points examined (Matcher::visitCounter, MatchersImpl.cpp:98). */
+int pmgpu_knn(pmgpu_ctx* ctx, const float* T, int k, float epsilon, float max_dist, int32_t* ids_out, float* dists_out, uint64_t* visit_out);
+
+/* ---- K3: OutlierFilters::compute (OutlierFilter.cpp:63-103) -----------------------------
+ * Evaluates the filter chain on the resident matches.  nfilters == 0 is the empty chain
+ * (weight = dist != inf).  weights_out: optional k x n download; limits_out: optional
+ * per-filter squared-distance limits (nfilters floats). */
+int pmgpu_weights(pmgpu_ctx* ctx, int nfilters, const int* types, const float* params, float* weights_out, float* limits_out);
+
+/* ---- K4-K7: ErrorMinimizer::compute (ErrorMinimizer.cpp:217-232) ------------------------
+ * Uses the resident reading (transformed by the T of the last pmgpu_knn), matches and
+ * weights.  T_out: the incremental 4x4; cov_out: 6x6 (WithCov variants, optional);
+ * stats_out[5] (optional) = {pointUsedRatio, weightedPointUsedRatio, nbRejectedMatches,
+ * nbRejectedPoints, nbKept} (ErrorMinimizer.cpp:92-140). */
+int pmgpu_minimize(pmgpu_ctx* ctx, int minimizer, float sensor_std_dev, float* T_out, float* cov_out, float* stats_out);
+
+/* ---- K8: SurfaceNormalDataPointsFilter::inPlaceFilter (SurfaceNormal.cpp:82-290) --------
+ * Self-kNN on `features` (rows x n) + per-point 3x3 eigen-solve.  Outputs are optional and
+ * written with column stride `ld` floats each: normals 3 x n, densities 1 x n, eig_values
+ * 3 x n, eig_vectors 9 x n (row-major serialisation, utils.h:89-103), matched_ids knn x n
+ * (as float, SurfaceNormal.cpp:254-257), mean_dists 1 x n.  If `attach` != 0 and the cloud
+ * is the current reference (same n), the normals also become the reference normals. */
+typedef struct pmgpu_normals_out {
+    float* normals;     int normals_ld;
+    float* densities;   int densities_ld;
+    float* eig_values;  int eig_values_ld;
+    float* eig_vectors; int eig_vectors_ld;
+    float* matched_ids; int matched_ids_ld;
+    float* mean_dists;  int mean_dists_ld;
+} pmgpu_normals_out;
+int pmgpu_normals(pmgpu_ctx* ctx, const float* features, int rows, int n, int knn, float epsilon, float max_dist, int flags,
+                  const pmgpu_normals_out* out, int* degenerate_out);
+/* same, on the resident reference; attaches the normals to it (config 3 pre-step) */
+int pmgpu_ref_compute_normals(pmgpu_ctx* ctx, int knn, float epsilon, float max_dist, int flags);
+
+/* ---- fused ICP loop: ICP::computeWithTransformedReference (ICP.cpp:371-430) -------------
+ * Runs iterations entirely on the device against the resident reference and reading:
+ * T_iter <- dT * T_iter with the Counter / Differential checkers evaluated on the device
+ * (TransformationCheckersImpl.cpp:45-158).  The reading is the one given to
+ * pmgpu_reading_set (already expressed in the reference frame).  T_iter_out: final T_iter. */
+typedef struct pmgpu_icp_params {
+    int knn;
+    float epsilon;
+    float max_dist;
+    int nfilters;
+    int filter_type[8];
+    float filter_param[8];
+    int minimizer;
+    float sensor_std_dev;
+    int max_iterations;       /* CounterTransformationChecker.maxIterationCount */
+    int use_differential;     /* DifferentialTransformationChecker on/off */
+    float min_diff_rot_err;
+    float min_diff_trans_err;
+    int smooth_length;
+} pmgpu_icp_params;
+int pmgpu_icp_run(pmgpu_ctx* ctx, const pmgpu_icp_params* params, const float* T_iter_init, float* T_iter_out, int* iterations_out,
+                  float* cov_out, float* stats_out);
+/* enqueue exactly `n_iterations` iterations without synchronising (bench inner loop) */
+int pmgpu_icp_enqueue(pmgpu_ctx* ctx, const pmgpu_icp_params* params, int n_iterations);
+int pmgpu_icp_reset(pmgpu_ctx* ctx, const float* T_iter_init);
+int pmgpu_icp_result(pmgpu_ctx* ctx, float* T_iter_out, int* iterations_out, float* cov_out, float* stats_out);
+
+/* ---- multi-GPU: queries sharded over ranks, replicated reference ------------------------
+ * After pmgpu_comm_init the quantile histograms and the normal-equation sums of
+ * pmgpu_weights / pmgpu_minimize / pmgpu_icp_* are all-reduced over the communicator, so
+ * every rank computes the same limit and the same T.  `unique_id` is the 128-byte
+ * ncclUniqueId produced by pmgpu_comm_unique_id on rank 0 and distributed by the caller. */
+int pmgpu_comm_unique_id(void* unique_id_128);
+int pmgpu_comm_init(pmgpu_ctx* ctx, const void* unique_id_128, int rank, int nranks);
+int pmgpu_comm_destroy(pmgpu_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMGPU_H */

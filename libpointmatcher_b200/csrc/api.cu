@@ -1,0 +1,514 @@
+// api.cu — the extern "C" entry points of include/pmgpu.h: argument checks, uploads/downloads,
+// kernel sequencing.  All work of a context is issued on its own stream.
+#include <string.h>
+
+#include <new>
+
+#include "core/linalg.h"
+#include "pmgpu_internal.cuh"
+
+using namespace pm;
+
+namespace {
+
+__global__ void pack_normals_kernel(const float* __restrict__ src, int ld, int n, f4* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* s = src + (size_t)i * ld;
+    dst[i] = make_float4(s[0], s[1], s[2], 0.f);
+}
+
+__global__ void unpack_f4_kernel(const f4* __restrict__ src, int n, float* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const f4 v = src[i];
+    dst[3 * (size_t)i] = v.x; dst[3 * (size_t)i + 1] = v.y; dst[3 * (size_t)i + 2] = v.z;
+}
+
+__global__ void ids_to_float_kernel(const int32_t* __restrict__ ids, size_t total, float* __restrict__ out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) out[i] = (float)ids[i];
+}
+
+__global__ void transform_inplace_kernel(f4* __restrict__ pts, int n, Mat4 T) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pts[i] = transform_point(T, pts[i]);
+}
+
+int fail(pmgpu_ctx* ctx, int code, const char* msg) {
+    ctx->set_error(msg);
+    return code;
+}
+
+int use_device(pmgpu_ctx* ctx) {
+    PM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return PMGPU_OK;
+}
+
+int push_state(pmgpu_ctx* ctx) {
+    PM_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->state, ctx->state_host, sizeof(IcpState), cudaMemcpyHostToDevice, ctx->stream));
+    return PMGPU_OK;
+}
+
+int pull_state(pmgpu_ctx* ctx) {
+    PM_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->state_host, ctx->state, sizeof(IcpState), cudaMemcpyDeviceToHost, ctx->stream));
+    PM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return PMGPU_OK;
+}
+
+const char* status_message(int s) {
+    switch (s) {
+        case PMGPU_OK: return "ok";
+        case PMGPU_ERR_CUDA: return "CUDA error";
+        case PMGPU_ERR_BAD_ARG: return "bad argument";
+        case PMGPU_ERR_UNSUPPORTED: return "GPU module: only float / 3-D clouds are supported";
+        case PMGPU_ERR_NO_REFERENCE: return "matcher not initialised: no reference";
+        case PMGPU_ERR_NO_READING: return "no reading";
+        case PMGPU_ERR_NO_MATCHES: return "no matches: findClosests must run first";
+        case PMGPU_ERR_NO_OUTLIER_TO_FILTER: return "no outlier to filter";
+        case PMGPU_ERR_BAD_QUANTILE: return "quantile must be between 0 and 1";
+        case PMGPU_ERR_NO_POINT_TO_MINIMIZE: return "ErrorMnimizer: no point to minimize";
+        case PMGPU_ERR_NO_NORMALS: return "Field normals not found";
+        case PMGPU_ERR_NOT_ORTHOGONAL: return "RigidTransformation: Error, rotation matrix is not orthogonal.";
+        case PMGPU_ERR_KNN_TOO_LARGE: return "knn is larger than the number of reference points";
+        case PMGPU_ERR_NAN: return "abs rotation norm not a number";
+        case PMGPU_ERR_COMM: return "NCCL error";
+    }
+    return "unknown status";
+}
+
+// status raised by a kernel -> API return value
+int device_status(pmgpu_ctx* ctx) {
+    const int s = ctx->state_host->status;
+    if (s != PMGPU_OK) ctx->set_error(status_message(s));
+    return s;
+}
+
+int upload_normals(pmgpu_ctx* ctx, const float* normals, int ld) {
+    if (ld < 3) return fail(ctx, PMGPU_ERR_BAD_ARG, "normals_ld must be >= 3");
+    const int n = ctx->nr;
+    PM_CUDA_TRY(ctx, ctx->ref_normals.reserve(n));
+    DevBuf<float> staging;
+    PM_CUDA_TRY(ctx, staging.reserve((size_t)n * ld));
+    // the last column may be shorter than ld in the caller's matrix: copy (n-1)*ld + 3 floats
+    PM_CUDA_TRY(ctx, cudaMemcpyAsync(staging.p, normals, ((size_t)(n - 1) * ld + 3) * sizeof(float), cudaMemcpyDefault, ctx->stream));
+    pack_normals_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(staging.p, ld, n, ctx->ref_normals.p);
+    ctx->launches += 1;
+    PM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    staging.release();
+    ctx->has_normals = true;
+    return PMGPU_OK;
+}
+
+int check_params(pmgpu_ctx* ctx, const pmgpu_icp_params* p) {
+    if (!p) return fail(ctx, PMGPU_ERR_BAD_ARG, "null parameters");
+    if (p->knn < 1) return fail(ctx, PMGPU_ERR_BAD_ARG, "knn must be >= 1");
+    if (p->knn > ctx->nr) return fail(ctx, PMGPU_ERR_KNN_TOO_LARGE, status_message(PMGPU_ERR_KNN_TOO_LARGE));
+    if (p->nfilters < 0 || p->nfilters > PM_MAX_FILTERS) return fail(ctx, PMGPU_ERR_BAD_ARG, "at most 8 outlier filters");
+    if (p->minimizer < 0 || p->minimizer > PMGPU_MIN_P2PLANE_COV) return fail(ctx, PMGPU_ERR_BAD_ARG, "unknown error minimizer");
+    if (p->use_differential && (p->smooth_length < 0 || p->smooth_length >= PM_MAX_HISTORY))
+        return fail(ctx, PMGPU_ERR_UNSUPPORTED, "DifferentialTransformationChecker: smoothLength must be < 64 on the GPU path");
+    if (p->max_iterations < 0) return fail(ctx, PMGPU_ERR_BAD_ARG, "maxIterationCount must be >= 0");
+    return PMGPU_OK;
+}
+
+int enqueue_iteration(pmgpu_ctx* ctx, const pmgpu_icp_params* p, bool gated) {
+    const float max_r2 = p->max_dist * p->max_dist;
+    PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, ctx->q_order.p, ctx->nq, true, gated, false, p->knn, max_r2, ctx->ids.p, ctx->dists.p));
+    PM_TRY(launch_weights(ctx, p->nfilters, p->filter_type, p->filter_param, gated));
+    PM_TRY(launch_minimize(ctx, p->minimizer, true, gated, p));
+    return PMGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pmgpu_status_string(int status) { return status_message(status); }
+
+int pmgpu_ctx_create(int device, pmgpu_ctx** ctx_out) {
+    if (!ctx_out) return PMGPU_ERR_BAD_ARG;
+    *ctx_out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return PMGPU_ERR_CUDA;
+    pmgpu_ctx* ctx = new (std::nothrow) pmgpu_ctx();
+    if (!ctx) return PMGPU_ERR_BAD_ARG;
+    ctx->device = device;
+    bool ok = cudaSetDevice(device) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&ctx->state, sizeof(IcpState)) == cudaSuccess;
+    ok = ok && cudaMallocHost((void**)&ctx->state_host, sizeof(IcpState)) == cudaSuccess;
+    int sms = 0;
+    ok = ok && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess;
+    if (!ok) {
+        pmgpu_ctx_destroy(ctx);
+        return PMGPU_ERR_CUDA;
+    }
+    ctx->num_sms = sms > 0 ? sms : 148;
+    memset(ctx->state_host, 0, sizeof(IcpState));
+    mat4_identity(ctx->state_host->T_iter);
+    mat4_identity(ctx->state_host->T_match);
+    mat4_identity(ctx->state_host->dT);
+    ctx->state_host->iterate = 1;
+    if (cudaMemcpy(ctx->state, ctx->state_host, sizeof(IcpState), cudaMemcpyHostToDevice) != cudaSuccess) {
+        pmgpu_ctx_destroy(ctx);
+        return PMGPU_ERR_CUDA;
+    }
+    *ctx_out = ctx;
+    return PMGPU_OK;
+}
+
+void pmgpu_ctx_destroy(pmgpu_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    pmgpu_comm_destroy(ctx);
+    ctx->ref_orig.release(); ctx->ref_sorted.release(); ctx->ref_normals.release(); ctx->nodes.release();
+    ctx->keys_a.release(); ctx->keys_b.release(); ctx->perm_a.release(); ctx->perm_b.release();
+    ctx->node_box.release(); ctx->node_dim.release(); ctx->cub_tmp.release();
+    ctx->reading.release(); ctx->q_order.release();
+    ctx->ids.release(); ctx->dists.release(); ctx->weights.release();
+    ctx->hist.release(); ctx->partials.release();
+    if (ctx->state) cudaFree(ctx->state);
+    if (ctx->state_host) cudaFreeHost(ctx->state_host);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* pmgpu_last_error(const pmgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+void* pmgpu_ctx_stream(pmgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+uint64_t pmgpu_launch_count(const pmgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int pmgpu_sync(pmgpu_ctx* ctx) {
+    if (!ctx) return PMGPU_ERR_BAD_ARG;
+    PM_TRY(use_device(ctx));
+    PM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return PMGPU_OK;
+}
+
+int pmgpu_ref_set(pmgpu_ctx* ctx, const float* features, int rows, int n, const float* normals, int normals_ld) {
+    if (!ctx) return PMGPU_ERR_BAD_ARG;
+    PM_TRY(use_device(ctx));
+    if (!features) return fail(ctx, PMGPU_ERR_BAD_ARG, "null reference features");
+    if (rows != 4) return fail(ctx, PMGPU_ERR_UNSUPPORTED, status_message(PMGPU_ERR_UNSUPPORTED));
+    if (n < 1) return fail(ctx, PMGPU_ERR_BAD_ARG, "the reference cloud is empty");
+    ctx->nr = 0;
+    ctx->has_normals = false;
+    ctx->have_matches = false;
+    PM_CUDA_TRY(ctx, ctx->ref_orig.reserve(n));
+    PM_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ref_orig.p, features, (size_t)n * sizeof(f4), cudaMemcpyDefault, ctx->stream));
+    ctx->nr = n;
+    const int s = build_tree(ctx);
+    if (s != PMGPU_OK) { ctx->nr = 0; return s; }
+    if (normals) PM_TRY(upload_normals(ctx, normals, normals_ld));
+    return PMGPU_OK;
+}
+
+int pmgpu_ref_set_normals(pmgpu_ctx* ctx, const float* normals, int normals_ld) {
+    if (!ctx) return PMGPU_ERR_BAD_ARG;
+    PM_TRY(use_device(ctx));
+    if (ctx->nr == 0) return fail(ctx, PMGPU_ERR_NO_REFERENCE, status_message(PMGPU_ERR_NO_REFERENCE));
+    if (!normals) { ctx->has_normals = false; return PMGPU_OK; }
+    return upload_normals(ctx, normals, normals_ld);
+}
+
+int pmgpu_reading_set(pmgpu_ctx* ctx, const float* features, int rows, int n) {
+    if (!ctx) return PMGPU_ERR_BAD_ARG;
+    PM_TRY(use_device(ctx));
+    if (!features) return fail(ctx, PMGPU_ERR_BAD_ARG, "null reading features");
+    if (rows != 4) return fail(ctx, PMGPU_ERR_UNSUPPORTED, status_message(PMGPU_ERR_UNSUPPORTED));
+    if (n < 0) return fail(ctx, PMGPU_ERR_BAD_ARG, "negative point count");
+    ctx->nq = 0;
+    ctx->have_matches = false;
+    ctx->have_weights = false;
+    PM_CUDA_TRY(ctx, ctx->reading.reserve(n > 0 ? n : 1));
+    if (n > 0) PM_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->reading.p, features, (size_t)n * sizeof(f4), cudaMemcpyDefault, ctx->stream));
+    ctx->nq = n;
+    if (n > 0) PM_TRY(morton_order(ctx));
+    PM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return PMGPU_OK;
+}
+
+int pmgpu_reading_apply_transform(pmgpu_ctx* ctx, const float* T) {
+    if (!ctx) return PMGPU_ERR_BAD_ARG;
+    PM_TRY(use_device(ctx));
+    if (!T) return fail(ctx, PMGPU_ERR_BAD_ARG, "null transform");
+    Mat4 M;
+    memcpy(M.m, T, sizeof(M.m));
+    if (!mat4_is_rigid(M)) return fail(ctx, PMGPU_ERR_NOT_ORTHOGONAL, status_message(PMGPU_ERR_NOT_ORTHOGONAL));
+    if (ctx->nq > 0) {
+        transform_inplace_kernel<<<(ctx->nq + 255) / 256, 256, 0, ctx->stream>>>(ctx->reading.p, ctx->nq, M);
+        ctx->launches += 1;
+        PM_CUDA_TRY(ctx, cudaGetLastError());
+    }
+    ctx->have_matches = false;
+    return PMGPU_OK;
+}
+
+int pmgpu_reading_get(pmgpu_ctx* ctx, float* features_out) {
+    if (!ctx) return PMGPU_ERR_BAD_ARG;
+    PM_TRY(use_device(ctx));
+    if (!features_out) return fail(ctx, PMGPU_ERR_BAD_ARG, "null output");
+    if (ctx->nq > 0) PM_CUDA_TRY(ctx, cudaMemcpyAsync(features_out, ctx->reading.p, (size_t)ctx->nq * sizeof(f4), cudaMemcpyDefault, ctx->stream));
+    PM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return PMGPU_OK;
+}
+
+int pmgpu_knn(pmgpu_ctx* ctx, const float* T, int k, float epsilon, float max_dist, int32_t* ids_out, float* dists_out, uint64_t* visit_out) {
+    if (!ctx) return PMGPU_ERR_BAD_ARG;
+    PM_TRY(use_device(ctx));
+    if (ctx->nr == 0) return fail(ctx, PMGPU_ERR_NO_REFERENCE, status_message(PMGPU_ERR_NO_REFERENCE));
+    if (k < 1) return fail(ctx, PMGPU_ERR_BAD_ARG, "knn must be >= 1");
+    if (k > ctx->nr) return fail(ctx, PMGPU_ERR_KNN_TOO_LARGE, status_message(PMGPU_ERR_KNN_TOO_LARGE));
+    if (!(epsilon >= 0.f)) return fail(ctx, PMGPU_ERR_BAD_ARG, "epsilon must be >= 0");
+    if (!(max_dist >= 0.f)) return fail(ctx, PMGPU_ERR_BAD_ARG, "maxDist must be >= 0");
+    IcpState* h = ctx->state_host;
+    if (T) {
+        memcpy(h->T_iter.m, T, sizeof(float) * 16);
+        if (!mat4_is_rigid(h->T_iter)) return fail(ctx, PMGPU_ERR_NOT_ORTHOGONAL, status_message(PMGPU_ERR_NOT_ORTHOGONAL));
+    } else {
+        mat4_identity(h->T_iter);
+    }
+    h->T_match = h->T_iter;
+    h->status = 0;
+    h->iterate = 1;
+    h->visits = 0;
+    PM_TRY(push_state(ctx));
+    const size_t total = (size_t)k * (ctx->nq > 0 ? ctx->nq : 1);
+    PM_CUDA_TRY(ctx, ctx->ids.reserve(total));
+    PM_CUDA_TRY(ctx, ctx->dists.reserve(total));
+    ctx->k = k;
+    ctx->have_weights = false;
+    const float max_r2 = max_dist * max_dist;
+    PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, ctx->q_order.p, ctx->nq, T != nullptr, false, false, k, max_r2, ctx->ids.p, ctx->dists.p));
+    ctx->have_matches = true;
+    const size_t out_n = (size_t)k * ctx->nq;
+    if (ids_out && out_n) PM_CUDA_TRY(ctx, cudaMemcpyAsync(ids_out, ctx->ids.p, out_n * sizeof(int32_t), cudaMemcpyDefault, ctx->stream));
+    if (dists_out && out_n) PM_CUDA_TRY(ctx, cudaMemcpyAsync(dists_out, ctx->dists.p, out_n * sizeof(float), cudaMemcpyDefault, ctx->stream));
+    PM_TRY(pull_state(ctx));
+    if (visit_out) *visit_out = ctx->state_host->visits;
+    return PMGPU_OK;
+}
+
+int pmgpu_weights(pmgpu_ctx* ctx, int nfilters, const int* types, const float* params, float* weights_out, float* limits_out) {
+    if (!ctx) return PMGPU_ERR_BAD_ARG;
+    PM_TRY(use_device(ctx));
+    if (!ctx->have_matches) return fail(ctx, PMGPU_ERR_NO_MATCHES, status_message(PMGPU_ERR_NO_MATCHES));
+    if (nfilters > 0 && (!types || !params)) return fail(ctx, PMGPU_ERR_BAD_ARG, "null filter arrays");
+    PM_TRY(launch_weights(ctx, nfilters, types, params, false));
+    const size_t total = (size_t)ctx->k * ctx->nq;
+    if (weights_out && total) {
+        PM_TRY(launch_materialize_weights(ctx));
+        PM_CUDA_TRY(ctx, cudaMemcpyAsync(weights_out, ctx->weights.p, total * sizeof(float), cudaMemcpyDefault, ctx->stream));
+    }
+    PM_TRY(pull_state(ctx));
+    const int s = device_status(ctx);
+    if (s != PMGPU_OK) {
+        ctx->have_weights = false;
+        ctx->state_host->status = 0;
+        ctx->state_host->iterate = 1;
+        PM_TRY(push_state(ctx));
+        PM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        return s;
+    }
+    if (limits_out)
+        for (int f = 0; f < nfilters; ++f) limits_out[f] = ctx->state_host->limit[f];
+    return PMGPU_OK;
+}
+
+int pmgpu_minimize(pmgpu_ctx* ctx, int minimizer, float sensor_std_dev, float* T_out, float* cov_out, float* stats_out) {
+    if (!ctx) return PMGPU_ERR_BAD_ARG;
+    PM_TRY(use_device(ctx));
+    if (!ctx->have_matches) return fail(ctx, PMGPU_ERR_NO_MATCHES, status_message(PMGPU_ERR_NO_MATCHES));
+    if (minimizer < 0 || minimizer > PMGPU_MIN_P2PLANE_COV) return fail(ctx, PMGPU_ERR_BAD_ARG, "unknown error minimizer");
+    if (!ctx->have_weights) PM_TRY(launch_weights(ctx, 0, nullptr, nullptr, false));  // empty chain
+    PM_TRY(launch_minimize(ctx, minimizer, false, false, nullptr));
+    const bool with_cov = minimizer == PMGPU_MIN_P2POINT_COV || minimizer == PMGPU_MIN_P2PLANE_COV;
+    if (with_cov) PM_TRY(launch_covariance(ctx, minimizer, sensor_std_dev));
+    PM_TRY(pull_state(ctx));
+    const int s = device_status(ctx);
+    if (s != PMGPU_OK) {
+        ctx->state_host->status = 0;
+        ctx->state_host->iterate = 1;
+        PM_TRY(push_state(ctx));
+        PM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        return s;
+    }
+    if (T_out) memcpy(T_out, ctx->state_host->dT.m, sizeof(float) * 16);
+    if (cov_out && with_cov) memcpy(cov_out, ctx->state_host->cov, sizeof(float) * 36);
+    if (stats_out) memcpy(stats_out, ctx->state_host->stats, sizeof(float) * 5);
+    return PMGPU_OK;
+}
+
+int pmgpu_icp_reset(pmgpu_ctx* ctx, const float* T_iter_init) {
+    if (!ctx) return PMGPU_ERR_BAD_ARG;
+    PM_TRY(use_device(ctx));
+    IcpState* h = ctx->state_host;
+    PM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (T_iter_init) memcpy(h->T_iter.m, T_iter_init, sizeof(float) * 16);
+    else mat4_identity(h->T_iter);
+    if (!mat4_is_rigid(h->T_iter)) return fail(ctx, PMGPU_ERR_NOT_ORTHOGONAL, status_message(PMGPU_ERR_NOT_ORTHOGONAL));
+    h->T_match = h->T_iter;
+    mat4_identity(h->dT);
+    h->status = 0;
+    h->iterate = 1;
+    h->iterations = 0;
+    h->counter = 0;
+    h->visits = 0;
+    // TransformationCheckers::init (TransformationCheckersImpl.cpp:107-124): history starts with T_iter
+    const Quat q = quat_from_mat4(h->T_iter);
+    h->hist_q[0][0] = q.w; h->hist_q[0][1] = q.x; h->hist_q[0][2] = q.y; h->hist_q[0][3] = q.z;
+    h->hist_t[0][0] = h->T_iter.m[12]; h->hist_t[0][1] = h->T_iter.m[13]; h->hist_t[0][2] = h->T_iter.m[14];
+    h->hist_len = 1;
+    PM_TRY(push_state(ctx));
+    PM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return PMGPU_OK;
+}
+
+int pmgpu_icp_enqueue(pmgpu_ctx* ctx, const pmgpu_icp_params* params, int n_iterations) {
+    if (!ctx) return PMGPU_ERR_BAD_ARG;
+    PM_TRY(use_device(ctx));
+    if (ctx->nr == 0) return fail(ctx, PMGPU_ERR_NO_REFERENCE, status_message(PMGPU_ERR_NO_REFERENCE));
+    if (ctx->nq == 0) return fail(ctx, PMGPU_ERR_NO_READING, status_message(PMGPU_ERR_NO_READING));
+    PM_TRY(check_params(ctx, params));
+    const bool plane = params->minimizer == PMGPU_MIN_P2PLANE || params->minimizer == PMGPU_MIN_P2PLANE_COV;
+    if (plane && !ctx->has_normals) return fail(ctx, PMGPU_ERR_NO_NORMALS, status_message(PMGPU_ERR_NO_NORMALS));
+    const size_t total = (size_t)params->knn * ctx->nq;
+    PM_CUDA_TRY(ctx, ctx->ids.reserve(total));
+    PM_CUDA_TRY(ctx, ctx->dists.reserve(total));
+    ctx->k = params->knn;
+    for (int it = 0; it < n_iterations; ++it) PM_TRY(enqueue_iteration(ctx, params, true));
+    ctx->have_matches = true;
+    ctx->have_weights = true;
+    return PMGPU_OK;
+}
+
+int pmgpu_icp_result(pmgpu_ctx* ctx, float* T_iter_out, int* iterations_out, float* cov_out, float* stats_out) {
+    if (!ctx) return PMGPU_ERR_BAD_ARG;
+    PM_TRY(use_device(ctx));
+    PM_TRY(pull_state(ctx));
+    if (T_iter_out) memcpy(T_iter_out, ctx->state_host->T_iter.m, sizeof(float) * 16);
+    if (iterations_out) *iterations_out = ctx->state_host->iterations;
+    if (cov_out) memcpy(cov_out, ctx->state_host->cov, sizeof(float) * 36);
+    if (stats_out) memcpy(stats_out, ctx->state_host->stats, sizeof(float) * 5);
+    return device_status(ctx);
+}
+
+int pmgpu_icp_run(pmgpu_ctx* ctx, const pmgpu_icp_params* params, const float* T_iter_init, float* T_iter_out, int* iterations_out, float* cov_out,
+                  float* stats_out) {
+    if (!ctx) return PMGPU_ERR_BAD_ARG;
+    PM_TRY(use_device(ctx));
+    if (ctx->nr == 0) return fail(ctx, PMGPU_ERR_NO_REFERENCE, status_message(PMGPU_ERR_NO_REFERENCE));
+    PM_TRY(check_params(ctx, params));
+    PM_TRY(pmgpu_icp_reset(ctx, T_iter_init));
+    // ICP.cpp:371: `while (iterate)` runs the body at least once, Counter stops it after
+    // maxIterationCount checks (max(1, maxIterationCount) iterations)
+    const int n = params->max_iterations > 1 ? params->max_iterations : 1;
+    PM_TRY(pmgpu_icp_enqueue(ctx, params, n));
+    const bool with_cov = params->minimizer == PMGPU_MIN_P2POINT_COV || params->minimizer == PMGPU_MIN_P2PLANE_COV;
+    if (with_cov) {
+        PM_TRY(pull_state(ctx));
+        if (ctx->state_host->status == PMGPU_OK) PM_TRY(launch_covariance(ctx, params->minimizer, params->sensor_std_dev));
+    }
+    return pmgpu_icp_result(ctx, T_iter_out, iterations_out, cov_out, stats_out);
+}
+
+int pmgpu_ref_compute_normals(pmgpu_ctx* ctx, int knn, float epsilon, float max_dist, int flags) {
+    if (!ctx) return PMGPU_ERR_BAD_ARG;
+    PM_TRY(use_device(ctx));
+    if (ctx->nr == 0) return fail(ctx, PMGPU_ERR_NO_REFERENCE, status_message(PMGPU_ERR_NO_REFERENCE));
+    if (knn < 1) return fail(ctx, PMGPU_ERR_BAD_ARG, "knn must be >= 1");
+    if (knn > ctx->nr) return fail(ctx, PMGPU_ERR_KNN_TOO_LARGE, status_message(PMGPU_ERR_KNN_TOO_LARGE));
+    if (!(epsilon >= 0.f) || !(max_dist >= 0.f)) return fail(ctx, PMGPU_ERR_BAD_ARG, "epsilon and maxDist must be >= 0");
+    if (flags & PMGPU_NORMALS_SMOOTH) return fail(ctx, PMGPU_ERR_UNSUPPORTED, "SurfaceNormalDataPointsFilter on GPU: smoothNormals is not supported");
+    const int n = ctx->nr;
+    DevBuf<int32_t> nids;
+    DevBuf<float> ndists;
+    PM_CUDA_TRY(ctx, nids.reserve((size_t)knn * n));
+    PM_CUDA_TRY(ctx, ndists.reserve((size_t)knn * n));
+    PM_CUDA_TRY(ctx, ctx->ref_normals.reserve(n));
+    int s = launch_knn(ctx, ctx->tree_view(), ctx->ref_sorted.p, nullptr, n, false, false, true, knn, max_dist * max_dist, nids.p, ndists.p);
+    if (s == PMGPU_OK) s = launch_normals(ctx, ctx->ref_orig.p, n, nids.p, ndists.p, knn, flags, ctx->ref_normals.p, nullptr, nullptr, nullptr, nullptr);
+    cudaStreamSynchronize(ctx->stream);
+    nids.release();
+    ndists.release();
+    if (s != PMGPU_OK) return s;
+    PM_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->has_normals = true;
+    return PMGPU_OK;
+}
+
+int pmgpu_normals(pmgpu_ctx* ctx, const float* features, int rows, int n, int knn, float epsilon, float max_dist, int flags,
+                  const pmgpu_normals_out* out, int* degenerate_out) {
+    if (!ctx) return PMGPU_ERR_BAD_ARG;
+    PM_TRY(use_device(ctx));
+    if (!features || !out) return fail(ctx, PMGPU_ERR_BAD_ARG, "null argument");
+    if (rows != 4) return fail(ctx, PMGPU_ERR_UNSUPPORTED, status_message(PMGPU_ERR_UNSUPPORTED));
+    if (n < 1) return fail(ctx, PMGPU_ERR_BAD_ARG, "empty cloud");
+    if (knn < 1) return fail(ctx, PMGPU_ERR_BAD_ARG, "knn must be >= 1");
+    if (knn > n) return fail(ctx, PMGPU_ERR_KNN_TOO_LARGE, status_message(PMGPU_ERR_KNN_TOO_LARGE));
+    if (!(epsilon >= 0.f) || !(max_dist >= 0.f)) return fail(ctx, PMGPU_ERR_BAD_ARG, "epsilon and maxDist must be >= 0");
+    if (flags & PMGPU_NORMALS_SMOOTH) return fail(ctx, PMGPU_ERR_UNSUPPORTED, "SurfaceNormalDataPointsFilter on GPU: smoothNormals is not supported");
+    // a private context holds the cloud's own search structure (the filter builds its own
+    // KDTreeMatcher, SurfaceNormal.cpp:153-162); it shares nothing with the ICP reference
+    pmgpu_ctx* sub = nullptr;
+    int s = pmgpu_ctx_create(ctx->device, &sub);
+    if (s != PMGPU_OK) return fail(ctx, s, "cannot create the filter's private context");
+    struct Guard {
+        pmgpu_ctx* c;
+        pmgpu_ctx* parent;
+        ~Guard() { parent->launches += c->launches; pmgpu_ctx_destroy(c); }
+    } guard{sub, ctx};
+    s = pmgpu_ref_set(sub, features, rows, n, nullptr, 0);
+    if (s != PMGPU_OK) return fail(ctx, s, sub->err.c_str());
+    DevBuf<int32_t> nids;
+    DevBuf<float> ndists, scratch;
+    DevBuf<f4> n4;
+    struct Release {
+        DevBuf<int32_t>& a; DevBuf<float>& b; DevBuf<float>& c; DevBuf<f4>& d;
+        ~Release() { a.release(); b.release(); c.release(); d.release(); }
+    } rel{nids, ndists, scratch, n4};
+    PM_CUDA_TRY(ctx, nids.reserve((size_t)knn * n));
+    PM_CUDA_TRY(ctx, ndists.reserve((size_t)knn * n));
+    PM_CUDA_TRY(ctx, n4.reserve(n));
+    // scratch: densities n | eig_values 3n | eig_vectors 9n | mean_dists n | normals3 3n | ids-as-float knn*n
+    const size_t off_den = 0, off_val = (size_t)n, off_vec = 4 * (size_t)n, off_md = 13 * (size_t)n, off_n3 = 14 * (size_t)n, off_ids = 17 * (size_t)n;
+    PM_CUDA_TRY(ctx, scratch.reserve(17 * (size_t)n + (out->matched_ids ? (size_t)knn * n : 0)));
+    cudaStream_t st = sub->stream;
+    IcpState* h = sub->state_host;
+    h->degenerate = 0;
+    s = push_state(sub);
+    if (s == PMGPU_OK) s = launch_knn(sub, sub->tree_view(), sub->ref_sorted.p, nullptr, n, false, false, true, knn, max_dist * max_dist, nids.p, ndists.p);
+    if (s == PMGPU_OK)
+        s = launch_normals(sub, sub->ref_orig.p, n, nids.p, ndists.p, knn, flags, n4.p, out->densities ? scratch.p + off_den : nullptr,
+                           out->eig_values ? scratch.p + off_val : nullptr, out->eig_vectors ? scratch.p + off_vec : nullptr,
+                           out->mean_dists ? scratch.p + off_md : nullptr);
+    if (s != PMGPU_OK) return fail(ctx, s, sub->err.c_str());
+    auto copy_out = [&](float* dst, int ld, const float* src, int span) -> cudaError_t {
+        if (!dst) return cudaSuccess;
+        if (ld == span) return cudaMemcpyAsync(dst, src, (size_t)span * n * sizeof(float), cudaMemcpyDefault, st);
+        return cudaMemcpy2DAsync(dst, (size_t)ld * sizeof(float), src, (size_t)span * sizeof(float), (size_t)span * sizeof(float), n, cudaMemcpyDefault, st);
+    };
+    if (out->normals) {
+        unpack_f4_kernel<<<(n + 255) / 256, 256, 0, st>>>(n4.p, n, scratch.p + off_n3);
+        sub->launches += 1;
+        PM_CUDA_TRY(ctx, copy_out(out->normals, out->normals_ld, scratch.p + off_n3, 3));
+    }
+    PM_CUDA_TRY(ctx, copy_out(out->densities, out->densities_ld, scratch.p + off_den, 1));
+    PM_CUDA_TRY(ctx, copy_out(out->eig_values, out->eig_values_ld, scratch.p + off_val, 3));
+    PM_CUDA_TRY(ctx, copy_out(out->eig_vectors, out->eig_vectors_ld, scratch.p + off_vec, 9));
+    PM_CUDA_TRY(ctx, copy_out(out->mean_dists, out->mean_dists_ld, scratch.p + off_md, 1));
+    if (out->matched_ids) {
+        const size_t total = (size_t)knn * n;
+        ids_to_float_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(nids.p, total, scratch.p + off_ids);
+        sub->launches += 1;
+        PM_CUDA_TRY(ctx, copy_out(out->matched_ids, out->matched_ids_ld, scratch.p + off_ids, knn));
+    }
+    s = pull_state(sub);
+    if (s != PMGPU_OK) return fail(ctx, s, sub->err.c_str());
+    PM_CUDA_TRY(ctx, cudaGetLastError());
+    if (degenerate_out) *degenerate_out = h->degenerate;
+    return PMGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,437 @@
+// minimize.cu — K4-K7: ErrorMinimizer::compute without ever building ErrorElements.
+//
+// Reference path per iteration (ErrorMinimizer.cpp:58-193, then PointToPlane.cpp:171-312 or
+// PointToPoint.cpp:61-101): compact the kept pairs into new matrices, gather the matched reference
+// columns, build F / wF / deltas temporaries, run a 6xM.Mx6 GEMM, solve.  Here one streaming
+// kernel re-derives the transformed reading point, reads (id, dist), applies the collapsed outlier
+// threshold (select.cu), gathers the matched reference point (+ normal) and accumulates the
+// normal-equation sums in fp64 registers; warp shuffles -> shared memory -> one partial row per
+// block; a one-block kernel reduces the rows in a fixed order (deterministic), solves, converts to
+// a 4x4, composes T_iter <- dT * T_iter and evaluates the Counter / Differential checkers, all on
+// the device.  Per-pair terms (cross product, residual dot product, w*F) are computed in float
+// with the reference's operation order; only the long sums are carried in fp64.
+//
+// Algorithmic bytes per match: reading 16 + id 4 + dist 4 + reference gather 16 (+ normal gather
+// 16 for point-to-plane) = 40 / 56 B.
+#include "core/linalg.h"
+#include "pmgpu_internal.cuh"
+
+namespace pm {
+
+namespace {
+
+// columns of a partial row
+//  point-to-plane : [0..20] upper triangle of A (row-major over i <= j), [21..26] sum wF*dot
+//  point-to-point : [0] sum w, [1..3] sum w p, [4..6] sum w q, [7..15] sum (w q_r) p_c  (r + 3 c)
+//  both           : [NS-4] kept pairs, [NS-3] rejected matches, [NS-2] rejected points, [NS-1] points seen
+constexpr int NS_PLANE = 27 + 4;
+constexpr int NS_POINT = 16 + 4;
+constexpr int NS_COV = 42;
+constexpr int NS_MAX = 42;
+constexpr int ACC_BLOCK = 256;
+
+template <int NS>
+__device__ __forceinline__ void block_reduce_store(double* acc, double* __restrict__ out_row) {
+    __shared__ double sh[ACC_BLOCK / 32][NS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < NS; ++c) {
+        double v = acc[c];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) sh[warp][c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NS) {
+        double v = 0.0;
+        for (int w = 0; w < ACC_BLOCK / 32; ++w) v += sh[w][threadIdx.x];
+        out_row[threadIdx.x] = v;
+    }
+}
+
+__device__ __forceinline__ float pair_weight(const IcpState* st, float d) {
+    if (d == pm_inf()) return 0.f;  // ErrorMinimizer.cpp:103-106: invalid matches are skipped
+    return st->has_filters ? ((d <= st->limit_all) ? 1.f : 0.f) : 1.f;
+}
+
+template <int MODE>  // 0 point-to-point, 1 point-to-plane
+__global__ void __launch_bounds__(ACC_BLOCK) accumulate_kernel(const f4* __restrict__ reading, int nq, int k, const int32_t* __restrict__ ids,
+                                                               const float* __restrict__ dists, const f4* __restrict__ ref,
+                                                               const f4* __restrict__ normals, const IcpState* __restrict__ state, int gated,
+                                                               double* __restrict__ partials) {
+    constexpr int NS = MODE == 1 ? NS_PLANE : NS_POINT;
+    __shared__ Mat4 sT;
+    if (gated && state->iterate == 0) return;
+    if (threadIdx.x < 16) sT.m[threadIdx.x] = state->T_iter.m[threadIdx.x];
+    __syncthreads();
+    double acc[NS];
+#pragma unroll
+    for (int c = 0; c < NS; ++c) acc[c] = 0.0;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
+        const f4 p = transform_point(sT, reading[i]);
+        bool match_exist = false;
+        for (int kk = 0; kk < k; ++kk) {
+            const float d = dists[(size_t)i * k + kk];
+            if (d == pm_inf()) continue;
+            const float w = pair_weight(state, d);
+            if (w == 0.f) { acc[NS - 3] += 1.0; continue; }
+            match_exist = true;
+            acc[NS - 4] += 1.0;
+            const int id = ids[(size_t)i * k + kk];
+            const f4 q = __ldg(ref + id);
+            if (MODE == 1) {
+                const f4 n = __ldg(normals + id);
+                float F[6], wF[6];
+                F[0] = fsub(fmul(p.y, n.z), fmul(p.z, n.y));  // crossProduct, ErrorMinimizer.cpp:304-306
+                F[1] = fsub(fmul(p.z, n.x), fmul(p.x, n.z));
+                F[2] = fsub(fmul(p.x, n.y), fmul(p.y, n.x));
+                F[3] = n.x; F[4] = n.y; F[5] = n.z;
+#pragma unroll
+                for (int a = 0; a < 6; ++a) wF[a] = fmul(w, F[a]);
+                // dot(deltas, normals) accumulated from zero, PointToPlane.cpp:233-240
+                float dot = fmul(fsub(p.x, q.x), n.x);
+                dot = fadd(dot, fmul(fsub(p.y, q.y), n.y));
+                dot = fadd(dot, fmul(fsub(p.z, q.z), n.z));
+                int c = 0;
+#pragma unroll
+                for (int a = 0; a < 6; ++a)
+#pragma unroll
+                    for (int b = a; b < 6; ++b) acc[c++] += (double)wF[a] * (double)F[b];
+#pragma unroll
+                for (int a = 0; a < 6; ++a) acc[21 + a] += (double)wF[a] * (double)dot;
+            } else {
+                acc[0] += (double)w;
+                const float wp[3] = {fmul(p.x, w), fmul(p.y, w), fmul(p.z, w)};
+                const float wq[3] = {fmul(q.x, w), fmul(q.y, w), fmul(q.z, w)};
+                const float pc[3] = {p.x, p.y, p.z};
+#pragma unroll
+                for (int a = 0; a < 3; ++a) { acc[1 + a] += (double)wp[a]; acc[4 + a] += (double)wq[a]; }
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) acc[7 + r + 3 * c] += (double)wq[r] * (double)pc[c];
+            }
+        }
+        if (!match_exist) acc[NS - 2] += 1.0;
+        acc[NS - 1] += 1.0;
+    }
+    block_reduce_store<NS>(acc, partials + (size_t)blockIdx.x * NS_MAX);
+}
+
+// Censi covariance sums (PointToPlaneWithCov.cpp:100-150, PointToPointWithCov.cpp:84-135):
+// [0..20] J_hessian upper triangle, [21..41] (d2J_dZdX d2J_dZdX^T) upper triangle.
+template <int MODE>
+__global__ void __launch_bounds__(ACC_BLOCK) cov_accumulate_kernel(const f4* __restrict__ reading, int nq, int k, const int32_t* __restrict__ ids,
+                                                                   const float* __restrict__ dists, const f4* __restrict__ ref,
+                                                                   const f4* __restrict__ normals, const IcpState* __restrict__ state,
+                                                                   double* __restrict__ partials) {
+    __shared__ Mat4 sT;
+    __shared__ float sPar[12];  // alpha beta gamma tx ty tz | mean_reading | mean_reference
+    if (threadIdx.x < 16) sT.m[threadIdx.x] = state->T_match.m[threadIdx.x];
+    if (threadIdx.x == 0) {
+        const float* t = state->dT.m;
+        const float beta = -asinf(t[2]);
+        const float alpha = atan2f(t[2 + 4], t[2 + 8]);
+        const float gamma = atan2f(t[1] / cosf(beta), t[0] / cosf(beta));
+        sPar[0] = alpha; sPar[1] = beta; sPar[2] = gamma;
+        sPar[3] = t[12]; sPar[4] = t[13]; sPar[5] = t[14];
+        for (int a = 0; a < 3; ++a) {
+            sPar[6 + a] = MODE == 0 ? (float)state->mean_reading[a] : 0.f;
+            sPar[9 + a] = MODE == 0 ? (float)state->mean_reference[a] : 0.f;
+        }
+    }
+    __syncthreads();
+    const float alpha = sPar[0], beta = sPar[1], gamma = sPar[2], t_x = sPar[3], t_y = sPar[4], t_z = sPar[5];
+    double acc[NS_COV];
+#pragma unroll
+    for (int c = 0; c < NS_COV; ++c) acc[c] = 0.0;
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
+        const f4 p = transform_point(sT, reading[i]);
+        for (int kk = 0; kk < k; ++kk) {
+            const float d = dists[(size_t)i * k + kk];
+            if (pair_weight(state, d) == 0.f) continue;
+            const int id = ids[(size_t)i * k + kk];
+            const f4 q = __ldg(ref + id);
+            float rp[3] = {p.x, p.y, p.z}, fp[3] = {q.x, q.y, q.z}, nrm[3] = {1.f, 1.f, 1.f};
+            if (MODE == 1) {
+                const f4 n = __ldg(normals + id);
+                nrm[0] = n.x; nrm[1] = n.y; nrm[2] = n.z;
+            } else {
+                // the reference evaluates the point-to-point covariance on the de-meaned clouds
+                for (int a = 0; a < 3; ++a) { rp[a] = fsub(rp[a], sPar[6 + a]); fp[a] = fsub(fp[a], sPar[9 + a]); }
+            }
+            const float reading_range = sqrtf(rp[0] * rp[0] + rp[1] * rp[1] + rp[2] * rp[2]);
+            const float rd[3] = {rp[0] / reading_range, rp[1] / reading_range, rp[2] / reading_range};
+            const float reference_range = sqrtf(fp[0] * fp[0] + fp[1] * fp[1] + fp[2] * fp[2]);
+            const float fd[3] = {fp[0] / reference_range, fp[1] / reference_range, fp[2] / reference_range};
+            const float n_alpha = nrm[2] * rd[1] - nrm[1] * rd[2];
+            const float n_beta = nrm[0] * rd[2] - nrm[2] * rd[0];
+            const float n_gamma = nrm[1] * rd[0] - nrm[0] * rd[1];
+            float E = nrm[0] * (rp[0] - gamma * rp[1] + beta * rp[2] + t_x - fp[0]);
+            E += nrm[1] * (gamma * rp[0] + rp[1] - alpha * rp[2] + t_y - fp[1]);
+            E += nrm[2] * (-beta * rp[0] + alpha * rp[1] + rp[2] + t_z - fp[2]);
+            float N_reading = nrm[0] * (rd[0] - gamma * rd[1] + beta * rd[2]);
+            N_reading += nrm[1] * (gamma * rd[0] + rd[1] - alpha * rd[2]);
+            N_reading += nrm[2] * (-beta * rd[0] + alpha * rd[1] + rd[2]);
+            const float N_reference = -(nrm[0] * fd[0] + nrm[1] * fd[1] + nrm[2] * fd[2]);
+            const float v[6] = {nrm[0], nrm[1], nrm[2], reading_range * n_alpha, reading_range * n_beta, reading_range * n_gamma};
+            const float er = E + reading_range * N_reading;
+            const float d1[6] = {nrm[0] * N_reading, nrm[1] * N_reading, nrm[2] * N_reading, n_alpha * er, n_beta * er, n_gamma * er};
+            const float d2[6] = {nrm[0] * N_reference, nrm[1] * N_reference, nrm[2] * N_reference, reference_range * n_alpha * N_reference,
+                                 reference_range * n_beta * N_reference, reference_range * n_gamma * N_reference};
+            int c = 0;
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int b = a; b < 6; ++b) {
+                    acc[c] += (double)v[a] * (double)v[b];
+                    acc[21 + c] += (double)d1[a] * (double)d1[b] + (double)d2[a] * (double)d2[b];
+                    ++c;
+                }
+        }
+    }
+    block_reduce_store<NS_COV>(acc, partials + (size_t)blockIdx.x * NS_MAX);
+}
+
+// fixed-order reduction of the per-block rows: 256 threads = 32 columns x 8 slices (two rounds
+// when there are more than 32 columns)
+__device__ void reduce_rows(const double* __restrict__ partials, int nblocks, int ns, double* sums) {
+    __shared__ double sh[8][NS_MAX];
+    const int slice = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c = lane; c < ns; c += 32) {
+        double v = 0.0;
+        for (int b = slice; b < nblocks; b += 8) v += partials[(size_t)b * NS_MAX + c];
+        sh[slice][c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < ns) {
+        double v = 0.0;
+        for (int s = 0; s < 8; ++s) v += sh[s][threadIdx.x];
+        sums[threadIdx.x] = v;
+    }
+    __syncthreads();
+}
+
+__device__ void expand_sym6(const double* tri, double* A) {
+    int c = 0;
+    for (int a = 0; a < 6; ++a)
+        for (int b = a; b < 6; ++b) { A[a + 6 * b] = tri[c]; A[b + 6 * a] = tri[c]; ++c; }
+}
+
+// CounterTransformationChecker + DifferentialTransformationChecker
+// (TransformationCheckersImpl.cpp:45-158), in the chain order the reference configs use.
+__device__ void run_checkers(IcpState* st, const pmgpu_icp_params& ck) {
+    st->counter += 1;
+    if (st->counter >= ck.max_iterations) { st->iterate = 0; return; }  // MaxNumIterationsReached, ICP.cpp:423-427
+    if (!ck.use_differential) return;
+    const int len = st->hist_len;
+    const Quat q = quat_from_mat4(st->T_iter);
+    float* hq = st->hist_q[len % PM_MAX_HISTORY];
+    float* ht = st->hist_t[len % PM_MAX_HISTORY];
+    hq[0] = q.w; hq[1] = q.x; hq[2] = q.y; hq[3] = q.z;
+    ht[0] = st->T_iter.m[12]; ht[1] = st->T_iter.m[13]; ht[2] = st->T_iter.m[14];
+    st->hist_len = len + 1;
+    const int size = len + 1;
+    float c0 = 0.f, c1 = 0.f;
+    if (size > ck.smooth_length) {
+        for (int i = size - 1; i >= size - ck.smooth_length; --i) {
+            const float* a = st->hist_q[i % PM_MAX_HISTORY];
+            const float* b = st->hist_q[(i - 1) % PM_MAX_HISTORY];
+            const Quat qa = {a[0], a[1], a[2], a[3]}, qb = {b[0], b[1], b[2], b[3]};
+            c0 += fabsf(quat_angular_distance(qa, qb));
+            const float* ta = st->hist_t[i % PM_MAX_HISTORY];
+            const float* tb = st->hist_t[(i - 1) % PM_MAX_HISTORY];
+            const float dx = ta[0] - tb[0], dy = ta[1] - tb[1], dz = ta[2] - tb[2];
+            c1 += fabsf(sqrtf(dx * dx + dy * dy + dz * dz));
+        }
+        c0 /= (float)ck.smooth_length;
+        c1 /= (float)ck.smooth_length;
+        if (c0 < ck.min_diff_rot_err && c1 < ck.min_diff_trans_err) st->iterate = 0;
+    }
+    if (c0 != c0 || c1 != c1) {
+        if (st->status == 0) st->status = PMGPU_ERR_NAN;
+        st->iterate = 0;
+    }
+}
+
+// mode bits: 1 = reduce partial rows into sums, 2 = solve from sums
+template <int MODE>
+__global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ sums, int phase,
+                                                       IcpState* state, int gated, int compose, pmgpu_icp_params ck, long long total_points_k) {
+    constexpr int NS = MODE == 1 ? NS_PLANE : NS_POINT;
+    if (gated && state->iterate == 0) return;
+    if (phase & 1) reduce_rows(partials, nblocks, NS, sums);
+    if (!(phase & 2) || threadIdx.x != 0) return;
+    (void)total_points_k;
+    const double kept = sums[NS - 4], rej_matches = sums[NS - 3], rej_points = sums[NS - 2], seen = sums[NS - 1];
+    // ErrorMinimizer.cpp:139-140: ratios over knn * number of reading points (all ranks)
+    const float denom = (float)(seen * (double)ck.knn);
+    state->stats[0] = (float)kept / denom;
+    state->stats[2] = (float)rej_matches;
+    state->stats[3] = (float)rej_points;
+    state->stats[4] = (float)kept;
+    state->T_match = state->T_iter;
+    if (!(kept > 0.0)) {
+        if (state->status == 0) state->status = PMGPU_ERR_NO_POINT_TO_MINIMIZE;
+        state->iterate = 0;
+        return;
+    }
+    Mat4 dT;
+    if (MODE == 1) {
+        state->stats[1] = (float)kept / denom;  // all weights are 1: sum w == kept
+        double A[36], b[6], x[6];
+        expand_sym6(sums, A);
+        for (int a = 0; a < 6; ++a) b[a] = -sums[21 + a];
+        solve_psd6(A, b, x);
+        float xf[6];
+        for (int a = 0; a < 6; ++a) xf[a] = (float)x[a];
+        angle_axis_to_mat4(xf, dT);
+    } else {
+        const double W = sums[0];
+        state->stats[1] = (float)W / denom;
+        const double inv = 1.0 / W;
+        double mp[3], mq[3], m[9], R[9];
+        for (int a = 0; a < 3; ++a) { mp[a] = sums[1 + a] * inv; mq[a] = sums[4 + a] * inv; }
+        // the reference keeps the centroids in float (PointToPoint.cpp:67-72)
+        float mpf[3], mqf[3];
+        for (int a = 0; a < 3; ++a) { mpf[a] = (float)mp[a]; mqf[a] = (float)mq[a]; state->mean_reading[a] = mpf[a]; state->mean_reference[a] = mqf[a]; }
+        // m = sum (w (q - mq)) (p - mp)^T = sum (w q) p^T - mq (sum w p)^T - (sum w q) mp^T + W mq mp^T
+        for (int c = 0; c < 3; ++c)
+            for (int r = 0; r < 3; ++r)
+                m[r + 3 * c] = sums[7 + r + 3 * c] - (double)mqf[r] * sums[1 + c] - sums[4 + r] * (double)mpf[c] + W * (double)mqf[r] * (double)mpf[c];
+        rotation_from_crosscov(m, R);
+        mat4_identity(dT);
+        for (int c = 0; c < 3; ++c)
+            for (int r = 0; r < 3; ++r) dT.m[r + 4 * c] = (float)R[r + 3 * c];
+        for (int r = 0; r < 3; ++r) {
+            double acc = 0.0;
+            for (int c = 0; c < 3; ++c) acc += (double)dT.m[r + 4 * c] * (double)mpf[c];
+            dT.m[12 + r] = (float)((double)mqf[r] - acc);  // PointToPoint.cpp:94
+        }
+    }
+    state->dT = dT;
+    if (compose) {
+        Mat4 Tn;
+        mat4_mul(dT, state->T_iter, Tn);  // ICP.cpp:411-412
+        state->T_iter = Tn;
+        state->iterations += 1;
+        run_checkers(state, ck);
+        // RigidTransformation::compute would throw on the next iteration (TransformationsImpl.cpp:62)
+        if (state->iterate && !mat4_is_rigid(Tn)) {
+            if (state->status == 0) state->status = PMGPU_ERR_NOT_ORTHOGONAL;
+            state->iterate = 0;
+        }
+    }
+}
+
+// inverse of a 6x6 by Gauss-Jordan with partial pivoting (J_hessian.inverse())
+__device__ void inverse6(const double* A, double* Inv) {
+    double M[36];
+    for (int i = 0; i < 36; ++i) { M[i] = A[i]; Inv[i] = (i % 7 == 0) ? 1.0 : 0.0; }
+    for (int k = 0; k < 6; ++k) {
+        int piv = k;
+        for (int i = k + 1; i < 6; ++i)
+            if (fabs(M[i + 6 * k]) > fabs(M[piv + 6 * k])) piv = i;
+        if (piv != k)
+            for (int j = 0; j < 6; ++j) {
+                double t = M[k + 6 * j]; M[k + 6 * j] = M[piv + 6 * j]; M[piv + 6 * j] = t;
+                t = Inv[k + 6 * j]; Inv[k + 6 * j] = Inv[piv + 6 * j]; Inv[piv + 6 * j] = t;
+            }
+        const double d = M[k + 6 * k];
+        for (int j = 0; j < 6; ++j) { M[k + 6 * j] /= d; Inv[k + 6 * j] /= d; }
+        for (int i = 0; i < 6; ++i) {
+            if (i == k) continue;
+            const double f = M[i + 6 * k];
+            if (f == 0.0) continue;
+            for (int j = 0; j < 6; ++j) { M[i + 6 * j] -= f * M[k + 6 * j]; Inv[i + 6 * j] -= f * Inv[k + 6 * j]; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) cov_finalize_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ sums, int phase,
+                                                           IcpState* state, float sensor_std_dev) {
+    if (phase & 1) reduce_rows(partials, nblocks, NS_COV, sums);
+    if (!(phase & 2) || threadIdx.x != 0) return;
+    double J[36], D[36], Ji[36], T1[36];
+    expand_sym6(sums, J);
+    expand_sym6(sums + 21, D);
+    inverse6(J, Ji);
+    for (int c = 0; c < 6; ++c)
+        for (int r = 0; r < 6; ++r) {
+            double s = 0.0;
+            for (int k = 0; k < 6; ++k) s += Ji[r + 6 * k] * D[k + 6 * c];
+            T1[r + 6 * c] = s;
+        }
+    const double s2 = (double)(sensor_std_dev * sensor_std_dev);
+    for (int c = 0; c < 6; ++c)
+        for (int r = 0; r < 6; ++r) {
+            double s = 0.0;
+            for (int k = 0; k < 6; ++k) s += T1[r + 6 * k] * Ji[k + 6 * c];
+            state->cov[r + 6 * c] = (float)(s2 * s);
+        }
+}
+
+}  // namespace
+
+int launch_minimize(pmgpu_ctx* ctx, int minimizer, bool compose_and_check, bool gated, const pmgpu_icp_params* checks) {
+    const bool plane = (minimizer == PMGPU_MIN_P2PLANE || minimizer == PMGPU_MIN_P2PLANE_COV);
+    if (plane && !ctx->has_normals) {
+        ctx->set_error("Field normals not found");
+        return PMGPU_ERR_NO_NORMALS;
+    }
+    cudaStream_t st = ctx->stream;
+    const int grid = grid_for(ctx->nq, ACC_BLOCK, ctx->num_sms, 4);
+    PM_CUDA_TRY(ctx, ctx->partials.reserve((size_t)(ctx->num_sms * 4 + 2) * NS_MAX));
+    double* sums = ctx->partials.p + (size_t)ctx->num_sms * 4 * NS_MAX;
+    pmgpu_icp_params ck;
+    if (checks) ck = *checks;
+    else {
+        ck = pmgpu_icp_params();
+        ck.max_iterations = 0x7fffffff;
+    }
+    ck.knn = ctx->k;
+    const int g = gated ? 1 : 0, comp = compose_and_check ? 1 : 0;
+    if (plane) accumulate_kernel<1><<<grid, ACC_BLOCK, 0, st>>>(ctx->reading.p, ctx->nq, ctx->k, ctx->ids.p, ctx->dists.p, ctx->ref_orig.p, ctx->ref_normals.p, ctx->state, g, ctx->partials.p);
+    else accumulate_kernel<0><<<grid, ACC_BLOCK, 0, st>>>(ctx->reading.p, ctx->nq, ctx->k, ctx->ids.p, ctx->dists.p, ctx->ref_orig.p, nullptr, ctx->state, g, ctx->partials.p);
+    ctx->launches += 1;
+    const int ns = plane ? NS_PLANE : NS_POINT;
+    if (ctx->nranks > 1) {
+        if (plane) finalize_kernel<1><<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 1, ctx->state, g, comp, ck, 0);
+        else finalize_kernel<0><<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 1, ctx->state, g, comp, ck, 0);
+        PM_TRY(comm_allreduce_f64(ctx, sums, ns));
+        if (plane) finalize_kernel<1><<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 2, ctx->state, g, comp, ck, 0);
+        else finalize_kernel<0><<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 2, ctx->state, g, comp, ck, 0);
+        ctx->launches += 2;
+    } else {
+        if (plane) finalize_kernel<1><<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 3, ctx->state, g, comp, ck, 0);
+        else finalize_kernel<0><<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 3, ctx->state, g, comp, ck, 0);
+        ctx->launches += 1;
+    }
+    PM_CUDA_TRY(ctx, cudaGetLastError());
+    return PMGPU_OK;
+}
+
+int launch_covariance(pmgpu_ctx* ctx, int minimizer, float sensor_std_dev) {
+    const bool plane = (minimizer == PMGPU_MIN_P2PLANE_COV);
+    cudaStream_t st = ctx->stream;
+    const int grid = grid_for(ctx->nq, ACC_BLOCK, ctx->num_sms, 4);
+    PM_CUDA_TRY(ctx, ctx->partials.reserve((size_t)(ctx->num_sms * 4 + 2) * NS_MAX));
+    double* sums = ctx->partials.p + (size_t)ctx->num_sms * 4 * NS_MAX;
+    if (plane) cov_accumulate_kernel<1><<<grid, ACC_BLOCK, 0, st>>>(ctx->reading.p, ctx->nq, ctx->k, ctx->ids.p, ctx->dists.p, ctx->ref_orig.p, ctx->ref_normals.p, ctx->state, ctx->partials.p);
+    else cov_accumulate_kernel<0><<<grid, ACC_BLOCK, 0, st>>>(ctx->reading.p, ctx->nq, ctx->k, ctx->ids.p, ctx->dists.p, ctx->ref_orig.p, nullptr, ctx->state, ctx->partials.p);
+    ctx->launches += 1;
+    if (ctx->nranks > 1) {
+        cov_finalize_kernel<<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 1, ctx->state, sensor_std_dev);
+        PM_TRY(comm_allreduce_f64(ctx, sums, NS_COV));
+        cov_finalize_kernel<<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 2, ctx->state, sensor_std_dev);
+        ctx->launches += 2;
+    } else {
+        cov_finalize_kernel<<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 3, ctx->state, sensor_std_dev);
+        ctx->launches += 1;
+    }
+    PM_CUDA_TRY(ctx, cudaGetLastError());
+    return PMGPU_OK;
+}
+
+}  // namespace pm

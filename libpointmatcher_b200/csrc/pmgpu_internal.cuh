@@ -1,0 +1,182 @@
+// pmgpu_internal.cuh — context, device-buffer bookkeeping and the kernel-launcher prototypes
+// shared by the translation units of libpmgpu.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/pmgpu.h"
+#include "core/common.h"
+#include "core/tree.h"
+
+namespace pm {
+
+// ---- error plumbing -------------------------------------------------------------------------
+#define PM_CUDA_TRY(ctx, expr)                                                                        \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess) {                                                                      \
+            (ctx)->set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" __FILE__ ":" + \
+                             std::to_string(__LINE__) + ")");                                         \
+            return PMGPU_ERR_CUDA;                                                                    \
+        }                                                                                             \
+    } while (0)
+
+#define PM_TRY(expr)                     \
+    do {                                 \
+        int _s = (expr);                 \
+        if (_s != PMGPU_OK) return _s;   \
+    } while (0)
+
+// growable device buffer
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc((void**)&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// ---- device-side state of one ICP registration -------------------------------------------------
+// Lives in device memory so that a whole iteration (match -> select -> weights -> minimise ->
+// compose -> check) runs without a host round trip.
+#define PM_MAX_FILTERS 8
+#define PM_HIST_BINS 2048
+#define PM_MAX_HISTORY 64   // ring of T_iter history for the Differential checker
+
+struct IcpState {
+    Mat4 T_iter;                 // cumulative transform applied to the reading (ICP.cpp:381)
+    Mat4 T_match;                // the transform the resident matches were computed with
+    Mat4 dT;                     // last incremental transform
+    int status;                  // first PMGPU_* error raised on the device, 0 if none
+    int iterate;                 // 1 while the checkers want another iteration
+    int iterations;              // iterations executed
+    int counter;                 // CounterTransformationChecker state
+    // select / weights
+    float limit[PM_MAX_FILTERS]; // per-filter squared-distance limit
+    float limit_all;             // min over filters: weight = dist <= limit_all
+    int has_filters;             // 0: empty chain (weight = dist != inf)
+    unsigned long long n_valid;  // number of finite distances (all ranks)
+    unsigned prefix;             // radix-select state
+    unsigned long long rank;     // remaining rank inside the current prefix bucket
+    // minimiser outputs
+    float cov[36];
+    float stats[5];              // pointUsedRatio, weightedPointUsedRatio, nbRejectedMatches, nbRejectedPoints, nbKept
+    double mean_reading[3], mean_reference[3]; // weighted centroids of the last point-to-point solve
+    // Differential checker history
+    float hist_q[PM_MAX_HISTORY][4];
+    float hist_t[PM_MAX_HISTORY][3];
+    int hist_len;
+    unsigned long long visits;   // reference points examined (Matcher::visitCounter)
+    int degenerate;              // degenerate normals counter (K8)
+};
+
+}  // namespace pm
+
+struct pmgpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    int num_sms = 148;
+
+    // reference (K1)
+    int nr = 0;
+    int depth = 0;
+    pm::DevBuf<f4> ref_orig;     // original order, (x, y, z, w)
+    pm::DevBuf<f4> ref_sorted;   // leaf order, w = original index bits
+    pm::DevBuf<f4> ref_normals;  // original order, (nx, ny, nz, 0)
+    pm::DevBuf<f4> nodes;        // 3 f4 per inner node
+    bool has_normals = false;
+    f4 root_lo, root_hi;
+    // build scratch
+    pm::DevBuf<uint64_t> keys_a, keys_b;
+    pm::DevBuf<uint32_t> perm_a, perm_b;
+    pm::DevBuf<uint32_t> node_box;  // 6 ordered-uint per node (lo xyz, hi xyz), heap index
+    pm::DevBuf<uint8_t> node_dim;
+    pm::DevBuf<uint8_t> cub_tmp;
+
+    // reading
+    int nq = 0;
+    pm::DevBuf<f4> reading;          // original order
+    pm::DevBuf<uint32_t> q_order;    // Morton order of the reading (query schedule)
+
+    // matches (K2)
+    int k = 0;
+    bool have_matches = false;
+    bool have_weights = false;
+    pm::DevBuf<int32_t> ids;     // k x nq
+    pm::DevBuf<float> dists;     // k x nq
+    pm::DevBuf<float> weights;   // k x nq, only materialised on request
+
+    // select (K3)
+    pm::DevBuf<unsigned> hist;   // PM_HIST_BINS
+    // minimiser partial sums (K4-K6)
+    pm::DevBuf<double> partials;
+    int partial_blocks = 0;
+
+    pm::IcpState* state = nullptr;   // device
+    pm::IcpState* state_host = nullptr;  // pinned host mirror
+
+    // multi-GPU
+    void* nccl_comm = nullptr;
+    int rank = 0, nranks = 1;
+
+    void set_error(const std::string& e) { err = e; }
+    pm::TreeView tree_view() const {
+        pm::TreeView t;
+        t.nodes = nodes.p;
+        t.pts = ref_sorted.p;
+        t.n = (uint32_t)nr;
+        t.depth = depth;
+        t.root_lo = root_lo;
+        t.root_hi = root_hi;
+        return t;
+    }
+};
+
+namespace pm {
+
+// tree_build.cu
+int build_tree(pmgpu_ctx* ctx);
+int morton_order(pmgpu_ctx* ctx);
+// knn.cu
+int launch_knn(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, const uint32_t* order, int nq, bool use_T, bool gated, bool qi_from_w, int k,
+               float max_r2, int32_t* ids, float* dists);
+// select.cu
+int launch_weights(pmgpu_ctx* ctx, int nfilters, const int* types, const float* params, bool gated);
+int launch_materialize_weights(pmgpu_ctx* ctx);
+// minimize.cu
+int launch_minimize(pmgpu_ctx* ctx, int minimizer, bool compose_and_check, bool gated, const pmgpu_icp_params* checks);
+int launch_covariance(pmgpu_ctx* ctx, int minimizer, float sensor_std_dev);
+// normals.cu
+int launch_normals(pmgpu_ctx* ctx, const f4* pts, int n, const int32_t* ids, const float* dists, int knn, int flags, f4* normals4,
+                   float* densities, float* eig_values, float* eig_vectors, float* mean_dists);
+// comm.cu
+int comm_allreduce_u32(pmgpu_ctx* ctx, unsigned* buf, size_t count);
+int comm_allreduce_u64(pmgpu_ctx* ctx, unsigned long long* buf, size_t count);
+int comm_allreduce_f64(pmgpu_ctx* ctx, double* buf, size_t count);
+
+inline int grid_for(int n, int block, int num_sms, int per_sm) {
+    long g = ((long)n + block - 1) / block;
+    const long cap = (long)num_sms * per_sm;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+}  // namespace pm

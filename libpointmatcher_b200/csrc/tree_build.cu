@@ -1,0 +1,197 @@
+// tree_build.cu — K1: builds the search structure of KDTreeMatcher::init (MatchersImpl.cpp:77-83)
+// on the device.  See core/tree.h for the layout.
+//
+// Level by level, top down: (1) every node's bounding box by warp-aggregated integer atomics on
+// order-preserving float keys, (2) the split axis = widest box extent, (3) one stable radix sort
+// of (segment id << 32 | ordered coordinate) which median-splits every segment of the level at
+// once (segments are position ranges, so the sort cannot move a point across segments).
+// The only library call is cub::DeviceRadixSort (part of the CUDA toolkit) — the build runs once
+// per init(); the per-iteration kernels are all hand-written.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "pmgpu_internal.cuh"
+
+namespace pm {
+
+namespace {
+
+__global__ void iota_kernel(uint32_t* perm, uint32_t n) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) perm[p] = p;
+}
+
+__global__ void init_boxes_kernel(uint32_t* box, uint32_t nnodes) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nnodes) {
+        box[6 * i + 0] = 0xffffffffu; box[6 * i + 1] = 0xffffffffu; box[6 * i + 2] = 0xffffffffu;
+        box[6 * i + 3] = 0u; box[6 * i + 4] = 0u; box[6 * i + 5] = 0u;
+    }
+}
+
+// boxes of all nodes of `level`: node (heap index) = 2^level + seg_of(position)
+__global__ void level_boxes_kernel(const f4* __restrict__ pts, const uint32_t* __restrict__ perm, uint32_t n, int level,
+                                   uint32_t* __restrict__ box) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = p < n;
+    uint32_t node = 0xffffffffu, ox = 0, oy = 0, oz = 0;
+    if (active) {
+        const f4 pt = pts[perm ? perm[p] : p];
+        node = (1u << level) + seg_of(p, level, n);
+        ox = float_ord(pt.x); oy = float_ord(pt.y); oz = float_ord(pt.z);
+    }
+    const unsigned amask = __ballot_sync(0xffffffffu, active);
+    if (!active) return;
+    const unsigned group = __match_any_sync(amask, node);
+    const uint32_t lx = __reduce_min_sync(group, ox), ly = __reduce_min_sync(group, oy), lz = __reduce_min_sync(group, oz);
+    const uint32_t hx = __reduce_max_sync(group, ox), hy = __reduce_max_sync(group, oy), hz = __reduce_max_sync(group, oz);
+    if ((threadIdx.x & 31) == (unsigned)(__ffs(group) - 1)) {
+        uint32_t* b = box + 6 * (size_t)node;
+        atomicMin(b + 0, lx); atomicMin(b + 1, ly); atomicMin(b + 2, lz);
+        atomicMax(b + 3, hx); atomicMax(b + 4, hy); atomicMax(b + 5, hz);
+    }
+}
+
+// sort key of every point for the split of `level`: (segment, coordinate along the widest axis)
+__global__ void level_keys_kernel(const f4* __restrict__ pts, const uint32_t* __restrict__ perm, uint32_t n, int level,
+                                  const uint32_t* __restrict__ box, uint64_t* __restrict__ keys) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t seg = seg_of(p, level, n);
+    const uint32_t* b = box + 6 * (size_t)((1u << level) + seg);
+    const float ex = fsub(ord_float(b[3]), ord_float(b[0]));
+    const float ey = fsub(ord_float(b[4]), ord_float(b[1]));
+    const float ez = fsub(ord_float(b[5]), ord_float(b[2]));
+    int dim = 0;
+    float best = ex;
+    if (ey > best) { dim = 1; best = ey; }
+    if (ez > best) { dim = 2; }
+    const f4 pt = pts[perm[p]];
+    const float c = dim == 0 ? pt.x : (dim == 1 ? pt.y : pt.z);
+    keys[p] = ((uint64_t)seg << 32) | (uint64_t)float_ord(c);
+}
+
+__global__ void gather_sorted_kernel(const f4* __restrict__ pts, const uint32_t* __restrict__ perm, uint32_t n, f4* __restrict__ out) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t src = perm[p];
+    const f4 pt = pts[src];
+    out[p] = make_float4(pt.x, pt.y, pt.z, __uint_as_float(src));
+}
+
+// inner node i (heap index) -> the boxes of its two children, interleaved per axis
+__global__ void pack_nodes_kernel(const uint32_t* __restrict__ box, uint32_t n_inner, f4* __restrict__ nodes) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (i > n_inner) return;
+    const uint32_t* l = box + 6 * (size_t)(2 * i);
+    const uint32_t* r = box + 6 * (size_t)(2 * i + 1);
+    f4* o = nodes + 3 * (size_t)(i - 1);
+    o[0] = make_float4(ord_float(l[0]), ord_float(l[3]), ord_float(r[0]), ord_float(r[3]));
+    o[1] = make_float4(ord_float(l[1]), ord_float(l[4]), ord_float(r[1]), ord_float(r[4]));
+    o[2] = make_float4(ord_float(l[2]), ord_float(l[5]), ord_float(r[2]), ord_float(r[5]));
+}
+
+// 30-bit Morton code of a point inside the cloud's bounding box
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__global__ void morton_keys_kernel(const f4* __restrict__ pts, uint32_t n, const uint32_t* __restrict__ box, uint32_t* __restrict__ keys,
+                                   uint32_t* __restrict__ vals) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const float lx = ord_float(box[6 + 0]), ly = ord_float(box[6 + 1]), lz = ord_float(box[6 + 2]);
+    const float hx = ord_float(box[6 + 3]), hy = ord_float(box[6 + 4]), hz = ord_float(box[6 + 5]);
+    const f4 pt = pts[p];
+    const float sx = hx > lx ? 1023.f / (hx - lx) : 0.f, sy = hy > ly ? 1023.f / (hy - ly) : 0.f, sz = hz > lz ? 1023.f / (hz - lz) : 0.f;
+    const uint32_t ix = (uint32_t)fminf(fmaxf((pt.x - lx) * sx, 0.f), 1023.f);
+    const uint32_t iy = (uint32_t)fminf(fmaxf((pt.y - ly) * sy, 0.f), 1023.f);
+    const uint32_t iz = (uint32_t)fminf(fmaxf((pt.z - lz) * sz, 0.f), 1023.f);
+    keys[p] = spread10(ix) | (spread10(iy) << 1) | (spread10(iz) << 2);
+    vals[p] = p;
+}
+
+inline unsigned blocks_for(uint32_t n, int block) { return (unsigned)((n + (uint32_t)block - 1) / (uint32_t)block); }
+
+}  // namespace
+
+int build_tree(pmgpu_ctx* ctx) {
+    const uint32_t n = (uint32_t)ctx->nr;
+    cudaStream_t st = ctx->stream;
+    const int D = tree_depth_for(n);
+    ctx->depth = D;
+    const uint32_t nnodes = 2u << D;  // heap indices 1 .. 2^(D+1)-1
+    PM_CUDA_TRY(ctx, ctx->node_box.reserve(6 * (size_t)nnodes));
+    PM_CUDA_TRY(ctx, ctx->perm_a.reserve(n));
+    PM_CUDA_TRY(ctx, ctx->perm_b.reserve(n));
+    PM_CUDA_TRY(ctx, ctx->keys_a.reserve(n));
+    PM_CUDA_TRY(ctx, ctx->keys_b.reserve(n));
+    PM_CUDA_TRY(ctx, ctx->ref_sorted.reserve(n));
+    PM_CUDA_TRY(ctx, ctx->nodes.reserve(3 * (size_t)(D > 0 ? (1u << D) : 1)));
+    size_t tmp_bytes = 0;
+    PM_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx->keys_a.p, ctx->keys_b.p, ctx->perm_a.p, ctx->perm_b.p, (int)n, 0, 64, st));
+    PM_CUDA_TRY(ctx, ctx->cub_tmp.reserve(tmp_bytes));
+
+    const int B = 256;
+    init_boxes_kernel<<<blocks_for(nnodes, B), B, 0, st>>>(ctx->node_box.p, nnodes);
+    iota_kernel<<<blocks_for(n, B), B, 0, st>>>(ctx->perm_a.p, n);
+    ctx->launches += 2;
+    uint32_t* perm = ctx->perm_a.p;
+    uint32_t* perm_alt = ctx->perm_b.p;
+    for (int l = 0; l <= D; ++l) {
+        level_boxes_kernel<<<blocks_for(n, B), B, 0, st>>>(ctx->ref_orig.p, perm, n, l, ctx->node_box.p);
+        ctx->launches += 1;
+        if (l == D) break;
+        level_keys_kernel<<<blocks_for(n, B), B, 0, st>>>(ctx->ref_orig.p, perm, n, l, ctx->node_box.p, ctx->keys_a.p);
+        size_t tb = ctx->cub_tmp.cap;
+        PM_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, ctx->keys_a.p, ctx->keys_b.p, perm, perm_alt, (int)n, 0, 32 + l, st));
+        ctx->launches += 2;
+        uint32_t* t = perm; perm = perm_alt; perm_alt = t;
+    }
+    gather_sorted_kernel<<<blocks_for(n, B), B, 0, st>>>(ctx->ref_orig.p, perm, n, ctx->ref_sorted.p);
+    ctx->launches += 1;
+    if (D > 0) {
+        const uint32_t n_inner = (1u << D) - 1;
+        pack_nodes_kernel<<<blocks_for(n_inner, B), B, 0, st>>>(ctx->node_box.p, n_inner, ctx->nodes.p);
+        ctx->launches += 1;
+    }
+    uint32_t rb[6];
+    PM_CUDA_TRY(ctx, cudaMemcpyAsync(rb, ctx->node_box.p + 6, sizeof(rb), cudaMemcpyDeviceToHost, st));
+    PM_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    PM_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->root_lo = make_float4(ord_float(rb[0]), ord_float(rb[1]), ord_float(rb[2]), 0.f);
+    ctx->root_hi = make_float4(ord_float(rb[3]), ord_float(rb[4]), ord_float(rb[5]), 0.f);
+    return PMGPU_OK;
+}
+
+// Query schedule: the reading is static during an ICP run (only T_iter changes), so its points
+// are visited in Morton order of their *untransformed* coordinates; a rigid motion preserves
+// locality, hence the 32 queries of a warp walk nearly the same tree path every iteration.
+int morton_order(pmgpu_ctx* ctx) {
+    const uint32_t n = (uint32_t)ctx->nq;
+    cudaStream_t st = ctx->stream;
+    PM_CUDA_TRY(ctx, ctx->q_order.reserve(n));
+    PM_CUDA_TRY(ctx, ctx->perm_a.reserve(n));
+    PM_CUDA_TRY(ctx, ctx->perm_b.reserve(n));
+    PM_CUDA_TRY(ctx, ctx->keys_a.reserve(n));  // reused as 2 x uint32 key arrays
+    PM_CUDA_TRY(ctx, ctx->node_box.reserve(12));
+    uint32_t* keys_in = reinterpret_cast<uint32_t*>(ctx->keys_a.p);
+    uint32_t* keys_out = keys_in + n;
+    size_t tmp_bytes = 0;
+    PM_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_in, keys_out, ctx->perm_a.p, ctx->q_order.p, (int)n, 0, 30, st));
+    PM_CUDA_TRY(ctx, ctx->cub_tmp.reserve(tmp_bytes));
+    const int B = 256;
+    init_boxes_kernel<<<1, 32, 0, st>>>(ctx->node_box.p, 2);
+    level_boxes_kernel<<<blocks_for(n, B), B, 0, st>>>(ctx->reading.p, nullptr, n, 0, ctx->node_box.p);
+    morton_keys_kernel<<<blocks_for(n, B), B, 0, st>>>(ctx->reading.p, n, ctx->node_box.p, keys_in, ctx->perm_a.p);
+    size_t tb = ctx->cub_tmp.cap;
+    PM_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, keys_in, keys_out, ctx->perm_a.p, ctx->q_order.p, (int)n, 0, 30, st));
+    ctx->launches += 4;
+    PM_CUDA_TRY(ctx, cudaGetLastError());
+    return PMGPU_OK;
+}
+
+}  // namespace pm

@@ -1,0 +1,495 @@
+"""Python mirror of the libpointmatcher plugin surface for the GPU hot path.
+
+Same module names, parameter names, defaults, bounds and error behaviour as the reference
+(`availableParameters()` of each class), so tests and configs read like
+the reference's.  Every module marshals to the C ABI (capi.py -> libpmgpu.so); nothing is
+computed in Python except the 4x4 bookkeeping of ICP::compute (ICP.cpp:264-313, 345-347, 448),
+which the reference also does on the host.  The C++ twin of this file is
+libpointmatcher_b200/host/PointMatcher.h.
+"""
+import numpy as np
+
+from . import capi
+
+
+# ---- exceptions (names of the reference) ----------------------------------------------------
+class InvalidParameter(RuntimeError):      # Parametrizable.h:101-104
+    pass
+
+
+class InvalidElement(RuntimeError):        # Registrar.h:69-72
+    pass
+
+
+class InvalidField(RuntimeError):          # PointMatcher.h:250-253
+    pass
+
+
+class ConvergenceError(RuntimeError):      # PointMatcher.h:148-151
+    pass
+
+
+class TransformationError(RuntimeError):   # PointMatcherSupport, TransformationsImpl.cpp:62
+    pass
+
+
+class ConfigurationError(RuntimeError):    # PointMatcher.h:83-100
+    pass
+
+
+_STATUS_TO_EXC = {
+    capi.ERR_UNSUPPORTED: ConfigurationError,
+    capi.ERR_NO_OUTLIER_TO_FILTER: ConvergenceError,
+    capi.ERR_BAD_QUANTILE: ConvergenceError,
+    capi.ERR_NO_POINT_TO_MINIMIZE: ConvergenceError,
+    capi.ERR_NAN: ConvergenceError,
+    capi.ERR_NO_NORMALS: InvalidField,
+    capi.ERR_NOT_ORTHOGONAL: TransformationError,
+    capi.ERR_BAD_ARG: InvalidParameter,
+}
+
+
+def _translate(fn, *a, **kw):
+    try:
+        return fn(*a, **kw)
+    except capi.PmGpuError as e:
+        exc = _STATUS_TO_EXC.get(e.code, RuntimeError)
+        raise exc(str(e)) from None
+
+
+# ---- Parametrizable (Parametrizable.cpp:170-207) ---------------------------------------------
+def _cast(kind, s):
+    s = str(s)
+    if kind is float:
+        return float(s)  # accepts "inf", "-inf", "nan" like lexical_cast_scalar_to_string (Parametrizable.h:53-64)
+    if kind is bool:
+        return bool(int(float(s)))
+    if kind is int:
+        return int(s)
+    return s
+
+
+class Parametrizable:
+    className = ""
+    #: rows of (name, doc, default, min, max, type) — availableParameters()
+    PARAMS = ()
+
+    def __init__(self, params=None):
+        params = dict(params or {})
+        self.parameters = {}
+        self.parametersUsed = set()
+        docs = {p[0]: p for p in self.PARAMS}
+        for name in params:
+            if name not in docs:
+                raise InvalidParameter("Parameter %s for module %s was set but is not used" % (name, self.className))
+        for name, _doc, default, lo, hi, kind in self.PARAMS:
+            val = str(params.get(name, default))
+            if kind in (int, float) and lo is not None:
+                try:
+                    v = _cast(kind, val)
+                except ValueError:
+                    raise InvalidParameter("Value %s of parameter %s in class %s cannot be parsed" % (val, name, self.className))
+                if v < _cast(kind, lo):
+                    raise InvalidParameter("Value %s of parameter %s in class %s is smaller than minimum admissible value %s"
+                                           % (val, name, self.className, lo))
+                if v > _cast(kind, hi):
+                    raise InvalidParameter("Value %s of parameter %s in class %s is larger than maximum admissible value %s"
+                                           % (val, name, self.className, hi))
+            self.parameters[name] = val
+
+    def get(self, name, kind=None):
+        if name not in self.parameters:
+            raise InvalidParameter("Parameter %s does not exist in class %s" % (name, self.className))
+        self.parametersUsed.add(name)
+        kind = kind or {p[0]: p[5] for p in self.PARAMS}[name]
+        return _cast(kind, self.parameters[name])
+
+    @classmethod
+    def availableParameters(cls):
+        return list(cls.PARAMS)
+
+
+# ---- DataPoints / Matches (PointMatcher.h:207-391) -------------------------------------------
+class DataPoints:
+    """features: (N, 4) float32 (x, y, z, 1); descriptors: dict name -> (N, span) float32."""
+
+    def __init__(self, features, descriptors=None):
+        self.features = np.ascontiguousarray(features, np.float32)
+        self.descriptors = dict(descriptors or {})
+
+    def descriptorExists(self, name):
+        return name in self.descriptors
+
+    def getDescriptorViewByName(self, name):
+        if name not in self.descriptors:
+            raise InvalidField("Field %s not found" % name)
+        return self.descriptors[name]
+
+    def copy(self):
+        return DataPoints(self.features.copy(), {k: v.copy() for k, v in self.descriptors.items()})
+
+
+class Matches:
+    InvalidId = -1
+    InvalidDist = np.float32(np.inf)
+
+    def __init__(self, dists, ids):
+        self.dists, self.ids = dists, ids
+
+    def getDistsQuantile(self, quantile):
+        """Matches.cpp:60-87 on the GPU select kernel (through a throw-away TrimmedDist filter)."""
+        raise NotImplementedError("use TrimmedDistOutlierFilter / the limits returned by OutlierFilters.compute")
+
+
+# ---- pipeline: the device context shared by the modules of one ICP chain ----------------------
+class _Bound:
+    """Modules talk to one capi.Context; a stand-alone module creates its own lazily."""
+    _ctx = None
+
+    def bind(self, ctx):
+        self._ctx = ctx
+
+    @property
+    def ctx(self):
+        if self._ctx is None:
+            self._ctx = capi.Context(0)
+        return self._ctx
+
+
+# ---- Matcher (MatchersImpl.h:74-103) -----------------------------------------------------------
+class KDTreeMatcher(Parametrizable, _Bound):
+    className = "KDTreeMatcher"
+    PARAMS = (
+        ("knn", "number of nearest neighbors to consider it the reference", "1", "1", "2147483647", int),
+        ("epsilon", "approximation to use for the nearest-neighbor search", "0", "0", "inf", float),
+        ("searchType", "Nabo search type. 0: brute force, 1: kd-tree linear heap, 2: kd-tree tree heap", "1", "0", "2", int),
+        ("maxDist", "maximum distance to consider for neighbors", "inf", "0", "inf", float),
+    )
+
+    def __init__(self, params=None):
+        Parametrizable.__init__(self, params)
+        self.knn = self.get("knn")
+        self.epsilon = self.get("epsilon")
+        self.searchType = self.get("searchType")
+        self.maxDist = self.get("maxDist")
+        self.visitCounter = 0
+
+    def init(self, filteredReference):
+        nrm = filteredReference.descriptors.get("normals")
+        _translate(self.ctx.set_reference, filteredReference.features, nrm)
+        self._ref = filteredReference
+
+    def findClosests(self, filteredReading, T=None):
+        """Matches of T * filteredReading against the reference passed to init()."""
+        ctx = self.ctx
+        if getattr(ctx, "_reading_obj", None) is not filteredReading:
+            _translate(ctx.set_reading, filteredReading.features)
+            ctx._reading_obj = filteredReading
+        ids, dists, visits = _translate(ctx.knn, T, self.knn, self.epsilon, self.maxDist)
+        self.visitCounter += visits
+        return Matches(dists, ids)
+
+    def getVisitCount(self):
+        return self.visitCounter
+
+    def resetVisitCount(self):
+        self.visitCounter = 0
+
+
+# ---- OutlierFilters (OutlierFiltersImpl.h:76-139) ---------------------------------------------
+class _DistFilter(Parametrizable, _Bound):
+    TYPE = None
+    PARAM = None
+
+    def __init__(self, params=None):
+        Parametrizable.__init__(self, params)
+        self.value = self.get(self.PARAM)
+
+    def spec(self):
+        return (self.TYPE, self.value)
+
+    def compute(self, filteredReading, filteredReference, matches):
+        w, _ = _translate(self.ctx.weights, [self.spec()])
+        return w
+
+
+class MaxDistOutlierFilter(_DistFilter):
+    className = "MaxDistOutlierFilter"
+    TYPE, PARAM = capi.FILTER_MAXDIST, "maxDist"
+    PARAMS = (("maxDist", "threshold distance (Euclidean norm)", "1", "0.0000001", "inf", float),)
+
+
+class MedianDistOutlierFilter(_DistFilter):
+    className = "MedianDistOutlierFilter"
+    TYPE, PARAM = capi.FILTER_MEDIANDIST, "factor"
+    PARAMS = (("factor", "points farther away factor * median will be considered outliers.", "3", "0.0000001", "inf", float),)
+
+
+class TrimmedDistOutlierFilter(_DistFilter):
+    className = "TrimmedDistOutlierFilter"
+    TYPE, PARAM = capi.FILTER_TRIMMEDDIST, "ratio"
+    PARAMS = (("ratio", "percentage to keep", "0.85", "0.0000001", "1.0", float),)
+
+
+class OutlierFilters(list, _Bound):
+    """OutlierFilter.cpp:63-103: product of all filters' weights; empty chain -> dist != inf."""
+
+    def compute(self, filteredReading, filteredReference, matches):
+        w, limits = _translate(self.ctx.weights, [f.spec() for f in self])
+        self.limits = limits
+        return w
+
+
+# ---- ErrorMinimizers ---------------------------------------------------------------------------
+class _Minimizer(Parametrizable, _Bound):
+    KIND = None
+
+    def __init__(self, params=None):
+        Parametrizable.__init__(self, params)
+        self.sensorStdDev = self.get("sensorStdDev") if any(p[0] == "sensorStdDev" for p in self.PARAMS) else 0.01
+        if any(p[0] == "force2D" for p in self.PARAMS):
+            force2D, force4DOF = self.get("force2D"), self.get("force4DOF")
+            if force2D and force4DOF:
+                raise ConfigurationError("Force 2D cannot be used together with force4DOF.")
+            if force2D or force4DOF:
+                raise ConfigurationError("GPU module: force2D / force4DOF are not supported")
+        self._cov = np.zeros((6, 6), np.float32)
+        self._stats = dict(pointUsedRatio=-1.0, weightedPointUsedRatio=-1.0)
+
+    def compute(self, filteredReading, filteredReference, outlierWeights, matches):
+        """Uses the matches / weights resident on the device (the arguments are the host copies
+        the reference interface passes around)."""
+        T, cov, stats = _translate(self.ctx.minimize, self.KIND, self.sensorStdDev)
+        if cov is not None:
+            self._cov = cov
+        self._stats = stats
+        return T
+
+    def getCovariance(self):
+        return self._cov
+
+    def getPointUsedRatio(self):
+        return self._stats["pointUsedRatio"]
+
+    def getWeightedPointUsedRatio(self):
+        return self._stats["weightedPointUsedRatio"]
+
+    def getOverlap(self):
+        return self._stats["weightedPointUsedRatio"]
+
+
+_P2PLANE_PARAMS = (
+    ("force2D", "If set to true(1), the minimization will be forced to give a solution in 2D.", "0", "0", "1", bool),
+    ("force4DOF", "If set to true(1), the minimization will optimize only yaw and translation.", "0", "0", "1", bool),
+)
+_COV_PARAM = (("sensorStdDev", "sensor standard deviation", "0.01", "0.", "inf", float),)
+
+
+class PointToPointErrorMinimizer(_Minimizer):
+    className = "PointToPointErrorMinimizer"
+    KIND = capi.MIN_P2POINT
+    PARAMS = ()
+
+
+class PointToPointWithCovErrorMinimizer(_Minimizer):
+    className = "PointToPointWithCovErrorMinimizer"
+    KIND = capi.MIN_P2POINT_COV
+    PARAMS = _COV_PARAM
+
+
+class PointToPlaneErrorMinimizer(_Minimizer):
+    className = "PointToPlaneErrorMinimizer"
+    KIND = capi.MIN_P2PLANE
+    PARAMS = _P2PLANE_PARAMS
+
+
+class PointToPlaneWithCovErrorMinimizer(_Minimizer):
+    className = "PointToPlaneWithCovErrorMinimizer"
+    KIND = capi.MIN_P2PLANE_COV
+    PARAMS = _P2PLANE_PARAMS + _COV_PARAM
+
+
+# ---- SurfaceNormalDataPointsFilter (SurfaceNormal.h:65-80) --------------------------------------
+class SurfaceNormalDataPointsFilter(Parametrizable, _Bound):
+    className = "SurfaceNormalDataPointsFilter"
+    PARAMS = (
+        ("knn", "number of nearest neighbors to consider, including the point itself", "5", "3", "2147483647", int),
+        ("maxDist", "maximum distance to consider for neighbors", "inf", "0", "inf", float),
+        ("epsilon", "approximation to use for the nearest-neighbor search", "0", "0", "inf", float),
+        ("keepNormals", "whether the normals should be added as descriptors to the resulting cloud", "1", None, None, bool),
+        ("keepDensities", "whether the point densities should be added as descriptors", "0", None, None, bool),
+        ("keepEigenValues", "whether the eigen values should be added as descriptors", "0", None, None, bool),
+        ("keepEigenVectors", "whether the eigen vectors should be added as descriptors", "0", None, None, bool),
+        ("keepMatchedIds", "whether the identifiers of matches points should be added as descriptors", "0", None, None, bool),
+        ("keepMeanDist", "whether the distance to the nearest neighbor mean should be added as descriptors", "0", None, None, bool),
+        ("sortEigen", "whether the eigenvalues and eigenvectors should be sorted (ascending)", "0", None, None, bool),
+        ("smoothNormals", "whether the normal vector should be average with the nearest neighbors", "0", None, None, bool),
+    )
+
+    def __init__(self, params=None):
+        Parametrizable.__init__(self, params)
+        for name, *_ in self.PARAMS:
+            setattr(self, name, self.get(name))
+        if self.smoothNormals:
+            raise ConfigurationError("GPU module: SurfaceNormalDataPointsFilter smoothNormals is not supported")
+
+    def init(self):
+        pass
+
+    def filter(self, cloud):
+        out = cloud.copy()
+        self.inPlaceFilter(out)
+        return out
+
+    def inPlaceFilter(self, cloud):
+        keep = [name for flag, name in ((self.keepNormals, "normals"), (self.keepDensities, "densities"),
+                                        (self.keepEigenValues, "eigValues"), (self.keepEigenVectors, "eigVectors"),
+                                        (self.keepMatchedIds, "matchedIds"), (self.keepMeanDist, "meanDists")) if flag]
+        res = _translate(self.ctx.normals, cloud.features, self.knn, self.epsilon, self.maxDist, self.sortEigen, keep)
+        self.degenerateCount = res.pop("degenerate")
+        cloud.descriptors.update(res)
+
+
+# ---- TransformationCheckers (host objects carrying the parameters; evaluated on the device
+#      inside the fused loop, TransformationCheckersImpl.cpp:45-158) ------------------------------
+class CounterTransformationChecker(Parametrizable):
+    className = "CounterTransformationChecker"
+    PARAMS = (("maxIterationCount", "maximum number of iterations ", "40", "0", "2147483647", int),)
+
+    def __init__(self, params=None):
+        Parametrizable.__init__(self, params)
+        self.maxIterationCount = self.get("maxIterationCount")
+
+
+class DifferentialTransformationChecker(Parametrizable):
+    className = "DifferentialTransformationChecker"
+    PARAMS = (
+        ("minDiffRotErr", "threshold for rotation error (radian)", "0.001", "0.", "6.2831854", float),
+        ("minDiffTransErr", "threshold for translation error", "0.001", "0.", "inf", float),
+        ("smoothLength", "number of iterations over which to average the differencial error", "3", "0", "2147483647", int),
+    )
+
+    def __init__(self, params=None):
+        Parametrizable.__init__(self, params)
+        self.minDiffRotErr = self.get("minDiffRotErr")
+        self.minDiffTransErr = self.get("minDiffTransErr")
+        self.smoothLength = self.get("smoothLength")
+
+
+# ---- Registrar (Registrar.h:75-218) --------------------------------------------------------------
+class Registrar(dict):
+    def create(self, name, params=None):
+        if name not in self:
+            raise InvalidElement("Trying to instanciate unknown element %s from registrar" % name)
+        return self[name](params)
+
+    def getDescription(self, name):
+        return self[name].__doc__ or ""
+
+
+MatcherRegistrar = Registrar(KDTreeMatcher=KDTreeMatcher)
+OutlierFilterRegistrar = Registrar(MaxDistOutlierFilter=MaxDistOutlierFilter, MedianDistOutlierFilter=MedianDistOutlierFilter,
+                                   TrimmedDistOutlierFilter=TrimmedDistOutlierFilter)
+ErrorMinimizerRegistrar = Registrar(PointToPointErrorMinimizer=PointToPointErrorMinimizer,
+                                    PointToPointWithCovErrorMinimizer=PointToPointWithCovErrorMinimizer,
+                                    PointToPlaneErrorMinimizer=PointToPlaneErrorMinimizer,
+                                    PointToPlaneWithCovErrorMinimizer=PointToPlaneWithCovErrorMinimizer)
+DataPointsFilterRegistrar = Registrar(SurfaceNormalDataPointsFilter=SurfaceNormalDataPointsFilter)
+TransformationCheckerRegistrar = Registrar(CounterTransformationChecker=CounterTransformationChecker,
+                                           DifferentialTransformationChecker=DifferentialTransformationChecker)
+
+
+# ---- float32 4x4 helpers with the reference's GEMM accumulation order -----------------------------
+def mat4_mul(A, B):
+    A = np.asarray(A, np.float32)
+    B = np.asarray(B, np.float32)
+    out = np.zeros((4, 4), np.float32)
+    for i in range(4):
+        for j in range(4):
+            acc = np.float32(A[i, 0] * B[0, j])
+            for k in range(1, 4):
+                acc = np.float32(acc + np.float32(A[i, k] * B[k, j]))
+            out[i, j] = acc
+    return out
+
+
+def sequential_mean(features):
+    """`features.rowwise().sum() / N` in float, column after column (ICP.cpp:292)."""
+    n = features.shape[0]
+    s = np.cumsum(features, axis=0, dtype=np.float32)[-1]
+    return (s / np.float32(n)).astype(np.float32)
+
+
+# ---- ICP (ICP.cpp:99-113, 243-449) -------------------------------------------------------------------
+class ICP:
+    """ICP chain over the GPU modules.  `icp(reading, reference[, T_init])` returns the 4x4
+    transform like `PointMatcher<T>::ICP::operator()`."""
+
+    def __init__(self, device=0):
+        self.ctx = capi.Context(device)
+        self.referenceDataPointsFilters = []
+        self.matcher = None
+        self.outlierFilters = OutlierFilters()
+        self.errorMinimizer = None
+        self.transformationCheckers = []
+        self.maxNumIterationsReached = False
+        self.iterationCount = 0
+
+    def setDefault(self):
+        """The hot-path part of ICP::setDefault (ICP.cpp:99-113): KDTreeMatcher, TrimmedDist(0.85),
+        PointToPlane, Counter(40) + Differential; reference normals from SurfaceNormal(knn 7) in
+        place of the CPU-only SamplingSurfaceNormal pre-filter."""
+        self.referenceDataPointsFilters = [SurfaceNormalDataPointsFilter({"knn": "7"})]
+        self.matcher = KDTreeMatcher()
+        self.outlierFilters = OutlierFilters([TrimmedDistOutlierFilter()])
+        self.errorMinimizer = PointToPlaneErrorMinimizer()
+        self.transformationCheckers = [CounterTransformationChecker(), DifferentialTransformationChecker()]
+
+    def _params(self):
+        counter = [c for c in self.transformationCheckers if isinstance(c, CounterTransformationChecker)]
+        diff = [c for c in self.transformationCheckers if isinstance(c, DifferentialTransformationChecker)]
+        m = self.matcher
+        return capi.make_params(
+            knn=m.knn, epsilon=m.epsilon, max_dist=m.maxDist, filters=[f.spec() for f in self.outlierFilters],
+            minimizer=self.errorMinimizer.KIND, sensor_std_dev=self.errorMinimizer.sensorStdDev,
+            max_iterations=counter[0].maxIterationCount if counter else 0x7FFFFFFF,
+            differential=(diff[0].minDiffRotErr, diff[0].minDiffTransErr, diff[0].smoothLength) if diff else None)
+
+    def __call__(self, readingIn, referenceIn, T_refIn_dataIn=None):
+        return self.compute(readingIn, referenceIn, T_refIn_dataIn)
+
+    def compute(self, readingIn, referenceIn, T_refIn_dataIn=None):
+        if self.matcher is None:
+            raise RuntimeError("You must setup a matcher before running ICP")
+        if self.errorMinimizer is None:
+            raise RuntimeError("You must setup an error minimizer before running ICP")
+        for mod in [self.matcher, self.outlierFilters, self.errorMinimizer] + list(self.outlierFilters) + list(self.referenceDataPointsFilters):
+            mod.bind(self.ctx)
+        T_init = np.eye(4, dtype=np.float32) if T_refIn_dataIn is None else np.asarray(T_refIn_dataIn, np.float32)
+        if T_init.shape != (4, 4):
+            raise RuntimeError("The initial transformation matrix must be squared.")
+        reference = referenceIn.copy() if isinstance(referenceIn, DataPoints) else DataPoints(np.array(referenceIn, np.float32))
+        reading = readingIn if isinstance(readingIn, DataPoints) else DataPoints(readingIn)
+        for f in self.referenceDataPointsFilters:
+            f.inPlaceFilter(reference)
+        # centre the reference on its mean (ICP.cpp:291-299)
+        mean = sequential_mean(reference.features)
+        T_refIn_refMean = np.eye(4, dtype=np.float32)
+        T_refIn_refMean[:3, 3] = mean[:3]
+        reference.features[:, :3] -= mean[:3]
+        self.matcher.init(reference)
+        # reading into the refMean frame (ICP.cpp:345-347)
+        T_refMean_refIn = np.eye(4, dtype=np.float32)
+        T_refMean_refIn[:3, 3] = -mean[:3]
+        T_refMean_dataIn = mat4_mul(T_refMean_refIn, T_init)
+        _translate(self.ctx.set_reading, reading.features)
+        self.ctx._reading_obj = None
+        _translate(self.ctx.reading_apply_transform, T_refMean_dataIn)
+        res = _translate(self.ctx.icp_run, self._params())
+        self.iterationCount = res["iterations"]
+        counter = [c for c in self.transformationCheckers if isinstance(c, CounterTransformationChecker)]
+        self.maxNumIterationsReached = bool(counter) and res["iterations"] >= max(1, counter[0].maxIterationCount)
+        self.errorMinimizer._stats = res["stats"]
+        self.errorMinimizer._cov = res["cov"]
+        self.T_iter = res["T_iter"]
+        return mat4_mul(mat4_mul(T_refIn_refMean, res["T_iter"]), T_refMean_dataIn)

@@ -1,0 +1,192 @@
+// tests/emu/emu.cpp — host harness for the PM_HD per-thread algorithms of
+// libpointmatcher_b200/csrc/core/*.h (tree addressing, traversal, top-k insertion, small solves).
+//
+// TEST INFRASTRUCTURE ONLY: it lets the CPU test-suite (pytest -m "not gpu") exercise the exact
+// device functions without a GPU.  It is compiled by tests/ into tests/emu/_build/libemu.so and is
+// never part of the product library; the product has no CPU path.
+// Built with -ffp-contract=off so that fmul/fadd/fsub round once, as the device intrinsics do.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "core/common.h"
+#include "core/linalg.h"
+#include "core/tree.h"
+
+using namespace pm;
+
+namespace {
+
+struct EmuTree {
+    std::vector<f4> nodes, pts;
+    TreeView view;
+};
+
+// the level-by-level build of tree_build.cu, sequentially
+EmuTree* build(const float* feat, int n) {
+    EmuTree* t = new EmuTree();
+    const uint32_t N = (uint32_t)n;
+    const int D = tree_depth_for(N);
+    const uint32_t nnodes = 2u << D;
+    std::vector<uint32_t> box(6 * (size_t)nnodes);
+    for (uint32_t i = 0; i < nnodes; ++i) {
+        for (int a = 0; a < 3; ++a) { box[6 * i + a] = 0xffffffffu; box[6 * i + 3 + a] = 0u; }
+    }
+    std::vector<uint32_t> perm(N);
+    std::iota(perm.begin(), perm.end(), 0u);
+    auto coord = [&](uint32_t i, int d) { return feat[4 * (size_t)i + d]; };
+    for (int l = 0; l <= D; ++l) {
+        for (uint32_t p = 0; p < N; ++p) {
+            const uint32_t node = (1u << l) + seg_of(p, l, N);
+            for (int a = 0; a < 3; ++a) {
+                const uint32_t o = float_ord(coord(perm[p], a));
+                box[6 * node + a] = std::min(box[6 * node + a], o);
+                box[6 * node + 3 + a] = std::max(box[6 * node + 3 + a], o);
+            }
+        }
+        if (l == D) break;
+        std::vector<std::pair<uint64_t, uint32_t>> kv(N);
+        for (uint32_t p = 0; p < N; ++p) {
+            const uint32_t seg = seg_of(p, l, N);
+            const uint32_t* b = &box[6 * (size_t)((1u << l) + seg)];
+            const float ex = fsub(ord_float(b[3]), ord_float(b[0]));
+            const float ey = fsub(ord_float(b[4]), ord_float(b[1]));
+            const float ez = fsub(ord_float(b[5]), ord_float(b[2]));
+            int dim = 0;
+            float best = ex;
+            if (ey > best) { dim = 1; best = ey; }
+            if (ez > best) { dim = 2; }
+            kv[p] = {((uint64_t)seg << 32) | float_ord(coord(perm[p], dim)), perm[p]};
+        }
+        std::stable_sort(kv.begin(), kv.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+        for (uint32_t p = 0; p < N; ++p) perm[p] = kv[p].second;
+    }
+    t->pts.resize(N);
+    for (uint32_t p = 0; p < N; ++p) t->pts[p] = make_f4(coord(perm[p], 0), coord(perm[p], 1), coord(perm[p], 2), u2f(perm[p]));
+    const uint32_t n_inner = (1u << D) - 1;
+    t->nodes.resize(3 * (size_t)std::max(1u, n_inner));
+    for (uint32_t i = 1; i <= n_inner; ++i) {
+        const uint32_t* l = &box[6 * (size_t)(2 * i)];
+        const uint32_t* r = &box[6 * (size_t)(2 * i + 1)];
+        for (int a = 0; a < 3; ++a)
+            t->nodes[3 * (size_t)(i - 1) + a] = make_f4(ord_float(l[a]), ord_float(l[3 + a]), ord_float(r[a]), ord_float(r[3 + a]));
+    }
+    t->view.nodes = t->nodes.data();
+    t->view.pts = t->pts.data();
+    t->view.n = N;
+    t->view.depth = D;
+    t->view.root_lo = make_f4(ord_float(box[6]), ord_float(box[7]), ord_float(box[8]), 0.f);
+    t->view.root_hi = make_f4(ord_float(box[9]), ord_float(box[10]), ord_float(box[11]), 0.f);
+    return t;
+}
+
+template <int KMAX>
+long run_knn(const EmuTree* t, const float* T16, const float* q, int nq, int k, float max_r2, int32_t* ids, float* dists) {
+    long visits = 0;
+    Mat4 T;
+    if (T16) std::memcpy(T.m, T16, sizeof(T.m));
+    for (int i = 0; i < nq; ++i) {
+        f4 p = make_f4(q[4 * (size_t)i], q[4 * (size_t)i + 1], q[4 * (size_t)i + 2], q[4 * (size_t)i + 3]);
+        if (T16) p = transform_point(T, p);
+        TopK<KMAX> best;
+        best.init(k, max_r2);
+        visits += knn_search<KMAX>(t->view, p.x, p.y, p.z, best);
+        for (int j = 0; j < k; ++j) {
+            const bool valid = best.id[j] != PM_NO_ID && best.d[j] != pm_inf();
+            ids[(size_t)i * k + j] = valid ? best.id[j] : -1;
+            dists[(size_t)i * k + j] = valid ? best.d[j] : pm_inf();
+        }
+    }
+    return visits;
+}
+
+}  // namespace
+
+extern "C" {
+
+void* emu_tree_build(const float* feat, int n) { return build(feat, n); }
+void emu_tree_free(void* t) { delete static_cast<EmuTree*>(t); }
+int emu_tree_depth(void* t) { return static_cast<EmuTree*>(t)->view.depth; }
+
+// leaf sizes and box containment invariants; returns 0 when the structure is consistent
+int emu_tree_check(void* tp) {
+    const EmuTree* t = static_cast<EmuTree*>(tp);
+    const TreeView& v = t->view;
+    const uint32_t leaves = 1u << v.depth;
+    std::vector<char> seen(v.n, 0);
+    for (uint32_t leaf = 0; leaf < leaves; ++leaf) {
+        const uint32_t b = seg_begin(v.depth, leaf, v.n), e = seg_begin(v.depth, leaf + 1, v.n);
+        if (e <= b || e - b > PM_LEAF_MAX) return 1;
+        for (uint32_t p = b; p < e; ++p) {
+            if (seg_of(p, v.depth, v.n) != leaf) return 2;
+            const uint32_t idx = f2u(v.pts[p].w);
+            if (idx >= v.n || seen[idx]) return 3;
+            seen[idx] = 1;
+            // every ancestor box contains the point
+            uint32_t node = leaves + leaf;
+            while (node > 1) {
+                const uint32_t parent = node >> 1;
+                const f4* nb = v.nodes + 3 * (size_t)(parent - 1);
+                const bool right = node & 1;
+                const float lo[3] = {right ? nb[0].z : nb[0].x, right ? nb[1].z : nb[1].x, right ? nb[2].z : nb[2].x};
+                const float hi[3] = {right ? nb[0].w : nb[0].y, right ? nb[1].w : nb[1].y, right ? nb[2].w : nb[2].y};
+                const float c[3] = {v.pts[p].x, v.pts[p].y, v.pts[p].z};
+                for (int a = 0; a < 3; ++a)
+                    if (c[a] < lo[a] || c[a] > hi[a]) return 4;
+                node = parent;
+            }
+        }
+    }
+    if (seg_begin(v.depth, leaves, v.n) != v.n) return 5;
+    return 0;
+}
+
+long emu_knn(void* tp, const float* T16, const float* q, int nq, int k, float max_dist, int32_t* ids, float* dists) {
+    const EmuTree* t = static_cast<EmuTree*>(tp);
+    const float r2 = max_dist * max_dist;
+    if (k == 1) return run_knn<1>(t, T16, q, nq, k, r2, ids, dists);
+    if (k <= 4) return run_knn<4>(t, T16, q, nq, k, r2, ids, dists);
+    if (k <= 8) return run_knn<8>(t, T16, q, nq, k, r2, ids, dists);
+    if (k <= 16) return run_knn<16>(t, T16, q, nq, k, r2, ids, dists);
+    if (k <= 32) return run_knn<32>(t, T16, q, nq, k, r2, ids, dists);
+    if (k <= 64) return run_knn<64>(t, T16, q, nq, k, r2, ids, dists);
+    return -1;
+}
+
+int emu_solve_psd6(const double* A, const double* b, double* x) { return solve_psd6(A, b, x); }
+void emu_rotation_from_crosscov(const double* m, double* R) { rotation_from_crosscov(m, R); }
+void emu_jacobi_eig3(const double* A, double* w, double* V) {
+    double M[9];
+    std::memcpy(M, A, sizeof(M));
+    jacobi_eig3(M, w, V);
+}
+int emu_rank3(const float* A) {
+    float M[9];
+    std::memcpy(M, A, sizeof(M));
+    return fullpiv_qr_rank3(M);
+}
+void emu_angle_axis(const float* x, float* T16) {
+    Mat4 T;
+    angle_axis_to_mat4(x, T);
+    std::memcpy(T16, T.m, sizeof(T.m));
+}
+float emu_angular_distance(const float* Ta, const float* Tb) {
+    Mat4 A, B;
+    std::memcpy(A.m, Ta, sizeof(A.m));
+    std::memcpy(B.m, Tb, sizeof(B.m));
+    return quat_angular_distance(quat_from_mat4(A), quat_from_mat4(B));
+}
+void emu_mat4_mul(const float* A, const float* B, float* C) {
+    Mat4 a, b, c;
+    std::memcpy(a.m, A, 64);
+    std::memcpy(b.m, B, 64);
+    mat4_mul(a, b, c);
+    std::memcpy(C, c.m, 64);
+}
+uint32_t emu_seg_begin(int level, uint32_t seg, uint32_t n) { return seg_begin(level, seg, n); }
+uint32_t emu_seg_of(uint32_t p, int level, uint32_t n) { return seg_of(p, level, n); }
+uint32_t emu_float_ord(float f) { return float_ord(f); }
+float emu_ord_float(uint32_t o) { return ord_float(o); }
+
+}  // extern "C"
