@@ -83,6 +83,12 @@ void* pmgpu_ctx_stream(pmgpu_ctx* ctx);
 int pmgpu_sync(pmgpu_ctx* ctx);
 /* number of kernel launches issued by this context since creation (bench `gpu_launches`) */
 uint64_t pmgpu_launch_count(const pmgpu_ctx* ctx);
+/* Per-stage device timing with CUDA events recorded on the context's stream around the kernels
+ * of each stage (0 = kNN match, 1 = select + weights, 2 = minimise / compose / check,
+ * 3 = covariance).  pmgpu_timing_collect synchronises, adds the elapsed milliseconds of all
+ * recorded intervals into ms_out[4] and their number into count_out[4], and clears them. */
+int pmgpu_timing_enable(pmgpu_ctx* ctx, int on);
+int pmgpu_timing_collect(pmgpu_ctx* ctx, double* ms_out, int* count_out);
 
 /* ---- K1: KDTreeMatcher::init (MatchersImpl.cpp:77-83) ----------------------------------
  * Uploads the reference features and builds the search structure over the first rows-1

@@ -64,6 +64,8 @@ SIGNATURES = {
     "pmgpu_ctx_stream": (C.c_void_p, [C.c_void_p]),
     "pmgpu_sync": (C.c_int, [C.c_void_p]),
     "pmgpu_launch_count": (C.c_uint64, [C.c_void_p]),
+    "pmgpu_timing_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "pmgpu_timing_collect": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "pmgpu_ref_set": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]),
     "pmgpu_ref_set_normals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "pmgpu_reading_set": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
@@ -182,6 +184,17 @@ class Context:
     @property
     def launch_count(self):
         return int(lib.pmgpu_launch_count(self.h))
+
+    def timing_enable(self, on=True):
+        self._check(lib.pmgpu_timing_enable(self.h, int(on)))
+
+    def timing_collect(self):
+        """{stage: (total ms, launches-of-that-stage)} since the last collect; synchronises."""
+        ms = (C.c_double * 4)()
+        cnt = (C.c_int * 4)()
+        self._check(lib.pmgpu_timing_collect(self.h, ms, cnt))
+        names = ("knn", "select", "minimize", "covariance")
+        return {n: (ms[i], cnt[i]) for i, n in enumerate(names)}
 
     # ---- K1
     def set_reference(self, features, normals=None):

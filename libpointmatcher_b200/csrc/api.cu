@@ -114,9 +114,15 @@ int check_params(pmgpu_ctx* ctx, const pmgpu_icp_params* p) {
 
 int enqueue_iteration(pmgpu_ctx* ctx, const pmgpu_icp_params* p, bool gated) {
     const float max_r2 = p->max_dist * p->max_dist;
+    ctx->stage_begin(0);
     PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, ctx->q_order.p, ctx->nq, true, gated, false, p->knn, max_r2, ctx->ids.p, ctx->dists.p));
+    ctx->stage_end();
+    ctx->stage_begin(1);
     PM_TRY(launch_weights(ctx, p->nfilters, p->filter_type, p->filter_param, gated));
+    ctx->stage_end();
+    ctx->stage_begin(2);
     PM_TRY(launch_minimize(ctx, p->minimizer, true, gated, p));
+    ctx->stage_end();
     return PMGPU_OK;
 }
 
@@ -169,6 +175,8 @@ void pmgpu_ctx_destroy(pmgpu_ctx* ctx) {
     ctx->reading.release(); ctx->q_order.release();
     ctx->ids.release(); ctx->dists.release(); ctx->weights.release();
     ctx->hist.release(); ctx->partials.release();
+    for (auto& iv : ctx->intervals) { cudaEventDestroy(iv.a); cudaEventDestroy(iv.b); }
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->state) cudaFree(ctx->state);
     if (ctx->state_host) cudaFreeHost(ctx->state_host);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -178,6 +186,33 @@ void pmgpu_ctx_destroy(pmgpu_ctx* ctx) {
 const char* pmgpu_last_error(const pmgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 void* pmgpu_ctx_stream(pmgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 uint64_t pmgpu_launch_count(const pmgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int pmgpu_timing_enable(pmgpu_ctx* ctx, int on) {
+    if (!ctx) return PMGPU_ERR_BAD_ARG;
+    ctx->timing = on != 0;
+    return PMGPU_OK;
+}
+
+int pmgpu_timing_collect(pmgpu_ctx* ctx, double* ms_out, int* count_out) {
+    if (!ctx) return PMGPU_ERR_BAD_ARG;
+    PM_TRY(use_device(ctx));
+    PM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int s = 0; s < 4; ++s) {
+        if (ms_out) ms_out[s] = 0.0;
+        if (count_out) count_out[s] = 0;
+    }
+    for (auto& iv : ctx->intervals) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, iv.a, iv.b) == cudaSuccess && iv.stage >= 0 && iv.stage < 4) {
+            if (ms_out) ms_out[iv.stage] += ms;
+            if (count_out) count_out[iv.stage] += 1;
+        }
+        ctx->event_pool.push_back(iv.a);
+        ctx->event_pool.push_back(iv.b);
+    }
+    ctx->intervals.clear();
+    return PMGPU_OK;
+}
 
 int pmgpu_sync(pmgpu_ctx* ctx) {
     if (!ctx) return PMGPU_ERR_BAD_ARG;
@@ -280,7 +315,9 @@ int pmgpu_knn(pmgpu_ctx* ctx, const float* T, int k, float epsilon, float max_di
     ctx->k = k;
     ctx->have_weights = false;
     const float max_r2 = max_dist * max_dist;
+    ctx->stage_begin(0);
     PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, ctx->q_order.p, ctx->nq, T != nullptr, false, false, k, max_r2, ctx->ids.p, ctx->dists.p));
+    ctx->stage_end();
     ctx->have_matches = true;
     const size_t out_n = (size_t)k * ctx->nq;
     if (ids_out && out_n) PM_CUDA_TRY(ctx, cudaMemcpyAsync(ids_out, ctx->ids.p, out_n * sizeof(int32_t), cudaMemcpyDefault, ctx->stream));
@@ -295,7 +332,9 @@ int pmgpu_weights(pmgpu_ctx* ctx, int nfilters, const int* types, const float* p
     PM_TRY(use_device(ctx));
     if (!ctx->have_matches) return fail(ctx, PMGPU_ERR_NO_MATCHES, status_message(PMGPU_ERR_NO_MATCHES));
     if (nfilters > 0 && (!types || !params)) return fail(ctx, PMGPU_ERR_BAD_ARG, "null filter arrays");
+    ctx->stage_begin(1);
     PM_TRY(launch_weights(ctx, nfilters, types, params, false));
+    ctx->stage_end();
     const size_t total = (size_t)ctx->k * ctx->nq;
     if (weights_out && total) {
         PM_TRY(launch_materialize_weights(ctx));
@@ -322,9 +361,15 @@ int pmgpu_minimize(pmgpu_ctx* ctx, int minimizer, float sensor_std_dev, float* T
     if (!ctx->have_matches) return fail(ctx, PMGPU_ERR_NO_MATCHES, status_message(PMGPU_ERR_NO_MATCHES));
     if (minimizer < 0 || minimizer > PMGPU_MIN_P2PLANE_COV) return fail(ctx, PMGPU_ERR_BAD_ARG, "unknown error minimizer");
     if (!ctx->have_weights) PM_TRY(launch_weights(ctx, 0, nullptr, nullptr, false));  // empty chain
+    ctx->stage_begin(2);
     PM_TRY(launch_minimize(ctx, minimizer, false, false, nullptr));
+    ctx->stage_end();
     const bool with_cov = minimizer == PMGPU_MIN_P2POINT_COV || minimizer == PMGPU_MIN_P2PLANE_COV;
-    if (with_cov) PM_TRY(launch_covariance(ctx, minimizer, sensor_std_dev));
+    if (with_cov) {
+        ctx->stage_begin(3);
+        PM_TRY(launch_covariance(ctx, minimizer, sensor_std_dev));
+        ctx->stage_end();
+    }
     PM_TRY(pull_state(ctx));
     const int s = device_status(ctx);
     if (s != PMGPU_OK) {

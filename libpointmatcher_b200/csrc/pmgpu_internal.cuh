@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 
 #include "../../include/pmgpu.h"
 #include "core/common.h"
@@ -135,6 +136,28 @@ struct pmgpu_ctx {
     // multi-GPU
     void* nccl_comm = nullptr;
     int rank = 0, nranks = 1;
+
+    // optional per-stage event timing (pmgpu_timing_enable)
+    struct Interval { cudaEvent_t a, b; int stage; };
+    bool timing = false;
+    std::vector<Interval> intervals;
+    std::vector<cudaEvent_t> event_pool;
+    cudaEvent_t take_event() {
+        cudaEvent_t e = nullptr;
+        if (!event_pool.empty()) { e = event_pool.back(); event_pool.pop_back(); }
+        else cudaEventCreate(&e);
+        return e;
+    }
+    void stage_begin(int stage) {
+        if (!timing) return;
+        Interval iv{take_event(), take_event(), stage};
+        cudaEventRecord(iv.a, stream);
+        intervals.push_back(iv);
+    }
+    void stage_end() {
+        if (!timing || intervals.empty()) return;
+        cudaEventRecord(intervals.back().b, stream);
+    }
 
     void set_error(const std::string& e) { err = e; }
     pm::TreeView tree_view() const {

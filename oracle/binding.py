@@ -81,6 +81,7 @@ def lib():
         _lib.orc_icp.argtypes = [_fp, C.c_int, _fp, C.c_int, _fp, _fp, C.POINTER(IcpConfig), _fp, _fp, C.POINTER(C.c_int), _fp, _fp]
         _lib.orc_quaternion_angular_distance.argtypes = [_fp, _fp, _fp]
         _lib.orc_num_threads.restype = C.c_int
+        _lib.orc_last_timings.argtypes = [C.POINTER(C.c_double)]
     return _lib
 
 
@@ -234,6 +235,13 @@ def icp(reading, reference, ref_normals=None, T_init=None, **kw):
                          _f(cov), _f(stats)))
     iters = [np.array(T_iters[i].reshape(4, 4, order="F")) for i in range(it.value)]
     return dict(T=np.array(T), iterations=it.value, T_iters=iters, cov=np.array(cov), stats=stats)
+
+
+def last_timings():
+    """dict(build_s, loop_s, match_s, iterations) of the last icp() call"""
+    t = (C.c_double * 4)()
+    lib().orc_last_timings(t)
+    return dict(build_s=t[0], loop_s=t[1], match_s=t[2], iterations=int(t[3]))
 
 
 def angular_distance(Ta, Tb):

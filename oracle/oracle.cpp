@@ -25,6 +25,7 @@
 #include <limits>
 #include <numeric>
 #include <vector>
+#include <chrono>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -32,6 +33,8 @@
 namespace {
 
 const float kInf = std::numeric_limits<float>::infinity();
+double g_timings[4] = {0, 0, 0, 0};  // last orc_icp: {build s, loop s, match s, iterations}
+inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 // ------------------------------------------------------------------------------------------
 // small dense helpers (column-major, runtime n <= 6)
@@ -1223,8 +1226,11 @@ int orc_icp(const float* readingIn, int nq, const float* referenceIn, int nr, co
     for (int p = 0; p < nr; ++p)
         for (int r = 0; r < 3; ++r) reference[4 * size_t(p) + r] -= meanRef[r];
 
+    const double t_build0 = now_s();
     KdTree* tree = nullptr;
     if (cfg->search_type != 0) tree = new KdTree(reference.data(), 4, nr);
+    g_timings[0] = now_s() - t_build0;
+    g_timings[2] = 0;
     if (cfg->knn > nr) { delete tree; return ORC_ERR_KNN_TOO_LARGE; }
 
     // computeWithTransformedReference (ICP.cpp:316-449)
@@ -1248,11 +1254,14 @@ int orc_icp(const float* readingIn, int nq, const float* referenceIn, int nr, co
     std::vector<int32_t> ids(size_t(knn) * nq);
     std::vector<float> dists(size_t(knn) * nq), w(size_t(knn) * nq);
     int rc = ORC_OK;
+    const double t_loop0 = now_s();
     while (iterate) {
         if (!check_rigid(T_iter)) { rc = ORC_ERR_NOT_ORTHOGONAL; break; }
         rigid_apply(T_iter, reading.data(), nq, stepReading.data());
+        const double t_m0 = now_s();
         if (tree) tree->knn(stepReading.data(), 4, nq, knn, cfg->epsilon, cfg->max_dist, ids.data(), dists.data(), cfg->nthreads);
         else orc_bruteforce_knn(reference.data(), 4, nr, stepReading.data(), nq, knn, cfg->max_dist, ids.data(), dists.data(), cfg->nthreads);
+        g_timings[2] += now_s() - t_m0;
         rc = outlier_weights(dists.data(), knn, nq, cfg->nfilters, cfg->filter_type, cfg->filter_param, w.data(), nullptr);
         if (rc) break;
         float dT[16];
@@ -1264,6 +1273,8 @@ int orc_icp(const float* readingIn, int nq, const float* referenceIn, int nr, co
         ++iterationCount;
         if (rc) break;
     }
+    g_timings[1] = now_s() - t_loop0;
+    g_timings[3] = iterationCount;
     delete tree;
     if (iterations_out) *iterations_out = iterationCount;
     if (rc) return rc;
@@ -1271,6 +1282,10 @@ int orc_icp(const float* readingIn, int nq, const float* referenceIn, int nr, co
     mat4_mul(T_refIn_refMean, T_iter, tmp);
     mat4_mul(tmp, T_refMean_dataIn, T_out);
     return ORC_OK;
+}
+
+void orc_last_timings(double* out4) {
+    for (int i = 0; i < 4; ++i) out4[i] = g_timings[i];
 }
 
 void orc_quaternion_angular_distance(const float* Ta, const float* Tb, float* out) {

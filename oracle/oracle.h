@@ -103,6 +103,9 @@ int orc_icp(const float* reading, int nq, const float* reference, int nr,
             float* T_out, float* T_iters_out, int* iterations_out, float* cov_out,
             float* stats_out);
 
+/* wall-clock of the last orc_icp call: {structure build s, iteration loop s, matching s, iterations} */
+void orc_last_timings(double* out4);
+
 /* misc helpers used by the tests */
 void orc_quaternion_angular_distance(const float* Ta16, const float* Tb16, float* out);
 int orc_num_threads(void);

@@ -1,0 +1,263 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (capi), against the oracle on the
+same seeded inputs.  Bars (BASELINE.json north_star): match indices bit-exact (exact ties
+excepted when the oracle is the kd-tree; none excepted against the brute-force oracle), squared
+distances bit-exact, quantile limits bit-exact, weights identical, transforms within
+1e-5 rad / 1e-5 m.
+"""
+import numpy as np
+import pytest
+
+from helpers import assert_transform_close, classify_id_mismatches, cloud, small_pose
+
+pytestmark = pytest.mark.gpu
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+# ---------------------------------------------------------------------------------- K1 + K2
+@pytest.mark.parametrize("kind", ["uniform", "grid", "plane", "cluster"])
+def test_knn_bit_exact_vs_bruteforce(gpu_ctx, oracle, kind):
+    rng = np.random.default_rng(100)
+    for n in (1, 2, 8, 9, 100, 3000):
+        ref, q = cloud(rng, n, kind), cloud(rng, 257, kind)
+        if kind != "grid":
+            q[:, :3] += rng.normal(0, 0.5, (257, 3)).astype(np.float32)
+        gpu_ctx.set_reference(ref)
+        gpu_ctx.set_reading(q)
+        for k in (1, 2, 5, 10, 20, 40):
+            if k > n:
+                continue
+            for md in (np.inf, 1.0):
+                ib, db = oracle.bruteforce_knn(ref, q, k, md, nthreads=4)
+                ig, dg, visits = gpu_ctx.knn(None, k, 0.0, md)
+                assert (ib == ig).all() and (bits(db) == bits(dg)).all(), (kind, n, k, md)
+                assert ((dg == np.inf) == (ig == -1)).all()
+
+
+def test_knn_fused_transform(gpu_ctx, oracle):
+    rng = np.random.default_rng(101)
+    ref, q = cloud(rng, 50000, "uniform"), cloud(rng, 4000, "uniform")
+    gpu_ctx.set_reference(ref)
+    gpu_ctx.set_reading(q)
+    for _ in range(3):
+        T = small_pose(rng)
+        qt = oracle.rigid_transform(T, q)
+        ib, db = oracle.bruteforce_knn(ref, qt, 3, nthreads=8)
+        ig, dg, _ = gpu_ctx.knn(T, 3)
+        assert (ib == ig).all() and (bits(db) == bits(dg)).all()
+
+
+def test_knn_lidar_vs_kdtree_oracle(gpu_ctx, oracle, synth):
+    rd, rf, _ = synth.scan_pair(200000)
+    tree = oracle.KdTree(rf)
+    gpu_ctx.set_reference(rf)
+    gpu_ctx.set_reading(rd)
+    for k, md in ((1, np.inf), (10, 2.0)):
+        ik, dk = tree.knn(rd, k, max_dist=md, nthreads=8)
+        ig, dg, visits = gpu_ctx.knn(None, k, 0.0, md)
+        assert (bits(dk) == bits(dg)).all()
+        ndiff, nties = classify_id_mismatches(ik, dk, ig, dg)
+        assert ndiff == nties, "%d id mismatches that are not exact ties" % (ndiff - nties)
+        assert visits > 0
+
+
+def test_knn_errors(gpu_ctx):
+    from libpointmatcher_b200 import capi
+    rng = np.random.default_rng(102)
+    ref = cloud(rng, 10)
+    gpu_ctx.set_reference(ref)
+    gpu_ctx.set_reading(ref)
+    with pytest.raises(capi.PmGpuError) as e:
+        gpu_ctx.knn(None, 11)
+    assert e.value.code == capi.ERR_KNN_TOO_LARGE
+    T = np.eye(4, dtype=np.float32)
+    T[0, 0] = 1.01
+    with pytest.raises(capi.PmGpuError) as e:
+        gpu_ctx.knn(T, 1)
+    assert e.value.code == capi.ERR_NOT_ORTHOGONAL
+    with pytest.raises(capi.PmGpuError) as e:
+        gpu_ctx.set_reference(np.ones((5, 3), np.float32))  # 2-D clouds: explicit error, never silently wrong
+    assert e.value.code == capi.ERR_UNSUPPORTED
+    # empty reading is fine
+    gpu_ctx.set_reference(ref)
+    gpu_ctx.set_reading(np.zeros((0, 4), np.float32))
+    ids, d, _ = gpu_ctx.knn(None, 1)
+    assert ids.shape == (0, 1)
+
+
+# ---------------------------------------------------------------------------------- K3
+def test_quantile_and_weights_bit_exact(gpu_ctx, oracle, synth):
+    rd, rf, _ = synth.scan_pair(100000)
+    gpu_ctx.set_reference(rf)
+    gpu_ctx.set_reading(rd)
+    for k, md in ((1, np.inf), (3, 0.7)):
+        ids, d, _ = gpu_ctx.knn(None, k, 0.0, md)
+        chains = [
+            [],
+            [(0, 0.5)],
+            [(2, 0.75)], [(2, 0.85)], [(2, 1.0)], [(2, 1e-7)], [(2, 0.3333333)],
+            [(1, 3.0)], [(1, 0.5)],
+            [(0, 1.0), (1, 3.0)], [(2, 0.9), (0, 0.3), (1, 2.0)],
+        ]
+        for chain in chains:
+            wo, lo = oracle.outlier_weights(d, chain)
+            wg, lg = gpu_ctx.weights(chain)
+            assert (bits(lo) == bits(lg)).all(), (chain, lo, lg)
+            assert (wo == wg).all(), chain
+
+
+def test_quantile_ties_and_errors(gpu_ctx, oracle):
+    from libpointmatcher_b200 import capi
+    # the {4,5,5,5,5} vector of utest/ui/Outliers.cpp:126-152, via a 5-point cloud on a line
+    ref = np.array([[0, 0, 0, 1]], np.float32)
+    rd = np.array([[2, 0, 0, 1], [0, np.sqrt(5), 0, 1], [0, 0, np.sqrt(5), 1], [np.sqrt(5), 0, 0, 1], [0, -np.sqrt(5), 0, 1]], np.float32)
+    gpu_ctx.set_reference(ref)
+    gpu_ctx.set_reading(rd)
+    ids, d, _ = gpu_ctx.knn(None, 1)
+    for ratio in (0.19, 0.2, 0.5, 1.0):
+        wo, lo = oracle.outlier_weights(d, [(2, ratio)])
+        wg, lg = gpu_ctx.weights([(2, ratio)])
+        assert (bits(lo) == bits(lg)).all() and (wo == wg).all()
+    # all matches beyond maxDist -> "no outlier to filter" (Matches.cpp:76-77)
+    gpu_ctx.knn(None, 1, 0.0, 0.5)
+    with pytest.raises(capi.PmGpuError) as e:
+        gpu_ctx.weights([(2, 0.85)])
+    assert e.value.code == capi.ERR_NO_OUTLIER_TO_FILTER
+    # ... and the empty chain then leaves nothing to minimise (ErrorMinimizer.cpp:76-77)
+    gpu_ctx.weights([])
+    with pytest.raises(capi.PmGpuError) as e:
+        gpu_ctx.minimize(0)
+    assert e.value.code == capi.ERR_NO_POINT_TO_MINIMIZE
+
+
+# ---------------------------------------------------------------------------------- K4-K7
+@pytest.mark.parametrize("k", [1, 4])
+def test_minimizers_match_oracle(gpu_ctx, oracle, synth, k):
+    rd, rf, _ = synth.scan_pair(100000)
+    nrm = oracle.surface_normals(rf, knn=10, nthreads=8)["normals"]
+    gpu_ctx.set_reference(rf, nrm)
+    gpu_ctx.set_reading(rd)
+    T0 = small_pose(np.random.default_rng(103), 0.05, 0.01)
+    ids, d, _ = gpu_ctx.knn(T0, k)
+    rdt = oracle.rigid_transform(T0, rd)
+    chain = [(2, 0.8), (0, 1.5)]
+    w, _ = gpu_ctx.weights(chain)
+    for mini in (0, 1, 2, 3):
+        Tg, covg, sg = gpu_ctx.minimize(mini, 0.02)
+        for acc in (False, True):
+            To, covo, so = oracle.minimize(mini, rdt, rf, nrm, ids, d, w, 0.02, acc_double=acc)
+            assert_transform_close(Tg, To, 1e-5, 1e-5)
+            assert sg["nbKept"] == so["nbKept"] and sg["nbRejectedMatches"] == so["nbRejectedMatches"]
+            assert sg["nbRejectedPoints"] == so["nbRejectedPoints"]
+            assert abs(sg["pointUsedRatio"] - so["pointUsedRatio"]) < 1e-6
+            assert abs(sg["weightedPointUsedRatio"] - so["weightedPointUsedRatio"]) < 1e-5
+        if mini >= 2:
+            # double-accumulated oracle: H^-1 is ill-conditioned in float -> relative tolerance
+            assert np.allclose(covg, covo, rtol=2e-3, atol=1e-3 * np.abs(covo).max()), (covg, covo)
+
+
+def test_point_to_plane_without_normals_is_invalid_field(gpu_ctx, oracle):
+    from libpointmatcher_b200 import capi
+    rng = np.random.default_rng(104)
+    ref = cloud(rng, 1000)
+    gpu_ctx.set_reference(ref)
+    gpu_ctx.set_reading(ref)
+    gpu_ctx.knn(None, 1)
+    with pytest.raises(capi.PmGpuError) as e:
+        gpu_ctx.minimize(1)
+    assert e.value.code == capi.ERR_NO_NORMALS
+
+
+def test_singular_plane_minimum_norm_solution(gpu_ctx):
+    """icpSingular (utest/utest.cpp:162-198) on the GPU modules: rank-deficient normal matrix"""
+    pts = np.array([[i, j, 0, 1] for i in range(-5, 5) for j in range(-5, 5)], np.float32)
+    nrm = np.tile(np.array([0, 0, 1], np.float32), (100, 1))
+    shifted = pts.copy()
+    shifted[:, 2] += 1.0
+    gpu_ctx.set_reference(shifted, nrm)
+    gpu_ctx.set_reading(pts)
+    gpu_ctx.knn(None, 1)
+    gpu_ctx.weights([(2, 0.85)])
+    T, _, _ = gpu_ctx.minimize(1)
+    expect = np.eye(4, dtype=np.float32)
+    expect[2, 3] = 1.0
+    assert np.allclose(T, expect, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------- K8
+def test_surface_normals_match_oracle(gpu_ctx, oracle, synth):
+    rf = synth.scan(60000, cache=False)
+    for knn in (5, 20):
+        o = oracle.surface_normals(rf, knn=knn, nthreads=8, sort_eigen=True)
+        g = gpu_ctx.normals(rf, knn=knn, sort_eigen=True, keep=("normals", "densities", "eigValues", "eigVectors", "matchedIds", "meanDists"))
+        mism = g["matchedIds"].astype(np.int32) != o["ids"]
+        same = ~mism.any(axis=1)  # points whose neighbourhood is identical (ties may reorder a few)
+        assert same.mean() > 0.999
+        well = same & (o["gap"] > 1e-3)
+        dots = np.abs((g["normals"] * o["normals"]).sum(1))
+        assert (1.0 - dots[well]).max() <= 1e-5, (1.0 - dots[well]).max()
+        assert np.allclose(g["densities"][same, 0], o["densities"][same], rtol=1e-5)
+        assert np.allclose(g["meanDists"][same, 0], o["meanDists"][same], rtol=1e-4, atol=1e-6)
+        scale = o["eigValues"][same].max(axis=1, keepdims=True)
+        assert (np.abs(g["eigValues"][same] - o["eigValues"][same]) <= 2e-5 * scale + 1e-9).all()
+        assert g["degenerate"] == o["degenerate"]
+
+
+def test_surface_normals_degenerate_points(gpu_ctx, oracle):
+    # an exact line: scatter matrix of rank 1 -> degenerate -> zero normal, zero density
+    line = np.array([[i, 0, 0, 1] for i in range(50)], np.float32)
+    o = oracle.surface_normals(line, knn=5)
+    g = gpu_ctx.normals(line, knn=5, keep=("normals", "densities"))
+    assert g["degenerate"] == o["degenerate"] == 50
+    assert (g["normals"] == 0).all() and (g["densities"] == 0).all()
+
+
+# ---------------------------------------------------------------------------------- ICP loop
+def _icp_both(oracle, synth, n, minimizer, filters, k=1, max_dist=np.inf, iters=15, differential=None, T_init=None):
+    from libpointmatcher_b200 import pm
+    rd, rf, T_gt = synth.scan_pair(n)
+    nrm = oracle.surface_normals(rf, knn=10, nthreads=8)["normals"]
+    res_o = oracle.icp(rd, rf, ref_normals=nrm, T_init=T_init, knn=k, max_dist=max_dist, filters=filters, minimizer=minimizer,
+                       max_iterations=iters, differential=differential, nthreads=8, acc_double=True)
+    icp = pm.ICP()
+    icp.matcher = pm.KDTreeMatcher({"knn": str(k), "maxDist": str(max_dist)})
+    names = {0: ("MaxDistOutlierFilter", "maxDist"), 1: ("MedianDistOutlierFilter", "factor"), 2: ("TrimmedDistOutlierFilter", "ratio")}
+    icp.outlierFilters = pm.OutlierFilters([pm.OutlierFilterRegistrar.create(names[t][0], {names[t][1]: repr(float(v))}) for t, v in filters])
+    icp.errorMinimizer = [pm.PointToPointErrorMinimizer, pm.PointToPlaneErrorMinimizer, pm.PointToPointWithCovErrorMinimizer,
+                          pm.PointToPlaneWithCovErrorMinimizer][minimizer]()
+    icp.transformationCheckers = [pm.CounterTransformationChecker({"maxIterationCount": str(iters)})]
+    if differential:
+        icp.transformationCheckers.append(pm.DifferentialTransformationChecker(
+            {"minDiffRotErr": repr(differential[0]), "minDiffTransErr": repr(differential[1]), "smoothLength": str(differential[2])}))
+    T = icp(pm.DataPoints(rd), pm.DataPoints(rf, {"normals": nrm}), T_init)
+    return T, icp, res_o, T_gt
+
+
+@pytest.mark.parametrize("minimizer", [0, 1])
+def test_icp_fixed_iterations_matches_oracle(oracle, synth, minimizer):
+    T, icp, res_o, T_gt = _icp_both(oracle, synth, 100000, minimizer, [(2, 0.75)], iters=15)
+    assert icp.iterationCount == res_o["iterations"] == 15
+    assert_transform_close(T, res_o["T"], 1e-5, 1e-5)
+
+
+def test_icp_knn10_median_maxdist_cov(oracle, synth):
+    """config 4 shape: knn 10, maxDist + MedianDist, PointToPlaneWithCov"""
+    T, icp, res_o, _ = _icp_both(oracle, synth, 50000, 3, [(0, 1.0), (1, 3.0)], k=10, max_dist=2.0, iters=8)
+    assert_transform_close(T, res_o["T"], 1e-5, 1e-5)
+    co, cg = res_o["cov"], icp.errorMinimizer.getCovariance()
+    assert np.allclose(cg, co, rtol=5e-3, atol=1e-3 * np.abs(co).max())
+
+
+def test_icp_differential_checker_stops_like_oracle(oracle, synth):
+    T, icp, res_o, T_gt = _icp_both(oracle, synth, 100000, 1, [(2, 0.85)], iters=40, differential=(0.001, 0.001, 3))
+    assert icp.iterationCount == res_o["iterations"] < 40
+    assert_transform_close(T, res_o["T"], 1e-5, 1e-5)
+    assert_transform_close(T, T_gt.astype(np.float32), 5e-3, 2e-2)  # and it is the right registration
+
+
+def test_icp_with_initial_guess(oracle, synth):
+    Ti = synth.pose_matrix((0.5, -0.3, 0.0), 3.0).astype(np.float32)
+    T, icp, res_o, _ = _icp_both(oracle, synth, 50000, 1, [(2, 0.8)], iters=10, T_init=Ti)
+    assert_transform_close(T, res_o["T"], 1e-5, 1e-5)
