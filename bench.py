@@ -48,7 +48,9 @@ def parse():
     ap.add_argument("--points", type=int, default=1_000_000)
     ap.add_argument("--mode", default="pairs", choices=["pairs", "shard"])
     ap.add_argument("--cpu-sample-iters", type=int, default=3)
-    ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the point-to-plane extra section")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end leg (profiling runs)")
     return ap.parse_args()
 
 
@@ -300,7 +302,7 @@ def run_ours(args, rank, world, local_rank):
         return T, n_it, dt
 
     e2e = None
-    if not sharded:
+    if not sharded and not args.no_e2e:
         e2e_once(pm.PointToPointErrorMinimizer, False)  # warm-up (allocations, first-use costs)
         barrier()
         T_e2e, n_it, dt = e2e_once(pm.PointToPointErrorMinimizer, False)
@@ -326,12 +328,13 @@ def run_ours(args, rank, world, local_rank):
             "stage_ms_per_iteration": {k: v[0] / max(1, args.steps + args.warmup) for k, v in st_pl.items()},
             "translation_error_vs_ground_truth_m": float(np.linalg.norm(T_full[:3, 3].astype(np.float64) - T_gt[:3, 3])),
         }
-        _, n_it, dt = e2e_once(pm.PointToPlaneErrorMinimizer, True)
-        extra["point_to_plane"]["e2e_iterations_per_s_incl_normals_knn20"] = n_it / dt
+        if not args.no_e2e:
+            _, n_it, dt = e2e_once(pm.PointToPlaneErrorMinimizer, True)
+            extra["point_to_plane"]["e2e_iterations_per_s_incl_normals_knn20"] = n_it / dt
 
     # ---- cpu_baseline on this box's host cores (rank 0, N = 1 only) -------------------------
     cpu = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import binding as orc
         orc.build()
         threads = orc.num_threads()

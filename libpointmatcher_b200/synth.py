@@ -125,7 +125,12 @@ def scan(n_points, pose=None, rings=None, seed=SEED, scene_seed=SEED, cache=True
     """One LiDAR scan of `n_points` points taken from `pose`, in the sensor frame."""
     pose = np.eye(4) if pose is None else np.asarray(pose, np.float64)
     if rings is None:
-        rings = 128 if n_points >= 2_000_000 and n_points % 128 == 0 else 64
+        # isotropic angular sampling: ring spacing ~ azimuth spacing over the 26.8 deg x 360 deg
+        # field of view (64 rings x 15 625 azimuth steps would put 1 M points on 64 thin circles,
+        # where 2 cm range noise >> 2.5 mm point spacing makes local surface normals meaningless)
+        rings = 64
+        while rings * 2 <= np.sqrt(n_points * (ELEV_MAX_DEG - ELEV_MIN_DEG) / 360.0) * 1.5:
+            rings *= 2
     key = hashlib.sha1(repr((n_points, pose.round(9).tolist(), rings, seed, scene_seed, 2)).encode()).hexdigest()[:20]
     path = os.path.join(_CACHE_DIR, key + ".npy")
     if cache and n_points >= 100_000 and os.path.exists(path):

@@ -148,7 +148,11 @@ def test_minimizers_match_oracle(gpu_ctx, oracle, synth, k):
         Tg, covg, sg = gpu_ctx.minimize(mini, 0.02)
         for acc in (False, True):
             To, covo, so = oracle.minimize(mini, rdt, rf, nrm, ids, d, w, 0.02, acc_double=acc)
-            assert_transform_close(Tg, To, 1e-5, 1e-5)
+            # acc=True: the oracle with fp64 sums, the 1e-5 rad / 1e-5 m bar.  acc=False: the
+            # float-faithful oracle, whose *sequential* float sums over ~1e5 un-centred points carry
+            # ~1e-4 m of their own rounding noise (Eigen's blocked reductions carry less), so it
+            # only bounds the deviation from the reference's float arithmetic from above.
+            assert_transform_close(Tg, To, 1e-5 if acc else 2e-5, 1e-5 if acc else 5e-4)
             assert sg["nbKept"] == so["nbKept"] and sg["nbRejectedMatches"] == so["nbRejectedMatches"]
             assert sg["nbRejectedPoints"] == so["nbRejectedPoints"]
             assert abs(sg["pointUsedRatio"] - so["pointUsedRatio"]) < 1e-6
