@@ -35,6 +35,16 @@ __global__ void transform_inplace_kernel(f4* __restrict__ pts, int n, Mat4 T) {
     if (i < n) pts[i] = transform_point(T, pts[i]);
 }
 
+// sorted position t -> caller's column order[t]; k values per column
+template <typename V>
+__global__ void unpermute_kernel(const V* __restrict__ src, const uint32_t* __restrict__ order, size_t n, int k, V* __restrict__ dst) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * (size_t)k) return;
+    const size_t t = e / k;
+    const int j = (int)(e - t * k);
+    dst[(size_t)order[t] * k + j] = src[e];
+}
+
 int fail(pmgpu_ctx* ctx, int code, const char* msg) {
     ctx->set_error(msg);
     return code;
@@ -100,6 +110,18 @@ int upload_normals(pmgpu_ctx* ctx, const float* normals, int ld) {
     return PMGPU_OK;
 }
 
+// download a k x nq device array that lives in Morton order into the caller's column order
+template <typename V>
+int download_unpermuted(pmgpu_ctx* ctx, const V* src, DevBuf<V>& staging, int k, V* dst) {
+    const size_t total = (size_t)k * ctx->nq;
+    if (!dst || total == 0) return PMGPU_OK;
+    PM_CUDA_TRY(ctx, staging.reserve(total));
+    unpermute_kernel<V><<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(src, ctx->q_order.p, (size_t)ctx->nq, k, staging.p);
+    ctx->launches += 1;
+    PM_CUDA_TRY(ctx, cudaMemcpyAsync(dst, staging.p, total * sizeof(V), cudaMemcpyDefault, ctx->stream));
+    return PMGPU_OK;
+}
+
 int check_params(pmgpu_ctx* ctx, const pmgpu_icp_params* p) {
     if (!p) return fail(ctx, PMGPU_ERR_BAD_ARG, "null parameters");
     if (p->knn < 1) return fail(ctx, PMGPU_ERR_BAD_ARG, "knn must be >= 1");
@@ -115,7 +137,7 @@ int check_params(pmgpu_ctx* ctx, const pmgpu_icp_params* p) {
 int enqueue_iteration(pmgpu_ctx* ctx, const pmgpu_icp_params* p, bool gated) {
     const float max_r2 = p->max_dist * p->max_dist;
     ctx->stage_begin(0);
-    PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, ctx->q_order.p, ctx->nq, true, gated, false, p->knn, max_r2, ctx->ids.p, ctx->dists.p));
+    PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, nullptr, ctx->nq, true, gated, false, p->knn, max_r2, ctx->ids.p, ctx->dists.p));
     ctx->stage_end();
     ctx->stage_begin(1);
     PM_TRY(launch_weights(ctx, p->nfilters, p->filter_type, p->filter_param, gated));
@@ -169,7 +191,8 @@ void pmgpu_ctx_destroy(pmgpu_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     pmgpu_comm_destroy(ctx);
-    ctx->ref_orig.release(); ctx->ref_sorted.release(); ctx->ref_normals.release(); ctx->nodes.release();
+    ctx->ref_orig.release(); ctx->ref_sorted.release(); ctx->ref_normals.release(); ctx->splits.release(); ctx->boxes.release();
+    ctx->reading_tmp.release(); ctx->ids_tmp.release(); ctx->dists_tmp.release();
     ctx->keys_a.release(); ctx->keys_b.release(); ctx->perm_a.release(); ctx->perm_b.release();
     ctx->node_box.release(); ctx->node_dim.release(); ctx->cub_tmp.release();
     ctx->reading.release(); ctx->q_order.release();
@@ -257,7 +280,8 @@ int pmgpu_reading_set(pmgpu_ctx* ctx, const float* features, int rows, int n) {
     ctx->have_matches = false;
     ctx->have_weights = false;
     PM_CUDA_TRY(ctx, ctx->reading.reserve(n > 0 ? n : 1));
-    if (n > 0) PM_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->reading.p, features, (size_t)n * sizeof(f4), cudaMemcpyDefault, ctx->stream));
+    PM_CUDA_TRY(ctx, ctx->reading_tmp.reserve(n > 0 ? n : 1));
+    if (n > 0) PM_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->reading_tmp.p, features, (size_t)n * sizeof(f4), cudaMemcpyDefault, ctx->stream));
     ctx->nq = n;
     if (n > 0) PM_TRY(morton_order(ctx));
     PM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -284,7 +308,7 @@ int pmgpu_reading_get(pmgpu_ctx* ctx, float* features_out) {
     if (!ctx) return PMGPU_ERR_BAD_ARG;
     PM_TRY(use_device(ctx));
     if (!features_out) return fail(ctx, PMGPU_ERR_BAD_ARG, "null output");
-    if (ctx->nq > 0) PM_CUDA_TRY(ctx, cudaMemcpyAsync(features_out, ctx->reading.p, (size_t)ctx->nq * sizeof(f4), cudaMemcpyDefault, ctx->stream));
+    PM_TRY(download_unpermuted<f4>(ctx, ctx->reading.p, ctx->reading_tmp, 1, reinterpret_cast<f4*>(features_out)));
     PM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return PMGPU_OK;
 }
@@ -316,12 +340,11 @@ int pmgpu_knn(pmgpu_ctx* ctx, const float* T, int k, float epsilon, float max_di
     ctx->have_weights = false;
     const float max_r2 = max_dist * max_dist;
     ctx->stage_begin(0);
-    PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, ctx->q_order.p, ctx->nq, T != nullptr, false, false, k, max_r2, ctx->ids.p, ctx->dists.p));
+    PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, nullptr, ctx->nq, T != nullptr, false, false, k, max_r2, ctx->ids.p, ctx->dists.p));
     ctx->stage_end();
     ctx->have_matches = true;
-    const size_t out_n = (size_t)k * ctx->nq;
-    if (ids_out && out_n) PM_CUDA_TRY(ctx, cudaMemcpyAsync(ids_out, ctx->ids.p, out_n * sizeof(int32_t), cudaMemcpyDefault, ctx->stream));
-    if (dists_out && out_n) PM_CUDA_TRY(ctx, cudaMemcpyAsync(dists_out, ctx->dists.p, out_n * sizeof(float), cudaMemcpyDefault, ctx->stream));
+    PM_TRY(download_unpermuted<int32_t>(ctx, ctx->ids.p, ctx->ids_tmp, k, ids_out));
+    PM_TRY(download_unpermuted<float>(ctx, ctx->dists.p, ctx->dists_tmp, k, dists_out));
     PM_TRY(pull_state(ctx));
     if (visit_out) *visit_out = ctx->state_host->visits;
     return PMGPU_OK;
@@ -338,7 +361,7 @@ int pmgpu_weights(pmgpu_ctx* ctx, int nfilters, const int* types, const float* p
     const size_t total = (size_t)ctx->k * ctx->nq;
     if (weights_out && total) {
         PM_TRY(launch_materialize_weights(ctx));
-        PM_CUDA_TRY(ctx, cudaMemcpyAsync(weights_out, ctx->weights.p, total * sizeof(float), cudaMemcpyDefault, ctx->stream));
+        PM_TRY(download_unpermuted<float>(ctx, ctx->weights.p, ctx->dists_tmp, ctx->k, weights_out));
     }
     PM_TRY(pull_state(ctx));
     const int s = device_status(ctx);

@@ -14,9 +14,11 @@
 #define PM_HD __host__ __device__ __forceinline__
 #define PM_D __device__ __forceinline__
 typedef float4 f4;
+typedef float2 f2;
 #else
 #define PM_HD inline
 struct alignas(16) f4 { float x, y, z, w; };
+struct alignas(8) f2 { float x, y; };
 #endif
 
 namespace pm {

@@ -6,16 +6,26 @@
 // [seg_begin(l, s), seg_begin(l, s + 1)) of the sorted point array, where
 // seg_begin(l, s) = floor(s * N / 2^l).  Ranges of children are exact halves of the parent
 // (median split along the parent's widest axis), so no child pointers, counts or leaf tables are
-// stored — only one axis-aligned bounding box per node.  Leaves (level D) hold
-// floor(N / 2^D) or ceil(N / 2^D) <= PM_LEAF_MAX points.
+// stored: per inner node one (split value, axis) pair, per node one axis-aligned bounding box.
+// Leaves (level D) hold floor(N / 2^D) or ceil(N / 2^D) <= PM_LEAF_MAX points.
 //
-// Exactness.  The traversal prunes a node only when its box distance is > the current k-th best
-// distance.  Box distances are evaluated with the same operation order and rounding as point
-// distances (core/common.h dist2); float rounding is monotone, hence for every point p inside a
-// box, dist2(q, p) >= box_dist2(q, box) holds *in float arithmetic*, and pruning can never drop a
-// point that belongs to the answer.  Candidates are ranked lexicographically by
-// (dist2, reference index): the answer is unique, independent of traversal order, and equals
-// what libnabo's brute-force search returns (index-ascending scan, strict '<').
+// Traversal (one thread per query, no stack):
+//   descent   root -> leaf by the split planes only (one 8-byte load + ~10 instructions per level).
+//             The tree is complete, so every lane of a warp runs exactly D steps: no divergence.
+//   backtrack a bit-trail holds one "far child pending" bit per level; the deepest pending level
+//             is popped with clz, the far child's heap index is rebuilt from the current node
+//             (ancestor >> shift, ^ 1), first filtered by the plane distance, then by its
+//             bounding-box distance (one 32-byte load), and only then descended.
+//
+// Exactness.  A subtree is skipped only when a lower bound of the distance to all of its points is
+// > the current k-th best distance.  Both bounds are evaluated with the same operation order and
+// rounding as point distances (core/common.h dist2); float rounding is monotone, hence for every
+// point p of the subtree dist2(q, p) >= bound holds *in float arithmetic*:
+//   plane : the far side satisfies |q[d] - p[d]| >= |q[d] - split| (left points <= split <= right)
+//   box   : per axis |q[a] - p[a]| >= gap(q[a], [lo[a], hi[a]])
+// so pruning never drops a point of the answer.  Candidates are ranked lexicographically by
+// (dist2, reference index): the answer is unique, independent of traversal order, and equals what
+// libnabo's brute-force search returns (index-ascending scan, strict '<').
 #pragma once
 #include "common.h"
 
@@ -37,16 +47,17 @@ PM_HD int tree_depth_for(uint32_t n) {
     return d;
 }
 
-// Read-only view handed to the kernels.
-//  nodes: 3 f4 per inner node i (heap index, root = 1, children 2i and 2i+1), at nodes[3*(i-1)]:
-//         {loL.x, hiL.x, loR.x, hiR.x}, {.. y ..}, {.. z ..}  (boxes of the two children)
-//  pts:   points in leaf order, w = bit pattern of the original column index
+// Read-only view handed to the kernels (all arrays indexed by heap index, root = 1, children
+// 2i and 2i + 1).
+//  splits: inner node i -> {split value, bit pattern of the split axis 0/1/2}
+//  boxes:  node i -> boxes[2i] = (lo.x, lo.y, lo.z, -), boxes[2i+1] = (hi.x, hi.y, hi.z, -)
+//  pts:    points in leaf order, w = bit pattern of the original column index
 struct TreeView {
-    const f4* nodes;
+    const f2* splits;
+    const f4* boxes;
     const f4* pts;
     uint32_t n;
     int depth;
-    f4 root_lo, root_hi;  // box of the whole cloud (w unused)
 };
 
 PM_HD f4 ldg4(const f4* p) {
@@ -56,12 +67,26 @@ PM_HD f4 ldg4(const f4* p) {
     return *p;
 #endif
 }
+PM_HD f2 ldg2(const f2* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+PM_HD int clz32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __clz((int)v);
+#else
+    return v ? __builtin_clz(v) : 32;
+#endif
+}
 
 // distance from q to the interval [lo, hi] on one axis (0 inside)
 PM_HD float axis_gap(float q, float lo, float hi) { return fmaxf(fmaxf(fsub(lo, q), fsub(q, hi)), 0.f); }
 
-PM_HD float box_dist2(float qx, float qy, float qz, float lox, float hix, float loy, float hiy, float loz, float hiz) {
-    const float dx = axis_gap(qx, lox, hix), dy = axis_gap(qy, loy, hiy), dz = axis_gap(qz, loz, hiz);
+PM_HD float box_dist2(float qx, float qy, float qz, f4 lo, f4 hi) {
+    const float dx = axis_gap(qx, lo.x, hi.x), dy = axis_gap(qy, lo.y, hi.y), dz = axis_gap(qz, lo.z, hi.z);
     return fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(dz, dz));
 }
 
@@ -120,50 +145,59 @@ template <int KMAX>
 PM_HD uint32_t knn_search(const TreeView& t, float qx, float qy, float qz, TopK<KMAX>& best) {
     uint32_t visited = 0;
     if (t.n == 0) return 0;
-    uint32_t stack_node[PM_MAX_DEPTH + 1];
-    float stack_d[PM_MAX_DEPTH + 1];
-    int sp = 0;
-    const uint32_t first_leaf = 1u << t.depth;
-    uint32_t node = 1;
+    const int D = t.depth;
+    const uint32_t first_leaf = 1u << D;
+    uint32_t node = 1;       // current node (heap index)
+    int level = 0;           // its level
+    uint32_t trail = 0;      // bit l set: the far child at level l (sibling of our level-l ancestor) is pending
     {
-        const float dr = box_dist2(qx, qy, qz, t.root_lo.x, t.root_hi.x, t.root_lo.y, t.root_hi.y, t.root_lo.z, t.root_hi.z);
+        const float dr = box_dist2(qx, qy, qz, ldg4(t.boxes + 2), ldg4(t.boxes + 3));
         if (dr > best.worst_d()) return 0;
     }
     for (;;) {
-        if (node >= first_leaf) {
+        // ---- descent by split planes: exactly D - level steps
+        while (level < D) {
+            const f2 s = ldg2(t.splits + node);
+            const uint32_t dim = f2u(s.y);
+            const float qd = dim == 0 ? qx : (dim == 1 ? qy : qz);
+            node = 2 * node + (qd >= s.x ? 1u : 0u);
+            ++level;
+            trail |= 1u << level;
+        }
+        // ---- leaf
+        {
             const uint32_t leaf = node - first_leaf;
-            const uint32_t b = seg_begin(t.depth, leaf, t.n), e = seg_begin(t.depth, leaf + 1, t.n);
-            for (uint32_t p = b; p < e; ++p) {
-                const f4 pt = ldg4(t.pts + p);
-                const float dd = dist2(qx, qy, qz, pt.x, pt.y, pt.z);
-                const int pi = (int)f2u(pt.w);
-                if (cand_less(dd, pi, best.worst_d(), best.worst_id())) best.insert(dd, pi);
+            const uint32_t b = seg_begin(D, leaf, t.n), e = seg_begin(D, leaf + 1, t.n);
+#pragma unroll
+            for (uint32_t j = 0; j < PM_LEAF_MAX; ++j) {
+                const uint32_t p = b + j;
+                if (p < e) {
+                    const f4 pt = ldg4(t.pts + p);
+                    const float dd = dist2(qx, qy, qz, pt.x, pt.y, pt.z);
+                    const int pi = (int)f2u(pt.w);
+                    if (cand_less(dd, pi, best.worst_d(), best.worst_id())) best.insert(dd, pi);
+                }
             }
             visited += e - b;
-        } else {
-            const f4* nb = t.nodes + 3 * (size_t)(node - 1);
-            const f4 bx = ldg4(nb), by = ldg4(nb + 1), bz = ldg4(nb + 2);
-            const float dl = box_dist2(qx, qy, qz, bx.x, bx.y, by.x, by.y, bz.x, bz.y);
-            const float dr = box_dist2(qx, qy, qz, bx.z, bx.w, by.z, by.w, bz.z, bz.w);
-            const float w = best.worst_d();
-            const bool vl = dl <= w, vr = dr <= w;
-            if (vl && vr) {
-                // nearer child first; ties go left (deterministic, does not affect the result)
-                const bool left_first = dl <= dr;
-                stack_node[sp] = left_first ? 2 * node + 1 : 2 * node;
-                stack_d[sp] = left_first ? dr : dl;
-                ++sp;
-                node = left_first ? 2 * node : 2 * node + 1;
-                continue;
-            }
-            if (vl) { node = 2 * node; continue; }
-            if (vr) { node = 2 * node + 1; continue; }
         }
-        // pop the next subtree that can still contain a better candidate
+        // ---- backtrack: deepest pending far child that can still hold a better candidate
         bool found = false;
-        while (sp > 0) {
-            --sp;
-            if (stack_d[sp] <= best.worst_d()) { node = stack_node[sp]; found = true; break; }
+        while (trail != 0) {
+            const int l = 31 - clz32(trail);
+            trail &= ~(1u << l);
+            const uint32_t far = (node >> (level - l)) ^ 1u;
+            const f2 s = ldg2(t.splits + (far >> 1));
+            const uint32_t dim = f2u(s.y);
+            const float qd = dim == 0 ? qx : (dim == 1 ? qy : qz);
+            const float diff = fsub(qd, s.x);
+            const float w = best.worst_d();
+            if (fmul(diff, diff) > w) continue;
+            const float db = box_dist2(qx, qy, qz, ldg4(t.boxes + 2 * (size_t)far), ldg4(t.boxes + 2 * (size_t)far + 1));
+            if (db > w) continue;
+            node = far;
+            level = l;
+            found = true;
+            break;
         }
         if (!found) break;
     }

@@ -101,9 +101,9 @@ struct pmgpu_ctx {
     pm::DevBuf<f4> ref_orig;     // original order, (x, y, z, w)
     pm::DevBuf<f4> ref_sorted;   // leaf order, w = original index bits
     pm::DevBuf<f4> ref_normals;  // original order, (nx, ny, nz, 0)
-    pm::DevBuf<f4> nodes;        // 3 f4 per inner node
+    pm::DevBuf<f2> splits;       // inner node (heap index) -> {split value, axis bits}
+    pm::DevBuf<f4> boxes;        // node (heap index) -> 2 f4 (lo, hi)
     bool has_normals = false;
-    f4 root_lo, root_hi;
     // build scratch
     pm::DevBuf<uint64_t> keys_a, keys_b;
     pm::DevBuf<uint32_t> perm_a, perm_b;
@@ -113,8 +113,11 @@ struct pmgpu_ctx {
 
     // reading
     int nq = 0;
-    pm::DevBuf<f4> reading;          // original order
-    pm::DevBuf<uint32_t> q_order;    // Morton order of the reading (query schedule)
+    pm::DevBuf<f4> reading;          // Morton order (position t holds original column q_order[t])
+    pm::DevBuf<f4> reading_tmp;      // upload staging (original order)
+    pm::DevBuf<uint32_t> q_order;    // sorted position -> original column
+    pm::DevBuf<int32_t> ids_tmp;     // un-permute staging for downloads
+    pm::DevBuf<float> dists_tmp;
 
     // matches (K2)
     int k = 0;
@@ -162,12 +165,11 @@ struct pmgpu_ctx {
     void set_error(const std::string& e) { err = e; }
     pm::TreeView tree_view() const {
         pm::TreeView t;
-        t.nodes = nodes.p;
+        t.splits = splits.p;
+        t.boxes = boxes.p;
         t.pts = ref_sorted.p;
         t.n = (uint32_t)nr;
         t.depth = depth;
-        t.root_lo = root_lo;
-        t.root_hi = root_hi;
         return t;
     }
 };

@@ -51,20 +51,15 @@ __global__ void level_boxes_kernel(const f4* __restrict__ pts, const uint32_t* _
     }
 }
 
+__device__ __forceinline__ int widest_axis(const uint32_t* b);
+
 // sort key of every point for the split of `level`: (segment, coordinate along the widest axis)
 __global__ void level_keys_kernel(const f4* __restrict__ pts, const uint32_t* __restrict__ perm, uint32_t n, int level,
                                   const uint32_t* __restrict__ box, uint64_t* __restrict__ keys) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const uint32_t seg = seg_of(p, level, n);
-    const uint32_t* b = box + 6 * (size_t)((1u << level) + seg);
-    const float ex = fsub(ord_float(b[3]), ord_float(b[0]));
-    const float ey = fsub(ord_float(b[4]), ord_float(b[1]));
-    const float ez = fsub(ord_float(b[5]), ord_float(b[2]));
-    int dim = 0;
-    float best = ex;
-    if (ey > best) { dim = 1; best = ey; }
-    if (ez > best) { dim = 2; }
+    const int dim = widest_axis(box + 6 * (size_t)((1u << level) + seg));
     const f4 pt = pts[perm[p]];
     const float c = dim == 0 ? pt.x : (dim == 1 ? pt.y : pt.z);
     keys[p] = ((uint64_t)seg << 32) | (uint64_t)float_ord(c);
@@ -78,16 +73,38 @@ __global__ void gather_sorted_kernel(const f4* __restrict__ pts, const uint32_t*
     out[p] = make_float4(pt.x, pt.y, pt.z, __uint_as_float(src));
 }
 
-// inner node i (heap index) -> the boxes of its two children, interleaved per axis
-__global__ void pack_nodes_kernel(const uint32_t* __restrict__ box, uint32_t n_inner, f4* __restrict__ nodes) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x + 1;
-    if (i > n_inner) return;
-    const uint32_t* l = box + 6 * (size_t)(2 * i);
-    const uint32_t* r = box + 6 * (size_t)(2 * i + 1);
-    f4* o = nodes + 3 * (size_t)(i - 1);
-    o[0] = make_float4(ord_float(l[0]), ord_float(l[3]), ord_float(r[0]), ord_float(r[3]));
-    o[1] = make_float4(ord_float(l[1]), ord_float(l[4]), ord_float(r[1]), ord_float(r[4]));
-    o[2] = make_float4(ord_float(l[2]), ord_float(l[5]), ord_float(r[2]), ord_float(r[5]));
+__device__ __forceinline__ int widest_axis(const uint32_t* b) {
+    const float ex = fsub(ord_float(b[3]), ord_float(b[0]));
+    const float ey = fsub(ord_float(b[4]), ord_float(b[1]));
+    const float ez = fsub(ord_float(b[5]), ord_float(b[2]));
+    int dim = 0;
+    float best = ex;
+    if (ey > best) { dim = 1; best = ey; }
+    if (ez > best) { dim = 2; }
+    return dim;
+}
+
+// after the sort of `level`: split value of node (level, s) = coordinate of the first point of its
+// right half (left points <= split <= right points along the split axis)
+__global__ void level_splits_kernel(const f4* __restrict__ pts, const uint32_t* __restrict__ perm, uint32_t n, int level,
+                                    const uint32_t* __restrict__ box, f2* __restrict__ splits) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= (1u << level)) return;
+    const uint32_t node = (1u << level) + s;
+    const int dim = widest_axis(box + 6 * (size_t)node);
+    const uint32_t mid = seg_begin(level + 1, 2 * s + 1, n);
+    const f4 pt = pts[perm[mid]];
+    const float c = dim == 0 ? pt.x : (dim == 1 ? pt.y : pt.z);
+    splits[node] = make_float2(c, __uint_as_float((uint32_t)dim));
+}
+
+// node i (heap index) -> boxes[2i] = lo, boxes[2i+1] = hi
+__global__ void pack_boxes_kernel(const uint32_t* __restrict__ box, uint32_t nnodes, f4* __restrict__ boxes) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnodes) return;
+    const uint32_t* b = box + 6 * (size_t)i;
+    boxes[2 * (size_t)i] = make_float4(ord_float(b[0]), ord_float(b[1]), ord_float(b[2]), 0.f);
+    boxes[2 * (size_t)i + 1] = make_float4(ord_float(b[3]), ord_float(b[4]), ord_float(b[5]), 0.f);
 }
 
 // 30-bit Morton code of a point inside the cloud's bounding box
@@ -114,6 +131,11 @@ __global__ void morton_keys_kernel(const f4* __restrict__ pts, uint32_t n, const
     vals[p] = p;
 }
 
+__global__ void gather_f4_kernel(const f4* __restrict__ src, const uint32_t* __restrict__ order, uint32_t n, f4* __restrict__ dst) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) dst[t] = src[order[t]];
+}
+
 inline unsigned blocks_for(uint32_t n, int block) { return (unsigned)((n + (uint32_t)block - 1) / (uint32_t)block); }
 
 }  // namespace
@@ -130,7 +152,8 @@ int build_tree(pmgpu_ctx* ctx) {
     PM_CUDA_TRY(ctx, ctx->keys_a.reserve(n));
     PM_CUDA_TRY(ctx, ctx->keys_b.reserve(n));
     PM_CUDA_TRY(ctx, ctx->ref_sorted.reserve(n));
-    PM_CUDA_TRY(ctx, ctx->nodes.reserve(3 * (size_t)(D > 0 ? (1u << D) : 1)));
+    PM_CUDA_TRY(ctx, ctx->splits.reserve((size_t)1 << D));
+    PM_CUDA_TRY(ctx, ctx->boxes.reserve(2 * (size_t)nnodes));
     size_t tmp_bytes = 0;
     PM_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, ctx->keys_a.p, ctx->keys_b.p, ctx->perm_a.p, ctx->perm_b.p, (int)n, 0, 64, st));
     PM_CUDA_TRY(ctx, ctx->cub_tmp.reserve(tmp_bytes));
@@ -148,28 +171,23 @@ int build_tree(pmgpu_ctx* ctx) {
         level_keys_kernel<<<blocks_for(n, B), B, 0, st>>>(ctx->ref_orig.p, perm, n, l, ctx->node_box.p, ctx->keys_a.p);
         size_t tb = ctx->cub_tmp.cap;
         PM_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, ctx->keys_a.p, ctx->keys_b.p, perm, perm_alt, (int)n, 0, 32 + l, st));
-        ctx->launches += 2;
         uint32_t* t = perm; perm = perm_alt; perm_alt = t;
+        level_splits_kernel<<<blocks_for(1u << l, B), B, 0, st>>>(ctx->ref_orig.p, perm, n, l, ctx->node_box.p, ctx->splits.p);
+        ctx->launches += 3;
     }
     gather_sorted_kernel<<<blocks_for(n, B), B, 0, st>>>(ctx->ref_orig.p, perm, n, ctx->ref_sorted.p);
     ctx->launches += 1;
-    if (D > 0) {
-        const uint32_t n_inner = (1u << D) - 1;
-        pack_nodes_kernel<<<blocks_for(n_inner, B), B, 0, st>>>(ctx->node_box.p, n_inner, ctx->nodes.p);
-        ctx->launches += 1;
-    }
-    uint32_t rb[6];
-    PM_CUDA_TRY(ctx, cudaMemcpyAsync(rb, ctx->node_box.p + 6, sizeof(rb), cudaMemcpyDeviceToHost, st));
-    PM_CUDA_TRY(ctx, cudaStreamSynchronize(st));
+    pack_boxes_kernel<<<blocks_for(nnodes, B), B, 0, st>>>(ctx->node_box.p, nnodes, ctx->boxes.p);
+    ctx->launches += 1;
     PM_CUDA_TRY(ctx, cudaGetLastError());
-    ctx->root_lo = make_float4(ord_float(rb[0]), ord_float(rb[1]), ord_float(rb[2]), 0.f);
-    ctx->root_hi = make_float4(ord_float(rb[3]), ord_float(rb[4]), ord_float(rb[5]), 0.f);
     return PMGPU_OK;
 }
 
-// Query schedule: the reading is static during an ICP run (only T_iter changes), so its points
-// are visited in Morton order of their *untransformed* coordinates; a rigid motion preserves
-// locality, hence the 32 queries of a warp walk nearly the same tree path every iteration.
+// Query schedule: the reading is static during an ICP run (only T_iter changes), so it is stored
+// once in Morton order of its *untransformed* coordinates (ctx->reading; q_order maps a sorted
+// position back to the caller's column).  A rigid motion preserves locality, hence the 32 queries
+// of a warp walk nearly the same tree path every iteration and all loads/stores are coalesced.
+// Expects the uploaded cloud in ctx->reading_tmp.
 int morton_order(pmgpu_ctx* ctx) {
     const uint32_t n = (uint32_t)ctx->nq;
     cudaStream_t st = ctx->stream;
@@ -185,11 +203,13 @@ int morton_order(pmgpu_ctx* ctx) {
     PM_CUDA_TRY(ctx, ctx->cub_tmp.reserve(tmp_bytes));
     const int B = 256;
     init_boxes_kernel<<<1, 32, 0, st>>>(ctx->node_box.p, 2);
-    level_boxes_kernel<<<blocks_for(n, B), B, 0, st>>>(ctx->reading.p, nullptr, n, 0, ctx->node_box.p);
-    morton_keys_kernel<<<blocks_for(n, B), B, 0, st>>>(ctx->reading.p, n, ctx->node_box.p, keys_in, ctx->perm_a.p);
+    level_boxes_kernel<<<blocks_for(n, B), B, 0, st>>>(ctx->reading_tmp.p, nullptr, n, 0, ctx->node_box.p);
+    morton_keys_kernel<<<blocks_for(n, B), B, 0, st>>>(ctx->reading_tmp.p, n, ctx->node_box.p, keys_in, ctx->perm_a.p);
     size_t tb = ctx->cub_tmp.cap;
     PM_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, keys_in, keys_out, ctx->perm_a.p, ctx->q_order.p, (int)n, 0, 30, st));
-    ctx->launches += 4;
+    // the reading itself is kept in that order so every per-iteration access is coalesced
+    gather_f4_kernel<<<blocks_for(n, B), B, 0, st>>>(ctx->reading_tmp.p, ctx->q_order.p, n, ctx->reading.p);
+    ctx->launches += 5;
     PM_CUDA_TRY(ctx, cudaGetLastError());
     return PMGPU_OK;
 }

@@ -19,7 +19,8 @@ using namespace pm;
 namespace {
 
 struct EmuTree {
-    std::vector<f4> nodes, pts;
+    std::vector<f2> splits;
+    std::vector<f4> boxes, pts;
     TreeView view;
 };
 
@@ -36,6 +37,18 @@ EmuTree* build(const float* feat, int n) {
     std::vector<uint32_t> perm(N);
     std::iota(perm.begin(), perm.end(), 0u);
     auto coord = [&](uint32_t i, int d) { return feat[4 * (size_t)i + d]; };
+    auto widest = [&](uint32_t node) {
+        const uint32_t* b = &box[6 * (size_t)node];
+        const float ex = fsub(ord_float(b[3]), ord_float(b[0]));
+        const float ey = fsub(ord_float(b[4]), ord_float(b[1]));
+        const float ez = fsub(ord_float(b[5]), ord_float(b[2]));
+        int dim = 0;
+        float best = ex;
+        if (ey > best) { dim = 1; best = ey; }
+        if (ez > best) { dim = 2; }
+        return dim;
+    };
+    t->splits.assign((size_t)1 << D, f2{0.f, 0.f});
     for (int l = 0; l <= D; ++l) {
         for (uint32_t p = 0; p < N; ++p) {
             const uint32_t node = (1u << l) + seg_of(p, l, N);
@@ -49,35 +62,31 @@ EmuTree* build(const float* feat, int n) {
         std::vector<std::pair<uint64_t, uint32_t>> kv(N);
         for (uint32_t p = 0; p < N; ++p) {
             const uint32_t seg = seg_of(p, l, N);
-            const uint32_t* b = &box[6 * (size_t)((1u << l) + seg)];
-            const float ex = fsub(ord_float(b[3]), ord_float(b[0]));
-            const float ey = fsub(ord_float(b[4]), ord_float(b[1]));
-            const float ez = fsub(ord_float(b[5]), ord_float(b[2]));
-            int dim = 0;
-            float best = ex;
-            if (ey > best) { dim = 1; best = ey; }
-            if (ez > best) { dim = 2; }
+            const int dim = widest((1u << l) + seg);
             kv[p] = {((uint64_t)seg << 32) | float_ord(coord(perm[p], dim)), perm[p]};
         }
         std::stable_sort(kv.begin(), kv.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
         for (uint32_t p = 0; p < N; ++p) perm[p] = kv[p].second;
+        for (uint32_t s = 0; s < (1u << l); ++s) {
+            const uint32_t node = (1u << l) + s;
+            const int dim = widest(node);
+            const uint32_t mid = seg_begin(l + 1, 2 * s + 1, N);
+            t->splits[node] = f2{coord(perm[mid], dim), u2f((uint32_t)dim)};
+        }
     }
     t->pts.resize(N);
     for (uint32_t p = 0; p < N; ++p) t->pts[p] = make_f4(coord(perm[p], 0), coord(perm[p], 1), coord(perm[p], 2), u2f(perm[p]));
-    const uint32_t n_inner = (1u << D) - 1;
-    t->nodes.resize(3 * (size_t)std::max(1u, n_inner));
-    for (uint32_t i = 1; i <= n_inner; ++i) {
-        const uint32_t* l = &box[6 * (size_t)(2 * i)];
-        const uint32_t* r = &box[6 * (size_t)(2 * i + 1)];
-        for (int a = 0; a < 3; ++a)
-            t->nodes[3 * (size_t)(i - 1) + a] = make_f4(ord_float(l[a]), ord_float(l[3 + a]), ord_float(r[a]), ord_float(r[3 + a]));
+    t->boxes.resize(2 * (size_t)nnodes);
+    for (uint32_t i = 0; i < nnodes; ++i) {
+        const uint32_t* b = &box[6 * (size_t)i];
+        t->boxes[2 * (size_t)i] = make_f4(ord_float(b[0]), ord_float(b[1]), ord_float(b[2]), 0.f);
+        t->boxes[2 * (size_t)i + 1] = make_f4(ord_float(b[3]), ord_float(b[4]), ord_float(b[5]), 0.f);
     }
-    t->view.nodes = t->nodes.data();
+    t->view.splits = t->splits.data();
+    t->view.boxes = t->boxes.data();
     t->view.pts = t->pts.data();
     t->view.n = N;
     t->view.depth = D;
-    t->view.root_lo = make_f4(ord_float(box[6]), ord_float(box[7]), ord_float(box[8]), 0.f);
-    t->view.root_hi = make_f4(ord_float(box[9]), ord_float(box[10]), ord_float(box[11]), 0.f);
     return t;
 }
 
@@ -123,18 +132,18 @@ int emu_tree_check(void* tp) {
             const uint32_t idx = f2u(v.pts[p].w);
             if (idx >= v.n || seen[idx]) return 3;
             seen[idx] = 1;
-            // every ancestor box contains the point
+            // every ancestor box contains the point, and every split separates its halves
             uint32_t node = leaves + leaf;
-            while (node > 1) {
-                const uint32_t parent = node >> 1;
-                const f4* nb = v.nodes + 3 * (size_t)(parent - 1);
-                const bool right = node & 1;
-                const float lo[3] = {right ? nb[0].z : nb[0].x, right ? nb[1].z : nb[1].x, right ? nb[2].z : nb[2].x};
-                const float hi[3] = {right ? nb[0].w : nb[0].y, right ? nb[1].w : nb[1].y, right ? nb[2].w : nb[2].y};
-                const float c[3] = {v.pts[p].x, v.pts[p].y, v.pts[p].z};
-                for (int a = 0; a < 3; ++a)
-                    if (c[a] < lo[a] || c[a] > hi[a]) return 4;
-                node = parent;
+            const float c[3] = {v.pts[p].x, v.pts[p].y, v.pts[p].z};
+            while (node >= 1) {
+                const f4 lo = v.boxes[2 * (size_t)node], hi = v.boxes[2 * (size_t)node + 1];
+                if (c[0] < lo.x || c[0] > hi.x || c[1] < lo.y || c[1] > hi.y || c[2] < lo.z || c[2] > hi.z) return 4;
+                if (node > 1) {
+                    const f2 s = v.splits[node >> 1];
+                    const float cd = c[f2u(s.y)];
+                    if ((node & 1) ? (cd < s.x) : (cd > s.x)) return 6;
+                }
+                node >>= 1;
             }
         }
     }

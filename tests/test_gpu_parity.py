@@ -146,20 +146,28 @@ def test_minimizers_match_oracle(gpu_ctx, oracle, synth, k):
     w, _ = gpu_ctx.weights(chain)
     for mini in (0, 1, 2, 3):
         Tg, covg, sg = gpu_ctx.minimize(mini, 0.02)
-        for acc in (False, True):
-            To, covo, so = oracle.minimize(mini, rdt, rf, nrm, ids, d, w, 0.02, acc_double=acc)
-            # acc=True: the oracle with fp64 sums, the 1e-5 rad / 1e-5 m bar.  acc=False: the
-            # float-faithful oracle, whose *sequential* float sums over ~1e5 un-centred points carry
-            # ~1e-4 m of their own rounding noise (Eigen's blocked reductions carry less), so it
-            # only bounds the deviation from the reference's float arithmetic from above.
-            assert_transform_close(Tg, To, 1e-5 if acc else 2e-5, 1e-5 if acc else 5e-4)
-            assert sg["nbKept"] == so["nbKept"] and sg["nbRejectedMatches"] == so["nbRejectedMatches"]
-            assert sg["nbRejectedPoints"] == so["nbRejectedPoints"]
-            assert abs(sg["pointUsedRatio"] - so["pointUsedRatio"]) < 1e-6
-            assert abs(sg["weightedPointUsedRatio"] - so["weightedPointUsedRatio"]) < 1e-5
-        if mini >= 2:
-            # double-accumulated oracle: H^-1 is ill-conditioned in float -> relative tolerance
+        # The bar (1e-5 rad / 1e-5 m) is checked against the oracle with fp64 sums.  The
+        # float-faithful oracle accumulates ~1e5..1e6 terms *sequentially* in float, which alone
+        # costs up to ~1e-3 m on un-centred clouds (Eigen's blocked reductions lose less), so it
+        # can only confirm that the GPU result lies within that oracle's own rounding noise.
+        To, covo, so = oracle.minimize(mini, rdt, rf, nrm, ids, d, w, 0.02, acc_double=True)
+        Tf, _, sf = oracle.minimize(mini, rdt, rf, nrm, ids, d, w, 0.02, acc_double=False)
+        assert_transform_close(Tg, To, 1e-5, 1e-5)
+        noise_t = float(np.linalg.norm(To[:3, 3].astype(np.float64) - Tf[:3, 3]))
+        assert float(np.linalg.norm(Tg[:3, 3].astype(np.float64) - Tf[:3, 3])) <= noise_t + 1e-5
+        for s_ in (so, sf):
+            assert sg["nbKept"] == s_["nbKept"] and sg["nbRejectedMatches"] == s_["nbRejectedMatches"]
+            assert sg["nbRejectedPoints"] == s_["nbRejectedPoints"]
+            assert abs(sg["pointUsedRatio"] - s_["pointUsedRatio"]) < 1e-6
+            assert abs(sg["weightedPointUsedRatio"] - s_["weightedPointUsedRatio"]) < 1e-5
+        if mini == 3:
+            # H^-1 is ill-conditioned in float -> relative tolerance
             assert np.allclose(covg, covo, rtol=2e-3, atol=1e-3 * np.abs(covo).max()), (covg, covo)
+        if mini == 2:
+            # PointToPointWithCov uses the pseudo-normal (1,1,1) (PointToPointWithCov.cpp:77): the
+            # first three rows of J_hessian are identical, the matrix is singular and its inverse
+            # (hence the reference's covariance) is not finite.  Same on the GPU.
+            assert not np.isfinite(covo).all() and not np.isfinite(covg).all()
 
 
 def test_point_to_plane_without_normals_is_invalid_field(gpu_ctx, oracle):
