@@ -1,5 +1,6 @@
 // api.cu — the extern "C" entry points of include/pmgpu.h: argument checks, uploads/downloads,
 // kernel sequencing.  All work of a context is issued on its own stream.
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -137,7 +138,9 @@ int check_params(pmgpu_ctx* ctx, const pmgpu_icp_params* p) {
 int enqueue_iteration(pmgpu_ctx* ctx, const pmgpu_icp_params* p, bool gated) {
     const float max_r2 = p->max_dist * p->max_dist;
     ctx->stage_begin(0);
-    PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, nullptr, ctx->nq, true, gated, false, p->knn, max_r2, ctx->ids.p, ctx->dists.p));
+    PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, ctx->nq, true, gated, false, p->knn, max_r2, ctx->hint.p,
+                      ctx->hint_valid && ctx->hints_enabled, ctx->ids.p, ctx->dists.p));
+    ctx->hint_valid = true;
     ctx->stage_end();
     ctx->stage_begin(1);
     PM_TRY(launch_weights(ctx, p->nfilters, p->filter_type, p->filter_param, gated));
@@ -173,6 +176,7 @@ int pmgpu_ctx_create(int device, pmgpu_ctx** ctx_out) {
         return PMGPU_ERR_CUDA;
     }
     ctx->num_sms = sms > 0 ? sms : 148;
+    ctx->hints_enabled = getenv("PMGPU_NO_HINTS") == nullptr;  // A/B switch for profiling
     memset(ctx->state_host, 0, sizeof(IcpState));
     mat4_identity(ctx->state_host->T_iter);
     mat4_identity(ctx->state_host->T_match);
@@ -192,7 +196,7 @@ void pmgpu_ctx_destroy(pmgpu_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     pmgpu_comm_destroy(ctx);
     ctx->ref_orig.release(); ctx->ref_sorted.release(); ctx->ref_normals.release(); ctx->splits.release(); ctx->boxes.release();
-    ctx->reading_tmp.release(); ctx->ids_tmp.release(); ctx->dists_tmp.release();
+    ctx->reading_tmp.release(); ctx->ids_tmp.release(); ctx->dists_tmp.release(); ctx->hint.release();
     ctx->keys_a.release(); ctx->keys_b.release(); ctx->perm_a.release(); ctx->perm_b.release();
     ctx->node_box.release(); ctx->node_dim.release(); ctx->cub_tmp.release();
     ctx->reading.release(); ctx->q_order.release();
@@ -253,6 +257,7 @@ int pmgpu_ref_set(pmgpu_ctx* ctx, const float* features, int rows, int n, const 
     ctx->nr = 0;
     ctx->has_normals = false;
     ctx->have_matches = false;
+    ctx->hint_valid = false;
     PM_CUDA_TRY(ctx, ctx->ref_orig.reserve(n));
     PM_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ref_orig.p, features, (size_t)n * sizeof(f4), cudaMemcpyDefault, ctx->stream));
     ctx->nr = n;
@@ -281,6 +286,8 @@ int pmgpu_reading_set(pmgpu_ctx* ctx, const float* features, int rows, int n) {
     ctx->have_weights = false;
     PM_CUDA_TRY(ctx, ctx->reading.reserve(n > 0 ? n : 1));
     PM_CUDA_TRY(ctx, ctx->reading_tmp.reserve(n > 0 ? n : 1));
+    PM_CUDA_TRY(ctx, ctx->hint.reserve(n > 0 ? n : 1));
+    ctx->hint_valid = false;
     if (n > 0) PM_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->reading_tmp.p, features, (size_t)n * sizeof(f4), cudaMemcpyDefault, ctx->stream));
     ctx->nq = n;
     if (n > 0) PM_TRY(morton_order(ctx));
@@ -340,7 +347,9 @@ int pmgpu_knn(pmgpu_ctx* ctx, const float* T, int k, float epsilon, float max_di
     ctx->have_weights = false;
     const float max_r2 = max_dist * max_dist;
     ctx->stage_begin(0);
-    PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, nullptr, ctx->nq, T != nullptr, false, false, k, max_r2, ctx->ids.p, ctx->dists.p));
+    PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, ctx->nq, T != nullptr, false, false, k, max_r2, ctx->hint.p,
+                      ctx->hint_valid && ctx->hints_enabled, ctx->ids.p, ctx->dists.p));
+    ctx->hint_valid = true;
     ctx->stage_end();
     ctx->have_matches = true;
     PM_TRY(download_unpermuted<int32_t>(ctx, ctx->ids.p, ctx->ids_tmp, k, ids_out));
@@ -495,7 +504,7 @@ int pmgpu_ref_compute_normals(pmgpu_ctx* ctx, int knn, float epsilon, float max_
     PM_CUDA_TRY(ctx, nids.reserve((size_t)knn * n));
     PM_CUDA_TRY(ctx, ndists.reserve((size_t)knn * n));
     PM_CUDA_TRY(ctx, ctx->ref_normals.reserve(n));
-    int s = launch_knn(ctx, ctx->tree_view(), ctx->ref_sorted.p, nullptr, n, false, false, true, knn, max_dist * max_dist, nids.p, ndists.p);
+    int s = launch_knn(ctx, ctx->tree_view(), ctx->ref_sorted.p, n, false, false, true, knn, max_dist * max_dist, nullptr, false, nids.p, ndists.p);
     if (s == PMGPU_OK) s = launch_normals(ctx, ctx->ref_orig.p, n, nids.p, ndists.p, knn, flags, ctx->ref_normals.p, nullptr, nullptr, nullptr, nullptr);
     cudaStreamSynchronize(ctx->stream);
     nids.release();
@@ -546,7 +555,7 @@ int pmgpu_normals(pmgpu_ctx* ctx, const float* features, int rows, int n, int kn
     IcpState* h = sub->state_host;
     h->degenerate = 0;
     s = push_state(sub);
-    if (s == PMGPU_OK) s = launch_knn(sub, sub->tree_view(), sub->ref_sorted.p, nullptr, n, false, false, true, knn, max_dist * max_dist, nids.p, ndists.p);
+    if (s == PMGPU_OK) s = launch_knn(sub, sub->tree_view(), sub->ref_sorted.p, n, false, false, true, knn, max_dist * max_dist, nullptr, false, nids.p, ndists.p);
     if (s == PMGPU_OK)
         s = launch_normals(sub, sub->ref_orig.p, n, nids.p, ndists.p, knn, flags, n4.p, out->densities ? scratch.p + off_den : nullptr,
                            out->eig_values ? scratch.p + off_val : nullptr, out->eig_vectors ? scratch.p + off_vec : nullptr,

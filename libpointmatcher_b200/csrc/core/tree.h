@@ -139,69 +139,127 @@ struct TopK<1> {
     PM_HD void insert(float nd, int ni) { d[0] = nd; id[0] = ni; }
 };
 
-// Exact k-nearest-neighbour search of one query.  Returns the number of reference points whose
-// distance was evaluated (the analogue of libnabo's visit count, MatchersImpl.cpp:98).
+#if defined(PM_EMU_STATS) && !defined(__CUDACC__)
+struct EmuStats { unsigned long long descent_steps, pops, box_tests, redescents, leaves; };
+static EmuStats g_emu_stats = {0, 0, 0, 0, 0};
+#define PM_STAT(field) (++g_emu_stats.field)
+#else
+#define PM_STAT(field) ((void)0)
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// Per-query search state and its three phases.  knn.cu runs the phases of the 32 lanes of a warp
+// in lock step (descend* | scan leaf | pop*), re-converging between phases, and hands a new query
+// to every lane that finished; knn_search_single() below composes the same phases sequentially
+// (host harness, and the definition of the result).
+// ------------------------------------------------------------------------------------------------
+struct Lane {
+    float qx, qy, qz;
+    uint32_t node;      // current node (heap index)
+    int level;          // its level
+    uint32_t trail;     // bit l set: the sibling of our level-l ancestor has not been examined yet
+    uint32_t best_leaf; // leaf (heap index) that produced the current nearest candidate
+    uint32_t visited;
+};
+
+// start at the root (cold) or at `start_leaf` (heap index of a leaf that probably holds the
+// answer: the previous iteration's match, or the query's own leaf for a self-query).  Any start
+// leaf is valid: every other subtree stays pending in the trail.
+PM_HD void lane_begin(Lane& s, const TreeView& t, float qx, float qy, float qz, uint32_t start_leaf) {
+    s.qx = qx; s.qy = qy; s.qz = qz;
+    s.visited = 0;
+    if (start_leaf != 0) {
+        s.node = start_leaf;
+        s.level = t.depth;
+        s.trail = (t.depth > 0) ? ((2u << t.depth) - 2u) : 0u;  // bits 1..D
+    } else {
+        s.node = 1;
+        s.level = 0;
+        s.trail = 0;
+    }
+    s.best_leaf = s.node;
+}
+
+PM_HD bool lane_descending(const Lane& s, const TreeView& t) { return s.level < t.depth; }
+
+// one step of the plane descent
+PM_HD void lane_descend_step(Lane& s, const TreeView& t) {
+    const f2 sp = ldg2(t.splits + s.node);
+    const uint32_t dim = f2u(sp.y);
+    const float qd = dim == 0 ? s.qx : (dim == 1 ? s.qy : s.qz);
+    s.node = 2 * s.node + (qd >= sp.x ? 1u : 0u);
+    ++s.level;
+    s.trail |= 1u << s.level;
+    PM_STAT(descent_steps);
+}
+
+// distances to all points of the current leaf
 template <int KMAX>
-PM_HD uint32_t knn_search(const TreeView& t, float qx, float qy, float qz, TopK<KMAX>& best) {
-    uint32_t visited = 0;
-    if (t.n == 0) return 0;
-    const int D = t.depth;
-    const uint32_t first_leaf = 1u << D;
-    uint32_t node = 1;       // current node (heap index)
-    int level = 0;           // its level
-    uint32_t trail = 0;      // bit l set: the far child at level l (sibling of our level-l ancestor) is pending
-    {
-        const float dr = box_dist2(qx, qy, qz, ldg4(t.boxes + 2), ldg4(t.boxes + 3));
-        if (dr > best.worst_d()) return 0;
-    }
-    for (;;) {
-        // ---- descent by split planes: exactly D - level steps
-        while (level < D) {
-            const f2 s = ldg2(t.splits + node);
-            const uint32_t dim = f2u(s.y);
-            const float qd = dim == 0 ? qx : (dim == 1 ? qy : qz);
-            node = 2 * node + (qd >= s.x ? 1u : 0u);
-            ++level;
-            trail |= 1u << level;
-        }
-        // ---- leaf
-        {
-            const uint32_t leaf = node - first_leaf;
-            const uint32_t b = seg_begin(D, leaf, t.n), e = seg_begin(D, leaf + 1, t.n);
+PM_HD void lane_scan_leaf(Lane& s, const TreeView& t, TopK<KMAX>& best) {
+    const uint32_t leaf = s.node - (1u << t.depth);
+    const uint32_t b = seg_begin(t.depth, leaf, t.n), e = seg_begin(t.depth, leaf + 1, t.n);
 #pragma unroll
-            for (uint32_t j = 0; j < PM_LEAF_MAX; ++j) {
-                const uint32_t p = b + j;
-                if (p < e) {
-                    const f4 pt = ldg4(t.pts + p);
-                    const float dd = dist2(qx, qy, qz, pt.x, pt.y, pt.z);
-                    const int pi = (int)f2u(pt.w);
-                    if (cand_less(dd, pi, best.worst_d(), best.worst_id())) best.insert(dd, pi);
-                }
+    for (uint32_t j = 0; j < PM_LEAF_MAX; ++j) {
+        const uint32_t p = b + j;
+        if (p < e) {
+            const f4 pt = ldg4(t.pts + p);
+            const float dd = dist2(s.qx, s.qy, s.qz, pt.x, pt.y, pt.z);
+            const int pi = (int)f2u(pt.w);
+            if (cand_less(dd, pi, best.worst_d(), best.worst_id())) {
+                if (cand_less(dd, pi, best.d[0], best.id[0])) s.best_leaf = s.node;
+                best.insert(dd, pi);
             }
-            visited += e - b;
         }
-        // ---- backtrack: deepest pending far child that can still hold a better candidate
-        bool found = false;
-        while (trail != 0) {
-            const int l = 31 - clz32(trail);
-            trail &= ~(1u << l);
-            const uint32_t far = (node >> (level - l)) ^ 1u;
-            const f2 s = ldg2(t.splits + (far >> 1));
-            const uint32_t dim = f2u(s.y);
-            const float qd = dim == 0 ? qx : (dim == 1 ? qy : qz);
-            const float diff = fsub(qd, s.x);
-            const float w = best.worst_d();
-            if (fmul(diff, diff) > w) continue;
-            const float db = box_dist2(qx, qy, qz, ldg4(t.boxes + 2 * (size_t)far), ldg4(t.boxes + 2 * (size_t)far + 1));
-            if (db > w) continue;
-            node = far;
-            level = l;
-            found = true;
-            break;
-        }
-        if (!found) break;
     }
-    return visited;
+    s.visited += e - b;
+    PM_STAT(leaves);
+}
+
+// examine pending siblings, deepest first; returns true when one has to be searched (the lane
+// then continues with descend steps from it), false when the search is complete.
+template <int KMAX>
+PM_HD bool lane_pop(Lane& s, const TreeView& t, const TopK<KMAX>& best) {
+    while (s.trail != 0) {
+        const int l = 31 - clz32(s.trail);
+        s.trail &= ~(1u << l);
+        const uint32_t far = (s.node >> (s.level - l)) ^ 1u;
+        PM_STAT(pops);
+        const float w = best.worst_d();
+        // plane bound, valid when the query lies on the other side of the parent's split
+        const f2 sp = ldg2(t.splits + (far >> 1));
+        const uint32_t dim = f2u(sp.y);
+        const float qd = dim == 0 ? s.qx : (dim == 1 ? s.qy : s.qz);
+        const bool q_right = qd >= sp.x;
+        if (q_right != ((far & 1u) != 0u)) {
+            const float diff = fsub(qd, sp.x);
+            if (fmul(diff, diff) > w) continue;
+        }
+        PM_STAT(box_tests);
+        const float db = box_dist2(s.qx, s.qy, s.qz, ldg4(t.boxes + 2 * (size_t)far), ldg4(t.boxes + 2 * (size_t)far + 1));
+        if (db > w) continue;
+        s.node = far;
+        s.level = l;
+        PM_STAT(redescents);
+        return true;
+    }
+    return false;
+}
+
+// Exact k-nearest-neighbour search of one query.  Returns the number of reference points whose
+// distance was evaluated (the analogue of libnabo's visit count, MatchersImpl.cpp:98);
+// *best_leaf_out receives the leaf of the nearest candidate (next iteration's start hint).
+template <int KMAX>
+PM_HD uint32_t knn_search_single(const TreeView& t, float qx, float qy, float qz, uint32_t start_leaf, TopK<KMAX>& best, uint32_t* best_leaf_out) {
+    if (t.n == 0) return 0;
+    Lane s;
+    lane_begin(s, t, qx, qy, qz, start_leaf);
+    for (;;) {
+        while (lane_descending(s, t)) lane_descend_step(s, t);
+        lane_scan_leaf<KMAX>(s, t, best);
+        if (!lane_pop<KMAX>(s, t, best)) break;
+    }
+    if (best_leaf_out) *best_leaf_out = s.best_leaf;
+    return s.visited;
 }
 
 }  // namespace pm

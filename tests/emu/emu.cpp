@@ -10,6 +10,7 @@
 #include <numeric>
 #include <vector>
 
+#define PM_EMU_STATS 1
 #include "core/common.h"
 #include "core/linalg.h"
 #include "core/tree.h"
@@ -90,6 +91,10 @@ EmuTree* build(const float* feat, int n) {
     return t;
 }
 
+uint32_t* g_visits_out = nullptr;  // optional per-query visit counts (analysis only)
+
+uint32_t* g_hint = nullptr;  // optional per-query start leaves (in: hint or 0, out: leaf of the nearest candidate)
+
 template <int KMAX>
 long run_knn(const EmuTree* t, const float* T16, const float* q, int nq, int k, float max_r2, int32_t* ids, float* dists) {
     long visits = 0;
@@ -100,7 +105,11 @@ long run_knn(const EmuTree* t, const float* T16, const float* q, int nq, int k, 
         if (T16) p = transform_point(T, p);
         TopK<KMAX> best;
         best.init(k, max_r2);
-        visits += knn_search<KMAX>(t->view, p.x, p.y, p.z, best);
+        uint32_t leaf_out = 0;
+        const uint32_t v = knn_search_single<KMAX>(t->view, p.x, p.y, p.z, g_hint ? g_hint[i] : 0u, best, &leaf_out);
+        if (g_hint) g_hint[i] = leaf_out;
+        visits += v;
+        if (g_visits_out) g_visits_out[i] = v;
         for (int j = 0; j < k; ++j) {
             const bool valid = best.id[j] != PM_NO_ID && best.d[j] != pm_inf();
             ids[(size_t)i * k + j] = valid ? best.id[j] : -1;
@@ -114,6 +123,13 @@ long run_knn(const EmuTree* t, const float* T16, const float* q, int nq, int k, 
 
 extern "C" {
 
+void emu_set_visits_out(uint32_t* p) { g_visits_out = p; }
+void emu_set_hint(uint32_t* p) { g_hint = p; }
+void emu_stats(unsigned long long* out5, int reset) {
+    out5[0] = g_emu_stats.descent_steps; out5[1] = g_emu_stats.pops; out5[2] = g_emu_stats.box_tests;
+    out5[3] = g_emu_stats.redescents; out5[4] = g_emu_stats.leaves;
+    if (reset) g_emu_stats = EmuStats{0, 0, 0, 0, 0};
+}
 void* emu_tree_build(const float* feat, int n) { return build(feat, n); }
 void emu_tree_free(void* t) { delete static_cast<EmuTree*>(t); }
 int emu_tree_depth(void* t) { return static_cast<EmuTree*>(t)->view.depth; }

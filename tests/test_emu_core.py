@@ -94,6 +94,28 @@ def test_knn_vs_kdtree_on_lidar(emu, oracle, synth):
     assert visits / len(rd) < 40  # box pruning keeps the leaf visits low on surface data
 
 
+def test_knn_any_start_leaf_gives_the_same_answer(emu, oracle):
+    """the warm start (previous match's leaf) is only a hint: even random start leaves are exact"""
+    rng = np.random.default_rng(16)
+    ref, q = cloud(rng, 5000, "uniform"), cloud(rng, 600, "uniform")
+    t = emu.emu_tree_build(f(ref), len(ref))
+    try:
+        depth = emu.emu_tree_depth(t)
+        for k in (1, 7):
+            ib, db = oracle.bruteforce_knn(ref, q, k)
+            for mode in ("random", "carried"):
+                hints = rng.integers(1 << depth, 2 << depth, len(q)).astype(np.uint32)
+                emu.emu_set_hint(hints.ctypes.data_as(C.c_void_p))
+                for _ in range(2 if mode == "carried" else 1):  # second pass starts at the leaves found by the first
+                    ids = np.empty((len(q), k), np.int32)
+                    dist = np.empty((len(q), k), np.float32)
+                    emu.emu_knn(t, None, f(q), len(q), k, np.inf, ids.ctypes.data_as(IP), f(dist))
+                    assert (ib == ids).all() and (db.view(np.uint32) == dist.view(np.uint32)).all()
+    finally:
+        emu.emu_set_hint(None)
+        emu.emu_tree_free(t)
+
+
 def test_solve_psd6(emu, oracle):
     rng = np.random.default_rng(12)
     x = np.zeros(6)
