@@ -168,16 +168,18 @@ struct Lane {
 PM_HD void lane_begin(Lane& s, const TreeView& t, float qx, float qy, float qz, uint32_t start_leaf) {
     s.qx = qx; s.qy = qy; s.qz = qz;
     s.visited = 0;
-    if (start_leaf != 0) {
+    // a hint that is not a leaf of THIS tree (0 = none) falls back to the cold start
+    if (start_leaf >= (1u << t.depth) && start_leaf < (2u << t.depth)) {
         s.node = start_leaf;
         s.level = t.depth;
         s.trail = (t.depth > 0) ? ((2u << t.depth) - 2u) : 0u;  // bits 1..D
+        s.best_leaf = start_leaf;
     } else {
         s.node = 1;
         s.level = 0;
         s.trail = 0;
+        s.best_leaf = 0;  // stays 0 (= no hint) when no candidate is accepted, e.g. all beyond maxDist
     }
-    s.best_leaf = s.node;
 }
 
 PM_HD bool lane_descending(const Lane& s, const TreeView& t) { return s.level < t.depth; }

@@ -101,16 +101,19 @@ def test_knn_any_start_leaf_gives_the_same_answer(emu, oracle):
     t = emu.emu_tree_build(f(ref), len(ref))
     try:
         depth = emu.emu_tree_depth(t)
-        for k in (1, 7):
-            ib, db = oracle.bruteforce_knn(ref, q, k)
-            for mode in ("random", "carried"):
+        for k, md in ((1, np.inf), (7, np.inf), (1, 0.3), (5, 0.5)):  # small maxDist: many queries find nothing
+            ib, db = oracle.bruteforce_knn(ref, q, k, md)
+            for mode in ("random", "carried", "cold-then-carried"):
                 hints = rng.integers(1 << depth, 2 << depth, len(q)).astype(np.uint32)
+                if mode == "cold-then-carried":
+                    hints[:] = 0
                 emu.emu_set_hint(hints.ctypes.data_as(C.c_void_p))
-                for _ in range(2 if mode == "carried" else 1):  # second pass starts at the leaves found by the first
+                for _ in range(1 if mode == "random" else 3):  # later passes start at the leaves found before
                     ids = np.empty((len(q), k), np.int32)
                     dist = np.empty((len(q), k), np.float32)
-                    emu.emu_knn(t, None, f(q), len(q), k, np.inf, ids.ctypes.data_as(IP), f(dist))
+                    emu.emu_knn(t, None, f(q), len(q), k, md, ids.ctypes.data_as(IP), f(dist))
                     assert (ib == ids).all() and (db.view(np.uint32) == dist.view(np.uint32)).all()
+                    assert ((hints == 0) | ((hints >= (1 << depth)) & (hints < (2 << depth)))).all()
     finally:
         emu.emu_set_hint(None)
         emu.emu_tree_free(t)
