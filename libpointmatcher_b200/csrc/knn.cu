@@ -8,7 +8,7 @@
 // as three phases — plane descent | leaf scan | pop pending siblings — and the lanes of a warp
 // RE-CONVERGE between phases (__syncwarp): without that, independent thread scheduling lets every
 // lane drift into its own phase and the warp executes ~3 of 32 lanes per instruction (measured,
-// profiles/).  Lanes that finish early are refilled with the next query of their warp's chunk.  T_iter is read from the device-resident IcpState, so no host round trip separates
+// profiles/).  T_iter is read from the device-resident IcpState, so no host round trip separates
 // iterations; in iterations >= 2 every query starts at the leaf of its previous match (hint),
 // which skips the root descent and makes the first leaf scan produce a tight bound.
 #include "pmgpu_internal.cuh"
@@ -16,11 +16,6 @@
 namespace pm {
 
 namespace {
-
-// queries per warp: each warp owns a contiguous chunk of the Morton-ordered reading and hands the
-// next query of the chunk to every lane that has finished ("lane refill"), so a lane with an easy
-// query does not idle until the hardest query of its warp is done.
-constexpr int CHUNK = 128;
 
 template <int KMAX>
 __global__ void __launch_bounds__(128) knn_kernel(TreeView tree, const f4* __restrict__ queries, int nq, const IcpState* __restrict__ state,
@@ -33,71 +28,56 @@ __global__ void __launch_bounds__(128) knn_kernel(TreeView tree, const f4* __res
         if (threadIdx.x < 16) sT.m[threadIdx.x] = state->T_iter.m[threadIdx.x];
         __syncthreads();
     }
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned lanes_lt = (1u << lane) - 1u;
-    const long long warp_id = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    long long next = warp_id * CHUNK;                       // warp-uniform: next unassigned query
-    const long long end = min((long long)nq, next + CHUNK);  // warp-uniform
-    bool running = false;
-    int t = 0;  // sorted position of this lane's current query
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    bool running = t < nq;
+    uint32_t qi = (uint32_t)t;
     Lane s;
     TopK<KMAX> best;
-    unsigned my_visits = 0;
+    best.init(k, max_r2);
     s.visited = 0;
-    for (;;) {
-        // ---- refill idle lanes with the next queries of the chunk, in lane order
-        const unsigned idle = __ballot_sync(0xffffffffu, !running);
-        if (idle) {
-            const long long mine = next + __popc(idle & lanes_lt);
-            next += __popc(idle);
-            if (!running && mine < end) {
-                t = (int)mine;
-                f4 q = queries[t];
-                uint32_t start = 0;
-                if (self_query) {
-                    // K8: the query is the reference point at leaf-order position t; its own leaf
-                    // is the perfect start (its original column travels in w)
-                    q.w = 1.f;
-                    start = (1u << tree.depth) + seg_of((uint32_t)t, tree.depth, tree.n);
-                } else if (use_hints) {
-                    start = hints[t];
-                }
-                if (use_T) q = transform_point(sT, q);
-                best.init(k, max_r2);
-                lane_begin(s, tree, q.x, q.y, q.z, start);
-                running = true;
-            }
+    s.best_leaf = 0;
+    if (running) {
+        f4 q = queries[t];
+        uint32_t start = 0;
+        if (self_query) {
+            // K8: the query is the reference point at leaf-order position t; its original column
+            // travels in w and its own leaf is the perfect start
+            qi = __float_as_uint(q.w);
+            q.w = 1.f;
+            start = (1u << tree.depth) + seg_of((uint32_t)t, tree.depth, tree.n);
+        } else if (use_hints) {
+            start = hints[t];
         }
-        if (!__any_sync(0xffffffffu, running)) break;
-        // ---- the three phases; the warp re-converges between them
+        if (use_T) q = transform_point(sT, q);
+        lane_begin(s, tree, q.x, q.y, q.z, start);
+    }
+    // all 32 lanes stay in the loop until the slowest is done; phases re-converge the warp
+    while (__any_sync(0xffffffffu, running)) {
         while (running && lane_descending(s, tree)) lane_descend_step(s, tree);
         __syncwarp();
         if (running) lane_scan_leaf<KMAX>(s, tree, best);
         __syncwarp();
-        if (running && !lane_pop<KMAX>(s, tree, best)) {
-            // search complete: emit the result of this query
-            running = false;
-            const uint32_t qi = self_query ? __float_as_uint(queries[t].w) : (uint32_t)t;
-            int32_t* oi = ids + (size_t)qi * k;
-            float* od = dists + (size_t)qi * k;
-#pragma unroll
-            for (int j = 0; j < KMAX; ++j) {
-                if (j < k) {
-                    const bool valid = best.id[j] != PM_NO_ID && best.d[j] != pm_inf();
-                    oi[j] = valid ? best.id[j] : -1;
-                    od[j] = valid ? best.d[j] : pm_inf();
-                }
-            }
-            if (hints && !self_query) hints[t] = s.best_leaf;
-            my_visits += s.visited;
-        }
+        if (running) running = lane_pop<KMAX>(s, tree, best);
         __syncwarp();
+    }
+    if (t < nq) {
+        int32_t* oi = ids + (size_t)qi * k;
+        float* od = dists + (size_t)qi * k;
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+            if (j < k) {
+                const bool valid = best.id[j] != PM_NO_ID && best.d[j] != pm_inf();
+                oi[j] = valid ? best.id[j] : -1;
+                od[j] = valid ? best.d[j] : pm_inf();
+            }
+        }
+        if (hints && !self_query) hints[t] = s.best_leaf;
     }
     if (visits) {
         // warp-aggregated statistics (Matcher::visitCounter)
-        unsigned v = my_visits;
+        unsigned v = (t < nq) ? s.visited : 0u;
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (lane == 0 && v) atomicAdd(visits, (unsigned long long)v);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(visits, (unsigned long long)v);
     }
 }
 
@@ -105,8 +85,7 @@ template <int KMAX>
 int launch_one(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, bool use_T, bool gated, bool self_query, int k, float max_r2,
                uint32_t* hints, bool use_hints, int32_t* ids, float* dists) {
     const int B = 128;
-    const long long per_block = (long long)CHUNK * (B / 32);
-    const int grid = (int)((nq + per_block - 1) / per_block);
+    const int grid = (nq + B - 1) / B;
     if (grid == 0) return PMGPU_OK;
     knn_kernel<KMAX><<<grid, B, 0, ctx->stream>>>(tree, queries, nq, ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k, max_r2, hints,
                                                  use_hints ? 1 : 0, ids, dists, &ctx->state->visits);
