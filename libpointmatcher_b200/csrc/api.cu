@@ -138,9 +138,9 @@ int check_params(pmgpu_ctx* ctx, const pmgpu_icp_params* p) {
 int enqueue_iteration(pmgpu_ctx* ctx, const pmgpu_icp_params* p, bool gated) {
     const float max_r2 = p->max_dist * p->max_dist;
     ctx->stage_begin(0);
-    PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, ctx->nq, true, gated, false, p->knn, max_r2, ctx->hint.p,
-                      ctx->hint_valid && ctx->hints_enabled, ctx->ids.p, ctx->dists.p));
-    ctx->hint_valid = true;
+    PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, ctx->nq, true, gated, false, p->knn, max_r2,
+                      ctx->seed_k == 1 && p->knn == 1 && ctx->hints_enabled, ctx->ids.p, ctx->dists.p));
+    ctx->seed_k = p->knn;
     ctx->stage_end();
     ctx->stage_begin(1);
     PM_TRY(launch_weights(ctx, p->nfilters, p->filter_type, p->filter_param, gated));
@@ -196,7 +196,7 @@ void pmgpu_ctx_destroy(pmgpu_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     pmgpu_comm_destroy(ctx);
     ctx->ref_orig.release(); ctx->ref_sorted.release(); ctx->ref_normals.release(); ctx->splits.release(); ctx->boxes.release();
-    ctx->reading_tmp.release(); ctx->ids_tmp.release(); ctx->dists_tmp.release(); ctx->hint.release();
+    ctx->reading_tmp.release(); ctx->ids_tmp.release(); ctx->dists_tmp.release();
     ctx->keys_a.release(); ctx->keys_b.release(); ctx->perm_a.release(); ctx->perm_b.release();
     ctx->node_box.release(); ctx->node_dim.release(); ctx->cub_tmp.release();
     ctx->reading.release(); ctx->q_order.release();
@@ -257,7 +257,7 @@ int pmgpu_ref_set(pmgpu_ctx* ctx, const float* features, int rows, int n, const 
     ctx->nr = 0;
     ctx->has_normals = false;
     ctx->have_matches = false;
-    ctx->hint_valid = false;
+    ctx->seed_k = 0;
     PM_CUDA_TRY(ctx, ctx->ref_orig.reserve(n));
     PM_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ref_orig.p, features, (size_t)n * sizeof(f4), cudaMemcpyDefault, ctx->stream));
     ctx->nr = n;
@@ -286,8 +286,7 @@ int pmgpu_reading_set(pmgpu_ctx* ctx, const float* features, int rows, int n) {
     ctx->have_weights = false;
     PM_CUDA_TRY(ctx, ctx->reading.reserve(n > 0 ? n : 1));
     PM_CUDA_TRY(ctx, ctx->reading_tmp.reserve(n > 0 ? n : 1));
-    PM_CUDA_TRY(ctx, ctx->hint.reserve(n > 0 ? n : 1));
-    ctx->hint_valid = false;
+    ctx->seed_k = 0;
     if (n > 0) PM_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->reading_tmp.p, features, (size_t)n * sizeof(f4), cudaMemcpyDefault, ctx->stream));
     ctx->nq = n;
     if (n > 0) PM_TRY(morton_order(ctx));
@@ -347,9 +346,9 @@ int pmgpu_knn(pmgpu_ctx* ctx, const float* T, int k, float epsilon, float max_di
     ctx->have_weights = false;
     const float max_r2 = max_dist * max_dist;
     ctx->stage_begin(0);
-    PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, ctx->nq, T != nullptr, false, false, k, max_r2, ctx->hint.p,
-                      ctx->hint_valid && ctx->hints_enabled, ctx->ids.p, ctx->dists.p));
-    ctx->hint_valid = true;
+    PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, ctx->nq, T != nullptr, false, false, k, max_r2,
+                      ctx->seed_k == 1 && k == 1 && ctx->hints_enabled, ctx->ids.p, ctx->dists.p));
+    ctx->seed_k = k;
     ctx->stage_end();
     ctx->have_matches = true;
     PM_TRY(download_unpermuted<int32_t>(ctx, ctx->ids.p, ctx->ids_tmp, k, ids_out));
@@ -504,7 +503,7 @@ int pmgpu_ref_compute_normals(pmgpu_ctx* ctx, int knn, float epsilon, float max_
     PM_CUDA_TRY(ctx, nids.reserve((size_t)knn * n));
     PM_CUDA_TRY(ctx, ndists.reserve((size_t)knn * n));
     PM_CUDA_TRY(ctx, ctx->ref_normals.reserve(n));
-    int s = launch_knn(ctx, ctx->tree_view(), ctx->ref_sorted.p, n, false, false, true, knn, max_dist * max_dist, nullptr, false, nids.p, ndists.p);
+    int s = launch_knn(ctx, ctx->tree_view(), ctx->ref_sorted.p, n, false, false, true, knn, max_dist * max_dist, false, nids.p, ndists.p);
     if (s == PMGPU_OK) s = launch_normals(ctx, ctx->ref_orig.p, n, nids.p, ndists.p, knn, flags, ctx->ref_normals.p, nullptr, nullptr, nullptr, nullptr);
     cudaStreamSynchronize(ctx->stream);
     nids.release();
@@ -555,7 +554,7 @@ int pmgpu_normals(pmgpu_ctx* ctx, const float* features, int rows, int n, int kn
     IcpState* h = sub->state_host;
     h->degenerate = 0;
     s = push_state(sub);
-    if (s == PMGPU_OK) s = launch_knn(sub, sub->tree_view(), sub->ref_sorted.p, n, false, false, true, knn, max_dist * max_dist, nullptr, false, nids.p, ndists.p);
+    if (s == PMGPU_OK) s = launch_knn(sub, sub->tree_view(), sub->ref_sorted.p, n, false, false, true, knn, max_dist * max_dist, false, nids.p, ndists.p);
     if (s == PMGPU_OK)
         s = launch_normals(sub, sub->ref_orig.p, n, nids.p, ndists.p, knn, flags, n4.p, out->densities ? scratch.p + off_den : nullptr,
                            out->eig_values ? scratch.p + off_val : nullptr, out->eig_vectors ? scratch.p + off_vec : nullptr,

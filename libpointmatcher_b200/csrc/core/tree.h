@@ -10,12 +10,13 @@
 // Leaves (level D) hold floor(N / 2^D) or ceil(N / 2^D) <= PM_LEAF_MAX points.
 //
 // Traversal (one thread per query, no stack):
-//   descent   root -> leaf by the split planes only (one 8-byte load + ~10 instructions per level).
+//   descent   root -> leaf by the split planes only (one 8-byte load + ~10 instructions per level);
+//             the squared plane distance of every level is cached in a per-lane scratch column.
 //             The tree is complete, so every lane of a warp runs exactly D steps: no divergence.
 //   backtrack a bit-trail holds one "far child pending" bit per level; the deepest pending level
-//             is popped with clz, the far child's heap index is rebuilt from the current node
-//             (ancestor >> shift, ^ 1), first filtered by the plane distance, then by its
-//             bounding-box distance (one 32-byte load), and only then descended.
+//             is popped with clz and filtered by its cached plane distance; survivors rebuild the
+//             far child's heap index from the current node (ancestor >> shift, ^ 1), test its
+//             bounding-box distance (one 32-byte load), and only then descend into it.
 //
 // Exactness.  A subtree is skipped only when a lower bound of the distance to all of its points is
 // > the current k-th best distance.  Both bounds are evaluated with the same operation order and
@@ -149,49 +150,42 @@ static EmuStats g_emu_stats = {0, 0, 0, 0, 0};
 
 // ------------------------------------------------------------------------------------------------
 // Per-query search state and its three phases.  knn.cu runs the phases of the 32 lanes of a warp
-// in lock step (descend* | scan leaf | pop*), re-converging between phases, and hands a new query
-// to every lane that finished; knn_search_single() below composes the same phases sequentially
-// (host harness, and the definition of the result).
+// in lock step (descend* | scan leaf | pop*), re-converging between phases;
+// knn_search_single() below composes the same phases sequentially (host harness, and the
+// definition of the result).
+//
+// `plane` is a per-lane scratch column (shared memory on the device, element l at
+// plane[l * stride]) that caches, for every level l, the squared distance from the query to the
+// split plane crossed at that level: the cheapest valid lower bound for the pending sibling.
 // ------------------------------------------------------------------------------------------------
 struct Lane {
     float qx, qy, qz;
     uint32_t node;      // current node (heap index)
     int level;          // its level
     uint32_t trail;     // bit l set: the sibling of our level-l ancestor has not been examined yet
-    uint32_t best_leaf; // leaf (heap index) that produced the current nearest candidate
     uint32_t visited;
 };
 
-// start at the root (cold) or at `start_leaf` (heap index of a leaf that probably holds the
-// answer: the previous iteration's match, or the query's own leaf for a self-query).  Any start
-// leaf is valid: every other subtree stays pending in the trail.
-PM_HD void lane_begin(Lane& s, const TreeView& t, float qx, float qy, float qz, uint32_t start_leaf) {
+PM_HD void lane_begin(Lane& s, float qx, float qy, float qz) {
     s.qx = qx; s.qy = qy; s.qz = qz;
     s.visited = 0;
-    // a hint that is not a leaf of THIS tree (0 = none) falls back to the cold start
-    if (start_leaf >= (1u << t.depth) && start_leaf < (2u << t.depth)) {
-        s.node = start_leaf;
-        s.level = t.depth;
-        s.trail = (t.depth > 0) ? ((2u << t.depth) - 2u) : 0u;  // bits 1..D
-        s.best_leaf = start_leaf;
-    } else {
-        s.node = 1;
-        s.level = 0;
-        s.trail = 0;
-        s.best_leaf = 0;  // stays 0 (= no hint) when no candidate is accepted, e.g. all beyond maxDist
-    }
+    s.node = 1;
+    s.level = 0;
+    s.trail = 0;
 }
 
 PM_HD bool lane_descending(const Lane& s, const TreeView& t) { return s.level < t.depth; }
 
 // one step of the plane descent
-PM_HD void lane_descend_step(Lane& s, const TreeView& t) {
+PM_HD void lane_descend_step(Lane& s, const TreeView& t, float* plane, int stride) {
     const f2 sp = ldg2(t.splits + s.node);
     const uint32_t dim = f2u(sp.y);
     const float qd = dim == 0 ? s.qx : (dim == 1 ? s.qy : s.qz);
+    const float diff = fsub(qd, sp.x);
     s.node = 2 * s.node + (qd >= sp.x ? 1u : 0u);
     ++s.level;
     s.trail |= 1u << s.level;
+    plane[s.level * stride] = fmul(diff, diff);
     PM_STAT(descent_steps);
 }
 
@@ -207,10 +201,7 @@ PM_HD void lane_scan_leaf(Lane& s, const TreeView& t, TopK<KMAX>& best) {
             const f4 pt = ldg4(t.pts + p);
             const float dd = dist2(s.qx, s.qy, s.qz, pt.x, pt.y, pt.z);
             const int pi = (int)f2u(pt.w);
-            if (cand_less(dd, pi, best.worst_d(), best.worst_id())) {
-                if (cand_less(dd, pi, best.d[0], best.id[0])) s.best_leaf = s.node;
-                best.insert(dd, pi);
-            }
+            if (cand_less(dd, pi, best.worst_d(), best.worst_id())) best.insert(dd, pi);
         }
     }
     s.visited += e - b;
@@ -220,22 +211,14 @@ PM_HD void lane_scan_leaf(Lane& s, const TreeView& t, TopK<KMAX>& best) {
 // examine pending siblings, deepest first; returns true when one has to be searched (the lane
 // then continues with descend steps from it), false when the search is complete.
 template <int KMAX>
-PM_HD bool lane_pop(Lane& s, const TreeView& t, const TopK<KMAX>& best) {
+PM_HD bool lane_pop(Lane& s, const TreeView& t, const TopK<KMAX>& best, const float* plane, int stride) {
     while (s.trail != 0) {
         const int l = 31 - clz32(s.trail);
         s.trail &= ~(1u << l);
-        const uint32_t far = (s.node >> (s.level - l)) ^ 1u;
         PM_STAT(pops);
         const float w = best.worst_d();
-        // plane bound, valid when the query lies on the other side of the parent's split
-        const f2 sp = ldg2(t.splits + (far >> 1));
-        const uint32_t dim = f2u(sp.y);
-        const float qd = dim == 0 ? s.qx : (dim == 1 ? s.qy : s.qz);
-        const bool q_right = qd >= sp.x;
-        if (q_right != ((far & 1u) != 0u)) {
-            const float diff = fsub(qd, sp.x);
-            if (fmul(diff, diff) > w) continue;
-        }
+        if (plane[l * stride] > w) continue;  // the whole far side of that split is out of reach
+        const uint32_t far = (s.node >> (s.level - l)) ^ 1u;
         PM_STAT(box_tests);
         const float db = box_dist2(s.qx, s.qy, s.qz, ldg4(t.boxes + 2 * (size_t)far), ldg4(t.boxes + 2 * (size_t)far + 1));
         if (db > w) continue;
@@ -247,20 +230,21 @@ PM_HD bool lane_pop(Lane& s, const TreeView& t, const TopK<KMAX>& best) {
     return false;
 }
 
-// Exact k-nearest-neighbour search of one query.  Returns the number of reference points whose
-// distance was evaluated (the analogue of libnabo's visit count, MatchersImpl.cpp:98);
-// *best_leaf_out receives the leaf of the nearest candidate (next iteration's start hint).
+// Exact k-nearest-neighbour search of one query.  `best` may already hold real candidates (e.g.
+// the previous iteration's match re-measured, k = 1): they only tighten the bounds.  Returns the
+// number of reference points whose distance was evaluated (the analogue of libnabo's visit count,
+// MatchersImpl.cpp:98).
 template <int KMAX>
-PM_HD uint32_t knn_search_single(const TreeView& t, float qx, float qy, float qz, uint32_t start_leaf, TopK<KMAX>& best, uint32_t* best_leaf_out) {
+PM_HD uint32_t knn_search_single(const TreeView& t, float qx, float qy, float qz, TopK<KMAX>& best) {
     if (t.n == 0) return 0;
+    float plane[PM_MAX_DEPTH + 2];
     Lane s;
-    lane_begin(s, t, qx, qy, qz, start_leaf);
+    lane_begin(s, qx, qy, qz);
     for (;;) {
-        while (lane_descending(s, t)) lane_descend_step(s, t);
+        while (lane_descending(s, t)) lane_descend_step(s, t, plane, 1);
         lane_scan_leaf<KMAX>(s, t, best);
-        if (!lane_pop<KMAX>(s, t, best)) break;
+        if (!lane_pop<KMAX>(s, t, best, plane, 1)) break;
     }
-    if (best_leaf_out) *best_leaf_out = s.best_leaf;
     return s.visited;
 }
 

@@ -8,26 +8,31 @@
 // as three phases — plane descent | leaf scan | pop pending siblings — and the lanes of a warp
 // RE-CONVERGE between phases (__syncwarp): without that, independent thread scheduling lets every
 // lane drift into its own phase and the warp executes ~3 of 32 lanes per instruction (measured,
-// profiles/).  T_iter is read from the device-resident IcpState, so no host round trip separates
-// iterations; in iterations >= 2 every query starts at the leaf of its previous match (hint),
-// which skips the root descent and makes the first leaf scan produce a tight bound.
+// profiles/).  The per-level plane distances of the descent are cached in shared memory (one
+// column per lane), so rejecting a pending sibling costs one LDS and a compare.  T_iter is read
+// from the device-resident IcpState, so no host round trip separates iterations; in iterations
+// >= 2 (k = 1) the previous match, re-measured, seeds the search with a tight bound.
 #include "pmgpu_internal.cuh"
 
 namespace pm {
 
 namespace {
 
+constexpr int KNN_BLOCK = 128;
+
 template <int KMAX>
-__global__ void __launch_bounds__(128) knn_kernel(TreeView tree, const f4* __restrict__ queries, int nq, const IcpState* __restrict__ state,
-                                                  int use_T, int gated, int self_query, int k, float max_r2, uint32_t* __restrict__ hints,
-                                                  int use_hints, int32_t* __restrict__ ids, float* __restrict__ dists,
-                                                  unsigned long long* visits) {
+__global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4* __restrict__ queries, int nq, const IcpState* __restrict__ state,
+                                                        int use_T, int gated, int self_query, int k, float max_r2,
+                                                        const f4* __restrict__ ref_orig, int use_seed, int32_t* __restrict__ ids,
+                                                        float* __restrict__ dists, unsigned long long* visits) {
+    extern __shared__ float s_plane[];  // [depth + 1][KNN_BLOCK]: cached plane distances, one column per lane
     __shared__ Mat4 sT;
     if (gated && state->iterate == 0) return;
     if (use_T) {
         if (threadIdx.x < 16) sT.m[threadIdx.x] = state->T_iter.m[threadIdx.x];
         __syncthreads();
     }
+    float* plane = s_plane + threadIdx.x;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     bool running = t < nq;
     uint32_t qi = (uint32_t)t;
@@ -35,29 +40,35 @@ __global__ void __launch_bounds__(128) knn_kernel(TreeView tree, const f4* __res
     TopK<KMAX> best;
     best.init(k, max_r2);
     s.visited = 0;
-    s.best_leaf = 0;
     if (running) {
         f4 q = queries[t];
-        uint32_t start = 0;
         if (self_query) {
             // K8: the query is the reference point at leaf-order position t; its original column
-            // travels in w and its own leaf is the perfect start
+            // travels in w
             qi = __float_as_uint(q.w);
             q.w = 1.f;
-            start = (1u << tree.depth) + seg_of((uint32_t)t, tree.depth, tree.n);
-        } else if (use_hints) {
-            start = hints[t];
         }
         if (use_T) q = transform_point(sT, q);
-        lane_begin(s, tree, q.x, q.y, q.z, start);
+        lane_begin(s, q.x, q.y, q.z);
+        if (KMAX == 1 && use_seed) {
+            // ICP iterations >= 2: the previous match of this query (still resident in ids),
+            // re-measured under the new T_iter, is a real candidate that makes the bound tight
+            // before the first leaf is reached.  It cannot change the answer, only the work.
+            const int prev = ids[t];
+            if (prev >= 0) {
+                const f4 r = __ldg(ref_orig + prev);
+                const float dd = dist2(q.x, q.y, q.z, r.x, r.y, r.z);
+                if (cand_less(dd, prev, best.worst_d(), best.worst_id())) best.insert(dd, prev);
+            }
+        }
     }
     // all 32 lanes stay in the loop until the slowest is done; phases re-converge the warp
     while (__any_sync(0xffffffffu, running)) {
-        while (running && lane_descending(s, tree)) lane_descend_step(s, tree);
+        while (running && lane_descending(s, tree)) lane_descend_step(s, tree, plane, KNN_BLOCK);
         __syncwarp();
         if (running) lane_scan_leaf<KMAX>(s, tree, best);
         __syncwarp();
-        if (running) running = lane_pop<KMAX>(s, tree, best);
+        if (running) running = lane_pop<KMAX>(s, tree, best, plane, KNN_BLOCK);
         __syncwarp();
     }
     if (t < nq) {
@@ -71,7 +82,6 @@ __global__ void __launch_bounds__(128) knn_kernel(TreeView tree, const f4* __res
                 od[j] = valid ? best.d[j] : pm_inf();
             }
         }
-        if (hints && !self_query) hints[t] = s.best_leaf;
     }
     if (visits) {
         // warp-aggregated statistics (Matcher::visitCounter)
@@ -83,12 +93,12 @@ __global__ void __launch_bounds__(128) knn_kernel(TreeView tree, const f4* __res
 
 template <int KMAX>
 int launch_one(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, bool use_T, bool gated, bool self_query, int k, float max_r2,
-               uint32_t* hints, bool use_hints, int32_t* ids, float* dists) {
-    const int B = 128;
-    const int grid = (nq + B - 1) / B;
+               bool use_seed, int32_t* ids, float* dists) {
+    const int grid = (nq + KNN_BLOCK - 1) / KNN_BLOCK;
     if (grid == 0) return PMGPU_OK;
-    knn_kernel<KMAX><<<grid, B, 0, ctx->stream>>>(tree, queries, nq, ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k, max_r2, hints,
-                                                 use_hints ? 1 : 0, ids, dists, &ctx->state->visits);
+    const size_t smem = (size_t)(tree.depth + 2) * KNN_BLOCK * sizeof(float);
+    knn_kernel<KMAX><<<grid, KNN_BLOCK, smem, ctx->stream>>>(tree, queries, nq, ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k, max_r2,
+                                                            ctx->ref_orig.p, use_seed ? 1 : 0, ids, dists, &ctx->state->visits);
     ctx->launches += 1;
     PM_CUDA_TRY(ctx, cudaGetLastError());
     return PMGPU_OK;
@@ -98,10 +108,10 @@ int launch_one(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, 
 
 // use_T: apply state->T_iter to every query; gated: no-op once state->iterate == 0;
 // self_query: `queries` is the leaf-ordered reference itself (results indexed by original column);
-// hints: per-query start leaves (read when use_hints, always written unless self_query / null)
+// use_seed (k = 1): `ids` still holds the previous matches of the same reading
 int launch_knn(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, bool use_T, bool gated, bool self_query, int k, float max_r2,
-               uint32_t* hints, bool use_hints, int32_t* ids, float* dists) {
-#define PM_KNN_CASE(K) return launch_one<K>(ctx, tree, queries, nq, use_T, gated, self_query, k, max_r2, hints, use_hints, ids, dists)
+               bool use_seed, int32_t* ids, float* dists) {
+#define PM_KNN_CASE(K) return launch_one<K>(ctx, tree, queries, nq, use_T, gated, self_query, k, max_r2, use_seed, ids, dists)
     if (k == 1) PM_KNN_CASE(1);
     if (k <= 4) PM_KNN_CASE(4);
     if (k <= 8) PM_KNN_CASE(8);

@@ -116,8 +116,7 @@ struct pmgpu_ctx {
     pm::DevBuf<f4> reading;          // Morton order (position t holds original column q_order[t])
     pm::DevBuf<f4> reading_tmp;      // upload staging (original order)
     pm::DevBuf<uint32_t> q_order;    // sorted position -> original column
-    pm::DevBuf<uint32_t> hint;       // per query: leaf of its previous match (start of the next search)
-    bool hint_valid = false;
+    int seed_k = 0;                  // k of the matches resident in `ids` for this reading / reference (0: none)
     bool hints_enabled = true;
     pm::DevBuf<int32_t> ids_tmp;     // un-permute staging for downloads
     pm::DevBuf<float> dists_tmp;
@@ -184,7 +183,7 @@ int build_tree(pmgpu_ctx* ctx);
 int morton_order(pmgpu_ctx* ctx);
 // knn.cu
 int launch_knn(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, bool use_T, bool gated, bool self_query, int k, float max_r2,
-               uint32_t* hints, bool use_hints, int32_t* ids, float* dists);
+               bool use_seed, int32_t* ids, float* dists);
 // select.cu
 int launch_weights(pmgpu_ctx* ctx, int nfilters, const int* types, const float* params, bool gated);
 int launch_materialize_weights(pmgpu_ctx* ctx);

@@ -43,7 +43,7 @@ def emu():
     lib.emu_tree_check.argtypes = [C.c_void_p]
     lib.emu_tree_free.argtypes = [C.c_void_p]
     lib.emu_tree_depth.argtypes = [C.c_void_p]
-    lib.emu_set_hint.argtypes = [C.c_void_p]
+    lib.emu_set_seed.argtypes = [C.c_void_p]
     lib.emu_knn.restype = C.c_long
     lib.emu_knn.argtypes = [C.c_void_p, fp, fp, C.c_int, C.c_int, C.c_float, ip, fp]
     lib.emu_solve_psd6.argtypes = [dp, dp, dp]

@@ -22,12 +22,14 @@ namespace {
 struct EmuTree {
     std::vector<f2> splits;
     std::vector<f4> boxes, pts;
+    const float* orig = nullptr;  // the caller's cloud (4 x n), original order
     TreeView view;
 };
 
 // the level-by-level build of tree_build.cu, sequentially
 EmuTree* build(const float* feat, int n) {
     EmuTree* t = new EmuTree();
+    t->orig = feat;
     const uint32_t N = (uint32_t)n;
     const int D = tree_depth_for(N);
     const uint32_t nnodes = 2u << D;
@@ -93,7 +95,7 @@ EmuTree* build(const float* feat, int n) {
 
 uint32_t* g_visits_out = nullptr;  // optional per-query visit counts (analysis only)
 
-uint32_t* g_hint = nullptr;  // optional per-query start leaves (in: hint or 0, out: leaf of the nearest candidate)
+const int32_t* g_seed = nullptr;  // optional per-query seed candidate (reference column or -1), k = 1 only
 
 template <int KMAX>
 long run_knn(const EmuTree* t, const float* T16, const float* q, int nq, int k, float max_r2, int32_t* ids, float* dists) {
@@ -105,9 +107,13 @@ long run_knn(const EmuTree* t, const float* T16, const float* q, int nq, int k, 
         if (T16) p = transform_point(T, p);
         TopK<KMAX> best;
         best.init(k, max_r2);
-        uint32_t leaf_out = 0;
-        const uint32_t v = knn_search_single<KMAX>(t->view, p.x, p.y, p.z, g_hint ? g_hint[i] : 0u, best, &leaf_out);
-        if (g_hint) g_hint[i] = leaf_out;
+        if (g_seed && KMAX == 1 && g_seed[i] >= 0) {
+            // re-measure the previous match (knn.cu does the same with the resident ids)
+            const float* r = t->orig + 4 * (size_t)g_seed[i];
+            const float dd = dist2(p.x, p.y, p.z, r[0], r[1], r[2]);
+            if (cand_less(dd, g_seed[i], best.worst_d(), best.worst_id())) best.insert(dd, g_seed[i]);
+        }
+        const uint32_t v = knn_search_single<KMAX>(t->view, p.x, p.y, p.z, best);
         visits += v;
         if (g_visits_out) g_visits_out[i] = v;
         for (int j = 0; j < k; ++j) {
@@ -124,7 +130,7 @@ long run_knn(const EmuTree* t, const float* T16, const float* q, int nq, int k, 
 extern "C" {
 
 void emu_set_visits_out(uint32_t* p) { g_visits_out = p; }
-void emu_set_hint(uint32_t* p) { g_hint = p; }
+void emu_set_seed(const int32_t* p) { g_seed = p; }
 void emu_stats(unsigned long long* out5, int reset) {
     out5[0] = g_emu_stats.descent_steps; out5[1] = g_emu_stats.pops; out5[2] = g_emu_stats.box_tests;
     out5[3] = g_emu_stats.redescents; out5[4] = g_emu_stats.leaves;

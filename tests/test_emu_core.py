@@ -94,29 +94,26 @@ def test_knn_vs_kdtree_on_lidar(emu, oracle, synth):
     assert visits / len(rd) < 40  # box pruning keeps the leaf visits low on surface data
 
 
-def test_knn_any_start_leaf_gives_the_same_answer(emu, oracle):
-    """the warm start (previous match's leaf) is only a hint: even random start leaves are exact"""
+def test_knn_seed_candidate_keeps_the_answer_exact(emu, oracle):
+    """k = 1: the previous match, re-measured, may seed the search (it only tightens the bounds);
+    any seed — right, wrong or missing — gives the same answer"""
     rng = np.random.default_rng(16)
-    ref, q = cloud(rng, 5000, "uniform"), cloud(rng, 600, "uniform")
-    t = emu.emu_tree_build(f(ref), len(ref))
-    try:
-        depth = emu.emu_tree_depth(t)
-        for k, md in ((1, np.inf), (7, np.inf), (1, 0.3), (5, 0.5)):  # small maxDist: many queries find nothing
-            ib, db = oracle.bruteforce_knn(ref, q, k, md)
-            for mode in ("random", "carried", "cold-then-carried"):
-                hints = rng.integers(1 << depth, 2 << depth, len(q)).astype(np.uint32)
-                if mode == "cold-then-carried":
-                    hints[:] = 0
-                emu.emu_set_hint(hints.ctypes.data_as(C.c_void_p))
-                for _ in range(1 if mode == "random" else 3):  # later passes start at the leaves found before
-                    ids = np.empty((len(q), k), np.int32)
-                    dist = np.empty((len(q), k), np.float32)
-                    emu.emu_knn(t, None, f(q), len(q), k, md, ids.ctypes.data_as(IP), f(dist))
+    ref, q = cloud(rng, 5000, "grid"), cloud(rng, 600, "grid")  # grid: exact ties with the seed
+    ref2, q2 = cloud(rng, 5000, "uniform"), cloud(rng, 600, "uniform")
+    for r_, q_ in ((ref, q), (ref2, q2)):
+        t = emu.emu_tree_build(f(r_), len(r_))
+        try:
+            for md in (np.inf, 0.3):
+                ib, db = oracle.bruteforce_knn(r_, q_, 1, md)
+                for seed in (ib[:, 0].copy(), rng.integers(-1, len(r_), len(q_)).astype(np.int32)):
+                    emu.emu_set_seed(seed.ctypes.data_as(C.c_void_p))
+                    ids = np.empty((len(q_), 1), np.int32)
+                    dist = np.empty((len(q_), 1), np.float32)
+                    emu.emu_knn(t, None, f(q_), len(q_), 1, md, ids.ctypes.data_as(IP), f(dist))
                     assert (ib == ids).all() and (db.view(np.uint32) == dist.view(np.uint32)).all()
-                    assert ((hints == 0) | ((hints >= (1 << depth)) & (hints < (2 << depth)))).all()
-    finally:
-        emu.emu_set_hint(None)
-        emu.emu_tree_free(t)
+        finally:
+            emu.emu_set_seed(None)
+            emu.emu_tree_free(t)
 
 
 def test_solve_psd6(emu, oracle):
