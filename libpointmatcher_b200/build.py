@@ -12,8 +12,11 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "_build")
-LIB = os.path.join(HERE, "libpmgpu.so")
+# tuning variants: PMGPU_VARIANT=<name> PMGPU_DEFINES="-DPM_LEAF_MAX=16 ..." builds libpmgpu_<name>.so
+VARIANT = os.environ.get("PMGPU_VARIANT", "")
+DEFINES = os.environ.get("PMGPU_DEFINES", "").split()
+OBJ = os.path.join(HERE, "_build" + ("_" + VARIANT if VARIANT else ""))
+LIB = os.path.join(HERE, "libpmgpu%s.so" % ("_" + VARIANT if VARIANT else ""))
 SOURCES = ["api.cu", "tree_build.cu", "knn.cu", "select.cu", "minimize.cu", "normals.cu", "comm.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
@@ -42,7 +45,7 @@ def _compile(src, verbose):
     path = os.path.join(CSRC, src)
     if not _stale(obj, [path] + _headers()):
         return obj
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
+    cmd = [NVCC] + FLAGS + DEFINES + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s" % (src, r.stdout))

@@ -138,12 +138,15 @@ int check_params(pmgpu_ctx* ctx, const pmgpu_icp_params* p) {
 int enqueue_iteration(pmgpu_ctx* ctx, const pmgpu_icp_params* p, bool gated) {
     const float max_r2 = p->max_dist * p->max_dist;
     ctx->stage_begin(0);
+    SelectSpec spec;
+    PM_TRY(make_select_spec(ctx, p->nfilters, p->filter_type, p->filter_param, &spec));
+    const bool fuse = ctx->nranks == 1;  // one GPU: the kNN kernel also runs select pass 0
     PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, ctx->nq, true, gated, false, p->knn, max_r2,
-                      ctx->seed_k == 1 && p->knn == 1 && ctx->hints_enabled, ctx->ids.p, ctx->dists.p));
+                      ctx->seed_k == 1 && p->knn == 1 && ctx->hints_enabled, ctx->ids.p, ctx->dists.p, fuse ? &spec : nullptr));
     ctx->seed_k = p->knn;
     ctx->stage_end();
     ctx->stage_begin(1);
-    PM_TRY(launch_weights(ctx, p->nfilters, p->filter_type, p->filter_param, gated));
+    PM_TRY(launch_weights(ctx, spec, gated, fuse));
     ctx->stage_end();
     ctx->stage_begin(2);
     PM_TRY(launch_minimize(ctx, p->minimizer, true, gated, p));
@@ -347,7 +350,7 @@ int pmgpu_knn(pmgpu_ctx* ctx, const float* T, int k, float epsilon, float max_di
     const float max_r2 = max_dist * max_dist;
     ctx->stage_begin(0);
     PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, ctx->nq, T != nullptr, false, false, k, max_r2,
-                      ctx->seed_k == 1 && k == 1 && ctx->hints_enabled, ctx->ids.p, ctx->dists.p));
+                      ctx->seed_k == 1 && k == 1 && ctx->hints_enabled, ctx->ids.p, ctx->dists.p, nullptr));
     ctx->seed_k = k;
     ctx->stage_end();
     ctx->have_matches = true;
@@ -363,8 +366,10 @@ int pmgpu_weights(pmgpu_ctx* ctx, int nfilters, const int* types, const float* p
     PM_TRY(use_device(ctx));
     if (!ctx->have_matches) return fail(ctx, PMGPU_ERR_NO_MATCHES, status_message(PMGPU_ERR_NO_MATCHES));
     if (nfilters > 0 && (!types || !params)) return fail(ctx, PMGPU_ERR_BAD_ARG, "null filter arrays");
+    SelectSpec spec;
+    PM_TRY(make_select_spec(ctx, nfilters, types, params, &spec));
     ctx->stage_begin(1);
-    PM_TRY(launch_weights(ctx, nfilters, types, params, false));
+    PM_TRY(launch_weights(ctx, spec, false, false));
     ctx->stage_end();
     const size_t total = (size_t)ctx->k * ctx->nq;
     if (weights_out && total) {
@@ -391,7 +396,7 @@ int pmgpu_minimize(pmgpu_ctx* ctx, int minimizer, float sensor_std_dev, float* T
     PM_TRY(use_device(ctx));
     if (!ctx->have_matches) return fail(ctx, PMGPU_ERR_NO_MATCHES, status_message(PMGPU_ERR_NO_MATCHES));
     if (minimizer < 0 || minimizer > PMGPU_MIN_P2PLANE_COV) return fail(ctx, PMGPU_ERR_BAD_ARG, "unknown error minimizer");
-    if (!ctx->have_weights) PM_TRY(launch_weights(ctx, 0, nullptr, nullptr, false));  // empty chain
+    if (!ctx->have_weights) PM_TRY(launch_weights(ctx, SelectSpec(), false, false));  // empty chain
     ctx->stage_begin(2);
     PM_TRY(launch_minimize(ctx, minimizer, false, false, nullptr));
     ctx->stage_end();
@@ -503,7 +508,7 @@ int pmgpu_ref_compute_normals(pmgpu_ctx* ctx, int knn, float epsilon, float max_
     PM_CUDA_TRY(ctx, nids.reserve((size_t)knn * n));
     PM_CUDA_TRY(ctx, ndists.reserve((size_t)knn * n));
     PM_CUDA_TRY(ctx, ctx->ref_normals.reserve(n));
-    int s = launch_knn(ctx, ctx->tree_view(), ctx->ref_sorted.p, n, false, false, true, knn, max_dist * max_dist, false, nids.p, ndists.p);
+    int s = launch_knn(ctx, ctx->tree_view(), ctx->ref_sorted.p, n, false, false, true, knn, max_dist * max_dist, false, nids.p, ndists.p, nullptr);
     if (s == PMGPU_OK) s = launch_normals(ctx, ctx->ref_orig.p, n, nids.p, ndists.p, knn, flags, ctx->ref_normals.p, nullptr, nullptr, nullptr, nullptr);
     cudaStreamSynchronize(ctx->stream);
     nids.release();
@@ -554,7 +559,7 @@ int pmgpu_normals(pmgpu_ctx* ctx, const float* features, int rows, int n, int kn
     IcpState* h = sub->state_host;
     h->degenerate = 0;
     s = push_state(sub);
-    if (s == PMGPU_OK) s = launch_knn(sub, sub->tree_view(), sub->ref_sorted.p, n, false, false, true, knn, max_dist * max_dist, false, nids.p, ndists.p);
+    if (s == PMGPU_OK) s = launch_knn(sub, sub->tree_view(), sub->ref_sorted.p, n, false, false, true, knn, max_dist * max_dist, false, nids.p, ndists.p, nullptr);
     if (s == PMGPU_OK)
         s = launch_normals(sub, sub->ref_orig.p, n, nids.p, ndists.p, knn, flags, n4.p, out->densities ? scratch.p + off_den : nullptr,
                            out->eig_values ? scratch.p + off_val : nullptr, out->eig_vectors ? scratch.p + off_vec : nullptr,

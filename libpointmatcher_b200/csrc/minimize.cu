@@ -14,7 +14,7 @@
 // Algorithmic bytes per match: reading 16 + id 4 + dist 4 + reference gather 16 (+ normal gather
 // 16 for point-to-plane) = 40 / 56 B.
 #include "core/linalg.h"
-#include "pmgpu_internal.cuh"
+#include "select.cuh"
 
 namespace pm {
 
@@ -53,11 +53,18 @@ __device__ __forceinline__ float pair_weight(const IcpState* st, float d) {
     return st->has_filters ? ((d <= st->limit_all) ? 1.f : 0.f) : 1.f;
 }
 
+template <int MODE>
+__device__ void finalize_body(const double* partials, int nblocks, double* sums, int phase, IcpState* state, int compose,
+                              const pmgpu_icp_params& ck);
+
+// `fuse`: the last block to finish reduces the partial rows, solves, composes T_iter and runs the
+// checkers (finalize_body), so the whole minimisation is one kernel
 template <int MODE>  // 0 point-to-point, 1 point-to-plane
 __global__ void __launch_bounds__(ACC_BLOCK) accumulate_kernel(const f4* __restrict__ reading, int nq, int k, const int32_t* __restrict__ ids,
                                                                const float* __restrict__ dists, const f4* __restrict__ ref,
                                                                const f4* __restrict__ normals, const IcpState* __restrict__ state, int gated,
-                                                               double* __restrict__ partials) {
+                                                               double* __restrict__ partials, int fuse, IcpState* state_rw, double* sums,
+                                                               int compose, pmgpu_icp_params ck) {
     constexpr int NS = MODE == 1 ? NS_PLANE : NS_POINT;
     __shared__ Mat4 sT;
     if (gated && state->iterate == 0) return;
@@ -116,6 +123,7 @@ __global__ void __launch_bounds__(ACC_BLOCK) accumulate_kernel(const f4* __restr
         acc[NS - 1] += 1.0;
     }
     block_reduce_store<NS>(acc, partials + (size_t)blockIdx.x * NS_MAX);
+    if (fuse && select_last_block(&state_rw->ticket[1])) finalize_body<MODE>(partials, gridDim.x, sums, 3, state_rw, compose, ck);
 }
 
 // Censi covariance sums (PointToPlaneWithCov.cpp:100-150, PointToPointWithCov.cpp:84-135):
@@ -201,7 +209,7 @@ __device__ void reduce_rows(const double* __restrict__ partials, int nblocks, in
     const int slice = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int c = lane; c < ns; c += 32) {
         double v = 0.0;
-        for (int b = slice; b < nblocks; b += 8) v += partials[(size_t)b * NS_MAX + c];
+        for (int b = slice; b < nblocks; b += 8) v += __ldcg(partials + (size_t)b * NS_MAX + c);
         sh[slice][c] = v;
     }
     __syncthreads();
@@ -255,15 +263,15 @@ __device__ void run_checkers(IcpState* st, const pmgpu_icp_params& ck) {
     }
 }
 
-// mode bits: 1 = reduce partial rows into sums, 2 = solve from sums
+// phase bits: 1 = reduce partial rows into sums, 2 = solve from sums.  Runs in one block of 256
+// threads: the last block of the accumulate kernel (one GPU) or finalize_kernel (sharded reading,
+// where the sums are all-reduced between the two phases).
 template <int MODE>
-__global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ sums, int phase,
-                                                       IcpState* state, int gated, int compose, pmgpu_icp_params ck, long long total_points_k) {
+__device__ void finalize_body(const double* partials, int nblocks, double* sums, int phase, IcpState* state, int compose,
+                              const pmgpu_icp_params& ck) {
     constexpr int NS = MODE == 1 ? NS_PLANE : NS_POINT;
-    if (gated && state->iterate == 0) return;
     if (phase & 1) reduce_rows(partials, nblocks, NS, sums);
     if (!(phase & 2) || threadIdx.x != 0) return;
-    (void)total_points_k;
     const double kept = sums[NS - 4], rej_matches = sums[NS - 3], rej_points = sums[NS - 2], seen = sums[NS - 1];
     // ErrorMinimizer.cpp:139-140: ratios over knn * number of reading points (all ranks)
     const float denom = (float)(seen * (double)ck.knn);
@@ -323,6 +331,13 @@ __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict_
             state->iterate = 0;
         }
     }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ sums, int phase,
+                                                       IcpState* state, int gated, int compose, pmgpu_icp_params ck) {
+    if (gated && state->iterate == 0) return;
+    finalize_body<MODE>(partials, nblocks, sums, phase, state, compose, ck);
 }
 
 // inverse of a 6x6 by Gauss-Jordan with partial pivoting (J_hessian.inverse())
@@ -392,21 +407,18 @@ int launch_minimize(pmgpu_ctx* ctx, int minimizer, bool compose_and_check, bool 
     }
     ck.knn = ctx->k;
     const int g = gated ? 1 : 0, comp = compose_and_check ? 1 : 0;
-    if (plane) accumulate_kernel<1><<<grid, ACC_BLOCK, 0, st>>>(ctx->reading.p, ctx->nq, ctx->k, ctx->ids.p, ctx->dists.p, ctx->ref_orig.p, ctx->ref_normals.p, ctx->state, g, ctx->partials.p);
-    else accumulate_kernel<0><<<grid, ACC_BLOCK, 0, st>>>(ctx->reading.p, ctx->nq, ctx->k, ctx->ids.p, ctx->dists.p, ctx->ref_orig.p, nullptr, ctx->state, g, ctx->partials.p);
+    const int fuse = ctx->nranks > 1 ? 0 : 1;
+    if (plane) accumulate_kernel<1><<<grid, ACC_BLOCK, 0, st>>>(ctx->reading.p, ctx->nq, ctx->k, ctx->ids.p, ctx->dists.p, ctx->ref_orig.p, ctx->ref_normals.p, ctx->state, g, ctx->partials.p, fuse, ctx->state, sums, comp, ck);
+    else accumulate_kernel<0><<<grid, ACC_BLOCK, 0, st>>>(ctx->reading.p, ctx->nq, ctx->k, ctx->ids.p, ctx->dists.p, ctx->ref_orig.p, nullptr, ctx->state, g, ctx->partials.p, fuse, ctx->state, sums, comp, ck);
     ctx->launches += 1;
-    const int ns = plane ? NS_PLANE : NS_POINT;
-    if (ctx->nranks > 1) {
-        if (plane) finalize_kernel<1><<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 1, ctx->state, g, comp, ck, 0);
-        else finalize_kernel<0><<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 1, ctx->state, g, comp, ck, 0);
+    if (!fuse) {
+        const int ns = plane ? NS_PLANE : NS_POINT;
+        if (plane) finalize_kernel<1><<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 1, ctx->state, g, comp, ck);
+        else finalize_kernel<0><<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 1, ctx->state, g, comp, ck);
         PM_TRY(comm_allreduce_f64(ctx, sums, ns));
-        if (plane) finalize_kernel<1><<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 2, ctx->state, g, comp, ck, 0);
-        else finalize_kernel<0><<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 2, ctx->state, g, comp, ck, 0);
+        if (plane) finalize_kernel<1><<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 2, ctx->state, g, comp, ck);
+        else finalize_kernel<0><<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 2, ctx->state, g, comp, ck);
         ctx->launches += 2;
-    } else {
-        if (plane) finalize_kernel<1><<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 3, ctx->state, g, comp, ck, 0);
-        else finalize_kernel<0><<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 3, ctx->state, g, comp, ck, 0);
-        ctx->launches += 1;
     }
     PM_CUDA_TRY(ctx, cudaGetLastError());
     return PMGPU_OK;

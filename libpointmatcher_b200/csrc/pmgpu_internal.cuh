@@ -72,8 +72,9 @@ struct IcpState {
     float limit_all;             // min over filters: weight = dist <= limit_all
     int has_filters;             // 0: empty chain (weight = dist != inf)
     unsigned long long n_valid;  // number of finite distances (all ranks)
-    unsigned prefix;             // radix-select state
-    unsigned long long rank;     // remaining rank inside the current prefix bucket
+    unsigned sel_prefix[PM_MAX_FILTERS];           // radix-select state per quantile filter
+    unsigned long long sel_rank[PM_MAX_FILTERS];   // remaining rank inside the selected bucket
+    unsigned ticket[4];          // "last block" counters: 0 select, 1 minimise, 2 covariance
     // minimiser outputs
     float cov[36];
     float stats[5];              // pointUsedRatio, weightedPointUsedRatio, nbRejectedMatches, nbRejectedPoints, nbKept
@@ -84,6 +85,21 @@ struct IcpState {
     int hist_len;
     unsigned long long visits;   // reference points examined (Matcher::visitCounter)
     int degenerate;              // degenerate normals counter (K8)
+};
+
+// the outlier-filter chain, by value in kernel arguments
+struct SelectSpec {
+    int nfilters;
+    int type[PM_MAX_FILTERS];
+    float param[PM_MAX_FILTERS];  // MaxDist: squared limit; MedianDist: factor; TrimmedDist: ratio
+    __host__ __device__ bool is_quantile(int f) const { return type[f] != PMGPU_FILTER_MAXDIST; }
+    __host__ __device__ float quantile(int f) const { return type[f] == PMGPU_FILTER_MEDIANDIST ? 0.5f : param[f]; }
+    __host__ __device__ float factor(int f) const { return type[f] == PMGPU_FILTER_MEDIANDIST ? param[f] : 0.f; }
+    __host__ __device__ int n_quantile() const {
+        int n = 0;
+        for (int f = 0; f < nfilters; ++f) n += is_quantile(f) ? 1 : 0;
+        return n;
+    }
 };
 
 }  // namespace pm
@@ -182,10 +198,13 @@ namespace pm {
 int build_tree(pmgpu_ctx* ctx);
 int morton_order(pmgpu_ctx* ctx);
 // knn.cu
+// `fused`: non-null = also initialise the filter limits and run select pass 0 on the way out
 int launch_knn(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, bool use_T, bool gated, bool self_query, int k, float max_r2,
-               bool use_seed, int32_t* ids, float* dists);
+               bool use_seed, int32_t* ids, float* dists, const SelectSpec* fused);
 // select.cu
-int launch_weights(pmgpu_ctx* ctx, int nfilters, const int* types, const float* params, bool gated);
+int make_select_spec(pmgpu_ctx* ctx, int nfilters, const int* types, const float* params, SelectSpec* spec);
+int select_reserve(pmgpu_ctx* ctx);
+int launch_weights(pmgpu_ctx* ctx, const SelectSpec& spec, bool gated, bool pass0_done);
 int launch_materialize_weights(pmgpu_ctx* ctx);
 // minimize.cu
 int launch_minimize(pmgpu_ctx* ctx, int minimizer, bool compose_and_check, bool gated, const pmgpu_icp_params* checks);

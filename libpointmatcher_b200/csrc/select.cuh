@@ -1,0 +1,144 @@
+// select.cuh — device-side pieces of the exact radix select (K3) shared by select.cu and by the
+// kNN kernel, which histograms the fresh distances of its own block on the way out (pass 0 costs
+// no extra kernel and no extra read of the distance matrix).
+//
+// Squared distances are non-negative floats, so their bit patterns order like unsigned integers:
+// pass 0 histograms bits 31..21, pass 1 bits 20..10 inside the selected bucket, pass 2 bits 9..0.
+// On one GPU the block that finishes last ("last block", ticket counter + __threadfence) scans
+// the 2048 bins and narrows the bucket for every quantile filter, so a pass is ONE kernel.  With
+// the reading sharded over GPUs the histograms are all-reduced first and a separate one-block
+// kernel does the scan (select.cu).
+#pragma once
+#include "pmgpu_internal.cuh"
+
+namespace pm {
+
+// MaxDist limits are known up front; quantile filters start at +inf and are lowered by pass 2
+__device__ __forceinline__ void select_init_limits(IcpState* st, const SelectSpec& sp) {
+    float all = pm_inf();
+    for (int f = 0; f < sp.nfilters; ++f) {
+        if (sp.type[f] == PMGPU_FILTER_MAXDIST) {
+            st->limit[f] = sp.param[f];
+            all = fminf(all, sp.param[f]);
+        } else {
+            st->limit[f] = pm_inf();
+        }
+    }
+    st->limit_all = all;
+    st->has_filters = sp.nfilters > 0 ? 1 : 0;
+}
+
+// bin of a distance in `pass`, or -1 when it lies outside the bucket selected so far
+__device__ __forceinline__ int select_bin(unsigned bits, int pass, unsigned prefix) {
+    if (bits == PM_INF_BITS) return -1;  // finite distances only (Matches.cpp:70)
+    if (pass == 0) return (int)(bits >> 21);
+    if (pass == 1) return ((bits >> 21) == prefix) ? (int)((bits >> 10) & 0x7ffu) : -1;
+    return ((bits >> 10) == prefix) ? (int)(bits & 0x3ffu) : -1;
+}
+
+// add the block's shared histogram to the global one
+__device__ __forceinline__ void select_flush(const unsigned* sh, unsigned* hist) {
+    for (int i = threadIdx.x; i < PM_HIST_BINS; i += blockDim.x) {
+        const unsigned v = sh[i];
+        if (v) atomicAdd(&hist[i], v);
+    }
+}
+
+// true (for every thread of the block) in the block that arrives last; resets the ticket
+__device__ __forceinline__ bool select_last_block(unsigned* ticket) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(ticket, 1u);
+        s_last = (t == gridDim.x - 1) ? 1 : 0;
+        if (s_last) *ticket = 0;
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last != 0;
+}
+
+// Scan the 2048 bins with the whole block (blockDim.x a multiple of 32, <= 1024, dividing 2048)
+// and pick the bin that holds `rank`.  pass 0 derives the rank from the number of finite
+// distances:  rank = size_t(float(n_valid) * quantile)  (Matches.cpp:85-86; quantile == 1 -> max
+// element); pass 2 finishes filter f: limit[f] = value (* factor for MedianDist), limit_all = min.
+// `clear`: zero the histogram afterwards.
+__device__ __forceinline__ void select_pick(unsigned* hist, int pass, float quantile, int f, float factor, IcpState* state, bool clear) {
+    __shared__ unsigned long long warp_tot[32];
+    __shared__ unsigned long long s_rank;
+    __shared__ int s_abort;
+    const int t = threadIdx.x;
+    const int per = PM_HIST_BINS / blockDim.x;  // consecutive bins per thread
+    unsigned long long mine = 0;
+    for (int j = 0; j < per; ++j) mine += __ldcg(hist + t * per + j);
+    unsigned long long incl = mine;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((t & 31) >= o) incl += v;
+    }
+    __syncthreads();  // warp_tot may still be read by a previous call
+    if ((t & 31) == 31) warp_tot[t >> 5] = incl;
+    __syncthreads();
+    const int nwarps = blockDim.x >> 5;
+    if (t < 32) {
+        unsigned long long w = t < nwarps ? warp_tot[t] : 0ull;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, w, o);
+            if (t >= o) w += v;
+        }
+        warp_tot[t] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    const unsigned long long before_warp = (t >> 5) ? warp_tot[(t >> 5) - 1] : 0ull;
+    unsigned long long excl = before_warp + incl - mine;  // elements in bins < t * per
+    const unsigned long long total = warp_tot[31];
+    if (t == 0) {
+        s_abort = 0;
+        if (pass == 0) {
+            state->n_valid = total;
+            if (total == 0) {
+                if (state->status == 0) state->status = PMGPU_ERR_NO_OUTLIER_TO_FILTER;
+                state->iterate = 0;
+                s_abort = 1;
+                s_rank = 0;
+            } else {
+                unsigned long long r;
+                if (quantile == 1.0f) r = total - 1;
+                else {
+                    r = (unsigned long long)(__ull2float_rn(total) * quantile);
+                    if (r > total - 1) r = total - 1;
+                }
+                s_rank = r;
+            }
+        } else {
+            s_rank = state->sel_rank[f];
+        }
+    }
+    __syncthreads();
+    if (!s_abort) {
+        const unsigned long long rank = s_rank;
+        for (int j = 0; j < per; ++j) {
+            const unsigned h = __ldcg(hist + t * per + j);
+            if (rank >= excl && rank < excl + h) {
+                const unsigned found = (unsigned)(t * per + j);
+                const unsigned long long rem = rank - excl;
+                if (pass == 0) { state->sel_prefix[f] = found; state->sel_rank[f] = rem; }
+                else if (pass == 1) { state->sel_prefix[f] = (state->sel_prefix[f] << 11) | found; state->sel_rank[f] = rem; }
+                else {
+                    const unsigned bits = (state->sel_prefix[f] << 10) | found;
+                    const float value = __uint_as_float(bits);
+                    const float lim = factor != 0.f ? __fmul_rn(factor, value) : value;
+                    state->limit[f] = lim;
+                    atomicMin(reinterpret_cast<int*>(&state->limit_all), __float_as_int(lim));  // non-negative floats order like ints
+                }
+            }
+            excl += h;
+        }
+    }
+    __syncthreads();
+    if (clear)
+        for (int j = 0; j < per; ++j) hist[t * per + j] = 0;
+}
+
+}  // namespace pm
