@@ -140,13 +140,12 @@ int enqueue_iteration(pmgpu_ctx* ctx, const pmgpu_icp_params* p, bool gated) {
     ctx->stage_begin(0);
     SelectSpec spec;
     PM_TRY(make_select_spec(ctx, p->nfilters, p->filter_type, p->filter_param, &spec));
-    const bool fuse = ctx->nranks == 1;  // one GPU: the kNN kernel also runs select pass 0
     PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, ctx->nq, true, gated, false, p->knn, max_r2,
-                      ctx->seed_k == 1 && p->knn == 1 && ctx->hints_enabled, ctx->ids.p, ctx->dists.p, fuse ? &spec : nullptr));
+                      ctx->seed_k == 1 && p->knn == 1 && ctx->hints_enabled, ctx->ids.p, ctx->dists.p));
     ctx->seed_k = p->knn;
     ctx->stage_end();
     ctx->stage_begin(1);
-    PM_TRY(launch_weights(ctx, spec, gated, fuse));
+    PM_TRY(launch_weights(ctx, spec, gated, false));
     ctx->stage_end();
     ctx->stage_begin(2);
     PM_TRY(launch_minimize(ctx, p->minimizer, true, gated, p));
@@ -350,7 +349,7 @@ int pmgpu_knn(pmgpu_ctx* ctx, const float* T, int k, float epsilon, float max_di
     const float max_r2 = max_dist * max_dist;
     ctx->stage_begin(0);
     PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, ctx->nq, T != nullptr, false, false, k, max_r2,
-                      ctx->seed_k == 1 && k == 1 && ctx->hints_enabled, ctx->ids.p, ctx->dists.p, nullptr));
+                      ctx->seed_k == 1 && k == 1 && ctx->hints_enabled, ctx->ids.p, ctx->dists.p));
     ctx->seed_k = k;
     ctx->stage_end();
     ctx->have_matches = true;
@@ -508,7 +507,7 @@ int pmgpu_ref_compute_normals(pmgpu_ctx* ctx, int knn, float epsilon, float max_
     PM_CUDA_TRY(ctx, nids.reserve((size_t)knn * n));
     PM_CUDA_TRY(ctx, ndists.reserve((size_t)knn * n));
     PM_CUDA_TRY(ctx, ctx->ref_normals.reserve(n));
-    int s = launch_knn(ctx, ctx->tree_view(), ctx->ref_sorted.p, n, false, false, true, knn, max_dist * max_dist, false, nids.p, ndists.p, nullptr);
+    int s = launch_knn(ctx, ctx->tree_view(), ctx->ref_sorted.p, n, false, false, true, knn, max_dist * max_dist, false, nids.p, ndists.p);
     if (s == PMGPU_OK) s = launch_normals(ctx, ctx->ref_orig.p, n, nids.p, ndists.p, knn, flags, ctx->ref_normals.p, nullptr, nullptr, nullptr, nullptr);
     cudaStreamSynchronize(ctx->stream);
     nids.release();
@@ -559,7 +558,7 @@ int pmgpu_normals(pmgpu_ctx* ctx, const float* features, int rows, int n, int kn
     IcpState* h = sub->state_host;
     h->degenerate = 0;
     s = push_state(sub);
-    if (s == PMGPU_OK) s = launch_knn(sub, sub->tree_view(), sub->ref_sorted.p, n, false, false, true, knn, max_dist * max_dist, false, nids.p, ndists.p, nullptr);
+    if (s == PMGPU_OK) s = launch_knn(sub, sub->tree_view(), sub->ref_sorted.p, n, false, false, true, knn, max_dist * max_dist, false, nids.p, ndists.p);
     if (s == PMGPU_OK)
         s = launch_normals(sub, sub->ref_orig.p, n, nids.p, ndists.p, knn, flags, n4.p, out->densities ? scratch.p + off_den : nullptr,
                            out->eig_values ? scratch.p + off_val : nullptr, out->eig_vectors ? scratch.p + off_vec : nullptr,

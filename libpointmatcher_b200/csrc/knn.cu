@@ -12,29 +12,22 @@
 // column per lane), so rejecting a pending sibling costs one LDS and a compare.  T_iter is read
 // from the device-resident IcpState, so no host round trip separates iterations; in iterations
 // >= 2 (k = 1) the previous match, re-measured, seeds the search with a tight bound.
-#include "select.cuh"
+#include "pmgpu_internal.cuh"
 
 namespace pm {
 
 namespace {
 
-#ifndef PM_KNN_BLOCK
-#define PM_KNN_BLOCK 128
-#endif
-constexpr int KNN_BLOCK = PM_KNN_BLOCK;
+constexpr int KNN_BLOCK = 128;
 
 template <int KMAX>
 __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4* __restrict__ queries, int nq, const IcpState* __restrict__ state,
                                                         int use_T, int gated, int self_query, int k, float max_r2,
                                                         const f4* __restrict__ ref_orig, int use_seed, int32_t* __restrict__ ids,
-                                                        float* __restrict__ dists, unsigned long long* visits, int fuse_select, SelectSpec sel,
-                                                        IcpState* state_rw, unsigned* __restrict__ hist) {
-    // [depth + 2][KNN_BLOCK] cached plane distances, one column per lane; re-used as the select
-    // histogram (2048 bins) once the searches of the block are over
-    extern __shared__ float s_plane[];
+                                                        float* __restrict__ dists, unsigned long long* visits) {
+    extern __shared__ float s_plane[];  // [depth + 1][KNN_BLOCK]: cached plane distances, one column per lane
     __shared__ Mat4 sT;
     if (gated && state->iterate == 0) return;
-    if (fuse_select && blockIdx.x == 0 && threadIdx.x == 0) select_init_limits(state_rw, sel);
     if (use_T) {
         if (threadIdx.x < 16) sT.m[threadIdx.x] = state->T_iter.m[threadIdx.x];
         __syncthreads();
@@ -96,46 +89,16 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
         if ((threadIdx.x & 31) == 0 && v) atomicAdd(visits, (unsigned long long)v);
     }
-    // ---- select pass 0 (K3) on the distances this block just produced
-    if (fuse_select && sel.n_quantile() > 0) {
-        unsigned* sh = reinterpret_cast<unsigned*>(s_plane);
-        __syncthreads();
-        for (int i = threadIdx.x; i < PM_HIST_BINS; i += blockDim.x) sh[i] = 0;
-        __syncthreads();
-        if (t < nq) {
-#pragma unroll
-            for (int j = 0; j < KMAX; ++j) {
-                if (j < k) {
-                    const bool valid = best.id[j] != PM_NO_ID && best.d[j] != pm_inf();
-                    if (valid) atomicAdd(&sh[__float_as_uint(best.d[j]) >> 21], 1u);
-                }
-            }
-        }
-        __syncthreads();
-        select_flush(sh, hist);
-        if (select_last_block(&state_rw->ticket[0])) {
-            const int nquant = sel.n_quantile();
-            int slot = 0;
-            for (int f = 0; f < sel.nfilters; ++f) {
-                if (!sel.is_quantile(f)) continue;
-                select_pick(hist, 0, sel.quantile(f), f, sel.factor(f), state_rw, slot == nquant - 1);
-                ++slot;
-            }
-        }
-    }
 }
 
 template <int KMAX>
 int launch_one(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, bool use_T, bool gated, bool self_query, int k, float max_r2,
-               bool use_seed, int32_t* ids, float* dists, const SelectSpec* fused) {
+               bool use_seed, int32_t* ids, float* dists) {
     const int grid = (nq + KNN_BLOCK - 1) / KNN_BLOCK;
     if (grid == 0) return PMGPU_OK;
-    size_t smem = (size_t)(tree.depth + 2) * KNN_BLOCK * sizeof(float);
-    if (fused && smem < PM_HIST_BINS * sizeof(unsigned)) smem = PM_HIST_BINS * sizeof(unsigned);
-    if (fused) PM_TRY(select_reserve(ctx));
+    const size_t smem = (size_t)(tree.depth + 2) * KNN_BLOCK * sizeof(float);
     knn_kernel<KMAX><<<grid, KNN_BLOCK, smem, ctx->stream>>>(tree, queries, nq, ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k, max_r2,
-                                                            ctx->ref_orig.p, use_seed ? 1 : 0, ids, dists, &ctx->state->visits, fused ? 1 : 0,
-                                                            fused ? *fused : SelectSpec(), ctx->state, ctx->hist.p);
+                                                            ctx->ref_orig.p, use_seed ? 1 : 0, ids, dists, &ctx->state->visits);
     ctx->launches += 1;
     PM_CUDA_TRY(ctx, cudaGetLastError());
     return PMGPU_OK;
@@ -147,8 +110,8 @@ int launch_one(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, 
 // self_query: `queries` is the leaf-ordered reference itself (results indexed by original column);
 // use_seed (k = 1): `ids` still holds the previous matches of the same reading
 int launch_knn(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, bool use_T, bool gated, bool self_query, int k, float max_r2,
-               bool use_seed, int32_t* ids, float* dists, const SelectSpec* fused) {
-#define PM_KNN_CASE(K) return launch_one<K>(ctx, tree, queries, nq, use_T, gated, self_query, k, max_r2, use_seed, ids, dists, fused)
+               bool use_seed, int32_t* ids, float* dists) {
+#define PM_KNN_CASE(K) return launch_one<K>(ctx, tree, queries, nq, use_T, gated, self_query, k, max_r2, use_seed, ids, dists)
     if (k == 1) PM_KNN_CASE(1);
     if (k <= 4) PM_KNN_CASE(4);
     if (k <= 8) PM_KNN_CASE(8);

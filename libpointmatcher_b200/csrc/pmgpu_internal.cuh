@@ -198,9 +198,8 @@ namespace pm {
 int build_tree(pmgpu_ctx* ctx);
 int morton_order(pmgpu_ctx* ctx);
 // knn.cu
-// `fused`: non-null = also initialise the filter limits and run select pass 0 on the way out
 int launch_knn(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, bool use_T, bool gated, bool self_query, int k, float max_r2,
-               bool use_seed, int32_t* ids, float* dists, const SelectSpec* fused);
+               bool use_seed, int32_t* ids, float* dists);
 // select.cu
 int make_select_spec(pmgpu_ctx* ctx, int nfilters, const int* types, const float* params, SelectSpec* spec);
 int select_reserve(pmgpu_ctx* ctx);

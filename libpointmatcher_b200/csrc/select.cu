@@ -4,8 +4,7 @@
 //
 // Every pass is one streaming read of the k x N distance matrix (4 B per match, HBM/L2 bound)
 // into a shared-memory histogram; the last block to finish scans the 2048 bins and narrows the
-// bucket (select.cuh).  Inside the fused ICP loop pass 0 rides on the kNN kernel, so the select
-// costs two small kernels per iteration.  The three in-scope filters all produce weights of the
+// bucket (select.cuh), so a pass is one kernel.  The three in-scope filters all produce weights of the
 // form (dist <= limit_f), and the chain multiplies them, so the whole chain collapses to ONE
 // threshold limit_all = min_f limit_f that the minimiser kernels apply on the fly: the weight
 // matrix is never written unless a caller asks for it.  With queries sharded over GPUs the
