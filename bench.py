@@ -188,6 +188,7 @@ def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     from libpointmatcher_b200 import capi, pm, synth
+    from libpointmatcher_b200 import dist as pmdist
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -196,7 +197,7 @@ def run_ours(args, rank, world, local_rank):
     pair_seed = 0 if (not dist_on or sharded) else rank
     rd, rf, T_gt = synth.scan_pair(args.points, pair_seed=pair_seed)
     if sharded:  # contiguous column range of the reading per rank
-        lo, hi = (rank * len(rd)) // world, ((rank + 1) * len(rd)) // world
+        lo, hi = pmdist.shard_range(len(rd), rank, world)
         rd_local = np.ascontiguousarray(rd[lo:hi])
     else:
         rd_local = rd
@@ -206,9 +207,7 @@ def run_ours(args, rank, world, local_rank):
 
     ctx = capi.Context(local_rank)
     if sharded:
-        uid = [capi.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        ctx.comm_init(uid[0], rank, world)
+        pmdist.init_comm(ctx, capi)
 
     # reference centred on its mean, reading moved into that frame — the host bookkeeping of
     # ICP::compute (ICP.cpp:291-299, 345-347), done once outside the timed loop
@@ -240,10 +239,7 @@ def run_ours(args, rank, world, local_rank):
     ctx.timing_enable(False)
     launches = ctx.launch_count - launches0
     total_ms = float(sum(ms))
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if dist_on:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
+    total_ms_max = pmdist.max_over_ranks(total_ms, dev)
     units = args.steps * (1 if (not dist_on or sharded) else world)
     value = units / (total_ms_max * 1e-3)
 
@@ -306,13 +302,11 @@ def run_ours(args, rank, world, local_rank):
         e2e_once(pm.PointToPointErrorMinimizer, False)  # warm-up (allocations, first-use costs)
         barrier()
         T_e2e, n_it, dt = e2e_once(pm.PointToPointErrorMinimizer, False)
-        td = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if dist_on:
-            dist.all_reduce(td, op=dist.ReduceOp.MAX)
-        e2e = {"value": n_it * (world if dist_on else 1) / float(td.item()), "unit": UNIT,
+        dt_max = pmdist.max_over_ranks(dt, dev)
+        e2e = {"value": n_it * (world if dist_on else 1) / dt_max, "unit": UNIT,
                "h2d_bytes_per_step": (rd_pin.nbytes + rf_pin.nbytes) / max(1, n_it), "d2h_bytes_per_step": 64.0 / max(1, n_it) + 0.0,
                "note": "one whole registration of %d iterations per call: H2D of both clouds (pinned) + structure build + loop + 4x4 D2H; "
-                       "bytes are per registration divided by iterations" % n_it, "seconds_per_registration": float(td.item())}
+                       "bytes are per registration divided by iterations" % n_it, "seconds_per_registration": dt_max}
 
     # ---- extra: the north-star target config (point-to-plane) ------------------------------
     if not args.no_extra and not sharded:

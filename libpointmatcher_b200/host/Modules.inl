@@ -1,0 +1,483 @@
+// host/Modules.inl — module implementations, included inside `struct PointMatcher<T>`.
+// Each class mirrors the reference class of the same name (file:line cited); the work is done by
+// the C ABI (include/pmgpu.h) on the pipeline the module is bound to.
+
+// ---- RigidTransformation (TransformationsImpl.{h,cpp}:49-151) ------------------------------------
+// Host-side utility with the reference's float operation order.  Inside ICP the transform is fused
+// into the kNN kernel (K2) and this class is only used for the 4x4 checks.
+struct RigidTransformation : public Transformation {
+    static const std::string description() { return "Rigid transformation."; }
+    RigidTransformation() : Transformation("RigidTransformation", ParametersDoc(), Parameters()) {}
+    static T det3(const TransformationParameters& p) {
+        return p(0, 0) * (p(1, 1) * p(2, 2) - p(1, 2) * p(2, 1)) - p(0, 1) * (p(1, 0) * p(2, 2) - p(1, 2) * p(2, 0)) +
+               p(0, 2) * (p(1, 0) * p(2, 1) - p(1, 1) * p(2, 0));
+    }
+    bool checkParameters(const TransformationParameters& parameters) const override {
+        const T epsilon = T(0.001);
+        if (parameters.rows() == 4) return !(std::fabs(T(1) - det3(parameters)) > epsilon);
+        const T det2 = parameters(0, 0) * parameters(1, 1) - parameters(0, 1) * parameters(1, 0);
+        return !(std::fabs(T(1) - det2) > epsilon);
+    }
+    DataPoints compute(const DataPoints& input, const TransformationParameters& parameters) const override {
+        if (!checkParameters(parameters)) throw TransformationError("RigidTransformation: Error, rotation matrix is not orthogonal.");
+        DataPoints out = input;
+        out.features = parameters * input.features;
+        // rotate the descriptors named normals / observationDirections (TransformationsImpl.cpp:72-84)
+        const int dim = parameters.rows() - 1;
+        unsigned row = 0;
+        for (const auto& label : input.descriptorLabels) {
+            if ((label.text == "normals" || label.text == "observationDirections") && (int)label.span == dim) {
+                for (int j = 0; j < input.descriptors.cols(); ++j)
+                    for (int i = 0; i < dim; ++i) {
+                        volatile T acc = parameters(i, 0) * input.descriptors(row, j);
+                        for (int k = 1; k < dim; ++k) {
+                            volatile T prod = parameters(i, k) * input.descriptors(row + k, j);
+                            acc = acc + prod;
+                        }
+                        out.descriptors(row + i, j) = acc;
+                    }
+            }
+            row += label.span;
+        }
+        return out;
+    }
+    TransformationParameters correctParameters(const TransformationParameters& parameters) const override {
+        TransformationParameters ortho = parameters;
+        if (ortho.cols() != 4) return ortho;
+        auto col = [&](int c, T* v) { for (int i = 0; i < 3; ++i) v[i] = parameters(i, c); };
+        auto normalize = [](T* v) { const T n = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); for (int i = 0; i < 3; ++i) v[i] /= n; };
+        auto cross = [](const T* a, const T* b, T* o) { o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0]; };
+        T c1[3], c2[3], n0[3], n1[3];
+        col(1, c1); col(2, c2);
+        normalize(c1); normalize(c2);
+        cross(c1, c2, n0);
+        cross(c2, n0, n1);
+        for (int i = 0; i < 3; ++i) { ortho(i, 0) = n0[i]; ortho(i, 1) = n1[i]; ortho(i, 2) = c2[i]; }
+        return ortho;
+    }
+};
+
+// ---- IdentityDataPointsFilter (DataPointsFilters/Identity.{h,cpp}) ----------------------------------
+struct IdentityDataPointsFilter : public DataPointsFilter {
+    static const std::string description() { return "Does nothing."; }
+    IdentityDataPointsFilter() : DataPointsFilter("IdentityDataPointsFilter", ParametersDoc(), Parameters()) {}
+    DataPoints filter(const DataPoints& input) override { return input; }
+    void inPlaceFilter(DataPoints&) override {}
+};
+
+// ---- SurfaceNormalDataPointsFilter (DataPointsFilters/SurfaceNormal.{h,cpp}) — K8 -------------------
+struct SurfaceNormalDataPointsFilter : public DataPointsFilter, public GpuBound {
+    static const std::string description() {
+        return "This filter extracts the surface normal vector and other statistics to each point by taking the eigenvector corresponding to "
+               "the smallest eigenvalue of its nearest neighbors (GPU: exact kNN + per-point 3x3 eigen-solve).";
+    }
+    static const ParametersDoc availableParameters() {
+        return {
+            {"knn", "number of nearest neighbors to consider, including the point itself", "5", "3", "2147483647", &Parametrizable::Comp<unsigned>},
+            {"maxDist", "maximum distance to consider for neighbors", "inf", "0", "inf", &Parametrizable::Comp<T>},
+            {"epsilon", "approximation to use for the nearest-neighbor search", "0", "0", "inf", &Parametrizable::Comp<T>},
+            {"keepNormals", "whether the normals should be added as descriptors to the resulting cloud", "1"},
+            {"keepDensities", "whether the point densities should be added as descriptors to the resulting cloud", "0"},
+            {"keepEigenValues", "whether the eigen values should be added as descriptors to the resulting cloud", "0"},
+            {"keepEigenVectors", "whether the eigen vectors should be added as descriptors to the resulting cloud", "0"},
+            {"keepMatchedIds", "whether the identifiers of matches points should be added as descriptors to the resulting cloud", "0"},
+            {"keepMeanDist", "whether the distance to the nearest neighbor mean should be added as descriptors to the resulting cloud", "0"},
+            {"sortEigen", "whether the eigenvalues and eigenvectors should be sorted (ascending) based on the eigenvalues", "0"},
+            {"smoothNormals", "whether the normal vector should be average with the nearest neighbors", "0"}};
+    }
+    const unsigned knn;
+    const T maxDist, epsilon;
+    const bool keepNormals, keepDensities, keepEigenValues, keepEigenVectors, keepMatchedIds, keepMeanDist, sortEigen, smoothNormals;
+    int degenerateCount = 0;
+
+    SurfaceNormalDataPointsFilter(const Parameters& params = Parameters())
+        : DataPointsFilter("SurfaceNormalDataPointsFilter", availableParameters(), params),
+          knn(Parametrizable::get<unsigned>("knn")), maxDist(Parametrizable::get<T>("maxDist")), epsilon(Parametrizable::get<T>("epsilon")),
+          keepNormals(Parametrizable::get<bool>("keepNormals")), keepDensities(Parametrizable::get<bool>("keepDensities")),
+          keepEigenValues(Parametrizable::get<bool>("keepEigenValues")), keepEigenVectors(Parametrizable::get<bool>("keepEigenVectors")),
+          keepMatchedIds(Parametrizable::get<bool>("keepMatchedIds")), keepMeanDist(Parametrizable::get<bool>("keepMeanDist")),
+          sortEigen(Parametrizable::get<bool>("sortEigen")), smoothNormals(Parametrizable::get<bool>("smoothNormals")) {
+        if (smoothNormals) throw ConfigurationError("SurfaceNormalDataPointsFilter: GPU module: smoothNormals is not supported");
+    }
+    DataPoints filter(const DataPoints& input) override {
+        DataPoints output(input);
+        inPlaceFilter(output);
+        return output;
+    }
+    void inPlaceFilter(DataPoints& cloud) override {
+        requireFloat3D(cloud.features.rows(), "SurfaceNormalDataPointsFilter");
+        unsigned insertDim = 0;
+        for (const auto& l : cloud.descriptorLabels) insertDim += l.span;
+        if (insertDim != cloud.getDescriptorDim())
+            throw typename DataPoints::InvalidField("SurfaceNormalDataPointsFilter: Error, descriptor labels do not match descriptor data");
+        if (keepNormals) cloud.allocateDescriptor("normals", 3);
+        if (keepDensities) cloud.allocateDescriptor("densities", 1);
+        if (keepEigenValues) cloud.allocateDescriptor("eigValues", 3);
+        if (keepEigenVectors) cloud.allocateDescriptor("eigVectors", 9);
+        if (keepMatchedIds) cloud.allocateDescriptor("matchedIds", knn);
+        if (keepMeanDist) cloud.allocateDescriptor("meanDists", 1);
+        // outputs land directly in the rows of the descriptor matrix (column stride = its row count)
+        pmgpu_normals_out out;
+        std::memset(&out, 0, sizeof(out));
+        const int ld = cloud.descriptors.rows();
+        float* base = reinterpret_cast<float*>(cloud.descriptors.data());
+        auto at = [&](const char* name) { return base + cloud.getDescriptorStartingRow(name); };
+        if (keepNormals) { out.normals = at("normals"); out.normals_ld = ld; }
+        if (keepDensities) { out.densities = at("densities"); out.densities_ld = ld; }
+        if (keepEigenValues) { out.eig_values = at("eigValues"); out.eig_values_ld = ld; }
+        if (keepEigenVectors) { out.eig_vectors = at("eigVectors"); out.eig_vectors_ld = ld; }
+        if (keepMatchedIds) { out.matched_ids = at("matchedIds"); out.matched_ids_ld = ld; }
+        if (keepMeanDist) { out.mean_dists = at("meanDists"); out.mean_dists_ld = ld; }
+        GpuPipeline& g = this->gpu();
+        g.check(pmgpu_normals(g.ctx, reinterpret_cast<const float*>(cloud.features.data()), cloud.features.rows(), cloud.features.cols(), (int)knn,
+                              (float)epsilon, (float)maxDist, sortEigen ? PMGPU_NORMALS_SORT_EIGEN : 0, &out, &degenerateCount));
+    }
+};
+
+// ---- KDTreeMatcher (MatchersImpl.{h,cpp}:74-101) — K1 + K2 ------------------------------------------
+struct KDTreeMatcher : public Matcher, public GpuBound {
+    static const std::string description() {
+        return "This matcher matches a point from the reading to its closest neighbors in the reference (GPU: exact search, answers of "
+               "libnabo's brute-force search).";
+    }
+    static const ParametersDoc availableParameters() {
+        return {{"knn", "number of nearest neighbors to consider it the reference", "1", "1", "2147483647", &Parametrizable::Comp<unsigned>},
+                {"epsilon", "approximation to use for the nearest-neighbor search", "0", "0", "inf", &Parametrizable::Comp<T>},
+                {"searchType", "Nabo search type. 0: brute force, check distance to every point in the data (very slow), 1: kd-tree with linear heap, good for small knn (~up to 30) and 2: kd-tree with tree heap, good for large knn (~from 30)", "1", "0", "2", &Parametrizable::Comp<unsigned>},
+                {"maxDist", "maximum distance to consider for neighbors", "inf", "0", "inf", &Parametrizable::Comp<T>}};
+    }
+    const int knn;
+    const T epsilon;
+    const int searchType;
+    const T maxDist;
+
+    KDTreeMatcher(const Parameters& params = Parameters())
+        : Matcher("KDTreeMatcher", availableParameters(), params), knn(Parametrizable::get<int>("knn")), epsilon(Parametrizable::get<T>("epsilon")),
+          searchType(Parametrizable::get<int>("searchType")), maxDist(Parametrizable::get<T>("maxDist")) {}
+
+    void init(const DataPoints& filteredReference) override {
+        requireFloat3D(filteredReference.features.rows(), "KDTreeMatcher");
+        GpuPipeline& g = this->gpu();
+        const float* normals = nullptr;
+        int ld = 0;
+        if (filteredReference.descriptorExists("normals", 3) && filteredReference.descriptors.cols() == filteredReference.features.cols()) {
+            normals = reinterpret_cast<const float*>(filteredReference.descriptors.data()) + filteredReference.getDescriptorStartingRow("normals");
+            ld = filteredReference.descriptors.rows();
+        }
+        g.check(pmgpu_ref_set(g.ctx, reinterpret_cast<const float*>(filteredReference.features.data()), filteredReference.features.rows(),
+                              filteredReference.features.cols(), normals, ld));
+        g.readingKey = nullptr;
+    }
+    // uploads the reading when it is not the resident one, then matches T * reading
+    Matches findClosestsTransformed(const DataPoints& reading, const TransformationParameters* Tr) {
+        requireFloat3D(reading.features.rows(), "KDTreeMatcher");
+        GpuPipeline& g = this->gpu();
+        if (g.readingKey != reading.features.data() || g.readingCols != reading.features.cols()) {
+            g.check(pmgpu_reading_set(g.ctx, reinterpret_cast<const float*>(reading.features.data()), reading.features.rows(), reading.features.cols()));
+            g.readingKey = reading.features.data();
+            g.readingCols = reading.features.cols();
+        }
+        Matches matches(knn, reading.features.cols());
+        uint64_t visits = 0;
+        g.check(pmgpu_knn(g.ctx, Tr ? reinterpret_cast<const float*>(Tr->data()) : nullptr, knn, (float)epsilon, (float)maxDist, matches.ids.data(),
+                          reinterpret_cast<float*>(matches.dists.data()), &visits));
+        this->visitCounter += visits;
+        return matches;
+    }
+    Matches findClosests(const DataPoints& filteredReading) override {
+        this->gpu().readingKey = nullptr;  // the caller may have modified the cloud in place: always upload
+        return findClosestsTransformed(filteredReading, nullptr);
+    }
+};
+
+// ---- outlier filters (OutlierFiltersImpl.{h,cpp}:66-147) — K3 ---------------------------------------
+struct NullOutlierFilter : public OutlierFilter {
+    static const std::string description() { return "Does nothing."; }
+    NullOutlierFilter() : OutlierFilter("NullOutlierFilter", ParametersDoc(), Parameters()) {}
+    OutlierWeights compute(const DataPoints&, const DataPoints&, const Matches& input) override {
+        return OutlierWeights::Constant(input.ids.rows(), input.ids.cols(), 1);
+    }
+};
+struct GpuDistOutlierFilter : public OutlierFilter, public GpuBound {
+    int filterType;
+    T value;
+    GpuDistOutlierFilter(const std::string& className, const ParametersDoc paramsDoc, const Parameters& params, int type, const char* paramName)
+        : OutlierFilter(className, paramsDoc, params), filterType(type), value(Parametrizable::get<T>(paramName)) {}
+    OutlierWeights compute(const DataPoints&, const DataPoints&, const Matches& input) override {
+        GpuPipeline& g = this->gpu();
+        OutlierWeights w(input.ids.rows(), input.ids.cols());
+        const float p = (float)value;
+        g.check(pmgpu_weights(g.ctx, 1, &filterType, &p, reinterpret_cast<float*>(w.data()), nullptr));
+        return w;
+    }
+};
+struct MaxDistOutlierFilter : public GpuDistOutlierFilter {
+    static const std::string description() { return "This filter considers as outlier links whose norms are above a fix threshold."; }
+    static const ParametersDoc availableParameters() { return {{"maxDist", "threshold distance (Euclidean norm)", "1", "0.0000001", "inf", &Parametrizable::Comp<T>}}; }
+    MaxDistOutlierFilter(const Parameters& params = Parameters()) : GpuDistOutlierFilter("MaxDistOutlierFilter", availableParameters(), params, PMGPU_FILTER_MAXDIST, "maxDist") {}
+};
+struct MedianDistOutlierFilter : public GpuDistOutlierFilter {
+    static const std::string description() { return "This filter considers as outlier links whose norms are above the median link norms times a factor."; }
+    static const ParametersDoc availableParameters() { return {{"factor", "points farther away factor * median will be considered outliers.", "3", "0.0000001", "inf", &Parametrizable::Comp<T>}}; }
+    MedianDistOutlierFilter(const Parameters& params = Parameters()) : GpuDistOutlierFilter("MedianDistOutlierFilter", availableParameters(), params, PMGPU_FILTER_MEDIANDIST, "factor") {}
+};
+struct TrimmedDistOutlierFilter : public GpuDistOutlierFilter {
+    static const std::string description() { return "Hard rejection threshold using quantile."; }
+    static const ParametersDoc availableParameters() { return {{"ratio", "percentage to keep", "0.85", "0.0000001", "1.0", &Parametrizable::Comp<T>}}; }
+    TrimmedDistOutlierFilter(const Parameters& params = Parameters()) : GpuDistOutlierFilter("TrimmedDistOutlierFilter", availableParameters(), params, PMGPU_FILTER_TRIMMEDDIST, "ratio") {}
+};
+
+// chain (OutlierFilter.cpp:63-103): product of the filters' weights; empty chain -> dist != inf.
+// A chain made of GPU distance filters is evaluated in one call (one collapsed threshold).
+struct OutlierFilters : public std::vector<std::shared_ptr<OutlierFilter>>, public GpuBound {
+    bool allGpu() const {
+        for (const auto& f : *this)
+            if (!dynamic_cast<GpuDistOutlierFilter*>(f.get())) return false;
+        return true;
+    }
+    void spec(int* types, float* params) const {
+        int i = 0;
+        for (const auto& f : *this) {
+            const auto* g = dynamic_cast<const GpuDistOutlierFilter*>(f.get());
+            types[i] = g->filterType;
+            params[i] = (float)g->value;
+            ++i;
+        }
+    }
+    OutlierWeights compute(const DataPoints& filteredReading, const DataPoints& filteredReference, const Matches& input) {
+        if (allGpu() && this->size() <= 8) {
+            GpuPipeline& g = this->gpu();
+            int types[8];
+            float params[8];
+            spec(types, params);
+            OutlierWeights w(input.ids.rows(), input.ids.cols());
+            g.check(pmgpu_weights(g.ctx, (int)this->size(), types, params, reinterpret_cast<float*>(w.data()), nullptr));
+            return w;
+        }
+        OutlierWeights w = (*this->begin())->compute(filteredReading, filteredReference, input);
+        for (auto it = this->begin() + 1; it != this->end(); ++it) {
+            const OutlierWeights o = (*it)->compute(filteredReading, filteredReference, input);
+            for (size_t i = 0; i < w.size(); ++i) w(i) = w(i) * o(i);
+        }
+        return w;
+    }
+};
+
+// ---- error minimizers (ErrorMinimizers/*.cpp) — K4-K7 ------------------------------------------------
+struct GpuErrorMinimizer : public ErrorMinimizer, public GpuBound {
+    int kind;
+    T sensorStdDev;
+    Matrix covMatrix;
+    GpuErrorMinimizer(const std::string& className, const ParametersDoc paramsDoc, const Parameters& params, int kind)
+        : ErrorMinimizer(className, paramsDoc, params), kind(kind), sensorStdDev(T(0.01)), covMatrix(Matrix::Zero(6, 6)) {}
+    // uses the matches / weights resident on the device; the host arguments are what the reference
+    // interface hands around (ErrorMinimizer.cpp:217-232)
+    TransformationParameters compute(const DataPoints& filteredReading, const DataPoints&, const OutlierWeights&, const Matches&) override {
+        requireFloat3D(filteredReading.features.rows(), "ErrorMinimizer");
+        GpuPipeline& g = this->gpu();
+        TransformationParameters out(4, 4);
+        float cov[36], stats[5];
+        g.check(pmgpu_minimize(g.ctx, kind, (float)sensorStdDev, reinterpret_cast<float*>(out.data()), cov, stats));
+        setResults(cov, stats);
+        return out;
+    }
+    void setResults(const float* cov, const float* stats) {
+        if (kind == PMGPU_MIN_P2POINT_COV || kind == PMGPU_MIN_P2PLANE_COV)
+            for (int i = 0; i < 36; ++i) covMatrix(i) = T(cov[i]);
+        this->lastErrorElements.pointUsedRatio = T(stats[0]);
+        this->lastErrorElements.weightedPointUsedRatio = T(stats[1]);
+        this->lastErrorElements.nbRejectedMatches = (int)stats[2];
+        this->lastErrorElements.nbRejectedPoints = (int)stats[3];
+    }
+    Matrix getCovariance() const override { return covMatrix; }
+};
+struct PointToPointErrorMinimizer : public GpuErrorMinimizer {
+    static const std::string description() { return "Point-to-point error. Based on SVD decomposition."; }
+    PointToPointErrorMinimizer() : GpuErrorMinimizer("PointToPointErrorMinimizer", ParametersDoc(), Parameters(), PMGPU_MIN_P2POINT) {}
+};
+struct PointToPointWithCovErrorMinimizer : public GpuErrorMinimizer {
+    static const std::string description() { return "Point-to-point error. Additionally, it computes the covariance (Censi 2007)."; }
+    static const ParametersDoc availableParameters() { return {{"sensorStdDev", "sensor standard deviation", "0.01", "0.", "inf", &Parametrizable::Comp<T>}}; }
+    PointToPointWithCovErrorMinimizer(const Parameters& params = Parameters())
+        : GpuErrorMinimizer("PointToPointWithCovErrorMinimizer", availableParameters(), params, PMGPU_MIN_P2POINT_COV) {
+        this->sensorStdDev = Parametrizable::get<T>("sensorStdDev");
+    }
+};
+struct PointToPlaneErrorMinimizer : public GpuErrorMinimizer {
+    static const std::string description() { return "Point-to-plane error (or point-to-line in 2D)."; }
+    static const ParametersDoc availableParameters() {
+        return {{"force2D", "If set to true(1), the minimization will be forced to give a solution in 2D (i.e., on the XY-plane) even with 3D inputs.", "0", "0", "1", &Parametrizable::Comp<bool>},
+                {"force4DOF", "If set to true(1), the minimization will optimize only yaw and translation, pitch and roll will follow the prior.", "0", "0", "1", &Parametrizable::Comp<bool>}};
+    }
+    PointToPlaneErrorMinimizer(const Parameters& params = Parameters()) : PointToPlaneErrorMinimizer("PointToPlaneErrorMinimizer", availableParameters(), params, PMGPU_MIN_P2PLANE) {}
+protected:
+    PointToPlaneErrorMinimizer(const std::string& className, const ParametersDoc paramsDoc, const Parameters& params, int kind)
+        : GpuErrorMinimizer(className, paramsDoc, params, kind) {
+        const bool force2D = Parametrizable::get<bool>("force2D"), force4DOF = Parametrizable::get<bool>("force4DOF");
+        if (force2D && force4DOF) throw ConfigurationError("Force 2D cannot be used together with force4DOF.");  // PointToPlane.cpp:59-64
+        if (force2D || force4DOF) throw ConfigurationError("PointToPlaneErrorMinimizer: GPU module: force2D / force4DOF are not supported");
+    }
+};
+struct PointToPlaneWithCovErrorMinimizer : public PointToPlaneErrorMinimizer {
+    static const std::string description() { return "Point-to-plane error (or point-to-line in 2D). Additionally, it computes the covariance (Censi 2007)."; }
+    static const ParametersDoc availableParameters() {
+        ParametersDoc d = PointToPlaneErrorMinimizer::availableParameters();
+        d.push_back({"sensorStdDev", "sensor standard deviation", "0.01", "0.", "inf", &Parametrizable::Comp<T>});
+        return d;
+    }
+    PointToPlaneWithCovErrorMinimizer(const Parameters& params = Parameters())
+        : PointToPlaneErrorMinimizer("PointToPlaneWithCovErrorMinimizer", availableParameters(), params, PMGPU_MIN_P2PLANE_COV) {
+        this->sensorStdDev = Parametrizable::get<T>("sensorStdDev");
+    }
+};
+
+// ---- transformation checkers (TransformationCheckersImpl.{h,cpp}) — host objects ------------------
+struct Quat {
+    T w, x, y, z;
+    static Quat fromMatrix(const TransformationParameters& m) {  // Eigen's matrix -> quaternion
+        Quat q;
+        T t = m(0, 0) + m(1, 1) + m(2, 2);
+        if (t > T(0)) {
+            t = std::sqrt(t + T(1));
+            q.w = T(0.5) * t;
+            t = T(0.5) / t;
+            q.x = (m(2, 1) - m(1, 2)) * t; q.y = (m(0, 2) - m(2, 0)) * t; q.z = (m(1, 0) - m(0, 1)) * t;
+        } else {
+            int i = 0;
+            if (m(1, 1) > m(0, 0)) i = 1;
+            if (m(2, 2) > m(i, i)) i = 2;
+            const int j = (i + 1) % 3, k = (j + 1) % 3;
+            t = std::sqrt(m(i, i) - m(j, j) - m(k, k) + T(1));
+            T v[3];
+            v[i] = T(0.5) * t;
+            t = T(0.5) / t;
+            q.w = (m(k, j) - m(j, k)) * t;
+            v[j] = (m(j, i) + m(i, j)) * t;
+            v[k] = (m(k, i) + m(i, k)) * t;
+            q.x = v[0]; q.y = v[1]; q.z = v[2];
+        }
+        return q;
+    }
+    T angularDistance(const Quat& b) const {  // Eigen 3.3: d = a * conj(b); 2 atan2(|d.vec|, |d.w|)
+        const T dw = w * b.w + x * b.x + y * b.y + z * b.z;
+        const T dx = -w * b.x + x * b.w - y * b.z + z * b.y;
+        const T dy = -w * b.y + y * b.w - z * b.x + x * b.z;
+        const T dz = -w * b.z + z * b.w - x * b.y + y * b.x;
+        return T(2) * std::atan2(std::sqrt(dx * dx + dy * dy + dz * dz), std::fabs(dw));
+    }
+};
+struct CounterTransformationChecker : public TransformationChecker {
+    struct MaxNumIterationsReached {};
+    static const std::string description() { return "This checker stops the ICP loop after a certain number of iterations."; }
+    static const ParametersDoc availableParameters() { return {{"maxIterationCount", "maximum number of iterations ", "40", "0", "2147483647", &Parametrizable::Comp<unsigned>}}; }
+    const unsigned maxIterationCount;
+    CounterTransformationChecker(const Parameters& params = Parameters())
+        : TransformationChecker("CounterTransformationChecker", availableParameters(), params), maxIterationCount(Parametrizable::get<unsigned>("maxIterationCount")) {
+        this->limits = Vector::Zero(1, 1);
+        this->limits(0) = T(maxIterationCount);
+        this->conditionVariableNames.push_back("Iteration");
+        this->limitNames.push_back("Max iteration");
+    }
+    void init(const TransformationParameters&, bool&) override { this->conditionVariables = Vector::Zero(1, 1); }
+    void check(const TransformationParameters&, bool& iterate) override {
+        this->conditionVariables(0) += T(1);
+        if (this->conditionVariables(0) >= this->limits(0)) {
+            iterate = false;
+            throw MaxNumIterationsReached();
+        }
+    }
+};
+struct DifferentialTransformationChecker : public TransformationChecker {
+    static const std::string description() { return "This checker stops the ICP loop when the relative motions (i.e. abs(currentIter - lastIter)) of rotation and translation components are below a fix thresholds."; }
+    static const ParametersDoc availableParameters() {
+        return {{"minDiffRotErr", "threshold for rotation error (radian)", "0.001", "0.", "6.2831854", &Parametrizable::Comp<T>},
+                {"minDiffTransErr", "threshold for translation error", "0.001", "0.", "inf", &Parametrizable::Comp<T>},
+                {"smoothLength", "number of iterations over which to average the differencial error", "3", "0", "2147483647", &Parametrizable::Comp<unsigned>}};
+    }
+    const T minDiffRotErr, minDiffTransErr;
+    const unsigned smoothLength;
+    std::vector<Quat> rotations;
+    std::vector<std::vector<T>> translations;
+    DifferentialTransformationChecker(const Parameters& params = Parameters())
+        : TransformationChecker("DifferentialTransformationChecker", availableParameters(), params), minDiffRotErr(Parametrizable::get<T>("minDiffRotErr")),
+          minDiffTransErr(Parametrizable::get<T>("minDiffTransErr")), smoothLength(Parametrizable::get<unsigned>("smoothLength")) {
+        this->limits = Vector::Zero(2, 1);
+        this->limits(0) = minDiffRotErr;
+        this->limits(1) = minDiffTransErr;
+        this->conditionVariableNames.push_back("Mean abs differential rot err");
+        this->conditionVariableNames.push_back("Mean abs differential trans err");
+        this->limitNames.push_back("Min differential rotation err");
+        this->limitNames.push_back("Min differential translation err");
+    }
+    void init(const TransformationParameters& parameters, bool&) override {
+        this->conditionVariables = Vector::Zero(2, 1);
+        rotations.clear();
+        translations.clear();
+        rotations.push_back(Quat::fromMatrix(parameters));
+        translations.push_back({parameters(0, 3), parameters(1, 3), parameters(2, 3)});
+    }
+    void check(const TransformationParameters& parameters, bool& iterate) override {
+        rotations.push_back(Quat::fromMatrix(parameters));
+        translations.push_back({parameters(0, 3), parameters(1, 3), parameters(2, 3)});
+        this->conditionVariables = Vector::Zero(2, 1);
+        if (rotations.size() > smoothLength) {
+            for (size_t i = rotations.size() - 1; i >= rotations.size() - smoothLength; --i) {
+                this->conditionVariables(0) += std::fabs(rotations[i].angularDistance(rotations[i - 1]));
+                const T dx = translations[i][0] - translations[i - 1][0], dy = translations[i][1] - translations[i - 1][1], dz = translations[i][2] - translations[i - 1][2];
+                this->conditionVariables(1) += std::fabs(std::sqrt(dx * dx + dy * dy + dz * dz));
+            }
+            this->conditionVariables(0) /= T(smoothLength);
+            this->conditionVariables(1) /= T(smoothLength);
+            if (this->conditionVariables(0) < this->limits(0) && this->conditionVariables(1) < this->limits(1)) iterate = false;
+        }
+        if (std::isnan(this->conditionVariables(0))) throw ConvergenceError("abs rotation norm not a number");
+        if (std::isnan(this->conditionVariables(1))) throw ConvergenceError("abs translation norm not a number");
+    }
+};
+struct BoundTransformationChecker : public TransformationChecker {
+    static const std::string description() { return "This checker stops the ICP loop with an exception when the transformation values exceed bounds."; }
+    static const ParametersDoc availableParameters() {
+        return {{"maxRotationNorm", "rotation bound", "1", "0", "inf", &Parametrizable::Comp<T>},
+                {"maxTranslationNorm", "translation bound", "1", "0", "inf", &Parametrizable::Comp<T>}};
+    }
+    const T maxRotationNorm, maxTranslationNorm;
+    Quat initialRotation3D;
+    std::vector<T> initialTranslation;
+    BoundTransformationChecker(const Parameters& params = Parameters())
+        : TransformationChecker("BoundTransformationChecker", availableParameters(), params), maxRotationNorm(Parametrizable::get<T>("maxRotationNorm")),
+          maxTranslationNorm(Parametrizable::get<T>("maxTranslationNorm")) {
+        this->limits = Vector::Zero(2, 1);
+        this->limits(0) = maxRotationNorm;
+        this->limits(1) = maxTranslationNorm;
+        this->limitNames.push_back("Max rotation angle");
+        this->limitNames.push_back("Max translation norm");
+        this->conditionVariableNames.push_back("Rotation angle");
+        this->conditionVariableNames.push_back("Translation norm");
+    }
+    void init(const TransformationParameters& parameters, bool&) override {
+        this->conditionVariables = Vector::Zero(2, 1);
+        if (parameters.rows() != 4) throw std::runtime_error("BoundTransformationChecker: GPU build supports 3D only");
+        initialRotation3D = Quat::fromMatrix(parameters);
+        initialTranslation = {parameters(0, 3), parameters(1, 3), parameters(2, 3)};
+    }
+    void check(const TransformationParameters& parameters, bool&) override {
+        this->conditionVariables(0) = Quat::fromMatrix(parameters).angularDistance(initialRotation3D);
+        const T dx = parameters(0, 3) - initialTranslation[0], dy = parameters(1, 3) - initialTranslation[1], dz = parameters(2, 3) - initialTranslation[2];
+        this->conditionVariables(1) = std::sqrt(dx * dx + dy * dy + dz * dz);
+        if (this->conditionVariables(0) > this->limits(0) || this->conditionVariables(1) > this->limits(1)) {
+            std::ostringstream oss;
+            oss << "limit out of bounds: rot: " << this->conditionVariables(0) << "/" << this->limits(0) << " tr: " << this->conditionVariables(1) << "/" << this->limits(1);
+            throw ConvergenceError(oss.str());
+        }
+    }
+};
+
+struct NullInspector : public Inspector {
+    static const std::string description() { return "Does nothing."; }
+    NullInspector() : Inspector("NullInspector", ParametersDoc(), Parameters()) {}
+    bool isNull() const override { return true; }
+};
+struct NullLogger : public Logger {
+    static const std::string description() { return "Does nothing."; }
+    NullLogger() : Logger("NullLogger", ParametersDoc(), Parameters()) {}
+};

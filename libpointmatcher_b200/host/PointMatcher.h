@@ -1,0 +1,429 @@
+// host/PointMatcher.h — the reference's public header (pointmatcher/PointMatcher.h, v1.3.1) for the
+// ICP hot path, with the GPU modules registered under the reference's names.
+//
+// Same class names, method signatures, parameter tables and exception types as the reference, so
+// code and YAML written against libpointmatcher compiles / loads unchanged for this path:
+//   PointMatcher<T>::DataPoints / Matches / OutlierWeights / TransformationParameters
+//   Matcher (KDTreeMatcher) . OutlierFilter(s) (MaxDist, MedianDist, TrimmedDist, Null)
+//   ErrorMinimizer (PointToPoint[WithCov], PointToPlane[WithCov]) . DataPointsFilter(s)
+//   (SurfaceNormal, Identity) . Transformation (Rigid) . TransformationChecker(s) (Counter,
+//   Differential, Bound) . Inspector (Null) . ICP (setDefault, loadFromYaml, operator())
+// Every module marshals to the C ABI of include/pmgpu.h; there is no CPU implementation of the hot
+// path behind these classes (no Eigen either: Matrix below is a minimal column-major container
+// with the memory layout of Eigen::Matrix<T, Dynamic, Dynamic>).
+//
+// Only T = float, 3-D (features.rows() == 4) runs on the GPU; PointMatcher<double> and 2-D clouds
+// are accepted by the interfaces and answered with ConfigurationError, never silently.
+#pragma once
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <iostream>
+
+#include "../../include/pmgpu.h"
+#include "Support.h"
+
+namespace pmb {
+
+// minimal column-major dense matrix, layout-compatible with Eigen's default
+template <typename T>
+class Matrix {
+public:
+    Matrix() : r_(0), c_(0) {}
+    Matrix(int rows, int cols) : r_(rows), c_(cols), d_((size_t)rows * cols) {}
+    static Matrix Zero(int rows, int cols) { Matrix m(rows, cols); std::fill(m.d_.begin(), m.d_.end(), T(0)); return m; }
+    static Matrix Constant(int rows, int cols, T v) { Matrix m(rows, cols); std::fill(m.d_.begin(), m.d_.end(), v); return m; }
+    static Matrix Identity(int rows, int cols) {
+        Matrix m = Zero(rows, cols);
+        for (int i = 0; i < std::min(rows, cols); ++i) m(i, i) = T(1);
+        return m;
+    }
+    int rows() const { return r_; }
+    int cols() const { return c_; }
+    size_t size() const { return d_.size(); }
+    T* data() { return d_.data(); }
+    const T* data() const { return d_.data(); }
+    T& operator()(int i, int j) { return d_[(size_t)j * r_ + i]; }
+    const T& operator()(int i, int j) const { return d_[(size_t)j * r_ + i]; }
+    T& operator()(int i) { return d_[i]; }
+    const T& operator()(int i) const { return d_[i]; }
+    void resize(int rows, int cols) { r_ = rows; c_ = cols; d_.assign((size_t)rows * cols, T(0)); }
+    // keeps the leading block, like Eigen's conservativeResize
+    void conservativeResize(int rows, int cols) {
+        Matrix m = Zero(rows, cols);
+        for (int j = 0; j < std::min(cols, c_); ++j)
+            for (int i = 0; i < std::min(rows, r_); ++i) m(i, j) = (*this)(i, j);
+        *this = m;
+    }
+    // dense product with a single accumulator per entry, k ascending and no FMA contraction
+    // assumed (the depth-4 GEMM order of the reference's 4x4 bookkeeping, ICP.cpp:411-412,448)
+    Matrix operator*(const Matrix& o) const {
+        Matrix out(r_, o.c_);
+        for (int j = 0; j < o.c_; ++j)
+            for (int i = 0; i < r_; ++i) {
+                volatile T acc = (*this)(i, 0) * o(0, j);
+                for (int k = 1; k < c_; ++k) {
+                    volatile T prod = (*this)(i, k) * o(k, j);
+                    acc = acc + prod;
+                }
+                out(i, j) = acc;
+            }
+        return out;
+    }
+    bool operator==(const Matrix& o) const { return r_ == o.r_ && c_ == o.c_ && d_ == o.d_; }
+
+private:
+    int r_, c_;
+    std::vector<T> d_;
+};
+
+}  // namespace pmb
+
+template <typename T>
+struct PointMatcher {
+    // ---------------------------------------------------------------------------------------------
+    // basic types (PointMatcher.h:160-200, 371-397)
+    // ---------------------------------------------------------------------------------------------
+    typedef T ScalarType;
+    typedef pmb::Matrix<T> Matrix;
+    typedef pmb::Matrix<T> Vector;
+    typedef pmb::Matrix<int> IntMatrix;
+    typedef Matrix TransformationParameters;
+    typedef Matrix OutlierWeights;
+    typedef PointMatcherSupport::Parametrizable Parametrizable;
+    typedef Parametrizable::Parameters Parameters;
+    typedef Parametrizable::ParameterDoc ParameterDoc;
+    typedef Parametrizable::ParametersDoc ParametersDoc;
+    typedef Parametrizable::InvalidParameter InvalidParameter;
+    typedef PointMatcherSupport::InvalidModuleType InvalidModuleType;
+    typedef PointMatcherSupport::TransformationError TransformationError;
+    typedef PointMatcherSupport::ConfigurationError ConfigurationError;
+    typedef PointMatcherSupport::InvalidElement InvalidElement;
+
+    struct ConvergenceError : std::runtime_error {  // PointMatcher.h:148-151
+        explicit ConvergenceError(const std::string& reason) : std::runtime_error(reason) {}
+    };
+
+    // ---- DataPoints (PointMatcher.h:207-358) -------------------------------------------------------
+    struct DataPoints {
+        struct Label {
+            std::string text;
+            size_t span;
+            Label(const std::string& text = "", const size_t span = 0) : text(text), span(span) {}
+            bool operator==(const Label& that) const { return text == that.text && span == that.span; }
+        };
+        struct Labels : std::vector<Label> {
+            bool contains(const std::string& text) const {
+                for (const Label& l : *this)
+                    if (l.text == text) return true;
+                return false;
+            }
+        };
+        struct InvalidField : std::runtime_error {  // PointMatcher.h:250-253
+            explicit InvalidField(const std::string& reason) : std::runtime_error(reason) {}
+        };
+
+        Matrix features;          // (dim + 1) x N, homogeneous row last
+        Labels featureLabels;
+        Matrix descriptors;       // (sum of spans) x N
+        Labels descriptorLabels;
+
+        DataPoints() {}
+        DataPoints(const Matrix& features, const Labels& featureLabels) : features(features), featureLabels(featureLabels) {}
+        DataPoints(const Matrix& features, const Labels& featureLabels, const Matrix& descriptors, const Labels& descriptorLabels)
+            : features(features), featureLabels(featureLabels), descriptors(descriptors), descriptorLabels(descriptorLabels) {}
+
+        unsigned getNbPoints() const { return features.cols(); }
+        unsigned getEuclideanDim() const { return features.rows() - 1; }
+        unsigned getHomogeneousDim() const { return features.rows(); }
+        unsigned getDescriptorDim() const { return descriptors.rows(); }
+        bool descriptorExists(const std::string& name) const { return descriptorLabels.contains(name); }
+        bool descriptorExists(const std::string& name, unsigned dim) const {
+            for (const Label& l : descriptorLabels)
+                if (l.text == name) return l.span == dim;
+            return false;
+        }
+        unsigned getDescriptorDimension(const std::string& name) const {
+            for (const Label& l : descriptorLabels)
+                if (l.text == name) return l.span;
+            return 0;
+        }
+        // DataPoints.cpp:917-942: row where the named descriptor starts
+        unsigned getDescriptorStartingRow(const std::string& name) const {
+            unsigned row = 0;
+            for (const Label& l : descriptorLabels) {
+                if (l.text == name) return row;
+                row += l.span;
+            }
+            throw InvalidField("Field " + name + " not found");
+        }
+        Matrix getDescriptorCopyByName(const std::string& name) const {
+            const unsigned row = getDescriptorStartingRow(name), span = getDescriptorDimension(name);
+            Matrix out(span, descriptors.cols());
+            for (int j = 0; j < descriptors.cols(); ++j)
+                for (unsigned i = 0; i < span; ++i) out(i, j) = descriptors(row + i, j);
+            return out;
+        }
+        // DataPoints.cpp:783-822: re-use an existing same-span descriptor or append rows
+        void allocateDescriptor(const std::string& name, const unsigned dim) {
+            for (const Label& l : descriptorLabels) {
+                if (l.text == name) {
+                    if (l.span == dim) return;
+                    throw InvalidField("Field " + name + " already exists but has a different dimension");
+                }
+            }
+            const int oldRows = descriptors.rows(), n = features.cols();
+            if (descriptors.cols() != n && oldRows > 0) throw InvalidField("descriptors and features have different point counts");
+            Matrix grown = Matrix::Zero(oldRows + dim, n);
+            for (int j = 0; j < n; ++j)
+                for (int i = 0; i < oldRows; ++i) grown(i, j) = descriptors(i, j);
+            descriptors = grown;
+            descriptorLabels.push_back(Label(name, dim));
+        }
+        void addDescriptor(const std::string& name, const Matrix& newDescriptor) {
+            allocateDescriptor(name, newDescriptor.rows());
+            const unsigned row = getDescriptorStartingRow(name);
+            for (int j = 0; j < newDescriptor.cols(); ++j)
+                for (int i = 0; i < newDescriptor.rows(); ++i) descriptors(row + i, j) = newDescriptor(i, j);
+        }
+    };
+
+    // ---- Matches (PointMatcher.h:371-391, Matches.cpp) -----------------------------------------------
+    struct Matches {
+        typedef Matrix Dists;
+        typedef IntMatrix Ids;
+        static constexpr int InvalidId = -1;
+        static T InvalidDist() { return std::numeric_limits<T>::infinity(); }
+        Dists dists;  // knn x N squared distances
+        Ids ids;      // knn x N reference columns
+        Matches() {}
+        Matches(const Dists& dists, const Ids ids) : dists(dists), ids(ids) {}
+        Matches(const int knn, const int pointsCount) : dists(knn, pointsCount), ids(knn, pointsCount) {}
+        // Matches.cpp:60-87 (host utility used outside the ICP loop, e.g. examples/icp_advance_api.cpp)
+        T getDistsQuantile(const T quantile) const {
+            std::vector<T> values;
+            values.reserve(dists.size());
+            for (size_t i = 0; i < dists.size(); ++i)
+                if (dists(i) != std::numeric_limits<T>::infinity()) values.push_back(dists(i));
+            if (values.size() == 0) throw ConvergenceError("no outlier to filter");
+            if (quantile < 0.0 || quantile > 1.0) throw ConvergenceError("quantile must be between 0 and 1");
+            if (quantile == 1.0) return *std::max_element(values.begin(), values.end());
+            const size_t idx = std::min(values.size() - 1, (size_t)(T(values.size()) * quantile));
+            std::nth_element(values.begin(), values.begin() + idx, values.end());
+            return values[idx];
+        }
+    };
+
+    // ---------------------------------------------------------------------------------------------
+    // the device context shared by the modules of one chain
+    // ---------------------------------------------------------------------------------------------
+    struct GpuPipeline {
+        pmgpu_ctx* ctx = nullptr;
+        const void* readingKey = nullptr;  // host features pointer of the resident reading
+        int readingCols = 0;
+        explicit GpuPipeline(int device = 0) {
+            const int rc = pmgpu_ctx_create(device, &ctx);
+            if (rc != PMGPU_OK)
+                throw std::runtime_error(std::string("GPU module: cannot create a pmgpu context (") + pmgpu_status_string(rc) +
+                                         "); there is no CPU fallback");
+        }
+        ~GpuPipeline() { pmgpu_ctx_destroy(ctx); }
+        GpuPipeline(const GpuPipeline&) = delete;
+        GpuPipeline& operator=(const GpuPipeline&) = delete;
+        // status -> the exception the reference throws at the same place (pmgpu.h)
+        void check(int rc) const {
+            if (rc == PMGPU_OK) return;
+            const std::string msg = pmgpu_last_error(ctx);
+            switch (rc) {
+                case PMGPU_ERR_UNSUPPORTED: throw ConfigurationError(msg);
+                case PMGPU_ERR_NO_OUTLIER_TO_FILTER:
+                case PMGPU_ERR_BAD_QUANTILE:
+                case PMGPU_ERR_NO_POINT_TO_MINIMIZE:
+                case PMGPU_ERR_NAN: throw ConvergenceError(msg);
+                case PMGPU_ERR_NO_NORMALS: throw typename DataPoints::InvalidField(msg);
+                case PMGPU_ERR_NOT_ORTHOGONAL: throw TransformationError(msg);
+                case PMGPU_ERR_BAD_ARG: throw InvalidParameter(msg);
+                default: throw std::runtime_error(msg + " (pmgpu status " + std::to_string(rc) + ")");
+            }
+        }
+        // modules created outside an ICP object share one pipeline per thread, so the stand-alone
+        // sequence init -> findClosests -> outlierFilters.compute -> errorMinimizer.compute
+        // (examples/icp_advance_api.cpp:164-217) works on resident data
+        static std::shared_ptr<GpuPipeline> threadDefault() {
+            static thread_local std::shared_ptr<GpuPipeline> p;
+            if (!p) p = std::make_shared<GpuPipeline>(0);
+            return p;
+        }
+    };
+    struct GpuBound {
+        std::shared_ptr<GpuPipeline> pipeline;
+        virtual ~GpuBound() {}
+        void bind(const std::shared_ptr<GpuPipeline>& p) { pipeline = p; }
+        GpuPipeline& gpu() {
+            if (!pipeline) pipeline = GpuPipeline::threadDefault();
+            return *pipeline;
+        }
+    };
+    static void requireFloat3D(int rows, const char* who) {
+        if (!std::is_same<T, float>::value || rows != 4)
+            throw ConfigurationError(std::string(who) + ": GPU module: only float / 3-D clouds are supported");
+    }
+
+    // ---------------------------------------------------------------------------------------------
+    // module interfaces (PointMatcher.h:404-641)
+    // ---------------------------------------------------------------------------------------------
+    struct Transformation : public Parametrizable {
+        Transformation() {}
+        Transformation(const std::string& className, const ParametersDoc paramsDoc, const Parameters& params) : Parametrizable(className, paramsDoc, params) {}
+        virtual ~Transformation() {}
+        virtual DataPoints compute(const DataPoints& input, const TransformationParameters& parameters) const = 0;
+        virtual bool checkParameters(const TransformationParameters& parameters) const = 0;
+        virtual TransformationParameters correctParameters(const TransformationParameters& parameters) const = 0;
+    };
+    struct Transformations : public std::vector<std::shared_ptr<Transformation>> {
+        void apply(DataPoints& cloud, const TransformationParameters& parameters) const {
+            DataPoints transformedCloud;
+            for (const auto& t : *this) {
+                transformedCloud = t->compute(cloud, parameters);
+                std::swap(cloud, transformedCloud);
+            }
+        }
+    };
+    DEF_REGISTRAR(Transformation)
+
+    struct DataPointsFilter : public Parametrizable {
+        DataPointsFilter() {}
+        DataPointsFilter(const std::string& className, const ParametersDoc paramsDoc, const Parameters& params) : Parametrizable(className, paramsDoc, params) {}
+        virtual ~DataPointsFilter() {}
+        virtual void init() {}
+        virtual DataPoints filter(const DataPoints& input) = 0;
+        virtual void inPlaceFilter(DataPoints& cloud) = 0;
+    };
+    struct DataPointsFilters : public std::vector<std::shared_ptr<DataPointsFilter>> {
+        void init() { for (auto& f : *this) f->init(); }
+        void apply(DataPoints& cloud) {
+            for (auto& f : *this) f->inPlaceFilter(cloud);  // DataPointsFilter.cpp:106-131
+        }
+    };
+    DEF_REGISTRAR(DataPointsFilter)
+
+    struct Matcher : public Parametrizable {
+        unsigned long visitCounter;
+        Matcher() : visitCounter(0) {}
+        Matcher(const std::string& className, const ParametersDoc paramsDoc, const Parameters& params) : Parametrizable(className, paramsDoc, params), visitCounter(0) {}
+        virtual ~Matcher() {}
+        void resetVisitCount() { visitCounter = 0; }
+        unsigned long getVisitCount() const { return visitCounter; }
+        virtual void init(const DataPoints& filteredReference) = 0;
+        virtual Matches findClosests(const DataPoints& filteredReading) = 0;
+    };
+    DEF_REGISTRAR(Matcher)
+
+    struct OutlierFilter : public Parametrizable {
+        OutlierFilter() {}
+        OutlierFilter(const std::string& className, const ParametersDoc paramsDoc, const Parameters& params) : Parametrizable(className, paramsDoc, params) {}
+        virtual ~OutlierFilter() {}
+        virtual OutlierWeights compute(const DataPoints& filteredReading, const DataPoints& filteredReference, const Matches& input) = 0;
+    };
+    struct OutlierFilters;  // below, needs the GPU filter base
+    DEF_REGISTRAR(OutlierFilter)
+
+    struct ErrorMinimizer : public Parametrizable {
+        // kept for source compatibility; the GPU minimisers never materialise the compacted clouds
+        struct ErrorElements {
+            DataPoints reading, reference;
+            OutlierWeights weights;
+            Matches matches;
+            int nbRejectedMatches = -1, nbRejectedPoints = -1;
+            T pointUsedRatio = T(-1), weightedPointUsedRatio = T(-1);
+        };
+        ErrorMinimizer() {}
+        ErrorMinimizer(const std::string& className, const ParametersDoc paramsDoc, const Parameters& params) : Parametrizable(className, paramsDoc, params) {}
+        virtual ~ErrorMinimizer() {}
+        T getPointUsedRatio() const { return lastErrorElements.pointUsedRatio; }
+        T getWeightedPointUsedRatio() const { return lastErrorElements.weightedPointUsedRatio; }
+        ErrorElements getErrorElements() const { return lastErrorElements; }
+        virtual T getOverlap() const { return lastErrorElements.weightedPointUsedRatio; }
+        virtual Matrix getCovariance() const { return Matrix::Zero(6, 6); }
+        virtual TransformationParameters compute(const DataPoints& filteredReading, const DataPoints& filteredReference,
+                                                 const OutlierWeights& outlierWeights, const Matches& matches) = 0;
+    protected:
+        ErrorElements lastErrorElements;
+    };
+    DEF_REGISTRAR(ErrorMinimizer)
+
+    struct TransformationChecker : public Parametrizable {
+    protected:
+        typedef std::vector<std::string> StringVector;
+        Vector limits, conditionVariables;
+        StringVector limitNames, conditionVariableNames;
+    public:
+        TransformationChecker() {}
+        TransformationChecker(const std::string& className, const ParametersDoc paramsDoc, const Parameters& params) : Parametrizable(className, paramsDoc, params) {}
+        virtual ~TransformationChecker() {}
+        virtual void init(const TransformationParameters& parameters, bool& iterate) = 0;
+        virtual void check(const TransformationParameters& parameters, bool& iterate) = 0;
+        const Vector& getLimits() const { return limits; }
+        const Vector& getConditionVariables() const { return conditionVariables; }
+        const StringVector& getLimitNames() const { return limitNames; }
+        const StringVector& getConditionVariableNames() const { return conditionVariableNames; }
+    };
+    struct TransformationCheckers : public std::vector<std::shared_ptr<TransformationChecker>> {
+        void init(const TransformationParameters& parameters, bool& iterate) { for (auto& c : *this) c->init(parameters, iterate); }
+        void check(const TransformationParameters& parameters, bool& iterate) { for (auto& c : *this) c->check(parameters, iterate); }
+    };
+    DEF_REGISTRAR(TransformationChecker)
+
+    struct Inspector : public Parametrizable {
+        Inspector() {}
+        Inspector(const std::string& className, const ParametersDoc paramsDoc, const Parameters& params) : Parametrizable(className, paramsDoc, params) {}
+        virtual ~Inspector() {}
+        virtual void init() {}
+        virtual void addStat(const std::string&, double) {}
+        virtual void dumpIteration(const size_t, const TransformationParameters&, const DataPoints&, const DataPoints&, const Matches&,
+                                   const OutlierWeights&, const TransformationCheckers&) {}
+        virtual void finish(const size_t) {}
+        virtual bool isNull() const { return false; }
+    };
+    DEF_REGISTRAR(Inspector)
+
+    struct Logger : public Parametrizable {
+        Logger() {}
+        Logger(const std::string& className, const ParametersDoc paramsDoc, const Parameters& params) : Parametrizable(className, paramsDoc, params) {}
+        virtual ~Logger() {}
+    };
+    DEF_REGISTRAR(Logger)
+
+#include "Modules.inl"
+
+    // ---------------------------------------------------------------------------------------------
+    // ICP (PointMatcher.h:652-764, ICP.cpp)
+    // ---------------------------------------------------------------------------------------------
+#include "ICP.inl"
+
+    // registry (Registry.cpp:60-126): the GPU classes under the reference's names
+    PointMatcher() {
+        ADD_TO_REGISTRAR_NO_PARAM(Transformation, RigidTransformation, RigidTransformation)
+        ADD_TO_REGISTRAR_NO_PARAM(DataPointsFilter, IdentityDataPointsFilter, IdentityDataPointsFilter)
+        ADD_TO_REGISTRAR(DataPointsFilter, SurfaceNormalDataPointsFilter, SurfaceNormalDataPointsFilter)
+        ADD_TO_REGISTRAR(Matcher, KDTreeMatcher, KDTreeMatcher)
+        ADD_TO_REGISTRAR_NO_PARAM(OutlierFilter, NullOutlierFilter, NullOutlierFilter)
+        ADD_TO_REGISTRAR(OutlierFilter, MaxDistOutlierFilter, MaxDistOutlierFilter)
+        ADD_TO_REGISTRAR(OutlierFilter, MedianDistOutlierFilter, MedianDistOutlierFilter)
+        ADD_TO_REGISTRAR(OutlierFilter, TrimmedDistOutlierFilter, TrimmedDistOutlierFilter)
+        ADD_TO_REGISTRAR_NO_PARAM(ErrorMinimizer, PointToPointErrorMinimizer, PointToPointErrorMinimizer)
+        ADD_TO_REGISTRAR(ErrorMinimizer, PointToPointWithCovErrorMinimizer, PointToPointWithCovErrorMinimizer)
+        ADD_TO_REGISTRAR(ErrorMinimizer, PointToPlaneErrorMinimizer, PointToPlaneErrorMinimizer)
+        ADD_TO_REGISTRAR(ErrorMinimizer, PointToPlaneWithCovErrorMinimizer, PointToPlaneWithCovErrorMinimizer)
+        ADD_TO_REGISTRAR(TransformationChecker, CounterTransformationChecker, CounterTransformationChecker)
+        ADD_TO_REGISTRAR(TransformationChecker, DifferentialTransformationChecker, DifferentialTransformationChecker)
+        ADD_TO_REGISTRAR(TransformationChecker, BoundTransformationChecker, BoundTransformationChecker)
+        ADD_TO_REGISTRAR_NO_PARAM(Inspector, NullInspector, NullInspector)
+        ADD_TO_REGISTRAR_NO_PARAM(Logger, NullLogger, NullLogger)
+    }
+    static const PointMatcher& get() {  // Registry.cpp:142-146
+        static const PointMatcher pm;
+        return pm;
+    }
+};

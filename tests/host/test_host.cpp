@@ -1,0 +1,185 @@
+// tests/host/test_host.cpp — exercises the C++ boundary classes (libpointmatcher_b200/host/).
+//   test_host cpu                                  : plugin runtime only (no GPU needed)
+//   test_host icp <config.yaml> <reading.f32> <nq> <reference.f32> <nr> [normals.f32]
+//                                                  : runs PM::ICP like examples/icp_simple.cpp and
+//                                                    prints iterations + the 4x4 (row-major)
+#include <cstdio>
+#include <fstream>
+#include <sstream>
+
+#include "PointMatcher.h"
+
+typedef PointMatcher<float> PM;
+typedef PM::DataPoints DP;
+
+#define CHECK(cond)                                                                  \
+    do {                                                                             \
+        if (!(cond)) {                                                               \
+            std::fprintf(stderr, "CHECK failed at %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+            return 1;                                                                \
+        }                                                                            \
+    } while (0)
+
+template <typename E, typename F>
+static bool throws(F f) {
+    try {
+        f();
+    } catch (const E&) {
+        return true;
+    } catch (...) {
+        return false;
+    }
+    return false;
+}
+
+static int run_cpu() {
+    const PM& pm = PM::get();
+    // registrar: names of the reference, parameter tables, bounds
+    auto m = pm.MatcherRegistrar.create("KDTreeMatcher", {{"knn", "3"}, {"maxDist", "inf"}});
+    CHECK(m->className == "KDTreeMatcher");
+    CHECK(m->get<int>("knn") == 3);
+    CHECK(std::isinf(m->get<float>("maxDist")));
+    CHECK(throws<PM::InvalidParameter>([&] { pm.MatcherRegistrar.create("KDTreeMatcher", {{"knn", "0"}}); }));
+    CHECK(throws<PM::InvalidParameter>([&] { pm.MatcherRegistrar.create("KDTreeMatcher", {{"bogus", "1"}}); }));
+    CHECK(throws<PM::InvalidElement>([&] { pm.MatcherRegistrar.create("NoSuchMatcher"); }));
+    CHECK(throws<PM::InvalidParameter>([&] { pm.OutlierFilterRegistrar.create("TrimmedDistOutlierFilter", {{"ratio", "1.5"}}); }));
+    CHECK(throws<PM::InvalidParameter>([&] { pm.ErrorMinimizerRegistrar.create("PointToPointErrorMinimizer", {{"x", "1"}}); }));
+    CHECK(throws<PM::ConfigurationError>([&] { pm.ErrorMinimizerRegistrar.create("PointToPlaneErrorMinimizer", {{"force2D", "1"}, {"force4DOF", "1"}}); }));
+    CHECK(throws<PM::InvalidParameter>([&] { pm.DataPointsFilterRegistrar.create("SurfaceNormalDataPointsFilter", {{"knn", "2"}}); }));
+    CHECK(pm.OutlierFilterRegistrar.getDescription("TrimmedDistOutlierFilter") == "Hard rejection threshold using quantile.");
+    CHECK(pm.TransformationCheckerRegistrar.create("CounterTransformationChecker")->get<unsigned>("maxIterationCount") == 40);
+
+    // YAML: the layout of examples/data/default.yaml
+    const char* yaml =
+        "readingDataPointsFilters:\n  - IdentityDataPointsFilter\n\n"
+        "referenceDataPointsFilters:\n  - SurfaceNormalDataPointsFilter:\n      knn: 10\n      keepDensities: 1 # comment\n\n"
+        "matcher:\n  KDTreeMatcher:\n    knn: 1\n    epsilon: 0\n\n"
+        "outlierFilters:\n  - TrimmedDistOutlierFilter:\n      ratio: 0.75\n  - MaxDistOutlierFilter:\n      maxDist: 2.5\n\n"
+        "errorMinimizer:\n  PointToPlaneErrorMinimizer\n\n"
+        "transformationCheckers:\n  - CounterTransformationChecker:\n      maxIterationCount: 40\n  - DifferentialTransformationChecker:\n"
+        "      minDiffRotErr: 0.001\n      minDiffTransErr: 0.01\n      smoothLength: 4\n\n"
+        "inspector:\n  NullInspector\n\nlogger:\n  NullLogger\n";
+    PM::ICP icp;
+    std::istringstream in(yaml);
+    icp.loadFromYaml(in);
+    CHECK(icp.readingDataPointsFilters.size() == 1 && icp.referenceDataPointsFilters.size() == 1);
+    CHECK(icp.matcher && icp.matcher->className == "KDTreeMatcher");
+    CHECK(icp.outlierFilters.size() == 2 && icp.outlierFilters[1]->className == "MaxDistOutlierFilter");
+    CHECK(icp.errorMinimizer->className == "PointToPlaneErrorMinimizer");
+    CHECK(icp.transformationCheckers.size() == 2 && icp.transformationCheckers[1]->get<unsigned>("smoothLength") == 4);
+    // unknown module type / unknown module / bad parameter (examples/data/unit_tests/badIcpConfig_*.yaml)
+    {
+        PM::ICP bad;
+        std::istringstream b1("matcher:\n  KDTreeMatcher\nnotAModuleType:\n  Foo\n");
+        CHECK(throws<PM::InvalidModuleType>([&] { bad.loadFromYaml(b1); }));
+        std::istringstream b2("matcher:\n  NotAMatcher\n");
+        CHECK(throws<PM::InvalidElement>([&] { bad.loadFromYaml(b2); }));
+        std::istringstream b3("outlierFilters:\n  - TrimmedDistOutlierFilter:\n      ratio: 7\n");
+        CHECK(throws<PM::InvalidParameter>([&] { bad.loadFromYaml(b3); }));
+    }
+    // host checkers: Counter throws at the limit, Differential needs smoothLength + 1 samples
+    {
+        PM::CounterTransformationChecker c(PM::Parameters{{"maxIterationCount", "2"}});
+        bool it = true;
+        PM::TransformationParameters I = PM::Matrix::Identity(4, 4);
+        c.init(I, it);
+        c.check(I, it);
+        CHECK(it);
+        CHECK(throws<PM::CounterTransformationChecker::MaxNumIterationsReached>([&] { c.check(I, it); }));
+        PM::DifferentialTransformationChecker d(PM::Parameters{{"smoothLength", "2"}});
+        it = true;
+        d.init(I, it);
+        d.check(I, it);
+        CHECK(it);  // only 2 samples
+        d.check(I, it);
+        CHECK(!it);  // identical transforms -> below thresholds
+        PM::BoundTransformationChecker b(PM::Parameters{{"maxTranslationNorm", "0.5"}});
+        b.init(I, it);
+        PM::TransformationParameters far = I;
+        far(0, 3) = 1.f;
+        CHECK(throws<PM::ConvergenceError>([&] { b.check(far, it); }));
+    }
+    // Matches::getDistsQuantile: float index arithmetic, infinite distances excluded
+    {
+        PM::Matches mt(1, 6);
+        const float v[6] = {4, 5, 5, 5, 5, std::numeric_limits<float>::infinity()};
+        for (int i = 0; i < 6; ++i) mt.dists(0, i) = v[i];
+        CHECK(mt.getDistsQuantile(0.19f) == 4.f && mt.getDistsQuantile(0.5f) == 5.f && mt.getDistsQuantile(1.f) == 5.f);
+    }
+    // rigid transformation: non-orthogonal matrices are rejected, correctParameters is idempotent
+    // (utest/ui/Transformations.cpp:40-131)
+    {
+        PM::RigidTransformation rigid;
+        PM::TransformationParameters Tm = PM::Matrix::Identity(4, 4);
+        Tm(0, 0) = 1.2f;
+        CHECK(!rigid.checkParameters(Tm));
+        DP cloud;
+        cloud.features = PM::Matrix::Constant(4, 3, 1.f);
+        CHECK(throws<PM::TransformationError>([&] { rigid.compute(cloud, Tm); }));
+        const PM::TransformationParameters c1 = rigid.correctParameters(Tm), c2 = rigid.correctParameters(c1);
+        CHECK(rigid.checkParameters(c1));
+        for (size_t i = 0; i < c1.size(); ++i) CHECK(std::fabs(c1(i) - c2(i)) < 1e-6f);
+    }
+    // double / 2-D: explicit ConfigurationError, never silently wrong
+    {
+        PointMatcher<double>::DataPoints d;
+        d.features = PointMatcher<double>::Matrix::Constant(4, 2, 1.0);
+        PointMatcher<double>::KDTreeMatcher km;
+        CHECK(throws<PointMatcher<double>::ConfigurationError>([&] { km.init(d); }));
+    }
+    std::printf("host cpu tests ok\n");
+    return 0;
+}
+
+static bool read_f32(const char* path, size_t count, float* dst) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return false;
+    f.read(reinterpret_cast<char*>(dst), count * sizeof(float));
+    return (size_t)f.gcount() == count * sizeof(float);
+}
+
+static int run_icp(int argc, char** argv) {
+    if (argc < 7) return 2;
+    const int nq = std::atoi(argv[4]), nr = std::atoi(argv[6]);
+    DP reading, reference;
+    reading.features = PM::Matrix(4, nq);
+    reference.features = PM::Matrix(4, nr);
+    if (!read_f32(argv[3], 4 * (size_t)nq, reading.features.data()) || !read_f32(argv[5], 4 * (size_t)nr, reference.features.data())) {
+        std::fprintf(stderr, "cannot read the clouds\n");
+        return 2;
+    }
+    if (argc > 7) {
+        PM::Matrix normals(3, nr);
+        if (!read_f32(argv[7], 3 * (size_t)nr, normals.data())) return 2;
+        reference.addDescriptor("normals", normals);
+    }
+    PM::ICP icp;
+    if (std::string(argv[2]) == "default") {
+        icp.setDefault();
+    } else {
+        std::ifstream cfg(argv[2]);
+        if (!cfg) return 2;
+        icp.loadFromYaml(cfg);
+    }
+    try {
+        const PM::TransformationParameters Tm = icp(reading, reference);
+        std::printf("iterations %zu fused %d maxreached %d overlap %.9g\n", icp.getIterationCount(), icp.usedFusedLoop() ? 1 : 0,
+                    icp.getMaxNumIterationsReached() ? 1 : 0, (double)icp.errorMinimizer->getWeightedPointUsedRatio());
+        for (int i = 0; i < 4; ++i) std::printf("%.9g %.9g %.9g %.9g\n", Tm(i, 0), Tm(i, 1), Tm(i, 2), Tm(i, 3));
+        const PM::Matrix cov = icp.errorMinimizer->getCovariance();
+        std::printf("cov");
+        for (int i = 0; i < 6; ++i) std::printf(" %.9g", cov(i, i));
+        std::printf("\n");
+    } catch (const std::exception& e) {
+        std::printf("exception %s\n", e.what());
+        return 3;
+    }
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    if (argc >= 2 && std::string(argv[1]) == "cpu") return run_cpu();
+    if (argc >= 2 && std::string(argv[1]) == "icp") return run_icp(argc, argv);
+    std::fprintf(stderr, "usage: test_host cpu | icp <config.yaml|default> <reading.f32> <nq> <reference.f32> <nr> [normals.f32]\n");
+    return 2;
+}

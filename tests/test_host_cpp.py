@@ -1,0 +1,125 @@
+"""The C++ boundary (libpointmatcher_b200/host/PointMatcher.h): same class names, YAML layout and
+exceptions as the reference.  The CPU part checks the plugin runtime; the GPU part runs PM::ICP
+the way examples/icp_simple.cpp does and compares with the oracle and with the Python mirror."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import assert_transform_close
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def host_bin():
+    src = os.path.join(ROOT, "tests", "host", "test_host.cpp")
+    out = os.path.join(ROOT, "tests", "host", "_build", "test_host")
+    host = os.path.join(ROOT, "libpointmatcher_b200", "host")
+    lib = os.path.join(ROOT, "libpointmatcher_b200", "libpmgpu.so")
+    deps = [src, lib, os.path.join(ROOT, "include", "pmgpu.h")] + [os.path.join(host, f) for f in os.listdir(host)]
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.check_call([cxx, "-O2", "-std=c++17", "-Wall", "-I", host, "-o", out, src, "-L", os.path.dirname(lib), "-lpmgpu",
+                               "-Wl,-rpath," + os.path.dirname(lib)])
+    return out
+
+
+def test_plugin_runtime(host_bin):
+    r = subprocess.run([host_bin, "cpu"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "host cpu tests ok" in r.stdout
+
+
+CONFIG = """
+referenceDataPointsFilters:
+  - IdentityDataPointsFilter
+
+matcher:
+  KDTreeMatcher:
+    knn: 1
+    epsilon: 0
+
+outlierFilters:
+  - TrimmedDistOutlierFilter:
+      ratio: 0.75
+
+errorMinimizer:
+  {minimizer}
+
+transformationCheckers:
+  - CounterTransformationChecker:
+      maxIterationCount: {iters}
+{differential}
+inspector:
+  NullInspector
+
+logger:
+  NullLogger
+"""
+DIFF = """  - DifferentialTransformationChecker:
+      minDiffRotErr: 0.001
+      minDiffTransErr: 0.001
+      smoothLength: 3
+"""
+BOUND = """  - BoundTransformationChecker:
+      maxRotationNorm: 0.8
+      maxTranslationNorm: 5
+"""
+
+
+def _run_icp(host_bin, tmp_path, config, rd, rf, nrm):
+    cfg = tmp_path / "cfg.yaml"
+    cfg.write_text(config)
+    rd.astype(np.float32).tofile(tmp_path / "rd.f32")
+    rf.astype(np.float32).tofile(tmp_path / "rf.f32")
+    args = [host_bin, "icp", str(cfg), str(tmp_path / "rd.f32"), str(len(rd)), str(tmp_path / "rf.f32"), str(len(rf))]
+    if nrm is not None:
+        np.ascontiguousarray(nrm, np.float32).tofile(tmp_path / "nrm.f32")
+        args.append(str(tmp_path / "nrm.f32"))
+    r = subprocess.run(args, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = r.stdout.strip().split("\n")
+    head = lines[0].split()
+    T = np.array([[float(x) for x in l.split()] for l in lines[1:5]], np.float32)
+    return dict(iterations=int(head[1]), fused=int(head[3]), maxreached=int(head[5]), T=T)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["counter", "differential", "bound"])
+def test_cpp_icp_matches_oracle_and_python(host_bin, tmp_path, oracle, synth, variant):
+    rd, rf, T_gt = synth.scan_pair(60000)
+    nrm = oracle.surface_normals(rf, knn=10, nthreads=8)["normals"]
+    iters = 12 if variant == "counter" else 40
+    extra = {"counter": "", "differential": DIFF, "bound": BOUND + DIFF}[variant]
+    cfg = CONFIG.format(minimizer="PointToPlaneErrorMinimizer", iters=iters, differential=extra)
+    res = _run_icp(host_bin, tmp_path, cfg, rd, rf, nrm)
+    diff = (0.001, 0.001, 3) if variant != "counter" else None
+    ref = oracle.icp(rd, rf, ref_normals=nrm, filters=[(2, 0.75)], minimizer=1, max_iterations=iters, differential=diff, nthreads=8, acc_double=True)
+    assert res["iterations"] == ref["iterations"]
+    assert_transform_close(res["T"], ref["T"], 1e-5, 1e-5)
+    # Counter / Differential chains run as one fused device loop; Bound needs the host checkers
+    assert res["fused"] == (0 if variant == "bound" else 1)
+    assert res["maxreached"] == (1 if variant == "counter" else 0)
+
+
+@pytest.mark.gpu
+def test_cpp_icp_default_chain(host_bin, tmp_path, oracle, synth):
+    """icp.setDefault(): normals from SurfaceNormalDataPointsFilter(knn 7) on the GPU"""
+    rd, rf, T_gt = synth.scan_pair(60000)
+    rd.astype(np.float32).tofile(tmp_path / "rd.f32")
+    rf.astype(np.float32).tofile(tmp_path / "rf.f32")
+    r = subprocess.run([host_bin, "icp", "default", str(tmp_path / "rd.f32"), str(len(rd)), str(tmp_path / "rf.f32"), str(len(rf))],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = r.stdout.strip().split("\n")
+    T = np.array([[float(x) for x in l.split()] for l in lines[1:5]], np.float64)
+    # the default chain converges to the true pose of the re-scan
+    assert np.linalg.norm(T[:3, 3] - T_gt[:3, 3]) < 0.02
+    nrm = oracle.surface_normals(rf, knn=7, nthreads=8)["normals"]
+    ref = oracle.icp(rd, rf, ref_normals=nrm, filters=[(2, 0.85)], minimizer=1, max_iterations=40, differential=(0.001, 0.001, 3), nthreads=8,
+                     acc_double=True)
+    assert int(lines[0].split()[1]) == ref["iterations"]
+    assert_transform_close(T, ref["T"], 2e-5, 2e-5)  # normals of near-degenerate neighbourhoods differ in sign/rounding only
