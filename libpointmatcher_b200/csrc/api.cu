@@ -57,6 +57,10 @@ int use_device(pmgpu_ctx* ctx) {
 }
 
 int push_state(pmgpu_ctx* ctx) {
+    // queue lengths and tickets are device-owned scratch: never push back a stale pulled copy
+    IcpState* h = ctx->state_host;
+    h->overflow_count[0] = h->overflow_count[1] = 0;
+    h->ticket[0] = h->ticket[1] = h->ticket[2] = h->ticket[3] = 0;
     PM_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->state, ctx->state_host, sizeof(IcpState), cudaMemcpyHostToDevice, ctx->stream));
     return PMGPU_OK;
 }
@@ -179,6 +183,7 @@ int pmgpu_ctx_create(int device, pmgpu_ctx** ctx_out) {
     }
     ctx->num_sms = sms > 0 ? sms : 148;
     ctx->hints_enabled = getenv("PMGPU_NO_HINTS") == nullptr;  // A/B switch for profiling
+    if (const char* b = getenv("PMGPU_KNN_BUDGET")) ctx->knn_budget = atoi(b) > 0 ? atoi(b) : 1;  // 1: (almost) everything through stage 2
     memset(ctx->state_host, 0, sizeof(IcpState));
     mat4_identity(ctx->state_host->T_iter);
     mat4_identity(ctx->state_host->T_match);
@@ -198,7 +203,7 @@ void pmgpu_ctx_destroy(pmgpu_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     pmgpu_comm_destroy(ctx);
     ctx->ref_orig.release(); ctx->ref_sorted.release(); ctx->ref_normals.release(); ctx->splits.release(); ctx->boxes.release();
-    ctx->reading_tmp.release(); ctx->ids_tmp.release(); ctx->dists_tmp.release();
+    ctx->reading_tmp.release(); ctx->ids_tmp.release(); ctx->dists_tmp.release(); ctx->overflow.release();
     ctx->keys_a.release(); ctx->keys_b.release(); ctx->perm_a.release(); ctx->perm_b.release();
     ctx->node_box.release(); ctx->node_dim.release(); ctx->cub_tmp.release();
     ctx->reading.release(); ctx->q_order.release();

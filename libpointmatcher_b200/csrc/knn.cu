@@ -11,7 +11,8 @@
 // profiles/).  The per-level plane distances of the descent are cached in shared memory (one
 // column per lane), so rejecting a pending sibling costs one LDS and a compare.  T_iter is read
 // from the device-resident IcpState, so no host round trip separates iterations; in iterations
-// >= 2 (k = 1) the previous match, re-measured, seeds the search with a tight bound.
+// >= 2 (k = 1) the previous match, re-measured, seeds the search with a tight bound.  Queries
+// still open after a budget of leaves go to a second, warp-per-query kernel (stage 2).
 #include "pmgpu_internal.cuh"
 
 namespace pm {
@@ -24,7 +25,8 @@ template <int KMAX>
 __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4* __restrict__ queries, int nq, const IcpState* __restrict__ state,
                                                         int use_T, int gated, int self_query, int k, float max_r2,
                                                         const f4* __restrict__ ref_orig, int use_seed, int32_t* __restrict__ ids,
-                                                        float* __restrict__ dists, unsigned long long* visits) {
+                                                        float* __restrict__ dists, unsigned long long* visits, int budget,
+                                                        uint32_t* __restrict__ overflow, unsigned* overflow_count) {
     extern __shared__ float s_plane[];  // [depth + 1][KNN_BLOCK]: cached plane distances, one column per lane
     __shared__ Mat4 sT;
     if (gated && state->iterate == 0) return;
@@ -62,13 +64,23 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
             }
         }
     }
-    // all 32 lanes stay in the loop until the slowest is done; phases re-converge the warp
+    // all 32 lanes stay in the loop until the slowest is done; phases re-converge the warp.
+    // A lane whose query is still open after `budget` leaves hands it (with the candidates found
+    // so far, written below like a final result) to the warp-cooperative stage 2: a few
+    // pathological queries (e.g. equidistant to a whole scan ring) would otherwise hold their
+    // warp — and the kernel — for thousands of rounds.
+    int rounds = 0;
     while (__any_sync(0xffffffffu, running)) {
         while (running && lane_descending(s, tree)) lane_descend_step(s, tree, plane, KNN_BLOCK);
         __syncwarp();
         if (running) lane_scan_leaf<KMAX>(s, tree, best);
         __syncwarp();
         if (running) running = lane_pop<KMAX>(s, tree, best, plane, KNN_BLOCK);
+        ++rounds;
+        if (running && rounds >= budget) {
+            running = false;
+            overflow[atomicAdd(overflow_count, 1u)] = (uint32_t)t;
+        }
         __syncwarp();
     }
     if (t < nq) {
@@ -91,15 +103,152 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
     }
 }
 
+
+// ---- stage 2: one warp per left-over query ------------------------------------------------------
+// The 32 lanes search ONE query together: a node is expanded 5 levels at a time (32 descendants,
+// one box test per lane), surviving inner nodes go on a small shared-memory stack, surviving
+// leaves are scanned four at a time (lane = leaf x point).  The candidate list is replicated in
+// every lane and updated with warp-uniform inserts, seeded with what stage 1 had found.  Same
+// bounds, same ranking: the result is the one the single-lane search would have produced.
+template <int KMAX>
+__device__ __forceinline__ bool topk_contains(const TopK<KMAX>& b, int id) {
+    bool f = false;
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) f = f || (b.id[j] == id);
+    return f;
+}
+
+constexpr int OVF_STACK = 224;  // <= 32 pushes per expansion level, <= 6 levels of expansion (depth <= 30)
+
+template <int KMAX>
+__global__ void __launch_bounds__(128) knn_overflow_kernel(TreeView tree, const f4* __restrict__ queries, const IcpState* __restrict__ state, int use_T,
+                                                           int gated, int self_query, int k, float max_r2, const uint32_t* __restrict__ overflow,
+                                                           unsigned* overflow_count, unsigned* next_count, int32_t* __restrict__ ids,
+                                                           float* __restrict__ dists, unsigned long long* visits) {
+    __shared__ uint32_t s_stack[4][OVF_STACK];
+    __shared__ Mat4 sT;
+    if (gated && state->iterate == 0) return;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *next_count = 0;  // the counter the NEXT launch of stage 1 will use
+    if (use_T) {
+        if (threadIdx.x < 16) sT.m[threadIdx.x] = state->T_iter.m[threadIdx.x];
+        __syncthreads();
+    }
+    const unsigned count = *overflow_count;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned lanes_lt = (1u << lane) - 1u;
+    uint32_t* stack = s_stack[warp];
+    const int D = tree.depth;
+    unsigned long long my_visits = 0;
+    for (unsigned w = blockIdx.x * 4 + warp; w < count; w += gridDim.x * 4) {
+        const uint32_t t = overflow[w];
+        f4 q = queries[t];
+        uint32_t qi = t;
+        if (self_query) { qi = __float_as_uint(q.w); q.w = 1.f; }
+        if (use_T) q = transform_point(sT, q);
+        TopK<KMAX> best;
+        best.init(k, max_r2);
+        // seed: the candidates stage 1 left in the result arrays (ascending, real points)
+#pragma unroll
+        for (int j = 0; j < KMAX; ++j) {
+            if (j < k) {
+                const int id = ids[(size_t)qi * k + j];
+                const float dd = dists[(size_t)qi * k + j];
+                if (id >= 0 && cand_less(dd, id, best.worst_d(), best.worst_id())) best.insert(dd, id);
+            }
+        }
+        int sp = 0;
+        if (lane == 0) stack[0] = 1u;
+        sp = 1;
+        __syncwarp();
+        while (sp > 0) {
+            const uint32_t n = stack[--sp];
+            __syncwarp();
+            const int L = 31 - __clz((int)n);
+            if (box_dist2(q.x, q.y, q.z, ldg4(tree.boxes + 2 * (size_t)n), ldg4(tree.boxes + 2 * (size_t)n + 1)) > best.worst_d()) continue;
+            const int step = min(5, D - L);
+            const uint32_t c = (n << step) + (uint32_t)lane;
+            bool pass = lane < (1 << step);
+            if (pass && step > 0) pass = box_dist2(q.x, q.y, q.z, ldg4(tree.boxes + 2 * (size_t)c), ldg4(tree.boxes + 2 * (size_t)c + 1)) <= best.worst_d();
+            unsigned mask = __ballot_sync(0xffffffffu, pass);
+            if (L + step < D) {
+                if (pass) stack[sp + __popc(mask & lanes_lt)] = c;
+                sp += __popc(mask);
+                __syncwarp();
+                continue;
+            }
+            // children are leaves: four leaves per pass, lane = (leaf slot, point)
+            const int slot = lane >> 3, pnt = lane & 7;
+            while (mask) {
+                unsigned m = mask;
+                for (int i = 0; i < slot; ++i) m &= m - 1;
+                const bool has = m != 0;
+                const uint32_t leaf = ((n << step) + (uint32_t)(__ffs(m) - 1)) - (1u << D);
+                uint32_t b = 0, e = 0;
+                if (has) {
+                    b = seg_begin(D, leaf, tree.n);
+                    e = seg_begin(D, leaf + 1, tree.n);
+                    if (pnt == 0) my_visits += e - b;
+                }
+#pragma unroll
+                for (uint32_t off = 0; off < PM_LEAF_MAX; off += 8) {  // one point per lane and pass
+                    const uint32_t p = b + off + pnt;
+                    float dd = 0.f;
+                    int pi = 0;
+                    bool cand = false;
+                    if (has && p < e) {
+                        const f4 pt = ldg4(tree.pts + p);
+                        dd = dist2(q.x, q.y, q.z, pt.x, pt.y, pt.z);
+                        pi = (int)__float_as_uint(pt.w);
+                        cand = cand_less(dd, pi, best.worst_d(), best.worst_id());
+                    }
+                    // candidates are rare once the list is good: insert them one by one, uniformly
+                    unsigned cm = __ballot_sync(0xffffffffu, cand);
+                    while (cm) {
+                        const int src = __ffs(cm) - 1;
+                        cm &= cm - 1;
+                        const float cd = __shfl_sync(0xffffffffu, dd, src);
+                        const int ci = __shfl_sync(0xffffffffu, pi, src);
+                        if (cand_less(cd, ci, best.worst_d(), best.worst_id()) && !topk_contains<KMAX>(best, ci)) best.insert(cd, ci);
+                    }
+                }
+                for (int i = 0; i < 4 && mask; ++i) mask &= mask - 1;
+            }
+        }
+        if (lane == 0) {
+            for (int j = 0; j < k; ++j) {
+                float bd = max_r2;
+                int bi = PM_NO_ID;
+#pragma unroll
+                for (int jj = 0; jj < KMAX; ++jj)
+                    if (jj == j) { bd = best.d[jj]; bi = best.id[jj]; }
+                const bool valid = bi != PM_NO_ID && bd != pm_inf();
+                ids[(size_t)qi * k + j] = valid ? bi : -1;
+                dists[(size_t)qi * k + j] = valid ? bd : pm_inf();
+            }
+        }
+        __syncwarp();
+    }
+    if (visits && my_visits) atomicAdd(visits, my_visits);
+}
+
 template <int KMAX>
 int launch_one(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, bool use_T, bool gated, bool self_query, int k, float max_r2,
                bool use_seed, int32_t* ids, float* dists) {
     const int grid = (nq + KNN_BLOCK - 1) / KNN_BLOCK;
     if (grid == 0) return PMGPU_OK;
     const size_t smem = (size_t)(tree.depth + 2) * KNN_BLOCK * sizeof(float);
+    PM_CUDA_TRY(ctx, ctx->overflow.reserve((size_t)nq));
+    // the two stages of one launch share counter[parity]; stage 2 clears counter[parity ^ 1] for the next launch
+    unsigned* cnt = &ctx->state->overflow_count[ctx->knn_parity];
+    unsigned* cnt_next = &ctx->state->overflow_count[ctx->knn_parity ^ 1];
+    ctx->knn_parity ^= 1;
     knn_kernel<KMAX><<<grid, KNN_BLOCK, smem, ctx->stream>>>(tree, queries, nq, ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k, max_r2,
-                                                            ctx->ref_orig.p, use_seed ? 1 : 0, ids, dists, &ctx->state->visits);
-    ctx->launches += 1;
+                                                            ctx->ref_orig.p, use_seed ? 1 : 0, ids, dists, &ctx->state->visits, ctx->knn_budget,
+                                                            ctx->overflow.p, cnt);
+    const int grid2 = min(ctx->num_sms * 4, (nq + 3) / 4);
+    knn_overflow_kernel<KMAX><<<grid2, 128, 0, ctx->stream>>>(tree, queries, ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k, max_r2,
+                                                           ctx->overflow.p, cnt, cnt_next, ids, dists, &ctx->state->visits);
+    ctx->launches += 2;
     PM_CUDA_TRY(ctx, cudaGetLastError());
     return PMGPU_OK;
 }

@@ -75,6 +75,7 @@ struct IcpState {
     unsigned sel_prefix[PM_MAX_FILTERS];           // radix-select state per quantile filter
     unsigned long long sel_rank[PM_MAX_FILTERS];   // remaining rank inside the selected bucket
     unsigned ticket[4];          // "last block" counters: 0 select, 1 minimise, 2 covariance
+    unsigned overflow_count[2];  // kNN stage-2 queue lengths (ping-pong between consecutive launches)
     // minimiser outputs
     float cov[36];
     float stats[5];              // pointUsedRatio, weightedPointUsedRatio, nbRejectedMatches, nbRejectedPoints, nbKept
@@ -133,6 +134,9 @@ struct pmgpu_ctx {
     pm::DevBuf<f4> reading_tmp;      // upload staging (original order)
     pm::DevBuf<uint32_t> q_order;    // sorted position -> original column
     int seed_k = 0;                  // k of the matches resident in `ids` for this reading / reference (0: none)
+    pm::DevBuf<uint32_t> overflow;   // kNN stage-2 queue: sorted positions of the queries stage 1 did not finish
+    int knn_parity = 0;
+    int knn_budget = 16;             // leaves a lane may scan before its query goes to stage 2
     bool hints_enabled = true;
     pm::DevBuf<int32_t> ids_tmp;     // un-permute staging for downloads
     pm::DevBuf<float> dists_tmp;
