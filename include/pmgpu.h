@@ -96,6 +96,11 @@ int pmgpu_timing_collect(pmgpu_ctx* ctx, double* ms_out, int* count_out);
  * (the "normals" descriptor rows inside DataPoints::descriptors, DataPoints.cpp:917-942);
  * needed by the point-to-plane minimizers.  Replaces any previous reference. */
 int pmgpu_ref_set(pmgpu_ctx* ctx, const float* features, int rows, int n, const float* normals, int normals_ld);
+/* ICP::compute's preamble fused with init (ICP.cpp:291-302): computes the float mean of the first
+ * rows-1 coordinates exactly as the reference does on the host (sequential row sums / n), uploads
+ * the cloud, subtracts the mean on the device (the same float subtraction) and builds the
+ * structure over the centred cloud.  mean_out[rows] receives the mean (last entry unused = 1). */
+int pmgpu_ref_set_centered(pmgpu_ctx* ctx, const float* features, int rows, int n, const float* normals, int normals_ld, float* mean_out);
 /* (re)attach normals to the current reference without rebuilding the tree */
 int pmgpu_ref_set_normals(pmgpu_ctx* ctx, const float* normals, int normals_ld);
 

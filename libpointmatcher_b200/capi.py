@@ -68,6 +68,7 @@ SIGNATURES = {
     "pmgpu_timing_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "pmgpu_timing_collect": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "pmgpu_ref_set": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]),
+    "pmgpu_ref_set_centered": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, _fp]),
     "pmgpu_ref_set_normals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "pmgpu_reading_set": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "pmgpu_reading_apply_transform": (C.c_int, [C.c_void_p, _fp]),
@@ -212,6 +213,17 @@ class Context:
             ld = 0 if nrm is None else nrm.shape[1]
             self._check(lib.pmgpu_ref_set(self.h, _ptr(f), rows, n, _ptr(nrm), ld))
         self.nr = n
+
+    def set_reference_centered(self, features, normals=None):
+        """ICP::compute's preamble + KDTreeMatcher::init: centre the reference on its mean (float row
+        sums / N, ICP.cpp:291-299) and build the structure.  Returns the mean (3,)."""
+        f = _cloud(features)
+        n, rows = f.shape
+        nrm = None if normals is None else np.ascontiguousarray(normals, np.float32)
+        mean = np.zeros(4, np.float32)
+        self._check(lib.pmgpu_ref_set_centered(self.h, _ptr(f), rows, n, _ptr(nrm), 0 if nrm is None else nrm.shape[1], _f(mean)))
+        self.nr = n
+        return mean[:3].copy()
 
     def set_reference_normals(self, normals):
         nrm = None if normals is None else np.ascontiguousarray(normals, np.float32)

@@ -31,6 +31,14 @@ __global__ void ids_to_float_kernel(const int32_t* __restrict__ ids, size_t tota
     if (i < total) out[i] = (float)ids[i];
 }
 
+__global__ void subtract_mean_kernel(f4* __restrict__ pts, int n, float mx, float my, float mz) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    f4 p = pts[i];
+    p.x = fsub(p.x, mx); p.y = fsub(p.y, my); p.z = fsub(p.z, mz);
+    pts[i] = p;
+}
+
 __global__ void transform_inplace_kernel(f4* __restrict__ pts, int n, Mat4 T) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) pts[i] = transform_point(T, pts[i]);
@@ -255,7 +263,18 @@ int pmgpu_sync(pmgpu_ctx* ctx) {
     return PMGPU_OK;
 }
 
+static int ref_set_impl(pmgpu_ctx* ctx, const float* features, int rows, int n, const float* normals, int normals_ld, float* mean_out);
+
 int pmgpu_ref_set(pmgpu_ctx* ctx, const float* features, int rows, int n, const float* normals, int normals_ld) {
+    return ref_set_impl(ctx, features, rows, n, normals, normals_ld, nullptr);
+}
+
+int pmgpu_ref_set_centered(pmgpu_ctx* ctx, const float* features, int rows, int n, const float* normals, int normals_ld, float* mean_out) {
+    if (!mean_out) return PMGPU_ERR_BAD_ARG;
+    return ref_set_impl(ctx, features, rows, n, normals, normals_ld, mean_out);
+}
+
+static int ref_set_impl(pmgpu_ctx* ctx, const float* features, int rows, int n, const float* normals, int normals_ld, float* mean_out) {
     if (!ctx) return PMGPU_ERR_BAD_ARG;
     PM_TRY(use_device(ctx));
     if (!features) return fail(ctx, PMGPU_ERR_BAD_ARG, "null reference features");
@@ -268,6 +287,23 @@ int pmgpu_ref_set(pmgpu_ctx* ctx, const float* features, int rows, int n, const 
     PM_CUDA_TRY(ctx, ctx->ref_orig.reserve(n));
     PM_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ref_orig.p, features, (size_t)n * sizeof(f4), cudaMemcpyDefault, ctx->stream));
     ctx->nr = n;
+    if (mean_out) {
+        // `reference.features.rowwise().sum() / nbPtsReference` in float, column after column
+        // (ICP.cpp:292); runs on the host while the upload is in flight
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, features) == cudaSuccess && attr.type == cudaMemoryTypeDevice)
+            return fail(ctx, PMGPU_ERR_BAD_ARG, "pmgpu_ref_set_centered needs a host pointer");
+        cudaGetLastError();
+        volatile float sx = 0.f, sy = 0.f, sz = 0.f;
+        for (int i = 0; i < n; ++i) {
+            sx = sx + features[4 * (size_t)i];
+            sy = sy + features[4 * (size_t)i + 1];
+            sz = sz + features[4 * (size_t)i + 2];
+        }
+        mean_out[0] = sx / (float)n; mean_out[1] = sy / (float)n; mean_out[2] = sz / (float)n; mean_out[3] = 1.f;
+        subtract_mean_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->ref_orig.p, n, mean_out[0], mean_out[1], mean_out[2]);
+        ctx->launches += 1;
+    }
     const int s = build_tree(ctx);
     if (s != PMGPU_OK) { ctx->nr = 0; return s; }
     if (normals) PM_TRY(upload_normals(ctx, normals, normals_ld));

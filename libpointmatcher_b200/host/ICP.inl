@@ -127,23 +127,27 @@ struct ICP : ICPChainBase {
         this->inspector->init();
         const int dim = referenceIn.features.rows();
 
-        DataPoints reference(referenceIn);
-        this->referenceDataPointsFilters.init();
-        this->referenceDataPointsFilters.apply(reference);
+        // inputs are never mutated (ICP.cpp:285); without reference filters no host copy is needed
+        DataPoints filtered;
+        if (!this->referenceDataPointsFilters.empty()) {
+            filtered = referenceIn;
+            this->referenceDataPointsFilters.init();
+            this->referenceDataPointsFilters.apply(filtered);
+        }
+        const DataPoints& reference = this->referenceDataPointsFilters.empty() ? referenceIn : filtered;
 
         // intermediate frame at the centre of mass of the reference (ICP.cpp:291-299): the mean is
-        // the float row sum over all columns, divided by N
-        const int nbPtsReference = reference.features.cols();
+        // the float row sum over all columns divided by N; the matcher is initialised with the
+        // centred cloud (ICP.cpp:302) — fused in pmgpu_ref_set_centered for the GPU matcher
+        auto* gpuMatcher = dynamic_cast<KDTreeMatcher*>(this->matcher.get());
+        if (!gpuMatcher) throw ConfigurationError("ICP: GPU build: the matcher must be the GPU KDTreeMatcher (there is no CPU path)");
+        float mean4[4];
+        gpuMatcher->initCentered(reference, mean4);
         TransformationParameters T_refIn_refMean = Matrix::Identity(dim, dim), T_refMean_refIn = Matrix::Identity(dim, dim);
         for (int r = 0; r < dim - 1; ++r) {
-            volatile T sum = T(0);
-            for (int c = 0; c < nbPtsReference; ++c) sum = sum + reference.features(r, c);
-            const T mean = sum / T(nbPtsReference);
-            T_refIn_refMean(r, dim - 1) = mean;
-            T_refMean_refIn(r, dim - 1) = -mean;
-            for (int c = 0; c < nbPtsReference; ++c) reference.features(r, c) -= mean;
+            T_refIn_refMean(r, dim - 1) = T(mean4[r]);
+            T_refMean_refIn(r, dim - 1) = T(-mean4[r]);
         }
-        this->matcher->init(reference);
         this->prefilteredReferencePtsCount = reference.features.cols();
         return computeWithTransformedReference(readingIn, reference, T_refIn_refMean, T_refMean_refIn, T_refIn_dataIn);
     }

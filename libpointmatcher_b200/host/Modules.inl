@@ -155,7 +155,11 @@ struct KDTreeMatcher : public Matcher, public GpuBound {
         : Matcher("KDTreeMatcher", availableParameters(), params), knn(Parametrizable::get<int>("knn")), epsilon(Parametrizable::get<T>("epsilon")),
           searchType(Parametrizable::get<int>("searchType")), maxDist(Parametrizable::get<T>("maxDist")) {}
 
-    void init(const DataPoints& filteredReference) override {
+    void init(const DataPoints& filteredReference) override { initImpl(filteredReference, nullptr); }
+    // init() on the reference centred on its mean — the preamble of ICP::compute (ICP.cpp:291-302)
+    // without a host copy of the cloud; mean4 receives the mean
+    void initCentered(const DataPoints& filteredReference, float* mean4) { initImpl(filteredReference, mean4); }
+    void initImpl(const DataPoints& filteredReference, float* mean4) {
         requireFloat3D(filteredReference.features.rows(), "KDTreeMatcher");
         GpuPipeline& g = this->gpu();
         const float* normals = nullptr;
@@ -164,8 +168,9 @@ struct KDTreeMatcher : public Matcher, public GpuBound {
             normals = reinterpret_cast<const float*>(filteredReference.descriptors.data()) + filteredReference.getDescriptorStartingRow("normals");
             ld = filteredReference.descriptors.rows();
         }
-        g.check(pmgpu_ref_set(g.ctx, reinterpret_cast<const float*>(filteredReference.features.data()), filteredReference.features.rows(),
-                              filteredReference.features.cols(), normals, ld));
+        const float* feat = reinterpret_cast<const float*>(filteredReference.features.data());
+        if (mean4) g.check(pmgpu_ref_set_centered(g.ctx, feat, filteredReference.features.rows(), filteredReference.features.cols(), normals, ld, mean4));
+        else g.check(pmgpu_ref_set(g.ctx, feat, filteredReference.features.rows(), filteredReference.features.cols(), normals, ld));
         g.readingKey = nullptr;
     }
     // uploads the reading when it is not the resident one, then matches T * reading

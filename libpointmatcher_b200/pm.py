@@ -179,6 +179,13 @@ class KDTreeMatcher(Parametrizable, _Bound):
         _translate(self.ctx.set_reference, filteredReference.features, nrm)
         self._ref = filteredReference
 
+    def initCentered(self, filteredReference):
+        """init() on the reference centred on its mean (the preamble of ICP::compute, ICP.cpp:291-302),
+        without a host copy of the cloud.  Returns the mean."""
+        nrm = filteredReference.descriptors.get("normals")
+        self._ref = filteredReference
+        return _translate(self.ctx.set_reference_centered, filteredReference.features, nrm)
+
     def findClosests(self, filteredReading, T=None):
         """Matches of T * filteredReading against the reference passed to init()."""
         ctx = self.ctx
@@ -468,16 +475,16 @@ class ICP:
         T_init = np.eye(4, dtype=np.float32) if T_refIn_dataIn is None else np.asarray(T_refIn_dataIn, np.float32)
         if T_init.shape != (4, 4):
             raise RuntimeError("The initial transformation matrix must be squared.")
-        reference = referenceIn.copy() if isinstance(referenceIn, DataPoints) else DataPoints(np.array(referenceIn, np.float32))
+        reference = referenceIn if isinstance(referenceIn, DataPoints) else DataPoints(referenceIn)
         reading = readingIn if isinstance(readingIn, DataPoints) else DataPoints(readingIn)
-        for f in self.referenceDataPointsFilters:
-            f.inPlaceFilter(reference)
-        # centre the reference on its mean (ICP.cpp:291-299)
-        mean = sequential_mean(reference.features)
+        if self.referenceDataPointsFilters:
+            reference = reference.copy()  # inputs are never mutated (ICP.cpp:285)
+            for f in self.referenceDataPointsFilters:
+                f.inPlaceFilter(reference)
+        # centre the reference on its mean and init the matcher with it (ICP.cpp:291-302)
+        mean = self.matcher.initCentered(reference)
         T_refIn_refMean = np.eye(4, dtype=np.float32)
         T_refIn_refMean[:3, 3] = mean[:3]
-        reference.features[:, :3] -= mean[:3]
-        self.matcher.init(reference)
         # reading into the refMean frame (ICP.cpp:345-347)
         T_refMean_refIn = np.eye(4, dtype=np.float32)
         T_refMean_refIn[:3, 3] = -mean[:3]
