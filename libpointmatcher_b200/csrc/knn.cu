@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
 // ---- stage 2: one warp per left-over query ------------------------------------------------------
 // The 32 lanes search ONE query together: a node is expanded 5 levels at a time (32 descendants,
 // one box test per lane), surviving inner nodes go on a small shared-memory stack, surviving
-// leaves are scanned four at a time (lane = leaf x point).  The candidate list is replicated in
+// leaves are scanned sixteen at a time (lane = leaf slot x point, four loads in flight per lane).  The candidate list is replicated in
 // every lane and updated with warp-uniform inserts, seeded with what stage 1 had found.  Same
 // bounds, same ranking: the result is the one the single-lane search would have produced.
 template <int KMAX>
@@ -176,42 +176,55 @@ __global__ void __launch_bounds__(128) knn_overflow_kernel(TreeView tree, const 
                 __syncwarp();
                 continue;
             }
-            // children are leaves: four leaves per pass, lane = (leaf slot, point)
+            // children are leaves: up to 16 leaves per pass — lane = (leaf slot, point), each lane
+            // keeps U = 4 independent loads in flight (this warp is alone on its query, so
+            // instruction-level parallelism is the only latency hiding it has)
+            constexpr int U = 4;
             const int slot = lane >> 3, pnt = lane & 7;
             while (mask) {
-                unsigned m = mask;
-                for (int i = 0; i < slot; ++i) m &= m - 1;
-                const bool has = m != 0;
-                const uint32_t leaf = ((n << step) + (uint32_t)(__ffs(m) - 1)) - (1u << D);
-                uint32_t b = 0, e = 0;
-                if (has) {
-                    b = seg_begin(D, leaf, tree.n);
-                    e = seg_begin(D, leaf + 1, tree.n);
-                    if (pnt == 0) my_visits += e - b;
+                const int nset = __popc(mask);
+                uint32_t b[U], e[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int sidx = slot + 4 * u;
+                    b[u] = e[u] = 0;
+                    if (sidx < nset) {
+                        const uint32_t leaf = ((n << step) + __fns(mask, 0, sidx + 1)) - (1u << D);
+                        b[u] = seg_begin(D, leaf, tree.n);
+                        e[u] = seg_begin(D, leaf + 1, tree.n);
+                        if (pnt == 0) my_visits += e[u] - b[u];
+                    }
                 }
 #pragma unroll
-                for (uint32_t off = 0; off < PM_LEAF_MAX; off += 8) {  // one point per lane and pass
-                    const uint32_t p = b + off + pnt;
-                    float dd = 0.f;
-                    int pi = 0;
-                    bool cand = false;
-                    if (has && p < e) {
-                        const f4 pt = ldg4(tree.pts + p);
-                        dd = dist2(q.x, q.y, q.z, pt.x, pt.y, pt.z);
-                        pi = (int)__float_as_uint(pt.w);
-                        cand = cand_less(dd, pi, best.worst_d(), best.worst_id());
+                for (uint32_t off = 0; off < PM_LEAF_MAX; off += 8) {  // one point per lane, slot and pass
+                    float dd[U];
+                    int pi[U];
+                    bool cand[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const uint32_t p = b[u] + off + pnt;
+                        dd[u] = 0.f; pi[u] = 0; cand[u] = false;
+                        if (p < e[u]) {
+                            const f4 pt = ldg4(tree.pts + p);
+                            dd[u] = dist2(q.x, q.y, q.z, pt.x, pt.y, pt.z);
+                            pi[u] = (int)__float_as_uint(pt.w);
+                            cand[u] = cand_less(dd[u], pi[u], best.worst_d(), best.worst_id());
+                        }
                     }
                     // candidates are rare once the list is good: insert them one by one, uniformly
-                    unsigned cm = __ballot_sync(0xffffffffu, cand);
-                    while (cm) {
-                        const int src = __ffs(cm) - 1;
-                        cm &= cm - 1;
-                        const float cd = __shfl_sync(0xffffffffu, dd, src);
-                        const int ci = __shfl_sync(0xffffffffu, pi, src);
-                        if (cand_less(cd, ci, best.worst_d(), best.worst_id()) && !topk_contains<KMAX>(best, ci)) best.insert(cd, ci);
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        unsigned cm = __ballot_sync(0xffffffffu, cand[u]);
+                        while (cm) {
+                            const int src = __ffs(cm) - 1;
+                            cm &= cm - 1;
+                            const float cd = __shfl_sync(0xffffffffu, dd[u], src);
+                            const int ci = __shfl_sync(0xffffffffu, pi[u], src);
+                            if (cand_less(cd, ci, best.worst_d(), best.worst_id()) && !topk_contains<KMAX>(best, ci)) best.insert(cd, ci);
+                        }
                     }
                 }
-                for (int i = 0; i < 4 && mask; ++i) mask &= mask - 1;
+                for (int i = 0; i < 4 * U && mask; ++i) mask &= mask - 1;
             }
         }
         if (lane == 0) {
