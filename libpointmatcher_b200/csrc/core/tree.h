@@ -28,6 +28,8 @@
 // (dist2, reference index): the answer is unique, independent of traversal order, and equals what
 // libnabo's brute-force search returns (index-ascending scan, strict '<').
 #pragma once
+#include <type_traits>
+
 #include "common.h"
 
 #ifndef PM_LEAF_MAX
@@ -96,7 +98,17 @@ PM_HD bool cand_less(float d, int i, float bd, int bi) { return d < bd || (d == 
 
 #define PM_NO_ID 0x7fffffff
 
-// k best candidates, ascending, held in registers when KMAX is small (all loops unrolled).
+// compile-time loop: every array index below is a constant, whatever the unroller decides, so
+// the candidate arrays can live in registers
+template <int I, int N, typename F>
+PM_HD void static_for(F&& f) {
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
+// k best candidates, ascending, held in registers (all indices are compile-time constants).
 template <int KMAX>
 struct TopK {
     float d[KMAX];
@@ -106,8 +118,7 @@ struct TopK {
     int wi;
     PM_HD void init(int k_, float max_r2) {
         k = k_;
-#pragma unroll
-        for (int j = 0; j < KMAX; ++j) { d[j] = max_r2; id[j] = PM_NO_ID; }
+        static_for<0, KMAX>([&](auto J) { d[J] = max_r2; id[J] = PM_NO_ID; });
         wd = max_r2;
         wi = PM_NO_ID;
     }
@@ -115,17 +126,30 @@ struct TopK {
     PM_HD int worst_id() const { return wi; }
     // insert (nd, ni); precondition: cand_less(nd, ni, worst)
     PM_HD void insert(float nd, int ni) {
-#pragma unroll
-        for (int j = KMAX - 1; j >= 1; --j) {
+        static_for<0, KMAX - 1>([&](auto I) {
+            constexpr int j = KMAX - 1 - I;  // j = KMAX-1 .. 1
             if (j < k) {
                 if (cand_less(nd, ni, d[j - 1], id[j - 1])) { d[j] = d[j - 1]; id[j] = id[j - 1]; }
                 else if (cand_less(nd, ni, d[j], id[j])) { d[j] = nd; id[j] = ni; }
             }
-        }
+        });
         if (cand_less(nd, ni, d[0], id[0])) { d[0] = nd; id[0] = ni; }
-#pragma unroll
-        for (int j = 0; j < KMAX; ++j)
-            if (j == k - 1) { wd = d[j]; wi = id[j]; }
+        static_for<0, KMAX>([&](auto J) {
+            if (J == k - 1) { wd = d[J]; wi = id[J]; }
+        });
+    }
+    // entry j (runtime index) without dynamic array addressing
+    PM_HD void get(int j, float& dj, int& ij) const {
+        dj = d[0];
+        ij = id[0];
+        static_for<1, KMAX>([&](auto J) {
+            if (J == j) { dj = d[J]; ij = id[J]; }
+        });
+    }
+    PM_HD bool contains(int q) const {
+        bool f = false;
+        static_for<0, KMAX>([&](auto J) { f = f || (id[J] == q); });
+        return f;
     }
 };
 
@@ -138,6 +162,8 @@ struct TopK<1> {
     PM_HD float worst_d() const { return d[0]; }
     PM_HD int worst_id() const { return id[0]; }
     PM_HD void insert(float nd, int ni) { d[0] = nd; id[0] = ni; }
+    PM_HD void get(int, float& dj, int& ij) const { dj = d[0]; ij = id[0]; }
+    PM_HD bool contains(int q) const { return id[0] == q; }
 };
 
 #if defined(PM_EMU_STATS) && !defined(__CUDACC__)
@@ -194,10 +220,22 @@ template <int KMAX>
 PM_HD void lane_scan_leaf(Lane& s, const TreeView& t, TopK<KMAX>& best) {
     const uint32_t leaf = s.node - (1u << t.depth);
     const uint32_t b = seg_begin(t.depth, leaf, t.n), e = seg_begin(t.depth, leaf + 1, t.n);
+    if (KMAX == 1) {
 #pragma unroll
-    for (uint32_t j = 0; j < PM_LEAF_MAX; ++j) {
-        const uint32_t p = b + j;
-        if (p < e) {
+        for (uint32_t j = 0; j < PM_LEAF_MAX; ++j) {
+            const uint32_t p = b + j;
+            if (p < e) {
+                const f4 pt = ldg4(t.pts + p);
+                const float dd = dist2(s.qx, s.qy, s.qz, pt.x, pt.y, pt.z);
+                const int pi = (int)f2u(pt.w);
+                if (cand_less(dd, pi, best.worst_d(), best.worst_id())) best.insert(dd, pi);
+            }
+        }
+    } else {
+        // k > 1: keep this a real loop — unrolling it around the (fully unrolled) insertion makes
+        // the compiler give up and demote the candidate arrays to local memory
+#pragma unroll 1
+        for (uint32_t p = b; p < e; ++p) {
             const f4 pt = ldg4(t.pts + p);
             const float dd = dist2(s.qx, s.qy, s.qz, pt.x, pt.y, pt.z);
             const int pi = (int)f2u(pt.w);

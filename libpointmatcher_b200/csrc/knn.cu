@@ -86,14 +86,13 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
     if (t < nq) {
         int32_t* oi = ids + (size_t)qi * k;
         float* od = dists + (size_t)qi * k;
-#pragma unroll
-        for (int j = 0; j < KMAX; ++j) {
-            if (j < k) {
-                const bool valid = best.id[j] != PM_NO_ID && best.d[j] != pm_inf();
-                oi[j] = valid ? best.id[j] : -1;
-                od[j] = valid ? best.d[j] : pm_inf();
+        static_for<0, KMAX>([&](auto J) {
+            if (J < k) {
+                const bool valid = best.id[J] != PM_NO_ID && best.d[J] != pm_inf();
+                oi[J] = valid ? best.id[J] : -1;
+                od[J] = valid ? best.d[J] : pm_inf();
             }
-        }
+        });
     }
     if (visits) {
         // warp-aggregated statistics (Matcher::visitCounter)
@@ -110,14 +109,6 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
 // leaves are scanned sixteen at a time (lane = leaf slot x point, four loads in flight per lane).  The candidate list is replicated in
 // every lane and updated with warp-uniform inserts, seeded with what stage 1 had found.  Same
 // bounds, same ranking: the result is the one the single-lane search would have produced.
-template <int KMAX>
-__device__ __forceinline__ bool topk_contains(const TopK<KMAX>& b, int id) {
-    bool f = false;
-#pragma unroll
-    for (int j = 0; j < KMAX; ++j) f = f || (b.id[j] == id);
-    return f;
-}
-
 constexpr int OVF_STACK = 224;  // <= 32 pushes per expansion level, <= 6 levels of expansion (depth <= 30)
 
 template <int KMAX>
@@ -148,13 +139,10 @@ __global__ void __launch_bounds__(128) knn_overflow_kernel(TreeView tree, const 
         TopK<KMAX> best;
         best.init(k, max_r2);
         // seed: the candidates stage 1 left in the result arrays (ascending, real points)
-#pragma unroll
-        for (int j = 0; j < KMAX; ++j) {
-            if (j < k) {
-                const int id = ids[(size_t)qi * k + j];
-                const float dd = dists[(size_t)qi * k + j];
-                if (id >= 0 && cand_less(dd, id, best.worst_d(), best.worst_id())) best.insert(dd, id);
-            }
+        for (int j = 0; j < k; ++j) {
+            const int id = ids[(size_t)qi * k + j];
+            const float dd = dists[(size_t)qi * k + j];
+            if (id >= 0 && cand_less(dd, id, best.worst_d(), best.worst_id())) best.insert(dd, id);
         }
         int sp = 0;
         if (lane == 0) stack[0] = 1u;
@@ -220,7 +208,7 @@ __global__ void __launch_bounds__(128) knn_overflow_kernel(TreeView tree, const 
                             cm &= cm - 1;
                             const float cd = __shfl_sync(0xffffffffu, dd[u], src);
                             const int ci = __shfl_sync(0xffffffffu, pi[u], src);
-                            if (cand_less(cd, ci, best.worst_d(), best.worst_id()) && !topk_contains<KMAX>(best, ci)) best.insert(cd, ci);
+                            if (cand_less(cd, ci, best.worst_d(), best.worst_id()) && !best.contains(ci)) best.insert(cd, ci);
                         }
                     }
                 }
@@ -229,11 +217,9 @@ __global__ void __launch_bounds__(128) knn_overflow_kernel(TreeView tree, const 
         }
         if (lane == 0) {
             for (int j = 0; j < k; ++j) {
-                float bd = max_r2;
-                int bi = PM_NO_ID;
-#pragma unroll
-                for (int jj = 0; jj < KMAX; ++jj)
-                    if (jj == j) { bd = best.d[jj]; bi = best.id[jj]; }
+                float bd;
+                int bi;
+                best.get(j, bd, bi);
                 const bool valid = bi != PM_NO_ID && bd != pm_inf();
                 ids[(size_t)qi * k + j] = valid ? bi : -1;
                 dists[(size_t)qi * k + j] = valid ? bd : pm_inf();
@@ -277,7 +263,9 @@ int launch_knn(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, 
     if (k == 1) PM_KNN_CASE(1);
     if (k <= 4) PM_KNN_CASE(4);
     if (k <= 8) PM_KNN_CASE(8);
+    if (k <= 10) PM_KNN_CASE(10);  // BASELINE config 4
     if (k <= 16) PM_KNN_CASE(16);
+    if (k <= 20) PM_KNN_CASE(20);  // BASELINE config 3 (normals)
     if (k <= 32) PM_KNN_CASE(32);
     if (k <= 64) PM_KNN_CASE(64);
 #undef PM_KNN_CASE

@@ -117,9 +117,12 @@ long run_knn(const EmuTree* t, const float* T16, const float* q, int nq, int k, 
         visits += v;
         if (g_visits_out) g_visits_out[i] = v;
         for (int j = 0; j < k; ++j) {
-            const bool valid = best.id[j] != PM_NO_ID && best.d[j] != pm_inf();
-            ids[(size_t)i * k + j] = valid ? best.id[j] : -1;
-            dists[(size_t)i * k + j] = valid ? best.d[j] : pm_inf();
+            float bd;
+            int bi;
+            best.get(j, bd, bi);
+            const bool valid = bi != PM_NO_ID && bd != pm_inf();
+            ids[(size_t)i * k + j] = valid ? bi : -1;
+            dists[(size_t)i * k + j] = valid ? bd : pm_inf();
         }
     }
     return visits;
@@ -179,7 +182,9 @@ long emu_knn(void* tp, const float* T16, const float* q, int nq, int k, float ma
     if (k == 1) return run_knn<1>(t, T16, q, nq, k, r2, ids, dists);
     if (k <= 4) return run_knn<4>(t, T16, q, nq, k, r2, ids, dists);
     if (k <= 8) return run_knn<8>(t, T16, q, nq, k, r2, ids, dists);
+    if (k <= 10) return run_knn<10>(t, T16, q, nq, k, r2, ids, dists);
     if (k <= 16) return run_knn<16>(t, T16, q, nq, k, r2, ids, dists);
+    if (k <= 20) return run_knn<20>(t, T16, q, nq, k, r2, ids, dists);
     if (k <= 32) return run_knn<32>(t, T16, q, nq, k, r2, ids, dists);
     if (k <= 64) return run_knn<64>(t, T16, q, nq, k, r2, ids, dists);
     return -1;
