@@ -10,6 +10,8 @@
 
 using namespace pm;
 
+thread_local cudaStream_t pm::g_alloc_stream = nullptr;
+
 namespace {
 
 __global__ void pack_normals_kernel(const float* __restrict__ src, int ld, int n, f4* __restrict__ dst) {
@@ -61,6 +63,7 @@ int fail(pmgpu_ctx* ctx, int code, const char* msg) {
 
 int use_device(pmgpu_ctx* ctx) {
     PM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    g_alloc_stream = ctx->stream;
     return PMGPU_OK;
 }
 
@@ -190,6 +193,15 @@ int pmgpu_ctx_create(int device, pmgpu_ctx** ctx_out) {
         return PMGPU_ERR_CUDA;
     }
     ctx->num_sms = sms > 0 ? sms : 148;
+    {
+        // keep freed buffers in the pool (see DevBuf)
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t threshold = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+        }
+        cudaGetLastError();
+    }
     ctx->hints_enabled = getenv("PMGPU_NO_HINTS") == nullptr;  // A/B switch for profiling
     if (const char* b = getenv("PMGPU_KNN_BUDGET")) ctx->knn_budget = atoi(b) > 0 ? atoi(b) : 1;  // 1: (almost) everything through stage 2
     memset(ctx->state_host, 0, sizeof(IcpState));
@@ -208,6 +220,7 @@ int pmgpu_ctx_create(int device, pmgpu_ctx** ctx_out) {
 void pmgpu_ctx_destroy(pmgpu_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    g_alloc_stream = ctx->stream;
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     pmgpu_comm_destroy(ctx);
     ctx->ref_orig.release(); ctx->ref_sorted.release(); ctx->ref_normals.release(); ctx->splits.release(); ctx->boxes.release();
@@ -221,7 +234,9 @@ void pmgpu_ctx_destroy(pmgpu_ctx* ctx) {
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->state) cudaFree(ctx->state);
     if (ctx->state_host) cudaFreeHost(ctx->state_host);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);  // the cudaFreeAsync calls above
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    g_alloc_stream = nullptr;
     delete ctx;
 }
 

@@ -13,8 +13,8 @@ def wall(f, reps=3):
         torch.cuda.synchronize(); t = time.perf_counter(); f(); torch.cuda.synchronize(); best = min(best, time.perf_counter() - t)
     return best * 1e3
 with capi.Context(0) as ctx:
-    print("set_reference (upload + build)      %.2f ms" % wall(lambda: ctx.set_reference(rf)))
     print("set_reference_centered              %.2f ms" % wall(lambda: ctx.set_reference_centered(rf)))
+    print("set_reference (upload + build)      %.2f ms" % wall(lambda: ctx.set_reference(rf)))
     print("set_reading (upload + morton)       %.2f ms" % wall(lambda: ctx.set_reading(rd)))
     print("ref_compute_normals knn=20          %.2f ms" % wall(lambda: ctx.ref_compute_normals(knn=20)))
     print("ref_compute_normals knn=7           %.2f ms" % wall(lambda: ctx.ref_compute_normals(knn=7)))
