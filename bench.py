@@ -267,8 +267,11 @@ def run_ours(args, rank, world, local_rank):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     knn_avg_ms = knn_ms / max(1, knn_n)
     achieved = alg_bytes / (knn_avg_ms * 1e-3) / 1e9 if knn_avg_ms > 0 else 0.0
+    # dram__bytes_read.sum + dram__bytes_write.sum of one knn_kernel<1> launch from the committed
+    # `ncu --set full` capture (profiles/r1_final_summary.txt; cold L2, 1 M x 1 M): 52.2 MB + 0.8 MB
+    ncu_traffic = 53.0e6 if (nq_local == 1_000_000 and nr == 1_000_000) else None
     roofline = {"bound": "hbm", "kernel": "knn_kernel<1> + knn_overflow_kernel<1> (K2: transform + exact nearest neighbour, stage 1 + stage 2)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": knn_avg_ms,
                 "note": "K2 is FP32-issue/latency bound, not HBM bound (SURVEY §8d); see DESIGN.md for the FP32 figure"}

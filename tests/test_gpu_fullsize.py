@@ -1,0 +1,106 @@
+"""Parity at BASELINE.json's full sizes (1 M x 1 M): against the oracle where it finishes in
+seconds on the box's host cores, and through size-independent properties."""
+import numpy as np
+import pytest
+
+from helpers import assert_transform_close, classify_id_mismatches
+
+pytestmark = pytest.mark.gpu
+N = 1_000_000
+
+
+@pytest.fixture(scope="module")
+def pair(synth):
+    return synth.scan_pair(N)
+
+
+def test_config2_knn_quantile_and_transform_at_1m(pair, oracle):
+    """BASELINE configs[1]: 1 M reading vs 1 M reference, knn 1, TrimmedDist 0.75, PointToPoint"""
+    from libpointmatcher_b200 import capi
+    rd, rf, T_gt = pair
+    threads = oracle.num_threads()
+    with capi.Context(0) as ctx:
+        ctx.set_reference(rf)
+        ctx.set_reading(rd)
+        ids, d, visits = ctx.knn(None, 1)
+        io, do = oracle.KdTree(rf).knn(rd, 1, nthreads=threads)
+        assert (d.view(np.uint32) == do.view(np.uint32)).all()          # distances bit-exact
+        ndiff, nties = classify_id_mismatches(io, do, ids, d)
+        assert ndiff == nties                                            # ids bit-exact, exact ties excepted
+        w, lim = ctx.weights([(capi.FILTER_TRIMMEDDIST, 0.75)])
+        wo, lo = oracle.outlier_weights(do, [(oracle.FILTER_TRIMMEDDIST, 0.75)])
+        assert lim[0] == lo[0] and (w == wo).all()                       # quantile bit-exact, weights identical
+        assert abs(w.mean() - 0.75) < 1e-3
+        T, _, st = ctx.minimize(capi.MIN_P2POINT)
+        To, _, so = oracle.minimize(oracle.MIN_P2POINT, rd, rf, None, ids, d, w, acc_double=True)
+        assert_transform_close(T, To, 1e-5, 1e-5)
+        assert st["nbKept"] == so["nbKept"]
+        # properties: sorted / idempotent self-match
+        ctx.set_reading(rf[:200000])
+        ids2, d2, _ = ctx.knn(None, 3)
+        assert (d2[:, 0] == 0).all() and (ids2[:, 0] == np.arange(200000)).all()   # a reference point's nearest neighbour is itself
+        assert (np.diff(d2, axis=1) >= 0).all()                                   # ascending distances
+
+
+def test_point_to_plane_icp_converges_at_1m(pair, oracle):
+    """the north-star target config: 1 M x 1 M point-to-plane, normals from K8 (knn 20)"""
+    from libpointmatcher_b200 import capi, pm
+    rd, rf, T_gt = pair
+    icp = pm.ICP()
+    icp.referenceDataPointsFilters = [pm.SurfaceNormalDataPointsFilter({"knn": "20"})]
+    icp.matcher = pm.KDTreeMatcher()
+    icp.outlierFilters = pm.OutlierFilters([pm.TrimmedDistOutlierFilter({"ratio": "0.75"})])
+    icp.errorMinimizer = pm.PointToPlaneErrorMinimizer()
+    icp.transformationCheckers = [pm.CounterTransformationChecker({"maxIterationCount": "40"})]
+    T = icp(pm.DataPoints(rd), pm.DataPoints(rf))
+    assert icp.iterationCount == 40
+    assert np.linalg.norm(T[:3, 3].astype(np.float64) - T_gt[:3, 3]) < 2e-3      # the true pose of the re-scan
+    R = T[:3, :3].astype(np.float64)
+    assert np.allclose(R.T @ R, np.eye(3), atol=1e-5)
+    icp.ctx.close()
+
+
+def test_config4_shape_knn10_filters_cov(oracle, synth):
+    """BASELINE configs[3] shape (knn 10, maxDist + MedianDist, PointToPlaneWithCov) on 500 k-point scans,
+    the largest size the oracle finishes in seconds"""
+    from libpointmatcher_b200 import capi
+    rd, rf, _ = synth.scan_pair(500_000)
+    threads = oracle.num_threads()
+    with capi.Context(0) as ctx:
+        ctx.set_reference(rf)
+        ctx.ref_compute_normals(knn=20)
+        ctx.set_reading(rd)
+        ids, d, _ = ctx.knn(None, 10, 0.0, 2.0)
+        io, do = oracle.KdTree(rf).knn(rd, 10, max_dist=2.0, nthreads=threads)
+        assert (d.view(np.uint32) == do.view(np.uint32)).all()
+        ndiff, nties = classify_id_mismatches(io, do, ids, d)
+        assert ndiff == nties
+        chain = [(capi.FILTER_MAXDIST, 1.0), (capi.FILTER_MEDIANDIST, 3.0)]
+        w, lim = ctx.weights(chain)
+        wo, lo = oracle.outlier_weights(do, chain)
+        assert (lim.view(np.uint32) == lo.view(np.uint32)).all() and (w == wo).all()
+
+
+def test_surface_normals_at_1m_properties(pair, oracle):
+    """K8 at 1 M points: unit normals, and agreement with the oracle on a random sample of points
+    (the oracle's neighbourhoods come from its own kd-tree over the full cloud)"""
+    from libpointmatcher_b200 import capi
+    rd, rf, _ = pair
+    with capi.Context(0) as ctx:
+        g = ctx.normals(rf, knn=20, keep=("normals", "matchedIds", "densities"))
+    n = g["normals"]
+    assert g["degenerate"] == 0
+    assert np.abs(np.linalg.norm(n, axis=1) - 1.0).max() < 1e-5
+    assert (g["matchedIds"][:, 0] == np.arange(len(rf))).all()       # every point is its own first neighbour
+    rng = np.random.default_rng(5)
+    sample = np.sort(rng.choice(len(rf), 20000, replace=False))
+    io, do = oracle.KdTree(rf).knn(rf[sample], 20, nthreads=oracle.num_threads())
+    same = (g["matchedIds"][sample].astype(np.int32) == io).all(axis=1)
+    assert same.mean() > 0.999
+    # normals from the oracle's neighbourhoods, in float64
+    P = rf[io[same]][:, :, :3].astype(np.float64)
+    C = np.einsum("nki,nkj->nij", P - P.mean(1, keepdims=True), P - P.mean(1, keepdims=True))
+    wv, V = np.linalg.eigh(C)
+    gap = (wv[:, 1] - wv[:, 0]) / wv.sum(1)
+    dots = np.abs((V[:, :, 0] * n[sample][same]).sum(1))
+    assert (1.0 - dots[gap > 1e-3]).max() < 1e-5
