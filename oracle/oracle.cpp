@@ -8,7 +8,8 @@
  * PARITY UNPINNED for kNN indices: libnabo is not under /root/reference; its published
  * algorithm (brute force, and the bucketed kd-tree with implicit bounds + sorted linear heap,
  * libnabo >= 1.0.7 `KDTreeUnbalancedPtInLeavesImplicitBoundsStackOpt`) is restated below.
- * Transforms are pinned against the reference's known-answer tests in tests/.
+ * Transforms are pinned against the reference's golden .ref_trans files, validT3d and its
+ * known-answer tests (tests/test_reference_goldens.py, tests/test_oracle_golden.py).
  *
  * Float semantics: compiled with -ffp-contract=off so every float op rounds once, like the
  * reference's default -O3 / SSE2 build (CMakeLists.txt:69-71).

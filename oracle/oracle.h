@@ -10,8 +10,10 @@
  *   - kNN match indices: PARITY UNPINNED by the reference (libnabo is an un-vendored external
  *     dependency, >= 1.0.7, and no reference test inspects Matches.ids).  The oracle restates
  *     libnabo's published algorithms (brute force; bucketed kd-tree, linear heap).
- *   - final transforms are pinned by the reference's own known-answer tests (icpSingular,
- *     icpIdentity: utest/utest.cpp:162-220) reproduced in tests/test_oracle_golden.py.
+ *   - final transforms ARE pinned by the reference's own fixtures: five golden
+ *     examples/data/icp_data/*.ref_trans (criterion of utest/utest.cpp:146-158, < 3 %), validT3d
+ *     (utest/utest.h:66-84) — tests/test_reference_goldens.py — and the known-answer tests
+ *     icpSingular / icpIdentity (utest/utest.cpp:162-220) — tests/test_oracle_golden.py.
  */
 #ifndef ORACLE_H
 #define ORACLE_H
