@@ -285,3 +285,65 @@ protected:
         return T_refIn_refMean * T_iter * T_refMean_dataIn;
     }
 };
+
+// ICPSequence (PointMatcher.h:726-764, ICP.cpp:455-609): ICP against a map that stays resident on
+// the device.  setMap() centres, filters and indexes the map once; every operator() registers a
+// new cloud against it (BASELINE config 3: a 10 M-point map, readings streaming in).
+struct ICPSequence : public ICP {
+    bool hasMap() const { return mapPointCloud.features.cols() != 0; }
+    // ICP.cpp:463-508
+    bool setMap(const DataPoints& inputCloud) {
+        if (!this->matcher) throw std::runtime_error("You must setup a matcher before running ICP");
+        if (!this->inspector) throw std::runtime_error("You must setup an inspector before running ICP");
+        const int dim = inputCloud.features.rows();
+        if (inputCloud.features.cols() == 0) return false;
+        requireFloat3D(dim, "ICPSequence");
+        this->bindPipeline();
+        auto* gpuMatcher = dynamic_cast<KDTreeMatcher*>(this->matcher.get());
+        if (!gpuMatcher) throw ConfigurationError("ICPSequence: GPU build: the matcher must be the GPU KDTreeMatcher (there is no CPU path)");
+        this->inspector->addStat("MapPointCount", inputCloud.features.cols());
+        mapPointCloud = inputCloud;
+        // the reference centres first and filters afterwards (ICP.cpp:486-496); the GPU filters on
+        // this path (SurfaceNormal, Identity) do not move points, so filtering the un-centred
+        // cloud and centring inside the matcher init is the same computation
+        this->referenceDataPointsFilters.init();
+        this->referenceDataPointsFilters.apply(mapPointCloud);
+        float mean4[4];
+        gpuMatcher->initCentered(mapPointCloud, mean4);
+        T_refIn_refMean = Matrix::Identity(dim, dim);
+        T_refMean_refIn = Matrix::Identity(dim, dim);
+        for (int r = 0; r < dim - 1; ++r) {
+            T_refIn_refMean(r, dim - 1) = T(mean4[r]);
+            T_refMean_refIn(r, dim - 1) = T(-mean4[r]);
+        }
+        this->prefilteredReferencePtsCount = mapPointCloud.features.cols();
+        return true;
+    }
+    void clearMap() { mapPointCloud = DataPoints(); }
+    // the map in its original frame (the host copy is kept un-centred here)
+    const DataPoints& getPrefilteredMap() const { return mapPointCloud; }
+    const DataPoints& getMap() const { return mapPointCloud; }
+
+    TransformationParameters operator()(const DataPoints& cloudIn) {
+        const int dim = cloudIn.features.rows();
+        return this->compute(cloudIn, Matrix::Identity(dim, dim));
+    }
+    TransformationParameters operator()(const DataPoints& cloudIn, const TransformationParameters& T_dataInOld_dataInNew) {
+        return this->compute(cloudIn, T_dataInOld_dataInNew);
+    }
+    // ICP.cpp:595-609
+    TransformationParameters compute(const DataPoints& cloudIn, const TransformationParameters& T_refIn_dataIn) {
+        if (!hasMap()) {
+            const int dim = cloudIn.features.rows();
+            return Matrix::Identity(dim, dim);  // "Ignoring attempt to perform ICP with an empty map"
+        }
+        this->bindPipeline();
+        this->inspector->init();
+        return this->computeWithTransformedReference(cloudIn, mapPointCloud, T_refIn_refMean, T_refMean_refIn, T_refIn_dataIn);
+    }
+
+protected:
+    DataPoints mapPointCloud;
+    TransformationParameters T_refIn_refMean, T_refMean_refIn;
+};
+

@@ -465,29 +465,35 @@ class ICP:
     def __call__(self, readingIn, referenceIn, T_refIn_dataIn=None):
         return self.compute(readingIn, referenceIn, T_refIn_dataIn)
 
-    def compute(self, readingIn, referenceIn, T_refIn_dataIn=None):
+    def _bind(self):
         if self.matcher is None:
             raise RuntimeError("You must setup a matcher before running ICP")
         if self.errorMinimizer is None:
             raise RuntimeError("You must setup an error minimizer before running ICP")
         for mod in [self.matcher, self.outlierFilters, self.errorMinimizer] + list(self.outlierFilters) + list(self.referenceDataPointsFilters):
             mod.bind(self.ctx)
-        T_init = np.eye(4, dtype=np.float32) if T_refIn_dataIn is None else np.asarray(T_refIn_dataIn, np.float32)
-        if T_init.shape != (4, 4):
-            raise RuntimeError("The initial transformation matrix must be squared.")
+
+    def _set_reference(self, referenceIn):
+        """reference filters, centring on the mean and matcher init (ICP.cpp:285-302).  Returns T_refIn_refMean."""
         reference = referenceIn if isinstance(referenceIn, DataPoints) else DataPoints(referenceIn)
-        reading = readingIn if isinstance(readingIn, DataPoints) else DataPoints(readingIn)
         if self.referenceDataPointsFilters:
             reference = reference.copy()  # inputs are never mutated (ICP.cpp:285)
             for f in self.referenceDataPointsFilters:
                 f.inPlaceFilter(reference)
-        # centre the reference on its mean and init the matcher with it (ICP.cpp:291-302)
         mean = self.matcher.initCentered(reference)
         T_refIn_refMean = np.eye(4, dtype=np.float32)
         T_refIn_refMean[:3, 3] = mean[:3]
-        # reading into the refMean frame (ICP.cpp:345-347)
+        return T_refIn_refMean
+
+    def _register(self, readingIn, T_refIn_refMean, T_refIn_dataIn):
+        """computeWithTransformedReference (ICP.cpp:316-449) against the resident reference"""
+        T_init = np.eye(4, dtype=np.float32) if T_refIn_dataIn is None else np.asarray(T_refIn_dataIn, np.float32)
+        if T_init.shape != (4, 4):
+            raise RuntimeError("The initial transformation matrix must be squared.")
+        reading = readingIn if isinstance(readingIn, DataPoints) else DataPoints(readingIn)
+        # reading into the refMean frame (ICP.cpp:345-347); T_refIn_refMean is a pure translation
         T_refMean_refIn = np.eye(4, dtype=np.float32)
-        T_refMean_refIn[:3, 3] = -mean[:3]
+        T_refMean_refIn[:3, 3] = -T_refIn_refMean[:3, 3]
         T_refMean_dataIn = mat4_mul(T_refMean_refIn, T_init)
         _translate(self.ctx.set_reading, reading.features)
         self.ctx._reading_obj = None
@@ -500,3 +506,37 @@ class ICP:
         self.errorMinimizer._cov = res["cov"]
         self.T_iter = res["T_iter"]
         return mat4_mul(mat4_mul(T_refIn_refMean, res["T_iter"]), T_refMean_dataIn)
+
+    def compute(self, readingIn, referenceIn, T_refIn_dataIn=None):
+        self._bind()
+        T_refIn_refMean = self._set_reference(referenceIn)
+        return self._register(readingIn, T_refIn_refMean, T_refIn_dataIn)
+
+
+class ICPSequence(ICP):
+    """ICP against a map that stays resident on the device (ICP.cpp:455-609): `setMap` filters,
+    centres and indexes the map once; every `icp(cloud[, T_init])` registers a new reading against
+    it without touching the reference structure (BASELINE config 3: a 10 M-point map, readings
+    streaming in)."""
+
+    def __init__(self, device=0):
+        super().__init__(device)
+        self._T_refIn_refMean = None
+
+    def hasMap(self):
+        return self._T_refIn_refMean is not None
+
+    def setMap(self, mapPointCloud):
+        self._bind()
+        self._T_refIn_refMean = self._set_reference(mapPointCloud)
+        return True
+
+    def clearMap(self):
+        self._T_refIn_refMean = None
+
+    def __call__(self, cloudIn, T_dataInOld_dataInNew=None):
+        # without a map the reference warns and answers the identity (ICP.cpp:598-604)
+        if not self.hasMap():
+            return np.eye(4, dtype=np.float32)
+        self._bind()
+        return self._register(cloudIn, self._T_refIn_refMean, T_dataInOld_dataInNew)

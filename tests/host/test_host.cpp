@@ -4,6 +4,7 @@
 //                                                  : runs PM::ICP like examples/icp_simple.cpp and
 //                                                    prints iterations + the 4x4 (row-major)
 #include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <sstream>
 
@@ -162,6 +163,23 @@ static int run_icp(int argc, char** argv) {
         icp.loadFromYaml(cfg);
     }
     try {
+        if (std::getenv("PM_TEST_SEQUENCE")) {
+            // ICPSequence: the map is indexed once, the reading is registered against it twice
+            PM::ICPSequence seq;
+            if (std::string(argv[2]) == "default") seq.setDefault();
+            else { std::ifstream cfg2(argv[2]); seq.loadFromYaml(cfg2); }
+            if (seq.hasMap()) return 4;
+            const PM::TransformationParameters I = seq(reading);  // no map yet: identity
+            if (!(I == PM::Matrix::Identity(4, 4))) return 4;
+            if (!seq.setMap(reference) || !seq.hasMap()) return 4;
+            const PM::TransformationParameters T1 = seq(reading), T2 = seq(reading);
+            if (!(T1 == T2)) return 5;  // the resident map is not disturbed by a registration
+            std::printf("iterations %zu fused %d maxreached %d overlap %.9g\n", seq.getIterationCount(), seq.usedFusedLoop() ? 1 : 0,
+                        seq.getMaxNumIterationsReached() ? 1 : 0, (double)seq.errorMinimizer->getWeightedPointUsedRatio());
+            for (int i = 0; i < 4; ++i) std::printf("%.9g %.9g %.9g %.9g\n", T1(i, 0), T1(i, 1), T1(i, 2), T1(i, 3));
+            std::printf("cov 0 0 0 0 0 0\n");
+            return 0;
+        }
         const PM::TransformationParameters Tm = icp(reading, reference);
         std::printf("iterations %zu fused %d maxreached %d overlap %.9g\n", icp.getIterationCount(), icp.usedFusedLoop() ? 1 : 0,
                     icp.getMaxNumIterationsReached() ? 1 : 0, (double)icp.errorMinimizer->getWeightedPointUsedRatio());

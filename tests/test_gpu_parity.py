@@ -273,3 +273,33 @@ def test_icp_with_initial_guess(oracle, synth):
     Ti = synth.pose_matrix((0.5, -0.3, 0.0), 3.0).astype(np.float32)
     T, icp, res_o, _ = _icp_both(oracle, synth, 50000, 1, [(2, 0.8)], iters=10, T_init=Ti)
     assert_transform_close(T, res_o["T"], 1e-5, 1e-5)
+
+
+def test_icp_sequence_resident_map(oracle, synth):
+    """ICPSequence (ICP.cpp:455-609): the map is indexed once; registering against it gives exactly
+    what ICP::operator() gives, before and after other registrations"""
+    from libpointmatcher_b200 import pm
+    rd, rf, _ = synth.scan_pair(50000)
+    rd2, _, _ = synth.scan_pair(50000, pair_seed=3)
+    nrm = oracle.surface_normals(rf, knn=10, nthreads=8)["normals"]
+
+    def chain(obj):
+        obj.matcher = pm.KDTreeMatcher()
+        obj.outlierFilters = pm.OutlierFilters([pm.TrimmedDistOutlierFilter({"ratio": "0.8"})])
+        obj.errorMinimizer = pm.PointToPlaneErrorMinimizer()
+        obj.transformationCheckers = [pm.CounterTransformationChecker({"maxIterationCount": "10"})]
+        return obj
+
+    ref = pm.DataPoints(rf, {"normals": nrm})
+    plain = chain(pm.ICP())
+    T_plain = plain(pm.DataPoints(rd), ref)
+    seq = chain(pm.ICPSequence())
+    assert not seq.hasMap()
+    assert (seq(pm.DataPoints(rd)) == np.eye(4)).all()      # no map yet: identity (ICP.cpp:598-604)
+    assert seq.setMap(ref) and seq.hasMap()
+    T1 = seq(pm.DataPoints(rd))
+    seq(pm.DataPoints(rd2))                                   # another reading in between
+    T3 = seq(pm.DataPoints(rd))
+    assert (T1 == T_plain).all() and (T3 == T_plain).all()
+    plain.ctx.close()
+    seq.ctx.close()

@@ -70,7 +70,7 @@ BOUND = """  - BoundTransformationChecker:
 """
 
 
-def _run_icp(host_bin, tmp_path, config, rd, rf, nrm):
+def _run_icp(host_bin, tmp_path, config, rd, rf, nrm, sequence=False):
     cfg = tmp_path / "cfg.yaml"
     cfg.write_text(config)
     rd.astype(np.float32).tofile(tmp_path / "rd.f32")
@@ -79,7 +79,8 @@ def _run_icp(host_bin, tmp_path, config, rd, rf, nrm):
     if nrm is not None:
         np.ascontiguousarray(nrm, np.float32).tofile(tmp_path / "nrm.f32")
         args.append(str(tmp_path / "nrm.f32"))
-    r = subprocess.run(args, capture_output=True, text=True)
+    env = dict(os.environ, PM_TEST_SEQUENCE="1") if sequence else None
+    r = subprocess.run(args, capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     lines = r.stdout.strip().split("\n")
     head = lines[0].split()
@@ -123,3 +124,15 @@ def test_cpp_icp_default_chain(host_bin, tmp_path, oracle, synth):
                      acc_double=True)
     assert int(lines[0].split()[1]) == ref["iterations"]
     assert_transform_close(T, ref["T"], 2e-5, 2e-5)  # normals of near-degenerate neighbourhoods differ in sign/rounding only
+
+
+@pytest.mark.gpu
+def test_cpp_icp_sequence_matches_plain_icp(host_bin, tmp_path, oracle, synth):
+    """ICPSequence (setMap once, register twice) gives the transform ICP::operator() gives"""
+    rd, rf, _ = synth.scan_pair(60000)
+    nrm = oracle.surface_normals(rf, knn=10, nthreads=8)["normals"]
+    cfg = CONFIG.format(minimizer="PointToPlaneErrorMinimizer", iters=15, differential="")
+    plain = _run_icp(host_bin, tmp_path, cfg, rd, rf, nrm)
+    seq = _run_icp(host_bin, tmp_path, cfg, rd, rf, nrm, sequence=True)
+    assert seq["iterations"] == plain["iterations"] == 15
+    assert (seq["T"] == plain["T"]).all()
