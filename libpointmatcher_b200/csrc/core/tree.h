@@ -176,7 +176,8 @@ static EmuStats g_emu_stats = {0, 0, 0, 0, 0};
 
 // ------------------------------------------------------------------------------------------------
 // Per-query search state and its three phases.  knn.cu runs the phases of the 32 lanes of a warp
-// in lock step (descend* | scan leaf | pop*), re-converging between phases;
+// in lock step (descend* | scan leaf + filter pending levels | box test*), one step of every lane
+// at a time, so the warp never diverges;
 // knn_search_single() below composes the same phases sequentially (host harness, and the
 // definition of the result).
 //
@@ -246,26 +247,34 @@ PM_HD void lane_scan_leaf(Lane& s, const TreeView& t, TopK<KMAX>& best) {
     PM_STAT(leaves);
 }
 
-// examine pending siblings, deepest first; returns true when one has to be searched (the lane
-// then continues with descend steps from it), false when the search is complete.
+// After a leaf: drop every pending level whose split plane is already out of reach.  Branch-free
+// over the levels (one LDS + compare + predicated bit-clear each), so the warp stays converged.
 template <int KMAX>
-PM_HD bool lane_pop(Lane& s, const TreeView& t, const TopK<KMAX>& best, const float* plane, int stride) {
-    while (s.trail != 0) {
-        const int l = 31 - clz32(s.trail);
-        s.trail &= ~(1u << l);
+PM_HD void lane_filter_trail(Lane& s, const TreeView& t, const TopK<KMAX>& best, const float* plane, int stride) {
+    const float w = best.worst_d();
+    uint32_t keep = s.trail;
+    for (int l = 1; l <= t.depth; ++l) {
         PM_STAT(pops);
-        const float w = best.worst_d();
-        if (plane[l * stride] > w) continue;  // the whole far side of that split is out of reach
-        const uint32_t far = (s.node >> (s.level - l)) ^ 1u;
-        PM_STAT(box_tests);
-        const float db = box_dist2(s.qx, s.qy, s.qz, ldg4(t.boxes + 2 * (size_t)far), ldg4(t.boxes + 2 * (size_t)far + 1));
-        if (db > w) continue;
-        s.node = far;
-        s.level = l;
-        PM_STAT(redescents);
-        return true;
+        if (plane[l * stride] > w) keep &= ~(1u << l);  // the whole far side of that split is out of reach
     }
-    return false;
+    s.trail = keep;
+}
+
+// One box test: the deepest pending sibling.  Returns true when it has to be searched (the lane
+// then continues with descend steps from it); false means "rejected", the caller tries the next
+// pending level while s.trail != 0.
+template <int KMAX>
+PM_HD bool lane_box_step(Lane& s, const TreeView& t, const TopK<KMAX>& best) {
+    const int l = 31 - clz32(s.trail);
+    s.trail &= ~(1u << l);
+    const uint32_t far = (s.node >> (s.level - l)) ^ 1u;
+    PM_STAT(box_tests);
+    const float db = box_dist2(s.qx, s.qy, s.qz, ldg4(t.boxes + 2 * (size_t)far), ldg4(t.boxes + 2 * (size_t)far + 1));
+    if (db > best.worst_d()) return false;
+    s.node = far;
+    s.level = l;
+    PM_STAT(redescents);
+    return true;
 }
 
 // Exact k-nearest-neighbour search of one query.  `best` may already hold real candidates (e.g.
@@ -281,7 +290,10 @@ PM_HD uint32_t knn_search_single(const TreeView& t, float qx, float qy, float qz
     for (;;) {
         while (lane_descending(s, t)) lane_descend_step(s, t, plane, 1);
         lane_scan_leaf<KMAX>(s, t, best);
-        if (!lane_pop<KMAX>(s, t, best, plane, 1)) break;
+        lane_filter_trail<KMAX>(s, t, best, plane, 1);
+        bool found = false;
+        while (!found && s.trail != 0) found = lane_box_step<KMAX>(s, t, best);
+        if (!found) break;
     }
     return s.visited;
 }

@@ -5,10 +5,10 @@
 // neighbouring points and walk almost the same part of the tree (the tree of a 1 M-point
 // reference is 1 MB of split planes + 8 MB of boxes + 16 MB of points, resident in the 126 MB L2;
 // leaf and node loads of a warp mostly hit the same L1 lines).  The search of core/tree.h is run
-// as three phases — plane descent | leaf scan | pop pending siblings — and the lanes of a warp
-// RE-CONVERGE between phases (__syncwarp): without that, independent thread scheduling lets every
-// lane drift into its own phase and the warp executes ~3 of 32 lanes per instruction (measured,
-// profiles/).  The per-level plane distances of the descent are cached in shared memory (one
+// as phases — plane descent | leaf scan + plane filter of the pending levels | box tests — and the
+// lanes of a warp advance through them in LOCK STEP (warp-vote loops: one step of every lane at a
+// time): without that, independent thread scheduling lets every lane drift into its own phase and
+// the warp executes ~3 of 32 lanes per instruction (measured, profiles/).  The per-level plane distances of the descent are cached in shared memory (one
 // column per lane), so rejecting a pending sibling costs one LDS and a compare.  T_iter is read
 // from the device-resident IcpState, so no host round trip separates iterations; in iterations
 // >= 2 (k = 1) the previous match, re-measured, seeds the search with a tight bound.  Queries
@@ -71,17 +71,25 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
     // warp — and the kernel — for thousands of rounds.
     int rounds = 0;
     while (__any_sync(0xffffffffu, running)) {
-        while (running && lane_descending(s, tree)) lane_descend_step(s, tree, plane, KNN_BLOCK);
-        __syncwarp();
-        if (running) lane_scan_leaf<KMAX>(s, tree, best);
-        __syncwarp();
-        if (running) running = lane_pop<KMAX>(s, tree, best, plane, KNN_BLOCK);
+        // descend: one level per step for every lane that is not at a leaf yet
+        while (__any_sync(0xffffffffu, running && lane_descending(s, tree)))
+            if (running && lane_descending(s, tree)) lane_descend_step(s, tree, plane, KNN_BLOCK);
+        // leaf + plane filter of the pending levels
+        if (running) {
+            lane_scan_leaf<KMAX>(s, tree, best);
+            lane_filter_trail<KMAX>(s, tree, best, plane, KNN_BLOCK);
+        }
+        // box tests, deepest pending sibling first, one per step, until every lane has either a
+        // subtree to search or nothing left
+        bool found = false;
+        while (__any_sync(0xffffffffu, running && !found && s.trail != 0))
+            if (running && !found && s.trail != 0) found = lane_box_step<KMAX>(s, tree, best);
+        if (running && !found) running = false;  // search complete
         ++rounds;
         if (running && rounds >= budget) {
             running = false;
             overflow[atomicAdd(overflow_count, 1u)] = (uint32_t)t;
         }
-        __syncwarp();
     }
     if (t < nq) {
         int32_t* oi = ids + (size_t)qi * k;
