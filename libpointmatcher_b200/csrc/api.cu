@@ -156,7 +156,7 @@ int enqueue_iteration(pmgpu_ctx* ctx, const pmgpu_icp_params* p, bool gated) {
     SelectSpec spec;
     PM_TRY(make_select_spec(ctx, p->nfilters, p->filter_type, p->filter_param, &spec));
     PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, ctx->nq, true, gated, false, p->knn, max_r2,
-                      ctx->seed_k == 1 && p->knn == 1 && ctx->hints_enabled, ctx->ids.p, ctx->dists.p));
+                      ctx->seed_k == 1 && p->knn == 1 && ctx->seed_enabled, ctx->ids.p, ctx->dists.p));
     ctx->seed_k = p->knn;
     ctx->stage_end();
     ctx->stage_begin(1);
@@ -202,7 +202,7 @@ int pmgpu_ctx_create(int device, pmgpu_ctx** ctx_out) {
         }
         cudaGetLastError();
     }
-    ctx->hints_enabled = getenv("PMGPU_NO_HINTS") == nullptr;  // A/B switch for profiling
+    ctx->seed_enabled = getenv("PMGPU_NO_SEED") == nullptr;
     if (const char* b = getenv("PMGPU_KNN_BUDGET")) ctx->knn_budget = atoi(b) > 0 ? atoi(b) : 1;  // 1: (almost) everything through stage 2
     memset(ctx->state_host, 0, sizeof(IcpState));
     mat4_identity(ctx->state_host->T_iter);
@@ -226,7 +226,7 @@ void pmgpu_ctx_destroy(pmgpu_ctx* ctx) {
     ctx->ref_orig.release(); ctx->ref_sorted.release(); ctx->ref_normals.release(); ctx->splits.release(); ctx->boxes.release();
     ctx->reading_tmp.release(); ctx->ids_tmp.release(); ctx->dists_tmp.release(); ctx->overflow.release();
     ctx->keys_a.release(); ctx->keys_b.release(); ctx->perm_a.release(); ctx->perm_b.release();
-    ctx->node_box.release(); ctx->node_dim.release(); ctx->cub_tmp.release();
+    ctx->node_box.release(); ctx->cub_tmp.release();
     ctx->reading.release(); ctx->q_order.release();
     ctx->ids.release(); ctx->dists.release(); ctx->weights.release();
     ctx->hist.release(); ctx->partials.release();
@@ -405,7 +405,7 @@ int pmgpu_knn(pmgpu_ctx* ctx, const float* T, int k, float epsilon, float max_di
     const float max_r2 = max_dist * max_dist;
     ctx->stage_begin(0);
     PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, ctx->nq, T != nullptr, false, false, k, max_r2,
-                      ctx->seed_k == 1 && k == 1 && ctx->hints_enabled, ctx->ids.p, ctx->dists.p));
+                      ctx->seed_k == 1 && k == 1 && ctx->seed_enabled, ctx->ids.p, ctx->dists.p));
     ctx->seed_k = k;
     ctx->stage_end();
     ctx->have_matches = true;

@@ -65,7 +65,6 @@ int allreduce(pmgpu_ctx* ctx, void* buf, size_t count, ncclDataType_t type) {
 }  // namespace
 
 int comm_allreduce_u32(pmgpu_ctx* ctx, unsigned* buf, size_t count) { return allreduce(ctx, buf, count, ncclUint32); }
-int comm_allreduce_u64(pmgpu_ctx* ctx, unsigned long long* buf, size_t count) { return allreduce(ctx, buf, count, ncclUint64); }
 int comm_allreduce_f64(pmgpu_ctx* ctx, double* buf, size_t count) { return allreduce(ctx, buf, count, ncclFloat64); }
 
 }  // namespace pm

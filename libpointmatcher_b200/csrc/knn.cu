@@ -8,8 +8,9 @@
 // as phases — plane descent | leaf scan + plane filter of the pending levels | box tests — and the
 // lanes of a warp advance through them in LOCK STEP (warp-vote loops: one step of every lane at a
 // time): without that, independent thread scheduling lets every lane drift into its own phase and
-// the warp executes ~3 of 32 lanes per instruction (measured, profiles/).  The per-level plane distances of the descent are cached in shared memory (one
-// column per lane), so rejecting a pending sibling costs one LDS and a compare.  T_iter is read
+// the warp executes ~3 of 32 lanes per instruction (measured, profiles/).  The per-level plane
+// distances of the descent are cached in shared memory (one column per lane), so rejecting a
+// pending sibling costs one LDS and a compare.  T_iter is read
 // from the device-resident IcpState, so no host round trip separates iterations; in iterations
 // >= 2 (k = 1) the previous match, re-measured, seeds the search with a tight bound.  Queries
 // still open after a budget of leaves go to a second, warp-per-query kernel (stage 2).
@@ -114,8 +115,8 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
 // ---- stage 2: one warp per left-over query ------------------------------------------------------
 // The 32 lanes search ONE query together: a node is expanded 5 levels at a time (32 descendants,
 // one box test per lane), surviving inner nodes go on a small shared-memory stack, surviving
-// leaves are scanned sixteen at a time (lane = leaf slot x point, four loads in flight per lane).  The candidate list is replicated in
-// every lane and updated with warp-uniform inserts, seeded with what stage 1 had found.  Same
+// leaves are scanned sixteen at a time (lane = leaf slot x point, four loads in flight per lane).
+// The candidate list is replicated in every lane and updated with warp-uniform inserts, seeded with what stage 1 had found.  Same
 // bounds, same ranking: the result is the one the single-lane search would have produced.
 constexpr int OVF_STACK = 224;  // <= 32 pushes per expansion level, <= 6 levels of expansion (depth <= 30)
 

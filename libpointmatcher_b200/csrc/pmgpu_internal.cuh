@@ -131,7 +131,6 @@ struct pmgpu_ctx {
     pm::DevBuf<uint64_t> keys_a, keys_b;
     pm::DevBuf<uint32_t> perm_a, perm_b;
     pm::DevBuf<uint32_t> node_box;  // 6 ordered-uint per node (lo xyz, hi xyz), heap index
-    pm::DevBuf<uint8_t> node_dim;
     pm::DevBuf<uint8_t> cub_tmp;
 
     // reading
@@ -143,7 +142,7 @@ struct pmgpu_ctx {
     pm::DevBuf<uint32_t> overflow;   // kNN stage-2 queue: sorted positions of the queries stage 1 did not finish
     int knn_parity = 0;
     int knn_budget = 16;             // leaves a lane may scan before its query goes to stage 2
-    bool hints_enabled = true;
+    bool seed_enabled = true;        // PMGPU_NO_SEED=1 switches the seeding off (A/B profiling)
     pm::DevBuf<int32_t> ids_tmp;     // un-permute staging for downloads
     pm::DevBuf<float> dists_tmp;
 
@@ -159,7 +158,6 @@ struct pmgpu_ctx {
     pm::DevBuf<unsigned> hist;   // PM_HIST_BINS
     // minimiser partial sums (K4-K6)
     pm::DevBuf<double> partials;
-    int partial_blocks = 0;
 
     pm::IcpState* state = nullptr;   // device
     pm::IcpState* state_host = nullptr;  // pinned host mirror
@@ -223,7 +221,6 @@ int launch_normals(pmgpu_ctx* ctx, const f4* pts, int n, const int32_t* ids, con
                    float* densities, float* eig_values, float* eig_vectors, float* mean_dists);
 // comm.cu
 int comm_allreduce_u32(pmgpu_ctx* ctx, unsigned* buf, size_t count);
-int comm_allreduce_u64(pmgpu_ctx* ctx, unsigned long long* buf, size_t count);
 int comm_allreduce_f64(pmgpu_ctx* ctx, double* buf, size_t count);
 
 inline int grid_for(int n, int block, int num_sms, int per_sm) {
