@@ -69,24 +69,63 @@ def config_dict(args, world):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks
+    line).  The timed region is only tens of milliseconds, so the sampler is an NVML polling thread
+    (~1 kHz); `nvidia-smi -lms` is the fallback when NVML cannot be loaded."""
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.proc, self.path = index, None, None
+    def __init__(self, index, uuid=None):
+        self.index, self.uuid = index, uuid
+        self.proc, self.path, self.thread, self.nvml = None, None, None, None
+        self.sm, self.mx, self.bits, self.running = [], None, 0, False
+
+    def _nvml_loop(self):
+        nv, h = self.nvml, self.handle
+        while self.running:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            try:
+                self.handle = nv.nvmlDeviceGetHandleByUUID(self.uuid) if self.uuid else nv.nvmlDeviceGetHandleByIndex(self.index)
+            except Exception:
+                self.handle = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM))
+            self.nvml, self.running = nv, True
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+                                          "-lms", "20"], stdout=f, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.nvml is not None:
+            self.running = False
+            self.thread.join(timeout=2)
+            nv, reasons = self.nvml, []
+            for name, bit in (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                              ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap)):
+                if self.bits & int(bit):
+                    reasons.append(name)
+            if self.sm:
+                out = {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.mx, "reasons": reasons, "samples": len(self.sm), "source": "nvml"}
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -112,8 +151,16 @@ class ClockSampler:
         except OSError:
             pass
         if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                   "source": "nvidia-smi"}
         return out
+
+
+def gpu_uuid(torch, index):
+    try:
+        return "GPU-" + str(torch.cuda.get_device_properties(index).uuid)
+    except Exception:
+        return None
 
 
 def pinned_copy(a):
@@ -228,7 +275,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- headline: point-to-point loop, resident data --------------------------------------
     params = make_params(capi, capi.MIN_P2POINT, args.steps)
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, gpu_uuid(torch, local_rank))
     launches0 = ctx.launch_count
     ctx.timing_enable(True)
     barrier()

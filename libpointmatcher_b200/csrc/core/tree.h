@@ -203,16 +203,30 @@ PM_HD void lane_begin(Lane& s, float qx, float qy, float qz) {
 
 PM_HD bool lane_descending(const Lane& s, const TreeView& t) { return s.level < t.depth; }
 
-// one step of the plane descent
-PM_HD void lane_descend_step(Lane& s, const TreeView& t, float* plane, int stride) {
+// coordinate `dim` of (x, y, z) without a branch (the ternary chain compiles to divergent branches)
+PM_HD float select3(uint32_t dim, float x, float y, float z) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("{\n\t.reg .pred p0, p2;\n\tsetp.eq.u32 p0, %1, 0;\n\tsetp.eq.u32 p2, %1, 2;\n\tselp.f32 %0, %2, %3, p0;\n\tselp.f32 %0, %4, %0, p2;\n\t}"
+        : "=f"(r) : "r"(dim), "f"(x), "f"(y), "f"(z));
+    return r;
+#else
+    return dim == 0 ? x : (dim == 1 ? y : z);
+#endif
+}
+
+// one step of the plane descent; `w` is the current k-th best distance: a sibling whose split
+// plane is already farther than that can never be needed (w only shrinks), so it is not even
+// recorded as pending
+PM_HD void lane_descend_step(Lane& s, const TreeView& t, float* plane, int stride, float w) {
     const f2 sp = ldg2(t.splits + s.node);
-    const uint32_t dim = f2u(sp.y);
-    const float qd = dim == 0 ? s.qx : (dim == 1 ? s.qy : s.qz);
+    const float qd = select3(f2u(sp.y), s.qx, s.qy, s.qz);
     const float diff = fsub(qd, sp.x);
+    const float pl = fmul(diff, diff);
     s.node = 2 * s.node + (qd >= sp.x ? 1u : 0u);
     ++s.level;
-    s.trail |= 1u << s.level;
-    plane[s.level * stride] = fmul(diff, diff);
+    if (!(pl > w)) s.trail |= 1u << s.level;
+    plane[s.level * stride] = pl;
     PM_STAT(descent_steps);
 }
 
@@ -247,8 +261,10 @@ PM_HD void lane_scan_leaf(Lane& s, const TreeView& t, TopK<KMAX>& best) {
     PM_STAT(leaves);
 }
 
-// After a leaf: drop every pending level whose split plane is already out of reach.  Branch-free
-// over the levels (one LDS + compare + predicated bit-clear each), so the warp stays converged.
+// Drop every pending level whose split plane is out of reach of the current bound.  Branch-free
+// over the levels (one LDS + compare + predicated bit-clear each).  Worth its ~4 instructions per
+// level only when the bound has just shrunk under many pending levels (lane_wants_filter): the
+// first leaf of an unseeded search, or a seed that turned out to be far off.
 template <int KMAX>
 PM_HD void lane_filter_trail(Lane& s, const TreeView& t, const TopK<KMAX>& best, const float* plane, int stride) {
     const float w = best.worst_d();
@@ -260,13 +276,29 @@ PM_HD void lane_filter_trail(Lane& s, const TreeView& t, const TopK<KMAX>& best,
     s.trail = keep;
 }
 
-// One box test: the deepest pending sibling.  Returns true when it has to be searched (the lane
-// then continues with descend steps from it); false means "rejected", the caller tries the next
+#define PM_FILTER_MIN_PENDING 6
+PM_HD int popc32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+// w_before: the bound the last descent was made with
+PM_HD bool lane_wants_filter(const Lane& s, float w_before, float w_now) {
+    return w_now < w_before && popc32(s.trail) >= PM_FILTER_MIN_PENDING;
+}
+
+// One pending sibling, the deepest: plane test against the current bound first (cached distance,
+// one LDS), then the box test.  Returns true when the sibling has to be searched (the lane then
+// continues with descend steps from it); false means "rejected", the caller tries the next
 // pending level while s.trail != 0.
 template <int KMAX>
-PM_HD bool lane_box_step(Lane& s, const TreeView& t, const TopK<KMAX>& best) {
+PM_HD bool lane_box_step(Lane& s, const TreeView& t, const TopK<KMAX>& best, const float* plane, int stride) {
     const int l = 31 - clz32(s.trail);
     s.trail &= ~(1u << l);
+    PM_STAT(pops);
+    if (plane[l * stride] > best.worst_d()) return false;
     const uint32_t far = (s.node >> (s.level - l)) ^ 1u;
     PM_STAT(box_tests);
     const float db = box_dist2(s.qx, s.qy, s.qz, ldg4(t.boxes + 2 * (size_t)far), ldg4(t.boxes + 2 * (size_t)far + 1));
@@ -288,11 +320,12 @@ PM_HD uint32_t knn_search_single(const TreeView& t, float qx, float qy, float qz
     Lane s;
     lane_begin(s, qx, qy, qz);
     for (;;) {
-        while (lane_descending(s, t)) lane_descend_step(s, t, plane, 1);
+        const float w0 = best.worst_d();
+        while (lane_descending(s, t)) lane_descend_step(s, t, plane, 1, w0);
         lane_scan_leaf<KMAX>(s, t, best);
-        lane_filter_trail<KMAX>(s, t, best, plane, 1);
+        if (lane_wants_filter(s, w0, best.worst_d())) lane_filter_trail<KMAX>(s, t, best, plane, 1);
         bool found = false;
-        while (!found && s.trail != 0) found = lane_box_step<KMAX>(s, t, best);
+        while (!found && s.trail != 0) found = lane_box_step<KMAX>(s, t, best, plane, 1);
         if (!found) break;
     }
     return s.visited;

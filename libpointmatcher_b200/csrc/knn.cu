@@ -73,18 +73,22 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
     int rounds = 0;
     while (__any_sync(0xffffffffu, running)) {
         // descend: one level per step for every lane that is not at a leaf yet
+        const float w0 = best.worst_d();
         while (__any_sync(0xffffffffu, running && lane_descending(s, tree)))
-            if (running && lane_descending(s, tree)) lane_descend_step(s, tree, plane, KNN_BLOCK);
-        // leaf + plane filter of the pending levels
+            if (running && lane_descending(s, tree)) lane_descend_step(s, tree, plane, KNN_BLOCK, w0);
+        // leaf; then the plane filter over all pending levels where it pays
+        bool refilter = false;
         if (running) {
             lane_scan_leaf<KMAX>(s, tree, best);
-            lane_filter_trail<KMAX>(s, tree, best, plane, KNN_BLOCK);
+            refilter = lane_wants_filter(s, w0, best.worst_d());
         }
-        // box tests, deepest pending sibling first, one per step, until every lane has either a
-        // subtree to search or nothing left
+        if (__any_sync(0xffffffffu, refilter))
+            if (refilter) lane_filter_trail<KMAX>(s, tree, best, plane, KNN_BLOCK);
+        // pending siblings, deepest first, one per step, until every lane has either a subtree to
+        // search or nothing left
         bool found = false;
         while (__any_sync(0xffffffffu, running && !found && s.trail != 0))
-            if (running && !found && s.trail != 0) found = lane_box_step<KMAX>(s, tree, best);
+            if (running && !found && s.trail != 0) found = lane_box_step<KMAX>(s, tree, best, plane, KNN_BLOCK);
         if (running && !found) running = false;  // search complete
         ++rounds;
         if (running && rounds >= budget) {
