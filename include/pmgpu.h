@@ -179,10 +179,21 @@ typedef struct pmgpu_icp_params {
 } pmgpu_icp_params;
 int pmgpu_icp_run(pmgpu_ctx* ctx, const pmgpu_icp_params* params, const float* T_iter_init, float* T_iter_out, int* iterations_out,
                   float* cov_out, float* stats_out);
-/* enqueue exactly `n_iterations` iterations without synchronising (bench inner loop) */
+/* enqueue exactly `n_iterations` iteration slots without synchronising (bench inner loop).
+ *
+ * Capped matching.  Inside the fused loop nothing outside can see the matches the outlier
+ * filters reject, so with maxDist = inf and a non-empty filter chain the matcher of iteration
+ * i+1 stops at a squared radius of 2 x the largest distance the filters of iteration i had to
+ * know exactly (their order statistics and limits).  The select kernels verify afterwards that
+ * the new order statistics and limits lie below the radius used; if they do, T is bit-identical
+ * to the uncapped loop.  If not, the slot is void (T_iter and the iteration count stay as they
+ * were) and the next slot matches without a cap.  pmgpu_icp_run tops up voided slots itself;
+ * a caller of pmgpu_icp_enqueue compares iterations_out with the slots it enqueued.
+ * pmgpu_icp_cap_redos: voided slots since pmgpu_icp_reset (valid after pmgpu_icp_result). */
 int pmgpu_icp_enqueue(pmgpu_ctx* ctx, const pmgpu_icp_params* params, int n_iterations);
 int pmgpu_icp_reset(pmgpu_ctx* ctx, const float* T_iter_init);
 int pmgpu_icp_result(pmgpu_ctx* ctx, float* T_iter_out, int* iterations_out, float* cov_out, float* stats_out);
+int pmgpu_icp_cap_redos(const pmgpu_ctx* ctx);
 
 /* ---- multi-GPU: queries sharded over ranks, replicated reference ------------------------
  * After pmgpu_comm_init the quantile histograms and the normal-equation sums of

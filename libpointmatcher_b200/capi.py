@@ -83,6 +83,7 @@ SIGNATURES = {
     "pmgpu_icp_enqueue": (C.c_int, [C.c_void_p, C.POINTER(IcpParams), C.c_int]),
     "pmgpu_icp_reset": (C.c_int, [C.c_void_p, _fp]),
     "pmgpu_icp_result": (C.c_int, [C.c_void_p, _fp, C.POINTER(C.c_int), _fp, _fp]),
+    "pmgpu_icp_cap_redos": (C.c_int, [C.c_void_p]),
     "pmgpu_comm_unique_id": (C.c_int, [C.c_void_p]),
     "pmgpu_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "pmgpu_comm_destroy": (C.c_int, [C.c_void_p]),
@@ -308,7 +309,7 @@ class Context:
         it = C.c_int(0)
         self._check(lib.pmgpu_icp_run(self.h, C.byref(params), _f(_T(T_iter_init)), _f(T), C.byref(it), _f(cov), _f(stats)))
         self.k = params.knn
-        return dict(T_iter=np.array(T), iterations=it.value, cov=np.array(cov), stats=_stats(stats))
+        return dict(T_iter=np.array(T), iterations=it.value, cov=np.array(cov), stats=_stats(stats), cap_redos=int(lib.pmgpu_icp_cap_redos(self.h)))
 
     def icp_reset(self, T_iter_init=None):
         self._check(lib.pmgpu_icp_reset(self.h, _f(_T(T_iter_init))))
@@ -323,7 +324,7 @@ class Context:
         stats = np.zeros(5, np.float32)
         it = C.c_int(0)
         self._check(lib.pmgpu_icp_result(self.h, _f(T), C.byref(it), _f(cov), _f(stats)))
-        return dict(T_iter=np.array(T), iterations=it.value, cov=np.array(cov), stats=_stats(stats))
+        return dict(T_iter=np.array(T), iterations=it.value, cov=np.array(cov), stats=_stats(stats), cap_redos=int(lib.pmgpu_icp_cap_redos(self.h)))
 
     # ---- multi-GPU
     def comm_init(self, unique_id, rank, nranks):

@@ -155,12 +155,16 @@ int enqueue_iteration(pmgpu_ctx* ctx, const pmgpu_icp_params* p, bool gated) {
     ctx->stage_begin(0);
     SelectSpec spec;
     PM_TRY(make_select_spec(ctx, p->nfilters, p->filter_type, p->filter_param, &spec));
+    // capped matching: only where nothing observable depends on the matches the filters reject —
+    // the fused loop, an unbounded maxDist (a finite one decides which matches count as missing),
+    // and a non-empty filter chain
+    const bool use_cap = gated && ctx->cap_enabled && p->nfilters > 0 && max_r2 == pm_inf();
     PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, ctx->nq, true, gated, false, p->knn, max_r2,
-                      ctx->seed_k == 1 && p->knn == 1 && ctx->seed_enabled, ctx->ids.p, ctx->dists.p));
+                      ctx->seed_k == 1 && p->knn == 1 && ctx->seed_enabled, ctx->ids.p, ctx->dists.p, use_cap));
     ctx->seed_k = p->knn;
     ctx->stage_end();
     ctx->stage_begin(1);
-    PM_TRY(launch_weights(ctx, spec, gated, false));
+    PM_TRY(launch_weights(ctx, spec, gated, use_cap));
     ctx->stage_end();
     ctx->stage_begin(2);
     PM_TRY(launch_minimize(ctx, p->minimizer, true, gated, p));
@@ -203,6 +207,9 @@ int pmgpu_ctx_create(int device, pmgpu_ctx** ctx_out) {
         cudaGetLastError();
     }
     ctx->seed_enabled = getenv("PMGPU_NO_SEED") == nullptr;
+    ctx->time_stage2 = getenv("PMGPU_TIME_STAGE2") != nullptr;
+    ctx->cap_enabled = getenv("PMGPU_NO_CAP") == nullptr;
+    if (const char* m = getenv("PMGPU_CAP_MARGIN")) ctx->cap_margin = (float)atof(m);
     if (const char* b = getenv("PMGPU_KNN_BUDGET")) ctx->knn_budget = atoi(b) > 0 ? atoi(b) : 1;  // 1: (almost) everything through stage 2
     memset(ctx->state_host, 0, sizeof(IcpState));
     mat4_identity(ctx->state_host->T_iter);
@@ -491,6 +498,10 @@ int pmgpu_icp_reset(pmgpu_ctx* ctx, const float* T_iter_init) {
     h->iterations = 0;
     h->counter = 0;
     h->visits = 0;
+    h->cap = pm_inf();
+    h->cap_need = 0.f;
+    h->redo = 0;
+    h->redo_count = 0;
     // TransformationCheckers::init (TransformationCheckersImpl.cpp:107-124): history starts with T_iter
     const Quat q = quat_from_mat4(h->T_iter);
     h->hist_q[0][0] = q.w; h->hist_q[0][1] = q.x; h->hist_q[0][2] = q.y; h->hist_q[0][3] = q.z;
@@ -530,6 +541,8 @@ int pmgpu_icp_result(pmgpu_ctx* ctx, float* T_iter_out, int* iterations_out, flo
     return device_status(ctx);
 }
 
+int pmgpu_icp_cap_redos(const pmgpu_ctx* ctx) { return ctx ? ctx->state_host->redo_count : 0; }
+
 int pmgpu_icp_run(pmgpu_ctx* ctx, const pmgpu_icp_params* params, const float* T_iter_init, float* T_iter_out, int* iterations_out, float* cov_out,
                   float* stats_out) {
     if (!ctx) return PMGPU_ERR_BAD_ARG;
@@ -540,7 +553,15 @@ int pmgpu_icp_run(pmgpu_ctx* ctx, const pmgpu_icp_params* params, const float* T
     // ICP.cpp:371: `while (iterate)` runs the body at least once, Counter stops it after
     // maxIterationCount checks (max(1, maxIterationCount) iterations)
     const int n = params->max_iterations > 1 ? params->max_iterations : 1;
-    PM_TRY(pmgpu_icp_enqueue(ctx, params, n));
+    // n iteration slots; a slot whose capped match was void (IcpState::redo) does not count as an
+    // iteration, so top up until the checkers have stopped the loop (rare: normally one pass)
+    for (int slots = n;;) {
+        PM_TRY(pmgpu_icp_enqueue(ctx, params, slots));
+        PM_TRY(pull_state(ctx));
+        const IcpState* h = ctx->state_host;
+        if (h->status != PMGPU_OK || !h->iterate || h->iterations >= n) break;
+        slots = n - h->iterations;
+    }
     const bool with_cov = params->minimizer == PMGPU_MIN_P2POINT_COV || params->minimizer == PMGPU_MIN_P2PLANE_COV;
     if (with_cov) {
         PM_TRY(pull_state(ctx));

@@ -22,12 +22,29 @@ namespace {
 
 constexpr int KNN_BLOCK = 128;
 
+// Search radius of one launch and what an empty result slot is written as.  Without a cap (or with
+// a cap that the caller's maxDist already undercuts) a miss is "no match within maxDist": id -1,
+// dist +inf, the pair the reference's Matches carry (MatchersImpl.cpp:95-99).  Under the cap a miss
+// only says "farther than the cap": it stays a finite, rejected match (id -2, dist FLT_MAX), so
+// the quantile population and the rejected-point statistics are the ones the exact search gives.
+struct Cap { float r2; int miss_id; float miss_d; };
+#define PM_CAPPED_ID (-2)
+#define PM_CAPPED_DIST 3.402823466e+38f
+__device__ __forceinline__ Cap knn_cap(const IcpState* state, int use_cap, float max_r2) {
+    Cap c = {max_r2, -1, pm_inf()};
+    if (use_cap) {
+        const float r = state->cap;
+        if (r < max_r2) { c.r2 = r; c.miss_id = PM_CAPPED_ID; c.miss_d = PM_CAPPED_DIST; }
+    }
+    return c;
+}
+
 template <int KMAX>
 __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4* __restrict__ queries, int nq, const IcpState* __restrict__ state,
                                                         int use_T, int gated, int self_query, int k, float max_r2,
                                                         const f4* __restrict__ ref_orig, int use_seed, int32_t* __restrict__ ids,
                                                         float* __restrict__ dists, unsigned long long* visits, int budget,
-                                                        uint32_t* __restrict__ overflow, unsigned* overflow_count) {
+                                                        uint32_t* __restrict__ overflow, unsigned* overflow_count, int use_cap) {
     extern __shared__ float s_plane[];  // [depth + 1][KNN_BLOCK]: cached plane distances, one column per lane
     __shared__ Mat4 sT;
     if (gated && state->iterate == 0) return;
@@ -41,7 +58,10 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
     uint32_t qi = (uint32_t)t;
     Lane s;
     TopK<KMAX> best;
-    best.init(k, max_r2);
+    // fused ICP loop: the search may stop at the radius the previous iteration's outlier filters
+    // make sufficient (state->cap, verified by the select kernels afterwards)
+    const Cap cap = knn_cap(state, use_cap, max_r2);
+    best.init(k, cap.r2);
     s.visited = 0;
     if (running) {
         f4 q = queries[t];
@@ -102,8 +122,8 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
         static_for<0, KMAX>([&](auto J) {
             if (J < k) {
                 const bool valid = best.id[J] != PM_NO_ID && best.d[J] != pm_inf();
-                oi[J] = valid ? best.id[J] : -1;
-                od[J] = valid ? best.d[J] : pm_inf();
+                oi[J] = valid ? best.id[J] : cap.miss_id;
+                od[J] = valid ? best.d[J] : cap.miss_d;
             }
         });
     }
@@ -128,7 +148,7 @@ template <int KMAX>
 __global__ void __launch_bounds__(128) knn_overflow_kernel(TreeView tree, const f4* __restrict__ queries, const IcpState* __restrict__ state, int use_T,
                                                            int gated, int self_query, int k, float max_r2, const uint32_t* __restrict__ overflow,
                                                            unsigned* overflow_count, unsigned* next_count, int32_t* __restrict__ ids,
-                                                           float* __restrict__ dists, unsigned long long* visits) {
+                                                           float* __restrict__ dists, unsigned long long* visits, int use_cap) {
     __shared__ uint32_t s_stack[4][OVF_STACK];
     __shared__ Mat4 sT;
     if (gated && state->iterate == 0) return;
@@ -138,6 +158,7 @@ __global__ void __launch_bounds__(128) knn_overflow_kernel(TreeView tree, const 
         __syncthreads();
     }
     const unsigned count = *overflow_count;
+    const Cap cap = knn_cap(state, use_cap, max_r2);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lanes_lt = (1u << lane) - 1u;
     uint32_t* stack = s_stack[warp];
@@ -150,7 +171,7 @@ __global__ void __launch_bounds__(128) knn_overflow_kernel(TreeView tree, const 
         if (self_query) { qi = __float_as_uint(q.w); q.w = 1.f; }
         if (use_T) q = transform_point(sT, q);
         TopK<KMAX> best;
-        best.init(k, max_r2);
+        best.init(k, cap.r2);
         // seed: the candidates stage 1 left in the result arrays (ascending, real points)
         for (int j = 0; j < k; ++j) {
             const int id = ids[(size_t)qi * k + j];
@@ -234,8 +255,8 @@ __global__ void __launch_bounds__(128) knn_overflow_kernel(TreeView tree, const 
                 int bi;
                 best.get(j, bd, bi);
                 const bool valid = bi != PM_NO_ID && bd != pm_inf();
-                ids[(size_t)qi * k + j] = valid ? bi : -1;
-                dists[(size_t)qi * k + j] = valid ? bd : pm_inf();
+                ids[(size_t)qi * k + j] = valid ? bi : cap.miss_id;
+                dists[(size_t)qi * k + j] = valid ? bd : cap.miss_d;
             }
         }
         __syncwarp();
@@ -245,7 +266,7 @@ __global__ void __launch_bounds__(128) knn_overflow_kernel(TreeView tree, const 
 
 template <int KMAX>
 int launch_one(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, bool use_T, bool gated, bool self_query, int k, float max_r2,
-               bool use_seed, int32_t* ids, float* dists) {
+               bool use_seed, int32_t* ids, float* dists, bool use_cap) {
     const int grid = (nq + KNN_BLOCK - 1) / KNN_BLOCK;
     if (grid == 0) return PMGPU_OK;
     const size_t smem = (size_t)(tree.depth + 2) * KNN_BLOCK * sizeof(float);
@@ -256,10 +277,11 @@ int launch_one(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, 
     ctx->knn_parity ^= 1;
     knn_kernel<KMAX><<<grid, KNN_BLOCK, smem, ctx->stream>>>(tree, queries, nq, ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k, max_r2,
                                                             ctx->ref_orig.p, use_seed ? 1 : 0, ids, dists, &ctx->state->visits, ctx->knn_budget,
-                                                            ctx->overflow.p, cnt);
+                                                            ctx->overflow.p, cnt, use_cap ? 1 : 0);
+    if (ctx->time_stage2) { ctx->stage_end(); ctx->stage_begin(3); }
     const int grid2 = min(ctx->num_sms * 4, (nq + 3) / 4);
     knn_overflow_kernel<KMAX><<<grid2, 128, 0, ctx->stream>>>(tree, queries, ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k, max_r2,
-                                                           ctx->overflow.p, cnt, cnt_next, ids, dists, &ctx->state->visits);
+                                                           ctx->overflow.p, cnt, cnt_next, ids, dists, &ctx->state->visits, use_cap ? 1 : 0);
     ctx->launches += 2;
     PM_CUDA_TRY(ctx, cudaGetLastError());
     return PMGPU_OK;
@@ -269,10 +291,11 @@ int launch_one(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, 
 
 // use_T: apply state->T_iter to every query; gated: no-op once state->iterate == 0;
 // self_query: `queries` is the leaf-ordered reference itself (results indexed by original column);
-// use_seed (k = 1): `ids` still holds the previous matches of the same reading
+// use_seed (k = 1): `ids` still holds the previous matches of the same reading;
+// use_cap: stop at min(max_r2, state->cap)
 int launch_knn(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, bool use_T, bool gated, bool self_query, int k, float max_r2,
-               bool use_seed, int32_t* ids, float* dists) {
-#define PM_KNN_CASE(K) return launch_one<K>(ctx, tree, queries, nq, use_T, gated, self_query, k, max_r2, use_seed, ids, dists)
+               bool use_seed, int32_t* ids, float* dists, bool use_cap) {
+#define PM_KNN_CASE(K) return launch_one<K>(ctx, tree, queries, nq, use_T, gated, self_query, k, max_r2, use_seed, ids, dists, use_cap)
     if (k == 1) PM_KNN_CASE(1);
     if (k <= 4) PM_KNN_CASE(4);
     if (k <= 8) PM_KNN_CASE(8);

@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(ACC_BLOCK) accumulate_kernel(const f4* __restr
                                                                int compose, pmgpu_icp_params ck) {
     constexpr int NS = MODE == 1 ? NS_PLANE : NS_POINT;
     __shared__ Mat4 sT;
-    if (gated && state->iterate == 0) return;
+    // redo: this iteration's capped match was void (select_finish) — leave T_iter as it is
+    if (gated && (state->iterate == 0 || state->redo)) return;
     if (threadIdx.x < 16) sT.m[threadIdx.x] = state->T_iter.m[threadIdx.x];
     __syncthreads();
     double acc[NS];
@@ -336,7 +337,7 @@ __device__ void finalize_body(const double* partials, int nblocks, double* sums,
 template <int MODE>
 __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ sums, int phase,
                                                        IcpState* state, int gated, int compose, pmgpu_icp_params ck) {
-    if (gated && state->iterate == 0) return;
+    if (gated && (state->iterate == 0 || state->redo)) return;
     finalize_body<MODE>(partials, nblocks, sums, phase, state, compose, ck);
 }
 

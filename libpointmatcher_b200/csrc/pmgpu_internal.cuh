@@ -82,6 +82,13 @@ struct IcpState {
     unsigned long long sel_rank[PM_MAX_FILTERS];   // remaining rank inside the selected bucket
     unsigned ticket[4];          // "last block" counters: 0 select, 1 minimise, 2 covariance
     unsigned overflow_count[2];  // kNN stage-2 queue lengths (ping-pong between consecutive launches)
+    // adaptive search radius of the fused loop (DESIGN.md "capped matching"): squared radius the
+    // NEXT match may stop at, the largest distance the filters of THIS iteration needed to know
+    // exactly, and the flag that voids an iteration whose cap turned out too small
+    float cap;
+    float cap_need;
+    int redo;
+    int redo_count;
     // minimiser outputs
     float cov[36];
     float stats[5];              // pointUsedRatio, weightedPointUsedRatio, nbRejectedMatches, nbRejectedPoints, nbKept
@@ -143,6 +150,9 @@ struct pmgpu_ctx {
     int knn_parity = 0;
     int knn_budget = 16;             // leaves a lane may scan before its query goes to stage 2
     bool seed_enabled = true;        // PMGPU_NO_SEED=1 switches the seeding off (A/B profiling)
+    bool cap_enabled = true;         // PMGPU_NO_CAP=1: the fused loop matches without the adaptive radius
+    float cap_margin = 2.0f;         // cap = margin x (largest squared distance the last filters needed); PMGPU_CAP_MARGIN
+    bool time_stage2 = false;        // PMGPU_TIME_STAGE2=1: report kNN stage 2 in the "covariance" timing slot (profiling)
     pm::DevBuf<int32_t> ids_tmp;     // un-permute staging for downloads
     pm::DevBuf<float> dists_tmp;
 
@@ -207,11 +217,11 @@ int build_tree(pmgpu_ctx* ctx);
 int morton_order(pmgpu_ctx* ctx);
 // knn.cu
 int launch_knn(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, bool use_T, bool gated, bool self_query, int k, float max_r2,
-               bool use_seed, int32_t* ids, float* dists);
+               bool use_seed, int32_t* ids, float* dists, bool use_cap = false);
 // select.cu
 int make_select_spec(pmgpu_ctx* ctx, int nfilters, const int* types, const float* params, SelectSpec* spec);
 int select_reserve(pmgpu_ctx* ctx);
-int launch_weights(pmgpu_ctx* ctx, const SelectSpec& spec, bool gated, bool pass0_done);
+int launch_weights(pmgpu_ctx* ctx, const SelectSpec& spec, bool gated, bool cap_active);
 int launch_materialize_weights(pmgpu_ctx* ctx);
 // minimize.cu
 int launch_minimize(pmgpu_ctx* ctx, int minimizer, bool compose_and_check, bool gated, const pmgpu_icp_params* checks);

@@ -20,7 +20,8 @@ constexpr int HIST_BLOCK = 256;
 
 // pass 0: one histogram serves every quantile filter (slot 0); pass 1, 2: one per filter
 __global__ void __launch_bounds__(HIST_BLOCK) hist_kernel(const float* __restrict__ dists, size_t total, int pass, SelectSpec spec, IcpState* state,
-                                                          int gated, int do_init, int do_pick, unsigned* __restrict__ hist) {
+                                                          int gated, int do_init, int do_pick, unsigned* __restrict__ hist, int cap_active,
+                                                          float cap_margin) {
     __shared__ unsigned sh[PM_HIST_BINS];
     if (gated && state->iterate == 0) return;
     if (do_init && blockIdx.x == 0 && threadIdx.x == 0) select_init_limits(state, spec);
@@ -51,10 +52,12 @@ __global__ void __launch_bounds__(HIST_BLOCK) hist_kernel(const float* __restric
         select_pick(hist + (size_t)(pass == 0 ? 0 : slot) * PM_HIST_BINS, pass, spec.quantile(f), f, spec.factor(f), state, pass != 0 || last);
         ++slot;
     }
+    if (pass == 2 && threadIdx.x == 0) select_finish(state, cap_active, cap_margin);
 }
 
 // sharded reading: the scan runs after the histograms have been all-reduced
-__global__ void __launch_bounds__(1024) pick_kernel(unsigned* __restrict__ hist, int pass, SelectSpec spec, IcpState* state, int gated) {
+__global__ void __launch_bounds__(1024) pick_kernel(unsigned* __restrict__ hist, int pass, SelectSpec spec, IcpState* state, int gated,
+                                                    int cap_active, float cap_margin) {
     if (gated && state->iterate == 0) return;
     const int nq = spec.n_quantile();
     int slot = 0;
@@ -64,11 +67,15 @@ __global__ void __launch_bounds__(1024) pick_kernel(unsigned* __restrict__ hist,
         select_pick(hist + (size_t)(pass == 0 ? 0 : slot) * PM_HIST_BINS, pass, spec.quantile(f), f, spec.factor(f), state, pass != 0 || last);
         ++slot;
     }
+    if (pass == 2 && threadIdx.x == 0) select_finish(state, cap_active, cap_margin);
 }
 
-__global__ void init_limits_kernel(IcpState* state, SelectSpec spec, int gated) {
+__global__ void init_limits_kernel(IcpState* state, SelectSpec spec, int gated, int cap_active, float cap_margin) {
     if (gated && state->iterate == 0) return;
-    if (threadIdx.x == 0 && blockIdx.x == 0) select_init_limits(state, spec);
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        select_init_limits(state, spec);
+        select_finish(state, cap_active, cap_margin);
+    }
 }
 
 __global__ void weights_kernel(const float* __restrict__ dists, size_t total, const IcpState* __restrict__ state, float* __restrict__ w) {
@@ -115,28 +122,28 @@ int select_reserve(pmgpu_ctx* ctx) {
     return PMGPU_OK;
 }
 
-// pass0_done: the kNN kernel already initialised the limits and ran pass 0 (fused ICP loop)
-int launch_weights(pmgpu_ctx* ctx, const SelectSpec& spec, bool gated, bool pass0_done) {
+// cap_active: the distances come from a capped match (fused ICP loop) — verify the cap and set the next
+int launch_weights(pmgpu_ctx* ctx, const SelectSpec& spec, bool gated, bool cap_active) {
     cudaStream_t st = ctx->stream;
     PM_TRY(select_reserve(ctx));
     const int g = gated ? 1 : 0;
     const int nquant = spec.n_quantile();
+    const int ca = cap_active ? 1 : 0;
     if (nquant == 0) {
-        if (!pass0_done) {
-            init_limits_kernel<<<1, 32, 0, st>>>(ctx->state, spec, g);
-            ctx->launches += 1;
-        }
+        init_limits_kernel<<<1, 32, 0, st>>>(ctx->state, spec, g, ca, ctx->cap_margin);
+        ctx->launches += 1;
     } else {
         const size_t total = (size_t)ctx->k * ctx->nq;
         const size_t want = (total + HIST_BLOCK * 4 - 1) / (HIST_BLOCK * 4);
         const int grid = grid_for((int)(want > 0x7fffffff ? 0x7fffffff : want) * HIST_BLOCK, HIST_BLOCK, ctx->num_sms, 4);
         const bool split = ctx->nranks > 1;
-        for (int pass = pass0_done ? 1 : 0; pass < 3; ++pass) {
-            hist_kernel<<<grid, HIST_BLOCK, 0, st>>>(ctx->dists.p, total, pass, spec, ctx->state, g, pass == 0 ? 1 : 0, split ? 0 : 1, ctx->hist.p);
+        for (int pass = 0; pass < 3; ++pass) {
+            hist_kernel<<<grid, HIST_BLOCK, 0, st>>>(ctx->dists.p, total, pass, spec, ctx->state, g, pass == 0 ? 1 : 0, split ? 0 : 1, ctx->hist.p, ca,
+                                                     ctx->cap_margin);
             ctx->launches += 1;
             if (split) {
                 PM_TRY(comm_allreduce_u32(ctx, ctx->hist.p, (size_t)(pass == 0 ? 1 : nquant) * PM_HIST_BINS));
-                pick_kernel<<<1, 1024, 0, st>>>(ctx->hist.p, pass, spec, ctx->state, g);
+                pick_kernel<<<1, 1024, 0, st>>>(ctx->hist.p, pass, spec, ctx->state, g, ca, ctx->cap_margin);
                 ctx->launches += 1;
             }
         }

@@ -27,6 +27,29 @@ __device__ __forceinline__ void select_init_limits(IcpState* st, const SelectSpe
     }
     st->limit_all = all;
     st->has_filters = sp.nfilters > 0 ? 1 : 0;
+    st->cap_need = 0.f;
+}
+
+// Capped matching (fused ICP loop).  The matcher of this iteration stopped at squared radius
+// state->cap, so every distance above it is only known to be "larger than the cap".  The filter
+// chain is exact as long as everything it had to know exactly — each order statistic and each
+// limit — lies below that radius; `need` is the largest of them.  If it does not, the iteration is
+// void: the minimiser kernels skip it (redo) and the next match runs without a cap.  Otherwise
+// the next match may stop at margin x need.  Called by one thread once all limits are final.
+__device__ __forceinline__ void select_finish(IcpState* st, int cap_active, float margin) {
+    if (!cap_active) {
+        st->redo = 0;
+        return;
+    }
+    const float need = st->has_filters ? fmaxf(st->cap_need, st->limit_all) : pm_inf();
+    if (st->cap != pm_inf() && !(need < st->cap)) {
+        st->cap = pm_inf();
+        st->redo = 1;
+        st->redo_count += 1;
+    } else {
+        st->cap = __fmul_rn(need, margin);  // +inf stays +inf
+        st->redo = 0;
+    }
 }
 
 // bin of a distance in `pass`, or -1 when it lies outside the bucket selected so far
@@ -132,6 +155,7 @@ __device__ __forceinline__ void select_pick(unsigned* hist, int pass, float quan
                     const float lim = factor != 0.f ? __fmul_rn(factor, value) : value;
                     state->limit[f] = lim;
                     atomicMin(reinterpret_cast<int*>(&state->limit_all), __float_as_int(lim));  // non-negative floats order like ints
+                    atomicMax(reinterpret_cast<int*>(&state->cap_need), __float_as_int(fmaxf(value, lim)));
                 }
             }
             excl += h;

@@ -303,3 +303,75 @@ def test_icp_sequence_resident_map(oracle, synth):
     assert (T1 == T_plain).all() and (T3 == T_plain).all()
     plain.ctx.close()
     seq.ctx.close()
+
+
+# ---------------------------------------------------------------------------------- capped matching
+def _fused_run(monkeypatch, env, rd, rf, nrm, params_kw, T0=None):
+    """One fused registration through the C ABI in a fresh context created under `env`."""
+    from libpointmatcher_b200 import capi
+    for k in ("PMGPU_NO_CAP", "PMGPU_CAP_MARGIN"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    with capi.Context(0) as ctx:
+        ctx.set_reference(rf, normals=nrm)
+        ctx.set_reading(rd)
+        return ctx.icp_run(capi.make_params(**params_kw), T0)
+
+
+@pytest.mark.parametrize("chain", [
+    dict(knn=1, filters=[(2, 0.75)], minimizer=0, max_iterations=12),
+    dict(knn=1, filters=[(2, 0.9)], minimizer=1, max_iterations=12),
+    dict(knn=3, filters=[(1, 2.5)], minimizer=1, max_iterations=8),
+    dict(knn=1, filters=[(0, 0.4), (1, 3.0)], minimizer=3, max_iterations=8),
+    dict(knn=1, filters=[(0, 0.05)], minimizer=0, max_iterations=6),
+])
+def test_capped_loop_is_bit_identical_to_uncapped(monkeypatch, oracle, synth, chain):
+    """The adaptive search radius of the fused loop (pmgpu.h "capped matching") must not change a
+    single bit of what the loop returns: T, iteration count, statistics, covariance."""
+    rd, rf, _ = synth.scan_pair(60000)
+    nrm = oracle.surface_normals(rf, knn=10, nthreads=8)["normals"]
+    plain = _fused_run(monkeypatch, {"PMGPU_NO_CAP": "1"}, rd, rf, nrm, chain)
+    capped = _fused_run(monkeypatch, {}, rd, rf, nrm, chain)
+    assert plain["cap_redos"] == 0
+    assert capped["iterations"] == plain["iterations"] == chain["max_iterations"]
+    assert (bits(capped["T_iter"]) == bits(plain["T_iter"])).all()
+    assert capped["stats"] == plain["stats"]
+    assert (bits(capped["cov"]) == bits(plain["cov"])).all()
+
+
+def test_cap_violation_voids_the_slot_and_is_repaired(monkeypatch, oracle, synth):
+    """A cap that is always too small (margin < 1) is detected by the select kernels every time it
+    is used: the slot is void, the next one runs uncapped, and the result is still exact."""
+    rd, rf, _ = synth.scan_pair(60000)
+    nrm = oracle.surface_normals(rf, knn=10, nthreads=8)["normals"]
+    chain = dict(knn=1, filters=[(2, 0.8)], minimizer=1, max_iterations=9)
+    plain = _fused_run(monkeypatch, {"PMGPU_NO_CAP": "1"}, rd, rf, nrm, chain)
+    tight = _fused_run(monkeypatch, {"PMGPU_CAP_MARGIN": "0.5"}, rd, rf, nrm, chain)
+    assert tight["cap_redos"] >= 4
+    assert tight["iterations"] == plain["iterations"] == 9
+    assert (bits(tight["T_iter"]) == bits(plain["T_iter"])).all()
+    assert tight["stats"] == plain["stats"]
+
+
+def test_cap_not_used_with_finite_maxdist_or_staged_calls(monkeypatch, oracle, synth):
+    """A finite matcher maxDist decides which matches count as missing (infinite distance, left out
+    of the quantile population), so the cap must stay off; and staged calls return exact matches."""
+    from libpointmatcher_b200 import capi
+    rd, rf, _ = synth.scan_pair(30000)
+    chain = dict(knn=2, max_dist=0.3, filters=[(2, 0.7)], minimizer=0, max_iterations=6)
+    plain = _fused_run(monkeypatch, {"PMGPU_NO_CAP": "1"}, rd, rf, None, chain)
+    capped = _fused_run(monkeypatch, {"PMGPU_CAP_MARGIN": "0.01"}, rd, rf, None, chain)
+    assert capped["cap_redos"] == 0
+    assert (bits(capped["T_iter"]) == bits(plain["T_iter"])).all() and capped["stats"] == plain["stats"]
+    monkeypatch.delenv("PMGPU_CAP_MARGIN", raising=False)
+    with capi.Context(0) as ctx:      # after a fused run, staged matching is still exact and uncapped
+        ctx.set_reference(rf)
+        ctx.set_reading(rd)
+        ctx.icp_run(capi.make_params(knn=1, filters=[(2, 0.5)], minimizer=0, max_iterations=5))
+        ids, dists, _ = ctx.knn(None, 1, 0.0, np.inf)
+        ib, db = oracle.bruteforce_knn(rf, rd, 1, np.inf, nthreads=8)
+        assert (bits(dists) == bits(db)).all() and (ids >= 0).all()
+        w, lim = ctx.weights([(2, 0.5)])
+        T, _, _ = ctx.minimize(0)
+        assert np.isfinite(T).all()
