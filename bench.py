@@ -211,7 +211,10 @@ def run_reference(args, rank, world):
 # ------------------------------------------------------------------------------------------------
 def timed_iterations(ctx, capi, torch, params, steps, warmup, flush_buf, T0=None):
     """W untimed warm-up iterations, reset, then exactly `steps` iterations, each bracketed by
-    CUDA events on the context's stream with an L2 flush in between.  Returns (ms list, result)."""
+    CUDA events on the context's stream with an L2 flush in between.  An iteration slot whose
+    capped match was void (pmgpu.h "capped matching") does not advance the loop: its time stays in
+    the total and further timed slots are enqueued until `steps` iterations have executed.
+    Returns (ms list, result)."""
     stream = torch.cuda.ExternalStream(ctx.stream)
     ctx.icp_reset(T0)
     if warmup > 0:
@@ -219,17 +222,21 @@ def timed_iterations(ctx, capi, torch, params, steps, warmup, flush_buf, T0=None
     ctx.sync()
     ctx.timing_collect()  # drop the warm-up intervals (they contain the lazy module load of the first launch)
     ctx.icp_reset(T0)
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
-    for i in range(steps):
-        with torch.cuda.stream(stream):
-            flush_buf.zero_()
-        starts[i].record(stream)
-        ctx.icp_enqueue(params, 1)
-        stops[i].record(stream)
-    ctx.sync()
-    res = ctx.icp_result()
-    return [s.elapsed_time(e) for s, e in zip(starts, stops)], res
+    ms, todo = [], steps
+    while todo > 0:
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(todo)]
+        stops = [torch.cuda.Event(enable_timing=True) for _ in range(todo)]
+        for i in range(todo):
+            with torch.cuda.stream(stream):
+                flush_buf.zero_()
+            starts[i].record(stream)
+            ctx.icp_enqueue(params, 1)
+            stops[i].record(stream)
+        ctx.sync()
+        res = ctx.icp_result()
+        ms += [s.elapsed_time(e) for s, e in zip(starts, stops)]
+        todo = steps - res["iterations"]
+    return ms, res
 
 
 def run_ours(args, rank, world, local_rank):
@@ -301,6 +308,7 @@ def run_ours(args, rank, world, local_rank):
     e1.record(stream)
     ctx.sync()
     b2b_ms = e0.elapsed_time(e1)
+    b2b_it = max(1, ctx.icp_result()["iterations"])
 
     # roofline of the dominant kernel (kNN match): algorithmic bytes / measured launch time
     knn_ms, knn_n = stage["knn"]
@@ -326,10 +334,25 @@ def run_ours(args, rank, world, local_rank):
     extra = {
         "stage_ms_per_iteration": {k: v[0] / max(1, args.steps) for k, v in stage.items()},
         "knn_queries_per_s": (nq_local * (world if dist_on else 1)) / (knn_avg_ms * 1e-3) if knn_avg_ms > 0 else None,
-        "back_to_back_iterations_per_s": args.steps / (b2b_ms * 1e-3),
-        "back_to_back_ms_per_step": b2b_ms / args.steps,
+        "back_to_back_iterations_per_s": b2b_it / (b2b_ms * 1e-3),
+        "back_to_back_ms_per_step": b2b_ms / b2b_it,
         "per_iteration_ms_first_last": [ms[0], ms[-1]],
+        "capped_matching": {"enabled": os.environ.get("PMGPU_NO_CAP") is None, "voided_slots": res["cap_redos"], "timed_slots": len(ms),
+                            "note": "fused loop only: the matcher stops at 1.5x the largest squared distance the previous iteration's "
+                                    "outlier filters needed; verified every iteration, T bit-identical to the uncapped loop (tests)"},
     }
+    if not args.no_extra and not sharded and os.environ.get("PMGPU_NO_CAP") is None:
+        # the same loop with the adaptive search radius switched off (every query searched to its true neighbour)
+        os.environ["PMGPU_NO_CAP"] = "1"
+        ctx_u = capi.Context(local_rank)
+        del os.environ["PMGPU_NO_CAP"]
+        ctx_u.set_reference(rf_c)
+        ctx_u.set_reading(rd_pin)
+        ctx_u.reading_apply_transform(T_in)
+        ms_u, res_u = timed_iterations(ctx_u, capi, torch, params, args.steps, args.warmup, flush_buf)
+        ctx_u.close()
+        extra["capped_matching"]["uncapped_iterations_per_s"] = args.steps / (sum(ms_u) * 1e-3)
+        extra["capped_matching"]["T_iter_identical_to_uncapped"] = bool((res_u["T_iter"].view(np.uint32) == res["T_iter"].view(np.uint32)).all())
 
     # ---- e2e: whole registration through the public API from pinned host buffers -----------
     def e2e_once(minimizer_cls, normals):
@@ -369,7 +392,7 @@ def run_ours(args, rank, world, local_rank):
         ctx.timing_enable(False)
         T_full = pm.mat4_mul(pm.mat4_mul(np.linalg.inv(T_in.astype(np.float64)).astype(np.float32), res_pl["T_iter"]), T_in)
         extra["point_to_plane"] = {
-            "iterations_per_s": args.steps / (sum(ms_pl) * 1e-3), "ms_per_step": sum(ms_pl) / args.steps,
+            "iterations_per_s": args.steps / (sum(ms_pl) * 1e-3), "ms_per_step": sum(ms_pl) / args.steps, "voided_slots": res_pl["cap_redos"],
             "stage_ms_per_iteration": {k: v[0] / max(1, args.steps) for k, v in st_pl.items()},
             "translation_error_vs_ground_truth_m": float(np.linalg.norm(T_full[:3, 3].astype(np.float64) - T_gt[:3, 3])),
         }

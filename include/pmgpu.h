@@ -183,7 +183,7 @@ int pmgpu_icp_run(pmgpu_ctx* ctx, const pmgpu_icp_params* params, const float* T
  *
  * Capped matching.  Inside the fused loop nothing outside can see the matches the outlier
  * filters reject, so with maxDist = inf and a non-empty filter chain the matcher of iteration
- * i+1 stops at a squared radius of 2 x the largest distance the filters of iteration i had to
+ * i+1 stops at a squared radius of 1.5 x the largest distance the filters of iteration i had to
  * know exactly (their order statistics and limits).  The select kernels verify afterwards that
  * the new order statistics and limits lie below the radius used; if they do, T is bit-identical
  * to the uncapped loop.  If not, the slot is void (T_iter and the iteration count stay as they

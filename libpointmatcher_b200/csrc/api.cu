@@ -209,8 +209,11 @@ int pmgpu_ctx_create(int device, pmgpu_ctx** ctx_out) {
     ctx->seed_enabled = getenv("PMGPU_NO_SEED") == nullptr;
     ctx->time_stage2 = getenv("PMGPU_TIME_STAGE2") != nullptr;
     ctx->cap_enabled = getenv("PMGPU_NO_CAP") == nullptr;
+    ctx->seeded_without_planes = getenv("PMGPU_SEED_PLANES") == nullptr;
     if (const char* m = getenv("PMGPU_CAP_MARGIN")) ctx->cap_margin = (float)atof(m);
-    if (const char* b = getenv("PMGPU_KNN_BUDGET")) ctx->knn_budget = atoi(b) > 0 ? atoi(b) : 1;  // 1: (almost) everything through stage 2
+    // 1: (almost) everything through stage 2
+    if (const char* b = getenv("PMGPU_KNN_BUDGET")) ctx->knn_budget = ctx->knn_budget_unseeded = atoi(b) > 0 ? atoi(b) : 1;
+    if (const char* b = getenv("PMGPU_KNN_BUDGET_UNSEEDED")) ctx->knn_budget_unseeded = atoi(b) > 0 ? atoi(b) : 1;
     memset(ctx->state_host, 0, sizeof(IcpState));
     mat4_identity(ctx->state_host->T_iter);
     mat4_identity(ctx->state_host->T_match);
@@ -316,11 +319,12 @@ static int ref_set_impl(pmgpu_ctx* ctx, const float* features, int rows, int n, 
         if (cudaPointerGetAttributes(&attr, features) == cudaSuccess && attr.type == cudaMemoryTypeDevice)
             return fail(ctx, PMGPU_ERR_BAD_ARG, "pmgpu_ref_set_centered needs a host pointer");
         cudaGetLastError();
-        volatile float sx = 0.f, sy = 0.f, sz = 0.f;
+        // three independent serial chains of float adds (no reassociation without -ffast-math)
+        float sx = 0.f, sy = 0.f, sz = 0.f;
         for (int i = 0; i < n; ++i) {
-            sx = sx + features[4 * (size_t)i];
-            sy = sy + features[4 * (size_t)i + 1];
-            sz = sz + features[4 * (size_t)i + 2];
+            sx += features[4 * (size_t)i];
+            sy += features[4 * (size_t)i + 1];
+            sz += features[4 * (size_t)i + 2];
         }
         mean_out[0] = sx / (float)n; mean_out[1] = sy / (float)n; mean_out[2] = sz / (float)n; mean_out[3] = 1.f;
         subtract_mean_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->ref_orig.p, n, mean_out[0], mean_out[1], mean_out[2]);

@@ -184,6 +184,8 @@ static EmuStats g_emu_stats = {0, 0, 0, 0, 0};
 // `plane` is a per-lane scratch column (shared memory on the device, element l at
 // plane[l * stride]) that caches, for every level l, the squared distance from the query to the
 // split plane crossed at that level: the cheapest valid lower bound for the pending sibling.
+// It may be null: pending siblings are then judged by their boxes alone (the right trade when the
+// search starts with a tight bound, so that hardly any sibling is pending at all).
 // ------------------------------------------------------------------------------------------------
 struct Lane {
     float qx, qy, qz;
@@ -226,7 +228,7 @@ PM_HD void lane_descend_step(Lane& s, const TreeView& t, float* plane, int strid
     s.node = 2 * s.node + (qd >= sp.x ? 1u : 0u);
     ++s.level;
     if (!(pl > w)) s.trail |= 1u << s.level;
-    plane[s.level * stride] = pl;
+    if (plane) plane[s.level * stride] = pl;
     PM_STAT(descent_steps);
 }
 
@@ -298,7 +300,7 @@ PM_HD bool lane_box_step(Lane& s, const TreeView& t, const TopK<KMAX>& best, con
     const int l = 31 - clz32(s.trail);
     s.trail &= ~(1u << l);
     PM_STAT(pops);
-    if (plane[l * stride] > best.worst_d()) return false;
+    if (plane && plane[l * stride] > best.worst_d()) return false;
     const uint32_t far = (s.node >> (s.level - l)) ^ 1u;
     PM_STAT(box_tests);
     const float db = box_dist2(s.qx, s.qy, s.qz, ldg4(t.boxes + 2 * (size_t)far), ldg4(t.boxes + 2 * (size_t)far + 1));

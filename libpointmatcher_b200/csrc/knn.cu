@@ -39,7 +39,7 @@ __device__ __forceinline__ Cap knn_cap(const IcpState* state, int use_cap, float
     return c;
 }
 
-template <int KMAX>
+template <int KMAX, bool PLANES>
 __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4* __restrict__ queries, int nq, const IcpState* __restrict__ state,
                                                         int use_T, int gated, int self_query, int k, float max_r2,
                                                         const f4* __restrict__ ref_orig, int use_seed, int32_t* __restrict__ ids,
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
         if (threadIdx.x < 16) sT.m[threadIdx.x] = state->T_iter.m[threadIdx.x];
         __syncthreads();
     }
-    float* plane = s_plane + threadIdx.x;
+    float* plane = PLANES ? s_plane + threadIdx.x : nullptr;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     bool running = t < nq;
     uint32_t qi = (uint32_t)t;
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
         bool refilter = false;
         if (running) {
             lane_scan_leaf<KMAX>(s, tree, best);
-            refilter = lane_wants_filter(s, w0, best.worst_d());
+            refilter = PLANES && lane_wants_filter(s, w0, best.worst_d());
         }
         if (__any_sync(0xffffffffu, refilter))
             if (refilter) lane_filter_trail<KMAX>(s, tree, best, plane, KNN_BLOCK);
@@ -270,14 +270,22 @@ int launch_one(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, 
     const int grid = (nq + KNN_BLOCK - 1) / KNN_BLOCK;
     if (grid == 0) return PMGPU_OK;
     const size_t smem = (size_t)(tree.depth + 2) * KNN_BLOCK * sizeof(float);
+    const bool seeded = KMAX == 1 && use_seed;
+    const bool planes = !(seeded && ctx->seeded_without_planes);
+    const int budget = seeded ? ctx->knn_budget : ctx->knn_budget_unseeded;
     PM_CUDA_TRY(ctx, ctx->overflow.reserve((size_t)nq));
     // the two stages of one launch share counter[parity]; stage 2 clears counter[parity ^ 1] for the next launch
     unsigned* cnt = &ctx->state->overflow_count[ctx->knn_parity];
     unsigned* cnt_next = &ctx->state->overflow_count[ctx->knn_parity ^ 1];
     ctx->knn_parity ^= 1;
-    knn_kernel<KMAX><<<grid, KNN_BLOCK, smem, ctx->stream>>>(tree, queries, nq, ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k, max_r2,
-                                                            ctx->ref_orig.p, use_seed ? 1 : 0, ids, dists, &ctx->state->visits, ctx->knn_budget,
-                                                            ctx->overflow.p, cnt, use_cap ? 1 : 0);
+    if (planes)
+        knn_kernel<KMAX, true><<<grid, KNN_BLOCK, smem, ctx->stream>>>(tree, queries, nq, ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k,
+                                                                      max_r2, ctx->ref_orig.p, use_seed ? 1 : 0, ids, dists, &ctx->state->visits,
+                                                                      budget, ctx->overflow.p, cnt, use_cap ? 1 : 0);
+    else
+        knn_kernel<KMAX, false><<<grid, KNN_BLOCK, 0, ctx->stream>>>(tree, queries, nq, ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k,
+                                                                    max_r2, ctx->ref_orig.p, use_seed ? 1 : 0, ids, dists, &ctx->state->visits,
+                                                                    budget, ctx->overflow.p, cnt, use_cap ? 1 : 0);
     if (ctx->time_stage2) { ctx->stage_end(); ctx->stage_begin(3); }
     const int grid2 = min(ctx->num_sms * 4, (nq + 3) / 4);
     knn_overflow_kernel<KMAX><<<grid2, 128, 0, ctx->stream>>>(tree, queries, ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k, max_r2,

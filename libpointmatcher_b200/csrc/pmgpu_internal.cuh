@@ -151,7 +151,9 @@ struct pmgpu_ctx {
     int knn_budget = 16;             // leaves a lane may scan before its query goes to stage 2
     bool seed_enabled = true;        // PMGPU_NO_SEED=1 switches the seeding off (A/B profiling)
     bool cap_enabled = true;         // PMGPU_NO_CAP=1: the fused loop matches without the adaptive radius
-    float cap_margin = 2.0f;         // cap = margin x (largest squared distance the last filters needed); PMGPU_CAP_MARGIN
+    float cap_margin = 1.5f;         // cap = margin x (largest squared distance the last filters needed); PMGPU_CAP_MARGIN
+    bool seeded_without_planes = true;   // seeded searches skip the plane cache (measured 18 % faster); PMGPU_SEED_PLANES=1 reverts
+    int knn_budget_unseeded = 32;        // same budget for searches that start without a bound (first iteration, k > 1)
     bool time_stage2 = false;        // PMGPU_TIME_STAGE2=1: report kNN stage 2 in the "covariance" timing slot (profiling)
     pm::DevBuf<int32_t> ids_tmp;     // un-permute staging for downloads
     pm::DevBuf<float> dists_tmp;
