@@ -48,6 +48,14 @@ __device__ __forceinline__ void block_reduce_store(double* acc, double* __restri
     }
 }
 
+#ifdef PM_PROFILE_NS
+__device__ __forceinline__ unsigned long long pm_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
 __device__ __forceinline__ float pair_weight(const IcpState* st, float d) {
     if (d == pm_inf()) return 0.f;  // ErrorMinimizer.cpp:103-106: invalid matches are skipped
     return st->has_filters ? ((d <= st->limit_all) ? 1.f : 0.f) : 1.f;
@@ -123,8 +131,25 @@ __global__ void __launch_bounds__(ACC_BLOCK) accumulate_kernel(const f4* __restr
         if (!match_exist) acc[NS - 2] += 1.0;
         acc[NS - 1] += 1.0;
     }
+#ifdef PM_PROFILE_NS
+    __shared__ unsigned long long s_t[3];
+    if (threadIdx.x == 0) s_t[0] = pm_globaltimer();
+#endif
     block_reduce_store<NS>(acc, partials + (size_t)blockIdx.x * NS_MAX);
-    if (fuse && select_last_block(&state_rw->ticket[1])) finalize_body<MODE>(partials, gridDim.x, sums, 3, state_rw, compose, ck);
+#ifdef PM_PROFILE_NS
+    if (threadIdx.x == 0) s_t[1] = pm_globaltimer();
+#endif
+    if (fuse && select_last_block(&state_rw->ticket[1])) {
+#ifdef PM_PROFILE_NS
+        if (threadIdx.x == 0) s_t[2] = pm_globaltimer();
+#endif
+        finalize_body<MODE>(partials, gridDim.x, sums, 3, state_rw, compose, ck);
+#ifdef PM_PROFILE_NS
+        if (threadIdx.x == 0)
+            printf("accumulate<%d> last block: block reduce %llu ns, ticket %llu ns, finalize %llu ns\n", MODE, s_t[1] - s_t[0], s_t[2] - s_t[1],
+                   pm_globaltimer() - s_t[2]);
+#endif
+    }
 }
 
 // Censi covariance sums (PointToPlaneWithCov.cpp:100-150, PointToPointWithCov.cpp:84-135):
@@ -204,13 +229,22 @@ __global__ void __launch_bounds__(ACC_BLOCK) cov_accumulate_kernel(const f4* __r
 }
 
 // fixed-order reduction of the per-block rows: 256 threads = 32 columns x 8 slices (two rounds
-// when there are more than 32 columns)
+// when there are more than 32 columns).  The loads of a slice are issued eight at a time before
+// they are added (in row order), so the reduction costs a few L2 round trips, not one per row.
 __device__ void reduce_rows(const double* __restrict__ partials, int nblocks, int ns, double* sums) {
     __shared__ double sh[8][NS_MAX];
     const int slice = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int c = lane; c < ns; c += 32) {
         double v = 0.0;
-        for (int b = slice; b < nblocks; b += 8) v += __ldcg(partials + (size_t)b * NS_MAX + c);
+        int b = slice;
+        for (; b + 56 < nblocks; b += 64) {
+            double r[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) r[u] = __ldcg(partials + (size_t)(b + 8 * u) * NS_MAX + c);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v += r[u];
+        }
+        for (; b < nblocks; b += 8) v += __ldcg(partials + (size_t)b * NS_MAX + c);
         sh[slice][c] = v;
     }
     __syncthreads();
@@ -271,8 +305,14 @@ template <int MODE>
 __device__ void finalize_body(const double* partials, int nblocks, double* sums, int phase, IcpState* state, int compose,
                               const pmgpu_icp_params& ck) {
     constexpr int NS = MODE == 1 ? NS_PLANE : NS_POINT;
+#ifdef PM_PROFILE_NS
+    const unsigned long long t_a = pm_globaltimer();
+#endif
     if (phase & 1) reduce_rows(partials, nblocks, NS, sums);
     if (!(phase & 2) || threadIdx.x != 0) return;
+#ifdef PM_PROFILE_NS
+    const unsigned long long t_b = pm_globaltimer();
+#endif
     const double kept = sums[NS - 4], rej_matches = sums[NS - 3], rej_points = sums[NS - 2], seen = sums[NS - 1];
     // ErrorMinimizer.cpp:139-140: ratios over knn * number of reading points (all ranks)
     const float denom = (float)(seen * (double)ck.knn);
@@ -319,6 +359,9 @@ __device__ void finalize_body(const double* partials, int nblocks, double* sums,
             dT.m[12 + r] = (float)((double)mqf[r] - acc);  // PointToPoint.cpp:94
         }
     }
+#ifdef PM_PROFILE_NS
+    const unsigned long long t_c = pm_globaltimer();
+#endif
     state->dT = dT;
     if (compose) {
         Mat4 Tn;
@@ -332,6 +375,9 @@ __device__ void finalize_body(const double* partials, int nblocks, double* sums,
             state->iterate = 0;
         }
     }
+#ifdef PM_PROFILE_NS
+    printf("finalize<%d>: reduce rows %llu ns, solve %llu ns, compose + checkers %llu ns\n", MODE, t_b - t_a, t_c - t_b, pm_globaltimer() - t_c);
+#endif
 }
 
 template <int MODE>
@@ -397,7 +443,9 @@ int launch_minimize(pmgpu_ctx* ctx, int minimizer, bool compose_and_check, bool 
         return PMGPU_ERR_NO_NORMALS;
     }
     cudaStream_t st = ctx->stream;
-    const int grid = grid_for(ctx->nq, ACC_BLOCK, ctx->num_sms, 4);
+    // the kernel holds 20-27 fp64 sums per thread: two 256-thread blocks are resident per SM, so
+    // that is the whole grid (one wave, and only 2 x SMs partial rows for the last block to reduce)
+    const int grid = grid_for(ctx->nq, ACC_BLOCK, ctx->num_sms, 2);
     PM_CUDA_TRY(ctx, ctx->partials.reserve((size_t)(ctx->num_sms * 4 + 2) * NS_MAX));
     double* sums = ctx->partials.p + (size_t)ctx->num_sms * 4 * NS_MAX;
     pmgpu_icp_params ck;
