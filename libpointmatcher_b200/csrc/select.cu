@@ -16,9 +16,16 @@ namespace pm {
 
 namespace {
 
-constexpr int HIST_BLOCK = 256;
+constexpr int HIST_BLOCK = 1024;
 
-// pass 0: one histogram serves every quantile filter (slot 0); pass 1, 2: one per filter
+__device__ __forceinline__ void hist_add(unsigned* sh, float d, int pass, unsigned prefix) {
+    const int bin = select_bin(__float_as_uint(d), pass, prefix);
+    if (bin >= 0) atomicAdd(&sh[bin], 1u);
+}
+
+// pass 0: one histogram serves every quantile filter (slot 0); pass 1, 2: one per filter.
+// One 1024-thread block per SM: every block flushes its 2048 bins with global atomics, so the fewer
+// blocks the shorter the serialised tail on the hot bins; the distances are read four at a time.
 __global__ void __launch_bounds__(HIST_BLOCK) hist_kernel(const float* __restrict__ dists, size_t total, int pass, SelectSpec spec, IcpState* state,
                                                           int gated, int do_init, int do_pick, unsigned* __restrict__ hist, int cap_active,
                                                           float cap_margin) {
@@ -26,16 +33,23 @@ __global__ void __launch_bounds__(HIST_BLOCK) hist_kernel(const float* __restric
     if (gated && state->iterate == 0) return;
     if (do_init && blockIdx.x == 0 && threadIdx.x == 0) select_init_limits(state, spec);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t gtid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t quads = total / 4;
+    const float4* __restrict__ d4 = reinterpret_cast<const float4*>(dists);
     int slot = 0;
     for (int f = 0; f < spec.nfilters; ++f) {
         if (!spec.is_quantile(f)) continue;
         for (int i = threadIdx.x; i < PM_HIST_BINS; i += blockDim.x) sh[i] = 0;
         __syncthreads();
         const unsigned prefix = pass == 0 ? 0u : state->sel_prefix[f];
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-            const int bin = select_bin(__float_as_uint(__ldg(dists + i)), pass, prefix);
-            if (bin >= 0) atomicAdd(&sh[bin], 1u);
+        for (size_t i = gtid; i < quads; i += stride) {
+            const float4 v = __ldg(d4 + i);
+            hist_add(sh, v.x, pass, prefix);
+            hist_add(sh, v.y, pass, prefix);
+            hist_add(sh, v.z, pass, prefix);
+            hist_add(sh, v.w, pass, prefix);
         }
+        if (gtid < total - 4 * quads) hist_add(sh, __ldg(dists + 4 * quads + gtid), pass, prefix);
         __syncthreads();
         select_flush(sh, hist + (size_t)slot * PM_HIST_BINS);
         __syncthreads();
@@ -135,7 +149,7 @@ int launch_weights(pmgpu_ctx* ctx, const SelectSpec& spec, bool gated, bool cap_
     } else {
         const size_t total = (size_t)ctx->k * ctx->nq;
         const size_t want = (total + HIST_BLOCK * 4 - 1) / (HIST_BLOCK * 4);
-        const int grid = grid_for((int)(want > 0x7fffffff ? 0x7fffffff : want) * HIST_BLOCK, HIST_BLOCK, ctx->num_sms, 4);
+        const int grid = grid_for((int)(want > 0x1fffff ? 0x1fffff : want) * HIST_BLOCK, HIST_BLOCK, ctx->num_sms, 1);
         const bool split = ctx->nranks > 1;
         for (int pass = 0; pass < 3; ++pass) {
             hist_kernel<<<grid, HIST_BLOCK, 0, st>>>(ctx->dists.p, total, pass, spec, ctx->state, g, pass == 0 ? 1 : 0, split ? 0 : 1, ctx->hist.p, ca,
