@@ -323,8 +323,8 @@ def run_ours(args, rank, world, local_rank):
     knn_avg_ms = knn_ms / max(1, knn_n)
     achieved = alg_bytes / (knn_avg_ms * 1e-3) / 1e9 if knn_avg_ms > 0 else 0.0
     # dram__bytes_read.sum + dram__bytes_write.sum of one knn_kernel<1> launch from the committed
-    # `ncu --set full` capture (profiles/r1_final_summary.txt; cold L2, 1 M x 1 M): 52.2 MB + 0.8 MB
-    ncu_traffic = 53.0e6 if (nq_local == 1_000_000 and nr == 1_000_000) else None
+    # `ncu --set full` capture (profiles/r1_final_summary.txt; cold L2, 1 M x 1 M): 51.6 MB read + 0.7 MB written
+    ncu_traffic = 52.2e6 if (nq_local == 1_000_000 and nr == 1_000_000) else None
     roofline = {"bound": "hbm", "kernel": "knn_kernel<1> + knn_overflow_kernel<1> (K2: transform + exact nearest neighbour, stage 1 + stage 2)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
@@ -397,8 +397,11 @@ def run_ours(args, rank, world, local_rank):
             "translation_error_vs_ground_truth_m": float(np.linalg.norm(T_full[:3, 3].astype(np.float64) - T_gt[:3, 3])),
         }
         if not args.no_e2e:
+            _, _, dt_first = e2e_once(pm.PointToPlaneErrorMinimizer, True)  # warm-up, like the headline e2e
             _, n_it, dt = e2e_once(pm.PointToPlaneErrorMinimizer, True)
             extra["point_to_plane"]["e2e_iterations_per_s_incl_normals_knn20"] = n_it / dt
+            extra["point_to_plane"]["e2e_seconds_per_registration"] = dt
+            extra["point_to_plane"]["e2e_first_call_seconds"] = dt_first
 
     # ---- cpu_baseline on this box's host cores (rank 0, N = 1 only) -------------------------
     cpu = None

@@ -20,7 +20,10 @@ namespace pm {
 
 namespace {
 
-constexpr int KNN_BLOCK = 128;
+#ifndef PM_KNN_BLOCK
+#define PM_KNN_BLOCK 128
+#endif
+constexpr int KNN_BLOCK = PM_KNN_BLOCK;
 
 // Search radius of one launch and what an empty result slot is written as.  Without a cap (or with
 // a cap that the caller's maxDist already undercuts) a miss is "no match within maxDist": id -1,
