@@ -1,10 +1,14 @@
 // tree_build.cu — K1: builds the search structure of KDTreeMatcher::init (MatchersImpl.cpp:77-83)
 // on the device.  See core/tree.h for the layout.
 //
-// Level by level, top down: (1) every node's bounding box by warp-aggregated integer atomics on
-// order-preserving float keys, (2) the split axis = widest box extent, (3) one stable radix sort
-// of (segment id << 32 | ordered coordinate) which median-splits every segment of the level at
-// once (segments are position ranges, so the sort cannot move a point across segments).
+// Upper levels, level by level, top down: (1) every node's bounding box by warp-aggregated integer
+// atomics on order-preserving float keys, (2) the split axis = widest box extent, (3) one stable
+// radix sort of (segment id << 32 | ordered coordinate) which median-splits every segment of the
+// level at once (segments are position ranges, so the sort cannot move a point across segments).
+// As soon as a segment fits one thread block (<= 4096 points) the rest of its subtree — boxes,
+// axes, median splits, leaf order — is finished by that block in shared memory (subtree_kernel,
+// a bitonic network on (node, coordinate, position) keys: the same total order as the stable
+// radix sort, so the tree is the one the level-by-level build produces).
 // The only library call is cub::DeviceRadixSort (part of the CUDA toolkit) — the build runs once
 // per init(); the per-iteration kernels are all hand-written.
 #include <cub/device/device_radix_sort.cuh>
@@ -136,6 +140,136 @@ __global__ void gather_f4_kernel(const f4* __restrict__ src, const uint32_t* __r
     if (t < n) dst[t] = src[order[t]];
 }
 
+// ---- lower levels: one block per subtree ---------------------------------------------------------
+constexpr int SUB_MAX = 4096;      // points of one block's subtree
+constexpr int SUB_THREADS = 1024;
+constexpr int SUB_NODES = 1024;    // nodes of one level inside a block: 4096 points / leaves of >= 4
+
+struct SubSmem {
+    union {
+        unsigned long long key[SUB_MAX];  // sort keys ...
+        uint32_t box[6 * SUB_NODES];      // ... and, before they are generated, the ordered-uint boxes of the level's nodes
+    };
+    float x[SUB_MAX], y[SUB_MAX], z[SUB_MAX];
+    uint16_t slot_a[SUB_MAX], slot_b[SUB_MAX];  // local position -> slot of the point (ping-pong)
+    uint32_t nbeg[SUB_NODES + 1];               // local begin of every node of the current level
+    uint8_t dim[SUB_NODES];                     // split axis of every node of the current level
+};
+static_assert(sizeof(SubSmem) <= 110 * 1024, "two subtree blocks per SM");
+
+// node (0-based inside the block) that owns local position i at the current level
+__device__ __forceinline__ uint32_t sub_node_of(const uint32_t* nbeg, uint32_t i, uint32_t nodes, uint32_t cnt) {
+    uint32_t k = (uint32_t)(((unsigned long long)i * nodes) / cnt);
+    if (k >= nodes) k = nodes - 1;
+    while (i < nbeg[k]) --k;
+    while (i >= nbeg[k + 1]) ++k;
+    return k;
+}
+
+__device__ __forceinline__ int widest_axis(const uint32_t* b);
+
+// Block b finishes the subtree of node (L0, b): levels L0 .. D.  perm_in: order after the upper
+// levels (null: identity, L0 == 0).
+__global__ void __launch_bounds__(SUB_THREADS) subtree_kernel(const f4* __restrict__ pts, const uint32_t* __restrict__ perm_in, uint32_t n, int L0, int D,
+                                                              uint32_t* __restrict__ node_box, f2* __restrict__ splits, f4* __restrict__ ref_sorted) {
+    extern __shared__ __align__(16) unsigned char sub_raw[];
+    SubSmem& sm = *reinterpret_cast<SubSmem*>(sub_raw);
+    const uint32_t tid = threadIdx.x, b = blockIdx.x;
+    const uint32_t gbeg = seg_begin(L0, b, n), cnt = seg_begin(L0, b + 1, n) - gbeg;
+    uint32_t sort_n = 64;  // power of two >= cnt
+    while (sort_n < cnt) sort_n <<= 1;
+    for (uint32_t i = tid; i < cnt; i += SUB_THREADS) {
+        const f4 p = pts[perm_in ? perm_in[gbeg + i] : gbeg + i];
+        sm.x[i] = p.x; sm.y[i] = p.y; sm.z[i] = p.z;
+        sm.slot_a[i] = (uint16_t)i;
+    }
+    uint16_t* cur = sm.slot_a;
+    uint16_t* nxt = sm.slot_b;
+    const uint32_t cnt32 = (cnt + 31u) & ~31u;
+    for (int l = L0; l <= D; ++l) {
+        const uint32_t nodes = 1u << (l - L0), first = b << (l - L0);
+        for (uint32_t k = tid; k <= nodes; k += SUB_THREADS) sm.nbeg[k] = seg_begin(l, first + k, n) - gbeg;
+        for (uint32_t k = tid; k < 6 * nodes; k += SUB_THREADS) sm.box[k] = (k % 6 < 3) ? 0xffffffffu : 0u;
+        __syncthreads();
+        // (1) boxes of the level's nodes
+        for (uint32_t i = tid; i < cnt32; i += SUB_THREADS) {
+            const bool active = i < cnt;
+            uint32_t k = 0xffffffffu, ox = 0, oy = 0, oz = 0;
+            if (active) {
+                const uint32_t s = cur[i];
+                k = sub_node_of(sm.nbeg, i, nodes, cnt);
+                ox = float_ord(sm.x[s]); oy = float_ord(sm.y[s]); oz = float_ord(sm.z[s]);
+            }
+            const unsigned amask = __ballot_sync(0xffffffffu, active);
+            if (active) {
+                const unsigned group = __match_any_sync(amask, k);
+                const uint32_t lx = __reduce_min_sync(group, ox), ly = __reduce_min_sync(group, oy), lz = __reduce_min_sync(group, oz);
+                const uint32_t hx = __reduce_max_sync(group, ox), hy = __reduce_max_sync(group, oy), hz = __reduce_max_sync(group, oz);
+                if ((tid & 31u) == (unsigned)(__ffs(group) - 1)) {
+                    uint32_t* bx = sm.box + 6 * k;
+                    atomicMin(bx + 0, lx); atomicMin(bx + 1, ly); atomicMin(bx + 2, lz);
+                    atomicMax(bx + 3, hx); atomicMax(bx + 4, hy); atomicMax(bx + 5, hz);
+                }
+            }
+        }
+        __syncthreads();
+        for (uint32_t k = tid; k < 6 * nodes; k += SUB_THREADS) node_box[6 * (size_t)((1u << l) + first) + k] = sm.box[k];
+        if (l == D) break;
+        for (uint32_t k = tid; k < nodes; k += SUB_THREADS) sm.dim[k] = (uint8_t)widest_axis(sm.box + 6 * k);
+        __syncthreads();  // the boxes are dead from here: the keys take their place
+        // (2) keys: node | coordinate along the node's widest axis | position (= stable)
+        for (uint32_t i = tid; i < sort_n; i += SUB_THREADS) {
+            unsigned long long key = ~0ull;
+            if (i < cnt) {
+                const uint32_t s = cur[i];
+                const uint32_t k = sub_node_of(sm.nbeg, i, nodes, cnt);
+                const int dim = sm.dim[k];
+                const float c = dim == 0 ? sm.x[s] : (dim == 1 ? sm.y[s] : sm.z[s]);
+                key = ((unsigned long long)k << 44) | ((unsigned long long)float_ord(c) << 12) | (unsigned long long)i;
+            }
+            sm.key[i] = key;
+        }
+        __syncthreads();
+        // (3) bitonic sort, ascending
+        for (uint32_t kk = 2; kk <= sort_n; kk <<= 1) {
+            for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+                for (uint32_t t = tid; t < (sort_n >> 1); t += SUB_THREADS) {
+                    const uint32_t i = 2 * t - (t & (j - 1));
+                    const unsigned long long a = sm.key[i], c = sm.key[i + j];
+                    const bool up = (i & kk) == 0;
+                    if ((a > c) == up) { sm.key[i] = c; sm.key[i + j] = a; }
+                }
+                __syncthreads();
+            }
+        }
+        // (4) the new order, (5) split values of the level's nodes
+        for (uint32_t i = tid; i < cnt; i += SUB_THREADS) nxt[i] = cur[(uint32_t)(sm.key[i] & 0xfffull)];
+        __syncthreads();
+        { uint16_t* t = cur; cur = nxt; nxt = t; }
+        for (uint32_t k = tid; k < nodes; k += SUB_THREADS) {
+            const int dim = sm.dim[k];
+            const uint32_t mid = seg_begin(l + 1, 2 * (first + k) + 1, n) - gbeg;
+            const uint32_t s = cur[mid];
+            const float c = dim == 0 ? sm.x[s] : (dim == 1 ? sm.y[s] : sm.z[s]);
+            splits[(1u << l) + first + k] = make_float2(c, __uint_as_float((uint32_t)dim));
+        }
+        __syncthreads();
+    }
+    // leaf order: the point and, in w, its original column
+    for (uint32_t i = tid; i < cnt; i += SUB_THREADS) {
+        const uint32_t s = cur[i];
+        const uint32_t src = perm_in ? perm_in[gbeg + s] : gbeg + s;
+        ref_sorted[gbeg + i] = make_float4(sm.x[s], sm.y[s], sm.z[s], __uint_as_float(src));
+    }
+}
+
+// first level whose segments fit one block
+inline int subtree_level(uint32_t n, int D) {
+    int l = 0;
+    while (l < D && (((uint64_t)n + ((1ull << l) - 1)) >> l) > (uint64_t)SUB_MAX) ++l;
+    return l;
+}
+
 inline unsigned blocks_for(uint32_t n, int block) { return (unsigned)((n + (uint32_t)block - 1) / (uint32_t)block); }
 
 }  // namespace
@@ -164,18 +298,19 @@ int build_tree(pmgpu_ctx* ctx) {
     ctx->launches += 2;
     uint32_t* perm = ctx->perm_a.p;
     uint32_t* perm_alt = ctx->perm_b.p;
-    for (int l = 0; l <= D; ++l) {
+    const int L0 = subtree_level(n, D);
+    for (int l = 0; l < L0; ++l) {
         level_boxes_kernel<<<blocks_for(n, B), B, 0, st>>>(ctx->ref_orig.p, perm, n, l, ctx->node_box.p);
-        ctx->launches += 1;
-        if (l == D) break;
         level_keys_kernel<<<blocks_for(n, B), B, 0, st>>>(ctx->ref_orig.p, perm, n, l, ctx->node_box.p, ctx->keys_a.p);
         size_t tb = ctx->cub_tmp.cap;
         PM_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, ctx->keys_a.p, ctx->keys_b.p, perm, perm_alt, (int)n, 0, 32 + l, st));
         uint32_t* t = perm; perm = perm_alt; perm_alt = t;
         level_splits_kernel<<<blocks_for(1u << l, B), B, 0, st>>>(ctx->ref_orig.p, perm, n, l, ctx->node_box.p, ctx->splits.p);
-        ctx->launches += 3;
+        ctx->launches += 4;
     }
-    gather_sorted_kernel<<<blocks_for(n, B), B, 0, st>>>(ctx->ref_orig.p, perm, n, ctx->ref_sorted.p);
+    PM_CUDA_TRY(ctx, cudaFuncSetAttribute(subtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SubSmem)));
+    subtree_kernel<<<1u << L0, SUB_THREADS, sizeof(SubSmem), st>>>(ctx->ref_orig.p, L0 > 0 ? perm : nullptr, n, L0, D, ctx->node_box.p, ctx->splits.p,
+                                                                   ctx->ref_sorted.p);
     ctx->launches += 1;
     pack_boxes_kernel<<<blocks_for(nnodes, B), B, 0, st>>>(ctx->node_box.p, nnodes, ctx->boxes.p);
     ctx->launches += 1;
