@@ -32,26 +32,52 @@ __global__ void init_boxes_kernel(uint32_t* box, uint32_t nnodes) {
     }
 }
 
-// boxes of all nodes of `level`: node (heap index) = 2^level + seg_of(position)
-__global__ void level_boxes_kernel(const f4* __restrict__ pts, const uint32_t* __restrict__ perm, uint32_t n, int level,
-                                   uint32_t* __restrict__ box) {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = p < n;
-    uint32_t node = 0xffffffffu, ox = 0, oy = 0, oz = 0;
-    if (active) {
+// Boxes of all nodes of `level` (node = 2^level + segment).  Precondition: every segment of the
+// level is longer than BOX_CHUNK (the upper levels; shorter segments belong to subtree_kernel), so
+// the BOX_CHUNK consecutive positions of a block touch at most two segments: min/max in
+// registers, one warp reduction, shared atomics, and 12 global atomics per block.
+constexpr int BOX_CHUNK = 4096;
+constexpr int BOX_THREADS = 256;
+__global__ void __launch_bounds__(BOX_THREADS) level_boxes_kernel(const f4* __restrict__ pts, const uint32_t* __restrict__ perm, uint32_t n, int level,
+                                                                  uint32_t* __restrict__ box) {
+    __shared__ uint32_t sbox[12];
+    const uint32_t c0 = blockIdx.x * BOX_CHUNK;
+    const uint32_t c1 = min(n, c0 + BOX_CHUNK);
+    const uint32_t seg0 = seg_of(c0, level, n);
+    const uint32_t nb = seg_begin(level, seg0 + 1, n);  // first position of the next segment
+    if (threadIdx.x < 12) sbox[threadIdx.x] = (threadIdx.x % 6 < 3) ? 0xffffffffu : 0u;
+    __syncthreads();
+    uint32_t lo[2][3], hi[2][3];
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { lo[k][a] = 0xffffffffu; hi[k][a] = 0u; }
+    for (uint32_t p = c0 + threadIdx.x; p < c1; p += BOX_THREADS) {
         const f4 pt = pts[perm ? perm[p] : p];
-        node = (1u << level) + seg_of(p, level, n);
-        ox = float_ord(pt.x); oy = float_ord(pt.y); oz = float_ord(pt.z);
+        const uint32_t o[3] = {float_ord(pt.x), float_ord(pt.y), float_ord(pt.z)};
+        const bool second = p >= nb;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            lo[0][a] = min(lo[0][a], second ? 0xffffffffu : o[a]);
+            hi[0][a] = max(hi[0][a], second ? 0u : o[a]);
+            lo[1][a] = min(lo[1][a], second ? o[a] : 0xffffffffu);
+            hi[1][a] = max(hi[1][a], second ? o[a] : 0u);
+        }
     }
-    const unsigned amask = __ballot_sync(0xffffffffu, active);
-    if (!active) return;
-    const unsigned group = __match_any_sync(amask, node);
-    const uint32_t lx = __reduce_min_sync(group, ox), ly = __reduce_min_sync(group, oy), lz = __reduce_min_sync(group, oz);
-    const uint32_t hx = __reduce_max_sync(group, ox), hy = __reduce_max_sync(group, oy), hz = __reduce_max_sync(group, oz);
-    if ((threadIdx.x & 31) == (unsigned)(__ffs(group) - 1)) {
-        uint32_t* b = box + 6 * (size_t)node;
-        atomicMin(b + 0, lx); atomicMin(b + 1, ly); atomicMin(b + 2, lz);
-        atomicMax(b + 3, hx); atomicMax(b + 4, hy); atomicMax(b + 5, hz);
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const uint32_t l = __reduce_min_sync(0xffffffffu, lo[k][a]), h = __reduce_max_sync(0xffffffffu, hi[k][a]);
+            if ((threadIdx.x & 31) == 0) { atomicMin(&sbox[6 * k + a], l); atomicMax(&sbox[6 * k + 3 + a], h); }
+        }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+        const uint32_t k = threadIdx.x / 6, a = threadIdx.x % 6;
+        if (k == 0 || nb < c1) {
+            uint32_t* dst = box + 6 * (size_t)((1u << level) + seg0 + k) + a;
+            if (a < 3) atomicMin(dst, sbox[threadIdx.x]); else atomicMax(dst, sbox[threadIdx.x]);
+        }
     }
 }
 
@@ -176,8 +202,6 @@ __global__ void __launch_bounds__(SUB_THREADS) subtree_kernel(const f4* __restri
     SubSmem& sm = *reinterpret_cast<SubSmem*>(sub_raw);
     const uint32_t tid = threadIdx.x, b = blockIdx.x;
     const uint32_t gbeg = seg_begin(L0, b, n), cnt = seg_begin(L0, b + 1, n) - gbeg;
-    uint32_t sort_n = 64;  // power of two >= cnt
-    while (sort_n < cnt) sort_n <<= 1;
     for (uint32_t i = tid; i < cnt; i += SUB_THREADS) {
         const f4 p = pts[perm_in ? perm_in[gbeg + i] : gbeg + i];
         sm.x[i] = p.x; sm.y[i] = p.y; sm.z[i] = p.z;
@@ -217,27 +241,41 @@ __global__ void __launch_bounds__(SUB_THREADS) subtree_kernel(const f4* __restri
         if (l == D) break;
         for (uint32_t k = tid; k < nodes; k += SUB_THREADS) sm.dim[k] = (uint8_t)widest_axis(sm.box + 6 * k);
         __syncthreads();  // the boxes are dead from here: the keys take their place
-        // (2) keys: node | coordinate along the node's widest axis | position (= stable)
-        for (uint32_t i = tid; i < sort_n; i += SUB_THREADS) {
-            unsigned long long key = ~0ull;
-            if (i < cnt) {
-                const uint32_t s = cur[i];
-                const uint32_t k = sub_node_of(sm.nbeg, i, nodes, cnt);
-                const int dim = sm.dim[k];
-                const float c = dim == 0 ? sm.x[s] : (dim == 1 ? sm.y[s] : sm.z[s]);
-                key = ((unsigned long long)k << 44) | ((unsigned long long)float_ord(c) << 12) | (unsigned long long)i;
-            }
-            sm.key[i] = key;
+        // (2) keys: coordinate along the node's widest axis | position (= stable)
+        for (uint32_t i = tid; i < cnt; i += SUB_THREADS) {
+            const uint32_t s = cur[i];
+            const int dim = sm.dim[sub_node_of(sm.nbeg, i, nodes, cnt)];
+            const float c = dim == 0 ? sm.x[s] : (dim == 1 ? sm.y[s] : sm.z[s]);
+            sm.key[i] = ((unsigned long long)float_ord(c) << 12) | (unsigned long long)i;
         }
         __syncthreads();
-        // (3) bitonic sort, ascending
-        for (uint32_t kk = 2; kk <= sort_n; kk <<= 1) {
+        // (3) every node's range sorted ascending by a bitonic network of P = 2^m >= node size
+        // virtual elements in which every compare-exchange points the same way (the first step of
+        // a merge mirrors its partner): a partner beyond the node's size is a virtual +inf and the
+        // exchange is a no-op, so ranges of any length sort in place without padding.
+        uint32_t P = 2;
+        while (P < sm.nbeg[1] + 1u) P <<= 1;  // node sizes of a level differ by at most one
+        const uint32_t halfP = P >> 1, pairs = nodes * halfP;
+        const int hs = 31 - __clz((int)halfP);
+        for (uint32_t kk = 2; kk <= P; kk <<= 1) {
             for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
-                for (uint32_t t = tid; t < (sort_n >> 1); t += SUB_THREADS) {
-                    const uint32_t i = 2 * t - (t & (j - 1));
-                    const unsigned long long a = sm.key[i], c = sm.key[i + j];
-                    const bool up = (i & kk) == 0;
-                    if ((a > c) == up) { sm.key[i] = c; sm.key[i + j] = a; }
+                const int js = 31 - __clz((int)j);
+                for (uint32_t v = tid; v < pairs; v += SUB_THREADS) {
+                    const uint32_t node = v >> hs, w = v & (halfP - 1);
+                    uint32_t r_lo, r_hi;
+                    if (j == (kk >> 1)) {  // flip step
+                        const uint32_t blk = w >> js, off = w & (j - 1);
+                        r_lo = blk * kk + off;
+                        r_hi = blk * kk + kk - 1 - off;
+                    } else {
+                        r_lo = 2 * w - (w & (j - 1));
+                        r_hi = r_lo + j;
+                    }
+                    const uint32_t base = sm.nbeg[node];
+                    if (base + r_hi < sm.nbeg[node + 1]) {
+                        const unsigned long long a = sm.key[base + r_lo], c = sm.key[base + r_hi];
+                        if (a > c) { sm.key[base + r_lo] = c; sm.key[base + r_hi] = a; }
+                    }
                 }
                 __syncthreads();
             }
@@ -300,7 +338,7 @@ int build_tree(pmgpu_ctx* ctx) {
     uint32_t* perm_alt = ctx->perm_b.p;
     const int L0 = subtree_level(n, D);
     for (int l = 0; l < L0; ++l) {
-        level_boxes_kernel<<<blocks_for(n, B), B, 0, st>>>(ctx->ref_orig.p, perm, n, l, ctx->node_box.p);
+        level_boxes_kernel<<<blocks_for(n, BOX_CHUNK), BOX_THREADS, 0, st>>>(ctx->ref_orig.p, perm, n, l, ctx->node_box.p);
         level_keys_kernel<<<blocks_for(n, B), B, 0, st>>>(ctx->ref_orig.p, perm, n, l, ctx->node_box.p, ctx->keys_a.p);
         size_t tb = ctx->cub_tmp.cap;
         PM_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, ctx->keys_a.p, ctx->keys_b.p, perm, perm_alt, (int)n, 0, 32 + l, st));
@@ -338,7 +376,7 @@ int morton_order(pmgpu_ctx* ctx) {
     PM_CUDA_TRY(ctx, ctx->cub_tmp.reserve(tmp_bytes));
     const int B = 256;
     init_boxes_kernel<<<1, 32, 0, st>>>(ctx->node_box.p, 2);
-    level_boxes_kernel<<<blocks_for(n, B), B, 0, st>>>(ctx->reading_tmp.p, nullptr, n, 0, ctx->node_box.p);
+    level_boxes_kernel<<<blocks_for(n, BOX_CHUNK), BOX_THREADS, 0, st>>>(ctx->reading_tmp.p, nullptr, n, 0, ctx->node_box.p);
     morton_keys_kernel<<<blocks_for(n, B), B, 0, st>>>(ctx->reading_tmp.p, n, ctx->node_box.p, keys_in, ctx->perm_a.p);
     size_t tb = ctx->cub_tmp.cap;
     PM_CUDA_TRY(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tb, keys_in, keys_out, ctx->perm_a.p, ctx->q_order.p, (int)n, 0, 30, st));
