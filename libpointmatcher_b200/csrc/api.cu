@@ -33,12 +33,31 @@ __global__ void ids_to_float_kernel(const int32_t* __restrict__ ids, size_t tota
     if (i < total) out[i] = (float)ids[i];
 }
 
-__global__ void subtract_mean_kernel(f4* __restrict__ pts, int n, float mx, float my, float mz) {
+// Moves a structure built on the caller's coordinates into the frame centred on `mean`: every
+// stored coordinate c becomes fsub(c, mean).  Rounding is monotone, so the order along every axis,
+// the median splits and the tight boxes of the shifted points are exactly the shifted ones.
+__global__ void center_structure_kernel(f4* __restrict__ ref_orig, f4* __restrict__ ref_sorted, int n, f2* __restrict__ splits, int nsplits,
+                                        f4* __restrict__ boxes, int nboxes, float mx, float my, float mz) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    f4 p = pts[i];
-    p.x = fsub(p.x, mx); p.y = fsub(p.y, my); p.z = fsub(p.z, mz);
-    pts[i] = p;
+    if (i < n) {
+        f4 p = ref_orig[i];
+        p.x = fsub(p.x, mx); p.y = fsub(p.y, my); p.z = fsub(p.z, mz);
+        ref_orig[i] = p;
+        p = ref_sorted[i];
+        p.x = fsub(p.x, mx); p.y = fsub(p.y, my); p.z = fsub(p.z, mz);
+        ref_sorted[i] = p;
+    }
+    if (i >= 1 && i < nsplits) {
+        f2 sp = splits[i];
+        const uint32_t dim = f2u(sp.y);
+        sp.x = fsub(sp.x, dim == 0 ? mx : (dim == 1 ? my : mz));
+        splits[i] = sp;
+    }
+    if (i < nboxes) {
+        f4 b = boxes[i];
+        b.x = fsub(b.x, mx); b.y = fsub(b.y, my); b.z = fsub(b.z, mz);
+        boxes[i] = b;
+    }
 }
 
 __global__ void transform_inplace_kernel(f4* __restrict__ pts, int n, Mat4 T) {
@@ -188,6 +207,7 @@ int pmgpu_ctx_create(int device, pmgpu_ctx** ctx_out) {
     ctx->device = device;
     bool ok = cudaSetDevice(device) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&ctx->state, sizeof(IcpState)) == cudaSuccess;
     ok = ok && cudaMallocHost((void**)&ctx->state_host, sizeof(IcpState)) == cudaSuccess;
     int sms = 0;
@@ -245,6 +265,7 @@ void pmgpu_ctx_destroy(pmgpu_ctx* ctx) {
     if (ctx->state) cudaFree(ctx->state);
     if (ctx->state_host) cudaFreeHost(ctx->state_host);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);  // the cudaFreeAsync calls above
+    if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     g_alloc_stream = nullptr;
     delete ctx;
@@ -312,14 +333,20 @@ static int ref_set_impl(pmgpu_ctx* ctx, const float* features, int rows, int n, 
     PM_CUDA_TRY(ctx, ctx->ref_orig.reserve(n));
     PM_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ref_orig.p, features, (size_t)n * sizeof(f4), cudaMemcpyDefault, ctx->stream));
     ctx->nr = n;
+    // the structure is built on the uploaded coordinates while, for the centred variant, the host
+    // is busy with the mean; it is shifted into the centred frame afterwards
+    const int s = build_tree(ctx);
+    if (s != PMGPU_OK) { ctx->nr = 0; return s; }
     if (mean_out) {
         // `reference.features.rowwise().sum() / nbPtsReference` in float, column after column
-        // (ICP.cpp:292); runs on the host while the upload is in flight
+        // (ICP.cpp:292): three independent serial chains of float adds (no reassociation without
+        // -ffast-math), overlapping the upload and the build
         cudaPointerAttributes attr;
-        if (cudaPointerGetAttributes(&attr, features) == cudaSuccess && attr.type == cudaMemoryTypeDevice)
+        if (cudaPointerGetAttributes(&attr, features) == cudaSuccess && attr.type == cudaMemoryTypeDevice) {
+            ctx->nr = 0;
             return fail(ctx, PMGPU_ERR_BAD_ARG, "pmgpu_ref_set_centered needs a host pointer");
+        }
         cudaGetLastError();
-        // three independent serial chains of float adds (no reassociation without -ffast-math)
         float sx = 0.f, sy = 0.f, sz = 0.f;
         for (int i = 0; i < n; ++i) {
             sx += features[4 * (size_t)i];
@@ -327,11 +354,13 @@ static int ref_set_impl(pmgpu_ctx* ctx, const float* features, int rows, int n, 
             sz += features[4 * (size_t)i + 2];
         }
         mean_out[0] = sx / (float)n; mean_out[1] = sy / (float)n; mean_out[2] = sz / (float)n; mean_out[3] = 1.f;
-        subtract_mean_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->ref_orig.p, n, mean_out[0], mean_out[1], mean_out[2]);
+        const int nsplits = 1 << ctx->depth, nboxes = 4 << ctx->depth;
+        const int m = n > nboxes ? n : nboxes;
+        center_structure_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(ctx->ref_orig.p, ctx->ref_sorted.p, n, ctx->splits.p, nsplits, ctx->boxes.p,
+                                                                         nboxes, mean_out[0], mean_out[1], mean_out[2]);
         ctx->launches += 1;
+        PM_CUDA_TRY(ctx, cudaGetLastError());
     }
-    const int s = build_tree(ctx);
-    if (s != PMGPU_OK) { ctx->nr = 0; return s; }
     if (normals) PM_TRY(upload_normals(ctx, normals, normals_ld));
     return PMGPU_OK;
 }
@@ -357,9 +386,11 @@ int pmgpu_reading_set(pmgpu_ctx* ctx, const float* features, int rows, int n) {
     PM_CUDA_TRY(ctx, ctx->reading_tmp.reserve(n > 0 ? n : 1));
     ctx->seed_k = 0;
     if (n > 0) PM_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->reading_tmp.p, features, (size_t)n * sizeof(f4), cudaMemcpyDefault, ctx->stream));
+    PM_CUDA_TRY(ctx, cudaEventRecord(ctx->copy_done, ctx->stream));
     ctx->nq = n;
     if (n > 0) PM_TRY(morton_order(ctx));
-    PM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    // the caller may release `features` on return: wait for the copy only, the ordering kernels run on
+    PM_CUDA_TRY(ctx, cudaEventSynchronize(ctx->copy_done));
     return PMGPU_OK;
 }
 

@@ -183,6 +183,7 @@ struct pmgpu_ctx {
     bool timing = false;
     std::vector<Interval> intervals;
     std::vector<cudaEvent_t> event_pool;
+    cudaEvent_t copy_done = nullptr;  // host buffers handed to *_set may be released once this has fired
     cudaEvent_t take_event() {
         cudaEvent_t e = nullptr;
         if (!event_pool.empty()) { e = event_pool.back(); event_pool.pop_back(); }

@@ -185,7 +185,8 @@ static_assert(sizeof(SubSmem) <= 110 * 1024, "two subtree blocks per SM");
 
 // node (0-based inside the block) that owns local position i at the current level
 __device__ __forceinline__ uint32_t sub_node_of(const uint32_t* nbeg, uint32_t i, uint32_t nodes, uint32_t cnt) {
-    uint32_t k = (uint32_t)(((unsigned long long)i * nodes) / cnt);
+    // estimate (i * nodes < 2^22 is exact in float), then walk to the exact range
+    uint32_t k = (uint32_t)(__fdividef((float)(i * nodes), (float)cnt));
     if (k >= nodes) k = nodes - 1;
     while (i < nbeg[k]) --k;
     while (i >= nbeg[k + 1]) ++k;
