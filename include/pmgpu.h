@@ -195,6 +195,32 @@ int pmgpu_icp_reset(pmgpu_ctx* ctx, const float* T_iter_init);
 int pmgpu_icp_result(pmgpu_ctx* ctx, float* T_iter_out, int* iterations_out, float* cov_out, float* stats_out);
 int pmgpu_icp_cap_redos(const pmgpu_ctx* ctx);
 
+/* ---- host-side pre-filters of the default chain (CPU, once per cloud) ----
+ * ICPChainBase::setDefault / examples/data/default.yaml put RandomSamplingDataPointsFilter on
+ * the reading and SamplingSurfaceNormalDataPointsFilter on the reference (ICP.cpp:100-113).
+ * Both draw from std::rand() in point order, and the second one's bins come from a recursive
+ * std::nth_element, so they run on the host exactly as in the reference; nothing here touches
+ * the device.
+ * pmgpu_host_random_sampling (RandomSampling.cpp:58-75): keep_out[0..return) = kept columns.
+ * pmgpu_host_sampling_surface_normal (SamplingSurfaceNormal.cpp:80-342): `features` (4 x n) and
+ * `descriptors` (desc_rows x n, may be null) are modified in place like the reference's cloud
+ * (samplingMethod 1 stores the bin mean in the kept column); outputs are written at the kept
+ * columns' ORIGINAL positions (normals 3 x n, densities n, eig_values 3 x n, eig_vectors 9 x n),
+ * the caller compacts by keep_out (sorted ascending).  Returns the number of kept points,
+ * -1 on a bad argument; unfit_out: points dropped for lack of a normal. */
+enum {
+    PMGPU_KEEP_NORMALS = 1,
+    PMGPU_KEEP_DENSITIES = 2,
+    PMGPU_KEEP_EIGEN_VALUES = 4,
+    PMGPU_KEEP_EIGEN_VECTORS = 8
+};
+void pmgpu_host_srand(unsigned seed);
+int pmgpu_host_random_sampling(int n, float prob, int32_t* keep_out);
+int pmgpu_host_sampling_surface_normal(float* features, int rows, int n, float* descriptors, int desc_rows, float ratio, int knn,
+                                       int sampling_method, float max_box_dim, int average_descriptors, int flags, int32_t* keep_out,
+                                       float* normals_out, float* densities_out, float* eig_values_out, float* eig_vectors_out,
+                                       int* unfit_out);
+
 /* ---- multi-GPU: queries sharded over ranks, replicated reference ------------------------
  * After pmgpu_comm_init the quantile histograms and the normal-equation sums of
  * pmgpu_weights / pmgpu_minimize / pmgpu_icp_* are all-reduced over the communicator, so

@@ -84,6 +84,10 @@ SIGNATURES = {
     "pmgpu_icp_reset": (C.c_int, [C.c_void_p, _fp]),
     "pmgpu_icp_result": (C.c_int, [C.c_void_p, _fp, C.POINTER(C.c_int), _fp, _fp]),
     "pmgpu_icp_cap_redos": (C.c_int, [C.c_void_p]),
+    "pmgpu_host_srand": (None, [C.c_uint]),
+    "pmgpu_host_random_sampling": (C.c_int, [C.c_int, C.c_float, C.c_void_p]),
+    "pmgpu_host_sampling_surface_normal": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_float, C.c_int,
+                                                    C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     "pmgpu_comm_unique_id": (C.c_int, [C.c_void_p]),
     "pmgpu_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "pmgpu_comm_destroy": (C.c_int, [C.c_void_p]),

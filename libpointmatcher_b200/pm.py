@@ -7,6 +7,8 @@ computed in Python except the 4x4 bookkeeping of ICP::compute (ICP.cpp:264-313, 
 which the reference also does on the host.  The C++ twin of this file is
 libpointmatcher_b200/host/PointMatcher.h.
 """
+import ctypes as C
+
 import numpy as np
 
 from . import capi
@@ -357,6 +359,148 @@ class SurfaceNormalDataPointsFilter(Parametrizable, _Bound):
         cloud.descriptors.update(res)
 
 
+# ---- host-side pre-filters of the default chain -------------------------------
+# Run once per cloud on the CPU, as in the reference: RandomSampling / SamplingSurfaceNormal go
+# through the C entry points of csrc/host_filters.cu (same std::rand stream and std::nth_element
+# order as the reference's C++), the threshold filters are plain column selections.
+def _select_columns(cloud, keep):
+    cloud.features = np.ascontiguousarray(cloud.features[keep])
+    cloud.descriptors = {k: np.ascontiguousarray(v[keep]) for k, v in cloud.descriptors.items()}
+
+
+class _HostFilter(Parametrizable):
+    def __init__(self, params=None):
+        Parametrizable.__init__(self, params)
+        for name, *_ in self.PARAMS:
+            setattr(self, name, self.get(name))
+
+    def bind(self, ctx):
+        pass
+
+    def init(self):
+        pass
+
+    def filter(self, cloud):
+        out = cloud.copy()
+        self.inPlaceFilter(out)
+        return out
+
+
+class IdentityDataPointsFilter(_HostFilter):
+    className = "IdentityDataPointsFilter"
+    PARAMS = ()
+
+    def inPlaceFilter(self, cloud):
+        pass
+
+
+class RandomSamplingDataPointsFilter(_HostFilter):
+    """RandomSampling.h:58-65, RandomSampling.cpp:58-75"""
+    className = "RandomSamplingDataPointsFilter"
+    PARAMS = (("prob", "probability to keep a point, one over decimation factor ", "0.75", "0", "1", float),)
+
+    def inPlaceFilter(self, cloud):
+        n = cloud.features.shape[0]
+        keep = np.empty(max(n, 1), np.int32)
+        m = capi.lib.pmgpu_host_random_sampling(n, float(np.float32(self.prob)), keep.ctypes.data)
+        _select_columns(cloud, keep[:m])
+
+
+class _AxisThresholdFilter(_HostFilter):
+    def _values(self, cloud):
+        if self.dim >= cloud.features.shape[1] - 1:
+            raise InvalidParameter("%s: Error, filtering on dimension number %d, larger than feature dimensionality %d"
+                                   % (self.className, self.dim, cloud.features.shape[1] - 2))
+        if self.dim == -1:  # Euclidean norm of the point, in float like Eigen's norm()
+            f = cloud.features[:, :-1]
+            acc = np.zeros(len(f), np.float32)
+            for a in range(f.shape[1]):
+                acc = (acc + f[:, a] * f[:, a]).astype(np.float32)
+            return np.sqrt(acc)
+        return cloud.features[:, self.dim]
+
+
+class MinDistDataPointsFilter(_AxisThresholdFilter):
+    """MinDist.h:56-62, MinDist.cpp:60-100"""
+    className = "MinDistDataPointsFilter"
+    PARAMS = (("dim", "dimension on which the filter will be applied. x=0, y=1, z=2, radius=-1", "-1", "-1", "2", int),
+              ("minDist", "minimum value authorized. If dim is set to -1 (radius), the absolute value of minDist will be used. "
+                          "All points before that will be filtered.", "1", "-inf", "inf", float))
+
+    def inPlaceFilter(self, cloud):
+        lim = np.float32(abs(self.minDist) if self.dim == -1 else self.minDist)
+        _select_columns(cloud, np.nonzero(self._values(cloud) > lim)[0])
+
+
+class MaxDistDataPointsFilter(_AxisThresholdFilter):
+    """MaxDist.h:56-62, MaxDist.cpp:60-100"""
+    className = "MaxDistDataPointsFilter"
+    PARAMS = (("dim", "dimension on which the filter will be applied. x=0, y=1, z=2, radius=-1", "-1", "-1", "2", int),
+              ("maxDist", "maximum distance authorized. If dim is set to -1 (radius), the absolute value of minDist will be used. "
+                          "All points beyond that will be filtered.", "1", "-inf", "inf", float))
+
+    def inPlaceFilter(self, cloud):
+        lim = np.float32(abs(self.maxDist) if self.dim == -1 else self.maxDist)
+        _select_columns(cloud, np.nonzero(self._values(cloud) < lim)[0])
+
+
+class SamplingSurfaceNormalDataPointsFilter(_HostFilter):
+    """SamplingSurfaceNormal.h:60-74, SamplingSurfaceNormal.cpp:80-342: kd-split bins of <= knn points,
+    one normal per bin, random (0) or one-per-bin (1) subsampling."""
+    className = "SamplingSurfaceNormalDataPointsFilter"
+    PARAMS = (
+        ("ratio", "ratio of points to keep with random subsampling. Matrix (normal, density, etc.) will be associated to all points in the same bin.",
+         "0.5", "0.0000001", "1.0", float),
+        ("knn", "determined how many points are used to compute the normals. Direct link with the rapidity of the computation (large = fast). "
+                "Technically, limit over which a box is splitted in two", "7", "3", "2147483647", int),
+        ("samplingMethod", "if set to 0, random subsampling using the parameter ratio. If set to 1, bin subsampling with the resulting number of "
+                           "points being 1/knn.", "0", "0", "1", int),
+        ("maxBoxDim", "maximum length of a box above which the box is discarded", "inf", None, None, float),
+        ("averageExistingDescriptors", "whether the filter keep the existing point descriptors and average them or should it drop them", "1", None, None, bool),
+        ("keepNormals", "whether the normals should be added as descriptors to the resulting cloud", "1", None, None, bool),
+        ("keepDensities", "whether the point densities should be added as descriptors to the resulting cloud", "0", None, None, bool),
+        ("keepEigenValues", "whether the eigen values should be added as descriptors to the resulting cloud", "0", None, None, bool),
+        ("keepEigenVectors", "whether the eigen vectors should be added as descriptors to the resulting cloud", "0", None, None, bool),
+    )
+
+    def inPlaceFilter(self, cloud):
+        n = cloud.features.shape[0]
+        names = list(cloud.descriptors)
+        spans = [cloud.descriptors[k].shape[1] for k in names]
+        desc = np.ascontiguousarray(np.concatenate([cloud.descriptors[k] for k in names], axis=1), np.float32) if names else None
+        feat = np.ascontiguousarray(cloud.features, np.float32).copy()
+        flags = (1 if self.keepNormals else 0) | (2 if self.keepDensities else 0) | (4 if self.keepEigenValues else 0) | (8 if self.keepEigenVectors else 0)
+        keep = np.empty(max(n, 1), np.int32)
+        normals = np.zeros((n, 3), np.float32)
+        dens = np.zeros(n, np.float32)
+        eva = np.zeros((n, 3), np.float32)
+        eve = np.zeros((n, 9), np.float32)
+        unfit = C.c_int(0)
+        m = capi.lib.pmgpu_host_sampling_surface_normal(
+            feat.ctypes.data, 4, n, desc.ctypes.data if desc is not None else None, desc.shape[1] if desc is not None else 0,
+            float(np.float32(self.ratio)), int(self.knn), int(self.samplingMethod), float(np.float32(self.maxBoxDim)),
+            1 if self.averageExistingDescriptors else 0, flags, keep.ctypes.data, normals.ctypes.data, dens.ctypes.data, eva.ctypes.data,
+            eve.ctypes.data, C.byref(unfit))
+        if m < 0:
+            raise RuntimeError("SamplingSurfaceNormalDataPointsFilter: bad argument")
+        k = keep[:m]
+        self.unfitPointsCount = unfit.value
+        cloud.features = np.ascontiguousarray(feat[k])
+        out, col = {}, 0
+        for name, span in zip(names, spans):
+            out[name] = np.ascontiguousarray(desc[k, col:col + span])
+            col += span
+        if self.keepNormals:
+            out["normals"] = normals[k]
+        if self.keepDensities:
+            out["densities"] = dens[k, None]
+        if self.keepEigenValues:
+            out["eigValues"] = eva[k]
+        if self.keepEigenVectors:
+            out["eigVectors"] = eve[k]
+        cloud.descriptors = out
+
+
 # ---- TransformationCheckers (host objects carrying the parameters; evaluated on the device
 #      inside the fused loop, TransformationCheckersImpl.cpp:45-158) ------------------------------
 class CounterTransformationChecker(Parametrizable):
@@ -401,7 +545,10 @@ ErrorMinimizerRegistrar = Registrar(PointToPointErrorMinimizer=PointToPointError
                                     PointToPointWithCovErrorMinimizer=PointToPointWithCovErrorMinimizer,
                                     PointToPlaneErrorMinimizer=PointToPlaneErrorMinimizer,
                                     PointToPlaneWithCovErrorMinimizer=PointToPlaneWithCovErrorMinimizer)
-DataPointsFilterRegistrar = Registrar(SurfaceNormalDataPointsFilter=SurfaceNormalDataPointsFilter)
+DataPointsFilterRegistrar = Registrar(SurfaceNormalDataPointsFilter=SurfaceNormalDataPointsFilter, IdentityDataPointsFilter=IdentityDataPointsFilter,
+                                      RandomSamplingDataPointsFilter=RandomSamplingDataPointsFilter,
+                                      SamplingSurfaceNormalDataPointsFilter=SamplingSurfaceNormalDataPointsFilter,
+                                      MinDistDataPointsFilter=MinDistDataPointsFilter, MaxDistDataPointsFilter=MaxDistDataPointsFilter)
 TransformationCheckerRegistrar = Registrar(CounterTransformationChecker=CounterTransformationChecker,
                                            DifferentialTransformationChecker=DifferentialTransformationChecker)
 
@@ -433,7 +580,8 @@ class ICP:
     transform like `PointMatcher<T>::ICP::operator()`."""
 
     def __init__(self, device=0):
-        self.ctx = capi.Context(device)
+        self._device, self._ctx = device, None  # the device context is created on first use
+        self.readingDataPointsFilters = []
         self.referenceDataPointsFilters = []
         self.matcher = None
         self.outlierFilters = OutlierFilters()
@@ -442,15 +590,51 @@ class ICP:
         self.maxNumIterationsReached = False
         self.iterationCount = 0
 
+    @property
+    def ctx(self):
+        if self._ctx is None:
+            self._ctx = capi.Context(self._device)
+        return self._ctx
+
     def setDefault(self):
-        """The hot-path part of ICP::setDefault (ICP.cpp:99-113): KDTreeMatcher, TrimmedDist(0.85),
-        PointToPlane, Counter(40) + Differential; reference normals from SurfaceNormal(knn 7) in
-        place of the CPU-only SamplingSurfaceNormal pre-filter."""
-        self.referenceDataPointsFilters = [SurfaceNormalDataPointsFilter({"knn": "7"})]
+        """ICPChainBase::setDefault (ICP.cpp:100-113): RandomSampling on the reading, SamplingSurfaceNormal
+        on the reference (both on the host, once per cloud), KDTreeMatcher, TrimmedDist(0.85), PointToPlane,
+        Counter(40) + Differential."""
+        self.readingDataPointsFilters = [RandomSamplingDataPointsFilter()]
+        self.referenceDataPointsFilters = [SamplingSurfaceNormalDataPointsFilter()]
         self.matcher = KDTreeMatcher()
         self.outlierFilters = OutlierFilters([TrimmedDistOutlierFilter()])
         self.errorMinimizer = PointToPlaneErrorMinimizer()
         self.transformationCheckers = [CounterTransformationChecker(), DifferentialTransformationChecker()]
+
+    def loadFromYaml(self, text):
+        """ICPChainBase::loadFromYaml (ICP.cpp:116-167): the reference's YAML layout — module lists for the
+        filters / outlier filters / checkers, a single module for matcher and errorMinimizer; a module is
+        `Name`, `Name:` or `Name: {param: value}`.  Unknown names raise InvalidElement (Registrar.h:150-162).
+        inspector / logger accept the Null modules only."""
+        import yaml
+        doc = yaml.safe_load(text) or {}
+
+        def one(node):
+            if isinstance(node, str):
+                return node, {}
+            if isinstance(node, dict) and len(node) == 1:
+                (name, params), = node.items()
+                return name, {k: str(v) for k, v in (params or {}).items()}
+            raise ConfigurationError("ICP YAML: a module must be `Name` or `Name: {parameters}`")
+
+        def many(key, registrar):
+            return [registrar.create(*one(n)) for n in (doc.get(key) or [])]
+
+        self.readingDataPointsFilters = many("readingDataPointsFilters", DataPointsFilterRegistrar)
+        self.referenceDataPointsFilters = many("referenceDataPointsFilters", DataPointsFilterRegistrar)
+        self.outlierFilters = OutlierFilters(many("outlierFilters", OutlierFilterRegistrar))
+        self.transformationCheckers = many("transformationCheckers", TransformationCheckerRegistrar)
+        self.matcher = MatcherRegistrar.create(*one(doc["matcher"])) if "matcher" in doc else KDTreeMatcher()
+        self.errorMinimizer = ErrorMinimizerRegistrar.create(*one(doc["errorMinimizer"])) if "errorMinimizer" in doc else PointToPlaneErrorMinimizer()
+        for key, allowed in (("inspector", "NullInspector"), ("logger", "NullLogger")):
+            if key in doc and one(doc[key])[0] != allowed:
+                raise InvalidElement("Trying to instanciate unknown element %s from registrar" % one(doc[key])[0])
 
     def _params(self):
         counter = [c for c in self.transformationCheckers if isinstance(c, CounterTransformationChecker)]
@@ -470,7 +654,8 @@ class ICP:
             raise RuntimeError("You must setup a matcher before running ICP")
         if self.errorMinimizer is None:
             raise RuntimeError("You must setup an error minimizer before running ICP")
-        for mod in [self.matcher, self.outlierFilters, self.errorMinimizer] + list(self.outlierFilters) + list(self.referenceDataPointsFilters):
+        for mod in ([self.matcher, self.outlierFilters, self.errorMinimizer] + list(self.outlierFilters) + list(self.referenceDataPointsFilters)
+                    + list(self.readingDataPointsFilters)):
             mod.bind(self.ctx)
 
     def _set_reference(self, referenceIn):
@@ -491,6 +676,10 @@ class ICP:
         if T_init.shape != (4, 4):
             raise RuntimeError("The initial transformation matrix must be squared.")
         reading = readingIn if isinstance(readingIn, DataPoints) else DataPoints(readingIn)
+        if self.readingDataPointsFilters:
+            reading = reading.copy()  # ICP.cpp:324-326
+            for f in self.readingDataPointsFilters:
+                f.inPlaceFilter(reading)
         # reading into the refMean frame (ICP.cpp:345-347); T_refIn_refMean is a pure translation
         T_refMean_refIn = np.eye(4, dtype=np.float32)
         T_refMean_refIn[:3, 3] = -T_refIn_refMean[:3, 3]

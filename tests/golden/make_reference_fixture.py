@@ -7,6 +7,7 @@ Contents (data only, no reference source code):
   cloud0, cloud1   examples/data/cloud.00000.vtk / cloud.00001.vtk   (N, 3) float32  — utest icpTest (utest/utest.cpp:81-160)
   car400, car401   examples/data/car_cloud400.csv / car_cloud401.csv (N, 6) float32 x y z nx ny nz — utest validate3dTransformation
   golden_<name>    examples/data/icp_data/<name>.ref_trans           (4, 4) float64
+  yaml_<name>      examples/data/icp_data/<name>.yaml, yaml_default = examples/data/default.yaml   (text)
   validT3d         utest/utest.cpp:352-356
 """
 import os
@@ -55,8 +56,15 @@ out = dict(
                        [0.111899, -0.156644, 0.981296, -0.0356313], [0, 0, 0, 1]]),
 )
 for name in ("defaultIdentityDataPointsFilter", "defaultPointToPlaneMinDistDataPointsFilter", "defaultPointToPointMinDistDataPointsFilter",
-             "defaultPointToPlaneWithCovErrorMinimizer", "defaultPointToPointWithCovErrorMinimizer"):
+             "defaultPointToPlaneWithCovErrorMinimizer", "defaultPointToPointWithCovErrorMinimizer", "defaultMaxDistDataPointsFilter",
+             "SamplingSurfaceNormalDataPointsFilter1", "SamplingSurfaceNormalDataPointsFilter2", "SamplingSurfaceNormalDataPointsFilter3"):
     out["golden_" + name] = load_trans(name)
+# the chain configurations themselves (YAML text = data), for the chains whose modules are all built
+for name in ("defaultIdentityDataPointsFilter", "defaultPointToPlaneMinDistDataPointsFilter", "defaultPointToPointMinDistDataPointsFilter",
+             "defaultMaxDistDataPointsFilter", "SamplingSurfaceNormalDataPointsFilter1", "SamplingSurfaceNormalDataPointsFilter2",
+             "SamplingSurfaceNormalDataPointsFilter3"):
+    out["yaml_" + name] = np.array(open(os.path.join(DATA, "icp_data", name + ".yaml")).read())
+out["yaml_default"] = np.array(open(os.path.join(DATA, "default.yaml")).read())  # BASELINE config 1
 path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_fixture.npz")
 np.savez_compressed(path, **out)
-print({k: v.shape for k, v in out.items()}, os.path.getsize(path))
+print({k: getattr(v, "shape", None) for k, v in out.items()}, os.path.getsize(path))

@@ -1,0 +1,166 @@
+"""the CPU pre-filters of the default chain (RandomSampling, SamplingSurfaceNormal,
+MinDist / MaxDist, Identity) and the YAML chain loader, against the oracle restatement in
+oracle/prefilters.py.  These run on the host in the reference too, so everything here is a CPU test;
+the chains that use them are run end to end against the reference's golden transforms with `-m gpu`
+(tests/test_reference_goldens.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import prefilters as orc  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def pm():
+    from libpointmatcher_b200 import pm
+    return pm
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from libpointmatcher_b200 import capi
+    return capi
+
+
+def surface_cloud(n, seed=0):
+    """a noisy curved sheet plus a wall: well-defined local normals, no repeated coordinates"""
+    rng = np.random.default_rng(seed)
+    xy = rng.uniform(-10, 10, (n, 2))
+    z = 0.05 * xy[:, 0] ** 2 * 0.1 + rng.normal(0, 0.002, n)
+    pts = np.c_[xy, z]
+    wall = n // 4
+    pts[:wall] = np.c_[rng.uniform(-10, 10, wall), np.full(wall, 10.0) + rng.normal(0, 0.002, wall), rng.uniform(0, 4, wall)]
+    return np.ascontiguousarray(np.c_[pts, np.ones(n)].astype(np.float32))
+
+
+@pytest.mark.parametrize("prob,seed", [(0.5, 1), (0.75, 7), (0.05, 123), (1.0, 3)])
+def test_random_sampling_is_the_reference_rand_stream(pm, capi, prob, seed):
+    cloud = surface_cloud(5000)
+    desc = {"intensity": np.arange(5000, dtype=np.float32)[:, None]}
+    capi.lib.pmgpu_host_srand(seed)
+    out = pm.RandomSamplingDataPointsFilter({"prob": repr(prob)}).filter(pm.DataPoints(cloud, desc))
+    orc.srand(seed)
+    keep = orc.random_sampling(5000, prob)
+    assert (out.descriptors["intensity"][:, 0].astype(np.int64) == keep).all()
+    assert (out.features == cloud[keep]).all()
+    assert abs(len(keep) / 5000 - min(prob, 1.0)) < 0.03
+
+
+def _match_rows(a, b, tol):
+    """rows of a and b as the same multiset (lexicographic order), within tol"""
+    ia, ib = np.lexsort(a[:, ::-1].T), np.lexsort(b[:, ::-1].T)
+    assert a.shape == b.shape
+    assert np.abs(a[ia] - b[ib]).max() < tol
+    return ia, ib
+
+
+def test_sampling_surface_normal_one_point_per_bin(pm):
+    cloud = surface_cloud(6000, seed=2)
+    colour = np.random.default_rng(5).uniform(0, 1, (6000, 2)).astype(np.float32)
+    f = pm.SamplingSurfaceNormalDataPointsFilter({"knn": "10", "samplingMethod": "1", "keepDensities": "1", "averageExistingDescriptors": "1"})
+    out = f.filter(pm.DataPoints(cloud, {"colour": colour}))
+    feats, normals, dens, descs, unfit = orc.sampling_surface_normal_method1(cloud, 10, descriptors=colour)
+    assert unfit == f.unfitPointsCount == 0
+    ia, ib = _match_rows(out.features, feats, 1e-4)                       # bins as sets: the same bin means
+    dots = np.abs((out.descriptors["normals"][ia] * normals[ib]).sum(axis=1))
+    assert (dots > 0.999).mean() > 0.99 and np.median(dots) > 0.999999    # one normal per bin, sign free
+    assert np.allclose(np.linalg.norm(out.descriptors["normals"], axis=1), 1, atol=1e-5)
+    assert np.allclose(out.descriptors["densities"][ia, 0], dens[ib], rtol=1e-3)
+    assert np.allclose(out.descriptors["colour"][ia], descs[ib], atol=1e-5)
+    assert (out.features[:, 3] == 1).all()
+    assert 6000 / 10 <= len(out.features) <= 6000 / 5                     # bins hold between knn/2 and knn points
+
+
+def test_sampling_surface_normal_random_subsampling(pm, capi):
+    cloud = surface_cloud(6000, seed=3)
+    tag = np.arange(6000, dtype=np.float32)[:, None]
+    capi.lib.pmgpu_host_srand(1)
+    f = pm.SamplingSurfaceNormalDataPointsFilter({"knn": "10", "samplingMethod": "0", "ratio": "0.7"})
+    out = f.filter(pm.DataPoints(cloud, {"tag": tag}))
+    kept = out.descriptors["tag"][:, 0].astype(np.int64)
+    assert (np.diff(kept) > 0).all()                                      # sorted by original index (SamplingSurfaceNormal.cpp:146)
+    assert (out.features == cloud[kept]).all()                            # points are kept as they are
+    assert abs(len(kept) / 6000 - 0.7) < 0.03
+    owner = np.empty(6000, np.int64)
+    fused = {}
+    for b, idx in enumerate(orc.bins(cloud, 10)):
+        owner[idx] = b
+        fused[b] = orc.fuse(cloud, idx)
+    dots = np.array([abs(float(out.descriptors["normals"][i] @ fused[owner[k]][1])) for i, k in enumerate(kept)])
+    assert (dots > 0.999).mean() > 0.99                                   # every kept point carries its bin's normal
+
+
+def test_sampling_surface_normal_drops_large_and_degenerate_bins(pm):
+    cloud = surface_cloud(3000, seed=4)
+    f = pm.SamplingSurfaceNormalDataPointsFilter({"knn": "12", "samplingMethod": "1", "maxBoxDim": "0.9"})
+    out = f.filter(pm.DataPoints(cloud))
+    feats, _, _, _, unfit = orc.sampling_surface_normal_method1(cloud, 12, max_box_dim=0.9)
+    assert f.unfitPointsCount == unfit > 0 and len(out.features) == len(feats) > 0
+    # collinear points: the covariance has rank 1 -> no normal, every point is dropped
+    line = np.zeros((64, 4), np.float32)
+    line[:, 0] = np.linspace(0, 1, 64, dtype=np.float32) ** 2
+    line[:, 3] = 1
+    f = pm.SamplingSurfaceNormalDataPointsFilter({"knn": "8", "samplingMethod": "1"})
+    out = f.filter(pm.DataPoints(line))
+    assert len(out.features) == 0 and f.unfitPointsCount == 64
+
+
+def test_min_max_dist_filters(pm):
+    cloud = surface_cloud(4000, seed=6)
+    for dim, val in ((-1, 6.5), (-1, -6.5), (0, 1.25), (2, 0.3)):
+        out = pm.MinDistDataPointsFilter({"dim": str(dim), "minDist": repr(val)}).filter(pm.DataPoints(cloud))
+        assert (out.features == cloud[orc.min_dist(cloud, dim, val)]).all()
+        out = pm.MaxDistDataPointsFilter({"dim": str(dim), "maxDist": repr(val)}).filter(pm.DataPoints(cloud))
+        assert (out.features == cloud[orc.max_dist(cloud, dim, val)]).all()
+    out = pm.IdentityDataPointsFilter().filter(pm.DataPoints(cloud))
+    assert (out.features == cloud).all()
+    with pytest.raises(pm.InvalidParameter):
+        pm.MinDistDataPointsFilter({"dim": "3"})
+
+
+def test_parameter_tables_of_the_prefilters(pm):
+    """names, defaults and bounds as in RandomSampling.h:58-63, SamplingSurfaceNormal.h:60-74, MinDist.h:56-62"""
+    assert pm.RandomSamplingDataPointsFilter().prob == 0.75
+    f = pm.SamplingSurfaceNormalDataPointsFilter()
+    assert (f.ratio, f.knn, f.samplingMethod, f.maxBoxDim) == (0.5, 7, 0, np.inf)
+    assert (f.averageExistingDescriptors, f.keepNormals, f.keepDensities, f.keepEigenValues, f.keepEigenVectors) == (True, True, False, False, False)
+    for bad in ({"knn": "2"}, {"ratio": "1.5"}, {"samplingMethod": "2"}, {"nope": "1"}):
+        with pytest.raises(pm.InvalidParameter):
+            pm.SamplingSurfaceNormalDataPointsFilter(bad)
+    with pytest.raises(pm.InvalidParameter):
+        pm.RandomSamplingDataPointsFilter({"prob": "1.5"})
+    m = pm.MinDistDataPointsFilter()
+    assert (m.dim, m.minDist) == (-1, 1.0)
+    for name in ("RandomSamplingDataPointsFilter", "SamplingSurfaceNormalDataPointsFilter", "MinDistDataPointsFilter", "MaxDistDataPointsFilter",
+                 "IdentityDataPointsFilter", "SurfaceNormalDataPointsFilter"):
+        assert name in pm.DataPointsFilterRegistrar
+
+
+def test_yaml_chains_of_the_reference_load(pm):
+    """ICPChainBase::loadFromYaml on the reference's own chain files (text packed into the fixture)"""
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "reference_fixture.npz"))
+    icp = pm.ICP()
+    icp.loadFromYaml(str(fx["yaml_defaultPointToPlaneMinDistDataPointsFilter"]))
+    assert [type(f).__name__ for f in icp.readingDataPointsFilters] == ["MinDistDataPointsFilter"]
+    ssn = icp.referenceDataPointsFilters[0]
+    assert type(ssn).__name__ == "SamplingSurfaceNormalDataPointsFilter" and (ssn.knn, ssn.samplingMethod, ssn.averageExistingDescriptors) == (10, 1, False)
+    assert abs(ssn.ratio - 0.666666) < 1e-7
+    assert type(icp.errorMinimizer).__name__ == "PointToPlaneErrorMinimizer" and icp.matcher.knn == 1
+    assert abs(icp.outlierFilters[0].get("ratio") - 0.75) < 1e-7
+    assert [type(c).__name__ for c in icp.transformationCheckers] == ["CounterTransformationChecker", "DifferentialTransformationChecker"]
+    assert icp.transformationCheckers[1].smoothLength == 4
+    icp.loadFromYaml(str(fx["yaml_defaultPointToPointMinDistDataPointsFilter"]))
+    assert type(icp.errorMinimizer).__name__ == "PointToPointErrorMinimizer"
+    assert [type(f).__name__ for f in icp.readingDataPointsFilters] == ["MinDistDataPointsFilter", "RandomSamplingDataPointsFilter"]
+    with pytest.raises(pm.InvalidElement):      # default.yaml asks for the VTKFileInspector, which is out of scope
+        icp.loadFromYaml(str(fx["yaml_default"]))
+    with pytest.raises(pm.InvalidElement):
+        icp.loadFromYaml("matcher:\n  KDTreeVarDistMatcher:\n    knn: 1\n")
+    icp.setDefault()                            # ICP.cpp:100-113
+    assert type(icp.readingDataPointsFilters[0]).__name__ == "RandomSamplingDataPointsFilter"
+    assert type(icp.referenceDataPointsFilters[0]).__name__ == "SamplingSurfaceNormalDataPointsFilter"
+    assert abs(icp.outlierFilters[0].get("ratio") - 0.85) < 1e-7

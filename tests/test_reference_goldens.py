@@ -9,6 +9,10 @@
   * validT3d — `IcpHelper::validate3dTransformation` (utest/utest.h:66-84): car_cloud401 onto
     car_cloud400, |t| within 0.1 and quaternion angular distance within 0.1 rad.
 
+  * the same goldens through the reference's own chain files (YAML text in the fixture) now that the
+    CPU pre-filters they name are built: `icp.loadFromYaml(...)`, `icp(data, ref)`,
+    exactly what `TEST(icpTest, icpTest)` does.
+
 The oracle is checked on the CPU; the GPU path (through the C ABI) is checked with `-m gpu`.
 """
 import os
@@ -98,3 +102,60 @@ def test_gpu_reproduces_validT3d(oracle, fx, mini):
     valid = fx["validT3d"]
     assert abs(np.linalg.norm(T[:3, 3]) - np.linalg.norm(valid[:3, 3])) < 0.1
     assert oracle.angular_distance(T, valid.astype(np.float32)) < 0.1
+
+
+# ---- the reference's chain files, end to end (pre-filters on the host, loop on the GPU) -----------
+YAML_CHAINS = ["defaultIdentityDataPointsFilter", "defaultPointToPlaneMinDistDataPointsFilter", "defaultPointToPointMinDistDataPointsFilter",
+               "defaultMaxDistDataPointsFilter", "SamplingSurfaceNormalDataPointsFilter1", "SamplingSurfaceNormalDataPointsFilter2",
+               "SamplingSurfaceNormalDataPointsFilter3"]
+
+
+@pytest.mark.parametrize("name", ["defaultIdentityDataPointsFilter", "defaultPointToPlaneMinDistDataPointsFilter"])
+def test_oracle_chain_with_prefilters_reproduces_golden(oracle, fx, name):
+    """oracle pre-filters (bin sampling, one point per bin) + oracle ICP = the chain of the YAML file"""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import prefilters as pre
+    ref, data = homog(fx["cloud0"]), homog(fx["cloud1"])
+    if "MinDist" in name:
+        data_f = data[pre.min_dist(data, -1, 1.0)]
+    else:
+        data_f = data
+    ref_f, normals, _, _, _ = pre.sampling_surface_normal_method1(ref, 10)
+    r = oracle.icp(np.ascontiguousarray(data_f), np.ascontiguousarray(ref_f), ref_normals=np.ascontiguousarray(normals),
+                   filters=[(oracle.FILTER_TRIMMEDDIST, 0.75)], minimizer=1, max_iterations=40, differential=(0.001, 0.01, 4), nthreads=4)
+    assert rel_err(r["T"], fx["golden_" + name], data) < 0.03
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", YAML_CHAINS)
+def test_gpu_runs_reference_yaml_chain_to_golden(fx, name):
+    from libpointmatcher_b200 import capi, pm
+    ref, data = homog(fx["cloud0"]), homog(fx["cloud1"])
+    capi.lib.pmgpu_host_srand(1)
+    icp = pm.ICP()
+    icp.loadFromYaml(str(fx["yaml_" + name]))
+    T = icp(pm.DataPoints(data), pm.DataPoints(ref))
+    icp.ctx.close()
+    assert rel_err(T, fx["golden_" + name], data) < 0.03
+    assert 1 <= icp.iterationCount <= 150
+
+
+@pytest.mark.gpu
+def test_gpu_default_chain_config1(fx):
+    """BASELINE config 1: examples/icp_simple = ICP::setDefault() on cloud.00001 -> cloud.00000; default.yaml is the
+    same chain with knn 10 and TrimmedDist 0.75 (its VTK inspector replaced by the Null one)."""
+    from libpointmatcher_b200 import capi, pm
+    ref, data = homog(fx["cloud0"]), homog(fx["cloud1"])
+    golden = fx["golden_SamplingSurfaceNormalDataPointsFilter1"]   # same clouds, same kind of chain
+    capi.lib.pmgpu_host_srand(1)
+    icp = pm.ICP()
+    icp.setDefault()
+    T = icp(pm.DataPoints(data), pm.DataPoints(ref))
+    assert rel_err(T, golden, data) < 0.03
+    text = str(fx["yaml_default"])
+    text = text[:text.index("inspector:\n VTKFileInspector")] + "inspector:\n  NullInspector\n\nlogger:\n  NullLogger\n"
+    icp.loadFromYaml(text)
+    T2 = icp(pm.DataPoints(data), pm.DataPoints(ref))
+    icp.ctx.close()
+    assert rel_err(T2, golden, data) < 0.03
