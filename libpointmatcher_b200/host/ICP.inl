@@ -19,13 +19,13 @@ struct ICPChainBase {
 
     virtual ~ICPChainBase() {}
 
-    // ICP.cpp:99-113.  The reference's default pre-filters (RandomSampling on the reading,
-    // SamplingSurfaceNormal on the reference) are CPU-only modules outside the GPU path; the
-    // reference normals that PointToPlane needs come from SurfaceNormalDataPointsFilter (K8).
+    // ICP.cpp:99-113.  The default pre-filters (RandomSampling on the reading, SamplingSurfaceNormal
+    // on the reference) run on the host, once per cloud, like the reference's.
     virtual void setDefault() {
         cleanup();
         this->transformations.push_back(std::make_shared<RigidTransformation>());
-        this->referenceDataPointsFilters.push_back(std::make_shared<SurfaceNormalDataPointsFilter>(Parameters{{"knn", "7"}}));
+        this->readingDataPointsFilters.push_back(std::make_shared<RandomSamplingDataPointsFilter>());          // ICP.cpp:105
+        this->referenceDataPointsFilters.push_back(std::make_shared<SamplingSurfaceNormalDataPointsFilter>());  // ICP.cpp:106
         this->matcher = std::make_shared<KDTreeMatcher>();
         this->outlierFilters.push_back(std::make_shared<TrimmedDistOutlierFilter>());
         this->errorMinimizer = std::make_shared<PointToPlaneErrorMinimizer>();

@@ -65,6 +65,163 @@ struct IdentityDataPointsFilter : public DataPointsFilter {
     void inPlaceFilter(DataPoints&) override {}
 };
 
+// ---- host-side pre-filters of the default chain -----------------------------------
+// CPU, once per cloud, like the reference; RandomSampling and SamplingSurfaceNormal run in
+// csrc/host_filters.cu behind the C ABI (same std::rand stream and std::nth_element as the reference).
+struct RandomSamplingDataPointsFilter : public DataPointsFilter {
+    static const std::string description() { return "Subsampling. This filter reduces the size of the point cloud by randomly dropping points. Based on \\cite{Masuda1996Random}"; }
+    static const ParametersDoc availableParameters() {
+        return {{"prob", "probability to keep a point, one over decimation factor ", "0.75", "0", "1", &Parametrizable::Comp<T>}};
+    }
+    const double prob;
+    RandomSamplingDataPointsFilter(const Parameters& params = Parameters())
+        : DataPointsFilter("RandomSamplingDataPointsFilter", availableParameters(), params), prob(Parametrizable::get<T>("prob")) {}
+    DataPoints filter(const DataPoints& input) override {
+        DataPoints output(input);
+        inPlaceFilter(output);
+        return output;
+    }
+    void inPlaceFilter(DataPoints& cloud) override {  // RandomSampling.cpp:58-75
+        const int n = cloud.features.cols();
+        std::vector<int32_t> keep(n > 0 ? n : 1);
+        const int m = pmgpu_host_random_sampling(n, (float)prob, keep.data());
+        cloud.keepColumns(std::vector<int>(keep.begin(), keep.begin() + m));
+    }
+};
+
+// MinDist.{h,cpp} / MaxDist.{h,cpp}: keep the points beyond / within a radius or an axis value
+template <bool KEEP_BEYOND>
+struct AxisThresholdDataPointsFilter : public DataPointsFilter {
+    const int dim;
+    const T limit;
+    AxisThresholdDataPointsFilter(const std::string& name, const ParametersDoc& doc, const Parameters& params, const char* limitName)
+        : DataPointsFilter(name, doc, params), dim(Parametrizable::get<int>("dim")), limit(Parametrizable::get<T>(limitName)) {}
+    DataPoints filter(const DataPoints& input) override {
+        DataPoints output(input);
+        inPlaceFilter(output);
+        return output;
+    }
+    void inPlaceFilter(DataPoints& cloud) override {
+        const int rows = cloud.features.rows(), n = cloud.features.cols();
+        if (dim >= rows - 1)
+            throw InvalidParameter(this->className + ": Error, filtering on dimension number " + std::to_string(dim) + ", larger than feature dimensionality " +
+                                   std::to_string(rows - 2));
+        std::vector<int> keep;
+        const T absLimit = limit < 0 ? -limit : limit;
+        for (int i = 0; i < n; ++i) {
+            T v, lim;
+            if (dim == -1) {  // Euclidean norm of the point
+                T acc = 0;
+                for (int r = 0; r < rows - 1; ++r) acc += cloud.features(r, i) * cloud.features(r, i);
+                v = std::sqrt(acc);
+                lim = absLimit;
+            } else {
+                v = cloud.features(dim, i);
+                lim = limit;
+            }
+            if (KEEP_BEYOND ? (v > lim) : (v < lim)) keep.push_back(i);
+        }
+        cloud.keepColumns(keep);
+    }
+};
+struct MinDistDataPointsFilter : public AxisThresholdDataPointsFilter<true> {
+    static const std::string description() { return "Subsampling. Filter points before a minimum distance measured on a specific axis. If dim is set to -1, points are filtered based on a minimum radius."; }
+    static const ParametersDoc availableParameters() {
+        return {{"dim", "dimension on which the filter will be applied. x=0, y=1, z=2, radius=-1", "-1", "-1", "2", &Parametrizable::Comp<int>},
+                {"minDist", "minimum value authorized. If dim is set to -1 (radius), the absolute value of minDist will be used. All points before that will be filtered.", "1", "-inf", "inf", &Parametrizable::Comp<T>}};
+    }
+    MinDistDataPointsFilter(const Parameters& params = Parameters())
+        : AxisThresholdDataPointsFilter<true>("MinDistDataPointsFilter", availableParameters(), params, "minDist") {}
+};
+struct MaxDistDataPointsFilter : public AxisThresholdDataPointsFilter<false> {
+    static const std::string description() { return "Subsampling. Filter points beyond a maximum distance measured on a specific axis. If dim is set to -1, points are filtered based on a maximum radius."; }
+    static const ParametersDoc availableParameters() {
+        return {{"dim", "dimension on which the filter will be applied. x=0, y=1, z=2, radius=-1", "-1", "-1", "2", &Parametrizable::Comp<int>},
+                {"maxDist", "maximum distance authorized. If dim is set to -1 (radius), the absolute value of minDist will be used. All points beyond that will be filtered.", "1", "-inf", "inf", &Parametrizable::Comp<T>}};
+    }
+    MaxDistDataPointsFilter(const Parameters& params = Parameters())
+        : AxisThresholdDataPointsFilter<false>("MaxDistDataPointsFilter", availableParameters(), params, "maxDist") {}
+};
+
+// SamplingSurfaceNormal.{h,cpp}: kd-split bins of <= knn points, one normal per bin
+struct SamplingSurfaceNormalDataPointsFilter : public DataPointsFilter {
+    static const std::string description() {
+        return "Subsampling, Normals. This filter decomposes the point-cloud space in boxes, by recursively splitting the cloud through axis-aligned "
+               "hyperplanes such as to maximize the evenness of the aspect ratio of the box. When the number of points in a box reaches a value knn or "
+               "lower, the filter computes the center of mass of these points and its normal by taking the eigenvector corresponding to the smallest "
+               "eigenvalue of all points in the box.";
+    }
+    static const ParametersDoc availableParameters() {
+        return {
+            {"ratio", "ratio of points to keep with random subsampling. Matrix (normal, density, etc.) will be associated to all points in the same bin.", "0.5", "0.0000001", "1.0", &Parametrizable::Comp<T>},
+            {"knn", "determined how many points are used to compute the normals. Direct link with the rapidity of the computation (large = fast). Technically, limit over which a box is splitted in two", "7", "3", "2147483647", &Parametrizable::Comp<unsigned>},
+            {"samplingMethod", "if set to 0, random subsampling using the parameter ratio. If set to 1, bin subsampling with the resulting number of points being 1/knn.", "0", "0", "1", &Parametrizable::Comp<unsigned>},
+            {"maxBoxDim", "maximum length of a box above which the box is discarded", "inf"},
+            {"averageExistingDescriptors", "whether the filter keep the existing point descriptors and average them or should it drop them", "1"},
+            {"keepNormals", "whether the normals should be added as descriptors to the resulting cloud", "1"},
+            {"keepDensities", "whether the point densities should be added as descriptors to the resulting cloud", "0"},
+            {"keepEigenValues", "whether the eigen values should be added as descriptors to the resulting cloud", "0"},
+            {"keepEigenVectors", "whether the eigen vectors should be added as descriptors to the resulting cloud", "0"}};
+    }
+    const T ratio;
+    const unsigned knn, samplingMethod;
+    const T maxBoxDim;
+    const bool averageExistingDescriptors, keepNormals, keepDensities, keepEigenValues, keepEigenVectors;
+    int unfitPointsCount = 0;
+    SamplingSurfaceNormalDataPointsFilter(const Parameters& params = Parameters())
+        : DataPointsFilter("SamplingSurfaceNormalDataPointsFilter", availableParameters(), params),
+          ratio(Parametrizable::get<T>("ratio")), knn(Parametrizable::get<unsigned>("knn")), samplingMethod(Parametrizable::get<unsigned>("samplingMethod")),
+          maxBoxDim(Parametrizable::get<T>("maxBoxDim")), averageExistingDescriptors(Parametrizable::get<bool>("averageExistingDescriptors")),
+          keepNormals(Parametrizable::get<bool>("keepNormals")), keepDensities(Parametrizable::get<bool>("keepDensities")),
+          keepEigenValues(Parametrizable::get<bool>("keepEigenValues")), keepEigenVectors(Parametrizable::get<bool>("keepEigenVectors")) {}
+    DataPoints filter(const DataPoints& input) override {
+        DataPoints output(input);
+        inPlaceFilter(output);
+        return output;
+    }
+    void inPlaceFilter(DataPoints& cloud) override {  // SamplingSurfaceNormal.cpp:80-170
+        requireFloat3D(cloud.features.rows(), "SamplingSurfaceNormalDataPointsFilter");
+        const int n = cloud.features.cols();
+        if (averageExistingDescriptors) {
+            unsigned insertDim = 0;
+            for (const auto& l : cloud.descriptorLabels) insertDim += l.span;
+            if (insertDim != cloud.getDescriptorDim())
+                throw typename DataPoints::InvalidField("SamplingSurfaceNormalDataPointsFilter: Error, descriptor labels do not match descriptor data");
+        }
+        const int oldDescRows = cloud.descriptors.rows();
+        if (keepNormals) cloud.allocateDescriptor("normals", 3);
+        if (keepDensities) cloud.allocateDescriptor("densities", 1);
+        if (keepEigenValues) cloud.allocateDescriptor("eigValues", 3);
+        if (keepEigenVectors) cloud.allocateDescriptor("eigVectors", 9);
+        std::vector<float> normals(keepNormals ? 3 * (size_t)n : 0), densities(keepDensities ? (size_t)n : 0), eigVa(keepEigenValues ? 3 * (size_t)n : 0),
+            eigVe(keepEigenVectors ? 9 * (size_t)n : 0);
+        // the existing descriptors as their own (rows x n) block for the averaging of bin sampling
+        std::vector<float> oldDesc((size_t)oldDescRows * n);
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i < oldDescRows; ++i) oldDesc[(size_t)j * oldDescRows + i] = (float)cloud.descriptors(i, j);
+        std::vector<int32_t> keep(n > 0 ? n : 1);
+        const int flags = (keepNormals ? PMGPU_KEEP_NORMALS : 0) | (keepDensities ? PMGPU_KEEP_DENSITIES : 0) | (keepEigenValues ? PMGPU_KEEP_EIGEN_VALUES : 0) |
+                          (keepEigenVectors ? PMGPU_KEEP_EIGEN_VECTORS : 0);
+        const int m = pmgpu_host_sampling_surface_normal(reinterpret_cast<float*>(cloud.features.data()), cloud.features.rows(), n,
+                                                         oldDescRows ? oldDesc.data() : nullptr, oldDescRows, (float)ratio, (int)knn, (int)samplingMethod,
+                                                         (float)maxBoxDim, averageExistingDescriptors ? 1 : 0, flags, keep.data(), normals.data(),
+                                                         densities.data(), eigVa.data(), eigVe.data(), &unfitPointsCount);
+        if (m < 0) throw std::runtime_error("SamplingSurfaceNormalDataPointsFilter: bad argument");
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i < oldDescRows; ++i) cloud.descriptors(i, j) = T(oldDesc[(size_t)j * oldDescRows + i]);
+        auto put = [&](const char* name, const std::vector<float>& src, int span) {
+            const unsigned row = cloud.getDescriptorStartingRow(name);
+            for (int j = 0; j < n; ++j)
+                for (int i = 0; i < span; ++i) cloud.descriptors(row + i, j) = T(src[(size_t)j * span + i]);
+        };
+        if (keepNormals) put("normals", normals, 3);
+        if (keepDensities) put("densities", densities, 1);
+        if (keepEigenValues) put("eigValues", eigVa, 3);
+        if (keepEigenVectors) put("eigVectors", eigVe, 9);
+        cloud.keepColumns(std::vector<int>(keep.begin(), keep.begin() + m));
+    }
+};
+
 // ---- SurfaceNormalDataPointsFilter (DataPointsFilters/SurfaceNormal.{h,cpp}) — K8 -------------------
 struct SurfaceNormalDataPointsFilter : public DataPointsFilter, public GpuBound {
     static const std::string description() {

@@ -181,6 +181,21 @@ struct PointMatcher {
             descriptors = grown;
             descriptorLabels.push_back(Label(name, dim));
         }
+        // keep the listed columns (ascending), in place: what the reference's filters do with
+        // setColFrom + conservativeResize (e.g. RandomSampling.cpp:63-74)
+        void keepColumns(const std::vector<int>& keep) {
+            const int m = (int)keep.size();
+            Matrix f(features.rows(), m);
+            for (int j = 0; j < m; ++j)
+                for (int i = 0; i < features.rows(); ++i) f(i, j) = features(i, keep[j]);
+            features = f;
+            if (descriptors.rows() > 0) {
+                Matrix d(descriptors.rows(), m);
+                for (int j = 0; j < m; ++j)
+                    for (int i = 0; i < descriptors.rows(); ++i) d(i, j) = descriptors(i, keep[j]);
+                descriptors = d;
+            }
+        }
         void addDescriptor(const std::string& name, const Matrix& newDescriptor) {
             allocateDescriptor(name, newDescriptor.rows());
             const unsigned row = getDescriptorStartingRow(name);
@@ -407,6 +422,10 @@ struct PointMatcher {
         ADD_TO_REGISTRAR_NO_PARAM(Transformation, RigidTransformation, RigidTransformation)
         ADD_TO_REGISTRAR_NO_PARAM(DataPointsFilter, IdentityDataPointsFilter, IdentityDataPointsFilter)
         ADD_TO_REGISTRAR(DataPointsFilter, SurfaceNormalDataPointsFilter, SurfaceNormalDataPointsFilter)
+        ADD_TO_REGISTRAR(DataPointsFilter, RandomSamplingDataPointsFilter, RandomSamplingDataPointsFilter)
+        ADD_TO_REGISTRAR(DataPointsFilter, SamplingSurfaceNormalDataPointsFilter, SamplingSurfaceNormalDataPointsFilter)
+        ADD_TO_REGISTRAR(DataPointsFilter, MinDistDataPointsFilter, MinDistDataPointsFilter)
+        ADD_TO_REGISTRAR(DataPointsFilter, MaxDistDataPointsFilter, MaxDistDataPointsFilter)
         ADD_TO_REGISTRAR(Matcher, KDTreeMatcher, KDTreeMatcher)
         ADD_TO_REGISTRAR_NO_PARAM(OutlierFilter, NullOutlierFilter, NullOutlierFilter)
         ADD_TO_REGISTRAR(OutlierFilter, MaxDistOutlierFilter, MaxDistOutlierFilter)

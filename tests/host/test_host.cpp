@@ -107,6 +107,64 @@ static int run_cpu() {
         for (int i = 0; i < 6; ++i) mt.dists(0, i) = v[i];
         CHECK(mt.getDistsQuantile(0.19f) == 4.f && mt.getDistsQuantile(0.5f) == 5.f && mt.getDistsQuantile(1.f) == 5.f);
     }
+    // host pre-filters of the default chain: registered under the reference's names,
+    // the default chain is the reference's (ICP.cpp:100-113), and the filters do on a small cloud what
+    // RandomSampling.cpp / MinDist.cpp / SamplingSurfaceNormal.cpp do
+    {
+        PM::ICP def;
+        def.setDefault();
+        CHECK(def.readingDataPointsFilters.size() == 1 && def.readingDataPointsFilters[0]->className == "RandomSamplingDataPointsFilter");
+        CHECK(def.referenceDataPointsFilters.size() == 1 && def.referenceDataPointsFilters[0]->className == "SamplingSurfaceNormalDataPointsFilter");
+        CHECK(def.referenceDataPointsFilters[0]->get<unsigned>("knn") == 7);
+        CHECK(throws<PM::InvalidParameter>([&] { pm.DataPointsFilterRegistrar.create("SamplingSurfaceNormalDataPointsFilter", {{"knn", "2"}}); }));
+        CHECK(throws<PM::InvalidParameter>([&] { pm.DataPointsFilterRegistrar.create("RandomSamplingDataPointsFilter", {{"prob", "2"}}); }));
+        const int n = 4000;
+        DP cloud;
+        cloud.features = PM::Matrix::Zero(4, n);
+        unsigned s = 12345u;
+        auto uni = [&]() { s = s * 1664525u + 1013904223u; return (float)(s >> 8) / 16777216.f; };
+        for (int i = 0; i < n; ++i) {  // a gently curved sheet: normals close to +-z
+            const float x = 20.f * uni() - 10.f, y = 20.f * uni() - 10.f;
+            cloud.features(0, i) = x; cloud.features(1, i) = y; cloud.features(2, i) = 0.01f * x * x + 0.002f * uni(); cloud.features(3, i) = 1.f;
+        }
+        cloud.featureLabels.push_back(DP::Label("x", 1)); cloud.featureLabels.push_back(DP::Label("y", 1));
+        cloud.featureLabels.push_back(DP::Label("z", 1)); cloud.featureLabels.push_back(DP::Label("pad", 1));
+        PM::Matrix tag(1, n);
+        for (int i = 0; i < n; ++i) tag(0, i) = (float)i;
+        cloud.addDescriptor("tag", tag);
+        pmgpu_host_srand(1);
+        DP half = pm.DataPointsFilterRegistrar.create("RandomSamplingDataPointsFilter", {{"prob", "0.5"}})->filter(cloud);
+        CHECK(half.features.cols() > 0.45 * n && half.features.cols() < 0.55 * n && half.descriptors.cols() == half.features.cols());
+        std::srand(1);  // the same std::rand stream decides (RandomSampling.cpp:66)
+        int j = 0;
+        for (int i = 0; i < n; ++i)
+            if ((double)((float)std::rand() / (float)RAND_MAX) < (double)0.5f) { CHECK(half.descriptors(0, j) == (float)i); ++j; }
+        CHECK(j == half.features.cols());
+        DP far = pm.DataPointsFilterRegistrar.create("MinDistDataPointsFilter", {{"minDist", "5"}})->filter(cloud);
+        DP near = pm.DataPointsFilterRegistrar.create("MaxDistDataPointsFilter", {{"maxDist", "5"}})->filter(cloud);
+        CHECK(far.features.cols() + near.features.cols() <= n && far.features.cols() > 0 && near.features.cols() > 0);
+        for (int i = 0; i < far.features.cols(); ++i)
+            CHECK(std::sqrt(far.features(0, i) * far.features(0, i) + far.features(1, i) * far.features(1, i) + far.features(2, i) * far.features(2, i)) > 5.f);
+        CHECK(throws<PM::InvalidParameter>([&] { pm.DataPointsFilterRegistrar.create("MinDistDataPointsFilter", {{"dim", "3"}}); }));
+        auto ssn = pm.DataPointsFilterRegistrar.create("SamplingSurfaceNormalDataPointsFilter", {{"knn", "10"}, {"samplingMethod", "1"}, {"keepDensities", "1"}});
+        DP bins = ssn->filter(cloud);
+        CHECK(bins.features.cols() >= n / 10 && bins.features.cols() <= n / 5);
+        CHECK(bins.descriptorExists("normals") && bins.descriptorExists("densities") && bins.descriptorExists("tag"));
+        const unsigned nr = bins.getDescriptorStartingRow("normals");
+        int upright = 0;
+        for (int i = 0; i < bins.features.cols(); ++i) {
+            const float nx = bins.descriptors(nr, i), ny = bins.descriptors(nr + 1, i), nz = bins.descriptors(nr + 2, i);
+            CHECK(std::fabs(nx * nx + ny * ny + nz * nz - 1.f) < 1e-4f);
+            if (std::fabs(nz) > 0.95f) ++upright;
+            CHECK(bins.features(3, i) == 1.f);
+        }
+        CHECK(upright > 0.95 * bins.features.cols());
+        pmgpu_host_srand(1);
+        DP sub = pm.DataPointsFilterRegistrar.create("SamplingSurfaceNormalDataPointsFilter", {{"knn", "10"}, {"ratio", "0.7"}})->filter(cloud);
+        CHECK(sub.features.cols() > 0.65 * n && sub.features.cols() < 0.75 * n);
+        const unsigned tr = sub.getDescriptorStartingRow("tag");
+        for (int i = 1; i < sub.features.cols(); ++i) CHECK(sub.descriptors(tr, i) > sub.descriptors(tr, i - 1));  // sorted by original index
+    }
     // rigid transformation: non-orthogonal matrices are rejected, correctParameters is idempotent
     // (utest/ui/Transformations.cpp:40-131)
     {
