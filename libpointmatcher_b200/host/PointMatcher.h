@@ -18,7 +18,9 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cctype>
 #include <cstring>
+#include <fstream>
 #include <iostream>
 
 #include "../../include/pmgpu.h"
@@ -180,6 +182,166 @@ struct PointMatcher {
                 for (int i = 0; i < oldRows; ++i) grown(i, j) = descriptors(i, j);
             descriptors = grown;
             descriptorLabels.push_back(Label(name, dim));
+        }
+        // DataPoints::load (IO.cpp:376-392): format from the extension.  The CSV reader (IO.cpp:535-760:
+        // header names x y z pad -> features, nx ny nz -> "normals", any other name -> its own
+        // descriptor; no header: 2 or 3 columns) and the ASCII legacy-VTK reader (IO.cpp:949-1250:
+        // POINTS, NORMALS, VECTORS, SCALARS) — the formats of the reference's example data.
+        static DataPoints load(const std::string& fileName) {
+            std::ifstream ifs(fileName.c_str());
+            if (!ifs.good()) throw std::runtime_error("Cannot open file " + fileName);
+            const size_t dot = fileName.rfind('.');
+            std::string ext = dot == std::string::npos ? "" : fileName.substr(dot);
+            for (auto& c : ext) c = (char)std::tolower(c);
+            if (ext == ".csv") return loadCSV(ifs);
+            if (ext == ".vtk") return loadVTK(ifs, fileName);
+            throw std::runtime_error("loadAnyFormat(): Unknown extension \"" + ext + "\" for file \"" + fileName +
+                                     "\", extension must be either \".vtk\" or \".csv\"");
+        }
+        static DataPoints loadCSV(std::istream& is) {
+            auto split = [](const std::string& line) {
+                std::vector<std::string> out;
+                std::string cur;
+                for (char c : line) {
+                    if (c == ' ' || c == '\t' || c == ',' || c == ';' || c == '\r') {
+                        if (!cur.empty()) { out.push_back(cur); cur.clear(); }
+                    } else cur.push_back(c);
+                }
+                if (!cur.empty()) out.push_back(cur);
+                return out;
+            };
+            std::string line;
+            if (!std::getline(is, line)) throw std::runtime_error("CSV parse error: empty file");
+            const bool hasHeader = line.find_first_not_of(" ,+-.1234567890Ee\r") != std::string::npos;
+            std::vector<std::string> header;
+            std::vector<std::vector<T>> rows;
+            auto pushRow = [&](const std::string& l) {
+                const auto tok = split(l);
+                if (tok.size() != header.size()) throw std::runtime_error("CSV parse error: a row does not have the width of the header");
+                std::vector<T> r(tok.size());
+                for (size_t i = 0; i < tok.size(); ++i) r[i] = (T)std::stod(tok[i]);
+                rows.push_back(r);
+            };
+            if (hasHeader) header = split(line);
+            else {
+                const size_t dim = split(line).size();
+                if (dim != 2 && dim != 3)
+                    throw std::runtime_error("CSV parse error: " + std::to_string(dim) + " columns and no header: not obvious which columns to load for x, y or z");
+                header = {"x", "y"};
+                if (dim == 3) header.push_back("z");
+                pushRow(line);
+            }
+            while (std::getline(is, line)) {
+                if (split(line).empty()) break;  // the reader stops at the first empty line
+                pushRow(line);
+            }
+            const int n = (int)rows.size();
+            auto column = [&](const std::string& name) {
+                for (size_t j = 0; j < header.size(); ++j)
+                    if (header[j] == name) return (int)j;
+                return -1;
+            };
+            if (column("x") < 0 || column("y") < 0) throw std::runtime_error("CSV parse error: no x / y column");
+            DataPoints out;
+            std::vector<int> featCols;
+            for (const char* f : {"x", "y", "z", "pad"})
+                if (column(f) >= 0) { featCols.push_back(column(f)); out.featureLabels.push_back(Label(f, 1)); }
+            const bool hasPad = column("pad") >= 0;
+            out.features = Matrix(featCols.size() + (hasPad ? 0 : 1), n);
+            for (int i = 0; i < n; ++i) {
+                for (size_t r = 0; r < featCols.size(); ++r) out.features(r, i) = rows[i][featCols[r]];
+                if (!hasPad) out.features(featCols.size(), i) = T(1);
+            }
+            if (!hasPad) out.featureLabels.push_back(Label("pad", 1));
+            // descriptors: columns with the same internal name are rows of one descriptor, in file order
+            auto internal = [](const std::string& name) -> std::string {
+                if (name == "nx" || name == "ny" || name == "nz" || name == "normal_x" || name == "normal_y" || name == "normal_z") return "normals";
+                if (name == "red" || name == "green" || name == "blue" || name == "alpha") return "color";
+                if (name.rfind("observationDirections", 0) == 0 && name.size() == 22) return "observationDirections";
+                if (name.rfind("eigValues", 0) == 0 && name.size() == 10) return "eigValues";
+                if (name.rfind("eigVectors", 0) == 0 && name.size() == 12) return "eigVectors";
+                return name;
+            };
+            std::vector<std::pair<std::string, std::vector<int>>> groups;
+            for (size_t j = 0; j < header.size(); ++j) {
+                const std::string& name = header[j];
+                if (name == "x" || name == "y" || name == "z" || name == "pad") continue;
+                if (name == "time") throw std::runtime_error("CSV parse error: time columns are not supported by this reader");
+                const std::string in = internal(name);
+                bool found = false;
+                for (auto& g : groups)
+                    if (g.first == in) { g.second.push_back((int)j); found = true; }
+                if (!found) groups.push_back({in, {(int)j}});
+            }
+            for (const auto& g : groups) {
+                Matrix d(g.second.size(), n);
+                for (int i = 0; i < n; ++i)
+                    for (size_t r = 0; r < g.second.size(); ++r) d(r, i) = rows[i][g.second[r]];
+                out.addDescriptor(g.first, d);
+            }
+            return out;
+        }
+        static DataPoints loadVTK(std::istream& is, const std::string& fileName = "") {
+            std::string l1, l2, l3;
+            std::getline(is, l1); std::getline(is, l2); std::getline(is, l3);
+            if (l1.rfind("# vtk DataFile Version", 0) != 0) throw std::runtime_error("Header in VTK file " + fileName + " is not valid");
+            while (!l3.empty() && (l3.back() == '\r' || l3.back() == ' ')) l3.pop_back();
+            if (l3 != "ASCII") throw std::runtime_error("VTK reader: only ASCII legacy files are supported here, got " + l3);
+            std::vector<std::string> tok;
+            for (std::string t; is >> t;) tok.push_back(t);
+            if (tok.size() < 2 || tok[0] != "DATASET" || (tok[1] != "POLYDATA" && tok[1] != "UNSTRUCTURED_GRID"))
+                throw std::runtime_error("Invalid data type in VTK file: only POLYDATA and UNSTRUCTURED_GRID are supported");
+            DataPoints out;
+            int n = -1;
+            size_t i = 2;
+            auto block = [&](size_t first, int rows_) {
+                if (first + (size_t)rows_ * n > tok.size()) throw std::runtime_error("VTK reader: truncated file");
+                Matrix m(rows_, n);
+                for (int c = 0; c < n; ++c)
+                    for (int r = 0; r < rows_; ++r) m(r, c) = (T)std::stod(tok[first + (size_t)c * rows_ + r]);
+                return m;
+            };
+            auto isNumber = [](const std::string& t) { return !t.empty() && t.find_first_not_of("0123456789") == std::string::npos; };
+            while (i < tok.size()) {
+                const std::string& key = tok[i];
+                if (key == "POINTS") {
+                    n = std::stoi(tok[i + 1]);
+                    const Matrix p = block(i + 3, 3);
+                    out.features = Matrix(4, n);
+                    for (int c = 0; c < n; ++c) {
+                        for (int r = 0; r < 3; ++r) out.features(r, c) = p(r, c);
+                        out.features(3, c) = T(1);
+                    }
+                    for (const char* f : {"x", "y", "z", "pad"}) out.featureLabels.push_back(Label(f, 1));
+                    i += 3 + 3 * (size_t)n;
+                } else if (key == "VERTICES" || key == "LINES" || key == "POLYGONS" || key == "TRIANGLE_STRIPS" || key == "CELLS") {
+                    i += 3 + (size_t)std::stol(tok[i + 2]);
+                } else if (key == "CELL_TYPES") {
+                    i += 2 + (size_t)std::stol(tok[i + 1]);
+                } else if (key == "POINT_DATA") {
+                    if (std::stoi(tok[i + 1]) != n) throw std::runtime_error("The number of points is greater than the amount of point data.");
+                    i += 2;
+                } else if (key == "NORMALS" || key == "VECTORS") {
+                    out.addDescriptor(key == "NORMALS" ? "normals" : tok[i + 1], block(i + 3, 3));
+                    i += 3 + 3 * (size_t)n;
+                } else if (key == "SCALARS") {
+                    const std::string name = tok[i + 1];
+                    int comps = 1;
+                    size_t j = i + 3;
+                    if (isNumber(tok[j])) { comps = std::stoi(tok[j]); ++j; }
+                    if (tok[j] == "LOOKUP_TABLE") j += 2;
+                    out.addDescriptor(name, block(j, comps));
+                    i = j + (size_t)comps * n;
+                } else if (key == "COLOR_SCALARS") {
+                    const int comps = std::stoi(tok[i + 2]);
+                    out.addDescriptor("color", block(i + 3, comps));
+                    i += 3 + (size_t)comps * n;
+                } else {
+                    throw std::runtime_error("VTK reader: unsupported section " + key);
+                }
+            }
+            if (n < 0) throw std::runtime_error("VTK reader: no POINTS section");
+            return out;
         }
         // keep the listed columns (ascending), in place: what the reference's filters do with
         // setColFrom + conservativeResize (e.g. RandomSampling.cpp:63-74)

@@ -8,6 +8,7 @@ which the reference also does on the host.  The C++ twin of this file is
 libpointmatcher_b200/host/PointMatcher.h.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -129,6 +130,114 @@ class DataPoints:
 
     def copy(self):
         return DataPoints(self.features.copy(), {k: v.copy() for k, v in self.descriptors.items()})
+
+    # external column name -> (internal name, kind): IO.h:117-157
+    _CSV_LABELS = dict(
+        [(n, (n, "feature")) for n in ("x", "y", "z", "pad")]
+        + [(n, ("normals", "descriptor")) for n in ("nx", "ny", "nz", "normal_x", "normal_y", "normal_z")]
+        + [("observationDirections%d" % i, ("observationDirections", "descriptor")) for i in range(3)]
+        + [(n, ("color", "descriptor")) for n in ("red", "green", "blue", "alpha")]
+        + [("eigValues%d" % i, ("eigValues", "descriptor")) for i in range(3)]
+        + [("eigVectors%d%s" % (i, a), ("eigVectors", "descriptor")) for i in range(3) for a in "XYZ"]
+        + [("intensity", ("intensity", "descriptor"))])
+
+    @staticmethod
+    def load(fileName):
+        """DataPoints::load (IO.cpp:376-392): format from the extension; the CSV and the ASCII legacy-VTK
+        readers (IO.cpp:535-760, 949-1250) — the formats of the reference's example data."""
+        ext = os.path.splitext(fileName)[1].lower()
+        if not os.path.isfile(fileName):
+            raise RuntimeError("Cannot open file " + os.path.abspath(fileName))
+        if ext == ".csv":
+            return DataPoints._load_csv(fileName)
+        if ext == ".vtk":
+            return DataPoints._load_vtk(fileName)
+        raise RuntimeError('loadAnyFormat(): Unknown extension "%s" for file "%s", extension must be either ".vtk" or ".csv"' % (ext, fileName))
+
+    @staticmethod
+    def _load_csv(fileName):
+        with open(fileName) as f:
+            lines = [ln.strip() for ln in f.read().splitlines()]
+        lines = lines[:lines.index("")] if "" in lines else lines  # the reader stops at the first empty line
+        if not lines:
+            raise RuntimeError("CSV parse error: empty file")
+
+        def split(ln):
+            return [t for t in ln.replace(",", " ").replace(";", " ").replace("\t", " ").split(" ") if t]
+
+        has_header = any(c not in " ,+-.1234567890Ee" for c in lines[0])
+        if has_header:
+            header, rows = split(lines[0]), lines[1:]
+        else:
+            rows = lines
+            dim = len(split(lines[0]))
+            if dim not in (2, 3):
+                raise RuntimeError("CSV parse error: %d columns and no header: not obvious which columns to load for x, y or z" % dim)
+            header = ["x", "y", "z"][:dim]
+        data = np.array([[float(t) for t in split(ln)] for ln in rows], np.float64).astype(np.float32).reshape(len(rows), len(header))
+        feats, descs = [], {}
+        for name in ("x", "y", "z", "pad"):  # features in the table's order, descriptors grouped by internal name
+            if name in header:
+                feats.append(data[:, header.index(name)])
+        if "x" not in header or "y" not in header:
+            raise RuntimeError("CSV parse error: no x / y column")
+        for j, name in enumerate(header):
+            internal, kind = DataPoints._CSV_LABELS.get(name, (name, "descriptor"))
+            if name == "time":
+                raise RuntimeError("CSV parse error: time columns are not supported by this reader")
+            if kind == "descriptor":
+                descs.setdefault(internal, []).append(data[:, j])
+        if "pad" not in header:
+            feats.append(np.ones(len(data), np.float32))  # homogeneous row (IO.cpp:752-757)
+        return DataPoints(np.stack(feats, axis=1), {k: np.stack(v, axis=1) for k, v in descs.items()})
+
+    @staticmethod
+    def _load_vtk(fileName):
+        with open(fileName, "rb") as f:
+            raw = f.read()
+        head = raw[:256].decode("ascii", "replace").splitlines()
+        if len(head) < 4 or not head[0].startswith("# vtk DataFile Version"):
+            raise RuntimeError("Header in VTK file " + fileName + " is not valid")
+        if head[2].strip() != "ASCII":
+            raise RuntimeError("VTK reader: only ASCII legacy files are supported here, got " + head[2].strip())
+        tok = raw.decode("ascii", "replace").split("\n", 3)[3].split()
+        if tok[0] != "DATASET" or tok[1] not in ("POLYDATA", "UNSTRUCTURED_GRID"):
+            raise RuntimeError("Invalid data type %s in VTK file: only POLYDATA and UNSTRUCTURED_GRID are supported" % " ".join(tok[:2]))
+        i, n, pts, descs = 2, None, None, {}
+        while i < len(tok):
+            key = tok[i]
+            if key == "POINTS":
+                n = int(tok[i + 1])
+                pts = np.array(tok[i + 3:i + 3 + 3 * n], np.float64).astype(np.float32).reshape(n, 3)
+                i += 3 + 3 * n
+            elif key in ("VERTICES", "LINES", "POLYGONS", "TRIANGLE_STRIPS", "CELLS"):
+                i += 3 + int(tok[i + 2])
+            elif key == "CELL_TYPES":
+                i += 2 + int(tok[i + 1])
+            elif key == "POINT_DATA":
+                if int(tok[i + 1]) != n:
+                    raise RuntimeError("The number of points is greater than the amount of point data.")
+                i += 2
+            elif key in ("NORMALS", "VECTORS"):
+                name = "normals" if key == "NORMALS" else tok[i + 1]
+                descs[name] = np.array(tok[i + 3:i + 3 + 3 * n], np.float64).astype(np.float32).reshape(n, 3)
+                i += 3 + 3 * n
+            elif key == "SCALARS":  # SCALARS name type [numComp] / LOOKUP_TABLE default / values
+                name = tok[i + 1]
+                comps, j = (int(tok[i + 3]), i + 4) if tok[i + 3].isdigit() else (1, i + 3)
+                if tok[j] == "LOOKUP_TABLE":
+                    j += 2
+                descs[name] = np.array(tok[j:j + comps * n], np.float64).astype(np.float32).reshape(n, comps)
+                i = j + comps * n
+            elif key == "COLOR_SCALARS":
+                comps = int(tok[i + 2])
+                descs["color"] = np.array(tok[i + 3:i + 3 + comps * n], np.float64).astype(np.float32).reshape(n, comps)
+                i += 3 + comps * n
+            else:
+                raise RuntimeError("VTK reader: unsupported section " + key)
+        if pts is None:
+            raise RuntimeError("VTK reader: no POINTS section")
+        return DataPoints(np.c_[pts, np.ones(n, np.float32)].astype(np.float32), descs)
 
 
 class Matches:

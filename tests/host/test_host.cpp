@@ -165,6 +165,35 @@ static int run_cpu() {
         const unsigned tr = sub.getDescriptorStartingRow("tag");
         for (int i = 1; i < sub.features.cols(); ++i) CHECK(sub.descriptors(tr, i) > sub.descriptors(tr, i - 1));  // sorted by original index
     }
+    // loaders (IO.cpp:376-392, 535-760, 949-1250): the layouts of examples/data/*.csv and *.vtk
+    {
+        const std::string dir = std::getenv("PM_TEST_TMP") ? std::getenv("PM_TEST_TMP") : "/tmp";
+        {
+            std::ofstream f(dir + "/pm_host_test.csv");
+            f << "x,y,z,nx,ny,nz,intensity\n-3.5376 , 0.639553 , -1.37678 , -0.060181,0.173729,0.982953, 7\n1 , 2 , 3 , 0,0,1, 9\n";
+        }
+        DP c = DP::load(dir + "/pm_host_test.csv");
+        CHECK(c.features.rows() == 4 && c.features.cols() == 2 && c.features(0, 0) == -3.5376f && c.features(2, 1) == 3.f && c.features(3, 0) == 1.f);
+        CHECK(c.descriptorExists("normals") && c.getDescriptorDimension("normals") == 3 && c.descriptorExists("intensity"));
+        CHECK(c.descriptors(c.getDescriptorStartingRow("normals") + 2, 0) == 0.982953f && c.descriptors(c.getDescriptorStartingRow("intensity"), 1) == 9.f);
+        {
+            std::ofstream f(dir + "/pm_host_test2.csv");
+            f << "0.5 1.5\n2.5 3.5\n";
+        }
+        DP c2 = DP::load(dir + "/pm_host_test2.csv");  // no header, two columns: a 2-D cloud
+        CHECK(c2.features.rows() == 3 && c2.features.cols() == 2 && c2.features(1, 1) == 3.5f && c2.features(2, 0) == 1.f);
+        {
+            std::ofstream f(dir + "/pm_host_test.vtk");
+            f << "# vtk DataFile Version 3.0\ndata\nASCII\nDATASET POLYDATA\nPOINTS 3 float\n-3.79521 0.0131325 -0.95763 \n1 2 3 \n4 5 6 \n"
+                 "VERTICES 3 6\n1 0\n1 1\n1 2\nPOINT_DATA 3\nNORMALS normals float\n0 0 1\n0 1 0\n1 0 0\nSCALARS densities float 1\nLOOKUP_TABLE default\n0.5\n1.5\n2.5\n";
+        }
+        DP v = DP::load(dir + "/pm_host_test.vtk");
+        CHECK(v.features.rows() == 4 && v.features.cols() == 3 && v.features(0, 0) == -3.79521f && v.features(2, 2) == 6.f && v.features(3, 1) == 1.f);
+        CHECK(v.descriptorExists("normals") && v.descriptors(v.getDescriptorStartingRow("normals") + 1, 1) == 1.f);
+        CHECK(v.descriptorExists("densities") && v.descriptors(v.getDescriptorStartingRow("densities"), 2) == 2.5f);
+        CHECK(throws<std::runtime_error>([&] { DP::load(dir + "/does_not_exist.vtk"); }));
+        CHECK(throws<std::runtime_error>([&] { DP::load(dir + "/pm_host_test.xyz"); }));
+    }
     // rigid transformation: non-orthogonal matrices are rejected, correctParameters is idempotent
     // (utest/ui/Transformations.cpp:40-131)
     {

@@ -164,3 +164,47 @@ def test_yaml_chains_of_the_reference_load(pm):
     assert type(icp.readingDataPointsFilters[0]).__name__ == "RandomSamplingDataPointsFilter"
     assert type(icp.referenceDataPointsFilters[0]).__name__ == "SamplingSurfaceNormalDataPointsFilter"
     assert abs(icp.outlierFilters[0].get("ratio") - 0.85) < 1e-7
+
+
+def test_loaders_read_the_reference_data_layouts(pm, tmp_path):
+    """DataPoints::load (IO.cpp:376-392): CSV with the header of examples/data/car_cloud400.csv, ASCII legacy VTK with the
+    layout of examples/data/cloud.00000.vtk; written from the packed fixture and read back bit for bit."""
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "reference_fixture.npz"))
+    car = fx["car400"][:500]
+    with open(tmp_path / "car.csv", "w") as f:
+        f.write("x,y,z,nx,ny,nz\n")
+        for r in car:
+            f.write("%r , %r , %r , %r,%r,%r\n" % tuple(float(v) for v in r))
+    c = pm.DataPoints.load(str(tmp_path / "car.csv"))
+    assert (c.features[:, :3] == car[:, :3]).all() and (c.features[:, 3] == 1).all()
+    assert (c.descriptors["normals"] == car[:, 3:6]).all()
+    pts = fx["cloud0"][:700]
+    with open(tmp_path / "cloud.vtk", "w") as f:
+        f.write("# vtk DataFile Version 3.0\ndata\nASCII\nDATASET POLYDATA\nPOINTS %d float\n" % len(pts))
+        for p in pts:
+            f.write("%r %r %r \n" % tuple(float(v) for v in p))
+        f.write("VERTICES %d %d\n" % (len(pts), 2 * len(pts)))
+        for i in range(len(pts)):
+            f.write("1 %d\n" % i)
+        f.write("POINT_DATA %d\nNORMALS normals float\n" % len(pts))
+        for i in range(len(pts)):
+            f.write("0 0 1\n")
+        f.write("SCALARS densities float 1\nLOOKUP_TABLE default\n" + "\n".join(str(float(i)) for i in range(len(pts))) + "\n")
+    v = pm.DataPoints.load(str(tmp_path / "cloud.vtk"))
+    assert (v.features[:, :3] == pts).all() and (v.features[:, 3] == 1).all()
+    assert (v.descriptors["normals"] == [0, 0, 1]).all() and (v.descriptors["densities"][:, 0] == np.arange(len(pts))).all()
+    (tmp_path / "two.csv").write_text("0.5 1.5\n2.5 3.5\n")
+    two = pm.DataPoints.load(str(tmp_path / "two.csv"))
+    assert two.features.tolist() == [[0.5, 1.5, 1.0], [2.5, 3.5, 1.0]]
+    (tmp_path / "five.csv").write_text("1 2 3 4 5\n")
+    with pytest.raises(RuntimeError):
+        pm.DataPoints.load(str(tmp_path / "five.csv"))           # the reference asks on stdin here
+    with pytest.raises(RuntimeError):
+        pm.DataPoints.load(str(tmp_path / "missing.vtk"))
+    with pytest.raises(RuntimeError):
+        pm.DataPoints.load(str(tmp_path / "cloud.xyz"))
+    ref_dir = "/root/reference/examples/data"                    # only in the build container
+    if os.path.isdir(ref_dir):
+        assert (pm.DataPoints.load(ref_dir + "/cloud.00000.vtk").features[:, :3] == fx["cloud0"]).all()
+        car_full = pm.DataPoints.load(ref_dir + "/car_cloud400.csv")
+        assert (car_full.features[:, :3] == fx["car400"][:, :3]).all() and (car_full.descriptors["normals"] == fx["car400"][:, 3:6]).all()
