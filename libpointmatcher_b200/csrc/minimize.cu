@@ -68,7 +68,7 @@ __device__ void finalize_body(const double* partials, int nblocks, double* sums,
 // `fuse`: the last block to finish reduces the partial rows, solves, composes T_iter and runs the
 // checkers (finalize_body), so the whole minimisation is one kernel
 template <int MODE>  // 0 point-to-point, 1 point-to-plane
-__global__ void __launch_bounds__(ACC_BLOCK) accumulate_kernel(const f4* __restrict__ reading, int nq, int k, const int32_t* __restrict__ ids,
+__global__ void __launch_bounds__(ACC_BLOCK, MODE == 1 ? 2 : 3) accumulate_kernel(const f4* __restrict__ reading, int nq, int k, const int32_t* __restrict__ ids,
                                                                const float* __restrict__ dists, const f4* __restrict__ ref,
                                                                const f4* __restrict__ normals, const IcpState* __restrict__ state, int gated,
                                                                double* __restrict__ partials, int fuse, IcpState* state_rw, double* sums,
@@ -443,9 +443,10 @@ int launch_minimize(pmgpu_ctx* ctx, int minimizer, bool compose_and_check, bool 
         return PMGPU_ERR_NO_NORMALS;
     }
     cudaStream_t st = ctx->stream;
-    // the kernel holds 20-27 fp64 sums per thread: two 256-thread blocks are resident per SM, so
-    // that is the whole grid (one wave, and only 2 x SMs partial rows for the last block to reduce)
-    const int grid = grid_for(ctx->nq, ACC_BLOCK, ctx->num_sms, 2);
+    // the kernel holds 20 (point) / 27 (plane) fp64 sums per thread: three / two 256-thread blocks are
+    // resident per SM (launch bounds), so that is the whole grid — one wave, and only that many
+    // partial rows for the last block to reduce
+    const int grid = grid_for(ctx->nq, ACC_BLOCK, ctx->num_sms, plane ? 2 : 3);
     PM_CUDA_TRY(ctx, ctx->partials.reserve((size_t)(ctx->num_sms * 4 + 2) * NS_MAX));
     double* sums = ctx->partials.p + (size_t)ctx->num_sms * 4 * NS_MAX;
     pmgpu_icp_params ck;
