@@ -57,8 +57,22 @@ enum pmgpu_status {
 enum pmgpu_filter_type {
     PMGPU_FILTER_MAXDIST = 0,    /* MaxDistOutlierFilter     param = maxDist (un-squared)  OutlierFiltersImpl.cpp:66-81   */
     PMGPU_FILTER_MEDIANDIST = 1, /* MedianDistOutlierFilter  param = factor                OutlierFiltersImpl.cpp:109-125 */
-    PMGPU_FILTER_TRIMMEDDIST = 2 /* TrimmedDistOutlierFilter param = ratio                 OutlierFiltersImpl.cpp:132-147 */
+    PMGPU_FILTER_TRIMMEDDIST = 2,/* TrimmedDistOutlierFilter param = ratio                 OutlierFiltersImpl.cpp:132-147 */
+    PMGPU_FILTER_ROBUST = 3      /* RobustOutlierFilter      param = tuning                OutlierFiltersImpl.cpp:420-598 */
 };
+/* RobustOutlierFilter: M-estimator weights w(e^2), e^2 = dist / scale^2.  Its discrete
+ * parameters travel in the filter word: bits 0-7 PMGPU_FILTER_ROBUST | bits 8-15 robustFct | bits 16-19
+ * scaleEstimator | bits 20-27 nbIterationForScale.  scaleEstimator "mad" = sqrt(median |d - median d|)
+ * (Matches.cpp:88-122) is two more exact radix selects on the device; "none" = 1.  distanceType
+ * point2point and approximation = inf only; "std" / "berg" are not built.  At most one robust filter per
+ * chain, not with a sharded reading.  limits_out[f] of pmgpu_weights returns the scale. */
+enum {
+    PMGPU_ROBUST_CAUCHY = 0, PMGPU_ROBUST_WELSCH, PMGPU_ROBUST_SC, PMGPU_ROBUST_GM, PMGPU_ROBUST_TUKEY, PMGPU_ROBUST_HUBER, PMGPU_ROBUST_L1,
+    PMGPU_ROBUST_STUDENT
+};
+enum { PMGPU_SCALE_NONE = 0, PMGPU_SCALE_MAD = 1 };
+#define PMGPU_ROBUST_WORD(fct, scale, nb_iter) (PMGPU_FILTER_ROBUST | ((fct) << 8) | ((scale) << 16) | ((nb_iter) << 20))
+
 
 enum pmgpu_minimizer {
     PMGPU_MIN_P2POINT = 0,     /* PointToPointErrorMinimizer          ErrorMinimizers/PointToPoint.cpp:61-101 */

@@ -177,7 +177,8 @@ int enqueue_iteration(pmgpu_ctx* ctx, const pmgpu_icp_params* p, bool gated) {
     // capped matching: only where nothing observable depends on the matches the filters reject —
     // the fused loop, an unbounded maxDist (a finite one decides which matches count as missing),
     // and a non-empty filter chain
-    const bool use_cap = gated && ctx->cap_enabled && p->nfilters > 0 && max_r2 == pm_inf();
+    // (a RobustOutlierFilter weighs every match, however far: nothing may be cut)
+    const bool use_cap = gated && ctx->cap_enabled && p->nfilters > 0 && max_r2 == pm_inf() && spec.robust_index() < 0;
     PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, ctx->nq, true, gated, false, p->knn, max_r2,
                       ctx->seed_k == 1 && p->knn == 1 && ctx->seed_enabled, ctx->ids.p, ctx->dists.p, use_cap));
     ctx->seed_k = p->knn;
@@ -235,6 +236,7 @@ int pmgpu_ctx_create(int device, pmgpu_ctx** ctx_out) {
     if (const char* b = getenv("PMGPU_KNN_BUDGET")) ctx->knn_budget = ctx->knn_budget_unseeded = atoi(b) > 0 ? atoi(b) : 1;
     if (const char* b = getenv("PMGPU_KNN_BUDGET_UNSEEDED")) ctx->knn_budget_unseeded = atoi(b) > 0 ? atoi(b) : 1;
     memset(ctx->state_host, 0, sizeof(IcpState));
+    ctx->state_host->robust_iteration = 1;
     mat4_identity(ctx->state_host->T_iter);
     mat4_identity(ctx->state_host->T_match);
     mat4_identity(ctx->state_host->dT);
@@ -484,7 +486,7 @@ int pmgpu_weights(pmgpu_ctx* ctx, int nfilters, const int* types, const float* p
         return s;
     }
     if (limits_out)
-        for (int f = 0; f < nfilters; ++f) limits_out[f] = ctx->state_host->limit[f];
+        for (int f = 0; f < nfilters; ++f) limits_out[f] = spec.is_robust(f) ? ctx->state_host->robust_scale : ctx->state_host->limit[f];
     return PMGPU_OK;
 }
 
@@ -533,6 +535,8 @@ int pmgpu_icp_reset(pmgpu_ctx* ctx, const float* T_iter_init) {
     h->iterations = 0;
     h->counter = 0;
     h->visits = 0;
+    h->robust_iteration = 1;  // a fresh RobustOutlierFilter (OutlierFiltersImpl.cpp:420-438)
+    h->robust_scale = 0.f;
     h->cap = pm_inf();
     h->cap_need = 0.f;
     h->redo = 0;

@@ -24,7 +24,7 @@ namespace {
 //  point-to-plane : [0..20] upper triangle of A (row-major over i <= j), [21..26] sum wF*dot
 //  point-to-point : [0] sum w, [1..3] sum w p, [4..6] sum w q, [7..15] sum (w q_r) p_c  (r + 3 c)
 //  both           : [NS-4] kept pairs, [NS-3] rejected matches, [NS-2] rejected points, [NS-1] points seen
-constexpr int NS_PLANE = 27 + 4;
+constexpr int NS_PLANE = 28 + 4;  // 21 A + 6 b + sum of weights, then the 4 counters
 constexpr int NS_POINT = 16 + 4;
 constexpr int NS_COV = 42;
 constexpr int NS_MAX = 42;
@@ -56,11 +56,6 @@ __device__ __forceinline__ unsigned long long pm_globaltimer() {
 }
 #endif
 
-__device__ __forceinline__ float pair_weight(const IcpState* st, float d) {
-    if (d == pm_inf()) return 0.f;  // ErrorMinimizer.cpp:103-106: invalid matches are skipped
-    return st->has_filters ? ((d <= st->limit_all) ? 1.f : 0.f) : 1.f;
-}
-
 template <int MODE>
 __device__ void finalize_body(const double* partials, int nblocks, double* sums, int phase, IcpState* state, int compose,
                               const pmgpu_icp_params& ck);
@@ -89,7 +84,7 @@ __global__ void __launch_bounds__(ACC_BLOCK, MODE == 1 ? 2 : 3) accumulate_kerne
         for (int kk = 0; kk < k; ++kk) {
             const float d = dists[(size_t)i * k + kk];
             if (d == pm_inf()) continue;
-            const float w = pair_weight(state, d);
+            const float w = pm_pair_weight(state, d);
             if (w == 0.f) { acc[NS - 3] += 1.0; continue; }
             match_exist = true;
             acc[NS - 4] += 1.0;
@@ -115,6 +110,7 @@ __global__ void __launch_bounds__(ACC_BLOCK, MODE == 1 ? 2 : 3) accumulate_kerne
                     for (int b = a; b < 6; ++b) acc[c++] += (double)wF[a] * (double)F[b];
 #pragma unroll
                 for (int a = 0; a < 6; ++a) acc[21 + a] += (double)wF[a] * (double)dot;
+                acc[27] += (double)w;
             } else {
                 acc[0] += (double)w;
                 const float wp[3] = {fmul(p.x, w), fmul(p.y, w), fmul(p.z, w)};
@@ -184,7 +180,7 @@ __global__ void __launch_bounds__(ACC_BLOCK) cov_accumulate_kernel(const f4* __r
         const f4 p = transform_point(sT, reading[i]);
         for (int kk = 0; kk < k; ++kk) {
             const float d = dists[(size_t)i * k + kk];
-            if (pair_weight(state, d) == 0.f) continue;
+            if (pm_pair_weight(state, d) == 0.f) continue;
             const int id = ids[(size_t)i * k + kk];
             const f4 q = __ldg(ref + id);
             float rp[3] = {p.x, p.y, p.z}, fp[3] = {q.x, q.y, q.z}, nrm[3] = {1.f, 1.f, 1.f};
@@ -328,7 +324,7 @@ __device__ void finalize_body(const double* partials, int nblocks, double* sums,
     }
     Mat4 dT;
     if (MODE == 1) {
-        state->stats[1] = (float)kept / denom;  // all weights are 1: sum w == kept
+        state->stats[1] = (float)sums[27] / denom;  // sum of weights (== kept for the 0/1 filters)
         double A[36], b[6], x[6];
         expand_sym6(sums, A);
         for (int a = 0; a < 6; ++a) b[a] = -sums[21 + a];

@@ -82,6 +82,16 @@ struct IcpState {
     unsigned long long sel_rank[PM_MAX_FILTERS];   // remaining rank inside the selected bucket
     unsigned ticket[4];          // "last block" counters: 0 select, 1 minimise, 2 covariance
     unsigned overflow_count[2];  // kNN stage-2 queue lengths (ping-pong between consecutive launches)
+    // RobustOutlierFilter (one per chain): set by select_init_limits / the robust select passes
+    int robust_on;               // chain has a robust filter
+    int robust_fct;              // PMGPU_ROBUST_*
+    float robust_k;              // tuning
+    float robust_scale;          // sqrt(MAD) or 1
+    int robust_iteration;        // RobustOutlierFilter::iteration (starts at 1)
+    int robust_recompute;        // this call re-estimates the scale (nbIterationForScale)
+    float robust_median;
+    unsigned robust_prefix;
+    unsigned long long robust_rank;
     // adaptive search radius of the fused loop (DESIGN.md "capped matching"): squared radius the
     // NEXT match may stop at, the largest distance the filters of THIS iteration needed to know
     // exactly, and the flag that voids an iteration whose cap turned out too small
@@ -106,9 +116,16 @@ struct SelectSpec {
     int nfilters;
     int type[PM_MAX_FILTERS];
     float param[PM_MAX_FILTERS];  // MaxDist: squared limit; MedianDist: factor; TrimmedDist: ratio
-    __host__ __device__ bool is_quantile(int f) const { return type[f] != PMGPU_FILTER_MAXDIST; }
+    __host__ __device__ int kind(int f) const { return type[f] & 0xff; }
+    __host__ __device__ bool is_robust(int f) const { return kind(f) == PMGPU_FILTER_ROBUST; }
+    __host__ __device__ bool is_quantile(int f) const { return kind(f) == PMGPU_FILTER_MEDIANDIST || kind(f) == PMGPU_FILTER_TRIMMEDDIST; }
     __host__ __device__ float quantile(int f) const { return type[f] == PMGPU_FILTER_MEDIANDIST ? 0.5f : param[f]; }
     __host__ __device__ float factor(int f) const { return type[f] == PMGPU_FILTER_MEDIANDIST ? param[f] : 0.f; }
+    __host__ __device__ int robust_index() const {
+        for (int f = 0; f < nfilters; ++f)
+            if (is_robust(f)) return f;
+        return -1;
+    }
     __host__ __device__ int n_quantile() const {
         int n = 0;
         for (int f = 0; f < nfilters; ++f) n += is_quantile(f) ? 1 : 0;

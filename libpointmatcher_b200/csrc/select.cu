@@ -69,6 +69,30 @@ __global__ void __launch_bounds__(HIST_BLOCK) hist_kernel(const float* __restric
     if (pass == 2 && threadIdx.x == 0) select_finish(state, cap_active, cap_margin);
 }
 
+// RobustOutlierFilter scale = sqrt(MAD): the same three passes twice, phase 0 on the distances
+// (median), phase 1 on |dist - median| (Matches.cpp:88-122); histogram slot PM_MAX_FILTERS
+__global__ void __launch_bounds__(HIST_BLOCK) robust_hist_kernel(const float* __restrict__ dists, size_t total, int pass, int phase, IcpState* state,
+                                                                 int gated, unsigned* __restrict__ hist) {
+    __shared__ unsigned sh[PM_HIST_BINS];
+    if (gated && state->iterate == 0) return;
+    if (!state->robust_recompute) return;  // the scale is frozen (nbIterationForScale)
+    for (int i = threadIdx.x; i < PM_HIST_BINS; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    const unsigned prefix = pass == 0 ? 0u : state->robust_prefix;
+    const float median = state->robust_median;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const float d = __ldg(dists + i);
+        if (d == pm_inf()) continue;
+        hist_add(sh, phase == 0 ? d : fabsf(__fsub_rn(d, median)), pass, prefix);
+    }
+    __syncthreads();
+    select_flush(sh, hist);
+    __syncthreads();
+    if (!select_last_block(&state->ticket[0])) return;
+    select_pick(hist, pass, 0.5f, 0, 0.f, state, true, phase + 1);
+}
+
 // sharded reading: the scan runs after the histograms have been all-reduced
 __global__ void __launch_bounds__(1024) pick_kernel(unsigned* __restrict__ hist, int pass, SelectSpec spec, IcpState* state, int gated,
                                                     int cap_active, float cap_margin) {
@@ -96,8 +120,8 @@ __global__ void weights_kernel(const float* __restrict__ dists, size_t total, co
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const float d = dists[i];
-    // empty chain: OutlierFilter.cpp:70-85; otherwise product of (dist <= limit_f)
-    w[i] = state->has_filters ? ((d <= state->limit_all) ? 1.f : 0.f) : ((d == pm_inf()) ? 0.f : 1.f);
+    // empty chain: OutlierFilter.cpp:70-85; otherwise the product of the filters' weights
+    w[i] = pm_pair_weight(state, d);
 }
 
 }  // namespace
@@ -120,18 +144,38 @@ int make_select_spec(pmgpu_ctx* ctx, int nfilters, const int* types, const float
                 ctx->set_error("quantile must be between 0 and 1");
                 return PMGPU_ERR_BAD_QUANTILE;
             }
+        } else if ((types[f] & 0xff) == PMGPU_FILTER_ROBUST) {
+            const int fct = (types[f] >> 8) & 0xff, est = (types[f] >> 16) & 0xf;
+            if (fct > PMGPU_ROBUST_STUDENT) {
+                ctx->set_error("Invalid robust function name.");
+                return PMGPU_ERR_BAD_ARG;
+            }
+            if (est != PMGPU_SCALE_NONE && est != PMGPU_SCALE_MAD) {
+                ctx->set_error("RobustOutlierFilter on GPU: scaleEstimator must be 'none' or 'mad'");
+                return PMGPU_ERR_UNSUPPORTED;
+            }
         } else if (types[f] != PMGPU_FILTER_MEDIANDIST) {
             ctx->set_error("unknown outlier filter type");
             return PMGPU_ERR_BAD_ARG;
         }
     }
+    int nrobust = 0;
+    for (int f = 0; f < nfilters; ++f) nrobust += spec->is_robust(f) ? 1 : 0;
+    if (nrobust > 1) {
+        ctx->set_error("at most one RobustOutlierFilter per chain on the GPU");
+        return PMGPU_ERR_UNSUPPORTED;
+    }
+    if (nrobust && ctx->nranks > 1) {
+        ctx->set_error("RobustOutlierFilter is not supported with a sharded reading");
+        return PMGPU_ERR_UNSUPPORTED;
+    }
     return PMGPU_OK;
 }
 
 int select_reserve(pmgpu_ctx* ctx) {
-    if (ctx->hist.cap < (size_t)PM_MAX_FILTERS * PM_HIST_BINS) {
-        PM_CUDA_TRY(ctx, ctx->hist.reserve((size_t)PM_MAX_FILTERS * PM_HIST_BINS));
-        PM_CUDA_TRY(ctx, cudaMemsetAsync(ctx->hist.p, 0, (size_t)PM_MAX_FILTERS * PM_HIST_BINS * sizeof(unsigned), ctx->stream));
+    if (ctx->hist.cap < (size_t)(PM_MAX_FILTERS + 1) * PM_HIST_BINS) {
+        PM_CUDA_TRY(ctx, ctx->hist.reserve((size_t)(PM_MAX_FILTERS + 1) * PM_HIST_BINS));
+        PM_CUDA_TRY(ctx, cudaMemsetAsync(ctx->hist.p, 0, (size_t)(PM_MAX_FILTERS + 1) * PM_HIST_BINS * sizeof(unsigned), ctx->stream));
     }
     return PMGPU_OK;
 }
@@ -161,6 +205,17 @@ int launch_weights(pmgpu_ctx* ctx, const SelectSpec& spec, bool gated, bool cap_
                 ctx->launches += 1;
             }
         }
+    }
+    const int r = spec.robust_index();
+    if (r >= 0 && ((spec.type[r] >> 16) & 0xf) == PMGPU_SCALE_MAD) {
+        const size_t total = (size_t)ctx->k * ctx->nq;
+        const size_t want = (total + HIST_BLOCK * 4 - 1) / (HIST_BLOCK * 4);
+        const int grid = grid_for((int)(want > 0x1fffff ? 0x1fffff : want) * HIST_BLOCK, HIST_BLOCK, ctx->num_sms, 1);
+        for (int phase = 0; phase < 2; ++phase)
+            for (int pass = 0; pass < 3; ++pass) {
+                robust_hist_kernel<<<grid, HIST_BLOCK, 0, st>>>(ctx->dists.p, total, pass, phase, ctx->state, g, ctx->hist.p + (size_t)PM_MAX_FILTERS * PM_HIST_BINS);
+                ctx->launches += 1;
+            }
     }
     PM_CUDA_TRY(ctx, cudaGetLastError());
     ctx->have_weights = true;

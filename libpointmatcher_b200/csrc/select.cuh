@@ -28,6 +28,43 @@ __device__ __forceinline__ void select_init_limits(IcpState* st, const SelectSpe
     st->limit_all = all;
     st->has_filters = sp.nfilters > 0 ? 1 : 0;
     st->cap_need = 0.f;
+    // RobustOutlierFilter::robustFiltering preamble (OutlierFiltersImpl.cpp:508-540)
+    const int r = sp.robust_index();
+    st->robust_on = r >= 0 ? 1 : 0;
+    if (r >= 0) {
+        const int word = sp.type[r], nb = (word >> 20) & 0xff, est = (word >> 16) & 0xf;
+        st->robust_fct = (word >> 8) & 0xff;
+        st->robust_k = sp.param[r];
+        st->robust_recompute = (est == PMGPU_SCALE_MAD && (st->robust_iteration <= nb || nb == 0)) ? 1 : 0;
+        if (est == PMGPU_SCALE_NONE) st->robust_scale = 1.f;
+        st->robust_iteration += 1;
+    }
+}
+
+// Weight of one match: product of the chain's filters (OutlierFilter.cpp:63-103).  The distance
+// filters are one threshold; a RobustOutlierFilter multiplies its M-estimator weight
+// (OutlierFiltersImpl.cpp:545-583), in float, e^2 = dist / (scale * scale).
+__device__ __forceinline__ float pm_robust_weight(const IcpState* st, float d) {
+    const float k = st->robust_k, k2 = __fmul_rn(k, k), sc = st->robust_scale;
+    const float e2 = __fdiv_rn(d, __fmul_rn(sc, sc));
+    float w;
+    switch (st->robust_fct) {
+        case PMGPU_ROBUST_CAUCHY: w = __fdiv_rn(1.f, __fadd_rn(1.f, __fdiv_rn(e2, k2))); break;
+        case PMGPU_ROBUST_WELSCH: w = expf(-__fdiv_rn(e2, k2)); break;
+        case PMGPU_ROBUST_SC: { const float a = __fadd_rn(k, e2); w = (e2 >= k) ? __fmul_rn(__fmul_rn(4.0f, k2), __fdiv_rn(1.f, __fmul_rn(a, a))) : 1.f; break; }
+        case PMGPU_ROBUST_GM: { const float a = __fadd_rn(k, e2); w = __fmul_rn(k2, __fdiv_rn(1.f, __fmul_rn(a, a))); break; }
+        case PMGPU_ROBUST_TUKEY: { const float a = __fsub_rn(1.f, __fdiv_rn(e2, k2)); w = (e2 >= k2) ? 0.f : __fmul_rn(a, a); break; }
+        case PMGPU_ROBUST_HUBER: w = (e2 >= k2) ? __fmul_rn(k, __fdiv_rn(1.f, sqrtf(e2))) : 1.f; break;
+        case PMGPU_ROBUST_L1: w = __fdiv_rn(1.f, sqrtf(e2)); break;
+        default: { const float dd = 3.f; w = powf(1.f + e2 / k, -(k + dd) / 2.f) * (k + dd) * (1.f / (k + e2)); break; }  // Student
+    }
+    return w <= 1e-50f ? 0.f : w;  // `w <= 1e-50 -> 1e-50` stored in a float array
+}
+__device__ __forceinline__ float pm_pair_weight(const IcpState* st, float d) {
+    if (d == pm_inf()) return 0.f;  // ErrorMinimizer.cpp:103-106: invalid matches are skipped
+    float w = st->has_filters ? ((d <= st->limit_all) ? 1.f : 0.f) : 1.f;
+    if (st->robust_on && w != 0.f) w = __fmul_rn(w, pm_robust_weight(st, d));
+    return w;
 }
 
 // Capped matching (fused ICP loop).  The matcher of this iteration stopped at squared radius
@@ -88,7 +125,10 @@ __device__ __forceinline__ bool select_last_block(unsigned* ticket) {
 // distances:  rank = size_t(float(n_valid) * quantile)  (Matches.cpp:85-86; quantile == 1 -> max
 // element); pass 2 finishes filter f: limit[f] = value (* factor for MedianDist), limit_all = min.
 // `clear`: zero the histogram afterwards.
-__device__ __forceinline__ void select_pick(unsigned* hist, int pass, float quantile, int f, float factor, IcpState* state, bool clear) {
+// target: 0 = quantile filter f; 1 = the median of a robust filter's MAD estimate, 2 = its median of
+// absolute deviations (both at position size / 2, Matches.cpp:107-120).
+__device__ __forceinline__ void select_pick(unsigned* hist, int pass, float quantile, int f, float factor, IcpState* state, bool clear,
+                                            int target = 0) {
     __shared__ unsigned long long warp_tot[32];
     __shared__ unsigned long long s_rank;
     __shared__ int s_abort;
@@ -128,7 +168,8 @@ __device__ __forceinline__ void select_pick(unsigned* hist, int pass, float quan
                 s_rank = 0;
             } else {
                 unsigned long long r;
-                if (quantile == 1.0f) r = total - 1;
+                if (target != 0) r = total / 2;
+                else if (quantile == 1.0f) r = total - 1;
                 else {
                     r = (unsigned long long)(__ull2float_rn(total) * quantile);
                     if (r > total - 1) r = total - 1;
@@ -136,7 +177,7 @@ __device__ __forceinline__ void select_pick(unsigned* hist, int pass, float quan
                 s_rank = r;
             }
         } else {
-            s_rank = state->sel_rank[f];
+            s_rank = target != 0 ? state->robust_rank : state->sel_rank[f];
         }
     }
     __syncthreads();
@@ -147,6 +188,15 @@ __device__ __forceinline__ void select_pick(unsigned* hist, int pass, float quan
             if (rank >= excl && rank < excl + h) {
                 const unsigned found = (unsigned)(t * per + j);
                 const unsigned long long rem = rank - excl;
+                if (target != 0) {
+                    if (pass == 0) { state->robust_prefix = found; state->robust_rank = rem; }
+                    else if (pass == 1) { state->robust_prefix = (state->robust_prefix << 11) | found; state->robust_rank = rem; }
+                    else {
+                        const float value = __uint_as_float((state->robust_prefix << 10) | found);
+                        if (target == 1) state->robust_median = value;
+                        else state->robust_scale = sqrtf(value);  // scale = sqrt(MAD), OutlierFiltersImpl.cpp:512
+                    }
+                } else
                 if (pass == 0) { state->sel_prefix[f] = found; state->sel_rank[f] = rem; }
                 else if (pass == 1) { state->sel_prefix[f] = (state->sel_prefix[f] << 11) | found; state->sel_rank[f] = rem; }
                 else {

@@ -389,6 +389,47 @@ struct TrimmedDistOutlierFilter : public GpuDistOutlierFilter {
     TrimmedDistOutlierFilter(const Parameters& params = Parameters()) : GpuDistOutlierFilter("TrimmedDistOutlierFilter", availableParameters(), params, PMGPU_FILTER_TRIMMEDDIST, "ratio") {}
 };
 
+// RobustOutlierFilter (OutlierFiltersImpl.h:199-262, .cpp:420-598): M-estimator weights on the GPU;
+// the discrete parameters travel in the filter word (pmgpu.h)
+struct RobustOutlierFilter : public GpuDistOutlierFilter {
+    static const std::string description() {
+        return "Robust weight function part of the M-Estimator familly. 8 robust functions to choose from (Cauchy, Welsch, Switchable Constraint, "
+               "Geman-McClure, Tukey, Huber, L1 and Student). All the functions are M-Estimator (\\cite{RobustWeightFunctions}) except L1 and Student.";
+    }
+    static const ParametersDoc availableParameters() {
+        return {
+            {"robustFct", "Type of robust function used. Available fct: 'cauchy', 'welsch', 'sc'(aka Switchable-Constraint), 'gm' (aka Geman-McClure), 'tukey', 'huber' and 'L1'. (Default: cauchy)", "cauchy"},
+            {"tuning", "Tuning parameter used to limit the influence of outliers.If the 'scaleEstimator' is 'mad' or 'none', this parameter acts as the tuning parameter.If the 'scaleEstimator' is 'berg' this parameter acts as the target scale (σ*).", "1.0", "0.0000001", "inf", &Parametrizable::Comp<T>},
+            {"scaleEstimator", "The scale estimator is used to convert the error distance into a Mahalanobis distance. 3 estimators are available: 'none': no estimator (scale = 1), 'mad': use the median of absolute deviation (a kind of robust standard deviation), 'berg': an iterative exponentially decreasing estimator", "mad"},
+            {"nbIterationForScale", "For how many iteration the 'scaleEstimator' is recalculated. After 'nbIterationForScale' iteration the previous scale is kept. A nbIterationForScale==0 means that the estiamtor is recalculated at each iteration.", "0", "0", "100", &Parametrizable::Comp<int>},
+            {"distanceType", "Type of error distance used, either point to point ('point2point') or point to plane('point2plane'). Point to point gives better result normally.", "point2point"},
+            {"approximation", "If the matched distance is larger than this threshold, its weight will be forced to zero. This can save computation as zero values are not minimized. If set to inf (default value), no approximation is done. The unit of this parameter is the same as the distance used, typically meters.", "inf", "0.0", "inf", &Parametrizable::Comp<T>}};
+    }
+    static int word(const Parameters& params) {
+        auto get = [&](const char* name, const char* def) {
+            const auto it = params.find(name);
+            return it == params.end() ? std::string(def) : it->second;
+        };
+        static const std::map<std::string, int> fcts = {{"cauchy", PMGPU_ROBUST_CAUCHY}, {"welsch", PMGPU_ROBUST_WELSCH}, {"sc", PMGPU_ROBUST_SC},
+                                                        {"gm", PMGPU_ROBUST_GM},         {"tukey", PMGPU_ROBUST_TUKEY},   {"huber", PMGPU_ROBUST_HUBER},
+                                                        {"L1", PMGPU_ROBUST_L1},         {"student", PMGPU_ROBUST_STUDENT}};
+        const auto f = fcts.find(get("robustFct", "cauchy"));
+        if (f == fcts.end()) throw InvalidParameter("Invalid robust function name.");
+        const std::string est = get("scaleEstimator", "mad");
+        if (est != "mad" && est != "none") throw ConfigurationError("RobustOutlierFilter: GPU module: scaleEstimator must be 'mad' or 'none'");
+        if (get("distanceType", "point2point") != "point2point") throw ConfigurationError("RobustOutlierFilter: GPU module: distanceType must be 'point2point'");
+        const std::string approx = get("approximation", "inf");
+        if (approx != "inf") throw ConfigurationError("RobustOutlierFilter: GPU module: approximation must be inf");
+        return PMGPU_ROBUST_WORD(f->second, est == "mad" ? PMGPU_SCALE_MAD : PMGPU_SCALE_NONE, std::stoi(get("nbIterationForScale", "0")));
+    }
+    RobustOutlierFilter(const Parameters& params = Parameters())
+        : GpuDistOutlierFilter("RobustOutlierFilter", availableParameters(), params, word(params), "tuning") {
+        // every declared parameter is read (Registrar.h:103-110)
+        Parametrizable::get<std::string>("robustFct"); Parametrizable::get<std::string>("scaleEstimator"); Parametrizable::get<int>("nbIterationForScale");
+        Parametrizable::get<std::string>("distanceType"); Parametrizable::get<T>("approximation");
+    }
+};
+
 // chain (OutlierFilter.cpp:63-103): product of the filters' weights; empty chain -> dist != inf.
 // A chain made of GPU distance filters is evaluated in one call (one collapsed threshold).
 struct OutlierFilters : public std::vector<std::shared_ptr<OutlierFilter>>, public GpuBound {

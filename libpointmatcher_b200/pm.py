@@ -349,6 +349,39 @@ class TrimmedDistOutlierFilter(_DistFilter):
     PARAMS = (("ratio", "percentage to keep", "0.85", "0.0000001", "1.0", float),)
 
 
+class RobustOutlierFilter(_DistFilter):
+    """OutlierFiltersImpl.h:199-262, OutlierFiltersImpl.cpp:420-598: M-estimator weights (cauchy, welsch, sc, gm, tukey,
+    huber, L1, student) of e^2 = dist / scale^2, scale = sqrt(MAD) or 1 — evaluated on the device."""
+    className = "RobustOutlierFilter"
+    TYPE, PARAM = capi.FILTER_ROBUST, "tuning"
+    FCTS = dict(cauchy=0, welsch=1, sc=2, gm=3, tukey=4, huber=5, L1=6, student=7)
+    PARAMS = (
+        ("robustFct", "Type of robust function used. Available fct: 'cauchy', 'welsch', 'sc'(aka Switchable-Constraint), 'gm' (aka Geman-McClure), "
+                      "'tukey', 'huber' and 'L1'. (Default: cauchy)", "cauchy", None, None, str),
+        ("tuning", "Tuning parameter used to limit the influence of outliers.", "1.0", "0.0000001", "inf", float),
+        ("scaleEstimator", "The scale estimator is used to convert the error distance into a Mahalanobis distance: 'none', 'mad', 'berg'", "mad", None, None, str),
+        ("nbIterationForScale", "For how many iteration the 'scaleEstimator' is recalculated. 0 means at each iteration.", "0", "0", "100", int),
+        ("distanceType", "Type of error distance used, either point to point ('point2point') or point to plane('point2plane').", "point2point", None, None, str),
+        ("approximation", "If the matched distance is larger than this threshold, its weight will be forced to zero.", "inf", "0.0", "inf", float),
+    )
+
+    def __init__(self, params=None):
+        _DistFilter.__init__(self, params)
+        fct, est = self.get("robustFct"), self.get("scaleEstimator")
+        if fct not in self.FCTS:
+            raise InvalidParameter("Invalid robust function name.")
+        if est not in ("mad", "none"):
+            raise ConfigurationError("RobustOutlierFilter: GPU module: scaleEstimator must be 'mad' or 'none'")
+        if self.get("distanceType") != "point2point":
+            raise ConfigurationError("RobustOutlierFilter: GPU module: distanceType must be 'point2point'")
+        if self.get("approximation") != float("inf"):
+            raise ConfigurationError("RobustOutlierFilter: GPU module: approximation must be inf")
+        self.word = capi.FILTER_ROBUST | (self.FCTS[fct] << 8) | ((1 if est == "mad" else 0) << 16) | (self.get("nbIterationForScale") << 20)
+
+    def spec(self):
+        return (self.word, self.value)
+
+
 class OutlierFilters(list, _Bound):
     """OutlierFilter.cpp:63-103: product of all filters' weights; empty chain -> dist != inf."""
 
@@ -649,7 +682,7 @@ class Registrar(dict):
 
 MatcherRegistrar = Registrar(KDTreeMatcher=KDTreeMatcher)
 OutlierFilterRegistrar = Registrar(MaxDistOutlierFilter=MaxDistOutlierFilter, MedianDistOutlierFilter=MedianDistOutlierFilter,
-                                   TrimmedDistOutlierFilter=TrimmedDistOutlierFilter)
+                                   TrimmedDistOutlierFilter=TrimmedDistOutlierFilter, RobustOutlierFilter=RobustOutlierFilter)
 ErrorMinimizerRegistrar = Registrar(PointToPointErrorMinimizer=PointToPointErrorMinimizer,
                                     PointToPointWithCovErrorMinimizer=PointToPointWithCovErrorMinimizer,
                                     PointToPlaneErrorMinimizer=PointToPlaneErrorMinimizer,

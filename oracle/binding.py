@@ -16,7 +16,14 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
 
-FILTER_MAXDIST, FILTER_MEDIANDIST, FILTER_TRIMMEDDIST = 0, 1, 2
+FILTER_MAXDIST, FILTER_MEDIANDIST, FILTER_TRIMMEDDIST, FILTER_ROBUST = 0, 1, 2, 3
+ROBUST_FCTS = dict(cauchy=0, welsch=1, sc=2, gm=3, tukey=4, huber=5, L1=6, student=7)
+SCALE_NONE, SCALE_MAD = 0, 1
+
+
+def robust_word(fct="cauchy", scale=SCALE_MAD, nb_iteration_for_scale=0):
+    """filter word of a RobustOutlierFilter (oracle.h): use as the filter type, with the tuning as the parameter"""
+    return FILTER_ROBUST | (ROBUST_FCTS[fct] << 8) | (scale << 16) | (nb_iteration_for_scale << 20)
 MIN_P2POINT, MIN_P2PLANE, MIN_P2POINT_COV, MIN_P2PLANE_COV = 0, 1, 2, 3
 ERRORS = {
     1: "ConvergenceError: no outlier to filter",

@@ -542,9 +542,73 @@ int dists_quantile(const float* dists, long n, float quantile, float* out) {
     return ORC_OK;
 }
 
-// OutlierFilters::compute (OutlierFilter.cpp:63-103) over the three in-scope filters
-// (OutlierFiltersImpl.cpp:66-81, 109-147).
-int outlier_weights(const float* dists, int knn, int n, int nfilters, const int* types, const float* params, float* w, float* limits_out) {
+// Matches::getMedianAbsDeviation (Matches.cpp:88-122): median(|x - median(x)|) over the finite
+// squared distances, both medians at position size/2.
+int median_abs_deviation(const float* dists, long n, float* out) {
+    std::vector<float> values;
+    values.reserve(n);
+    for (long i = 0; i < n; ++i)
+        if (dists[i] != kInf) values.push_back(dists[i]);
+    if (values.empty()) return ORC_ERR_NO_OUTLIER_TO_FILTER;
+    std::nth_element(values.begin(), values.begin() + values.size() / 2, values.end());
+    const float median = values[values.size() / 2];
+    for (float& v : values) v = std::fabs(v - median);
+    std::nth_element(values.begin(), values.begin() + values.size() / 2, values.end());
+    *out = values[values.size() / 2];
+    return ORC_OK;
+}
+
+// state a RobustOutlierFilter object carries from one compute() to the next (OutlierFiltersImpl.cpp:420-438)
+struct RobustState {
+    int iteration = 1;
+    float scale = 0.f;
+};
+
+// RobustOutlierFilter::robustFiltering (OutlierFiltersImpl.cpp:503-598), distanceType point2point,
+// approximation = inf.  All array arithmetic in float, as Eigen's Array<T> evaluates it.
+int robust_weights(const float* dists, long total, int word, float tuning, RobustState& st, float* w_out, float* scale_out) {
+    const int fct = (word >> 8) & 0xff, scale_est = (word >> 16) & 0xf, nb_iter = (word >> 20) & 0xff;
+    if (scale_est == ORC_SCALE_MAD) {
+        if (st.iteration <= nb_iter || nb_iter == 0) {
+            float mad;
+            const int rc = median_abs_deviation(dists, total, &mad);
+            if (rc) return rc;
+            st.scale = std::sqrt(mad);
+        }
+    } else if (scale_est == ORC_SCALE_NONE) {
+        st.scale = 1.f;
+    } else {
+        return ORC_ERR_BAD_ARG;
+    }
+    st.iteration++;
+    if (scale_out) *scale_out = st.scale;
+    const float k = tuning, k2 = k * k, s2 = st.scale * st.scale;
+    for (long i = 0; i < total; ++i) {
+        const float e2 = dists[i] / s2;
+        float w;
+        switch (fct) {
+            case ORC_ROBUST_CAUCHY: w = 1.f / (1.f + e2 / k2); break;
+            case ORC_ROBUST_WELSCH: w = std::exp(-e2 / k2); break;
+            case ORC_ROBUST_SC: { const float a = k + e2; w = (e2 >= k) ? 4.0f * k2 * (1.f / (a * a)) : 1.f; break; }
+            case ORC_ROBUST_GM: { const float a = k + e2; w = k2 * (1.f / (a * a)); break; }
+            case ORC_ROBUST_TUKEY: { const float a = 1.f - e2 / k2; w = (e2 >= k2) ? 0.f : a * a; break; }
+            case ORC_ROBUST_HUBER: w = (e2 >= k2) ? k * (1.f / std::sqrt(e2)) : 1.f; break;
+            case ORC_ROBUST_L1: w = 1.f / std::sqrt(e2); break;
+            case ORC_ROBUST_STUDENT: { const float d = 3.f; w = std::pow(1.f + e2 / k, -(k + d) / 2.f) * (k + d) * (1.f / (k + e2)); break; }
+            default: return ORC_ERR_BAD_ARG;
+        }
+        // `w <= 1e-50` -> 1e-50, which is 0 once stored in a float array; an infinite distance gives weight 0
+        // for every function but is dropped by ErrorElements anyway
+        if (w <= 1e-50f) w = (float)1e-50;
+        w_out[i] = w;
+    }
+    return ORC_OK;
+}
+
+// OutlierFilters::compute (OutlierFilter.cpp:63-103) over the in-scope filters
+// (OutlierFiltersImpl.cpp:66-81, 109-147, 420-598).
+int outlier_weights(const float* dists, int knn, int n, int nfilters, const int* types, const float* params, float* w, float* limits_out,
+                    RobustState* robust = nullptr) {
     const long total = long(knn) * n;
     if (nfilters == 0) {
         for (long i = 0; i < total; ++i) w[i] = (dists[i] == kInf) ? 0.f : 1.f;
@@ -563,6 +627,15 @@ int outlier_weights(const float* dists, int knn, int n, int nfilters, const int*
         } else if (types[f] == ORC_FILTER_TRIMMEDDIST) {
             const int rc = dists_quantile(dists, total, params[f], &limit);
             if (rc) return rc;
+        } else if ((types[f] & 0xff) == ORC_FILTER_ROBUST) {
+            RobustState fresh;
+            std::vector<float> wr(total);
+            float scale = 0.f;
+            const int rc = robust_weights(dists, total, types[f], params[f], robust ? robust[f] : fresh, wr.data(), &scale);
+            if (rc) return rc;
+            if (limits_out) limits_out[f] = scale;  // the scale, for the tests
+            for (long i = 0; i < total; ++i) w[i] = (f == 0) ? wr[i] : w[i] * wr[i];
+            continue;
         } else {
             return ORC_ERR_BAD_ARG;
         }
@@ -1255,6 +1328,7 @@ int orc_icp(const float* readingIn, int nq, const float* referenceIn, int nr, co
     std::vector<int32_t> ids(size_t(knn) * nq);
     std::vector<float> dists(size_t(knn) * nq), w(size_t(knn) * nq);
     int rc = ORC_OK;
+    RobustState robustState[8];  // one per filter slot: the filter objects live as long as the ICP object
     const double t_loop0 = now_s();
     while (iterate) {
         if (!check_rigid(T_iter)) { rc = ORC_ERR_NOT_ORTHOGONAL; break; }
@@ -1263,7 +1337,7 @@ int orc_icp(const float* readingIn, int nq, const float* referenceIn, int nr, co
         if (tree) tree->knn(stepReading.data(), 4, nq, knn, cfg->epsilon, cfg->max_dist, ids.data(), dists.data(), cfg->nthreads);
         else orc_bruteforce_knn(reference.data(), 4, nr, stepReading.data(), nq, knn, cfg->max_dist, ids.data(), dists.data(), cfg->nthreads);
         g_timings[2] += now_s() - t_m0;
-        rc = outlier_weights(dists.data(), knn, nq, cfg->nfilters, cfg->filter_type, cfg->filter_param, w.data(), nullptr);
+        rc = outlier_weights(dists.data(), knn, nq, cfg->nfilters, cfg->filter_type, cfg->filter_param, w.data(), nullptr, robustState);
         if (rc) break;
         float dT[16];
         rc = orc_minimize(cfg->minimizer, stepReading.data(), nq, reference.data(), nr, ref_normals, ids.data(), dists.data(), w.data(), knn, cfg->sensor_std_dev, cfg->acc_double, dT, cov_out, stats_out);

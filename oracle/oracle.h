@@ -23,7 +23,14 @@ extern "C" {
 #endif
 
 /* filter types for the outlier chain (OutlierFiltersImpl.cpp) */
-enum { ORC_FILTER_MAXDIST = 0, ORC_FILTER_MEDIANDIST = 1, ORC_FILTER_TRIMMEDDIST = 2 };
+enum { ORC_FILTER_MAXDIST = 0, ORC_FILTER_MEDIANDIST = 1, ORC_FILTER_TRIMMEDDIST = 2, ORC_FILTER_ROBUST = 3 };
+/* RobustOutlierFilter (OutlierFiltersImpl.cpp:420-598): the filter word carries its discrete parameters:
+ *   bits 0-7  ORC_FILTER_ROBUST | bits 8-15 robust function | bits 16-19 scale estimator |
+ *   bits 20-27 nbIterationForScale;   filter_param = tuning.  distanceType point2point, approximation inf. */
+enum { ORC_ROBUST_CAUCHY = 0, ORC_ROBUST_WELSCH, ORC_ROBUST_SC, ORC_ROBUST_GM, ORC_ROBUST_TUKEY, ORC_ROBUST_HUBER, ORC_ROBUST_L1,
+       ORC_ROBUST_STUDENT };
+enum { ORC_SCALE_NONE = 0, ORC_SCALE_MAD = 1 };
+#define ORC_ROBUST_WORD(fct, scale, nb_iter) (ORC_FILTER_ROBUST | ((fct) << 8) | ((scale) << 16) | ((nb_iter) << 20))
 /* error minimizers */
 enum { ORC_MIN_P2POINT = 0, ORC_MIN_P2PLANE = 1, ORC_MIN_P2POINT_COV = 2, ORC_MIN_P2PLANE_COV = 3 };
 /* status codes */

@@ -375,3 +375,56 @@ def test_cap_not_used_with_finite_maxdist_or_staged_calls(monkeypatch, oracle, s
         w, lim = ctx.weights([(2, 0.5)])
         T, _, _ = ctx.minimize(0)
         assert np.isfinite(T).all()
+
+
+# ---------------------------------------------------------------------------------- RobustOutlierFilter (8f row 3)
+@pytest.mark.parametrize("fct", ["cauchy", "welsch", "sc", "gm", "tukey", "huber", "L1", "student"])
+def test_robust_filter_weights_match_oracle(gpu_ctx, oracle, synth, fct):
+    """scale = sqrt(MAD) bit-exact (two exact selects), weights in float like Eigen's arrays"""
+    rd, rf, _ = synth.scan_pair(40000)
+    gpu_ctx.set_reference(rf)
+    gpu_ctx.set_reading(rd)
+    ids, dists, _ = gpu_ctx.knn(None, 3, 0.0, np.inf)
+    for scale in (oracle.SCALE_MAD, oracle.SCALE_NONE):
+        word, tuning = oracle.robust_word(fct, scale), 1.3
+        wo, so = oracle.outlier_weights(dists, [(word, tuning)])
+        wg, sg = gpu_ctx.weights([(word, tuning)])
+        assert bits(sg)[0] == bits(so)[0], (fct, scale, sg, so)
+        if fct in ("cauchy", "sc", "gm", "tukey"):
+            assert (bits(wg) == bits(wo)).all()
+        else:                       # exp / pow / sqrt differ from libm in the last places
+            assert np.allclose(wg, wo, rtol=2e-6, atol=1e-30)
+    # in a chain the weights multiply (OutlierFilter.cpp:96)
+    chain = [(2, 0.8), (oracle.robust_word(fct, oracle.SCALE_MAD), 0.7)]
+    wo, _ = oracle.outlier_weights(dists, chain)
+    wg, _ = gpu_ctx.weights(chain)
+    assert np.allclose(wg, wo, rtol=2e-6, atol=1e-30) and ((wg == 0) == (wo == 0)).all()
+
+
+@pytest.mark.parametrize("minimizer,k", [(0, 1), (0, 4), (1, 2)])
+def test_icp_with_robust_filter_matches_oracle(oracle, synth, minimizer, k):
+    from libpointmatcher_b200 import capi
+    rd, rf, _ = synth.scan_pair(50000)
+    nrm = oracle.surface_normals(rf, knn=10, nthreads=8)["normals"]
+    word = oracle.robust_word("cauchy", oracle.SCALE_MAD)
+    res_o = oracle.icp(rd, rf, ref_normals=nrm, knn=k, filters=[(word, 1.0)], minimizer=minimizer, max_iterations=12, nthreads=8, acc_double=True)
+    with capi.Context(0) as ctx:
+        ctx.set_reference(rf, normals=nrm)
+        ctx.set_reading(rd)
+        res = ctx.icp_run(capi.make_params(knn=k, filters=[(word, 1.0)], minimizer=minimizer, max_iterations=12))
+    assert res["iterations"] == res_o["iterations"] == 12 and res["cap_redos"] == 0
+    assert_transform_close(res["T_iter"], res_o["T"], 1e-5, 1e-5)
+    assert abs(res["stats"]["weightedPointUsedRatio"] - float(res_o["stats"][1])) < 1e-4
+
+
+def test_robust_filter_scale_frozen_after_n_iterations(oracle, synth):
+    """nbIterationForScale: the scale is re-estimated in the first n calls only (OutlierFiltersImpl.cpp:510-514)"""
+    from libpointmatcher_b200 import capi
+    rd, rf, _ = synth.scan_pair(30000)
+    word = oracle.robust_word("huber", oracle.SCALE_MAD, 2)
+    res_o = oracle.icp(rd, rf, knn=1, filters=[(word, 1.0)], minimizer=0, max_iterations=8, nthreads=8, acc_double=True)
+    with capi.Context(0) as ctx:
+        ctx.set_reference(rf)
+        ctx.set_reading(rd)
+        res = ctx.icp_run(capi.make_params(knn=1, filters=[(word, 1.0)], minimizer=0, max_iterations=8))
+    assert_transform_close(res["T_iter"], res_o["T"], 1e-5, 1e-5)

@@ -107,7 +107,7 @@ def test_gpu_reproduces_validT3d(oracle, fx, mini):
 # ---- the reference's chain files, end to end (pre-filters on the host, loop on the GPU) -----------
 YAML_CHAINS = ["defaultIdentityDataPointsFilter", "defaultPointToPlaneMinDistDataPointsFilter", "defaultPointToPointMinDistDataPointsFilter",
                "defaultMaxDistDataPointsFilter", "SamplingSurfaceNormalDataPointsFilter1", "SamplingSurfaceNormalDataPointsFilter2",
-               "SamplingSurfaceNormalDataPointsFilter3"]
+               "SamplingSurfaceNormalDataPointsFilter3", "defaultRobustOutlierFilter"]
 
 
 @pytest.mark.parametrize("name", ["defaultIdentityDataPointsFilter", "defaultPointToPlaneMinDistDataPointsFilter"])
@@ -125,6 +125,14 @@ def test_oracle_chain_with_prefilters_reproduces_golden(oracle, fx, name):
     r = oracle.icp(np.ascontiguousarray(data_f), np.ascontiguousarray(ref_f), ref_normals=np.ascontiguousarray(normals),
                    filters=[(oracle.FILTER_TRIMMEDDIST, 0.75)], minimizer=1, max_iterations=40, differential=(0.001, 0.01, 4), nthreads=4)
     assert rel_err(r["T"], fx["golden_" + name], data) < 0.03
+
+
+def test_oracle_robust_chain_reproduces_golden(oracle, fx):
+    """defaultRobustOutlierFilter.yaml: knn 10, RobustOutlierFilter(cauchy, mad, tuning 1), PointToPoint"""
+    ref, data = homog(fx["cloud0"]), homog(fx["cloud1"])
+    r = oracle.icp(data, ref, knn=10, filters=[(oracle.robust_word("cauchy", oracle.SCALE_MAD), 1.0)], minimizer=0, max_iterations=40,
+                   differential=(0.001, 0.01, 4), nthreads=4)
+    assert rel_err(r["T"], fx["golden_defaultRobustOutlierFilter"], data) < 0.03
 
 
 @pytest.mark.gpu
