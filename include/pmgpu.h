@@ -80,6 +80,10 @@ enum pmgpu_minimizer {
     PMGPU_MIN_P2POINT_COV = 2, /* PointToPointWithCovErrorMinimizer   ErrorMinimizers/PointToPointWithCov.cpp:49-145 */
     PMGPU_MIN_P2PLANE_COV = 3  /* PointToPlaneWithCovErrorMinimizer   ErrorMinimizers/PointToPlaneWithCov.cpp:60-162 */
 };
+/* or-ed into PMGPU_MIN_P2PLANE[_COV]: PointToPlaneErrorMinimizer force4DOF (PointToPlane.cpp:203-214,
+ * 266-281) — the unknowns are the rotation about z and the translation: the 4x4 sub-system
+ * (cross_z, n) of the same sums, T = AngleAxis(x0, unitZ) + translation. */
+#define PMGPU_MIN_FORCE4DOF 0x100
 
 /* SurfaceNormalDataPointsFilter keep* flags (DataPointsFilters/SurfaceNormal.h:65-80) */
 enum pmgpu_normals_flags {

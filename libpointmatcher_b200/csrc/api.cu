@@ -162,7 +162,10 @@ int check_params(pmgpu_ctx* ctx, const pmgpu_icp_params* p) {
     if (p->knn < 1) return fail(ctx, PMGPU_ERR_BAD_ARG, "knn must be >= 1");
     if (p->knn > ctx->nr) return fail(ctx, PMGPU_ERR_KNN_TOO_LARGE, status_message(PMGPU_ERR_KNN_TOO_LARGE));
     if (p->nfilters < 0 || p->nfilters > PM_MAX_FILTERS) return fail(ctx, PMGPU_ERR_BAD_ARG, "at most 8 outlier filters");
-    if (p->minimizer < 0 || p->minimizer > PMGPU_MIN_P2PLANE_COV) return fail(ctx, PMGPU_ERR_BAD_ARG, "unknown error minimizer");
+    if (p->minimizer < 0 || (p->minimizer & 0xff) > PMGPU_MIN_P2PLANE_COV || (p->minimizer & ~0x1ff))
+        return fail(ctx, PMGPU_ERR_BAD_ARG, "unknown error minimizer");
+    if ((p->minimizer & PMGPU_MIN_FORCE4DOF) && !((p->minimizer & 0xff) == PMGPU_MIN_P2PLANE || (p->minimizer & 0xff) == PMGPU_MIN_P2PLANE_COV))
+        return fail(ctx, PMGPU_ERR_BAD_ARG, "force4DOF is a point-to-plane parameter");
     if (p->use_differential && (p->smooth_length < 0 || p->smooth_length >= PM_MAX_HISTORY))
         return fail(ctx, PMGPU_ERR_UNSUPPORTED, "DifferentialTransformationChecker: smoothLength must be < 64 on the GPU path");
     if (p->max_iterations < 0) return fail(ctx, PMGPU_ERR_BAD_ARG, "maxIterationCount must be >= 0");
@@ -494,12 +497,14 @@ int pmgpu_minimize(pmgpu_ctx* ctx, int minimizer, float sensor_std_dev, float* T
     if (!ctx) return PMGPU_ERR_BAD_ARG;
     PM_TRY(use_device(ctx));
     if (!ctx->have_matches) return fail(ctx, PMGPU_ERR_NO_MATCHES, status_message(PMGPU_ERR_NO_MATCHES));
-    if (minimizer < 0 || minimizer > PMGPU_MIN_P2PLANE_COV) return fail(ctx, PMGPU_ERR_BAD_ARG, "unknown error minimizer");
+    if (minimizer < 0 || (minimizer & 0xff) > PMGPU_MIN_P2PLANE_COV || (minimizer & ~0x1ff)) return fail(ctx, PMGPU_ERR_BAD_ARG, "unknown error minimizer");
+    if ((minimizer & PMGPU_MIN_FORCE4DOF) && (minimizer & 0xff) != PMGPU_MIN_P2PLANE && (minimizer & 0xff) != PMGPU_MIN_P2PLANE_COV)
+        return fail(ctx, PMGPU_ERR_BAD_ARG, "force4DOF is a point-to-plane parameter");
     if (!ctx->have_weights) PM_TRY(launch_weights(ctx, SelectSpec(), false, false));  // empty chain
     ctx->stage_begin(2);
     PM_TRY(launch_minimize(ctx, minimizer, false, false, nullptr));
     ctx->stage_end();
-    const bool with_cov = minimizer == PMGPU_MIN_P2POINT_COV || minimizer == PMGPU_MIN_P2PLANE_COV;
+    const bool with_cov = (minimizer & 0xff) == PMGPU_MIN_P2POINT_COV || (minimizer & 0xff) == PMGPU_MIN_P2PLANE_COV;
     if (with_cov) {
         ctx->stage_begin(3);
         PM_TRY(launch_covariance(ctx, minimizer, sensor_std_dev));
@@ -557,7 +562,7 @@ int pmgpu_icp_enqueue(pmgpu_ctx* ctx, const pmgpu_icp_params* params, int n_iter
     if (ctx->nr == 0) return fail(ctx, PMGPU_ERR_NO_REFERENCE, status_message(PMGPU_ERR_NO_REFERENCE));
     if (ctx->nq == 0) return fail(ctx, PMGPU_ERR_NO_READING, status_message(PMGPU_ERR_NO_READING));
     PM_TRY(check_params(ctx, params));
-    const bool plane = params->minimizer == PMGPU_MIN_P2PLANE || params->minimizer == PMGPU_MIN_P2PLANE_COV;
+    const bool plane = (params->minimizer & 0xff) == PMGPU_MIN_P2PLANE || (params->minimizer & 0xff) == PMGPU_MIN_P2PLANE_COV;
     if (plane && !ctx->has_normals) return fail(ctx, PMGPU_ERR_NO_NORMALS, status_message(PMGPU_ERR_NO_NORMALS));
     const size_t total = (size_t)params->knn * ctx->nq;
     PM_CUDA_TRY(ctx, ctx->ids.reserve(total));
@@ -601,7 +606,7 @@ int pmgpu_icp_run(pmgpu_ctx* ctx, const pmgpu_icp_params* params, const float* T
         if (h->status != PMGPU_OK || !h->iterate || h->iterations >= n) break;
         slots = n - h->iterations;
     }
-    const bool with_cov = params->minimizer == PMGPU_MIN_P2POINT_COV || params->minimizer == PMGPU_MIN_P2PLANE_COV;
+    const bool with_cov = (params->minimizer & 0xff) == PMGPU_MIN_P2POINT_COV || (params->minimizer & 0xff) == PMGPU_MIN_P2PLANE_COV;
     if (with_cov) {
         PM_TRY(pull_state(ctx));
         if (ctx->state_host->status == PMGPU_OK) PM_TRY(launch_covariance(ctx, params->minimizer, params->sensor_std_dev));

@@ -17,13 +17,13 @@ namespace pm {
 // solution x = P L (L^T L)^-2 L^T P^T b, which is what the reference's
 // R1^T (R1 R1^T)^-1 Q1^T b evaluates to.  Returns the rank.
 // ------------------------------------------------------------------------------------------
-PM_HD int solve_psd6(const double* A, const double* b, double* x) {
-    const int n = 6;
+// (n x n, n <= 6: 6 for the full problem, 4 with force4DOF; the rank threshold is n * eps_float)
+PM_HD int solve_psd(const double* A, const double* b, double* x, const int n) {
     double M[36], L[36];
     int perm[6];
-    for (int i = 0; i < 36; ++i) { M[i] = A[i]; L[i] = 0.0; }
+    for (int i = 0; i < n * n; ++i) { M[i] = A[i]; L[i] = 0.0; }
     for (int i = 0; i < n; ++i) perm[i] = i;
-    const double thr = 6.0 * PM_FLT_EPS;
+    const double thr = (double)n * PM_FLT_EPS;
     double d0 = 0.0;
     int rank = 0;
     for (int k = 0; k < n; ++k) {
@@ -110,6 +110,7 @@ PM_HD int solve_psd6(const double* A, const double* b, double* x) {
     for (int i = 0; i < n; ++i) x[perm[i]] = z[i];
     return rank;
 }
+PM_HD int solve_psd6(const double* A, const double* b, double* x) { return solve_psd(A, b, x, 6); }
 
 // ------------------------------------------------------------------------------------------
 // Cyclic Jacobi eigen-decomposition of a symmetric 3x3 matrix (double).  A is destroyed;

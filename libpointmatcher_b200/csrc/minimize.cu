@@ -328,9 +328,21 @@ __device__ void finalize_body(const double* partials, int nblocks, double* sums,
         double A[36], b[6], x[6];
         expand_sym6(sums, A);
         for (int a = 0; a < 6; ++a) b[a] = -sums[21 + a];
-        solve_psd6(A, b, x);
         float xf[6];
-        for (int a = 0; a < 6; ++a) xf[a] = (float)x[a];
+        if (ck.minimizer & PMGPU_MIN_FORCE4DOF) {
+            // rows / columns (cross_z, nx, ny, nz) of the same normal equations (PointToPlane.cpp:203-214)
+            double A4[16], b4[4], x4[4];
+            for (int c = 0; c < 4; ++c) {
+                b4[c] = b[2 + c];
+                for (int r = 0; r < 4; ++r) A4[r + 4 * c] = A[(2 + r) + 6 * (2 + c)];
+            }
+            solve_psd(A4, b4, x4, 4);
+            xf[0] = 0.f; xf[1] = 0.f;
+            for (int a = 0; a < 4; ++a) xf[2 + a] = (float)x4[a];  // AngleAxis(x(0), unitZ), translation x(1..3)
+        } else {
+            solve_psd6(A, b, x);
+            for (int a = 0; a < 6; ++a) xf[a] = (float)x[a];
+        }
         angle_axis_to_mat4(xf, dT);
     } else {
         const double W = sums[0];
@@ -432,7 +444,8 @@ __global__ void __launch_bounds__(256) cov_finalize_kernel(const double* __restr
 
 }  // namespace
 
-int launch_minimize(pmgpu_ctx* ctx, int minimizer, bool compose_and_check, bool gated, const pmgpu_icp_params* checks) {
+int launch_minimize(pmgpu_ctx* ctx, int minimizer_word, bool compose_and_check, bool gated, const pmgpu_icp_params* checks) {
+    const int minimizer = minimizer_word & 0xff;
     const bool plane = (minimizer == PMGPU_MIN_P2PLANE || minimizer == PMGPU_MIN_P2PLANE_COV);
     if (plane && !ctx->has_normals) {
         ctx->set_error("Field normals not found");
@@ -452,6 +465,7 @@ int launch_minimize(pmgpu_ctx* ctx, int minimizer, bool compose_and_check, bool 
         ck.max_iterations = 0x7fffffff;
     }
     ck.knn = ctx->k;
+    ck.minimizer = minimizer_word;
     const int g = gated ? 1 : 0, comp = compose_and_check ? 1 : 0;
     const int fuse = ctx->nranks > 1 ? 0 : 1;
     if (plane) accumulate_kernel<1><<<grid, ACC_BLOCK, 0, st>>>(ctx->reading.p, ctx->nq, ctx->k, ctx->ids.p, ctx->dists.p, ctx->ref_orig.p, ctx->ref_normals.p, ctx->state, g, ctx->partials.p, fuse, ctx->state, sums, comp, ck);
@@ -471,7 +485,7 @@ int launch_minimize(pmgpu_ctx* ctx, int minimizer, bool compose_and_check, bool 
 }
 
 int launch_covariance(pmgpu_ctx* ctx, int minimizer, float sensor_std_dev) {
-    const bool plane = (minimizer == PMGPU_MIN_P2PLANE_COV);
+    const bool plane = ((minimizer & 0xff) == PMGPU_MIN_P2PLANE_COV);
     cudaStream_t st = ctx->stream;
     const int grid = grid_for(ctx->nq, ACC_BLOCK, ctx->num_sms, 4);
     PM_CUDA_TRY(ctx, ctx->partials.reserve((size_t)(ctx->num_sms * 4 + 2) * NS_MAX));

@@ -485,7 +485,7 @@ struct GpuErrorMinimizer : public ErrorMinimizer, public GpuBound {
         return out;
     }
     void setResults(const float* cov, const float* stats) {
-        if (kind == PMGPU_MIN_P2POINT_COV || kind == PMGPU_MIN_P2PLANE_COV)
+        if ((kind & 0xff) == PMGPU_MIN_P2POINT_COV || (kind & 0xff) == PMGPU_MIN_P2PLANE_COV)
             for (int i = 0; i < 36; ++i) covMatrix(i) = T(cov[i]);
         this->lastErrorElements.pointUsedRatio = T(stats[0]);
         this->lastErrorElements.weightedPointUsedRatio = T(stats[1]);
@@ -518,7 +518,8 @@ protected:
         : GpuErrorMinimizer(className, paramsDoc, params, kind) {
         const bool force2D = Parametrizable::get<bool>("force2D"), force4DOF = Parametrizable::get<bool>("force4DOF");
         if (force2D && force4DOF) throw ConfigurationError("Force 2D cannot be used together with force4DOF.");  // PointToPlane.cpp:59-64
-        if (force2D || force4DOF) throw ConfigurationError("PointToPlaneErrorMinimizer: GPU module: force2D / force4DOF are not supported");
+        if (force2D) throw ConfigurationError("PointToPlaneErrorMinimizer: GPU module: force2D is not supported");
+        if (force4DOF) this->kind |= PMGPU_MIN_FORCE4DOF;  // the 4x4 sub-system, PointToPlane.cpp:203-214
     }
 };
 struct PointToPlaneWithCovErrorMinimizer : public PointToPlaneErrorMinimizer {

@@ -402,19 +402,24 @@ class _Minimizer(Parametrizable, _Bound):
             force2D, force4DOF = self.get("force2D"), self.get("force4DOF")
             if force2D and force4DOF:
                 raise ConfigurationError("Force 2D cannot be used together with force4DOF.")
-            if force2D or force4DOF:
-                raise ConfigurationError("GPU module: force2D / force4DOF are not supported")
+            if force2D:
+                raise ConfigurationError("GPU module: force2D is not supported")
+            self.force4DOF = bool(force4DOF)
         self._cov = np.zeros((6, 6), np.float32)
         self._stats = dict(pointUsedRatio=-1.0, weightedPointUsedRatio=-1.0)
 
     def compute(self, filteredReading, filteredReference, outlierWeights, matches):
         """Uses the matches / weights resident on the device (the arguments are the host copies
         the reference interface passes around)."""
-        T, cov, stats = _translate(self.ctx.minimize, self.KIND, self.sensorStdDev)
+        T, cov, stats = _translate(self.ctx.minimize, self.kind_word(), self.sensorStdDev)
         if cov is not None:
             self._cov = cov
         self._stats = stats
         return T
+
+    def kind_word(self):
+        """minimiser id with the force4DOF bit (pmgpu.h)"""
+        return self.KIND | (capi.MIN_FORCE4DOF if getattr(self, "force4DOF", False) else 0)
 
     def getCovariance(self):
         return self._cov
@@ -784,7 +789,7 @@ class ICP:
         m = self.matcher
         return capi.make_params(
             knn=m.knn, epsilon=m.epsilon, max_dist=m.maxDist, filters=[f.spec() for f in self.outlierFilters],
-            minimizer=self.errorMinimizer.KIND, sensor_std_dev=self.errorMinimizer.sensorStdDev,
+            minimizer=self.errorMinimizer.kind_word(), sensor_std_dev=self.errorMinimizer.sensorStdDev,
             max_iterations=counter[0].maxIterationCount if counter else 0x7FFFFFFF,
             differential=(diff[0].minDiffRotErr, diff[0].minDiffTransErr, diff[0].smoothLength) if diff else None)
 

@@ -823,6 +823,48 @@ void angle_axis_to_T(const float x[6], float* T) {
             for (int i = 0; i < 3; ++i) T[i + 4 * j] = (i == j) ? 1.f : 0.f;
 }
 
+// force4DOF (PointToPlane.cpp:203-214, 266-281): the unknowns are the rotation about z and the translation;
+// `cross` collapses to its z row, (matrixGamma * p)^T n = -p_y n_x + p_x n_y.
+template <typename S>
+int minimize_p2plane_4dof(const ErrorElements& e, float* T_out) {
+    const int M = e.M;
+    Mat<S> A(4, 4);
+    std::vector<S> b(4, S(0));
+    for (int p = 0; p < M; ++p) {
+        const float* r = &e.reading[4 * size_t(p)];
+        const float* q = &e.reference[4 * size_t(p)];
+        const float* nr = &e.normals[3 * size_t(p)];
+        const float w = e.weights[p];
+        float F[4], wF[4];
+        F[0] = (-r[1]) * nr[0] + r[0] * nr[1];
+        F[1] = nr[0]; F[2] = nr[1]; F[3] = nr[2];
+        for (int i = 0; i < 4; ++i) wF[i] = w * F[i];
+        float dot = 0.f;
+        for (int i = 0; i < 3; ++i) dot += (r[i] - q[i]) * nr[i];
+        for (int j = 0; j < 4; ++j)
+            for (int i = 0; i < 4; ++i) A(i, j) += S(wF[i]) * S(F[j]);
+        for (int i = 0; i < 4; ++i) b[i] += S(wF[i]) * S(dot);
+    }
+    for (int i = 0; i < 4; ++i) b[i] = -b[i];
+    float x4[4];
+    if (sizeof(S) == sizeof(float)) {
+        Mat<float> Af(4, 4);
+        std::vector<float> bf(4), xf;
+        for (int j = 0; j < 4; ++j)
+            for (int i = 0; i < 4; ++i) Af(i, j) = float(A(i, j));
+        for (int i = 0; i < 4; ++i) bf[i] = float(b[i]);
+        solve_possibly_underdetermined<float>(Af, bf, xf);
+        for (int i = 0; i < 4; ++i) x4[i] = xf[i];
+    } else {
+        std::vector<S> xs;
+        solve_possibly_underdetermined<S>(A, b, xs);
+        for (int i = 0; i < 4; ++i) x4[i] = float(xs[i]);
+    }
+    const float x[6] = {0.f, 0.f, x4[0], x4[1], x4[2], x4[3]};  // AngleAxis(x(0), unitZ), translation x(1..3)
+    angle_axis_to_T(x, T_out);
+    return ORC_OK;
+}
+
 template <typename S>
 int minimize_p2plane(const ErrorElements& e, float* T_out) {
     const int M = e.M;
@@ -961,10 +1003,12 @@ int minimize_p2point(ErrorElements& e, float* T_out) {
 }
 
 template <typename S>
-int minimize_impl(int minimizer, ErrorElements& e, float sensorStdDev, float* T_out, float* cov_out) {
+int minimize_impl(int minimizer_word, ErrorElements& e, float sensorStdDev, float* T_out, float* cov_out) {
+    const int minimizer = minimizer_word & 0xff;
+    const bool force4dof = (minimizer_word & ORC_MIN_FORCE4DOF) != 0;
     if (minimizer == ORC_MIN_P2PLANE || minimizer == ORC_MIN_P2PLANE_COV) {
         if (e.normals.empty()) return ORC_ERR_BAD_ARG;
-        const int rc = minimize_p2plane<S>(e, T_out);
+        const int rc = force4dof ? minimize_p2plane_4dof<S>(e, T_out) : minimize_p2plane<S>(e, T_out);
         if (rc) return rc;
         if (minimizer == ORC_MIN_P2PLANE_COV && cov_out)
             estimate_covariance<S>(e.reading.data(), e.reference.data(), e.normals.data(), e.M, T_out, sensorStdDev, cov_out);

@@ -428,3 +428,36 @@ def test_robust_filter_scale_frozen_after_n_iterations(oracle, synth):
         ctx.set_reading(rd)
         res = ctx.icp_run(capi.make_params(knn=1, filters=[(word, 1.0)], minimizer=0, max_iterations=8))
     assert_transform_close(res["T_iter"], res_o["T"], 1e-5, 1e-5)
+
+
+# ---------------------------------------------------------------------------------- force4DOF (8f row 3)
+def test_point_to_plane_force4dof_matches_oracle(gpu_ctx, oracle, synth):
+    """PointToPlaneErrorMinimizer force4DOF (PointToPlane.cpp:203-214, 266-281): rotation about z + translation,
+    one minimiser call and a whole ICP run against the oracle"""
+    from libpointmatcher_b200 import capi, pm
+    rd, rf, _ = synth.scan_pair(50000)
+    nrm = oracle.surface_normals(rf, knn=10, nthreads=8)["normals"]
+    gpu_ctx.set_reference(rf, normals=nrm)
+    gpu_ctx.set_reading(rd)
+    ids, dists, _ = gpu_ctx.knn(None, 1, 0.0, np.inf)
+    w, _ = gpu_ctx.weights([(2, 0.8)])
+    Tg, _, _ = gpu_ctx.minimize(capi.MIN_P2PLANE | capi.MIN_FORCE4DOF)
+    To, _, _ = oracle.minimize(oracle.MIN_P2PLANE | oracle.MIN_FORCE4DOF, rd, rf, nrm, ids, dists, w, acc_double=True)
+    assert_transform_close(Tg, To, 1e-5, 1e-5)
+    assert Tg[2, 0] == 0 and Tg[2, 1] == 0 and Tg[0, 2] == 0 and Tg[1, 2] == 0 and abs(Tg[2, 2] - 1) < 1e-6   # a yaw-only rotation
+    T6, _, _ = gpu_ctx.minimize(capi.MIN_P2PLANE)
+    assert np.abs(T6[:3, :3] - Tg[:3, :3]).max() > 1e-7                                                       # and not the 6-DOF answer
+    res_o = oracle.icp(rd, rf, ref_normals=nrm, filters=[(2, 0.8)], minimizer=oracle.MIN_P2PLANE | oracle.MIN_FORCE4DOF, max_iterations=10,
+                       nthreads=8, acc_double=True)
+    icp = pm.ICP()
+    icp.matcher = pm.KDTreeMatcher()
+    icp.outlierFilters = pm.OutlierFilters([pm.TrimmedDistOutlierFilter({"ratio": "0.8"})])
+    icp.errorMinimizer = pm.PointToPlaneErrorMinimizer({"force4DOF": "1"})
+    icp.transformationCheckers = [pm.CounterTransformationChecker({"maxIterationCount": "10"})]
+    T = icp(pm.DataPoints(rd), pm.DataPoints(rf, {"normals": nrm}))
+    icp.ctx.close()
+    assert_transform_close(T, res_o["T"], 1e-5, 1e-5)
+    with pytest.raises(pm.ConfigurationError):
+        pm.PointToPlaneErrorMinimizer({"force2D": "1"})
+    with pytest.raises(capi.PmGpuError):
+        gpu_ctx.minimize(capi.MIN_P2POINT | capi.MIN_FORCE4DOF)
