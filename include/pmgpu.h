@@ -78,7 +78,11 @@ enum pmgpu_minimizer {
     PMGPU_MIN_P2POINT = 0,     /* PointToPointErrorMinimizer          ErrorMinimizers/PointToPoint.cpp:61-101 */
     PMGPU_MIN_P2PLANE = 1,     /* PointToPlaneErrorMinimizer          ErrorMinimizers/PointToPlane.cpp:171-312 */
     PMGPU_MIN_P2POINT_COV = 2, /* PointToPointWithCovErrorMinimizer   ErrorMinimizers/PointToPointWithCov.cpp:49-145 */
-    PMGPU_MIN_P2PLANE_COV = 3  /* PointToPlaneWithCovErrorMinimizer   ErrorMinimizers/PointToPlaneWithCov.cpp:60-162 */
+    PMGPU_MIN_P2PLANE_COV = 3, /* PointToPlaneWithCovErrorMinimizer   ErrorMinimizers/PointToPlaneWithCov.cpp:60-162 */
+    PMGPU_MIN_P2POINT_SIM = 4  /* PointToPointSimilarityErrorMinimizer ErrorMinimizers/PointToPointSimilarity.cpp:49-101:
+                                  rotation + translation + one scale; T_iter is then a similarity, applied as it is
+                                  (SimilarityTransformation, TransformationsImpl.cpp:156-210) — fused loop and
+                                  pmgpu_minimize; pmgpu_knn still insists on a rigid T */
 };
 /* or-ed into PMGPU_MIN_P2PLANE[_COV]: PointToPlaneErrorMinimizer force4DOF (PointToPlane.cpp:203-214,
  * 266-281) — the unknowns are the rotation about z and the translation: the 4x4 sub-system

@@ -19,7 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpmgpu%s.so" % ("_" + os.environ["PMGPU_VARIANT"] if os.environ.get("PMGPU_VARIANT") else ""))
 
 FILTER_MAXDIST, FILTER_MEDIANDIST, FILTER_TRIMMEDDIST, FILTER_ROBUST = 0, 1, 2, 3
-MIN_P2POINT, MIN_P2PLANE, MIN_P2POINT_COV, MIN_P2PLANE_COV = 0, 1, 2, 3
+MIN_P2POINT, MIN_P2PLANE, MIN_P2POINT_COV, MIN_P2PLANE_COV, MIN_P2POINT_SIM = 0, 1, 2, 3, 4
 MIN_FORCE4DOF = 0x100  # or-ed into a point-to-plane minimiser id
 NORMALS_SORT_EIGEN, NORMALS_SMOOTH = 1, 2
 
@@ -280,7 +280,7 @@ class Context:
         cov = np.zeros((6, 6), np.float32, order="F")
         stats = np.zeros(5, np.float32)
         self._check(lib.pmgpu_minimize(self.h, minimizer, sensor_std_dev, _f(T), _f(cov), _f(stats)))
-        return np.array(T), (np.array(cov) if (minimizer & 0xff) >= 2 else None), _stats(stats)
+        return np.array(T), (np.array(cov) if (minimizer & 0xff) in (2, 3) else None), _stats(stats)
 
     # ---- K8
     def normals(self, features, knn=5, epsilon=0.0, max_dist=np.inf, sort_eigen=False, keep=("normals",)):

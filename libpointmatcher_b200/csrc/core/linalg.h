@@ -154,7 +154,9 @@ PM_HD void jacobi_eig3(double* A, double* w, double* V) {
 // reflection fix of PointToPoint.cpp:82-93 (negate the last row of V^T when det(U V^T) < 0).
 // V from the eigen-decomposition of m^T m, U = m V / sigma, rank-deficient columns completed.
 // ------------------------------------------------------------------------------------------
-PM_HD void rotation_from_crosscov(const double* m, double* R) {
+// sv (optional): the singular values, descending, the last one negated when the reflection fix was
+// applied (what PointToPointSimilarity.cpp:78-89 sums for the scale)
+PM_HD void rotation_from_crosscov(const double* m, double* R, double* sv = nullptr) {
     double MtM[9], w[3], V[9];
     for (int j = 0; j < 3; ++j)
         for (int i = 0; i < 3; ++i) {
@@ -214,9 +216,10 @@ PM_HD void rotation_from_crosscov(const double* m, double* R) {
         for (int j = 0; j < 3; ++j)
             for (int i = 0; i < 3; ++i) R[i + 3 * j] = U[i] * Vs[j] + U[i + 3] * Vs[j + 3] + U[i + 6] * Vs[j + 6];
         const double det = R[0] * (R[4] * R[8] - R[7] * R[5]) - R[3] * (R[1] * R[8] - R[7] * R[2]) + R[6] * (R[1] * R[5] - R[4] * R[2]);
-        if (det < 0.0 && rep == 0) { Vs[6] = -Vs[6]; Vs[7] = -Vs[7]; Vs[8] = -Vs[8]; }
+        if (det < 0.0 && rep == 0) { Vs[6] = -Vs[6]; Vs[7] = -Vs[7]; Vs[8] = -Vs[8]; sig[2] = -sig[2]; }
         else break;
     }
+    if (sv) { sv[0] = sig[0]; sv[1] = sig[1]; sv[2] = sig[2]; }
 }
 
 // ------------------------------------------------------------------------------------------

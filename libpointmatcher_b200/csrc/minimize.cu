@@ -25,7 +25,7 @@ namespace {
 //  point-to-point : [0] sum w, [1..3] sum w p, [4..6] sum w q, [7..15] sum (w q_r) p_c  (r + 3 c)
 //  both           : [NS-4] kept pairs, [NS-3] rejected matches, [NS-2] rejected points, [NS-1] points seen
 constexpr int NS_PLANE = 28 + 4;  // 21 A + 6 b + sum of weights, then the 4 counters
-constexpr int NS_POINT = 16 + 4;
+constexpr int NS_POINT = 17 + 4;  // W, 3 + 3 weighted sums, 9 cross terms, sum w |p|^2, then the 4 counters
 constexpr int NS_COV = 42;
 constexpr int NS_MAX = 42;
 constexpr int ACC_BLOCK = 256;
@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(ACC_BLOCK, MODE == 1 ? 2 : 3) accumulate_kerne
                 for (int c = 0; c < 3; ++c)
 #pragma unroll
                     for (int r = 0; r < 3; ++r) acc[7 + r + 3 * c] += (double)wq[r] * (double)pc[c];
+                acc[16] += (double)w * ((double)p.x * (double)p.x + (double)p.y * (double)p.y + (double)p.z * (double)p.z);
             }
         }
         if (!match_exist) acc[NS - 2] += 1.0;
@@ -357,10 +358,18 @@ __device__ void finalize_body(const double* partials, int nblocks, double* sums,
         for (int c = 0; c < 3; ++c)
             for (int r = 0; r < 3; ++r)
                 m[r + 3 * c] = sums[7 + r + 3 * c] - (double)mqf[r] * sums[1 + c] - sums[4 + r] * (double)mpf[c] + W * (double)mqf[r] * (double)mpf[c];
-        rotation_from_crosscov(m, R);
+        double sv[3], scale = 1.0;
+        rotation_from_crosscov(m, R, sv);
+        if ((ck.minimizer & 0xff) == PMGPU_MIN_P2POINT_SIM) {
+            // sigma = sum w |p - mp|^2 from the raw sums (PointToPointSimilarity.cpp:69)
+            double sigma = sums[16] + W * ((double)mpf[0] * mpf[0] + (double)mpf[1] * mpf[1] + (double)mpf[2] * mpf[2]);
+            for (int a = 0; a < 3; ++a) sigma -= 2.0 * (double)mpf[a] * sums[1 + a];
+            scale = (sv[0] + sv[1] + sv[2]) / sigma;
+            if (sigma < 0.0001) scale = 1.0;
+        }
         mat4_identity(dT);
         for (int c = 0; c < 3; ++c)
-            for (int r = 0; r < 3; ++r) dT.m[r + 4 * c] = (float)R[r + 3 * c];
+            for (int r = 0; r < 3; ++r) dT.m[r + 4 * c] = (float)(scale * R[r + 3 * c]);
         for (int r = 0; r < 3; ++r) {
             double acc = 0.0;
             for (int c = 0; c < 3; ++c) acc += (double)dT.m[r + 4 * c] * (double)mpf[c];
@@ -378,7 +387,7 @@ __device__ void finalize_body(const double* partials, int nblocks, double* sums,
         state->iterations += 1;
         run_checkers(state, ck);
         // RigidTransformation::compute would throw on the next iteration (TransformationsImpl.cpp:62)
-        if (state->iterate && !mat4_is_rigid(Tn)) {
+        if (state->iterate && (ck.minimizer & 0xff) != PMGPU_MIN_P2POINT_SIM && !mat4_is_rigid(Tn)) {
             if (state->status == 0) state->status = PMGPU_ERR_NOT_ORTHOGONAL;
             state->iterate = 0;
         }

@@ -506,6 +506,10 @@ struct PointToPointWithCovErrorMinimizer : public GpuErrorMinimizer {
         this->sensorStdDev = Parametrizable::get<T>("sensorStdDev");
     }
 };
+struct PointToPointSimilarityErrorMinimizer : public GpuErrorMinimizer {
+    static const std::string description() { return "Point-to-point similarity error (rotation + translation + scale). The scale is the same for all coordinates. Based on SVD decomposition."; }
+    PointToPointSimilarityErrorMinimizer() : GpuErrorMinimizer("PointToPointSimilarityErrorMinimizer", ParametersDoc(), Parameters(), PMGPU_MIN_P2POINT_SIM) {}
+};
 struct PointToPlaneErrorMinimizer : public GpuErrorMinimizer {
     static const std::string description() { return "Point-to-plane error (or point-to-line in 2D)."; }
     static const ParametersDoc availableParameters() {

@@ -596,6 +596,7 @@ struct PointMatcher {
         ADD_TO_REGISTRAR(OutlierFilter, RobustOutlierFilter, RobustOutlierFilter)
         ADD_TO_REGISTRAR_NO_PARAM(ErrorMinimizer, PointToPointErrorMinimizer, PointToPointErrorMinimizer)
         ADD_TO_REGISTRAR(ErrorMinimizer, PointToPointWithCovErrorMinimizer, PointToPointWithCovErrorMinimizer)
+        ADD_TO_REGISTRAR_NO_PARAM(ErrorMinimizer, PointToPointSimilarityErrorMinimizer, PointToPointSimilarityErrorMinimizer)
         ADD_TO_REGISTRAR(ErrorMinimizer, PointToPlaneErrorMinimizer, PointToPlaneErrorMinimizer)
         ADD_TO_REGISTRAR(ErrorMinimizer, PointToPlaneWithCovErrorMinimizer, PointToPlaneWithCovErrorMinimizer)
         ADD_TO_REGISTRAR(TransformationChecker, CounterTransformationChecker, CounterTransformationChecker)

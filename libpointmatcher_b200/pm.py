@@ -453,6 +453,13 @@ class PointToPointWithCovErrorMinimizer(_Minimizer):
     PARAMS = _COV_PARAM
 
 
+class PointToPointSimilarityErrorMinimizer(_Minimizer):
+    """PointToPointSimilarity.cpp:49-101: rotation, translation and one scale factor"""
+    className = "PointToPointSimilarityErrorMinimizer"
+    KIND = capi.MIN_P2POINT_SIM
+    PARAMS = ()
+
+
 class PointToPlaneErrorMinimizer(_Minimizer):
     className = "PointToPlaneErrorMinimizer"
     KIND = capi.MIN_P2PLANE
@@ -690,6 +697,7 @@ OutlierFilterRegistrar = Registrar(MaxDistOutlierFilter=MaxDistOutlierFilter, Me
                                    TrimmedDistOutlierFilter=TrimmedDistOutlierFilter, RobustOutlierFilter=RobustOutlierFilter)
 ErrorMinimizerRegistrar = Registrar(PointToPointErrorMinimizer=PointToPointErrorMinimizer,
                                     PointToPointWithCovErrorMinimizer=PointToPointWithCovErrorMinimizer,
+                                    PointToPointSimilarityErrorMinimizer=PointToPointSimilarityErrorMinimizer,
                                     PointToPlaneErrorMinimizer=PointToPlaneErrorMinimizer,
                                     PointToPlaneWithCovErrorMinimizer=PointToPlaneWithCovErrorMinimizer)
 DataPointsFilterRegistrar = Registrar(SurfaceNormalDataPointsFilter=SurfaceNormalDataPointsFilter, IdentityDataPointsFilter=IdentityDataPointsFilter,

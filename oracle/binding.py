@@ -24,7 +24,7 @@ SCALE_NONE, SCALE_MAD = 0, 1
 def robust_word(fct="cauchy", scale=SCALE_MAD, nb_iteration_for_scale=0):
     """filter word of a RobustOutlierFilter (oracle.h): use as the filter type, with the tuning as the parameter"""
     return FILTER_ROBUST | (ROBUST_FCTS[fct] << 8) | (scale << 16) | (nb_iteration_for_scale << 20)
-MIN_P2POINT, MIN_P2PLANE, MIN_P2POINT_COV, MIN_P2PLANE_COV = 0, 1, 2, 3
+MIN_P2POINT, MIN_P2PLANE, MIN_P2POINT_COV, MIN_P2PLANE_COV, MIN_P2POINT_SIM = 0, 1, 2, 3, 4
 MIN_FORCE4DOF = 0x100  # or-ed into a point-to-plane minimizer id
 ERRORS = {
     1: "ConvergenceError: no outlier to filter",
@@ -192,7 +192,7 @@ def minimize(minimizer, reading, reference, ref_normals, ids, dists, weights, se
                               sensor_std_dev, int(acc_double), _f(T), _f(cov), _f(stats)))
     st = dict(pointUsedRatio=stats[0], weightedPointUsedRatio=stats[1], nbRejectedMatches=int(stats[2]),
               nbRejectedPoints=int(stats[3]), nbKept=int(stats[4]))
-    return np.array(T), (np.array(cov) if (minimizer & 0xff) >= 2 else None), st
+    return np.array(T), (np.array(cov) if (minimizer & 0xff) in (2, 3) else None), st
 
 
 def surface_normals(cloud, knn=5, eps=0.0, max_dist=np.inf, sort_eigen=False, smooth_normals=False, nthreads=1):

@@ -958,8 +958,10 @@ void estimate_covariance(const float* pts_reading, const float* pts_reference, c
 
 // PointToPoint (PointToPoint.cpp:61-101).  De-means e.reading / e.reference in place, as the
 // reference does (the WithCov variant depends on it).
+// `similarity`: PointToPointSimilarityErrorMinimizer (PointToPointSimilarity.cpp:55-101) — the same solve plus
+// the scale  sum(singular values, sign-fixed) / sum_p w |reading_p - mean|^2  (1 when that spread is < 1e-4).
 template <typename S>
-int minimize_p2point(ErrorElements& e, float* T_out) {
+int minimize_p2point(ErrorElements& e, float* T_out, bool similarity = false) {
     const int M = e.M;
     S wsum = 0;
     for (int p = 0; p < M; ++p) wsum += S(e.weights[p]);
@@ -990,13 +992,24 @@ int minimize_p2point(ErrorElements& e, float* T_out) {
     if (det3(R) < S(0)) {
         for (int j = 0; j < 3; ++j) Vt(2, j) = -Vt(2, j);
         R = mul(U, Vt);
+        sv[2] = -sv[2];
+    }
+    S scale = S(1);
+    if (similarity) {
+        S sigma = 0;
+        for (int p = 0; p < M; ++p) {
+            const float* r = &e.reading[4 * size_t(p)];
+            sigma += S(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]) * S(e.weights[p]);
+        }
+        scale = (sv[0] + sv[1] + sv[2]) / sigma;
+        if (sigma < S(0.0001)) scale = S(1);
     }
     mat4_identity(T_out);
     for (int j = 0; j < 3; ++j)
-        for (int i = 0; i < 3; ++i) T_out[i + 4 * j] = float(R(i, j));
+        for (int i = 0; i < 3; ++i) T_out[i + 4 * j] = float(scale * R(i, j));
     for (int i = 0; i < 3; ++i) {
         S acc = 0;
-        for (int j = 0; j < 3; ++j) acc += S(float(R(i, j))) * S(meanReading[j]);
+        for (int j = 0; j < 3; ++j) acc += S(T_out[i + 4 * j]) * S(meanReading[j]);
         T_out[12 + i] = float(S(meanReference[i]) - acc);
     }
     return ORC_OK;
@@ -1014,7 +1027,7 @@ int minimize_impl(int minimizer_word, ErrorElements& e, float sensorStdDev, floa
             estimate_covariance<S>(e.reading.data(), e.reference.data(), e.normals.data(), e.M, T_out, sensorStdDev, cov_out);
         return ORC_OK;
     }
-    const int rc = minimize_p2point<S>(e, T_out);
+    const int rc = minimize_p2point<S>(e, T_out, minimizer == ORC_MIN_P2POINT_SIM);
     if (rc) return rc;
     if (minimizer == ORC_MIN_P2POINT_COV && cov_out)
         estimate_covariance<S>(e.reading.data(), e.reference.data(), nullptr, e.M, T_out, sensorStdDev, cov_out);
@@ -1375,7 +1388,8 @@ int orc_icp(const float* readingIn, int nq, const float* referenceIn, int nr, co
     RobustState robustState[8];  // one per filter slot: the filter objects live as long as the ICP object
     const double t_loop0 = now_s();
     while (iterate) {
-        if (!check_rigid(T_iter)) { rc = ORC_ERR_NOT_ORTHOGONAL; break; }
+        // SimilarityTransformation::checkParameters accepts anything (TransformationsImpl.cpp:199-204)
+        if ((cfg->minimizer & 0xff) != ORC_MIN_P2POINT_SIM && !check_rigid(T_iter)) { rc = ORC_ERR_NOT_ORTHOGONAL; break; }
         rigid_apply(T_iter, reading.data(), nq, stepReading.data());
         const double t_m0 = now_s();
         if (tree) tree->knn(stepReading.data(), 4, nq, knn, cfg->epsilon, cfg->max_dist, ids.data(), dists.data(), cfg->nthreads);

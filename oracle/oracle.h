@@ -32,7 +32,7 @@ enum { ORC_ROBUST_CAUCHY = 0, ORC_ROBUST_WELSCH, ORC_ROBUST_SC, ORC_ROBUST_GM, O
 enum { ORC_SCALE_NONE = 0, ORC_SCALE_MAD = 1 };
 #define ORC_ROBUST_WORD(fct, scale, nb_iter) (ORC_FILTER_ROBUST | ((fct) << 8) | ((scale) << 16) | ((nb_iter) << 20))
 /* error minimizers */
-enum { ORC_MIN_P2POINT = 0, ORC_MIN_P2PLANE = 1, ORC_MIN_P2POINT_COV = 2, ORC_MIN_P2PLANE_COV = 3 };
+enum { ORC_MIN_P2POINT = 0, ORC_MIN_P2PLANE = 1, ORC_MIN_P2POINT_COV = 2, ORC_MIN_P2PLANE_COV = 3, ORC_MIN_P2POINT_SIM = 4 };
 #define ORC_MIN_FORCE4DOF 0x100 /* or-ed into a point-to-plane minimizer id: PointToPlaneErrorMinimizer force4DOF */
 /* status codes */
 enum {

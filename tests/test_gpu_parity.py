@@ -461,3 +461,28 @@ def test_point_to_plane_force4dof_matches_oracle(gpu_ctx, oracle, synth):
         pm.PointToPlaneErrorMinimizer({"force2D": "1"})
     with pytest.raises(capi.PmGpuError):
         gpu_ctx.minimize(capi.MIN_P2POINT | capi.MIN_FORCE4DOF)
+
+
+# ---------------------------------------------------------------------------------- PointToPointSimilarity (8f row 3)
+def test_similarity_minimizer_matches_oracle(gpu_ctx, oracle, synth):
+    from libpointmatcher_b200 import capi
+    rd, rf, _ = synth.scan_pair(50000)
+    rd = rd.copy()
+    rd[:, :3] *= np.float32(1.03)                       # a reading that really needs a scale
+    gpu_ctx.set_reference(rf)
+    gpu_ctx.set_reading(rd)
+    ids, dists, _ = gpu_ctx.knn(None, 2, 0.0, np.inf)
+    w, _ = gpu_ctx.weights([(2, 0.8)])
+    Tg, _, _ = gpu_ctx.minimize(capi.MIN_P2POINT_SIM)
+    To, _, _ = oracle.minimize(oracle.MIN_P2POINT_SIM, rd, rf, None, ids, dists, w, acc_double=True)
+    assert np.abs(Tg - To).max() < 2e-5
+    s_g = np.cbrt(np.linalg.det(Tg[:3, :3].astype(np.float64)))
+    assert 0.9 < s_g < 1.0                              # it shrinks the inflated reading
+    res_o = oracle.icp(rd, rf, filters=[(2, 0.8)], minimizer=oracle.MIN_P2POINT_SIM, max_iterations=15, nthreads=8, acc_double=True)
+    with capi.Context(0) as ctx:
+        ctx.set_reference(rf)
+        ctx.set_reading(rd)
+        res = ctx.icp_run(capi.make_params(knn=1, filters=[(2, 0.8)], minimizer=capi.MIN_P2POINT_SIM, max_iterations=15))
+    assert res["iterations"] == res_o["iterations"] == 15
+    assert np.abs(res["T_iter"] - res_o["T"]).max() < 5e-5
+    assert abs(np.cbrt(np.linalg.det(res["T_iter"][:3, :3].astype(np.float64))) - 1 / 1.03) < 1.5e-2   # on its way to 1 / 1.03

@@ -135,14 +135,27 @@ def test_oracle_robust_chain_reproduces_golden(oracle, fx):
     assert rel_err(r["T"], fx["golden_defaultRobustOutlierFilter"], data) < 0.03
 
 
+def test_oracle_similarity_chain_reproduces_golden(oracle, fx):
+    """defaultSimilarityPointToPointMinDistDataPointsFilter.yaml: MinDist 1 on both clouds, TrimmedDist 0.75,
+    PointToPointSimilarityErrorMinimizer, 150 iterations"""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import prefilters as pre
+    ref, data = homog(fx["cloud0"]), homog(fx["cloud1"])
+    ref_f, data_f = ref[pre.min_dist(ref, -1, 1.0)], data[pre.min_dist(data, -1, 1.0)]
+    r = oracle.icp(np.ascontiguousarray(data_f), np.ascontiguousarray(ref_f), filters=[(oracle.FILTER_TRIMMEDDIST, 0.75)],
+                   minimizer=oracle.MIN_P2POINT_SIM, max_iterations=150, differential=(0.001, 0.01, 4), nthreads=4)
+    assert rel_err(r["T"], fx["golden_defaultSimilarityPointToPointMinDistDataPointsFilter"], data) < 0.03
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", YAML_CHAINS)
+@pytest.mark.parametrize("name", YAML_CHAINS + ["defaultSimilarityPointToPointMinDistDataPointsFilter"])
 def test_gpu_runs_reference_yaml_chain_to_golden(fx, name):
     from libpointmatcher_b200 import capi, pm
     ref, data = homog(fx["cloud0"]), homog(fx["cloud1"])
     capi.lib.pmgpu_host_srand(1)
     icp = pm.ICP()
-    icp.loadFromYaml(str(fx["yaml_" + name]))
+    icp.loadFromYaml(str(fx["yaml_" + name]).replace("PerformanceInspector", "NullInspector"))  # inspectors are out of scope
     T = icp(pm.DataPoints(data), pm.DataPoints(ref))
     icp.ctx.close()
     assert rel_err(T, fx["golden_" + name], data) < 0.03
