@@ -58,7 +58,10 @@ enum pmgpu_filter_type {
     PMGPU_FILTER_MAXDIST = 0,    /* MaxDistOutlierFilter     param = maxDist (un-squared)  OutlierFiltersImpl.cpp:66-81   */
     PMGPU_FILTER_MEDIANDIST = 1, /* MedianDistOutlierFilter  param = factor                OutlierFiltersImpl.cpp:109-125 */
     PMGPU_FILTER_TRIMMEDDIST = 2,/* TrimmedDistOutlierFilter param = ratio                 OutlierFiltersImpl.cpp:132-147 */
-    PMGPU_FILTER_ROBUST = 3      /* RobustOutlierFilter      param = tuning                OutlierFiltersImpl.cpp:420-598 */
+    PMGPU_FILTER_ROBUST = 3,     /* RobustOutlierFilter      param = tuning                OutlierFiltersImpl.cpp:420-598 */
+    PMGPU_FILTER_SURFACENORMAL = 4 /* SurfaceNormalOutlierFilter param = maxAngle: weight 0 where |n_reading . n_reference| <
+                                      cos(maxAngle), both normalised (OutlierFiltersImpl.cpp:222-285); needs the reference
+                                      normals and pmgpu_reading_set_normals, otherwise all ones like the reference */
 };
 /* RobustOutlierFilter: M-estimator weights w(e^2), e^2 = dist / scale^2.  Its discrete
  * parameters travel in the filter word: bits 0-7 PMGPU_FILTER_ROBUST | bits 8-15 robustFct | bits 16-19
@@ -132,6 +135,9 @@ int pmgpu_reading_set(pmgpu_ctx* ctx, const float* features, int rows, int n);
 /* RigidTransformation::compute on the resident reading, in place (TransformationsImpl.cpp:49-87;
  * the `transformations.apply(reading, T_refMean_dataIn)` of ICP.cpp:345-347).  Returns
  * PMGPU_ERR_NOT_ORTHOGONAL if |1 - det R| > 1e-3. */
+/* the reading's "normals" descriptor (3 rows of a descriptor matrix with column stride `ld`), after pmgpu_reading_set; they turn with
+ * the reading (pmgpu_reading_apply_transform, T_iter) as RigidTransformation::compute turns them (TransformationsImpl.cpp:71-84) */
+int pmgpu_reading_set_normals(pmgpu_ctx* ctx, const float* normals, int ld);
 int pmgpu_reading_apply_transform(pmgpu_ctx* ctx, const float* T);
 /* optional download of the resident reading (4 x n) */
 int pmgpu_reading_get(pmgpu_ctx* ctx, float* features_out);

@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # PMGPU_VARIANT selects a tuning build (libpmgpu_<name>.so, see build.py); default: libpmgpu.so
 LIB_PATH = os.path.join(_HERE, "libpmgpu%s.so" % ("_" + os.environ["PMGPU_VARIANT"] if os.environ.get("PMGPU_VARIANT") else ""))
 
-FILTER_MAXDIST, FILTER_MEDIANDIST, FILTER_TRIMMEDDIST, FILTER_ROBUST = 0, 1, 2, 3
+FILTER_MAXDIST, FILTER_MEDIANDIST, FILTER_TRIMMEDDIST, FILTER_ROBUST, FILTER_SURFACENORMAL = 0, 1, 2, 3, 4
 MIN_P2POINT, MIN_P2PLANE, MIN_P2POINT_COV, MIN_P2PLANE_COV, MIN_P2POINT_SIM = 0, 1, 2, 3, 4
 MIN_FORCE4DOF = 0x100  # or-ed into a point-to-plane minimiser id
 NORMALS_SORT_EIGEN, NORMALS_SMOOTH = 1, 2
@@ -72,6 +72,7 @@ SIGNATURES = {
     "pmgpu_ref_set_centered": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, _fp]),
     "pmgpu_ref_set_normals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "pmgpu_reading_set": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "pmgpu_reading_set_normals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "pmgpu_reading_apply_transform": (C.c_int, [C.c_void_p, _fp]),
     "pmgpu_reading_get": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pmgpu_knn": (C.c_int, [C.c_void_p, _fp, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
@@ -247,6 +248,11 @@ class Context:
 
     def reading_apply_transform(self, T):
         self._check(lib.pmgpu_reading_apply_transform(self.h, _f(_T(T))))
+
+    def set_reading_normals(self, normals):
+        """the reading's "normals" descriptor (N, 3), after set_reading; used by SurfaceNormalOutlierFilter"""
+        nrm = None if normals is None else np.ascontiguousarray(normals, np.float32)
+        self._check(lib.pmgpu_reading_set_normals(self.h, _ptr(nrm), 0 if nrm is None else nrm.shape[1]))
 
     def get_reading(self):
         out = np.empty((self.nq, 4), np.float32)

@@ -21,6 +21,27 @@ __global__ void pack_normals_kernel(const float* __restrict__ src, int ld, int n
     dst[i] = make_float4(s[0], s[1], s[2], 0.f);
 }
 
+// reading normals arrive in the caller's column order and are kept in the reading's Morton order
+__global__ void pack_normals_permuted_kernel(const float* __restrict__ src, int ld, const uint32_t* __restrict__ order, int n, f4* __restrict__ dst) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const float* s = src + (size_t)order[t] * ld;
+    dst[t] = make_float4(s[0], s[1], s[2], 0.f);
+}
+
+// `R * inputDesc` for the "normals" descriptor (TransformationsImpl.cpp:71-84)
+__global__ void rotate_normals_inplace_kernel(f4* __restrict__ nrm, int n, Mat4 T) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const f4 v = nrm[i];
+    f4 r;
+    r.x = fadd(fadd(fmul(T.m[0], v.x), fmul(T.m[4], v.y)), fmul(T.m[8], v.z));
+    r.y = fadd(fadd(fmul(T.m[1], v.x), fmul(T.m[5], v.y)), fmul(T.m[9], v.z));
+    r.z = fadd(fadd(fmul(T.m[2], v.x), fmul(T.m[6], v.y)), fmul(T.m[10], v.z));
+    r.w = 0.f;
+    nrm[i] = r;
+}
+
 __global__ void unpack_f4_kernel(const f4* __restrict__ src, int n, float* __restrict__ dst) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -387,6 +408,7 @@ int pmgpu_reading_set(pmgpu_ctx* ctx, const float* features, int rows, int n) {
     ctx->nq = 0;
     ctx->have_matches = false;
     ctx->have_weights = false;
+    ctx->has_reading_normals = false;
     PM_CUDA_TRY(ctx, ctx->reading.reserve(n > 0 ? n : 1));
     PM_CUDA_TRY(ctx, ctx->reading_tmp.reserve(n > 0 ? n : 1));
     ctx->seed_k = 0;
@@ -396,6 +418,25 @@ int pmgpu_reading_set(pmgpu_ctx* ctx, const float* features, int rows, int n) {
     if (n > 0) PM_TRY(morton_order(ctx));
     // the caller may release `features` on return: wait for the copy only, the ordering kernels run on
     PM_CUDA_TRY(ctx, cudaEventSynchronize(ctx->copy_done));
+    return PMGPU_OK;
+}
+
+int pmgpu_reading_set_normals(pmgpu_ctx* ctx, const float* normals, int ld) {
+    if (!ctx) return PMGPU_ERR_BAD_ARG;
+    PM_TRY(use_device(ctx));
+    if (ctx->nq == 0) return fail(ctx, PMGPU_ERR_NO_READING, status_message(PMGPU_ERR_NO_READING));
+    if (!normals) { ctx->has_reading_normals = false; return PMGPU_OK; }
+    if (ld < 3) return fail(ctx, PMGPU_ERR_BAD_ARG, "normals_ld must be >= 3");
+    const int n = ctx->nq;
+    PM_CUDA_TRY(ctx, ctx->reading_normals.reserve(n));
+    DevBuf<float> staging;
+    PM_CUDA_TRY(ctx, staging.reserve((size_t)n * ld));
+    PM_CUDA_TRY(ctx, cudaMemcpyAsync(staging.p, normals, ((size_t)(n - 1) * ld + 3) * sizeof(float), cudaMemcpyDefault, ctx->stream));
+    pack_normals_permuted_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(staging.p, ld, ctx->q_order.p, n, ctx->reading_normals.p);
+    ctx->launches += 1;
+    PM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    staging.release();
+    ctx->has_reading_normals = true;
     return PMGPU_OK;
 }
 
@@ -409,6 +450,10 @@ int pmgpu_reading_apply_transform(pmgpu_ctx* ctx, const float* T) {
     if (ctx->nq > 0) {
         transform_inplace_kernel<<<(ctx->nq + 255) / 256, 256, 0, ctx->stream>>>(ctx->reading.p, ctx->nq, M);
         ctx->launches += 1;
+        if (ctx->has_reading_normals) {
+            rotate_normals_inplace_kernel<<<(ctx->nq + 255) / 256, 256, 0, ctx->stream>>>(ctx->reading_normals.p, ctx->nq, M);
+            ctx->launches += 1;
+        }
         PM_CUDA_TRY(ctx, cudaGetLastError());
     }
     ctx->have_matches = false;

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(ACC_BLOCK, MODE == 1 ? 2 : 3) accumulate_kerne
                                                                const float* __restrict__ dists, const f4* __restrict__ ref,
                                                                const f4* __restrict__ normals, const IcpState* __restrict__ state, int gated,
                                                                double* __restrict__ partials, int fuse, IcpState* state_rw, double* sums,
-                                                               int compose, pmgpu_icp_params ck) {
+                                                               int compose, pmgpu_icp_params ck, const f4* __restrict__ reading_normals) {
     constexpr int NS = MODE == 1 ? NS_PLANE : NS_POINT;
     __shared__ Mat4 sT;
     // redo: this iteration's capped match was void (select_finish) — leave T_iter as it is
@@ -84,11 +84,16 @@ __global__ void __launch_bounds__(ACC_BLOCK, MODE == 1 ? 2 : 3) accumulate_kerne
         for (int kk = 0; kk < k; ++kk) {
             const float d = dists[(size_t)i * k + kk];
             if (d == pm_inf()) continue;
-            const float w = pm_pair_weight(state, d);
+            float w = pm_pair_weight(state, d);
+            int id = 0;
+            if (w != 0.f) {
+                id = ids[(size_t)i * k + kk];
+                // SurfaceNormalOutlierFilter: `normals` is the reference's descriptor whenever it exists
+                if (state->sn_on) w = __fmul_rn(w, pm_sn_weight(sT, reading_normals[i], __ldg(normals + id), state->sn_eps));
+            }
             if (w == 0.f) { acc[NS - 3] += 1.0; continue; }
             match_exist = true;
             acc[NS - 4] += 1.0;
-            const int id = ids[(size_t)i * k + kk];
             const f4 q = __ldg(ref + id);
             if (MODE == 1) {
                 const f4 n = __ldg(normals + id);
@@ -155,7 +160,8 @@ template <int MODE>
 __global__ void __launch_bounds__(ACC_BLOCK) cov_accumulate_kernel(const f4* __restrict__ reading, int nq, int k, const int32_t* __restrict__ ids,
                                                                    const float* __restrict__ dists, const f4* __restrict__ ref,
                                                                    const f4* __restrict__ normals, const IcpState* __restrict__ state,
-                                                                   double* __restrict__ partials) {
+                                                                   double* __restrict__ partials, const f4* __restrict__ reading_normals,
+                                                                   const f4* __restrict__ sn_normals) {
     __shared__ Mat4 sT;
     __shared__ float sPar[12];  // alpha beta gamma tx ty tz | mean_reading | mean_reference
     if (threadIdx.x < 16) sT.m[threadIdx.x] = state->T_match.m[threadIdx.x];
@@ -183,6 +189,7 @@ __global__ void __launch_bounds__(ACC_BLOCK) cov_accumulate_kernel(const f4* __r
             const float d = dists[(size_t)i * k + kk];
             if (pm_pair_weight(state, d) == 0.f) continue;
             const int id = ids[(size_t)i * k + kk];
+            if (state->sn_on && pm_sn_weight(sT, reading_normals[i], __ldg(sn_normals + id), state->sn_eps) == 0.f) continue;
             const f4 q = __ldg(ref + id);
             float rp[3] = {p.x, p.y, p.z}, fp[3] = {q.x, q.y, q.z}, nrm[3] = {1.f, 1.f, 1.f};
             if (MODE == 1) {
@@ -477,8 +484,8 @@ int launch_minimize(pmgpu_ctx* ctx, int minimizer_word, bool compose_and_check, 
     ck.minimizer = minimizer_word;
     const int g = gated ? 1 : 0, comp = compose_and_check ? 1 : 0;
     const int fuse = ctx->nranks > 1 ? 0 : 1;
-    if (plane) accumulate_kernel<1><<<grid, ACC_BLOCK, 0, st>>>(ctx->reading.p, ctx->nq, ctx->k, ctx->ids.p, ctx->dists.p, ctx->ref_orig.p, ctx->ref_normals.p, ctx->state, g, ctx->partials.p, fuse, ctx->state, sums, comp, ck);
-    else accumulate_kernel<0><<<grid, ACC_BLOCK, 0, st>>>(ctx->reading.p, ctx->nq, ctx->k, ctx->ids.p, ctx->dists.p, ctx->ref_orig.p, nullptr, ctx->state, g, ctx->partials.p, fuse, ctx->state, sums, comp, ck);
+    if (plane) accumulate_kernel<1><<<grid, ACC_BLOCK, 0, st>>>(ctx->reading.p, ctx->nq, ctx->k, ctx->ids.p, ctx->dists.p, ctx->ref_orig.p, ctx->ref_normals.p, ctx->state, g, ctx->partials.p, fuse, ctx->state, sums, comp, ck, ctx->reading_normals.p);
+    else accumulate_kernel<0><<<grid, ACC_BLOCK, 0, st>>>(ctx->reading.p, ctx->nq, ctx->k, ctx->ids.p, ctx->dists.p, ctx->ref_orig.p, ctx->has_normals ? ctx->ref_normals.p : nullptr, ctx->state, g, ctx->partials.p, fuse, ctx->state, sums, comp, ck, ctx->reading_normals.p);
     ctx->launches += 1;
     if (!fuse) {
         const int ns = plane ? NS_PLANE : NS_POINT;
@@ -499,8 +506,8 @@ int launch_covariance(pmgpu_ctx* ctx, int minimizer, float sensor_std_dev) {
     const int grid = grid_for(ctx->nq, ACC_BLOCK, ctx->num_sms, 4);
     PM_CUDA_TRY(ctx, ctx->partials.reserve((size_t)(ctx->num_sms * 4 + 2) * NS_MAX));
     double* sums = ctx->partials.p + (size_t)ctx->num_sms * 4 * NS_MAX;
-    if (plane) cov_accumulate_kernel<1><<<grid, ACC_BLOCK, 0, st>>>(ctx->reading.p, ctx->nq, ctx->k, ctx->ids.p, ctx->dists.p, ctx->ref_orig.p, ctx->ref_normals.p, ctx->state, ctx->partials.p);
-    else cov_accumulate_kernel<0><<<grid, ACC_BLOCK, 0, st>>>(ctx->reading.p, ctx->nq, ctx->k, ctx->ids.p, ctx->dists.p, ctx->ref_orig.p, nullptr, ctx->state, ctx->partials.p);
+    if (plane) cov_accumulate_kernel<1><<<grid, ACC_BLOCK, 0, st>>>(ctx->reading.p, ctx->nq, ctx->k, ctx->ids.p, ctx->dists.p, ctx->ref_orig.p, ctx->ref_normals.p, ctx->state, ctx->partials.p, ctx->reading_normals.p, ctx->ref_normals.p);
+    else cov_accumulate_kernel<0><<<grid, ACC_BLOCK, 0, st>>>(ctx->reading.p, ctx->nq, ctx->k, ctx->ids.p, ctx->dists.p, ctx->ref_orig.p, nullptr, ctx->state, ctx->partials.p, ctx->reading_normals.p, ctx->ref_normals.p);
     ctx->launches += 1;
     if (ctx->nranks > 1) {
         cov_finalize_kernel<<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 1, ctx->state, sensor_std_dev);

@@ -82,6 +82,8 @@ struct IcpState {
     unsigned long long sel_rank[PM_MAX_FILTERS];   // remaining rank inside the selected bucket
     unsigned ticket[4];          // "last block" counters: 0 select, 1 minimise, 2 covariance
     unsigned overflow_count[2];  // kNN stage-2 queue lengths (ping-pong between consecutive launches)
+    int sn_on;                   // SurfaceNormalOutlierFilter active (both clouds have normals)
+    float sn_eps;                // cos(maxAngle)
     // RobustOutlierFilter (one per chain): set by select_init_limits / the robust select passes
     int robust_on;               // chain has a robust filter
     int robust_fct;              // PMGPU_ROBUST_*
@@ -121,6 +123,12 @@ struct SelectSpec {
     __host__ __device__ bool is_quantile(int f) const { return kind(f) == PMGPU_FILTER_MEDIANDIST || kind(f) == PMGPU_FILTER_TRIMMEDDIST; }
     __host__ __device__ float quantile(int f) const { return type[f] == PMGPU_FILTER_MEDIANDIST ? 0.5f : param[f]; }
     __host__ __device__ float factor(int f) const { return type[f] == PMGPU_FILTER_MEDIANDIST ? param[f] : 0.f; }
+    int sn_active;  // the chain's SurfaceNormalOutlierFilter has normals on both sides to work with
+    __host__ __device__ int sn_index() const {
+        for (int f = 0; f < nfilters; ++f)
+            if (kind(f) == PMGPU_FILTER_SURFACENORMAL) return f;
+        return -1;
+    }
     __host__ __device__ int robust_index() const {
         for (int f = 0; f < nfilters; ++f)
             if (is_robust(f)) return f;
@@ -148,6 +156,8 @@ struct pmgpu_ctx {
     pm::DevBuf<f4> ref_orig;     // original order, (x, y, z, w)
     pm::DevBuf<f4> ref_sorted;   // leaf order, w = original index bits
     pm::DevBuf<f4> ref_normals;  // original order, (nx, ny, nz, 0)
+    pm::DevBuf<f4> reading_normals;  // Morton order like `reading`
+    bool has_reading_normals = false;
     pm::DevBuf<f2> splits;       // inner node (heap index) -> {split value, axis bits}
     pm::DevBuf<f4> boxes;        // node (heap index) -> 2 f4 (lo, hi)
     bool has_normals = false;

@@ -116,12 +116,15 @@ __global__ void init_limits_kernel(IcpState* state, SelectSpec spec, int gated, 
     }
 }
 
-__global__ void weights_kernel(const float* __restrict__ dists, size_t total, const IcpState* __restrict__ state, float* __restrict__ w) {
+__global__ void weights_kernel(const float* __restrict__ dists, const int32_t* __restrict__ ids, int k, size_t total, const IcpState* __restrict__ state,
+                               const f4* __restrict__ reading_normals, const f4* __restrict__ ref_normals, float* __restrict__ w) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const float d = dists[i];
     // empty chain: OutlierFilter.cpp:70-85; otherwise the product of the filters' weights
-    w[i] = pm_pair_weight(state, d);
+    float wt = pm_pair_weight(state, d);
+    if (wt != 0.f && state->sn_on) wt = __fmul_rn(wt, pm_sn_weight(state->T_iter, reading_normals[i / k], __ldg(ref_normals + ids[i]), state->sn_eps));
+    w[i] = wt;
 }
 
 }  // namespace
@@ -144,6 +147,8 @@ int make_select_spec(pmgpu_ctx* ctx, int nfilters, const int* types, const float
                 ctx->set_error("quantile must be between 0 and 1");
                 return PMGPU_ERR_BAD_QUANTILE;
             }
+        } else if (types[f] == PMGPU_FILTER_SURFACENORMAL) {
+            spec->param[f] = cosf(params[f]);  // eps(cos(maxAngle)) on the host, OutlierFiltersImpl.cpp:227
         } else if ((types[f] & 0xff) == PMGPU_FILTER_ROBUST) {
             const int fct = (types[f] >> 8) & 0xff, est = (types[f] >> 16) & 0xf;
             if (fct > PMGPU_ROBUST_STUDENT) {
@@ -158,6 +163,13 @@ int make_select_spec(pmgpu_ctx* ctx, int nfilters, const int* types, const float
             ctx->set_error("unknown outlier filter type");
             return PMGPU_ERR_BAD_ARG;
         }
+    }
+    spec->sn_active = (ctx->has_normals && ctx->has_reading_normals) ? 1 : 0;
+    int nsn = 0;
+    for (int f = 0; f < nfilters; ++f) nsn += spec->kind(f) == PMGPU_FILTER_SURFACENORMAL ? 1 : 0;
+    if (nsn > 1) {
+        ctx->set_error("at most one SurfaceNormalOutlierFilter per chain on the GPU");
+        return PMGPU_ERR_UNSUPPORTED;
     }
     int nrobust = 0;
     for (int f = 0; f < nfilters; ++f) nrobust += spec->is_robust(f) ? 1 : 0;
@@ -226,7 +238,8 @@ int launch_materialize_weights(pmgpu_ctx* ctx) {
     const size_t total = (size_t)ctx->k * ctx->nq;
     PM_CUDA_TRY(ctx, ctx->weights.reserve(total));
     const int B = 256;
-    weights_kernel<<<(unsigned)((total + B - 1) / B), B, 0, ctx->stream>>>(ctx->dists.p, total, ctx->state, ctx->weights.p);
+    weights_kernel<<<(unsigned)((total + B - 1) / B), B, 0, ctx->stream>>>(ctx->dists.p, ctx->ids.p, ctx->k, total, ctx->state, ctx->reading_normals.p,
+                                                                            ctx->ref_normals.p, ctx->weights.p);
     ctx->launches += 1;
     PM_CUDA_TRY(ctx, cudaGetLastError());
     return PMGPU_OK;

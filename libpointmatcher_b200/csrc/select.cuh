@@ -28,6 +28,9 @@ __device__ __forceinline__ void select_init_limits(IcpState* st, const SelectSpe
     st->limit_all = all;
     st->has_filters = sp.nfilters > 0 ? 1 : 0;
     st->cap_need = 0.f;
+    const int sn = sp.sn_index();
+    st->sn_on = (sn >= 0 && sp.sn_active) ? 1 : 0;
+    if (sn >= 0) { st->sn_eps = sp.param[sn]; st->limit[sn] = sp.param[sn]; }
     // RobustOutlierFilter::robustFiltering preamble (OutlierFiltersImpl.cpp:508-540)
     const int r = sp.robust_index();
     st->robust_on = r >= 0 ? 1 : 0;
@@ -60,6 +63,26 @@ __device__ __forceinline__ float pm_robust_weight(const IcpState* st, float d) {
     }
     return w <= 1e-50f ? 0.f : w;  // `w <= 1e-50 -> 1e-50` stored in a float array
 }
+// SurfaceNormalOutlierFilter (OutlierFiltersImpl.cpp:248-265): rn = the reading normal as stored, turned by the
+// rotation block of T like `R * inputDesc`; both normals `.normalized()`; weight 0 where |dot| < eps
+__device__ __forceinline__ void pm_normalized(float& x, float& y, float& z) {
+    const float n2 = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+    if (n2 > 0.f) {
+        const float n = __fsqrt_rn(n2);
+        x = __fdiv_rn(x, n); y = __fdiv_rn(y, n); z = __fdiv_rn(z, n);
+    }
+}
+__device__ __forceinline__ float pm_sn_weight(const Mat4& T, f4 rn, f4 qn, float eps) {
+    float ax = __fadd_rn(__fadd_rn(__fmul_rn(T.m[0], rn.x), __fmul_rn(T.m[4], rn.y)), __fmul_rn(T.m[8], rn.z));
+    float ay = __fadd_rn(__fadd_rn(__fmul_rn(T.m[1], rn.x), __fmul_rn(T.m[5], rn.y)), __fmul_rn(T.m[9], rn.z));
+    float az = __fadd_rn(__fadd_rn(__fmul_rn(T.m[2], rn.x), __fmul_rn(T.m[6], rn.y)), __fmul_rn(T.m[10], rn.z));
+    pm_normalized(ax, ay, az);
+    float bx = qn.x, by = qn.y, bz = qn.z;
+    pm_normalized(bx, by, bz);
+    const float value = fabsf(__fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz)));
+    return value < eps ? 0.f : 1.f;
+}
+
 __device__ __forceinline__ float pm_pair_weight(const IcpState* st, float d) {
     if (d == pm_inf()) return 0.f;  // ErrorMinimizer.cpp:103-106: invalid matches are skipped
     float w = st->has_filters ? ((d <= st->limit_all) ? 1.f : 0.f) : 1.f;

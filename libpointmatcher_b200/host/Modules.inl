@@ -389,6 +389,17 @@ struct TrimmedDistOutlierFilter : public GpuDistOutlierFilter {
     TrimmedDistOutlierFilter(const Parameters& params = Parameters()) : GpuDistOutlierFilter("TrimmedDistOutlierFilter", availableParameters(), params, PMGPU_FILTER_TRIMMEDDIST, "ratio") {}
 };
 
+struct SurfaceNormalOutlierFilter : public GpuDistOutlierFilter {
+    static const std::string description() {
+        return "Hard rejection threshold using the angle between the surface normal vector of the reading and the reference. "
+               "If normal vectors or not in the descriptor for both of the point clouds, does nothing.";
+    }
+    static const ParametersDoc availableParameters() {
+        return {{"maxAngle", "Maximum authorised angle between the 2 surface normals (in radian)", "1.57", "0.0", "3.1416", &Parametrizable::Comp<T>}};
+    }
+    SurfaceNormalOutlierFilter(const Parameters& params = Parameters())
+        : GpuDistOutlierFilter("SurfaceNormalOutlierFilter", availableParameters(), params, PMGPU_FILTER_SURFACENORMAL, "maxAngle") {}
+};
 // RobustOutlierFilter (OutlierFiltersImpl.h:199-262, .cpp:420-598): M-estimator weights on the GPU;
 // the discrete parameters travel in the filter word (pmgpu.h)
 struct RobustOutlierFilter : public GpuDistOutlierFilter {

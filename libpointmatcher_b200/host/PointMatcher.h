@@ -594,6 +594,7 @@ struct PointMatcher {
         ADD_TO_REGISTRAR(OutlierFilter, MedianDistOutlierFilter, MedianDistOutlierFilter)
         ADD_TO_REGISTRAR(OutlierFilter, TrimmedDistOutlierFilter, TrimmedDistOutlierFilter)
         ADD_TO_REGISTRAR(OutlierFilter, RobustOutlierFilter, RobustOutlierFilter)
+        ADD_TO_REGISTRAR(OutlierFilter, SurfaceNormalOutlierFilter, SurfaceNormalOutlierFilter)
         ADD_TO_REGISTRAR_NO_PARAM(ErrorMinimizer, PointToPointErrorMinimizer, PointToPointErrorMinimizer)
         ADD_TO_REGISTRAR(ErrorMinimizer, PointToPointWithCovErrorMinimizer, PointToPointWithCovErrorMinimizer)
         ADD_TO_REGISTRAR_NO_PARAM(ErrorMinimizer, PointToPointSimilarityErrorMinimizer, PointToPointSimilarityErrorMinimizer)

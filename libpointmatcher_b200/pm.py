@@ -349,6 +349,14 @@ class TrimmedDistOutlierFilter(_DistFilter):
     PARAMS = (("ratio", "percentage to keep", "0.85", "0.0000001", "1.0", float),)
 
 
+class SurfaceNormalOutlierFilter(_DistFilter):
+    """OutlierFiltersImpl.h:180-197, OutlierFiltersImpl.cpp:222-285: weight 0 where the angle between the reading's and the
+    matched reference point's normal exceeds maxAngle (|n_r . n_q| < cos maxAngle); all ones when a cloud has no normals."""
+    className = "SurfaceNormalOutlierFilter"
+    TYPE, PARAM = capi.FILTER_SURFACENORMAL, "maxAngle"
+    PARAMS = (("maxAngle", "Maximum authorised angle between the 2 surface normals (in radian)", "1.57", "0.0", "3.1416", float),)
+
+
 class RobustOutlierFilter(_DistFilter):
     """OutlierFiltersImpl.h:199-262, OutlierFiltersImpl.cpp:420-598: M-estimator weights (cauchy, welsch, sc, gm, tukey,
     huber, L1, student) of e^2 = dist / scale^2, scale = sqrt(MAD) or 1 — evaluated on the device."""
@@ -694,7 +702,8 @@ class Registrar(dict):
 
 MatcherRegistrar = Registrar(KDTreeMatcher=KDTreeMatcher)
 OutlierFilterRegistrar = Registrar(MaxDistOutlierFilter=MaxDistOutlierFilter, MedianDistOutlierFilter=MedianDistOutlierFilter,
-                                   TrimmedDistOutlierFilter=TrimmedDistOutlierFilter, RobustOutlierFilter=RobustOutlierFilter)
+                                   TrimmedDistOutlierFilter=TrimmedDistOutlierFilter, RobustOutlierFilter=RobustOutlierFilter,
+                                   SurfaceNormalOutlierFilter=SurfaceNormalOutlierFilter)
 ErrorMinimizerRegistrar = Registrar(PointToPointErrorMinimizer=PointToPointErrorMinimizer,
                                     PointToPointWithCovErrorMinimizer=PointToPointWithCovErrorMinimizer,
                                     PointToPointSimilarityErrorMinimizer=PointToPointSimilarityErrorMinimizer,
@@ -841,6 +850,8 @@ class ICP:
         T_refMean_dataIn = mat4_mul(T_refMean_refIn, T_init)
         _translate(self.ctx.set_reading, reading.features)
         self.ctx._reading_obj = None
+        if reading.descriptorExists("normals"):  # they turn with the reading (TransformationsImpl.cpp:71-84)
+            _translate(self.ctx.set_reading_normals, reading.descriptors["normals"])
         _translate(self.ctx.reading_apply_transform, T_refMean_dataIn)
         res = _translate(self.ctx.icp_run, self._params())
         self.iterationCount = res["iterations"]

@@ -16,7 +16,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
 
-FILTER_MAXDIST, FILTER_MEDIANDIST, FILTER_TRIMMEDDIST, FILTER_ROBUST = 0, 1, 2, 3
+FILTER_MAXDIST, FILTER_MEDIANDIST, FILTER_TRIMMEDDIST, FILTER_ROBUST, FILTER_SURFACENORMAL = 0, 1, 2, 3, 4
 ROBUST_FCTS = dict(cauchy=0, welsch=1, sc=2, gm=3, tukey=4, huber=5, L1=6, student=7)
 SCALE_NONE, SCALE_MAD = 0, 1
 
@@ -177,6 +177,24 @@ def outlier_weights(dists, filters):
     return w, limits[: len(filters)]
 
 
+def outlier_weights_sn(dists, ids, filters, reading_normals, ref_normals):
+    """a chain that may contain SurfaceNormalOutlierFilter (type FILTER_SURFACENORMAL, param maxAngle); reading_normals
+    (N, 3) already rotated like the reading, ref_normals (Nr, 3)"""
+    d = np.ascontiguousarray(dists, np.float32)
+    i = np.ascontiguousarray(ids, np.int32)
+    n, k = d.shape
+    types = np.array([f[0] for f in filters], np.int32)
+    params = np.array([f[1] for f in filters], np.float32)
+    rn = None if reading_normals is None else np.ascontiguousarray(reading_normals, np.float32)
+    qn = None if ref_normals is None else np.ascontiguousarray(ref_normals, np.float32)
+    w = np.empty_like(d)
+    limits = np.zeros(max(1, len(filters)), np.float32)
+    L = lib()
+    L.orc_outlier_weights_sn.argtypes = [_fp, _ip, C.c_int, C.c_int, C.c_int, _ip, _fp, _fp, _fp, _fp, _fp]
+    _check(L.orc_outlier_weights_sn(_f(d), _i(i), k, n, len(filters), _i(types), _f(params), _f(rn), _f(qn), _f(w), _f(limits)))
+    return w, limits[: len(filters)]
+
+
 def minimize(minimizer, reading, reference, ref_normals, ids, dists, weights, sensor_std_dev=0.01, acc_double=False):
     """Returns (T (4,4), cov (6,6) or None, stats dict)."""
     rd, rf = _cloud(reading), _cloud(reference)
@@ -228,9 +246,14 @@ def make_config(knn=1, epsilon=0.0, max_dist=np.inf, search_type=1, filters=(), 
     return cfg
 
 
-def icp(reading, reference, ref_normals=None, T_init=None, **kw):
-    """ICP::operator() (ICP.cpp:243-449).  Returns dict(T, iterations, T_iters, cov, stats)."""
+def icp(reading, reference, ref_normals=None, T_init=None, reading_normals=None, **kw):
+    """ICP::operator() (ICP.cpp:243-449).  Returns dict(T, iterations, T_iters, cov, stats).  reading_normals: the
+    reading's "normals" descriptor, used by SurfaceNormalOutlierFilter only."""
     cfg = kw.pop("config", None) or make_config(**kw)
+    rn = None if reading_normals is None else np.ascontiguousarray(reading_normals, np.float32)
+    lib().orc_set_reading_normals.argtypes = [_fp]
+    lib().orc_set_reading_normals.restype = None
+    lib().orc_set_reading_normals(_f(rn))
     rd, rf = _cloud(reading), _cloud(reference)
     nr = None if ref_normals is None else np.ascontiguousarray(ref_normals, np.float32)
     Ti = np.asfortranarray(np.eye(4, dtype=np.float32) if T_init is None else np.asarray(T_init, np.float32))

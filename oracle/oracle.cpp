@@ -607,8 +607,26 @@ int robust_weights(const float* dists, long total, int word, float tuning, Robus
 
 // OutlierFilters::compute (OutlierFilter.cpp:63-103) over the in-scope filters
 // (OutlierFiltersImpl.cpp:66-81, 109-147, 420-598).
+// what SurfaceNormalOutlierFilter::compute reads besides the distances (OutlierFiltersImpl.cpp:236-285)
+struct SnContext {
+    const int32_t* ids = nullptr;
+    const float* reading_normals = nullptr;  // 3 x n, rotated like the reading
+    const float* ref_normals = nullptr;      // 3 x nr
+};
+
+// `.normalized()`: v / |v| when |v|^2 > 0 (Eigen >= 3.3), in float
+inline void normalized3(const float* v, float* out) {
+    const float n2 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    if (n2 > 0.f) {
+        const float n = std::sqrt(n2);
+        out[0] = v[0] / n; out[1] = v[1] / n; out[2] = v[2] / n;
+    } else {
+        out[0] = v[0]; out[1] = v[1]; out[2] = v[2];
+    }
+}
+
 int outlier_weights(const float* dists, int knn, int n, int nfilters, const int* types, const float* params, float* w, float* limits_out,
-                    RobustState* robust = nullptr) {
+                    RobustState* robust = nullptr, const SnContext* sn = nullptr) {
     const long total = long(knn) * n;
     if (nfilters == 0) {
         for (long i = 0; i < total; ++i) w[i] = (dists[i] == kInf) ? 0.f : 1.f;
@@ -627,6 +645,30 @@ int outlier_weights(const float* dists, int knn, int n, int nfilters, const int*
         } else if (types[f] == ORC_FILTER_TRIMMEDDIST) {
             const int rc = dists_quantile(dists, total, params[f], &limit);
             if (rc) return rc;
+        } else if (types[f] == ORC_FILTER_SURFACENORMAL) {
+            const float eps = std::cos(params[f]);  // eps(cos(maxAngle)), OutlierFiltersImpl.cpp:227
+            if (limits_out) limits_out[f] = eps;
+            const bool have = sn && sn->ids && sn->reading_normals && sn->ref_normals;
+            for (int x = 0; x < n; ++x) {
+                float nr[3] = {0.f, 0.f, 0.f};
+                if (have) normalized3(sn->reading_normals + 3 * size_t(x), nr);
+                for (int y = 0; y < knn; ++y) {
+                    const long i = long(x) * knn + y;
+                    float wf = 1.f;  // no normals: "Skipping filtering", all ones
+                    if (have) {
+                        const int id = sn->ids[i];
+                        if (id < 0) wf = 0.f;
+                        else {
+                            float nq[3];
+                            normalized3(sn->ref_normals + 3 * size_t(id), nq);
+                            const float value = std::fabs(nr[0] * nq[0] + nr[1] * nq[1] + nr[2] * nq[2]);
+                            wf = (value < eps) ? 0.f : 1.f;
+                        }
+                    }
+                    w[i] = (f == 0) ? wf : w[i] * wf;
+                }
+            }
+            continue;
         } else if ((types[f] & 0xff) == ORC_FILTER_ROBUST) {
             RobustState fresh;
             std::vector<float> wr(total);
@@ -1191,6 +1233,16 @@ int orc_rotate_normals(const float* T, const float* in3, int n, float* out3) {
     return ORC_OK;
 }
 
+static const float* g_reading_normals = nullptr;
+void orc_set_reading_normals(const float* normals3xn) { g_reading_normals = normals3xn; }
+
+int orc_outlier_weights_sn(const float* dists, const int32_t* ids, int knn, int n, int nfilters, const int* types, const float* params,
+                           const float* reading_normals, const float* ref_normals, float* weights, float* limits_out) {
+    SnContext sn;
+    sn.ids = ids; sn.reading_normals = reading_normals; sn.ref_normals = ref_normals;
+    return outlier_weights(dists, knn, n, nfilters, types, params, weights, limits_out, nullptr, &sn);
+}
+
 int orc_dists_quantile(const float* dists, long n, float quantile, float* out) { return dists_quantile(dists, n, quantile, out); }
 
 int orc_outlier_weights(const float* dists, int knn, int n, int nfilters, const int* types, const float* params, float* weights, float* limits_out) {
@@ -1386,6 +1438,7 @@ int orc_icp(const float* readingIn, int nq, const float* referenceIn, int nr, co
     std::vector<float> dists(size_t(knn) * nq), w(size_t(knn) * nq);
     int rc = ORC_OK;
     RobustState robustState[8];  // one per filter slot: the filter objects live as long as the ICP object
+    std::vector<float> stepNormals, baseNormals;
     const double t_loop0 = now_s();
     while (iterate) {
         // SimilarityTransformation::checkParameters accepts anything (TransformationsImpl.cpp:199-204)
@@ -1395,7 +1448,19 @@ int orc_icp(const float* readingIn, int nq, const float* referenceIn, int nr, co
         if (tree) tree->knn(stepReading.data(), 4, nq, knn, cfg->epsilon, cfg->max_dist, ids.data(), dists.data(), cfg->nthreads);
         else orc_bruteforce_knn(reference.data(), 4, nr, stepReading.data(), nq, knn, cfg->max_dist, ids.data(), dists.data(), cfg->nthreads);
         g_timings[2] += now_s() - t_m0;
-        rc = outlier_weights(dists.data(), knn, nq, cfg->nfilters, cfg->filter_type, cfg->filter_param, w.data(), nullptr, robustState);
+        SnContext sn;
+        if (g_reading_normals && ref_normals) {
+            // the reading's normals turn with it (RigidTransformation::compute, TransformationsImpl.cpp:71-84):
+            // T_iter * (T_refMean_dataIn * n), rotation blocks only
+            if (stepNormals.empty()) {
+                stepNormals.resize(3 * size_t(nq));
+                baseNormals.resize(3 * size_t(nq));
+                orc_rotate_normals(T_refMean_dataIn, g_reading_normals, nq, baseNormals.data());
+            }
+            orc_rotate_normals(T_iter, baseNormals.data(), nq, stepNormals.data());
+            sn.ids = ids.data(); sn.reading_normals = stepNormals.data(); sn.ref_normals = ref_normals;
+        }
+        rc = outlier_weights(dists.data(), knn, nq, cfg->nfilters, cfg->filter_type, cfg->filter_param, w.data(), nullptr, robustState, &sn);
         if (rc) break;
         float dT[16];
         rc = orc_minimize(cfg->minimizer, stepReading.data(), nq, reference.data(), nr, ref_normals, ids.data(), dists.data(), w.data(), knn, cfg->sensor_std_dev, cfg->acc_double, dT, cov_out, stats_out);

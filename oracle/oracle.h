@@ -23,7 +23,7 @@ extern "C" {
 #endif
 
 /* filter types for the outlier chain (OutlierFiltersImpl.cpp) */
-enum { ORC_FILTER_MAXDIST = 0, ORC_FILTER_MEDIANDIST = 1, ORC_FILTER_TRIMMEDDIST = 2, ORC_FILTER_ROBUST = 3 };
+enum { ORC_FILTER_MAXDIST = 0, ORC_FILTER_MEDIANDIST = 1, ORC_FILTER_TRIMMEDDIST = 2, ORC_FILTER_ROBUST = 3, ORC_FILTER_SURFACENORMAL = 4 };
 /* RobustOutlierFilter (OutlierFiltersImpl.cpp:420-598): the filter word carries its discrete parameters:
  *   bits 0-7  ORC_FILTER_ROBUST | bits 8-15 robust function | bits 16-19 scale estimator |
  *   bits 20-27 nbIterationForScale;   filter_param = tuning.  distanceType point2point, approximation inf. */
@@ -82,6 +82,13 @@ int orc_rotate_normals(const float* T16, const float* in3, int n, float* out3);
 int orc_dists_quantile(const float* dists, long n, float quantile, float* out);
 int orc_outlier_weights(const float* dists, int knn, int n, int nfilters, const int* types,
                         const float* params, float* weights, float* limits_out);
+/* SurfaceNormalOutlierFilter (OutlierFiltersImpl.cpp:222-285, type ORC_FILTER_SURFACENORMAL, param = maxAngle)
+ * needs the matches and both clouds' normals: the reading's (3 x n, already rotated like the reading) and the
+ * reference's (3 x nr).  orc_outlier_weights_sn evaluates a chain that may contain it; orc_icp takes the
+ * un-rotated reading normals through orc_set_reading_normals (NULL switches the filter to "all ones"). */
+int orc_outlier_weights_sn(const float* dists, const int32_t* ids, int knn, int n, int nfilters, const int* types, const float* params,
+                           const float* reading_normals, const float* ref_normals, float* weights, float* limits_out);
+void orc_set_reading_normals(const float* normals3xn);
 
 /* --- ErrorElements + minimizers -------------------------------------------------------- */
 /* reading: 4 x nq (already transformed), reference 4 x nr, ref_normals 3 x nr or NULL.

@@ -486,3 +486,38 @@ def test_similarity_minimizer_matches_oracle(gpu_ctx, oracle, synth):
     assert res["iterations"] == res_o["iterations"] == 15
     assert np.abs(res["T_iter"] - res_o["T"]).max() < 5e-5
     assert abs(np.cbrt(np.linalg.det(res["T_iter"][:3, :3].astype(np.float64))) - 1 / 1.03) < 1.5e-2   # on its way to 1 / 1.03
+
+
+# ---------------------------------------------------------------------------------- SurfaceNormalOutlierFilter (8f row 3)
+def test_surface_normal_outlier_filter_matches_oracle(gpu_ctx, oracle, synth):
+    from libpointmatcher_b200 import capi, pm
+    rd, rf, _ = synth.scan_pair(40000)
+    nq = oracle.surface_normals(rf, knn=10, nthreads=8)["normals"]
+    nr = oracle.surface_normals(rd, knn=10, nthreads=8)["normals"]
+    gpu_ctx.set_reference(rf, normals=nq)
+    gpu_ctx.set_reading(rd)
+    gpu_ctx.set_reading_normals(nr)
+    T = synth.pose_matrix((0.05, -0.02, 0.01), 2.0).astype(np.float32)
+    ids, dists, _ = gpu_ctx.knn(T, 3, 0.0, np.inf)
+    nr_rot = (nr @ T[:3, :3].T).astype(np.float32)
+    for chain in ([(4, 0.3)], [(2, 0.8), (4, 0.5)], [(4, 1.57)]):
+        wo, lo = oracle.outlier_weights_sn(dists, ids, chain, nr_rot, nq)
+        wg, lg = gpu_ctx.weights(chain)
+        assert (wg != wo).mean() < 2e-4, chain      # |dot| within an ulp of cos(maxAngle) may fall either side (rotation rounding)
+        assert 0.02 < (wg == 0).mean() < 0.98 or chain == [(4, 1.57)]
+    # without reading normals the filter does nothing (OutlierFiltersImpl.cpp:268-277)
+    gpu_ctx.set_reading_normals(None)
+    gpu_ctx.knn(T, 3, 0.0, np.inf)
+    wg, _ = gpu_ctx.weights([(4, 0.3)])
+    assert (wg == 1).all()
+    # whole loop: point-to-plane with Trimmed + SurfaceNormal filters, reading normals turning with the reading
+    chain = [(2, 0.8), (4, 0.4)]
+    res_o = oracle.icp(rd, rf, ref_normals=nq, reading_normals=nr, knn=2, filters=chain, minimizer=1, max_iterations=10, nthreads=8, acc_double=True)
+    icp = pm.ICP()
+    icp.matcher = pm.KDTreeMatcher({"knn": "2"})
+    icp.outlierFilters = pm.OutlierFilters([pm.TrimmedDistOutlierFilter({"ratio": "0.8"}), pm.SurfaceNormalOutlierFilter({"maxAngle": "0.4"})])
+    icp.errorMinimizer = pm.PointToPlaneErrorMinimizer()
+    icp.transformationCheckers = [pm.CounterTransformationChecker({"maxIterationCount": "10"})]
+    Tg = icp(pm.DataPoints(rd, {"normals": nr}), pm.DataPoints(rf, {"normals": nq}))
+    icp.ctx.close()
+    assert_transform_close(Tg, res_o["T"], 2e-5, 2e-5)
