@@ -143,6 +143,64 @@ struct MaxDistDataPointsFilter : public AxisThresholdDataPointsFilter<false> {
         : AxisThresholdDataPointsFilter<false>("MaxDistDataPointsFilter", availableParameters(), params, "maxDist") {}
 };
 
+// ObservationDirection.{h,cpp}: descriptor observationDirections = sensor centre - point
+struct ObservationDirectionDataPointsFilter : public DataPointsFilter {
+    static const std::string description() { return "Observation direction. This filter extracts observation directions (vector from point to sensor), considering a sensor at position (x,y,z)."; }
+    static const ParametersDoc availableParameters() {
+        return {{"x", "x-coordinate of sensor", "0"}, {"y", "y-coordinate of sensor", "0"}, {"z", "z-coordinate of sensor", "0"}};
+    }
+    const T centerX, centerY, centerZ;
+    ObservationDirectionDataPointsFilter(const Parameters& params = Parameters())
+        : DataPointsFilter("ObservationDirectionDataPointsFilter", availableParameters(), params), centerX(Parametrizable::get<T>("x")),
+          centerY(Parametrizable::get<T>("y")), centerZ(Parametrizable::get<T>("z")) {}
+    DataPoints filter(const DataPoints& input) override {
+        DataPoints output(input);
+        inPlaceFilter(output);
+        return output;
+    }
+    void inPlaceFilter(DataPoints& cloud) override {
+        const int dim = cloud.features.rows() - 1, n = cloud.features.cols();
+        if (dim != 2 && dim != 3)
+            throw typename DataPoints::InvalidField("ObservationDirectionDataPointsFilter: Error, works only in 2 or 3 dimensions, cloud has " +
+                                                    std::to_string(dim) + " dimensions.");
+        const T center[3] = {centerX, centerY, centerZ};
+        cloud.allocateDescriptor("observationDirections", dim);
+        const unsigned row = cloud.getDescriptorStartingRow("observationDirections");
+        for (int i = 0; i < n; ++i)
+            for (int r = 0; r < dim; ++r) cloud.descriptors(row + r, i) = center[r] - cloud.features(r, i);
+    }
+};
+
+// OrientNormals.{h,cpp}: flip the normals toward (or away from) the observation point
+struct OrientNormalsDataPointsFilter : public DataPointsFilter {
+    static const std::string description() { return "Normals. Reorient normals so that they all point in the same direction, with respect to the observation points."; }
+    static const ParametersDoc availableParameters() {
+        return {{"towardCenter", "If set to true(1), all the normals will point inside the surface (i.e. toward the observation points).", "1", "0", "1", &Parametrizable::Comp<bool>}};
+    }
+    const bool towardCenter;
+    OrientNormalsDataPointsFilter(const Parameters& params = Parameters())
+        : DataPointsFilter("OrientNormalsDataPointsFilter", availableParameters(), params), towardCenter(Parametrizable::get<bool>("towardCenter")) {}
+    DataPoints filter(const DataPoints& input) override {
+        DataPoints output(input);
+        inPlaceFilter(output);
+        return output;
+    }
+    void inPlaceFilter(DataPoints& cloud) override {
+        if (!cloud.descriptorExists("normals")) throw typename DataPoints::InvalidField("OrientNormalsDataPointsFilter: Error, cannot find normals in descriptors.");
+        if (!cloud.descriptorExists("observationDirections"))
+            throw typename DataPoints::InvalidField("OrientNormalsDataPointsFilter: Error, cannot find observation directions in descriptors.");
+        const unsigned rn = cloud.getDescriptorStartingRow("normals"), ro = cloud.getDescriptorStartingRow("observationDirections");
+        const int dim = cloud.getDescriptorDimension("normals"), n = cloud.features.cols();
+        for (int i = 0; i < n; ++i) {
+            T acc = 0;
+            for (int r = 0; r < dim; ++r) acc += cloud.descriptors(ro + r, i) * cloud.descriptors(rn + r, i);
+            const double scalar = acc;
+            if (towardCenter ? (scalar < 0) : (scalar > 0))
+                for (int r = 0; r < dim; ++r) cloud.descriptors(rn + r, i) = -cloud.descriptors(rn + r, i);
+        }
+    }
+};
+
 // SamplingSurfaceNormal.{h,cpp}: kd-split bins of <= knn points, one normal per bin
 struct SamplingSurfaceNormalDataPointsFilter : public DataPointsFilter {
     static const std::string description() {

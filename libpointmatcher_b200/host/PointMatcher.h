@@ -588,6 +588,8 @@ struct PointMatcher {
         ADD_TO_REGISTRAR(DataPointsFilter, SamplingSurfaceNormalDataPointsFilter, SamplingSurfaceNormalDataPointsFilter)
         ADD_TO_REGISTRAR(DataPointsFilter, MinDistDataPointsFilter, MinDistDataPointsFilter)
         ADD_TO_REGISTRAR(DataPointsFilter, MaxDistDataPointsFilter, MaxDistDataPointsFilter)
+        ADD_TO_REGISTRAR(DataPointsFilter, ObservationDirectionDataPointsFilter, ObservationDirectionDataPointsFilter)
+        ADD_TO_REGISTRAR(DataPointsFilter, OrientNormalsDataPointsFilter, OrientNormalsDataPointsFilter)
         ADD_TO_REGISTRAR(Matcher, KDTreeMatcher, KDTreeMatcher)
         ADD_TO_REGISTRAR_NO_PARAM(OutlierFilter, NullOutlierFilter, NullOutlierFilter)
         ADD_TO_REGISTRAR(OutlierFilter, MaxDistOutlierFilter, MaxDistOutlierFilter)

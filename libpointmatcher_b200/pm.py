@@ -606,6 +606,43 @@ class MaxDistDataPointsFilter(_AxisThresholdFilter):
         _select_columns(cloud, np.nonzero(self._values(cloud) < lim)[0])
 
 
+class ObservationDirectionDataPointsFilter(_HostFilter):
+    """ObservationDirection.h:63-70, ObservationDirection.cpp:61-88: descriptor observationDirections = sensor centre - point"""
+    className = "ObservationDirectionDataPointsFilter"
+    PARAMS = (("x", "x-coordinate of sensor", "0", None, None, float), ("y", "y-coordinate of sensor", "0", None, None, float),
+              ("z", "z-coordinate of sensor", "0", None, None, float))
+
+    def inPlaceFilter(self, cloud):
+        dim = cloud.features.shape[1] - 1
+        if dim not in (2, 3):
+            raise InvalidField("ObservationDirectionDataPointsFilter: Error, works only in 2 or 3 dimensions, cloud has %d dimensions." % dim)
+        centre = np.array([self.x, self.y, self.z][:dim], np.float32)
+        cloud.descriptors["observationDirections"] = (centre[None, :] - cloud.features[:, :dim]).astype(np.float32)
+
+
+class OrientNormalsDataPointsFilter(_HostFilter):
+    """OrientNormals.h:59-64, OrientNormals.cpp:60-92: flip the normals toward (or away from) the observation point"""
+    className = "OrientNormalsDataPointsFilter"
+    PARAMS = (("towardCenter", "If set to true(1), all the normals will point inside the surface (i.e. toward the observation points).",
+               "1", "0", "1", bool),)
+
+    def inPlaceFilter(self, cloud):
+        if not cloud.descriptorExists("normals"):
+            raise InvalidField("OrientNormalsDataPointsFilter: Error, cannot find normals in descriptors.")
+        if not cloud.descriptorExists("observationDirections"):
+            raise InvalidField("OrientNormalsDataPointsFilter: Error, cannot find observation directions in descriptors.")
+        n, o = cloud.descriptors["normals"], cloud.descriptors["observationDirections"]
+        scalar = np.zeros(len(n), np.float64)          # `const double scalar = vecP.dot(vecN)`: a float dot product
+        acc = np.zeros(len(n), np.float32)
+        for a in range(n.shape[1]):
+            acc = (acc + o[:, a] * n[:, a]).astype(np.float32)
+        scalar[:] = acc
+        flip = scalar < 0 if self.towardCenter else scalar > 0
+        out = n.copy()
+        out[flip] = -out[flip]
+        cloud.descriptors["normals"] = out
+
+
 class SamplingSurfaceNormalDataPointsFilter(_HostFilter):
     """SamplingSurfaceNormal.h:60-74, SamplingSurfaceNormal.cpp:80-342: kd-split bins of <= knn points,
     one normal per bin, random (0) or one-per-bin (1) subsampling."""
@@ -689,6 +726,61 @@ class DifferentialTransformationChecker(Parametrizable):
         self.smoothLength = self.get("smoothLength")
 
 
+def _quat_from_matrix(m):
+    """Eigen's rotation matrix -> quaternion (w, x, y, z), in float"""
+    m = np.asarray(m, np.float32)
+    t = np.float32(m[0, 0] + m[1, 1] + m[2, 2])
+    q = np.zeros(4, np.float32)
+    if t > 0:
+        t = np.sqrt(np.float32(t + np.float32(1)))
+        q[0] = np.float32(0.5) * t
+        t = np.float32(0.5) / t
+        q[1], q[2], q[3] = (m[2, 1] - m[1, 2]) * t, (m[0, 2] - m[2, 0]) * t, (m[1, 0] - m[0, 1]) * t
+    else:
+        i = 0
+        if m[1, 1] > m[0, 0]:
+            i = 1
+        if m[2, 2] > m[i, i]:
+            i = 2
+        j, k = (i + 1) % 3, (i + 2) % 3
+        t = np.sqrt(np.float32(m[i, i] - m[j, j] - m[k, k] + np.float32(1)))
+        q[1 + i] = np.float32(0.5) * t
+        t = np.float32(0.5) / t
+        q[0] = (m[k, j] - m[j, k]) * t
+        q[1 + j] = (m[j, i] + m[i, j]) * t
+        q[1 + k] = (m[k, i] + m[i, k]) * t
+    return q
+
+
+class BoundTransformationChecker(Parametrizable):
+    """TransformationCheckersImpl.h:117-123, TransformationCheckersImpl.cpp:165-225: ConvergenceError when the transform leaves a
+    bound around its initial value.  A host checker: with it in the chain the loop runs one device iteration per step."""
+    className = "BoundTransformationChecker"
+    PARAMS = (("maxRotationNorm", "rotation bound", "1", "0", "inf", float), ("maxTranslationNorm", "translation bound", "1", "0", "inf", float))
+
+    def __init__(self, params=None):
+        Parametrizable.__init__(self, params)
+        self.maxRotationNorm, self.maxTranslationNorm = self.get("maxRotationNorm"), self.get("maxTranslationNorm")
+        self.conditionVariables = [0.0, 0.0]
+
+    def init(self, T):
+        self._q0 = _quat_from_matrix(np.asarray(T)[:3, :3])
+        self._t0 = np.asarray(T, np.float32)[:3, 3].copy()
+
+    def check(self, T):
+        q, q0 = _quat_from_matrix(np.asarray(T)[:3, :3]), self._q0
+        # angularDistance: d = q * conj(q0); 2 * atan2(|d.vec|, |d.w|)
+        w = q[0] * q0[0] + q[1] * q0[1] + q[2] * q0[2] + q[3] * q0[3]
+        v = np.array([-q[0] * q0[1] + q[1] * q0[0] - q[2] * q0[3] + q[3] * q0[2],
+                      -q[0] * q0[2] + q[1] * q0[3] + q[2] * q0[0] - q[3] * q0[1],
+                      -q[0] * q0[3] - q[1] * q0[2] + q[2] * q0[1] + q[3] * q0[0]], np.float32)
+        rot = float(2 * np.arctan2(np.float32(np.linalg.norm(v)), np.float32(abs(w))))
+        tr = float(np.linalg.norm(np.asarray(T, np.float32)[:3, 3] - self._t0))
+        self.conditionVariables = [rot, tr]
+        if rot > self.maxRotationNorm or tr > self.maxTranslationNorm:
+            raise ConvergenceError("limit out of bounds: rot: %g/%g tr: %g/%g" % (rot, self.maxRotationNorm, tr, self.maxTranslationNorm))
+
+
 # ---- Registrar (Registrar.h:75-218) --------------------------------------------------------------
 class Registrar(dict):
     def create(self, name, params=None):
@@ -712,9 +804,12 @@ ErrorMinimizerRegistrar = Registrar(PointToPointErrorMinimizer=PointToPointError
 DataPointsFilterRegistrar = Registrar(SurfaceNormalDataPointsFilter=SurfaceNormalDataPointsFilter, IdentityDataPointsFilter=IdentityDataPointsFilter,
                                       RandomSamplingDataPointsFilter=RandomSamplingDataPointsFilter,
                                       SamplingSurfaceNormalDataPointsFilter=SamplingSurfaceNormalDataPointsFilter,
-                                      MinDistDataPointsFilter=MinDistDataPointsFilter, MaxDistDataPointsFilter=MaxDistDataPointsFilter)
+                                      MinDistDataPointsFilter=MinDistDataPointsFilter, MaxDistDataPointsFilter=MaxDistDataPointsFilter,
+                                      ObservationDirectionDataPointsFilter=ObservationDirectionDataPointsFilter,
+                                      OrientNormalsDataPointsFilter=OrientNormalsDataPointsFilter)
 TransformationCheckerRegistrar = Registrar(CounterTransformationChecker=CounterTransformationChecker,
-                                           DifferentialTransformationChecker=DifferentialTransformationChecker)
+                                           DifferentialTransformationChecker=DifferentialTransformationChecker,
+                                           BoundTransformationChecker=BoundTransformationChecker)
 
 
 # ---- float32 4x4 helpers with the reference's GEMM accumulation order -----------------------------
@@ -853,7 +948,11 @@ class ICP:
         if reading.descriptorExists("normals"):  # they turn with the reading (TransformationsImpl.cpp:71-84)
             _translate(self.ctx.set_reading_normals, reading.descriptors["normals"])
         _translate(self.ctx.reading_apply_transform, T_refMean_dataIn)
-        res = _translate(self.ctx.icp_run, self._params())
+        bounds = [c for c in self.transformationCheckers if isinstance(c, BoundTransformationChecker)]
+        if bounds:
+            res = self._run_with_host_checkers(bounds)
+        else:
+            res = _translate(self.ctx.icp_run, self._params())
         self.iterationCount = res["iterations"]
         counter = [c for c in self.transformationCheckers if isinstance(c, CounterTransformationChecker)]
         self.maxNumIterationsReached = bool(counter) and res["iterations"] >= max(1, counter[0].maxIterationCount)
@@ -861,6 +960,29 @@ class ICP:
         self.errorMinimizer._cov = res["cov"]
         self.T_iter = res["T_iter"]
         return mat4_mul(mat4_mul(T_refIn_refMean, res["T_iter"]), T_refMean_dataIn)
+
+    def _run_with_host_checkers(self, bounds):
+        """Counter / Differential still decide on the device; the host checkers see T_iter after every iteration
+        (TransformationCheckers::check, ICP.cpp:414-427), so the loop is enqueued one iteration at a time."""
+        params = self._params()
+        if (params.minimizer & 0xff) in (capi.MIN_P2POINT_COV, capi.MIN_P2PLANE_COV):
+            raise ConfigurationError("GPU module (Python mirror): BoundTransformationChecker with a WithCov minimiser is not supported")
+        _translate(self.ctx.icp_reset, None)
+        for b in bounds:
+            b.init(np.eye(4, dtype=np.float32))
+        done, redos, res = 0, 0, None
+        while True:
+            _translate(self.ctx.icp_enqueue, params, 1)
+            res = _translate(self.ctx.icp_result)
+            if res["iterations"] == done:
+                if res["cap_redos"] > redos:   # a void slot of capped matching: not an iteration
+                    redos = res["cap_redos"]
+                    continue
+                break                          # the device checkers had already stopped the loop
+            done = res["iterations"]
+            for b in bounds:
+                b.check(res["T_iter"])
+        return res
 
     def compute(self, readingIn, referenceIn, T_refIn_dataIn=None):
         self._bind()

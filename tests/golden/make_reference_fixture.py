@@ -58,12 +58,13 @@ out = dict(
 for name in ("defaultIdentityDataPointsFilter", "defaultPointToPlaneMinDistDataPointsFilter", "defaultPointToPointMinDistDataPointsFilter",
              "defaultPointToPlaneWithCovErrorMinimizer", "defaultPointToPointWithCovErrorMinimizer", "defaultMaxDistDataPointsFilter",
              "SamplingSurfaceNormalDataPointsFilter1", "SamplingSurfaceNormalDataPointsFilter2", "SamplingSurfaceNormalDataPointsFilter3",
-             "defaultRobustOutlierFilter", "defaultSimilarityPointToPointMinDistDataPointsFilter"):
+             "defaultRobustOutlierFilter", "defaultSimilarityPointToPointMinDistDataPointsFilter", "force4DOFForPointToPlaneMinimizer"):
     out["golden_" + name] = load_trans(name)
 # the chain configurations themselves (YAML text = data), for the chains whose modules are all built
 for name in ("defaultIdentityDataPointsFilter", "defaultPointToPlaneMinDistDataPointsFilter", "defaultPointToPointMinDistDataPointsFilter",
              "defaultMaxDistDataPointsFilter", "SamplingSurfaceNormalDataPointsFilter1", "SamplingSurfaceNormalDataPointsFilter2",
-             "SamplingSurfaceNormalDataPointsFilter3", "defaultRobustOutlierFilter", "defaultSimilarityPointToPointMinDistDataPointsFilter"):
+             "SamplingSurfaceNormalDataPointsFilter3", "defaultRobustOutlierFilter", "defaultSimilarityPointToPointMinDistDataPointsFilter",
+             "force4DOFForPointToPlaneMinimizer"):
     out["yaml_" + name] = np.array(open(os.path.join(DATA, "icp_data", name + ".yaml")).read())
 out["yaml_default"] = np.array(open(os.path.join(DATA, "default.yaml")).read())  # BASELINE config 1
 path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_fixture.npz")

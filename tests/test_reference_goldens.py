@@ -149,7 +149,7 @@ def test_oracle_similarity_chain_reproduces_golden(oracle, fx):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", YAML_CHAINS + ["defaultSimilarityPointToPointMinDistDataPointsFilter"])
+@pytest.mark.parametrize("name", YAML_CHAINS + ["defaultSimilarityPointToPointMinDistDataPointsFilter", "force4DOFForPointToPlaneMinimizer"])
 def test_gpu_runs_reference_yaml_chain_to_golden(fx, name):
     from libpointmatcher_b200 import capi, pm
     ref, data = homog(fx["cloud0"]), homog(fx["cloud1"])
