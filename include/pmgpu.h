@@ -135,6 +135,10 @@ int pmgpu_reading_set(pmgpu_ctx* ctx, const float* features, int rows, int n);
 /* RigidTransformation::compute on the resident reading, in place (TransformationsImpl.cpp:49-87;
  * the `transformations.apply(reading, T_refMean_dataIn)` of ICP.cpp:345-347).  Returns
  * PMGPU_ERR_NOT_ORTHOGONAL if |1 - det R| > 1e-3. */
+/* KDTreeVarDistMatcher (MatchersImpl.cpp:105-150): one maximum search distance per reading point — the reading's `maxDistField`
+ * descriptor (1 row, column stride `ld`).  After this call a NEGATIVE max_dist in pmgpu_knn / pmgpu_icp_params means "use the per-point
+ * distances" (a match farther than its point's distance is missing: id -1, dist inf).  Capped matching stays off in that mode. */
+int pmgpu_reading_set_max_dists(pmgpu_ctx* ctx, const float* max_dists, int ld);
 /* the reading's "normals" descriptor (3 rows of a descriptor matrix with column stride `ld`), after pmgpu_reading_set; they turn with
  * the reading (pmgpu_reading_apply_transform, T_iter) as RigidTransformation::compute turns them (TransformationsImpl.cpp:71-84) */
 int pmgpu_reading_set_normals(pmgpu_ctx* ctx, const float* normals, int ld);

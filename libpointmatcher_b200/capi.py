@@ -73,6 +73,7 @@ SIGNATURES = {
     "pmgpu_ref_set_normals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "pmgpu_reading_set": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "pmgpu_reading_set_normals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "pmgpu_reading_set_max_dists": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "pmgpu_reading_apply_transform": (C.c_int, [C.c_void_p, _fp]),
     "pmgpu_reading_get": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pmgpu_knn": (C.c_int, [C.c_void_p, _fp, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
@@ -253,6 +254,11 @@ class Context:
         """the reading's "normals" descriptor (N, 3), after set_reading; used by SurfaceNormalOutlierFilter"""
         nrm = None if normals is None else np.ascontiguousarray(normals, np.float32)
         self._check(lib.pmgpu_reading_set_normals(self.h, _ptr(nrm), 0 if nrm is None else nrm.shape[1]))
+
+    def set_reading_max_dists(self, max_dists):
+        """KDTreeVarDistMatcher: one maximum search distance per reading point (N,) — then pass max_dist < 0 to knn / make_params"""
+        md = None if max_dists is None else np.ascontiguousarray(np.asarray(max_dists, np.float32).reshape(-1))
+        self._check(lib.pmgpu_reading_set_max_dists(self.h, _ptr(md), 1))
 
     def get_reading(self):
         out = np.empty((self.nq, 4), np.float32)

@@ -29,6 +29,14 @@ __global__ void pack_normals_permuted_kernel(const float* __restrict__ src, int 
     dst[t] = make_float4(s[0], s[1], s[2], 0.f);
 }
 
+// KDTreeVarDistMatcher: per-point search distance -> squared (maxRadius * maxRadius in float, like libnabo), Morton order
+__global__ void pack_max_r2_kernel(const float* __restrict__ src, int ld, const uint32_t* __restrict__ order, int n, float* __restrict__ dst) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const float r = src[(size_t)order[t] * ld];
+    dst[t] = fmul(r, r);
+}
+
 // `R * inputDesc` for the "normals" descriptor (TransformationsImpl.cpp:71-84)
 __global__ void rotate_normals_inplace_kernel(f4* __restrict__ nrm, int n, Mat4 T) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -194,7 +202,8 @@ int check_params(pmgpu_ctx* ctx, const pmgpu_icp_params* p) {
 }
 
 int enqueue_iteration(pmgpu_ctx* ctx, const pmgpu_icp_params* p, bool gated) {
-    const float max_r2 = p->max_dist * p->max_dist;
+    const bool var_dist = p->max_dist < 0.f;  // KDTreeVarDistMatcher
+    const float max_r2 = var_dist ? pm_inf() : p->max_dist * p->max_dist;
     ctx->stage_begin(0);
     SelectSpec spec;
     PM_TRY(make_select_spec(ctx, p->nfilters, p->filter_type, p->filter_param, &spec));
@@ -202,9 +211,10 @@ int enqueue_iteration(pmgpu_ctx* ctx, const pmgpu_icp_params* p, bool gated) {
     // the fused loop, an unbounded maxDist (a finite one decides which matches count as missing),
     // and a non-empty filter chain
     // (a RobustOutlierFilter weighs every match, however far: nothing may be cut)
-    const bool use_cap = gated && ctx->cap_enabled && p->nfilters > 0 && max_r2 == pm_inf() && spec.robust_index() < 0;
+    const bool use_cap = gated && ctx->cap_enabled && p->nfilters > 0 && max_r2 == pm_inf() && spec.robust_index() < 0 && !var_dist;
     PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, ctx->nq, true, gated, false, p->knn, max_r2,
-                      ctx->seed_k == 1 && p->knn == 1 && ctx->seed_enabled, ctx->ids.p, ctx->dists.p, use_cap));
+                      ctx->seed_k == 1 && p->knn == 1 && ctx->seed_enabled, ctx->ids.p, ctx->dists.p, use_cap,
+                      var_dist ? ctx->reading_max_r2.p : nullptr));
     ctx->seed_k = p->knn;
     ctx->stage_end();
     ctx->stage_begin(1);
@@ -409,6 +419,7 @@ int pmgpu_reading_set(pmgpu_ctx* ctx, const float* features, int rows, int n) {
     ctx->have_matches = false;
     ctx->have_weights = false;
     ctx->has_reading_normals = false;
+    ctx->has_reading_max_r2 = false;
     PM_CUDA_TRY(ctx, ctx->reading.reserve(n > 0 ? n : 1));
     PM_CUDA_TRY(ctx, ctx->reading_tmp.reserve(n > 0 ? n : 1));
     ctx->seed_k = 0;
@@ -418,6 +429,26 @@ int pmgpu_reading_set(pmgpu_ctx* ctx, const float* features, int rows, int n) {
     if (n > 0) PM_TRY(morton_order(ctx));
     // the caller may release `features` on return: wait for the copy only, the ordering kernels run on
     PM_CUDA_TRY(ctx, cudaEventSynchronize(ctx->copy_done));
+    return PMGPU_OK;
+}
+
+int pmgpu_reading_set_max_dists(pmgpu_ctx* ctx, const float* max_dists, int ld) {
+    if (!ctx) return PMGPU_ERR_BAD_ARG;
+    PM_TRY(use_device(ctx));
+    if (ctx->nq == 0) return fail(ctx, PMGPU_ERR_NO_READING, status_message(PMGPU_ERR_NO_READING));
+    if (!max_dists) { ctx->has_reading_max_r2 = false; return PMGPU_OK; }
+    if (ld < 1) return fail(ctx, PMGPU_ERR_BAD_ARG, "ld must be >= 1");
+    const int n = ctx->nq;
+    PM_CUDA_TRY(ctx, ctx->reading_max_r2.reserve(n));
+    DevBuf<float> staging;
+    PM_CUDA_TRY(ctx, staging.reserve((size_t)n * ld));
+    PM_CUDA_TRY(ctx, cudaMemcpyAsync(staging.p, max_dists, ((size_t)(n - 1) * ld + 1) * sizeof(float), cudaMemcpyDefault, ctx->stream));
+    pack_max_r2_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(staging.p, ld, ctx->q_order.p, n, ctx->reading_max_r2.p);
+    ctx->launches += 1;
+    PM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    staging.release();
+    ctx->has_reading_max_r2 = true;
+    ctx->seed_k = 0;
     return PMGPU_OK;
 }
 
@@ -476,7 +507,9 @@ int pmgpu_knn(pmgpu_ctx* ctx, const float* T, int k, float epsilon, float max_di
     if (k < 1) return fail(ctx, PMGPU_ERR_BAD_ARG, "knn must be >= 1");
     if (k > ctx->nr) return fail(ctx, PMGPU_ERR_KNN_TOO_LARGE, status_message(PMGPU_ERR_KNN_TOO_LARGE));
     if (!(epsilon >= 0.f)) return fail(ctx, PMGPU_ERR_BAD_ARG, "epsilon must be >= 0");
-    if (!(max_dist >= 0.f)) return fail(ctx, PMGPU_ERR_BAD_ARG, "maxDist must be >= 0");
+    const bool var_dist = max_dist < 0.f;  // KDTreeVarDistMatcher: per-point distances (pmgpu_reading_set_max_dists)
+    if (var_dist && !ctx->has_reading_max_r2) return fail(ctx, PMGPU_ERR_BAD_ARG, "maxDist < 0 needs pmgpu_reading_set_max_dists first");
+    if (!var_dist && !(max_dist >= 0.f)) return fail(ctx, PMGPU_ERR_BAD_ARG, "maxDist must be >= 0");
     IcpState* h = ctx->state_host;
     if (T) {
         memcpy(h->T_iter.m, T, sizeof(float) * 16);
@@ -494,10 +527,10 @@ int pmgpu_knn(pmgpu_ctx* ctx, const float* T, int k, float epsilon, float max_di
     PM_CUDA_TRY(ctx, ctx->dists.reserve(total));
     ctx->k = k;
     ctx->have_weights = false;
-    const float max_r2 = max_dist * max_dist;
+    const float max_r2 = var_dist ? pm_inf() : max_dist * max_dist;
     ctx->stage_begin(0);
     PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, ctx->nq, T != nullptr, false, false, k, max_r2,
-                      ctx->seed_k == 1 && k == 1 && ctx->seed_enabled, ctx->ids.p, ctx->dists.p));
+                      ctx->seed_k == 1 && k == 1 && ctx->seed_enabled, ctx->ids.p, ctx->dists.p, false, var_dist ? ctx->reading_max_r2.p : nullptr));
     ctx->seed_k = k;
     ctx->stage_end();
     ctx->have_matches = true;
@@ -607,6 +640,7 @@ int pmgpu_icp_enqueue(pmgpu_ctx* ctx, const pmgpu_icp_params* params, int n_iter
     if (ctx->nr == 0) return fail(ctx, PMGPU_ERR_NO_REFERENCE, status_message(PMGPU_ERR_NO_REFERENCE));
     if (ctx->nq == 0) return fail(ctx, PMGPU_ERR_NO_READING, status_message(PMGPU_ERR_NO_READING));
     PM_TRY(check_params(ctx, params));
+    if (params->max_dist < 0.f && !ctx->has_reading_max_r2) return fail(ctx, PMGPU_ERR_BAD_ARG, "maxDist < 0 needs pmgpu_reading_set_max_dists first");
     const bool plane = (params->minimizer & 0xff) == PMGPU_MIN_P2PLANE || (params->minimizer & 0xff) == PMGPU_MIN_P2PLANE_COV;
     if (plane && !ctx->has_normals) return fail(ctx, PMGPU_ERR_NO_NORMALS, status_message(PMGPU_ERR_NO_NORMALS));
     const size_t total = (size_t)params->knn * ctx->nq;

@@ -47,7 +47,8 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
                                                         int use_T, int gated, int self_query, int k, float max_r2,
                                                         const f4* __restrict__ ref_orig, int use_seed, int32_t* __restrict__ ids,
                                                         float* __restrict__ dists, unsigned long long* visits, int budget,
-                                                        uint32_t* __restrict__ overflow, unsigned* overflow_count, int use_cap) {
+                                                        uint32_t* __restrict__ overflow, unsigned* overflow_count, int use_cap,
+                                                        const float* __restrict__ var_r2) {
     extern __shared__ float s_plane[];  // [depth + 1][KNN_BLOCK]: cached plane distances, one column per lane
     __shared__ Mat4 sT;
     if (gated && state->iterate == 0) return;
@@ -63,7 +64,8 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
     TopK<KMAX> best;
     // fused ICP loop: the search may stop at the radius the previous iteration's outlier filters
     // make sufficient (state->cap, verified by the select kernels afterwards)
-    const Cap cap = knn_cap(state, use_cap, max_r2);
+    Cap cap = knn_cap(state, use_cap, max_r2);
+    if (var_r2 && t < nq) cap.r2 = var_r2[t];  // KDTreeVarDistMatcher: the query's own radius
     best.init(k, cap.r2);
     s.visited = 0;
     if (running) {
@@ -151,7 +153,8 @@ template <int KMAX>
 __global__ void __launch_bounds__(128) knn_overflow_kernel(TreeView tree, const f4* __restrict__ queries, const IcpState* __restrict__ state, int use_T,
                                                            int gated, int self_query, int k, float max_r2, const uint32_t* __restrict__ overflow,
                                                            unsigned* overflow_count, unsigned* next_count, int32_t* __restrict__ ids,
-                                                           float* __restrict__ dists, unsigned long long* visits, int use_cap) {
+                                                           float* __restrict__ dists, unsigned long long* visits, int use_cap,
+                                                           const float* __restrict__ var_r2) {
     __shared__ uint32_t s_stack[4][OVF_STACK];
     __shared__ Mat4 sT;
     if (gated && state->iterate == 0) return;
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(128) knn_overflow_kernel(TreeView tree, const 
         if (self_query) { qi = __float_as_uint(q.w); q.w = 1.f; }
         if (use_T) q = transform_point(sT, q);
         TopK<KMAX> best;
-        best.init(k, cap.r2);
+        best.init(k, var_r2 ? var_r2[t] : cap.r2);
         // seed: the candidates stage 1 left in the result arrays (ascending, real points)
         for (int j = 0; j < k; ++j) {
             const int id = ids[(size_t)qi * k + j];
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(128) knn_overflow_kernel(TreeView tree, const 
 
 template <int KMAX>
 int launch_one(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, bool use_T, bool gated, bool self_query, int k, float max_r2,
-               bool use_seed, int32_t* ids, float* dists, bool use_cap) {
+               bool use_seed, int32_t* ids, float* dists, bool use_cap, const float* var_r2) {
     const int grid = (nq + KNN_BLOCK - 1) / KNN_BLOCK;
     if (grid == 0) return PMGPU_OK;
     const size_t smem = (size_t)(tree.depth + 2) * KNN_BLOCK * sizeof(float);
@@ -292,15 +295,15 @@ int launch_one(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, 
     if (planes)
         knn_kernel<KMAX, true><<<grid, KNN_BLOCK, smem, ctx->stream>>>(tree, queries, nq, ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k,
                                                                       max_r2, ctx->ref_orig.p, use_seed ? 1 : 0, ids, dists, &ctx->state->visits,
-                                                                      budget, ctx->overflow.p, cnt, use_cap ? 1 : 0);
+                                                                      budget, ctx->overflow.p, cnt, use_cap ? 1 : 0, var_r2);
     else
         knn_kernel<KMAX, false><<<grid, KNN_BLOCK, 0, ctx->stream>>>(tree, queries, nq, ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k,
                                                                     max_r2, ctx->ref_orig.p, use_seed ? 1 : 0, ids, dists, &ctx->state->visits,
-                                                                    budget, ctx->overflow.p, cnt, use_cap ? 1 : 0);
+                                                                    budget, ctx->overflow.p, cnt, use_cap ? 1 : 0, var_r2);
     if (ctx->time_stage2) { ctx->stage_end(); ctx->stage_begin(3); }
     const int grid2 = min(ctx->num_sms * 4, (nq + 3) / 4);
     knn_overflow_kernel<KMAX><<<grid2, 128, 0, ctx->stream>>>(tree, queries, ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k, max_r2,
-                                                           ctx->overflow.p, cnt, cnt_next, ids, dists, &ctx->state->visits, use_cap ? 1 : 0);
+                                                           ctx->overflow.p, cnt, cnt_next, ids, dists, &ctx->state->visits, use_cap ? 1 : 0, var_r2);
     ctx->launches += 2;
     PM_CUDA_TRY(ctx, cudaGetLastError());
     return PMGPU_OK;
@@ -313,8 +316,8 @@ int launch_one(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, 
 // use_seed (k = 1): `ids` still holds the previous matches of the same reading;
 // use_cap: stop at min(max_r2, state->cap)
 int launch_knn(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, bool use_T, bool gated, bool self_query, int k, float max_r2,
-               bool use_seed, int32_t* ids, float* dists, bool use_cap) {
-#define PM_KNN_CASE(K) return launch_one<K>(ctx, tree, queries, nq, use_T, gated, self_query, k, max_r2, use_seed, ids, dists, use_cap)
+               bool use_seed, int32_t* ids, float* dists, bool use_cap, const float* var_r2) {
+#define PM_KNN_CASE(K) return launch_one<K>(ctx, tree, queries, nq, use_T, gated, self_query, k, max_r2, use_seed, ids, dists, use_cap, var_r2)
     if (k == 1) PM_KNN_CASE(1);
     if (k <= 4) PM_KNN_CASE(4);
     if (k <= 8) PM_KNN_CASE(8);

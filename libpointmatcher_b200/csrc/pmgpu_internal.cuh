@@ -158,6 +158,8 @@ struct pmgpu_ctx {
     pm::DevBuf<f4> ref_normals;  // original order, (nx, ny, nz, 0)
     pm::DevBuf<f4> reading_normals;  // Morton order like `reading`
     bool has_reading_normals = false;
+    pm::DevBuf<float> reading_max_r2;  // KDTreeVarDistMatcher: squared per-point search radius, Morton order
+    bool has_reading_max_r2 = false;
     pm::DevBuf<f2> splits;       // inner node (heap index) -> {split value, axis bits}
     pm::DevBuf<f4> boxes;        // node (heap index) -> 2 f4 (lo, hi)
     bool has_normals = false;
@@ -247,7 +249,7 @@ int build_tree(pmgpu_ctx* ctx);
 int morton_order(pmgpu_ctx* ctx);
 // knn.cu
 int launch_knn(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, bool use_T, bool gated, bool self_query, int k, float max_r2,
-               bool use_seed, int32_t* ids, float* dists, bool use_cap = false);
+               bool use_seed, int32_t* ids, float* dists, bool use_cap = false, const float* var_r2 = nullptr);
 // select.cu
 int make_select_spec(pmgpu_ctx* ctx, int nfilters, const int* types, const float* params, SelectSpec* spec);
 int select_reserve(pmgpu_ctx* ctx);

@@ -199,6 +199,7 @@ protected:
 
         // the reading lives on the device, expressed in the refMean frame
         g.check(pmgpu_reading_set(g.ctx, reinterpret_cast<const float*>(reading.features.data()), reading.features.rows(), reading.features.cols()));
+        gpuMatcher->uploadMaxDists(g, reading);  // KDTreeVarDistMatcher
         if (reading.descriptorExists("normals"))  // they turn with the reading (TransformationsImpl.cpp:71-84)
             g.check(pmgpu_reading_set_normals(g.ctx, reinterpret_cast<const float*>(reading.descriptors.data()) + reading.getDescriptorStartingRow("normals"),
                                               reading.descriptors.rows()));

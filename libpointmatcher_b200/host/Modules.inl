@@ -366,9 +366,22 @@ struct KDTreeMatcher : public Matcher, public GpuBound {
     const int searchType;
     const T maxDist;
 
+    std::string maxDistField;  // KDTreeVarDistMatcher: the reading descriptor that holds one search distance per point
+
     KDTreeMatcher(const Parameters& params = Parameters())
         : Matcher("KDTreeMatcher", availableParameters(), params), knn(Parametrizable::get<int>("knn")), epsilon(Parametrizable::get<T>("epsilon")),
           searchType(Parametrizable::get<int>("searchType")), maxDist(Parametrizable::get<T>("maxDist")) {}
+    // the per-point distances of `reading` for the resident reading (no-op for the plain matcher)
+    void uploadMaxDists(GpuPipeline& g, const DataPoints& reading) const {
+        if (maxDistField.empty()) return;
+        const unsigned row = reading.getDescriptorStartingRow(maxDistField);  // throws InvalidField like getDescriptorViewByName
+        g.check(pmgpu_reading_set_max_dists(g.ctx, reinterpret_cast<const float*>(reading.descriptors.data()) + row, reading.descriptors.rows()));
+    }
+protected:
+    KDTreeMatcher(const std::string& className, const ParametersDoc& doc, const Parameters& params, const std::string& field)
+        : Matcher(className, doc, params), knn(Parametrizable::get<int>("knn")), epsilon(Parametrizable::get<T>("epsilon")),
+          searchType(Parametrizable::get<int>("searchType")), maxDist(T(-1)), maxDistField(field) {}
+public:
 
     void init(const DataPoints& filteredReference) override { initImpl(filteredReference, nullptr); }
     // init() on the reference centred on its mean — the preamble of ICP::compute (ICP.cpp:291-302)
@@ -396,6 +409,7 @@ struct KDTreeMatcher : public Matcher, public GpuBound {
             g.check(pmgpu_reading_set(g.ctx, reinterpret_cast<const float*>(reading.features.data()), reading.features.rows(), reading.features.cols()));
             g.readingKey = reading.features.data();
             g.readingCols = reading.features.cols();
+            uploadMaxDists(g, reading);
         }
         Matches matches(knn, reading.features.cols());
         uint64_t visits = 0;
@@ -407,6 +421,27 @@ struct KDTreeMatcher : public Matcher, public GpuBound {
     Matches findClosests(const DataPoints& filteredReading) override {
         this->gpu().readingKey = nullptr;  // the caller may have modified the cloud in place: always upload
         return findClosestsTransformed(filteredReading, nullptr);
+    }
+};
+
+// KDTreeVarDistMatcher (MatchersImpl.h:105-127, MatchersImpl.cpp:105-150): one maximum search distance per reading point
+struct KDTreeVarDistMatcher : public KDTreeMatcher {
+    static const std::string description() {
+        return "This matcher matches a point from the reading to its closest neighbors in the reference. A maximum search radius per point can be "
+               "defined.";
+    }
+    static const ParametersDoc availableParameters() {
+        return {{"knn", "number of nearest neighbors to consider it the reference", "1", "1", "2147483647", &Parametrizable::Comp<unsigned>},
+                {"epsilon", "approximation to use for the nearest-neighbor search", "0", "0", "inf", &Parametrizable::Comp<T>},
+                {"searchType", "Nabo search type. 0: brute force, check distance to every point in the data (very slow), 1: kd-tree with linear heap, good for small knn (~up to 30) and 2: kd-tree with tree heap, good for large knn (~from 30)", "1", "0", "2", &Parametrizable::Comp<unsigned>},
+                {"maxDistField", "descriptor field name used to set a maximum distance to consider for neighbors per point", "maxSearchDist"}};
+    }
+    static std::string field(const Parameters& params) {
+        const auto it = params.find("maxDistField");
+        return it == params.end() ? std::string("maxSearchDist") : it->second;
+    }
+    KDTreeVarDistMatcher(const Parameters& params = Parameters()) : KDTreeMatcher("KDTreeVarDistMatcher", availableParameters(), params, field(params)) {
+        Parametrizable::get<std::string>("maxDistField");
     }
 };
 

@@ -591,6 +591,7 @@ struct PointMatcher {
         ADD_TO_REGISTRAR(DataPointsFilter, ObservationDirectionDataPointsFilter, ObservationDirectionDataPointsFilter)
         ADD_TO_REGISTRAR(DataPointsFilter, OrientNormalsDataPointsFilter, OrientNormalsDataPointsFilter)
         ADD_TO_REGISTRAR(Matcher, KDTreeMatcher, KDTreeMatcher)
+        ADD_TO_REGISTRAR(Matcher, KDTreeVarDistMatcher, KDTreeVarDistMatcher)
         ADD_TO_REGISTRAR_NO_PARAM(OutlierFilter, NullOutlierFilter, NullOutlierFilter)
         ADD_TO_REGISTRAR(OutlierFilter, MaxDistOutlierFilter, MaxDistOutlierFilter)
         ADD_TO_REGISTRAR(OutlierFilter, MedianDistOutlierFilter, MedianDistOutlierFilter)

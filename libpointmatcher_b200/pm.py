@@ -314,6 +314,34 @@ class KDTreeMatcher(Parametrizable, _Bound):
         self.visitCounter = 0
 
 
+class KDTreeVarDistMatcher(KDTreeMatcher):
+    """MatchersImpl.h:105-127, MatchersImpl.cpp:105-150: like KDTreeMatcher, with one maximum search distance per reading
+    point, read from the reading's `maxDistField` descriptor."""
+    className = "KDTreeVarDistMatcher"
+    PARAMS = KDTreeMatcher.PARAMS[:3] + (
+        ("maxDistField", "descriptor field name used to set a maximum distance to consider for neighbors per point", "maxSearchDist", None, None, str),)
+
+    def __init__(self, params=None):
+        Parametrizable.__init__(self, params)
+        self.knn, self.epsilon, self.searchType = self.get("knn"), self.get("epsilon"), self.get("searchType")
+        self.maxDistField = self.get("maxDistField")
+        self.maxDist = -1.0   # "per-point distances" for pmgpu_knn / pmgpu_icp_params
+        self.visitCounter = 0
+
+    def uploadMaxDists(self, reading):
+        _translate(self.ctx.set_reading_max_dists, reading.getDescriptorViewByName(self.maxDistField))
+
+    def findClosests(self, filteredReading, T=None):
+        ctx = self.ctx
+        if getattr(ctx, "_reading_obj", None) is not filteredReading:
+            _translate(ctx.set_reading, filteredReading.features)
+            ctx._reading_obj = filteredReading
+            self.uploadMaxDists(filteredReading)
+        ids, dists, visits = _translate(ctx.knn, T, self.knn, self.epsilon, -1.0)
+        self.visitCounter += visits
+        return Matches(dists, ids)
+
+
 # ---- OutlierFilters (OutlierFiltersImpl.h:76-139) ---------------------------------------------
 class _DistFilter(Parametrizable, _Bound):
     TYPE = None
@@ -792,7 +820,7 @@ class Registrar(dict):
         return self[name].__doc__ or ""
 
 
-MatcherRegistrar = Registrar(KDTreeMatcher=KDTreeMatcher)
+MatcherRegistrar = Registrar(KDTreeMatcher=KDTreeMatcher, KDTreeVarDistMatcher=KDTreeVarDistMatcher)
 OutlierFilterRegistrar = Registrar(MaxDistOutlierFilter=MaxDistOutlierFilter, MedianDistOutlierFilter=MedianDistOutlierFilter,
                                    TrimmedDistOutlierFilter=TrimmedDistOutlierFilter, RobustOutlierFilter=RobustOutlierFilter,
                                    SurfaceNormalOutlierFilter=SurfaceNormalOutlierFilter)
@@ -945,6 +973,8 @@ class ICP:
         T_refMean_dataIn = mat4_mul(T_refMean_refIn, T_init)
         _translate(self.ctx.set_reading, reading.features)
         self.ctx._reading_obj = None
+        if isinstance(self.matcher, KDTreeVarDistMatcher):
+            self.matcher.uploadMaxDists(reading)
         if reading.descriptorExists("normals"):  # they turn with the reading (TransformationsImpl.cpp:71-84)
             _translate(self.ctx.set_reading_normals, reading.descriptors["normals"])
         _translate(self.ctx.reading_apply_transform, T_refMean_dataIn)

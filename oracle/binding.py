@@ -177,6 +177,21 @@ def outlier_weights(dists, filters):
     return w, limits[: len(filters)]
 
 
+def bruteforce_knn_var(reference, query, k, max_radii, nthreads=1):
+    """KDTreeVarDistMatcher semantics: per-query maximum radius.  Returns (ids (N, k), dists (N, k))."""
+    rf, q = _cloud(reference), _cloud(query)
+    mr = np.ascontiguousarray(max_radii, np.float32).ravel()
+    ids = np.empty((q.shape[0], k), np.int32)
+    dists = np.empty((q.shape[0], k), np.float32)
+    L = lib()
+    L.orc_bruteforce_knn_var.restype = C.c_long
+    L.orc_bruteforce_knn_var.argtypes = [_fp, C.c_int, C.c_int, _fp, C.c_int, C.c_int, _fp, _ip, _fp, C.c_int]
+    rc = L.orc_bruteforce_knn_var(_f(rf), 4, rf.shape[0], _f(q), q.shape[0], k, _f(mr), _i(ids), _f(dists), nthreads)
+    if rc < 0:
+        _check(-rc)
+    return ids, dists
+
+
 def outlier_weights_sn(dists, ids, filters, reading_normals, ref_normals):
     """a chain that may contain SurfaceNormalOutlierFilter (type FILTER_SURFACENORMAL, param maxAngle); reading_normals
     (N, 3) already rotated like the reading, ref_normals (Nr, 3)"""

@@ -1214,6 +1214,34 @@ long orc_bruteforce_knn(const float* ref, int rows, int nr, const float* query, 
     return long(nq) * nr;
 }
 
+// KDTreeVarDistMatcher (MatchersImpl.cpp:132-150): libnabo's knn with one maximum radius per query
+long orc_bruteforce_knn_var(const float* ref, int rows, int nr, const float* query, int nq, int k, const float* max_radii, int32_t* ids, float* dists,
+                            int nthreads) {
+    if (k > nr) return -ORC_ERR_KNN_TOO_LARGE;
+    const int dim = rows - 1;
+#pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
+    {
+        LinearHeap heap(k);
+#pragma omp for schedule(static)
+        for (int i = 0; i < nq; ++i) {
+            heap.reset();
+            const float maxRadius2 = max_radii[i] * max_radii[i];
+            const float* q = query + size_t(i) * rows;
+            for (int j = 0; j < nr; ++j) {
+                const float* p = ref + size_t(j) * rows;
+                float dist = 0.f;
+                for (int d = 0; d < dim; ++d) {
+                    const float diff = q[d] - p[d];
+                    dist += diff * diff;
+                }
+                if (dist <= maxRadius2 && dist < heap.headValue()) heap.replaceHead(j, dist);
+            }
+            heap.get(ids + size_t(i) * k, dists + size_t(i) * k);
+        }
+    }
+    return long(nq) * nr;
+}
+
 int orc_rigid_transform(const float* T16, const float* in, int n, float* out) {
     if (!check_rigid(T16)) return ORC_ERR_NOT_ORTHOGONAL;
     rigid_apply(T16, in, n, out);

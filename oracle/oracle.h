@@ -74,6 +74,10 @@ long orc_kdtree_knn(void* tree, const float* query, int rows, int nq, int k, flo
 long orc_bruteforce_knn(const float* ref, int rows, int nr, const float* query, int nq, int k,
                         float max_radius, int32_t* ids, float* dists, int nthreads);
 
+/* KDTreeVarDistMatcher (MatchersImpl.cpp:132-150): one maximum radius per query (the reading's maxDistField descriptor) */
+long orc_bruteforce_knn_var(const float* ref, int rows, int nr, const float* query, int nq, int k,
+                            const float* max_radii, int32_t* ids, float* dists, int nthreads);
+
 /* --- RigidTransformation::compute (TransformationsImpl.cpp:49-105) -------------------- */
 int orc_rigid_transform(const float* T16, const float* in, int n, float* out);
 int orc_rotate_normals(const float* T16, const float* in3, int n, float* out3);

@@ -521,3 +521,47 @@ def test_surface_normal_outlier_filter_matches_oracle(gpu_ctx, oracle, synth):
     Tg = icp(pm.DataPoints(rd, {"normals": nr}), pm.DataPoints(rf, {"normals": nq}))
     icp.ctx.close()
     assert_transform_close(Tg, res_o["T"], 2e-5, 2e-5)
+
+
+# ---------------------------------------------------------------------------------- KDTreeVarDistMatcher (8f row 3)
+def test_var_dist_matcher_bit_exact_vs_bruteforce(gpu_ctx, oracle, synth):
+    """one maximum search distance per reading point (MatchersImpl.cpp:132-150): ids and dists as libnabo's brute force"""
+    from libpointmatcher_b200 import capi, pm
+    rd, rf, _ = synth.scan_pair(20000)
+    rng = np.random.default_rng(7)
+    radii = rng.uniform(0.0, 0.3, len(rd)).astype(np.float32)
+    radii[::17] = np.inf
+    radii[::23] = 0.0
+    gpu_ctx.set_reference(rf)
+    gpu_ctx.set_reading(rd)
+    gpu_ctx.set_reading_max_dists(radii)
+    for k in (1, 5):
+        ib, db = oracle.bruteforce_knn_var(rf, rd, k, radii, nthreads=8)
+        ig, dg, _ = gpu_ctx.knn(None, k, 0.0, -1.0)
+        assert (ib == ig).all() and (bits(db) == bits(dg)).all()
+        assert 0.05 < (ig[:, 0] == -1).mean() < 0.95
+        ig2, dg2, _ = gpu_ctx.knn(None, k, 0.0, -1.0)          # seeded second call (k = 1): same answer
+        assert (ig2 == ig).all() and (bits(dg2) == bits(dg)).all()
+    gpu_ctx.set_reading(rd)                                    # a new reading forgets the distances
+    with pytest.raises(capi.PmGpuError):
+        gpu_ctx.knn(None, 1, 0.0, -1.0)
+    # the module: fused loop == staged calls, and a missing descriptor is an InvalidField
+    m = pm.KDTreeVarDistMatcher({"knn": "1"})
+    m.bind(gpu_ctx)
+    with pytest.raises(pm.InvalidField):
+        m.findClosests(pm.DataPoints(rd))
+    reading = pm.DataPoints(rd, {"maxSearchDist": radii[:, None]})
+    mt = m.findClosests(reading)
+    ib, db = oracle.bruteforce_knn_var(rf, rd, 1, radii, nthreads=8)
+    assert (mt.ids == ib).all()
+    icp = pm.ICP()
+    icp.matcher = pm.KDTreeVarDistMatcher()
+    icp.outlierFilters = pm.OutlierFilters([pm.TrimmedDistOutlierFilter({"ratio": "0.9"})])
+    icp.errorMinimizer = pm.PointToPointErrorMinimizer()
+    icp.transformationCheckers = [pm.CounterTransformationChecker({"maxIterationCount": "6"})]
+    wide = pm.DataPoints(rd, {"maxSearchDist": np.full((len(rd), 1), 1e3, np.float32)})
+    T_var = icp(wide, pm.DataPoints(rf))
+    icp.matcher = pm.KDTreeMatcher()
+    T_plain = icp(pm.DataPoints(rd), pm.DataPoints(rf))
+    icp.ctx.close()
+    assert (bits(T_var) == bits(T_plain)).all()                # radii that never bind: the plain matcher's answer

@@ -159,7 +159,7 @@ def test_yaml_chains_of_the_reference_load(pm):
     with pytest.raises(pm.InvalidElement):      # default.yaml asks for the VTKFileInspector, which is out of scope
         icp.loadFromYaml(str(fx["yaml_default"]))
     with pytest.raises(pm.InvalidElement):
-        icp.loadFromYaml("matcher:\n  KDTreeVarDistMatcher:\n    knn: 1\n")
+        icp.loadFromYaml("matcher:\n  NoSuchMatcher:\n    knn: 1\n")
     icp.setDefault()                            # ICP.cpp:100-113
     assert type(icp.readingDataPointsFilters[0]).__name__ == "RandomSamplingDataPointsFilter"
     assert type(icp.referenceDataPointsFilters[0]).__name__ == "SamplingSurfaceNormalDataPointsFilter"
