@@ -165,6 +165,39 @@ static int run_cpu() {
         const unsigned tr = sub.getDescriptorStartingRow("tag");
         for (int i = 1; i < sub.features.cols(); ++i) CHECK(sub.descriptors(tr, i) > sub.descriptors(tr, i - 1));  // sorted by original index
     }
+    // modules of SURVEY 8f rows 3-4: registered under the reference's names, parameters checked at construction
+    {
+        auto rob = pm.OutlierFilterRegistrar.create("RobustOutlierFilter", {{"robustFct", "huber"}, {"tuning", "1.5"}, {"scaleEstimator", "mad"}, {"nbIterationForScale", "3"}});
+        auto* g = dynamic_cast<PM::GpuDistOutlierFilter*>(rob.get());
+        CHECK(g && g->filterType == PMGPU_ROBUST_WORD(PMGPU_ROBUST_HUBER, PMGPU_SCALE_MAD, 3) && g->value == 1.5f);
+        CHECK(throws<PM::InvalidParameter>([&] { pm.OutlierFilterRegistrar.create("RobustOutlierFilter", {{"robustFct", "nope"}}); }));
+        CHECK(throws<PM::ConfigurationError>([&] { pm.OutlierFilterRegistrar.create("RobustOutlierFilter", {{"scaleEstimator", "berg"}}); }));
+        CHECK(pm.OutlierFilterRegistrar.create("SurfaceNormalOutlierFilter", {{"maxAngle", "0.42"}})->get<float>("maxAngle") == 0.42f);
+        auto var = pm.MatcherRegistrar.create("KDTreeVarDistMatcher", {{"knn", "3"}, {"maxDistField", "radius"}});
+        auto* vm = dynamic_cast<PM::KDTreeMatcher*>(var.get());
+        CHECK(vm && vm->maxDistField == "radius" && vm->maxDist == -1.f && vm->knn == 3);
+        CHECK(throws<PM::InvalidParameter>([&] { pm.MatcherRegistrar.create("KDTreeVarDistMatcher", {{"maxDist", "1"}}); }));
+        CHECK(pm.ErrorMinimizerRegistrar.create("PointToPointSimilarityErrorMinimizer")->className == "PointToPointSimilarityErrorMinimizer");
+        auto p4 = pm.ErrorMinimizerRegistrar.create("PointToPlaneErrorMinimizer", {{"force4DOF", "1"}});
+        CHECK(dynamic_cast<PM::GpuErrorMinimizer*>(p4.get())->kind == (PMGPU_MIN_P2PLANE | PMGPU_MIN_FORCE4DOF));
+        CHECK(throws<PM::ConfigurationError>([&] { pm.ErrorMinimizerRegistrar.create("PointToPlaneErrorMinimizer", {{"force2D", "1"}}); }));
+        DP c;
+        c.features = PM::Matrix::Zero(4, 2);
+        c.features(0, 0) = 1.f; c.features(1, 1) = 2.f; c.features(3, 0) = c.features(3, 1) = 1.f;
+        PM::Matrix nrm = PM::Matrix::Zero(3, 2);
+        nrm(0, 0) = 1.f; nrm(1, 1) = 1.f;  // both point away from the sensor at the origin
+        c.addDescriptor("normals", nrm);
+        pm.DataPointsFilterRegistrar.create("ObservationDirectionDataPointsFilter")->inPlaceFilter(c);
+        const unsigned ro = c.getDescriptorStartingRow("observationDirections"), rn = c.getDescriptorStartingRow("normals");
+        CHECK(c.descriptors(ro, 0) == -1.f && c.descriptors(ro + 1, 1) == -2.f);
+        pm.DataPointsFilterRegistrar.create("OrientNormalsDataPointsFilter")->inPlaceFilter(c);
+        CHECK(c.descriptors(rn, 0) == -1.f && c.descriptors(rn + 1, 1) == -1.f);  // flipped toward the sensor
+        pm.DataPointsFilterRegistrar.create("OrientNormalsDataPointsFilter", {{"towardCenter", "0"}})->inPlaceFilter(c);
+        CHECK(c.descriptors(rn, 0) == 1.f && c.descriptors(rn + 1, 1) == 1.f);
+        DP bare;
+        bare.features = c.features;
+        CHECK(throws<DP::InvalidField>([&] { pm.DataPointsFilterRegistrar.create("OrientNormalsDataPointsFilter")->inPlaceFilter(bare); }));
+    }
     // loaders (IO.cpp:376-392, 535-760, 949-1250): the layouts of examples/data/*.csv and *.vtk
     {
         const std::string dir = std::getenv("PM_TEST_TMP") ? std::getenv("PM_TEST_TMP") : "/tmp";
