@@ -140,3 +140,20 @@ def test_cpp_icp_sequence_matches_plain_icp(host_bin, tmp_path, oracle, synth):
     seq = _run_icp(host_bin, tmp_path, cfg, rd, rf, nrm, sequence=True)
     assert seq["iterations"] == plain["iterations"] == 15
     assert (seq["T"] == plain["T"]).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["defaultPointToPlaneMinDistDataPointsFilter", "defaultRobustOutlierFilter", "force4DOFForPointToPlaneMinimizer",
+                                  "defaultSimilarityPointToPointMinDistDataPointsFilter"])
+def test_cpp_runs_reference_yaml_chain_to_golden(host_bin, tmp_path, name):
+    """the reference's own chain files through the C++ mirror (`icp.loadFromYaml(ifs); icp(data, ref)`, utest/utest.cpp:81-160):
+    host pre-filters, GPU loop (fused, or staged with the host Bound checker for the force4DOF chain), 3 % criterion"""
+    fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_fixture.npz"))
+    ref = np.ascontiguousarray(np.c_[fx["cloud0"], np.ones(len(fx["cloud0"]))].astype(np.float32))
+    data = np.ascontiguousarray(np.c_[fx["cloud1"], np.ones(len(fx["cloud1"]))].astype(np.float32))
+    cfg = str(fx["yaml_" + name]).replace("PerformanceInspector", "NullInspector")
+    res = _run_icp(host_bin, tmp_path, cfg, data, ref, None)
+    cur = res["T"].astype(np.float64) @ data.T.astype(np.float64)
+    gold = fx["golden_" + name].astype(np.float64) @ data.T.astype(np.float64)
+    assert np.median(np.abs(cur - gold)) / np.median(np.abs(cur)) < 0.03
+    assert res["fused"] == (0 if name.startswith("force4DOF") else 1)
