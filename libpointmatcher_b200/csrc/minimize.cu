@@ -78,60 +78,80 @@ __global__ void __launch_bounds__(ACC_BLOCK, MODE == 1 ? 2 : 3) accumulate_kerne
 #pragma unroll
     for (int c = 0; c < NS; ++c) acc[c] = 0.0;
     const int stride = gridDim.x * blockDim.x;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
-        const f4 p = transform_point(sT, reading[i]);
-        bool match_exist = false;
-        for (int kk = 0; kk < k; ++kk) {
-            const float d = dists[(size_t)i * k + kk];
-            if (d == pm_inf()) continue;
-            float w = pm_pair_weight(state, d);
-            int id = 0;
-            if (w != 0.f) {
-                id = ids[(size_t)i * k + kk];
-                // SurfaceNormalOutlierFilter: `normals` is the reference's descriptor whenever it exists
-                if (state->sn_on) w = __fmul_rn(w, pm_sn_weight(sT, reading_normals[i], __ldg(normals + id), state->sn_eps));
-            }
-            if (w == 0.f) { acc[NS - 3] += 1.0; continue; }
-            match_exist = true;
-            acc[NS - 4] += 1.0;
-            const f4 q = __ldg(ref + id);
-            if (MODE == 1) {
-                const f4 n = __ldg(normals + id);
-                float F[6], wF[6];
-                F[0] = fsub(fmul(p.y, n.z), fmul(p.z, n.y));  // crossProduct, ErrorMinimizer.cpp:304-306
-                F[1] = fsub(fmul(p.z, n.x), fmul(p.x, n.z));
-                F[2] = fsub(fmul(p.x, n.y), fmul(p.y, n.x));
-                F[3] = n.x; F[4] = n.y; F[5] = n.z;
+    // one (reading point, match) pair; `id` is only meaningful where the weight is not zero
+    auto pair = [&](const f4& p, const int i, const float d, const int id, bool& match_exist) {
+        if (d == pm_inf()) return;
+        float w = pm_pair_weight(state, d);
+        // SurfaceNormalOutlierFilter: `normals` is the reference's descriptor whenever it exists
+        if (w != 0.f && state->sn_on) w = __fmul_rn(w, pm_sn_weight(sT, reading_normals[i], __ldg(normals + id), state->sn_eps));
+        if (w == 0.f) { acc[NS - 3] += 1.0; return; }
+        match_exist = true;
+        acc[NS - 4] += 1.0;
+        const f4 q = __ldg(ref + id);
+        if (MODE == 1) {
+            const f4 n = __ldg(normals + id);
+            float F[6], wF[6];
+            F[0] = fsub(fmul(p.y, n.z), fmul(p.z, n.y));  // crossProduct, ErrorMinimizer.cpp:304-306
+            F[1] = fsub(fmul(p.z, n.x), fmul(p.x, n.z));
+            F[2] = fsub(fmul(p.x, n.y), fmul(p.y, n.x));
+            F[3] = n.x; F[4] = n.y; F[5] = n.z;
 #pragma unroll
-                for (int a = 0; a < 6; ++a) wF[a] = fmul(w, F[a]);
-                // dot(deltas, normals) accumulated from zero, PointToPlane.cpp:233-240
-                float dot = fmul(fsub(p.x, q.x), n.x);
-                dot = fadd(dot, fmul(fsub(p.y, q.y), n.y));
-                dot = fadd(dot, fmul(fsub(p.z, q.z), n.z));
-                int c = 0;
+            for (int a = 0; a < 6; ++a) wF[a] = fmul(w, F[a]);
+            // dot(deltas, normals) accumulated from zero, PointToPlane.cpp:233-240
+            float dot = fmul(fsub(p.x, q.x), n.x);
+            dot = fadd(dot, fmul(fsub(p.y, q.y), n.y));
+            dot = fadd(dot, fmul(fsub(p.z, q.z), n.z));
+            int c = 0;
 #pragma unroll
-                for (int a = 0; a < 6; ++a)
+            for (int a = 0; a < 6; ++a)
 #pragma unroll
-                    for (int b = a; b < 6; ++b) acc[c++] += (double)wF[a] * (double)F[b];
+                for (int b = a; b < 6; ++b) acc[c++] += (double)wF[a] * (double)F[b];
 #pragma unroll
-                for (int a = 0; a < 6; ++a) acc[21 + a] += (double)wF[a] * (double)dot;
-                acc[27] += (double)w;
-            } else {
-                acc[0] += (double)w;
-                const float wp[3] = {fmul(p.x, w), fmul(p.y, w), fmul(p.z, w)};
-                const float wq[3] = {fmul(q.x, w), fmul(q.y, w), fmul(q.z, w)};
-                const float pc[3] = {p.x, p.y, p.z};
+            for (int a = 0; a < 6; ++a) acc[21 + a] += (double)wF[a] * (double)dot;
+            acc[27] += (double)w;
+        } else {
+            acc[0] += (double)w;
+            const float wp[3] = {fmul(p.x, w), fmul(p.y, w), fmul(p.z, w)};
+            const float wq[3] = {fmul(q.x, w), fmul(q.y, w), fmul(q.z, w)};
+            const float pc[3] = {p.x, p.y, p.z};
 #pragma unroll
-                for (int a = 0; a < 3; ++a) { acc[1 + a] += (double)wp[a]; acc[4 + a] += (double)wq[a]; }
+            for (int a = 0; a < 3; ++a) { acc[1 + a] += (double)wp[a]; acc[4 + a] += (double)wq[a]; }
 #pragma unroll
-                for (int c = 0; c < 3; ++c)
+            for (int c = 0; c < 3; ++c)
 #pragma unroll
-                    for (int r = 0; r < 3; ++r) acc[7 + r + 3 * c] += (double)wq[r] * (double)pc[c];
-                acc[16] += (double)w * ((double)p.x * (double)p.x + (double)p.y * (double)p.y + (double)p.z * (double)p.z);
-            }
+                for (int r = 0; r < 3; ++r) acc[7 + r + 3 * c] += (double)wq[r] * (double)pc[c];
+            acc[16] += (double)w * ((double)p.x * (double)p.x + (double)p.y * (double)p.y + (double)p.z * (double)p.z);
         }
-        if (!match_exist) acc[NS - 2] += 1.0;
-        acc[NS - 1] += 1.0;
+    };
+    if (k == 1) {
+        // the common case, software-pipelined: the (point, distance, id) of the thread's next element are
+        // in flight while the current one gathers its reference point — the kernel is latency bound
+        int i = blockIdx.x * blockDim.x + threadIdx.x;
+        f4 rp = make_float4(0.f, 0.f, 0.f, 0.f);
+        float d = 0.f;
+        int id = 0;
+        if (i < nq) { rp = reading[i]; d = dists[i]; id = ids[i]; }
+        while (i < nq) {
+            const int inext = i + stride;
+            f4 rp_n = rp;
+            float d_n = 0.f;
+            int id_n = 0;
+            if (inext < nq) { rp_n = reading[inext]; d_n = dists[inext]; id_n = ids[inext]; }
+            const f4 p = transform_point(sT, rp);
+            bool match_exist = false;
+            pair(p, i, d, id, match_exist);
+            if (!match_exist) acc[NS - 2] += 1.0;
+            acc[NS - 1] += 1.0;
+            i = inext; rp = rp_n; d = d_n; id = id_n;
+        }
+    } else {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
+            const f4 p = transform_point(sT, reading[i]);
+            bool match_exist = false;
+            for (int kk = 0; kk < k; ++kk) pair(p, i, dists[(size_t)i * k + kk], ids[(size_t)i * k + kk], match_exist);
+            if (!match_exist) acc[NS - 2] += 1.0;
+            acc[NS - 1] += 1.0;
+        }
     }
 #ifdef PM_PROFILE_NS
     __shared__ unsigned long long s_t[3];
