@@ -53,7 +53,7 @@ enum pmgpu_status {
     PMGPU_ERR_COMM = 14                 /* NCCL failure */
 };
 
-/* OutlierFiltersImpl.h: the three filters on the hot path */
+/* OutlierFiltersImpl.h: the distance filters of the hot path and the two row-8f-3 filters */
 enum pmgpu_filter_type {
     PMGPU_FILTER_MAXDIST = 0,    /* MaxDistOutlierFilter     param = maxDist (un-squared)  OutlierFiltersImpl.cpp:66-81   */
     PMGPU_FILTER_MEDIANDIST = 1, /* MedianDistOutlierFilter  param = factor                OutlierFiltersImpl.cpp:109-125 */

@@ -504,8 +504,11 @@ int launch_minimize(pmgpu_ctx* ctx, int minimizer_word, bool compose_and_check, 
     ck.minimizer = minimizer_word;
     const int g = gated ? 1 : 0, comp = compose_and_check ? 1 : 0;
     const int fuse = ctx->nranks > 1 ? 0 : 1;
-    if (plane) accumulate_kernel<1><<<grid, ACC_BLOCK, 0, st>>>(ctx->reading.p, ctx->nq, ctx->k, ctx->ids.p, ctx->dists.p, ctx->ref_orig.p, ctx->ref_normals.p, ctx->state, g, ctx->partials.p, fuse, ctx->state, sums, comp, ck, ctx->reading_normals.p);
-    else accumulate_kernel<0><<<grid, ACC_BLOCK, 0, st>>>(ctx->reading.p, ctx->nq, ctx->k, ctx->ids.p, ctx->dists.p, ctx->ref_orig.p, ctx->has_normals ? ctx->ref_normals.p : nullptr, ctx->state, g, ctx->partials.p, fuse, ctx->state, sums, comp, ck, ctx->reading_normals.p);
+    if (plane) accumulate_kernel<1><<<grid, ACC_BLOCK, 0, st>>>(ctx->reading.p, ctx->nq, ctx->k, ctx->ids.p, ctx->dists.p, ctx->ref_orig.p,
+            ctx->ref_normals.p, ctx->state, g, ctx->partials.p, fuse, ctx->state, sums, comp, ck, ctx->reading_normals.p);
+    else accumulate_kernel<0><<<grid, ACC_BLOCK, 0, st>>>(ctx->reading.p, ctx->nq, ctx->k, ctx->ids.p, ctx->dists.p, ctx->ref_orig.p,
+            ctx->has_normals ? ctx->ref_normals.p : nullptr, ctx->state, g, ctx->partials.p, fuse, ctx->state, sums, comp, ck,
+            ctx->reading_normals.p);
     ctx->launches += 1;
     if (!fuse) {
         const int ns = plane ? NS_PLANE : NS_POINT;
@@ -526,8 +529,10 @@ int launch_covariance(pmgpu_ctx* ctx, int minimizer, float sensor_std_dev) {
     const int grid = grid_for(ctx->nq, ACC_BLOCK, ctx->num_sms, 4);
     PM_CUDA_TRY(ctx, ctx->partials.reserve((size_t)(ctx->num_sms * 4 + 2) * NS_MAX));
     double* sums = ctx->partials.p + (size_t)ctx->num_sms * 4 * NS_MAX;
-    if (plane) cov_accumulate_kernel<1><<<grid, ACC_BLOCK, 0, st>>>(ctx->reading.p, ctx->nq, ctx->k, ctx->ids.p, ctx->dists.p, ctx->ref_orig.p, ctx->ref_normals.p, ctx->state, ctx->partials.p, ctx->reading_normals.p, ctx->ref_normals.p);
-    else cov_accumulate_kernel<0><<<grid, ACC_BLOCK, 0, st>>>(ctx->reading.p, ctx->nq, ctx->k, ctx->ids.p, ctx->dists.p, ctx->ref_orig.p, nullptr, ctx->state, ctx->partials.p, ctx->reading_normals.p, ctx->ref_normals.p);
+    if (plane) cov_accumulate_kernel<1><<<grid, ACC_BLOCK, 0, st>>>(ctx->reading.p, ctx->nq, ctx->k, ctx->ids.p, ctx->dists.p, ctx->ref_orig.p,
+            ctx->ref_normals.p, ctx->state, ctx->partials.p, ctx->reading_normals.p, ctx->ref_normals.p);
+    else cov_accumulate_kernel<0><<<grid, ACC_BLOCK, 0, st>>>(ctx->reading.p, ctx->nq, ctx->k, ctx->ids.p, ctx->dists.p, ctx->ref_orig.p, nullptr,
+            ctx->state, ctx->partials.p, ctx->reading_normals.p, ctx->ref_normals.p);
     ctx->launches += 1;
     if (ctx->nranks > 1) {
         cov_finalize_kernel<<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 1, ctx->state, sensor_std_dev);

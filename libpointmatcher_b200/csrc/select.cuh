@@ -219,9 +219,10 @@ __device__ __forceinline__ void select_pick(unsigned* hist, int pass, float quan
                         if (target == 1) state->robust_median = value;
                         else state->robust_scale = sqrtf(value);  // scale = sqrt(MAD), OutlierFiltersImpl.cpp:512
                     }
-                } else
-                if (pass == 0) { state->sel_prefix[f] = found; state->sel_rank[f] = rem; }
-                else if (pass == 1) { state->sel_prefix[f] = (state->sel_prefix[f] << 11) | found; state->sel_rank[f] = rem; }
+                } else if (pass == 0) {
+                    state->sel_prefix[f] = found;
+                    state->sel_rank[f] = rem;
+                } else if (pass == 1) { state->sel_prefix[f] = (state->sel_prefix[f] << 11) | found; state->sel_rank[f] = rem; }
                 else {
                     const unsigned bits = (state->sel_prefix[f] << 10) | found;
                     const float value = __uint_as_float(bits);
