@@ -188,6 +188,11 @@ int pmgpu_normals(pmgpu_ctx* ctx, const float* features, int rows, int n, int kn
                   const pmgpu_normals_out* out, int* degenerate_out);
 /* same, on the resident reference; attaches the normals to it (config 3 pre-step) */
 int pmgpu_ref_compute_normals(pmgpu_ctx* ctx, int knn, float epsilon, float max_dist, int flags);
+/* Centres the RESIDENT reference on the mean of `features` (the host cloud it was set from) and returns the mean — the second
+ * half of pmgpu_ref_set_centered as its own step, so that a chain whose last reference filter is SurfaceNormalDataPointsFilter
+ * can run  pmgpu_ref_set -> pmgpu_ref_compute_normals -> pmgpu_ref_center  on one upload and one structure (normals do not
+ * change under a translation; they are computed on the caller's coordinates, exactly like the filter's own output). */
+int pmgpu_ref_center(pmgpu_ctx* ctx, const float* features, int rows, int n, float* mean_out);
 
 /* ---- fused ICP loop: ICP::computeWithTransformedReference (ICP.cpp:371-430) -------------
  * Runs iterations entirely on the device against the resident reference and reading:

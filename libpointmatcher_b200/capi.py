@@ -82,6 +82,7 @@ SIGNATURES = {
     "pmgpu_normals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int,
                                 C.POINTER(NormalsOut), C.POINTER(C.c_int)]),
     "pmgpu_ref_compute_normals": (C.c_int, [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int]),
+    "pmgpu_ref_center": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, _fp]),
     "pmgpu_icp_run": (C.c_int, [C.c_void_p, C.POINTER(IcpParams), _fp, _fp, C.POINTER(C.c_int), _fp, _fp]),
     "pmgpu_icp_enqueue": (C.c_int, [C.c_void_p, C.POINTER(IcpParams), C.c_int]),
     "pmgpu_icp_reset": (C.c_int, [C.c_void_p, _fp]),
@@ -316,6 +317,13 @@ class Context:
 
     def ref_compute_normals(self, knn=5, epsilon=0.0, max_dist=np.inf):
         self._check(lib.pmgpu_ref_compute_normals(self.h, knn, epsilon, max_dist, 0))
+
+    def ref_center(self, features):
+        """centre the resident reference on the mean of the host cloud it was set from; returns the mean (4,)"""
+        f = _cloud(features)
+        mean = np.zeros(4, np.float32)
+        self._check(lib.pmgpu_ref_center(self.h, _ptr(f), f.shape[1], f.shape[0], _f(mean)))
+        return mean
 
     # ---- fused loop
     def icp_run(self, params, T_iter_init=None):

@@ -356,6 +356,43 @@ int pmgpu_ref_set_centered(pmgpu_ctx* ctx, const float* features, int rows, int 
     return ref_set_impl(ctx, features, rows, n, normals, normals_ld, mean_out);
 }
 
+// Shifts the resident structure (built on the caller's coordinates) into the frame centred on the cloud's mean.
+// `reference.features.rowwise().sum() / nbPtsReference` in float, column after column (ICP.cpp:292): three
+// independent serial chains of float adds on the host (no reassociation without -ffast-math), which overlap
+// whatever the stream is still doing (upload, build, normals).
+static int center_resident_reference(pmgpu_ctx* ctx, const float* features, int n, float* mean_out) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, features) == cudaSuccess && attr.type == cudaMemoryTypeDevice) {
+        ctx->nr = 0;
+        return fail(ctx, PMGPU_ERR_BAD_ARG, "centring the reference needs a host pointer");
+    }
+    cudaGetLastError();
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    for (int i = 0; i < n; ++i) {
+        sx += features[4 * (size_t)i];
+        sy += features[4 * (size_t)i + 1];
+        sz += features[4 * (size_t)i + 2];
+    }
+    mean_out[0] = sx / (float)n; mean_out[1] = sy / (float)n; mean_out[2] = sz / (float)n; mean_out[3] = 1.f;
+    const int nsplits = 1 << ctx->depth, nboxes = 4 << ctx->depth;
+    const int m = n > nboxes ? n : nboxes;
+    center_structure_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(ctx->ref_orig.p, ctx->ref_sorted.p, n, ctx->splits.p, nsplits, ctx->boxes.p, nboxes,
+                                                                     mean_out[0], mean_out[1], mean_out[2]);
+    ctx->launches += 1;
+    PM_CUDA_TRY(ctx, cudaGetLastError());
+    return PMGPU_OK;
+}
+
+int pmgpu_ref_center(pmgpu_ctx* ctx, const float* features, int rows, int n, float* mean_out) {
+    if (!ctx || !features || !mean_out) return PMGPU_ERR_BAD_ARG;
+    PM_TRY(use_device(ctx));
+    if (ctx->nr == 0) return fail(ctx, PMGPU_ERR_NO_REFERENCE, status_message(PMGPU_ERR_NO_REFERENCE));
+    if (rows != 4 || n != ctx->nr) return fail(ctx, PMGPU_ERR_BAD_ARG, "pmgpu_ref_center: `features` must be the cloud given to pmgpu_ref_set");
+    ctx->have_matches = false;
+    ctx->seed_k = 0;
+    return center_resident_reference(ctx, features, n, mean_out);
+}
+
 static int ref_set_impl(pmgpu_ctx* ctx, const float* features, int rows, int n, const float* normals, int normals_ld, float* mean_out) {
     if (!ctx) return PMGPU_ERR_BAD_ARG;
     PM_TRY(use_device(ctx));
@@ -373,30 +410,7 @@ static int ref_set_impl(pmgpu_ctx* ctx, const float* features, int rows, int n, 
     // is busy with the mean; it is shifted into the centred frame afterwards
     const int s = build_tree(ctx);
     if (s != PMGPU_OK) { ctx->nr = 0; return s; }
-    if (mean_out) {
-        // `reference.features.rowwise().sum() / nbPtsReference` in float, column after column
-        // (ICP.cpp:292): three independent serial chains of float adds (no reassociation without
-        // -ffast-math), overlapping the upload and the build
-        cudaPointerAttributes attr;
-        if (cudaPointerGetAttributes(&attr, features) == cudaSuccess && attr.type == cudaMemoryTypeDevice) {
-            ctx->nr = 0;
-            return fail(ctx, PMGPU_ERR_BAD_ARG, "pmgpu_ref_set_centered needs a host pointer");
-        }
-        cudaGetLastError();
-        float sx = 0.f, sy = 0.f, sz = 0.f;
-        for (int i = 0; i < n; ++i) {
-            sx += features[4 * (size_t)i];
-            sy += features[4 * (size_t)i + 1];
-            sz += features[4 * (size_t)i + 2];
-        }
-        mean_out[0] = sx / (float)n; mean_out[1] = sy / (float)n; mean_out[2] = sz / (float)n; mean_out[3] = 1.f;
-        const int nsplits = 1 << ctx->depth, nboxes = 4 << ctx->depth;
-        const int m = n > nboxes ? n : nboxes;
-        center_structure_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(ctx->ref_orig.p, ctx->ref_sorted.p, n, ctx->splits.p, nsplits, ctx->boxes.p,
-                                                                         nboxes, mean_out[0], mean_out[1], mean_out[2]);
-        ctx->launches += 1;
-        PM_CUDA_TRY(ctx, cudaGetLastError());
-    }
+    if (mean_out) PM_TRY(center_resident_reference(ctx, features, n, mean_out));
     if (normals) PM_TRY(upload_normals(ctx, normals, normals_ld));
     return PMGPU_OK;
 }

@@ -948,11 +948,27 @@ class ICP:
     def _set_reference(self, referenceIn):
         """reference filters, centring on the mean and matcher init (ICP.cpp:285-302).  Returns T_refIn_refMean."""
         reference = referenceIn if isinstance(referenceIn, DataPoints) else DataPoints(referenceIn)
-        if self.referenceDataPointsFilters:
+        filters = list(self.referenceDataPointsFilters)
+        # A trailing SurfaceNormalDataPointsFilter that only adds normals is run on the structure the matcher needs anyway
+        # (one upload, one build): set -> normals on the resident cloud -> centre.  Same kernel on the same coordinates as the
+        # filter's own private run, and normals do not change under the centring translation.
+        last = filters[-1] if filters else None
+        fuse_normals = (type(last) is SurfaceNormalDataPointsFilter and type(self.matcher) is KDTreeMatcher and last.keepNormals
+                        and not (last.keepDensities or last.keepEigenValues or last.keepEigenVectors or last.keepMatchedIds or last.keepMeanDist
+                                 or last.sortEigen))
+        if fuse_normals:
+            filters = filters[:-1]
+        if filters:
             reference = reference.copy()  # inputs are never mutated (ICP.cpp:285)
-            for f in self.referenceDataPointsFilters:
+            for f in filters:
                 f.inPlaceFilter(reference)
-        mean = self.matcher.initCentered(reference)
+        if fuse_normals:
+            _translate(self.ctx.set_reference, reference.features, None)
+            _translate(self.ctx.ref_compute_normals, last.knn, last.epsilon, last.maxDist)
+            mean = _translate(self.ctx.ref_center, reference.features)
+            self.matcher._ref = reference
+        else:
+            mean = self.matcher.initCentered(reference)
         T_refIn_refMean = np.eye(4, dtype=np.float32)
         T_refIn_refMean[:3, 3] = mean[:3]
         return T_refIn_refMean

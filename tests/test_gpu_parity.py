@@ -565,3 +565,38 @@ def test_var_dist_matcher_bit_exact_vs_bruteforce(gpu_ctx, oracle, synth):
     T_plain = icp(pm.DataPoints(rd), pm.DataPoints(rf))
     icp.ctx.close()
     assert (bits(T_var) == bits(T_plain)).all()                # radii that never bind: the plain matcher's answer
+
+
+def test_trailing_normals_filter_runs_on_the_matchers_structure(synth):
+    """a chain whose last reference filter is SurfaceNormalDataPointsFilter computes the normals on the structure the matcher needs
+    anyway (pmgpu_ref_set -> pmgpu_ref_compute_normals -> pmgpu_ref_center): the same transform, bit for bit, as filtering first"""
+    from libpointmatcher_b200 import pm
+    rd, rf, _ = synth.scan_pair(50000)
+
+    def chain(filters):
+        icp = pm.ICP()
+        icp.referenceDataPointsFilters = filters
+        icp.matcher = pm.KDTreeMatcher()
+        icp.outlierFilters = pm.OutlierFilters([pm.TrimmedDistOutlierFilter({"ratio": "0.8"})])
+        icp.errorMinimizer = pm.PointToPlaneErrorMinimizer()
+        icp.transformationCheckers = [pm.CounterTransformationChecker({"maxIterationCount": "8"})]
+        return icp
+
+    fused = chain([pm.SurfaceNormalDataPointsFilter({"knn": "12"})])
+    T_fused = fused(pm.DataPoints(rd), pm.DataPoints(rf))
+    fused.ctx.close()
+    filtered = pm.SurfaceNormalDataPointsFilter({"knn": "12"}).filter(pm.DataPoints(rf))
+    plain = chain([])
+    T_plain = plain(pm.DataPoints(rd), filtered)
+    plain.ctx.close()
+    assert (bits(T_fused) == bits(T_plain)).all()
+    # earlier filters stay on the host: the same chain with the pre-filter applied by hand
+    cut = pm.MinDistDataPointsFilter({"minDist": "8"}).filter(pm.DataPoints(rf))
+    assert 0 < len(cut.features) < len(rf)
+    both = chain([pm.MinDistDataPointsFilter({"minDist": "8"}), pm.SurfaceNormalDataPointsFilter({"knn": "12"})])
+    T_both = both(pm.DataPoints(rd), pm.DataPoints(rf))
+    both.ctx.close()
+    by_hand = chain([pm.SurfaceNormalDataPointsFilter({"knn": "12"})])
+    T_hand = by_hand(pm.DataPoints(rd), cut)
+    by_hand.ctx.close()
+    assert (bits(T_both) == bits(T_hand)).all() and not (bits(T_both) == bits(T_fused)).all()
