@@ -127,14 +127,26 @@ struct ICP : ICPChainBase {
         this->inspector->init();
         const int dim = referenceIn.features.rows();
 
+        // A trailing SurfaceNormalDataPointsFilter that only adds normals is run on the structure the matcher needs anyway
+        // (pmgpu_ref_set -> pmgpu_ref_compute_normals -> pmgpu_ref_center: one upload, one build).  Same kernel on the same
+        // coordinates as the filter's own run, and normals do not change under the centring translation.
+        SurfaceNormalDataPointsFilter* trailingNormals = nullptr;
+        if (!this->referenceDataPointsFilters.empty()) {
+            auto* last = dynamic_cast<SurfaceNormalDataPointsFilter*>(this->referenceDataPointsFilters.back().get());
+            auto* plainMatcher = dynamic_cast<KDTreeMatcher*>(this->matcher.get());
+            if (last && plainMatcher && last->keepNormals && !last->keepDensities && !last->keepEigenValues && !last->keepEigenVectors &&
+                !last->keepMatchedIds && !last->keepMeanDist && !last->sortEigen)
+                trailingNormals = last;
+        }
         // inputs are never mutated (ICP.cpp:285); without reference filters no host copy is needed
         DataPoints filtered;
-        if (!this->referenceDataPointsFilters.empty()) {
+        const size_t hostFilters = this->referenceDataPointsFilters.size() - (trailingNormals ? 1 : 0);
+        if (hostFilters > 0) {
             filtered = referenceIn;
             this->referenceDataPointsFilters.init();
-            this->referenceDataPointsFilters.apply(filtered);
+            for (size_t i = 0; i < hostFilters; ++i) this->referenceDataPointsFilters[i]->inPlaceFilter(filtered);
         }
-        const DataPoints& reference = this->referenceDataPointsFilters.empty() ? referenceIn : filtered;
+        const DataPoints& reference = hostFilters > 0 ? filtered : referenceIn;
 
         // intermediate frame at the centre of mass of the reference (ICP.cpp:291-299): the mean is
         // the float row sum over all columns divided by N; the matcher is initialised with the
@@ -142,7 +154,16 @@ struct ICP : ICPChainBase {
         auto* gpuMatcher = dynamic_cast<KDTreeMatcher*>(this->matcher.get());
         if (!gpuMatcher) throw ConfigurationError("ICP: GPU build: the matcher must be the GPU KDTreeMatcher (there is no CPU path)");
         float mean4[4];
-        gpuMatcher->initCentered(reference, mean4);
+        if (trailingNormals) {
+            GpuPipeline& g = *pipeline;
+            const float* feat = reinterpret_cast<const float*>(reference.features.data());
+            g.check(pmgpu_ref_set(g.ctx, feat, reference.features.rows(), reference.features.cols(), nullptr, 0));
+            g.check(pmgpu_ref_compute_normals(g.ctx, (int)trailingNormals->knn, (float)trailingNormals->epsilon, (float)trailingNormals->maxDist, 0));
+            g.check(pmgpu_ref_center(g.ctx, feat, reference.features.rows(), reference.features.cols(), mean4));
+            g.readingKey = nullptr;
+        } else {
+            gpuMatcher->initCentered(reference, mean4);
+        }
         TransformationParameters T_refIn_refMean = Matrix::Identity(dim, dim), T_refMean_refIn = Matrix::Identity(dim, dim);
         for (int r = 0; r < dim - 1; ++r) {
             T_refIn_refMean(r, dim - 1) = T(mean4[r]);

@@ -157,3 +157,20 @@ def test_cpp_runs_reference_yaml_chain_to_golden(host_bin, tmp_path, name):
     gold = fx["golden_" + name].astype(np.float64) @ data.T.astype(np.float64)
     assert np.median(np.abs(cur - gold)) / np.median(np.abs(cur)) < 0.03
     assert res["fused"] == (0 if name.startswith("force4DOF") else 1)
+
+
+@pytest.mark.gpu
+def test_cpp_trailing_normals_filter_matches_python(host_bin, tmp_path, synth):
+    """reference filters ending in SurfaceNormalDataPointsFilter: both mirrors compute the normals on the matcher's structure
+    (pmgpu_ref_set -> pmgpu_ref_compute_normals -> pmgpu_ref_center) and agree"""
+    from libpointmatcher_b200 import pm
+    rd, rf, _ = synth.scan_pair(60000)
+    cfg = CONFIG.format(minimizer="PointToPlaneErrorMinimizer", iters=10, differential="").replace(
+        "  - IdentityDataPointsFilter\n", "  - IdentityDataPointsFilter\n  - SurfaceNormalDataPointsFilter:\n      knn: 12\n")
+    res = _run_icp(host_bin, tmp_path, cfg, rd, rf, None)
+    icp = pm.ICP()
+    icp.loadFromYaml(cfg)
+    Tp = icp(pm.DataPoints(rd), pm.DataPoints(rf))
+    icp.ctx.close()
+    assert res["iterations"] == icp.iterationCount == 10 and res["fused"] == 1
+    assert_transform_close(res["T"], Tp, 1e-6, 1e-6)
