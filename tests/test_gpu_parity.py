@@ -600,3 +600,31 @@ def test_trailing_normals_filter_runs_on_the_matchers_structure(synth):
     T_hand = by_hand(pm.DataPoints(rd), cut)
     by_hand.ctx.close()
     assert (bits(T_both) == bits(T_hand)).all() and not (bits(T_both) == bits(T_fused)).all()
+
+
+def test_new_entry_points_reject_misuse(gpu_ctx, synth):
+    """argument checking of the row-8f entry points: loud errors, never a silent answer"""
+    from libpointmatcher_b200 import capi
+    rd, rf, _ = synth.scan_pair(5000)
+    with capi.Context(0) as fresh:
+        with pytest.raises(capi.PmGpuError) as e:       # no reading yet
+            fresh.set_reading_normals(np.zeros((10, 3), np.float32))
+        assert e.value.code == capi.ERR_NO_READING
+        with pytest.raises(capi.PmGpuError) as e:       # no reference yet
+            fresh.ref_center(rf)
+        assert e.value.code == capi.ERR_NO_REFERENCE
+    gpu_ctx.set_reference(rf)
+    gpu_ctx.set_reading(rd)
+    with pytest.raises(capi.PmGpuError):                # a different cloud than the resident one
+        gpu_ctx.ref_center(rf[:-1])
+    gpu_ctx.knn(None, 1, 0.0, np.inf)
+    for bad in ([(capi.FILTER_ROBUST | (99 << 8), 1.0)],                       # unknown robust function
+                [(capi.FILTER_ROBUST | (5 << 16), 1.0)],                       # scale estimator that is not built
+                [(capi.FILTER_ROBUST, 1.0), (capi.FILTER_ROBUST, 2.0)],        # two robust filters
+                [(7, 1.0)]):                                                   # unknown filter
+        with pytest.raises(capi.PmGpuError):
+            gpu_ctx.weights(bad)
+    with pytest.raises(capi.PmGpuError):
+        gpu_ctx.minimize(capi.MIN_P2POINT_SIM + 1)
+    w, _ = gpu_ctx.weights([(2, 0.9)])                  # and the context is still usable afterwards
+    assert w.shape == (len(rd), 1) and 0.85 < w.mean() < 0.95
