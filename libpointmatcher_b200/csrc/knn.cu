@@ -301,7 +301,7 @@ int launch_one(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, 
                                                                     max_r2, ctx->ref_orig.p, use_seed ? 1 : 0, ids, dists, &ctx->state->visits,
                                                                     budget, ctx->overflow.p, cnt, use_cap ? 1 : 0, var_r2);
     if (ctx->time_stage2) { ctx->stage_end(); ctx->stage_begin(3); }
-    const int grid2 = min(ctx->num_sms * 4, (nq + 3) / 4);
+    const int grid2 = min(ctx->num_sms * 10, (nq + 3) / 4);  // 48 registers: ten 128-thread blocks are resident per SM
     knn_overflow_kernel<KMAX><<<grid2, 128, 0, ctx->stream>>>(tree, queries, ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k, max_r2,
                                                            ctx->overflow.p, cnt, cnt_next, ids, dists, &ctx->state->visits, use_cap ? 1 : 0, var_r2);
     ctx->launches += 2;
