@@ -253,6 +253,16 @@ enum {
 };
 void pmgpu_host_srand(unsigned seed);
 int pmgpu_host_random_sampling(int n, float prob, int32_t* keep_out);
+/* The other std::rand() consumers among the reference's DataPointsFilters (same libc stream):
+ * pmgpu_host_rand = std::rand() (FixStepSampling.cpp:82 draws its phase from it);
+ * pmgpu_host_max_point_count (MaxPointCount.cpp:71-110): srand(seed), order_out[0..return) = the
+ *   ORIGINAL column each kept column holds (the reference's swap through an Eigen view copies
+ *   column idx onto column j and leaves idx in place, so duplicates are possible); the identity
+ *   and n when max_count > n - 1;
+ * pmgpu_host_max_density (MaxDensity.cpp:60-105): densities[i * stride]; keep_out = kept columns. */
+int pmgpu_host_rand(void);
+int pmgpu_host_max_point_count(int n, uint64_t seed, uint64_t max_count, int32_t* order_out);
+int pmgpu_host_max_density(const float* densities, int stride, int n, float max_density, int32_t* keep_out);
 int pmgpu_host_sampling_surface_normal(float* features, int rows, int n, float* descriptors, int desc_rows, float ratio, int knn,
                                        int sampling_method, float max_box_dim, int average_descriptors, int flags, int32_t* keep_out,
                                        float* normals_out, float* densities_out, float* eig_values_out, float* eig_vectors_out,

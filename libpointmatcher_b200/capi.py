@@ -90,6 +90,9 @@ SIGNATURES = {
     "pmgpu_icp_cap_redos": (C.c_int, [C.c_void_p]),
     "pmgpu_host_srand": (None, [C.c_uint]),
     "pmgpu_host_random_sampling": (C.c_int, [C.c_int, C.c_float, C.c_void_p]),
+    "pmgpu_host_rand": (C.c_int, []),
+    "pmgpu_host_max_point_count": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "pmgpu_host_max_density": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "pmgpu_host_sampling_surface_normal": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_int, C.c_float, C.c_int,
                                                     C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     "pmgpu_comm_unique_id": (C.c_int, [C.c_void_p]),

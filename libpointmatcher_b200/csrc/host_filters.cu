@@ -166,6 +166,49 @@ int pmgpu_host_random_sampling(int n, float prob, int32_t* keep_out) {
     return j;
 }
 
+int pmgpu_host_rand(void) { return std::rand(); }
+
+// MaxPointCount.cpp:71-110.  The reference means to swap columns j and idx, but `const auto feat =
+// cloud.features.col(j)` is an Eigen view, not a copy: column j takes column idx and column idx stays
+// as it is.  idx >= j and only positions < j have been overwritten, so kept column j is ORIGINAL
+// column idx_j (duplicates possible) — restated as that.
+int pmgpu_host_max_point_count(int n, uint64_t seed, uint64_t max_count, int32_t* order_out) {
+    if (n < 0 || !order_out) return -1;
+    if (n == 0) return 0;
+    const size_t N = (size_t)(n - 1);  // as the reference: cols() - 1 converted to size_t
+    if (!(max_count <= N)) {
+        for (int i = 0; i < n; ++i) order_out[i] = i;
+        return n;
+    }
+    std::srand((unsigned)seed);
+    for (size_t j = 0; j < max_count; ++j) {
+        const size_t idx = j + static_cast<size_t>((N - j) * (static_cast<float>(std::rand() / static_cast<float>(RAND_MAX))));
+        order_out[j] = (int32_t)idx;
+    }
+    return (int)max_count;
+}
+
+// MaxDensity.cpp:60-105: points denser than max_density survive with probability max_density / density
+int pmgpu_host_max_density(const float* densities, int stride, int n, float max_density, int32_t* keep_out) {
+    if (n < 0 || !keep_out || (n > 0 && !densities) || stride < 1) return -1;
+    float last = -std::numeric_limits<float>::infinity();
+    for (int i = 0; i < n; ++i) last = std::max(last, densities[(size_t)i * stride]);
+    int saturated = 0;
+    for (int i = 0; i < n; ++i) saturated += densities[(size_t)i * stride] == last;
+    int j = 0;
+    for (int i = 0; i < n; ++i) {
+        const float density = densities[(size_t)i * stride];
+        if (density > max_density) {
+            const float r = (float)std::rand() / (float)RAND_MAX;
+            float accept = max_density / density;
+            if (density == last) accept = accept * (1 - saturated / n);  // integer division, as the reference
+            if (r < accept) keep_out[j++] = i;
+        } else
+            keep_out[j++] = i;
+    }
+    return j;
+}
+
 int pmgpu_host_sampling_surface_normal(float* features, int rows, int n, float* descriptors, int desc_rows, float ratio, int knn, int sampling_method,
                                        float max_box_dim, int average_descriptors, int flags, int32_t* keep_out, float* normals_out,
                                        float* densities_out, float* eig_values_out, float* eig_vectors_out, int* unfit_out) {

@@ -280,6 +280,269 @@ struct SamplingSurfaceNormalDataPointsFilter : public DataPointsFilter {
     }
 };
 
+// ---- the remaining per-cloud host filters of the reference's golden chain files --------------------
+// (examples/data/icp_data/default*DataPointsFilter.yaml): O(N) host passes, once per cloud, as in the
+// reference.  The std::rand() consumers go through pmgpu_host_* so both mirrors draw from one place.
+#define PM_FILTER_COPY_THEN_IN_PLACE                  \
+    DataPoints filter(const DataPoints& input) override { \
+        DataPoints output(input);                     \
+        inPlaceFilter(output);                        \
+        return output;                                \
+    }
+
+struct BoundingBoxDataPointsFilter : public DataPointsFilter {  // BoundingBox.{h,cpp}
+    static const std::string description() { return "Subsampling. Remove points laying in a bounding box which is axis aligned."; }
+    static const ParametersDoc availableParameters() {
+        return {{"xMin", "minimum value on x-axis defining one side of the bounding box", "-1", "-inf", "inf", &Parametrizable::Comp<T>},
+                {"xMax", "maximum value on x-axis defining one side of the bounding box", "1", "-inf", "inf", &Parametrizable::Comp<T>},
+                {"yMin", "minimum value on y-axis defining one side of the bounding box", "-1", "-inf", "inf", &Parametrizable::Comp<T>},
+                {"yMax", "maximum value on y-axis defining one side of the bounding box", "1", "-inf", "inf", &Parametrizable::Comp<T>},
+                {"zMin", "minimum value on z-axis defining one side of the bounding box", "-1", "-inf", "inf", &Parametrizable::Comp<T>},
+                {"zMax", "maximum value on z-axis defining one side of the bounding box", "1", "-inf", "inf", &Parametrizable::Comp<T>},
+                {"removeInside", "If set to true (1), remove points inside the bounding box; else (0), remove points outside the bounding box", "1", "0", "1", &Parametrizable::Comp<bool>}};
+    }
+    const T xMin, xMax, yMin, yMax, zMin, zMax;
+    const bool removeInside;
+    BoundingBoxDataPointsFilter(const Parameters& params = Parameters())
+        : DataPointsFilter("BoundingBoxDataPointsFilter", availableParameters(), params), xMin(Parametrizable::get<T>("xMin")),
+          xMax(Parametrizable::get<T>("xMax")), yMin(Parametrizable::get<T>("yMin")), yMax(Parametrizable::get<T>("yMax")),
+          zMin(Parametrizable::get<T>("zMin")), zMax(Parametrizable::get<T>("zMax")), removeInside(Parametrizable::get<bool>("removeInside")) {}
+    PM_FILTER_COPY_THEN_IN_PLACE
+    void inPlaceFilter(DataPoints& cloud) override {  // BoundingBox.cpp:71-103
+        const int n = cloud.features.cols(), rows = cloud.features.rows();
+        std::vector<int> keep;
+        for (int i = 0; i < n; ++i) {
+            const bool x_in = cloud.features(0, i) > xMin && cloud.features(0, i) < xMax;
+            const bool y_in = cloud.features(1, i) > yMin && cloud.features(1, i) < yMax;
+            const bool z_in = rows == 3 || (cloud.features(2, i) > zMin && cloud.features(2, i) < zMax);
+            const bool in_box = x_in && y_in && z_in;
+            if (removeInside ? !in_box : in_box) keep.push_back(i);
+        }
+        cloud.keepColumns(keep);
+    }
+};
+
+struct DistanceLimitDataPointsFilter : public DataPointsFilter {  // DistanceLimit.{h,cpp}
+    static const std::string description() { return "Subsampling. Filter points based on distance measured on a specific axis. If dim is set to -1, points are filtered based on radius."; }
+    static const ParametersDoc availableParameters() {
+        return {{"dim", "dimension on which the filter will be applied. x=0, y=1, z=2, radius=-1", "-1", "-1", "2", &Parametrizable::Comp<int>},
+                {"dist", "distance limit of the filter. If dim is set to -1 (radius), the absolute value of dist will be used", "1", "-inf", "inf", &Parametrizable::Comp<T>},
+                {"removeInside", "If set to true (1), remove points before the distance limit; else (0), remove points beyond the distance limit", "1", "0", "1", &Parametrizable::Comp<bool>}};
+    }
+    const int dim;
+    const T dist;
+    const bool removeInside;
+    DistanceLimitDataPointsFilter(const Parameters& params = Parameters())
+        : DataPointsFilter("DistanceLimitDataPointsFilter", availableParameters(), params), dim(Parametrizable::get<int>("dim")),
+          dist(Parametrizable::get<T>("dist")), removeInside(Parametrizable::get<bool>("removeInside")) {}
+    PM_FILTER_COPY_THEN_IN_PLACE
+    void inPlaceFilter(DataPoints& cloud) override {  // DistanceLimit.cpp:66-127
+        const int n = cloud.features.cols(), rows = cloud.features.rows();
+        if (dim >= rows - 1)
+            throw InvalidParameter("DistanceLimitDataPointsFilter: Error, filtering on dimension number " + std::to_string(dim) +
+                                   ", larger than authorized axis id " + std::to_string(rows - 2));
+        std::vector<int> keep;
+        const T absDist = dist < 0 ? -dist : dist;
+        for (int i = 0; i < n; ++i) {
+            T v, lim;
+            if (dim == -1) {
+                T acc = 0;
+                for (int r = 0; r < rows - 1; ++r) acc += cloud.features(r, i) * cloud.features(r, i);
+                v = std::sqrt(acc);
+                lim = absDist;
+            } else {
+                v = cloud.features(dim, i);
+                lim = dist;
+            }
+            if (removeInside ? (v > lim) : (v < lim)) keep.push_back(i);
+        }
+        cloud.keepColumns(keep);
+    }
+};
+
+struct FixStepSamplingDataPointsFilter : public DataPointsFilter {  // FixStepSampling.{h,cpp}
+    static const std::string description() { return "Subsampling. This filter reduces the size of the point cloud by only keeping one point over step ones; with step varying in time from startStep to endStep, each iteration getting multiplied by stepMult. If use as prefilter (i.e. before the iterations), only startStep is used."; }
+    static const ParametersDoc availableParameters() {
+        return {{"startStep", "initial number of point to skip (initial decimation factor)", "10", "1", "2147483647", &Parametrizable::Comp<unsigned>},
+                {"endStep", "maximal or minimal number of points to skip (final decimation factor)", "10", "1", "2147483647", &Parametrizable::Comp<unsigned>},
+                {"stepMult", "multiplication factor to compute the new decimation factor for each iteration", "1", "0.0000001", "inf", &Parametrizable::Comp<double>}};
+    }
+    const unsigned startStep, endStep;
+    const double stepMult;
+    double step;
+    FixStepSamplingDataPointsFilter(const Parameters& params = Parameters())
+        : DataPointsFilter("FixStepSamplingDataPointsFilter", availableParameters(), params), startStep(Parametrizable::get<unsigned>("startStep")),
+          endStep(Parametrizable::get<unsigned>("endStep")), stepMult(Parametrizable::get<double>("stepMult")), step(startStep) {}
+    void init() override { step = startStep; }
+    PM_FILTER_COPY_THEN_IN_PLACE
+    void inPlaceFilter(DataPoints& cloud) override {  // FixStepSampling.cpp:76-110
+        const int iStep(step);
+        const int n = cloud.features.cols();
+        const int phase(pmgpu_host_rand() % iStep);
+        std::vector<int> keep;
+        for (int i = phase; i < n; i += iStep) keep.push_back(i);
+        cloud.keepColumns(keep);
+        const double deltaStep(startStep * stepMult - startStep);
+        step *= stepMult;
+        if (deltaStep < 0 && step < endStep) step = endStep;
+        if (deltaStep > 0 && step > endStep) step = endStep;
+    }
+};
+
+struct MaxPointCountDataPointsFilter : public DataPointsFilter {  // MaxPointCount.{h,cpp}
+    static const std::string description() { return "Conditional subsampling. This filter reduces the size of the point cloud by randomly dropping points if their number is above maxCount. Based on \\cite{Masuda1996Random}"; }
+    static const ParametersDoc availableParameters() {
+        return {{"seed", "srand seed", "1", "0", "2147483647", &Parametrizable::Comp<size_t>},
+                {"maxCount", "maximum number of points", "1000", "0", "2147483647", &Parametrizable::Comp<size_t>}};
+    }
+    const size_t maxCount;
+    size_t seed;
+    MaxPointCountDataPointsFilter(const Parameters& params = Parameters())
+        : DataPointsFilter("MaxPointCountDataPointsFilter", availableParameters(), params), maxCount(Parametrizable::get<size_t>("maxCount")),
+          seed(Parametrizable::get<size_t>("seed")) {}
+    PM_FILTER_COPY_THEN_IN_PLACE
+    void inPlaceFilter(DataPoints& cloud) override {  // MaxPointCount.cpp:71-110 (see pmgpu.h on the reference's view "swap")
+        const int n = cloud.features.cols();
+        if (n == 0 || !(maxCount <= (size_t)(n - 1))) return;
+        std::vector<int32_t> order(n);
+        const int m = pmgpu_host_max_point_count(n, seed, maxCount, order.data());
+        cloud.keepColumns(std::vector<int>(order.begin(), order.begin() + m));
+    }
+};
+
+struct MaxQuantileOnAxisDataPointsFilter : public DataPointsFilter {  // MaxQuantileOnAxis.{h,cpp}
+    static const std::string description() { return "Subsampling. Filter points beyond a maximum quantile measured on a specific axis."; }
+    static const ParametersDoc availableParameters() {
+        return {{"dim", "dimension on which the filter will be applied. x=0, y=1, z=2", "0", "0", "2", &Parametrizable::Comp<unsigned>},
+                {"ratio", "maximum quantile authorized. All points beyond that will be filtered.", "0.5", "0.0000001", "0.9999999", &Parametrizable::Comp<T>}};
+    }
+    const unsigned dim;
+    const T ratio;
+    MaxQuantileOnAxisDataPointsFilter(const Parameters& params = Parameters())
+        : DataPointsFilter("MaxQuantileOnAxisDataPointsFilter", availableParameters(), params), dim(Parametrizable::get<unsigned>("dim")),
+          ratio(Parametrizable::get<T>("ratio")) {}
+    PM_FILTER_COPY_THEN_IN_PLACE
+    void inPlaceFilter(DataPoints& cloud) override {  // MaxQuantileOnAxis.cpp:65-103
+        if (int(dim) >= cloud.features.rows())
+            throw InvalidParameter("MaxQuantileOnAxisDataPointsFilter: Error, filtering on dimension number " + std::to_string(dim) +
+                                   ", larger than feature dimensionality " + std::to_string(cloud.features.rows()));
+        const int n = cloud.features.cols();
+        if (n == 0) return;
+        const int nbPointsOut = n * ratio;
+        std::vector<T> values;
+        values.reserve(n);
+        for (int x = 0; x < n; ++x) values.push_back(cloud.features(dim, x));
+        std::nth_element(values.begin(), values.begin() + (std::ptrdiff_t)(values.size() * ratio), values.end());
+        const T limit = values[nbPointsOut];
+        std::vector<int> keep;
+        for (int i = 0; i < n; ++i)
+            if (cloud.features(dim, i) < limit) keep.push_back(i);
+        cloud.keepColumns(keep);
+    }
+};
+
+struct RemoveNaNDataPointsFilter : public DataPointsFilter {  // RemoveNaN.{h,cpp}
+    static const std::string description() { return "Remove points having NaN as coordinate."; }
+    RemoveNaNDataPointsFilter() : DataPointsFilter("RemoveNaNDataPointsFilter", ParametersDoc(), Parameters()) {}
+    PM_FILTER_COPY_THEN_IN_PLACE
+    void inPlaceFilter(DataPoints& cloud) override {  // RemoveNaN.cpp:52-72
+        const int n = cloud.features.cols(), rows = cloud.features.rows();
+        std::vector<int> keep;
+        for (int i = 0; i < n; ++i) {
+            bool hasNaN = false;
+            for (int r = 0; r < rows; ++r) hasNaN |= !(cloud.features(r, i) == cloud.features(r, i));
+            if (!hasNaN) keep.push_back(i);
+        }
+        cloud.keepColumns(keep);
+    }
+};
+
+struct MaxDensityDataPointsFilter : public DataPointsFilter {  // MaxDensity.{h,cpp}
+    static const std::string description() { return "Subsampling. Reduce the points number by randomly removing points with a density highler than a treshold."; }
+    static const ParametersDoc availableParameters() {
+        return {{"maxDensity", "Maximum density of points to target. Unit: number of points per m^3.", "10", "0.0000001", "inf", &Parametrizable::Comp<T>}};
+    }
+    const T maxDensity;
+    MaxDensityDataPointsFilter(const Parameters& params = Parameters())
+        : DataPointsFilter("MaxDensityDataPointsFilter", availableParameters(), params), maxDensity(Parametrizable::get<T>("maxDensity")) {}
+    PM_FILTER_COPY_THEN_IN_PLACE
+    void inPlaceFilter(DataPoints& cloud) override {  // MaxDensity.cpp:60-105
+        if (!cloud.descriptorExists("densities")) throw typename DataPoints::InvalidField("MaxDensityDataPointsFilter: Error, no densities found in descriptors.");
+        const int n = cloud.features.cols();
+        const unsigned row = cloud.getDescriptorStartingRow("densities");
+        std::vector<float> dens(n > 0 ? n : 1);
+        for (int i = 0; i < n; ++i) dens[i] = (float)cloud.descriptors(row, i);
+        std::vector<int32_t> keep(n > 0 ? n : 1);
+        const int m = pmgpu_host_max_density(dens.data(), 1, n, (float)maxDensity, keep.data());
+        cloud.keepColumns(std::vector<int>(keep.begin(), keep.begin() + (m > 0 ? m : 0)));
+    }
+};
+
+struct ShadowDataPointsFilter : public DataPointsFilter {  // Shadow.{h,cpp}
+    static const std::string description() { return "Remove ghost points appearing on edge discontinuties. Assume that the origine of the point cloud is close to where the laser center was. Requires surface normal for every points"; }
+    static const ParametersDoc availableParameters() {
+        return {{"eps", "Small angle (in rad) around which a normal shoudn't be observable", "0.1", "0.0", "3.1416", &Parametrizable::Comp<T>}};
+    }
+    const T eps;  // sin of the parameter (Shadow.cpp:46)
+    ShadowDataPointsFilter(const Parameters& params = Parameters())
+        : DataPointsFilter("ShadowDataPointsFilter", availableParameters(), params), eps(std::sin(Parametrizable::get<T>("eps"))) {}
+    PM_FILTER_COPY_THEN_IN_PLACE
+    void inPlaceFilter(DataPoints& cloud) override {  // Shadow.cpp:62-90
+        if (!cloud.descriptorExists("normals")) throw typename DataPoints::InvalidField("ShadowDataPointsFilter, Error: cannot find normals in descriptors");
+        const int dim = cloud.features.rows(), n = cloud.features.cols();
+        const unsigned rn = cloud.getDescriptorStartingRow("normals");
+        const int nd = cloud.getDescriptorDimension("normals");
+        std::vector<int> keep;
+        for (int i = 0; i < n; ++i) {
+            T nn = 0, pn = 0;
+            for (int r = 0; r < nd; ++r) nn += cloud.descriptors(rn + r, i) * cloud.descriptors(rn + r, i);
+            for (int r = 0; r < dim - 1; ++r) pn += cloud.features(r, i) * cloud.features(r, i);
+            nn = std::sqrt(nn);
+            pn = std::sqrt(pn);
+            T dot = 0;  // normalized() leaves a zero vector as it is
+            for (int r = 0; r < nd && r < dim - 1; ++r)
+                dot += (nn > 0 ? cloud.descriptors(rn + r, i) / nn : cloud.descriptors(rn + r, i)) * (pn > 0 ? cloud.features(r, i) / pn : cloud.features(r, i));
+            if ((dot < 0 ? -dot : dot) > eps) keep.push_back(i);
+        }
+        cloud.keepColumns(keep);
+    }
+};
+
+struct SimpleSensorNoiseDataPointsFilter : public DataPointsFilter {  // SimpleSensorNoise.{h,cpp}
+    static const std::string description() { return "Add a 1D descriptor named <sensorNoise> that would represent the noise radius expressed in meter based on SICK LMS specifications \\cite{Pomerleau2012Noise}."; }
+    static const ParametersDoc availableParameters() {
+        return {{"sensorType", "Type of the sensor used. Choices: 0=Sick LMS-1xx, 1=Hokuyo URG-04LX, 2=Hokuyo UTM-30LX, 3=Kinect/Xtion", "0", "0", "2147483647", &Parametrizable::Comp<unsigned>},
+                {"gain", "If the point cloud is coming from an untrusty source, you can use the gain to augment the uncertainty", "1", "1", "inf", &Parametrizable::Comp<T>}};
+    }
+    const unsigned sensorType;
+    const T gain;  // read and never used, as in the reference
+    SimpleSensorNoiseDataPointsFilter(const Parameters& params = Parameters())
+        : DataPointsFilter("SimpleSensorNoiseDataPointsFilter", availableParameters(), params), sensorType(Parametrizable::get<unsigned>("sensorType")),
+          gain(Parametrizable::get<T>("gain")) {
+        if (sensorType >= 5) throw InvalidParameter("SimpleSensorNoiseDataPointsFilter: Error, sensorType id " + std::to_string(sensorType) + " does not exist.");
+    }
+    PM_FILTER_COPY_THEN_IN_PLACE
+    void inPlaceFilter(DataPoints& cloud) override {  // SimpleSensorNoise.cpp:75-140
+        static const T laser[5][3] = {{T(0.012), T(0.0068), T(0.0008)}, {T(0.028), T(0.0013), T(0.0001)}, {T(0.018), T(0.0006), T(0.0015)},
+                                      {0, 0, 0}, {T(0.004), T(0.0053), T(-0.0092)}};
+        cloud.allocateDescriptor("simpleSensorNoise", 1);
+        const unsigned row = cloud.getDescriptorStartingRow("simpleSensorNoise");
+        const int dim = cloud.features.rows(), n = cloud.features.cols();
+        for (int i = 0; i < n; ++i) {
+            T acc = 0;
+            for (int r = 0; r < dim - 1; ++r) acc += cloud.features(r, i) * cloud.features(r, i);
+            const T norm = std::sqrt(acc);
+            if (sensorType == 3)
+                cloud.descriptors(row, i) = (norm * norm) * T(0.5 * 0.00285);
+            else {
+                const T v = laser[sensorType][1] * norm + laser[sensorType][2];
+                cloud.descriptors(row, i) = v < laser[sensorType][0] ? laser[sensorType][0] : v;  // maxCoeff over (v, minRadius): a NaN stays
+            }
+        }
+    }
+};
+#undef PM_FILTER_COPY_THEN_IN_PLACE
+
 // ---- SurfaceNormalDataPointsFilter (DataPointsFilters/SurfaceNormal.{h,cpp}) — K8 -------------------
 struct SurfaceNormalDataPointsFilter : public DataPointsFilter, public GpuBound {
     static const std::string description() {

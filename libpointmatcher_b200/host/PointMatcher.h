@@ -590,6 +590,15 @@ struct PointMatcher {
         ADD_TO_REGISTRAR(DataPointsFilter, MaxDistDataPointsFilter, MaxDistDataPointsFilter)
         ADD_TO_REGISTRAR(DataPointsFilter, ObservationDirectionDataPointsFilter, ObservationDirectionDataPointsFilter)
         ADD_TO_REGISTRAR(DataPointsFilter, OrientNormalsDataPointsFilter, OrientNormalsDataPointsFilter)
+        ADD_TO_REGISTRAR(DataPointsFilter, BoundingBoxDataPointsFilter, BoundingBoxDataPointsFilter)
+        ADD_TO_REGISTRAR(DataPointsFilter, DistanceLimitDataPointsFilter, DistanceLimitDataPointsFilter)
+        ADD_TO_REGISTRAR(DataPointsFilter, FixStepSamplingDataPointsFilter, FixStepSamplingDataPointsFilter)
+        ADD_TO_REGISTRAR(DataPointsFilter, MaxPointCountDataPointsFilter, MaxPointCountDataPointsFilter)
+        ADD_TO_REGISTRAR(DataPointsFilter, MaxQuantileOnAxisDataPointsFilter, MaxQuantileOnAxisDataPointsFilter)
+        ADD_TO_REGISTRAR_NO_PARAM(DataPointsFilter, RemoveNaNDataPointsFilter, RemoveNaNDataPointsFilter)
+        ADD_TO_REGISTRAR(DataPointsFilter, MaxDensityDataPointsFilter, MaxDensityDataPointsFilter)
+        ADD_TO_REGISTRAR(DataPointsFilter, ShadowDataPointsFilter, ShadowDataPointsFilter)
+        ADD_TO_REGISTRAR(DataPointsFilter, SimpleSensorNoiseDataPointsFilter, SimpleSensorNoiseDataPointsFilter)
         ADD_TO_REGISTRAR(Matcher, KDTreeMatcher, KDTreeMatcher)
         ADD_TO_REGISTRAR(Matcher, KDTreeVarDistMatcher, KDTreeVarDistMatcher)
         ADD_TO_REGISTRAR_NO_PARAM(OutlierFilter, NullOutlierFilter, NullOutlierFilter)

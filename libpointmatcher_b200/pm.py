@@ -671,6 +671,177 @@ class OrientNormalsDataPointsFilter(_HostFilter):
         cloud.descriptors["normals"] = out
 
 
+def _float_norm(f):
+    """Eigen's norm() of each row's first columns in float: sqrt of the squares summed left to right"""
+    acc = np.zeros(len(f), np.float32)
+    for a in range(f.shape[1]):
+        acc = (acc + f[:, a] * f[:, a]).astype(np.float32)
+    return np.sqrt(acc)
+
+
+class BoundingBoxDataPointsFilter(_HostFilter):
+    """BoundingBox.h:56-66, BoundingBox.cpp:71-103: keep (or remove) the points strictly inside an axis-aligned box"""
+    className = "BoundingBoxDataPointsFilter"
+    PARAMS = tuple((a + m, "%simum value on %s-axis defining one side of the bounding box" % (m.lower(), a), "-1" if m == "Min" else "1",
+                    "-inf", "inf", float) for a in "xyz" for m in ("Min", "Max")) + (
+        ("removeInside", "If set to true (1), remove points inside the bounding box; else (0), remove points outside the bounding box",
+         "1", "0", "1", bool),)
+
+    def inPlaceFilter(self, cloud):
+        f = cloud.features
+        lo = np.array([self.xMin, self.yMin, self.zMin], np.float32)
+        hi = np.array([self.xMax, self.yMax, self.zMax], np.float32)
+        dims = f.shape[1] - 1            # a 2-D cloud (3 rows) has no z test
+        inside = np.all((f[:, :dims] > lo[:dims]) & (f[:, :dims] < hi[:dims]), axis=1)
+        _select_columns(cloud, np.nonzero(~inside if self.removeInside else inside)[0])
+
+
+class DistanceLimitDataPointsFilter(_AxisThresholdFilter):
+    """DistanceLimit.h:56-62, DistanceLimit.cpp:66-127: MinDist (removeInside 1) or MaxDist (0) in one filter"""
+    className = "DistanceLimitDataPointsFilter"
+    PARAMS = (("dim", "dimension on which the filter will be applied. x=0, y=1, z=2, radius=-1", "-1", "-1", "2", int),
+              ("dist", "distance limit of the filter. If dim is set to -1 (radius), the absolute value of dist will be used", "1", "-inf", "inf", float),
+              ("removeInside", "If set to true (1), remove points before the distance limit; else (0), remove points beyond the distance limit",
+               "1", "0", "1", bool))
+
+    def _values(self, cloud):
+        if self.dim >= cloud.features.shape[1] - 1:
+            raise InvalidParameter("DistanceLimitDataPointsFilter: Error, filtering on dimension number %d, larger than authorized axis id %d"
+                                   % (self.dim, cloud.features.shape[1] - 2))
+        return _AxisThresholdFilter._values(self, cloud)
+
+    def inPlaceFilter(self, cloud):
+        lim = np.float32(abs(self.dist) if self.dim == -1 else self.dist)
+        v = self._values(cloud)
+        _select_columns(cloud, np.nonzero(v > lim if self.removeInside else v < lim)[0])
+
+
+class FixStepSamplingDataPointsFilter(_HostFilter):
+    """FixStepSampling.h:56-80, FixStepSampling.cpp:62-110: every step-th point from a random phase; the step
+    is multiplied by stepMult after every call until it reaches endStep, init() rewinds it"""
+    className = "FixStepSamplingDataPointsFilter"
+    PARAMS = (("startStep", "initial number of point to skip (initial decimation factor)", "10", "1", "2147483647", int),
+              ("endStep", "maximal or minimal number of points to skip (final decimation factor)", "10", "1", "2147483647", int),
+              ("stepMult", "multiplication factor to compute the new decimation factor for each iteration", "1", "0.0000001", "inf", float))
+
+    def __init__(self, params=None):
+        _HostFilter.__init__(self, params)
+        self.step = float(self.startStep)
+
+    def init(self):
+        self.step = float(self.startStep)
+
+    def inPlaceFilter(self, cloud):
+        i_step = int(self.step)
+        phase = capi.lib.pmgpu_host_rand() % i_step
+        _select_columns(cloud, np.arange(phase, cloud.features.shape[0], i_step))
+        delta = self.startStep * self.stepMult - self.startStep
+        self.step *= self.stepMult
+        if (delta < 0 and self.step < self.endStep) or (delta > 0 and self.step > self.endStep):
+            self.step = float(self.endStep)
+
+
+class MaxPointCountDataPointsFilter(_HostFilter):
+    """MaxPointCount.h:56-66, MaxPointCount.cpp:71-110: maxCount columns drawn with srand(seed); the draw itself
+    (and the reference's swap through an Eigen view, which copies rather than swaps) is pmgpu_host_max_point_count"""
+    className = "MaxPointCountDataPointsFilter"
+    PARAMS = (("seed", "srand seed", "1", "0", "2147483647", int), ("maxCount", "maximum number of points", "1000", "0", "2147483647", int))
+
+    def inPlaceFilter(self, cloud):
+        n = cloud.features.shape[0]
+        if n > 0 and self.maxCount <= n - 1:
+            order = np.empty(n, np.int32)
+            m = capi.lib.pmgpu_host_max_point_count(n, self.seed, self.maxCount, order.ctypes.data)
+            _select_columns(cloud, order[:m])
+
+
+class MaxQuantileOnAxisDataPointsFilter(_HostFilter):
+    """MaxQuantileOnAxis.h:56-62, MaxQuantileOnAxis.cpp:65-103: keep the points below the ratio-quantile of one coordinate"""
+    className = "MaxQuantileOnAxisDataPointsFilter"
+    PARAMS = (("dim", "dimension on which the filter will be applied. x=0, y=1, z=2", "0", "0", "2", int),
+              ("ratio", "maximum quantile authorized. All points beyond that will be filtered.", "0.5", "0.0000001", "0.9999999", float))
+
+    def inPlaceFilter(self, cloud):
+        rows = cloud.features.shape[1]
+        if self.dim >= rows:
+            raise InvalidParameter("MaxQuantileOnAxisDataPointsFilter: Error, filtering on dimension number %d, larger than feature dimensionality %d"
+                                   % (self.dim, rows))
+        values = cloud.features[:, self.dim]
+        if len(values) == 0:
+            return
+        rank = int(np.float32(len(values)) * np.float32(self.ratio))   # `nbPointsIn * ratio` in T, truncated
+        limit = np.partition(values, rank)[rank]
+        _select_columns(cloud, np.nonzero(values < limit)[0])
+
+
+class RemoveNaNDataPointsFilter(_HostFilter):
+    """RemoveNaN.cpp:52-72: drop the points with a NaN among their features"""
+    className = "RemoveNaNDataPointsFilter"
+    PARAMS = ()
+
+    def inPlaceFilter(self, cloud):
+        _select_columns(cloud, np.nonzero(~np.isnan(cloud.features).any(axis=1))[0])
+
+
+class MaxDensityDataPointsFilter(_HostFilter):
+    """MaxDensity.h:56-61, MaxDensity.cpp:60-105: thin out the points whose "densities" descriptor exceeds maxDensity"""
+    className = "MaxDensityDataPointsFilter"
+    PARAMS = (("maxDensity", "Maximum density of points to target. Unit: number of points per m^3.", "10", "0.0000001", "inf", float),)
+
+    def inPlaceFilter(self, cloud):
+        if not cloud.descriptorExists("densities"):
+            raise InvalidField("MaxDensityDataPointsFilter: Error, no densities found in descriptors.")
+        dens = np.ascontiguousarray(cloud.descriptors["densities"][:, 0], np.float32)
+        keep = np.empty(max(len(dens), 1), np.int32)
+        m = capi.lib.pmgpu_host_max_density(dens.ctypes.data, 1, len(dens), float(np.float32(self.maxDensity)), keep.ctypes.data)
+        _select_columns(cloud, keep[:m])
+
+
+class ShadowDataPointsFilter(_HostFilter):
+    """Shadow.h:58-63, Shadow.cpp:42-90: drop the points whose normal is (within eps) perpendicular to the line of sight"""
+    className = "ShadowDataPointsFilter"
+    PARAMS = (("eps", "Small angle (in rad) around which a normal shoudn't be observable", "0.1", "0.0", "3.1416", float),)
+
+    def inPlaceFilter(self, cloud):
+        if not cloud.descriptorExists("normals"):
+            raise InvalidField("ShadowDataPointsFilter, Error: cannot find normals in descriptors")
+        n = cloud.descriptors["normals"]
+        p = cloud.features[:, :-1]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            nn = _float_norm(n)
+            pn = _float_norm(p)
+            nu = np.where(nn[:, None] > 0, n / nn[:, None], n).astype(np.float32)   # Eigen's normalized() leaves a zero vector alone
+            pu = np.where(pn[:, None] > 0, p / pn[:, None], p).astype(np.float32)
+        dot = np.zeros(len(n), np.float32)
+        for a in range(n.shape[1]):
+            dot = (dot + nu[:, a] * pu[:, a]).astype(np.float32)
+        _select_columns(cloud, np.nonzero(np.abs(dot) > np.sin(np.float32(self.eps)))[0])
+
+
+class SimpleSensorNoiseDataPointsFilter(_HostFilter):
+    """SimpleSensorNoise.h:58-82, SimpleSensorNoise.cpp:44-140: descriptor simpleSensorNoise from a per-sensor range model
+    (the reference reads `gain` and never uses it; so does this)"""
+    className = "SimpleSensorNoiseDataPointsFilter"
+    PARAMS = (("sensorType", "Type of the sensor used. Choices: 0=Sick LMS-1xx, 1=Hokuyo URG-04LX, 2=Hokuyo UTM-30LX, 3=Kinect/Xtion",
+               "0", "0", "2147483647", int),
+              ("gain", "If the point cloud is coming from an untrusty source, you can use the gain to augment the uncertainty", "1", "1", "inf", float))
+    LASERS = {0: (0.012, 0.0068, 0.0008), 1: (0.028, 0.0013, 0.0001), 2: (0.018, 0.0006, 0.0015), 4: (0.004, 0.0053, -0.0092)}
+
+    def __init__(self, params=None):
+        _HostFilter.__init__(self, params)
+        if self.sensorType >= 5:
+            raise InvalidParameter("SimpleSensorNoiseDataPointsFilter: Error, sensorType id %d does not exist." % self.sensorType)
+
+    def inPlaceFilter(self, cloud):
+        norm = _float_norm(cloud.features[:, :-1])
+        if self.sensorType == 3:     # Kinect / Xtion
+            noise = ((norm * norm).astype(np.float32) * np.float32(0.5 * 0.00285)).astype(np.float32)
+        else:
+            min_radius, beam_angle, beam_const = (np.float32(v) for v in self.LASERS[self.sensorType])
+            noise = np.maximum(((beam_angle * norm).astype(np.float32) + beam_const).astype(np.float32), min_radius)
+        cloud.descriptors["simpleSensorNoise"] = noise[:, None]
+
+
 class SamplingSurfaceNormalDataPointsFilter(_HostFilter):
     """SamplingSurfaceNormal.h:60-74, SamplingSurfaceNormal.cpp:80-342: kd-split bins of <= knn points,
     one normal per bin, random (0) or one-per-bin (1) subsampling."""
@@ -834,7 +1005,16 @@ DataPointsFilterRegistrar = Registrar(SurfaceNormalDataPointsFilter=SurfaceNorma
                                       SamplingSurfaceNormalDataPointsFilter=SamplingSurfaceNormalDataPointsFilter,
                                       MinDistDataPointsFilter=MinDistDataPointsFilter, MaxDistDataPointsFilter=MaxDistDataPointsFilter,
                                       ObservationDirectionDataPointsFilter=ObservationDirectionDataPointsFilter,
-                                      OrientNormalsDataPointsFilter=OrientNormalsDataPointsFilter)
+                                      OrientNormalsDataPointsFilter=OrientNormalsDataPointsFilter,
+                                      BoundingBoxDataPointsFilter=BoundingBoxDataPointsFilter,
+                                      DistanceLimitDataPointsFilter=DistanceLimitDataPointsFilter,
+                                      FixStepSamplingDataPointsFilter=FixStepSamplingDataPointsFilter,
+                                      MaxPointCountDataPointsFilter=MaxPointCountDataPointsFilter,
+                                      MaxQuantileOnAxisDataPointsFilter=MaxQuantileOnAxisDataPointsFilter,
+                                      RemoveNaNDataPointsFilter=RemoveNaNDataPointsFilter,
+                                      MaxDensityDataPointsFilter=MaxDensityDataPointsFilter,
+                                      ShadowDataPointsFilter=ShadowDataPointsFilter,
+                                      SimpleSensorNoiseDataPointsFilter=SimpleSensorNoiseDataPointsFilter)
 TransformationCheckerRegistrar = Registrar(CounterTransformationChecker=CounterTransformationChecker,
                                            DifferentialTransformationChecker=DifferentialTransformationChecker,
                                            BoundTransformationChecker=BoundTransformationChecker)

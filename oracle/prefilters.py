@@ -132,3 +132,128 @@ def max_dist(features, dim, max_dist_value):
         elif f[i, dim] < np.float32(max_dist_value):
             keep.append(i)
     return np.array(keep, np.int64)
+
+
+# ---- the other per-cloud filters of the reference's golden chain files (plain loops, one point at a time) ----
+#   BoundingBox.cpp:71-103, DistanceLimit.cpp:66-127, FixStepSampling.cpp:76-110, MaxPointCount.cpp:71-110,
+#   MaxQuantileOnAxis.cpp:65-103, RemoveNaN.cpp:52-72, MaxDensity.cpp:60-105, Shadow.cpp:62-90,
+#   SimpleSensorNoise.cpp:75-140.  The rand()-driven ones are pinned through libc like random_sampling above.
+def _f32(x):
+    return np.float32(x)
+
+
+def _norm3(v):
+    acc = _f32(0)
+    for a in v:
+        acc = _f32(acc + _f32(a) * _f32(a))
+    return _f32(np.sqrt(acc))
+
+
+def bounding_box(features, lo, hi, remove_inside):
+    keep = []
+    for i, p in enumerate(np.asarray(features, np.float32)):
+        inside = all(p[a] > _f32(lo[a]) and p[a] < _f32(hi[a]) for a in range(len(p) - 1))
+        if inside != bool(remove_inside):
+            keep.append(i)
+    return np.array(keep, np.int64)
+
+
+def distance_limit(features, dim, dist, remove_inside):
+    keep = []
+    for i, p in enumerate(np.asarray(features, np.float32)):
+        v, lim = (_norm3(p[:-1]), _f32(abs(dist))) if dim == -1 else (p[dim], _f32(dist))
+        if (v > lim) if remove_inside else (v < lim):
+            keep.append(i)
+    return np.array(keep, np.int64)
+
+
+def fix_step(n, step):
+    """one call: phase = rand() % int(step), then every int(step)-th column"""
+    i_step = int(step)
+    phase = _libc.rand() % i_step
+    return np.arange(phase, n, i_step)
+
+
+def fix_step_next(step, start, end, mult):
+    delta = start * mult - start
+    step *= mult
+    if delta < 0 and step < end:
+        step = end
+    if delta > 0 and step > end:
+        step = end
+    return step
+
+
+def max_point_count(n, seed, max_count):
+    """the columns the reference ends up with: column j takes column idx (the Eigen-view 'swap' never writes idx back)"""
+    N = n - 1
+    if not max_count <= N:
+        return np.arange(n)
+    srand(seed)
+    cur = list(range(n))
+    for j in range(max_count):
+        r = np.float32(np.float32(_libc.rand()) / np.float32(RAND_MAX))
+        idx = j + int(np.float32(N - j) * r)
+        view_j = j                      # `const auto feat = col(j)`: a view of column j, not its value
+        cur[j] = cur[idx]
+        cur[idx] = cur[view_j]          # reads the NEW column j: no-op
+    return np.array(cur[:max_count], np.int64)
+
+
+def max_quantile_on_axis(features, dim, ratio):
+    v = np.asarray(features, np.float32)[:, dim]
+    rank = int(np.float32(len(v)) * np.float32(ratio))
+    limit = np.sort(v)[rank]
+    return np.array([i for i in range(len(v)) if v[i] < limit], np.int64)
+
+
+def remove_nan(features):
+    return np.array([i for i, p in enumerate(np.asarray(features, np.float32)) if not any(x != x for x in p)], np.int64)
+
+
+def max_density(densities, max_density_):
+    d = np.asarray(densities, np.float32)
+    last = d.max()
+    saturated = int((d == last).sum())
+    keep = []
+    for i in range(len(d)):
+        if d[i] > _f32(max_density_):
+            r = np.float32(_libc.rand()) / np.float32(RAND_MAX)
+            accept = _f32(_f32(max_density_) / d[i])
+            if d[i] == last:
+                accept = _f32(accept * _f32(1 - saturated // len(d)))
+            if r < accept:
+                keep.append(i)
+        else:
+            keep.append(i)
+    return np.array(keep, np.int64)
+
+
+def shadow(features, normals, eps):
+    lim = np.sin(np.float32(eps))
+    keep = []
+    for i, (p, nrm) in enumerate(zip(np.asarray(features, np.float32), np.asarray(normals, np.float32))):
+        nn, pn = _norm3(nrm), _norm3(p[:-1])
+        nu = [_f32(x / nn) if nn > 0 else x for x in nrm]
+        pu = [_f32(x / pn) if pn > 0 else x for x in p[:-1]]
+        dot = _f32(0)
+        for a, b in zip(nu, pu):
+            dot = _f32(dot + _f32(a * b))
+        if abs(dot) > lim:
+            keep.append(i)
+    return np.array(keep, np.int64)
+
+
+_LASERS = {0: (0.012, 0.0068, 0.0008), 1: (0.028, 0.0013, 0.0001), 2: (0.018, 0.0006, 0.0015), 4: (0.004, 0.0053, -0.0092)}
+
+
+def simple_sensor_noise(features, sensor_type):
+    out = []
+    for p in np.asarray(features, np.float32):
+        norm = _norm3(p[:-1])
+        if sensor_type == 3:
+            out.append(_f32(_f32(norm * norm) * _f32(0.5 * 0.00285)))
+        else:
+            mn, ang, cst = (_f32(v) for v in _LASERS[sensor_type])
+            out.append(max(_f32(_f32(ang * norm) + cst), mn))
+    return np.array(out, np.float32)

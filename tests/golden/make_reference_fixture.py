@@ -55,17 +55,14 @@ out = dict(
     validT3d=np.array([[0.982304, 0.166685, -0.0854066, 0.0446816], [-0.150189, 0.973488, 0.172524, 0.191998],
                        [0.111899, -0.156644, 0.981296, -0.0356313], [0, 0, 0, 1]]),
 )
-for name in ("defaultIdentityDataPointsFilter", "defaultPointToPlaneMinDistDataPointsFilter", "defaultPointToPointMinDistDataPointsFilter",
-             "defaultPointToPlaneWithCovErrorMinimizer", "defaultPointToPointWithCovErrorMinimizer", "defaultMaxDistDataPointsFilter",
-             "SamplingSurfaceNormalDataPointsFilter1", "SamplingSurfaceNormalDataPointsFilter2", "SamplingSurfaceNormalDataPointsFilter3",
-             "defaultRobustOutlierFilter", "defaultSimilarityPointToPointMinDistDataPointsFilter", "force4DOFForPointToPlaneMinimizer"):
+ICP_DATA = os.path.join(DATA, "icp_data")
+# every chain file of utest icpTest (utest/utest.cpp:81-160) with its golden transform
+for name in sorted(f[:-5] for f in os.listdir(ICP_DATA) if f.endswith(".yaml")):
     out["golden_" + name] = load_trans(name)
-# the chain configurations themselves (YAML text = data), for the chains whose modules are all built
-for name in ("defaultIdentityDataPointsFilter", "defaultPointToPlaneMinDistDataPointsFilter", "defaultPointToPointMinDistDataPointsFilter",
-             "defaultMaxDistDataPointsFilter", "SamplingSurfaceNormalDataPointsFilter1", "SamplingSurfaceNormalDataPointsFilter2",
-             "SamplingSurfaceNormalDataPointsFilter3", "defaultRobustOutlierFilter", "defaultSimilarityPointToPointMinDistDataPointsFilter",
-             "force4DOFForPointToPlaneMinimizer"):
-    out["yaml_" + name] = np.array(open(os.path.join(DATA, "icp_data", name + ".yaml")).read())
+    out["yaml_" + name] = np.array(open(os.path.join(ICP_DATA, name + ".yaml")).read())
+for name in ("defaultPointToPlaneWithCovErrorMinimizer", "defaultPointToPointWithCovErrorMinimizer"):
+    if os.path.exists(os.path.join(ICP_DATA, name + ".ref_trans")):
+        out["golden_" + name] = load_trans(name)
 out["yaml_default"] = np.array(open(os.path.join(DATA, "default.yaml")).read())  # BASELINE config 1
 path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_fixture.npz")
 np.savez_compressed(path, **out)

@@ -315,9 +315,56 @@ static int run_icp(int argc, char** argv) {
     return 0;
 }
 
+// test_host filters <features.f32> <n> <normals.f32> <densities.f32> <out.bin>
+// applies each of the per-cloud host filters of the golden chain files to a fresh copy of the cloud
+// (srand(1) before each) and writes, per filter: int32 count, int32 descriptor rows, features (4 x count),
+// descriptors (rows x count) — compared bit for bit with the Python mirror (tests/test_prefilters.py).
+static int run_filters(int argc, char** argv) {
+    if (argc < 7) return 2;
+    const int n = std::atoi(argv[3]);
+    DP cloud;
+    cloud.features = PM::Matrix(4, n);
+    PM::Matrix normals(3, n), densities(1, n);
+    if (!read_f32(argv[2], 4 * (size_t)n, cloud.features.data()) || !read_f32(argv[4], 3 * (size_t)n, normals.data()) ||
+        !read_f32(argv[5], (size_t)n, densities.data()))
+        return 2;
+    cloud.addDescriptor("normals", normals);
+    cloud.addDescriptor("densities", densities);
+    const std::vector<std::pair<std::string, PM::Parameters>> list = {
+        {"BoundingBoxDataPointsFilter", {{"xMin", "0.2"}}},
+        {"BoundingBoxDataPointsFilter", {{"xMin", "-3"}, {"xMax", "2"}, {"yMin", "-1"}, {"yMax", "4"}, {"zMin", "-2"}, {"zMax", "2"}, {"removeInside", "0"}}},
+        {"DistanceLimitDataPointsFilter", {{"dist", "3"}, {"removeInside", "0"}}},
+        {"DistanceLimitDataPointsFilter", {{"dim", "1"}, {"dist", "-0.5"}}},
+        {"FixStepSamplingDataPointsFilter", {{"startStep", "7"}, {"endStep", "3"}, {"stepMult", "0.7"}}},
+        {"MaxPointCountDataPointsFilter", {{"maxCount", "500"}}},
+        {"MaxPointCountDataPointsFilter", {{"maxCount", "100000"}, {"seed", "5"}}},
+        {"MaxQuantileOnAxisDataPointsFilter", {{"ratio", "0.72"}}},
+        {"MaxQuantileOnAxisDataPointsFilter", {{"dim", "2"}, {"ratio", "0.333"}}},
+        {"RemoveNaNDataPointsFilter", {}},
+        {"MaxDensityDataPointsFilter", {{"maxDensity", "0.3"}}},
+        {"ShadowDataPointsFilter", {{"eps", "0.3"}}},
+        {"SimpleSensorNoiseDataPointsFilter", {{"gain", "2"}}},
+        {"SimpleSensorNoiseDataPointsFilter", {{"sensorType", "3"}}},
+        {"SimpleSensorNoiseDataPointsFilter", {{"sensorType", "4"}}},
+    };
+    std::ofstream out(argv[6], std::ios::binary);
+    for (const auto& item : list) {
+        pmgpu_host_srand(1);
+        auto f = PM::get().DataPointsFilterRegistrar.create(item.first, item.second);
+        DP c = f->filter(cloud);
+        if (item.first == "FixStepSamplingDataPointsFilter") c = f->filter(c);  // second call: the step has moved on
+        const int32_t head[2] = {(int32_t)c.features.cols(), (int32_t)c.descriptors.rows()};
+        out.write(reinterpret_cast<const char*>(head), sizeof(head));
+        out.write(reinterpret_cast<const char*>(c.features.data()), sizeof(float) * 4 * (size_t)head[0]);
+        out.write(reinterpret_cast<const char*>(c.descriptors.data()), sizeof(float) * (size_t)head[1] * (size_t)head[0]);
+    }
+    return out.good() ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
     if (argc >= 2 && std::string(argv[1]) == "cpu") return run_cpu();
     if (argc >= 2 && std::string(argv[1]) == "icp") return run_icp(argc, argv);
+    if (argc >= 2 && std::string(argv[1]) == "filters") return run_filters(argc, argv);
     std::fprintf(stderr, "usage: test_host cpu | icp <config.yaml|default> <reading.f32> <nq> <reference.f32> <nr> [normals.f32]\n");
     return 2;
 }

@@ -144,7 +144,8 @@ def test_cpp_icp_sequence_matches_plain_icp(host_bin, tmp_path, oracle, synth):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["defaultPointToPlaneMinDistDataPointsFilter", "defaultRobustOutlierFilter", "force4DOFForPointToPlaneMinimizer",
-                                  "defaultSimilarityPointToPointMinDistDataPointsFilter"])
+                                  "defaultSimilarityPointToPointMinDistDataPointsFilter", "defaultMaxDensityDataPointsFilter",
+                                  "defaultShadowDataPointsFilter", "defaultMaxPointCountDataPointsFilter", "defaultMaxQuantileOnAxisDataPointsFilter"])
 def test_cpp_runs_reference_yaml_chain_to_golden(host_bin, tmp_path, name):
     """the reference's own chain files through the C++ mirror (`icp.loadFromYaml(ifs); icp(data, ref)`, utest/utest.cpp:81-160):
     host pre-filters, GPU loop (fused, or staged with the host Bound checker for the force4DOF chain), 3 % criterion"""
@@ -174,3 +175,54 @@ def test_cpp_trailing_normals_filter_matches_python(host_bin, tmp_path, synth):
     icp.ctx.close()
     assert res["iterations"] == icp.iterationCount == 10 and res["fused"] == 1
     assert_transform_close(res["T"], Tp, 1e-6, 1e-6)
+
+
+def test_cpp_host_filters_match_python_mirror(host_bin, tmp_path):
+    """the nine per-cloud host filters of the golden chain files: C++ mirror == Python mirror, bit for bit"""
+    from libpointmatcher_b200 import capi, pm
+    rng = np.random.default_rng(3)
+    n = 3000
+    f = np.c_[rng.normal(0, 2.5, (n, 3)), np.ones(n)].astype(np.float32)
+    f[3, 1] = f[77, 1] = np.nan      # not on an axis MaxQuantileOnAxis selects on: NaN has no rank
+    normals = rng.normal(0, 1, (n, 3)).astype(np.float32)
+    normals[::97] = 0
+    dens = rng.uniform(0, 1, (n, 1)).astype(np.float32)
+    dens[::50] = dens.max()
+    for name, arr in (("f", f), ("n", normals), ("d", dens)):
+        arr.tofile(tmp_path / (name + ".f32"))
+    out = tmp_path / "out.bin"
+    subprocess.check_call([host_bin, "filters", str(tmp_path / "f.f32"), str(n), str(tmp_path / "n.f32"), str(tmp_path / "d.f32"), str(out)])
+    raw = np.fromfile(out, np.uint8)
+    configs = [("BoundingBoxDataPointsFilter", {"xMin": "0.2"}),
+               ("BoundingBoxDataPointsFilter", {"xMin": "-3", "xMax": "2", "yMin": "-1", "yMax": "4", "zMin": "-2", "zMax": "2", "removeInside": "0"}),
+               ("DistanceLimitDataPointsFilter", {"dist": "3", "removeInside": "0"}),
+               ("DistanceLimitDataPointsFilter", {"dim": "1", "dist": "-0.5"}),
+               ("FixStepSamplingDataPointsFilter", {"startStep": "7", "endStep": "3", "stepMult": "0.7"}),
+               ("MaxPointCountDataPointsFilter", {"maxCount": "500"}),
+               ("MaxPointCountDataPointsFilter", {"maxCount": "100000", "seed": "5"}),
+               ("MaxQuantileOnAxisDataPointsFilter", {"ratio": "0.72"}),
+               ("MaxQuantileOnAxisDataPointsFilter", {"dim": "2", "ratio": "0.333"}),
+               ("RemoveNaNDataPointsFilter", {}),
+               ("MaxDensityDataPointsFilter", {"maxDensity": "0.3"}),
+               ("ShadowDataPointsFilter", {"eps": "0.3"}),
+               ("SimpleSensorNoiseDataPointsFilter", {"gain": "2"}),
+               ("SimpleSensorNoiseDataPointsFilter", {"sensorType": "3"}),
+               ("SimpleSensorNoiseDataPointsFilter", {"sensorType": "4"})]
+    pos = 0
+    for name, params in configs:
+        capi.lib.pmgpu_host_srand(1)
+        flt = pm.DataPointsFilterRegistrar.create(name, params)
+        c = flt.filter(pm.DataPoints(f, {"normals": normals, "densities": dens}))
+        if name.startswith("FixStep"):
+            c = flt.filter(c)
+        count, rows = raw[pos:pos + 8].view(np.int32)
+        pos += 8
+        feat = raw[pos:pos + 16 * count].view(np.float32).reshape(count, 4)
+        pos += 16 * count
+        desc = raw[pos:pos + 4 * rows * count].view(np.float32).reshape(count, rows)
+        pos += 4 * rows * count
+        mine = np.concatenate(list(c.descriptors.values()), axis=1)
+        assert count == len(c.features) and rows == mine.shape[1], name
+        assert feat.tobytes() == c.features.tobytes(), name
+        assert desc.tobytes() == np.ascontiguousarray(mine).tobytes(), name
+    assert pos == len(raw)

@@ -208,3 +208,127 @@ def test_loaders_read_the_reference_data_layouts(pm, tmp_path):
         assert (pm.DataPoints.load(ref_dir + "/cloud.00000.vtk").features[:, :3] == fx["cloud0"]).all()
         car_full = pm.DataPoints.load(ref_dir + "/car_cloud400.csv")
         assert (car_full.features[:, :3] == fx["car400"][:, :3]).all() and (car_full.descriptors["normals"] == fx["car400"][:, 3:6]).all()
+
+
+# ---- the other per-cloud host filters of the reference's golden chain files ------------------------
+def chain_cloud(n=3000, seed=3):
+    rng = np.random.default_rng(seed)
+    f = np.c_[rng.normal(0, 2.5, (n, 3)), np.ones(n)].astype(np.float32)
+    normals = rng.normal(0, 1, (n, 3)).astype(np.float32)
+    normals[::97] = 0                                  # zero normals: normalized() leaves them alone
+    dens = rng.uniform(0, 1, (n, 1)).astype(np.float32)
+    dens[::50] = dens.max()                            # saturated densities
+    return f, normals, dens
+
+
+def _run(pm, name, params, f, normals, dens):
+    cloud = pm.DataPoints(f, {"normals": normals, "densities": dens, "index": np.arange(len(f), dtype=np.float32)[:, None]})
+    return pm.DataPointsFilterRegistrar.create(name, params).filter(cloud)
+
+
+@pytest.mark.parametrize("params,lo,hi,inside", [({"xMin": "0.2"}, (0.2, -1, -1), (1, 1, 1), True),
+                                                  ({"xMin": "-3", "xMax": "2", "yMin": "-1", "yMax": "4", "zMin": "-2", "zMax": "2", "removeInside": "0"},
+                                                   (-3, -1, -2), (2, 4, 2), False)])
+def test_bounding_box_filter(pm, params, lo, hi, inside):
+    f, nrm, dens = chain_cloud()
+    out = _run(pm, "BoundingBoxDataPointsFilter", params, f, nrm, dens)
+    keep = orc.bounding_box(f, lo, hi, inside)
+    assert 0 < len(keep) < len(f)
+    assert (out.descriptors["index"][:, 0] == keep).all() and (out.features == f[keep]).all() and (out.descriptors["normals"] == nrm[keep]).all()
+
+
+@pytest.mark.parametrize("dim,dist,inside", [(-1, 3.0, 0), (-1, -3.0, 1), (1, -0.5, 1), (2, 0.7, 0)])
+def test_distance_limit_filter(pm, dim, dist, inside):
+    f, nrm, dens = chain_cloud()
+    out = _run(pm, "DistanceLimitDataPointsFilter", {"dim": str(dim), "dist": repr(dist), "removeInside": str(inside)}, f, nrm, dens)
+    keep = orc.distance_limit(f, dim, dist, inside)
+    assert 0 < len(keep) < len(f) and (out.descriptors["index"][:, 0] == keep).all()
+    with pytest.raises(pm.InvalidParameter):
+        pm.DistanceLimitDataPointsFilter({"dim": "2"}).filter(pm.DataPoints(np.ones((5, 3), np.float32)))
+
+
+def test_fix_step_sampling_filter_walks_its_step(pm, capi):
+    f, nrm, dens = chain_cloud()
+    flt = pm.FixStepSamplingDataPointsFilter({"startStep": "7", "endStep": "3", "stepMult": "0.7"})
+    capi.lib.pmgpu_host_srand(11)
+    got = []
+    for _ in range(5):
+        got.append(flt.filter(pm.DataPoints(f, {"index": np.arange(len(f), dtype=np.float32)[:, None]})).descriptors["index"][:, 0])
+    orc.srand(11)
+    step = 7.0
+    for g in got:
+        assert (g == orc.fix_step(len(f), step)).all()
+        step = orc.fix_step_next(step, 7, 3, 0.7)
+    assert step == 3.0 and len(got[0]) in (428, 429) and len(got[-1]) == 1000
+    flt.init()
+    assert flt.step == 7.0
+
+
+@pytest.mark.parametrize("count,seed", [(500, 1), (1, 9), (2999, 4), (3000, 1), (100000, 5)])
+def test_max_point_count_filter(pm, count, seed):
+    f, nrm, dens = chain_cloud()
+    out = _run(pm, "MaxPointCountDataPointsFilter", {"maxCount": str(count), "seed": str(seed)}, f, nrm, dens)
+    keep = orc.max_point_count(len(f), seed, count)
+    assert len(keep) == min(count, len(f))
+    assert (out.descriptors["index"][:, 0] == keep).all() and (out.features == f[keep]).all()
+
+
+@pytest.mark.parametrize("dim,ratio", [(0, 0.72), (2, 0.333), (1, 0.9999999), (0, 0.0000001)])
+def test_max_quantile_on_axis_filter(pm, dim, ratio):
+    f, nrm, dens = chain_cloud()
+    f[5:25, dim] = f[100, dim]                         # ties at one value
+    out = _run(pm, "MaxQuantileOnAxisDataPointsFilter", {"dim": str(dim), "ratio": repr(ratio)}, f, nrm, dens)
+    keep = orc.max_quantile_on_axis(f, dim, ratio)
+    assert (out.descriptors["index"][:, 0] == keep).all()
+    assert len(keep) <= int(np.float32(len(f)) * np.float32(ratio))
+
+
+def test_remove_nan_filter(pm):
+    f, nrm, dens = chain_cloud()
+    f[3, 0] = f[77, 2] = f[2999, 1] = np.nan
+    out = _run(pm, "RemoveNaNDataPointsFilter", {}, f, nrm, dens)
+    keep = orc.remove_nan(f)
+    assert len(keep) == len(f) - 3 and (out.descriptors["index"][:, 0] == keep).all()
+
+
+@pytest.mark.parametrize("limit,seed", [(0.3, 1), (0.05, 8), (2.0, 1)])
+def test_max_density_filter(pm, capi, limit, seed):
+    f, nrm, dens = chain_cloud()
+    capi.lib.pmgpu_host_srand(seed)
+    out = _run(pm, "MaxDensityDataPointsFilter", {"maxDensity": repr(limit)}, f, nrm, dens)
+    orc.srand(seed)
+    keep = orc.max_density(dens[:, 0], limit)
+    assert (out.descriptors["index"][:, 0] == keep).all()
+    assert (len(keep) == len(f)) == (limit > 1)
+    with pytest.raises(pm.InvalidField):
+        pm.MaxDensityDataPointsFilter().filter(pm.DataPoints(f))
+
+
+@pytest.mark.parametrize("eps", [0.00001, 0.3, 1.2])
+def test_shadow_filter(pm, eps):
+    f, nrm, dens = chain_cloud()
+    out = _run(pm, "ShadowDataPointsFilter", {"eps": repr(eps)}, f, nrm, dens)
+    keep = orc.shadow(f, nrm, eps)
+    assert 0 < len(keep) < len(f) and (out.descriptors["index"][:, 0] == keep).all()
+    with pytest.raises(pm.InvalidField):
+        pm.ShadowDataPointsFilter().filter(pm.DataPoints(f))
+
+
+@pytest.mark.parametrize("sensor", [0, 1, 2, 3, 4])
+def test_simple_sensor_noise_filter(pm, sensor):
+    f, nrm, dens = chain_cloud(500)
+    out = _run(pm, "SimpleSensorNoiseDataPointsFilter", {"sensorType": str(sensor), "gain": "2"}, f, nrm, dens)
+    assert (out.descriptors["simpleSensorNoise"][:, 0] == orc.simple_sensor_noise(f, sensor)).all() and len(out.features) == 500
+    with pytest.raises(pm.InvalidParameter):
+        pm.SimpleSensorNoiseDataPointsFilter({"sensorType": "5"})
+
+
+def test_all_21_reference_chain_files_load(pm):
+    """every chain file of utest icpTest parses into modules registered under the reference's names"""
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "reference_fixture.npz"))
+    names = [k for k in fx.files if k.startswith("yaml_") and k != "yaml_default"]
+    assert len(names) == 21
+    for k in names:
+        icp = pm.ICP()
+        icp.loadFromYaml(str(fx[k]).replace("PerformanceInspector", "NullInspector"))
+        assert icp.matcher is not None and icp.errorMinimizer is not None and len(icp.transformationCheckers) >= 1

@@ -148,8 +148,42 @@ def test_oracle_similarity_chain_reproduces_golden(oracle, fx):
     assert rel_err(r["T"], fx["golden_defaultSimilarityPointToPointMinDistDataPointsFilter"], data) < 0.03
 
 
+@pytest.mark.parametrize("name", ["defaultBoundingBoxDataPointsFilter", "defaultDistanceLimitDataPointsFilter", "defaultMaxQuantileOnAxisDataPointsFilter",
+                                  "defaultRemoveNaNDataPointsFilter", "defaultMaxPointCountDataPointsFilter"])
+def test_oracle_chain_with_more_prefilters_reproduces_golden(oracle, fx, name):
+    """oracle restatement of the reading filter (oracle/prefilters.py, parameters of the YAML file) + bin sampling of the
+    reference + oracle ICP (knn 1, TrimmedDist 0.75, PointToPlane) against the reference's golden transform"""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import prefilters as pre
+    ref, data = homog(fx["cloud0"]), homog(fx["cloud1"])
+    keep = {"defaultBoundingBoxDataPointsFilter": lambda: pre.bounding_box(data, (0.2, -1, -1), (1, 1, 1), True),
+            "defaultDistanceLimitDataPointsFilter": lambda: pre.distance_limit(data, -1, 200, 0),
+            "defaultMaxQuantileOnAxisDataPointsFilter": lambda: pre.max_quantile_on_axis(data, 0, 0.72),
+            "defaultRemoveNaNDataPointsFilter": lambda: pre.remove_nan(data),
+            "defaultMaxPointCountDataPointsFilter": lambda: pre.max_point_count(len(data), 1, 500)}[name]()
+    ref_f, normals, _, _, _ = pre.sampling_surface_normal_method1(ref, 10)
+    r = oracle.icp(np.ascontiguousarray(data[keep]), np.ascontiguousarray(ref_f), ref_normals=np.ascontiguousarray(normals),
+                   filters=[(oracle.FILTER_TRIMMEDDIST, 0.75)], minimizer=1, max_iterations=40, differential=(0.001, 0.01, 4), nthreads=4)
+    assert rel_err(r["T"], fx["golden_" + name], data) < 0.03
+
+
+# the per-cloud host filters of the remaining chain files (BoundingBox, DistanceLimit, FixStepSampling, MaxDensity, MaxPointCount,
+# MaxQuantileOnAxis, RemoveNaN, Shadow, SimpleSensorNoise, ObservationDirection, OrientNormals): all 21 files of utest icpTest
+MORE_CHAINS = ["defaultBoundingBoxDataPointsFilter", "defaultDistanceLimitDataPointsFilter", "defaultFixStepSamplingDataPointsFilter",
+               "defaultMaxDensityDataPointsFilter", "defaultMaxPointCountDataPointsFilter", "defaultMaxQuantileOnAxisDataPointsFilter",
+               "defaultObservationDirectionDataPointsFilter", "defaultOrientNormalsDataPointsFilter", "defaultRemoveNaNDataPointsFilter",
+               "defaultShadowDataPointsFilter", "defaultSimpleSensorNoiseDataPointsFilter"]
+
+
+def test_fixture_holds_all_21_chain_files(fx):
+    names = sorted(k[5:] for k in fx.files if k.startswith("yaml_") and k != "yaml_default")
+    assert len(names) == 21 and all("golden_" + n in fx.files for n in names)
+    assert sorted(YAML_CHAINS + MORE_CHAINS + ["defaultSimilarityPointToPointMinDistDataPointsFilter", "force4DOFForPointToPlaneMinimizer"]) == names
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", YAML_CHAINS + ["defaultSimilarityPointToPointMinDistDataPointsFilter", "force4DOFForPointToPlaneMinimizer"])
+@pytest.mark.parametrize("name", YAML_CHAINS + MORE_CHAINS + ["defaultSimilarityPointToPointMinDistDataPointsFilter", "force4DOFForPointToPlaneMinimizer"])
 def test_gpu_runs_reference_yaml_chain_to_golden(fx, name):
     from libpointmatcher_b200 import capi, pm
     ref, data = homog(fx["cloud0"]), homog(fx["cloud1"])
