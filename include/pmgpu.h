@@ -91,6 +91,11 @@ enum pmgpu_minimizer {
  * 266-281) — the unknowns are the rotation about z and the translation: the 4x4 sub-system
  * (cross_z, n) of the same sums, T = AngleAxis(x0, unitZ) + translation. */
 #define PMGPU_MIN_FORCE4DOF 0x100
+/* or-ed into PMGPU_MIN_P2PLANE: force2D on 3-D clouds (PointToPlane.cpp:177-186, 294-310) — the unknowns are
+ * the rotation about z and the x/y translation: the 3x3 sub-system (cross_z, nx, ny) with the residual
+ * n . (p - q) taken over x and y only; T = identity with Rotation2D(x0) and (x1, x2) in its xy block.
+ * Not combinable with force4DOF (the reference throws, PointToPlane.cpp:59-64) nor, here, with the covariance. */
+#define PMGPU_MIN_FORCE2D 0x200
 
 /* SurfaceNormalDataPointsFilter keep* flags (DataPointsFilters/SurfaceNormal.h:65-80) */
 enum pmgpu_normals_flags {

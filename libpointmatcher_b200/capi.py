@@ -21,6 +21,7 @@ LIB_PATH = os.path.join(_HERE, "libpmgpu%s.so" % ("_" + os.environ["PMGPU_VARIAN
 FILTER_MAXDIST, FILTER_MEDIANDIST, FILTER_TRIMMEDDIST, FILTER_ROBUST, FILTER_SURFACENORMAL = 0, 1, 2, 3, 4
 MIN_P2POINT, MIN_P2PLANE, MIN_P2POINT_COV, MIN_P2PLANE_COV, MIN_P2POINT_SIM = 0, 1, 2, 3, 4
 MIN_FORCE4DOF = 0x100  # or-ed into a point-to-plane minimiser id
+MIN_FORCE2D = 0x200    # likewise (PointToPlaneErrorMinimizer only)
 NORMALS_SORT_EIGEN, NORMALS_SMOOTH = 1, 2
 
 OK = 0

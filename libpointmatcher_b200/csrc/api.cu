@@ -191,10 +191,12 @@ int check_params(pmgpu_ctx* ctx, const pmgpu_icp_params* p) {
     if (p->knn < 1) return fail(ctx, PMGPU_ERR_BAD_ARG, "knn must be >= 1");
     if (p->knn > ctx->nr) return fail(ctx, PMGPU_ERR_KNN_TOO_LARGE, status_message(PMGPU_ERR_KNN_TOO_LARGE));
     if (p->nfilters < 0 || p->nfilters > PM_MAX_FILTERS) return fail(ctx, PMGPU_ERR_BAD_ARG, "at most 8 outlier filters");
-    if (p->minimizer < 0 || (p->minimizer & 0xff) > PMGPU_MIN_P2POINT_SIM || (p->minimizer & ~0x1ff))
+    if (p->minimizer < 0 || (p->minimizer & 0xff) > PMGPU_MIN_P2POINT_SIM || (p->minimizer & ~0x3ff))
         return fail(ctx, PMGPU_ERR_BAD_ARG, "unknown error minimizer");
     if ((p->minimizer & PMGPU_MIN_FORCE4DOF) && !((p->minimizer & 0xff) == PMGPU_MIN_P2PLANE || (p->minimizer & 0xff) == PMGPU_MIN_P2PLANE_COV))
         return fail(ctx, PMGPU_ERR_BAD_ARG, "force4DOF is a point-to-plane parameter");
+    if ((p->minimizer & PMGPU_MIN_FORCE2D) && p->minimizer != (PMGPU_MIN_P2PLANE | PMGPU_MIN_FORCE2D))
+        return fail(ctx, PMGPU_ERR_BAD_ARG, "force2D goes with PointToPlaneErrorMinimizer alone (no force4DOF, no covariance)");
     if (p->use_differential && (p->smooth_length < 0 || p->smooth_length >= PM_MAX_HISTORY))
         return fail(ctx, PMGPU_ERR_UNSUPPORTED, "DifferentialTransformationChecker: smoothLength must be < 64 on the GPU path");
     if (p->max_iterations < 0) return fail(ctx, PMGPU_ERR_BAD_ARG, "maxIterationCount must be >= 0");
@@ -589,9 +591,11 @@ int pmgpu_minimize(pmgpu_ctx* ctx, int minimizer, float sensor_std_dev, float* T
     if (!ctx) return PMGPU_ERR_BAD_ARG;
     PM_TRY(use_device(ctx));
     if (!ctx->have_matches) return fail(ctx, PMGPU_ERR_NO_MATCHES, status_message(PMGPU_ERR_NO_MATCHES));
-    if (minimizer < 0 || (minimizer & 0xff) > PMGPU_MIN_P2POINT_SIM || (minimizer & ~0x1ff)) return fail(ctx, PMGPU_ERR_BAD_ARG, "unknown error minimizer");
+    if (minimizer < 0 || (minimizer & 0xff) > PMGPU_MIN_P2POINT_SIM || (minimizer & ~0x3ff)) return fail(ctx, PMGPU_ERR_BAD_ARG, "unknown error minimizer");
     if ((minimizer & PMGPU_MIN_FORCE4DOF) && (minimizer & 0xff) != PMGPU_MIN_P2PLANE && (minimizer & 0xff) != PMGPU_MIN_P2PLANE_COV)
         return fail(ctx, PMGPU_ERR_BAD_ARG, "force4DOF is a point-to-plane parameter");
+    if ((minimizer & PMGPU_MIN_FORCE2D) && minimizer != (PMGPU_MIN_P2PLANE | PMGPU_MIN_FORCE2D))
+        return fail(ctx, PMGPU_ERR_BAD_ARG, "force2D goes with PointToPlaneErrorMinimizer alone (no force4DOF, no covariance)");
     if (!ctx->have_weights) PM_TRY(launch_weights(ctx, SelectSpec(), false, false));  // empty chain
     ctx->stage_begin(2);
     PM_TRY(launch_minimize(ctx, minimizer, false, false, nullptr));

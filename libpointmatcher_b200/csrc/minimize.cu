@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(ACC_BLOCK, MODE == 1 ? 2 : 3) accumulate_kerne
             // dot(deltas, normals) accumulated from zero, PointToPlane.cpp:233-240
             float dot = fmul(fsub(p.x, q.x), n.x);
             dot = fadd(dot, fmul(fsub(p.y, q.y), n.y));
-            dot = fadd(dot, fmul(fsub(p.z, q.z), n.z));
+            if (!(ck.minimizer & PMGPU_MIN_FORCE2D)) dot = fadd(dot, fmul(fsub(p.z, q.z), n.z));  // force2D: clouds are [x, y, 1]
             int c = 0;
 #pragma unroll
             for (int a = 0; a < 6; ++a)
@@ -357,7 +357,22 @@ __device__ void finalize_body(const double* partials, int nblocks, double* sums,
         expand_sym6(sums, A);
         for (int a = 0; a < 6; ++a) b[a] = -sums[21 + a];
         float xf[6];
-        if (ck.minimizer & PMGPU_MIN_FORCE4DOF) {
+        if (ck.minimizer & PMGPU_MIN_FORCE2D) {
+            // rows / columns (cross_z, nx, ny): the pseudo cross product of ErrorMinimizer.cpp:308-313 is cross_z, and the
+            // accumulate kernel left z out of the residual (PointToPlane.cpp:177-186, 294-310)
+            double A3[9], b3[3], x3[3];
+            for (int c = 0; c < 3; ++c) {
+                b3[c] = b[2 + c];
+                for (int r = 0; r < 3; ++r) A3[r + 3 * c] = A[(2 + r) + 6 * (2 + c)];
+            }
+            solve_psd(A3, b3, x3, 3);
+            const float ang = (float)x3[0];
+            const float sn = sinf(ang), cs = cosf(ang);  // Eigen::Rotation2D<float>
+            mat4_identity(dT);
+            dT.m[0] = cs; dT.m[4] = -sn;
+            dT.m[1] = sn; dT.m[5] = cs;
+            dT.m[12] = (float)x3[1]; dT.m[13] = (float)x3[2];
+        } else if (ck.minimizer & PMGPU_MIN_FORCE4DOF) {
             // rows / columns (cross_z, nx, ny, nz) of the same normal equations (PointToPlane.cpp:203-214)
             double A4[16], b4[4], x4[4];
             for (int c = 0; c < 4; ++c) {
@@ -371,7 +386,7 @@ __device__ void finalize_body(const double* partials, int nblocks, double* sums,
             solve_psd6(A, b, x);
             for (int a = 0; a < 6; ++a) xf[a] = (float)x[a];
         }
-        angle_axis_to_mat4(xf, dT);
+        if (!(ck.minimizer & PMGPU_MIN_FORCE2D)) angle_axis_to_mat4(xf, dT);
     } else {
         const double W = sums[0];
         state->stats[1] = (float)W / denom;

@@ -889,7 +889,8 @@ protected:
         : GpuErrorMinimizer(className, paramsDoc, params, kind) {
         const bool force2D = Parametrizable::get<bool>("force2D"), force4DOF = Parametrizable::get<bool>("force4DOF");
         if (force2D && force4DOF) throw ConfigurationError("Force 2D cannot be used together with force4DOF.");  // PointToPlane.cpp:59-64
-        if (force2D) throw ConfigurationError("PointToPlaneErrorMinimizer: GPU module: force2D is not supported");
+        if (force2D && kind != PMGPU_MIN_P2PLANE) throw ConfigurationError(className + ": GPU module: force2D is not supported together with the covariance");
+        if (force2D) this->kind |= PMGPU_MIN_FORCE2D;  // the 3x3 sub-system without z, PointToPlane.cpp:177-186
         if (force4DOF) this->kind |= PMGPU_MIN_FORCE4DOF;  // the 4x4 sub-system, PointToPlane.cpp:203-214
     }
 };

@@ -438,8 +438,9 @@ class _Minimizer(Parametrizable, _Bound):
             force2D, force4DOF = self.get("force2D"), self.get("force4DOF")
             if force2D and force4DOF:
                 raise ConfigurationError("Force 2D cannot be used together with force4DOF.")
-            if force2D:
-                raise ConfigurationError("GPU module: force2D is not supported")
+            if force2D and self.KIND != capi.MIN_P2PLANE:
+                raise ConfigurationError("GPU module: force2D is not supported together with the covariance")
+            self.force2D = bool(force2D)
             self.force4DOF = bool(force4DOF)
         self._cov = np.zeros((6, 6), np.float32)
         self._stats = dict(pointUsedRatio=-1.0, weightedPointUsedRatio=-1.0)
@@ -454,8 +455,8 @@ class _Minimizer(Parametrizable, _Bound):
         return T
 
     def kind_word(self):
-        """minimiser id with the force4DOF bit (pmgpu.h)"""
-        return self.KIND | (capi.MIN_FORCE4DOF if getattr(self, "force4DOF", False) else 0)
+        """minimiser id with the force4DOF / force2D bit (pmgpu.h)"""
+        return self.KIND | (capi.MIN_FORCE4DOF if getattr(self, "force4DOF", False) else 0) | (capi.MIN_FORCE2D if getattr(self, "force2D", False) else 0)
 
     def getCovariance(self):
         return self._cov

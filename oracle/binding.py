@@ -26,6 +26,7 @@ def robust_word(fct="cauchy", scale=SCALE_MAD, nb_iteration_for_scale=0):
     return FILTER_ROBUST | (ROBUST_FCTS[fct] << 8) | (scale << 16) | (nb_iteration_for_scale << 20)
 MIN_P2POINT, MIN_P2PLANE, MIN_P2POINT_COV, MIN_P2PLANE_COV, MIN_P2POINT_SIM = 0, 1, 2, 3, 4
 MIN_FORCE4DOF = 0x100  # or-ed into a point-to-plane minimizer id
+MIN_FORCE2D = 0x200
 ERRORS = {
     1: "ConvergenceError: no outlier to filter",
     2: "ConvergenceError: ErrorMnimizer: no point to minimize",

@@ -907,6 +907,53 @@ int minimize_p2plane_4dof(const ErrorElements& e, float* T_out) {
     return ORC_OK;
 }
 
+// force2D on 3-D clouds (PointToPlane.cpp:177-186, 294-310): the clouds become [x, y, 1], the normals (nx, ny);
+// `cross` is the pseudo cross product x*ny - y*nx (ErrorMinimizer.cpp:308-313), the residual has no z term, the
+// unknowns are (angle, tx, ty), and the result is the identity with Rotation2D / translation in its xy block.
+template <typename S>
+int minimize_p2plane_2d(const ErrorElements& e, float* T_out) {
+    const int M = e.M;
+    Mat<S> A(3, 3);
+    std::vector<S> b(3, S(0));
+    for (int p = 0; p < M; ++p) {
+        const float* r = &e.reading[4 * size_t(p)];
+        const float* q = &e.reference[4 * size_t(p)];
+        const float* nr = &e.normals[3 * size_t(p)];
+        const float w = e.weights[p];
+        float F[3], wF[3];
+        F[0] = r[0] * nr[1] - r[1] * nr[0];
+        F[1] = nr[0]; F[2] = nr[1];
+        for (int i = 0; i < 3; ++i) wF[i] = w * F[i];
+        float dot = 0.f;
+        for (int i = 0; i < 2; ++i) dot += (r[i] - q[i]) * nr[i];
+        for (int j = 0; j < 3; ++j)
+            for (int i = 0; i < 3; ++i) A(i, j) += S(wF[i]) * S(F[j]);
+        for (int i = 0; i < 3; ++i) b[i] += S(wF[i]) * S(dot);
+    }
+    for (int i = 0; i < 3; ++i) b[i] = -b[i];
+    float x[3];
+    if (sizeof(S) == sizeof(float)) {
+        Mat<float> Af(3, 3);
+        std::vector<float> bf(3), xf;
+        for (int j = 0; j < 3; ++j)
+            for (int i = 0; i < 3; ++i) Af(i, j) = float(A(i, j));
+        for (int i = 0; i < 3; ++i) bf[i] = float(b[i]);
+        solve_possibly_underdetermined<float>(Af, bf, xf);
+        for (int i = 0; i < 3; ++i) x[i] = xf[i];
+    } else {
+        std::vector<S> xs;
+        solve_possibly_underdetermined<S>(A, b, xs);
+        for (int i = 0; i < 3; ++i) x[i] = float(xs[i]);
+    }
+    for (int j = 0; j < 4; ++j)
+        for (int i = 0; i < 4; ++i) T_out[i + 4 * j] = (i == j) ? 1.f : 0.f;
+    const float s = std::sin(x[0]), c = std::cos(x[0]);  // Eigen::Rotation2D<float>::toRotationMatrix
+    T_out[0] = c; T_out[4] = -s;
+    T_out[1] = s; T_out[5] = c;
+    T_out[12] = x[1]; T_out[13] = x[2];
+    return ORC_OK;
+}
+
 template <typename S>
 int minimize_p2plane(const ErrorElements& e, float* T_out) {
     const int M = e.M;
@@ -1063,7 +1110,9 @@ int minimize_impl(int minimizer_word, ErrorElements& e, float sensorStdDev, floa
     const bool force4dof = (minimizer_word & ORC_MIN_FORCE4DOF) != 0;
     if (minimizer == ORC_MIN_P2PLANE || minimizer == ORC_MIN_P2PLANE_COV) {
         if (e.normals.empty()) return ORC_ERR_BAD_ARG;
-        const int rc = force4dof ? minimize_p2plane_4dof<S>(e, T_out) : minimize_p2plane<S>(e, T_out);
+        const bool force2d = (minimizer_word & ORC_MIN_FORCE2D) != 0;
+        if (force2d && (force4dof || minimizer == ORC_MIN_P2PLANE_COV)) return ORC_ERR_BAD_ARG;
+        const int rc = force2d ? minimize_p2plane_2d<S>(e, T_out) : force4dof ? minimize_p2plane_4dof<S>(e, T_out) : minimize_p2plane<S>(e, T_out);
         if (rc) return rc;
         if (minimizer == ORC_MIN_P2PLANE_COV && cov_out)
             estimate_covariance<S>(e.reading.data(), e.reference.data(), e.normals.data(), e.M, T_out, sensorStdDev, cov_out);

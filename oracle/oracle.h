@@ -34,6 +34,7 @@ enum { ORC_SCALE_NONE = 0, ORC_SCALE_MAD = 1 };
 /* error minimizers */
 enum { ORC_MIN_P2POINT = 0, ORC_MIN_P2PLANE = 1, ORC_MIN_P2POINT_COV = 2, ORC_MIN_P2PLANE_COV = 3, ORC_MIN_P2POINT_SIM = 4 };
 #define ORC_MIN_FORCE4DOF 0x100 /* or-ed into a point-to-plane minimizer id: PointToPlaneErrorMinimizer force4DOF */
+#define ORC_MIN_FORCE2D 0x200  /* likewise: force2D (rotation about z + x/y translation on 3-D clouds) */
 /* status codes */
 enum {
     ORC_OK = 0,

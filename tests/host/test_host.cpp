@@ -180,7 +180,8 @@ static int run_cpu() {
         CHECK(pm.ErrorMinimizerRegistrar.create("PointToPointSimilarityErrorMinimizer")->className == "PointToPointSimilarityErrorMinimizer");
         auto p4 = pm.ErrorMinimizerRegistrar.create("PointToPlaneErrorMinimizer", {{"force4DOF", "1"}});
         CHECK(dynamic_cast<PM::GpuErrorMinimizer*>(p4.get())->kind == (PMGPU_MIN_P2PLANE | PMGPU_MIN_FORCE4DOF));
-        CHECK(throws<PM::ConfigurationError>([&] { pm.ErrorMinimizerRegistrar.create("PointToPlaneErrorMinimizer", {{"force2D", "1"}}); }));
+        CHECK(pm.ErrorMinimizerRegistrar.create("PointToPlaneErrorMinimizer", {{"force2D", "1"}})->get<bool>("force2D"));
+        CHECK(throws<PM::ConfigurationError>([&] { pm.ErrorMinimizerRegistrar.create("PointToPlaneWithCovErrorMinimizer", {{"force2D", "1"}}); }));
         DP c;
         c.features = PM::Matrix::Zero(4, 2);
         c.features(0, 0) = 1.f; c.features(1, 1) = 2.f; c.features(3, 0) = c.features(3, 1) = 1.f;

@@ -458,7 +458,7 @@ def test_point_to_plane_force4dof_matches_oracle(gpu_ctx, oracle, synth):
     icp.ctx.close()
     assert_transform_close(T, res_o["T"], 1e-5, 1e-5)
     with pytest.raises(pm.ConfigurationError):
-        pm.PointToPlaneErrorMinimizer({"force2D": "1"})
+        pm.PointToPlaneErrorMinimizer({"force2D": "1", "force4DOF": "1"})
     with pytest.raises(capi.PmGpuError):
         gpu_ctx.minimize(capi.MIN_P2POINT | capi.MIN_FORCE4DOF)
 
@@ -628,3 +628,39 @@ def test_new_entry_points_reject_misuse(gpu_ctx, synth):
         gpu_ctx.minimize(capi.MIN_P2POINT_SIM + 1)
     w, _ = gpu_ctx.weights([(2, 0.9)])                  # and the context is still usable afterwards
     assert w.shape == (len(rd), 1) and 0.85 < w.mean() < 0.95
+
+
+# ---------------------------------------------------------------------------------- force2D (8a row a11)
+@pytest.mark.gpu
+def test_point_to_plane_force2d_matches_oracle(gpu_ctx, oracle, synth):
+    """PointToPlaneErrorMinimizer force2D on 3-D clouds (PointToPlane.cpp:177-186, 294-310): rotation about z and x/y
+    translation from the 3x3 system without z; one minimiser call and a whole ICP run against the oracle"""
+    from libpointmatcher_b200 import capi, pm
+    rd, rf, _ = synth.scan_pair(50000)
+    nrm = oracle.surface_normals(rf, knn=10, nthreads=8)["normals"]
+    gpu_ctx.set_reference(rf, normals=nrm)
+    gpu_ctx.set_reading(rd)
+    ids, dists, _ = gpu_ctx.knn(None, 1, 0.0, np.inf)
+    w, _ = gpu_ctx.weights([(2, 0.8)])
+    Tg, _, _ = gpu_ctx.minimize(capi.MIN_P2PLANE | capi.MIN_FORCE2D)
+    To, _, _ = oracle.minimize(oracle.MIN_P2PLANE | oracle.MIN_FORCE2D, rd, rf, nrm, ids, dists, w, acc_double=True)
+    assert_transform_close(Tg, To, 1e-5, 1e-5)
+    assert (Tg[2] == [0, 0, 1, 0]).all() and (Tg[:, 2] == [0, 0, 1, 0]).all() and (Tg[3] == [0, 0, 0, 1]).all()   # z is left alone
+    T4, _, _ = gpu_ctx.minimize(capi.MIN_P2PLANE | capi.MIN_FORCE4DOF)
+    assert np.abs(T4[:2, :] - Tg[:2, :]).max() > 1e-7                                                             # not the 4-DOF answer
+    res_o = oracle.icp(rd, rf, ref_normals=nrm, filters=[(2, 0.8)], minimizer=oracle.MIN_P2PLANE | oracle.MIN_FORCE2D, max_iterations=10,
+                       nthreads=8, acc_double=True)
+    icp = pm.ICP()
+    icp.matcher = pm.KDTreeMatcher()
+    icp.outlierFilters = pm.OutlierFilters([pm.TrimmedDistOutlierFilter({"ratio": "0.8"})])
+    icp.errorMinimizer = pm.PointToPlaneErrorMinimizer({"force2D": "1"})
+    icp.transformationCheckers = [pm.CounterTransformationChecker({"maxIterationCount": "10"})]
+    T = icp(pm.DataPoints(rd), pm.DataPoints(rf, {"normals": nrm}))
+    icp.ctx.close()
+    assert_transform_close(T, res_o["T"], 1e-5, 1e-5)
+    assert T[2, 3] == 0 and T[2, 2] == 1
+    with pytest.raises(pm.ConfigurationError):
+        pm.PointToPlaneWithCovErrorMinimizer({"force2D": "1"})
+    for bad in (capi.MIN_P2POINT | capi.MIN_FORCE2D, capi.MIN_P2PLANE_COV | capi.MIN_FORCE2D, capi.MIN_P2PLANE | capi.MIN_FORCE2D | capi.MIN_FORCE4DOF):
+        with pytest.raises(capi.PmGpuError):
+            gpu_ctx.minimize(bad)
