@@ -59,6 +59,8 @@ enum pmgpu_filter_type {
     PMGPU_FILTER_MEDIANDIST = 1, /* MedianDistOutlierFilter  param = factor                OutlierFiltersImpl.cpp:109-125 */
     PMGPU_FILTER_TRIMMEDDIST = 2,/* TrimmedDistOutlierFilter param = ratio                 OutlierFiltersImpl.cpp:132-147 */
     PMGPU_FILTER_ROBUST = 3,     /* RobustOutlierFilter      param = tuning                OutlierFiltersImpl.cpp:420-598 */
+    PMGPU_FILTER_VARTRIMMEDDIST = 5, /* VarTrimmedDistOutlierFilter param = lambda; minRatio / maxRatio through
+                                     pmgpu_set_var_trimmed_ratios       OutlierFiltersImpl.cpp:152-218 */
     PMGPU_FILTER_SURFACENORMAL = 4 /* SurfaceNormalOutlierFilter param = maxAngle: weight 0 where |n_reading . n_reference| <
                                       cos(maxAngle), both normalised (OutlierFiltersImpl.cpp:222-285); needs the reference
                                       normals and pmgpu_reading_set_normals, otherwise all ones like the reference */
@@ -167,6 +169,15 @@ int pmgpu_knn(pmgpu_ctx* ctx, const float* T, int k, float epsilon, float max_di
  * (weight = dist != inf).  weights_out: optional k x n download; limits_out: optional
  * per-filter squared-distance limits (nfilters floats). */
 int pmgpu_weights(pmgpu_ctx* ctx, int nfilters, const int* types, const float* params, float* weights_out, float* limits_out);
+/* VarTrimmedDistOutlierFilter (OutlierFiltersImpl.h:147-172, OutlierFiltersImpl.cpp:152-218): TrimmedDist with the ratio
+ * that minimises FRMS(i) = cumsum(sorted dists)[i] / i / (i / N)^(2 lambda) over minRatio N <= i < maxRatio N.  The
+ * distances are sorted on the device, the running sum is taken in float one element after the other exactly like the
+ * reference's std::partial_sum (one warp, ~2 ns per match), FRMS and its first minimum in parallel, and the limit is
+ * read from the sorted array.  One such filter per chain; it switches capped matching off (every distance counts).
+ * pmgpu_set_var_trimmed_ratios sets minRatio / maxRatio (defaults 0.05 / 0.99) of the context's VarTrimmedDist filter;
+ * PMGPU_ERR_BAD_ARG unless 0 < min_ratio < max_ratio <= 1.  pmgpu_var_trimmed_ratio: the ratio the last evaluation chose. */
+int pmgpu_set_var_trimmed_ratios(pmgpu_ctx* ctx, float min_ratio, float max_ratio);
+int pmgpu_var_trimmed_ratio(pmgpu_ctx* ctx, float* ratio_out);
 
 /* ---- K4-K7: ErrorMinimizer::compute (ErrorMinimizer.cpp:217-232) ------------------------
  * Uses the resident reading (transformed by the T of the last pmgpu_knn), matches and

@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # PMGPU_VARIANT selects a tuning build (libpmgpu_<name>.so, see build.py); default: libpmgpu.so
 LIB_PATH = os.path.join(_HERE, "libpmgpu%s.so" % ("_" + os.environ["PMGPU_VARIANT"] if os.environ.get("PMGPU_VARIANT") else ""))
 
-FILTER_MAXDIST, FILTER_MEDIANDIST, FILTER_TRIMMEDDIST, FILTER_ROBUST, FILTER_SURFACENORMAL = 0, 1, 2, 3, 4
+FILTER_MAXDIST, FILTER_MEDIANDIST, FILTER_TRIMMEDDIST, FILTER_ROBUST, FILTER_SURFACENORMAL, FILTER_VARTRIMMEDDIST = 0, 1, 2, 3, 4, 5
 MIN_P2POINT, MIN_P2PLANE, MIN_P2POINT_COV, MIN_P2PLANE_COV, MIN_P2POINT_SIM = 0, 1, 2, 3, 4
 MIN_FORCE4DOF = 0x100  # or-ed into a point-to-plane minimiser id
 MIN_FORCE2D = 0x200    # likewise (PointToPlaneErrorMinimizer only)
@@ -89,6 +89,8 @@ SIGNATURES = {
     "pmgpu_icp_reset": (C.c_int, [C.c_void_p, _fp]),
     "pmgpu_icp_result": (C.c_int, [C.c_void_p, _fp, C.POINTER(C.c_int), _fp, _fp]),
     "pmgpu_icp_cap_redos": (C.c_int, [C.c_void_p]),
+    "pmgpu_set_var_trimmed_ratios": (C.c_int, [C.c_void_p, C.c_float, C.c_float]),
+    "pmgpu_var_trimmed_ratio": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pmgpu_host_srand": (None, [C.c_uint]),
     "pmgpu_host_random_sampling": (C.c_int, [C.c_int, C.c_float, C.c_void_p]),
     "pmgpu_host_rand": (C.c_int, []),
@@ -289,6 +291,16 @@ class Context:
         limits = np.zeros(max(1, len(filters)), np.float32)
         self._check(lib.pmgpu_weights(self.h, len(filters), types.ctypes.data_as(_ip), _f(params), _ptr(w), _f(limits)))
         return w, limits[: len(filters)]
+
+    def set_var_trimmed_ratios(self, min_ratio=0.05, max_ratio=0.99):
+        """minRatio / maxRatio of the chain's VarTrimmedDistOutlierFilter (type FILTER_VARTRIMMEDDIST, param lambda)"""
+        self._check(lib.pmgpu_set_var_trimmed_ratios(self.h, min_ratio, max_ratio))
+
+    def var_trimmed_ratio(self):
+        """the inlier ratio the last evaluation of a VarTrimmedDist filter chose"""
+        out = np.zeros(1, np.float32)
+        self._check(lib.pmgpu_var_trimmed_ratio(self.h, _f(out)))
+        return out[0]
 
     # ---- K4-K7
     def minimize(self, minimizer, sensor_std_dev=0.01):

@@ -213,7 +213,7 @@ int enqueue_iteration(pmgpu_ctx* ctx, const pmgpu_icp_params* p, bool gated) {
     // the fused loop, an unbounded maxDist (a finite one decides which matches count as missing),
     // and a non-empty filter chain
     // (a RobustOutlierFilter weighs every match, however far: nothing may be cut)
-    const bool use_cap = gated && ctx->cap_enabled && p->nfilters > 0 && max_r2 == pm_inf() && spec.robust_index() < 0 && !var_dist;
+    const bool use_cap = gated && ctx->cap_enabled && p->nfilters > 0 && max_r2 == pm_inf() && spec.robust_index() < 0 && spec.var_index() < 0 && !var_dist;
     PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, ctx->nq, true, gated, false, p->knn, max_r2,
                       ctx->seed_k == 1 && p->knn == 1 && ctx->seed_enabled, ctx->ids.p, ctx->dists.p, use_cap,
                       var_dist ? ctx->reading_max_r2.p : nullptr));
@@ -584,6 +584,24 @@ int pmgpu_weights(pmgpu_ctx* ctx, int nfilters, const int* types, const float* p
     }
     if (limits_out)
         for (int f = 0; f < nfilters; ++f) limits_out[f] = spec.is_robust(f) ? ctx->state_host->robust_scale : ctx->state_host->limit[f];
+    return PMGPU_OK;
+}
+
+int pmgpu_set_var_trimmed_ratios(pmgpu_ctx* ctx, float min_ratio, float max_ratio) {
+    if (!ctx) return PMGPU_ERR_BAD_ARG;
+    if (!(min_ratio > 0.f) || !(max_ratio <= 1.f) || !(min_ratio < max_ratio))
+        return fail(ctx, PMGPU_ERR_BAD_ARG, "VarTrimmedDistOutlierFilter: 0 < minRatio < maxRatio <= 1");  // OutlierFiltersImpl.cpp:161-164, .h:156-157
+    ctx->var_min_ratio = min_ratio;
+    ctx->var_max_ratio = max_ratio;
+    return PMGPU_OK;
+}
+
+int pmgpu_var_trimmed_ratio(pmgpu_ctx* ctx, float* ratio_out) {
+    if (!ctx || !ratio_out) return PMGPU_ERR_BAD_ARG;
+    PM_TRY(use_device(ctx));
+    if (!ctx->have_weights) return fail(ctx, PMGPU_ERR_NO_MATCHES, "no outlier weights have been evaluated");
+    PM_TRY(pull_state(ctx));
+    *ratio_out = ctx->state_host->var_ratio;
     return PMGPU_OK;
 }
 

@@ -94,6 +94,7 @@ struct IcpState {
     float robust_median;
     unsigned robust_prefix;
     unsigned long long robust_rank;
+    float var_ratio;             // VarTrimmedDistOutlierFilter: the optimised inlier ratio of the last evaluation
     // adaptive search radius of the fused loop (DESIGN.md "capped matching"): squared radius the
     // NEXT match may stop at, the largest distance the filters of THIS iteration needed to know
     // exactly, and the flag that voids an iteration whose cap turned out too small
@@ -132,6 +133,11 @@ struct SelectSpec {
     __host__ __device__ int robust_index() const {
         for (int f = 0; f < nfilters; ++f)
             if (is_robust(f)) return f;
+        return -1;
+    }
+    __host__ __device__ int var_index() const {
+        for (int f = 0; f < nfilters; ++f)
+            if (kind(f) == PMGPU_FILTER_VARTRIMMEDDIST) return f;
         return -1;
     }
     __host__ __device__ int n_quantile() const {
@@ -197,6 +203,10 @@ struct pmgpu_ctx {
 
     // select (K3)
     pm::DevBuf<unsigned> hist;   // PM_HIST_BINS
+    // VarTrimmedDistOutlierFilter: minRatio / maxRatio (pmgpu_set_var_trimmed_ratios), sorted distance bits, running sums
+    float var_min_ratio = 0.05f, var_max_ratio = 0.99f;
+    pm::DevBuf<unsigned> var_sorted;
+    pm::DevBuf<float> var_cum;
     // minimiser partial sums (K4-K6)
     pm::DevBuf<double> partials;
 

@@ -10,6 +10,8 @@
 // matrix is never written unless a caller asks for it.  With queries sharded over GPUs the
 // histograms are all-reduced between the histogram kernel and a one-block pick kernel, so every
 // rank selects the same global order statistic.
+#include <cub/device/device_radix_sort.cuh>
+
 #include "select.cuh"
 
 namespace pm {
@@ -108,6 +110,112 @@ __global__ void __launch_bounds__(1024) pick_kernel(unsigned* __restrict__ hist,
     if (pass == 2 && threadIdx.x == 0) select_finish(state, cap_active, cap_margin);
 }
 
+// ---- VarTrimmedDistOutlierFilter::optimizeInlierRatio (OutlierFiltersImpl.cpp:177-218) --------------------------
+// `sorted`: the bit patterns of all k x N distances in ascending order (zeros first, +inf last).
+__device__ __forceinline__ size_t lower_bound_bits(const unsigned* __restrict__ a, size_t n, unsigned key) {
+    size_t lo = 0, hi = n;
+    while (lo < hi) {
+        const size_t mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+struct VarRange {
+    size_t n_zero, n_finite;  // the qualifying distances (finite, > 0) are sorted[n_zero .. n_finite)
+    long long min_el, end;    // FRMS candidates: cum[min_el .. end)
+    int points_nbr;
+};
+__device__ __forceinline__ VarRange var_range(const unsigned* sorted, size_t total, float min_ratio, float max_ratio) {
+    VarRange r;
+    r.n_zero = lower_bound_bits(sorted, total, 1u);
+    r.n_finite = lower_bound_bits(sorted, total, PM_INF_BITS);
+    r.points_nbr = (int)total;
+    r.min_el = (long long)floorf(__fmul_rn(min_ratio, (float)r.points_nbr));
+    const long long max_el = (long long)floorf(__fmul_rn(max_ratio, (float)r.points_nbr));
+    const long long count = (long long)(r.n_finite - r.n_zero);
+    r.end = max_el < count ? max_el : count;  // past `count` the reference reads uninitialised memory
+    return r;
+}
+// std::partial_sum in float: cum[i] = fl(cum[i - 1] + d[i]).  The rounding of every step depends on the one before,
+// so this is a serial chain by definition; one warp walks it 32 elements at a time (coalesced load, 32 dependent
+// adds on values passed round by shuffle, coalesced store).
+__global__ void __launch_bounds__(32) vartrim_scan_kernel(const unsigned* __restrict__ sorted, size_t total, float min_ratio, float max_ratio,
+                                                          IcpState* state, int gated, float* __restrict__ cum) {
+    if (gated && state->iterate == 0) return;
+    const VarRange r = var_range(sorted, total, min_ratio, max_ratio);
+    const int lane = threadIdx.x;
+    if (r.n_finite == r.n_zero) {
+        if (lane == 0) {
+            if (state->status == 0) state->status = PMGPU_ERR_NO_OUTLIER_TO_FILTER;
+            state->iterate = 0;
+        }
+        return;
+    }
+    const unsigned* __restrict__ src = sorted + r.n_zero;
+    float acc = 0.f;
+    float x = lane < r.end ? __uint_as_float(src[lane]) : 0.f;
+    for (long long base = 0; base < r.end; base += 32) {
+        const long long nxt = base + 32 + lane;
+        const float x_next = nxt < r.end ? __uint_as_float(src[nxt]) : 0.f;
+        float mine = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, x, j));
+            if (lane == j) mine = acc;
+        }
+        if (base + lane < r.end) cum[base + lane] = mine;
+        x = x_next;
+    }
+}
+// FRMS = trunkSortedDist * ids.inverse() * deno.inverse().square(), per coefficient in float; minCoeff = first minimum;
+// then limit = getDistsQuantile(optRatio) read from the sorted array (Matches.cpp:60-87).  pow: Eigen calls powf; the
+// double-precision pow rounded to float is the correctly rounded value glibc's powf returns in all but rare cases.
+__global__ void __launch_bounds__(1024) vartrim_pick_kernel(const unsigned* __restrict__ sorted, size_t total, float min_ratio, float max_ratio,
+                                                            float lambda, int f, IcpState* state, int gated, const float* __restrict__ cum) {
+    if (gated && state->iterate == 0) return;
+    __shared__ float s_best[32];
+    __shared__ long long s_idx[32];
+    const VarRange r = var_range(sorted, total, min_ratio, max_ratio);
+    const float n_f = (float)r.points_nbr;
+    float best = pm_inf();
+    long long idx = -1;
+    for (long long e = r.min_el + threadIdx.x; e < r.end; e += blockDim.x) {
+        const float id = __fadd_rn((float)(r.min_el + 1), __fmul_rn((float)(e - r.min_el), 1.f));  // LinSpaced, step 1
+        const float ratio = __fdiv_rn(id, n_f);
+        const float deno = (float)pow((double)ratio, (double)lambda);
+        const float inv = __fdiv_rn(1.f, deno);
+        const float frms = __fmul_rn(__fmul_rn(cum[e], __fdiv_rn(1.f, id)), __fmul_rn(inv, inv));
+        if (idx < 0 || frms < best) { best = frms; idx = e; }  // ascending e per thread: strict < keeps the first
+    }
+    auto better = [](float a, long long ia, float b, long long ib) { return ib < 0 ? true : (ia < 0 ? false : (a < b || (a == b && ia < ib))); };
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_down_sync(0xffffffffu, best, o);
+        const long long oi = __shfl_down_sync(0xffffffffu, idx, o);
+        if (!better(best, idx, ob, oi)) { best = ob; idx = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_best[threadIdx.x >> 5] = best; s_idx[threadIdx.x >> 5] = idx; }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+        if (!better(best, idx, s_best[w], s_idx[w])) { best = s_best[w]; idx = s_idx[w]; }
+    const long long min_index = idx < 0 ? 0 : idx - r.min_el;
+    const float opt = __fdiv_rn((float)(min_index + r.min_el), n_f);
+    state->var_ratio = opt;
+    const unsigned long long n_valid = r.n_finite;  // zeros count for the quantile
+    if (n_valid == 0 || !(opt >= 0.f && opt <= 1.f)) {
+        if (state->status == 0) state->status = n_valid == 0 ? PMGPU_ERR_NO_OUTLIER_TO_FILTER : PMGPU_ERR_BAD_QUANTILE;
+        state->iterate = 0;
+        return;
+    }
+    unsigned long long rank = opt == 1.0f ? n_valid - 1 : (unsigned long long)(__ull2float_rn(n_valid) * opt);
+    if (rank > n_valid - 1) rank = n_valid - 1;
+    const float lim = __uint_as_float(sorted[rank]);
+    state->n_valid = n_valid;
+    state->limit[f] = lim;
+    state->limit_all = fminf(state->limit_all, lim);
+}
+
 __global__ void init_limits_kernel(IcpState* state, SelectSpec spec, int gated, int cap_active, float cap_margin) {
     if (gated && state->iterate == 0) return;
     if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -159,6 +267,8 @@ int make_select_spec(pmgpu_ctx* ctx, int nfilters, const int* types, const float
                 ctx->set_error("RobustOutlierFilter on GPU: scaleEstimator must be 'none' or 'mad'");
                 return PMGPU_ERR_UNSUPPORTED;
             }
+        } else if (types[f] == PMGPU_FILTER_VARTRIMMEDDIST) {
+            // lambda: any value, like the reference's parameter table (OutlierFiltersImpl.h:158)
         } else if (types[f] != PMGPU_FILTER_MEDIANDIST) {
             ctx->set_error("unknown outlier filter type");
             return PMGPU_ERR_BAD_ARG;
@@ -175,6 +285,16 @@ int make_select_spec(pmgpu_ctx* ctx, int nfilters, const int* types, const float
     for (int f = 0; f < nfilters; ++f) nrobust += spec->is_robust(f) ? 1 : 0;
     if (nrobust > 1) {
         ctx->set_error("at most one RobustOutlierFilter per chain on the GPU");
+        return PMGPU_ERR_UNSUPPORTED;
+    }
+    int nvar = 0;
+    for (int f = 0; f < nfilters; ++f) nvar += spec->kind(f) == PMGPU_FILTER_VARTRIMMEDDIST ? 1 : 0;
+    if (nvar > 1) {
+        ctx->set_error("at most one VarTrimmedDistOutlierFilter per chain on the GPU");
+        return PMGPU_ERR_UNSUPPORTED;
+    }
+    if (nvar && ctx->nranks > 1) {
+        ctx->set_error("VarTrimmedDistOutlierFilter is not supported with a sharded reading");
         return PMGPU_ERR_UNSUPPORTED;
     }
     if (nrobust && ctx->nranks > 1) {
@@ -228,6 +348,24 @@ int launch_weights(pmgpu_ctx* ctx, const SelectSpec& spec, bool gated, bool cap_
                 robust_hist_kernel<<<grid, HIST_BLOCK, 0, st>>>(ctx->dists.p, total, pass, phase, ctx->state, g, ctx->hist.p + (size_t)PM_MAX_FILTERS * PM_HIST_BINS);
                 ctx->launches += 1;
             }
+    }
+    const int v = spec.var_index();
+    if (v >= 0) {
+        // sort all k x N distance bit patterns (non-negative floats order like unsigned integers), then the serial
+        // running sum and the parallel FRMS minimum; runs after the other filters have set their limits
+        const size_t total = (size_t)ctx->k * ctx->nq;
+        PM_CUDA_TRY(ctx, ctx->var_sorted.reserve(total));
+        PM_CUDA_TRY(ctx, ctx->var_cum.reserve(total));
+        const unsigned* keys = reinterpret_cast<const unsigned*>(ctx->dists.p);
+        size_t tmp_bytes = 0;
+        PM_CUDA_TRY(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys, ctx->var_sorted.p, (int)total, 0, 32, st));
+        PM_CUDA_TRY(ctx, ctx->cub_tmp.reserve(tmp_bytes));
+        size_t tb = ctx->cub_tmp.cap;
+        PM_CUDA_TRY(ctx, cub::DeviceRadixSort::SortKeys(ctx->cub_tmp.p, tb, keys, ctx->var_sorted.p, (int)total, 0, 32, st));
+        vartrim_scan_kernel<<<1, 32, 0, st>>>(ctx->var_sorted.p, total, ctx->var_min_ratio, ctx->var_max_ratio, ctx->state, g, ctx->var_cum.p);
+        vartrim_pick_kernel<<<1, 1024, 0, st>>>(ctx->var_sorted.p, total, ctx->var_min_ratio, ctx->var_max_ratio, spec.param[v], v, ctx->state, g,
+                                                ctx->var_cum.p);
+        ctx->launches += 3;
     }
     PM_CUDA_TRY(ctx, cudaGetLastError());
     ctx->have_weights = true;

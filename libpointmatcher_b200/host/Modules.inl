@@ -721,13 +721,34 @@ struct GpuDistOutlierFilter : public OutlierFilter, public GpuBound {
     T value;
     GpuDistOutlierFilter(const std::string& className, const ParametersDoc paramsDoc, const Parameters& params, int type, const char* paramName)
         : OutlierFilter(className, paramsDoc, params), filterType(type), value(Parametrizable::get<T>(paramName)) {}
+    // parameters that do not fit the (type, value) pair go to the context before the chain is evaluated
+    virtual void prepare(GpuPipeline&) const {}
     OutlierWeights compute(const DataPoints&, const DataPoints&, const Matches& input) override {
         GpuPipeline& g = this->gpu();
+        prepare(g);
         OutlierWeights w(input.ids.rows(), input.ids.cols());
         const float p = (float)value;
         g.check(pmgpu_weights(g.ctx, 1, &filterType, &p, reinterpret_cast<float*>(w.data()), nullptr));
         return w;
     }
+};
+// OutlierFiltersImpl.h:147-172, OutlierFiltersImpl.cpp:152-218: TrimmedDist with the ratio minimising the fractional RMS distance
+struct VarTrimmedDistOutlierFilter : public GpuDistOutlierFilter {
+    static const std::string description() { return "Hard rejection threshold using quantile and variable ratio. Based on \\cite{Phillips2007VarTrimmed}."; }
+    static const ParametersDoc availableParameters() {
+        return {{"minRatio", "min ratio", "0.05", "0.0000001", "1", &Parametrizable::Comp<T>},
+                {"maxRatio", "max ratio", "0.99", "0.0000001", "1", &Parametrizable::Comp<T>},
+                {"lambda", "lambda (part of the term that balance the rmsd: 1/ratio^lambda", "2.35"}};
+    }
+    const T minRatio, maxRatio, lambda;
+    VarTrimmedDistOutlierFilter(const Parameters& params = Parameters())
+        : GpuDistOutlierFilter("VarTrimmedDistOutlierFilter", availableParameters(), params, PMGPU_FILTER_VARTRIMMEDDIST, "lambda"),
+          minRatio(Parametrizable::get<T>("minRatio")), maxRatio(Parametrizable::get<T>("maxRatio")), lambda(Parametrizable::get<T>("lambda")) {
+        if (this->minRatio >= this->maxRatio)
+            throw InvalidParameter("VarTrimmedDistOutlierFilter: minRatio (" + std::to_string(minRatio) + ") should be smaller than maxRatio (" +
+                                   std::to_string(maxRatio) + ")");
+    }
+    void prepare(GpuPipeline& g) const override { g.check(pmgpu_set_var_trimmed_ratios(g.ctx, (float)minRatio, (float)maxRatio)); }
 };
 struct MaxDistOutlierFilter : public GpuDistOutlierFilter {
     static const std::string description() { return "This filter considers as outlier links whose norms are above a fix threshold."; }
@@ -805,10 +826,11 @@ struct OutlierFilters : public std::vector<std::shared_ptr<OutlierFilter>>, publ
             if (!dynamic_cast<GpuDistOutlierFilter*>(f.get())) return false;
         return true;
     }
-    void spec(int* types, float* params) const {
+    void spec(int* types, float* params, GpuPipeline& pipeline) const {
         int i = 0;
         for (const auto& f : *this) {
             const auto* g = dynamic_cast<const GpuDistOutlierFilter*>(f.get());
+            g->prepare(pipeline);
             types[i] = g->filterType;
             params[i] = (float)g->value;
             ++i;
@@ -819,7 +841,7 @@ struct OutlierFilters : public std::vector<std::shared_ptr<OutlierFilter>>, publ
             GpuPipeline& g = this->gpu();
             int types[8];
             float params[8];
-            spec(types, params);
+            spec(types, params, g);
             OutlierWeights w(input.ids.rows(), input.ids.cols());
             g.check(pmgpu_weights(g.ctx, (int)this->size(), types, params, reinterpret_cast<float*>(w.data()), nullptr));
             return w;

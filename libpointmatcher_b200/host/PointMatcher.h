@@ -605,6 +605,7 @@ struct PointMatcher {
         ADD_TO_REGISTRAR(OutlierFilter, MaxDistOutlierFilter, MaxDistOutlierFilter)
         ADD_TO_REGISTRAR(OutlierFilter, MedianDistOutlierFilter, MedianDistOutlierFilter)
         ADD_TO_REGISTRAR(OutlierFilter, TrimmedDistOutlierFilter, TrimmedDistOutlierFilter)
+        ADD_TO_REGISTRAR(OutlierFilter, VarTrimmedDistOutlierFilter, VarTrimmedDistOutlierFilter)
         ADD_TO_REGISTRAR(OutlierFilter, RobustOutlierFilter, RobustOutlierFilter)
         ADD_TO_REGISTRAR(OutlierFilter, SurfaceNormalOutlierFilter, SurfaceNormalOutlierFilter)
         ADD_TO_REGISTRAR_NO_PARAM(ErrorMinimizer, PointToPointErrorMinimizer, PointToPointErrorMinimizer)

@@ -354,7 +354,11 @@ class _DistFilter(Parametrizable, _Bound):
     def spec(self):
         return (self.TYPE, self.value)
 
+    def prepare(self, ctx):
+        """parameters that do not fit the (type, value) pair go to the context before the chain is evaluated"""
+
     def compute(self, filteredReading, filteredReference, matches):
+        self.prepare(self.ctx)
         w, _ = _translate(self.ctx.weights, [self.spec()])
         return w
 
@@ -375,6 +379,24 @@ class TrimmedDistOutlierFilter(_DistFilter):
     className = "TrimmedDistOutlierFilter"
     TYPE, PARAM = capi.FILTER_TRIMMEDDIST, "ratio"
     PARAMS = (("ratio", "percentage to keep", "0.85", "0.0000001", "1.0", float),)
+
+
+class VarTrimmedDistOutlierFilter(_DistFilter):
+    """OutlierFiltersImpl.h:147-172, OutlierFiltersImpl.cpp:152-218: TrimmedDist with the ratio that minimises the
+    fractional RMS distance; sorted, summed (serially, in float) and minimised on the device."""
+    className = "VarTrimmedDistOutlierFilter"
+    TYPE, PARAM = capi.FILTER_VARTRIMMEDDIST, "lambda"
+    PARAMS = (("minRatio", "min ratio", "0.05", "0.0000001", "1", float), ("maxRatio", "max ratio", "0.99", "0.0000001", "1", float),
+              ("lambda", "lambda (part of the term that balance the rmsd: 1/ratio^lambda", "2.35", None, None, float))
+
+    def __init__(self, params=None):
+        _DistFilter.__init__(self, params)
+        self.minRatio, self.maxRatio = self.get("minRatio"), self.get("maxRatio")
+        if self.minRatio >= self.maxRatio:
+            raise InvalidParameter("VarTrimmedDistOutlierFilter: minRatio (%g) should be smaller than maxRatio (%g)" % (self.minRatio, self.maxRatio))
+
+    def prepare(self, ctx):
+        _translate(ctx.set_var_trimmed_ratios, self.minRatio, self.maxRatio)
 
 
 class SurfaceNormalOutlierFilter(_DistFilter):
@@ -422,6 +444,8 @@ class OutlierFilters(list, _Bound):
     """OutlierFilter.cpp:63-103: product of all filters' weights; empty chain -> dist != inf."""
 
     def compute(self, filteredReading, filteredReference, matches):
+        for f in self:
+            f.prepare(self.ctx)
         w, limits = _translate(self.ctx.weights, [f.spec() for f in self])
         self.limits = limits
         return w
@@ -995,6 +1019,7 @@ class Registrar(dict):
 MatcherRegistrar = Registrar(KDTreeMatcher=KDTreeMatcher, KDTreeVarDistMatcher=KDTreeVarDistMatcher)
 OutlierFilterRegistrar = Registrar(MaxDistOutlierFilter=MaxDistOutlierFilter, MedianDistOutlierFilter=MedianDistOutlierFilter,
                                    TrimmedDistOutlierFilter=TrimmedDistOutlierFilter, RobustOutlierFilter=RobustOutlierFilter,
+                                   VarTrimmedDistOutlierFilter=VarTrimmedDistOutlierFilter,
                                    SurfaceNormalOutlierFilter=SurfaceNormalOutlierFilter)
 ErrorMinimizerRegistrar = Registrar(PointToPointErrorMinimizer=PointToPointErrorMinimizer,
                                     PointToPointWithCovErrorMinimizer=PointToPointWithCovErrorMinimizer,
@@ -1108,6 +1133,8 @@ class ICP:
         counter = [c for c in self.transformationCheckers if isinstance(c, CounterTransformationChecker)]
         diff = [c for c in self.transformationCheckers if isinstance(c, DifferentialTransformationChecker)]
         m = self.matcher
+        for f in self.outlierFilters:
+            f.prepare(self.ctx)
         return capi.make_params(
             knn=m.knn, epsilon=m.epsilon, max_dist=m.maxDist, filters=[f.spec() for f in self.outlierFilters],
             minimizer=self.errorMinimizer.kind_word(), sensor_std_dev=self.errorMinimizer.sensorStdDev,

@@ -16,7 +16,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
 
-FILTER_MAXDIST, FILTER_MEDIANDIST, FILTER_TRIMMEDDIST, FILTER_ROBUST, FILTER_SURFACENORMAL = 0, 1, 2, 3, 4
+FILTER_MAXDIST, FILTER_MEDIANDIST, FILTER_TRIMMEDDIST, FILTER_ROBUST, FILTER_SURFACENORMAL, FILTER_VARTRIMMEDDIST = 0, 1, 2, 3, 4, 5
 ROBUST_FCTS = dict(cauchy=0, welsch=1, sc=2, gm=3, tukey=4, huber=5, L1=6, student=7)
 SCALE_NONE, SCALE_MAD = 0, 1
 
@@ -83,6 +83,9 @@ def lib():
         _lib.orc_rigid_transform.argtypes = [_fp, _fp, C.c_int, _fp]
         _lib.orc_rotate_normals.argtypes = [_fp, _fp, C.c_int, _fp]
         _lib.orc_dists_quantile.argtypes = [_fp, C.c_long, C.c_float, _fp]
+        _lib.orc_set_var_trimmed_ratios.argtypes = [C.c_float, C.c_float]
+        _lib.orc_set_var_trimmed_ratios.restype = None
+        _lib.orc_var_trimmed_ratio.argtypes = [_fp, C.c_long, C.c_float, C.c_float, C.c_float, _fp]
         _lib.orc_outlier_weights.argtypes = [_fp, C.c_int, C.c_int, C.c_int, _ip, _fp, _fp, _fp]
         _lib.orc_minimize.argtypes = [C.c_int, _fp, C.c_int, _fp, C.c_int, _fp, _ip, _fp, _fp, C.c_int, C.c_float, C.c_int, _fp, _fp, _fp]
         _lib.orc_surface_normals.argtypes = [_fp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int,
@@ -163,6 +166,19 @@ def dists_quantile(dists, quantile):
     d = np.ascontiguousarray(dists, np.float32)
     out = np.zeros(1, np.float32)
     _check(lib().orc_dists_quantile(_f(d), d.size, quantile, _f(out)))
+    return out[0]
+
+
+def set_var_trimmed_ratios(min_ratio=0.05, max_ratio=0.99):
+    """minRatio / maxRatio of the VarTrimmedDist filters (type FILTER_VARTRIMMEDDIST, param lambda) evaluated from now on"""
+    lib().orc_set_var_trimmed_ratios(min_ratio, max_ratio)
+
+
+def var_trimmed_ratio(dists, min_ratio=0.05, max_ratio=0.99, lam=2.35):
+    """VarTrimmedDistOutlierFilter::optimizeInlierRatio (OutlierFiltersImpl.cpp:177-218)"""
+    d = np.ascontiguousarray(dists, np.float32)
+    out = np.zeros(1, np.float32)
+    _check(lib().orc_var_trimmed_ratio(_f(d), d.size, min_ratio, max_ratio, lam, _f(out)))
     return out[0]
 
 

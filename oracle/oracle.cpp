@@ -542,6 +542,40 @@ int dists_quantile(const float* dists, long n, float quantile, float* out) {
     return ORC_OK;
 }
 
+// VarTrimmedDistOutlierFilter::optimizeInlierRatio (OutlierFiltersImpl.cpp:177-218).  The reference sorts the finite,
+// positive distances, takes their running sum in float (std::partial_sum), and minimises
+// FRMS(i) = cumsum[i] / i / (i / N)^(2 lambda) over minEl <= i < maxEl, N = rows * cols of the distance matrix, every
+// array expression evaluated per coefficient in float.  Where fewer than maxEl distances qualify the reference reads
+// past the end of its vector (undefined); the candidates are cut at the number of qualifying distances here.
+float g_var_min_ratio = 0.05f, g_var_max_ratio = 0.99f;
+int var_trimmed_ratio(const float* dists, long n, float min_ratio, float max_ratio, float lambda, float* ratio_out) {
+    std::vector<float> sorted;
+    sorted.reserve(n);
+    for (long i = 0; i < n; ++i)
+        if (dists[i] != kInf && dists[i] > 0) sorted.push_back(dists[i]);
+    if (sorted.empty()) return ORC_ERR_NO_OUTLIER_TO_FILTER;
+    std::sort(sorted.begin(), sorted.end());
+    std::vector<float> cum(sorted.size());
+    std::partial_sum(sorted.begin(), sorted.end(), cum.begin());  // running sum in float, one element after the other
+    const int points_nbr = (int)n;
+    const int minEl = (int)std::floor(min_ratio * points_nbr);
+    const int maxEl = (int)std::floor(max_ratio * points_nbr);
+    const long end = std::min<long>(maxEl, (long)cum.size());
+    int minIndex = 0;
+    float best = 0.f;
+    bool have = false;
+    for (long e = minEl; e < end; ++e) {
+        const float id = float(minEl + 1) + float(e - minEl) * 1.f;  // LinSpaced(maxEl - minEl, minEl + 1, maxEl): step 1
+        const float ratio = id / float(points_nbr);
+        const float deno = std::pow(ratio, lambda);
+        const float inv = 1.f / deno;
+        const float frms = (cum[e] * (1.f / id)) * (inv * inv);
+        if (!have || frms < best) { best = frms; minIndex = int(e - minEl); have = true; }  // minCoeff: the first minimum
+    }
+    *ratio_out = (float)(minIndex + minEl) / (float)points_nbr;
+    return ORC_OK;
+}
+
 // Matches::getMedianAbsDeviation (Matches.cpp:88-122): median(|x - median(x)|) over the finite
 // squared distances, both medians at position size/2.
 int median_abs_deviation(const float* dists, long n, float* out) {
@@ -644,6 +678,12 @@ int outlier_weights(const float* dists, int knn, int n, int nfilters, const int*
             limit = params[f] * median;
         } else if (types[f] == ORC_FILTER_TRIMMEDDIST) {
             const int rc = dists_quantile(dists, total, params[f], &limit);
+            if (rc) return rc;
+        } else if (types[f] == ORC_FILTER_VARTRIMMEDDIST) {
+            float tuned;
+            int rc = var_trimmed_ratio(dists, total, g_var_min_ratio, g_var_max_ratio, params[f], &tuned);
+            if (rc) return rc;
+            rc = dists_quantile(dists, total, tuned, &limit);
             if (rc) return rc;
         } else if (types[f] == ORC_FILTER_SURFACENORMAL) {
             const float eps = std::cos(params[f]);  // eps(cos(maxAngle)), OutlierFiltersImpl.cpp:227
@@ -1321,6 +1361,10 @@ int orc_outlier_weights_sn(const float* dists, const int32_t* ids, int knn, int 
 }
 
 int orc_dists_quantile(const float* dists, long n, float quantile, float* out) { return dists_quantile(dists, n, quantile, out); }
+void orc_set_var_trimmed_ratios(float min_ratio, float max_ratio) { g_var_min_ratio = min_ratio; g_var_max_ratio = max_ratio; }
+int orc_var_trimmed_ratio(const float* dists, long n, float min_ratio, float max_ratio, float lambda, float* ratio_out) {
+    return var_trimmed_ratio(dists, n, min_ratio, max_ratio, lambda, ratio_out);
+}
 
 int orc_outlier_weights(const float* dists, int knn, int n, int nfilters, const int* types, const float* params, float* weights, float* limits_out) {
     return outlier_weights(dists, knn, n, nfilters, types, params, weights, limits_out);

@@ -23,7 +23,8 @@ extern "C" {
 #endif
 
 /* filter types for the outlier chain (OutlierFiltersImpl.cpp) */
-enum { ORC_FILTER_MAXDIST = 0, ORC_FILTER_MEDIANDIST = 1, ORC_FILTER_TRIMMEDDIST = 2, ORC_FILTER_ROBUST = 3, ORC_FILTER_SURFACENORMAL = 4 };
+enum { ORC_FILTER_MAXDIST = 0, ORC_FILTER_MEDIANDIST = 1, ORC_FILTER_TRIMMEDDIST = 2, ORC_FILTER_ROBUST = 3, ORC_FILTER_SURFACENORMAL = 4,
+       ORC_FILTER_VARTRIMMEDDIST = 5 /* param = lambda; minRatio / maxRatio through orc_set_var_trimmed_ratios */ };
 /* RobustOutlierFilter (OutlierFiltersImpl.cpp:420-598): the filter word carries its discrete parameters:
  *   bits 0-7  ORC_FILTER_ROBUST | bits 8-15 robust function | bits 16-19 scale estimator |
  *   bits 20-27 nbIterationForScale;   filter_param = tuning.  distanceType point2point, approximation inf. */
@@ -85,6 +86,10 @@ int orc_rotate_normals(const float* T16, const float* in3, int n, float* out3);
 
 /* --- Matches::getDistsQuantile / outlier chain ----------------------------------------- */
 int orc_dists_quantile(const float* dists, long n, float quantile, float* out);
+/* VarTrimmedDistOutlierFilter (OutlierFiltersImpl.cpp:152-218): minRatio / maxRatio of the filters evaluated from now on
+ * (defaults 0.05 / 0.99), and optimizeInlierRatio on its own */
+void orc_set_var_trimmed_ratios(float min_ratio, float max_ratio);
+int orc_var_trimmed_ratio(const float* dists, long n, float min_ratio, float max_ratio, float lambda, float* ratio_out);
 int orc_outlier_weights(const float* dists, int knn, int n, int nfilters, const int* types,
                         const float* params, float* weights, float* limits_out);
 /* SurfaceNormalOutlierFilter (OutlierFiltersImpl.cpp:222-285, type ORC_FILTER_SURFACENORMAL, param = maxAngle)

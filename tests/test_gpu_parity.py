@@ -664,3 +664,77 @@ def test_point_to_plane_force2d_matches_oracle(gpu_ctx, oracle, synth):
     for bad in (capi.MIN_P2POINT | capi.MIN_FORCE2D, capi.MIN_P2PLANE_COV | capi.MIN_FORCE2D, capi.MIN_P2PLANE | capi.MIN_FORCE2D | capi.MIN_FORCE4DOF):
         with pytest.raises(capi.PmGpuError):
             gpu_ctx.minimize(bad)
+
+
+# ---------------------------------------------------------------------------------- VarTrimmedDist (8f row 3)
+def test_var_trimmed_reference_known_answer_on_gpu(gpu_ctx):
+    """utest/ui/Outliers.cpp:126-152 on the device: squared distances {4,5,5,5,5}"""
+    from libpointmatcher_b200 import capi
+    ref = np.array([[20.0 * i, 0, 0, 1] for i in range(5)], np.float32)
+    rd = ref.copy()
+    rd[0, 0] += 2
+    rd[1:, 0] += 1
+    rd[1:, 1] += 2
+    gpu_ctx.set_reference(ref)
+    gpu_ctx.set_reading(rd)
+    _, dists, _ = gpu_ctx.knn(None, 1, 0.0, np.inf)
+    assert dists[:, 0].tolist() == [4, 5, 5, 5, 5]
+    gpu_ctx.set_var_trimmed_ratios(0.0000001, 1.0)
+    w, lim = gpu_ctx.weights([(capi.FILTER_VARTRIMMEDDIST, 0.0)])
+    assert w[:, 0].tolist() == [1, 0, 0, 0, 0] and lim[0] == 4 and gpu_ctx.var_trimmed_ratio() == 0
+    w, lim = gpu_ctx.weights([(capi.FILTER_VARTRIMMEDDIST, 1.0)])
+    assert w[:, 0].tolist() == [1, 1, 1, 1, 1] and lim[0] == 5 and gpu_ctx.var_trimmed_ratio() == np.float32(0.8)
+    with pytest.raises(capi.PmGpuError):
+        gpu_ctx.set_var_trimmed_ratios(0.5, 0.5)
+    with pytest.raises(capi.PmGpuError):
+        gpu_ctx.weights([(capi.FILTER_VARTRIMMEDDIST, 1.0), (capi.FILTER_VARTRIMMEDDIST, 2.0)])
+    gpu_ctx.set_var_trimmed_ratios()
+
+
+@pytest.mark.parametrize("n,k,max_dist,ratios,lam", [(50000, 1, np.inf, (0.05, 0.99), 2.35), (200000, 1, np.inf, (0.3, 0.95), 1.0),
+                                                      (30000, 5, 0.8, (0.05, 0.99), 2.35), (1000000, 1, np.inf, (0.05, 0.99), 2.35)])
+def test_var_trimmed_ratio_limit_and_weights_match_oracle(gpu_ctx, oracle, synth, n, k, max_dist, ratios, lam):
+    """optimizeInlierRatio (OutlierFiltersImpl.cpp:177-218): ratio, limit and weights against the oracle — bit for bit; with a finite
+    maxDist some matches are +inf and (k > 1, exact duplicates) some zero, which both sides leave out of the sorted list"""
+    from libpointmatcher_b200 import capi
+    rd, rf, _ = synth.scan_pair(n)
+    rd = rd.copy()
+    rd[:50] = rf[:50]                                     # zero distances
+    gpu_ctx.set_reference(rf)
+    gpu_ctx.set_reading(rd)
+    _, dists, _ = gpu_ctx.knn(None, k, 0.0, max_dist)
+    gpu_ctx.set_var_trimmed_ratios(*ratios)
+    oracle.set_var_trimmed_ratios(*ratios)
+    try:
+        w, lim = gpu_ctx.weights([(capi.FILTER_VARTRIMMEDDIST, lam), (capi.FILTER_MAXDIST, 3.0)])
+        wo, limo = oracle.outlier_weights(dists, [(oracle.FILTER_VARTRIMMEDDIST, lam), (oracle.FILTER_MAXDIST, 3.0)])
+        ro = oracle.var_trimmed_ratio(dists, ratios[0], ratios[1], lam)
+    finally:
+        oracle.set_var_trimmed_ratios()
+        rg = gpu_ctx.var_trimmed_ratio()
+        gpu_ctx.set_var_trimmed_ratios()
+    assert ratios[0] <= rg <= ratios[1]
+    assert rg == ro and lim[0] == limo[0] and lim[1] == limo[1]
+    assert (w == wo).all() and 0 < w.sum() < w.size
+
+
+@pytest.mark.parametrize("minimizer", [0, 1])
+def test_icp_with_var_trimmed_filter_matches_oracle(oracle, synth, minimizer):
+    from libpointmatcher_b200 import pm
+    rd, rf, _ = synth.scan_pair(60000)
+    nrm = oracle.surface_normals(rf, knn=10, nthreads=8)["normals"]
+    oracle.set_var_trimmed_ratios(0.05, 0.99)
+    res_o = oracle.icp(rd, rf, ref_normals=nrm, filters=[(oracle.FILTER_VARTRIMMEDDIST, 2.35)], minimizer=minimizer, max_iterations=12, nthreads=8,
+                       acc_double=True)
+    icp = pm.ICP()
+    icp.matcher = pm.KDTreeMatcher()
+    icp.outlierFilters = pm.OutlierFilters([pm.VarTrimmedDistOutlierFilter()])
+    icp.errorMinimizer = pm.PointToPlaneErrorMinimizer() if minimizer else pm.PointToPointErrorMinimizer()
+    icp.transformationCheckers = [pm.CounterTransformationChecker({"maxIterationCount": "12"})]
+    T = icp(pm.DataPoints(rd), pm.DataPoints(rf, {"normals": nrm}))
+    ratio = icp.ctx.var_trimmed_ratio()
+    icp.ctx.close()
+    assert_transform_close(T, res_o["T"], 1e-5, 1e-5)
+    assert 0.5 < ratio < 0.99
+    with pytest.raises(pm.InvalidParameter):
+        pm.VarTrimmedDistOutlierFilter({"minRatio": "0.9", "maxRatio": "0.5"})
