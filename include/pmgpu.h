@@ -169,6 +169,14 @@ int pmgpu_knn(pmgpu_ctx* ctx, const float* T, int k, float epsilon, float max_di
  * (weight = dist != inf).  weights_out: optional k x n download; limits_out: optional
  * per-filter squared-distance limits (nfilters floats). */
 int pmgpu_weights(pmgpu_ctx* ctx, int nfilters, const int* types, const float* params, float* weights_out, float* limits_out);
+/* The matches and weights resident on the device, for what the reference derives from ErrorElements after the fact
+ * (ErrorMinimizer::getErrorElements, getResidualError, getOverlap; ErrorMinimizer.cpp:58-193, PointToPlane.cpp:314-470,
+ * PointToPoint.cpp:101-165): ids / dists / weights (k x nq, column-major like Matches, any may be null) of the last
+ * evaluation — staged calls or the last executed iteration of the fused loop — and T_match (4 x 4 column-major), the
+ * transform of the reading those matches were made with.  After a capped fused loop the matches the filters rejected beyond
+ * the search radius read id -2 / dist FLT_MAX / weight 0: ErrorElements drops them like any other rejected match. */
+int pmgpu_matches_get(pmgpu_ctx* ctx, int32_t* ids_out, float* dists_out, float* weights_out, float* T_match_out);
+
 /* VarTrimmedDistOutlierFilter (OutlierFiltersImpl.h:147-172, OutlierFiltersImpl.cpp:152-218): TrimmedDist with the ratio
  * that minimises FRMS(i) = cumsum(sorted dists)[i] / i / (i / N)^(2 lambda) over minRatio N <= i < maxRatio N.  The
  * distances are sorted on the device, the running sum is taken in float one element after the other exactly like the

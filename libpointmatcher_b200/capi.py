@@ -89,6 +89,7 @@ SIGNATURES = {
     "pmgpu_icp_reset": (C.c_int, [C.c_void_p, _fp]),
     "pmgpu_icp_result": (C.c_int, [C.c_void_p, _fp, C.POINTER(C.c_int), _fp, _fp]),
     "pmgpu_icp_cap_redos": (C.c_int, [C.c_void_p]),
+    "pmgpu_matches_get": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pmgpu_set_var_trimmed_ratios": (C.c_int, [C.c_void_p, C.c_float, C.c_float]),
     "pmgpu_var_trimmed_ratio": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pmgpu_host_srand": (None, [C.c_uint]),
@@ -291,6 +292,15 @@ class Context:
         limits = np.zeros(max(1, len(filters)), np.float32)
         self._check(lib.pmgpu_weights(self.h, len(filters), types.ctypes.data_as(_ip), _f(params), _ptr(w), _f(limits)))
         return w, limits[: len(filters)]
+
+    def matches(self, weights=True):
+        """the resident matches of the last evaluation: (ids (nq, k), dists (nq, k), weights (nq, k) or None, T_match (4, 4))"""
+        ids = np.empty((self.nq, self.k), np.int32)
+        dists = np.empty((self.nq, self.k), np.float32)
+        w = np.empty((self.nq, self.k), np.float32) if weights else None
+        T = np.zeros((4, 4), np.float32, order="F")
+        self._check(lib.pmgpu_matches_get(self.h, _ptr(ids), _ptr(dists), _ptr(w), _f(T)))
+        return ids, dists, w, np.array(T)
 
     def set_var_trimmed_ratios(self, min_ratio=0.05, max_ratio=0.99):
         """minRatio / maxRatio of the chain's VarTrimmedDistOutlierFilter (type FILTER_VARTRIMMEDDIST, param lambda)"""

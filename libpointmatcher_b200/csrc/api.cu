@@ -587,6 +587,23 @@ int pmgpu_weights(pmgpu_ctx* ctx, int nfilters, const int* types, const float* p
     return PMGPU_OK;
 }
 
+int pmgpu_matches_get(pmgpu_ctx* ctx, int32_t* ids_out, float* dists_out, float* weights_out, float* T_match_out) {
+    if (!ctx) return PMGPU_ERR_BAD_ARG;
+    PM_TRY(use_device(ctx));
+    if (!ctx->have_matches) return fail(ctx, PMGPU_ERR_NO_MATCHES, status_message(PMGPU_ERR_NO_MATCHES));
+    if (weights_out && !ctx->have_weights) return fail(ctx, PMGPU_ERR_NO_MATCHES, "no outlier weights have been evaluated");
+    const size_t total = (size_t)ctx->k * ctx->nq;
+    if (ids_out && total) PM_TRY(download_unpermuted<int32_t>(ctx, ctx->ids.p, ctx->ids_tmp, ctx->k, ids_out));
+    if (dists_out && total) PM_TRY(download_unpermuted<float>(ctx, ctx->dists.p, ctx->dists_tmp, ctx->k, dists_out));
+    if (weights_out && total) {
+        PM_TRY(launch_materialize_weights(ctx));
+        PM_TRY(download_unpermuted<float>(ctx, ctx->weights.p, ctx->dists_tmp, ctx->k, weights_out));
+    }
+    PM_TRY(pull_state(ctx));
+    if (T_match_out) memcpy(T_match_out, ctx->state_host->T_match.m, sizeof(float) * 16);
+    return PMGPU_OK;
+}
+
 int pmgpu_set_var_trimmed_ratios(pmgpu_ctx* ctx, float min_ratio, float max_ratio) {
     if (!ctx) return PMGPU_ERR_BAD_ARG;
     if (!(min_ratio > 0.f) || !(max_ratio <= 1.f) || !(min_ratio < max_ratio))

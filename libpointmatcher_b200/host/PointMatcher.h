@@ -358,6 +358,39 @@ struct PointMatcher {
                 descriptors = d;
             }
         }
+        // DataPoints::concatenate (DataPoints.cpp:225-330): append dp's points; only the descriptors both clouds carry
+        // (same name, same span) survive, in this cloud's order
+        void concatenate(const DataPoints& dp) {
+            const int n1 = features.cols(), n2 = dp.features.cols();
+            if (features.rows() != dp.features.rows())
+                throw InvalidField("Cannot concatenate DataPoints because the dimension of the features are not the same. Actual dimension: " +
+                                   std::to_string(features.rows()) + " New dimension: " + std::to_string(dp.features.rows()));
+            Labels kept;
+            for (const Label& a : descriptorLabels)
+                for (const Label& b : dp.descriptorLabels)
+                    if (a.text == b.text) {
+                        if (a.span != b.span)
+                            throw InvalidField("The field " + a.text + " has dimension " + std::to_string(a.span) + " in this, different than dimension " +
+                                               std::to_string(b.span) + " in that");
+                        kept.push_back(a);
+                        break;
+                    }
+            size_t rows = 0;
+            for (const Label& l : kept) rows += l.span;
+            Matrix f(features.rows(), n1 + n2), d((int)rows, rows ? n1 + n2 : 0);
+            for (int j = 0; j < n1 + n2; ++j)
+                for (int i = 0; i < features.rows(); ++i) f(i, j) = j < n1 ? features(i, j) : dp.features(i, j - n1);
+            unsigned row = 0;
+            for (const Label& l : kept) {
+                const unsigned ra = getDescriptorStartingRow(l.text), rb = dp.getDescriptorStartingRow(l.text);
+                for (int j = 0; j < n1 + n2; ++j)
+                    for (unsigned i = 0; i < l.span; ++i) d(row + i, j) = j < n1 ? descriptors(ra + i, j) : dp.descriptors(rb + i, j - n1);
+                row += l.span;
+            }
+            features = f;
+            descriptors = d;
+            descriptorLabels = kept;
+        }
         void addDescriptor(const std::string& name, const Matrix& newDescriptor) {
             allocateDescriptor(name, newDescriptor.rows());
             const unsigned row = getDescriptorStartingRow(name);

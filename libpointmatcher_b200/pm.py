@@ -131,6 +131,22 @@ class DataPoints:
     def copy(self):
         return DataPoints(self.features.copy(), {k: v.copy() for k, v in self.descriptors.items()})
 
+    def concatenate(self, dp):
+        """DataPoints::concatenate (DataPoints.cpp:225-330): append dp's points; only the descriptors both clouds carry
+        (same name, same dimension) survive, in this cloud's order — what align_sequence / build_map grow their map with"""
+        if self.features.shape[1] != dp.features.shape[1]:
+            raise InvalidField("Cannot concatenate DataPoints because the dimension of the features are not the same. Actual dimension: %d New dimension: %d"
+                               % (self.features.shape[1], dp.features.shape[1]))
+        merged = {}
+        for name, mine in self.descriptors.items():
+            if name in dp.descriptors:
+                theirs = dp.descriptors[name]
+                if mine.shape[1] != theirs.shape[1]:
+                    raise InvalidField("The field %s has dimension %d in this, different than dimension %d in that" % (name, mine.shape[1], theirs.shape[1]))
+                merged[name] = np.ascontiguousarray(np.concatenate([mine, theirs], axis=0))
+        self.features = np.ascontiguousarray(np.concatenate([self.features, dp.features], axis=0))
+        self.descriptors = merged
+
     # external column name -> (internal name, kind): IO.h:117-157
     _CSV_LABELS = dict(
         [(n, (n, "feature")) for n in ("x", "y", "z", "pad")]
@@ -1214,6 +1230,13 @@ class ICP:
         self.errorMinimizer._cov = res["cov"]
         self.T_iter = res["T_iter"]
         return mat4_mul(mat4_mul(T_refIn_refMean, res["T_iter"]), T_refMean_dataIn)
+
+    def getMatches(self):
+        """What the reference's inspectors and ErrorMinimizer::getErrorElements read after the fact (ErrorMinimizer.cpp:58-193):
+        the matches, outlier weights and reading transform of the last executed iteration, downloaded on request only.
+        Returns (Matches, weights (nq, k), T_match); after a capped fused loop the rejected far matches read id -2 / FLT_MAX / 0."""
+        ids, dists, w, T = _translate(self.ctx.matches)
+        return Matches(ids, dists), w, T
 
     def _run_with_host_checkers(self, bounds):
         """Counter / Differential still decide on the device; the host checkers see T_iter after every iteration

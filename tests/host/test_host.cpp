@@ -182,6 +182,31 @@ static int run_cpu() {
         CHECK(dynamic_cast<PM::GpuErrorMinimizer*>(p4.get())->kind == (PMGPU_MIN_P2PLANE | PMGPU_MIN_FORCE4DOF));
         CHECK(pm.ErrorMinimizerRegistrar.create("PointToPlaneErrorMinimizer", {{"force2D", "1"}})->get<bool>("force2D"));
         CHECK(throws<PM::ConfigurationError>([&] { pm.ErrorMinimizerRegistrar.create("PointToPlaneWithCovErrorMinimizer", {{"force2D", "1"}}); }));
+        {   // DataPoints::concatenate (DataPoints.cpp:225-330): common descriptors only, this cloud's order
+            DP a, b;
+            a.features = PM::Matrix::Constant(4, 2, 1);
+            b.features = PM::Matrix::Constant(4, 3, 2);
+            a.addDescriptor("normals", PM::Matrix::Constant(3, 2, 5));
+            a.addDescriptor("densities", PM::Matrix::Constant(1, 2, 6));
+            b.addDescriptor("densities", PM::Matrix::Constant(1, 3, 7));
+            b.addDescriptor("color", PM::Matrix::Constant(4, 3, 8));
+            a.concatenate(b);
+            CHECK(a.features.cols() == 5 && a.features(0, 1) == 1 && a.features(3, 4) == 2);
+            CHECK(a.descriptorLabels.size() == 1 && a.descriptorExists("densities") && !a.descriptorExists("normals"));
+            CHECK(a.descriptors.rows() == 1 && a.descriptors(0, 1) == 6 && a.descriptors(0, 2) == 7);
+            DP c2;
+            c2.features = PM::Matrix::Zero(3, 1);
+            CHECK(throws<DP::InvalidField>([&] { a.concatenate(c2); }));
+            DP d1, d2;
+            d1.features = PM::Matrix::Zero(4, 1);
+            d2.features = PM::Matrix::Zero(4, 1);
+            d1.addDescriptor("normals", PM::Matrix::Zero(3, 1));
+            d2.addDescriptor("normals", PM::Matrix::Zero(2, 1));
+            CHECK(throws<DP::InvalidField>([&] { d1.concatenate(d2); }));
+        }
+        auto vt = pm.OutlierFilterRegistrar.create("VarTrimmedDistOutlierFilter", {{"minRatio", "0.1"}, {"lambda", "1.5"}});
+        CHECK(vt->get<float>("lambda") == 1.5f && vt->get<float>("maxRatio") == 0.99f);
+        CHECK(throws<PM::InvalidParameter>([&] { pm.OutlierFilterRegistrar.create("VarTrimmedDistOutlierFilter", {{"minRatio", "0.9"}, {"maxRatio", "0.5"}}); }));
         DP c;
         c.features = PM::Matrix::Zero(4, 2);
         c.features(0, 0) = 1.f; c.features(1, 1) = 2.f; c.features(3, 0) = c.features(3, 1) = 1.f;

@@ -738,3 +738,33 @@ def test_icp_with_var_trimmed_filter_matches_oracle(oracle, synth, minimizer):
     assert 0.5 < ratio < 0.99
     with pytest.raises(pm.InvalidParameter):
         pm.VarTrimmedDistOutlierFilter({"minRatio": "0.9", "maxRatio": "0.5"})
+
+
+# ---------------------------------------------------------------------------------- resident matches on request (8f row 4)
+def test_matches_get_after_staged_calls_and_after_the_fused_loop(gpu_ctx, oracle, synth):
+    """pmgpu_matches_get: what getErrorElements / the inspectors read after the fact — identical to the staged outputs, and after a
+    fused (capped) loop the kept pairs are those of an exact search at T_match with the chain's weights"""
+    from libpointmatcher_b200 import capi, pm
+    rd, rf, _ = synth.scan_pair(40000)
+    gpu_ctx.set_reference(rf)
+    gpu_ctx.set_reading(rd)
+    ids, dists, _ = gpu_ctx.knn(None, 2, 0.0, np.inf)
+    w, _ = gpu_ctx.weights([(capi.FILTER_TRIMMEDDIST, 0.7)])
+    ids2, dists2, w2, T = gpu_ctx.matches()
+    assert (ids2 == ids).all() and (dists2 == dists).all() and (w2 == w).all() and (T == np.eye(4, dtype=np.float32)).all()
+    icp = pm.ICP()
+    icp.matcher = pm.KDTreeMatcher()
+    icp.outlierFilters = pm.OutlierFilters([pm.TrimmedDistOutlierFilter({"ratio": "0.7"})])
+    icp.errorMinimizer = pm.PointToPointErrorMinimizer()
+    icp.transformationCheckers = [pm.CounterTransformationChecker({"maxIterationCount": "6"})]
+    icp(pm.DataPoints(rd), pm.DataPoints(rf))
+    m, wf, Tm = icp.getMatches()
+    stats = icp.errorMinimizer._stats
+    assert abs(wf.sum() / wf.size - stats["weightedPointUsedRatio"]) < 1e-6
+    # the same search, staged and uncapped, at the same transform: kept pairs agree exactly
+    ids_e, dists_e, _ = icp.ctx.knn(Tm, 1, 0.0, np.inf)
+    we, _ = icp.ctx.weights([(capi.FILTER_TRIMMEDDIST, 0.7)])
+    icp.ctx.close()
+    kept = wf[:, 0] != 0
+    assert (we == wf).all() and (m.ids[kept] == ids_e[kept]).all() and (m.dists[kept] == dists_e[kept]).all()
+    assert ((m.ids[~kept] == ids_e[~kept]) | (m.ids[~kept] == -2)).all()

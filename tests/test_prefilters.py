@@ -332,3 +332,17 @@ def test_all_21_reference_chain_files_load(pm):
         icp = pm.ICP()
         icp.loadFromYaml(str(fx[k]).replace("PerformanceInspector", "NullInspector"))
         assert icp.matcher is not None and icp.errorMinimizer is not None and len(icp.transformationCheckers) >= 1
+
+
+def test_datapoints_concatenate(pm):
+    """DataPoints::concatenate (DataPoints.cpp:225-330): only the descriptors both clouds carry survive"""
+    a = pm.DataPoints(np.ones((2, 4), np.float32), {"normals": np.full((2, 3), 5, np.float32), "densities": np.full((2, 1), 6, np.float32)})
+    b = pm.DataPoints(np.full((3, 4), 2, np.float32), {"densities": np.full((3, 1), 7, np.float32), "color": np.full((3, 4), 8, np.float32)})
+    a.concatenate(b)
+    assert a.features.shape == (5, 4) and a.features[1, 0] == 1 and a.features[4, 3] == 2
+    assert list(a.descriptors) == ["densities"] and a.descriptors["densities"][:, 0].tolist() == [6, 6, 7, 7, 7]
+    with pytest.raises(pm.InvalidField):
+        a.concatenate(pm.DataPoints(np.zeros((1, 3), np.float32)))
+    c = pm.DataPoints(np.zeros((1, 4), np.float32), {"normals": np.zeros((1, 3), np.float32)})
+    with pytest.raises(pm.InvalidField):
+        c.concatenate(pm.DataPoints(np.zeros((1, 4), np.float32), {"normals": np.zeros((1, 2), np.float32)}))
