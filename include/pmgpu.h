@@ -137,6 +137,9 @@ int pmgpu_ref_set_centered(pmgpu_ctx* ctx, const float* features, int rows, int 
 int pmgpu_ref_set_normals(pmgpu_ctx* ctx, const float* normals, int normals_ld);
 
 /* ---- reading (the `filteredReading` argument of findClosests / compute) ---------------- */
+/* the reference's normals as resident (3 x nr, the caller's column order) — those pmgpu_ref_compute_normals made on the
+ * device never visit the host otherwise; for ErrorElements / residual-error consumers (PointToPlane.cpp:314-352) */
+int pmgpu_ref_get_normals(pmgpu_ctx* ctx, float* normals_out);
 int pmgpu_reading_set(pmgpu_ctx* ctx, const float* features, int rows, int n);
 
 /* RigidTransformation::compute on the resident reading, in place (TransformationsImpl.cpp:49-87;

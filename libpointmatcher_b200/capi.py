@@ -77,6 +77,7 @@ SIGNATURES = {
     "pmgpu_reading_set_max_dists": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "pmgpu_reading_apply_transform": (C.c_int, [C.c_void_p, _fp]),
     "pmgpu_reading_get": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pmgpu_ref_get_normals": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pmgpu_knn": (C.c_int, [C.c_void_p, _fp, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
     "pmgpu_weights": (C.c_int, [C.c_void_p, C.c_int, _ip, _fp, C.c_void_p, _fp]),
     "pmgpu_minimize": (C.c_int, [C.c_void_p, C.c_int, C.c_float, _fp, _fp, _fp]),
@@ -292,6 +293,12 @@ class Context:
         limits = np.zeros(max(1, len(filters)), np.float32)
         self._check(lib.pmgpu_weights(self.h, len(filters), types.ctypes.data_as(_ip), _f(params), _ptr(w), _f(limits)))
         return w, limits[: len(filters)]
+
+    def ref_normals(self):
+        """the reference's normals as resident on the device (nr, 3)"""
+        out = np.empty((self.nr, 3), np.float32)
+        self._check(lib.pmgpu_ref_get_normals(self.h, _ptr(out)))
+        return out
 
     def matches(self, weights=True):
         """the resident matches of the last evaluation: (ids (nq, k), dists (nq, k), weights (nq, k) or None, T_match (4, 4))"""

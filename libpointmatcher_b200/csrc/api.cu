@@ -425,6 +425,23 @@ int pmgpu_ref_set_normals(pmgpu_ctx* ctx, const float* normals, int normals_ld) 
     return upload_normals(ctx, normals, normals_ld);
 }
 
+int pmgpu_ref_get_normals(pmgpu_ctx* ctx, float* normals_out) {
+    if (!ctx) return PMGPU_ERR_BAD_ARG;
+    PM_TRY(use_device(ctx));
+    if (!normals_out) return fail(ctx, PMGPU_ERR_BAD_ARG, "null output");
+    if (ctx->nr == 0) return fail(ctx, PMGPU_ERR_NO_REFERENCE, status_message(PMGPU_ERR_NO_REFERENCE));
+    if (!ctx->has_normals) return fail(ctx, PMGPU_ERR_NO_NORMALS, status_message(PMGPU_ERR_NO_NORMALS));
+    std::vector<f4> host((size_t)ctx->nr);
+    PM_CUDA_TRY(ctx, cudaMemcpyAsync(host.data(), ctx->ref_normals.p, host.size() * sizeof(f4), cudaMemcpyDeviceToHost, ctx->stream));
+    PM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < ctx->nr; ++i) {
+        normals_out[3 * (size_t)i + 0] = host[i].x;
+        normals_out[3 * (size_t)i + 1] = host[i].y;
+        normals_out[3 * (size_t)i + 2] = host[i].z;
+    }
+    return PMGPU_OK;
+}
+
 int pmgpu_reading_set(pmgpu_ctx* ctx, const float* features, int rows, int n) {
     if (!ctx) return PMGPU_ERR_BAD_ARG;
     PM_TRY(use_device(ctx));

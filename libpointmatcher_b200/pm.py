@@ -467,6 +467,114 @@ class OutlierFilters(list, _Bound):
         return w
 
 
+# ---- ErrorElements, materialised on request (ErrorMinimizer.cpp:58-193) -------------------------------
+def rigid_apply(T, cloud):
+    """RigidTransformation::compute (TransformationsImpl.cpp:49-87) on a host cloud, float, the GEMM's left-to-right sums:
+    features' = T * features; "normals" / "observationDirections" turn with the rotation block"""
+    T = np.asarray(T, np.float32)
+    f = cloud.features
+    out = np.empty_like(f)
+    for r in range(4):
+        acc = T[r, 0] * f[:, 0]
+        for c in range(1, 4):
+            acc = (acc + T[r, c] * f[:, c]).astype(np.float32)
+        out[:, r] = acc
+    desc = dict(cloud.descriptors)
+    for name in ("normals", "observationDirections"):
+        if name in desc:
+            d = desc[name]
+            rot = np.empty_like(d)
+            for r in range(d.shape[1]):
+                acc = T[r, 0] * d[:, 0]
+                for c in range(1, d.shape[1]):
+                    acc = (acc + T[r, c] * d[:, c]).astype(np.float32)
+                rot[:, r] = acc
+            desc[name] = rot
+    return DataPoints(out, desc)
+
+
+class ErrorElements:
+    """ErrorMinimizer::ErrorElements (PointMatcher.h:507-525, ErrorMinimizer.cpp:58-193): the kept (reading point, match) pairs in
+    reading order, k innermost; `reading` repeats a point once per kept match, `reference` gathers the matched columns."""
+
+    def __init__(self, requestedPts, sourcePts, outlierWeights, matches):
+        ids, dists, w = np.asarray(matches.ids), np.asarray(matches.dists), np.asarray(outlierWeights, np.float32)
+        n, knn = ids.shape
+        keep = (dists != Matches.InvalidDist) & (w != 0)
+        if not (w != 0).any():
+            raise ConvergenceError("ErrorMnimizer: no point to minimize")
+        i_idx, k_idx = np.nonzero(keep)                       # row-major over (point, k): i outer, k inner
+        self.reading = DataPoints(requestedPts.features[i_idx], {k: v[i_idx] for k, v in requestedPts.descriptors.items()})
+        kept_ids = ids[i_idx, k_idx]
+        self.reference = DataPoints(sourcePts.features[kept_ids], {k: v[kept_ids] for k, v in sourcePts.descriptors.items()})
+        self.weights = w[i_idx, k_idx]
+        self.matches = Matches(dists[i_idx, k_idx][:, None], kept_ids[:, None])
+        self.nbRejectedMatches = int(((dists != Matches.InvalidDist) & (w == 0)).sum())
+        self.nbRejectedPoints = int((~keep.any(axis=1)).sum())
+        self.pointUsedRatio = float(np.float32(len(i_idx)) / np.float32(knn * n))
+        self.weightedPointUsedRatio = float(np.float32(self.weights.sum(dtype=np.float64)) / np.float32(knn * n))
+
+
+def _delta_norms(ee):
+    d = (ee.reading.features[:, :-1] - ee.reference.features[:, :-1]).astype(np.float32)
+    return _float_norm(d)
+
+
+def point_to_point_residual(ee):
+    """PointToPointErrorMinimizer::computeResidualError (PointToPoint.cpp:153-163): sum of |reading - reference| over the kept pairs"""
+    return float(_delta_norms(ee).sum(dtype=np.float64))
+
+
+def point_to_plane_residual(ee, force2D=False):
+    """PointToPlaneErrorMinimizer::computeResidualError (PointToPlane.cpp:314-352): sum w (n . (reading - reference))^2"""
+    dims = 2 if force2D else ee.reading.features.shape[1] - 1
+    n = ee.reference.getDescriptorViewByName("normals")
+    dot = np.zeros(len(n), np.float32)
+    for a in range(dims):
+        dot = (dot + (ee.reading.features[:, a] - ee.reference.features[:, a]).astype(np.float32) * n[:, a]).astype(np.float32)
+    return float((ee.weights * (dot * dot).astype(np.float32)).astype(np.float32).sum(dtype=np.float64))
+
+
+def point_to_point_overlap(ee):
+    """PointToPointErrorMinimizer::getOverlap (PointToPoint.cpp:116-151); None: no sensor noise, use weightedPointUsedRatio"""
+    if not ee.reading.descriptorExists("simpleSensorNoise"):
+        return None
+    dists = _delta_norms(ee)
+    mean = np.float32(np.float32(dists.sum(dtype=np.float64)) / np.float32(len(dists)))
+    return float(np.float32(int((dists < mean + ee.reading.descriptors["simpleSensorNoise"][:, 0]).sum())) / np.float32(len(dists)))
+
+
+def point_to_plane_overlap(ee):
+    """PointToPlaneErrorMinimizer::getOverlap (PointToPlane.cpp:369-466); None: neither cloud has sensor noise"""
+    rn = ee.reading.descriptors.get("simpleSensorNoise")
+    fn = ee.reference.descriptors.get("simpleSensorNoise")
+    dens = ee.reference.descriptors.get("densities")
+    if rn is not None and fn is not None and dens is not None:
+        values = dens.reshape(-1)
+        median = np.partition(values, int(len(values) * 0.5))[int(len(values) * 0.5)]
+        radius = np.float32(1.0 / np.power(np.float64(median), 1 / 3.0))
+        unc = ((radius + rn[:, 0]).astype(np.float32) + fn[:, 0]).astype(np.float32)
+    elif rn is not None and fn is not None:
+        unc = (rn[:, 0] + fn[:, 0]).astype(np.float32)
+    elif rn is not None:
+        unc = rn[:, 0]
+    elif fn is not None:
+        unc = fn[:, 0]
+    else:
+        return None
+    dists = _delta_norms(ee)
+    f = ee.reading.features
+    count, unique = 0, 1
+    last = f[0] * 2
+    for i in range(len(f)):            # sequential by construction: "last valid point" carries from one pair to the next
+        if (last != f[i]).any() and abs(dists[i]) < unc[i]:
+            last = f[i]
+            count += 1
+        if i > 0 and (f[i] != f[i - 1]).any():
+            unique += 1
+    return float(np.float32(count) / np.float32(unique + ee.nbRejectedPoints))
+
+
 # ---- ErrorMinimizers ---------------------------------------------------------------------------
 class _Minimizer(Parametrizable, _Bound):
     KIND = None
@@ -507,7 +615,31 @@ class _Minimizer(Parametrizable, _Bound):
     def getWeightedPointUsedRatio(self):
         return self._stats["weightedPointUsedRatio"]
 
+    #: set by ICP: builds the ErrorElements of the last iteration from the resident matches (downloaded on request only)
+    _error_elements_provider = None
+
+    def getErrorElements(self):
+        """ErrorMinimizer::getErrorElements (ErrorMinimizer.cpp:232-236) — lazily: nothing is copied back unless this is called"""
+        if self._error_elements_provider is None:
+            raise RuntimeError("Error, last error element empty. Error minimizer needs to be called at least once before using this method.")
+        return self._error_elements_provider()
+
+    def getResidualError(self, *_):
+        """PointToPoint.cpp:101-114 / PointToPlane.cpp:354-367; the reference's four arguments are the host copies of what is resident"""
+        ee = self.getErrorElements()
+        if self.KIND in (capi.MIN_P2PLANE, capi.MIN_P2PLANE_COV):
+            return point_to_plane_residual(ee, getattr(self, "force2D", False))
+        return point_to_point_residual(ee)
+
     def getOverlap(self):
+        """ErrorMinimizer.cpp:227-230, PointToPoint.cpp:116-151, PointToPlane.cpp:369-466: the noise-based estimate when the clouds
+        carry simpleSensorNoise, else the weighted ratio of the outlier filters"""
+        if self._error_elements_provider is not None and self.KIND != capi.MIN_P2POINT_SIM:
+            ee = self.getErrorElements()
+            plane = self.KIND in (capi.MIN_P2PLANE, capi.MIN_P2PLANE_COV)
+            ov = point_to_plane_overlap(ee) if plane else point_to_point_overlap(ee)
+            if ov is not None:
+                return ov
         return self._stats["weightedPointUsedRatio"]
 
 
@@ -1193,6 +1325,7 @@ class ICP:
             self.matcher._ref = reference
         else:
             mean = self.matcher.initCentered(reference)
+        self._reference_filtered, self._normals_on_device = reference, fuse_normals
         T_refIn_refMean = np.eye(4, dtype=np.float32)
         T_refIn_refMean[:3, 3] = mean[:3]
         return T_refIn_refMean
@@ -1213,6 +1346,9 @@ class ICP:
         T_refMean_dataIn = mat4_mul(T_refMean_refIn, T_init)
         _translate(self.ctx.set_reading, reading.features)
         self.ctx._reading_obj = None
+        self._reading_filtered, self._T_refMean_dataIn = reading, T_refMean_dataIn
+        self._T_refMean_refIn = T_refMean_refIn
+        self.errorMinimizer._error_elements_provider = self.getErrorElements
         if isinstance(self.matcher, KDTreeVarDistMatcher):
             self.matcher.uploadMaxDists(reading)
         if reading.descriptorExists("normals"):  # they turn with the reading (TransformationsImpl.cpp:71-84)
@@ -1231,12 +1367,25 @@ class ICP:
         self.T_iter = res["T_iter"]
         return mat4_mul(mat4_mul(T_refIn_refMean, res["T_iter"]), T_refMean_dataIn)
 
+    def getErrorElements(self):
+        """ErrorElements of the last executed iteration (ErrorMinimizer.cpp:58-193), from the resident matches: the reading as that
+        iteration saw it (T_match * T_refMean_dataIn * filtered reading, ICP.cpp:345-347,381), the centred reference, the kept pairs"""
+        matches, w, T_match = self.getMatches()
+        step = rigid_apply(T_match, rigid_apply(self._T_refMean_dataIn, self._reading_filtered))
+        ref = self._reference_filtered
+        desc = dict(ref.descriptors)
+        if self._normals_on_device:
+            desc["normals"] = _translate(self.ctx.ref_normals)
+        centred = ref.features.copy()
+        centred[:, :3] = (centred[:, :3] + self._T_refMean_refIn[:3, 3][None, :]).astype(np.float32)   # minus the mean (ICP.cpp:291-299)
+        return ErrorElements(step, DataPoints(centred, desc), w, matches)
+
     def getMatches(self):
         """What the reference's inspectors and ErrorMinimizer::getErrorElements read after the fact (ErrorMinimizer.cpp:58-193):
         the matches, outlier weights and reading transform of the last executed iteration, downloaded on request only.
         Returns (Matches, weights (nq, k), T_match); after a capped fused loop the rejected far matches read id -2 / FLT_MAX / 0."""
         ids, dists, w, T = _translate(self.ctx.matches)
-        return Matches(ids, dists), w, T
+        return Matches(dists, ids), w, T
 
     def _run_with_host_checkers(self, bounds):
         """Counter / Differential still decide on the device; the host checkers see T_iter after every iteration

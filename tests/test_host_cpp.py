@@ -226,3 +226,30 @@ def test_cpp_host_filters_match_python_mirror(host_bin, tmp_path):
         assert feat.tobytes() == c.features.tobytes(), name
         assert desc.tobytes() == np.ascontiguousarray(mine).tobytes(), name
     assert pos == len(raw)
+
+
+@pytest.mark.gpu
+def test_cpp_var_trimmed_and_force2d_chain_matches_oracle_and_python(host_bin, tmp_path, oracle, synth):
+    """VarTrimmedDistOutlierFilter + PointToPlaneErrorMinimizer force2D from a YAML file through the C++ mirror: same answer as
+    the oracle (1e-5) and as the Python mirror"""
+    from libpointmatcher_b200 import pm
+    rd, rf, _ = synth.scan_pair(60000)
+    nrm = oracle.surface_normals(rf, knn=10, nthreads=8)["normals"]
+    cfg = CONFIG.format(minimizer="PointToPlaneErrorMinimizer:\n    force2D: 1", iters=10, differential="")
+    cfg = cfg.replace("  - TrimmedDistOutlierFilter:\n      ratio: 0.75", "  - VarTrimmedDistOutlierFilter:\n      minRatio: 0.2\n      maxRatio: 0.95\n      lambda: 2.0")
+    assert "VarTrimmedDistOutlierFilter" in cfg
+    res = _run_icp(host_bin, tmp_path, cfg, rd, rf, nrm)
+    oracle.set_var_trimmed_ratios(0.2, 0.95)
+    try:
+        ref = oracle.icp(rd, rf, ref_normals=nrm, filters=[(oracle.FILTER_VARTRIMMEDDIST, 2.0)], minimizer=oracle.MIN_P2PLANE | oracle.MIN_FORCE2D,
+                         max_iterations=10, nthreads=8, acc_double=True)
+    finally:
+        oracle.set_var_trimmed_ratios()
+    assert res["iterations"] == ref["iterations"] == 10 and res["fused"] == 1
+    assert_transform_close(res["T"], ref["T"], 1e-5, 1e-5)
+    icp = pm.ICP()
+    icp.loadFromYaml(cfg)
+    Tp = icp(pm.DataPoints(rd), pm.DataPoints(rf, {"normals": nrm}))
+    icp.ctx.close()
+    assert_transform_close(res["T"], Tp, 1e-6, 1e-6)
+    assert Tp[2, 3] == 0 and Tp[2, 2] == 1

@@ -34,10 +34,11 @@ for r in rows[hi + 1:]:
     a[0] += 1
     a[1] += v
 tot = sum(a[1] for a in agg.values())
-p("== launch list of `python bench.py --steps 4 --warmup 3 --no-extra --no-cpu --no-e2e` (ns, share of all launches incl. the one-off build)")
+import os
+p("== launch list of `python bench.py --steps %s --warmup 3 --no-extra --no-cpu --no-e2e` (ns, share of all launches incl. the one-off build)" % os.environ.get("PROF_STEPS", "4"))
 for k, a in sorted(agg.items(), key=lambda x: -x[1][1])[:16]:
     p("%-72s n=%4d total=%12.0f share=%5.1f%% avg=%10.0f" % (k, a[0], a[1], 100 * a[1] / tot, a[1] / a[0]))
-loop = {k: a for k, a in agg.items() if any(s in k for s in ("knn_kernel", "accumulate", "finalize", "hist_kernel", "pick_kernel", "init_limits"))}
+loop = {k: a for k, a in agg.items() if any(s in k for s in ("knn_kernel", "knn_overflow", "accumulate", "finalize", "hist_kernel", "pick_kernel", "init_limits"))}
 lt = sum(a[1] for a in loop.values())
 p("-- share inside the iteration loop only")
 for k, a in sorted(loop.items(), key=lambda x: -x[1][1]):
