@@ -139,7 +139,8 @@ struct ICP : ICPChainBase {
                 trailingNormals = last;
         }
         // inputs are never mutated (ICP.cpp:285); without reference filters no host copy is needed
-        DataPoints filtered;
+        DataPoints& filtered = referenceFilteredHost;  // a member: ErrorElements may be asked for after this call returns
+        filtered = DataPoints();
         const size_t hostFilters = this->referenceDataPointsFilters.size() - (trailingNormals ? 1 : 0);
         if (hostFilters > 0) {
             filtered = referenceIn;
@@ -175,6 +176,7 @@ struct ICP : ICPChainBase {
 
 protected:
     DataPoints readingFiltered;
+    DataPoints referenceFilteredHost;
     size_t iterationCount = 0;
     bool fusedLoop = false;
     std::shared_ptr<GpuPipeline> pipeline;
@@ -306,6 +308,30 @@ protected:
         this->matcher->resetVisitCount();
         this->inspector->addStat("OverlapRatio", this->errorMinimizer->getWeightedPointUsedRatio());
         this->inspector->finish(iterationCount);
+        // ErrorElements of the last executed iteration, on request (ErrorMinimizer.cpp:58-193): the reading as that iteration saw
+        // it (T_match * T_refMean_dataIn * filtered reading, ICP.cpp:345-347,381), the centred reference (device-made normals are
+        // fetched), the kept pairs.  `reference` is the caller's cloud when there are no host reference filters: like the
+        // reference's matcher (MatchersImpl.cpp:77-83, libnabo keeps a reference), it must stay alive while this is used.
+        const DataPoints* referencePtr = &reference;
+        const int knnUsed = p.knn;
+        gpuMinimizer->materialize = [this, referencePtr, T_refMean_dataIn, T_refMean_refIn, knnUsed](typename ErrorMinimizer::ErrorElements& out) {
+            GpuPipeline& gp = *pipeline;
+            const int n = readingFiltered.features.cols();
+            Matches m(knnUsed, n);
+            OutlierWeights w(knnUsed, n);
+            TransformationParameters T_match(4, 4);
+            gp.check(pmgpu_matches_get(gp.ctx, m.ids.data(), reinterpret_cast<float*>(m.dists.data()), reinterpret_cast<float*>(w.data()),
+                                       reinterpret_cast<float*>(T_match.data())));
+            const DataPoints step = RigidTransformation::apply(RigidTransformation::apply(readingFiltered, T_refMean_dataIn), T_match);
+            DataPoints centred = *referencePtr;
+            for (int j = 0; j < centred.features.cols(); ++j)
+                for (int r = 0; r < centred.features.rows() - 1; ++r) centred.features(r, j) = centred.features(r, j) + T_refMean_refIn(r, centred.features.rows() - 1);
+            if (!centred.descriptorExists("normals")) {
+                Matrix normals(3, centred.features.cols());
+                if (pmgpu_ref_get_normals(gp.ctx, reinterpret_cast<float*>(normals.data())) == PMGPU_OK) centred.addDescriptor("normals", normals);
+            }
+            out = typename ErrorMinimizer::ErrorElements(step, centred, w, m);
+        };
         // ICP.cpp:448
         return T_refIn_refMean * T_iter * T_refMean_dataIn;
     }

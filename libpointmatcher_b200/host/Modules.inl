@@ -20,6 +20,9 @@ struct RigidTransformation : public Transformation {
     }
     DataPoints compute(const DataPoints& input, const TransformationParameters& parameters) const override {
         if (!checkParameters(parameters)) throw TransformationError("RigidTransformation: Error, rotation matrix is not orthogonal.");
+        return apply(input, parameters);
+    }
+    static DataPoints apply(const DataPoints& input, const TransformationParameters& parameters) {
         DataPoints out = input;
         out.features = parameters * input.features;
         // rotate the descriptors named normals / observationDirections (TransformationsImpl.cpp:72-84)
@@ -857,6 +860,7 @@ struct OutlierFilters : public std::vector<std::shared_ptr<OutlierFilter>>, publ
 
 // ---- error minimizers (ErrorMinimizers/*.cpp) — K4-K7 ------------------------------------------------
 struct GpuErrorMinimizer : public ErrorMinimizer, public GpuBound {
+    typedef typename ErrorMinimizer::ErrorElements ErrorElements;
     int kind;
     T sensorStdDev;
     Matrix covMatrix;
@@ -882,6 +886,95 @@ struct GpuErrorMinimizer : public ErrorMinimizer, public GpuBound {
         this->lastErrorElements.nbRejectedPoints = (int)stats[3];
     }
     Matrix getCovariance() const override { return covMatrix; }
+    bool isPlane() const { return (kind & 0xff) == PMGPU_MIN_P2PLANE || (kind & 0xff) == PMGPU_MIN_P2PLANE_COV; }
+    static T deltaNorm(const ErrorElements& e, int i) {
+        T acc = 0;
+        for (int r = 0; r < e.reading.features.rows() - 1; ++r) {
+            const T d = e.reading.features(r, i) - e.reference.features(r, i);
+            acc += d * d;
+        }
+        return std::sqrt(acc);
+    }
+    // PointToPoint.cpp:153-163: sum |reading - reference|;  PointToPlane.cpp:314-352: sum w (n . (reading - reference))^2
+    static T computeResidualError(const ErrorElements& e, bool plane, bool force2D) {
+        const int m = e.reading.features.cols();
+        double total = 0;
+        if (!plane) {
+            for (int i = 0; i < m; ++i) total += deltaNorm(e, i);
+            return T(total);
+        }
+        const unsigned rn = e.reference.getDescriptorStartingRow("normals");
+        const int dims = force2D ? 2 : e.reading.features.rows() - 1;
+        for (int i = 0; i < m; ++i) {
+            T dot = 0;
+            for (int r = 0; r < dims; ++r) dot += (e.reading.features(r, i) - e.reference.features(r, i)) * e.reference.descriptors(rn + r, i);
+            total += e.weights(0, i) * (dot * dot);
+        }
+        return T(total);
+    }
+    T getResidualError(const DataPoints& filteredReading, const DataPoints& filteredReference, const OutlierWeights& outlierWeights,
+                       const Matches& matches) const override {
+        const ErrorElements mPts(filteredReading, filteredReference, outlierWeights, matches);
+        return computeResidualError(mPts, isPlane(), (kind & PMGPU_MIN_FORCE2D) != 0);
+    }
+    // the same number for the last iteration of a registration, from the resident matches
+    T getResidualError() const { return computeResidualError(this->getErrorElements(), isPlane(), (kind & PMGPU_MIN_FORCE2D) != 0); }
+    // PointToPoint.cpp:116-151, PointToPlane.cpp:369-466: the noise-based estimate when the clouds carry simpleSensorNoise,
+    // else the weighted ratio of the outlier filters (ErrorMinimizer.cpp:227-230)
+    T getOverlap() const override {
+        if (!this->materialize || (kind & 0xff) == PMGPU_MIN_P2POINT_SIM) return this->lastErrorElements.weightedPointUsedRatio;
+        const ErrorElements e = this->getErrorElements();
+        const int m = e.reading.features.cols();
+        if (m == 0) throw std::runtime_error("Error, last error element empty. Error minimizer needs to be called at least once before using this method.");
+        const bool rNoise = e.reading.descriptorExists("simpleSensorNoise"), fNoise = e.reference.descriptorExists("simpleSensorNoise");
+        if (!isPlane()) {
+            if (!rNoise) return this->lastErrorElements.weightedPointUsedRatio;
+            const unsigned row = e.reading.getDescriptorStartingRow("simpleSensorNoise");
+            std::vector<T> dists(m);
+            double sum = 0;
+            for (int i = 0; i < m; ++i) sum += (dists[i] = deltaNorm(e, i));
+            const T mean = T(sum) / T(m);
+            int count = 0;
+            for (int i = 0; i < m; ++i) count += dists[i] < (mean + e.reading.descriptors(row, i)) ? 1 : 0;
+            return T(count) / T(m);
+        }
+        if (!rNoise && !fNoise) return this->lastErrorElements.weightedPointUsedRatio;
+        const unsigned rr = rNoise ? e.reading.getDescriptorStartingRow("simpleSensorNoise") : 0;
+        const unsigned fr = fNoise ? e.reference.getDescriptorStartingRow("simpleSensorNoise") : 0;
+        T medianRadius = 0;
+        const bool optimal = rNoise && fNoise && e.reference.descriptorExists("densities");
+        if (optimal) {
+            const unsigned dr = e.reference.getDescriptorStartingRow("densities");
+            std::vector<T> values(m);
+            for (int i = 0; i < m; ++i) values[i] = e.reference.descriptors(dr, i);
+            std::nth_element(values.begin(), values.begin() + (std::ptrdiff_t)(values.size() * 0.5), values.end());
+            const T medianDensity = values[(size_t)(values.size() * 0.5)];
+            medianRadius = T(1.0 / std::pow((double)medianDensity, 1 / 3.0));
+        }
+        int count = 0, nbUniquePoint = 1;
+        const int rows = e.reading.features.rows();
+        std::vector<T> last(rows);
+        for (int r = 0; r < rows; ++r) last[r] = e.reading.features(r, 0) * T(2);
+        auto differs = [&](const T* a, int col) {
+            for (int r = 0; r < rows; ++r)
+                if (a[r] != e.reading.features(r, col)) return true;
+            return false;
+        };
+        std::vector<T> prev(rows);
+        for (int i = 0; i < m; ++i) {
+            T unc;
+            if (optimal) unc = (medianRadius + e.reading.descriptors(rr, i)) + e.reference.descriptors(fr, i);
+            else if (rNoise && fNoise) unc = e.reading.descriptors(rr, i) + e.reference.descriptors(fr, i);
+            else unc = rNoise ? e.reading.descriptors(rr, i) : e.reference.descriptors(fr, i);
+            if (differs(last.data(), i) && deltaNorm(e, i) < unc) {
+                for (int r = 0; r < rows; ++r) last[r] = e.reading.features(r, i);
+                ++count;
+            }
+            if (i > 0 && differs(prev.data(), i)) ++nbUniquePoint;
+            for (int r = 0; r < rows; ++r) prev[r] = e.reading.features(r, i);
+        }
+        return T(count) / T(nbUniquePoint + e.nbRejectedPoints);
+    }
 };
 struct PointToPointErrorMinimizer : public GpuErrorMinimizer {
     static const std::string description() { return "Point-to-point error. Based on SVD decomposition."; }

@@ -21,6 +21,7 @@
 #include <cctype>
 #include <cstring>
 #include <fstream>
+#include <functional>
 #include <iostream>
 
 #include "../../include/pmgpu.h"
@@ -540,26 +541,81 @@ struct PointMatcher {
     DEF_REGISTRAR(OutlierFilter)
 
     struct ErrorMinimizer : public Parametrizable {
-        // kept for source compatibility; the GPU minimisers never materialise the compacted clouds
+        // The GPU minimisers never need the compacted clouds; they are built on request only (getErrorElements, getOverlap,
+        // getResidualError), from the matches resident on the device (pmgpu_matches_get).
         struct ErrorElements {
             DataPoints reading, reference;
             OutlierWeights weights;
             Matches matches;
             int nbRejectedMatches = -1, nbRejectedPoints = -1;
             T pointUsedRatio = T(-1), weightedPointUsedRatio = T(-1);
+            ErrorElements() {}
+            // ErrorMinimizer.cpp:58-193: the kept (reading point, match) pairs in reading order, k innermost
+            ErrorElements(const DataPoints& requestedPts, const DataPoints& sourcePts, const OutlierWeights& outlierWeights, const Matches& matchesIn) {
+                const int knn = outlierWeights.rows(), n = requestedPts.features.cols();
+                int pointsCount = 0;
+                for (size_t i = 0; i < outlierWeights.size(); ++i) pointsCount += outlierWeights(i) != T(0) ? 1 : 0;
+                if (pointsCount == 0) throw ConvergenceError("ErrorMnimizer: no point to minimize");
+                std::vector<int> keptPoint, keptId;
+                std::vector<T> keptDist, keptWeight;
+                int rejectedMatchCount = 0, rejectedPointCount = 0;
+                T weightSum = 0;
+                for (int i = 0; i < n; ++i) {
+                    bool matchExist = false;
+                    for (int k = 0; k < knn; ++k) {
+                        const T matchDist = matchesIn.dists(k, i);
+                        if (matchDist == Matches::InvalidDist()) continue;
+                        if (outlierWeights(k, i) != T(0)) {
+                            keptPoint.push_back(i);
+                            keptId.push_back(matchesIn.ids(k, i));
+                            keptDist.push_back(matchDist);
+                            keptWeight.push_back(outlierWeights(k, i));
+                            weightSum += outlierWeights(k, i);
+                            matchExist = true;
+                        } else
+                            ++rejectedMatchCount;
+                    }
+                    if (!matchExist) ++rejectedPointCount;
+                }
+                const int m = (int)keptPoint.size();
+                pointUsedRatio = T(m) / T(knn * n);
+                weightedPointUsedRatio = weightSum / T(knn * n);
+                reading = requestedPts;
+                reading.keepColumns(keptPoint);
+                reference = sourcePts;
+                reference.keepColumns(keptId);
+                weights = OutlierWeights(1, m);
+                matches = Matches(1, m);
+                for (int j = 0; j < m; ++j) {
+                    weights(0, j) = keptWeight[j];
+                    matches.ids(0, j) = keptId[j];
+                    matches.dists(0, j) = keptDist[j];
+                }
+                nbRejectedMatches = rejectedMatchCount;
+                nbRejectedPoints = rejectedPointCount;
+            }
         };
         ErrorMinimizer() {}
         ErrorMinimizer(const std::string& className, const ParametersDoc paramsDoc, const Parameters& params) : Parametrizable(className, paramsDoc, params) {}
         virtual ~ErrorMinimizer() {}
         T getPointUsedRatio() const { return lastErrorElements.pointUsedRatio; }
         T getWeightedPointUsedRatio() const { return lastErrorElements.weightedPointUsedRatio; }
-        ErrorElements getErrorElements() const { return lastErrorElements; }
+        // ErrorMinimizer.cpp:232-236 — materialised on request: nothing is copied back from the device unless this is called
+        ErrorElements getErrorElements() const {
+            if (materialize) materialize(lastErrorElements);
+            return lastErrorElements;
+        }
         virtual T getOverlap() const { return lastErrorElements.weightedPointUsedRatio; }
+        virtual T getResidualError(const DataPoints&, const DataPoints&, const OutlierWeights&, const Matches&) const {
+            throw std::runtime_error("You must implement getResidualError() in your ErrorMinimizer");  // ErrorMinimizer.cpp:205-210
+        }
+        // set by ICP after a registration: fills lastErrorElements from the resident matches
+        std::function<void(ErrorElements&)> materialize;
         virtual Matrix getCovariance() const { return Matrix::Zero(6, 6); }
         virtual TransformationParameters compute(const DataPoints& filteredReading, const DataPoints& filteredReference,
                                                  const OutlierWeights& outlierWeights, const Matches& matches) = 0;
     protected:
-        ErrorElements lastErrorElements;
+        mutable ErrorElements lastErrorElements;
     };
     DEF_REGISTRAR(ErrorMinimizer)
 

@@ -204,6 +204,37 @@ static int run_cpu() {
             d2.addDescriptor("normals", PM::Matrix::Zero(2, 1));
             CHECK(throws<DP::InvalidField>([&] { d1.concatenate(d2); }));
         }
+        {   // ErrorElements (ErrorMinimizer.cpp:58-193) and the residuals derived from them, host arguments only
+            DP rd, rf;
+            rd.features = PM::Matrix::Zero(4, 3);
+            rf.features = PM::Matrix::Zero(4, 2);
+            for (int j = 0; j < 3; ++j) { rd.features(0, j) = float(j); rd.features(3, j) = 1; }
+            rf.features(0, 0) = 0.5f; rf.features(1, 0) = 2; rf.features(3, 0) = 1;
+            rf.features(0, 1) = 5;    rf.features(2, 1) = 1; rf.features(3, 1) = 1;
+            PM::Matrix nrm = PM::Matrix::Zero(3, 2);
+            nrm(1, 0) = 1; nrm(2, 1) = 1;
+            rf.addDescriptor("normals", nrm);
+            PM::Matches m(2, 3);
+            PM::OutlierWeights w(2, 3);
+            const float inf = std::numeric_limits<float>::infinity();
+            const int ids[6] = {0, 1, 1, 0, 0, -1};
+            const float dd[6] = {1, 2, 3, 4, 5, inf}, ww[6] = {1, 0, 0.5f, 1, 0, 0};
+            for (int i = 0; i < 6; ++i) { m.ids(i) = ids[i]; m.dists(i) = dd[i]; w(i) = ww[i]; }
+            const PM::ErrorMinimizer::ErrorElements ee(rd, rf, w, m);
+            CHECK(ee.reading.features.cols() == 3 && ee.nbRejectedMatches == 2 && ee.nbRejectedPoints == 1);
+            CHECK(ee.matches.ids(0, 0) == 0 && ee.matches.ids(0, 1) == 1 && ee.matches.ids(0, 2) == 0 && ee.weights(0, 1) == 0.5f);
+            CHECK(ee.reading.features(0, 1) == 1 && ee.reading.features(0, 2) == 1 && ee.reference.features(0, 1) == 5);
+            CHECK(ee.reference.descriptors(2, 1) == 1 && ee.pointUsedRatio == 0.5f && std::fabs(ee.weightedPointUsedRatio - 2.5f / 6) < 1e-7f);
+            auto p2p = pm.ErrorMinimizerRegistrar.create("PointToPointErrorMinimizer");
+            const float r1 = std::sqrt(0.25f + 4.f), r2 = std::sqrt(16.f + 1.f), r3 = std::sqrt(0.25f + 4.f);
+            CHECK(std::fabs(p2p->getResidualError(rd, rf, w, m) - (r1 + r2 + r3)) < 1e-5f);
+            auto p2l = pm.ErrorMinimizerRegistrar.create("PointToPlaneErrorMinimizer");
+            CHECK(std::fabs(p2l->getResidualError(rd, rf, w, m) - (1 * 4.f + 0.5f * 1.f + 1 * 4.f)) < 1e-5f);
+            auto p2d = pm.ErrorMinimizerRegistrar.create("PointToPlaneErrorMinimizer", {{"force2D", "1"}});
+            CHECK(std::fabs(p2d->getResidualError(rd, rf, w, m) - (4.f + 0.f + 4.f)) < 1e-5f);
+            PM::OutlierWeights none = PM::OutlierWeights::Zero(2, 3);
+            CHECK(throws<PM::ConvergenceError>([&] { PM::ErrorMinimizer::ErrorElements bad(rd, rf, none, m); }));
+        }
         auto vt = pm.OutlierFilterRegistrar.create("VarTrimmedDistOutlierFilter", {{"minRatio", "0.1"}, {"lambda", "1.5"}});
         CHECK(vt->get<float>("lambda") == 1.5f && vt->get<float>("maxRatio") == 0.99f);
         CHECK(throws<PM::InvalidParameter>([&] { pm.OutlierFilterRegistrar.create("VarTrimmedDistOutlierFilter", {{"minRatio", "0.9"}, {"maxRatio", "0.5"}}); }));
@@ -334,6 +365,14 @@ static int run_icp(int argc, char** argv) {
         std::printf("cov");
         for (int i = 0; i < 6; ++i) std::printf(" %.9g", cov(i, i));
         std::printf("\n");
+        if (std::getenv("PM_TEST_ELEMENTS")) {
+            // ErrorElements of the last iteration on request, and what the reference derives from them
+            const auto ee = icp.errorMinimizer->getErrorElements();
+            auto* gm = dynamic_cast<PM::GpuErrorMinimizer*>(icp.errorMinimizer.get());
+            std::printf("elements %d rejM %d rejP %d used %.9g weighted %.9g residual %.9g noiseOverlap %.9g\n", (int)ee.reading.features.cols(), ee.nbRejectedMatches,
+                        ee.nbRejectedPoints, (double)ee.pointUsedRatio, (double)ee.weightedPointUsedRatio, (double)gm->getResidualError(),
+                        (double)icp.errorMinimizer->getOverlap());
+        }
     } catch (const std::exception& e) {
         std::printf("exception %s\n", e.what());
         return 3;

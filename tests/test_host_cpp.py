@@ -70,7 +70,7 @@ BOUND = """  - BoundTransformationChecker:
 """
 
 
-def _run_icp(host_bin, tmp_path, config, rd, rf, nrm, sequence=False):
+def _run_icp(host_bin, tmp_path, config, rd, rf, nrm, sequence=False, elements=False):
     cfg = tmp_path / "cfg.yaml"
     cfg.write_text(config)
     rd.astype(np.float32).tofile(tmp_path / "rd.f32")
@@ -79,13 +79,17 @@ def _run_icp(host_bin, tmp_path, config, rd, rf, nrm, sequence=False):
     if nrm is not None:
         np.ascontiguousarray(nrm, np.float32).tofile(tmp_path / "nrm.f32")
         args.append(str(tmp_path / "nrm.f32"))
-    env = dict(os.environ, PM_TEST_SEQUENCE="1") if sequence else None
+    env = dict(os.environ, PM_TEST_SEQUENCE="1") if sequence else (dict(os.environ, PM_TEST_ELEMENTS="1") if elements else None)
     r = subprocess.run(args, capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     lines = r.stdout.strip().split("\n")
     head = lines[0].split()
     T = np.array([[float(x) for x in l.split()] for l in lines[1:5]], np.float32)
-    return dict(iterations=int(head[1]), fused=int(head[3]), maxreached=int(head[5]), T=T)
+    out = dict(iterations=int(head[1]), fused=int(head[3]), maxreached=int(head[5]), T=T)
+    if elements:
+        tok = lines[6].split()
+        out.update({tok[i]: float(tok[i + 1]) for i in range(0, len(tok), 2)})
+    return out
 
 
 @pytest.mark.gpu
@@ -253,3 +257,29 @@ def test_cpp_var_trimmed_and_force2d_chain_matches_oracle_and_python(host_bin, t
     icp.ctx.close()
     assert_transform_close(res["T"], Tp, 1e-6, 1e-6)
     assert Tp[2, 3] == 0 and Tp[2, 2] == 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("minimizer", ["PointToPointErrorMinimizer", "PointToPlaneErrorMinimizer"])
+def test_cpp_error_elements_residual_and_overlap_match_python(host_bin, tmp_path, oracle, synth, minimizer):
+    """errorMinimizer->getErrorElements() / getOverlap() / the residual error after icp(reading, reference) through the C++ mirror:
+    built on request from the resident matches, equal to the Python mirror's (whose numbers are checked against the oracle)"""
+    from libpointmatcher_b200 import pm
+    rd, rf, _ = synth.scan_pair(30000)
+    cfg = CONFIG.format(minimizer=minimizer, iters=8, differential="")
+    cfg = cfg.replace("referenceDataPointsFilters:\n  - IdentityDataPointsFilter", "readingDataPointsFilters:\n  - SimpleSensorNoiseDataPointsFilter\n\n"
+                      "referenceDataPointsFilters:\n  - SimpleSensorNoiseDataPointsFilter\n  - SurfaceNormalDataPointsFilter:\n      knn: 10\n      keepDensities: 1")
+    cfg = cfg.replace("    knn: 1\n", "    knn: 2\n")
+    assert "keepDensities" in cfg and "knn: 2" in cfg
+    res = _run_icp(host_bin, tmp_path, cfg, rd, rf, None, elements=True)
+    icp = pm.ICP()
+    icp.loadFromYaml(cfg)
+    Tp = icp(pm.DataPoints(rd), pm.DataPoints(rf))
+    ee = icp.errorMinimizer.getErrorElements()
+    assert_transform_close(res["T"], Tp, 1e-6, 1e-6)
+    assert (res["elements"], res["rejM"], res["rejP"]) == (len(ee.reading.features), ee.nbRejectedMatches, ee.nbRejectedPoints)
+    assert abs(res["used"] - ee.pointUsedRatio) < 1e-6 and abs(res["weighted"] - ee.weightedPointUsedRatio) < 1e-6
+    residual, overlap = icp.errorMinimizer.getResidualError(), icp.errorMinimizer.getOverlap()
+    icp.ctx.close()
+    assert abs(res["residual"] - residual) < 1e-5 * residual
+    assert abs(res["noiseOverlap"] - overlap) < 1e-6 and 0 < overlap <= 1
