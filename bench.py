@@ -452,10 +452,15 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries the one JSON line and nothing else: whatever a library writes on fd 1 meanwhile (NCCL's version banner
+    # under NCCL_DEBUG=VERSION, for one) is sent to stderr
+    sys.stdout.flush()
+    out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         line = run_reference(args, rank, world)
         if line is not None:
-            print(json.dumps(line))
+            print(json.dumps(line), file=out, flush=True)
         return 0
     import torch
     import torch.distributed as dist
@@ -468,7 +473,7 @@ def main():
         if world > 1:
             dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
     return 0
 
 
