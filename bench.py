@@ -176,6 +176,14 @@ def make_params(capi, minimizer, steps):
 
 
 # ------------------------------------------------------------------------------------------------
+def host_threads():
+    """every core this process may run on — not OMP_NUM_THREADS, which torchrun sets to 1 for each rank it launches"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def run_reference(args, rank, world):
     """CPU arm: the oracle port of the reference path on all host threads (rank 0 only)."""
     if rank != 0:
@@ -183,7 +191,7 @@ def run_reference(args, rank, world):
     from libpointmatcher_b200 import synth
     from oracle import binding as orc
     orc.build()
-    threads = orc.num_threads()
+    threads = host_threads()
     rd, rf, _ = synth.scan_pair(args.points)
     kw = dict(filters=[(orc.FILTER_TRIMMEDDIST, RATIO)], minimizer=orc.MIN_P2POINT, nthreads=threads)
     if args.warmup > 0:
@@ -425,7 +433,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0 and world == 1 and not args.no_cpu:
         from oracle import binding as orc
         orc.build()
-        threads = orc.num_threads()
+        threads = host_threads()
         n_it = max(1, args.cpu_sample_iters)
         orc.icp(rd, rf, filters=[(orc.FILTER_TRIMMEDDIST, RATIO)], minimizer=orc.MIN_P2POINT, max_iterations=n_it, nthreads=threads)
         tm = orc.last_timings()
