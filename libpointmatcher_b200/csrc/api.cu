@@ -215,7 +215,7 @@ int enqueue_iteration(pmgpu_ctx* ctx, const pmgpu_icp_params* p, bool gated) {
     // (a RobustOutlierFilter weighs every match, however far: nothing may be cut)
     const bool use_cap = gated && ctx->cap_enabled && p->nfilters > 0 && max_r2 == pm_inf() && spec.robust_index() < 0 && spec.var_index() < 0 && !var_dist;
     PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, ctx->nq, true, gated, false, p->knn, max_r2,
-                      ctx->seed_k == 1 && p->knn == 1 && ctx->seed_enabled, ctx->ids.p, ctx->dists.p, use_cap,
+                      ctx->seed_k == p->knn && ctx->seed_enabled, ctx->ids.p, ctx->dists.p, use_cap,
                       var_dist ? ctx->reading_max_r2.p : nullptr));
     ctx->seed_k = p->knn;
     ctx->stage_end();
@@ -563,7 +563,7 @@ int pmgpu_knn(pmgpu_ctx* ctx, const float* T, int k, float epsilon, float max_di
     const float max_r2 = var_dist ? pm_inf() : max_dist * max_dist;
     ctx->stage_begin(0);
     PM_TRY(launch_knn(ctx, ctx->tree_view(), ctx->reading.p, ctx->nq, T != nullptr, false, false, k, max_r2,
-                      ctx->seed_k == 1 && k == 1 && ctx->seed_enabled, ctx->ids.p, ctx->dists.p, false, var_dist ? ctx->reading_max_r2.p : nullptr));
+                      ctx->seed_k == k && ctx->seed_enabled, ctx->ids.p, ctx->dists.p, false, var_dist ? ctx->reading_max_r2.p : nullptr));
     ctx->seed_k = k;
     ctx->stage_end();
     ctx->have_matches = true;

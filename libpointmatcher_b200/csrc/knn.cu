@@ -89,6 +89,21 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
                 if (cand_less(dd, prev, best.worst_d(), best.worst_id())) best.insert(dd, prev);
             }
         }
+        if (KMAX > 1 && use_seed) {
+            // k > 1: the previous k matches of this query, re-measured under the new T_iter, are k distinct real points, so
+            // the largest of their distances bounds the k-th nearest distance from above: the search may start with that
+            // radius.  Nothing is inserted — the points themselves lie within the radius (<=) and are found again — so the
+            // result is the unseeded one; only the pruning starts earlier.  Unusable when a slot was empty or capped.
+            float bound = 0.f;
+            bool usable = true;
+            for (int j = 0; j < k; ++j) {
+                const int prev = ids[(size_t)t * k + j];
+                if (prev < 0) { usable = false; break; }
+                const f4 r = __ldg(ref_orig + prev);
+                bound = fmaxf(bound, dist2(q.x, q.y, q.z, r.x, r.y, r.z));
+            }
+            if (usable && bound < best.worst_d()) best.init(k, bound);
+        }
     }
     // all 32 lanes stay in the loop until the slowest is done; phases re-converge the warp.
     // A lane whose query is still open after `budget` leaves hands it (with the candidates found
@@ -313,7 +328,7 @@ int launch_one(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, 
 
 // use_T: apply state->T_iter to every query; gated: no-op once state->iterate == 0;
 // self_query: `queries` is the leaf-ordered reference itself (results indexed by original column);
-// use_seed (k = 1): `ids` still holds the previous matches of the same reading;
+// use_seed: `ids` still holds the previous matches (same k) of the same reading — a candidate for k = 1, a radius for k > 1;
 // use_cap: stop at min(max_r2, state->cap)
 int launch_knn(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, bool use_T, bool gated, bool self_query, int k, float max_r2,
                bool use_seed, int32_t* ids, float* dists, bool use_cap, const float* var_r2) {
