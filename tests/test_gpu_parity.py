@@ -768,3 +768,25 @@ def test_matches_get_after_staged_calls_and_after_the_fused_loop(gpu_ctx, oracle
     kept = wf[:, 0] != 0
     assert (we == wf).all() and (m.ids[kept] == ids_e[kept]).all() and (m.dists[kept] == dists_e[kept]).all()
     assert ((m.ids[~kept] == ids_e[~kept]) | (m.ids[~kept] == -2)).all()
+
+
+# ---------------------------------------------------------------------------------- k > 1 starting radius from the previous matches
+def test_knn_k_gt_1_seeded_radius_is_exact(gpu_ctx, oracle):
+    """consecutive searches of the same reading with the same k: the previous k matches, re-measured, set the starting radius (knn.cu).
+    Whatever the change of transform in between, and with empty slots under a finite maxDist, the answer is the brute-force one."""
+    rng = np.random.default_rng(202)
+    ref, q = cloud(rng, 60000, "uniform"), cloud(rng, 5000, "uniform")   # mean spacing ~0.5: both maxDist values leave some slots empty
+    gpu_ctx.set_reference(ref)
+    gpu_ctx.set_reading(q)
+    poses = [np.eye(4, dtype=np.float32), small_pose(rng), small_pose(rng)]
+    big = np.eye(4, dtype=np.float32)
+    big[:3, 3] = (3.0, -2.0, 1.0)                                  # far from the previous answer: the radius is loose but valid
+    poses.append(big)
+    for k, md in ((10, np.inf), (10, 0.6), (4, 0.3)):
+        for T in poses:
+            qt = oracle.rigid_transform(T, q)
+            ib, db = oracle.bruteforce_knn(ref, qt, k, md, nthreads=8)
+            ig, dg, _ = gpu_ctx.knn(T, k, 0.0, md)
+            assert (ib == ig).all() and (bits(db) == bits(dg)).all(), (k, md)
+        if md != np.inf:
+            assert (ig == -1).any() and (ig[:, 0] >= 0).any()      # some slots empty: those queries search unseeded next time
