@@ -331,7 +331,7 @@ def run_ours(args, rank, world, local_rank):
     knn_avg_ms = knn_ms / max(1, knn_n)
     achieved = alg_bytes / (knn_avg_ms * 1e-3) / 1e9 if knn_avg_ms > 0 else 0.0
     # dram__bytes_read.sum + dram__bytes_write.sum of one knn_kernel<1> launch from the committed
-    # `ncu --set full` capture (profiles/r1_final_summary.txt; cold L2, 1 M x 1 M): 51.6 MB read + 0.7 MB written
+    # `ncu --set full` capture (profiles/r1_end_summary.txt; cold L2, 1 M x 1 M): 51.6 MB read + 0.7 MB written
     ncu_traffic = 52.2e6 if (nq_local == 1_000_000 and nr == 1_000_000) else None
     roofline = {"bound": "hbm", "kernel": "knn_kernel<1> + knn_overflow_kernel<1> (K2: transform + exact nearest neighbour, stage 1 + stage 2)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic,
@@ -356,7 +356,17 @@ def run_ours(args, rank, world, local_rank):
     except Exception as e:  # never let the explanatory figure break the bench line
         roofline["fp32"] = {"error": str(e)}
 
+    # the HBM-bound stages next to it (select = one 4 B read per match and pass, three passes; point-to-point
+    # normal equations = 40 B per match), same peak, from the same per-stage CUDA-event timings
+    sel_ms, min_ms = stage["select"][0] / max(1, args.steps), stage["minimize"][0] / max(1, args.steps)
+    hbm_stages = {}
+    for name, nbytes, t_ms in (("select (3 x hist_kernel)", 3 * 4 * nq_local, sel_ms), ("minimize (accumulate_kernel<0>)", 40 * nq_local, min_ms)):
+        if t_ms > 0:
+            gbs = nbytes / (t_ms * 1e-3) / 1e9
+            hbm_stages[name] = {"algorithmic_bytes_per_iteration": nbytes, "ms_per_iteration": t_ms, "achieved": gbs, "peak": peak, "unit": "GB/s",
+                                "frac": gbs / peak}
     extra = {
+        "hbm_stage_rooflines": hbm_stages,
         "stage_ms_per_iteration": {k: v[0] / max(1, args.steps) for k, v in stage.items()},
         "knn_queries_per_s": (nq_local * (world if dist_on else 1)) / (knn_avg_ms * 1e-3) if knn_avg_ms > 0 else None,
         "back_to_back_iterations_per_s": b2b_it / (b2b_ms * 1e-3),
