@@ -3,7 +3,7 @@ seconds on the box's host cores, and through size-independent properties."""
 import numpy as np
 import pytest
 
-from helpers import assert_transform_close, classify_id_mismatches
+from helpers import assert_transform_close, classify_id_mismatches, small_pose
 
 pytestmark = pytest.mark.gpu
 N = 1_000_000
@@ -79,6 +79,14 @@ def test_config4_shape_knn10_filters_cov(oracle, synth):
         w, lim = ctx.weights(chain)
         wo, lo = oracle.outlier_weights(do, chain)
         assert (lim.view(np.uint32) == lo.view(np.uint32)).all() and (w == wo).all()
+        # a second search of the same reading under a new transform starts from the radius the first one's matches give (knn.cu,
+        # k > 1): still the exact answer
+        T = small_pose(np.random.default_rng(7), trans=0.2, ang=0.02)
+        ids2, d2, _ = ctx.knn(T, 10, 0.0, 2.0)
+        io2, do2 = oracle.KdTree(rf).knn(oracle.rigid_transform(T, rd), 10, max_dist=2.0, nthreads=threads)
+        assert (d2.view(np.uint32) == do2.view(np.uint32)).all()
+        ndiff, nties = classify_id_mismatches(io2, do2, ids2, d2)
+        assert ndiff == nties
 
 
 def test_surface_normals_at_1m_properties(pair, oracle):
