@@ -183,7 +183,7 @@ int pmgpu_matches_get(pmgpu_ctx* ctx, int32_t* ids_out, float* dists_out, float*
 /* VarTrimmedDistOutlierFilter (OutlierFiltersImpl.h:147-172, OutlierFiltersImpl.cpp:152-218): TrimmedDist with the ratio
  * that minimises FRMS(i) = cumsum(sorted dists)[i] / i / (i / N)^(2 lambda) over minRatio N <= i < maxRatio N.  The
  * distances are sorted on the device, the running sum is taken in float one element after the other exactly like the
- * reference's std::partial_sum (one warp, ~2 ns per match), FRMS and its first minimum in parallel, and the limit is
+ * reference's std::partial_sum (one thread walks the chain, four warps feed it: ~4 ns per match), FRMS and its first minimum in parallel, and the limit is
  * read from the sorted array.  One such filter per chain; it switches capped matching off (every distance counts).
  * pmgpu_set_var_trimmed_ratios sets minRatio / maxRatio (defaults 0.05 / 0.99) of the context's VarTrimmedDist filter;
  * PMGPU_ERR_BAD_ARG unless 0 < min_ratio < max_ratio <= 1.  pmgpu_var_trimmed_ratio: the ratio the last evaluation chose. */

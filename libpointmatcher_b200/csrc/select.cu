@@ -137,36 +137,86 @@ __device__ __forceinline__ VarRange var_range(const unsigned* sorted, size_t tot
     r.end = max_el < count ? max_el : count;  // past `count` the reference reads uninitialised memory
     return r;
 }
-// std::partial_sum in float: cum[i] = fl(cum[i - 1] + d[i]).  The rounding of every step depends on the one before,
-// so this is a serial chain by definition; one warp walks it 32 elements at a time (coalesced load, 32 dependent
-// adds on values passed round by shuffle, coalesced store).
-__global__ void __launch_bounds__(32) vartrim_scan_kernel(const unsigned* __restrict__ sorted, size_t total, float min_ratio, float max_ratio,
-                                                          IcpState* state, int gated, float* __restrict__ cum) {
+// std::partial_sum in float: cum[i] = fl(cum[i - 1] + d[i]).  The rounding of every step depends on the one before, so
+// the sum is a serial chain of dependent adds by definition (4 cycles each).  One thread walks it; everything else is
+// taken off that thread: the other warps of the block stage the next tile of sorted distances into shared memory and
+// write the previous tile of running sums back (coalesced), so the chain thread issues one 16-byte shared load, four
+// adds and one 16-byte shared store per four elements.  (A single warp doing loads, shuffles and selects itself was
+// issue-bound at ~10 cycles per element: 6.5 ms per 1 M.)
+constexpr int VT_TILE = 2048;
+constexpr int VT_COPY = 128;               // threads that stage tiles (warps 1..4); warp 0 holds the chain thread
+constexpr int VT_THREADS = 32 + VT_COPY;
+__global__ void __launch_bounds__(VT_THREADS) vartrim_scan_kernel(const unsigned* __restrict__ sorted, size_t total, float min_ratio, float max_ratio,
+                                                                  IcpState* state, int gated, float* __restrict__ cum) {
+    __shared__ __align__(16) float s_in[2][VT_TILE];
+    __shared__ __align__(16) float s_out[2][VT_TILE];
     if (gated && state->iterate == 0) return;
     const VarRange r = var_range(sorted, total, min_ratio, max_ratio);
-    const int lane = threadIdx.x;
     if (r.n_finite == r.n_zero) {
-        if (lane == 0) {
+        if (threadIdx.x == 0) {
             if (state->status == 0) state->status = PMGPU_ERR_NO_OUTLIER_TO_FILTER;
             state->iterate = 0;
         }
         return;
     }
     const unsigned* __restrict__ src = sorted + r.n_zero;
-    float acc = 0.f;
-    float x = lane < r.end ? __uint_as_float(src[lane]) : 0.f;
-    for (long long base = 0; base < r.end; base += 32) {
-        const long long nxt = base + 32 + lane;
-        const float x_next = nxt < r.end ? __uint_as_float(src[nxt]) : 0.f;
-        float mine = 0.f;
+    const long long ntiles = (r.end + VT_TILE - 1) / VT_TILE;
+    const int tid = threadIdx.x;
+    // fixed trip counts, fully unrolled: the 16 loads of a thread are in flight together (a rolled loop issues load, dependent
+    // shared store, next load ... and pays the memory latency 16 times per tile — more than the chain takes)
+    auto stage_in = [&](long long tile, int c) {
+        float v[VT_TILE / VT_COPY];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            acc = __fadd_rn(acc, __shfl_sync(0xffffffffu, x, j));
-            if (lane == j) mine = acc;
+        for (int k = 0; k < VT_TILE / VT_COPY; ++k) {
+            const long long g = tile * VT_TILE + c + VT_COPY * k;
+            v[k] = g < r.end ? __uint_as_float(__ldg(src + g)) : 0.f;  // + 0 leaves the sum as it is
         }
-        if (base + lane < r.end) cum[base + lane] = mine;
-        x = x_next;
+#pragma unroll
+        for (int k = 0; k < VT_TILE / VT_COPY; ++k) s_in[tile & 1][c + VT_COPY * k] = v[k];
+    };
+    auto stage_out = [&](long long tile, int c) {
+#pragma unroll
+        for (int k = 0; k < VT_TILE / VT_COPY; ++k) {
+            const long long g = tile * VT_TILE + c + VT_COPY * k;
+            if (g < r.end) cum[g] = s_out[tile & 1][c + VT_COPY * k];
+        }
+    };
+    if (ntiles > 0 && tid >= 32) stage_in(0, tid - 32);
+    __syncthreads();
+    float acc = 0.f;
+    for (long long t = 0; t < ntiles; ++t) {
+        if (tid == 0) {
+            const float4* in4 = reinterpret_cast<const float4*>(s_in[t & 1]);
+            float4* out4 = reinterpret_cast<float4*>(s_out[t & 1]);
+            // batches of 32 elements, the next batch's shared loads issued before this batch's adds: left to the compiler, every
+            // 16-byte load sat between the store before it and the adds after it, and its latency was on the chain
+            constexpr int B = 8;
+            float4 cur[B], nxt[B];
+#pragma unroll
+            for (int k = 0; k < B; ++k) cur[k] = in4[k];
+            for (int i = 0; i < VT_TILE / 4; i += B) {
+                const int ni = (i + B < VT_TILE / 4) ? i + B : i;  // the last batch re-reads itself, unused
+#pragma unroll
+                for (int k = 0; k < B; ++k) nxt[k] = in4[ni + k];
+#pragma unroll
+                for (int k = 0; k < B; ++k) {
+                    acc = __fadd_rn(acc, cur[k].x); cur[k].x = acc;
+                    acc = __fadd_rn(acc, cur[k].y); cur[k].y = acc;
+                    acc = __fadd_rn(acc, cur[k].z); cur[k].z = acc;
+                    acc = __fadd_rn(acc, cur[k].w); cur[k].w = acc;
+                }
+#pragma unroll
+                for (int k = 0; k < B; ++k) out4[i + k] = cur[k];
+#pragma unroll
+                for (int k = 0; k < B; ++k) cur[k] = nxt[k];
+            }
+        } else if (tid >= 32) {  // warps 1..4: the next tile in, the previous tile out
+            if (t + 1 < ntiles) stage_in(t + 1, tid - 32);
+            if (t > 0) stage_out(t - 1, tid - 32);
+        }
+        __syncthreads();
     }
+    if (ntiles > 0 && tid >= 32) stage_out(ntiles - 1, tid - 32);
 }
 // FRMS = trunkSortedDist * ids.inverse() * deno.inverse().square(), per coefficient in float; minCoeff = first minimum;
 // then limit = getDistsQuantile(optRatio) read from the sorted array (Matches.cpp:60-87).  pow: Eigen calls powf; the
@@ -362,7 +412,7 @@ int launch_weights(pmgpu_ctx* ctx, const SelectSpec& spec, bool gated, bool cap_
         PM_CUDA_TRY(ctx, ctx->cub_tmp.reserve(tmp_bytes));
         size_t tb = ctx->cub_tmp.cap;
         PM_CUDA_TRY(ctx, cub::DeviceRadixSort::SortKeys(ctx->cub_tmp.p, tb, keys, ctx->var_sorted.p, (int)total, 0, 32, st));
-        vartrim_scan_kernel<<<1, 32, 0, st>>>(ctx->var_sorted.p, total, ctx->var_min_ratio, ctx->var_max_ratio, ctx->state, g, ctx->var_cum.p);
+        vartrim_scan_kernel<<<1, VT_THREADS, 0, st>>>(ctx->var_sorted.p, total, ctx->var_min_ratio, ctx->var_max_ratio, ctx->state, g, ctx->var_cum.p);
         vartrim_pick_kernel<<<1, 1024, 0, st>>>(ctx->var_sorted.p, total, ctx->var_min_ratio, ctx->var_max_ratio, spec.param[v], v, ctx->state, g,
                                                 ctx->var_cum.p);
         ctx->launches += 3;
