@@ -95,6 +95,7 @@ struct IcpState {
     unsigned robust_prefix;
     unsigned long long robust_rank;
     float var_ratio;             // VarTrimmedDistOutlierFilter: the optimised inlier ratio of the last evaluation
+    unsigned long long var_best; // (FRMS bits << 32 | candidate index): atomicMin over the blocks = the first minimum
     // adaptive search radius of the fused loop (DESIGN.md "capped matching"): squared radius the
     // NEXT match may stop at, the largest distance the filters of THIS iteration needed to know
     // exactly, and the flag that voids an iteration whose cap turned out too small

@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(VT_THREADS) vartrim_scan_kernel(const unsigned
     __shared__ __align__(16) float s_in[2][VT_TILE];
     __shared__ __align__(16) float s_out[2][VT_TILE];
     if (gated && state->iterate == 0) return;
+    if (threadIdx.x == 0) state->var_best = ~0ull;  // the pick kernel behind this one takes its minimum into it
     const VarRange r = var_range(sorted, total, min_ratio, max_ratio);
     if (r.n_finite == r.n_zero) {
         if (threadIdx.x == 0) {
@@ -224,32 +225,37 @@ __global__ void __launch_bounds__(VT_THREADS) vartrim_scan_kernel(const unsigned
 __global__ void __launch_bounds__(1024) vartrim_pick_kernel(const unsigned* __restrict__ sorted, size_t total, float min_ratio, float max_ratio,
                                                             float lambda, int f, IcpState* state, int gated, const float* __restrict__ cum) {
     if (gated && state->iterate == 0) return;
-    __shared__ float s_best[32];
-    __shared__ long long s_idx[32];
+    __shared__ unsigned long long s_best[32];
     const VarRange r = var_range(sorted, total, min_ratio, max_ratio);
     const float n_f = (float)r.points_nbr;
-    float best = pm_inf();
-    long long idx = -1;
-    for (long long e = r.min_el + threadIdx.x; e < r.end; e += blockDim.x) {
+    // FRMS >= 0, so its bit pattern orders like an unsigned integer: the minimum of (bits << 32 | offset) over all candidates
+    // is the smallest FRMS and, among equals, the smallest index — Eigen's minCoeff (first minimum)
+    unsigned long long best = ~0ull;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = r.min_el + (long long)blockIdx.x * blockDim.x + threadIdx.x; e < r.end; e += stride) {
         const float id = __fadd_rn((float)(r.min_el + 1), __fmul_rn((float)(e - r.min_el), 1.f));  // LinSpaced, step 1
         const float ratio = __fdiv_rn(id, n_f);
         const float deno = (float)pow((double)ratio, (double)lambda);
         const float inv = __fdiv_rn(1.f, deno);
         const float frms = __fmul_rn(__fmul_rn(cum[e], __fdiv_rn(1.f, id)), __fmul_rn(inv, inv));
-        if (idx < 0 || frms < best) { best = frms; idx = e; }  // ascending e per thread: strict < keeps the first
+        const unsigned long long key = ((unsigned long long)__float_as_uint(frms) << 32) | (unsigned long long)(unsigned)(e - r.min_el);
+        if (frms == frms && key < best) best = key;  // a NaN is never smaller (minCoeff skips it)
     }
-    auto better = [](float a, long long ia, float b, long long ib) { return ib < 0 ? true : (ia < 0 ? false : (a < b || (a == b && ia < ib))); };
     for (int o = 16; o > 0; o >>= 1) {
-        const float ob = __shfl_down_sync(0xffffffffu, best, o);
-        const long long oi = __shfl_down_sync(0xffffffffu, idx, o);
-        if (!better(best, idx, ob, oi)) { best = ob; idx = oi; }
+        const unsigned long long other = __shfl_down_sync(0xffffffffu, best, o);
+        if (other < best) best = other;
     }
-    if ((threadIdx.x & 31) == 0) { s_best[threadIdx.x >> 5] = best; s_idx[threadIdx.x >> 5] = idx; }
+    if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = best;
     __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+            if (s_best[w] < best) best = s_best[w];
+        if (best != ~0ull) atomicMin(&state->var_best, best);
+    }
+    if (!select_last_block(&state->ticket[0])) return;
     if (threadIdx.x != 0) return;
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
-        if (!better(best, idx, s_best[w], s_idx[w])) { best = s_best[w]; idx = s_idx[w]; }
-    const long long min_index = idx < 0 ? 0 : idx - r.min_el;
+    const unsigned long long winner = __ldcg(&state->var_best);
+    const long long min_index = winner == ~0ull ? 0 : (long long)(winner & 0xffffffffull);
     const float opt = __fdiv_rn((float)(min_index + r.min_el), n_f);
     state->var_ratio = opt;
     const unsigned long long n_valid = r.n_finite;  // zeros count for the quantile
@@ -413,7 +419,7 @@ int launch_weights(pmgpu_ctx* ctx, const SelectSpec& spec, bool gated, bool cap_
         size_t tb = ctx->cub_tmp.cap;
         PM_CUDA_TRY(ctx, cub::DeviceRadixSort::SortKeys(ctx->cub_tmp.p, tb, keys, ctx->var_sorted.p, (int)total, 0, 32, st));
         vartrim_scan_kernel<<<1, VT_THREADS, 0, st>>>(ctx->var_sorted.p, total, ctx->var_min_ratio, ctx->var_max_ratio, ctx->state, g, ctx->var_cum.p);
-        vartrim_pick_kernel<<<1, 1024, 0, st>>>(ctx->var_sorted.p, total, ctx->var_min_ratio, ctx->var_max_ratio, spec.param[v], v, ctx->state, g,
+        vartrim_pick_kernel<<<ctx->num_sms, 1024, 0, st>>>(ctx->var_sorted.p, total, ctx->var_min_ratio, ctx->var_max_ratio, spec.param[v], v, ctx->state, g,
                                                 ctx->var_cum.p);
         ctx->launches += 3;
     }
