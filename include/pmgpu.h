@@ -50,7 +50,7 @@ enum pmgpu_status {
     PMGPU_ERR_NOT_ORTHOGONAL = 11,      /* TransformationError                            TransformationsImpl.cpp:62-63 */
     PMGPU_ERR_KNN_TOO_LARGE = 12,       /* libnabo: "knn larger than the number of points" */
     PMGPU_ERR_NAN = 13,                 /* ConvergenceError("abs rotation norm not a number") TransformationCheckersImpl.cpp:154-157 */
-    PMGPU_ERR_COMM = 14                 /* NCCL failure */
+    PMGPU_ERR_COMM = 14                 /* NCCL failure, or the peers of a sharded registration did not arrive */
 };
 
 /* OutlierFiltersImpl.h: the distance filters of the hot path and the two row-8f-3 filters */
@@ -302,6 +302,18 @@ int pmgpu_host_sampling_surface_normal(float* features, int rows, int n, float* 
  * ncclUniqueId produced by pmgpu_comm_unique_id on rank 0 and distributed by the caller. */
 int pmgpu_comm_unique_id(void* unique_id_128);
 int pmgpu_comm_init(pmgpu_ctx* ctx, const void* unique_id_128, int rank, int nranks);
+/* Peer mailboxes: the per-iteration exchanges without any library collective.  Each rank's context owns a ~1 MB mailbox in
+ * its GPU's memory; pmgpu_comm_peer_handle allocates it and writes a 128-byte handle, the caller distributes the handles
+ * (rank order, nranks x 128 bytes) and pmgpu_comm_peer_init maps every peer's mailbox (cudaIpcOpenMemHandle across
+ * processes; direct pointers + peer access between contexts of one process).  From then on the last block of the
+ * histogram / accumulate / covariance kernels stores its rank's histograms or sums into every peer's mailbox over NVLink,
+ * raises a flag and sums the ranks' contributions in rank order itself — one kernel per stage as on one GPU, every rank
+ * bit-identical (libpointmatcher_b200/csrc/comm.cuh).  At most 8 ranks.  Both inits may be combined: the mailboxes take
+ * the per-iteration exchanges, NCCL the one-off all-gather of pmgpu_ref_compute_normals, which under a communicator
+ * computes only this rank's slice of the map's normals.  A rank whose peers do not arrive within 2 s
+ * stops with PMGPU_ERR_COMM.  All ranks must issue the same sequence of calls; a rank's reading slice may be empty. */
+int pmgpu_comm_peer_handle(pmgpu_ctx* ctx, void* handle_128);
+int pmgpu_comm_peer_init(pmgpu_ctx* ctx, const void* handles, int rank, int nranks);
 int pmgpu_comm_destroy(pmgpu_ctx* ctx);
 
 #ifdef __cplusplus

@@ -17,7 +17,7 @@ VARIANT = os.environ.get("PMGPU_VARIANT", "")
 DEFINES = os.environ.get("PMGPU_DEFINES", "").split()
 OBJ = os.path.join(HERE, "_build" + ("_" + VARIANT if VARIANT else ""))
 LIB = os.path.join(HERE, "libpmgpu%s.so" % ("_" + VARIANT if VARIANT else ""))
-SOURCES = ["api.cu", "tree_build.cu", "knn.cu", "select.cu", "minimize.cu", "normals.cu", "comm.cu", "host_filters.cu"]
+SOURCES = ["api.cu", "tree_build.cu", "knn.cu", "select.cu", "minimize.cu", "comm.cu", "host_filters.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

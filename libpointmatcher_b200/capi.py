@@ -102,6 +102,8 @@ SIGNATURES = {
                                                     C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     "pmgpu_comm_unique_id": (C.c_int, [C.c_void_p]),
     "pmgpu_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "pmgpu_comm_peer_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "pmgpu_comm_peer_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "pmgpu_comm_destroy": (C.c_int, [C.c_void_p]),
 }
 
@@ -388,6 +390,21 @@ class Context:
     def comm_init(self, unique_id, rank, nranks):
         buf = C.create_string_buffer(bytes(unique_id), 128)
         self._check(lib.pmgpu_comm_init(self.h, buf, rank, nranks))
+
+    def comm_peer_handle(self):
+        """allocate this context's peer mailbox; returns its 128-byte handle (to be gathered over all ranks)"""
+        buf = C.create_string_buffer(128)
+        self._check(lib.pmgpu_comm_peer_handle(self.h, buf))
+        return bytes(buf.raw)
+
+    def comm_peer_init(self, handles, rank):
+        """handles: the ranks' mailbox handles in rank order"""
+        blob = b"".join(bytes(h) for h in handles)
+        buf = C.create_string_buffer(blob, len(blob))
+        self._check(lib.pmgpu_comm_peer_init(self.h, buf, rank, len(handles)))
+
+    def comm_destroy(self):
+        self._check(lib.pmgpu_comm_destroy(self.h))
 
 
 def comm_unique_id():

@@ -6,6 +6,7 @@
 #include <new>
 
 #include "core/linalg.h"
+#include "normals.cuh"
 #include "pmgpu_internal.cuh"
 
 using namespace pm;
@@ -57,11 +58,6 @@ __global__ void unpack_f4_kernel(const f4* __restrict__ src, int n, float* __res
     dst[3 * (size_t)i] = v.x; dst[3 * (size_t)i + 1] = v.y; dst[3 * (size_t)i + 2] = v.z;
 }
 
-__global__ void ids_to_float_kernel(const int32_t* __restrict__ ids, size_t total, float* __restrict__ out) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < total) out[i] = (float)ids[i];
-}
-
 // Moves a structure built on the caller's coordinates into the frame centred on `mean`: every
 // stored coordinate c becomes fsub(c, mean).  Rounding is monotone, so the order along every axis,
 // the median splits and the tight boxes of the shifted points are exactly the shifted ones.
@@ -87,6 +83,13 @@ __global__ void center_structure_kernel(f4* __restrict__ ref_orig, f4* __restric
         b.x = fsub(b.x, mx); b.y = fsub(b.y, my); b.z = fsub(b.z, mz);
         boxes[i] = b;
     }
+}
+
+// sharded K8: normals arrive in leaf order (one contiguous slice per rank); position t holds the point whose original
+// column travels in ref_sorted[t].w
+__global__ void scatter_by_leaf_order_kernel(const f4* __restrict__ src, const f4* __restrict__ ref_sorted, int n, f4* __restrict__ dst) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) dst[f2u(ref_sorted[t].w)] = src[t];
 }
 
 __global__ void transform_inplace_kernel(f4* __restrict__ pts, int n, Mat4 T) {
@@ -162,14 +165,13 @@ int upload_normals(pmgpu_ctx* ctx, const float* normals, int ld) {
     if (ld < 3) return fail(ctx, PMGPU_ERR_BAD_ARG, "normals_ld must be >= 3");
     const int n = ctx->nr;
     PM_CUDA_TRY(ctx, ctx->ref_normals.reserve(n));
-    DevBuf<float> staging;
+    ScopedBuf<float> staging;
     PM_CUDA_TRY(ctx, staging.reserve((size_t)n * ld));
     // the last column may be shorter than ld in the caller's matrix: copy (n-1)*ld + 3 floats
     PM_CUDA_TRY(ctx, cudaMemcpyAsync(staging.p, normals, ((size_t)(n - 1) * ld + 3) * sizeof(float), cudaMemcpyDefault, ctx->stream));
     pack_normals_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(staging.p, ld, n, ctx->ref_normals.p);
     ctx->launches += 1;
     PM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    staging.release();
     ctx->has_normals = true;
     return PMGPU_OK;
 }
@@ -298,6 +300,7 @@ void pmgpu_ctx_destroy(pmgpu_ctx* ctx) {
     ctx->reading.release(); ctx->q_order.release();
     ctx->ids.release(); ctx->dists.release(); ctx->weights.release();
     ctx->hist.release(); ctx->partials.release();
+    ctx->reading_normals.release(); ctx->reading_max_r2.release(); ctx->var_sorted.release(); ctx->var_cum.release();
     for (auto& iv : ctx->intervals) { cudaEventDestroy(iv.a); cudaEventDestroy(iv.b); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
     if (ctx->state) cudaFree(ctx->state);
@@ -473,13 +476,12 @@ int pmgpu_reading_set_max_dists(pmgpu_ctx* ctx, const float* max_dists, int ld) 
     if (ld < 1) return fail(ctx, PMGPU_ERR_BAD_ARG, "ld must be >= 1");
     const int n = ctx->nq;
     PM_CUDA_TRY(ctx, ctx->reading_max_r2.reserve(n));
-    DevBuf<float> staging;
+    ScopedBuf<float> staging;
     PM_CUDA_TRY(ctx, staging.reserve((size_t)n * ld));
     PM_CUDA_TRY(ctx, cudaMemcpyAsync(staging.p, max_dists, ((size_t)(n - 1) * ld + 1) * sizeof(float), cudaMemcpyDefault, ctx->stream));
     pack_max_r2_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(staging.p, ld, ctx->q_order.p, n, ctx->reading_max_r2.p);
     ctx->launches += 1;
     PM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    staging.release();
     ctx->has_reading_max_r2 = true;
     ctx->seed_k = 0;
     return PMGPU_OK;
@@ -493,13 +495,12 @@ int pmgpu_reading_set_normals(pmgpu_ctx* ctx, const float* normals, int ld) {
     if (ld < 3) return fail(ctx, PMGPU_ERR_BAD_ARG, "normals_ld must be >= 3");
     const int n = ctx->nq;
     PM_CUDA_TRY(ctx, ctx->reading_normals.reserve(n));
-    DevBuf<float> staging;
+    ScopedBuf<float> staging;
     PM_CUDA_TRY(ctx, staging.reserve((size_t)n * ld));
     PM_CUDA_TRY(ctx, cudaMemcpyAsync(staging.p, normals, ((size_t)(n - 1) * ld + 3) * sizeof(float), cudaMemcpyDefault, ctx->stream));
     pack_normals_permuted_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(staging.p, ld, ctx->q_order.p, n, ctx->reading_normals.p);
     ctx->launches += 1;
     PM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    staging.release();
     ctx->has_reading_normals = true;
     return PMGPU_OK;
 }
@@ -694,6 +695,9 @@ int pmgpu_icp_reset(pmgpu_ctx* ctx, const float* T_iter_init) {
     h->cap_need = 0.f;
     h->redo = 0;
     h->redo_count = 0;
+    // a fresh registration never starts from an earlier run's matches (they would only be a seed, but a seed a first
+    // iteration does not have)
+    ctx->seed_k = 0;
     // TransformationCheckers::init (TransformationCheckersImpl.cpp:107-124): history starts with T_iter
     const Quat q = quat_from_mat4(h->T_iter);
     h->hist_q[0][0] = q.w; h->hist_q[0][1] = q.x; h->hist_q[0][2] = q.y; h->hist_q[0][3] = q.z;
@@ -708,7 +712,9 @@ int pmgpu_icp_enqueue(pmgpu_ctx* ctx, const pmgpu_icp_params* params, int n_iter
     if (!ctx) return PMGPU_ERR_BAD_ARG;
     PM_TRY(use_device(ctx));
     if (ctx->nr == 0) return fail(ctx, PMGPU_ERR_NO_REFERENCE, status_message(PMGPU_ERR_NO_REFERENCE));
-    if (ctx->nq == 0) return fail(ctx, PMGPU_ERR_NO_READING, status_message(PMGPU_ERR_NO_READING));
+    // a rank of a sharded registration may hold an empty slice: its kernels still run (one block each) and take part in
+    // the exchanges, or its peers would wait for it
+    if (ctx->nq == 0 && ctx->nranks <= 1) return fail(ctx, PMGPU_ERR_NO_READING, status_message(PMGPU_ERR_NO_READING));
     PM_TRY(check_params(ctx, params));
     if (params->max_dist < 0.f && !ctx->has_reading_max_r2) return fail(ctx, PMGPU_ERR_BAD_ARG, "maxDist < 0 needs pmgpu_reading_set_max_dists first");
     const bool plane = (params->minimizer & 0xff) == PMGPU_MIN_P2PLANE || (params->minimizer & 0xff) == PMGPU_MIN_P2PLANE_COV;
@@ -746,14 +752,17 @@ int pmgpu_icp_run(pmgpu_ctx* ctx, const pmgpu_icp_params* params, const float* T
     // ICP.cpp:371: `while (iterate)` runs the body at least once, Counter stops it after
     // maxIterationCount checks (max(1, maxIterationCount) iterations)
     const int n = params->max_iterations > 1 ? params->max_iterations : 1;
-    // n iteration slots; a slot whose capped match was void (IcpState::redo) does not count as an
-    // iteration, so top up until the checkers have stopped the loop (rare: normally one pass)
-    for (int slots = n;;) {
-        PM_TRY(pmgpu_icp_enqueue(ctx, params, slots));
-        PM_TRY(pull_state(ctx));
+    // Iteration slots are enqueued in bounded chunks with a look at the state in between: a chain without a Counter
+    // (max_iterations = INT_MAX, Differential only) or with a large one must not queue millions of gated no-op launches
+    // before the host learns that the checkers have stopped the loop.  A slot whose capped match was void
+    // (IcpState::redo) does not count as an iteration, so slots are topped up until the checkers stop the loop.
+    const int chunk = 64;
+    for (;;) {
         const IcpState* h = ctx->state_host;
+        const int left = n - h->iterations;
+        PM_TRY(pmgpu_icp_enqueue(ctx, params, left < chunk ? left : chunk));
+        PM_TRY(pull_state(ctx));
         if (h->status != PMGPU_OK || !h->iterate || h->iterations >= n) break;
-        slots = n - h->iterations;
     }
     const bool with_cov = (params->minimizer & 0xff) == PMGPU_MIN_P2POINT_COV || (params->minimizer & 0xff) == PMGPU_MIN_P2PLANE_COV;
     if (with_cov) {
@@ -772,17 +781,34 @@ int pmgpu_ref_compute_normals(pmgpu_ctx* ctx, int knn, float epsilon, float max_
     if (!(epsilon >= 0.f) || !(max_dist >= 0.f)) return fail(ctx, PMGPU_ERR_BAD_ARG, "epsilon and maxDist must be >= 0");
     if (flags & PMGPU_NORMALS_SMOOTH) return fail(ctx, PMGPU_ERR_UNSUPPORTED, "SurfaceNormalDataPointsFilter on GPU: smoothNormals is not supported");
     const int n = ctx->nr;
-    DevBuf<int32_t> nids;
-    DevBuf<float> ndists;
-    PM_CUDA_TRY(ctx, nids.reserve((size_t)knn * n));
-    PM_CUDA_TRY(ctx, ndists.reserve((size_t)knn * n));
     PM_CUDA_TRY(ctx, ctx->ref_normals.reserve(n));
-    int s = launch_knn(ctx, ctx->tree_view(), ctx->ref_sorted.p, n, false, false, true, knn, max_dist * max_dist, false, nids.p, ndists.p);
-    if (s == PMGPU_OK) s = launch_normals(ctx, ctx->ref_orig.p, n, nids.p, ndists.p, knn, flags, ctx->ref_normals.p, nullptr, nullptr, nullptr, nullptr);
-    cudaStreamSynchronize(ctx->stream);
-    nids.release();
-    ndists.release();
-    if (s != PMGPU_OK) return s;
+    NormalsSink sink;
+    memset(&sink, 0, sizeof(sink));
+    sink.pts = ctx->ref_orig.p;
+    sink.degenerate = &ctx->state->degenerate;
+    const float max_r2 = max_dist * max_dist;
+    if (ctx->nranks > 1 && ctx->nccl_comm) {
+        // every rank holds the whole structure and computes the normals of one slice of it (leaf-order
+        // positions, so the slice is spatially compact and its output contiguous); one all-gather of float4[N / G] and a
+        // local scatter into the caller's column order complete every rank's copy
+        const int chunk = (n + ctx->nranks - 1) / ctx->nranks;
+        const int lo = ctx->rank * chunk < n ? ctx->rank * chunk : n;
+        const int hi = lo + chunk < n ? lo + chunk : n;
+        PM_CUDA_TRY(ctx, ctx->gather_tmp.reserve((size_t)chunk * ctx->nranks));
+        sink.normals4 = ctx->gather_tmp.p;
+        sink.by_position = 1;
+        ctx->stage_begin(0);
+        PM_TRY(launch_knn_normals(ctx, ctx->tree_view(), lo, hi, knn, max_r2, sink));
+        ctx->stage_end();
+        PM_TRY(comm_allgather_bytes(ctx, ctx->gather_tmp.p, (size_t)chunk * sizeof(f4)));
+        scatter_by_leaf_order_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->gather_tmp.p, ctx->ref_sorted.p, n, ctx->ref_normals.p);
+        ctx->launches += 1;
+    } else {
+        sink.normals4 = ctx->ref_normals.p;
+        ctx->stage_begin(0);
+        PM_TRY(launch_knn_normals(ctx, ctx->tree_view(), 0, n, knn, max_r2, sink));
+        ctx->stage_end();
+    }
     PM_CUDA_TRY(ctx, cudaGetLastError());
     ctx->has_normals = true;
     return PMGPU_OK;
@@ -807,20 +833,13 @@ int pmgpu_normals(pmgpu_ctx* ctx, const float* features, int rows, int n, int kn
     struct Guard {
         pmgpu_ctx* c;
         pmgpu_ctx* parent;
-        ~Guard() { parent->launches += c->launches; pmgpu_ctx_destroy(c); }
+        ~Guard() { parent->launches += c->launches; pmgpu_ctx_destroy(c); g_alloc_stream = parent->stream; }
     } guard{sub, ctx};
     s = pmgpu_ref_set(sub, features, rows, n, nullptr, 0);
     if (s != PMGPU_OK) return fail(ctx, s, sub->err.c_str());
-    DevBuf<int32_t> nids;
-    DevBuf<float> ndists, scratch;
-    DevBuf<f4> n4;
-    struct Release {
-        DevBuf<int32_t>& a; DevBuf<float>& b; DevBuf<float>& c; DevBuf<f4>& d;
-        ~Release() { a.release(); b.release(); c.release(); d.release(); }
-    } rel{nids, ndists, scratch, n4};
-    PM_CUDA_TRY(ctx, nids.reserve((size_t)knn * n));
-    PM_CUDA_TRY(ctx, ndists.reserve((size_t)knn * n));
-    PM_CUDA_TRY(ctx, n4.reserve(n));
+    ScopedBuf<float> scratch;
+    ScopedBuf<f4> n4;
+    if (out->normals) PM_CUDA_TRY(ctx, n4.reserve(n));
     // scratch: densities n | eig_values 3n | eig_vectors 9n | mean_dists n | normals3 3n | ids-as-float knn*n
     const size_t off_den = 0, off_val = (size_t)n, off_vec = 4 * (size_t)n, off_md = 13 * (size_t)n, off_n3 = 14 * (size_t)n, off_ids = 17 * (size_t)n;
     PM_CUDA_TRY(ctx, scratch.reserve(17 * (size_t)n + (out->matched_ids ? (size_t)knn * n : 0)));
@@ -828,11 +847,18 @@ int pmgpu_normals(pmgpu_ctx* ctx, const float* features, int rows, int n, int kn
     IcpState* h = sub->state_host;
     h->degenerate = 0;
     s = push_state(sub);
-    if (s == PMGPU_OK) s = launch_knn(sub, sub->tree_view(), sub->ref_sorted.p, n, false, false, true, knn, max_dist * max_dist, false, nids.p, ndists.p);
-    if (s == PMGPU_OK)
-        s = launch_normals(sub, sub->ref_orig.p, n, nids.p, ndists.p, knn, flags, n4.p, out->densities ? scratch.p + off_den : nullptr,
-                           out->eig_values ? scratch.p + off_val : nullptr, out->eig_vectors ? scratch.p + off_vec : nullptr,
-                           out->mean_dists ? scratch.p + off_md : nullptr);
+    // K8 as the epilogue of the self-kNN: only what the caller asked for is computed and written
+    NormalsSink sink;
+    memset(&sink, 0, sizeof(sink));
+    sink.pts = sub->ref_orig.p;
+    sink.normals4 = out->normals ? n4.p : nullptr;
+    sink.densities = out->densities ? scratch.p + off_den : nullptr;
+    sink.eig_values = out->eig_values ? scratch.p + off_val : nullptr;
+    sink.eig_vectors = out->eig_vectors ? scratch.p + off_vec : nullptr;
+    sink.mean_dists = out->mean_dists ? scratch.p + off_md : nullptr;
+    sink.matched_ids = out->matched_ids ? scratch.p + off_ids : nullptr;
+    sink.degenerate = &sub->state->degenerate;
+    if (s == PMGPU_OK) s = launch_knn_normals(sub, sub->tree_view(), 0, n, knn, max_dist * max_dist, sink);
     if (s != PMGPU_OK) return fail(ctx, s, sub->err.c_str());
     auto copy_out = [&](float* dst, int ld, const float* src, int span) -> cudaError_t {
         if (!dst) return cudaSuccess;
@@ -848,12 +874,7 @@ int pmgpu_normals(pmgpu_ctx* ctx, const float* features, int rows, int n, int kn
     PM_CUDA_TRY(ctx, copy_out(out->eig_values, out->eig_values_ld, scratch.p + off_val, 3));
     PM_CUDA_TRY(ctx, copy_out(out->eig_vectors, out->eig_vectors_ld, scratch.p + off_vec, 9));
     PM_CUDA_TRY(ctx, copy_out(out->mean_dists, out->mean_dists_ld, scratch.p + off_md, 1));
-    if (out->matched_ids) {
-        const size_t total = (size_t)knn * n;
-        ids_to_float_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(nids.p, total, scratch.p + off_ids);
-        sub->launches += 1;
-        PM_CUDA_TRY(ctx, copy_out(out->matched_ids, out->matched_ids_ld, scratch.p + off_ids, knn));
-    }
+    PM_CUDA_TRY(ctx, copy_out(out->matched_ids, out->matched_ids_ld, scratch.p + off_ids, knn));
     s = pull_state(sub);
     if (s != PMGPU_OK) return fail(ctx, s, sub->err.c_str());
     PM_CUDA_TRY(ctx, cudaGetLastError());

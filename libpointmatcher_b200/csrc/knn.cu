@@ -14,6 +14,9 @@
 // from the device-resident IcpState, so no host round trip separates iterations; in iterations
 // >= 2 (k = 1) the previous match, re-measured, seeds the search with a tight bound.  Queries
 // still open after a budget of leaves go to a second, warp-per-query kernel (stage 2).
+#include <string.h>
+
+#include "normals.cuh"
 #include "pmgpu_internal.cuh"
 
 namespace pm {
@@ -42,13 +45,15 @@ __device__ __forceinline__ Cap knn_cap(const IcpState* state, int use_cap, float
     return c;
 }
 
-template <int KMAX, bool PLANES>
+// NORMALS: K8 — a self-query whose epilogue turns the k neighbours into the point's surface normal (normals.cuh) instead of
+// writing them out; `ids` / `dists` are then unused
+template <int KMAX, bool PLANES, bool NORMALS>
 __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4* __restrict__ queries, int nq, const IcpState* __restrict__ state,
                                                         int use_T, int gated, int self_query, int k, float max_r2,
                                                         const f4* __restrict__ ref_orig, int use_seed, int32_t* __restrict__ ids,
                                                         float* __restrict__ dists, unsigned long long* visits, int budget,
                                                         uint32_t* __restrict__ overflow, unsigned* overflow_count, int use_cap,
-                                                        const float* __restrict__ var_r2) {
+                                                        const float* __restrict__ var_r2, NormalsSink ns, int pos_offset) {
     extern __shared__ float s_plane[];  // [depth + 1][KNN_BLOCK]: cached plane distances, one column per lane
     __shared__ Mat4 sT;
     if (gated && state->iterate == 0) return;
@@ -111,6 +116,7 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
     // pathological queries (e.g. equidistant to a whole scan ring) would otherwise hold their
     // warp — and the kernel — for thousands of rounds.
     int rounds = 0;
+    unsigned my_slot = 0xffffffffu;  // K8: the stage-2 queue slot this query was handed over at
     while (__any_sync(0xffffffffu, running)) {
         // descend: one level per step for every lane that is not at a leaf yet
         const float w0 = best.worst_d();
@@ -132,11 +138,34 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
         if (running && !found) running = false;  // search complete
         ++rounds;
         if (running && rounds >= budget) {
-            running = false;
-            overflow[atomicAdd(overflow_count, 1u)] = (uint32_t)t;
+            const unsigned slot = atomicAdd(overflow_count, 1u);
+            if (!NORMALS || slot < ns.scratch_cap) {
+                running = false;
+                overflow[slot] = (uint32_t)t;
+                my_slot = slot;
+            } else {
+                budget = 0x7fffffff;  // K8: the hand-over scratch is full — this lane finishes its query here
+            }
         }
     }
-    if (t < nq) {
+    if (NORMALS) {
+        bool deg = false;
+        if (t < nq) {
+            if (my_slot != 0xffffffffu) {
+                // handed to stage 2: the candidates found so far travel in the scratch, by queue slot
+                static_for<0, KMAX>([&](auto J) {
+                    if (J < k) {
+                        ns.scratch_ids[(size_t)my_slot * k + J] = best.id[J];
+                        ns.scratch_d[(size_t)my_slot * k + J] = best.d[J];
+                    }
+                });
+            } else {
+                deg = normals_epilogue<KMAX>(best, k, ns, ns.by_position ? (size_t)(pos_offset + t) : (size_t)qi, s.qx, s.qy, s.qz);
+            }
+        }
+        const unsigned dm = __ballot_sync(0xffffffffu, deg);
+        if ((threadIdx.x & 31) == 0 && dm) atomicAdd(ns.degenerate, __popc(dm));
+    } else if (t < nq) {
         int32_t* oi = ids + (size_t)qi * k;
         float* od = dists + (size_t)qi * k;
         static_for<0, KMAX>([&](auto J) {
@@ -164,12 +193,12 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
 // bounds, same ranking: the result is the one the single-lane search would have produced.
 constexpr int OVF_STACK = 224;  // <= 32 pushes per expansion level, <= 6 levels of expansion (depth <= 30)
 
-template <int KMAX>
+template <int KMAX, bool NORMALS>
 __global__ void __launch_bounds__(128) knn_overflow_kernel(TreeView tree, const f4* __restrict__ queries, const IcpState* __restrict__ state, int use_T,
                                                            int gated, int self_query, int k, float max_r2, const uint32_t* __restrict__ overflow,
                                                            unsigned* overflow_count, unsigned* next_count, int32_t* __restrict__ ids,
                                                            float* __restrict__ dists, unsigned long long* visits, int use_cap,
-                                                           const float* __restrict__ var_r2) {
+                                                           const float* __restrict__ var_r2, NormalsSink ns, int pos_offset) {
     __shared__ uint32_t s_stack[4][OVF_STACK];
     __shared__ Mat4 sT;
     if (gated && state->iterate == 0) return;
@@ -178,7 +207,8 @@ __global__ void __launch_bounds__(128) knn_overflow_kernel(TreeView tree, const 
         if (threadIdx.x < 16) sT.m[threadIdx.x] = state->T_iter.m[threadIdx.x];
         __syncthreads();
     }
-    const unsigned count = *overflow_count;
+    unsigned count = *overflow_count;
+    if (NORMALS && count > ns.scratch_cap) count = ns.scratch_cap;  // later arrivals finished in stage 1
 #ifdef PM_PROFILE_NS
     if (blockIdx.x == 0 && threadIdx.x == 0) printf("stage 2: %u queries\n", count);
 #endif
@@ -196,11 +226,11 @@ __global__ void __launch_bounds__(128) knn_overflow_kernel(TreeView tree, const 
         if (use_T) q = transform_point(sT, q);
         TopK<KMAX> best;
         best.init(k, var_r2 ? var_r2[t] : cap.r2);
-        // seed: the candidates stage 1 left in the result arrays (ascending, real points)
+        // seed: the candidates stage 1 left in the result arrays (K8: in the scratch, by queue slot); ascending, real points
         for (int j = 0; j < k; ++j) {
-            const int id = ids[(size_t)qi * k + j];
-            const float dd = dists[(size_t)qi * k + j];
-            if (id >= 0 && cand_less(dd, id, best.worst_d(), best.worst_id())) best.insert(dd, id);
+            const int id = NORMALS ? ns.scratch_ids[(size_t)w * k + j] : ids[(size_t)qi * k + j];
+            const float dd = NORMALS ? ns.scratch_d[(size_t)w * k + j] : dists[(size_t)qi * k + j];
+            if (id >= 0 && id != PM_NO_ID && cand_less(dd, id, best.worst_d(), best.worst_id())) best.insert(dd, id);
         }
         int sp = 0;
         if (lane == 0) stack[0] = 1u;
@@ -278,7 +308,11 @@ __global__ void __launch_bounds__(128) knn_overflow_kernel(TreeView tree, const 
                 for (int i = 0; i < 4 * U && mask; ++i) mask &= mask - 1;
             }
         }
-        if (lane == 0) {
+        if (NORMALS) {
+            // the list is replicated in every lane: lane 0 finishes the point
+            if (lane == 0 && normals_epilogue<KMAX>(best, k, ns, ns.by_position ? (size_t)(pos_offset + t) : (size_t)qi, q.x, q.y, q.z))
+                atomicAdd(ns.degenerate, 1);
+        } else if (lane == 0) {
             for (int j = 0; j < k; ++j) {
                 float bd;
                 int bi;
@@ -293,32 +327,41 @@ __global__ void __launch_bounds__(128) knn_overflow_kernel(TreeView tree, const 
     if (visits && my_visits) atomicAdd(visits, my_visits);
 }
 
-template <int KMAX>
+template <int KMAX, bool NORMALS>
 int launch_one(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, bool use_T, bool gated, bool self_query, int k, float max_r2,
-               bool use_seed, int32_t* ids, float* dists, bool use_cap, const float* var_r2) {
+               bool use_seed, int32_t* ids, float* dists, bool use_cap, const float* var_r2, NormalsSink ns, int pos_offset) {
     const int grid = (nq + KNN_BLOCK - 1) / KNN_BLOCK;
     if (grid == 0) return PMGPU_OK;
     const size_t smem = (size_t)(tree.depth + 2) * KNN_BLOCK * sizeof(float);
     const bool seeded = KMAX == 1 && use_seed;
-    const bool planes = !(seeded && ctx->seeded_without_planes);
+    const bool planes = NORMALS || !(seeded && ctx->seeded_without_planes);
     const int budget = seeded ? ctx->knn_budget : ctx->knn_budget_unseeded;
     PM_CUDA_TRY(ctx, ctx->overflow.reserve((size_t)nq));
+    if (NORMALS) {
+        // hand-over scratch for the queries stage 1 gives up on: one in eight at most, the rest finish where they are
+        ns.scratch_cap = (unsigned)(nq / 8 + 1024);
+        PM_CUDA_TRY(ctx, ctx->ids_tmp.reserve((size_t)ns.scratch_cap * k));
+        PM_CUDA_TRY(ctx, ctx->dists_tmp.reserve((size_t)ns.scratch_cap * k));
+        ns.scratch_ids = ctx->ids_tmp.p;
+        ns.scratch_d = ctx->dists_tmp.p;
+    }
     // the two stages of one launch share counter[parity]; stage 2 clears counter[parity ^ 1] for the next launch
     unsigned* cnt = &ctx->state->overflow_count[ctx->knn_parity];
     unsigned* cnt_next = &ctx->state->overflow_count[ctx->knn_parity ^ 1];
     ctx->knn_parity ^= 1;
     if (planes)
-        knn_kernel<KMAX, true><<<grid, KNN_BLOCK, smem, ctx->stream>>>(tree, queries, nq, ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k,
-                                                                      max_r2, ctx->ref_orig.p, use_seed ? 1 : 0, ids, dists, &ctx->state->visits,
-                                                                      budget, ctx->overflow.p, cnt, use_cap ? 1 : 0, var_r2);
-    else
-        knn_kernel<KMAX, false><<<grid, KNN_BLOCK, 0, ctx->stream>>>(tree, queries, nq, ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k,
-                                                                    max_r2, ctx->ref_orig.p, use_seed ? 1 : 0, ids, dists, &ctx->state->visits,
-                                                                    budget, ctx->overflow.p, cnt, use_cap ? 1 : 0, var_r2);
+        knn_kernel<KMAX, true, NORMALS><<<grid, KNN_BLOCK, smem, ctx->stream>>>(tree, queries, nq, ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k,
+                                                                               max_r2, ctx->ref_orig.p, use_seed ? 1 : 0, ids, dists, &ctx->state->visits,
+                                                                               budget, ctx->overflow.p, cnt, use_cap ? 1 : 0, var_r2, ns, pos_offset);
+    else if constexpr (!NORMALS)
+        knn_kernel<KMAX, false, false><<<grid, KNN_BLOCK, 0, ctx->stream>>>(tree, queries, nq, ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k,
+                                                                           max_r2, ctx->ref_orig.p, use_seed ? 1 : 0, ids, dists, &ctx->state->visits,
+                                                                           budget, ctx->overflow.p, cnt, use_cap ? 1 : 0, var_r2, ns, pos_offset);
     if (ctx->time_stage2) { ctx->stage_end(); ctx->stage_begin(3); }
     const int grid2 = min(ctx->num_sms * 10, (nq + 3) / 4);  // 48 registers: ten 128-thread blocks are resident per SM
-    knn_overflow_kernel<KMAX><<<grid2, 128, 0, ctx->stream>>>(tree, queries, ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k, max_r2,
-                                                           ctx->overflow.p, cnt, cnt_next, ids, dists, &ctx->state->visits, use_cap ? 1 : 0, var_r2);
+    knn_overflow_kernel<KMAX, NORMALS><<<grid2, 128, 0, ctx->stream>>>(tree, queries, ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k, max_r2,
+                                                                    ctx->overflow.p, cnt, cnt_next, ids, dists, &ctx->state->visits, use_cap ? 1 : 0, var_r2,
+                                                                    ns, pos_offset);
     ctx->launches += 2;
     PM_CUDA_TRY(ctx, cudaGetLastError());
     return PMGPU_OK;
@@ -332,7 +375,9 @@ int launch_one(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, 
 // use_cap: stop at min(max_r2, state->cap)
 int launch_knn(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, bool use_T, bool gated, bool self_query, int k, float max_r2,
                bool use_seed, int32_t* ids, float* dists, bool use_cap, const float* var_r2) {
-#define PM_KNN_CASE(K) return launch_one<K>(ctx, tree, queries, nq, use_T, gated, self_query, k, max_r2, use_seed, ids, dists, use_cap, var_r2)
+    NormalsSink none;
+    memset(&none, 0, sizeof(none));
+#define PM_KNN_CASE(K) return launch_one<K, false>(ctx, tree, queries, nq, use_T, gated, self_query, k, max_r2, use_seed, ids, dists, use_cap, var_r2, none, 0)
     if (k == 1) PM_KNN_CASE(1);
     if (k <= 4) PM_KNN_CASE(4);
     if (k <= 8) PM_KNN_CASE(8);
@@ -343,6 +388,24 @@ int launch_knn(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, 
     if (k <= 64) PM_KNN_CASE(64);
 #undef PM_KNN_CASE
     ctx->set_error("KDTreeMatcher on GPU: knn > 64 is not supported");
+    return PMGPU_ERR_UNSUPPORTED;
+}
+
+// K8: surface normals of the leaf-order positions [pos_lo, pos_hi) of the resident cloud as the epilogue of their self-kNN
+// (normals.cuh); nothing but the sink's outputs is written
+int launch_knn_normals(pmgpu_ctx* ctx, const TreeView& tree, int pos_lo, int pos_hi, int k, float max_r2, const NormalsSink& sink) {
+    const f4* queries = tree.pts + pos_lo;
+    const int nq = pos_hi - pos_lo;
+#define PM_KNN_CASE(K) return launch_one<K, true>(ctx, tree, queries, nq, false, false, true, k, max_r2, false, nullptr, nullptr, false, nullptr, sink, pos_lo)
+    if (k <= 4) PM_KNN_CASE(4);
+    if (k <= 8) PM_KNN_CASE(8);
+    if (k <= 10) PM_KNN_CASE(10);
+    if (k <= 16) PM_KNN_CASE(16);
+    if (k <= 20) PM_KNN_CASE(20);  // BASELINE config 3
+    if (k <= 32) PM_KNN_CASE(32);
+    if (k <= 64) PM_KNN_CASE(64);
+#undef PM_KNN_CASE
+    ctx->set_error("SurfaceNormalDataPointsFilter on GPU: knn > 64 is not supported");
     return PMGPU_ERR_UNSUPPORTED;
 }
 

@@ -13,6 +13,7 @@
 //
 // Algorithmic bytes per match: reading 16 + id 4 + dist 4 + reference gather 16 (+ normal gather
 // 16 for point-to-plane) = 40 / 56 B.
+#include "comm.cuh"
 #include "core/linalg.h"
 #include "select.cuh"
 
@@ -58,7 +59,7 @@ __device__ __forceinline__ unsigned long long pm_globaltimer() {
 
 template <int MODE>
 __device__ void finalize_body(const double* partials, int nblocks, double* sums, int phase, IcpState* state, int compose,
-                              const pmgpu_icp_params& ck);
+                              const pmgpu_icp_params& ck, const PeerComm& pc);
 
 // `fuse`: the last block to finish reduces the partial rows, solves, composes T_iter and runs the
 // checkers (finalize_body), so the whole minimisation is one kernel
@@ -67,7 +68,7 @@ __global__ void __launch_bounds__(ACC_BLOCK, MODE == 1 ? 2 : 3) accumulate_kerne
                                                                const float* __restrict__ dists, const f4* __restrict__ ref,
                                                                const f4* __restrict__ normals, const IcpState* __restrict__ state, int gated,
                                                                double* __restrict__ partials, int fuse, IcpState* state_rw, double* sums,
-                                                               int compose, pmgpu_icp_params ck, const f4* __restrict__ reading_normals) {
+                                                               int compose, pmgpu_icp_params ck, const f4* __restrict__ reading_normals, PeerComm pc) {
     constexpr int NS = MODE == 1 ? NS_PLANE : NS_POINT;
     __shared__ Mat4 sT;
     // redo: this iteration's capped match was void (select_finish) — leave T_iter as it is
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(ACC_BLOCK, MODE == 1 ? 2 : 3) accumulate_kerne
 #ifdef PM_PROFILE_NS
         if (threadIdx.x == 0) s_t[2] = pm_globaltimer();
 #endif
-        finalize_body<MODE>(partials, gridDim.x, sums, 3, state_rw, compose, ck);
+        finalize_body<MODE>(partials, gridDim.x, sums, 3, state_rw, compose, ck, pc);
 #ifdef PM_PROFILE_NS
         if (threadIdx.x == 0)
             printf("accumulate<%d> last block: block reduce %llu ns, ticket %llu ns, finalize %llu ns\n", MODE, s_t[1] - s_t[0], s_t[2] - s_t[1],
@@ -327,12 +328,15 @@ __device__ void run_checkers(IcpState* st, const pmgpu_icp_params& ck) {
 // where the sums are all-reduced between the two phases).
 template <int MODE>
 __device__ void finalize_body(const double* partials, int nblocks, double* sums, int phase, IcpState* state, int compose,
-                              const pmgpu_icp_params& ck) {
+                              const pmgpu_icp_params& ck, const PeerComm& pc) {
     constexpr int NS = MODE == 1 ? NS_PLANE : NS_POINT;
 #ifdef PM_PROFILE_NS
     const unsigned long long t_a = pm_globaltimer();
 #endif
     if (phase & 1) reduce_rows(partials, nblocks, NS, sums);
+    // sharded reading: this rank's sums become the sums over all ranks, in rank order on every rank (comm.cuh), so every
+    // rank solves the same system to the same bits
+    if (phase == 3 && pc.nranks > 1 && !peer_allreduce<true>(pc, sums, (2 * NS + 3) & ~3, state)) return;
     if (!(phase & 2) || threadIdx.x != 0) return;
 #ifdef PM_PROFILE_NS
     const unsigned long long t_b = pm_globaltimer();
@@ -443,7 +447,9 @@ template <int MODE>
 __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ sums, int phase,
                                                        IcpState* state, int gated, int compose, pmgpu_icp_params ck) {
     if (gated && (state->iterate == 0 || state->redo)) return;
-    finalize_body<MODE>(partials, nblocks, sums, phase, state, compose, ck);
+    PeerComm none;
+    none.nranks = 1;
+    finalize_body<MODE>(partials, nblocks, sums, phase, state, compose, ck, none);
 }
 
 // inverse of a 6x6 by Gauss-Jordan with partial pivoting (J_hessian.inverse())
@@ -471,8 +477,9 @@ __device__ void inverse6(const double* A, double* Inv) {
 }
 
 __global__ void __launch_bounds__(256) cov_finalize_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ sums, int phase,
-                                                           IcpState* state, float sensor_std_dev) {
+                                                           IcpState* state, float sensor_std_dev, PeerComm pc) {
     if (phase & 1) reduce_rows(partials, nblocks, NS_COV, sums);
+    if (phase == 3 && pc.nranks > 1 && !peer_allreduce<true>(pc, sums, (2 * NS_COV + 3) & ~3, state)) return;
     if (!(phase & 2) || threadIdx.x != 0) return;
     double J[36], D[36], Ji[36], T1[36];
     expand_sym6(sums, J);
@@ -518,12 +525,15 @@ int launch_minimize(pmgpu_ctx* ctx, int minimizer_word, bool compose_and_check, 
     ck.knn = ctx->k;
     ck.minimizer = minimizer_word;
     const int g = gated ? 1 : 0, comp = compose_and_check ? 1 : 0;
-    const int fuse = ctx->nranks > 1 ? 0 : 1;
+    // sharded reading: the exchange of the sums is the last block's epilogue over the peer mailboxes (comm.cuh); without
+    // mailboxes, NCCL between two finalize kernels
+    const int fuse = (ctx->nranks > 1 && !ctx->peer_on) ? 0 : 1;
+    const PeerComm pc = fuse ? comm_peers(ctx) : PeerComm{0, 1, {}};
     if (plane) accumulate_kernel<1><<<grid, ACC_BLOCK, 0, st>>>(ctx->reading.p, ctx->nq, ctx->k, ctx->ids.p, ctx->dists.p, ctx->ref_orig.p,
-            ctx->ref_normals.p, ctx->state, g, ctx->partials.p, fuse, ctx->state, sums, comp, ck, ctx->reading_normals.p);
+            ctx->ref_normals.p, ctx->state, g, ctx->partials.p, fuse, ctx->state, sums, comp, ck, ctx->reading_normals.p, pc);
     else accumulate_kernel<0><<<grid, ACC_BLOCK, 0, st>>>(ctx->reading.p, ctx->nq, ctx->k, ctx->ids.p, ctx->dists.p, ctx->ref_orig.p,
             ctx->has_normals ? ctx->ref_normals.p : nullptr, ctx->state, g, ctx->partials.p, fuse, ctx->state, sums, comp, ck,
-            ctx->reading_normals.p);
+            ctx->reading_normals.p, pc);
     ctx->launches += 1;
     if (!fuse) {
         const int ns = plane ? NS_PLANE : NS_POINT;
@@ -549,13 +559,14 @@ int launch_covariance(pmgpu_ctx* ctx, int minimizer, float sensor_std_dev) {
     else cov_accumulate_kernel<0><<<grid, ACC_BLOCK, 0, st>>>(ctx->reading.p, ctx->nq, ctx->k, ctx->ids.p, ctx->dists.p, ctx->ref_orig.p, nullptr,
             ctx->state, ctx->partials.p, ctx->reading_normals.p, ctx->ref_normals.p);
     ctx->launches += 1;
-    if (ctx->nranks > 1) {
-        cov_finalize_kernel<<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 1, ctx->state, sensor_std_dev);
+    const PeerComm none{0, 1, {}};
+    if (ctx->nranks > 1 && !ctx->peer_on) {
+        cov_finalize_kernel<<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 1, ctx->state, sensor_std_dev, none);
         PM_TRY(comm_allreduce_f64(ctx, sums, NS_COV));
-        cov_finalize_kernel<<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 2, ctx->state, sensor_std_dev);
+        cov_finalize_kernel<<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 2, ctx->state, sensor_std_dev, none);
         ctx->launches += 2;
     } else {
-        cov_finalize_kernel<<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 3, ctx->state, sensor_std_dev);
+        cov_finalize_kernel<<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 3, ctx->state, sensor_std_dev, comm_peers(ctx));
         ctx->launches += 1;
     }
     PM_CUDA_TRY(ctx, cudaGetLastError());

@@ -58,12 +58,23 @@ struct DevBuf {
     }
 };
 
+// a temporary device buffer of one API call: released on every return path
+template <typename T>
+struct ScopedBuf : DevBuf<T> {
+    ScopedBuf() = default;
+    ScopedBuf(const ScopedBuf&) = delete;
+    ScopedBuf& operator=(const ScopedBuf&) = delete;
+    ~ScopedBuf() { this->release(); }
+};
+
 // ---- device-side state of one ICP registration -------------------------------------------------
 // Lives in device memory so that a whole iteration (match -> select -> weights -> minimise ->
 // compose -> check) runs without a host round trip.
 #define PM_MAX_FILTERS 8
 #define PM_HIST_BINS 2048
 #define PM_MAX_HISTORY 64   // ring of T_iter history for the Differential checker
+#define PM_MAX_RANKS 8      // GPUs one registration can be sharded over (one NVSwitch node)
+#define PM_MAILBOX_SLOT_WORDS (PM_MAX_FILTERS * PM_HIST_BINS)  // 64 KB: the largest message (one histogram per quantile filter)
 
 struct IcpState {
     Mat4 T_iter;                 // cumulative transform applied to the reading (ICP.cpp:381)
@@ -148,6 +159,20 @@ struct SelectSpec {
     }
 };
 
+// peer mailboxes of a sharded registration (protocol and device side: comm.cuh)
+struct Mailbox {
+    unsigned flag[2][PM_MAX_RANKS];                         // epoch of the last exchange rank r completed into bank b
+    unsigned seq;                                           // exchanges THIS rank has executed (local; the epoch counter)
+    unsigned pad[31 - 2 * PM_MAX_RANKS];
+    unsigned slot[2][PM_MAX_RANKS][PM_MAILBOX_SLOT_WORDS];  // rank r's contribution, bank b
+};
+static_assert(2 * PM_MAX_RANKS <= 31, "flag block");
+// by value in the kernel arguments
+struct PeerComm {
+    int rank, nranks;            // nranks <= 1: no exchange
+    Mailbox* box[PM_MAX_RANKS];  // box[r]: rank r's mailbox as mapped here; box[rank] is local memory
+};
+
 }  // namespace pm
 
 struct pmgpu_ctx {
@@ -217,6 +242,12 @@ struct pmgpu_ctx {
     // multi-GPU
     void* nccl_comm = nullptr;
     int rank = 0, nranks = 1;
+    // peer mailboxes (comm.cuh): mine, and every rank's as mapped into this process
+    void* mailbox = nullptr;
+    void* peer_box[PM_MAX_RANKS] = {};
+    bool peer_opened[PM_MAX_RANKS] = {};   // mapped with cudaIpcOpenMemHandle (to be closed)
+    bool peer_on = false;
+    pm::DevBuf<f4> gather_tmp;             // sharded K8: leaf-order normals of all ranks before the un-permute
 
     // optional per-stage event timing (pmgpu_timing_enable)
     struct Interval { cudaEvent_t a, b; int stage; };
@@ -269,12 +300,11 @@ int launch_materialize_weights(pmgpu_ctx* ctx);
 // minimize.cu
 int launch_minimize(pmgpu_ctx* ctx, int minimizer, bool compose_and_check, bool gated, const pmgpu_icp_params* checks);
 int launch_covariance(pmgpu_ctx* ctx, int minimizer, float sensor_std_dev);
-// normals.cu
-int launch_normals(pmgpu_ctx* ctx, const f4* pts, int n, const int32_t* ids, const float* dists, int knn, int flags, f4* normals4,
-                   float* densities, float* eig_values, float* eig_vectors, float* mean_dists);
 // comm.cu
 int comm_allreduce_u32(pmgpu_ctx* ctx, unsigned* buf, size_t count);
 int comm_allreduce_f64(pmgpu_ctx* ctx, double* buf, size_t count);
+int comm_allgather_bytes(pmgpu_ctx* ctx, void* buf, size_t bytes_per_rank);  // in place: rank r's block at r * bytes_per_rank
+PeerComm comm_peers(pmgpu_ctx* ctx);  // the kernel argument of a fused exchange
 
 inline int grid_for(int n, int block, int num_sms, int per_sm) {
     long g = ((long)n + block - 1) / block;

@@ -12,6 +12,7 @@
 // rank selects the same global order statistic.
 #include <cub/device/device_radix_sort.cuh>
 
+#include "comm.cuh"
 #include "select.cuh"
 
 namespace pm {
@@ -30,7 +31,7 @@ __device__ __forceinline__ void hist_add(unsigned* sh, float d, int pass, unsign
 // blocks the shorter the serialised tail on the hot bins; the distances are read four at a time.
 __global__ void __launch_bounds__(HIST_BLOCK) hist_kernel(const float* __restrict__ dists, size_t total, int pass, SelectSpec spec, IcpState* state,
                                                           int gated, int do_init, int do_pick, unsigned* __restrict__ hist, int cap_active,
-                                                          float cap_margin) {
+                                                          float cap_margin, PeerComm pc) {
     __shared__ unsigned sh[PM_HIST_BINS];
     if (gated && state->iterate == 0) return;
     if (do_init && blockIdx.x == 0 && threadIdx.x == 0) select_init_limits(state, spec);
@@ -61,6 +62,8 @@ __global__ void __launch_bounds__(HIST_BLOCK) hist_kernel(const float* __restric
     if (!do_pick || slot == 0) return;
     if (!select_last_block(&state->ticket[0])) return;
     const int nq = spec.n_quantile();
+    // sharded reading: this rank's histograms become the sum over all ranks, exchanged over the peer mailboxes right here
+    if (pc.nranks > 1 && !peer_allreduce<false>(pc, hist, (pass == 0 ? 1 : nq) * PM_HIST_BINS, state)) return;
     slot = 0;
     for (int f = 0; f < spec.nfilters; ++f) {
         if (!spec.is_quantile(f)) continue;
@@ -287,7 +290,9 @@ __global__ void weights_kernel(const float* __restrict__ dists, const int32_t* _
     const float d = dists[i];
     // empty chain: OutlierFilter.cpp:70-85; otherwise the product of the filters' weights
     float wt = pm_pair_weight(state, d);
-    if (wt != 0.f && state->sn_on) wt = __fmul_rn(wt, pm_sn_weight(state->T_iter, reading_normals[i / k], __ldg(ref_normals + ids[i]), state->sn_eps));
+    // the reading normal turns with the transform the MATCHES were made with: after a fused iteration T_iter is already
+    // the composed one, T_match the one the minimiser used
+    if (wt != 0.f && state->sn_on) wt = __fmul_rn(wt, pm_sn_weight(state->T_match, reading_normals[i / k], __ldg(ref_normals + ids[i]), state->sn_eps));
     w[i] = wt;
 }
 
@@ -382,10 +387,12 @@ int launch_weights(pmgpu_ctx* ctx, const SelectSpec& spec, bool gated, bool cap_
         const size_t total = (size_t)ctx->k * ctx->nq;
         const size_t want = (total + HIST_BLOCK * 4 - 1) / (HIST_BLOCK * 4);
         const int grid = grid_for((int)(want > 0x1fffff ? 0x1fffff : want) * HIST_BLOCK, HIST_BLOCK, ctx->num_sms, 1);
-        const bool split = ctx->nranks > 1;
+        // sharded reading: fused peer exchange in the last block (comm.cuh) when the mailboxes are up, else NCCL between
+        // the histogram kernel and a one-block pick kernel
+        const bool split = ctx->nranks > 1 && !ctx->peer_on;
         for (int pass = 0; pass < 3; ++pass) {
             hist_kernel<<<grid, HIST_BLOCK, 0, st>>>(ctx->dists.p, total, pass, spec, ctx->state, g, pass == 0 ? 1 : 0, split ? 0 : 1, ctx->hist.p, ca,
-                                                     ctx->cap_margin);
+                                                     ctx->cap_margin, comm_peers(ctx));
             ctx->launches += 1;
             if (split) {
                 PM_TRY(comm_allreduce_u32(ctx, ctx->hist.p, (size_t)(pass == 0 ? 1 : nquant) * PM_HIST_BINS));

@@ -38,8 +38,23 @@ def broadcast_bytes(payload, src=0):
     return box[0]
 
 
-def init_comm(ctx, capi):
-    """give `ctx` (capi.Context) an NCCL communicator spanning the default process group"""
+def gather_bytes(payload):
+    """every rank passes bytes, every rank returns the list of all ranks' bytes in rank order"""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [payload]
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, payload)
+    return out
+
+
+def init_comm(ctx, capi, peer=True, nccl=True):
+    """shard `ctx` (capi.Context) over the default process group: peer mailboxes for the per-iteration exchanges
+    (fused into the kernels, comm.cuh) and an NCCL communicator for the all-gather of sharded map normals"""
     rank, world = dist.get_rank(), dist.get_world_size()
-    uid = broadcast_bytes(capi.comm_unique_id() if rank == 0 else None, 0)
-    ctx.comm_init(uid, rank, world)
+    if nccl:
+        uid = broadcast_bytes(capi.comm_unique_id() if rank == 0 else None, 0)
+        ctx.comm_init(uid, rank, world)
+    if peer:
+        handles = gather_bytes(ctx.comm_peer_handle())
+        ctx.comm_peer_init(handles, rank)
+        dist.barrier()  # every mailbox is mapped everywhere before the first exchange

@@ -1230,6 +1230,13 @@ class ICP:
         self.transformationCheckers = []
         self.maxNumIterationsReached = False
         self.iterationCount = 0
+        self._shard = None
+
+    def setSharded(self, rank, world):
+        """this process registers columns [rank n / world, (rank + 1) n / world) of every (filtered)
+        reading against the replicated reference; `self.ctx` must have been given the communicator of the `world`
+        ranks (libpointmatcher_b200.dist.init_comm).  Every rank returns the same transform."""
+        self._shard = (int(rank), int(world)) if world > 1 else None
 
     @property
     def ctx(self):
@@ -1344,6 +1351,11 @@ class ICP:
         T_refMean_refIn = np.eye(4, dtype=np.float32)
         T_refMean_refIn[:3, 3] = -T_refIn_refMean[:3, 3]
         T_refMean_dataIn = mat4_mul(T_refMean_refIn, T_init)
+        if self._shard is not None:
+            rank, world = self._shard
+            n = reading.features.shape[0]
+            lo, hi = (rank * n) // world, ((rank + 1) * n) // world
+            reading = DataPoints(reading.features[lo:hi], {k: v[lo:hi] for k, v in reading.descriptors.items()})
         _translate(self.ctx.set_reading, reading.features)
         self.ctx._reading_obj = None
         self._reading_filtered, self._T_refMean_dataIn = reading, T_refMean_dataIn

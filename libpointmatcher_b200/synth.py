@@ -100,6 +100,16 @@ class Scene:
         return t
 
 
+def _threads():
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    # several ranks of one node generate their clouds at the same time
+    world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
+    return max(1, min(16, n // max(1, world)))
+
+
 def _scan_uncached(n_points, pose, rings, seed, scene_seed):
     scene = Scene(scene_seed)
     az_steps = -(-n_points // rings)
@@ -108,16 +118,31 @@ def _scan_uncached(n_points, pose, rings, seed, scene_seed):
     out = np.empty((az_steps * rings, 4), np.float32)
     R, origin = pose[:3, :3], pose[:3, 3]
     chunk = max(1, (1 << 18) // rings)
-    for a0 in range(0, az_steps, chunk):
+    starts = list(range(0, az_steps, chunk))
+    # the range noise is one sequential stream (drawn chunk after chunk, as always); the ray casting of the chunks is
+    # independent and runs on a thread pool (numpy releases the GIL)
+    noise = [rng.normal(0.0, RANGE_SIGMA, (min(az_steps, a0 + chunk) - a0) * rings) for a0 in starts]
+
+    def cast(i):
+        a0 = starts[i]
         a1 = min(az_steps, a0 + chunk)
         az = 2 * np.pi * (np.arange(a0, a1) + 0.5) / az_steps
         azg, elg = np.meshgrid(az, el, indexing="ij")  # firing order: azimuth-major
         d = np.stack([np.cos(elg) * np.cos(azg), np.cos(elg) * np.sin(azg), np.sin(elg)], axis=-1).reshape(-1, 3)
         t = scene.raycast(origin, d @ R.T)
-        t = t + rng.normal(0.0, RANGE_SIGMA, t.shape[0])
+        t = t + noise[i]
         sl = slice(a0 * rings, a1 * rings)
         out[sl, :3] = (d * t[:, None]).astype(np.float32)
         out[sl, 3] = 1.0
+
+    nthreads = _threads()
+    if nthreads > 1 and len(starts) > 1:
+        import concurrent.futures
+        with concurrent.futures.ThreadPoolExecutor(max_workers=nthreads) as ex:
+            list(ex.map(cast, range(len(starts))))
+    else:
+        for i in range(len(starts)):
+            cast(i)
     return out[:n_points]
 
 
@@ -150,10 +175,11 @@ def scan(n_points, pose=None, rings=None, seed=SEED, scene_seed=SEED, cache=True
     return out
 
 
-def scan_pair(n_reading, n_reference=None, pair_seed=0):
+def scan_pair(n_reading, n_reference=None, pair_seed=0, rings=None):
     """(reading, reference, T_gt): `reading` is a re-scan from READING_POSE (pair_seed = 0) or
     from a random pose with |t| <= 1 m and |angle| <= 6 deg (pair_seed > 0), `T_gt` (float64 4x4)
-    maps reading coordinates into the reference frame."""
+    maps reading coordinates into the reference frame.  rings: None = isotropic angular sampling (see scan), 64 = the
+    64 x (N / 64) layout SURVEY 8d names."""
     n_reference = n_reading if n_reference is None else n_reference
     if pair_seed == 0:
         pose = READING_POSE
@@ -164,8 +190,8 @@ def scan_pair(n_reading, n_reference=None, pair_seed=0):
         t[2] *= 0.1
         ang = rng.uniform(-6.0, 6.0, 3) * np.array([1.0, 0.15, 0.15])
         pose = pose_matrix(t, *ang)
-    reference = scan(n_reference, np.eye(4), seed=SEED + 2 * pair_seed)
-    reading = scan(n_reading, pose, seed=SEED + 2 * pair_seed + 1)
+    reference = scan(n_reference, np.eye(4), rings=rings, seed=SEED + 2 * pair_seed)
+    reading = scan(n_reading, pose, rings=rings, seed=SEED + 2 * pair_seed + 1)
     return reading, reference, pose
 
 

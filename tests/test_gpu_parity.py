@@ -790,3 +790,51 @@ def test_knn_k_gt_1_seeded_radius_is_exact(gpu_ctx, oracle):
             assert (ib == ig).all() and (bits(db) == bits(dg)).all(), (k, md)
         if md != np.inf:
             assert (ig == -1).any() and (ig[:, 0] >= 0).any()      # some slots empty: those queries search unseeded next time
+
+
+# ---------------------------------------------------------------------------------- round-2 review items
+@pytest.mark.gpu
+def test_differential_only_chain_stops_without_a_counter(oracle, synth):
+    """A chain with no CounterTransformationChecker is valid (max_iterations = INT_MAX): the fused loop is enqueued in
+    bounded chunks and stops when the Differential checker says so, with the oracle's iteration count."""
+    from libpointmatcher_b200 import pm
+    rd, rf, _ = synth.scan_pair(30000)
+    nrm = oracle.surface_normals(rf, knn=10, nthreads=8)["normals"]
+    res_o = oracle.icp(rd, rf, ref_normals=nrm, filters=[(2, 0.8)], minimizer=1, max_iterations=1000, differential=(1e-3, 1e-3, 3), nthreads=8, acc_double=True)
+    icp = pm.ICP()
+    icp.matcher = pm.KDTreeMatcher()
+    icp.outlierFilters = pm.OutlierFilters([pm.TrimmedDistOutlierFilter({"ratio": "0.8"})])
+    icp.errorMinimizer = pm.PointToPlaneErrorMinimizer()
+    icp.transformationCheckers = [pm.DifferentialTransformationChecker({"minDiffRotErr": "0.001", "minDiffTransErr": "0.001", "smoothLength": "3"})]
+    launches0 = icp.ctx.launch_count
+    T = icp(pm.DataPoints(rd), pm.DataPoints(rf, {"normals": nrm}))
+    assert icp.iterationCount == res_o["iterations"] < 200
+    assert icp.ctx.launch_count - launches0 < 8 * 64 * (icp.iterationCount // 64 + 2)   # bounded: chunks of 64 slots
+    icp.ctx.close()
+    assert_transform_close(T, res_o["T"], 2e-5, 2e-5)
+
+
+@pytest.mark.gpu
+def test_materialised_weights_after_fused_loop_use_the_match_transform(oracle, synth):
+    """After a fused iteration T_iter is already the composed transform; the SurfaceNormalOutlierFilter weights that
+    pmgpu_matches_get materialises must turn the reading normals with T_match, the transform the matches (and the
+    minimiser) saw."""
+    from libpointmatcher_b200 import capi
+    rd, rf, _ = synth.scan_pair(30000)
+    nq = oracle.surface_normals(rf, knn=10, nthreads=8)["normals"]
+    nr = oracle.surface_normals(rd, knn=10, nthreads=8)["normals"]
+    chain = [(capi.FILTER_TRIMMEDDIST, 0.8), (capi.FILTER_SURFACENORMAL, 0.4)]
+    with capi.Context(0) as ctx:
+        ctx.set_reference(rf, nq)
+        ctx.set_reading(rd)
+        ctx.set_reading_normals(nr)
+        p = capi.make_params(knn=2, filters=chain, minimizer=capi.MIN_P2PLANE, max_iterations=3)
+        res = ctx.icp_run(p)
+        ids, dists, w, T_match = ctx.matches()
+        assert not np.array_equal(T_match, res["T_iter"])     # the loop has composed one more increment
+        nr_rot = (nr @ T_match[:3, :3].T).astype(np.float32)
+        real = ids >= 0
+        wo, _ = oracle.outlier_weights_sn(np.where(real, dists, np.inf).astype(np.float32), np.where(real, ids, 0).astype(np.int32), chain, nr_rot, nq)
+        # capped far matches (id -2) are rejected on both sides; |dot| within an ulp of the limit may fall either side
+        assert ((w != wo) & real).mean() < 2e-4
+        assert res["stats"]["nbKept"] == int((w != 0).sum())   # what the minimiser used is what is materialised
