@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
             if (!NORMALS || slot < ns.scratch_cap) {
                 running = false;
                 overflow[slot] = (uint32_t)t;
-                my_slot = slot;
+                my_slot = slot;  // handed over: unfilled slots below carry the radius this search ran with
             } else {
                 budget = 0x7fffffff;  // K8: the hand-over scratch is full — this lane finishes its query here
             }
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
                 // handed to stage 2: the candidates found so far travel in the scratch, by queue slot
                 static_for<0, KMAX>([&](auto J) {
                     if (J < k) {
-                        ns.scratch_ids[(size_t)my_slot * k + J] = best.id[J];
+                        ns.scratch_ids[(size_t)my_slot * k + J] = best.id[J] != PM_NO_ID ? best.id[J] : -1;
                         ns.scratch_d[(size_t)my_slot * k + J] = best.d[J];
                     }
                 });
@@ -168,11 +168,14 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
     } else if (t < nq) {
         int32_t* oi = ids + (size_t)qi * k;
         float* od = dists + (size_t)qi * k;
+        const bool handed = my_slot != 0xffffffffu;
         static_for<0, KMAX>([&](auto J) {
             if (J < k) {
                 const bool valid = best.id[J] != PM_NO_ID && best.d[J] != pm_inf();
                 oi[J] = valid ? best.id[J] : cap.miss_id;
-                od[J] = valid ? best.d[J] : cap.miss_d;
+                // a query handed to stage 2 passes on the radius it was searching with (a seeded bound, a per-point
+                // distance) in its unfilled slots, so that stage 2 does not start again from the caller's maxDist
+                od[J] = valid ? best.d[J] : (handed ? best.d[J] : cap.miss_d);
             }
         });
     }
@@ -225,12 +228,19 @@ __global__ void __launch_bounds__(128) knn_overflow_kernel(TreeView tree, const 
         if (self_query) { qi = __float_as_uint(q.w); q.w = 1.f; }
         if (use_T) q = transform_point(sT, q);
         TopK<KMAX> best;
-        best.init(k, var_r2 ? var_r2[t] : cap.r2);
-        // seed: the candidates stage 1 left in the result arrays (K8: in the scratch, by queue slot); ascending, real points
+        // seed: the candidates stage 1 left in the result arrays (K8: in the scratch, by queue slot) — real points,
+        // ascending; its unfilled slots (id < 0) carry the radius it was searching with
+        float r0 = var_r2 ? var_r2[t] : cap.r2;
         for (int j = 0; j < k; ++j) {
             const int id = NORMALS ? ns.scratch_ids[(size_t)w * k + j] : ids[(size_t)qi * k + j];
             const float dd = NORMALS ? ns.scratch_d[(size_t)w * k + j] : dists[(size_t)qi * k + j];
-            if (id >= 0 && id != PM_NO_ID && cand_less(dd, id, best.worst_d(), best.worst_id())) best.insert(dd, id);
+            if (id < 0) r0 = fminf(r0, dd);
+        }
+        best.init(k, r0);
+        for (int j = 0; j < k; ++j) {
+            const int id = NORMALS ? ns.scratch_ids[(size_t)w * k + j] : ids[(size_t)qi * k + j];
+            const float dd = NORMALS ? ns.scratch_d[(size_t)w * k + j] : dists[(size_t)qi * k + j];
+            if (id >= 0 && cand_less(dd, id, best.worst_d(), best.worst_id())) best.insert(dd, id);
         }
         int sp = 0;
         if (lane == 0) stack[0] = 1u;

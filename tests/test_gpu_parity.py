@@ -834,7 +834,8 @@ def test_materialised_weights_after_fused_loop_use_the_match_transform(oracle, s
         assert not np.array_equal(T_match, res["T_iter"])     # the loop has composed one more increment
         nr_rot = (nr @ T_match[:3, :3].T).astype(np.float32)
         real = ids >= 0
-        wo, _ = oracle.outlier_weights_sn(np.where(real, dists, np.inf).astype(np.float32), np.where(real, ids, 0).astype(np.int32), chain, nr_rot, nq)
-        # capped far matches (id -2) are rejected on both sides; |dot| within an ulp of the limit may fall either side
+        # capped far matches (id -2, dist FLT_MAX) stay in the quantile population as finite, rejected matches
+        wo, _ = oracle.outlier_weights_sn(dists, np.where(real, ids, 0).astype(np.int32), chain, nr_rot, nq)
+        # |dot| within an ulp of the limit may fall either side
         assert ((w != wo) & real).mean() < 2e-4
         assert res["stats"]["nbKept"] == int((w != 0).sum())   # what the minimiser used is what is materialised
