@@ -293,7 +293,7 @@ void pmgpu_ctx_destroy(pmgpu_ctx* ctx) {
     g_alloc_stream = ctx->stream;
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     pmgpu_comm_destroy(ctx);
-    ctx->ref_orig.release(); ctx->ref_sorted.release(); ctx->ref_normals.release(); ctx->splits.release(); ctx->boxes.release();
+    ctx->ref_orig.release(); ctx->ref_sorted.release(); ctx->ref_normals.release(); ctx->splits.release(); ctx->boxes.release(); ctx->gather_tmp.release();
     ctx->reading_tmp.release(); ctx->ids_tmp.release(); ctx->dists_tmp.release(); ctx->overflow.release();
     ctx->keys_a.release(); ctx->keys_b.release(); ctx->perm_a.release(); ctx->perm_b.release();
     ctx->node_box.release(); ctx->cub_tmp.release();

@@ -108,47 +108,51 @@ PM_HD void static_for(F&& f) {
     }
 }
 
-// k best candidates, ascending, held in registers (all indices are compile-time constants).
+// k best candidates, ascending, held in registers (all indices are compile-time constants).  A candidate is ONE 64-bit
+// key, (distance bits << 32) | index: squared distances are non-negative floats, whose bit patterns order like unsigned
+// integers, and indices are non-negative, so the lexicographic (dist, index) ranking is a single unsigned compare (half
+// the instructions of the two-float-one-int version in the insertion chain, which is what a k > 1 search spends its
+// time in).  A NaN distance is larger than +inf as a bit pattern: never accepted, as with float compares.
 template <int KMAX>
 struct TopK {
-    float d[KMAX];
-    int id[KMAX];
+    unsigned long long key[KMAX];
     int k;
-    float wd;  // cached k-th best (d[k-1], id[k-1])
-    int wi;
+    unsigned long long wkey;  // cached k-th best
+    PM_HD static unsigned long long pack(float d, int i) { return ((unsigned long long)f2u(d) << 32) | (unsigned long long)(uint32_t)i; }
     PM_HD void init(int k_, float max_r2) {
         k = k_;
-        static_for<0, KMAX>([&](auto J) { d[J] = max_r2; id[J] = PM_NO_ID; });
-        wd = max_r2;
-        wi = PM_NO_ID;
+        wkey = pack(max_r2, PM_NO_ID);
+        static_for<0, KMAX>([&](auto J) { key[J] = wkey; });
     }
-    PM_HD float worst_d() const { return wd; }
-    PM_HD int worst_id() const { return wi; }
-    // insert (nd, ni); precondition: cand_less(nd, ni, worst)
+    PM_HD float worst_d() const { return u2f((uint32_t)(wkey >> 32)); }
+    PM_HD int worst_id() const { return (int)(uint32_t)wkey; }
+    PM_HD bool accepts(float d, int i) const { return pack(d, i) < wkey; }
+    template <int J> PM_HD float D(std::integral_constant<int, J>) const { return u2f((uint32_t)(key[J] >> 32)); }
+    template <int J> PM_HD int I(std::integral_constant<int, J>) const { return (int)(uint32_t)key[J]; }
+    // insert (nd, ni); precondition: accepts(nd, ni)
     PM_HD void insert(float nd, int ni) {
+        const unsigned long long c = pack(nd, ni);
         static_for<0, KMAX - 1>([&](auto I) {
-            constexpr int j = KMAX - 1 - I;  // j = KMAX-1 .. 1
-            if (j < k) {
-                if (cand_less(nd, ni, d[j - 1], id[j - 1])) { d[j] = d[j - 1]; id[j] = id[j - 1]; }
-                else if (cand_less(nd, ni, d[j], id[j])) { d[j] = nd; id[j] = ni; }
-            }
+            constexpr int j = KMAX - 1 - I;  // j = KMAX-1 .. 1; slot j - 1 is still untouched when slot j is rewritten
+            if (j < k) key[j] = c < key[j - 1] ? key[j - 1] : (c < key[j] ? c : key[j]);
         });
-        if (cand_less(nd, ni, d[0], id[0])) { d[0] = nd; id[0] = ni; }
+        if (c < key[0]) key[0] = c;
         static_for<0, KMAX>([&](auto J) {
-            if (J == k - 1) { wd = d[J]; wi = id[J]; }
+            if (J == k - 1) wkey = key[J];
         });
     }
     // entry j (runtime index) without dynamic array addressing
     PM_HD void get(int j, float& dj, int& ij) const {
-        dj = d[0];
-        ij = id[0];
+        unsigned long long e = key[0];
         static_for<1, KMAX>([&](auto J) {
-            if (J == j) { dj = d[J]; ij = id[J]; }
+            if (J == j) e = key[J];
         });
+        dj = u2f((uint32_t)(e >> 32));
+        ij = (int)(uint32_t)e;
     }
     PM_HD bool contains(int q) const {
         bool f = false;
-        static_for<0, KMAX>([&](auto J) { f = f || (id[J] == q); });
+        static_for<0, KMAX>([&](auto J) { f = f || ((int)(uint32_t)key[J] == q); });
         return f;
     }
 };
@@ -161,6 +165,9 @@ struct TopK<1> {
     PM_HD void init(int, float max_r2) { k = 1; d[0] = max_r2; id[0] = PM_NO_ID; }
     PM_HD float worst_d() const { return d[0]; }
     PM_HD int worst_id() const { return id[0]; }
+    PM_HD bool accepts(float nd, int ni) const { return cand_less(nd, ni, d[0], id[0]); }
+    template <int J> PM_HD float D(std::integral_constant<int, J>) const { return d[0]; }
+    template <int J> PM_HD int I(std::integral_constant<int, J>) const { return id[0]; }
     PM_HD void insert(float nd, int ni) { d[0] = nd; id[0] = ni; }
     PM_HD void get(int, float& dj, int& ij) const { dj = d[0]; ij = id[0]; }
     PM_HD bool contains(int q) const { return id[0] == q; }
@@ -217,6 +224,10 @@ PM_HD float select3(uint32_t dim, float x, float y, float z) {
 #endif
 }
 
+// (Measured and dropped, round 2: the same planes stored three levels per 32-byte block, so that one load serves three
+// levels and the chain of dependent loads is ~6 long instead of ~17.  Exact — same planes, same order — but the
+// run-time select of one of seven plane registers per level costs more issue slots than the shorter chain saves: the
+// seeded k = 1 match went from 0.173 to 0.207 ms per 1 M queries.  The kernel is issue bound before it is latency bound.)
 // one step of the plane descent; `w` is the current k-th best distance: a sibling whose split
 // plane is already farther than that can never be needed (w only shrinks), so it is not even
 // recorded as pending
@@ -245,18 +256,43 @@ PM_HD void lane_scan_leaf(Lane& s, const TreeView& t, TopK<KMAX>& best) {
                 const f4 pt = ldg4(t.pts + p);
                 const float dd = dist2(s.qx, s.qy, s.qz, pt.x, pt.y, pt.z);
                 const int pi = (int)f2u(pt.w);
-                if (cand_less(dd, pi, best.worst_d(), best.worst_id())) best.insert(dd, pi);
+                if (best.accepts(dd, pi)) best.insert(dd, pi);
             }
         }
-    } else {
-        // k > 1: keep this a real loop — unrolling it around the (fully unrolled) insertion makes
-        // the compiler give up and demote the candidate arrays to local memory
+#ifdef PM_LEAF_ONE_PHASE
+    } else if (true) {
+        // (A/B builds) the one-phase scan: a real loop around the insertion
 #pragma unroll 1
         for (uint32_t p = b; p < e; ++p) {
             const f4 pt = ldg4(t.pts + p);
             const float dd = dist2(s.qx, s.qy, s.qz, pt.x, pt.y, pt.z);
             const int pi = (int)f2u(pt.w);
-            if (cand_less(dd, pi, best.worst_d(), best.worst_id())) best.insert(dd, pi);
+            if (best.accepts(dd, pi)) best.insert(dd, pi);
+        }
+#endif
+    } else {
+        // k > 1, two phases.  (1) all distances of the leaf (independent loads, unrolled) -> a bit mask of the points
+        // that beat the current k-th best; (2) only those are inserted, one per trip, re-derived from the (L1-resident)
+        // point.  The insertion chain is ~6 k instructions and the lanes of a warp run in lock step: with the insert
+        // inside the scan loop a warp paid for it at EVERY point position where ANY lane had a candidate (nearly all
+        // eight), now it pays max over lanes of the number of candidates (one or two once the lists are good).
+        uint32_t mask = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < PM_LEAF_MAX; ++j) {
+            const uint32_t p = b + j;
+            if (p < e) {
+                const f4 pt = ldg4(t.pts + p);
+                const float dd = dist2(s.qx, s.qy, s.qz, pt.x, pt.y, pt.z);
+                if (best.accepts(dd, (int)f2u(pt.w))) mask |= 1u << j;
+            }
+        }
+        while (mask) {
+            const uint32_t j = 31u - (uint32_t)clz32(mask & (0u - mask));  // lowest set bit: index order, like the one-phase scan
+            mask &= mask - 1u;
+            const f4 pt = ldg4(t.pts + b + j);
+            const float dd = dist2(s.qx, s.qy, s.qz, pt.x, pt.y, pt.z);
+            const int pi = (int)f2u(pt.w);
+            if (best.accepts(dd, pi)) best.insert(dd, pi);  // the bound may have shrunk since phase 1
         }
     }
     s.visited += e - b;

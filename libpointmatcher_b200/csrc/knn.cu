@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
             if (prev >= 0) {
                 const f4 r = __ldg(ref_orig + prev);
                 const float dd = dist2(q.x, q.y, q.z, r.x, r.y, r.z);
-                if (cand_less(dd, prev, best.worst_d(), best.worst_id())) best.insert(dd, prev);
+                if (best.accepts(dd, prev)) best.insert(dd, prev);
             }
         }
         if (KMAX > 1 && use_seed) {
@@ -155,8 +155,8 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
                 // handed to stage 2: the candidates found so far travel in the scratch, by queue slot
                 static_for<0, KMAX>([&](auto J) {
                     if (J < k) {
-                        ns.scratch_ids[(size_t)my_slot * k + J] = best.id[J] != PM_NO_ID ? best.id[J] : -1;
-                        ns.scratch_d[(size_t)my_slot * k + J] = best.d[J];
+                        ns.scratch_ids[(size_t)my_slot * k + J] = best.I(J) != PM_NO_ID ? best.I(J) : -1;
+                        ns.scratch_d[(size_t)my_slot * k + J] = best.D(J);
                     }
                 });
             } else {
@@ -171,11 +171,11 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
         const bool handed = my_slot != 0xffffffffu;
         static_for<0, KMAX>([&](auto J) {
             if (J < k) {
-                const bool valid = best.id[J] != PM_NO_ID && best.d[J] != pm_inf();
-                oi[J] = valid ? best.id[J] : cap.miss_id;
+                const bool valid = best.I(J) != PM_NO_ID && best.D(J) != pm_inf();
+                oi[J] = valid ? best.I(J) : cap.miss_id;
                 // a query handed to stage 2 passes on the radius it was searching with (a seeded bound, a per-point
                 // distance) in its unfilled slots, so that stage 2 does not start again from the caller's maxDist
-                od[J] = valid ? best.d[J] : (handed ? best.d[J] : cap.miss_d);
+                od[J] = valid ? best.D(J) : (handed ? best.D(J) : cap.miss_d);
             }
         });
     }
@@ -240,7 +240,7 @@ __global__ void __launch_bounds__(128) knn_overflow_kernel(TreeView tree, const 
         for (int j = 0; j < k; ++j) {
             const int id = NORMALS ? ns.scratch_ids[(size_t)w * k + j] : ids[(size_t)qi * k + j];
             const float dd = NORMALS ? ns.scratch_d[(size_t)w * k + j] : dists[(size_t)qi * k + j];
-            if (id >= 0 && cand_less(dd, id, best.worst_d(), best.worst_id())) best.insert(dd, id);
+            if (id >= 0 && best.accepts(dd, id)) best.insert(dd, id);
         }
         int sp = 0;
         if (lane == 0) stack[0] = 1u;
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(128) knn_overflow_kernel(TreeView tree, const 
                             const f4 pt = ldg4(tree.pts + p);
                             dd[u] = dist2(q.x, q.y, q.z, pt.x, pt.y, pt.z);
                             pi[u] = (int)__float_as_uint(pt.w);
-                            cand[u] = cand_less(dd[u], pi[u], best.worst_d(), best.worst_id());
+                            cand[u] = best.accepts(dd[u], pi[u]);
                         }
                     }
                     // candidates are rare once the list is good: insert them one by one, uniformly
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(128) knn_overflow_kernel(TreeView tree, const 
                             cm &= cm - 1;
                             const float cd = __shfl_sync(0xffffffffu, dd[u], src);
                             const int ci = __shfl_sync(0xffffffffu, pi[u], src);
-                            if (cand_less(cd, ci, best.worst_d(), best.worst_id()) && !best.contains(ci)) best.insert(cd, ci);
+                            if (best.accepts(cd, ci) && !best.contains(ci)) best.insert(cd, ci);
                         }
                     }
                 }

@@ -47,8 +47,8 @@ __device__ __forceinline__ bool normals_epilogue(const TopK<KMAX>& best, int k, 
     float sx = 0.f, sy = 0.f, sz = 0.f;
     int real_knn = 0;
     static_for<0, KMAX>([&](auto J) {
-        if (J < k && best.id[J] != PM_NO_ID && best.d[J] != pm_inf()) {
-            const f4 p = __ldg(ns.pts + best.id[J]);
+        if (J < k && best.I(J) != PM_NO_ID && best.D(J) != pm_inf()) {
+            const f4 p = __ldg(ns.pts + best.I(J));
             sx = fadd(sx, p.x); sy = fadd(sy, p.y); sz = fadd(sz, p.z);
             ++real_knn;
         }
@@ -58,8 +58,8 @@ __device__ __forceinline__ bool normals_epilogue(const TopK<KMAX>& best, int k, 
     // C = NN * NN^T (un-normalised), and the largest neighbour radius for the density
     float c00 = 0.f, c01 = 0.f, c02 = 0.f, c11 = 0.f, c12 = 0.f, c22 = 0.f, max_norm = 0.f;
     static_for<0, KMAX>([&](auto J) {
-        if (J < k && best.id[J] != PM_NO_ID && best.d[J] != pm_inf()) {
-            const f4 p = __ldg(ns.pts + best.id[J]);
+        if (J < k && best.I(J) != PM_NO_ID && best.D(J) != pm_inf()) {
+            const f4 p = __ldg(ns.pts + best.I(J));
             const float dx = fsub(p.x, mx), dy = fsub(p.y, my), dz = fsub(p.z, mz);
             c00 = fadd(c00, fmul(dx, dx)); c01 = fadd(c01, fmul(dx, dy)); c02 = fadd(c02, fmul(dx, dz));
             c11 = fadd(c11, fmul(dy, dy)); c12 = fadd(c12, fmul(dy, dz)); c22 = fadd(c22, fmul(dz, dz));
@@ -69,8 +69,8 @@ __device__ __forceinline__ bool normals_epilogue(const TopK<KMAX>& best, int k, 
     if (ns.matched_ids) {
         static_for<0, KMAX>([&](auto J) {
             if (J < k) {
-                const bool valid = best.id[J] != PM_NO_ID && best.d[J] != pm_inf();
-                ns.matched_ids[out * k + J] = (float)(valid ? best.id[J] : -1);
+                const bool valid = best.I(J) != PM_NO_ID && best.D(J) != pm_inf();
+                ns.matched_ids[out * k + J] = (float)(valid ? best.I(J) : -1);
             }
         });
     }

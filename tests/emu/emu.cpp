@@ -111,7 +111,7 @@ long run_knn(const EmuTree* t, const float* T16, const float* q, int nq, int k, 
             // re-measure the previous match (knn.cu does the same with the resident ids)
             const float* r = t->orig + 4 * (size_t)g_seed[i];
             const float dd = dist2(p.x, p.y, p.z, r[0], r[1], r[2]);
-            if (cand_less(dd, g_seed[i], best.worst_d(), best.worst_id())) best.insert(dd, g_seed[i]);
+            if (best.accepts(dd, g_seed[i])) best.insert(dd, g_seed[i]);
         }
         const uint32_t v = knn_search_single<KMAX>(t->view, p.x, p.y, p.z, best);
         visits += v;

@@ -192,3 +192,4 @@ def test_angle_axis_and_checkers_match_oracle(emu, oracle):
         assert abs(a - oracle.angular_distance(T, T2)) < 1e-6
     emu.emu_angle_axis(f(np.zeros(6, np.float32)), f(T))  # zero motion -> identity (PointToPlane.cpp:286-292)
     assert (T == np.eye(4)).all()
+
