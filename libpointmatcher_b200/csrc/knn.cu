@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
         }
         if (use_T) q = transform_point(sT, q);
         lane_begin(s, q.x, q.y, q.z);
+        lane_fetch<PLANES>(s, tree);   // look-ahead descents in the unseeded variants (core/tree.h lane_fetch)
         if (KMAX == 1 && use_seed) {
             // ICP iterations >= 2: the previous match of this query (still resident in ids),
             // re-measured under the new T_iter, is a real candidate that makes the bound tight
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
         // descend: one level per step for every lane that is not at a leaf yet
         const float w0 = best.worst_d();
         while (__any_sync(0xffffffffu, running && lane_descending(s, tree)))
-            if (running && lane_descending(s, tree)) lane_descend_step(s, tree, plane, KNN_BLOCK, w0);
+            if (running && lane_descending(s, tree)) lane_descend_step<PLANES>(s, tree, plane, KNN_BLOCK, w0);
         // leaf; then the plane filter over all pending levels where it pays
         bool refilter = false;
         if (running) {
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
         // search or nothing left
         bool found = false;
         while (__any_sync(0xffffffffu, running && !found && s.trail != 0))
-            if (running && !found && s.trail != 0) found = lane_box_step<KMAX>(s, tree, best, plane, KNN_BLOCK);
+            if (running && !found && s.trail != 0) found = lane_box_step<KMAX, PLANES>(s, tree, best, plane, KNN_BLOCK);
         if (running && !found) running = false;  // search complete
         ++rounds;
         if (running && rounds >= budget) {
@@ -194,6 +195,64 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
 // leaves are scanned sixteen at a time (lane = leaf slot x point, four loads in flight per lane).
 // The candidate list is replicated in every lane and updated with warp-uniform inserts, seeded with what stage 1 had found.  Same
 // bounds, same ranking: the result is the one the single-lane search would have produced.
+// The candidate list of stage 2 is DISTRIBUTED over the warp: slot s lives in lane s & 31 (register s >> 5), ascending in
+// (dist, index) like TopK.  An insertion is then one compare per lane, a ballot that gives the position, and one shuffle
+// that moves the tail up by a lane — ~15 warp instructions instead of the ~10 k of a list replicated in every lane
+// (which was 60 % of this kernel's instructions at k = 10, profiles/r2_knn_overflow_k10_hot_lines.txt).
+template <int KMAX>
+struct WarpTopK {
+    static constexpr int R = (KMAX + 31) / 32;
+    static constexpr unsigned FULL = 0xffffffffu;
+    unsigned long long key[R];
+    unsigned long long wkey;  // the k-th best, replicated
+    int k, lane;
+    __device__ __forceinline__ static unsigned long long pack(float d, int i) { return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(uint32_t)i; }
+    __device__ __forceinline__ float worst_d() const { return __uint_as_float((uint32_t)(wkey >> 32)); }
+    __device__ __forceinline__ bool accepts(float d, int i) const { return pack(d, i) < wkey; }
+    __device__ __forceinline__ void refresh_worst() { wkey = __shfl_sync(FULL, key[(k - 1) >> 5], (k - 1) & 31); }
+    // all slots (radius, no point) except the real candidates the caller fills in
+    __device__ __forceinline__ void init(int k_, int lane_, float r0) {
+        k = k_; lane = lane_;
+#pragma unroll
+        for (int r = 0; r < R; ++r) key[r] = (r * 32 + lane < k) ? pack(r0, PM_NO_ID) : ~0ull;  // slots >= k: never smaller than anything
+        wkey = pack(r0, PM_NO_ID);
+    }
+    __device__ __forceinline__ bool contains(int q) const {
+        bool f = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) f = f || ((int)(uint32_t)key[r] == q && key[r] != ~0ull);
+        return __any_sync(FULL, f);
+    }
+    // warp-uniform (nd, ni); precondition: accepts(nd, ni) and not contained
+    __device__ __forceinline__ void insert(float nd, int ni) {
+        const unsigned long long c = pack(nd, ni);
+        int pos = 0;  // entries smaller than c = its slot
+#pragma unroll
+        for (int r = 0; r < R; ++r) pos += __popc(__ballot_sync(FULL, key[r] < c));
+#pragma unroll
+        for (int r = R - 1; r >= 0; --r) {
+            unsigned long long up = __shfl_up_sync(FULL, key[r], 1);
+            if (r > 0) {
+                const unsigned long long wrap = __shfl_sync(FULL, key[r - 1], 31);
+                if (lane == 0) up = wrap;
+            }
+            const int s = r * 32 + lane;
+            key[r] = (s > pos && s < k) ? up : (s == pos ? c : key[r]);
+        }
+        refresh_worst();
+    }
+    // slot j (warp-uniform j), in every lane
+    __device__ __forceinline__ unsigned long long slot(int j) const {
+        unsigned long long e = __shfl_sync(FULL, key[0], j & 31);
+#pragma unroll
+        for (int r = 1; r < R; ++r) {
+            const unsigned long long o = __shfl_sync(FULL, key[r], j & 31);
+            if ((j >> 5) == r) e = o;
+        }
+        return e;
+    }
+};
+
 constexpr int OVF_STACK = 224;  // <= 32 pushes per expansion level, <= 6 levels of expansion (depth <= 30)
 
 template <int KMAX, bool NORMALS>
@@ -227,20 +286,30 @@ __global__ void __launch_bounds__(128) knn_overflow_kernel(TreeView tree, const 
         uint32_t qi = t;
         if (self_query) { qi = __float_as_uint(q.w); q.w = 1.f; }
         if (use_T) q = transform_point(sT, q);
-        TopK<KMAX> best;
         // seed: the candidates stage 1 left in the result arrays (K8: in the scratch, by queue slot) — real points,
-        // ascending; its unfilled slots (id < 0) carry the radius it was searching with
-        float r0 = var_r2 ? var_r2[t] : cap.r2;
-        for (int j = 0; j < k; ++j) {
-            const int id = NORMALS ? ns.scratch_ids[(size_t)w * k + j] : ids[(size_t)qi * k + j];
-            const float dd = NORMALS ? ns.scratch_d[(size_t)w * k + j] : dists[(size_t)qi * k + j];
-            if (id < 0) r0 = fminf(r0, dd);
-        }
-        best.init(k, r0);
-        for (int j = 0; j < k; ++j) {
-            const int id = NORMALS ? ns.scratch_ids[(size_t)w * k + j] : ids[(size_t)qi * k + j];
-            const float dd = NORMALS ? ns.scratch_d[(size_t)w * k + j] : dists[(size_t)qi * k + j];
-            if (id >= 0 && best.accepts(dd, id)) best.insert(dd, id);
+        // ascending, so lane j takes entry j as it is; the unfilled slots (id < 0) carry the radius stage 1 searched with
+        WarpTopK<KMAX> best;
+        {
+            int sid[WarpTopK<KMAX>::R];
+            float sd[WarpTopK<KMAX>::R];
+            unsigned rbits = __float_as_uint(var_r2 ? var_r2[t] : cap.r2);
+#pragma unroll
+            for (int r = 0; r < WarpTopK<KMAX>::R; ++r) {
+                const int j = r * 32 + lane;
+                sid[r] = -1;
+                sd[r] = pm_inf();
+                if (j < k) {
+                    sid[r] = NORMALS ? ns.scratch_ids[(size_t)w * k + j] : ids[(size_t)qi * k + j];
+                    sd[r] = NORMALS ? ns.scratch_d[(size_t)w * k + j] : dists[(size_t)qi * k + j];
+                    if (sid[r] < 0) rbits = min(rbits, __float_as_uint(sd[r]));  // non-negative floats order like their bits
+                }
+            }
+            rbits = __reduce_min_sync(0xffffffffu, rbits);
+            best.init(k, lane, __uint_as_float(rbits));
+#pragma unroll
+            for (int r = 0; r < WarpTopK<KMAX>::R; ++r)
+                if (sid[r] >= 0) best.key[r] = WarpTopK<KMAX>::pack(sd[r], sid[r]);
+            best.refresh_worst();
         }
         int sp = 0;
         if (lane == 0) stack[0] = 1u;
@@ -318,18 +387,24 @@ __global__ void __launch_bounds__(128) knn_overflow_kernel(TreeView tree, const 
                 for (int i = 0; i < 4 * U && mask; ++i) mask &= mask - 1;
             }
         }
-        if (NORMALS) {
-            // the list is replicated in every lane: lane 0 finishes the point
-            if (lane == 0 && normals_epilogue<KMAX>(best, k, ns, ns.by_position ? (size_t)(pos_offset + t) : (size_t)qi, q.x, q.y, q.z))
+        if constexpr (NORMALS) {
+            // the epilogue wants the whole list in one thread: gather it (every lane takes part in the shuffles), lane 0 finishes
+            TopK<KMAX> all;
+            all.k = k;
+            static_for<0, KMAX>([&](auto J) { all.key[J] = __shfl_sync(0xffffffffu, best.key[J / 32], J % 32); });
+            if (lane == 0 && normals_epilogue<KMAX>(all, k, ns, ns.by_position ? (size_t)(pos_offset + t) : (size_t)qi, q.x, q.y, q.z))
                 atomicAdd(ns.degenerate, 1);
-        } else if (lane == 0) {
-            for (int j = 0; j < k; ++j) {
-                float bd;
-                int bi;
-                best.get(j, bd, bi);
-                const bool valid = bi != PM_NO_ID && bd != pm_inf();
-                ids[(size_t)qi * k + j] = valid ? bi : cap.miss_id;
-                dists[(size_t)qi * k + j] = valid ? bd : cap.miss_d;
+        } else {
+#pragma unroll
+            for (int r = 0; r < WarpTopK<KMAX>::R; ++r) {
+                const int j = r * 32 + lane;
+                if (j < k) {
+                    const float bd = __uint_as_float((uint32_t)(best.key[r] >> 32));
+                    const int bi = (int)(uint32_t)best.key[r];
+                    const bool valid = bi != PM_NO_ID && bd != pm_inf();
+                    ids[(size_t)qi * k + j] = valid ? bi : cap.miss_id;
+                    dists[(size_t)qi * k + j] = valid ? bd : cap.miss_d;
+                }
             }
         }
         __syncwarp();
