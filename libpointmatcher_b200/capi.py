@@ -331,7 +331,7 @@ class Context:
         return np.array(T), (np.array(cov) if (minimizer & 0xff) in (2, 3) else None), _stats(stats)
 
     # ---- K8
-    def normals(self, features, knn=5, epsilon=0.0, max_dist=np.inf, sort_eigen=False, keep=("normals",)):
+    def normals(self, features, knn=5, epsilon=0.0, max_dist=np.inf, sort_eigen=False, keep=("normals",), smooth=False):
         """SurfaceNormalDataPointsFilter on a cloud.  keep: subset of normals, densities, eigValues,
         eigVectors, matchedIds, meanDists.  Returns dict of arrays (+ 'degenerate')."""
         f = _cloud(features)
@@ -345,13 +345,13 @@ class Context:
                 setattr(o, field, _f(arrays[name]))
                 setattr(o, field + "_ld", spans[name])
         deg = C.c_int(0)
-        flags = NORMALS_SORT_EIGEN if sort_eigen else 0
+        flags = (NORMALS_SORT_EIGEN if sort_eigen else 0) | (NORMALS_SMOOTH if smooth else 0)
         self._check(lib.pmgpu_normals(self.h, _ptr(f), f.shape[1], n, knn, epsilon, max_dist, flags, C.byref(o), C.byref(deg)))
         arrays["degenerate"] = deg.value
         return arrays
 
-    def ref_compute_normals(self, knn=5, epsilon=0.0, max_dist=np.inf):
-        self._check(lib.pmgpu_ref_compute_normals(self.h, knn, epsilon, max_dist, 0))
+    def ref_compute_normals(self, knn=5, epsilon=0.0, max_dist=np.inf, smooth=False):
+        self._check(lib.pmgpu_ref_compute_normals(self.h, knn, epsilon, max_dist, NORMALS_SMOOTH if smooth else 0))
 
     def ref_center(self, features):
         """centre the resident reference on the mean of the host cloud it was set from; returns the mean (4,)"""

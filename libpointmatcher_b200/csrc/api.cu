@@ -107,6 +107,26 @@ __global__ void unpermute_kernel(const V* __restrict__ src, const uint32_t* __re
     dst[(size_t)order[t] * k + j] = src[e];
 }
 
+// smoothNormals (SurfaceNormal.cpp:259-283): in place and in point order, like the reference — normal i becomes the mean of
+// its valid neighbours' CURRENT normals, each flipped to the side of normal i.  `n4`: (nx, ny, nz, 0) per point.
+void smooth_normals_host(f4* n4, const int32_t* ids, int knn, int n) {
+    for (int i = 0; i < n; ++i) {
+        const f4 cur = n4[i];
+        float mx = 0.f, my = 0.f, mz = 0.f;
+        int cnt = 0;
+        for (int j = 0; j < knn; ++j) {
+            const int r = ids[(size_t)i * knn + j];
+            if (r < 0) continue;
+            const f4 nb = n4[r];
+            const float dot = cur.x * nb.x + cur.y * nb.y + cur.z * nb.z;
+            if (dot > 0.f) { mx += nb.x; my += nb.y; mz += nb.z; }
+            else { mx -= nb.x; my -= nb.y; mz -= nb.z; }
+            ++cnt;
+        }
+        n4[i] = make_float4(mx / (float)cnt, my / (float)cnt, mz / (float)cnt, 0.f);
+    }
+}
+
 int fail(pmgpu_ctx* ctx, int code, const char* msg) {
     ctx->set_error(msg);
     return code;
@@ -779,7 +799,7 @@ int pmgpu_ref_compute_normals(pmgpu_ctx* ctx, int knn, float epsilon, float max_
     if (knn < 1) return fail(ctx, PMGPU_ERR_BAD_ARG, "knn must be >= 1");
     if (knn > ctx->nr) return fail(ctx, PMGPU_ERR_KNN_TOO_LARGE, status_message(PMGPU_ERR_KNN_TOO_LARGE));
     if (!(epsilon >= 0.f) || !(max_dist >= 0.f)) return fail(ctx, PMGPU_ERR_BAD_ARG, "epsilon and maxDist must be >= 0");
-    if (flags & PMGPU_NORMALS_SMOOTH) return fail(ctx, PMGPU_ERR_UNSUPPORTED, "SurfaceNormalDataPointsFilter on GPU: smoothNormals is not supported");
+    const bool smooth = (flags & PMGPU_NORMALS_SMOOTH) != 0;
     const int n = ctx->nr;
     PM_CUDA_TRY(ctx, ctx->ref_normals.reserve(n));
     NormalsSink sink;
@@ -787,7 +807,12 @@ int pmgpu_ref_compute_normals(pmgpu_ctx* ctx, int knn, float epsilon, float max_
     sink.pts = ctx->ref_orig.p;
     sink.degenerate = &ctx->state->degenerate;
     const float max_r2 = max_dist * max_dist;
-    if (ctx->nranks > 1 && ctx->nccl_comm) {
+    ScopedBuf<int32_t> nids;
+    if (smooth) {
+        PM_CUDA_TRY(ctx, nids.reserve((size_t)knn * n));
+        sink.ids_i32 = nids.p;
+    }
+    if (ctx->nranks > 1 && ctx->nccl_comm && !smooth) {
         // every rank holds the whole structure and computes the normals of one slice of it (leaf-order
         // positions, so the slice is spatially compact and its output contiguous); one all-gather of float4[N / G] and a
         // local scatter into the caller's column order complete every rank's copy
@@ -810,6 +835,17 @@ int pmgpu_ref_compute_normals(pmgpu_ctx* ctx, int knn, float epsilon, float max_
         ctx->stage_end();
     }
     PM_CUDA_TRY(ctx, cudaGetLastError());
+    if (smooth) {
+        // the serial pass of the reference, on the host (see normals.cuh)
+        std::vector<f4> h_n((size_t)n);
+        std::vector<int32_t> h_ids((size_t)knn * n);
+        PM_CUDA_TRY(ctx, cudaMemcpyAsync(h_n.data(), ctx->ref_normals.p, h_n.size() * sizeof(f4), cudaMemcpyDeviceToHost, ctx->stream));
+        PM_CUDA_TRY(ctx, cudaMemcpyAsync(h_ids.data(), nids.p, h_ids.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        PM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        smooth_normals_host(h_n.data(), h_ids.data(), knn, n);
+        PM_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ref_normals.p, h_n.data(), h_n.size() * sizeof(f4), cudaMemcpyHostToDevice, ctx->stream));
+        PM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     ctx->has_normals = true;
     return PMGPU_OK;
 }
@@ -824,7 +860,7 @@ int pmgpu_normals(pmgpu_ctx* ctx, const float* features, int rows, int n, int kn
     if (knn < 1) return fail(ctx, PMGPU_ERR_BAD_ARG, "knn must be >= 1");
     if (knn > n) return fail(ctx, PMGPU_ERR_KNN_TOO_LARGE, status_message(PMGPU_ERR_KNN_TOO_LARGE));
     if (!(epsilon >= 0.f) || !(max_dist >= 0.f)) return fail(ctx, PMGPU_ERR_BAD_ARG, "epsilon and maxDist must be >= 0");
-    if (flags & PMGPU_NORMALS_SMOOTH) return fail(ctx, PMGPU_ERR_UNSUPPORTED, "SurfaceNormalDataPointsFilter on GPU: smoothNormals is not supported");
+    const bool smooth = (flags & PMGPU_NORMALS_SMOOTH) != 0 && out->normals;
     // a private context holds the cloud's own search structure (the filter builds its own
     // KDTreeMatcher, SurfaceNormal.cpp:153-162); it shares nothing with the ICP reference
     pmgpu_ctx* sub = nullptr;
@@ -839,7 +875,9 @@ int pmgpu_normals(pmgpu_ctx* ctx, const float* features, int rows, int n, int kn
     if (s != PMGPU_OK) return fail(ctx, s, sub->err.c_str());
     ScopedBuf<float> scratch;
     ScopedBuf<f4> n4;
+    ScopedBuf<int32_t> nids;
     if (out->normals) PM_CUDA_TRY(ctx, n4.reserve(n));
+    if (smooth) PM_CUDA_TRY(ctx, nids.reserve((size_t)knn * n));
     // scratch: densities n | eig_values 3n | eig_vectors 9n | mean_dists n | normals3 3n | ids-as-float knn*n
     const size_t off_den = 0, off_val = (size_t)n, off_vec = 4 * (size_t)n, off_md = 13 * (size_t)n, off_n3 = 14 * (size_t)n, off_ids = 17 * (size_t)n;
     PM_CUDA_TRY(ctx, scratch.reserve(17 * (size_t)n + (out->matched_ids ? (size_t)knn * n : 0)));
@@ -858,8 +896,19 @@ int pmgpu_normals(pmgpu_ctx* ctx, const float* features, int rows, int n, int kn
     sink.mean_dists = out->mean_dists ? scratch.p + off_md : nullptr;
     sink.matched_ids = out->matched_ids ? scratch.p + off_ids : nullptr;
     sink.degenerate = &sub->state->degenerate;
+    sink.ids_i32 = smooth ? nids.p : nullptr;
     if (s == PMGPU_OK) s = launch_knn_normals(sub, sub->tree_view(), 0, n, knn, max_dist * max_dist, sink);
     if (s != PMGPU_OK) return fail(ctx, s, sub->err.c_str());
+    if (smooth) {
+        std::vector<f4> h_n((size_t)n);
+        std::vector<int32_t> h_ids((size_t)knn * n);
+        PM_CUDA_TRY(ctx, cudaMemcpyAsync(h_n.data(), n4.p, h_n.size() * sizeof(f4), cudaMemcpyDeviceToHost, sub->stream));
+        PM_CUDA_TRY(ctx, cudaMemcpyAsync(h_ids.data(), nids.p, h_ids.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, sub->stream));
+        PM_CUDA_TRY(ctx, cudaStreamSynchronize(sub->stream));
+        smooth_normals_host(h_n.data(), h_ids.data(), knn, n);
+        PM_CUDA_TRY(ctx, cudaMemcpyAsync(n4.p, h_n.data(), h_n.size() * sizeof(f4), cudaMemcpyHostToDevice, sub->stream));
+        PM_CUDA_TRY(ctx, cudaStreamSynchronize(sub->stream));
+    }
     auto copy_out = [&](float* dst, int ld, const float* src, int span) -> cudaError_t {
         if (!dst) return cudaSuccess;
         if (ld == span) return cudaMemcpyAsync(dst, src, (size_t)span * n * sizeof(float), cudaMemcpyDefault, st);

@@ -209,7 +209,13 @@ struct WarpTopK {
     __device__ __forceinline__ static unsigned long long pack(float d, int i) { return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned long long)(uint32_t)i; }
     __device__ __forceinline__ float worst_d() const { return __uint_as_float((uint32_t)(wkey >> 32)); }
     __device__ __forceinline__ bool accepts(float d, int i) const { return pack(d, i) < wkey; }
-    __device__ __forceinline__ void refresh_worst() { wkey = __shfl_sync(FULL, key[(k - 1) >> 5], (k - 1) & 31); }
+    __device__ __forceinline__ void refresh_worst() {
+        unsigned long long src = key[0];  // the register that holds slot k - 1, without dynamic register indexing
+#pragma unroll
+        for (int r = 1; r < R; ++r)
+            if (((k - 1) >> 5) == r) src = key[r];
+        wkey = __shfl_sync(FULL, src, (k - 1) & 31);
+    }
     // all slots (radius, no point) except the real candidates the caller fills in
     __device__ __forceinline__ void init(int k_, int lane_, float r0) {
         k = k_; lane = lane_;
@@ -412,6 +418,39 @@ __global__ void __launch_bounds__(128) knn_overflow_kernel(TreeView tree, const 
     if (visits && my_visits) atomicAdd(visits, my_visits);
 }
 
+// knn > 64: every query goes straight to the warp-per-query kernel, whose distributed list holds up to 32 candidates per
+// register (WarpTopK): the queue is the identity and every result slot starts unfilled at the caller's radius
+__global__ void all_to_stage2_kernel(int nq, int k, float max_r2, const float* __restrict__ var_r2, uint32_t* __restrict__ overflow, unsigned* count,
+                                     int32_t* __restrict__ ids, float* __restrict__ dists) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e == 0) *count = (unsigned)nq;
+    if (e < (size_t)nq) overflow[e] = (uint32_t)e;
+    if (e < (size_t)nq * k) {
+        ids[e] = -1;
+        dists[e] = var_r2 ? var_r2[e / k] : max_r2;
+    }
+}
+
+template <int KMAX>
+int launch_wide(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, bool use_T, bool gated, int k, float max_r2, int32_t* ids, float* dists,
+                const float* var_r2) {
+    if (nq == 0) return PMGPU_OK;
+    PM_CUDA_TRY(ctx, ctx->overflow.reserve((size_t)nq));
+    unsigned* cnt = &ctx->state->overflow_count[ctx->knn_parity];
+    unsigned* cnt_next = &ctx->state->overflow_count[ctx->knn_parity ^ 1];
+    ctx->knn_parity ^= 1;
+    const size_t total = (size_t)nq * k;
+    all_to_stage2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(nq, k, max_r2, var_r2, ctx->overflow.p, cnt, ids, dists);
+    NormalsSink none;
+    memset(&none, 0, sizeof(none));
+    const int grid2 = min(ctx->num_sms * 8, (nq + 3) / 4);
+    knn_overflow_kernel<KMAX, false><<<grid2, 128, 0, ctx->stream>>>(tree, queries, ctx->state, use_T ? 1 : 0, gated ? 1 : 0, 0, k, max_r2, ctx->overflow.p, cnt,
+                                                                 cnt_next, ids, dists, &ctx->state->visits, 0, var_r2, none, 0);
+    ctx->launches += 2;
+    PM_CUDA_TRY(ctx, cudaGetLastError());
+    return PMGPU_OK;
+}
+
 template <int KMAX, bool NORMALS>
 int launch_one(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, bool use_T, bool gated, bool self_query, int k, float max_r2,
                bool use_seed, int32_t* ids, float* dists, bool use_cap, const float* var_r2, NormalsSink ns, int pos_offset) {
@@ -472,7 +511,16 @@ int launch_knn(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, 
     if (k <= 32) PM_KNN_CASE(32);
     if (k <= 64) PM_KNN_CASE(64);
 #undef PM_KNN_CASE
-    ctx->set_error("KDTreeMatcher on GPU: knn > 64 is not supported");
+    // larger k (MatchersImpl.h:80 allows any unsigned): the warp-per-query kernel alone, list distributed over the lanes
+    if (self_query || use_cap) {
+        ctx->set_error("KDTreeMatcher on GPU: knn > 64 is supported for plain matching only");
+        return PMGPU_ERR_UNSUPPORTED;
+    }
+    if (k <= 128) return launch_wide<128>(ctx, tree, queries, nq, use_T, gated, k, max_r2, ids, dists, var_r2);
+    if (k <= 256) return launch_wide<256>(ctx, tree, queries, nq, use_T, gated, k, max_r2, ids, dists, var_r2);
+    if (k <= 512) return launch_wide<512>(ctx, tree, queries, nq, use_T, gated, k, max_r2, ids, dists, var_r2);
+    if (k <= 1024) return launch_wide<1024>(ctx, tree, queries, nq, use_T, gated, k, max_r2, ids, dists, var_r2);
+    ctx->set_error("KDTreeMatcher on GPU: knn > 1024 is not supported");
     return PMGPU_ERR_UNSUPPORTED;
 }
 

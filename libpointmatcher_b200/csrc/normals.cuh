@@ -13,6 +13,10 @@
 // EigenSolver leaves it), clamped to [-1, 1].  Eigenvalues / eigenvectors are reported in ascending
 // eigenvalue order whether or not sortEigen is set (the reference's unsorted order is whatever
 // Eigen's Hessenberg QR produces: unpinned).
+// smoothNormals (SurfaceNormal.cpp:259-283) replaces every normal by the sign-aligned mean of its neighbours' normals IN
+// PLACE, point after point, so point i sees the already smoothed normals of every neighbour j < i: a serial recurrence
+// by definition.  It runs on the host (api.cu smooth_normals_host), once per cloud like the reference's, on the normals
+// and exact neighbour ids this epilogue wrote.
 #pragma once
 #include "core/linalg.h"
 #include "pmgpu_internal.cuh"
@@ -28,6 +32,7 @@ struct NormalsSink {
     float* eig_vectors;  // optional, 9 per point (row-major serialisation, utils.h:89-103)
     float* mean_dists;   // optional, 1 per point
     float* matched_ids;  // optional, k per point, as float (SurfaceNormal.cpp:254-257)
+    int32_t* ids_i32;    // optional, k per point, exact (-1 = no neighbour): what smoothNormals walks on the host
     int* degenerate;     // counter
     int by_position;     // 1: outputs indexed by the query's leaf-order position (sharded K8: contiguous per rank), 0: by original column
     // stage-2 hand-over of the candidates stage 1 found for queries that ran out of budget
@@ -71,6 +76,14 @@ __device__ __forceinline__ bool normals_epilogue(const TopK<KMAX>& best, int k, 
             if (J < k) {
                 const bool valid = best.I(J) != PM_NO_ID && best.D(J) != pm_inf();
                 ns.matched_ids[out * k + J] = (float)(valid ? best.I(J) : -1);
+            }
+        });
+    }
+    if (ns.ids_i32) {
+        static_for<0, KMAX>([&](auto J) {
+            if (J < k) {
+                const bool valid = best.I(J) != PM_NO_ID && best.D(J) != pm_inf();
+                ns.ids_i32[out * k + J] = valid ? best.I(J) : -1;
             }
         });
     }

@@ -135,7 +135,7 @@ struct ICP : ICPChainBase {
             auto* last = dynamic_cast<SurfaceNormalDataPointsFilter*>(this->referenceDataPointsFilters.back().get());
             auto* plainMatcher = dynamic_cast<KDTreeMatcher*>(this->matcher.get());
             if (last && plainMatcher && last->keepNormals && !last->keepDensities && !last->keepEigenValues && !last->keepEigenVectors &&
-                !last->keepMatchedIds && !last->keepMeanDist && !last->sortEigen)
+                !last->keepMatchedIds && !last->keepMeanDist && !last->sortEigen && !last->smoothNormals)
                 trailingNormals = last;
         }
         // inputs are never mutated (ICP.cpp:285); without reference filters no host copy is needed

@@ -577,9 +577,7 @@ struct SurfaceNormalDataPointsFilter : public DataPointsFilter, public GpuBound 
           keepNormals(Parametrizable::get<bool>("keepNormals")), keepDensities(Parametrizable::get<bool>("keepDensities")),
           keepEigenValues(Parametrizable::get<bool>("keepEigenValues")), keepEigenVectors(Parametrizable::get<bool>("keepEigenVectors")),
           keepMatchedIds(Parametrizable::get<bool>("keepMatchedIds")), keepMeanDist(Parametrizable::get<bool>("keepMeanDist")),
-          sortEigen(Parametrizable::get<bool>("sortEigen")), smoothNormals(Parametrizable::get<bool>("smoothNormals")) {
-        if (smoothNormals) throw ConfigurationError("SurfaceNormalDataPointsFilter: GPU module: smoothNormals is not supported");
-    }
+          sortEigen(Parametrizable::get<bool>("sortEigen")), smoothNormals(Parametrizable::get<bool>("smoothNormals")) {}
     DataPoints filter(const DataPoints& input) override {
         DataPoints output(input);
         inPlaceFilter(output);
@@ -611,7 +609,8 @@ struct SurfaceNormalDataPointsFilter : public DataPointsFilter, public GpuBound 
         if (keepMeanDist) { out.mean_dists = at("meanDists"); out.mean_dists_ld = ld; }
         GpuPipeline& g = this->gpu();
         g.check(pmgpu_normals(g.ctx, reinterpret_cast<const float*>(cloud.features.data()), cloud.features.rows(), cloud.features.cols(), (int)knn,
-                              (float)epsilon, (float)maxDist, sortEigen ? PMGPU_NORMALS_SORT_EIGEN : 0, &out, &degenerateCount));
+                              (float)epsilon, (float)maxDist, (sortEigen ? PMGPU_NORMALS_SORT_EIGEN : 0) | (smoothNormals ? PMGPU_NORMALS_SMOOTH : 0), &out,
+                              &degenerateCount));
     }
 };
 

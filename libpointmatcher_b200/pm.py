@@ -702,8 +702,6 @@ class SurfaceNormalDataPointsFilter(Parametrizable, _Bound):
         Parametrizable.__init__(self, params)
         for name, *_ in self.PARAMS:
             setattr(self, name, self.get(name))
-        if self.smoothNormals:
-            raise ConfigurationError("GPU module: SurfaceNormalDataPointsFilter smoothNormals is not supported")
 
     def init(self):
         pass
@@ -717,7 +715,7 @@ class SurfaceNormalDataPointsFilter(Parametrizable, _Bound):
         keep = [name for flag, name in ((self.keepNormals, "normals"), (self.keepDensities, "densities"),
                                         (self.keepEigenValues, "eigValues"), (self.keepEigenVectors, "eigVectors"),
                                         (self.keepMatchedIds, "matchedIds"), (self.keepMeanDist, "meanDists")) if flag]
-        res = _translate(self.ctx.normals, cloud.features, self.knn, self.epsilon, self.maxDist, self.sortEigen, keep)
+        res = _translate(self.ctx.normals, cloud.features, self.knn, self.epsilon, self.maxDist, self.sortEigen, keep, self.smoothNormals)
         self.degenerateCount = res.pop("degenerate")
         cloud.descriptors.update(res)
 
@@ -1318,7 +1316,7 @@ class ICP:
         last = filters[-1] if filters else None
         fuse_normals = (type(last) is SurfaceNormalDataPointsFilter and type(self.matcher) is KDTreeMatcher and last.keepNormals
                         and not (last.keepDensities or last.keepEigenValues or last.keepEigenVectors or last.keepMatchedIds or last.keepMeanDist
-                                 or last.sortEigen))
+                                 or last.sortEigen or last.smoothNormals))
         if fuse_normals:
             filters = filters[:-1]
         if filters:

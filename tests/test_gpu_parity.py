@@ -839,3 +839,37 @@ def test_materialised_weights_after_fused_loop_use_the_match_transform(oracle, s
         # |dot| within an ulp of the limit may fall either side
         assert ((w != wo) & real).mean() < 2e-4
         assert res["stats"]["nbKept"] == int((w != 0).sum())   # what the minimiser used is what is materialised
+
+
+@pytest.mark.gpu
+def test_knn_larger_than_64_is_exact(gpu_ctx, oracle):
+    """knn > 64 (MatchersImpl.h:80 allows any unsigned): the warp-per-query kernel with the list distributed over the lanes;
+    ids and dists bit-exact against libnabo's brute-force semantics, misses included"""
+    rng = np.random.default_rng(21)
+    ref, q = cloud(rng, 3000, "uniform"), cloud(rng, 500, "uniform")
+    gpu_ctx.set_reference(ref)
+    gpu_ctx.set_reading(q)
+    for k, md in ((65, np.inf), (100, np.inf), (200, 3.0), (700, np.inf), (1024, 8.0)):
+        ib, db = oracle.bruteforce_knn(ref, q, k, md)
+        ig, dg, _ = gpu_ctx.knn(None, k, 0.0, md)
+        assert (ib == ig).all() and (db.view(np.uint32) == dg.view(np.uint32)).all(), (k, md)
+    with pytest.raises(Exception):
+        gpu_ctx.knn(None, 1025)
+
+
+@pytest.mark.gpu
+def test_smooth_normals_match_oracle(gpu_ctx, oracle, synth):
+    """smoothNormals (SurfaceNormal.cpp:259-283): the in-place, point-after-point average of the neighbours' normals — a serial
+    recurrence, run on the host over the device's normals and neighbour ids; equal to the oracle's up to each normal's sign"""
+    rf = synth.scan(30000, cache=False)
+    o = oracle.surface_normals(rf, knn=8, nthreads=8, smooth_normals=True)
+    g = gpu_ctx.normals(rf, knn=8, keep=("normals",), smooth=True)
+    no, ng = np.linalg.norm(o["normals"], axis=1), np.linalg.norm(g["normals"], axis=1)
+    ok = np.abs(no - ng) <= 1e-4
+    cos = np.abs((o["normals"] * g["normals"]).sum(1)) / np.maximum(no * ng, 1e-12)
+    ok &= (cos >= 1 - 1e-4) | (no < 1e-3)
+    assert ok.mean() > 0.995, ok.mean()     # a tie-reordered neighbourhood or an ill-conditioned normal spreads to its neighbours
+    # and the resident-reference variant takes the same path
+    gpu_ctx.set_reference(rf)
+    gpu_ctx.ref_compute_normals(knn=8, smooth=True)
+    assert np.array_equal(gpu_ctx.ref_normals(), g["normals"])
