@@ -10,12 +10,18 @@
  *
  * Conventions
  *  - clouds are `rows x n` column-major float matrices exactly as `DataPoints::features`
- *    (pointmatcher/PointMatcher.h:169,331): rows == 4 (x, y, z, w) for 3-D.  Only float / 3-D
- *    is implemented on the GPU; anything else returns PMGPU_ERR_UNSUPPORTED (there is no CPU
- *    fallback by design).
+ *    (pointmatcher/PointMatcher.h:169,331): rows == 4 (x, y, z, w) for 3-D clouds, rows == 3 (x, y, w) for
+ *    2-D clouds — every module of the reference branches on it (PointToPlane.cpp:294-310,
+ *    ErrorMinimizer.cpp:308-313, TransformationCheckersImpl.cpp:114-131).  A 2-D cloud lives on the device as
+ *    (x, y, 0, w), where every z term of the 3-D kernels is an exact zero; transforms of a 2-D context cross
+ *    this ABI as 3 x 3 matrices, normals have 2 rows, eigenvalues 2, eigenvectors 4.  2-D supports the
+ *    matchers, the distance outlier filters, PointToPoint / PointToPlane, Counter / Differential (with the
+ *    reference's 3 x 3 quaternion quirk) and SurfaceNormal; the covariance, similarity and force2D / 4DOF
+ *    variants return PMGPU_ERR_UNSUPPORTED.  Only float is implemented; anything else returns
+ *    PMGPU_ERR_UNSUPPORTED (there is no CPU fallback by design).
  *  - match results are `k x n` column-major (`Matches::ids/dists`, PointMatcher.h:373-374):
  *    ids int32 (-1 = Matches::InvalidId), dists float SQUARED distances (+inf = InvalidDist).
- *  - 4x4 transforms are column-major float[16] (Eigen default).
+ *  - transforms are `rows x rows` column-major (Eigen default): float[16], or float[9] for 2-D clouds.
  *  - every pointer argument may be a host pointer (pageable or pinned) or a device pointer
  *    (copies use cudaMemcpyDefault); NULL for an optional output skips that download.
  *  - all functions return a PMGPU_* status; pmgpu_last_error(ctx) gives the message.  The

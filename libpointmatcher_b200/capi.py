@@ -176,6 +176,7 @@ class Context:
         self.h = h
         self.device = device
         self.nq = self.nr = self.k = 0
+        self.dimh = 4   # features.rows() of the resident clouds: 4, or 3 for 2-D clouds (transforms are then 3 x 3)
 
     def close(self):
         if getattr(self, "h", None):
@@ -231,6 +232,7 @@ class Context:
             nrm = None if normals is None else np.ascontiguousarray(normals, np.float32)
             ld = 0 if nrm is None else nrm.shape[1]
             self._check(lib.pmgpu_ref_set(self.h, _ptr(f), rows, n, _ptr(nrm), ld))
+            self.dimh = rows
         self.nr = n
 
     def set_reference_centered(self, features, normals=None):
@@ -241,8 +243,8 @@ class Context:
         nrm = None if normals is None else np.ascontiguousarray(normals, np.float32)
         mean = np.zeros(4, np.float32)
         self._check(lib.pmgpu_ref_set_centered(self.h, _ptr(f), rows, n, _ptr(nrm), 0 if nrm is None else nrm.shape[1], _f(mean)))
-        self.nr = n
-        return mean[:3].copy()
+        self.nr, self.dimh = n, rows
+        return mean[:rows - 1].copy()
 
     def set_reference_normals(self, normals):
         nrm = None if normals is None else np.ascontiguousarray(normals, np.float32)
@@ -256,6 +258,8 @@ class Context:
             f = _cloud(features)
             n, rows = f.shape
             self._check(lib.pmgpu_reading_set(self.h, _ptr(f), rows, n))
+            if self.nr == 0:
+                self.dimh = rows
         self.nq = n
 
     def reading_apply_transform(self, T):
@@ -272,7 +276,7 @@ class Context:
         self._check(lib.pmgpu_reading_set_max_dists(self.h, _ptr(md), 1))
 
     def get_reading(self):
-        out = np.empty((self.nq, 4), np.float32)
+        out = np.empty((self.nq, self.dimh), np.float32)
         self._check(lib.pmgpu_reading_get(self.h, _ptr(out)))
         return out
 
@@ -298,7 +302,7 @@ class Context:
 
     def ref_normals(self):
         """the reference's normals as resident on the device (nr, 3)"""
-        out = np.empty((self.nr, 3), np.float32)
+        out = np.empty((self.nr, self.dimh - 1), np.float32)
         self._check(lib.pmgpu_ref_get_normals(self.h, _ptr(out)))
         return out
 
@@ -307,7 +311,7 @@ class Context:
         ids = np.empty((self.nq, self.k), np.int32)
         dists = np.empty((self.nq, self.k), np.float32)
         w = np.empty((self.nq, self.k), np.float32) if weights else None
-        T = np.zeros((4, 4), np.float32, order="F")
+        T = np.zeros((self.dimh, self.dimh), np.float32, order="F")
         self._check(lib.pmgpu_matches_get(self.h, _ptr(ids), _ptr(dists), _ptr(w), _f(T)))
         return ids, dists, w, np.array(T)
 
@@ -324,7 +328,7 @@ class Context:
     # ---- K4-K7
     def minimize(self, minimizer, sensor_std_dev=0.01):
         """ErrorMinimizer::compute.  Returns (T (4,4), cov (6,6) or None, stats dict)."""
-        T = np.zeros((4, 4), np.float32, order="F")
+        T = np.zeros((self.dimh, self.dimh), np.float32, order="F")
         cov = np.zeros((6, 6), np.float32, order="F")
         stats = np.zeros(5, np.float32)
         self._check(lib.pmgpu_minimize(self.h, minimizer, sensor_std_dev, _f(T), _f(cov), _f(stats)))
@@ -335,8 +339,8 @@ class Context:
         """SurfaceNormalDataPointsFilter on a cloud.  keep: subset of normals, densities, eigValues,
         eigVectors, matchedIds, meanDists.  Returns dict of arrays (+ 'degenerate')."""
         f = _cloud(features)
-        n = f.shape[0]
-        spans = dict(normals=3, densities=1, eigValues=3, eigVectors=9, matchedIds=knn, meanDists=1)
+        n, dn = f.shape[0], f.shape[1] - 1
+        spans = dict(normals=dn, densities=1, eigValues=dn, eigVectors=dn * dn, matchedIds=knn, meanDists=1)
         arrays = {name: np.zeros((n, spans[name]), np.float32) for name in keep}
         o = NormalsOut()
         for name, field in (("normals", "normals"), ("densities", "densities"), ("eigValues", "eig_values"),
@@ -358,12 +362,12 @@ class Context:
         f = _cloud(features)
         mean = np.zeros(4, np.float32)
         self._check(lib.pmgpu_ref_center(self.h, _ptr(f), f.shape[1], f.shape[0], _f(mean)))
-        return mean
+        return mean[:f.shape[1]]
 
     # ---- fused loop
     def icp_run(self, params, T_iter_init=None):
         """ICP::computeWithTransformedReference loop.  Returns dict(T_iter, iterations, cov, stats)."""
-        T = np.zeros((4, 4), np.float32, order="F")
+        T = np.zeros((self.dimh, self.dimh), np.float32, order="F")
         cov = np.zeros((6, 6), np.float32, order="F")
         stats = np.zeros(5, np.float32)
         it = C.c_int(0)
@@ -379,7 +383,7 @@ class Context:
         self.k = params.knn
 
     def icp_result(self):
-        T = np.zeros((4, 4), np.float32, order="F")
+        T = np.zeros((self.dimh, self.dimh), np.float32, order="F")
         cov = np.zeros((6, 6), np.float32, order="F")
         stats = np.zeros(5, np.float32)
         it = C.c_int(0)

@@ -15,19 +15,20 @@ thread_local cudaStream_t pm::g_alloc_stream = nullptr;
 
 namespace {
 
-__global__ void pack_normals_kernel(const float* __restrict__ src, int ld, int n, f4* __restrict__ dst) {
+__global__ void pack_normals_kernel(const float* __restrict__ src, int ld, int n, f4* __restrict__ dst, int comps) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float* s = src + (size_t)i * ld;
-    dst[i] = make_float4(s[0], s[1], s[2], 0.f);
+    dst[i] = make_float4(s[0], s[1], comps == 3 ? s[2] : 0.f, 0.f);
 }
 
 // reading normals arrive in the caller's column order and are kept in the reading's Morton order
-__global__ void pack_normals_permuted_kernel(const float* __restrict__ src, int ld, const uint32_t* __restrict__ order, int n, f4* __restrict__ dst) {
+__global__ void pack_normals_permuted_kernel(const float* __restrict__ src, int ld, const uint32_t* __restrict__ order, int n, f4* __restrict__ dst,
+                                             int comps) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const float* s = src + (size_t)order[t] * ld;
-    dst[t] = make_float4(s[0], s[1], s[2], 0.f);
+    dst[t] = make_float4(s[0], s[1], comps == 3 ? s[2] : 0.f, 0.f);
 }
 
 // KDTreeVarDistMatcher: per-point search distance -> squared (maxRadius * maxRadius in float, like libnabo), Morton order
@@ -51,11 +52,27 @@ __global__ void rotate_normals_inplace_kernel(f4* __restrict__ nrm, int n, Mat4 
     nrm[i] = r;
 }
 
-__global__ void unpack_f4_kernel(const f4* __restrict__ src, int n, float* __restrict__ dst) {
+// comps = 3 (3-D) or 2 (2-D clouds)
+__global__ void unpack_f4_kernel(const f4* __restrict__ src, int n, float* __restrict__ dst, int comps) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const f4 v = src[i];
-    dst[3 * (size_t)i] = v.x; dst[3 * (size_t)i + 1] = v.y; dst[3 * (size_t)i + 2] = v.z;
+    dst[comps * (size_t)i] = v.x; dst[comps * (size_t)i + 1] = v.y;
+    if (comps == 3) dst[3 * (size_t)i + 2] = v.z;
+}
+
+// a 2-D cloud (3 x n: x, y, w) as resident points (x, y, 0, w): every kernel then computes what the reference computes on
+// the 3-row matrices, bit for bit — the z terms are exact zeros (x + 0 and 0 * t round to themselves)
+__global__ void expand_2d_kernel(const float* __restrict__ src, int n, f4* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    dst[i] = make_float4(src[3 * (size_t)i], src[3 * (size_t)i + 1], 0.f, src[3 * (size_t)i + 2]);
+}
+__global__ void collapse_2d_kernel(const f4* __restrict__ src, int n, float* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const f4 v = src[i];
+    dst[3 * (size_t)i] = v.x; dst[3 * (size_t)i + 1] = v.y; dst[3 * (size_t)i + 2] = v.w;
 }
 
 // Moves a structure built on the caller's coordinates into the frame centred on `mean`: every
@@ -127,6 +144,38 @@ void smooth_normals_host(f4* n4, const int32_t* ids, int knn, int n) {
     }
 }
 
+// transforms cross the ABI as dimh x dimh column-major matrices (PointMatcher.h TransformationParameters): 4x4, or 3x3 for
+// 2-D clouds, which live on the device embedded in a 4x4 with an identity z row / column
+void T_load(int dimh, const float* T, Mat4& M) {
+    if (dimh == 4) { memcpy(M.m, T, sizeof(M.m)); return; }
+    mat4_identity(M);
+    M.m[0] = T[0]; M.m[1] = T[1];
+    M.m[4] = T[3]; M.m[5] = T[4];
+    M.m[12] = T[6]; M.m[13] = T[7];
+}
+void T_store(int dimh, const Mat4& M, float* T) {
+    if (dimh == 4) { memcpy(T, M.m, sizeof(M.m)); return; }
+    T[0] = M.m[0]; T[1] = M.m[1]; T[2] = 0.f;
+    T[3] = M.m[4]; T[4] = M.m[5]; T[5] = 0.f;
+    T[6] = M.m[12]; T[7] = M.m[13]; T[8] = 1.f;
+}
+
+// clouds: `rows` x n column-major, rows = 4 or 3; 2-D clouds are expanded to (x, y, 0, w) on the device
+int upload_cloud(pmgpu_ctx* ctx, const float* features, int rows, int n, f4* dst) {
+    if (n <= 0) return PMGPU_OK;
+    if (rows == 4) {
+        PM_CUDA_TRY(ctx, cudaMemcpyAsync(dst, features, (size_t)n * sizeof(f4), cudaMemcpyDefault, ctx->stream));
+        return PMGPU_OK;
+    }
+    ScopedBuf<float> staging;
+    PM_CUDA_TRY(ctx, staging.reserve(3 * (size_t)n));
+    PM_CUDA_TRY(ctx, cudaMemcpyAsync(staging.p, features, 3 * (size_t)n * sizeof(float), cudaMemcpyDefault, ctx->stream));
+    expand_2d_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(staging.p, n, dst);
+    ctx->launches += 1;
+    PM_CUDA_TRY(ctx, cudaGetLastError());
+    return PMGPU_OK;
+}
+
 int fail(pmgpu_ctx* ctx, int code, const char* msg) {
     ctx->set_error(msg);
     return code;
@@ -158,7 +207,7 @@ const char* status_message(int s) {
         case PMGPU_OK: return "ok";
         case PMGPU_ERR_CUDA: return "CUDA error";
         case PMGPU_ERR_BAD_ARG: return "bad argument";
-        case PMGPU_ERR_UNSUPPORTED: return "GPU module: only float / 3-D clouds are supported";
+        case PMGPU_ERR_UNSUPPORTED: return "GPU module: only float clouds of 2 or 3 dimensions are supported";
         case PMGPU_ERR_NO_REFERENCE: return "matcher not initialised: no reference";
         case PMGPU_ERR_NO_READING: return "no reading";
         case PMGPU_ERR_NO_MATCHES: return "no matches: findClosests must run first";
@@ -182,14 +231,15 @@ int device_status(pmgpu_ctx* ctx) {
 }
 
 int upload_normals(pmgpu_ctx* ctx, const float* normals, int ld) {
-    if (ld < 3) return fail(ctx, PMGPU_ERR_BAD_ARG, "normals_ld must be >= 3");
+    const int comps = ctx->dimh - 1;
+    if (ld < comps) return fail(ctx, PMGPU_ERR_BAD_ARG, "normals_ld must be >= the cloud's dimension");
     const int n = ctx->nr;
     PM_CUDA_TRY(ctx, ctx->ref_normals.reserve(n));
     ScopedBuf<float> staging;
     PM_CUDA_TRY(ctx, staging.reserve((size_t)n * ld));
     // the last column may be shorter than ld in the caller's matrix: copy (n-1)*ld + 3 floats
-    PM_CUDA_TRY(ctx, cudaMemcpyAsync(staging.p, normals, ((size_t)(n - 1) * ld + 3) * sizeof(float), cudaMemcpyDefault, ctx->stream));
-    pack_normals_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(staging.p, ld, n, ctx->ref_normals.p);
+    PM_CUDA_TRY(ctx, cudaMemcpyAsync(staging.p, normals, ((size_t)(n - 1) * ld + comps) * sizeof(float), cudaMemcpyDefault, ctx->stream));
+    pack_normals_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(staging.p, ld, n, ctx->ref_normals.p, comps);
     ctx->launches += 1;
     PM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->has_normals = true;
@@ -222,6 +272,8 @@ int check_params(pmgpu_ctx* ctx, const pmgpu_icp_params* p) {
     if (p->use_differential && (p->smooth_length < 0 || p->smooth_length >= PM_MAX_HISTORY))
         return fail(ctx, PMGPU_ERR_UNSUPPORTED, "DifferentialTransformationChecker: smoothLength must be < 64 on the GPU path");
     if (p->max_iterations < 0) return fail(ctx, PMGPU_ERR_BAD_ARG, "maxIterationCount must be >= 0");
+    if (ctx->dimh == 3 && (p->minimizer & 0xff) != PMGPU_MIN_P2POINT && p->minimizer != PMGPU_MIN_P2PLANE)
+        return fail(ctx, PMGPU_ERR_UNSUPPORTED, "2-D clouds: PointToPoint and PointToPlane error minimizers only (no covariance, similarity, force2D / force4DOF)");
     return PMGPU_OK;
 }
 
@@ -393,16 +445,20 @@ static int center_resident_reference(pmgpu_ctx* ctx, const float* features, int 
     }
     cudaGetLastError();
     float sx = 0.f, sy = 0.f, sz = 0.f;
+    const int rows = ctx->dimh;
     for (int i = 0; i < n; ++i) {
-        sx += features[4 * (size_t)i];
-        sy += features[4 * (size_t)i + 1];
-        sz += features[4 * (size_t)i + 2];
+        sx += features[rows * (size_t)i];
+        sy += features[rows * (size_t)i + 1];
+        if (rows == 4) sz += features[4 * (size_t)i + 2];
     }
-    mean_out[0] = sx / (float)n; mean_out[1] = sy / (float)n; mean_out[2] = sz / (float)n; mean_out[3] = 1.f;
+    mean_out[0] = sx / (float)n; mean_out[1] = sy / (float)n;
+    if (rows == 4) { mean_out[2] = sz / (float)n; mean_out[3] = 1.f; }
+    else mean_out[2] = 1.f;
+    const float mean_z = rows == 4 ? mean_out[2] : 0.f;
     const int nsplits = 1 << ctx->depth, nboxes = 4 << ctx->depth;
     const int m = n > nboxes ? n : nboxes;
     center_structure_kernel<<<(m + 255) / 256, 256, 0, ctx->stream>>>(ctx->ref_orig.p, ctx->ref_sorted.p, n, ctx->splits.p, nsplits, ctx->boxes.p, nboxes,
-                                                                     mean_out[0], mean_out[1], mean_out[2]);
+                                                                     mean_out[0], mean_out[1], mean_z);
     ctx->launches += 1;
     PM_CUDA_TRY(ctx, cudaGetLastError());
     return PMGPU_OK;
@@ -412,7 +468,7 @@ int pmgpu_ref_center(pmgpu_ctx* ctx, const float* features, int rows, int n, flo
     if (!ctx || !features || !mean_out) return PMGPU_ERR_BAD_ARG;
     PM_TRY(use_device(ctx));
     if (ctx->nr == 0) return fail(ctx, PMGPU_ERR_NO_REFERENCE, status_message(PMGPU_ERR_NO_REFERENCE));
-    if (rows != 4 || n != ctx->nr) return fail(ctx, PMGPU_ERR_BAD_ARG, "pmgpu_ref_center: `features` must be the cloud given to pmgpu_ref_set");
+    if (rows != ctx->dimh || n != ctx->nr) return fail(ctx, PMGPU_ERR_BAD_ARG, "pmgpu_ref_center: `features` must be the cloud given to pmgpu_ref_set");
     ctx->have_matches = false;
     ctx->seed_k = 0;
     return center_resident_reference(ctx, features, n, mean_out);
@@ -422,14 +478,15 @@ static int ref_set_impl(pmgpu_ctx* ctx, const float* features, int rows, int n, 
     if (!ctx) return PMGPU_ERR_BAD_ARG;
     PM_TRY(use_device(ctx));
     if (!features) return fail(ctx, PMGPU_ERR_BAD_ARG, "null reference features");
-    if (rows != 4) return fail(ctx, PMGPU_ERR_UNSUPPORTED, status_message(PMGPU_ERR_UNSUPPORTED));
+    if (rows != 4 && rows != 3) return fail(ctx, PMGPU_ERR_UNSUPPORTED, status_message(PMGPU_ERR_UNSUPPORTED));
     if (n < 1) return fail(ctx, PMGPU_ERR_BAD_ARG, "the reference cloud is empty");
     ctx->nr = 0;
     ctx->has_normals = false;
     ctx->have_matches = false;
     ctx->seed_k = 0;
+    ctx->dimh = rows;
     PM_CUDA_TRY(ctx, ctx->ref_orig.reserve(n));
-    PM_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ref_orig.p, features, (size_t)n * sizeof(f4), cudaMemcpyDefault, ctx->stream));
+    PM_TRY(upload_cloud(ctx, features, rows, n, ctx->ref_orig.p));
     ctx->nr = n;
     // the structure is built on the uploaded coordinates while, for the centred variant, the host
     // is busy with the mean; it is shifted into the centred frame afterwards
@@ -457,10 +514,11 @@ int pmgpu_ref_get_normals(pmgpu_ctx* ctx, float* normals_out) {
     std::vector<f4> host((size_t)ctx->nr);
     PM_CUDA_TRY(ctx, cudaMemcpyAsync(host.data(), ctx->ref_normals.p, host.size() * sizeof(f4), cudaMemcpyDeviceToHost, ctx->stream));
     PM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    const int comps = ctx->dimh - 1;
     for (int i = 0; i < ctx->nr; ++i) {
-        normals_out[3 * (size_t)i + 0] = host[i].x;
-        normals_out[3 * (size_t)i + 1] = host[i].y;
-        normals_out[3 * (size_t)i + 2] = host[i].z;
+        normals_out[comps * (size_t)i + 0] = host[i].x;
+        normals_out[comps * (size_t)i + 1] = host[i].y;
+        if (comps == 3) normals_out[3 * (size_t)i + 2] = host[i].z;
     }
     return PMGPU_OK;
 }
@@ -469,8 +527,10 @@ int pmgpu_reading_set(pmgpu_ctx* ctx, const float* features, int rows, int n) {
     if (!ctx) return PMGPU_ERR_BAD_ARG;
     PM_TRY(use_device(ctx));
     if (!features) return fail(ctx, PMGPU_ERR_BAD_ARG, "null reading features");
-    if (rows != 4) return fail(ctx, PMGPU_ERR_UNSUPPORTED, status_message(PMGPU_ERR_UNSUPPORTED));
+    if (rows != 4 && rows != 3) return fail(ctx, PMGPU_ERR_UNSUPPORTED, status_message(PMGPU_ERR_UNSUPPORTED));
+    if (ctx->nr > 0 && rows != ctx->dimh) return fail(ctx, PMGPU_ERR_BAD_ARG, "reading and reference must have the same dimension");
     if (n < 0) return fail(ctx, PMGPU_ERR_BAD_ARG, "negative point count");
+    if (ctx->nr == 0) ctx->dimh = rows;
     ctx->nq = 0;
     ctx->have_matches = false;
     ctx->have_weights = false;
@@ -479,7 +539,7 @@ int pmgpu_reading_set(pmgpu_ctx* ctx, const float* features, int rows, int n) {
     PM_CUDA_TRY(ctx, ctx->reading.reserve(n > 0 ? n : 1));
     PM_CUDA_TRY(ctx, ctx->reading_tmp.reserve(n > 0 ? n : 1));
     ctx->seed_k = 0;
-    if (n > 0) PM_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->reading_tmp.p, features, (size_t)n * sizeof(f4), cudaMemcpyDefault, ctx->stream));
+    PM_TRY(upload_cloud(ctx, features, rows, n, ctx->reading_tmp.p));
     PM_CUDA_TRY(ctx, cudaEventRecord(ctx->copy_done, ctx->stream));
     ctx->nq = n;
     if (n > 0) PM_TRY(morton_order(ctx));
@@ -512,13 +572,14 @@ int pmgpu_reading_set_normals(pmgpu_ctx* ctx, const float* normals, int ld) {
     PM_TRY(use_device(ctx));
     if (ctx->nq == 0) return fail(ctx, PMGPU_ERR_NO_READING, status_message(PMGPU_ERR_NO_READING));
     if (!normals) { ctx->has_reading_normals = false; return PMGPU_OK; }
-    if (ld < 3) return fail(ctx, PMGPU_ERR_BAD_ARG, "normals_ld must be >= 3");
+    const int comps = ctx->dimh - 1;
+    if (ld < comps) return fail(ctx, PMGPU_ERR_BAD_ARG, "normals_ld must be >= the cloud's dimension");
     const int n = ctx->nq;
     PM_CUDA_TRY(ctx, ctx->reading_normals.reserve(n));
     ScopedBuf<float> staging;
     PM_CUDA_TRY(ctx, staging.reserve((size_t)n * ld));
-    PM_CUDA_TRY(ctx, cudaMemcpyAsync(staging.p, normals, ((size_t)(n - 1) * ld + 3) * sizeof(float), cudaMemcpyDefault, ctx->stream));
-    pack_normals_permuted_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(staging.p, ld, ctx->q_order.p, n, ctx->reading_normals.p);
+    PM_CUDA_TRY(ctx, cudaMemcpyAsync(staging.p, normals, ((size_t)(n - 1) * ld + comps) * sizeof(float), cudaMemcpyDefault, ctx->stream));
+    pack_normals_permuted_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(staging.p, ld, ctx->q_order.p, n, ctx->reading_normals.p, comps);
     ctx->launches += 1;
     PM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->has_reading_normals = true;
@@ -530,7 +591,7 @@ int pmgpu_reading_apply_transform(pmgpu_ctx* ctx, const float* T) {
     PM_TRY(use_device(ctx));
     if (!T) return fail(ctx, PMGPU_ERR_BAD_ARG, "null transform");
     Mat4 M;
-    memcpy(M.m, T, sizeof(M.m));
+    T_load(ctx->dimh, T, M);
     if (!mat4_is_rigid(M)) return fail(ctx, PMGPU_ERR_NOT_ORTHOGONAL, status_message(PMGPU_ERR_NOT_ORTHOGONAL));
     if (ctx->nq > 0) {
         transform_inplace_kernel<<<(ctx->nq + 255) / 256, 256, 0, ctx->stream>>>(ctx->reading.p, ctx->nq, M);
@@ -549,7 +610,19 @@ int pmgpu_reading_get(pmgpu_ctx* ctx, float* features_out) {
     if (!ctx) return PMGPU_ERR_BAD_ARG;
     PM_TRY(use_device(ctx));
     if (!features_out) return fail(ctx, PMGPU_ERR_BAD_ARG, "null output");
-    PM_TRY(download_unpermuted<f4>(ctx, ctx->reading.p, ctx->reading_tmp, 1, reinterpret_cast<f4*>(features_out)));
+    if (ctx->dimh == 4) {
+        PM_TRY(download_unpermuted<f4>(ctx, ctx->reading.p, ctx->reading_tmp, 1, reinterpret_cast<f4*>(features_out)));
+    } else if (ctx->nq > 0) {
+        PM_CUDA_TRY(ctx, ctx->reading_tmp.reserve(ctx->nq));
+        unpermute_kernel<f4><<<(ctx->nq + 255) / 256, 256, 0, ctx->stream>>>(ctx->reading.p, ctx->q_order.p, (size_t)ctx->nq, 1, ctx->reading_tmp.p);
+        ScopedBuf<float> flat;
+        PM_CUDA_TRY(ctx, flat.reserve(3 * (size_t)ctx->nq));
+        collapse_2d_kernel<<<(ctx->nq + 255) / 256, 256, 0, ctx->stream>>>(ctx->reading_tmp.p, ctx->nq, flat.p);
+        ctx->launches += 2;
+        PM_CUDA_TRY(ctx, cudaMemcpyAsync(features_out, flat.p, 3 * (size_t)ctx->nq * sizeof(float), cudaMemcpyDefault, ctx->stream));
+        PM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        return PMGPU_OK;
+    }
     PM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return PMGPU_OK;
 }
@@ -566,7 +639,7 @@ int pmgpu_knn(pmgpu_ctx* ctx, const float* T, int k, float epsilon, float max_di
     if (!var_dist && !(max_dist >= 0.f)) return fail(ctx, PMGPU_ERR_BAD_ARG, "maxDist must be >= 0");
     IcpState* h = ctx->state_host;
     if (T) {
-        memcpy(h->T_iter.m, T, sizeof(float) * 16);
+        T_load(ctx->dimh, T, h->T_iter);
         if (!mat4_is_rigid(h->T_iter)) return fail(ctx, PMGPU_ERR_NOT_ORTHOGONAL, status_message(PMGPU_ERR_NOT_ORTHOGONAL));
     } else {
         mat4_identity(h->T_iter);
@@ -638,7 +711,7 @@ int pmgpu_matches_get(pmgpu_ctx* ctx, int32_t* ids_out, float* dists_out, float*
         PM_TRY(download_unpermuted<float>(ctx, ctx->weights.p, ctx->dists_tmp, ctx->k, weights_out));
     }
     PM_TRY(pull_state(ctx));
-    if (T_match_out) memcpy(T_match_out, ctx->state_host->T_match.m, sizeof(float) * 16);
+    if (T_match_out) T_store(ctx->dimh, ctx->state_host->T_match, T_match_out);
     return PMGPU_OK;
 }
 
@@ -669,6 +742,8 @@ int pmgpu_minimize(pmgpu_ctx* ctx, int minimizer, float sensor_std_dev, float* T
         return fail(ctx, PMGPU_ERR_BAD_ARG, "force4DOF is a point-to-plane parameter");
     if ((minimizer & PMGPU_MIN_FORCE2D) && minimizer != (PMGPU_MIN_P2PLANE | PMGPU_MIN_FORCE2D))
         return fail(ctx, PMGPU_ERR_BAD_ARG, "force2D goes with PointToPlaneErrorMinimizer alone (no force4DOF, no covariance)");
+    if (ctx->dimh == 3 && minimizer != PMGPU_MIN_P2POINT && minimizer != PMGPU_MIN_P2PLANE)
+        return fail(ctx, PMGPU_ERR_UNSUPPORTED, "2-D clouds: PointToPoint and PointToPlane error minimizers only (no covariance, similarity, force2D / force4DOF)");
     if (!ctx->have_weights) PM_TRY(launch_weights(ctx, SelectSpec(), false, false));  // empty chain
     ctx->stage_begin(2);
     PM_TRY(launch_minimize(ctx, minimizer, false, false, nullptr));
@@ -688,7 +763,7 @@ int pmgpu_minimize(pmgpu_ctx* ctx, int minimizer, float sensor_std_dev, float* T
         PM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         return s;
     }
-    if (T_out) memcpy(T_out, ctx->state_host->dT.m, sizeof(float) * 16);
+    if (T_out) T_store(ctx->dimh, ctx->state_host->dT, T_out);
     if (cov_out && with_cov) memcpy(cov_out, ctx->state_host->cov, sizeof(float) * 36);
     if (stats_out) memcpy(stats_out, ctx->state_host->stats, sizeof(float) * 5);
     return PMGPU_OK;
@@ -699,7 +774,7 @@ int pmgpu_icp_reset(pmgpu_ctx* ctx, const float* T_iter_init) {
     PM_TRY(use_device(ctx));
     IcpState* h = ctx->state_host;
     PM_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    if (T_iter_init) memcpy(h->T_iter.m, T_iter_init, sizeof(float) * 16);
+    if (T_iter_init) T_load(ctx->dimh, T_iter_init, h->T_iter);
     else mat4_identity(h->T_iter);
     if (!mat4_is_rigid(h->T_iter)) return fail(ctx, PMGPU_ERR_NOT_ORTHOGONAL, status_message(PMGPU_ERR_NOT_ORTHOGONAL));
     h->T_match = h->T_iter;
@@ -753,7 +828,7 @@ int pmgpu_icp_result(pmgpu_ctx* ctx, float* T_iter_out, int* iterations_out, flo
     if (!ctx) return PMGPU_ERR_BAD_ARG;
     PM_TRY(use_device(ctx));
     PM_TRY(pull_state(ctx));
-    if (T_iter_out) memcpy(T_iter_out, ctx->state_host->T_iter.m, sizeof(float) * 16);
+    if (T_iter_out) T_store(ctx->dimh, ctx->state_host->T_iter, T_iter_out);
     if (iterations_out) *iterations_out = ctx->state_host->iterations;
     if (cov_out) memcpy(cov_out, ctx->state_host->cov, sizeof(float) * 36);
     if (stats_out) memcpy(stats_out, ctx->state_host->stats, sizeof(float) * 5);
@@ -806,6 +881,7 @@ int pmgpu_ref_compute_normals(pmgpu_ctx* ctx, int knn, float epsilon, float max_
     memset(&sink, 0, sizeof(sink));
     sink.pts = ctx->ref_orig.p;
     sink.degenerate = &ctx->state->degenerate;
+    sink.dim2 = ctx->dimh == 3 ? 1 : 0;
     const float max_r2 = max_dist * max_dist;
     ScopedBuf<int32_t> nids;
     if (smooth) {
@@ -855,8 +931,9 @@ int pmgpu_normals(pmgpu_ctx* ctx, const float* features, int rows, int n, int kn
     if (!ctx) return PMGPU_ERR_BAD_ARG;
     PM_TRY(use_device(ctx));
     if (!features || !out) return fail(ctx, PMGPU_ERR_BAD_ARG, "null argument");
-    if (rows != 4) return fail(ctx, PMGPU_ERR_UNSUPPORTED, status_message(PMGPU_ERR_UNSUPPORTED));
+    if (rows != 4 && rows != 3) return fail(ctx, PMGPU_ERR_UNSUPPORTED, status_message(PMGPU_ERR_UNSUPPORTED));
     if (n < 1) return fail(ctx, PMGPU_ERR_BAD_ARG, "empty cloud");
+    const int dn = rows - 1;  // spans: normals dn, eig_values dn, eig_vectors dn * dn
     if (knn < 1) return fail(ctx, PMGPU_ERR_BAD_ARG, "knn must be >= 1");
     if (knn > n) return fail(ctx, PMGPU_ERR_KNN_TOO_LARGE, status_message(PMGPU_ERR_KNN_TOO_LARGE));
     if (!(epsilon >= 0.f) || !(max_dist >= 0.f)) return fail(ctx, PMGPU_ERR_BAD_ARG, "epsilon and maxDist must be >= 0");
@@ -878,7 +955,7 @@ int pmgpu_normals(pmgpu_ctx* ctx, const float* features, int rows, int n, int kn
     ScopedBuf<int32_t> nids;
     if (out->normals) PM_CUDA_TRY(ctx, n4.reserve(n));
     if (smooth) PM_CUDA_TRY(ctx, nids.reserve((size_t)knn * n));
-    // scratch: densities n | eig_values 3n | eig_vectors 9n | mean_dists n | normals3 3n | ids-as-float knn*n
+    // scratch (laid out for the 3-D spans): densities n | eig_values 3n | eig_vectors 9n | mean_dists n | normals 3n | ids-as-float knn*n
     const size_t off_den = 0, off_val = (size_t)n, off_vec = 4 * (size_t)n, off_md = 13 * (size_t)n, off_n3 = 14 * (size_t)n, off_ids = 17 * (size_t)n;
     PM_CUDA_TRY(ctx, scratch.reserve(17 * (size_t)n + (out->matched_ids ? (size_t)knn * n : 0)));
     cudaStream_t st = sub->stream;
@@ -896,6 +973,7 @@ int pmgpu_normals(pmgpu_ctx* ctx, const float* features, int rows, int n, int kn
     sink.mean_dists = out->mean_dists ? scratch.p + off_md : nullptr;
     sink.matched_ids = out->matched_ids ? scratch.p + off_ids : nullptr;
     sink.degenerate = &sub->state->degenerate;
+    sink.dim2 = rows == 3 ? 1 : 0;
     sink.ids_i32 = smooth ? nids.p : nullptr;
     if (s == PMGPU_OK) s = launch_knn_normals(sub, sub->tree_view(), 0, n, knn, max_dist * max_dist, sink);
     if (s != PMGPU_OK) return fail(ctx, s, sub->err.c_str());
@@ -915,13 +993,13 @@ int pmgpu_normals(pmgpu_ctx* ctx, const float* features, int rows, int n, int kn
         return cudaMemcpy2DAsync(dst, (size_t)ld * sizeof(float), src, (size_t)span * sizeof(float), (size_t)span * sizeof(float), n, cudaMemcpyDefault, st);
     };
     if (out->normals) {
-        unpack_f4_kernel<<<(n + 255) / 256, 256, 0, st>>>(n4.p, n, scratch.p + off_n3);
+        unpack_f4_kernel<<<(n + 255) / 256, 256, 0, st>>>(n4.p, n, scratch.p + off_n3, dn);
         sub->launches += 1;
-        PM_CUDA_TRY(ctx, copy_out(out->normals, out->normals_ld, scratch.p + off_n3, 3));
+        PM_CUDA_TRY(ctx, copy_out(out->normals, out->normals_ld, scratch.p + off_n3, dn));
     }
     PM_CUDA_TRY(ctx, copy_out(out->densities, out->densities_ld, scratch.p + off_den, 1));
-    PM_CUDA_TRY(ctx, copy_out(out->eig_values, out->eig_values_ld, scratch.p + off_val, 3));
-    PM_CUDA_TRY(ctx, copy_out(out->eig_vectors, out->eig_vectors_ld, scratch.p + off_vec, 9));
+    PM_CUDA_TRY(ctx, copy_out(out->eig_values, out->eig_values_ld, scratch.p + off_val, dn));
+    PM_CUDA_TRY(ctx, copy_out(out->eig_vectors, out->eig_vectors_ld, scratch.p + off_vec, dn * dn));
     PM_CUDA_TRY(ctx, copy_out(out->mean_dists, out->mean_dists_ld, scratch.p + off_md, 1));
     PM_CUDA_TRY(ctx, copy_out(out->matched_ids, out->matched_ids_ld, scratch.p + off_ids, knn));
     s = pull_state(sub);

@@ -150,6 +150,25 @@ PM_HD void jacobi_eig3(double* A, double* w, double* V) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Eigen-decomposition of the symmetric 2x2 [a b; b c] in closed form (2-D clouds): w ascending,
+// V = unit eigenvectors as columns (column-major 2x2).
+// ------------------------------------------------------------------------------------------
+PM_HD void sym_eig2(double a, double b, double c, double* w, double* V) {
+    const double half = 0.5 * (a + c), d = 0.5 * (a - c);
+    const double r = sqrt(d * d + b * b);
+    w[0] = half - r;
+    w[1] = half + r;
+    // eigenvector of w[1]: (b, w1 - a) or (w1 - c, b), whichever is better conditioned; the other one is orthogonal to it
+    double x1 = b, y1 = w[1] - a;
+    const double x2 = w[1] - c, y2 = b;
+    if (x2 * x2 + y2 * y2 > x1 * x1 + y1 * y1) { x1 = x2; y1 = y2; }
+    const double n1 = sqrt(x1 * x1 + y1 * y1);
+    if (n1 > 0.0) { x1 /= n1; y1 /= n1; } else { x1 = 0.0; y1 = 1.0; }  // a multiple of the identity: any basis
+    V[2] = x1; V[3] = y1;     // column 1: the larger eigenvalue
+    V[0] = -y1; V[1] = x1;    // column 0: the smaller one
+}
+
+// ------------------------------------------------------------------------------------------
 // Rotation of point-to-point: R = U V^T from the SVD of the 3x3 cross-covariance m, with the
 // reflection fix of PointToPoint.cpp:82-93 (negate the last row of V^T when det(U V^T) < 0).
 // V from the eigen-decomposition of m^T m, U = m V / sigma, rank-deficient columns completed.
@@ -297,9 +316,11 @@ PM_HD float quat_angular_distance(const Quat& a, const Quat& b) {
 // (SurfaceNormal.cpp:193 `C.fullPivHouseholderQr().rank()`): full pivoting, Householder
 // reflections, pivots compared with 3 * eps * max|pivot|.  A is destroyed.
 // ------------------------------------------------------------------------------------------
-PM_HD int fullpiv_qr_rank3(float* A) {
+// `size`: the matrix is size x size in the top-left corner of the 3x3 (the rest zero): a 2-D cloud's 2x2 scatter matrix
+// takes the same pivots as its zero-padded 3x3, with Eigen's threshold for a 2x2 (eps * diagonalSize).
+PM_HD int fullpiv_qr_rank3(float* A, int size = 3) {
     const int n = 3;
-    const float precision = (float)PM_FLT_EPS * 3.f;
+    const float precision = (float)PM_FLT_EPS * (float)size;
     float biggest = 0.f, maxpivot = 0.f;
     float diag[3] = {0.f, 0.f, 0.f};
     int nonzero = n;

@@ -42,7 +42,7 @@ struct BinBuild {
 // SamplingSurfaceNormal.cpp:232-342
 void fuse_range(BinBuild& d, int first, int last) {
     const int count = last - first;
-    const int dimN = d.rows - 1;  // 3
+    const int dimN = d.rows - 1;  // 3, or 2 for 2-D clouds
     float lo[3], hi[3], sum[3] = {0.f, 0.f, 0.f};
     for (int a = 0; a < dimN; ++a) { lo[a] = std::numeric_limits<float>::max(); hi[a] = -std::numeric_limits<float>::max(); }
     for (int i = 0; i < count; ++i)
@@ -61,7 +61,7 @@ void fuse_range(BinBuild& d, int first, int last) {
     float C[9] = {0};
     float max_norm = 0.f;
     for (int i = 0; i < count; ++i) {
-        float v[3];
+        float v[3] = {0.f, 0.f, 0.f};
         for (int a = 0; a < dimN; ++a) v[a] = d.f(a, d.indices[first + i]) - mean[a];
         for (int c = 0; c < 3; ++c)
             for (int r = 0; r < 3; ++r) C[r + 3 * c] += v[r] * v[c];
@@ -73,12 +73,19 @@ void fuse_range(BinBuild& d, int first, int last) {
     if (want_eig) {
         float Cq[9];
         std::memcpy(Cq, C, sizeof(Cq));
-        if (pm::fullpiv_qr_rank3(Cq) + 1 >= dimN) {  // SamplingSurfaceNormal.cpp:258
-            double A[9], w[3], V[9];
-            for (int i = 0; i < 9; ++i) A[i] = (double)C[i];
-            pm::jacobi_eig3(A, w, V);
-            for (int i = 0; i < 3; ++i) eig_va[i] = (float)w[i];
-            for (int i = 0; i < 9; ++i) eig_ve[i] = (float)V[i];
+        if (pm::fullpiv_qr_rank3(Cq, dimN) + 1 >= dimN) {  // SamplingSurfaceNormal.cpp:258
+            if (dimN == 2) {
+                double w[2], V[4];
+                pm::sym_eig2((double)C[0], (double)C[1], (double)C[4], w, V);
+                eig_va[0] = (float)w[0]; eig_va[1] = (float)w[1];
+                eig_ve[0] = (float)V[0]; eig_ve[1] = (float)V[1]; eig_ve[3] = (float)V[2]; eig_ve[4] = (float)V[3];
+            } else {
+                double A[9], w[3], V[9];
+                for (int i = 0; i < 9; ++i) A[i] = (double)C[i];
+                pm::jacobi_eig3(A, w, V);
+                for (int i = 0; i < 3; ++i) eig_va[i] = (float)w[i];
+                for (int i = 0; i < 9; ++i) eig_ve[i] = (float)V[i];
+            }
         } else {
             d.unfit += count;
             return;
@@ -88,9 +95,9 @@ void fuse_range(BinBuild& d, int first, int last) {
     if (d.flags & PMGPU_KEEP_NORMALS) {  // computeNormal, utils.h:122-139: first smallest eigenvalue
         int smallest = 0;
         float value = std::numeric_limits<float>::max();
-        for (int j = 0; j < 3; ++j)
+        for (int j = 0; j < dimN; ++j)
             if (eig_va[j] < value) { smallest = j; value = eig_va[j]; }
-        for (int a = 0; a < 3; ++a) normal[a] = eig_ve[a + 3 * smallest];
+        for (int a = 0; a < dimN; ++a) normal[a] = eig_ve[a + 3 * smallest];
     }
     float density = 0.f;
     if (d.flags & PMGPU_KEEP_DENSITIES) {  // computeDensity, utils.h:105-120
@@ -98,12 +105,13 @@ void fuse_range(BinBuild& d, int first, int last) {
         density = (float)count / volume;
     }
     auto write = [&](int k) {
-        if (d.flags & PMGPU_KEEP_NORMALS) std::memcpy(d.normals + 3 * (size_t)k, normal, sizeof(normal));
+        // spans follow the cloud's dimension: normals dimN, eigValues dimN, eigVectors dimN * dimN
+        if (d.flags & PMGPU_KEEP_NORMALS) std::memcpy(d.normals + dimN * (size_t)k, normal, dimN * sizeof(float));
         if (d.flags & PMGPU_KEEP_DENSITIES) d.densities[k] = density;
-        if (d.flags & PMGPU_KEEP_EIGEN_VALUES) std::memcpy(d.eig_values + 3 * (size_t)k, eig_va, sizeof(eig_va));
+        if (d.flags & PMGPU_KEEP_EIGEN_VALUES) std::memcpy(d.eig_values + dimN * (size_t)k, eig_va, dimN * sizeof(float));
         if (d.flags & PMGPU_KEEP_EIGEN_VECTORS)
-            for (int r = 0; r < 3; ++r)
-                for (int c = 0; c < 3; ++c) d.eig_vectors[9 * (size_t)k + 3 * r + c] = eig_ve[r + 3 * c];
+            for (int r = 0; r < dimN; ++r)
+                for (int c = 0; c < dimN; ++c) d.eig_vectors[dimN * dimN * (size_t)k + dimN * r + c] = eig_ve[r + 3 * c];
     };
     if (d.sampling_method == 0) {
         for (int i = 0; i < count; ++i) {
@@ -212,7 +220,7 @@ int pmgpu_host_max_density(const float* densities, int stride, int n, float max_
 int pmgpu_host_sampling_surface_normal(float* features, int rows, int n, float* descriptors, int desc_rows, float ratio, int knn, int sampling_method,
                                        float max_box_dim, int average_descriptors, int flags, int32_t* keep_out, float* normals_out,
                                        float* densities_out, float* eig_values_out, float* eig_vectors_out, int* unfit_out) {
-    if (!features || rows != 4 || n < 0 || !keep_out || knn < 1) return -1;
+    if (!features || (rows != 4 && rows != 3) || n < 0 || !keep_out || knn < 1) return -1;
     if ((flags & PMGPU_KEEP_NORMALS) && !normals_out) return -1;
     if ((flags & PMGPU_KEEP_DENSITIES) && !densities_out) return -1;
     if ((flags & PMGPU_KEEP_EIGEN_VALUES) && !eig_values_out) return -1;

@@ -294,7 +294,14 @@ __device__ void run_checkers(IcpState* st, const pmgpu_icp_params& ck) {
     if (st->counter >= ck.max_iterations) { st->iterate = 0; return; }  // MaxNumIterationsReached, ICP.cpp:423-427
     if (!ck.use_differential) return;
     const int len = st->hist_len;
-    const Quat q = quat_from_mat4(st->T_iter);
+    Mat4 Tq = st->T_iter;
+    if (ck.minimizer & PM_MIN_DIM2) {
+        // 2-D: check() builds the quaternion from topLeftCorner(3, 3) of the 3x3 HOMOGENEOUS matrix, translation column
+        // included (TransformationCheckersImpl.cpp:131) — reproduced as it is (init() embeds the 2x2 properly, :116-121)
+        Tq.m[8] = st->T_iter.m[12]; Tq.m[9] = st->T_iter.m[13]; Tq.m[10] = 1.f;
+        Tq.m[2] = 0.f; Tq.m[6] = 0.f;
+    }
+    const Quat q = quat_from_mat4(Tq);
     float* hq = st->hist_q[len % PM_MAX_HISTORY];
     float* ht = st->hist_t[len % PM_MAX_HISTORY];
     hq[0] = q.w; hq[1] = q.x; hq[2] = q.y; hq[3] = q.z;
@@ -405,7 +412,19 @@ __device__ void finalize_body(const double* partials, int nblocks, double* sums,
             for (int r = 0; r < 3; ++r)
                 m[r + 3 * c] = sums[7 + r + 3 * c] - (double)mqf[r] * sums[1 + c] - sums[4 + r] * (double)mpf[c] + W * (double)mqf[r] * (double)mpf[c];
         double sv[3], scale = 1.0;
-        rotation_from_crosscov(m, R, sv);
+        if (ck.minimizer & PM_MIN_DIM2) {
+            // 2-D clouds: the rotation that maximises trace(R^T m) of the 2x2 cross-covariance in closed form — what
+            // U V^T with the reflection fix of PointToPoint.cpp:88-93 (row dimCount - 2 of V^T) evaluates to
+            const double cs = m[0] + m[4], sn = m[1] - m[3];
+            const double h = sqrt(cs * cs + sn * sn);
+            const double c = h > 0.0 ? cs / h : 1.0, s_ = h > 0.0 ? sn / h : 0.0;
+            for (int i = 0; i < 9; ++i) R[i] = (i % 4 == 0) ? 1.0 : 0.0;
+            R[0] = c; R[3] = -s_;
+            R[1] = s_; R[4] = c;
+            sv[0] = sv[1] = sv[2] = 0.0;
+        } else {
+            rotation_from_crosscov(m, R, sv);
+        }
         if ((ck.minimizer & 0xff) == PMGPU_MIN_P2POINT_SIM) {
             // sigma = sum w |p - mp|^2 from the raw sums (PointToPointSimilarity.cpp:69)
             double sigma = sums[16] + W * ((double)mpf[0] * mpf[0] + (double)mpf[1] * mpf[1] + (double)mpf[2] * mpf[2]);
@@ -524,6 +543,9 @@ int launch_minimize(pmgpu_ctx* ctx, int minimizer_word, bool compose_and_check, 
     }
     ck.knn = ctx->k;
     ck.minimizer = minimizer_word;
+    // 2-D clouds: point-to-plane is the force2D system (cross_z, nx, ny) with the xy residual (PointToPlane.cpp:171-312 with
+    // dim == 3), point-to-point the 2x2 rotation, the Differential checker its 3x3 quirk
+    if (ctx->dimh == 3) ck.minimizer |= PM_MIN_DIM2 | (plane ? PMGPU_MIN_FORCE2D : 0);
     const int g = gated ? 1 : 0, comp = compose_and_check ? 1 : 0;
     // sharded reading: the exchange of the sums is the last block's epilogue over the peer mailboxes (comm.cuh); without
     // mailboxes, NCCL between two finalize kernels

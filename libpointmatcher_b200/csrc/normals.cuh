@@ -34,6 +34,7 @@ struct NormalsSink {
     float* matched_ids;  // optional, k per point, as float (SurfaceNormal.cpp:254-257)
     int32_t* ids_i32;    // optional, k per point, exact (-1 = no neighbour): what smoothNormals walks on the host
     int* degenerate;     // counter
+    int dim2;            // the cloud is 2-D (z = 0): 2x2 scatter matrix, eig_values 2 and eig_vectors 4 per point (SurfaceNormal.cpp featDim - 1 = 2)
     int by_position;     // 1: outputs indexed by the query's leaf-order position (sharded K8: contiguous per rank), 0: by original column
     // stage-2 hand-over of the candidates stage 1 found for queries that ran out of budget
     int32_t* scratch_ids;
@@ -95,7 +96,18 @@ __device__ __forceinline__ bool normals_epilogue(const TopK<KMAX>& best, int k, 
     float ve[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // column-major, ascending eigenvalue
     if (wants_eigen) {
         float Cq[9] = {c00, c01, c02, c01, c11, c12, c02, c12, c22};
-        if (real_knn > 0 && fullpiv_qr_rank3(Cq) + 1 >= 3) {
+        if (ns.dim2) {
+            // 2-D cloud: C is 2x2, the test is rank + 1 >= 2 with the 2x2 threshold, the eigen-solve is closed-form
+            if (real_knn > 0 && fullpiv_qr_rank3(Cq, 2) + 1 >= 2) {
+                double w[2], V[4];
+                sym_eig2((double)c00, (double)c01, (double)c11, w, V);
+                va[0] = (float)w[0]; va[1] = (float)w[1];
+                ve[0] = (float)V[0]; ve[1] = (float)V[1];  // column 0 (3-row layout: the third row stays 0)
+                ve[3] = (float)V[2]; ve[4] = (float)V[3];
+            } else {
+                is_degenerate = true;
+            }
+        } else if (real_knn > 0 && fullpiv_qr_rank3(Cq) + 1 >= 3) {
             double A[9] = {c00, c01, c02, c01, c11, c12, c02, c12, c22}, w[3], V[9];
             jacobi_eig3(A, w, V);
             int o[3] = {0, 1, 2};
@@ -120,11 +132,12 @@ __device__ __forceinline__ bool normals_epilogue(const TopK<KMAX>& best, int k, 
             ns.densities[out] = (float)real_knn / volume;
         }
     }
+    const int dn = ns.dim2 ? 2 : 3;
     if (ns.eig_values)
-        for (int r = 0; r < 3; ++r) ns.eig_values[3 * out + r] = va[r];
+        for (int r = 0; r < dn; ++r) ns.eig_values[dn * out + r] = va[r];
     if (ns.eig_vectors)  // serializeEigVec: row-major (utils.h:89-103)
-        for (int r = 0; r < 3; ++r)
-            for (int c = 0; c < 3; ++c) ns.eig_vectors[9 * out + 3 * r + c] = ve[r + 3 * c];
+        for (int r = 0; r < dn; ++r)
+            for (int c = 0; c < dn; ++c) ns.eig_vectors[dn * dn * out + dn * r + c] = ve[r + 3 * c];
     if (ns.mean_dists) {
         if (is_degenerate) ns.mean_dists[out] = 18446744073709551615.f;  // numeric_limits<size_t>::max() as float, SurfaceNormal.cpp:245
         else {

@@ -73,6 +73,8 @@ struct ScopedBuf : DevBuf<T> {
 #define PM_MAX_FILTERS 8
 #define PM_HIST_BINS 2048
 #define PM_MAX_HISTORY 64   // ring of T_iter history for the Differential checker
+// internal bit of the minimiser word: the clouds are 2-D (features.rows() == 3), embedded with z = 0
+#define PM_MIN_DIM2 0x400
 #define PM_MAX_RANKS 8      // GPUs one registration can be sharded over (one NVSwitch node)
 #define PM_MAILBOX_SLOT_WORDS (PM_MAX_FILTERS * PM_HIST_BINS)  // 64 KB: the largest message (one histogram per quantile filter)
 
@@ -183,6 +185,7 @@ struct pmgpu_ctx {
     int num_sms = 148;
 
     // reference (K1)
+    int dimh = 4;                // features.rows() of the resident clouds: 4 (3-D) or 3 (2-D, held as (x, y, 0, w))
     int nr = 0;
     int depth = 0;
     pm::DevBuf<f4> ref_orig;     // original order, (x, y, z, w)

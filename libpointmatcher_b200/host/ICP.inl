@@ -319,7 +319,7 @@ protected:
             const int n = readingFiltered.features.cols();
             Matches m(knnUsed, n);
             OutlierWeights w(knnUsed, n);
-            TransformationParameters T_match(4, 4);
+            TransformationParameters T_match(readingFiltered.features.rows(), readingFiltered.features.rows());
             gp.check(pmgpu_matches_get(gp.ctx, m.ids.data(), reinterpret_cast<float*>(m.dists.data()), reinterpret_cast<float*>(w.data()),
                                        reinterpret_cast<float*>(T_match.data())));
             const DataPoints step = RigidTransformation::apply(RigidTransformation::apply(readingFiltered, T_refMean_dataIn), T_match);
@@ -327,7 +327,7 @@ protected:
             for (int j = 0; j < centred.features.cols(); ++j)
                 for (int r = 0; r < centred.features.rows() - 1; ++r) centred.features(r, j) = centred.features(r, j) + T_refMean_refIn(r, centred.features.rows() - 1);
             if (!centred.descriptorExists("normals")) {
-                Matrix normals(3, centred.features.cols());
+                Matrix normals(centred.features.rows() - 1, centred.features.cols());
                 if (pmgpu_ref_get_normals(gp.ctx, reinterpret_cast<float*>(normals.data())) == PMGPU_OK) centred.addDescriptor("normals", normals);
             }
             out = typename ErrorMinimizer::ErrorElements(step, centred, w, m);

@@ -250,12 +250,13 @@ struct SamplingSurfaceNormalDataPointsFilter : public DataPointsFilter {
                 throw typename DataPoints::InvalidField("SamplingSurfaceNormalDataPointsFilter: Error, descriptor labels do not match descriptor data");
         }
         const int oldDescRows = cloud.descriptors.rows();
-        if (keepNormals) cloud.allocateDescriptor("normals", 3);
+        const int dn = cloud.features.rows() - 1;  // spans follow the cloud's dimension (SamplingSurfaceNormal.cpp:100-112)
+        if (keepNormals) cloud.allocateDescriptor("normals", dn);
         if (keepDensities) cloud.allocateDescriptor("densities", 1);
-        if (keepEigenValues) cloud.allocateDescriptor("eigValues", 3);
-        if (keepEigenVectors) cloud.allocateDescriptor("eigVectors", 9);
-        std::vector<float> normals(keepNormals ? 3 * (size_t)n : 0), densities(keepDensities ? (size_t)n : 0), eigVa(keepEigenValues ? 3 * (size_t)n : 0),
-            eigVe(keepEigenVectors ? 9 * (size_t)n : 0);
+        if (keepEigenValues) cloud.allocateDescriptor("eigValues", dn);
+        if (keepEigenVectors) cloud.allocateDescriptor("eigVectors", dn * dn);
+        std::vector<float> normals(keepNormals ? dn * (size_t)n : 0), densities(keepDensities ? (size_t)n : 0), eigVa(keepEigenValues ? dn * (size_t)n : 0),
+            eigVe(keepEigenVectors ? dn * dn * (size_t)n : 0);
         // the existing descriptors as their own (rows x n) block for the averaging of bin sampling
         std::vector<float> oldDesc((size_t)oldDescRows * n);
         for (int j = 0; j < n; ++j)
@@ -275,10 +276,10 @@ struct SamplingSurfaceNormalDataPointsFilter : public DataPointsFilter {
             for (int j = 0; j < n; ++j)
                 for (int i = 0; i < span; ++i) cloud.descriptors(row + i, j) = T(src[(size_t)j * span + i]);
         };
-        if (keepNormals) put("normals", normals, 3);
+        if (keepNormals) put("normals", normals, dn);
         if (keepDensities) put("densities", densities, 1);
-        if (keepEigenValues) put("eigValues", eigVa, 3);
-        if (keepEigenVectors) put("eigVectors", eigVe, 9);
+        if (keepEigenValues) put("eigValues", eigVa, dn);
+        if (keepEigenVectors) put("eigVectors", eigVe, dn * dn);
         cloud.keepColumns(std::vector<int>(keep.begin(), keep.begin() + m));
     }
 };
@@ -589,10 +590,11 @@ struct SurfaceNormalDataPointsFilter : public DataPointsFilter, public GpuBound 
         for (const auto& l : cloud.descriptorLabels) insertDim += l.span;
         if (insertDim != cloud.getDescriptorDim())
             throw typename DataPoints::InvalidField("SurfaceNormalDataPointsFilter: Error, descriptor labels do not match descriptor data");
-        if (keepNormals) cloud.allocateDescriptor("normals", 3);
+        const int dn = cloud.features.rows() - 1;  // spans follow the cloud's dimension (SurfaceNormal.cpp:105-125)
+        if (keepNormals) cloud.allocateDescriptor("normals", dn);
         if (keepDensities) cloud.allocateDescriptor("densities", 1);
-        if (keepEigenValues) cloud.allocateDescriptor("eigValues", 3);
-        if (keepEigenVectors) cloud.allocateDescriptor("eigVectors", 9);
+        if (keepEigenValues) cloud.allocateDescriptor("eigValues", dn);
+        if (keepEigenVectors) cloud.allocateDescriptor("eigVectors", dn * dn);
         if (keepMatchedIds) cloud.allocateDescriptor("matchedIds", knn);
         if (keepMeanDist) cloud.allocateDescriptor("meanDists", 1);
         // outputs land directly in the rows of the descriptor matrix (column stride = its row count)
@@ -657,7 +659,7 @@ public:
         GpuPipeline& g = this->gpu();
         const float* normals = nullptr;
         int ld = 0;
-        if (filteredReference.descriptorExists("normals", 3) && filteredReference.descriptors.cols() == filteredReference.features.cols()) {
+        if (filteredReference.descriptorExists("normals", filteredReference.features.rows() - 1) && filteredReference.descriptors.cols() == filteredReference.features.cols()) {
             normals = reinterpret_cast<const float*>(filteredReference.descriptors.data()) + filteredReference.getDescriptorStartingRow("normals");
             ld = filteredReference.descriptors.rows();
         }
@@ -870,7 +872,7 @@ struct GpuErrorMinimizer : public ErrorMinimizer, public GpuBound {
     TransformationParameters compute(const DataPoints& filteredReading, const DataPoints&, const OutlierWeights&, const Matches&) override {
         requireFloat3D(filteredReading.features.rows(), "ErrorMinimizer");
         GpuPipeline& g = this->gpu();
-        TransformationParameters out(4, 4);
+        TransformationParameters out(filteredReading.features.rows(), filteredReading.features.rows());
         float cov[36], stats[5];
         g.check(pmgpu_minimize(g.ctx, kind, (float)sensorStdDev, reinterpret_cast<float*>(out.data()), cov, stats));
         setResults(cov, stats);
@@ -1103,12 +1105,25 @@ struct DifferentialTransformationChecker : public TransformationChecker {
         this->conditionVariables = Vector::Zero(2, 1);
         rotations.clear();
         translations.clear();
-        rotations.push_back(Quat::fromMatrix(parameters));
-        translations.push_back({parameters(0, 3), parameters(1, 3), parameters(2, 3)});
+        if (parameters.rows() == 4) {
+            rotations.push_back(Quat::fromMatrix(parameters));
+        } else {  // the 2-D case: the 2x2 rotation embedded in an identity (TransformationCheckersImpl.cpp:116-121)
+            TransformationParameters m = Matrix::Identity(3, 3);
+            for (int c = 0; c < 2; ++c)
+                for (int r = 0; r < 2; ++r) m(r, c) = parameters(r, c);
+            rotations.push_back(Quat::fromMatrix(m));
+        }
+        translations.push_back(translationOf(parameters));
+    }
+    static std::vector<T> translationOf(const TransformationParameters& p) {
+        const int d = p.rows();
+        return {p(0, d - 1), p(1, d - 1), d == 4 ? p(2, 3) : T(0)};
     }
     void check(const TransformationParameters& parameters, bool& iterate) override {
+        // 2-D: the reference builds the quaternion from topLeftCorner(3, 3) of the 3x3 homogeneous matrix, translation column
+        // included (TransformationCheckersImpl.cpp:131); fromMatrix reads exactly those nine entries
         rotations.push_back(Quat::fromMatrix(parameters));
-        translations.push_back({parameters(0, 3), parameters(1, 3), parameters(2, 3)});
+        translations.push_back(translationOf(parameters));
         this->conditionVariables = Vector::Zero(2, 1);
         if (rotations.size() > smoothLength) {
             for (size_t i = rotations.size() - 1; i >= rotations.size() - smoothLength; --i) {
@@ -1132,6 +1147,7 @@ struct BoundTransformationChecker : public TransformationChecker {
     }
     const T maxRotationNorm, maxTranslationNorm;
     Quat initialRotation3D;
+    T initialRotation2D = T(0);
     std::vector<T> initialTranslation;
     BoundTransformationChecker(const Parameters& params = Parameters())
         : TransformationChecker("BoundTransformationChecker", availableParameters(), params), maxRotationNorm(Parametrizable::get<T>("maxRotationNorm")),
@@ -1146,13 +1162,22 @@ struct BoundTransformationChecker : public TransformationChecker {
     }
     void init(const TransformationParameters& parameters, bool&) override {
         this->conditionVariables = Vector::Zero(2, 1);
-        if (parameters.rows() != 4) throw std::runtime_error("BoundTransformationChecker: GPU build supports 3D only");
-        initialRotation3D = Quat::fromMatrix(parameters);
-        initialTranslation = {parameters(0, 3), parameters(1, 3), parameters(2, 3)};
+        if (parameters.rows() == 4) initialRotation3D = Quat::fromMatrix(parameters);
+        else if (parameters.rows() == 3) initialRotation2D = std::acos(parameters(0, 0));
+        else throw std::runtime_error("BoundTransformationChecker only works in 2D or 3D");
+        initialTranslation = DifferentialTransformationChecker::translationOf(parameters);
     }
     void check(const TransformationParameters& parameters, bool&) override {
-        this->conditionVariables(0) = Quat::fromMatrix(parameters).angularDistance(initialRotation3D);
-        const T dx = parameters(0, 3) - initialTranslation[0], dy = parameters(1, 3) - initialTranslation[1], dz = parameters(2, 3) - initialTranslation[2];
+        if (parameters.rows() == 4) {
+            this->conditionVariables(0) = Quat::fromMatrix(parameters).angularDistance(initialRotation3D);
+        } else {  // TransformationCheckersImpl.cpp:207-211, normalizeAngle :229-236
+            T a = std::acos(parameters(0, 0)) - initialRotation2D;
+            while (a > T(M_PI)) a -= T(2 * M_PI);
+            while (a < T(-M_PI)) a += T(2 * M_PI);
+            this->conditionVariables(0) = a;
+        }
+        const std::vector<T> tr = DifferentialTransformationChecker::translationOf(parameters);
+        const T dx = tr[0] - initialTranslation[0], dy = tr[1] - initialTranslation[1], dz = tr[2] - initialTranslation[2];
         this->conditionVariables(1) = std::sqrt(dx * dx + dy * dy + dz * dz);
         if (this->conditionVariables(0) > this->limits(0) || this->conditionVariables(1) > this->limits(1)) {
             std::ostringstream oss;

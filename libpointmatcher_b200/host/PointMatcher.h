@@ -476,9 +476,10 @@ struct PointMatcher {
             return *pipeline;
         }
     };
+    // the GPU path computes in float on 3-D clouds (features.rows() == 4) and 2-D clouds (features.rows() == 3)
     static void requireFloat3D(int rows, const char* who) {
-        if (!std::is_same<T, float>::value || rows != 4)
-            throw ConfigurationError(std::string(who) + ": GPU module: only float / 3-D clouds are supported");
+        if (!std::is_same<T, float>::value || (rows != 4 && rows != 3))
+            throw ConfigurationError(std::string(who) + ": GPU module: only float clouds of 2 or 3 dimensions are supported");
     }
 
     // ---------------------------------------------------------------------------------------------

@@ -114,7 +114,7 @@ class Parametrizable:
 
 # ---- DataPoints / Matches (PointMatcher.h:207-391) -------------------------------------------
 class DataPoints:
-    """features: (N, 4) float32 (x, y, z, 1); descriptors: dict name -> (N, span) float32."""
+    """features: (N, 4) float32 (x, y, z, 1), or (N, 3) (x, y, 1) for a 2-D cloud; descriptors: dict name -> (N, span) float32."""
 
     def __init__(self, features, descriptors=None):
         self.features = np.ascontiguousarray(features, np.float32)
@@ -474,9 +474,10 @@ def rigid_apply(T, cloud):
     T = np.asarray(T, np.float32)
     f = cloud.features
     out = np.empty_like(f)
-    for r in range(4):
+    dim = f.shape[1]  # 4, or 3 for a 2-D cloud
+    for r in range(dim):
         acc = T[r, 0] * f[:, 0]
-        for c in range(1, 4):
+        for c in range(1, dim):
             acc = (acc + T[r, c] * f[:, c]).astype(np.float32)
         out[:, r] = acc
     desc = dict(cloud.descriptors)
@@ -1040,13 +1041,15 @@ class SamplingSurfaceNormalDataPointsFilter(_HostFilter):
         feat = np.ascontiguousarray(cloud.features, np.float32).copy()
         flags = (1 if self.keepNormals else 0) | (2 if self.keepDensities else 0) | (4 if self.keepEigenValues else 0) | (8 if self.keepEigenVectors else 0)
         keep = np.empty(max(n, 1), np.int32)
-        normals = np.zeros((n, 3), np.float32)
+        rows = feat.shape[1]
+        dn = rows - 1          # spans follow the cloud's dimension (2-D clouds: normals 2, eigVectors 4)
+        normals = np.zeros((n, dn), np.float32)
         dens = np.zeros(n, np.float32)
-        eva = np.zeros((n, 3), np.float32)
-        eve = np.zeros((n, 9), np.float32)
+        eva = np.zeros((n, dn), np.float32)
+        eve = np.zeros((n, dn * dn), np.float32)
         unfit = C.c_int(0)
         m = capi.lib.pmgpu_host_sampling_surface_normal(
-            feat.ctypes.data, 4, n, desc.ctypes.data if desc is not None else None, desc.shape[1] if desc is not None else 0,
+            feat.ctypes.data, rows, n, desc.ctypes.data if desc is not None else None, desc.shape[1] if desc is not None else 0,
             float(np.float32(self.ratio)), int(self.knn), int(self.samplingMethod), float(np.float32(self.maxBoxDim)),
             1 if self.averageExistingDescriptors else 0, flags, keep.ctypes.data, normals.ctypes.data, dens.ctypes.data, eva.ctypes.data,
             eve.ctypes.data, C.byref(unfit))
@@ -1134,10 +1137,28 @@ class BoundTransformationChecker(Parametrizable):
         self.conditionVariables = [0.0, 0.0]
 
     def init(self, T):
-        self._q0 = _quat_from_matrix(np.asarray(T)[:3, :3])
-        self._t0 = np.asarray(T, np.float32)[:3, 3].copy()
+        T = np.asarray(T, np.float32)
+        self._dim = T.shape[0]
+        if self._dim == 3:   # 2-D: the rotation is acos(T(0, 0)) (TransformationCheckersImpl.cpp:190-191)
+            self._a0 = np.float32(np.arccos(T[0, 0]))
+            self._t0 = T[:2, 2].copy()
+            return
+        self._q0 = _quat_from_matrix(T[:3, :3])
+        self._t0 = T[:3, 3].copy()
 
     def check(self, T):
+        if self._dim == 3:
+            T = np.asarray(T, np.float32)
+            a = np.float32(np.arccos(T[0, 0])) - self._a0
+            while a > np.pi:     # normalizeAngle (TransformationCheckersImpl.cpp:229-236)
+                a -= 2 * np.pi
+            while a < -np.pi:
+                a += 2 * np.pi
+            rot, tr = float(a), float(np.linalg.norm(T[:2, 2] - self._t0))
+            self.conditionVariables = [rot, tr]
+            if rot > self.maxRotationNorm or tr > self.maxTranslationNorm:
+                raise ConvergenceError("limit out of bounds: rot: %g/%g tr: %g/%g" % (rot, self.maxRotationNorm, tr, self.maxTranslationNorm))
+            return
         q, q0 = _quat_from_matrix(np.asarray(T)[:3, :3]), self._q0
         # angularDistance: d = q * conj(q0); 2 * atan2(|d.vec|, |d.w|)
         w = q[0] * q0[0] + q[1] * q0[1] + q[2] * q0[2] + q[3] * q0[3]
@@ -1194,13 +1215,15 @@ TransformationCheckerRegistrar = Registrar(CounterTransformationChecker=CounterT
 
 # ---- float32 4x4 helpers with the reference's GEMM accumulation order -----------------------------
 def mat4_mul(A, B):
+    """dim x dim product (4 x 4, or 3 x 3 for 2-D clouds) in float32, left-to-right sums"""
     A = np.asarray(A, np.float32)
     B = np.asarray(B, np.float32)
-    out = np.zeros((4, 4), np.float32)
-    for i in range(4):
-        for j in range(4):
+    d = A.shape[0]
+    out = np.zeros((d, d), np.float32)
+    for i in range(d):
+        for j in range(d):
             acc = np.float32(A[i, 0] * B[0, j])
-            for k in range(1, 4):
+            for k in range(1, d):
                 acc = np.float32(acc + np.float32(A[i, k] * B[k, j]))
             out[i, j] = acc
     return out
@@ -1331,23 +1354,27 @@ class ICP:
         else:
             mean = self.matcher.initCentered(reference)
         self._reference_filtered, self._normals_on_device = reference, fuse_normals
-        T_refIn_refMean = np.eye(4, dtype=np.float32)
-        T_refIn_refMean[:3, 3] = mean[:3]
+        d = reference.features.shape[1]  # 4, or 3 for 2-D clouds
+        T_refIn_refMean = np.eye(d, dtype=np.float32)
+        T_refIn_refMean[:d - 1, d - 1] = mean[:d - 1]
         return T_refIn_refMean
 
     def _register(self, readingIn, T_refIn_refMean, T_refIn_dataIn):
         """computeWithTransformedReference (ICP.cpp:316-449) against the resident reference"""
-        T_init = np.eye(4, dtype=np.float32) if T_refIn_dataIn is None else np.asarray(T_refIn_dataIn, np.float32)
-        if T_init.shape != (4, 4):
+        d = T_refIn_refMean.shape[0]
+        T_init = np.eye(d, dtype=np.float32) if T_refIn_dataIn is None else np.asarray(T_refIn_dataIn, np.float32)
+        if T_init.ndim != 2 or T_init.shape[0] != T_init.shape[1]:
             raise RuntimeError("The initial transformation matrix must be squared.")
+        if T_init.shape[0] != d:
+            raise RuntimeError("The shape of initial transformation matrix must be NxN. Where N is the number of rows in the read/reference scans.")
         reading = readingIn if isinstance(readingIn, DataPoints) else DataPoints(readingIn)
         if self.readingDataPointsFilters:
             reading = reading.copy()  # ICP.cpp:324-326
             for f in self.readingDataPointsFilters:
                 f.inPlaceFilter(reading)
         # reading into the refMean frame (ICP.cpp:345-347); T_refIn_refMean is a pure translation
-        T_refMean_refIn = np.eye(4, dtype=np.float32)
-        T_refMean_refIn[:3, 3] = -T_refIn_refMean[:3, 3]
+        T_refMean_refIn = np.eye(d, dtype=np.float32)
+        T_refMean_refIn[:d - 1, d - 1] = -T_refIn_refMean[:d - 1, d - 1]
         T_refMean_dataIn = mat4_mul(T_refMean_refIn, T_init)
         if self._shard is not None:
             rank, world = self._shard
@@ -1387,7 +1414,8 @@ class ICP:
         if self._normals_on_device:
             desc["normals"] = _translate(self.ctx.ref_normals)
         centred = ref.features.copy()
-        centred[:, :3] = (centred[:, :3] + self._T_refMean_refIn[:3, 3][None, :]).astype(np.float32)   # minus the mean (ICP.cpp:291-299)
+        d = centred.shape[1]
+        centred[:, :d - 1] = (centred[:, :d - 1] + self._T_refMean_refIn[:d - 1, d - 1][None, :]).astype(np.float32)   # minus the mean (ICP.cpp:291-299)
         return ErrorElements(step, DataPoints(centred, desc), w, matches)
 
     def getMatches(self):
@@ -1405,7 +1433,7 @@ class ICP:
             raise ConfigurationError("GPU module (Python mirror): BoundTransformationChecker with a WithCov minimiser is not supported")
         _translate(self.ctx.icp_reset, None)
         for b in bounds:
-            b.init(np.eye(4, dtype=np.float32))
+            b.init(np.eye(self.ctx.dimh, dtype=np.float32))
         done, redos, res = 0, 0, None
         while True:
             _translate(self.ctx.icp_enqueue, params, 1)

@@ -144,10 +144,12 @@ class KdTree:
 
 
 def bruteforce_knn(reference, query, k=1, max_dist=np.inf, nthreads=1):
-    r, q = _cloud(reference), _cloud(query)
+    """clouds (N, 4), or (N, 3) for 2-D clouds: the search runs over the first rows - 1 coordinates (MatchersImpl.cpp:82)"""
+    r, q = np.ascontiguousarray(reference, np.float32), np.ascontiguousarray(query, np.float32)
+    assert r.ndim == 2 and r.shape[1] in (3, 4) and q.shape[1] == r.shape[1], "clouds are (N, 4) or (N, 3) float32"
     ids = np.empty((q.shape[0], k), np.int32)
     dists = np.empty((q.shape[0], k), np.float32)
-    rc = lib().orc_bruteforce_knn(_f(r), 4, r.shape[0], _f(q), q.shape[0], k, max_dist, _i(ids), _f(dists), nthreads)
+    rc = lib().orc_bruteforce_knn(_f(r), r.shape[1], r.shape[0], _f(q), q.shape[0], k, max_dist, _i(ids), _f(dists), nthreads)
     if rc < 0:
         raise OracleError(-rc)
     return ids, dists

@@ -9,6 +9,8 @@ Contents (data only, no reference source code):
   golden_<name>    examples/data/icp_data/<name>.ref_trans           (4, 4) float64
   yaml_<name>      examples/data/icp_data/<name>.yaml, yaml_default = examples/data/default.yaml   (text)
   validT3d         utest/utest.cpp:352-356
+  box2d_one, box2d_two   examples/data/2D_oneBox.csv / 2D_twoBoxes.csv   (N, 2) float32 — utest validate2dTransformation
+  validT2d         utest/utest.cpp:347-350
 """
 import os
 
@@ -54,6 +56,9 @@ out = dict(
     car401=load_csv(os.path.join(DATA, "car_cloud401.csv")),
     validT3d=np.array([[0.982304, 0.166685, -0.0854066, 0.0446816], [-0.150189, 0.973488, 0.172524, 0.191998],
                        [0.111899, -0.156644, 0.981296, -0.0356313], [0, 0, 0, 1]]),
+    box2d_one=load_csv(os.path.join(DATA, "2D_oneBox.csv")),
+    box2d_two=load_csv(os.path.join(DATA, "2D_twoBoxes.csv")),
+    validT2d=np.array([[0.987498, 0.157629, 0.0859918], [-0.157629, 0.987498, 0.203247], [0, 0, 1]]),
 )
 ICP_DATA = os.path.join(DATA, "icp_data")
 # every chain file of utest icpTest (utest/utest.cpp:81-160) with its golden transform

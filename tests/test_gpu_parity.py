@@ -78,7 +78,7 @@ def test_knn_errors(gpu_ctx):
         gpu_ctx.knn(T, 1)
     assert e.value.code == capi.ERR_NOT_ORTHOGONAL
     with pytest.raises(capi.PmGpuError) as e:
-        gpu_ctx.set_reference(np.ones((5, 3), np.float32))  # 2-D clouds: explicit error, never silently wrong
+        gpu_ctx.set_reference(np.ones((5, 5), np.float32))  # neither 2-D nor 3-D: explicit error, never silently wrong
     assert e.value.code == capi.ERR_UNSUPPORTED
     # empty reading is fine
     gpu_ctx.set_reference(ref)
