@@ -214,9 +214,6 @@ struct Lane {
     int level;          // its level
     uint32_t trail;     // bit l set: the sibling of our level-l ancestor has not been examined yet
     uint32_t visited;
-    // look-ahead descents only (lane_fetch / lane_descend_step<true>); dead registers otherwise
-    f2 sp;              // the split plane of `node` ...
-    f4 kids;            // ... and those of its two children, requested before the side is known
 };
 
 PM_HD void lane_begin(Lane& s, float qx, float qy, float qz) {
@@ -228,20 +225,6 @@ PM_HD void lane_begin(Lane& s, float qx, float qy, float qz) {
 }
 
 PM_HD bool lane_descending(const Lane& s, const TreeView& t) { return s.level < t.depth; }
-
-// One level of look-ahead (PF = true): the planes of both children (adjacent, one 16-byte load) are requested as soon as
-// the node is known, so the load of level l + 1 is in flight while level l is being decided — the chain of dependent
-// loads that a descent is runs at two levels per round trip.  Measured (1 M x 1 M, profiles/r2_ab_pair_prefetch.txt): the
-// unseeded searches gain a lot (first k = 1 match 0.49 -> 0.24 ms, knn-20 normals 1.50 -> 1.05 ms), the seeded k = 1 match
-// of the loop loses a little (0.172 -> 0.177 ms: its descents mostly hit L1 and the six extra registers cost occupancy),
-// so the kernels choose per variant.
-template <bool PF>
-PM_HD void lane_fetch(Lane& s, const TreeView& t) {
-    if (PF && s.level < t.depth) {
-        s.sp = ldg2(t.splits + s.node);
-        if (s.level + 1 < t.depth) s.kids = ldg4(reinterpret_cast<const f4*>(t.splits + 2 * (size_t)s.node));
-    }
-}
 
 // coordinate `dim` of (x, y, z) without a branch (the ternary chain compiles to divergent branches)
 PM_HD float select3(uint32_t dim, float x, float y, float z) {
@@ -262,20 +245,16 @@ PM_HD float select3(uint32_t dim, float x, float y, float z) {
 // one step of the plane descent; `w` is the current k-th best distance: a sibling whose split
 // plane is already farther than that can never be needed (w only shrinks), so it is not even
 // recorded as pending
-template <bool PF>
+// (Measured and dropped, round 2: one level of look-ahead — the planes of both children requested as soon as the node is
+// known, so that the load of level l + 1 is in flight while level l is decided.  No gain: 0.56 vs 0.50 ms for the first,
+// unseeded k = 1 match of 1 M queries; the descent's loads mostly hit L1 and the extra selects and registers cost more.)
 PM_HD void lane_descend_step(Lane& s, const TreeView& t, float* plane, int stride, float w) {
-    const f2 sp = PF ? s.sp : ldg2(t.splits + s.node);
+    const f2 sp = ldg2(t.splits + s.node);
     const float qd = select3(f2u(sp.y), s.qx, s.qy, s.qz);
     const float diff = fsub(qd, sp.x);
     const float pl = fmul(diff, diff);
-    const bool right = qd >= sp.x;
-    s.node = 2 * s.node + (right ? 1u : 0u);
+    s.node = 2 * s.node + (qd >= sp.x ? 1u : 0u);
     ++s.level;
-    if (PF) {
-        s.sp.x = right ? s.kids.z : s.kids.x;
-        s.sp.y = right ? s.kids.w : s.kids.y;
-        if (s.level + 1 < t.depth) s.kids = ldg4(reinterpret_cast<const f4*>(t.splits + 2 * (size_t)s.node));
-    }
     if (!(pl > w)) s.trail |= 1u << s.level;
     if (plane) plane[s.level * stride] = pl;
     PM_STAT(descent_steps);
@@ -369,7 +348,7 @@ PM_HD bool lane_wants_filter(const Lane& s, float w_before, float w_now) {
 // one LDS), then the box test.  Returns true when the sibling has to be searched (the lane then
 // continues with descend steps from it); false means "rejected", the caller tries the next
 // pending level while s.trail != 0.
-template <int KMAX, bool PF>
+template <int KMAX>
 PM_HD bool lane_box_step(Lane& s, const TreeView& t, const TopK<KMAX>& best, const float* plane, int stride) {
     const int l = 31 - clz32(s.trail);
     s.trail &= ~(1u << l);
@@ -381,7 +360,6 @@ PM_HD bool lane_box_step(Lane& s, const TreeView& t, const TopK<KMAX>& best, con
     if (db > best.worst_d()) return false;
     s.node = far;
     s.level = l;
-    lane_fetch<PF>(s, t);
     PM_STAT(redescents);
     return true;
 }
@@ -390,20 +368,19 @@ PM_HD bool lane_box_step(Lane& s, const TreeView& t, const TopK<KMAX>& best, con
 // the previous iteration's match re-measured, k = 1): they only tighten the bounds.  Returns the
 // number of reference points whose distance was evaluated (the analogue of libnabo's visit count,
 // MatchersImpl.cpp:98).
-template <int KMAX, bool PF = true>
+template <int KMAX>
 PM_HD uint32_t knn_search_single(const TreeView& t, float qx, float qy, float qz, TopK<KMAX>& best) {
     if (t.n == 0) return 0;
     float plane[PM_MAX_DEPTH + 2];
     Lane s;
     lane_begin(s, qx, qy, qz);
-    lane_fetch<PF>(s, t);
     for (;;) {
         const float w0 = best.worst_d();
-        while (lane_descending(s, t)) lane_descend_step<PF>(s, t, plane, 1, w0);
+        while (lane_descending(s, t)) lane_descend_step(s, t, plane, 1, w0);
         lane_scan_leaf<KMAX>(s, t, best);
         if (lane_wants_filter(s, w0, best.worst_d())) lane_filter_trail<KMAX>(s, t, best, plane, 1);
         bool found = false;
-        while (!found && s.trail != 0) found = lane_box_step<KMAX, PF>(s, t, best, plane, 1);
+        while (!found && s.trail != 0) found = lane_box_step<KMAX>(s, t, best, plane, 1);
         if (!found) break;
     }
     return s.visited;

@@ -83,7 +83,6 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
         }
         if (use_T) q = transform_point(sT, q);
         lane_begin(s, q.x, q.y, q.z);
-        lane_fetch<PLANES>(s, tree);   // look-ahead descents in the unseeded variants (core/tree.h lane_fetch)
         if (KMAX == 1 && use_seed) {
             // ICP iterations >= 2: the previous match of this query (still resident in ids),
             // re-measured under the new T_iter, is a real candidate that makes the bound tight
@@ -122,7 +121,7 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
         // descend: one level per step for every lane that is not at a leaf yet
         const float w0 = best.worst_d();
         while (__any_sync(0xffffffffu, running && lane_descending(s, tree)))
-            if (running && lane_descending(s, tree)) lane_descend_step<PLANES>(s, tree, plane, KNN_BLOCK, w0);
+            if (running && lane_descending(s, tree)) lane_descend_step(s, tree, plane, KNN_BLOCK, w0);
         // leaf; then the plane filter over all pending levels where it pays
         bool refilter = false;
         if (running) {
@@ -135,7 +134,7 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
         // search or nothing left
         bool found = false;
         while (__any_sync(0xffffffffu, running && !found && s.trail != 0))
-            if (running && !found && s.trail != 0) found = lane_box_step<KMAX, PLANES>(s, tree, best, plane, KNN_BLOCK);
+            if (running && !found && s.trail != 0) found = lane_box_step<KMAX>(s, tree, best, plane, KNN_BLOCK);
         if (running && !found) running = false;  // search complete
         ++rounds;
         if (running && rounds >= budget) {

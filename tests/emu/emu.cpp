@@ -93,7 +93,6 @@ EmuTree* build(const float* feat, int n) {
     return t;
 }
 
-bool g_lookahead = true;  // descents with one level of look-ahead (core/tree.h lane_fetch) or plain
 uint32_t* g_visits_out = nullptr;  // optional per-query visit counts (analysis only)
 
 const int32_t* g_seed = nullptr;  // optional per-query seed candidate (reference column or -1), k = 1 only
@@ -114,7 +113,7 @@ long run_knn(const EmuTree* t, const float* T16, const float* q, int nq, int k, 
             const float dd = dist2(p.x, p.y, p.z, r[0], r[1], r[2]);
             if (best.accepts(dd, g_seed[i])) best.insert(dd, g_seed[i]);
         }
-        const uint32_t v = g_lookahead ? knn_search_single<KMAX, true>(t->view, p.x, p.y, p.z, best) : knn_search_single<KMAX, false>(t->view, p.x, p.y, p.z, best);
+        const uint32_t v = knn_search_single<KMAX>(t->view, p.x, p.y, p.z, best);
         visits += v;
         if (g_visits_out) g_visits_out[i] = v;
         for (int j = 0; j < k; ++j) {
@@ -134,7 +133,6 @@ long run_knn(const EmuTree* t, const float* T16, const float* q, int nq, int k, 
 extern "C" {
 
 void emu_set_visits_out(uint32_t* p) { g_visits_out = p; }
-void emu_set_lookahead(int on) { g_lookahead = on != 0; }
 void emu_set_seed(const int32_t* p) { g_seed = p; }
 void emu_stats(unsigned long long* out5, int reset) {
     out5[0] = g_emu_stats.descent_steps; out5[1] = g_emu_stats.pops; out5[2] = g_emu_stats.box_tests;

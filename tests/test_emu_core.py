@@ -194,24 +194,3 @@ def test_angle_axis_and_checkers_match_oracle(emu, oracle):
     assert (T == np.eye(4)).all()
 
 
-
-def test_lookahead_descent_equals_plain_descent(emu, oracle, synth):
-    """the descent with one level of look-ahead (both children's planes requested before the side is known) walks the
-    same path: ids, dists and the number of points examined equal the plain descent's, for depths 0 .. 13"""
-    emu.emu_set_lookahead.argtypes = [C.c_int]
-    rng = np.random.default_rng(12)
-    try:
-        for n in (1, 7, 9, 17, 70, 600, 5000, 40000):
-            ref = cloud(rng, n, "uniform") if n < 40000 else synth.scan(n)
-            q = ref[rng.integers(0, n, 300)].copy()
-            q[:, :3] += rng.normal(0, 0.2, (300, 3)).astype(np.float32)
-            for k in (1, 5):
-                if k > n:
-                    continue
-                emu.emu_set_lookahead(0)
-                i0, d0, v0 = emu_knn(emu, ref, q, k)
-                emu.emu_set_lookahead(1)
-                i1, d1, v1 = emu_knn(emu, ref, q, k)
-                assert (i0 == i1).all() and (d0.view(np.uint32) == d1.view(np.uint32)).all() and v0 == v1, (n, k)
-    finally:
-        emu.emu_set_lookahead(1)

@@ -29,6 +29,11 @@ def child(configs):
         r = {"it_per_s": round(m["value"], 1), "ms_per_step": round(m["ms_per_step"], 4), "first_ms": round(m["first_iteration_ms"], 3),
              "last_ms": round(m["last_iteration_ms"], 3), "b2b_ms": round(m["back_to_back_ms_per_step"], 4),
              "stage": {k: round(v, 4) for k, v in m["stage_ms_per_iteration"].items()}, "normals_ms": round(m["normals_ms"] or 0, 3)}
+        # fingerprint of the RESULTS: variants must agree on it, or the faster one is computing something else
+        import hashlib
+        T_bits = m["tm"].ctx.icp_result()["T_iter"].tobytes()
+        ids, dists, _ = m["ctx"].knn(m["tm"].ctx.icp_result()["T_iter"], cfg["knn"], 0.0, cfg["max_dist"])
+        r["fingerprint"] = hashlib.sha1(T_bits + dists.tobytes()).hexdigest()[:12]
         if name == "c2plane":
             r["knn"] = {k: {a: round(b, 3) for a, b in v.items() if a.endswith("_ms")} for k, v in bench.knn_throughput(args, m, capi, 0).items() if k.startswith("k")}
         m["ctx"].close()
