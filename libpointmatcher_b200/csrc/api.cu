@@ -192,6 +192,8 @@ int push_state(pmgpu_ctx* ctx) {
     IcpState* h = ctx->state_host;
     h->overflow_count[0] = h->overflow_count[1] = 0;
     h->ticket[0] = h->ticket[1] = h->ticket[2] = h->ticket[3] = 0;
+    h->bar_count = 0;
+    for (int f = 0; f < PM_MAX_FILTERS; ++f) h->sel_cand_count[f] = 0;
     PM_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->state, ctx->state_host, sizeof(IcpState), cudaMemcpyHostToDevice, ctx->stream));
     return PMGPU_OK;
 }
@@ -293,6 +295,13 @@ int enqueue_iteration(pmgpu_ctx* ctx, const pmgpu_icp_params* p, bool gated) {
                       var_dist ? ctx->reading_max_r2.p : nullptr));
     ctx->seed_k = p->knn;
     ctx->stage_end();
+    if (gated && fused_select_applies(ctx, spec)) {
+        // outlier-filter select + minimiser + compose / checkers as one kernel (timing slot 2)
+        ctx->stage_begin(2);
+        PM_TRY(launch_select_minimize(ctx, spec, p->minimizer, p, use_cap));
+        ctx->stage_end();
+        return PMGPU_OK;
+    }
     ctx->stage_begin(1);
     PM_TRY(launch_weights(ctx, spec, gated, use_cap));
     ctx->stage_end();
@@ -340,6 +349,7 @@ int pmgpu_ctx_create(int device, pmgpu_ctx** ctx_out) {
     ctx->seed_enabled = getenv("PMGPU_NO_SEED") == nullptr;
     ctx->time_stage2 = getenv("PMGPU_TIME_STAGE2") != nullptr;
     ctx->cap_enabled = getenv("PMGPU_NO_CAP") == nullptr;
+    ctx->fused_select = getenv("PMGPU_NO_FUSED_SELECT") == nullptr;
     ctx->seeded_without_planes = getenv("PMGPU_SEED_PLANES") == nullptr;
     if (const char* m = getenv("PMGPU_CAP_MARGIN")) ctx->cap_margin = (float)atof(m);
     // 1: (almost) everything through stage 2
@@ -371,7 +381,7 @@ void pmgpu_ctx_destroy(pmgpu_ctx* ctx) {
     ctx->node_box.release(); ctx->cub_tmp.release();
     ctx->reading.release(); ctx->q_order.release();
     ctx->ids.release(); ctx->dists.release(); ctx->weights.release();
-    ctx->hist.release(); ctx->partials.release();
+    ctx->hist.release(); ctx->sel_cand.release(); ctx->partials.release();
     ctx->reading_normals.release(); ctx->reading_max_r2.release(); ctx->var_sorted.release(); ctx->var_cum.release();
     for (auto& iv : ctx->intervals) { cudaEventDestroy(iv.a); cudaEventDestroy(iv.b); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);
@@ -790,6 +800,8 @@ int pmgpu_icp_reset(pmgpu_ctx* ctx, const float* T_iter_init) {
     h->cap_need = 0.f;
     h->redo = 0;
     h->redo_count = 0;
+    for (int f = 0; f < PM_MAX_FILTERS; ++f) { h->sel_guess[f] = 0; h->sel_prev[f] = 0; h->sel_inner[f] = 64; }  // no previous order statistic: the first select is the generic one
+    h->sel_passes = 0;
     // a fresh registration never starts from an earlier run's matches (they would only be a seed, but a seed a first
     // iteration does not have)
     ctx->seed_k = 0;

@@ -61,30 +61,21 @@ template <int MODE>
 __device__ void finalize_body(const double* partials, int nblocks, double* sums, int phase, IcpState* state, int compose,
                               const pmgpu_icp_params& ck, const PeerComm& pc);
 
-// `fuse`: the last block to finish reduces the partial rows, solves, composes T_iter and runs the
-// checkers (finalize_body), so the whole minimisation is one kernel
-template <int MODE>  // 0 point-to-point, 1 point-to-plane
-__global__ void __launch_bounds__(ACC_BLOCK, MODE == 1 ? 2 : 3) accumulate_kernel(const f4* __restrict__ reading, int nq, int k, const int32_t* __restrict__ ids,
-                                                               const float* __restrict__ dists, const f4* __restrict__ ref,
-                                                               const f4* __restrict__ normals, const IcpState* __restrict__ state, int gated,
-                                                               double* __restrict__ partials, int fuse, IcpState* state_rw, double* sums,
-                                                               int compose, pmgpu_icp_params ck, const f4* __restrict__ reading_normals, PeerComm pc) {
+// The streaming part of K4 / K5: this thread's share of the (reading point, match) pairs into its fp64 sums.
+// W: where the weight of a match is read from — the IcpState itself, or the PairW copy of a kernel that computed the limits
+// in the same launch (select_accumulate_kernel).
+template <int MODE, typename W>
+__device__ __forceinline__ void accumulate_pairs(double* acc, const Mat4& sT, const W* wst, const f4* __restrict__ reading, int nq, int k,
+                                                 const int32_t* __restrict__ ids, const float* __restrict__ dists, const f4* __restrict__ ref,
+                                                 const f4* __restrict__ normals, const pmgpu_icp_params& ck, const f4* __restrict__ reading_normals) {
     constexpr int NS = MODE == 1 ? NS_PLANE : NS_POINT;
-    __shared__ Mat4 sT;
-    // redo: this iteration's capped match was void (select_finish) — leave T_iter as it is
-    if (gated && (state->iterate == 0 || state->redo)) return;
-    if (threadIdx.x < 16) sT.m[threadIdx.x] = state->T_iter.m[threadIdx.x];
-    __syncthreads();
-    double acc[NS];
-#pragma unroll
-    for (int c = 0; c < NS; ++c) acc[c] = 0.0;
     const int stride = gridDim.x * blockDim.x;
     // one (reading point, match) pair; `id` is only meaningful where the weight is not zero
     auto pair = [&](const f4& p, const int i, const float d, const int id, bool& match_exist) {
         if (d == pm_inf()) return;
-        float w = pm_pair_weight(state, d);
+        float w = pm_pair_weight(wst, d);
         // SurfaceNormalOutlierFilter: `normals` is the reference's descriptor whenever it exists
-        if (w != 0.f && state->sn_on) w = __fmul_rn(w, pm_sn_weight(sT, reading_normals[i], __ldg(normals + id), state->sn_eps));
+        if (w != 0.f && wst->sn_on) w = __fmul_rn(w, pm_sn_weight(sT, reading_normals[i], __ldg(normals + id), wst->sn_eps));
         if (w == 0.f) { acc[NS - 3] += 1.0; return; }
         match_exist = true;
         acc[NS - 4] += 1.0;
@@ -154,6 +145,26 @@ __global__ void __launch_bounds__(ACC_BLOCK, MODE == 1 ? 2 : 3) accumulate_kerne
             acc[NS - 1] += 1.0;
         }
     }
+}
+
+// `fuse`: the last block to finish reduces the partial rows, solves, composes T_iter and runs the
+// checkers (finalize_body), so the whole minimisation is one kernel
+template <int MODE>  // 0 point-to-point, 1 point-to-plane
+__global__ void __launch_bounds__(ACC_BLOCK, MODE == 1 ? 2 : 3) accumulate_kernel(const f4* __restrict__ reading, int nq, int k, const int32_t* __restrict__ ids,
+                                                               const float* __restrict__ dists, const f4* __restrict__ ref,
+                                                               const f4* __restrict__ normals, const IcpState* __restrict__ state, int gated,
+                                                               double* __restrict__ partials, int fuse, IcpState* state_rw, double* sums,
+                                                               int compose, pmgpu_icp_params ck, const f4* __restrict__ reading_normals, PeerComm pc) {
+    constexpr int NS = MODE == 1 ? NS_PLANE : NS_POINT;
+    __shared__ Mat4 sT;
+    // redo: this iteration's capped match was void (select_finish) — leave T_iter as it is
+    if (gated && (state->iterate == 0 || state->redo)) return;
+    if (threadIdx.x < 16) sT.m[threadIdx.x] = state->T_iter.m[threadIdx.x];
+    __syncthreads();
+    double acc[NS];
+#pragma unroll
+    for (int c = 0; c < NS; ++c) acc[c] = 0.0;
+    accumulate_pairs<MODE>(acc, sT, state, reading, nq, k, ids, dists, ref, normals, ck, reading_normals);
 #ifdef PM_PROFILE_NS
     __shared__ unsigned long long s_t[3];
     if (threadIdx.x == 0) s_t[0] = pm_globaltimer();
@@ -173,6 +184,109 @@ __global__ void __launch_bounds__(ACC_BLOCK, MODE == 1 ? 2 : 3) accumulate_kerne
                    pm_globaltimer() - s_t[2]);
 #endif
     }
+}
+
+// K3 + K4/K5 + K7 as ONE kernel of the fused loop: the exact quantile select runs as the first phase of the minimiser kernel,
+// whose grid is one resident wave (cooperative launch), so a pass is "histogram my share, grid barrier" instead of a kernel:
+// the block that arrives last at the barrier scans the bins (sharded reading: after the peer exchange of the histograms),
+// writes the next plan or the limits, and releases the others.  With the window plan of select.cuh an iteration needs two
+// passes (three or four when the order statistic left the window or there is none yet, e.g. the first iteration).  Limits,
+// weights, sums and T are bit for bit those of hist_kernel x 3 + accumulate_kernel; what is gone is three launches, their
+// drains and the DRAM round trips between them (0.037 + 0.043 ms -> see DESIGN.md K3).
+template <int MODE>
+__global__ void __launch_bounds__(ACC_BLOCK, MODE == 1 ? 2 : 3) select_accumulate_kernel(const f4* __restrict__ reading, int nq, int k, const int32_t* __restrict__ ids,
+                                                               const float* __restrict__ dists, const f4* __restrict__ ref,
+                                                               const f4* __restrict__ normals, IcpState* state, double* __restrict__ partials,
+                                                               double* sums, pmgpu_icp_params ck, const f4* __restrict__ reading_normals, PeerComm pc,
+                                                               SelectSpec spec, unsigned* __restrict__ hist, int cap_active, float cap_margin, unsigned* __restrict__ cand) {
+    constexpr int NS = MODE == 1 ? NS_PLANE : NS_POINT;
+    __shared__ SelScratch s_sel;
+    __shared__ Mat4 sT;
+    __shared__ PairW s_w;
+    __shared__ int s_flags[2];
+    if (__ldcg(&state->iterate) == 0) return;  // the fused loop is always gated; written by an earlier kernel
+#ifdef PM_PROFILE_NS
+    unsigned long long tp[16];
+    int ntp = 0;
+    tp[ntp++] = pm_globaltimer();
+#endif
+    const size_t total = (size_t)nq * k;
+    const int nquant = spec.n_quantile();
+    const int collect = pc.nranks <= 1 ? 1 : 0;  // the collected distances are not exchanged between ranks: two passes there
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        select_init_limits(state, spec);
+        select_plans_begin(state, spec, collect);
+    }
+    for (int pass = 0;; ++pass) {
+        int slot = 0;
+        for (int f = 0; f < spec.nfilters; ++f) {
+            if (!spec.is_quantile(f)) continue;
+            SelPlan p;
+            bool done = false;
+            if (pass == 0) {
+                // what block 0 writes into the state: no need to wait for it
+                p = select_first_plan(__ldcg(&state->sel_guess[f]), collect ? __ldcg(&state->sel_inner[f]) : 0);
+            } else {
+                done = __ldcg(&state->sel_done[f]) != 0;
+                p.lo = __ldcg(&state->sel_prefix[f]); p.shift = __ldcg(&state->sel_shift[f]);
+                p.nb = __ldcg(&state->sel_nb[f]); p.outside = __ldcg(&state->sel_outside[f]);
+                p.c0 = p.c1 = 0;
+            }
+            if (!done) select_pass_block(dists, total, p, &s_sel, hist + (size_t)slot * PM_HIST_BINS, cand + (size_t)f * PM_SEL_CAND_CAP, &state->sel_cand_count[f]);
+            ++slot;
+        }
+#ifdef PM_PROFILE_NS
+        if (ntp < 14) tp[ntp++] = pm_globaltimer();
+#endif
+        unsigned gen;
+        if (grid_bar_arrive(state, gen)) {
+            bool ok = true;
+            // sharded reading: this rank's histograms become the sums over all ranks (comm.cuh), right here
+            if (nquant > 0 && pc.nranks > 1 && !peer_allreduce<false>(pc, hist, nquant * PM_HIST_BINS, state)) ok = false;
+            if (ok) {
+                slot = 0;
+                for (int f = 0; f < spec.nfilters; ++f) {
+                    if (!spec.is_quantile(f)) continue;
+                    if (!state->sel_done[f] && state->sel_pending > 0)
+                        select_pick_plan(hist + (size_t)slot * PM_HIST_BINS, f, spec.quantile(f), spec.factor(f), state, &s_sel,
+                                         cand + (size_t)f * PM_SEL_CAND_CAP, &state->sel_cand_count[f]);
+                    ++slot;
+                    __syncthreads();
+                }
+            }
+            if (threadIdx.x == 0) {
+                if (!ok) state->sel_pending = 0;  // the peers never arrived: status is raised, the loop has stopped
+                if (nquant > 0) state->sel_passes += 1;
+                if (state->sel_pending == 0 && ok && state->iterate) select_finish(state, cap_active, cap_margin);
+            }
+            grid_bar_release(state, gen);
+        } else {
+            grid_bar_wait(state, gen);
+        }
+#ifdef PM_PROFILE_NS
+        if (ntp < 14) tp[ntp++] = pm_globaltimer();
+#endif
+        if (__ldcg(&state->sel_pending) == 0) break;
+    }
+    // redo: this iteration's capped match was void (select_finish) — leave T_iter as it is
+    if (threadIdx.x == 0) { s_flags[0] = __ldcg(&state->iterate); s_flags[1] = __ldcg(&state->redo); }
+    if (threadIdx.x < 16) sT.m[threadIdx.x] = __ldcg(&state->T_iter.m[threadIdx.x]);
+    if (threadIdx.x == 32) load_pairw(state, &s_w);
+    __syncthreads();
+    if (s_flags[0] == 0 || s_flags[1]) return;
+    double acc[NS];
+#pragma unroll
+    for (int c = 0; c < NS; ++c) acc[c] = 0.0;
+    accumulate_pairs<MODE>(acc, sT, &s_w, reading, nq, k, ids, dists, ref, normals, ck, reading_normals);
+#ifdef PM_PROFILE_NS
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        printf("select_accumulate<%d> block 0 (ns since start):", MODE);
+        for (int i = 1; i < ntp; ++i) printf(" %llu", tp[i] - tp[0]);
+        printf(" | accumulated at %llu, passes %d\n", pm_globaltimer() - tp[0], state->sel_passes);
+    }
+#endif
+    block_reduce_store<NS>(acc, partials + (size_t)blockIdx.x * NS_MAX);
+    if (select_last_block(&state->ticket[1])) finalize_body<MODE>(partials, gridDim.x, sums, 3, state, 1, ck, pc);
 }
 
 // Censi covariance sums (PointToPlaneWithCov.cpp:100-150, PointToPointWithCov.cpp:84-135):
@@ -568,6 +682,69 @@ int launch_minimize(pmgpu_ctx* ctx, int minimizer_word, bool compose_and_check, 
     }
     PM_CUDA_TRY(ctx, cudaGetLastError());
     return PMGPU_OK;
+}
+
+// The fused loop's K3 + K4/K5 + K7 in one cooperative launch (select_accumulate_kernel).  Applies to chains of distance
+// filters (MaxDist / MedianDist / TrimmedDist / SurfaceNormal); chains with a Robust or VarTrimmedDist filter, and a sharded
+// reading without peer mailboxes, keep the separate kernels.
+bool fused_select_applies(const pmgpu_ctx* ctx, const SelectSpec& spec) {
+    if (!ctx->fused_select) return false;
+    if (spec.robust_index() >= 0 || spec.var_index() >= 0) return false;
+    if (ctx->nranks > 1 && !ctx->peer_on) return false;
+    return true;
+}
+
+template <int MODE>
+static int launch_select_minimize_mode(pmgpu_ctx* ctx, const SelectSpec& spec, const pmgpu_icp_params& ck, bool cap_active, const f4* normals) {
+    auto kernel = select_accumulate_kernel<MODE>;
+    if (ctx->fused_grid[MODE] == 0) {
+        int per_sm = 0;
+        PM_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, ACC_BLOCK, 0));
+        if (per_sm < 1) {
+            ctx->set_error("select_accumulate_kernel does not fit on an SM");
+            return PMGPU_ERR_CUDA;
+        }
+        const int want = MODE == 1 ? 2 : 3;  // the launch bounds
+        ctx->fused_grid[MODE] = ctx->num_sms * (per_sm < want ? per_sm : want);
+    }
+    int grid = (ctx->nq + ACC_BLOCK - 1) / ACC_BLOCK;
+    if (grid > ctx->fused_grid[MODE]) grid = ctx->fused_grid[MODE];
+    if (grid < 1) grid = 1;
+    PM_CUDA_TRY(ctx, ctx->partials.reserve((size_t)(ctx->num_sms * 4 + 2) * NS_MAX));
+    double* sums = ctx->partials.p + (size_t)ctx->num_sms * 4 * NS_MAX;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(ACC_BLOCK);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;  // all blocks resident at once: the in-kernel grid barrier cannot deadlock
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PM_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, kernel, (const f4*)ctx->reading.p, ctx->nq, ctx->k, (const int32_t*)ctx->ids.p, (const float*)ctx->dists.p,
+                                        (const f4*)ctx->ref_orig.p, normals, ctx->state, ctx->partials.p, sums, ck, (const f4*)ctx->reading_normals.p,
+                                        comm_peers(ctx), spec, ctx->hist.p, cap_active ? 1 : 0, ctx->cap_margin, ctx->sel_cand.p));
+    ctx->launches += 1;
+    return PMGPU_OK;
+}
+
+int launch_select_minimize(pmgpu_ctx* ctx, const SelectSpec& spec, int minimizer_word, const pmgpu_icp_params* checks, bool cap_active) {
+    const int minimizer = minimizer_word & 0xff;
+    const bool plane = (minimizer == PMGPU_MIN_P2PLANE || minimizer == PMGPU_MIN_P2PLANE_COV);
+    if (plane && !ctx->has_normals) {
+        ctx->set_error("Field normals not found");
+        return PMGPU_ERR_NO_NORMALS;
+    }
+    PM_TRY(select_reserve(ctx));
+    PM_CUDA_TRY(ctx, ctx->sel_cand.reserve((size_t)PM_MAX_FILTERS * PM_SEL_CAND_CAP));
+    pmgpu_icp_params ck = *checks;
+    ck.knn = ctx->k;
+    ck.minimizer = minimizer_word;
+    if (ctx->dimh == 3) ck.minimizer |= PM_MIN_DIM2 | (plane ? PMGPU_MIN_FORCE2D : 0);  // as launch_minimize
+    ctx->have_weights = true;
+    if (plane) return launch_select_minimize_mode<1>(ctx, spec, ck, cap_active, ctx->ref_normals.p);
+    return launch_select_minimize_mode<0>(ctx, spec, ck, cap_active, ctx->has_normals ? ctx->ref_normals.p : nullptr);
 }
 
 int launch_covariance(pmgpu_ctx* ctx, int minimizer, float sensor_std_dev) {

@@ -94,6 +94,18 @@ struct IcpState {
     unsigned sel_prefix[PM_MAX_FILTERS];           // radix-select state per quantile filter
     unsigned long long sel_rank[PM_MAX_FILTERS];   // remaining rank inside the selected bucket
     unsigned ticket[4];          // "last block" counters: 0 select, 1 minimise, 2 covariance
+    // select inside the minimiser kernel (minimize.cu select_accumulate_kernel): grid barrier words, and per quantile filter
+    // the plan of the next histogram pass — bins (bits - sel_prefix) >> sel_shift, sel_nb of them — plus the bit pattern
+    // of the previous iteration's order statistic, around which the first pass of the next iteration opens its window
+    unsigned bar_count, bar_gen;
+    unsigned sel_guess[PM_MAX_FILTERS], sel_prev[PM_MAX_FILTERS];  // centre of the next window; the last order statistic (0: none)
+    int sel_shift[PM_MAX_FILTERS], sel_nb[PM_MAX_FILTERS], sel_outside[PM_MAX_FILTERS];
+    int sel_inner[PM_MAX_FILTERS];            // half-width (window bins) of the bins whose distances the first pass collects
+    int sel_c0[PM_MAX_FILTERS], sel_c1[PM_MAX_FILTERS];
+    unsigned sel_cand_count[PM_MAX_FILTERS];  // collected distances (device-owned scratch counter)
+    int sel_have_rank[PM_MAX_FILTERS], sel_done[PM_MAX_FILTERS];
+    int sel_pending;             // quantile filters whose order statistic is not final yet
+    int sel_passes;              // histogram passes of the last in-kernel select (statistics)
     unsigned overflow_count[2];  // kNN stage-2 queue lengths (ping-pong between consecutive launches)
     int sn_on;                   // SurfaceNormalOutlierFilter active (both clouds have normals)
     float sn_eps;                // cos(maxAngle)
@@ -232,12 +244,15 @@ struct pmgpu_ctx {
 
     // select (K3)
     pm::DevBuf<unsigned> hist;   // PM_HIST_BINS
+    pm::DevBuf<unsigned> sel_cand;   // distances collected by the in-kernel select's first pass, PM_SEL_CAND_CAP per filter
     // VarTrimmedDistOutlierFilter: minRatio / maxRatio (pmgpu_set_var_trimmed_ratios), sorted distance bits, running sums
     float var_min_ratio = 0.05f, var_max_ratio = 0.99f;
     pm::DevBuf<unsigned> var_sorted;
     pm::DevBuf<float> var_cum;
     // minimiser partial sums (K4-K6)
     pm::DevBuf<double> partials;
+    bool fused_select = true;        // fused loop: quantile select inside the minimiser kernel; PMGPU_NO_FUSED_SELECT=1 reverts
+    int fused_grid[2] = {0, 0};      // co-resident blocks of select_accumulate_kernel<MODE> (occupancy query, once)
 
     pm::IcpState* state = nullptr;   // device
     pm::IcpState* state_host = nullptr;  // pinned host mirror
@@ -303,6 +318,8 @@ int launch_materialize_weights(pmgpu_ctx* ctx);
 // minimize.cu
 int launch_minimize(pmgpu_ctx* ctx, int minimizer, bool compose_and_check, bool gated, const pmgpu_icp_params* checks);
 int launch_covariance(pmgpu_ctx* ctx, int minimizer, float sensor_std_dev);
+bool fused_select_applies(const pmgpu_ctx* ctx, const SelectSpec& spec);
+int launch_select_minimize(pmgpu_ctx* ctx, const SelectSpec& spec, int minimizer, const pmgpu_icp_params* checks, bool cap_active);
 // comm.cu
 int comm_allreduce_u32(pmgpu_ctx* ctx, unsigned* buf, size_t count);
 int comm_allreduce_f64(pmgpu_ctx* ctx, double* buf, size_t count);

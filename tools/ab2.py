@@ -2,6 +2,7 @@
 stage times of the c2plane and c4 loops, the resident normals and the staged kNN throughput.
 
     python tools/ab2.py base narrow onephase          (parent: one subprocess per variant)
+    python tools/ab2.py base env:PMGPU_NO_FUSED_SELECT=1   (run-time switches of the base build)
 """
 import argparse
 import json
@@ -50,6 +51,11 @@ if __name__ == "__main__":
         env = dict(os.environ)
         if v == "base":
             env.pop("PMGPU_VARIANT", None)
+        elif v.startswith("env:"):   # env:NAME=value[,NAME=value]: the base build with run-time switches
+            env.pop("PMGPU_VARIANT", None)
+            for kv in v[4:].split(","):
+                name, _, val = kv.partition("=")
+                env[name] = val
         else:
             env["PMGPU_VARIANT"] = v
         r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", configs], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
