@@ -181,9 +181,11 @@ int fail(pmgpu_ctx* ctx, int code, const char* msg) {
     return code;
 }
 
-int use_device(pmgpu_ctx* ctx) {
+// keep_window: the entry point neither touches the reading nor the ordering scratch (see pmgpu_ctx::overlap_window)
+int use_device(pmgpu_ctx* ctx, bool keep_window = false) {
     PM_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     g_alloc_stream = ctx->stream;
+    if (!keep_window) ctx->overlap_window = false;
     return PMGPU_OK;
 }
 
@@ -328,6 +330,9 @@ int pmgpu_ctx_create(int device, pmgpu_ctx** ctx_out) {
     bool ok = cudaSetDevice(device) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->copy_done, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_build, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->ev_reading, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&ctx->state, sizeof(IcpState)) == cudaSuccess;
     ok = ok && cudaMallocHost((void**)&ctx->state_host, sizeof(IcpState)) == cudaSuccess;
     int sms = 0;
@@ -350,6 +355,7 @@ int pmgpu_ctx_create(int device, pmgpu_ctx** ctx_out) {
     ctx->time_stage2 = getenv("PMGPU_TIME_STAGE2") != nullptr;
     ctx->cap_enabled = getenv("PMGPU_NO_CAP") == nullptr;
     ctx->fused_select = getenv("PMGPU_NO_FUSED_SELECT") == nullptr;
+    ctx->overlap_enabled = getenv("PMGPU_NO_OVERLAP") == nullptr;
     ctx->seeded_without_planes = getenv("PMGPU_SEED_PLANES") == nullptr;
     if (const char* m = getenv("PMGPU_CAP_MARGIN")) ctx->cap_margin = (float)atof(m);
     // 1: (almost) everything through stage 2
@@ -389,6 +395,9 @@ void pmgpu_ctx_destroy(pmgpu_ctx* ctx) {
     if (ctx->state_host) cudaFreeHost(ctx->state_host);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);  // the cudaFreeAsync calls above
     if (ctx->copy_done) cudaEventDestroy(ctx->copy_done);
+    if (ctx->ev_build) cudaEventDestroy(ctx->ev_build);
+    if (ctx->ev_reading) cudaEventDestroy(ctx->ev_reading);
+    if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     g_alloc_stream = nullptr;
     delete ctx;
@@ -476,7 +485,7 @@ static int center_resident_reference(pmgpu_ctx* ctx, const float* features, int 
 
 int pmgpu_ref_center(pmgpu_ctx* ctx, const float* features, int rows, int n, float* mean_out) {
     if (!ctx || !features || !mean_out) return PMGPU_ERR_BAD_ARG;
-    PM_TRY(use_device(ctx));
+    PM_TRY(use_device(ctx, true));
     if (ctx->nr == 0) return fail(ctx, PMGPU_ERR_NO_REFERENCE, status_message(PMGPU_ERR_NO_REFERENCE));
     if (rows != ctx->dimh || n != ctx->nr) return fail(ctx, PMGPU_ERR_BAD_ARG, "pmgpu_ref_center: `features` must be the cloud given to pmgpu_ref_set");
     ctx->have_matches = false;
@@ -502,14 +511,16 @@ static int ref_set_impl(pmgpu_ctx* ctx, const float* features, int rows, int n, 
     // is busy with the mean; it is shifted into the centred frame afterwards
     const int s = build_tree(ctx);
     if (s != PMGPU_OK) { ctx->nr = 0; return s; }
+    PM_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_build, ctx->stream));
     if (mean_out) PM_TRY(center_resident_reference(ctx, features, n, mean_out));
     if (normals) PM_TRY(upload_normals(ctx, normals, normals_ld));
+    ctx->overlap_window = ctx->overlap_enabled;  // what follows on the stream (normals, centring) leaves the reading's buffers alone
     return PMGPU_OK;
 }
 
 int pmgpu_ref_set_normals(pmgpu_ctx* ctx, const float* normals, int normals_ld) {
     if (!ctx) return PMGPU_ERR_BAD_ARG;
-    PM_TRY(use_device(ctx));
+    PM_TRY(use_device(ctx, true));
     if (ctx->nr == 0) return fail(ctx, PMGPU_ERR_NO_REFERENCE, status_message(PMGPU_ERR_NO_REFERENCE));
     if (!normals) { ctx->has_normals = false; return PMGPU_OK; }
     return upload_normals(ctx, normals, normals_ld);
@@ -535,6 +546,7 @@ int pmgpu_ref_get_normals(pmgpu_ctx* ctx, float* normals_out) {
 
 int pmgpu_reading_set(pmgpu_ctx* ctx, const float* features, int rows, int n) {
     if (!ctx) return PMGPU_ERR_BAD_ARG;
+    const bool window = ctx->overlap_window;
     PM_TRY(use_device(ctx));
     if (!features) return fail(ctx, PMGPU_ERR_BAD_ARG, "null reading features");
     if (rows != 4 && rows != 3) return fail(ctx, PMGPU_ERR_UNSUPPORTED, status_message(PMGPU_ERR_UNSUPPORTED));
@@ -546,13 +558,32 @@ int pmgpu_reading_set(pmgpu_ctx* ctx, const float* features, int rows, int n) {
     ctx->have_weights = false;
     ctx->has_reading_normals = false;
     ctx->has_reading_max_r2 = false;
-    PM_CUDA_TRY(ctx, ctx->reading.reserve(n > 0 ? n : 1));
-    PM_CUDA_TRY(ctx, ctx->reading_tmp.reserve(n > 0 ? n : 1));
+    // Upload + ordering on the second stream, behind the structure build only, while the main stream is still computing
+    // the reference's normals: possible when no buffer has to grow (allocations are ordered on the main stream) and the
+    // cloud needs no staging (3-D).
+    const size_t need = (size_t)(n > 0 ? n : 1);
+    const bool overlap = window && rows == 4 && n > 0 && ctx->reading.cap >= need && ctx->reading_tmp.cap >= need && ctx->q_order.cap >= need &&
+                         ctx->perm_a.cap >= need && ctx->perm_b.cap >= need && ctx->keys_a.cap >= need && ctx->node_box.cap >= 12 && ctx->cub_tmp.cap >= morton_scratch_bytes((uint32_t)n);
+    PM_CUDA_TRY(ctx, ctx->reading.reserve(need));
+    PM_CUDA_TRY(ctx, ctx->reading_tmp.reserve(need));
     ctx->seed_k = 0;
-    PM_TRY(upload_cloud(ctx, features, rows, n, ctx->reading_tmp.p));
-    PM_CUDA_TRY(ctx, cudaEventRecord(ctx->copy_done, ctx->stream));
-    ctx->nq = n;
-    if (n > 0) PM_TRY(morton_order(ctx));
+    cudaStream_t main_stream = ctx->stream;
+    if (overlap) {
+        PM_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_build, 0));
+        ctx->stream = ctx->stream2;
+    }
+    int s = upload_cloud(ctx, features, rows, n, ctx->reading_tmp.p);
+    if (s == PMGPU_OK && cudaEventRecord(ctx->copy_done, ctx->stream) != cudaSuccess) s = fail(ctx, PMGPU_ERR_CUDA, "cudaEventRecord");
+    if (s == PMGPU_OK) {
+        ctx->nq = n;
+        if (n > 0) s = morton_order(ctx);
+    }
+    ctx->stream = main_stream;
+    PM_TRY(s);
+    if (overlap) {
+        PM_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_reading, ctx->stream2));
+        PM_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_reading, 0));  // everything queued from here on sees the reading
+    }
     // the caller may release `features` on return: wait for the copy only, the ordering kernels run on
     PM_CUDA_TRY(ctx, cudaEventSynchronize(ctx->copy_done));
     return PMGPU_OK;
@@ -881,7 +912,7 @@ int pmgpu_icp_run(pmgpu_ctx* ctx, const pmgpu_icp_params* params, const float* T
 
 int pmgpu_ref_compute_normals(pmgpu_ctx* ctx, int knn, float epsilon, float max_dist, int flags) {
     if (!ctx) return PMGPU_ERR_BAD_ARG;
-    PM_TRY(use_device(ctx));
+    PM_TRY(use_device(ctx, true));
     if (ctx->nr == 0) return fail(ctx, PMGPU_ERR_NO_REFERENCE, status_message(PMGPU_ERR_NO_REFERENCE));
     if (knn < 1) return fail(ctx, PMGPU_ERR_BAD_ARG, "knn must be >= 1");
     if (knn > ctx->nr) return fail(ctx, PMGPU_ERR_KNN_TOO_LARGE, status_message(PMGPU_ERR_KNN_TOO_LARGE));

@@ -248,8 +248,9 @@ PM_HD float select3(uint32_t dim, float x, float y, float z) {
 // (Measured and dropped, round 2: one level of look-ahead — the planes of both children requested as soon as the node is
 // known, so that the load of level l + 1 is in flight while level l is decided.  No gain: 0.56 vs 0.50 ms for the first,
 // unseeded k = 1 match of 1 M queries; the descent's loads mostly hit L1 and the extra selects and registers cost more.)
-PM_HD void lane_descend_step(Lane& s, const TreeView& t, float* plane, int stride, float w) {
-    const f2 sp = ldg2(t.splits + s.node);
+// `top` (optional): the split planes of the nodes with heap index < top_n, staged in shared memory by the kernel
+PM_HD void lane_descend_step(Lane& s, const TreeView& t, float* plane, int stride, float w, const f2* top = nullptr, uint32_t top_n = 0) {
+    const f2 sp = (top && s.node < top_n) ? top[s.node] : ldg2(t.splits + s.node);
     const float qd = select3(f2u(sp.y), s.qx, s.qy, s.qz);
     const float diff = fsub(qd, sp.x);
     const float pl = fmul(diff, diff);

@@ -57,6 +57,31 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
     extern __shared__ float s_plane[];  // [depth + 1][KNN_BLOCK]: cached plane distances, one column per lane
     __shared__ Mat4 sT;
     if (gated && state->iterate == 0) return;
+#ifdef PM_TOP_SMEM
+    // (A/B build) the split planes of the top PM_TOP_SMEM levels staged in shared memory by one bulk copy (TMA, 1-D): the
+    // first PM_TOP_SMEM dependent loads of every descent become shared-memory loads
+    __shared__ __align__(128) f2 s_top[1 << PM_TOP_SMEM];
+    __shared__ __align__(8) unsigned long long s_top_bar;
+    const uint32_t top_n = min(1u << PM_TOP_SMEM, 1u << tree.depth);
+    {
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_top_bar), dst = (unsigned)__cvta_generic_to_shared(s_top);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned bytes = top_n * (unsigned)sizeof(f2);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(tree.splits), "r"(bytes), "r"(bar)
+                         : "memory");
+        }
+    }
+    const f2* top = s_top;
+#else
+    const f2* top = nullptr;
+    const uint32_t top_n = 0;
+#endif
     if (use_T) {
         if (threadIdx.x < 16) sT.m[threadIdx.x] = state->T_iter.m[threadIdx.x];
         __syncthreads();
@@ -117,11 +142,26 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
     // warp — and the kernel — for thousands of rounds.
     int rounds = 0;
     unsigned my_slot = 0xffffffffu;  // K8: the stage-2 queue slot this query was handed over at
+#ifdef PM_TOP_SMEM
+    {   // the staged planes have landed (the copy ran behind the query load, the transform and the seed gather)
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_top_bar);
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar) : "memory");
+    }
+#endif
     while (__any_sync(0xffffffffu, running)) {
         // descend: one level per step for every lane that is not at a leaf yet
         const float w0 = best.worst_d();
         while (__any_sync(0xffffffffu, running && lane_descending(s, tree)))
-            if (running && lane_descending(s, tree)) lane_descend_step(s, tree, plane, KNN_BLOCK, w0);
+        {
+            if (running && lane_descending(s, tree)) lane_descend_step(s, tree, plane, KNN_BLOCK, w0, top, top_n);
+#ifdef PM_DESCENT_STEPS  // (A/B builds) more levels per warp vote
+#pragma unroll
+            for (int u = 1; u < PM_DESCENT_STEPS; ++u)
+                if (running && lane_descending(s, tree)) lane_descend_step(s, tree, plane, KNN_BLOCK, w0, top, top_n);
+#endif
+        }
         // leaf; then the plane filter over all pending levels where it pays
         bool refilter = false;
         if (running) {

@@ -273,6 +273,13 @@ struct pmgpu_ctx {
     std::vector<Interval> intervals;
     std::vector<cudaEvent_t> event_pool;
     cudaEvent_t copy_done = nullptr;  // host buffers handed to *_set may be released once this has fired
+    // The reading's upload and Morton ordering run on a second stream when the main stream is still busy with work that
+    // does not touch the reading or the ordering scratch (the reference's normals, the centring): `overlap_window` is
+    // opened by pmgpu_ref_set after the structure build (ev_build) and closed by every other entry point.
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_build = nullptr, ev_reading = nullptr;
+    bool overlap_window = false;
+    bool overlap_enabled = true;      // PMGPU_NO_OVERLAP=1: everything on the one stream
     cudaEvent_t take_event() {
         cudaEvent_t e = nullptr;
         if (!event_pool.empty()) { e = event_pool.back(); event_pool.pop_back(); }
@@ -307,6 +314,7 @@ namespace pm {
 // tree_build.cu
 int build_tree(pmgpu_ctx* ctx);
 int morton_order(pmgpu_ctx* ctx);
+size_t morton_scratch_bytes(uint32_t n);
 // knn.cu
 int launch_knn(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, bool use_T, bool gated, bool self_query, int k, float max_r2,
                bool use_seed, int32_t* ids, float* dists, bool use_cap = false, const float* var_r2 = nullptr);

@@ -362,6 +362,14 @@ int build_tree(pmgpu_ctx* ctx) {
 // position back to the caller's column).  A rigid motion preserves locality, hence the 32 queries
 // of a warp walk nearly the same tree path every iteration and all loads/stores are coalesced.
 // Expects the uploaded cloud in ctx->reading_tmp.
+// bytes of sort scratch (ctx->cub_tmp) morton_order needs for n points
+size_t morton_scratch_bytes(uint32_t n) {
+    size_t tmp_bytes = 0;
+    uint32_t* none = nullptr;
+    if (cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, none, none, none, none, (int)n, 0, 30, nullptr) != cudaSuccess) return ~(size_t)0;
+    return tmp_bytes;
+}
+
 int morton_order(pmgpu_ctx* ctx) {
     const uint32_t n = (uint32_t)ctx->nq;
     cudaStream_t st = ctx->stream;
