@@ -356,6 +356,8 @@ int pmgpu_ctx_create(int device, pmgpu_ctx** ctx_out) {
     ctx->cap_enabled = getenv("PMGPU_NO_CAP") == nullptr;
     ctx->fused_select = getenv("PMGPU_NO_FUSED_SELECT") == nullptr;
     ctx->overlap_enabled = getenv("PMGPU_NO_OVERLAP") == nullptr;
+    if (const char* c = getenv("PMGPU_COOP")) ctx->fused_cooperative = atoi(c) != 0;
+    if (const char* c = getenv("PMGPU_DEFER_FINALIZE")) ctx->defer_finalize = atoi(c) != 0;
     ctx->seeded_without_planes = getenv("PMGPU_SEED_PLANES") == nullptr;
     if (const char* m = getenv("PMGPU_CAP_MARGIN")) ctx->cap_margin = (float)atof(m);
     // 1: (almost) everything through stage 2

@@ -70,18 +70,32 @@ __device__ __forceinline__ void accumulate_pairs(double* acc, const Mat4& sT, co
                                                  const f4* __restrict__ normals, const pmgpu_icp_params& ck, const f4* __restrict__ reading_normals) {
     constexpr int NS = MODE == 1 ? NS_PLANE : NS_POINT;
     const int stride = gridDim.x * blockDim.x;
-    // one (reading point, match) pair; `id` is only meaningful where the weight is not zero
-    auto pair = [&](const f4& p, const int i, const float d, const int id, bool& match_exist) {
-        if (d == pm_inf()) return;
-        float w = pm_pair_weight(wst, d);
-        // SurfaceNormalOutlierFilter: `normals` is the reference's descriptor whenever it exists
-        if (w != 0.f && wst->sn_on) w = __fmul_rn(w, pm_sn_weight(sT, reading_normals[i], __ldg(normals + id), wst->sn_eps));
-        if (w == 0.f) { acc[NS - 3] += 1.0; return; }
+    // A (reading point, match) pair in two steps, so that the gathers of SEVERAL pairs are in flight before the first one is
+    // consumed — the kernel waits on 16-byte random reads of the matched reference point and normal, nothing else:
+    //   pair_begin : weight from the distance alone (limits, M-estimator); where it is not zero, the gathers are issued
+    //   pair_end   : SurfaceNormal factor, then the sums
+    struct Pend { float w; f4 q, n; bool live; };
+    int kept = 0, rej_matches = 0, rej_points = 0, seen = 0;  // the four counters, integers until the end
+    auto pair_begin = [&](Pend& e, const float d, const int id) {
+        e.live = d != pm_inf();  // an invalid match is not even counted as rejected (ErrorMinimizer.cpp:103-106)
+        e.w = 0.f;
+        if (!e.live) return;
+        e.w = pm_pair_weight(wst, d);
+        if (e.w != 0.f) {
+            e.q = __ldg(ref + id);
+            if (MODE == 1 || wst->sn_on) e.n = __ldg(normals + id);  // SurfaceNormalOutlierFilter: the reference's descriptor whenever it exists
+        }
+    };
+    auto pair_end = [&](const Pend& e, const f4& p, const int i, bool& match_exist) {
+        if (!e.live) return;
+        float w = e.w;
+        if (w != 0.f && wst->sn_on) w = __fmul_rn(w, pm_sn_weight(sT, reading_normals[i], e.n, wst->sn_eps));
+        if (w == 0.f) { ++rej_matches; return; }
         match_exist = true;
-        acc[NS - 4] += 1.0;
-        const f4 q = __ldg(ref + id);
+        ++kept;
+        const f4 q = e.q;
         if (MODE == 1) {
-            const f4 n = __ldg(normals + id);
+            const f4 n = e.n;
             float F[6], wF[6];
             F[0] = fsub(fmul(p.y, n.z), fmul(p.z, n.y));  // crossProduct, ErrorMinimizer.cpp:304-306
             F[1] = fsub(fmul(p.z, n.x), fmul(p.x, n.z));
@@ -116,35 +130,61 @@ __device__ __forceinline__ void accumulate_pairs(double* acc, const Mat4& sT, co
         }
     };
     if (k == 1) {
-        // the common case, software-pipelined: the (point, distance, id) of the thread's next element are
-        // in flight while the current one gathers its reference point — the kernel is latency bound
+        // the common case: two reading points per trip — both gathers issued before either is consumed — and the
+        // (point, distance, id) of the next two already requested
         int i = blockIdx.x * blockDim.x + threadIdx.x;
-        f4 rp = make_float4(0.f, 0.f, 0.f, 0.f);
-        float d = 0.f;
-        int id = 0;
-        if (i < nq) { rp = reading[i]; d = dists[i]; id = ids[i]; }
+        f4 rp[2];
+        float d[2];
+        int id[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            rp[u] = make_float4(0.f, 0.f, 0.f, 0.f); d[u] = pm_inf(); id[u] = 0;
+            if (i + u * stride < nq) { rp[u] = reading[i + u * stride]; d[u] = dists[i + u * stride]; id[u] = ids[i + u * stride]; }
+        }
         while (i < nq) {
-            const int inext = i + stride;
-            f4 rp_n = rp;
-            float d_n = 0.f;
-            int id_n = 0;
-            if (inext < nq) { rp_n = reading[inext]; d_n = dists[inext]; id_n = ids[inext]; }
-            const f4 p = transform_point(sT, rp);
-            bool match_exist = false;
-            pair(p, i, d, id, match_exist);
-            if (!match_exist) acc[NS - 2] += 1.0;
-            acc[NS - 1] += 1.0;
-            i = inext; rp = rp_n; d = d_n; id = id_n;
+            Pend e[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) pair_begin(e[u], d[u], id[u]);
+            const int inext = i + 2 * stride;
+            f4 rp_n[2];
+            float d_n[2];
+            int id_n[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                rp_n[u] = rp[u]; d_n[u] = pm_inf(); id_n[u] = 0;
+                if (inext + u * stride < nq) { rp_n[u] = reading[inext + u * stride]; d_n[u] = dists[inext + u * stride]; id_n[u] = ids[inext + u * stride]; }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (i + u * stride < nq) {
+                    const f4 p = transform_point(sT, rp[u]);
+                    bool match_exist = false;
+                    pair_end(e[u], p, i + u * stride, match_exist);
+                    if (!match_exist) ++rej_points;
+                    ++seen;
+                }
+            }
+            i = inext;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) { rp[u] = rp_n[u]; d[u] = d_n[u]; id[u] = id_n[u]; }
         }
     } else {
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
             const f4 p = transform_point(sT, reading[i]);
             bool match_exist = false;
-            for (int kk = 0; kk < k; ++kk) pair(p, i, dists[(size_t)i * k + kk], ids[(size_t)i * k + kk], match_exist);
-            if (!match_exist) acc[NS - 2] += 1.0;
-            acc[NS - 1] += 1.0;
+            for (int kk = 0; kk < k; kk += 2) {
+                Pend e[2];
+                const bool two = kk + 1 < k;
+                pair_begin(e[0], dists[(size_t)i * k + kk], ids[(size_t)i * k + kk]);
+                if (two) pair_begin(e[1], dists[(size_t)i * k + kk + 1], ids[(size_t)i * k + kk + 1]);
+                pair_end(e[0], p, i, match_exist);
+                if (two) pair_end(e[1], p, i, match_exist);
+            }
+            if (!match_exist) ++rej_points;
+            ++seen;
         }
     }
+    acc[NS - 4] = (double)kept; acc[NS - 3] = (double)rej_matches; acc[NS - 2] = (double)rej_points; acc[NS - 1] = (double)seen;
 }
 
 // `fuse`: the last block to finish reduces the partial rows, solves, composes T_iter and runs the
@@ -193,12 +233,15 @@ __global__ void __launch_bounds__(ACC_BLOCK, MODE == 1 ? 2 : 3) accumulate_kerne
 // passes (three or four when the order statistic left the window or there is none yet, e.g. the first iteration).  Limits,
 // weights, sums and T are bit for bit those of hist_kernel x 3 + accumulate_kernel; what is gone is three launches, their
 // drains and the DRAM round trips between them (0.037 + 0.043 ms -> see DESIGN.md K3).
+#ifndef PM_FUSED_MIN_BLOCKS
+#define PM_FUSED_MIN_BLOCKS(MODE) ((MODE) == 1 ? 2 : 3)
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(ACC_BLOCK, MODE == 1 ? 2 : 3) select_accumulate_kernel(const f4* __restrict__ reading, int nq, int k, const int32_t* __restrict__ ids,
+__global__ void __launch_bounds__(ACC_BLOCK, PM_FUSED_MIN_BLOCKS(MODE)) select_accumulate_kernel(const f4* __restrict__ reading, int nq, int k, const int32_t* __restrict__ ids,
                                                                const float* __restrict__ dists, const f4* __restrict__ ref,
                                                                const f4* __restrict__ normals, IcpState* state, double* __restrict__ partials,
                                                                double* sums, pmgpu_icp_params ck, const f4* __restrict__ reading_normals, PeerComm pc,
-                                                               SelectSpec spec, unsigned* __restrict__ hist, int cap_active, float cap_margin, unsigned* __restrict__ cand) {
+                                                               SelectSpec spec, unsigned* __restrict__ hist, int cap_active, float cap_margin, unsigned* __restrict__ cand, int defer_finalize) {
     constexpr int NS = MODE == 1 ? NS_PLANE : NS_POINT;
     __shared__ SelScratch s_sel;
     __shared__ Mat4 sT;
@@ -279,14 +322,28 @@ __global__ void __launch_bounds__(ACC_BLOCK, MODE == 1 ? 2 : 3) select_accumulat
     for (int c = 0; c < NS; ++c) acc[c] = 0.0;
     accumulate_pairs<MODE>(acc, sT, &s_w, reading, nq, k, ids, dists, ref, normals, ck, reading_normals);
 #ifdef PM_PROFILE_NS
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        printf("select_accumulate<%d> block 0 (ns since start):", MODE);
-        for (int i = 1; i < ntp; ++i) printf(" %llu", tp[i] - tp[0]);
-        printf(" | accumulated at %llu, passes %d\n", pm_globaltimer() - tp[0], state->sel_passes);
-    }
+    const unsigned long long t_acc = pm_globaltimer();
 #endif
     block_reduce_store<NS>(acc, partials + (size_t)blockIdx.x * NS_MAX);
-    if (select_last_block(&state->ticket[1])) finalize_body<MODE>(partials, gridDim.x, sums, 3, state, 1, ck, pc);
+#ifdef PM_PROFILE_NS
+    const unsigned long long t_red = pm_globaltimer();
+#endif
+    if (defer_finalize) return;  // the reduction of the rows, the solve and the composition follow as finalize_kernel
+    if (select_last_block(&state->ticket[1])) {
+#ifdef PM_PROFILE_NS
+        const unsigned long long t_last = pm_globaltimer();
+#endif
+        finalize_body<MODE>(partials, gridDim.x, sums, 3, state, 1, ck, pc);
+#ifdef PM_PROFILE_NS
+        if (threadIdx.x == 0)
+            printf("select_accumulate<%d> LAST block %d (ns since ITS start): select done %llu, accumulated %llu, block-reduced %llu, ticket %llu, finalized %llu, passes %d\n",
+                   MODE, blockIdx.x, tp[ntp - 1] - tp[0], t_acc - tp[0], t_red - tp[0], t_last - tp[0], pm_globaltimer() - tp[0], state->sel_passes);
+#endif
+    }
+#ifdef PM_PROFILE_NS
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        printf("select_accumulate<%d> block 0: select done %llu, accumulated %llu, block-reduced %llu\n", MODE, tp[ntp - 1] - tp[0], t_acc - tp[0], t_red - tp[0]);
+#endif
 }
 
 // Censi covariance sums (PointToPlaneWithCov.cpp:100-150, PointToPointWithCov.cpp:84-135):
@@ -368,22 +425,20 @@ __global__ void __launch_bounds__(ACC_BLOCK) cov_accumulate_kernel(const f4* __r
 }
 
 // fixed-order reduction of the per-block rows: 256 threads = 32 columns x 8 slices (two rounds
-// when there are more than 32 columns).  The loads of a slice are issued eight at a time before
+// when there are more than 32 columns).  The loads of a slice are issued sixteen at a time before
 // they are added (in row order), so the reduction costs a few L2 round trips, not one per row.
 __device__ void reduce_rows(const double* __restrict__ partials, int nblocks, int ns, double* sums) {
     __shared__ double sh[8][NS_MAX];
     const int slice = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int c = lane; c < ns; c += 32) {
         double v = 0.0;
-        int b = slice;
-        for (; b + 56 < nblocks; b += 64) {
-            double r[8];
+        for (int b = slice; b < nblocks; b += 128) {  // sixteen rows requested at once (rows past the end read as + 0)
+            double r[16];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) r[u] = __ldcg(partials + (size_t)(b + 8 * u) * NS_MAX + c);
+            for (int u = 0; u < 16; ++u) r[u] = (b + 8 * u < nblocks) ? __ldcg(partials + (size_t)(b + 8 * u) * NS_MAX + c) : 0.0;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v += r[u];
+            for (int u = 0; u < 16; ++u) v += r[u];
         }
-        for (; b < nblocks; b += 8) v += __ldcg(partials + (size_t)b * NS_MAX + c);
         sh[slice][c] = v;
     }
     __syncthreads();
@@ -444,6 +499,94 @@ __device__ void run_checkers(IcpState* st, const pmgpu_icp_params& ck) {
     }
 }
 
+// solve_psd (core/linalg.h) by one warp: the same diagonally pivoted Cholesky, element for element the same operations (so
+// the same bits), but the pivot search, the column of L and the rank-1 update of every step run across the lanes on
+// shared-memory matrices.  The serial routine is ~1 900 dependent instructions of ONE thread on an otherwise idle SM — 13 us,
+// a fifth of the iteration's minimiser kernel — of which the arithmetic (6 square roots, 27 divisions, ~150 fused
+// multiply-adds; tools/fp64_latency.cu: 99 / 132 / 7 cycles each on this GPU) is a small part: the rest is local-memory
+// indexing.  N is a template parameter so that all index arithmetic is constant folding.  A, b, x in shared memory; every
+// lane of warp 0 calls it.  A rank-deficient system takes the one-thread routine.
+__device__ __noinline__ int solve_psd_serial(const double* A, const double* b, double* x, int n) { return solve_psd(A, b, x, n); }
+
+template <int N>
+__device__ __forceinline__ int solve_psd_warp(const double* A, const double* b, double* x) {
+    __shared__ double sM[36], sL[36], sc[6];
+    __shared__ int sperm[6];
+    const int lane = threadIdx.x & 31;
+    // the two matrix elements of this lane: e0 = lane, e1 = lane + 32 (column-major i + N j)
+    const int e0 = lane, e1 = lane + 32;
+    const int i0 = e0 % N, j0 = e0 / N, i1 = e1 % N, j1 = e1 / N;
+    const bool in0 = e0 < N * N, in1 = e1 < N * N;
+    if (in0) { sM[e0] = A[e0]; sL[e0] = 0.0; }
+    if (in1) { sM[e1] = A[e1]; sL[e1] = 0.0; }
+    if (lane < N) sperm[lane] = lane;
+    __syncwarp();
+    const double thr = (double)N * PM_FLT_EPS;
+    double d0 = 0.0;
+    int rank = 0;
+#pragma unroll 1
+    for (int k = 0; k < N; ++k) {
+        // the first largest remaining diagonal entry
+        double dv = (lane >= k && lane < N) ? sM[lane + N * lane] : -1.0;
+        int pi = lane;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            const double ov = __shfl_down_sync(0xffffffffu, dv, o);
+            const int oi = __shfl_down_sync(0xffffffffu, pi, o);
+            const bool mine_valid = pi >= k && pi < N, other_valid = oi >= k && oi < N;
+            if (other_valid && (!mine_valid || ov > dv || (ov == dv && oi < pi))) { dv = ov; pi = oi; }
+        }
+        const int p = __shfl_sync(0xffffffffu, pi, 0);
+        const double dmax = __shfl_sync(0xffffffffu, dv, 0);
+        if (k == 0) d0 = dmax;
+        if (!(dmax > thr * d0) || !(dmax > 0.0)) break;
+        if (p != k) {
+            if (lane < N) { const double t = sM[k + N * lane]; sM[k + N * lane] = sM[p + N * lane]; sM[p + N * lane] = t; }
+            __syncwarp();
+            if (lane < N) { const double t = sM[lane + N * k]; sM[lane + N * k] = sM[lane + N * p]; sM[lane + N * p] = t; }
+            if (lane < k) { const double t = sL[k + N * lane]; sL[k + N * lane] = sL[p + N * lane]; sL[p + N * lane] = t; }
+            if (lane == 0) { const int t = sperm[k]; sperm[k] = sperm[p]; sperm[p] = t; }
+            __syncwarp();
+        }
+        const double lkk = sqrt(dmax);
+        if (lane == k) sL[k + N * k] = lkk;
+        if (lane > k && lane < N) sL[lane + N * k] = sM[lane + N * k] / lkk;
+        __syncwarp();
+        if (in0 && i0 > k && j0 > k) sM[e0] -= sL[i0 + N * k] * sL[j0 + N * k];
+        if (in1 && i1 > k && j1 > k) sM[e1] -= sL[i1 + N * k] * sL[j1 + N * k];
+        __syncwarp();
+        ++rank;
+    }
+    if (rank < N) {
+        if (lane == 0) solve_psd_serial(A, b, x, N);  // minimum-norm solution: rare
+        __syncwarp();
+        return rank;
+    }
+    if (lane < N) sc[lane] = b[sperm[lane]];
+    __syncwarp();
+    if (lane == 0) {
+        double y[N], z[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double s = sc[i];
+#pragma unroll
+            for (int j = 0; j < i; ++j) s -= sL[i + N * j] * y[j];
+            y[i] = s / sL[i + N * i];
+        }
+#pragma unroll
+        for (int i = N - 1; i >= 0; --i) {
+            double s = y[i];
+#pragma unroll
+            for (int j = i + 1; j < N; ++j) s -= sL[j + N * i] * z[j];
+            z[i] = s / sL[i + N * i];
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[sperm[i]] = z[i];
+    }
+    __syncwarp();
+    return rank;
+}
+
 // phase bits: 1 = reduce partial rows into sums, 2 = solve from sums.  Runs in one block of 256
 // threads: the last block of the accumulate kernel (one GPU) or finalize_kernel (sharded reading,
 // where the sums are all-reduced between the two phases).
@@ -458,61 +601,70 @@ __device__ void finalize_body(const double* partials, int nblocks, double* sums,
     // sharded reading: this rank's sums become the sums over all ranks, in rank order on every rank (comm.cuh), so every
     // rank solves the same system to the same bits
     if (phase == 3 && pc.nranks > 1 && !peer_allreduce<true>(pc, sums, (2 * NS + 3) & ~3, state)) return;
-    if (!(phase & 2) || threadIdx.x != 0) return;
+    if (!(phase & 2) || threadIdx.x >= 32) return;  // warp 0: the solve is a warp's work, everything around it lane 0's
+    const bool lead = threadIdx.x == 0;
 #ifdef PM_PROFILE_NS
     const unsigned long long t_b = pm_globaltimer();
 #endif
     const double kept = sums[NS - 4], rej_matches = sums[NS - 3], rej_points = sums[NS - 2], seen = sums[NS - 1];
     // ErrorMinimizer.cpp:139-140: ratios over knn * number of reading points (all ranks)
     const float denom = (float)(seen * (double)ck.knn);
-    state->stats[0] = (float)kept / denom;
-    state->stats[2] = (float)rej_matches;
-    state->stats[3] = (float)rej_points;
-    state->stats[4] = (float)kept;
-    state->T_match = state->T_iter;
+    if (lead) {
+        state->stats[0] = (float)kept / denom;
+        state->stats[2] = (float)rej_matches;
+        state->stats[3] = (float)rej_points;
+        state->stats[4] = (float)kept;
+        state->T_match = state->T_iter;
+    }
     if (!(kept > 0.0)) {
-        if (state->status == 0) state->status = PMGPU_ERR_NO_POINT_TO_MINIMIZE;
-        state->iterate = 0;
+        if (lead) {
+            if (state->status == 0) state->status = PMGPU_ERR_NO_POINT_TO_MINIMIZE;
+            state->iterate = 0;
+        }
         return;
     }
     Mat4 dT;
     if (MODE == 1) {
-        state->stats[1] = (float)sums[27] / denom;  // sum of weights (== kept for the 0/1 filters)
-        double A[36], b[6], x[6];
-        expand_sym6(sums, A);
-        for (int a = 0; a < 6; ++a) b[a] = -sums[21 + a];
+        __shared__ double sA[36], sb[6], sx[6];
+        if (lead) state->stats[1] = (float)sums[27] / denom;  // sum of weights (== kept for the 0/1 filters)
+        // rows / columns of the system actually solved: all six (rotation vector, translation); force4DOF: (cross_z, nx, ny,
+        // nz) (PointToPlane.cpp:203-214); force2D / 2-D clouds: (cross_z, nx, ny) — the pseudo cross product of
+        // ErrorMinimizer.cpp:308-313 is cross_z, and the accumulate kernel left z out of the residual (PointToPlane.cpp:177-186, 294-310)
+        const int n = (ck.minimizer & PMGPU_MIN_FORCE2D) ? 3 : ((ck.minimizer & PMGPU_MIN_FORCE4DOF) ? 4 : 6), off = n == 6 ? 0 : 2;
+        for (int e = threadIdx.x; e < n * n; e += 32) {
+            const int r = off + e % n, c = off + e / n;
+            const int a = r < c ? r : c, bb = r < c ? c : r;
+            sA[e] = sums[a * 6 - a * (a - 1) / 2 + (bb - a)];  // upper triangle, row-major over a <= bb
+        }
+        if ((int)threadIdx.x < n) sb[threadIdx.x] = -sums[21 + off + threadIdx.x];
+        __syncwarp();
+#ifdef PM_PROFILE_NS
+        const unsigned long long t_s0 = pm_globaltimer();
+#endif
+        const int rank_ = n == 6 ? solve_psd_warp<6>(sA, sb, sx) : (n == 4 ? solve_psd_warp<4>(sA, sb, sx) : solve_psd_warp<3>(sA, sb, sx));
+#ifdef PM_PROFILE_NS
+        if (lead) printf("   finalize: prologue %llu ns, solve_psd_warp %llu ns (n %d rank %d)\n", t_s0 - t_b, pm_globaltimer() - t_s0, n, rank_);
+#else
+        (void)rank_;
+#endif
+        if (!lead) return;
         float xf[6];
         if (ck.minimizer & PMGPU_MIN_FORCE2D) {
-            // rows / columns (cross_z, nx, ny): the pseudo cross product of ErrorMinimizer.cpp:308-313 is cross_z, and the
-            // accumulate kernel left z out of the residual (PointToPlane.cpp:177-186, 294-310)
-            double A3[9], b3[3], x3[3];
-            for (int c = 0; c < 3; ++c) {
-                b3[c] = b[2 + c];
-                for (int r = 0; r < 3; ++r) A3[r + 3 * c] = A[(2 + r) + 6 * (2 + c)];
-            }
-            solve_psd(A3, b3, x3, 3);
-            const float ang = (float)x3[0];
+            const float ang = (float)sx[0];
             const float sn = sinf(ang), cs = cosf(ang);  // Eigen::Rotation2D<float>
             mat4_identity(dT);
             dT.m[0] = cs; dT.m[4] = -sn;
             dT.m[1] = sn; dT.m[5] = cs;
-            dT.m[12] = (float)x3[1]; dT.m[13] = (float)x3[2];
+            dT.m[12] = (float)sx[1]; dT.m[13] = (float)sx[2];
         } else if (ck.minimizer & PMGPU_MIN_FORCE4DOF) {
-            // rows / columns (cross_z, nx, ny, nz) of the same normal equations (PointToPlane.cpp:203-214)
-            double A4[16], b4[4], x4[4];
-            for (int c = 0; c < 4; ++c) {
-                b4[c] = b[2 + c];
-                for (int r = 0; r < 4; ++r) A4[r + 4 * c] = A[(2 + r) + 6 * (2 + c)];
-            }
-            solve_psd(A4, b4, x4, 4);
             xf[0] = 0.f; xf[1] = 0.f;
-            for (int a = 0; a < 4; ++a) xf[2 + a] = (float)x4[a];  // AngleAxis(x(0), unitZ), translation x(1..3)
+            for (int a = 0; a < 4; ++a) xf[2 + a] = (float)sx[a];  // AngleAxis(x(0), unitZ), translation x(1..3)
         } else {
-            solve_psd6(A, b, x);
-            for (int a = 0; a < 6; ++a) xf[a] = (float)x[a];
+            for (int a = 0; a < 6; ++a) xf[a] = (float)sx[a];
         }
         if (!(ck.minimizer & PMGPU_MIN_FORCE2D)) angle_axis_to_mat4(xf, dT);
     } else {
+        if (!lead) return;
         const double W = sums[0];
         state->stats[1] = (float)W / denom;
         const double inv = 1.0 / W;
@@ -578,11 +730,9 @@ __device__ void finalize_body(const double* partials, int nblocks, double* sums,
 
 template <int MODE>
 __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ sums, int phase,
-                                                       IcpState* state, int gated, int compose, pmgpu_icp_params ck) {
+                                                       IcpState* state, int gated, int compose, pmgpu_icp_params ck, PeerComm pc) {
     if (gated && (state->iterate == 0 || state->redo)) return;
-    PeerComm none;
-    none.nranks = 1;
-    finalize_body<MODE>(partials, nblocks, sums, phase, state, compose, ck, none);
+    finalize_body<MODE>(partials, nblocks, sums, phase, state, compose, ck, pc);
 }
 
 // inverse of a 6x6 by Gauss-Jordan with partial pivoting (J_hessian.inverse())
@@ -673,11 +823,11 @@ int launch_minimize(pmgpu_ctx* ctx, int minimizer_word, bool compose_and_check, 
     ctx->launches += 1;
     if (!fuse) {
         const int ns = plane ? NS_PLANE : NS_POINT;
-        if (plane) finalize_kernel<1><<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 1, ctx->state, g, comp, ck);
-        else finalize_kernel<0><<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 1, ctx->state, g, comp, ck);
+        if (plane) finalize_kernel<1><<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 1, ctx->state, g, comp, ck, pc);
+        else finalize_kernel<0><<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 1, ctx->state, g, comp, ck, pc);
         PM_TRY(comm_allreduce_f64(ctx, sums, ns));
-        if (plane) finalize_kernel<1><<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 2, ctx->state, g, comp, ck);
-        else finalize_kernel<0><<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 2, ctx->state, g, comp, ck);
+        if (plane) finalize_kernel<1><<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 2, ctx->state, g, comp, ck, pc);
+        else finalize_kernel<0><<<1, 256, 0, st>>>(ctx->partials.p, grid, sums, 2, ctx->state, g, comp, ck, pc);
         ctx->launches += 2;
     }
     PM_CUDA_TRY(ctx, cudaGetLastError());
@@ -704,7 +854,7 @@ static int launch_select_minimize_mode(pmgpu_ctx* ctx, const SelectSpec& spec, c
             ctx->set_error("select_accumulate_kernel does not fit on an SM");
             return PMGPU_ERR_CUDA;
         }
-        const int want = MODE == 1 ? 2 : 3;  // the launch bounds
+        const int want = PM_FUSED_MIN_BLOCKS(MODE);  // the launch bounds
         ctx->fused_grid[MODE] = ctx->num_sms * (per_sm < want ? per_sm : want);
     }
     int grid = (ctx->nq + ACC_BLOCK - 1) / ACC_BLOCK;
@@ -721,11 +871,16 @@ static int launch_select_minimize_mode(pmgpu_ctx* ctx, const SelectSpec& spec, c
     attr[0].id = cudaLaunchAttributeCooperative;  // all blocks resident at once: the in-kernel grid barrier cannot deadlock
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = ctx->fused_cooperative ? 1 : 0;
     PM_CUDA_TRY(ctx, cudaLaunchKernelEx(&cfg, kernel, (const f4*)ctx->reading.p, ctx->nq, ctx->k, (const int32_t*)ctx->ids.p, (const float*)ctx->dists.p,
                                         (const f4*)ctx->ref_orig.p, normals, ctx->state, ctx->partials.p, sums, ck, (const f4*)ctx->reading_normals.p,
-                                        comm_peers(ctx), spec, ctx->hist.p, cap_active ? 1 : 0, ctx->cap_margin, ctx->sel_cand.p));
+                                        comm_peers(ctx), spec, ctx->hist.p, cap_active ? 1 : 0, ctx->cap_margin, ctx->sel_cand.p, ctx->defer_finalize ? 1 : 0));
     ctx->launches += 1;
+    if (ctx->defer_finalize) {
+        finalize_kernel<MODE><<<1, 256, 0, ctx->stream>>>(ctx->partials.p, grid, sums, 3, ctx->state, 1, 1, ck, comm_peers(ctx));
+        ctx->launches += 1;
+        PM_CUDA_TRY(ctx, cudaGetLastError());
+    }
     return PMGPU_OK;
 }
 

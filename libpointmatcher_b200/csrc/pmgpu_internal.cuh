@@ -252,6 +252,8 @@ struct pmgpu_ctx {
     // minimiser partial sums (K4-K6)
     pm::DevBuf<double> partials;
     bool fused_select = true;        // fused loop: quantile select inside the minimiser kernel; PMGPU_NO_FUSED_SELECT=1 reverts
+    bool defer_finalize = true;      // PMGPU_DEFER_FINALIZE=1: rows + solve + compose as a second, one-block kernel (A/B)
+    bool fused_cooperative = true;   // PMGPU_COOP=0: plain launch of the same one-wave grid (A/B)
     int fused_grid[2] = {0, 0};      // co-resident blocks of select_accumulate_kernel<MODE> (occupancy query, once)
 
     pm::IcpState* state = nullptr;   // device

@@ -47,5 +47,6 @@ tot_i = sum(a[1] for a in agg.values())
 tot_s = sum(a[3] for a in agg.values())
 print("total warp instructions %.0f, lanes/inst %.2f, samples %.0f" % (tot_i, sum(a[2] for a in agg.values()) / max(tot_i, 1), tot_s))
 print("%-12s %5s %6s %6s %5s  %s" % ("file", "line", "inst%", "samp%", "lanes", "source"))
-for (f, ln), a in sorted(agg.items(), key=lambda x: -x[1][1])[:top]:
+by = 3 if "--by-samples" in sys.argv else 1
+for (f, ln), a in sorted(agg.items(), key=lambda x: -x[1][by])[:top]:
     print("%-12s %5d %6.2f %6.2f %5.1f  %s" % (f[:12], ln, 100 * a[1] / tot_i, 100 * a[3] / max(tot_s, 1), a[2] / max(a[1], 1), a[0]))
