@@ -618,7 +618,9 @@ def run_ours(args, rank, world, local_rank):
     k = cfg["knn"]
     alg_bytes = 16 * m["nq_local"] + 16 * m["nr"] + 8 * k * m["nq_local"]
     achieved = alg_bytes / (knn_ms * 1e-3) / 1e9 if knn_ms > 0 else 0.0
-    traffic = {("c2plane", 1_000_000): None}.get((args.config, m["nq_local"]))
+    # dram__bytes_read + dram__bytes_write of K2 per launch (stage 1 + stage 2) from the ncu --set full capture of this workload
+    # (profiles/r2_end_knn_c2plane_summary.txt: 51.8 + 0.6 MB and 0.2 MB); null for the workloads that were not captured
+    traffic = {("c2plane", 1_000_000): 52.6e6, ("c2", 1_000_000): 52.6e6}.get((args.config, m["nq_local"]))
     roofline = {"bound": "hbm", "kernel": "knn_kernel<%d> + knn_overflow_kernel<%d> (K2: transform + exact nearest neighbours, stage 1 + 2)" % (k, k),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": "measured (MEASURED_PEAKS.json)" if pk else "fallback (B200_PROFILING.md)",
