@@ -74,14 +74,18 @@ enum pmgpu_filter_type {
 /* RobustOutlierFilter: M-estimator weights w(e^2), e^2 = dist / scale^2.  Its discrete
  * parameters travel in the filter word: bits 0-7 PMGPU_FILTER_ROBUST | bits 8-15 robustFct | bits 16-19
  * scaleEstimator | bits 20-27 nbIterationForScale.  scaleEstimator "mad" = sqrt(median |d - median d|)
- * (Matches.cpp:88-122) is two more exact radix selects on the device; "none" = 1.  distanceType
- * point2point and approximation = inf only; "std" / "berg" are not built.  At most one robust filter per
- * chain, not with a sharded reading.  limits_out[f] of pmgpu_weights returns the scale. */
+ * (Matches.cpp:88-122) is two more exact radix selects on the device; "berg" (OutlierFiltersImpl.cpp:420-432, 523-537:
+ * 1.9 sqrt(median d) at the first iteration, then 0.85 (scale - target) + target with target = the tuning given and the
+ * tuning constant of Bergstrom for cauchy / tukey / huber) one select at the first iteration; "std" =
+ * sqrt(Matches::getStandardDeviation()) (Matches.cpp:124-129) two fp64 reductions; "none" = 1.
+ * `approximation` (weight 0 where e^2 >= approximation^2) through pmgpu_set_robust_approximation.  distanceType
+ * point2point only.  At most one robust filter per chain, not with a sharded reading.  limits_out[f] of pmgpu_weights
+ * returns the scale. */
 enum {
     PMGPU_ROBUST_CAUCHY = 0, PMGPU_ROBUST_WELSCH, PMGPU_ROBUST_SC, PMGPU_ROBUST_GM, PMGPU_ROBUST_TUKEY, PMGPU_ROBUST_HUBER, PMGPU_ROBUST_L1,
     PMGPU_ROBUST_STUDENT
 };
-enum { PMGPU_SCALE_NONE = 0, PMGPU_SCALE_MAD = 1 };
+enum { PMGPU_SCALE_NONE = 0, PMGPU_SCALE_MAD = 1, PMGPU_SCALE_BERG = 2, PMGPU_SCALE_STD = 3 };
 #define PMGPU_ROBUST_WORD(fct, scale, nb_iter) (PMGPU_FILTER_ROBUST | ((fct) << 8) | ((scale) << 16) | ((nb_iter) << 20))
 
 
@@ -194,6 +198,9 @@ int pmgpu_matches_get(pmgpu_ctx* ctx, int32_t* ids_out, float* dists_out, float*
  * pmgpu_set_var_trimmed_ratios sets minRatio / maxRatio (defaults 0.05 / 0.99) of the context's VarTrimmedDist filter;
  * PMGPU_ERR_BAD_ARG unless 0 < min_ratio < max_ratio <= 1.  pmgpu_var_trimmed_ratio: the ratio the last evaluation chose. */
 int pmgpu_set_var_trimmed_ratios(pmgpu_ctx* ctx, float min_ratio, float max_ratio);
+/* RobustOutlierFilter `approximation` (OutlierFiltersImpl.cpp:400, 591-595; metres, un-squared; +inf = none, the default):
+ * of the context's robust filter. */
+int pmgpu_set_robust_approximation(pmgpu_ctx* ctx, float approximation);
 int pmgpu_var_trimmed_ratio(pmgpu_ctx* ctx, float* ratio_out);
 
 /* ---- K4-K7: ErrorMinimizer::compute (ErrorMinimizer.cpp:217-232) ------------------------

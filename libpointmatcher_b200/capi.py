@@ -92,6 +92,7 @@ SIGNATURES = {
     "pmgpu_icp_cap_redos": (C.c_int, [C.c_void_p]),
     "pmgpu_matches_get": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pmgpu_set_var_trimmed_ratios": (C.c_int, [C.c_void_p, C.c_float, C.c_float]),
+    "pmgpu_set_robust_approximation": (C.c_int, [C.c_void_p, C.c_float]),
     "pmgpu_var_trimmed_ratio": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pmgpu_host_srand": (None, [C.c_uint]),
     "pmgpu_host_random_sampling": (C.c_int, [C.c_int, C.c_float, C.c_void_p]),
@@ -314,6 +315,10 @@ class Context:
         T = np.zeros((self.dimh, self.dimh), np.float32, order="F")
         self._check(lib.pmgpu_matches_get(self.h, _ptr(ids), _ptr(dists), _ptr(w), _f(T)))
         return ids, dists, w, np.array(T)
+
+    def set_robust_approximation(self, approximation=float("inf")):
+        """RobustOutlierFilter `approximation` (metres; inf: none) of the chain evaluated from here on"""
+        self._check(lib.pmgpu_set_robust_approximation(self.h, approximation))
 
     def set_var_trimmed_ratios(self, min_ratio=0.05, max_ratio=0.99):
         """minRatio / maxRatio of the chain's VarTrimmedDistOutlierFilter (type FILTER_VARTRIMMEDDIST, param lambda)"""

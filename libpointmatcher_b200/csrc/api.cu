@@ -767,6 +767,14 @@ int pmgpu_set_var_trimmed_ratios(pmgpu_ctx* ctx, float min_ratio, float max_rati
     return PMGPU_OK;
 }
 
+int pmgpu_set_robust_approximation(pmgpu_ctx* ctx, float approximation) {
+    if (!ctx) return PMGPU_ERR_BAD_ARG;
+    if (!(approximation >= 0.f)) return fail(ctx, PMGPU_ERR_BAD_ARG, "RobustOutlierFilter: approximation must be >= 0");
+    // squaredApproximation(pow(get<T>("approximation"), 2)): the square is taken in double (OutlierFiltersImpl.cpp:400)
+    ctx->robust_approx2 = (float)((double)approximation * (double)approximation);
+    return PMGPU_OK;
+}
+
 int pmgpu_var_trimmed_ratio(pmgpu_ctx* ctx, float* ratio_out) {
     if (!ctx || !ratio_out) return PMGPU_ERR_BAD_ARG;
     PM_TRY(use_device(ctx));

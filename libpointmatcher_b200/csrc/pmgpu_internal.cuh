@@ -115,7 +115,9 @@ struct IcpState {
     float robust_k;              // tuning
     float robust_scale;          // sqrt(MAD) or 1
     int robust_iteration;        // RobustOutlierFilter::iteration (starts at 1)
-    int robust_recompute;        // this call re-estimates the scale (nbIterationForScale)
+    int robust_recompute;        // this call re-estimates the scale (nbIterationForScale): 1 mad, 2 berg's first median, 3 std
+    float robust_target;         // berg: the scale the estimator converges to (the tuning the caller gave)
+    float robust_approx2;        // weight 0 where e^2 >= this (`approximation` squared; +inf: none)
     float robust_median;
     unsigned robust_prefix;
     unsigned long long robust_rank;
@@ -151,6 +153,7 @@ struct SelectSpec {
     __host__ __device__ float quantile(int f) const { return type[f] == PMGPU_FILTER_MEDIANDIST ? 0.5f : param[f]; }
     __host__ __device__ float factor(int f) const { return type[f] == PMGPU_FILTER_MEDIANDIST ? param[f] : 0.f; }
     int sn_active;  // the chain's SurfaceNormalOutlierFilter has normals on both sides to work with
+    float robust_approx2;  // RobustOutlierFilter: squared `approximation`
     __host__ __device__ int sn_index() const {
         for (int f = 0; f < nfilters; ++f)
             if (kind(f) == PMGPU_FILTER_SURFACENORMAL) return f;
@@ -247,6 +250,7 @@ struct pmgpu_ctx {
     pm::DevBuf<unsigned> sel_cand;   // distances collected by the in-kernel select's first pass, PM_SEL_CAND_CAP per filter
     // VarTrimmedDistOutlierFilter: minRatio / maxRatio (pmgpu_set_var_trimmed_ratios), sorted distance bits, running sums
     float var_min_ratio = 0.05f, var_max_ratio = 0.99f;
+    float robust_approx2 = __builtin_inff();   // RobustOutlierFilter `approximation`, squared (pmgpu_set_robust_approximation)
     pm::DevBuf<unsigned> var_sorted;
     pm::DevBuf<float> var_cum;
     // minimiser partial sums (K4-K6)

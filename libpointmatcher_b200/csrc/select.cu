@@ -76,11 +76,12 @@ __global__ void __launch_bounds__(HIST_BLOCK) hist_kernel(const float* __restric
 
 // RobustOutlierFilter scale = sqrt(MAD): the same three passes twice, phase 0 on the distances
 // (median), phase 1 on |dist - median| (Matches.cpp:88-122); histogram slot PM_MAX_FILTERS
+// `want`: the estimator these passes belong to (robust_recompute: 1 mad, 2 berg's first median)
 __global__ void __launch_bounds__(HIST_BLOCK) robust_hist_kernel(const float* __restrict__ dists, size_t total, int pass, int phase, IcpState* state,
-                                                                 int gated, unsigned* __restrict__ hist) {
+                                                                 int gated, unsigned* __restrict__ hist, int want) {
     __shared__ unsigned sh[PM_HIST_BINS];
     if (gated && state->iterate == 0) return;
-    if (!state->robust_recompute) return;  // the scale is frozen (nbIterationForScale)
+    if (state->robust_recompute != want) return;  // the scale is frozen (nbIterationForScale), or not this estimator's turn
     for (int i = threadIdx.x; i < PM_HIST_BINS; i += blockDim.x) sh[i] = 0;
     __syncthreads();
     const unsigned prefix = pass == 0 ? 0u : state->robust_prefix;
@@ -95,7 +96,39 @@ __global__ void __launch_bounds__(HIST_BLOCK) robust_hist_kernel(const float* __
     select_flush(sh, hist);
     __syncthreads();
     if (!select_last_block(&state->ticket[0])) return;
-    select_pick(hist, pass, 0.5f, 0, 0.f, state, true, phase + 1);
+    select_pick(hist, pass, 0.5f, 0, 0.f, state, true, want == 2 ? 3 : phase + 1);
+}
+
+// scaleEstimator "std": scale = sqrt(Matches::getStandardDeviation()) = sqrt(sqrt(sum (d - mean)^2 / (size - 1))) over ALL
+// entries of the distance matrix (Matches.cpp:124-129).  Two reductions: phase 0 the mean, phase 1 the squared deviations
+// (terms in float like Eigen's array expression, sums in fp64, block partials added in block order by the last block).
+__global__ void __launch_bounds__(HIST_BLOCK) robust_std_kernel(const float* __restrict__ dists, size_t total, int phase, IcpState* state, int gated,
+                                                                double* __restrict__ partials) {
+    __shared__ double s_warp[HIST_BLOCK / 32];
+    if (gated && state->iterate == 0) return;
+    if (state->robust_recompute != 3) return;
+    const float mean = state->robust_median;  // phase 1: the mean of phase 0
+    double acc = 0.0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const float d = __ldg(dists + i);
+        if (phase == 0) acc += (double)d;
+        else { const float t = __fsub_rn(d, mean); acc += (double)__fmul_rn(t, t); }
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v = 0.0;
+        for (int w = 0; w < HIST_BLOCK / 32; ++w) v += s_warp[w];
+        partials[blockIdx.x] = v;
+    }
+    if (!select_last_block(&state->ticket[0])) return;
+    if (threadIdx.x != 0) return;
+    double sum = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) sum += __ldcg(partials + b);
+    if (phase == 0) state->robust_median = (float)(sum / (double)total);
+    else state->robust_scale = sqrtf(sqrtf((float)(sum / (double)(total - 1))));
 }
 
 // sharded reading: the scan runs after the histograms have been all-reduced
@@ -324,9 +357,9 @@ int make_select_spec(pmgpu_ctx* ctx, int nfilters, const int* types, const float
                 ctx->set_error("Invalid robust function name.");
                 return PMGPU_ERR_BAD_ARG;
             }
-            if (est != PMGPU_SCALE_NONE && est != PMGPU_SCALE_MAD) {
-                ctx->set_error("RobustOutlierFilter on GPU: scaleEstimator must be 'none' or 'mad'");
-                return PMGPU_ERR_UNSUPPORTED;
+            if (est > PMGPU_SCALE_STD) {
+                ctx->set_error("Invalid scale estimator name.");
+                return PMGPU_ERR_BAD_ARG;
             }
         } else if (types[f] == PMGPU_FILTER_VARTRIMMEDDIST) {
             // lambda: any value, like the reference's parameter table (OutlierFiltersImpl.h:158)
@@ -336,6 +369,7 @@ int make_select_spec(pmgpu_ctx* ctx, int nfilters, const int* types, const float
         }
     }
     spec->sn_active = (ctx->has_normals && ctx->has_reading_normals) ? 1 : 0;
+    spec->robust_approx2 = ctx->robust_approx2;
     int nsn = 0;
     for (int f = 0; f < nfilters; ++f) nsn += spec->kind(f) == PMGPU_FILTER_SURFACENORMAL ? 1 : 0;
     if (nsn > 1) {
@@ -402,15 +436,25 @@ int launch_weights(pmgpu_ctx* ctx, const SelectSpec& spec, bool gated, bool cap_
         }
     }
     const int r = spec.robust_index();
-    if (r >= 0 && ((spec.type[r] >> 16) & 0xf) == PMGPU_SCALE_MAD) {
+    const int est = r >= 0 ? ((spec.type[r] >> 16) & 0xf) : PMGPU_SCALE_NONE;
+    if (est == PMGPU_SCALE_MAD || est == PMGPU_SCALE_BERG) {
         const size_t total = (size_t)ctx->k * ctx->nq;
         const size_t want = (total + HIST_BLOCK * 4 - 1) / (HIST_BLOCK * 4);
         const int grid = grid_for((int)(want > 0x1fffff ? 0x1fffff : want) * HIST_BLOCK, HIST_BLOCK, ctx->num_sms, 1);
-        for (int phase = 0; phase < 2; ++phase)
+        // mad: median, then median of the absolute deviations; berg: the median alone (used at the filter's first iteration)
+        for (int phase = 0; phase < (est == PMGPU_SCALE_MAD ? 2 : 1); ++phase)
             for (int pass = 0; pass < 3; ++pass) {
-                robust_hist_kernel<<<grid, HIST_BLOCK, 0, st>>>(ctx->dists.p, total, pass, phase, ctx->state, g, ctx->hist.p + (size_t)PM_MAX_FILTERS * PM_HIST_BINS);
+                robust_hist_kernel<<<grid, HIST_BLOCK, 0, st>>>(ctx->dists.p, total, pass, phase, ctx->state, g, ctx->hist.p + (size_t)PM_MAX_FILTERS * PM_HIST_BINS,
+                                                                est == PMGPU_SCALE_MAD ? 1 : 2);
                 ctx->launches += 1;
             }
+    } else if (est == PMGPU_SCALE_STD) {
+        const size_t total = (size_t)ctx->k * ctx->nq;
+        PM_CUDA_TRY(ctx, ctx->partials.reserve((size_t)(ctx->num_sms * 4 + 2) * 42));
+        for (int phase = 0; phase < 2; ++phase) {
+            robust_std_kernel<<<ctx->num_sms, HIST_BLOCK, 0, st>>>(ctx->dists.p, total, phase, ctx->state, g, ctx->partials.p);
+            ctx->launches += 1;
+        }
     }
     const int v = spec.var_index();
     if (v >= 0) {

@@ -36,10 +36,29 @@ __device__ __forceinline__ void select_init_limits(IcpState* st, const SelectSpe
     st->robust_on = r >= 0 ? 1 : 0;
     if (r >= 0) {
         const int word = sp.type[r], nb = (word >> 20) & 0xff, est = (word >> 16) & 0xf;
-        st->robust_fct = (word >> 8) & 0xff;
+        const int fct = (word >> 8) & 0xff;
+        st->robust_fct = fct;
         st->robust_k = sp.param[r];
-        st->robust_recompute = (est == PMGPU_SCALE_MAD && (st->robust_iteration <= nb || nb == 0)) ? 1 : 0;
-        if (est == PMGPU_SCALE_NONE) st->robust_scale = 1.f;
+        st->robust_approx2 = sp.robust_approx2;
+        const bool re = st->robust_iteration <= nb || nb == 0;  // nbIterationForScale
+        st->robust_recompute = 0;
+        if (est == PMGPU_SCALE_MAD) {
+            st->robust_recompute = re ? 1 : 0;
+        } else if (est == PMGPU_SCALE_BERG) {
+            // OutlierFiltersImpl.cpp:420-432: the tuning given is the target scale, the tuning constant is Bergstrom's
+            st->robust_target = sp.param[r];
+            if (fct == PMGPU_ROBUST_CAUCHY) st->robust_k = 4.3040f;
+            else if (fct == PMGPU_ROBUST_TUKEY) st->robust_k = 7.0589f;
+            else if (fct == PMGPU_ROBUST_HUBER) st->robust_k = 2.0138f;
+            if (re) {
+                if (st->robust_iteration == 1) st->robust_recompute = 2;  // 1.9 sqrt(median): one select, then select_pick
+                else st->robust_scale = __fadd_rn(__fmul_rn(0.85f, __fsub_rn(st->robust_scale, st->robust_target)), st->robust_target);
+            }
+        } else if (est == PMGPU_SCALE_STD) {
+            st->robust_recompute = re ? 3 : 0;
+        } else {
+            st->robust_scale = 1.f;
+        }
         st->robust_iteration += 1;
     }
 }
@@ -63,6 +82,7 @@ __device__ __forceinline__ float pm_robust_weight(const S* st, float d) {
         case PMGPU_ROBUST_L1: w = __fdiv_rn(1.f, sqrtf(e2)); break;
         default: { const float dd = 3.f; w = powf(1.f + e2 / k, -(k + dd) / 2.f) * (k + dd) * (1.f / (k + e2)); break; }  // Student
     }
+    if (e2 >= st->robust_approx2 && st->robust_approx2 != pm_inf()) return 0.f;  // `approximation`, OutlierFiltersImpl.cpp:591-595
     return w <= 1e-50f ? 0.f : w;  // `w <= 1e-50 -> 1e-50` stored in a float array
 }
 // SurfaceNormalOutlierFilter (OutlierFiltersImpl.cpp:248-265): rn = the reading normal as stored, turned by the
@@ -91,7 +111,7 @@ __device__ __forceinline__ float pm_sn_weight(const Mat4& T, f4 rn, f4 qn, float
 struct PairW {
     float limit_all;
     int has_filters, robust_on, robust_fct;
-    float robust_k, robust_scale;
+    float robust_k, robust_scale, robust_approx2;
     int sn_on;
     float sn_eps;
 };
@@ -102,6 +122,7 @@ __device__ __forceinline__ void load_pairw(const IcpState* st, PairW* w) {
     w->robust_fct = __ldcg(&st->robust_fct);
     w->robust_k = __ldcg(&st->robust_k);
     w->robust_scale = __ldcg(&st->robust_scale);
+    w->robust_approx2 = __ldcg(&st->robust_approx2);
     w->sn_on = __ldcg(&st->sn_on);
     w->sn_eps = __ldcg(&st->sn_eps);
 }
@@ -173,7 +194,8 @@ __device__ __forceinline__ bool select_last_block(unsigned* ticket) {
 // element); pass 2 finishes filter f: limit[f] = value (* factor for MedianDist), limit_all = min.
 // `clear`: zero the histogram afterwards.
 // target: 0 = quantile filter f; 1 = the median of a robust filter's MAD estimate, 2 = its median of
-// absolute deviations (both at position size / 2, Matches.cpp:107-120).
+// absolute deviations (both at position size / 2, Matches.cpp:107-120); 3 = the median of the berg estimator's first
+// iteration (getDistsQuantile(0.5)).
 __device__ __forceinline__ void select_pick(unsigned* hist, int pass, float quantile, int f, float factor, IcpState* state, bool clear,
                                             int target = 0) {
     __shared__ unsigned long long warp_tot[32];
@@ -215,7 +237,7 @@ __device__ __forceinline__ void select_pick(unsigned* hist, int pass, float quan
                 s_rank = 0;
             } else {
                 unsigned long long r;
-                if (target != 0) r = total / 2;
+                if (target == 1 || target == 2) r = total / 2;  // Matches.cpp:107-120; target 3 (berg) is getDistsQuantile(0.5)
                 else if (quantile == 1.0f) r = total - 1;
                 else {
                     r = (unsigned long long)(__ull2float_rn(total) * quantile);
@@ -241,6 +263,7 @@ __device__ __forceinline__ void select_pick(unsigned* hist, int pass, float quan
                     else {
                         const float value = __uint_as_float((state->robust_prefix << 10) | found);
                         if (target == 1) state->robust_median = value;
+                        else if (target == 3) state->robust_scale = (float)(1.9 * (double)sqrtf(value));  // berg, OutlierFiltersImpl.cpp:529
                         else state->robust_scale = sqrtf(value);  // scale = sqrt(MAD), OutlierFiltersImpl.cpp:512
                     }
                 } else if (pass == 0) {

@@ -808,17 +808,22 @@ struct RobustOutlierFilter : public GpuDistOutlierFilter {
         const auto f = fcts.find(get("robustFct", "cauchy"));
         if (f == fcts.end()) throw InvalidParameter("Invalid robust function name.");
         const std::string est = get("scaleEstimator", "mad");
-        if (est != "mad" && est != "none") throw ConfigurationError("RobustOutlierFilter: GPU module: scaleEstimator must be 'mad' or 'none'");
-        if (get("distanceType", "point2point") != "point2point") throw ConfigurationError("RobustOutlierFilter: GPU module: distanceType must be 'point2point'");
-        const std::string approx = get("approximation", "inf");
-        if (approx != "inf") throw ConfigurationError("RobustOutlierFilter: GPU module: approximation must be inf");
-        return PMGPU_ROBUST_WORD(f->second, est == "mad" ? PMGPU_SCALE_MAD : PMGPU_SCALE_NONE, std::stoi(get("nbIterationForScale", "0")));
+        static const std::map<std::string, int> ests = {{"none", PMGPU_SCALE_NONE}, {"mad", PMGPU_SCALE_MAD}, {"berg", PMGPU_SCALE_BERG}, {"std", PMGPU_SCALE_STD}};
+        const auto e = ests.find(est);
+        if (e == ests.end()) throw InvalidParameter("Invalid scale estimator name.");
+        const std::string dt = get("distanceType", "point2point");
+        if (dt != "point2point" && dt != "point2plane") throw InvalidParameter("Invalid distance type name.");
+        if (dt != "point2point") throw ConfigurationError("RobustOutlierFilter: GPU module: distanceType must be 'point2point'");
+        return PMGPU_ROBUST_WORD(f->second, e->second, std::stoi(get("nbIterationForScale", "0")));
     }
+    T approximation;
+    void prepare(GpuPipeline& g) const override { g.check(pmgpu_set_robust_approximation(g.ctx, (float)approximation)); }
     RobustOutlierFilter(const Parameters& params = Parameters())
         : GpuDistOutlierFilter("RobustOutlierFilter", availableParameters(), params, word(params), "tuning") {
         // every declared parameter is read (Registrar.h:103-110)
         Parametrizable::get<std::string>("robustFct"); Parametrizable::get<std::string>("scaleEstimator"); Parametrizable::get<int>("nbIterationForScale");
-        Parametrizable::get<std::string>("distanceType"); Parametrizable::get<T>("approximation");
+        Parametrizable::get<std::string>("distanceType");
+        approximation = Parametrizable::get<T>("approximation");
     }
 };
 

@@ -425,10 +425,12 @@ class SurfaceNormalOutlierFilter(_DistFilter):
 
 class RobustOutlierFilter(_DistFilter):
     """OutlierFiltersImpl.h:199-262, OutlierFiltersImpl.cpp:420-598: M-estimator weights (cauchy, welsch, sc, gm, tukey,
-    huber, L1, student) of e^2 = dist / scale^2, scale = sqrt(MAD) or 1 — evaluated on the device."""
+    huber, L1, student) of e^2 = dist / scale^2, scale = sqrt(MAD), Bergstrom's decreasing estimator, sqrt(std) or 1, with the
+    `approximation` cut — evaluated on the device."""
     className = "RobustOutlierFilter"
     TYPE, PARAM = capi.FILTER_ROBUST, "tuning"
     FCTS = dict(cauchy=0, welsch=1, sc=2, gm=3, tukey=4, huber=5, L1=6, student=7)
+    ESTIMATORS = dict(none=0, mad=1, berg=2, std=3)
     PARAMS = (
         ("robustFct", "Type of robust function used. Available fct: 'cauchy', 'welsch', 'sc'(aka Switchable-Constraint), 'gm' (aka Geman-McClure), "
                       "'tukey', 'huber' and 'L1'. (Default: cauchy)", "cauchy", None, None, str),
@@ -444,13 +446,17 @@ class RobustOutlierFilter(_DistFilter):
         fct, est = self.get("robustFct"), self.get("scaleEstimator")
         if fct not in self.FCTS:
             raise InvalidParameter("Invalid robust function name.")
-        if est not in ("mad", "none"):
-            raise ConfigurationError("RobustOutlierFilter: GPU module: scaleEstimator must be 'mad' or 'none'")
+        if est not in self.ESTIMATORS:
+            raise InvalidParameter("Invalid scale estimator name.")
+        if self.get("distanceType") not in ("point2point", "point2plane"):
+            raise InvalidParameter("Invalid distance type name.")
         if self.get("distanceType") != "point2point":
             raise ConfigurationError("RobustOutlierFilter: GPU module: distanceType must be 'point2point'")
-        if self.get("approximation") != float("inf"):
-            raise ConfigurationError("RobustOutlierFilter: GPU module: approximation must be inf")
-        self.word = capi.FILTER_ROBUST | (self.FCTS[fct] << 8) | ((1 if est == "mad" else 0) << 16) | (self.get("nbIterationForScale") << 20)
+        self.approximation = self.get("approximation")
+        self.word = capi.FILTER_ROBUST | (self.FCTS[fct] << 8) | (self.ESTIMATORS[est] << 16) | (self.get("nbIterationForScale") << 20)
+
+    def prepare(self, ctx):
+        _translate(ctx.set_robust_approximation, self.approximation)
 
     def spec(self):
         return (self.word, self.value)

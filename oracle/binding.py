@@ -18,7 +18,7 @@ _LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
 
 FILTER_MAXDIST, FILTER_MEDIANDIST, FILTER_TRIMMEDDIST, FILTER_ROBUST, FILTER_SURFACENORMAL, FILTER_VARTRIMMEDDIST = 0, 1, 2, 3, 4, 5
 ROBUST_FCTS = dict(cauchy=0, welsch=1, sc=2, gm=3, tukey=4, huber=5, L1=6, student=7)
-SCALE_NONE, SCALE_MAD = 0, 1
+SCALE_NONE, SCALE_MAD, SCALE_BERG, SCALE_STD = 0, 1, 2, 3
 
 
 def robust_word(fct="cauchy", scale=SCALE_MAD, nb_iteration_for_scale=0):
@@ -83,6 +83,8 @@ def lib():
         _lib.orc_rigid_transform.argtypes = [_fp, _fp, C.c_int, _fp]
         _lib.orc_rotate_normals.argtypes = [_fp, _fp, C.c_int, _fp]
         _lib.orc_dists_quantile.argtypes = [_fp, C.c_long, C.c_float, _fp]
+        _lib.orc_set_robust_approximation.argtypes = [C.c_float]
+        _lib.orc_set_robust_approximation.restype = None
         _lib.orc_set_var_trimmed_ratios.argtypes = [C.c_float, C.c_float]
         _lib.orc_set_var_trimmed_ratios.restype = None
         _lib.orc_var_trimmed_ratio.argtypes = [_fp, C.c_long, C.c_float, C.c_float, C.c_float, _fp]
@@ -169,6 +171,11 @@ def dists_quantile(dists, quantile):
     out = np.zeros(1, np.float32)
     _check(lib().orc_dists_quantile(_f(d), d.size, quantile, _f(out)))
     return out[0]
+
+
+def set_robust_approximation(approximation=float("inf")):
+    """`approximation` of the RobustOutlierFilters evaluated from now on (metres; inf: none)"""
+    lib().orc_set_robust_approximation(approximation)
 
 
 def set_var_trimmed_ratios(min_ratio=0.05, max_ratio=0.99):

@@ -598,16 +598,51 @@ struct RobustState {
     float scale = 0.f;
 };
 
-// RobustOutlierFilter::robustFiltering (OutlierFiltersImpl.cpp:503-598), distanceType point2point,
-// approximation = inf.  All array arithmetic in float, as Eigen's Array<T> evaluates it.
+// `approximation` of the RobustOutlierFilter under test, squared like the constructor squares it (OutlierFiltersImpl.cpp:400);
+// set through orc_set_robust_approximation (the filter-chain arrays carry one float per filter)
+static float g_robust_approx2 = std::numeric_limits<float>::infinity();
+
+// Matches::getStandardDeviation (Matches.cpp:124-129): sqrt(sum (d - mean)^2 / (size - 1)) over all entries.  Eigen sums a float
+// array packet-wise; the restatement sums in double and rounds once (the difference is the reference's own summation noise).
+static float standard_deviation(const float* dists, long total) {
+    double s = 0.0;
+    for (long i = 0; i < total; ++i) s += dists[i];
+    const float mean = (float)(s / (double)total);
+    double v = 0.0;
+    for (long i = 0; i < total; ++i) { const float t = dists[i] - mean; v += (double)(t * t); }
+    return std::sqrt((float)(v / (double)(total - 1)));
+}
+
+// RobustOutlierFilter::robustFiltering (OutlierFiltersImpl.cpp:503-598), distanceType point2point.
+// All array arithmetic in float, as Eigen's Array<T> evaluates it.
 int robust_weights(const float* dists, long total, int word, float tuning, RobustState& st, float* w_out, float* scale_out) {
     const int fct = (word >> 8) & 0xff, scale_est = (word >> 16) & 0xf, nb_iter = (word >> 20) & 0xff;
+    const bool re = st.iteration <= nb_iter || nb_iter == 0;
     if (scale_est == ORC_SCALE_MAD) {
-        if (st.iteration <= nb_iter || nb_iter == 0) {
+        if (re) {
             float mad;
             const int rc = median_abs_deviation(dists, total, &mad);
             if (rc) return rc;
             st.scale = std::sqrt(mad);
+        }
+    } else if (scale_est == ORC_SCALE_STD) {
+        if (re) st.scale = std::sqrt(standard_deviation(dists, total));
+    } else if (scale_est == ORC_SCALE_BERG) {
+        // constructor (OutlierFiltersImpl.cpp:420-432): the tuning given is the target scale, the tuning constant Bergstrom's
+        const float target = tuning;
+        if (fct == ORC_ROBUST_CAUCHY) tuning = 4.3040f;
+        else if (fct == ORC_ROBUST_TUKEY) tuning = 7.0589f;
+        else if (fct == ORC_ROBUST_HUBER) tuning = 2.0138f;
+        if (re) {
+            if (st.iteration == 1) {
+                float median;
+                const int rc = dists_quantile(dists, total, 0.5f, &median);
+                if (rc) return rc;
+                st.scale = (float)(1.9 * (double)std::sqrt(median));
+            } else {
+                const float rate = 0.85f;
+                st.scale = rate * (st.scale - target) + target;
+            }
         }
     } else if (scale_est == ORC_SCALE_NONE) {
         st.scale = 1.f;
@@ -634,6 +669,7 @@ int robust_weights(const float* dists, long total, int word, float tuning, Robus
         // `w <= 1e-50` -> 1e-50, which is 0 once stored in a float array; an infinite distance gives weight 0
         // for every function but is dropped by ErrorElements anyway
         if (w <= 1e-50f) w = (float)1e-50;
+        if (g_robust_approx2 != std::numeric_limits<float>::infinity() && e2 >= g_robust_approx2) w = 0.f;  // OutlierFiltersImpl.cpp:591-595
         w_out[i] = w;
     }
     return ORC_OK;
@@ -1361,6 +1397,7 @@ int orc_outlier_weights_sn(const float* dists, const int32_t* ids, int knn, int 
 }
 
 int orc_dists_quantile(const float* dists, long n, float quantile, float* out) { return dists_quantile(dists, n, quantile, out); }
+void orc_set_robust_approximation(float approximation) { g_robust_approx2 = (float)((double)approximation * (double)approximation); }
 void orc_set_var_trimmed_ratios(float min_ratio, float max_ratio) { g_var_min_ratio = min_ratio; g_var_max_ratio = max_ratio; }
 int orc_var_trimmed_ratio(const float* dists, long n, float min_ratio, float max_ratio, float lambda, float* ratio_out) {
     return var_trimmed_ratio(dists, n, min_ratio, max_ratio, lambda, ratio_out);

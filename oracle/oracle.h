@@ -30,7 +30,7 @@ enum { ORC_FILTER_MAXDIST = 0, ORC_FILTER_MEDIANDIST = 1, ORC_FILTER_TRIMMEDDIST
  *   bits 20-27 nbIterationForScale;   filter_param = tuning.  distanceType point2point, approximation inf. */
 enum { ORC_ROBUST_CAUCHY = 0, ORC_ROBUST_WELSCH, ORC_ROBUST_SC, ORC_ROBUST_GM, ORC_ROBUST_TUKEY, ORC_ROBUST_HUBER, ORC_ROBUST_L1,
        ORC_ROBUST_STUDENT };
-enum { ORC_SCALE_NONE = 0, ORC_SCALE_MAD = 1 };
+enum { ORC_SCALE_NONE = 0, ORC_SCALE_MAD = 1, ORC_SCALE_BERG = 2, ORC_SCALE_STD = 3 };
 #define ORC_ROBUST_WORD(fct, scale, nb_iter) (ORC_FILTER_ROBUST | ((fct) << 8) | ((scale) << 16) | ((nb_iter) << 20))
 /* error minimizers */
 enum { ORC_MIN_P2POINT = 0, ORC_MIN_P2PLANE = 1, ORC_MIN_P2POINT_COV = 2, ORC_MIN_P2PLANE_COV = 3, ORC_MIN_P2POINT_SIM = 4 };
@@ -85,6 +85,8 @@ int orc_rigid_transform(const float* T16, const float* in, int n, float* out);
 int orc_rotate_normals(const float* T16, const float* in3, int n, float* out3);
 
 /* --- Matches::getDistsQuantile / outlier chain ----------------------------------------- */
+/* RobustOutlierFilter `approximation` (metres; +inf: none) of the filters evaluated from here on */
+void orc_set_robust_approximation(float approximation);
 int orc_dists_quantile(const float* dists, long n, float quantile, float* out);
 /* VarTrimmedDistOutlierFilter (OutlierFiltersImpl.cpp:152-218): minRatio / maxRatio of the filters evaluated from now on
  * (defaults 0.05 / 0.99), and optimizeInlierRatio on its own */

@@ -171,7 +171,9 @@ static int run_cpu() {
         auto* g = dynamic_cast<PM::GpuDistOutlierFilter*>(rob.get());
         CHECK(g && g->filterType == PMGPU_ROBUST_WORD(PMGPU_ROBUST_HUBER, PMGPU_SCALE_MAD, 3) && g->value == 1.5f);
         CHECK(throws<PM::InvalidParameter>([&] { pm.OutlierFilterRegistrar.create("RobustOutlierFilter", {{"robustFct", "nope"}}); }));
-        CHECK(throws<PM::ConfigurationError>([&] { pm.OutlierFilterRegistrar.create("RobustOutlierFilter", {{"scaleEstimator", "berg"}}); }));
+        CHECK(!throws<PM::ConfigurationError>([&] { pm.OutlierFilterRegistrar.create("RobustOutlierFilter", {{"scaleEstimator", "berg"}}); }));
+        CHECK(throws<PM::InvalidParameter>([&] { pm.OutlierFilterRegistrar.create("RobustOutlierFilter", {{"scaleEstimator", "bogus"}}); }));
+        CHECK(throws<PM::ConfigurationError>([&] { pm.OutlierFilterRegistrar.create("RobustOutlierFilter", {{"distanceType", "point2plane"}}); }));
         CHECK(pm.OutlierFilterRegistrar.create("SurfaceNormalOutlierFilter", {{"maxAngle", "0.42"}})->get<float>("maxAngle") == 0.42f);
         auto var = pm.MatcherRegistrar.create("KDTreeVarDistMatcher", {{"knn", "3"}, {"maxDistField", "radius"}});
         auto* vm = dynamic_cast<PM::KDTreeMatcher*>(var.get());

@@ -430,6 +430,50 @@ def test_robust_filter_scale_frozen_after_n_iterations(oracle, synth):
     assert_transform_close(res["T_iter"], res_o["T"], 1e-5, 1e-5)
 
 
+@pytest.mark.parametrize("est", ["berg", "std"])
+@pytest.mark.parametrize("fct", ["cauchy", "tukey", "welsch"])
+def test_robust_filter_berg_and_std_scale_estimators(oracle, synth, est, fct):
+    """scaleEstimator "berg" (1.9 sqrt(median) at the first call, then 0.85 (scale - target) + target, Bergstrom's tuning constants)
+    and "std" (sqrt of the standard deviation of all distances), OutlierFiltersImpl.cpp:420-432, 516-537; with `approximation`"""
+    from libpointmatcher_b200 import capi
+    rd, rf, _ = synth.scan_pair(40000)
+    scale = oracle.SCALE_BERG if est == "berg" else oracle.SCALE_STD
+    word, tuning = oracle.robust_word(fct, scale), 0.6
+    for approx in (float("inf"), 0.9):
+        oracle.set_robust_approximation(approx)
+        try:
+            with capi.Context(0) as ctx:   # a fresh context = a fresh filter object (iteration 1)
+                ctx.set_reference(rf)
+                ctx.set_reading(rd)
+                ids, dists, _ = ctx.knn(None, 2, 0.0, np.inf)
+                ctx.set_robust_approximation(approx)
+                wo, so = oracle.outlier_weights(dists, [(word, tuning)])
+                wg, sg = ctx.weights([(word, tuning)])
+        finally:
+            oracle.set_robust_approximation(float("inf"))
+        if est == "berg":
+            assert bits(sg)[0] == bits(so)[0], (fct, sg, so)   # an exact select and one rounding
+        else:
+            assert abs(sg[0] - so[0]) <= 2e-6 * abs(so[0])      # two fp64 sums against the restatement's
+        assert np.allclose(wg, wo, rtol=2e-5, atol=1e-30) and ((wg == 0) == (wo == 0)).mean() > 0.9999
+        if approx != float("inf"):
+            assert (wg == 0).any() and (wg != 0).any()
+
+
+def test_icp_with_berg_scale_matches_oracle(oracle, synth):
+    """the berg scale decays from iteration to iteration inside the fused loop exactly as in the oracle's filter object"""
+    from libpointmatcher_b200 import capi
+    rd, rf, _ = synth.scan_pair(40000)
+    word = oracle.robust_word("cauchy", oracle.SCALE_BERG, 0)
+    res_o = oracle.icp(rd, rf, knn=1, filters=[(word, 0.1)], minimizer=0, max_iterations=8, nthreads=8, acc_double=True)
+    with capi.Context(0) as ctx:
+        ctx.set_reference(rf)
+        ctx.set_reading(rd)
+        res = ctx.icp_run(capi.make_params(knn=1, filters=[(word, 0.1)], minimizer=0, max_iterations=8))
+    assert res["iterations"] == res_o["iterations"] == 8
+    assert_transform_close(res["T_iter"], res_o["T"], 1e-5, 1e-5)
+
+
 # ---------------------------------------------------------------------------------- force4DOF (8f row 3)
 def test_point_to_plane_force4dof_matches_oracle(gpu_ctx, oracle, synth):
     """PointToPlaneErrorMinimizer force4DOF (PointToPlane.cpp:203-214, 266-281): rotation about z + translation,
