@@ -113,4 +113,110 @@ __device__ __forceinline__ bool peer_allreduce(const PeerComm& pc, void* data, i
     return true;
 }
 
+// The in-kernel select of a sharded registration (select.cuh, minimize.cu): one exchange carries this rank's histogram slot
+// (PM_HIST_BINS words, summed over the ranks in rank order) AND the distances its window pass collected (concatenated in rank
+// order), so that a sharded iteration finds its order statistic in one pass like a single GPU does.  Message layout in a
+// mailbox slot: [0, 2048) histogram | [2048] number of collected distances (0xffffffff: more than fit) | [2052, ...) distances.
+// Same protocol and guarantees as peer_allreduce; called by every thread of the one picking block.  On return `hist` holds
+// the summed histogram, cand[0 .. *cand_count) all ranks' collected distances (*cand_count > cap: the list is incomplete).
+#define PM_SEL_MSG_CAND_OFFSET (PM_HIST_BINS + 4)
+#define PM_SEL_MSG_CAND_MAX (PM_MAILBOX_SLOT_WORDS - PM_SEL_MSG_CAND_OFFSET)
+__device__ __forceinline__ bool peer_select_exchange(const PeerComm& pc, unsigned* hist, unsigned* cand, unsigned* cand_count, unsigned cand_cap,
+                                                     IcpState* state) {
+    __shared__ int s_ok;
+    __shared__ unsigned s_epoch, s_total;
+    if (threadIdx.x == 0) {
+        s_epoch = pc.box[pc.rank]->seq + 1u;
+        pc.box[pc.rank]->seq = s_epoch;
+        s_ok = 1;
+    }
+    __syncthreads();
+    const unsigned epoch = s_epoch;
+    const int bank = (int)(epoch & 1u);
+    const unsigned n_mine = __ldcg(cand_count);
+    const bool fits = n_mine <= (unsigned)PM_SEL_MSG_CAND_MAX - 4u && n_mine <= cand_cap - 4u;
+    // lists travel in 16-byte units: the tail of the last unit is padded with 0xffffffff, which is not the bit pattern of a
+    // distance and is skipped by the pick
+    const unsigned n_pad = (n_mine + 3u) & ~3u;
+    if (fits && threadIdx.x < n_pad - n_mine) cand[n_mine + threadIdx.x] = 0xffffffffu;
+    __syncthreads();
+    // 1. my histogram, count and collected distances into slot[bank][rank] of every rank (16-byte stores, loads issued ahead)
+    const uint4* hist4 = reinterpret_cast<const uint4*>(hist);
+    const uint4* cand4 = reinterpret_cast<const uint4*>(cand);
+    const unsigned nq4 = fits ? n_pad >> 2 : 0u;
+    for (unsigned i0 = threadIdx.x; i0 < (unsigned)(PM_HIST_BINS / 4) + nq4; i0 += 4u * blockDim.x) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned i = i0 + (unsigned)u * blockDim.x;
+            if (i < (unsigned)(PM_HIST_BINS / 4)) v[u] = __ldcg(hist4 + i);
+            else if (i < (unsigned)(PM_HIST_BINS / 4) + nq4) v[u] = __ldcg(cand4 + (i - PM_HIST_BINS / 4));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned i = i0 + (unsigned)u * blockDim.x;
+            if (i >= (unsigned)(PM_HIST_BINS / 4) + nq4) continue;
+            const unsigned w = i < (unsigned)(PM_HIST_BINS / 4) ? 4u * i : (unsigned)PM_SEL_MSG_CAND_OFFSET + 4u * (i - PM_HIST_BINS / 4);
+            for (int r = 0; r < pc.nranks; ++r) *reinterpret_cast<uint4*>(&pc.box[r]->slot[bank][pc.rank][w]) = v[u];
+        }
+    }
+    if (threadIdx.x == 0)
+        for (int r = 0; r < pc.nranks; ++r) pc.box[r]->slot[bank][pc.rank][PM_HIST_BINS] = fits ? n_pad : 0xffffffffu;
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < pc.nranks) st_release_sys(&pc.box[threadIdx.x]->flag[bank][pc.rank], epoch);
+    if ((int)threadIdx.x < pc.nranks) {
+        const unsigned* f = &pc.box[pc.rank]->flag[bank][threadIdx.x];
+        const unsigned long long t0 = pm_globaltimer_ns();
+        unsigned spins = 0;
+        while ((int)(ld_acquire_sys(f) - epoch) < 0) {
+            if ((++spins & 0x3ffu) == 0 && pm_globaltimer_ns() - t0 > PM_COMM_TIMEOUT_NS) { s_ok = 0; break; }
+        }
+    }
+    __syncthreads();
+    if (!s_ok) {
+        if (threadIdx.x == 0) {
+            if (state->status == 0) state->status = PMGPU_ERR_COMM;
+            state->iterate = 0;
+        }
+        return false;
+    }
+    // 2. histogram summed in rank order; collected distances concatenated in rank order
+    const Mailbox* mine = pc.box[pc.rank];
+    for (int i = threadIdx.x; i < PM_HIST_BINS / 4; i += blockDim.x) {
+        uint4 acc = ld_volatile_u4(reinterpret_cast<const uint4*>(mine->slot[bank][0]) + i);
+        for (int r = 1; r < pc.nranks; ++r) {
+            const uint4 v = ld_volatile_u4(reinterpret_cast<const uint4*>(mine->slot[bank][r]) + i);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        reinterpret_cast<uint4*>(hist)[i] = acc;
+    }
+    unsigned base = 0;
+    bool complete = true;
+    for (int r = 0; r < pc.nranks; ++r) {
+        const unsigned n_r = *(volatile const unsigned*)&mine->slot[bank][r][PM_HIST_BINS];  // a multiple of 4
+        if (n_r == 0xffffffffu) { complete = false; break; }
+        if (base + n_r <= cand_cap) {
+            const uint4* src = reinterpret_cast<const uint4*>(&mine->slot[bank][r][PM_SEL_MSG_CAND_OFFSET]);
+            uint4* dst = reinterpret_cast<uint4*>(cand + base);
+            for (unsigned i0 = threadIdx.x; i0 < (n_r >> 2); i0 += 4u * blockDim.x) {
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i0 + (unsigned)u * blockDim.x < (n_r >> 2)) v[u] = ld_volatile_u4(src + i0 + (unsigned)u * blockDim.x);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i0 + (unsigned)u * blockDim.x < (n_r >> 2)) dst[i0 + (unsigned)u * blockDim.x] = v[u];
+            }
+        }
+        base += n_r;
+    }
+    if (threadIdx.x == 0) s_total = complete ? base : cand_cap + 1u;
+    __syncthreads();
+    if (threadIdx.x == 0) *cand_count = s_total;
+    __threadfence();
+    __syncthreads();
+    return true;
+}
+
 }  // namespace pm

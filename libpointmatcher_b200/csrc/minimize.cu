@@ -255,7 +255,9 @@ __global__ void __launch_bounds__(ACC_BLOCK, PM_FUSED_MIN_BLOCKS(MODE)) select_a
 #endif
     const size_t total = (size_t)nq * k;
     const int nquant = spec.n_quantile();
-    const int collect = pc.nranks <= 1 ? 1 : 0;  // the collected distances are not exchanged between ranks: two passes there
+    // sharded reading: the collected distances travel with the histogram when the chain has one quantile filter (one mailbox
+    // slot holds both); with several, the histograms alone are exchanged and the select takes its second pass
+    const int collect = (pc.nranks <= 1 || nquant == 1) ? 1 : 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         select_init_limits(state, spec);
         select_plans_begin(state, spec, collect);
@@ -285,7 +287,15 @@ __global__ void __launch_bounds__(ACC_BLOCK, PM_FUSED_MIN_BLOCKS(MODE)) select_a
         if (grid_bar_arrive(state, gen)) {
             bool ok = true;
             // sharded reading: this rank's histograms become the sums over all ranks (comm.cuh), right here
-            if (nquant > 0 && pc.nranks > 1 && !peer_allreduce<false>(pc, hist, nquant * PM_HIST_BINS, state)) ok = false;
+            if (nquant > 0 && pc.nranks > 1) {
+                if (nquant == 1) {
+                    int fq = 0;
+                    while (!spec.is_quantile(fq)) ++fq;
+                    ok = peer_select_exchange(pc, hist, cand + (size_t)fq * PM_SEL_CAND_CAP, &state->sel_cand_count[fq], PM_SEL_CAND_CAP, state);
+                } else {
+                    ok = peer_allreduce<false>(pc, hist, nquant * PM_HIST_BINS, state);
+                }
+            }
             if (ok) {
                 slot = 0;
                 for (int f = 0; f < spec.nfilters; ++f) {
