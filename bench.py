@@ -100,7 +100,7 @@ def config_dict(args, cfg, world, mode):
         "iterations": args.steps, "repetitions": args.reps,
         "ring_layout": ("%d rings" % args.rings) if args.rings else "isotropic angular sampling (256 rings x 3906 azimuth steps at 1M; see extra.ring_layout_64)",
         "multi_gpu": {"single": "one GPU", "pairs": "one independent scan pair per rank, no collective",
-                      "shard": "queries of ONE registration sharded over the ranks, reference replicated; select histograms and normal-equation sums "
+                      "shard": "queries of ONE registration dealt out to the ranks (round-robin columns), reference replicated; select histograms and normal-equation sums "
                                "exchanged inside the producing kernels over NVLink peer mailboxes; map normals per slice + ncclAllGather"}[mode],
         "l2": "flushed between timed iterations (256 MiB memset)",
         "world_size": world,
@@ -369,8 +369,7 @@ def measure(args, cfg, torch, capi, pm, pmdist, rank, world, local_rank, mode, r
     sharded = dist_on and mode == "shard"
     rd, rf, T_gt = clouds if clouds is not None else make_clouds(cfg, args, pair_seed=0 if (not dist_on or sharded) else rank)
     if sharded:
-        lo, hi = pmdist.shard_range(len(rd), rank, world)
-        rd_local = np.ascontiguousarray(rd[lo:hi])
+        rd_local = np.ascontiguousarray(rd[pmdist.shard_columns(len(rd), rank, world)])
     else:
         rd_local = rd
     rd_pin, _k1 = pinned_copy(rd)          # e2e hands pm.ICP the WHOLE reading; the sharded ICP takes its slice

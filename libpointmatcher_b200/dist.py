@@ -2,9 +2,11 @@
 
 Two ways the path shards:
   pairs  — independent registrations, pair j -> rank j mod G, no data-path collective
-  shard  — the queries of ONE registration split into contiguous column ranges, reference
-           replicated; the select histograms and the normal-equation sums are all-reduced inside
-           libpmgpu (comm.cu, NCCL), bootstrapped with an ncclUniqueId broadcast from rank 0.
+  shard  — the queries of ONE registration dealt out to the ranks in chunks of 4096 consecutive columns, round-robin (every
+           rank gets pieces of every part of the scan, so the ranks' kNN times are balanced — with one contiguous range per
+           rank, one rank's slice of a 2 M-point scan was 1.6 x more expensive than another's and the others waited for it
+           inside the exchange — and every piece keeps the scan's full local density), reference replicated; the select histograms and the
+           normal-equation sums are exchanged inside the kernels (comm.cuh), bootstrapped by init_comm below.
 """
 import torch
 import torch.distributed as dist
@@ -13,6 +15,21 @@ import torch.distributed as dist
 def shard_range(n, rank, world):
     """contiguous column range [lo, hi) of rank `rank`; ranges tile [0, n) exactly"""
     return (rank * n) // world, ((rank + 1) * n) // world
+
+
+SHARD_CHUNK = 4096
+
+
+def shard_columns(n, rank, world, chunk=SHARD_CHUNK):
+    """the columns of rank `rank`: chunks of `chunk` consecutive columns dealt out round-robin (chunk c -> rank c mod world), as an
+    index array; the ranks' arrays tile [0, n) exactly.  Consecutive columns of a scan are neighbours in space, so a rank's subset
+    keeps the full local density (the lanes of a warp stay as close together as on one GPU) while every rank gets pieces of
+    every part of the scan (balanced kNN times)."""
+    import numpy as np
+    if world <= 1:
+        return np.arange(n)
+    idx = np.arange(n)
+    return idx[(idx // chunk) % world == rank]
 
 
 def pair_assignment(n_pairs, rank, world):

@@ -1383,10 +1383,11 @@ class ICP:
         T_refMean_refIn[:d - 1, d - 1] = -T_refIn_refMean[:d - 1, d - 1]
         T_refMean_dataIn = mat4_mul(T_refMean_refIn, T_init)
         if self._shard is not None:
+            # chunks of columns dealt out round-robin (dist.shard_columns): balanced ranks, full local density
+            from . import dist as _pmdist
             rank, world = self._shard
-            n = reading.features.shape[0]
-            lo, hi = (rank * n) // world, ((rank + 1) * n) // world
-            reading = DataPoints(reading.features[lo:hi], {k: v[lo:hi] for k, v in reading.descriptors.items()})
+            mine = _pmdist.shard_columns(reading.features.shape[0], rank, world)
+            reading = DataPoints(np.ascontiguousarray(reading.features[mine]), {k: np.ascontiguousarray(v[mine]) for k, v in reading.descriptors.items()})
         _translate(self.ctx.set_reading, reading.features)
         self.ctx._reading_obj = None
         self._reading_filtered, self._T_refMean_dataIn = reading, T_refMean_dataIn

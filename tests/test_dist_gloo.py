@@ -60,6 +60,16 @@ def test_world_size_2_host_logic():
         assert dict(out) == {0: 1, 1: 1}
 
 
+def test_shard_columns_tile_exactly():
+    from libpointmatcher_b200 import dist as pd
+    for n in (0, 1, 7, 1000, 1000003):
+        for world in (1, 2, 3, 8):
+            cols = np.concatenate([np.arange(n)[pd.shard_columns(n, k, world)] for k in range(world)])
+            assert len(cols) == n and (np.sort(cols) == np.arange(n)).all()
+            sizes = [len(np.arange(n)[pd.shard_columns(n, k, world)]) for k in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+
+
 def test_shard_range_tiles_exactly():
     from libpointmatcher_b200 import dist as pd
     for n in (0, 1, 7, 1000, 1_000_003):
