@@ -67,7 +67,7 @@ def test_shard_columns_tile_exactly():
             cols = np.concatenate([np.arange(n)[pd.shard_columns(n, k, world)] for k in range(world)])
             assert len(cols) == n and (np.sort(cols) == np.arange(n)).all()
             sizes = [len(np.arange(n)[pd.shard_columns(n, k, world)]) for k in range(world)]
-            assert max(sizes) - min(sizes) <= 1
+            assert max(sizes) - min(sizes) <= pd.SHARD_CHUNK   # balanced to within one chunk
 
 
 def test_shard_range_tiles_exactly():
