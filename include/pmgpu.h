@@ -33,6 +33,7 @@
 #ifndef PMGPU_H
 #define PMGPU_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -301,6 +302,10 @@ int pmgpu_host_random_sampling(int n, float prob, int32_t* keep_out);
  *   and n when max_count > n - 1;
  * pmgpu_host_max_density (MaxDensity.cpp:60-105): densities[i * stride]; keep_out = kept columns. */
 int pmgpu_host_rand(void);
+/* Page-locks / releases a host buffer the caller keeps handing to pmgpu_*_set (cudaHostRegister): uploads from registered
+ * memory run at the link's full rate and asynchronously (the reference has no counterpart; Eigen owns its matrices). */
+int pmgpu_host_pin(void* ptr, size_t bytes);
+int pmgpu_host_unpin(void* ptr);
 int pmgpu_host_max_point_count(int n, uint64_t seed, uint64_t max_count, int32_t* order_out);
 int pmgpu_host_max_density(const float* densities, int stride, int n, float max_density, int32_t* keep_out);
 int pmgpu_host_sampling_surface_normal(float* features, int rows, int n, float* descriptors, int desc_rows, float ratio, int knn,

@@ -93,6 +93,8 @@ SIGNATURES = {
     "pmgpu_matches_get": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pmgpu_set_var_trimmed_ratios": (C.c_int, [C.c_void_p, C.c_float, C.c_float]),
     "pmgpu_set_robust_approximation": (C.c_int, [C.c_void_p, C.c_float]),
+    "pmgpu_host_pin": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "pmgpu_host_unpin": (C.c_int, [C.c_void_p]),
     "pmgpu_var_trimmed_ratio": (C.c_int, [C.c_void_p, C.c_void_p]),
     "pmgpu_host_srand": (None, [C.c_uint]),
     "pmgpu_host_random_sampling": (C.c_int, [C.c_int, C.c_float, C.c_void_p]),

@@ -888,6 +888,15 @@ int pmgpu_icp_result(pmgpu_ctx* ctx, float* T_iter_out, int* iterations_out, flo
     return device_status(ctx);
 }
 
+int pmgpu_host_pin(void* ptr, size_t bytes) {
+    if (!ptr || bytes == 0) return PMGPU_ERR_BAD_ARG;
+    return cudaHostRegister(ptr, bytes, cudaHostRegisterDefault) == cudaSuccess ? PMGPU_OK : (cudaGetLastError(), PMGPU_ERR_CUDA);
+}
+int pmgpu_host_unpin(void* ptr) {
+    if (!ptr) return PMGPU_ERR_BAD_ARG;
+    return cudaHostUnregister(ptr) == cudaSuccess ? PMGPU_OK : (cudaGetLastError(), PMGPU_ERR_CUDA);
+}
+
 int pmgpu_icp_cap_redos(const pmgpu_ctx* ctx) { return ctx ? ctx->state_host->redo_count : 0; }
 
 int pmgpu_icp_run(pmgpu_ctx* ctx, const pmgpu_icp_params* params, const float* T_iter_init, float* T_iter_out, int* iterations_out, float* cov_out,

@@ -202,10 +202,21 @@ protected:
         if (dim != T_refIn_dataIn.cols())
             throw std::runtime_error("The shape of initial transformation matrix must be NxN. Where N is the number of rows in the read/reference scans.");
 
-        DataPoints reading(readingIn);
-        this->readingDataPointsFilters.init();
-        this->readingDataPointsFilters.apply(reading);
-        readingFiltered = reading;
+        // inputs are never mutated (ICP.cpp:324-326): with reading filters they work on a copy; without, the caller's matrix is
+        // uploaded as it is (page-locked if the caller registered it, pmgpu_host_pin) and the copy the reference keeps as
+        // readingFiltered (ICP.h) is made on a second host thread while the device runs the loop
+        DataPoints filteredStorage;
+        if (!this->readingDataPointsFilters.empty()) {
+            filteredStorage = readingIn;
+            this->readingDataPointsFilters.init();
+            this->readingDataPointsFilters.apply(filteredStorage);
+        }
+        const DataPoints& reading = this->readingDataPointsFilters.empty() ? readingIn : filteredStorage;
+        struct KeepCopy {  // joins on every exit path, exceptions included
+            std::future<void> f;
+            ~KeepCopy() { if (f.valid()) f.get(); }
+        } keep;
+        keep.f = std::async(std::launch::async, [this, &reading] { readingFiltered = reading; });
         requireFloat3D(reading.features.rows(), "ICP");
         this->prefilteredReadingPtsCount = reading.features.cols();
 
@@ -278,6 +289,19 @@ protected:
                 throw ConfigurationError("ICP: GPU build: readingStepDataPointsFilters are not supported (the reading stays on the device)");
             this->transformationCheckers.init(T_iter, iterate);
             const bool wantHostData = !this->inspector->isNull();
+            // what Inspector::dumpIteration is shown (ICP.cpp:345-347, 381, 403-405): the reading as the iteration sees it and the
+            // reference in the frame of its mean — host copies, made only for an inspector that is not the NullInspector
+            DataPoints readingRefMean, referenceCentred;
+            if (wantHostData) {
+                readingRefMean = RigidTransformation::apply(reading, T_refMean_dataIn);
+                referenceCentred = reference;  // minus the mean, as ICP.cpp:291-299 subtracts it (a pure translation)
+                for (int j = 0; j < referenceCentred.features.cols(); ++j)
+                    for (int r = 0; r < dim - 1; ++r) referenceCentred.features(r, j) = referenceCentred.features(r, j) + T_refMean_refIn(r, dim - 1);
+                if (!referenceCentred.descriptorExists("normals")) {  // made on the device by a trailing SurfaceNormal filter
+                    Matrix normals(dim - 1, referenceCentred.features.cols());
+                    if (pmgpu_ref_get_normals(g.ctx, reinterpret_cast<float*>(normals.data())) == PMGPU_OK) referenceCentred.addDescriptor("normals", normals);
+                }
+            }
             while (iterate) {
                 // one iteration, stage by stage through the C ABI (ICP.cpp:371-430); host copies of
                 // matches / weights are only made when an inspector wants to see them
@@ -288,7 +312,9 @@ protected:
                                   wantHostData ? reinterpret_cast<float*>(matches.dists.data()) : nullptr, &visits));
                 gpuMatcher->visitCounter += visits;
                 g.check(pmgpu_weights(g.ctx, p.nfilters, p.filter_type, p.filter_param, wantHostData ? reinterpret_cast<float*>(weights.data()) : nullptr, nullptr));
-                if (wantHostData) this->inspector->dumpIteration(iterationCount, T_iter, reference, reading, matches, weights, this->transformationCheckers);
+                if (wantHostData)
+                    this->inspector->dumpIteration(iterationCount, T_iter, referenceCentred, RigidTransformation::apply(readingRefMean, T_iter), matches, weights,
+                                                   this->transformationCheckers);
                 TransformationParameters dT(dim, dim);
                 g.check(pmgpu_minimize(g.ctx, p.minimizer, p.sensor_std_dev, reinterpret_cast<float*>(dT.data()), cov, stats));
                 gpuMinimizer->setResults(cov, stats);

@@ -22,6 +22,7 @@
 #include <cstring>
 #include <fstream>
 #include <functional>
+#include <future>
 #include <iostream>
 
 #include "../../include/pmgpu.h"

@@ -334,6 +334,31 @@ static int run_icp(int argc, char** argv) {
         reference.addDescriptor("normals", normals);
     }
     PM::ICP icp;
+    // PM_TEST_INSPECTOR: an inspector that is not the NullInspector sees every iteration (ICP.cpp:403-405) — matches, weights and
+    // the clouds of that iteration materialised on the host for it, and only for it
+    struct Recorder : public PM::Inspector {
+        int calls = 0, bad = 0;
+        size_t lastIteration = 0;
+        double kept = 0;
+        void dumpIteration(const size_t it, const PM::TransformationParameters&, const DP& ref, const DP& rd, const PM::Matches& m, const PM::OutlierWeights& w,
+                           const PM::TransformationCheckers&) override {
+            ++calls;
+            lastIteration = it;
+            kept = 0;
+            // the match distances are the squared distances between the clouds the inspector is shown, bit for bit
+            for (int j = 0; j < m.ids.cols(); j += 97) {
+                const int id = m.ids(0, j);
+                if (id < 0) continue;
+                const float dx = rd.features(0, j) - ref.features(0, id), dy = rd.features(1, j) - ref.features(1, id), dz = rd.features(2, j) - ref.features(2, id);
+                volatile float a = dx * dx, b = dy * dy, c = dz * dz;
+                volatile float ab = a + b;
+                const float d2 = ab + c;
+                if (d2 != m.dists(0, j)) ++bad;
+            }
+            for (int j = 0; j < w.cols(); ++j) kept += w(0, j);
+        }
+    };
+    auto recorder = std::make_shared<Recorder>();
     if (std::string(argv[2]) == "default") {
         icp.setDefault();
     } else {
@@ -359,7 +384,10 @@ static int run_icp(int argc, char** argv) {
             std::printf("cov 0 0 0 0 0 0\n");
             return 0;
         }
+        if (std::getenv("PM_TEST_INSPECTOR")) icp.inspector = recorder;
         const PM::TransformationParameters Tm = icp(reading, reference);
+        if (std::getenv("PM_TEST_INSPECTOR"))
+            std::printf("inspector calls %d last %zu mismatches %d kept %.9g\n", recorder->calls, recorder->lastIteration, recorder->bad, recorder->kept);
         std::printf("iterations %zu fused %d maxreached %d overlap %.9g\n", icp.getIterationCount(), icp.usedFusedLoop() ? 1 : 0,
                     icp.getMaxNumIterationsReached() ? 1 : 0, (double)icp.errorMinimizer->getWeightedPointUsedRatio());
         for (int i = 0; i < 4; ++i) std::printf("%.9g %.9g %.9g %.9g\n", Tm(i, 0), Tm(i, 1), Tm(i, 2), Tm(i, 3));

@@ -70,7 +70,7 @@ BOUND = """  - BoundTransformationChecker:
 """
 
 
-def _run_icp(host_bin, tmp_path, config, rd, rf, nrm, sequence=False, elements=False):
+def _run_icp(host_bin, tmp_path, config, rd, rf, nrm, sequence=False, elements=False, inspector=False):
     cfg = tmp_path / "cfg.yaml"
     cfg.write_text(config)
     rd.astype(np.float32).tofile(tmp_path / "rd.f32")
@@ -80,16 +80,40 @@ def _run_icp(host_bin, tmp_path, config, rd, rf, nrm, sequence=False, elements=F
         np.ascontiguousarray(nrm, np.float32).tofile(tmp_path / "nrm.f32")
         args.append(str(tmp_path / "nrm.f32"))
     env = dict(os.environ, PM_TEST_SEQUENCE="1") if sequence else (dict(os.environ, PM_TEST_ELEMENTS="1") if elements else None)
+    if inspector:
+        env = dict(os.environ, PM_TEST_INSPECTOR="1")
     r = subprocess.run(args, capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     lines = r.stdout.strip().split("\n")
+    seen = None
+    if inspector:
+        tok = lines.pop(0).split()
+        seen = dict(calls=int(tok[2]), last=int(tok[4]), mismatches=int(tok[6]), kept=float(tok[8]))
     head = lines[0].split()
     T = np.array([[float(x) for x in l.split()] for l in lines[1:5]], np.float32)
-    out = dict(iterations=int(head[1]), fused=int(head[3]), maxreached=int(head[5]), T=T)
+    out = dict(iterations=int(head[1]), fused=int(head[3]), maxreached=int(head[5]), T=T, inspector=seen)
     if elements:
         tok = lines[6].split()
         out.update({tok[i]: float(tok[i + 1]) for i in range(0, len(tok), 2)})
     return out
+
+
+@pytest.mark.gpu
+def test_cpp_inspector_sees_every_iteration(host_bin, tmp_path, oracle, synth):
+    """Inspector::dumpIteration (ICP.cpp:403-405): a non-Null inspector switches the loop to one stage at a time and is shown, every
+    iteration, the reading as that iteration sees it, the centred reference, the exact matches and the outlier weights — host copies
+    made for it alone; the registration itself is the fused loop's (same transform, same iteration count)"""
+    rd, rf, _ = synth.scan_pair(40000)
+    nrm = oracle.surface_normals(rf, knn=10, nthreads=8)["normals"]
+    cfg = CONFIG.format(minimizer="PointToPlaneErrorMinimizer", iters=9, differential="")
+    plain = _run_icp(host_bin, tmp_path, cfg, rd, rf, nrm)
+    seen = _run_icp(host_bin, tmp_path, cfg, rd, rf, nrm, inspector=True)
+    assert plain["fused"] == 1 and seen["fused"] == 0
+    ins = seen["inspector"]
+    assert ins["calls"] == 9 == seen["iterations"] == plain["iterations"] and ins["last"] == 8
+    assert ins["mismatches"] == 0                              # dists == |stepReading - reference[id]|^2 on what it was shown
+    assert abs(ins["kept"] / len(rd) - 0.75) < 0.01            # TrimmedDist 0.75 weights
+    assert_transform_close(seen["T"], plain["T"], 1e-5, 1e-5)
 
 
 @pytest.mark.gpu
