@@ -80,13 +80,16 @@ enum pmgpu_filter_type {
  * tuning constant of Bergstrom for cauchy / tukey / huber) one select at the first iteration; "std" =
  * sqrt(Matches::getStandardDeviation()) (Matches.cpp:124-129) two fp64 reductions; "none" = 1.
  * `approximation` (weight 0 where e^2 >= approximation^2) through pmgpu_set_robust_approximation.  distanceType
- * point2point only.  At most one robust filter per chain, not with a sharded reading.  limits_out[f] of pmgpu_weights
- * returns the scale. */
+ * point2plane = PMGPU_ROBUST_P2PLANE or-ed into the word: the weight function then sees dot(n / |n|, p - q)^2 instead of the
+ * match distance (computePointToPlaneDistance, OutlierFiltersImpl.cpp:468-500; needs the reference normals, 3-D clouds; the
+ * scale estimators keep reading the match distances).  At most one robust filter per chain, not with a sharded reading.
+ * limits_out[f] of pmgpu_weights returns the scale. */
 enum {
     PMGPU_ROBUST_CAUCHY = 0, PMGPU_ROBUST_WELSCH, PMGPU_ROBUST_SC, PMGPU_ROBUST_GM, PMGPU_ROBUST_TUKEY, PMGPU_ROBUST_HUBER, PMGPU_ROBUST_L1,
     PMGPU_ROBUST_STUDENT
 };
 enum { PMGPU_SCALE_NONE = 0, PMGPU_SCALE_MAD = 1, PMGPU_SCALE_BERG = 2, PMGPU_SCALE_STD = 3 };
+#define PMGPU_ROBUST_P2PLANE (1 << 28)
 #define PMGPU_ROBUST_WORD(fct, scale, nb_iter) (PMGPU_FILTER_ROBUST | ((fct) << 8) | ((scale) << 16) | ((nb_iter) << 20))
 
 

@@ -357,6 +357,7 @@ int pmgpu_ctx_create(int device, pmgpu_ctx** ctx_out) {
     ctx->fused_select = getenv("PMGPU_NO_FUSED_SELECT") == nullptr;
     ctx->overlap_enabled = getenv("PMGPU_NO_OVERLAP") == nullptr;
     if (const char* c = getenv("PMGPU_COOP")) ctx->fused_cooperative = atoi(c) != 0;
+    ctx->pdl = getenv("PMGPU_NO_PDL") == nullptr;
     if (const char* c = getenv("PMGPU_DEFER_FINALIZE")) ctx->defer_finalize = atoi(c) != 0;
     ctx->seeded_without_planes = getenv("PMGPU_SEED_PLANES") == nullptr;
     if (const char* m = getenv("PMGPU_CAP_MARGIN")) ctx->cap_margin = (float)atof(m);

@@ -56,6 +56,8 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
                                                         const float* __restrict__ var_r2, NormalsSink ns, int pos_offset) {
     extern __shared__ float s_plane[];  // [depth + 1][KNN_BLOCK]: cached plane distances, one column per lane
     __shared__ Mat4 sT;
+    pdl_wait();     // (dependent of the previous iteration's last kernel)
+    pdl_release();  // stage 2 may be set up from here on; it waits for this grid's completion itself
     if (gated && state->iterate == 0) return;
 #ifdef PM_TOP_SMEM
     // (A/B build) the split planes of the top PM_TOP_SMEM levels staged in shared memory by one bulk copy (TMA, 1-D): the
@@ -308,6 +310,7 @@ __global__ void __launch_bounds__(128) knn_overflow_kernel(TreeView tree, const 
                                                            const float* __restrict__ var_r2, NormalsSink ns, int pos_offset) {
     __shared__ uint32_t s_stack[4][OVF_STACK];
     __shared__ Mat4 sT;
+    pdl_wait();  // dependent of stage 1
     if (gated && state->iterate == 0) return;
     if (blockIdx.x == 0 && threadIdx.x == 0) *next_count = 0;  // the counter the NEXT launch of stage 1 will use
     if (use_T) {
@@ -513,18 +516,18 @@ int launch_one(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, 
     unsigned* cnt_next = &ctx->state->overflow_count[ctx->knn_parity ^ 1];
     ctx->knn_parity ^= 1;
     if (planes)
-        knn_kernel<KMAX, true, NORMALS><<<grid, KNN_BLOCK, smem, ctx->stream>>>(tree, queries, nq, ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k,
-                                                                               max_r2, ctx->ref_orig.p, use_seed ? 1 : 0, ids, dists, &ctx->state->visits,
-                                                                               budget, ctx->overflow.p, cnt, use_cap ? 1 : 0, var_r2, ns, pos_offset);
+        PM_CUDA_TRY(ctx, launch_dependent(ctx->pdl && gated, knn_kernel<KMAX, true, NORMALS>, dim3(grid), dim3(KNN_BLOCK), smem, ctx->stream, tree, queries, nq,
+                                          ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k, max_r2, ctx->ref_orig.p, use_seed ? 1 : 0, ids, dists,
+                                          &ctx->state->visits, budget, ctx->overflow.p, cnt, use_cap ? 1 : 0, var_r2, ns, pos_offset));
     else if constexpr (!NORMALS)
-        knn_kernel<KMAX, false, false><<<grid, KNN_BLOCK, 0, ctx->stream>>>(tree, queries, nq, ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k,
-                                                                           max_r2, ctx->ref_orig.p, use_seed ? 1 : 0, ids, dists, &ctx->state->visits,
-                                                                           budget, ctx->overflow.p, cnt, use_cap ? 1 : 0, var_r2, ns, pos_offset);
+        PM_CUDA_TRY(ctx, launch_dependent(ctx->pdl && gated, knn_kernel<KMAX, false, false>, dim3(grid), dim3(KNN_BLOCK), 0, ctx->stream, tree, queries, nq,
+                                          ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k, max_r2, ctx->ref_orig.p, use_seed ? 1 : 0, ids, dists,
+                                          &ctx->state->visits, budget, ctx->overflow.p, cnt, use_cap ? 1 : 0, var_r2, ns, pos_offset));
     if (ctx->time_stage2) { ctx->stage_end(); ctx->stage_begin(3); }
     const int grid2 = min(ctx->num_sms * 10, (nq + 3) / 4);  // 48 registers: ten 128-thread blocks are resident per SM
-    knn_overflow_kernel<KMAX, NORMALS><<<grid2, 128, 0, ctx->stream>>>(tree, queries, ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k, max_r2,
-                                                                    ctx->overflow.p, cnt, cnt_next, ids, dists, &ctx->state->visits, use_cap ? 1 : 0, var_r2,
-                                                                    ns, pos_offset);
+    PM_CUDA_TRY(ctx, launch_dependent(ctx->pdl && !ctx->time_stage2, knn_overflow_kernel<KMAX, NORMALS>, dim3(grid2), dim3(128), 0, ctx->stream, tree, queries,
+                                      ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k, max_r2, ctx->overflow.p, cnt, cnt_next, ids, dists,
+                                      &ctx->state->visits, use_cap ? 1 : 0, var_r2, ns, pos_offset));
     ctx->launches += 2;
     PM_CUDA_TRY(ctx, cudaGetLastError());
     return PMGPU_OK;

@@ -83,13 +83,15 @@ __device__ __forceinline__ void accumulate_pairs(double* acc, const Mat4& sT, co
         e.w = pm_pair_weight(wst, d);
         if (e.w != 0.f) {
             e.q = __ldg(ref + id);
-            if (MODE == 1 || wst->sn_on) e.n = __ldg(normals + id);  // SurfaceNormalOutlierFilter: the reference's descriptor whenever it exists
+            // SurfaceNormalOutlierFilter / Robust point2plane: the reference's descriptor whenever it exists
+            if (MODE == 1 || wst->sn_on || (wst->robust_on && wst->robust_p2plane)) e.n = __ldg(normals + id);
         }
     };
     auto pair_end = [&](const Pend& e, const f4& p, const int i, bool& match_exist) {
         if (!e.live) return;
         float w = e.w;
         if (w != 0.f && wst->sn_on) w = __fmul_rn(w, pm_sn_weight(sT, reading_normals[i], e.n, wst->sn_eps));
+        if (w != 0.f && wst->robust_on && wst->robust_p2plane) w = __fmul_rn(w, pm_robust_p2plane_weight(wst, p, e.q, e.n));
         if (w == 0.f) { ++rej_matches; return; }
         match_exist = true;
         ++kept;
@@ -246,7 +248,8 @@ __global__ void __launch_bounds__(ACC_BLOCK, PM_FUSED_MIN_BLOCKS(MODE)) select_a
     __shared__ SelScratch s_sel;
     __shared__ Mat4 sT;
     __shared__ PairW s_w;
-    __shared__ int s_flags[2];
+    __shared__ int s_flags[3];
+    pdl_release();  // the one-block finalize kernel behind this one may be set up; it waits for this grid's completion itself
     if (__ldcg(&state->iterate) == 0) return;  // the fused loop is always gated; written by an earlier kernel
 #ifdef PM_PROFILE_NS
     unsigned long long tp[16];
@@ -308,9 +311,11 @@ __global__ void __launch_bounds__(ACC_BLOCK, PM_FUSED_MIN_BLOCKS(MODE)) select_a
                 }
             }
             if (threadIdx.x == 0) {
+                // (loads first, decisions after: the picking thread's round trips to the L2 are the critical path here)
+                const int pending = state->sel_pending, iterate = state->iterate, passes = state->sel_passes;
                 if (!ok) state->sel_pending = 0;  // the peers never arrived: status is raised, the loop has stopped
-                if (nquant > 0) state->sel_passes += 1;
-                if (state->sel_pending == 0 && ok && state->iterate) select_finish(state, cap_active, cap_margin);
+                if (nquant > 0) state->sel_passes = passes + 1;
+                if (pending == 0 && ok && iterate) select_finish(state, cap_active, cap_margin);
             }
             grid_bar_release(state, gen);
         } else {
@@ -319,13 +324,15 @@ __global__ void __launch_bounds__(ACC_BLOCK, PM_FUSED_MIN_BLOCKS(MODE)) select_a
 #ifdef PM_PROFILE_NS
         if (ntp < 14) tp[ntp++] = pm_globaltimer();
 #endif
-        if (__ldcg(&state->sel_pending) == 0) break;
+        // everything the rest of the kernel reads from the state, requested at once (used only when the select is complete)
+        if (threadIdx.x == 0) { s_flags[0] = __ldcg(&state->iterate); s_flags[1] = __ldcg(&state->redo); s_flags[2] = __ldcg(&state->sel_pending); }
+        if (threadIdx.x >= 1 && threadIdx.x <= 16) sT.m[threadIdx.x - 1] = __ldcg(&state->T_iter.m[threadIdx.x - 1]);
+        if (threadIdx.x == 32) load_pairw(state, &s_w);
+        __syncthreads();
+        if (s_flags[2] == 0) break;
+        __syncthreads();  // s_flags is rewritten after the next pass
     }
     // redo: this iteration's capped match was void (select_finish) — leave T_iter as it is
-    if (threadIdx.x == 0) { s_flags[0] = __ldcg(&state->iterate); s_flags[1] = __ldcg(&state->redo); }
-    if (threadIdx.x < 16) sT.m[threadIdx.x] = __ldcg(&state->T_iter.m[threadIdx.x]);
-    if (threadIdx.x == 32) load_pairw(state, &s_w);
-    __syncthreads();
     if (s_flags[0] == 0 || s_flags[1]) return;
     double acc[NS];
 #pragma unroll
@@ -393,6 +400,7 @@ __global__ void __launch_bounds__(ACC_BLOCK) cov_accumulate_kernel(const f4* __r
             const int id = ids[(size_t)i * k + kk];
             if (state->sn_on && pm_sn_weight(sT, reading_normals[i], __ldg(sn_normals + id), state->sn_eps) == 0.f) continue;
             const f4 q = __ldg(ref + id);
+            if (state->robust_on && state->robust_p2plane && pm_robust_p2plane_weight(state, p, q, __ldg(sn_normals + id)) == 0.f) continue;
             float rp[3] = {p.x, p.y, p.z}, fp[3] = {q.x, q.y, q.z}, nrm[3] = {1.f, 1.f, 1.f};
             if (MODE == 1) {
                 const f4 n = __ldg(normals + id);
@@ -741,6 +749,8 @@ __device__ void finalize_body(const double* partials, int nblocks, double* sums,
 template <int MODE>
 __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ sums, int phase,
                                                        IcpState* state, int gated, int compose, pmgpu_icp_params ck, PeerComm pc) {
+    pdl_wait();     // dependent of the accumulate kernel when launched as such
+    pdl_release();  // the next iteration's match may be set up
     if (gated && (state->iterate == 0 || state->redo)) return;
     finalize_body<MODE>(partials, nblocks, sums, phase, state, compose, ck, pc);
 }
@@ -887,9 +897,9 @@ static int launch_select_minimize_mode(pmgpu_ctx* ctx, const SelectSpec& spec, c
                                         comm_peers(ctx), spec, ctx->hist.p, cap_active ? 1 : 0, ctx->cap_margin, ctx->sel_cand.p, ctx->defer_finalize ? 1 : 0));
     ctx->launches += 1;
     if (ctx->defer_finalize) {
-        finalize_kernel<MODE><<<1, 256, 0, ctx->stream>>>(ctx->partials.p, grid, sums, 3, ctx->state, 1, 1, ck, comm_peers(ctx));
+        PM_CUDA_TRY(ctx, launch_dependent(ctx->pdl, finalize_kernel<MODE>, dim3(1), dim3(256), 0, ctx->stream, (const double*)ctx->partials.p, grid, sums, 3,
+                                          ctx->state, 1, 1, ck, comm_peers(ctx)));
         ctx->launches += 1;
-        PM_CUDA_TRY(ctx, cudaGetLastError());
     }
     return PMGPU_OK;
 }

@@ -67,6 +67,29 @@ struct ScopedBuf : DevBuf<T> {
     ~ScopedBuf() { this->release(); }
 };
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------
+// The kernels of an iteration form a strict chain on one stream.  A kernel launched with launch_dependent() may be set up and
+// have its blocks made resident while its predecessor is still running (the predecessor says when with pdl_release(), at its
+// top: by then all of its own blocks have been scheduled); it must call pdl_wait() before it touches anything the
+// predecessor writes — the wait returns when the predecessor has completed and its writes are visible.  Launched normally, both
+// calls are no-ops.  What it buys is the launch latency of a ~2 us boundary, twice or three times per iteration.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_dependent(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---- device-side state of one ICP registration -------------------------------------------------
 // Lives in device memory so that a whole iteration (match -> select -> weights -> minimise ->
 // compose -> check) runs without a host round trip.
@@ -116,6 +139,7 @@ struct IcpState {
     float robust_scale;          // sqrt(MAD) or 1
     int robust_iteration;        // RobustOutlierFilter::iteration (starts at 1)
     int robust_recompute;        // this call re-estimates the scale (nbIterationForScale): 1 mad, 2 berg's first median, 3 std
+    int robust_p2plane;          // distanceType point2plane: the weight function sees dot(n / |n|, p - q)^2
     float robust_target;         // berg: the scale the estimator converges to (the tuning the caller gave)
     float robust_approx2;        // weight 0 where e^2 >= this (`approximation` squared; +inf: none)
     float robust_median;
@@ -257,6 +281,7 @@ struct pmgpu_ctx {
     pm::DevBuf<double> partials;
     bool fused_select = true;        // fused loop: quantile select inside the minimiser kernel; PMGPU_NO_FUSED_SELECT=1 reverts
     bool defer_finalize = true;      // PMGPU_DEFER_FINALIZE=1: rows + solve + compose as a second, one-block kernel (A/B)
+    bool pdl = true;                 // PMGPU_NO_PDL=1: every kernel waits for its predecessor's completion before it is set up
     bool fused_cooperative = true;   // PMGPU_COOP=0: plain launch of the same one-wave grid (A/B)
     int fused_grid[2] = {0, 0};      // co-resident blocks of select_accumulate_kernel<MODE> (occupancy query, once)
 

@@ -317,7 +317,8 @@ __global__ void init_limits_kernel(IcpState* state, SelectSpec spec, int gated, 
 }
 
 __global__ void weights_kernel(const float* __restrict__ dists, const int32_t* __restrict__ ids, int k, size_t total, const IcpState* __restrict__ state,
-                               const f4* __restrict__ reading_normals, const f4* __restrict__ ref_normals, float* __restrict__ w) {
+                               const f4* __restrict__ reading_normals, const f4* __restrict__ ref_normals, float* __restrict__ w,
+                               const f4* __restrict__ reading, const f4* __restrict__ ref) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const float d = dists[i];
@@ -326,6 +327,9 @@ __global__ void weights_kernel(const float* __restrict__ dists, const int32_t* _
     // the reading normal turns with the transform the MATCHES were made with: after a fused iteration T_iter is already
     // the composed one, T_match the one the minimiser used
     if (wt != 0.f && state->sn_on) wt = __fmul_rn(wt, pm_sn_weight(state->T_match, reading_normals[i / k], __ldg(ref_normals + ids[i]), state->sn_eps));
+    // Robust distanceType point2plane: the reading point as the matches saw it, the matched point and its normal
+    if (wt != 0.f && state->robust_on && state->robust_p2plane)
+        wt = __fmul_rn(wt, pm_robust_p2plane_weight(state, transform_point(state->T_match, reading[i / k]), __ldg(ref + ids[i]), __ldg(ref_normals + ids[i])));
     w[i] = wt;
 }
 
@@ -360,6 +364,16 @@ int make_select_spec(pmgpu_ctx* ctx, int nfilters, const int* types, const float
             if (est > PMGPU_SCALE_STD) {
                 ctx->set_error("Invalid scale estimator name.");
                 return PMGPU_ERR_BAD_ARG;
+            }
+            if (types[f] & PMGPU_ROBUST_P2PLANE) {
+                if (!ctx->has_normals) {
+                    ctx->set_error("Field normals not found");  // getDescriptorViewByName("normals"), OutlierFiltersImpl.cpp:477
+                    return PMGPU_ERR_NO_NORMALS;
+                }
+                if (ctx->dimh != 4) {
+                    ctx->set_error("RobustOutlierFilter on GPU: distanceType point2plane needs 3-D clouds");
+                    return PMGPU_ERR_UNSUPPORTED;
+                }
             }
         } else if (types[f] == PMGPU_FILTER_VARTRIMMEDDIST) {
             // lambda: any value, like the reference's parameter table (OutlierFiltersImpl.h:158)
@@ -484,7 +498,7 @@ int launch_materialize_weights(pmgpu_ctx* ctx) {
     PM_CUDA_TRY(ctx, ctx->weights.reserve(total));
     const int B = 256;
     weights_kernel<<<(unsigned)((total + B - 1) / B), B, 0, ctx->stream>>>(ctx->dists.p, ctx->ids.p, ctx->k, total, ctx->state, ctx->reading_normals.p,
-                                                                            ctx->ref_normals.p, ctx->weights.p);
+                                                                            ctx->ref_normals.p, ctx->weights.p, ctx->reading.p, ctx->ref_orig.p);
     ctx->launches += 1;
     PM_CUDA_TRY(ctx, cudaGetLastError());
     return PMGPU_OK;

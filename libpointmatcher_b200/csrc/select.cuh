@@ -38,6 +38,7 @@ __device__ __forceinline__ void select_init_limits(IcpState* st, const SelectSpe
         const int word = sp.type[r], nb = (word >> 20) & 0xff, est = (word >> 16) & 0xf;
         const int fct = (word >> 8) & 0xff;
         st->robust_fct = fct;
+        st->robust_p2plane = (word & PMGPU_ROBUST_P2PLANE) ? 1 : 0;
         st->robust_k = sp.param[r];
         st->robust_approx2 = sp.robust_approx2;
         const bool re = st->robust_iteration <= nb || nb == 0;  // nbIterationForScale
@@ -112,6 +113,7 @@ struct PairW {
     float limit_all;
     int has_filters, robust_on, robust_fct;
     float robust_k, robust_scale, robust_approx2;
+    int robust_p2plane;
     int sn_on;
     float sn_eps;
 };
@@ -123,6 +125,7 @@ __device__ __forceinline__ void load_pairw(const IcpState* st, PairW* w) {
     w->robust_k = __ldcg(&st->robust_k);
     w->robust_scale = __ldcg(&st->robust_scale);
     w->robust_approx2 = __ldcg(&st->robust_approx2);
+    w->robust_p2plane = __ldcg(&st->robust_p2plane);
     w->sn_on = __ldcg(&st->sn_on);
     w->sn_eps = __ldcg(&st->sn_eps);
 }
@@ -131,8 +134,18 @@ template <typename S>
 __device__ __forceinline__ float pm_pair_weight(const S* st, float d) {
     if (d == pm_inf()) return 0.f;  // ErrorMinimizer.cpp:103-106: invalid matches are skipped
     float w = st->has_filters ? ((d <= st->limit_all) ? 1.f : 0.f) : 1.f;
-    if (st->robust_on && w != 0.f) w = __fmul_rn(w, pm_robust_weight(st, d));
+    // (distanceType point2plane: the robust factor needs the matched point and its normal — pm_robust_p2plane_weight, applied
+    // by the caller once it has gathered them)
+    if (st->robust_on && !st->robust_p2plane && w != 0.f) w = __fmul_rn(w, pm_robust_weight(st, d));
     return w;
+}
+// RobustOutlierFilter::computePointToPlaneDistance (OutlierFiltersImpl.cpp:468-500): dot(n.normalized(), p - q)^2 in float
+template <typename S>
+__device__ __forceinline__ float pm_robust_p2plane_weight(const S* st, const f4& p, const f4& q, const f4& n) {
+    float nx = n.x, ny = n.y, nz = n.z;
+    pm_normalized(nx, ny, nz);
+    const float dot = __fadd_rn(__fadd_rn(__fmul_rn(nx, __fsub_rn(p.x, q.x)), __fmul_rn(ny, __fsub_rn(p.y, q.y))), __fmul_rn(nz, __fsub_rn(p.z, q.z)));
+    return pm_robust_weight(st, __fmul_rn(dot, dot));
 }
 
 // Capped matching (fused ICP loop).  The matcher of this iteration stopped at squared radius
@@ -146,11 +159,14 @@ __device__ __forceinline__ void select_finish(IcpState* st, int cap_active, floa
         st->redo = 0;
         return;
     }
-    const float need = st->has_filters ? fmaxf(st->cap_need, st->limit_all) : pm_inf();
-    if (st->cap != pm_inf() && !(need < st->cap)) {
+    // all five values requested before the first is used: one round trip, not one per branch
+    const int has_filters = st->has_filters, redo_count = st->redo_count;
+    const float cap_need = st->cap_need, limit_all = st->limit_all, cap = st->cap;
+    const float need = has_filters ? fmaxf(cap_need, limit_all) : pm_inf();
+    if (cap != pm_inf() && !(need < cap)) {
         st->cap = pm_inf();
         st->redo = 1;
-        st->redo_count += 1;
+        st->redo_count = redo_count + 1;
     } else {
         st->cap = __fmul_rn(need, margin);  // +inf stays +inf
         st->redo = 0;
@@ -456,16 +472,19 @@ __device__ __forceinline__ void select_find(const SelScan& sc, unsigned long lon
 
 // one thread: filter f's order statistic is `bits` — limit[f], limit_all, cap_need exactly as select_pick's last pass — and
 // what the next iteration's first pass is centred on
-__device__ __forceinline__ void select_finish_filter(IcpState* st, int f, float factor, unsigned bits, int inner_next) {
+// (`pre`: limit_all, cap_need, sel_prev[f], sel_pending as the picking thread read them on entry — one round trip to the L2
+// for all four instead of one each, on the critical path of every iteration)
+struct SelFinishPre { float limit_all, cap_need; unsigned prev; int pending; };
+__device__ __forceinline__ void select_finish_filter(IcpState* st, int f, float factor, unsigned bits, int inner_next, const SelFinishPre& pre) {
     const float value = __uint_as_float(bits);
     const float lim = factor != 0.f ? __fmul_rn(factor, value) : value;
     st->limit[f] = lim;
-    st->limit_all = fminf(st->limit_all, lim);  // one thread at a time: the filters are picked in turn
-    st->cap_need = fmaxf(st->cap_need, fmaxf(value, lim));
+    st->limit_all = fminf(pre.limit_all, lim);  // one thread at a time: the filters are picked in turn
+    st->cap_need = fmaxf(pre.cap_need, fmaxf(value, lim));
     // the next iteration's window is centred where the value is heading: this value plus its last move (in bit patterns, i.e.
     // roughly geometric — the limit of a converging registration shrinks by a few per cent per iteration, hundreds of window
     // bins, but steadily: extrapolated, the first pass lands within a few dozen bins)
-    const unsigned prev = st->sel_prev[f];
+    const unsigned prev = pre.prev;
     long long next = (long long)bits;
     if (prev != 0u) next += (long long)bits - (long long)prev;
     if (next < 1) next = 1;
@@ -474,7 +493,7 @@ __device__ __forceinline__ void select_finish_filter(IcpState* st, int f, float 
     st->sel_guess[f] = (unsigned)next;
     if (inner_next >= 0) st->sel_inner[f] = inner_next;  // < 0: set by the window pass before this one, or unknown (kept)
     st->sel_done[f] = 1;
-    st->sel_pending -= 1;
+    st->sel_pending = pre.pending - 1;
 }
 // half-width (in window bins) of the next inner window: twice the move just seen, as far as the collected list can hold
 __device__ __forceinline__ int select_next_inner(int moved_bins, unsigned bin_count, int half_now) {
@@ -502,6 +521,13 @@ __device__ __forceinline__ void select_pick_plan(unsigned* hist, int f, float qu
     const unsigned long long below = outside ? __ldcg(hist + PM_SEL_WINDOW_BINS) : 0ull;
     const unsigned long long above = outside ? __ldcg(hist + PM_SEL_WINDOW_BINS + 1) : 0ull;
     const unsigned ncand = c1 > c0 ? __ldcg(cand_count) : 0u;
+    // requested now, used at the end: what the finishing thread needs, and the first batch of collected distances (the list's
+    // length is not known yet; the buffer is)
+    SelFinishPre pre = {0.f, 0.f, 0u, 0};
+    if (t == 0) { pre.limit_all = st->limit_all; pre.cap_need = st->cap_need; pre.prev = st->sel_prev[f]; pre.pending = st->sel_pending; }
+    unsigned c_first[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) c_first[u] = c1 > c0 ? __ldcg(cand + (unsigned)u * blockDim.x + t) : 0u;
     SelScan sc;
     select_scan<false>(hist, nb, sc, &s_loc, warp_tot);
     if (t == 0) {
@@ -543,7 +569,7 @@ __device__ __forceinline__ void select_pick_plan(unsigned* hist, int f, float qu
         const int moved = bin > PM_SEL_CENTRE ? bin - PM_SEL_CENTRE : PM_SEL_CENTRE - bin;
         const int inner_next = outside ? select_next_inner(moved, s_loc.count, (c1 - c0) / 2) : -1;
         if (shift == 0) {
-            if (t == 0) select_finish_filter(st, f, factor, nlo, -1);
+            if (t == 0) select_finish_filter(st, f, factor, nlo, -1, pre);
         } else if (bin >= c0 && bin < c1 && ncand <= PM_SEL_CAND_CAP) {
             // the bin was collected: its distances, by their low 11 bits, into the shared histogram -> the exact value now.
             // (ncand <= cap also says no block overflowed its staging, so the list holds every distance of bins [c0, c1).)
@@ -555,7 +581,7 @@ __device__ __forceinline__ void select_pick_plan(unsigned* hist, int f, float qu
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const unsigned i = base + (unsigned)u * blockDim.x + t;
-                    c[u] = i < ncand ? __ldcg(cand + i) : 0xffffffffu;  // not the bit pattern of a distance
+                    c[u] = i < ncand ? (base == 0 ? c_first[u] : __ldcg(cand + i)) : 0xffffffffu;  // not the bit pattern of a distance
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
@@ -566,7 +592,7 @@ __device__ __forceinline__ void select_pick_plan(unsigned* hist, int f, float qu
             __syncthreads();
             select_scan<true>(sh->hist, PM_HIST_BINS, sc, &s_loc, warp_tot);
             select_find(sc, rem, &s_loc);
-            if (t == 0) select_finish_filter(st, f, factor, nlo + (unsigned)s_loc.bin, inner_next);
+            if (t == 0) select_finish_filter(st, f, factor, nlo + (unsigned)s_loc.bin, inner_next, pre);
         } else if (t == 0) {
             const int nshift = shift > 11 ? shift - 11 : 0;
             st->sel_prefix[f] = nlo;

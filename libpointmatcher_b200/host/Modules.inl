@@ -813,8 +813,7 @@ struct RobustOutlierFilter : public GpuDistOutlierFilter {
         if (e == ests.end()) throw InvalidParameter("Invalid scale estimator name.");
         const std::string dt = get("distanceType", "point2point");
         if (dt != "point2point" && dt != "point2plane") throw InvalidParameter("Invalid distance type name.");
-        if (dt != "point2point") throw ConfigurationError("RobustOutlierFilter: GPU module: distanceType must be 'point2point'");
-        return PMGPU_ROBUST_WORD(f->second, e->second, std::stoi(get("nbIterationForScale", "0")));
+        return PMGPU_ROBUST_WORD(f->second, e->second, std::stoi(get("nbIterationForScale", "0"))) | (dt == "point2plane" ? PMGPU_ROBUST_P2PLANE : 0);
     }
     T approximation;
     void prepare(GpuPipeline& g) const override { g.check(pmgpu_set_robust_approximation(g.ctx, (float)approximation)); }

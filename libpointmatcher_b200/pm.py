@@ -450,10 +450,10 @@ class RobustOutlierFilter(_DistFilter):
             raise InvalidParameter("Invalid scale estimator name.")
         if self.get("distanceType") not in ("point2point", "point2plane"):
             raise InvalidParameter("Invalid distance type name.")
-        if self.get("distanceType") != "point2point":
-            raise ConfigurationError("RobustOutlierFilter: GPU module: distanceType must be 'point2point'")
         self.approximation = self.get("approximation")
         self.word = capi.FILTER_ROBUST | (self.FCTS[fct] << 8) | (self.ESTIMATORS[est] << 16) | (self.get("nbIterationForScale") << 20)
+        if self.get("distanceType") == "point2plane":
+            self.word |= capi.ROBUST_P2PLANE
 
     def prepare(self, ctx):
         _translate(ctx.set_robust_approximation, self.approximation)

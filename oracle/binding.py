@@ -21,6 +21,9 @@ ROBUST_FCTS = dict(cauchy=0, welsch=1, sc=2, gm=3, tukey=4, huber=5, L1=6, stude
 SCALE_NONE, SCALE_MAD, SCALE_BERG, SCALE_STD = 0, 1, 2, 3
 
 
+ROBUST_P2PLANE = 1 << 28   # distanceType point2plane, or-ed into the robust filter word
+
+
 def robust_word(fct="cauchy", scale=SCALE_MAD, nb_iteration_for_scale=0):
     """filter word of a RobustOutlierFilter (oracle.h): use as the filter type, with the tuning as the parameter"""
     return FILTER_ROBUST | (ROBUST_FCTS[fct] << 8) | (scale << 16) | (nb_iteration_for_scale << 20)
@@ -216,6 +219,24 @@ def bruteforce_knn_var(reference, query, k, max_radii, nthreads=1):
     if rc < 0:
         _check(-rc)
     return ids, dists
+
+
+def outlier_weights_geom(dists, ids, filters, reading, reference, ref_normals):
+    """a chain that may contain a RobustOutlierFilter with distanceType point2plane (robust_word(...) | ROBUST_P2PLANE): reading
+    (N, 4) as the iteration sees it, reference (Nr, 4), ref_normals (Nr, 3)"""
+    d = np.ascontiguousarray(dists, np.float32)
+    i = np.ascontiguousarray(ids, np.int32)
+    n, k = d.shape
+    types = np.array([f[0] for f in filters], np.int32)
+    params = np.array([f[1] for f in filters], np.float32)
+    rd, rf = _cloud(reading), _cloud(reference)
+    qn = np.ascontiguousarray(ref_normals, np.float32)
+    w = np.empty_like(d)
+    limits = np.zeros(max(1, len(filters)), np.float32)
+    L = lib()
+    L.orc_outlier_weights_geom.argtypes = [_fp, _ip, C.c_int, C.c_int, C.c_int, _ip, _fp, _fp, _fp, _fp, _fp, _fp]
+    _check(L.orc_outlier_weights_geom(_f(d), _i(i), k, n, len(filters), _i(types), _f(params), _f(rd), _f(rf), _f(qn), _f(w), _f(limits)))
+    return w, limits[: len(filters)]
 
 
 def outlier_weights_sn(dists, ids, filters, reading_normals, ref_normals):

@@ -615,7 +615,8 @@ static float standard_deviation(const float* dists, long total) {
 
 // RobustOutlierFilter::robustFiltering (OutlierFiltersImpl.cpp:503-598), distanceType point2point.
 // All array arithmetic in float, as Eigen's Array<T> evaluates it.
-int robust_weights(const float* dists, long total, int word, float tuning, RobustState& st, float* w_out, float* scale_out) {
+int robust_weights(const float* dists, long total, int word, float tuning, RobustState& st, float* w_out, float* scale_out,
+                   const float* weight_dists = nullptr) {
     const int fct = (word >> 8) & 0xff, scale_est = (word >> 16) & 0xf, nb_iter = (word >> 20) & 0xff;
     const bool re = st.iteration <= nb_iter || nb_iter == 0;
     if (scale_est == ORC_SCALE_MAD) {
@@ -652,8 +653,9 @@ int robust_weights(const float* dists, long total, int word, float tuning, Robus
     st.iteration++;
     if (scale_out) *scale_out = st.scale;
     const float k = tuning, k2 = k * k, s2 = st.scale * st.scale;
+    const float* wd = weight_dists ? weight_dists : dists;
     for (long i = 0; i < total; ++i) {
-        const float e2 = dists[i] / s2;
+        const float e2 = wd[i] / s2;
         float w;
         switch (fct) {
             case ORC_ROBUST_CAUCHY: w = 1.f / (1.f + e2 / k2); break;
@@ -682,6 +684,9 @@ struct SnContext {
     const int32_t* ids = nullptr;
     const float* reading_normals = nullptr;  // 3 x n, rotated like the reading
     const float* ref_normals = nullptr;      // 3 x nr
+    // RobustOutlierFilter distanceType point2plane (OutlierFiltersImpl.cpp:468-500) also reads the clouds themselves
+    const float* reading = nullptr;          // 4 x n, the reading as this iteration sees it
+    const float* reference = nullptr;        // 4 x nr
 };
 
 // `.normalized()`: v / |v| when |v|^2 > 0 (Eigen >= 3.3), in float
@@ -749,7 +754,26 @@ int outlier_weights(const float* dists, int knn, int n, int nfilters, const int*
             RobustState fresh;
             std::vector<float> wr(total);
             float scale = 0.f;
-            const int rc = robust_weights(dists, total, types[f], params[f], robust ? robust[f] : fresh, wr.data(), &scale);
+            // the scale estimators always read the match distances; distanceType point2plane (bit 28) replaces the distances the
+            // weight function sees by dot(n / |n|, p - q)^2 (computePointToPlaneDistance, OutlierFiltersImpl.cpp:468-500)
+            std::vector<float> pp;
+            if (types[f] & ORC_ROBUST_P2PLANE) {
+                if (!sn || !sn->ids || !sn->ref_normals || !sn->reading || !sn->reference) return ORC_ERR_BAD_ARG;  // the reference throws InvalidField("Field normals not found")
+                pp.assign(total, 0.f);
+                for (int x = 0; x < n; ++x)
+                    for (int y = 0; y < knn; ++y) {
+                        const long i = long(x) * knn + y;
+                        const int id = sn->ids[i];
+                        if (id < 0) continue;
+                        float nq[3];
+                        normalized3(sn->ref_normals + 3 * size_t(id), nq);
+                        const float* pr = sn->reading + 4 * size_t(x);
+                        const float* qr = sn->reference + 4 * size_t(id);
+                        const float dot = (nq[0] * (pr[0] - qr[0]) + nq[1] * (pr[1] - qr[1])) + nq[2] * (pr[2] - qr[2]);
+                        pp[i] = dot * dot;
+                    }
+            }
+            const int rc = robust_weights(dists, total, types[f], params[f], robust ? robust[f] : fresh, wr.data(), &scale, pp.empty() ? nullptr : pp.data());
             if (rc) return rc;
             if (limits_out) limits_out[f] = scale;  // the scale, for the tests
             for (long i = 0; i < total; ++i) w[i] = (f == 0) ? wr[i] : w[i] * wr[i];
@@ -1396,6 +1420,13 @@ int orc_outlier_weights_sn(const float* dists, const int32_t* ids, int knn, int 
     return outlier_weights(dists, knn, n, nfilters, types, params, weights, limits_out, nullptr, &sn);
 }
 
+int orc_outlier_weights_geom(const float* dists, const int32_t* ids, int knn, int n, int nfilters, const int* types, const float* params,
+                             const float* reading4xn, const float* reference4xnr, const float* ref_normals, float* weights, float* limits_out) {
+    SnContext sn;
+    sn.ids = ids; sn.ref_normals = ref_normals; sn.reading = reading4xn; sn.reference = reference4xnr;
+    return outlier_weights(dists, knn, n, nfilters, types, params, weights, limits_out, nullptr, &sn);
+}
+
 int orc_dists_quantile(const float* dists, long n, float quantile, float* out) { return dists_quantile(dists, n, quantile, out); }
 void orc_set_robust_approximation(float approximation) { g_robust_approx2 = (float)((double)approximation * (double)approximation); }
 void orc_set_var_trimmed_ratios(float min_ratio, float max_ratio) { g_var_min_ratio = min_ratio; g_var_max_ratio = max_ratio; }
@@ -1607,6 +1638,7 @@ int orc_icp(const float* readingIn, int nq, const float* referenceIn, int nr, co
         else orc_bruteforce_knn(reference.data(), 4, nr, stepReading.data(), nq, knn, cfg->max_dist, ids.data(), dists.data(), cfg->nthreads);
         g_timings[2] += now_s() - t_m0;
         SnContext sn;
+        sn.ids = ids.data(); sn.ref_normals = ref_normals; sn.reading = stepReading.data(); sn.reference = reference.data();
         if (g_reading_normals && ref_normals) {
             // the reading's normals turn with it (RigidTransformation::compute, TransformationsImpl.cpp:71-84):
             // T_iter * (T_refMean_dataIn * n), rotation blocks only

@@ -31,6 +31,7 @@ enum { ORC_FILTER_MAXDIST = 0, ORC_FILTER_MEDIANDIST = 1, ORC_FILTER_TRIMMEDDIST
 enum { ORC_ROBUST_CAUCHY = 0, ORC_ROBUST_WELSCH, ORC_ROBUST_SC, ORC_ROBUST_GM, ORC_ROBUST_TUKEY, ORC_ROBUST_HUBER, ORC_ROBUST_L1,
        ORC_ROBUST_STUDENT };
 enum { ORC_SCALE_NONE = 0, ORC_SCALE_MAD = 1, ORC_SCALE_BERG = 2, ORC_SCALE_STD = 3 };
+#define ORC_ROBUST_P2PLANE (1 << 28) /* distanceType point2plane, or-ed into the word */
 #define ORC_ROBUST_WORD(fct, scale, nb_iter) (ORC_FILTER_ROBUST | ((fct) << 8) | ((scale) << 16) | ((nb_iter) << 20))
 /* error minimizers */
 enum { ORC_MIN_P2POINT = 0, ORC_MIN_P2PLANE = 1, ORC_MIN_P2POINT_COV = 2, ORC_MIN_P2PLANE_COV = 3, ORC_MIN_P2POINT_SIM = 4 };
@@ -92,6 +93,9 @@ int orc_dists_quantile(const float* dists, long n, float quantile, float* out);
  * (defaults 0.05 / 0.99), and optimizeInlierRatio on its own */
 void orc_set_var_trimmed_ratios(float min_ratio, float max_ratio);
 int orc_var_trimmed_ratio(const float* dists, long n, float min_ratio, float max_ratio, float lambda, float* ratio_out);
+/* the chain with what RobustOutlierFilter distanceType point2plane reads: ids, the clouds (4 x n) and the reference normals */
+int orc_outlier_weights_geom(const float* dists, const int32_t* ids, int knn, int n, int nfilters, const int* types, const float* params,
+                             const float* reading4xn, const float* reference4xnr, const float* ref_normals, float* weights, float* limits_out);
 int orc_outlier_weights(const float* dists, int knn, int n, int nfilters, const int* types,
                         const float* params, float* weights, float* limits_out);
 /* SurfaceNormalOutlierFilter (OutlierFiltersImpl.cpp:222-285, type ORC_FILTER_SURFACENORMAL, param = maxAngle)

@@ -173,7 +173,11 @@ static int run_cpu() {
         CHECK(throws<PM::InvalidParameter>([&] { pm.OutlierFilterRegistrar.create("RobustOutlierFilter", {{"robustFct", "nope"}}); }));
         CHECK(!throws<PM::ConfigurationError>([&] { pm.OutlierFilterRegistrar.create("RobustOutlierFilter", {{"scaleEstimator", "berg"}}); }));
         CHECK(throws<PM::InvalidParameter>([&] { pm.OutlierFilterRegistrar.create("RobustOutlierFilter", {{"scaleEstimator", "bogus"}}); }));
-        CHECK(throws<PM::ConfigurationError>([&] { pm.OutlierFilterRegistrar.create("RobustOutlierFilter", {{"distanceType", "point2plane"}}); }));
+        CHECK(throws<PM::InvalidParameter>([&] { pm.OutlierFilterRegistrar.create("RobustOutlierFilter", {{"distanceType", "point2line"}}); }));
+        {
+            auto pp = pm.OutlierFilterRegistrar.create("RobustOutlierFilter", {{"distanceType", "point2plane"}, {"scaleEstimator", "berg"}});
+            CHECK(dynamic_cast<PM::GpuDistOutlierFilter*>(pp.get())->filterType == (PMGPU_ROBUST_WORD(PMGPU_ROBUST_CAUCHY, PMGPU_SCALE_BERG, 0) | PMGPU_ROBUST_P2PLANE));
+        }
         CHECK(pm.OutlierFilterRegistrar.create("SurfaceNormalOutlierFilter", {{"maxAngle", "0.42"}})->get<float>("maxAngle") == 0.42f);
         auto var = pm.MatcherRegistrar.create("KDTreeVarDistMatcher", {{"knn", "3"}, {"maxDistField", "radius"}});
         auto* vm = dynamic_cast<PM::KDTreeMatcher*>(var.get());

@@ -460,6 +460,38 @@ def test_robust_filter_berg_and_std_scale_estimators(oracle, synth, est, fct):
             assert (wg == 0).any() and (wg != 0).any()
 
 
+def test_robust_filter_point_to_plane_distance(oracle, synth):
+    """distanceType point2plane (computePointToPlaneDistance, OutlierFiltersImpl.cpp:468-500): the weight function sees
+    dot(n / |n|, p - q)^2, the scale estimator still the match distances; one evaluation and a fused ICP run against the oracle"""
+    from libpointmatcher_b200 import capi
+    rd, rf, _ = synth.scan_pair(40000)
+    nrm = oracle.surface_normals(rf, knn=10, nthreads=8)["normals"]
+    word = oracle.robust_word("cauchy", oracle.SCALE_MAD) | oracle.ROBUST_P2PLANE
+    with capi.Context(0) as ctx:
+        ctx.set_reference(rf, normals=nrm)
+        ctx.set_reading(rd)
+        ids, dists, _ = ctx.knn(None, 2, 0.0, np.inf)
+        wo, so = oracle.outlier_weights_geom(dists, ids, [(word, 1.0)], rd, rf, nrm)
+        wg, sg = ctx.weights([(word, 1.0)])
+        assert bits(sg)[0] == bits(so)[0]
+        assert np.allclose(wg, wo, rtol=2e-5, atol=1e-30)
+        w_p2p, _ = ctx.weights([(oracle.robust_word("cauchy", oracle.SCALE_MAD), 1.0)])
+        assert np.abs(wg - w_p2p).max() > 0.1                       # it is a different distance
+        for minimizer in (0, 1):
+            res_o = oracle.icp(rd, rf, ref_normals=nrm, knn=1, filters=[(word, 1.0)], minimizer=minimizer, max_iterations=8, nthreads=8, acc_double=True)
+            ctx.set_reading(rd)
+            res = ctx.icp_run(capi.make_params(knn=1, filters=[(word, 1.0)], minimizer=minimizer, max_iterations=8))
+            assert res["iterations"] == res_o["iterations"] == 8
+            assert_transform_close(res["T_iter"], res_o["T"], 1e-5, 1e-5)
+    with capi.Context(0) as ctx:                                    # without reference normals: the reference's InvalidField
+        ctx.set_reference(rf)
+        ctx.set_reading(rd)
+        ctx.knn(None, 1, 0.0, np.inf)
+        with pytest.raises(capi.PmGpuError) as e:
+            ctx.weights([(word, 1.0)])
+        assert e.value.code == capi.ERR_NO_NORMALS
+
+
 def test_icp_with_berg_scale_matches_oracle(oracle, synth):
     """the berg scale decays from iteration to iteration inside the fused loop exactly as in the oracle's filter object"""
     from libpointmatcher_b200 import capi
