@@ -358,6 +358,7 @@ int pmgpu_ctx_create(int device, pmgpu_ctx** ctx_out) {
     ctx->overlap_enabled = getenv("PMGPU_NO_OVERLAP") == nullptr;
     if (const char* c = getenv("PMGPU_COOP")) ctx->fused_cooperative = atoi(c) != 0;
     ctx->pdl = getenv("PMGPU_NO_PDL") == nullptr;
+    ctx->stage2_resume = getenv("PMGPU_NO_RESUME") == nullptr;
     if (const char* c = getenv("PMGPU_DEFER_FINALIZE")) ctx->defer_finalize = atoi(c) != 0;
     ctx->seeded_without_planes = getenv("PMGPU_SEED_PLANES") == nullptr;
     if (const char* m = getenv("PMGPU_CAP_MARGIN")) ctx->cap_margin = (float)atof(m);
@@ -390,7 +391,7 @@ void pmgpu_ctx_destroy(pmgpu_ctx* ctx) {
     ctx->node_box.release(); ctx->cub_tmp.release();
     ctx->reading.release(); ctx->q_order.release();
     ctx->ids.release(); ctx->dists.release(); ctx->weights.release();
-    ctx->hist.release(); ctx->sel_cand.release(); ctx->partials.release();
+    ctx->hist.release(); ctx->sel_cand.release(); ctx->partials.release(); ctx->overflow_resume.release();
     ctx->reading_normals.release(); ctx->reading_max_r2.release(); ctx->var_sorted.release(); ctx->var_cum.release();
     for (auto& iv : ctx->intervals) { cudaEventDestroy(iv.a); cudaEventDestroy(iv.b); }
     for (auto e : ctx->event_pool) cudaEventDestroy(e);

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
                                                         const f4* __restrict__ ref_orig, int use_seed, int32_t* __restrict__ ids,
                                                         float* __restrict__ dists, unsigned long long* visits, int budget,
                                                         uint32_t* __restrict__ overflow, unsigned* overflow_count, int use_cap,
-                                                        const float* __restrict__ var_r2, NormalsSink ns, int pos_offset) {
+                                                        const float* __restrict__ var_r2, NormalsSink ns, int pos_offset, uint2* __restrict__ resume) {
     extern __shared__ float s_plane[];  // [depth + 1][KNN_BLOCK]: cached plane distances, one column per lane
     __shared__ Mat4 sT;
     pdl_wait();     // (dependent of the previous iteration's last kernel)
@@ -184,6 +184,9 @@ __global__ void __launch_bounds__(KNN_BLOCK) knn_kernel(TreeView tree, const f4*
             if (!NORMALS || slot < ns.scratch_cap) {
                 running = false;
                 overflow[slot] = (uint32_t)t;
+                // where the search stands: the subtree it was about to enter and the siblings still pending above it — the
+                // whole of what is left, so stage 2 continues instead of walking down from the root again
+                resume[slot] = make_uint2(s.node, s.trail);
                 my_slot = slot;  // handed over: unfilled slots below carry the radius this search ran with
             } else {
                 budget = 0x7fffffff;  // K8: the hand-over scratch is full — this lane finishes its query here
@@ -307,7 +310,7 @@ __global__ void __launch_bounds__(128) knn_overflow_kernel(TreeView tree, const 
                                                            int gated, int self_query, int k, float max_r2, const uint32_t* __restrict__ overflow,
                                                            unsigned* overflow_count, unsigned* next_count, int32_t* __restrict__ ids,
                                                            float* __restrict__ dists, unsigned long long* visits, int use_cap,
-                                                           const float* __restrict__ var_r2, NormalsSink ns, int pos_offset) {
+                                                           const float* __restrict__ var_r2, NormalsSink ns, int pos_offset, const uint2* __restrict__ resume) {
     __shared__ uint32_t s_stack[4][OVF_STACK];
     __shared__ Mat4 sT;
     pdl_wait();  // dependent of stage 1
@@ -359,9 +362,26 @@ __global__ void __launch_bounds__(128) knn_overflow_kernel(TreeView tree, const 
                 if (sid[r] >= 0) best.key[r] = WarpTopK<KMAX>::pack(sd[r], sid[r]);
             best.refresh_worst();
         }
+        // the work list: the whole tree (queries that come straight here), or what stage 1 left — the pending siblings of its
+        // path, shallowest first, and on top the subtree it was about to enter
         int sp = 0;
-        if (lane == 0) stack[0] = 1u;
-        sp = 1;
+        if (resume) {
+            const uint2 rs = resume[w];
+            const int lvl = 31 - __clz((int)rs.x);
+            unsigned tr = rs.y;
+            if (lane == 0) {
+                while (tr) {
+                    const int l = __ffs((int)tr) - 1;
+                    tr &= tr - 1u;
+                    stack[sp++] = (rs.x >> (lvl - l)) ^ 1u;
+                }
+                stack[sp++] = rs.x;
+            }
+            sp = __shfl_sync(0xffffffffu, sp, 0);
+        } else {
+            if (lane == 0) stack[0] = 1u;
+            sp = 1;
+        }
         __syncwarp();
         while (sp > 0) {
             const uint32_t n = stack[--sp];
@@ -487,7 +507,7 @@ int launch_wide(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq,
     memset(&none, 0, sizeof(none));
     const int grid2 = min(ctx->num_sms * 8, (nq + 3) / 4);
     knn_overflow_kernel<KMAX, false><<<grid2, 128, 0, ctx->stream>>>(tree, queries, ctx->state, use_T ? 1 : 0, gated ? 1 : 0, 0, k, max_r2, ctx->overflow.p, cnt,
-                                                                 cnt_next, ids, dists, &ctx->state->visits, 0, var_r2, none, 0);
+                                                                 cnt_next, ids, dists, &ctx->state->visits, 0, var_r2, none, 0, nullptr);
     ctx->launches += 2;
     PM_CUDA_TRY(ctx, cudaGetLastError());
     return PMGPU_OK;
@@ -503,6 +523,7 @@ int launch_one(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, 
     const bool planes = NORMALS || !(seeded && ctx->seeded_without_planes);
     const int budget = seeded ? ctx->knn_budget : ctx->knn_budget_unseeded;
     PM_CUDA_TRY(ctx, ctx->overflow.reserve((size_t)nq));
+    PM_CUDA_TRY(ctx, ctx->overflow_resume.reserve((size_t)nq));
     if (NORMALS) {
         // hand-over scratch for the queries stage 1 gives up on: one in eight at most, the rest finish where they are
         ns.scratch_cap = (unsigned)(nq / 8 + 1024);
@@ -518,16 +539,16 @@ int launch_one(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, 
     if (planes)
         PM_CUDA_TRY(ctx, launch_dependent(ctx->pdl && gated, knn_kernel<KMAX, true, NORMALS>, dim3(grid), dim3(KNN_BLOCK), smem, ctx->stream, tree, queries, nq,
                                           ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k, max_r2, ctx->ref_orig.p, use_seed ? 1 : 0, ids, dists,
-                                          &ctx->state->visits, budget, ctx->overflow.p, cnt, use_cap ? 1 : 0, var_r2, ns, pos_offset));
+                                          &ctx->state->visits, budget, ctx->overflow.p, cnt, use_cap ? 1 : 0, var_r2, ns, pos_offset, ctx->overflow_resume.p));
     else if constexpr (!NORMALS)
         PM_CUDA_TRY(ctx, launch_dependent(ctx->pdl && gated, knn_kernel<KMAX, false, false>, dim3(grid), dim3(KNN_BLOCK), 0, ctx->stream, tree, queries, nq,
                                           ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k, max_r2, ctx->ref_orig.p, use_seed ? 1 : 0, ids, dists,
-                                          &ctx->state->visits, budget, ctx->overflow.p, cnt, use_cap ? 1 : 0, var_r2, ns, pos_offset));
+                                          &ctx->state->visits, budget, ctx->overflow.p, cnt, use_cap ? 1 : 0, var_r2, ns, pos_offset, ctx->overflow_resume.p));
     if (ctx->time_stage2) { ctx->stage_end(); ctx->stage_begin(3); }
     const int grid2 = min(ctx->num_sms * 10, (nq + 3) / 4);  // 48 registers: ten 128-thread blocks are resident per SM
     PM_CUDA_TRY(ctx, launch_dependent(ctx->pdl && !ctx->time_stage2, knn_overflow_kernel<KMAX, NORMALS>, dim3(grid2), dim3(128), 0, ctx->stream, tree, queries,
                                       ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k, max_r2, ctx->overflow.p, cnt, cnt_next, ids, dists,
-                                      &ctx->state->visits, use_cap ? 1 : 0, var_r2, ns, pos_offset));
+                                      &ctx->state->visits, use_cap ? 1 : 0, var_r2, ns, pos_offset, (const uint2*)(ctx->stage2_resume ? ctx->overflow_resume.p : nullptr)));
     ctx->launches += 2;
     PM_CUDA_TRY(ctx, cudaGetLastError());
     return PMGPU_OK;

@@ -250,6 +250,7 @@ struct pmgpu_ctx {
     pm::DevBuf<uint32_t> q_order;    // sorted position -> original column
     int seed_k = 0;                  // k of the matches resident in `ids` for this reading / reference (0: none)
     pm::DevBuf<uint32_t> overflow;   // kNN stage-2 queue: sorted positions of the queries stage 1 did not finish
+    pm::DevBuf<uint2> overflow_resume;  // ... and where each of them stood: (node to search next, pending-sibling trail)
     int knn_parity = 0;
     int knn_budget = 16;             // leaves a lane may scan before its query goes to stage 2
     bool seed_enabled = true;        // PMGPU_NO_SEED=1 switches the seeding off (A/B profiling)
@@ -281,6 +282,7 @@ struct pmgpu_ctx {
     pm::DevBuf<double> partials;
     bool fused_select = true;        // fused loop: quantile select inside the minimiser kernel; PMGPU_NO_FUSED_SELECT=1 reverts
     bool defer_finalize = true;      // PMGPU_DEFER_FINALIZE=1: rows + solve + compose as a second, one-block kernel (A/B)
+    bool stage2_resume = true;       // PMGPU_NO_RESUME=1: stage 2 restarts every handed-over query from the root (A/B)
     bool pdl = true;                 // PMGPU_NO_PDL=1: every kernel waits for its predecessor's completion before it is set up
     bool fused_cooperative = true;   // PMGPU_COOP=0: plain launch of the same one-wave grid (A/B)
     int fused_grid[2] = {0, 0};      // co-resident blocks of select_accumulate_kernel<MODE> (occupancy query, once)
