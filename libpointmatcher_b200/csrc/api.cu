@@ -359,6 +359,7 @@ int pmgpu_ctx_create(int device, pmgpu_ctx** ctx_out) {
     if (const char* c = getenv("PMGPU_COOP")) ctx->fused_cooperative = atoi(c) != 0;
     ctx->pdl = getenv("PMGPU_NO_PDL") == nullptr;
     ctx->stage2_resume = getenv("PMGPU_NO_RESUME") == nullptr;
+    ctx->build_select = getenv("PMGPU_BUILD_SORT") == nullptr;
     if (const char* c = getenv("PMGPU_DEFER_FINALIZE")) ctx->defer_finalize = atoi(c) != 0;
     ctx->seeded_without_planes = getenv("PMGPU_SEED_PLANES") == nullptr;
     if (const char* m = getenv("PMGPU_CAP_MARGIN")) ctx->cap_margin = (float)atof(m);
@@ -388,7 +389,7 @@ void pmgpu_ctx_destroy(pmgpu_ctx* ctx) {
     ctx->ref_orig.release(); ctx->ref_sorted.release(); ctx->ref_normals.release(); ctx->splits.release(); ctx->boxes.release(); ctx->gather_tmp.release();
     ctx->reading_tmp.release(); ctx->ids_tmp.release(); ctx->dists_tmp.release(); ctx->overflow.release();
     ctx->keys_a.release(); ctx->keys_b.release(); ctx->perm_a.release(); ctx->perm_b.release();
-    ctx->node_box.release(); ctx->cub_tmp.release();
+    ctx->node_box.release(); ctx->cub_tmp.release(); ctx->seg_state.release(); ctx->seg_hist.release();
     ctx->reading.release(); ctx->q_order.release();
     ctx->ids.release(); ctx->dists.release(); ctx->weights.release();
     ctx->hist.release(); ctx->sel_cand.release(); ctx->partials.release(); ctx->overflow_resume.release();

@@ -242,6 +242,9 @@ struct pmgpu_ctx {
     pm::DevBuf<uint32_t> perm_a, perm_b;
     pm::DevBuf<uint32_t> node_box;  // 6 ordered-uint per node (lo xyz, hi xyz), heap index
     pm::DevBuf<uint8_t> cub_tmp;
+    pm::DevBuf<uint8_t> seg_state;   // per-segment radix-select / partition state of the level being split (tree_build.cu SegState)
+    pm::DevBuf<unsigned> seg_hist;   // ... and its histograms: PM_HIST_BINS per segment
+    bool build_select = true;        // PMGPU_BUILD_SORT=1: the upper levels by cub::DeviceRadixSort as in round 1 (A/B)
 
     // reading
     int nq = 0;

@@ -14,6 +14,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "pmgpu_internal.cuh"
+#include "select.cuh"
 
 namespace pm {
 
@@ -93,6 +94,170 @@ __global__ void level_keys_kernel(const f4* __restrict__ pts, const uint32_t* __
     const f4 pt = pts[perm[p]];
     const float c = dim == 0 ? pt.x : (dim == 1 ? pt.y : pt.z);
     keys[p] = ((uint64_t)seg << 32) | (uint64_t)float_ord(c);
+}
+
+// ---- upper levels: exact median split of every segment of a level by radix SELECT + partition ------------------------------
+// A level only has to put the (mid - lo) smallest coordinates of every segment into its left half — a full sort (round 1: one
+// cub::DeviceRadixSort::SortPairs of 64-bit keys per level, five passes over 12 bytes per point) orders far more than that.  Here:
+// 32-bit ordered coordinate per point (seg_keys_kernel), three histogram passes that find every segment's median key exactly
+// (bits 31..21, 20..10, 9..0; the chunk's block that completes a segment's histogram also scans it — per-segment ticket),
+// one partition pass.  Points equal to the median key are dealt to the left half until it is full (atomic tickets), so left
+// <= split <= right holds and both halves have their exact sizes; which of several EQUAL coordinates lands left, and the order
+// inside a half, depend on the order of the atomics — the tree may differ between two builds of a cloud with duplicate
+// coordinates, the matches never do (core/tree.h: the answer is unique whatever the traversal).
+struct SegState {
+    unsigned prefix, rank;        // radix-select state: selected bucket so far, remaining rank inside it
+    unsigned ticket;              // chunks that have added their histogram
+    unsigned key, ties_left;      // the median's ordered key; how many points equal to it go left
+    unsigned left_cursor, right_cursor, tie_cursor;
+};
+constexpr int SEG_CHUNK = 4096;   // positions per block: touches at most two segments of an upper level (their length is >= 4096)
+constexpr int SEG_THREADS = 256;
+
+__global__ void seg_keys_kernel(const f4* __restrict__ pts, const uint32_t* __restrict__ perm, uint32_t n, int level, const uint32_t* __restrict__ box,
+                                uint32_t* __restrict__ k32) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t seg = seg_of(p, level, n);
+    const int dim = widest_axis(box + 6 * (size_t)((1u << level) + seg));
+    const f4 pt = pts[perm[p]];
+    k32[p] = float_ord(dim == 0 ? pt.x : (dim == 1 ? pt.y : pt.z));
+}
+
+__device__ __forceinline__ uint32_t seg_chunks(uint32_t lo, uint32_t hi) { return (hi - 1) / SEG_CHUNK - lo / SEG_CHUNK + 1; }
+
+template <int PASS>
+__global__ void __launch_bounds__(SEG_THREADS) seg_hist_kernel(const uint32_t* __restrict__ k32, uint32_t n, int level, SegState* __restrict__ seg,
+                                                               unsigned* __restrict__ hist, const uint32_t* __restrict__ box, f2* __restrict__ splits) {
+    __shared__ unsigned sh[2][PM_HIST_BINS];
+    __shared__ unsigned long long warp_tot[32];
+    __shared__ SelLocate s_loc;
+    __shared__ int s_last[2];
+    const uint32_t c0 = blockIdx.x * SEG_CHUNK, c1 = min(n, c0 + SEG_CHUNK);
+    const uint32_t seg0 = seg_of(c0, level, n);
+    const uint32_t nb = seg_begin(level, seg0 + 1, n);  // first position of the next segment
+    const bool two = nb < c1;
+    for (int i = threadIdx.x; i < 2 * PM_HIST_BINS; i += SEG_THREADS) (&sh[0][0])[i] = 0;
+    __syncthreads();
+    const unsigned pf0 = PASS == 0 ? 0u : seg[seg0].prefix, pf1 = (PASS == 0 || !two) ? 0u : seg[seg0 + 1].prefix;
+    for (uint32_t p = c0 + threadIdx.x; p < c1; p += SEG_THREADS) {
+        const uint32_t key = k32[p];
+        const int s = p >= nb ? 1 : 0;
+        const unsigned pf = s ? pf1 : pf0;
+        if (PASS == 0) atomicAdd(&sh[s][key >> 21], 1u);
+        else if (PASS == 1) { if ((key >> 21) == pf) atomicAdd(&sh[s][(key >> 10) & 0x7ffu], 1u); }
+        else { if ((key >> 10) == pf) atomicAdd(&sh[s][key & 0x3ffu], 1u); }
+    }
+    __syncthreads();
+    for (int s = 0; s < (two ? 2 : 1); ++s) select_flush(sh[s], hist + (size_t)(seg0 + s) * PM_HIST_BINS);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        s_last[threadIdx.x] = 0;
+        if (threadIdx.x == 0 || two) {
+            const uint32_t sg = seg0 + threadIdx.x;
+            const uint32_t lo = seg_begin(level, sg, n), hi = seg_begin(level, sg + 1, n);
+            const unsigned t = atomicAdd(&seg[sg].ticket, 1u);
+            if (t == seg_chunks(lo, hi) - 1) { s_last[threadIdx.x] = 1; seg[sg].ticket = 0; }
+        }
+    }
+    __syncthreads();
+    for (int s = 0; s < 2; ++s) {
+        if (!s_last[s]) continue;  // block-uniform
+        __threadfence();
+        const uint32_t sg = seg0 + s;
+        unsigned* h = hist + (size_t)sg * PM_HIST_BINS;
+        const uint32_t lo = seg_begin(level, sg, n), mid = seg_begin(level + 1, 2 * sg + 1, n);
+        const unsigned long long rank = PASS == 0 ? (unsigned long long)(mid - lo) : (unsigned long long)seg[sg].rank;
+        const unsigned prefix = PASS == 0 ? 0u : seg[sg].prefix;
+        SelScan sc;
+        select_scan<false>(h, PASS == 2 ? 1024 : PM_HIST_BINS, sc, &s_loc, warp_tot);
+        select_find(sc, rank, &s_loc);
+        if (threadIdx.x == 0) {
+            const unsigned bin = (unsigned)s_loc.bin;
+            if (PASS == 0) { seg[sg].prefix = bin; seg[sg].rank = (unsigned)s_loc.rem; }
+            else if (PASS == 1) { seg[sg].prefix = (prefix << 11) | bin; seg[sg].rank = (unsigned)s_loc.rem; }
+            else {
+                const unsigned key = (prefix << 10) | bin;
+                seg[sg].key = key;
+                seg[sg].ties_left = (unsigned)s_loc.rem;  // points equal to the median key that belong to the left half
+                seg[sg].left_cursor = 0; seg[sg].right_cursor = 0; seg[sg].tie_cursor = 0;
+                // split value of node (level, sg) = coordinate of the first point of its right half (left <= split <= right)
+                const uint32_t node = (1u << level) + sg;
+                splits[node] = make_float2(ord_float(key), __uint_as_float((uint32_t)widest_axis(box + 6 * (size_t)node)));
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < PM_HIST_BINS; i += SEG_THREADS) h[i] = 0;
+        __syncthreads();
+    }
+}
+
+// every point to its half: < median key left, > right, == left while the left half has room
+__global__ void __launch_bounds__(SEG_THREADS) seg_partition_kernel(const uint32_t* __restrict__ k32, const uint32_t* __restrict__ perm_in, uint32_t n, int level,
+                                                                    SegState* __restrict__ seg, uint32_t* __restrict__ perm_out) {
+    constexpr int PER = SEG_CHUNK / SEG_THREADS;  // 16 positions per thread, strided
+    __shared__ unsigned s_warp[SEG_THREADS / 32][4];
+    __shared__ unsigned s_base[4];
+    const uint32_t c0 = blockIdx.x * SEG_CHUNK, c1 = min(n, c0 + SEG_CHUNK);
+    const uint32_t seg0 = seg_of(c0, level, n);
+    const uint32_t nb = seg_begin(level, seg0 + 1, n);
+    const bool two = nb < c1;
+    const unsigned m0 = seg[seg0].key, m1 = two ? seg[seg0 + 1].key : 0u;
+    const unsigned tl0 = seg[seg0].ties_left, tl1 = two ? seg[seg0 + 1].ties_left : 0u;
+    unsigned cls = 0;                 // 2 bits per position: bit 0 = right half, bit 1 = second segment
+    unsigned cnt[4] = {0, 0, 0, 0};   // [segment * 2 + side]
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        const uint32_t p = c0 + threadIdx.x + SEG_THREADS * j;
+        if (p >= c1) continue;
+        const uint32_t key = k32[p];
+        const unsigned s = p >= nb ? 1u : 0u;
+        const unsigned m = s ? m1 : m0;
+        unsigned right = key > m ? 1u : 0u;
+        if (key == m) right = atomicAdd(&seg[seg0 + s].tie_cursor, 1u) < (s ? tl1 : tl0) ? 0u : 1u;
+        cls |= (right | (s << 1)) << (2 * j);
+        cnt[s * 2 + right] += 1;
+    }
+    // block-wide exclusive offsets of the four classes
+    unsigned excl[4];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        unsigned v = cnt[c];
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned u = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += u;
+        }
+        excl[c] = v - cnt[c];
+        if (lane == 31) s_warp[warp][c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        unsigned run = 0;
+        for (int w = 0; w < SEG_THREADS / 32; ++w) { const unsigned v = s_warp[w][threadIdx.x]; s_warp[w][threadIdx.x] = run; run += v; }
+        const unsigned s = threadIdx.x >> 1, right = threadIdx.x & 1;
+        s_base[threadIdx.x] = 0;
+        if (run && (s == 0 || two)) {
+            const uint32_t sg = seg0 + s;
+            const uint32_t start = right ? seg_begin(level + 1, 2 * sg + 1, n) : seg_begin(level, sg, n);
+            s_base[threadIdx.x] = start + atomicAdd(right ? &seg[sg].right_cursor : &seg[sg].left_cursor, run);
+        }
+    }
+    __syncthreads();
+    unsigned pos[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) pos[c] = s_base[c] + s_warp[warp][c] + excl[c];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        const uint32_t p = c0 + threadIdx.x + SEG_THREADS * j;
+        if (p >= c1) continue;
+        const unsigned c = (cls >> (2 * j)) & 3u;
+        unsigned dst = pos[0];
+        if (c == 1) dst = pos[1]; else if (c == 2) dst = pos[2]; else if (c == 3) dst = pos[3];
+        if (c == 0) pos[0]++; else if (c == 1) pos[1]++; else if (c == 2) pos[2]++; else pos[3]++;
+        perm_out[dst] = perm_in[p];
+    }
 }
 
 __global__ void gather_sorted_kernel(const f4* __restrict__ pts, const uint32_t* __restrict__ perm, uint32_t n, f4* __restrict__ out) {
@@ -338,6 +503,27 @@ int build_tree(pmgpu_ctx* ctx) {
     uint32_t* perm = ctx->perm_a.p;
     uint32_t* perm_alt = ctx->perm_b.p;
     const int L0 = subtree_level(n, D);
+    if (L0 > 0 && ctx->build_select) {
+        // upper levels by radix select + partition (see SegState)
+        const size_t nseg = (size_t)1 << (L0 - 1);
+        PM_CUDA_TRY(ctx, ctx->seg_state.reserve(nseg * sizeof(SegState)));
+        PM_CUDA_TRY(ctx, ctx->seg_hist.reserve(nseg * PM_HIST_BINS));
+        PM_CUDA_TRY(ctx, cudaMemsetAsync(ctx->seg_state.p, 0, nseg * sizeof(SegState), st));
+        PM_CUDA_TRY(ctx, cudaMemsetAsync(ctx->seg_hist.p, 0, nseg * PM_HIST_BINS * sizeof(unsigned), st));
+        SegState* seg = reinterpret_cast<SegState*>(ctx->seg_state.p);
+        uint32_t* k32 = reinterpret_cast<uint32_t*>(ctx->keys_a.p);
+        const unsigned chunks = blocks_for(n, SEG_CHUNK);
+        for (int l = 0; l < L0; ++l) {
+            level_boxes_kernel<<<blocks_for(n, BOX_CHUNK), BOX_THREADS, 0, st>>>(ctx->ref_orig.p, perm, n, l, ctx->node_box.p);
+            seg_keys_kernel<<<blocks_for(n, B), B, 0, st>>>(ctx->ref_orig.p, perm, n, l, ctx->node_box.p, k32);
+            seg_hist_kernel<0><<<chunks, SEG_THREADS, 0, st>>>(k32, n, l, seg, ctx->seg_hist.p, ctx->node_box.p, ctx->splits.p);
+            seg_hist_kernel<1><<<chunks, SEG_THREADS, 0, st>>>(k32, n, l, seg, ctx->seg_hist.p, ctx->node_box.p, ctx->splits.p);
+            seg_hist_kernel<2><<<chunks, SEG_THREADS, 0, st>>>(k32, n, l, seg, ctx->seg_hist.p, ctx->node_box.p, ctx->splits.p);
+            seg_partition_kernel<<<chunks, SEG_THREADS, 0, st>>>(k32, perm, n, l, seg, perm_alt);
+            uint32_t* t = perm; perm = perm_alt; perm_alt = t;
+            ctx->launches += 6;
+        }
+    } else {
     for (int l = 0; l < L0; ++l) {
         level_boxes_kernel<<<blocks_for(n, BOX_CHUNK), BOX_THREADS, 0, st>>>(ctx->ref_orig.p, perm, n, l, ctx->node_box.p);
         level_keys_kernel<<<blocks_for(n, B), B, 0, st>>>(ctx->ref_orig.p, perm, n, l, ctx->node_box.p, ctx->keys_a.p);
@@ -346,6 +532,7 @@ int build_tree(pmgpu_ctx* ctx) {
         uint32_t* t = perm; perm = perm_alt; perm_alt = t;
         level_splits_kernel<<<blocks_for(1u << l, B), B, 0, st>>>(ctx->ref_orig.p, perm, n, l, ctx->node_box.p, ctx->splits.p);
         ctx->launches += 4;
+    }
     }
     PM_CUDA_TRY(ctx, cudaFuncSetAttribute(subtree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SubSmem)));
     subtree_kernel<<<1u << L0, SUB_THREADS, sizeof(SubSmem), st>>>(ctx->ref_orig.p, L0 > 0 ? perm : nullptr, n, L0, D, ctx->node_box.p, ctx->splits.p,
