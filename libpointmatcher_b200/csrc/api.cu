@@ -13,6 +13,10 @@ using namespace pm;
 
 thread_local cudaStream_t pm::g_alloc_stream = nullptr;
 
+#include <atomic>
+static std::atomic<int> g_live_contexts{0};
+bool pm::pdl_enabled(const pmgpu_ctx* ctx) { return ctx->pdl && g_live_contexts.load(std::memory_order_relaxed) == 1; }
+
 namespace {
 
 __global__ void pack_normals_kernel(const float* __restrict__ src, int ld, int n, f4* __restrict__ dst, int comps) {
@@ -376,12 +380,15 @@ int pmgpu_ctx_create(int device, pmgpu_ctx** ctx_out) {
         pmgpu_ctx_destroy(ctx);
         return PMGPU_ERR_CUDA;
     }
+    g_live_contexts.fetch_add(1);
+    ctx->counted = true;
     *ctx_out = ctx;
     return PMGPU_OK;
 }
 
 void pmgpu_ctx_destroy(pmgpu_ctx* ctx) {
     if (!ctx) return;
+    if (ctx->counted) g_live_contexts.fetch_sub(1);
     cudaSetDevice(ctx->device);
     g_alloc_stream = ctx->stream;
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);

@@ -537,16 +537,16 @@ int launch_one(pmgpu_ctx* ctx, const TreeView& tree, const f4* queries, int nq, 
     unsigned* cnt_next = &ctx->state->overflow_count[ctx->knn_parity ^ 1];
     ctx->knn_parity ^= 1;
     if (planes)
-        PM_CUDA_TRY(ctx, launch_dependent(ctx->pdl && gated, knn_kernel<KMAX, true, NORMALS>, dim3(grid), dim3(KNN_BLOCK), smem, ctx->stream, tree, queries, nq,
+        PM_CUDA_TRY(ctx, launch_dependent(pdl_enabled(ctx) && gated, knn_kernel<KMAX, true, NORMALS>, dim3(grid), dim3(KNN_BLOCK), smem, ctx->stream, tree, queries, nq,
                                           ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k, max_r2, ctx->ref_orig.p, use_seed ? 1 : 0, ids, dists,
                                           &ctx->state->visits, budget, ctx->overflow.p, cnt, use_cap ? 1 : 0, var_r2, ns, pos_offset, ctx->overflow_resume.p));
     else if constexpr (!NORMALS)
-        PM_CUDA_TRY(ctx, launch_dependent(ctx->pdl && gated, knn_kernel<KMAX, false, false>, dim3(grid), dim3(KNN_BLOCK), 0, ctx->stream, tree, queries, nq,
+        PM_CUDA_TRY(ctx, launch_dependent(pdl_enabled(ctx) && gated, knn_kernel<KMAX, false, false>, dim3(grid), dim3(KNN_BLOCK), 0, ctx->stream, tree, queries, nq,
                                           ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k, max_r2, ctx->ref_orig.p, use_seed ? 1 : 0, ids, dists,
                                           &ctx->state->visits, budget, ctx->overflow.p, cnt, use_cap ? 1 : 0, var_r2, ns, pos_offset, ctx->overflow_resume.p));
     if (ctx->time_stage2) { ctx->stage_end(); ctx->stage_begin(3); }
     const int grid2 = min(ctx->num_sms * 10, (nq + 3) / 4);  // 48 registers: ten 128-thread blocks are resident per SM
-    PM_CUDA_TRY(ctx, launch_dependent(ctx->pdl && !ctx->time_stage2, knn_overflow_kernel<KMAX, NORMALS>, dim3(grid2), dim3(128), 0, ctx->stream, tree, queries,
+    PM_CUDA_TRY(ctx, launch_dependent(pdl_enabled(ctx) && !ctx->time_stage2, knn_overflow_kernel<KMAX, NORMALS>, dim3(grid2), dim3(128), 0, ctx->stream, tree, queries,
                                       ctx->state, use_T ? 1 : 0, gated ? 1 : 0, self_query ? 1 : 0, k, max_r2, ctx->overflow.p, cnt, cnt_next, ids, dists,
                                       &ctx->state->visits, use_cap ? 1 : 0, var_r2, ns, pos_offset, (const uint2*)(ctx->stage2_resume ? ctx->overflow_resume.p : nullptr)));
     ctx->launches += 2;

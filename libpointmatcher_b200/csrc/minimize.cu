@@ -897,7 +897,7 @@ static int launch_select_minimize_mode(pmgpu_ctx* ctx, const SelectSpec& spec, c
                                         comm_peers(ctx), spec, ctx->hist.p, cap_active ? 1 : 0, ctx->cap_margin, ctx->sel_cand.p, ctx->defer_finalize ? 1 : 0));
     ctx->launches += 1;
     if (ctx->defer_finalize) {
-        PM_CUDA_TRY(ctx, launch_dependent(ctx->pdl, finalize_kernel<MODE>, dim3(1), dim3(256), 0, ctx->stream, (const double*)ctx->partials.p, grid, sums, 3,
+        PM_CUDA_TRY(ctx, launch_dependent(pdl_enabled(ctx), finalize_kernel<MODE>, dim3(1), dim3(256), 0, ctx->stream, (const double*)ctx->partials.p, grid, sums, 3,
                                           ctx->state, 1, 1, ck, comm_peers(ctx)));
         ctx->launches += 1;
     }

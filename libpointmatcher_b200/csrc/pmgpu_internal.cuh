@@ -285,6 +285,7 @@ struct pmgpu_ctx {
     pm::DevBuf<double> partials;
     bool fused_select = true;        // fused loop: quantile select inside the minimiser kernel; PMGPU_NO_FUSED_SELECT=1 reverts
     bool defer_finalize = true;      // PMGPU_DEFER_FINALIZE=1: rows + solve + compose as a second, one-block kernel (A/B)
+    bool counted = false;            // in the process-wide count of live contexts (api.cu)
     bool stage2_resume = true;       // PMGPU_NO_RESUME=1: stage 2 restarts every handed-over query from the root (A/B)
     bool pdl = true;                 // PMGPU_NO_PDL=1: every kernel waits for its predecessor's completion before it is set up
     bool fused_cooperative = true;   // PMGPU_COOP=0: plain launch of the same one-wave grid (A/B)
@@ -347,6 +348,10 @@ struct pmgpu_ctx {
 
 namespace pm {
 
+// api.cu: programmatic dependent launch is used while this is the process's only live context — a dependent's blocks sit on
+// SM slots while they wait, which costs nothing when the stream's own predecessor is all that runs, and a quarter of the
+// throughput when other contexts' kernels could have had those slots (config 5: three contexts per GPU, 420 vs 528 pairs/s)
+bool pdl_enabled(const pmgpu_ctx* ctx);
 // tree_build.cu
 int build_tree(pmgpu_ctx* ctx);
 int morton_order(pmgpu_ctx* ctx);
