@@ -219,7 +219,11 @@ int pmgpu_minimize(pmgpu_ctx* ctx, int minimizer, float sensor_std_dev, float* T
  * written with column stride `ld` floats each: normals 3 x n, densities 1 x n, eig_values
  * 3 x n, eig_vectors 9 x n (row-major serialisation, utils.h:89-103), matched_ids knn x n
  * (as float, SurfaceNormal.cpp:254-257), mean_dists 1 x n.  If `attach` != 0 and the cloud
- * is the current reference (same n), the normals also become the reference normals. */
+ * is the current reference (same n), the normals also become the reference normals.
+ * epsilon > 0 is accepted and answered exactly (a valid, different answer from libnabo's approximate search).  Eigenvalues /
+ * eigenvectors are always reported in ascending order of the eigenvalue (the reference's `sortEigen` order; without sortEigen
+ * it reports them in Eigen::EigenSolver's unspecified order), and the rank test of SurfaceNormal.cpp:190-232 is applied
+ * whichever outputs are asked for: a degenerate neighbourhood reads normal 0, density 0. */
 typedef struct pmgpu_normals_out {
     float* normals;     int normals_ld;
     float* densities;   int densities_ld;

@@ -11,7 +11,7 @@ timeout 300 $A > gpurun_out/prof_plain_e1.log 2>&1 &&
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"knn_kernel|knn_overflow" -s 8 -c 6 -o gpurun_out/r2_end_knn_c2plane $A > gpurun_out/ncu_e1.log 2>&1
 echo "knn rc=$?"
 timeout 300 $A > gpurun_out/prof_plain_e2.log 2>&1 &&
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"select_accumulate" -s 3 -c 4 -o gpurun_out/r2_end_select_accumulate $A > gpurun_out/ncu_e2.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"select_accumulate|finalize_kernel" -s 6 -c 6 -o gpurun_out/r2_end_select_accumulate $A > gpurun_out/ncu_e2.log 2>&1
 echo "select_accumulate rc=$?"
 tail -3 gpurun_out/ncu_e2.log
 ls -la gpurun_out | tail -8
