@@ -369,7 +369,7 @@ def measure(args, cfg, torch, capi, pm, pmdist, rank, world, local_rank, mode, r
     sharded = dist_on and mode == "shard"
     rd, rf, T_gt = clouds if clouds is not None else make_clouds(cfg, args, pair_seed=0 if (not dist_on or sharded) else rank)
     if sharded:
-        rd_local = np.ascontiguousarray(rd[pmdist.shard_columns(len(rd), rank, world)])
+        rd_local = pmdist.shard_take(rd, rank, world)
     else:
         rd_local = rd
     rd_pin, _k1 = pinned_copy(rd)          # e2e hands pm.ICP the WHOLE reading; the sharded ICP takes its slice

@@ -155,6 +155,10 @@ int pmgpu_ref_set_normals(pmgpu_ctx* ctx, const float* normals, int normals_ld);
  * device never visit the host otherwise; for ErrorElements / residual-error consumers (PointToPlane.cpp:314-352) */
 int pmgpu_ref_get_normals(pmgpu_ctx* ctx, float* normals_out);
 int pmgpu_reading_set(pmgpu_ctx* ctx, const float* features, int rows, int n);
+/* Sharded registration: uploads THIS rank's share of the whole reading `features` (4 x n, host) — the chunks of `chunk` consecutive
+ * columns c with c mod nranks == rank, in order — straight from the caller's matrix (one strided copy, no host-side gather).
+ * Equivalent to pmgpu_reading_set on those columns.  3-D clouds. */
+int pmgpu_reading_set_sharded(pmgpu_ctx* ctx, const float* features, int rows, int n, int rank, int nranks, int chunk);
 
 /* RigidTransformation::compute on the resident reading, in place (TransformationsImpl.cpp:49-87;
  * the `transformations.apply(reading, T_refMean_dataIn)` of ICP.cpp:345-347).  Returns

@@ -74,6 +74,7 @@ SIGNATURES = {
     "pmgpu_ref_set_centered": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, _fp]),
     "pmgpu_ref_set_normals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "pmgpu_reading_set": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "pmgpu_reading_set_sharded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "pmgpu_reading_set_normals": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "pmgpu_reading_set_max_dists": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "pmgpu_reading_apply_transform": (C.c_int, [C.c_void_p, _fp]),
@@ -265,6 +266,15 @@ class Context:
             if self.nr == 0:
                 self.dimh = rows
         self.nq = n
+
+    def set_reading_sharded(self, features, rank, world, chunk):
+        """this rank's chunks of the whole reading (N, 4), uploaded straight from `features` (dist.shard_columns' columns)"""
+        f = _cloud(features)
+        n, rows = f.shape
+        self._check(lib.pmgpu_reading_set_sharded(self.h, _ptr(f), rows, n, rank, world, chunk))
+        nchunks = n // chunk
+        mine = (nchunks - rank + world - 1) // world if nchunks > rank else 0
+        self.nq = mine * chunk + (n - nchunks * chunk if nchunks % world == rank else 0)
 
     def reading_apply_transform(self, T):
         self._check(lib.pmgpu_reading_apply_transform(self.h, _f(_T(T))))

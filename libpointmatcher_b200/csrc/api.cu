@@ -396,7 +396,7 @@ void pmgpu_ctx_destroy(pmgpu_ctx* ctx) {
     ctx->ref_orig.release(); ctx->ref_sorted.release(); ctx->ref_normals.release(); ctx->splits.release(); ctx->boxes.release(); ctx->gather_tmp.release();
     ctx->reading_tmp.release(); ctx->ids_tmp.release(); ctx->dists_tmp.release(); ctx->overflow.release();
     ctx->keys_a.release(); ctx->keys_b.release(); ctx->perm_a.release(); ctx->perm_b.release();
-    ctx->node_box.release(); ctx->cub_tmp.release(); ctx->seg_state.release(); ctx->seg_hist.release();
+    ctx->node_box.release(); ctx->cub_tmp.release(); ctx->seg_state.release(); ctx->seg_hist.release(); ctx->seg_cnt.release();
     ctx->reading.release(); ctx->q_order.release();
     ctx->ids.release(); ctx->dists.release(); ctx->weights.release();
     ctx->hist.release(); ctx->sel_cand.release(); ctx->partials.release(); ctx->overflow_resume.release();
@@ -556,8 +556,21 @@ int pmgpu_ref_get_normals(pmgpu_ctx* ctx, float* normals_out) {
     return PMGPU_OK;
 }
 
-int pmgpu_reading_set(pmgpu_ctx* ctx, const float* features, int rows, int n) {
+// shard: rank / nranks / chunk of pmgpu_reading_set_sharded (nranks <= 1: the whole cloud); `n` is then the WHOLE cloud's size
+static int reading_set_impl(pmgpu_ctx* ctx, const float* features, int rows, int n_total, int rank, int nranks, int chunk) {
     if (!ctx) return PMGPU_ERR_BAD_ARG;
+    int n = n_total;
+    int my_chunks = 0, tail = 0;
+    if (nranks > 1) {
+        if (rows != 4 || chunk < 1 || rank < 0 || rank >= nranks || n_total < 0) {
+            ctx->set_error("pmgpu_reading_set_sharded: 3-D clouds, chunk >= 1, 0 <= rank < nranks");
+            return PMGPU_ERR_BAD_ARG;
+        }
+        const int nchunks = n_total / chunk;
+        my_chunks = nchunks > rank ? (nchunks - rank + nranks - 1) / nranks : 0;
+        tail = (nchunks % nranks == rank) ? n_total - nchunks * chunk : 0;
+        n = my_chunks * chunk + tail;
+    }
     const bool window = ctx->overlap_window;
     PM_TRY(use_device(ctx));
     if (!features) return fail(ctx, PMGPU_ERR_BAD_ARG, "null reading features");
@@ -584,7 +597,20 @@ int pmgpu_reading_set(pmgpu_ctx* ctx, const float* features, int rows, int n) {
         PM_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_build, 0));
         ctx->stream = ctx->stream2;
     }
-    int s = upload_cloud(ctx, features, rows, n, ctx->reading_tmp.p);
+    int s = PMGPU_OK;
+    if (nranks > 1) {
+        // my chunks sit at a regular stride in the caller's matrix: one 2-D copy (rows of `chunk` points), then the tail
+        const size_t row_bytes = (size_t)chunk * sizeof(f4);
+        if (my_chunks > 0 && cudaMemcpy2DAsync(ctx->reading_tmp.p, row_bytes, features + (size_t)rank * chunk * 4, row_bytes * nranks, row_bytes, my_chunks,
+                                               cudaMemcpyDefault, ctx->stream) != cudaSuccess)
+            s = fail(ctx, PMGPU_ERR_CUDA, "cudaMemcpy2DAsync");
+        if (s == PMGPU_OK && tail > 0 &&
+            cudaMemcpyAsync(ctx->reading_tmp.p + (size_t)my_chunks * chunk, features + (size_t)(n_total - tail) * 4, (size_t)tail * sizeof(f4), cudaMemcpyDefault,
+                            ctx->stream) != cudaSuccess)
+            s = fail(ctx, PMGPU_ERR_CUDA, "cudaMemcpyAsync");
+    } else {
+        s = upload_cloud(ctx, features, rows, n, ctx->reading_tmp.p);
+    }
     if (s == PMGPU_OK && cudaEventRecord(ctx->copy_done, ctx->stream) != cudaSuccess) s = fail(ctx, PMGPU_ERR_CUDA, "cudaEventRecord");
     if (s == PMGPU_OK) {
         ctx->nq = n;
@@ -599,6 +625,12 @@ int pmgpu_reading_set(pmgpu_ctx* ctx, const float* features, int rows, int n) {
     // the caller may release `features` on return: wait for the copy only, the ordering kernels run on
     PM_CUDA_TRY(ctx, cudaEventSynchronize(ctx->copy_done));
     return PMGPU_OK;
+}
+
+int pmgpu_reading_set(pmgpu_ctx* ctx, const float* features, int rows, int n) { return reading_set_impl(ctx, features, rows, n, 0, 1, 0); }
+int pmgpu_reading_set_sharded(pmgpu_ctx* ctx, const float* features, int rows, int n, int rank, int nranks, int chunk) {
+    if (nranks <= 1) return reading_set_impl(ctx, features, rows, n, 0, 1, 0);
+    return reading_set_impl(ctx, features, rows, n, rank, nranks, chunk);
 }
 
 int pmgpu_reading_set_max_dists(pmgpu_ctx* ctx, const float* max_dists, int ld) {

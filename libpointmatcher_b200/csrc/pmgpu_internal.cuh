@@ -244,6 +244,7 @@ struct pmgpu_ctx {
     pm::DevBuf<uint8_t> cub_tmp;
     pm::DevBuf<uint8_t> seg_state;   // per-segment radix-select / partition state of the level being split (tree_build.cu SegState)
     pm::DevBuf<unsigned> seg_hist;   // ... and its histograms: PM_HIST_BINS per segment
+    pm::DevBuf<unsigned> seg_cnt;    // ... and, per chunk of 4096 positions, the counts / offsets of its two segments' three classes
     bool build_select = true;        // PMGPU_BUILD_SORT=1: the upper levels by cub::DeviceRadixSort as in round 1 (A/B)
 
     // reading

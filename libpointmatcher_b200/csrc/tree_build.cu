@@ -101,15 +101,15 @@ __global__ void level_keys_kernel(const f4* __restrict__ pts, const uint32_t* __
 // cub::DeviceRadixSort::SortPairs of 64-bit keys per level, five passes over 12 bytes per point) orders far more than that.  Here:
 // 32-bit ordered coordinate per point (seg_keys_kernel), three histogram passes that find every segment's median key exactly
 // (bits 31..21, 20..10, 9..0; the chunk's block that completes a segment's histogram also scans it — per-segment ticket),
-// one partition pass.  Points equal to the median key are dealt to the left half until it is full (atomic tickets), so left
-// <= split <= right holds and both halves have their exact sizes; which of several EQUAL coordinates lands left, and the order
-// inside a half, depend on the order of the atomics — the tree may differ between two builds of a cloud with duplicate
-// coordinates, the matches never do (core/tree.h: the answer is unique whatever the traversal).
+// a count + a scatter pass.  Points equal to the median key fill the left half up to its exact size, so left <= split <= right
+// holds and both halves have their exact sizes; the order is fixed by position (no atomics decide anything), so the same cloud
+// gives the same tree on every GPU and in every run.
 struct SegState {
     unsigned prefix, rank;        // radix-select state: selected bucket so far, remaining rank inside it
     unsigned ticket;              // chunks that have added their histogram
     unsigned key, ties_left;      // the median's ordered key; how many points equal to it go left
-    unsigned left_cursor, right_cursor, tie_cursor;
+    unsigned eq_total;            // points equal to the median key
+    unsigned pad[2];
 };
 constexpr int SEG_CHUNK = 4096;   // positions per block: touches at most two segments of an upper level (their length is >= 4096)
 constexpr int SEG_THREADS = 256;
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(SEG_THREADS) seg_hist_kernel(const uint32_t* _
                 const unsigned key = (prefix << 10) | bin;
                 seg[sg].key = key;
                 seg[sg].ties_left = (unsigned)s_loc.rem;  // points equal to the median key that belong to the left half
-                seg[sg].left_cursor = 0; seg[sg].right_cursor = 0; seg[sg].tie_cursor = 0;
+                seg[sg].eq_total = s_loc.count;
                 // split value of node (level, sg) = coordinate of the first point of its right half (left <= split <= right)
                 const uint32_t node = (1u << level) + sg;
                 splits[node] = make_float2(ord_float(key), __uint_as_float((uint32_t)widest_axis(box + 6 * (size_t)node)));
@@ -193,69 +193,170 @@ __global__ void __launch_bounds__(SEG_THREADS) seg_hist_kernel(const uint32_t* _
     }
 }
 
-// every point to its half: < median key left, > right, == left while the left half has room
-__global__ void __launch_bounds__(SEG_THREADS) seg_partition_kernel(const uint32_t* __restrict__ k32, const uint32_t* __restrict__ perm_in, uint32_t n, int level,
-                                                                    SegState* __restrict__ seg, uint32_t* __restrict__ perm_out) {
-    constexpr int PER = SEG_CHUNK / SEG_THREADS;  // 16 positions per thread, strided
-    __shared__ unsigned s_warp[SEG_THREADS / 32][4];
-    __shared__ unsigned s_base[4];
+// Every point to its half: < median key left, > right, == left while the left half has room.  DETERMINISTIC: the same cloud gives
+// the same tree on every GPU (a sharded registration computes map normals per slice of leaf-order positions, so the ranks' trees
+// must agree position by position) and in every run.  Two kernels: seg_count_kernel counts, per chunk and segment, the points below /
+// equal to / above the median key, and the block that completes a segment's counts turns them into exclusive offsets in chunk
+// order; seg_scatter_kernel classifies again and writes every point to  lo + [less | first ties_left equal] and
+// mid + [other equal | greater],  ranked by chunk, then by thread, then by position within the thread.
+constexpr int SEG_PER = SEG_CHUNK / SEG_THREADS;  // 16 positions per thread, strided
+
+__global__ void __launch_bounds__(SEG_THREADS) seg_count_kernel(const uint32_t* __restrict__ k32, uint32_t n, int level, SegState* __restrict__ seg,
+                                                                unsigned* __restrict__ chunk_cnt) {
+    __shared__ unsigned s_tot[SEG_THREADS / 32][6];
+    __shared__ int s_last[2];
+    __shared__ unsigned s_scan[SEG_THREADS];
     const uint32_t c0 = blockIdx.x * SEG_CHUNK, c1 = min(n, c0 + SEG_CHUNK);
     const uint32_t seg0 = seg_of(c0, level, n);
     const uint32_t nb = seg_begin(level, seg0 + 1, n);
     const bool two = nb < c1;
     const unsigned m0 = seg[seg0].key, m1 = two ? seg[seg0 + 1].key : 0u;
-    const unsigned tl0 = seg[seg0].ties_left, tl1 = two ? seg[seg0 + 1].ties_left : 0u;
-    unsigned cls = 0;                 // 2 bits per position: bit 0 = right half, bit 1 = second segment
-    unsigned cnt[4] = {0, 0, 0, 0};   // [segment * 2 + side]
+    unsigned cnt[6] = {0, 0, 0, 0, 0, 0};
 #pragma unroll
-    for (int j = 0; j < PER; ++j) {
+    for (int j = 0; j < SEG_PER; ++j) {
         const uint32_t p = c0 + threadIdx.x + SEG_THREADS * j;
         if (p >= c1) continue;
         const uint32_t key = k32[p];
         const unsigned s = p >= nb ? 1u : 0u;
         const unsigned m = s ? m1 : m0;
-        unsigned right = key > m ? 1u : 0u;
-        if (key == m) right = atomicAdd(&seg[seg0 + s].tie_cursor, 1u) < (s ? tl1 : tl0) ? 0u : 1u;
-        cls |= (right | (s << 1)) << (2 * j);
-        cnt[s * 2 + right] += 1;
+        const unsigned c = key < m ? 0u : (key == m ? 1u : 2u);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) cnt[q] += (s * 3 + c == (unsigned)q) ? 1u : 0u;
     }
-    // block-wide exclusive offsets of the four classes
-    unsigned excl[4];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        unsigned v = cnt[c];
+    for (int q = 0; q < 6; ++q) {
+        const unsigned v = __reduce_add_sync(0xffffffffu, cnt[q]);
+        if (lane == 0) s_tot[warp][q] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        unsigned v = 0;
+        for (int w = 0; w < SEG_THREADS / 32; ++w) v += s_tot[w][threadIdx.x];
+        chunk_cnt[(size_t)blockIdx.x * 6 + threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        s_last[threadIdx.x] = 0;
+        if (threadIdx.x == 0 || two) {
+            const uint32_t sg = seg0 + threadIdx.x;
+            const uint32_t lo = seg_begin(level, sg, n), hi = seg_begin(level, sg + 1, n);
+            const unsigned t = atomicAdd(&seg[sg].ticket, 1u);
+            if (t == seg_chunks(lo, hi) - 1) { s_last[threadIdx.x] = 1; seg[sg].ticket = 0; }
+        }
+    }
+    __syncthreads();
+    for (int s = 0; s < 2; ++s) {
+        if (!s_last[s]) continue;  // block-uniform
+        __threadfence();
+        // exclusive offsets of this segment's three classes over its chunks, in chunk order
+        const uint32_t sg = seg0 + s;
+        const uint32_t lo = seg_begin(level, sg, n), hi = seg_begin(level, sg + 1, n);
+        const uint32_t cf = lo / SEG_CHUNK, nch = seg_chunks(lo, hi);
+        const uint32_t per = (nch + SEG_THREADS - 1) / SEG_THREADS;
+        const uint32_t i0 = min(nch, threadIdx.x * per), i1 = min(nch, i0 + per);
+        for (int c = 0; c < 3; ++c) {
+            // the segment is slot 0 of every chunk that starts inside it and slot 1 of the chunk that straddles its lower end
+            auto slot_of = [&](uint32_t i) { return (i == 0 && (uint32_t)(cf * SEG_CHUNK) < lo) ? 1u : 0u; };
+            unsigned sum = 0;
+            for (uint32_t i = i0; i < i1; ++i) sum += __ldcg(chunk_cnt + (size_t)(cf + i) * 6 + slot_of(i) * 3 + c);
+            // block exclusive scan of the threads' sums (warp shuffles, then the eight warp totals)
+            unsigned incl = sum;
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            if (lane == 31) s_scan[warp] = incl;
+            __syncthreads();
+            unsigned wbase = 0;
+            for (int w = 0; w < warp; ++w) wbase += s_scan[w];
+            __syncthreads();
+            s_scan[threadIdx.x] = wbase + incl - sum;
+            __syncthreads();
+            unsigned off = s_scan[threadIdx.x];
+            for (uint32_t i = i0; i < i1; ++i) {
+                unsigned* e = chunk_cnt + (size_t)(cf + i) * 6 + slot_of(i) * 3 + c;
+                const unsigned v = __ldcg(e);
+                *e = off;
+                off += v;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SEG_THREADS) seg_scatter_kernel(const uint32_t* __restrict__ k32, const uint32_t* __restrict__ perm_in, uint32_t n, int level,
+                                                                  const SegState* __restrict__ seg, const unsigned* __restrict__ chunk_off,
+                                                                  uint32_t* __restrict__ perm_out) {
+    __shared__ unsigned s_warp[SEG_THREADS / 32][6];
+    const uint32_t c0 = blockIdx.x * SEG_CHUNK, c1 = min(n, c0 + SEG_CHUNK);
+    const uint32_t seg0 = seg_of(c0, level, n);
+    const uint32_t nb = seg_begin(level, seg0 + 1, n);
+    const bool two = nb < c1;
+    const unsigned m0 = seg[seg0].key, m1 = two ? seg[seg0 + 1].key : 0u;
+    unsigned long long cls = 0;  // 3 bits per position
+    unsigned cnt[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < SEG_PER; ++j) {
+        const uint32_t p = c0 + threadIdx.x + SEG_THREADS * j;
+        if (p >= c1) continue;
+        const uint32_t key = k32[p];
+        const unsigned s = p >= nb ? 1u : 0u;
+        const unsigned m = s ? m1 : m0;
+        const unsigned c = key < m ? 0u : (key == m ? 1u : 2u);
+        cls |= (unsigned long long)(s * 3 + c) << (3 * j);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) cnt[q] += (s * 3 + c == (unsigned)q) ? 1u : 0u;
+    }
+    // rank of this thread's first point of every class inside the block: warps in order, lanes in order
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned excl[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        unsigned v = cnt[q];
         for (int o = 1; o < 32; o <<= 1) {
             const unsigned u = __shfl_up_sync(0xffffffffu, v, o);
             if (lane >= o) v += u;
         }
-        excl[c] = v - cnt[c];
-        if (lane == 31) s_warp[warp][c] = v;
+        excl[q] = v - cnt[q];
+        if (lane == 31) s_warp[warp][q] = v;
     }
     __syncthreads();
-    if (threadIdx.x < 4) {
+    if (threadIdx.x < 6) {
         unsigned run = 0;
         for (int w = 0; w < SEG_THREADS / 32; ++w) { const unsigned v = s_warp[w][threadIdx.x]; s_warp[w][threadIdx.x] = run; run += v; }
-        const unsigned s = threadIdx.x >> 1, right = threadIdx.x & 1;
-        s_base[threadIdx.x] = 0;
-        if (run && (s == 0 || two)) {
-            const uint32_t sg = seg0 + s;
-            const uint32_t start = right ? seg_begin(level + 1, 2 * sg + 1, n) : seg_begin(level, sg, n);
-            s_base[threadIdx.x] = start + atomicAdd(right ? &seg[sg].right_cursor : &seg[sg].left_cursor, run);
-        }
     }
     __syncthreads();
-    unsigned pos[4];
+    // where class q of segment slot s starts for this thread
+    unsigned pos[6];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) pos[c] = s_base[c] + s_warp[warp][c] + excl[c];
+    for (int q = 0; q < 6; ++q) pos[q] = chunk_off[(size_t)blockIdx.x * 6 + q] + s_warp[warp][q] + excl[q];
+    uint32_t lo[2], mid[2];
+    unsigned ties[2], eq_total[2];
 #pragma unroll
-    for (int j = 0; j < PER; ++j) {
+    for (int s = 0; s < 2; ++s) {
+        const uint32_t sg = seg0 + s;
+        lo[s] = seg_begin(level, sg, n);
+        mid[s] = seg_begin(level + 1, 2 * sg + 1, n);
+        ties[s] = (s == 0 || two) ? seg[sg].ties_left : 0u;
+        eq_total[s] = (s == 0 || two) ? seg[sg].eq_total : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < SEG_PER; ++j) {
         const uint32_t p = c0 + threadIdx.x + SEG_THREADS * j;
         if (p >= c1) continue;
-        const unsigned c = (cls >> (2 * j)) & 3u;
-        unsigned dst = pos[0];
-        if (c == 1) dst = pos[1]; else if (c == 2) dst = pos[2]; else if (c == 3) dst = pos[3];
-        if (c == 0) pos[0]++; else if (c == 1) pos[1]++; else if (c == 2) pos[2]++; else pos[3]++;
+        const unsigned q = (unsigned)((cls >> (3 * j)) & 7ull);
+        unsigned r = 0;
+#pragma unroll
+        for (int qq = 0; qq < 6; ++qq)
+            if ((unsigned)qq == q) { r = pos[qq]; pos[qq] += 1; }
+        const unsigned s = q >= 3 ? 1u : 0u, c = q - 3 * s;
+        const unsigned n_less = (mid[s] - lo[s]) - ties[s];
+        uint32_t dst;
+        if (c == 0) dst = lo[s] + r;
+        else if (c == 1) dst = r < ties[s] ? lo[s] + n_less + r : mid[s] + (r - ties[s]);
+        else dst = mid[s] + (eq_total[s] - ties[s]) + r;
         perm_out[dst] = perm_in[p];
     }
 }
@@ -508,6 +609,7 @@ int build_tree(pmgpu_ctx* ctx) {
         const size_t nseg = (size_t)1 << (L0 - 1);
         PM_CUDA_TRY(ctx, ctx->seg_state.reserve(nseg * sizeof(SegState)));
         PM_CUDA_TRY(ctx, ctx->seg_hist.reserve(nseg * PM_HIST_BINS));
+        PM_CUDA_TRY(ctx, ctx->seg_cnt.reserve((size_t)blocks_for(n, SEG_CHUNK) * 6));
         PM_CUDA_TRY(ctx, cudaMemsetAsync(ctx->seg_state.p, 0, nseg * sizeof(SegState), st));
         PM_CUDA_TRY(ctx, cudaMemsetAsync(ctx->seg_hist.p, 0, nseg * PM_HIST_BINS * sizeof(unsigned), st));
         SegState* seg = reinterpret_cast<SegState*>(ctx->seg_state.p);
@@ -519,9 +621,10 @@ int build_tree(pmgpu_ctx* ctx) {
             seg_hist_kernel<0><<<chunks, SEG_THREADS, 0, st>>>(k32, n, l, seg, ctx->seg_hist.p, ctx->node_box.p, ctx->splits.p);
             seg_hist_kernel<1><<<chunks, SEG_THREADS, 0, st>>>(k32, n, l, seg, ctx->seg_hist.p, ctx->node_box.p, ctx->splits.p);
             seg_hist_kernel<2><<<chunks, SEG_THREADS, 0, st>>>(k32, n, l, seg, ctx->seg_hist.p, ctx->node_box.p, ctx->splits.p);
-            seg_partition_kernel<<<chunks, SEG_THREADS, 0, st>>>(k32, perm, n, l, seg, perm_alt);
+            seg_count_kernel<<<chunks, SEG_THREADS, 0, st>>>(k32, n, l, seg, ctx->seg_cnt.p);
+            seg_scatter_kernel<<<chunks, SEG_THREADS, 0, st>>>(k32, perm, n, l, seg, ctx->seg_cnt.p, perm_alt);
             uint32_t* t = perm; perm = perm_alt; perm_alt = t;
-            ctx->launches += 6;
+            ctx->launches += 7;
         }
     } else {
     for (int l = 0; l < L0; ++l) {

@@ -32,6 +32,22 @@ def shard_columns(n, rank, world, chunk=SHARD_CHUNK):
     return idx[(idx // chunk) % world == rank]
 
 
+def shard_take(a, rank, world, chunk=SHARD_CHUNK):
+    """a[shard_columns(len(a), rank, world)] as ONE strided copy (no index array: this sits inside a registration's timed region)"""
+    import numpy as np
+    a = np.asarray(a)
+    n = len(a)
+    if world <= 1:
+        return a
+    nchunks = n // chunk
+    body = a[:nchunks * chunk].reshape((nchunks, chunk) + a.shape[1:])[rank::world]
+    tail = a[nchunks * chunk:] if (nchunks % world == rank) else a[:0]
+    out = np.empty((body.shape[0] * chunk + len(tail),) + a.shape[1:], a.dtype)
+    out[:body.shape[0] * chunk].reshape(body.shape)[...] = body
+    out[body.shape[0] * chunk:] = tail
+    return out
+
+
 def pair_assignment(n_pairs, rank, world):
     """static round-robin: pair j -> rank j mod world (evaluations/eval_solution.cpp:250-271 shards pairs over threads)"""
     return list(range(rank, n_pairs, world))

@@ -1382,13 +1382,20 @@ class ICP:
         T_refMean_refIn = np.eye(d, dtype=np.float32)
         T_refMean_refIn[:d - 1, d - 1] = -T_refIn_refMean[:d - 1, d - 1]
         T_refMean_dataIn = mat4_mul(T_refMean_refIn, T_init)
-        if self._shard is not None:
-            # chunks of columns dealt out round-robin (dist.shard_columns): balanced ranks, full local density
+        if self._shard is not None and not reading.descriptors and reading.features.shape[1] == 4:
+            # chunks of columns dealt out round-robin (dist.shard_columns): balanced ranks, full local density; uploaded straight
+            # from the caller's matrix (one strided copy on the device side, no gather on the host)
             from . import dist as _pmdist
             rank, world = self._shard
-            mine = _pmdist.shard_columns(reading.features.shape[0], rank, world)
-            reading = DataPoints(np.ascontiguousarray(reading.features[mine]), {k: np.ascontiguousarray(v[mine]) for k, v in reading.descriptors.items()})
-        _translate(self.ctx.set_reading, reading.features)
+            _translate(self.ctx.set_reading_sharded, reading.features, rank, world, _pmdist.SHARD_CHUNK)
+            full = reading
+            reading = _LazyShard(full, rank, world)   # the host copy of the slice is only made if ErrorElements are asked for
+        else:
+            if self._shard is not None:
+                from . import dist as _pmdist
+                rank, world = self._shard
+                reading = DataPoints(_pmdist.shard_take(reading.features, rank, world), {k: _pmdist.shard_take(v, rank, world) for k, v in reading.descriptors.items()})
+            _translate(self.ctx.set_reading, reading.features)
         self.ctx._reading_obj = None
         self._reading_filtered, self._T_refMean_dataIn = reading, T_refMean_dataIn
         self._T_refMean_refIn = T_refMean_refIn
@@ -1415,7 +1422,8 @@ class ICP:
         """ErrorElements of the last executed iteration (ErrorMinimizer.cpp:58-193), from the resident matches: the reading as that
         iteration saw it (T_match * T_refMean_dataIn * filtered reading, ICP.cpp:345-347,381), the centred reference, the kept pairs"""
         matches, w, T_match = self.getMatches()
-        step = rigid_apply(T_match, rigid_apply(self._T_refMean_dataIn, self._reading_filtered))
+        filtered = self._reading_filtered.get() if isinstance(self._reading_filtered, _LazyShard) else self._reading_filtered
+        step = rigid_apply(T_match, rigid_apply(self._T_refMean_dataIn, filtered))
         ref = self._reference_filtered
         desc = dict(ref.descriptors)
         if self._normals_on_device:
@@ -1459,6 +1467,22 @@ class ICP:
         self._bind()
         T_refIn_refMean = self._set_reference(referenceIn)
         return self._register(readingIn, T_refIn_refMean, T_refIn_dataIn)
+
+
+class _LazyShard:
+    """this rank's slice of a sharded reading, gathered on the host only when somebody asks (ErrorElements)"""
+
+    def __init__(self, full, rank, world):
+        self.full, self.rank, self.world, self._slice = full, rank, world, None
+
+    def descriptorExists(self, name):
+        return False
+
+    def get(self):
+        if self._slice is None:
+            from . import dist as _pmdist
+            self._slice = DataPoints(_pmdist.shard_take(self.full.features, self.rank, self.world))
+        return self._slice
 
 
 class ICPSequence(ICP):

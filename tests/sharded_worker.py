@@ -43,7 +43,6 @@ def main():
     mean = rf[:, :3].mean(axis=0).astype(np.float32)
     rf = rf.copy(); rf[:, :3] -= mean
     rd = rd.copy(); rd[:, :3] -= mean
-    mine = pmdist.shard_columns(len(rd), rank, world)
     configs = {
         "A": dict(knn=1, max_dist=np.inf, filters=[(capi.FILTER_TRIMMEDDIST, 0.75)], minimizer=capi.MIN_P2PLANE, iters=12),
         "B": dict(knn=10, max_dist=2.0, filters=[(capi.FILTER_MAXDIST, 1.0), (capi.FILTER_MEDIANDIST, 3.0)], minimizer=capi.MIN_P2PLANE_COV, iters=6),
@@ -79,7 +78,7 @@ def main():
     ctx.set_reference(rf)
     ctx.ref_compute_normals(knn=10)          # this rank's slice + all-gather
     normals_sharded = ctx.ref_normals()
-    sharded = {name: run(ctx, np.ascontiguousarray(rd[mine]), cfg) for name, cfg in configs.items()}
+    sharded = {name: run(ctx, pmdist.shard_take(rd, rank, world), cfg) for name, cfg in configs.items()}
 
     # every rank must hold rank 0's T bit for bit
     report = {"world": world, "points": args.points, "exchange": "nccl" if args.nccl_only else "peer mailboxes", "configs": {}}

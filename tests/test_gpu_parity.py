@@ -949,3 +949,18 @@ def test_smooth_normals_match_oracle(gpu_ctx, oracle, synth):
     gpu_ctx.set_reference(rf)
     gpu_ctx.ref_compute_normals(knn=8, smooth=True)
     assert np.array_equal(gpu_ctx.ref_normals(), g["normals"])
+
+
+def test_reading_set_sharded_uploads_the_ranks_chunks(gpu_ctx, synth):
+    """pmgpu_reading_set_sharded: one strided copy straight from the whole reading = pmgpu_reading_set on dist.shard_take's slice"""
+    from libpointmatcher_b200 import dist as pmdist
+    rd, rf, _ = synth.scan_pair(30000)
+    gpu_ctx.set_reference(rf)
+    for n in (len(rd), 4096 * 3, 4096 * 3 + 5, 100):
+        for world in (2, 3):
+            for rank in range(world):
+                gpu_ctx.set_reading_sharded(rd[:n], rank, world, pmdist.SHARD_CHUNK)
+                want = pmdist.shard_take(rd[:n], rank, world)
+                assert gpu_ctx.nq == len(want)
+                if len(want):
+                    assert (gpu_ctx.get_reading().view(np.uint32) == np.ascontiguousarray(want).view(np.uint32)).all()
