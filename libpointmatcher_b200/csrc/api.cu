@@ -14,8 +14,10 @@ using namespace pm;
 thread_local cudaStream_t pm::g_alloc_stream = nullptr;
 
 #include <atomic>
-static std::atomic<int> g_live_contexts{0};
-bool pm::pdl_enabled(const pmgpu_ctx* ctx) { return ctx->pdl && g_live_contexts.load(std::memory_order_relaxed) == 1; }
+static std::atomic<int> g_live_contexts[64];  // per device
+static std::atomic<int>& live_on(int device) { return g_live_contexts[device & 63]; }
+bool pm::alone_on_device(const pmgpu_ctx* ctx) { return live_on(ctx->device).load(std::memory_order_relaxed) == 1; }
+bool pm::pdl_enabled(const pmgpu_ctx* ctx) { return ctx->pdl && alone_on_device(ctx); }
 
 namespace {
 
@@ -380,7 +382,7 @@ int pmgpu_ctx_create(int device, pmgpu_ctx** ctx_out) {
         pmgpu_ctx_destroy(ctx);
         return PMGPU_ERR_CUDA;
     }
-    g_live_contexts.fetch_add(1);
+    live_on(device).fetch_add(1);
     ctx->counted = true;
     *ctx_out = ctx;
     return PMGPU_OK;
@@ -388,7 +390,7 @@ int pmgpu_ctx_create(int device, pmgpu_ctx** ctx_out) {
 
 void pmgpu_ctx_destroy(pmgpu_ctx* ctx) {
     if (!ctx) return;
-    if (ctx->counted) g_live_contexts.fetch_sub(1);
+    if (ctx->counted) live_on(ctx->device).fetch_sub(1);
     cudaSetDevice(ctx->device);
     g_alloc_stream = ctx->stream;
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);

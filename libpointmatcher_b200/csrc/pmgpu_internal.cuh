@@ -349,9 +349,11 @@ struct pmgpu_ctx {
 
 namespace pm {
 
-// api.cu: programmatic dependent launch is used while this is the process's only live context — a dependent's blocks sit on
-// SM slots while they wait, which costs nothing when the stream's own predecessor is all that runs, and a quarter of the
-// throughput when other contexts' kernels could have had those slots (config 5: three contexts per GPU, 420 vs 528 pairs/s)
+// api.cu: is this the process's only live context on its GPU?  Two things are reserved for that case, because they hold SM
+// slots while they wait and that only costs nothing when nothing else could have used them (config 5 runs three contexts per
+// GPU): programmatic dependent launch (a pre-launched dependent's blocks: 420 vs 528 pairs/s) and the select inside the
+// minimiser kernel (a whole-GPU cooperative grid spinning at its barrier: 525 vs 627 pairs/s).  Results do not depend on it.
+bool alone_on_device(const pmgpu_ctx* ctx);
 bool pdl_enabled(const pmgpu_ctx* ctx);
 // tree_build.cu
 int build_tree(pmgpu_ctx* ctx);
