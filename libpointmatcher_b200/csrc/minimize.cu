@@ -858,7 +858,10 @@ int launch_minimize(pmgpu_ctx* ctx, int minimizer_word, bool compose_and_check, 
 // filters (MaxDist / MedianDist / TrimmedDist / SurfaceNormal); chains with a Robust or VarTrimmedDist filter, and a sharded
 // reading without peer mailboxes, keep the separate kernels.
 bool fused_select_applies(const pmgpu_ctx* ctx, const SelectSpec& spec) {
-    if (!ctx->fused_select || !alone_on_device(ctx)) return false;
+    if (!ctx->fused_select) return false;
+    // a sharded registration never consults the neighbourhood: every rank must take the same path (the two paths exchange
+    // different messages), and a rank cannot know how many contexts its peers' GPUs hold
+    if (ctx->nranks <= 1 && !alone_on_device(ctx)) return false;
     if (spec.robust_index() >= 0 || spec.var_index() >= 0) return false;
     if (ctx->nranks > 1 && !ctx->peer_on) return false;
     return true;
