@@ -71,7 +71,7 @@ def parse():
     ap.add_argument("--pairs", type=int, default=0, help="c5: number of pairs (default 1024, bounded by --max-seconds)")
     ap.add_argument("--mode", default="auto", choices=["auto", "pairs", "shard"])
     ap.add_argument("--reps", type=int, default=11, help="repetitions of the K-iteration timed loop (median reported)")
-    ap.add_argument("--e2e-reps", type=int, default=5)
+    ap.add_argument("--e2e-reps", type=int, default=10, help="whole registrations timed for e2e (median)")
     ap.add_argument("--rings", type=int, default=0, help="scan rings (0: isotropic sampling, 64: SURVEY 8d's 64 x N/64 layout)")
     ap.add_argument("--cpu-sample-iters", type=int, default=3)
     ap.add_argument("--no-extra", action="store_true", help="skip the explanatory extra sections")
