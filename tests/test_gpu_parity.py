@@ -36,6 +36,35 @@ def test_knn_bit_exact_vs_bruteforce(gpu_ctx, oracle, kind):
                 assert ((dg == np.inf) == (ig == -1)).all()
 
 
+@pytest.mark.parametrize("kind", ["uniform", "grid", "plane"])
+def test_knn_bit_exact_with_upper_build_levels(gpu_ctx, oracle, kind):
+    """clouds large enough for the level-by-level part of the structure build (segments > 4096 points: radix select + count +
+    scatter, tree_build.cu) at sizes where segments straddle the 4096-position chunks unevenly, and with many EQUAL coordinates
+    (grid / plane: the median key has ties that must fill the left half exactly)"""
+    rng = np.random.default_rng(104)
+    for n in (4097, 8191, 8193, 12289, 40961, 100003):
+        ref, q = cloud(rng, n, kind), cloud(rng, 300, kind)
+        if kind == "plane":
+            ref[:, 0] = np.round(ref[:, 0], 1)   # ~100 distinct x values: long runs of equal keys whenever x is the split axis
+        if kind != "grid":
+            q[:, :3] += rng.normal(0, 0.3, (300, 3)).astype(np.float32)
+        gpu_ctx.set_reference(ref)
+        gpu_ctx.set_reading(q)
+        for k in (1, 7):
+            ib, db = oracle.bruteforce_knn(ref, q, k, np.inf, nthreads=8)
+            ig, dg, _ = gpu_ctx.knn(None, k, 0.0, np.inf)
+            assert (ib == ig).all() and (bits(db) == bits(dg)).all(), (kind, n, k)
+    # the same cloud builds the same structure: two contexts agree on the leaf order (sharded map normals rely on it)
+    from libpointmatcher_b200 import capi
+    ref = cloud(rng, 50000, kind)
+    with capi.Context(0) as other:
+        other.set_reference(ref)
+        other.ref_compute_normals(knn=8)
+        gpu_ctx.set_reference(ref)
+        gpu_ctx.ref_compute_normals(knn=8)
+        assert (bits(other.ref_normals()) == bits(gpu_ctx.ref_normals())).all()
+
+
 def test_knn_fused_transform(gpu_ctx, oracle):
     rng = np.random.default_rng(101)
     ref, q = cloud(rng, 50000, "uniform"), cloud(rng, 4000, "uniform")
