@@ -276,7 +276,7 @@ protected:
             p.smooth_length = (int)differential->smoothLength;
         }
 
-        fusedLoop = onlyDeviceCheckers && (counter || differential) && this->readingStepDataPointsFilters.empty() && this->inspector->isNull();
+        fusedLoop = onlyDeviceCheckers && (counter || differential) && this->readingStepDataPointsFilters.empty() && !this->inspector->needsIterationData();
         float cov[36], stats[5];
         if (fusedLoop) {
             int iterations = 0;
@@ -288,7 +288,7 @@ protected:
             if (!this->readingStepDataPointsFilters.empty())
                 throw ConfigurationError("ICP: GPU build: readingStepDataPointsFilters are not supported (the reading stays on the device)");
             this->transformationCheckers.init(T_iter, iterate);
-            const bool wantHostData = !this->inspector->isNull();
+            const bool wantHostData = this->inspector->needsIterationData();
             // what Inspector::dumpIteration is shown (ICP.cpp:345-347, 381, 403-405): the reading as the iteration sees it and the
             // reference in the frame of its mean — host copies, made only for an inspector that is not the NullInspector
             DataPoints readingRefMean, referenceCentred;

@@ -1196,6 +1196,201 @@ struct NullInspector : public Inspector {
     NullInspector() : Inspector("NullInspector", ParametersDoc(), Parameters()) {}
     bool isNull() const override { return true; }
 };
+// PerformanceInspector (InspectorsImpl.h:66-98, InspectorsImpl.cpp:61-103): collects the statistics ICP reports through addStat; it
+// has no use for the per-iteration data (Inspector::dumpIteration stays the empty base version), so the loop stays fused
+struct PerformanceInspector : public Inspector {
+    static const std::string description() { return "Keep statistics on performance."; }
+    static const ParametersDoc availableParameters() {
+        return {{"baseFileName", "base file name for the statistics files (if empty, disabled)", ""},
+                {"dumpPerfOnExit", "dump performance statistics to stderr on exit", "0"},
+                {"dumpStats", "dump the statistics on first and last step", "0"}};
+    }
+    const std::string baseFileName;
+    const bool bDumpPerfOnExit, bDumpStats;
+    std::map<std::string, std::vector<double>> stats;
+    PerformanceInspector(const std::string& className, const ParametersDoc paramsDoc, const Parameters& params)
+        : Inspector(className, paramsDoc, params), baseFileName(Parametrizable::get<std::string>("baseFileName")),
+          bDumpPerfOnExit(Parametrizable::get<bool>("dumpPerfOnExit")), bDumpStats(Parametrizable::get<bool>("dumpStats")) {}
+    PerformanceInspector(const Parameters& params = Parameters()) : PerformanceInspector("PerformanceInspector", availableParameters(), params) {}
+    void addStat(const std::string& name, double data) override {
+        if (!bDumpStats) return;
+        stats[name].push_back(data);
+    }
+    // one "name: count mean min max" group per statistic (the reference prints its Histogram class's bins; the dump format is
+    // documented there as "will most probably change")
+    virtual void dumpStats(std::ostream& stream) {
+        bool first = true;
+        for (const auto& kv : stats) {
+            if (!first) stream << ", ";
+            first = false;
+            double sum = 0, lo = 0, hi = 0;
+            for (size_t i = 0; i < kv.second.size(); ++i) {
+                const double v = kv.second[i];
+                sum += v;
+                lo = i ? std::min(lo, v) : v;
+                hi = i ? std::max(hi, v) : v;
+            }
+            stream << kv.first << ": " << kv.second.size() << " " << (kv.second.empty() ? 0.0 : sum / kv.second.size()) << " " << lo << " " << hi;
+        }
+    }
+    ~PerformanceInspector() override {
+        if (bDumpPerfOnExit && !stats.empty()) { dumpStats(std::cerr); std::cerr << "\n"; }
+    }
+    bool isNull() const override { return false; }
+    bool needsIterationData() const override { return false; }
+};
+
+// VTKFileInspector (InspectorsImpl.h:100-193, InspectorsImpl.cpp:138-790), ASCII files: every iteration it may write the match
+// links with their outlier weights (<base>-link-N.vtk), the reading as that iteration sees it (<base>-reading-N.vtk), the
+// reference (<base>-reference-N.vtk) and one line of the checkers' condition variables and limits (<base>-iterationInfo.csv).
+// Numbers are written the way Eigen's operator<< writes a matrix: stream precision, every coefficient right-aligned to the
+// widest one, a blank between columns.
+struct VTKFileInspector : public PerformanceInspector {
+    static const std::string description() { return "Dump the different steps into VTK files."; }
+    static const ParametersDoc availableParameters() {
+        return {{"baseFileName", "base file name for the VTK files ", "point-matcher-output"},
+                {"dumpPerfOnExit", "dump performance statistics to stderr on exit", "0"},
+                {"dumpStats", "dump the statistics on first and last step", "0"},
+                {"dumpIterationInfo", "dump iteration info", "0"},
+                {"dumpDataLinks", "dump data links at each iteration", "0"},
+                {"dumpReading", "dump the reading cloud at each iteration", "0"},
+                {"dumpReference", "dump the reference cloud at each iteration", "0"},
+                {"writeBinary", "write binary VTK files", "0"}};
+    }
+    const bool bDumpIterationInfo, bDumpDataLinks, bDumpReading, bDumpReference;
+    std::unique_ptr<std::ofstream> streamIter;
+    VTKFileInspector(const Parameters& params = Parameters())
+        : PerformanceInspector("VTKFileInspector", availableParameters(), params), bDumpIterationInfo(Parametrizable::get<bool>("dumpIterationInfo")),
+          bDumpDataLinks(Parametrizable::get<bool>("dumpDataLinks")), bDumpReading(Parametrizable::get<bool>("dumpReading")),
+          bDumpReference(Parametrizable::get<bool>("dumpReference")) {
+        if (Parametrizable::get<bool>("writeBinary")) throw ConfigurationError("VTKFileInspector: GPU host layer: writeBinary is not supported (ASCII files only)");
+    }
+    bool needsIterationData() const override { return bDumpIterationInfo || bDumpDataLinks || bDumpReading || bDumpReference; }
+
+    // rows x cols block the way Eigen prints it: at(r, c), aligned columns
+    template <typename F>
+    static void writeMatrix(std::ostream& stream, int rows, int cols, F at) {
+        std::vector<std::string> cells((size_t)rows * cols);
+        size_t width = 0;
+        for (int r = 0; r < rows; ++r)
+            for (int c = 0; c < cols; ++c) {
+                std::ostringstream o;
+                o.copyfmt(stream);
+                o << at(r, c);
+                cells[(size_t)r * cols + c] = o.str();
+                width = std::max(width, o.str().size());
+            }
+        for (int r = 0; r < rows; ++r) {
+            if (r) stream << "\n";
+            for (int c = 0; c < cols; ++c) {
+                if (c) stream << " ";
+                const std::string& v = cells[(size_t)r * cols + c];
+                stream << std::string(width - v.size(), ' ') << v;
+            }
+        }
+    }
+    static void writePoints(std::ostream& stream, const Matrix& features) {  // features.topLeftCorner(dim, n).transpose()
+        const int dim = features.rows() == 4 ? 3 : features.rows();
+        writeMatrix(stream, features.cols(), dim, [&](int r, int c) { return features(c, r); });
+    }
+    // InspectorsImpl.cpp:158-238 (ASCII branch)
+    static void dumpDataPoints(const DataPoints& data, std::ostream& stream) {
+        const Matrix& features = data.features;
+        stream << "# vtk DataFile Version 3.0\nFile created by libpointmatcher\nASCII\nDATASET POLYDATA\n";
+        stream << "POINTS " << features.cols() << " float\n";
+        writePoints(stream, features);
+        stream << "\n";
+        stream << "VERTICES " << features.cols() << " " << features.cols() * 2 << "\n";
+        for (int i = 0; i < features.cols(); ++i) stream << "1 " << i << "\n";
+        stream << "POINT_DATA " << features.cols() << "\n";
+        unsigned row = 0;
+        for (const auto& label : data.descriptorLabels) {
+            const int span = (int)label.span;
+            const char* attribute = nullptr;
+            int forced = 0;
+            if (label.text == "normals") { attribute = "NORMALS"; forced = 3; }
+            else if (label.text == "eigVectors") { attribute = "TENSORS"; forced = 9; }
+            else if (label.text == "color") { attribute = "COLOR_SCALARS"; forced = 4; }
+            else if (span == 1) { attribute = "SCALARS"; forced = 1; }
+            else if (span == 3 || span == 2) { attribute = "VECTORS"; forced = 3; }
+            if (attribute && span > 0 && span <= forced) {
+                const bool color = std::string(attribute) == "COLOR_SCALARS";
+                if (color) stream << attribute << " " << label.text << " " << forced << "\n";
+                else {
+                    stream << attribute << " " << label.text << " float\n";
+                    if (std::string(attribute) == "SCALARS") stream << "LOOKUP_TABLE default\n";
+                }
+                const unsigned r0 = row;
+                // padWithZeros / padWithOnes (colours) to the attribute's dimension, transposed: one point per line
+                writeMatrix(stream, data.descriptors.cols(), forced,
+                            [&](int r, int c) { return c < span ? data.descriptors(r0 + c, r) : (color ? T(1) : T(0)); });
+                stream << "\n";
+            }
+            row += label.span;
+        }
+    }
+    // InspectorsImpl.cpp:285-362
+    static void dumpDataLinks(const DataPoints& ref, const DataPoints& reading, const Matches& matches, const OutlierWeights& w, std::ostream& stream) {
+        const int refPtCount = ref.features.cols(), readingPtCount = reading.features.cols();
+        stream << "# vtk DataFile Version 3.0\ncomment\nASCII\nDATASET POLYDATA\n";
+        stream << "POINTS " << refPtCount + readingPtCount << " float\n";
+        writePoints(stream, ref.features);
+        stream << "\n";
+        writePoints(stream, reading.features);
+        stream << "\n";
+        const int knn = matches.ids.rows();
+        size_t matchCount = 0;
+        for (int k = 0; k < knn; ++k)
+            for (int i = 0; i < readingPtCount; ++i) matchCount += matches.ids(k, i) != Matches::InvalidId ? 1 : 0;
+        stream << "LINES " << matchCount << " " << matchCount * 3 << "\n";
+        for (int k = 0; k < knn; ++k)
+            for (int i = 0; i < readingPtCount; ++i)
+                if (matches.ids(k, i) != Matches::InvalidId) stream << "2 " << refPtCount + i << " " << matches.ids(k, i) << "\n";
+        stream << "CELL_DATA " << matchCount << "\nSCALARS outlier float 1\nLOOKUP_TABLE default\n";
+        for (int k = 0; k < knn; ++k)
+            for (int i = 0; i < readingPtCount; ++i)
+                if (matches.ids(k, i) != Matches::InvalidId) stream << w(k, i) << "\n";
+    }
+    std::string fileName(const std::string& role, size_t iteration) const {
+        std::ostringstream oss;
+        oss << this->baseFileName << "-" << role << "-" << iteration << ".vtk";
+        return oss.str();
+    }
+    static std::unique_ptr<std::ofstream> open(const std::string& name) {
+        std::unique_ptr<std::ofstream> f(new std::ofstream(name.c_str()));
+        if (f->fail()) throw std::runtime_error("Couldn't open the file \"" + name + "\". Check if directory exist.");
+        return f;
+    }
+    void init() override {
+        if (!bDumpIterationInfo) return;
+        streamIter = open(this->baseFileName + "-iterationInfo.csv");
+    }
+    // InspectorsImpl.cpp:384-450
+    void dumpIteration(const size_t iterationNumber, const TransformationParameters&, const DataPoints& filteredReference, const DataPoints& reading,
+                       const Matches& matches, const OutlierWeights& outlierWeights, const TransformationCheckers& transCheck) override {
+        if (bDumpDataLinks) dumpDataLinks(filteredReference, reading, matches, outlierWeights, *open(fileName("link", iterationNumber)));
+        if (bDumpReading) dumpDataPoints(reading, *open(fileName("reading", iterationNumber)));
+        if (bDumpReference) dumpDataPoints(filteredReference, *open(fileName("reference", iterationNumber)));
+        if (!bDumpIterationInfo || !streamIter) return;
+        std::ostream& out = *streamIter;
+        if (iterationNumber == 0) {
+            for (size_t j = 0; j < transCheck.size(); ++j)
+                for (size_t i = 0; i < transCheck[j]->getConditionVariableNames().size(); ++i) {
+                    if (!(j == 0 && i == 0)) out << ", ";
+                    out << transCheck[j]->getConditionVariableNames()[i] << ", " << transCheck[j]->getLimitNames()[i];
+                }
+            out << "\n";
+        }
+        for (size_t j = 0; j < transCheck.size(); ++j)
+            for (int i = 0; i < (int)transCheck[j]->getConditionVariables().size(); ++i) {
+                if (!(j == 0 && i == 0)) out << ", ";
+                out << transCheck[j]->getConditionVariables()(i) << ", " << transCheck[j]->getLimits()(i);
+            }
+        out << "\n";
+    }
+    void finish(const size_t) override { streamIter.reset(); }
+};
+
 struct NullLogger : public Logger {
     static const std::string description() { return "Does nothing."; }
     NullLogger() : Logger("NullLogger", ParametersDoc(), Parameters()) {}

@@ -22,6 +22,8 @@
 #include <cstring>
 #include <fstream>
 #include <functional>
+#include <sstream>
+#include <memory>
 #include <future>
 #include <iostream>
 
@@ -653,6 +655,8 @@ struct PointMatcher {
                                    const OutlierWeights&, const TransformationCheckers&) {}
         virtual void finish(const size_t) {}
         virtual bool isNull() const { return false; }
+        // does dumpIteration read its arguments?  (host copies of matches / weights / clouds are made only if it does)
+        virtual bool needsIterationData() const { return !isNull(); }
     };
     DEF_REGISTRAR(Inspector)
 
@@ -708,6 +712,8 @@ struct PointMatcher {
         ADD_TO_REGISTRAR(TransformationChecker, DifferentialTransformationChecker, DifferentialTransformationChecker)
         ADD_TO_REGISTRAR(TransformationChecker, BoundTransformationChecker, BoundTransformationChecker)
         ADD_TO_REGISTRAR_NO_PARAM(Inspector, NullInspector, NullInspector)
+        ADD_TO_REGISTRAR(Inspector, PerformanceInspector, PerformanceInspector)
+        ADD_TO_REGISTRAR(Inspector, VTKFileInspector, VTKFileInspector)
         ADD_TO_REGISTRAR_NO_PARAM(Logger, NullLogger, NullLogger)
     }
     static const PointMatcher& get() {  // Registry.cpp:142-146

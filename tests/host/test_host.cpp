@@ -311,6 +311,59 @@ static int run_cpu() {
         PointMatcher<double>::KDTreeMatcher km;
         CHECK(throws<PointMatcher<double>::ConfigurationError>([&] { km.init(d); }));
     }
+    {
+        // VTKFileInspector (InspectorsImpl.cpp:158-450, ASCII): the files of one iteration, byte for byte as the reference's
+        // stream operators lay them out (Eigen's aligned columns), on a hand-made case
+        const char* tmp = std::getenv("PM_TEST_TMP");
+        const std::string base = std::string(tmp ? tmp : "/tmp") + "/pm_vtk_test";
+        auto insp = pm.InspectorRegistrar.create("VTKFileInspector", {{"baseFileName", base}, {"dumpIterationInfo", "1"}, {"dumpDataLinks", "1"},
+                                                                      {"dumpReading", "1"}, {"dumpReference", "1"}});
+        CHECK(!insp->isNull() && insp->needsIterationData());
+        CHECK(throws<PM::ConfigurationError>([&] { pm.InspectorRegistrar.create("VTKFileInspector", {{"writeBinary", "1"}}); }));
+        auto perf = pm.InspectorRegistrar.create("PerformanceInspector", {{"dumpStats", "1"}});
+        CHECK(!perf->isNull() && !perf->needsIterationData());  // statistics only: the loop stays on the device
+        DP ref, rd;
+        ref.features = PM::Matrix(4, 3);
+        const float rp[3][3] = {{0, 0, 0}, {1, 0, 0}, {0, 2.5f, 0}};
+        for (int j = 0; j < 3; ++j) { for (int i = 0; i < 3; ++i) ref.features(i, j) = rp[j][i]; ref.features(3, j) = 1; }
+        PM::Matrix nrm(3, 3);
+        for (int j = 0; j < 3; ++j) { nrm(0, j) = 0; nrm(1, j) = 0; nrm(2, j) = 1; }
+        ref.addDescriptor("normals", nrm);
+        rd.features = PM::Matrix(4, 2);
+        const float qp[2][3] = {{0.1f, 0, 0}, {1, 0.25f, 0}};
+        for (int j = 0; j < 2; ++j) { for (int i = 0; i < 3; ++i) rd.features(i, j) = qp[j][i]; rd.features(3, j) = 1; }
+        PM::Matches m(1, 2);
+        m.ids(0, 0) = 0; m.ids(0, 1) = 1;
+        m.dists(0, 0) = 0.01f; m.dists(0, 1) = 0.0625f;
+        PM::OutlierWeights w(1, 2);
+        w(0, 0) = 1.f; w(0, 1) = 0.5f;
+        PM::TransformationCheckers checkers;
+        checkers.push_back(pm.TransformationCheckerRegistrar.create("CounterTransformationChecker", {{"maxIterationCount", "40"}}));
+        bool it = true;
+        checkers.init(PM::Matrix::Identity(4, 4), it);
+        insp->init();
+        insp->dumpIteration(0, PM::Matrix::Identity(4, 4), ref, rd, m, w, checkers);
+        insp->finish(1);
+        auto slurp = [](const std::string& path) {
+            std::ifstream f(path);
+            std::stringstream ss;
+            ss << f.rdbuf();
+            return ss.str();
+        };
+        CHECK(slurp(base + "-link-0.vtk") ==
+              "# vtk DataFile Version 3.0\ncomment\nASCII\nDATASET POLYDATA\nPOINTS 5 float\n"
+              "  0   0   0\n  1   0   0\n  0 2.5   0\n"
+              " 0.1    0    0\n   1 0.25    0\n"
+              "LINES 2 6\n2 3 0\n2 4 1\nCELL_DATA 2\nSCALARS outlier float 1\nLOOKUP_TABLE default\n1\n0.5\n");
+        CHECK(slurp(base + "-reading-0.vtk") ==
+              "# vtk DataFile Version 3.0\nFile created by libpointmatcher\nASCII\nDATASET POLYDATA\nPOINTS 2 float\n"
+              " 0.1    0    0\n   1 0.25    0\nVERTICES 2 4\n1 0\n1 1\nPOINT_DATA 2\n");
+        CHECK(slurp(base + "-reference-0.vtk") ==
+              "# vtk DataFile Version 3.0\nFile created by libpointmatcher\nASCII\nDATASET POLYDATA\nPOINTS 3 float\n"
+              "  0   0   0\n  1   0   0\n  0 2.5   0\nVERTICES 3 6\n1 0\n1 1\n1 2\nPOINT_DATA 3\nNORMALS normals float\n0 0 1\n0 0 1\n0 0 1\n");
+        const std::string info = slurp(base + "-iterationInfo.csv");
+        CHECK(info.find(", ") != std::string::npos && std::count(info.begin(), info.end(), '\n') == 2 && info.find("40") != std::string::npos);
+    }
     std::printf("host cpu tests ok\n");
     return 0;
 }
