@@ -117,6 +117,31 @@ def test_cpp_inspector_sees_every_iteration(host_bin, tmp_path, oracle, synth):
 
 
 @pytest.mark.gpu
+def test_cpp_vtk_file_inspector_dumps_every_iteration(host_bin, tmp_path, oracle, synth):
+    """a chain with the reference's VTKFileInspector (examples/data/default.yaml has one): one link / reading file per iteration, the
+    match count of the link file = the finite matches, the same transform as with the NullInspector"""
+    rd, rf, _ = synth.scan_pair(6000)
+    nrm = oracle.surface_normals(rf, knn=10, nthreads=8)["normals"]
+    base = str(tmp_path / "dump")
+    cfg = CONFIG.format(minimizer="PointToPlaneErrorMinimizer", iters=4, differential="")
+    plain = _run_icp(host_bin, tmp_path, cfg, rd, rf, nrm)
+    vtk = cfg.replace("inspector:\n  NullInspector", "inspector:\n  VTKFileInspector:\n    baseFileName: %s\n    dumpDataLinks: 1\n    dumpReading: 1\n    dumpIterationInfo: 1" % base)
+    assert vtk != cfg
+    seen = _run_icp(host_bin, tmp_path, vtk, rd, rf, nrm)
+    assert seen["fused"] == 0 and seen["iterations"] == plain["iterations"] == 4
+    assert_transform_close(seen["T"], plain["T"], 1e-5, 1e-5)
+    for it in range(4):
+        link = open("%s-link-%d.vtk" % (base, it)).read().split("\n")
+        assert link[4] == "POINTS %d float" % (len(rd) + len(rf))
+        lines_at = link.index("LINES %d %d" % (len(rd), 3 * len(rd)))          # knn 1, maxDist inf: every reading point has a match
+        assert link[lines_at + 1].startswith("2 %d " % len(rf))
+        reading = open("%s-reading-%d.vtk" % (base, it)).read().split("\n")
+        assert reading[4] == "POINTS %d float" % len(rd) and "VERTICES %d %d" % (len(rd), 2 * len(rd)) in reading
+    info = open(base + "-iterationInfo.csv").read().strip().split("\n")
+    assert len(info) == 5                                                       # header + one line per iteration
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("variant", ["counter", "differential", "bound"])
 def test_cpp_icp_matches_oracle_and_python(host_bin, tmp_path, oracle, synth, variant):
     rd, rf, T_gt = synth.scan_pair(60000)
