@@ -112,3 +112,90 @@ def test_surface_normals_at_1m_properties(pair, oracle):
     gap = (wv[:, 1] - wv[:, 0]) / wv.sum(1)
     dots = np.abs((V[:, :, 0] * n[sample][same]).sum(1))
     assert (1.0 - dots[gap > 1e-3]).max() < 1e-5
+
+
+def _run_host_icp(rd, rf, nrm, matcher, filters, minimizer, iters):
+    from libpointmatcher_b200 import pm
+    icp = pm.ICP()
+    icp.matcher = pm.KDTreeMatcher(matcher)
+    icp.outlierFilters = pm.OutlierFilters([pm.OutlierFilterRegistrar.create(n, p) for n, p in filters])
+    icp.errorMinimizer = getattr(pm, minimizer)()
+    icp.transformationCheckers = [pm.CounterTransformationChecker({"maxIterationCount": str(iters)})]
+    return icp(pm.DataPoints(rd), pm.DataPoints(rf, {"normals": nrm})), icp
+
+
+def test_config3_10m_map_1m_reading(oracle, synth):
+    """BASELINE configs[2] at its full size: a 10 M-point map (10 scans in the world frame), 1 M-point reading, knn 1, TrimmedDist
+    0.75, PointToPlane, SurfaceNormal knn 20 on the map.  The oracle finishes this in seconds on the box's host threads (kd-tree
+    build ~2 s, 1 M queries ~0.1 s), so matching is compared in full; the map's normals on a random sample."""
+    from libpointmatcher_b200 import capi
+    rf = synth.world_map(10_000_000, 10)
+    rd = synth.scan(1_000_000, synth.READING_POSE, seed=synth.SEED + 1)
+    threads = oracle.num_threads()
+    chain = [(capi.FILTER_TRIMMEDDIST, 0.75)]
+    with capi.Context(0) as ctx:
+        ctx.set_reference(rf)
+        ctx.ref_compute_normals(knn=20)
+        nrm = ctx.ref_normals()
+        ctx.set_reading(rd)
+        ids, d, _ = ctx.knn(None, 1)
+        tree = oracle.KdTree(rf)
+        io, do = tree.knn(rd, 1, nthreads=threads)
+        assert (d.view(np.uint32) == do.view(np.uint32)).all()
+        ndiff, nties = classify_id_mismatches(io, do, ids, d)
+        assert ndiff == nties
+        w, lim = ctx.weights(chain)
+        wo, lo = oracle.outlier_weights(do, chain)
+        assert lim[0] == lo[0] and (w == wo).all()
+        # map normals: unit length everywhere, and the oracle's neighbourhoods / float64 eigenvectors on a sample
+        assert np.abs(np.linalg.norm(nrm, axis=1) - 1.0).max() < 1e-5
+        rng = np.random.default_rng(11)
+        sample = np.sort(rng.choice(len(rf), 20000, replace=False))
+        isamp, _ = tree.knn(rf[sample], 20, nthreads=threads)
+        del tree
+        P = rf[isamp][:, :, :3].astype(np.float64)
+        Pc = P - P.mean(1, keepdims=True)
+        wv, V = np.linalg.eigh(np.einsum("nki,nkj->nij", Pc, Pc))
+        gap = (wv[:, 1] - wv[:, 0]) / wv.sum(1)
+        dots = np.abs((V[:, :, 0] * nrm[sample]).sum(1))
+        # a neighbourhood with an exact distance tie at rank 20 may hold a different 20th point: allow 0.1 % of the sample
+        assert ((1.0 - dots[gap > 1e-3]) > 1e-5).mean() < 1e-3
+    # the whole registration through the host driver (which centres both clouds on the map's mean like ICP.cpp:291-299, as the
+    # oracle's loop does) against the oracle's loop over the same normals
+    res_o = oracle.icp(rd, rf, ref_normals=nrm, knn=1, filters=chain, minimizer=capi.MIN_P2PLANE, max_iterations=6,
+                       nthreads=threads, acc_double=True)
+    T, icp = _run_host_icp(rd, rf, nrm, {"knn": "1"}, [("TrimmedDistOutlierFilter", {"ratio": "0.75"})], "PointToPlaneErrorMinimizer", 6)
+    assert icp.iterationCount == res_o["iterations"] == 6
+    assert_transform_close(T, res_o["T"], 1e-5, 1e-5)
+    icp.ctx.close()
+
+
+def test_config4_at_2m(oracle, synth):
+    """BASELINE configs[3] at its full size: 2 M x 2 M, knn 10, maxDist 2, MaxDist 1 x MedianDist 3, PointToPlaneWithCov"""
+    from libpointmatcher_b200 import capi
+    rd, rf, _ = synth.scan_pair(2_000_000)
+    threads = oracle.num_threads()
+    chain = [(capi.FILTER_MAXDIST, 1.0), (capi.FILTER_MEDIANDIST, 3.0)]
+    with capi.Context(0) as ctx:
+        ctx.set_reference(rf)
+        ctx.ref_compute_normals(knn=20)
+        nrm = ctx.ref_normals()
+        ctx.set_reading(rd)
+        ids, d, _ = ctx.knn(None, 10, 0.0, 2.0)
+        io, do = oracle.KdTree(rf).knn(rd, 10, max_dist=2.0, nthreads=threads)
+        assert (d.view(np.uint32) == do.view(np.uint32)).all()
+        ndiff, nties = classify_id_mismatches(io, do, ids, d)
+        assert ndiff == nties
+        w, lim = ctx.weights(chain)
+        wo, lo = oracle.outlier_weights(do, chain)
+        assert (lim.view(np.uint32) == lo.view(np.uint32)).all() and (w == wo).all()
+        res_o = oracle.icp(rd, rf, ref_normals=nrm, knn=10, max_dist=2.0, filters=chain, minimizer=capi.MIN_P2PLANE_COV,
+                           max_iterations=4, nthreads=threads, acc_double=True)
+    T, icp = _run_host_icp(rd, rf, nrm, {"knn": "10", "maxDist": "2.0"},
+                           [("MaxDistOutlierFilter", {"maxDist": "1.0"}), ("MedianDistOutlierFilter", {"factor": "3.0"})],
+                           "PointToPlaneWithCovErrorMinimizer", 4)
+    assert icp.iterationCount == res_o["iterations"] == 4
+    assert_transform_close(T, res_o["T"], 1e-5, 1e-5)
+    c, co = np.asarray(icp.errorMinimizer.getCovariance(), np.float64), res_o["cov"].astype(np.float64)
+    assert np.abs(c - co).max() <= 2e-3 * np.abs(co).max()
+    icp.ctx.close()
