@@ -283,6 +283,12 @@ int pmgpu_icp_enqueue(pmgpu_ctx* ctx, const pmgpu_icp_params* params, int n_iter
 int pmgpu_icp_reset(pmgpu_ctx* ctx, const float* T_iter_init);
 int pmgpu_icp_result(pmgpu_ctx* ctx, float* T_iter_out, int* iterations_out, float* cov_out, float* stats_out);
 int pmgpu_icp_cap_redos(const pmgpu_ctx* ctx);
+/* One iteration of the loop for a host that looks at every iteration (Inspector::dumpIteration, ICP.cpp:403-405; a host-side
+ * TransformationChecker such as Bound, ICP.cpp:414-427): exactly one slot, matched WITHOUT the cap — pmgpu_matches_get then shows
+ * what the reference's inspector is shown, every match with its weight — then the state as pmgpu_icp_result returns it; with a
+ * WithCov minimiser, the covariance of this iteration.  iterations_out unchanged from the previous call = the device checkers
+ * (Counter, Differential) had already stopped the loop.  Call pmgpu_icp_reset first. */
+int pmgpu_icp_step(pmgpu_ctx* ctx, const pmgpu_icp_params* params, float* T_iter_out, int* iterations_out, float* cov_out, float* stats_out);
 
 /* ---- host-side pre-filters of the default chain (CPU, once per cloud) ----
  * ICPChainBase::setDefault / examples/data/default.yaml put RandomSamplingDataPointsFilter on

@@ -91,6 +91,7 @@ SIGNATURES = {
     "pmgpu_icp_enqueue": (C.c_int, [C.c_void_p, C.POINTER(IcpParams), C.c_int]),
     "pmgpu_icp_reset": (C.c_int, [C.c_void_p, _fp]),
     "pmgpu_icp_result": (C.c_int, [C.c_void_p, _fp, C.POINTER(C.c_int), _fp, _fp]),
+    "pmgpu_icp_step": (C.c_int, [C.c_void_p, C.POINTER(IcpParams), _fp, C.POINTER(C.c_int), _fp, _fp]),
     "pmgpu_icp_cap_redos": (C.c_int, [C.c_void_p]),
     "pmgpu_matches_get": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pmgpu_set_var_trimmed_ratios": (C.c_int, [C.c_void_p, C.c_float, C.c_float]),
@@ -399,6 +400,16 @@ class Context:
     def icp_enqueue(self, params, n_iterations):
         self._check(lib.pmgpu_icp_enqueue(self.h, C.byref(params), n_iterations))
         self.k = params.knn
+
+    def icp_step(self, params):
+        """one exactly-matched iteration slot (after icp_reset), then the state: dict as icp_result"""
+        T = np.zeros((self.dimh, self.dimh), np.float32, order="F")
+        cov = np.zeros((6, 6), np.float32, order="F")
+        stats = np.zeros(5, np.float32)
+        it = C.c_int(0)
+        self._check(lib.pmgpu_icp_step(self.h, C.byref(params), _f(T), C.byref(it), _f(cov), _f(stats)))
+        self.k = params.knn
+        return dict(T_iter=np.array(T), iterations=it.value, cov=np.array(cov), stats=_stats(stats), cap_redos=int(lib.pmgpu_icp_cap_redos(self.h)))
 
     def icp_result(self):
         T = np.zeros((self.dimh, self.dimh), np.float32, order="F")

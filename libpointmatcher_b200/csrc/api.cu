@@ -943,6 +943,22 @@ int pmgpu_host_unpin(void* ptr) {
 
 int pmgpu_icp_cap_redos(const pmgpu_ctx* ctx) { return ctx ? ctx->state_host->redo_count : 0; }
 
+int pmgpu_icp_step(pmgpu_ctx* ctx, const pmgpu_icp_params* params, float* T_iter_out, int* iterations_out, float* cov_out, float* stats_out) {
+    if (!ctx || !params) return PMGPU_ERR_BAD_ARG;
+    // exact matching for this slot: whoever asks for single iterations is going to look at the matches
+    const bool cap = ctx->cap_enabled;
+    ctx->cap_enabled = false;
+    const int rc = pmgpu_icp_enqueue(ctx, params, 1);
+    ctx->cap_enabled = cap;
+    PM_TRY(rc);
+    const bool with_cov = (params->minimizer & 0xff) == PMGPU_MIN_P2POINT_COV || (params->minimizer & 0xff) == PMGPU_MIN_P2PLANE_COV;
+    if (with_cov) {
+        PM_TRY(pull_state(ctx));
+        if (ctx->state_host->status == PMGPU_OK) PM_TRY(launch_covariance(ctx, params->minimizer, params->sensor_std_dev));
+    }
+    return pmgpu_icp_result(ctx, T_iter_out, iterations_out, cov_out, stats_out);
+}
+
 int pmgpu_icp_run(pmgpu_ctx* ctx, const pmgpu_icp_params* params, const float* T_iter_init, float* T_iter_out, int* iterations_out, float* cov_out,
                   float* stats_out) {
     if (!ctx) return PMGPU_ERR_BAD_ARG;

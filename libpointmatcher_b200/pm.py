@@ -1178,6 +1178,70 @@ class BoundTransformationChecker(Parametrizable):
             raise ConvergenceError("limit out of bounds: rot: %g/%g tr: %g/%g" % (rot, self.maxRotationNorm, tr, self.maxTranslationNorm))
 
 
+# ---- Inspector (PointMatcher.h:640-664, InspectorsImpl.h:47-98) -------------------------------------
+class Inspector(Parametrizable):
+    """What ICP reports to while it runs.  `dumpIteration` is called once per iteration with host copies of what that iteration
+    matched (ICP.cpp:403-405); they are only made — and the loop only leaves the fused device path — for an inspector whose
+    `needsIterationData()` is true, which is the case for every subclass that overrides `dumpIteration`."""
+    className = "Inspector"
+
+    def init(self):
+        pass
+
+    def addStat(self, name, data):
+        pass
+
+    def dumpStats(self, stream):
+        pass
+
+    def dumpStatsHeader(self, stream):
+        pass
+
+    def dumpIteration(self, iterationNumber, parameters, filteredReference, reading, matches, outlierWeights, transformationCheckers):
+        pass
+
+    def finish(self, iterationCount):
+        pass
+
+    def needsIterationData(self):
+        return type(self).dumpIteration is not Inspector.dumpIteration
+
+
+class NullInspector(Inspector):
+    """Does nothing."""
+    className = "NullInspector"
+
+
+class PerformanceInspector(Inspector):
+    """Keep statistics on performance."""
+    className = "PerformanceInspector"
+    PARAMS = (("baseFileName", "base file name for the statistics files (if empty, disabled)", "", None, None, str),
+              ("dumpPerfOnExit", "dump performance statistics to stderr on exit", "0", None, None, int),
+              ("dumpStats", "dump the statistics on first and last step", "0", None, None, int))
+
+    def __init__(self, params=None):
+        Inspector.__init__(self, params)
+        self.baseFileName = self.get("baseFileName")
+        self.bDumpPerfOnExit, self.bDumpStats = bool(self.get("dumpPerfOnExit")), bool(self.get("dumpStats"))
+        self.stats = {}
+
+    def addStat(self, name, data):          # InspectorsImpl.cpp:74-84
+        if self.bDumpStats:
+            self.stats.setdefault(name, []).append(float(data))
+
+    def dumpStats(self, stream):
+        """one "name: count mean min max" group per statistic, like the C++ host layer (the reference prints its Histogram
+        class's bins in a format it documents as bound to change)"""
+        stream.write(", ".join("%s: %d %g %g %g" % (k, len(v), sum(v) / len(v) if v else 0.0, min(v) if v else 0.0, max(v) if v else 0.0)
+                               for k, v in sorted(self.stats.items())))
+
+    def dumpStatsHeader(self, stream):
+        stream.write(", ".join(sorted(self.stats)))
+
+
+InspectorRegistrar = None  # filled in below, after Registrar
+
+
 # ---- Registrar (Registrar.h:75-218) --------------------------------------------------------------
 class Registrar(dict):
     def create(self, name, params=None):
@@ -1217,6 +1281,7 @@ DataPointsFilterRegistrar = Registrar(SurfaceNormalDataPointsFilter=SurfaceNorma
 TransformationCheckerRegistrar = Registrar(CounterTransformationChecker=CounterTransformationChecker,
                                            DifferentialTransformationChecker=DifferentialTransformationChecker,
                                            BoundTransformationChecker=BoundTransformationChecker)
+InspectorRegistrar = Registrar(NullInspector=NullInspector, PerformanceInspector=PerformanceInspector)
 
 
 # ---- float32 4x4 helpers with the reference's GEMM accumulation order -----------------------------
@@ -1255,6 +1320,7 @@ class ICP:
         self.outlierFilters = OutlierFilters()
         self.errorMinimizer = None
         self.transformationCheckers = []
+        self.inspector = NullInspector()
         self.maxNumIterationsReached = False
         self.iterationCount = 0
         self._shard = None
@@ -1281,12 +1347,13 @@ class ICP:
         self.outlierFilters = OutlierFilters([TrimmedDistOutlierFilter()])
         self.errorMinimizer = PointToPlaneErrorMinimizer()
         self.transformationCheckers = [CounterTransformationChecker(), DifferentialTransformationChecker()]
+        self.inspector = NullInspector()
 
     def loadFromYaml(self, text):
         """ICPChainBase::loadFromYaml (ICP.cpp:116-167): the reference's YAML layout — module lists for the
         filters / outlier filters / checkers, a single module for matcher and errorMinimizer; a module is
         `Name`, `Name:` or `Name: {param: value}`.  Unknown names raise InvalidElement (Registrar.h:150-162).
-        inspector / logger accept the Null modules only."""
+        inspector: NullInspector or PerformanceInspector (VTKFileInspector lives in the C++ host layer); logger: NullLogger only."""
         import yaml
         doc = yaml.safe_load(text) or {}
 
@@ -1307,9 +1374,9 @@ class ICP:
         self.transformationCheckers = many("transformationCheckers", TransformationCheckerRegistrar)
         self.matcher = MatcherRegistrar.create(*one(doc["matcher"])) if "matcher" in doc else KDTreeMatcher()
         self.errorMinimizer = ErrorMinimizerRegistrar.create(*one(doc["errorMinimizer"])) if "errorMinimizer" in doc else PointToPlaneErrorMinimizer()
-        for key, allowed in (("inspector", "NullInspector"), ("logger", "NullLogger")):
-            if key in doc and one(doc[key])[0] != allowed:
-                raise InvalidElement("Trying to instanciate unknown element %s from registrar" % one(doc[key])[0])
+        self.inspector = InspectorRegistrar.create(*one(doc["inspector"])) if "inspector" in doc else NullInspector()
+        if "logger" in doc and one(doc["logger"])[0] != "NullLogger":
+            raise InvalidElement("Trying to instanciate unknown element %s from registrar" % one(doc["logger"])[0])
 
     def _params(self):
         counter = [c for c in self.transformationCheckers if isinstance(c, CounterTransformationChecker)]
@@ -1406,8 +1473,11 @@ class ICP:
             _translate(self.ctx.set_reading_normals, reading.descriptors["normals"])
         _translate(self.ctx.reading_apply_transform, T_refMean_dataIn)
         bounds = [c for c in self.transformationCheckers if isinstance(c, BoundTransformationChecker)]
-        if bounds:
-            res = self._run_with_host_checkers(bounds)
+        if self.inspector is None:
+            raise RuntimeError("You must setup an inspector before running ICP")
+        self.inspector.init()
+        if bounds or self.inspector.needsIterationData():
+            res = self._run_stepwise(bounds)
         else:
             res = _translate(self.ctx.icp_run, self._params())
         self.iterationCount = res["iterations"]
@@ -1416,6 +1486,9 @@ class ICP:
         self.errorMinimizer._stats = res["stats"]
         self.errorMinimizer._cov = res["cov"]
         self.T_iter = res["T_iter"]
+        self.inspector.addStat("IterationsCount", float(res["iterations"]))     # ICP.cpp:432-437
+        self.inspector.addStat("OverlapRatio", float(res["stats"]["weightedPointUsedRatio"]))
+        self.inspector.finish(res["iterations"])
         return mat4_mul(mat4_mul(T_refIn_refMean, res["T_iter"]), T_refMean_dataIn)
 
     def getErrorElements(self):
@@ -1424,14 +1497,7 @@ class ICP:
         matches, w, T_match = self.getMatches()
         filtered = self._reading_filtered.get() if isinstance(self._reading_filtered, _LazyShard) else self._reading_filtered
         step = rigid_apply(T_match, rigid_apply(self._T_refMean_dataIn, filtered))
-        ref = self._reference_filtered
-        desc = dict(ref.descriptors)
-        if self._normals_on_device:
-            desc["normals"] = _translate(self.ctx.ref_normals)
-        centred = ref.features.copy()
-        d = centred.shape[1]
-        centred[:, :d - 1] = (centred[:, :d - 1] + self._T_refMean_refIn[:d - 1, d - 1][None, :]).astype(np.float32)   # minus the mean (ICP.cpp:291-299)
-        return ErrorElements(step, DataPoints(centred, desc), w, matches)
+        return ErrorElements(step, self._centred_reference(), w, matches)
 
     def getMatches(self):
         """What the reference's inspectors and ErrorMinimizer::getErrorElements read after the fact (ErrorMinimizer.cpp:58-193):
@@ -1440,28 +1506,44 @@ class ICP:
         ids, dists, w, T = _translate(self.ctx.matches)
         return Matches(dists, ids), w, T
 
-    def _run_with_host_checkers(self, bounds):
-        """Counter / Differential still decide on the device; the host checkers see T_iter after every iteration
-        (TransformationCheckers::check, ICP.cpp:414-427), so the loop is enqueued one iteration at a time."""
+    def _run_stepwise(self, bounds):
+        """The loop one iteration at a time (pmgpu_icp_step: exact matching, the covariance of every iteration), for a host that
+        looks at every iteration: host-side checkers see T_iter after it (TransformationCheckers::check, ICP.cpp:414-427) and an
+        inspector that wants them is shown the iteration's reading, matches and weights (ICP.cpp:403-405).  Counter / Differential
+        still decide on the device."""
         params = self._params()
-        if (params.minimizer & 0xff) in (capi.MIN_P2POINT_COV, capi.MIN_P2PLANE_COV):
-            raise ConfigurationError("GPU module (Python mirror): BoundTransformationChecker with a WithCov minimiser is not supported")
         _translate(self.ctx.icp_reset, None)
         for b in bounds:
             b.init(np.eye(self.ctx.dimh, dtype=np.float32))
-        done, redos, res = 0, 0, None
+        want = self.inspector.needsIterationData()
+        reference = reading0 = None
+        if want:
+            reference = self._centred_reference()
+            filtered = self._reading_filtered.get() if isinstance(self._reading_filtered, _LazyShard) else self._reading_filtered
+            reading0 = rigid_apply(self._T_refMean_dataIn, filtered)
+        done, res = 0, None
         while True:
-            _translate(self.ctx.icp_enqueue, params, 1)
-            res = _translate(self.ctx.icp_result)
+            res = _translate(self.ctx.icp_step, params)
             if res["iterations"] == done:
-                if res["cap_redos"] > redos:   # a void slot of capped matching: not an iteration
-                    redos = res["cap_redos"]
-                    continue
                 break                          # the device checkers had already stopped the loop
+            if want:
+                matches, w, T_match = self.getMatches()
+                self.inspector.dumpIteration(done, T_match, reference, rigid_apply(T_match, reading0), matches, w, self.transformationCheckers)
             done = res["iterations"]
             for b in bounds:
                 b.check(res["T_iter"])
         return res
+
+    def _centred_reference(self):
+        """the filtered reference in the frame of its mean, with the normals a fused SurfaceNormal filter made on the device"""
+        ref = self._reference_filtered
+        desc = dict(ref.descriptors)
+        if self._normals_on_device:
+            desc["normals"] = _translate(self.ctx.ref_normals)
+        centred = ref.features.copy()
+        d = centred.shape[1]
+        centred[:, :d - 1] = (centred[:, :d - 1] + self._T_refMean_refIn[:d - 1, d - 1][None, :]).astype(np.float32)   # minus the mean (ICP.cpp:291-299)
+        return DataPoints(centred, desc)
 
     def compute(self, readingIn, referenceIn, T_refIn_dataIn=None):
         self._bind()

@@ -89,29 +89,34 @@ def test_config4_shape_knn10_filters_cov(oracle, synth):
         assert ndiff == nties
 
 
-def test_surface_normals_at_1m_properties(pair, oracle):
-    """K8 at 1 M points: unit normals, and agreement with the oracle on a random sample of points
-    (the oracle's neighbourhoods come from its own kd-tree over the full cloud)"""
+def test_surface_normals_at_1m(pair, oracle):
+    """K8 at 1 M points, knn 20, every point against the oracle's SurfaceNormalDataPointsFilter (its own kd-tree over the
+    full cloud, float eigen-solver) and against float64 eigenvectors of the same neighbourhoods"""
     from libpointmatcher_b200 import capi
     rd, rf, _ = pair
     with capi.Context(0) as ctx:
-        g = ctx.normals(rf, knn=20, keep=("normals", "matchedIds", "densities"))
+        g = ctx.normals(rf, knn=20, sort_eigen=True, keep=("normals", "matchedIds", "densities", "eigValues"))
     n = g["normals"]
-    assert g["degenerate"] == 0
+    o = oracle.surface_normals(rf, knn=20, nthreads=oracle.num_threads(), sort_eigen=True)
+    assert g["degenerate"] == o["degenerate"] == 0
     assert np.abs(np.linalg.norm(n, axis=1) - 1.0).max() < 1e-5
     assert (g["matchedIds"][:, 0] == np.arange(len(rf))).all()       # every point is its own first neighbour
-    rng = np.random.default_rng(5)
-    sample = np.sort(rng.choice(len(rf), 20000, replace=False))
-    io, do = oracle.KdTree(rf).knn(rf[sample], 20, nthreads=oracle.num_threads())
-    same = (g["matchedIds"][sample].astype(np.int32) == io).all(axis=1)
+    same = (g["matchedIds"].astype(np.int32) == o["ids"]).all(axis=1)  # exact distance ties may reorder a few neighbourhoods
     assert same.mean() > 0.999
-    # normals from the oracle's neighbourhoods, in float64
-    P = rf[io[same]][:, :, :3].astype(np.float64)
-    C = np.einsum("nki,nkj->nij", P - P.mean(1, keepdims=True), P - P.mean(1, keepdims=True))
-    wv, V = np.linalg.eigh(C)
+    well = same & (o["gap"] > 1e-3)
+    dots = np.abs((n * o["normals"]).sum(1))
+    assert (1.0 - dots[well]).max() <= 1e-5
+    assert np.allclose(g["densities"][same, 0], o["densities"][same], rtol=1e-5)
+    scale = o["eigValues"][same].max(axis=1, keepdims=True)
+    assert (np.abs(g["eigValues"][same] - o["eigValues"][same]) <= 2e-5 * scale + 1e-9).all()
+    # and against float64 arithmetic on a sample of the agreed neighbourhoods
+    sample = np.flatnonzero(same)[:: max(1, int(same.sum()) // 20000)]
+    P = rf[o["ids"][sample]][:, :, :3].astype(np.float64)
+    Pc = P - P.mean(1, keepdims=True)
+    wv, V = np.linalg.eigh(np.einsum("nki,nkj->nij", Pc, Pc))
     gap = (wv[:, 1] - wv[:, 0]) / wv.sum(1)
-    dots = np.abs((V[:, :, 0] * n[sample][same]).sum(1))
-    assert (1.0 - dots[gap > 1e-3]).max() < 1e-5
+    d64 = np.abs((V[:, :, 0] * n[sample]).sum(1))
+    assert (1.0 - d64[gap > 1e-3]).max() < 1e-5
 
 
 def _run_host_icp(rd, rf, nrm, matcher, filters, minimizer, iters):

@@ -993,3 +993,79 @@ def test_reading_set_sharded_uploads_the_ranks_chunks(gpu_ctx, synth):
                 assert gpu_ctx.nq == len(want)
                 if len(want):
                     assert (gpu_ctx.get_reading().view(np.uint32) == np.ascontiguousarray(want).view(np.uint32)).all()
+
+
+# ---------------------------------------------------------------------------------- Inspector / host checkers of the Python mirror
+def test_python_inspector_is_shown_every_iteration(oracle, synth):
+    """Inspector::dumpIteration (ICP.cpp:403-405) through the Python mirror: an inspector that overrides it takes the loop off the
+    fused path (pmgpu_icp_step: one exactly-matched slot at a time) and is shown, per iteration, T_iter, the centred reference, the
+    reading as the iteration sees it, every match and weight; the registration itself is the NullInspector's, bit for bit.  A
+    BoundTransformationChecker rides on the same path, now with a WithCov minimiser too."""
+    from libpointmatcher_b200 import pm
+    rd, rf, _ = synth.scan_pair(40000)
+    nrm = oracle.surface_normals(rf, knn=10, nthreads=8)["normals"]
+
+    def chain(inspector=None, extra=()):
+        icp = pm.ICP()
+        icp.matcher = pm.KDTreeMatcher({"knn": "3"})
+        icp.outlierFilters = pm.OutlierFilters([pm.TrimmedDistOutlierFilter({"ratio": "0.8"})])
+        icp.errorMinimizer = pm.PointToPlaneWithCovErrorMinimizer()
+        icp.transformationCheckers = [pm.CounterTransformationChecker({"maxIterationCount": "12"}),
+                                      pm.DifferentialTransformationChecker({"minDiffRotErr": "0.001", "minDiffTransErr": "0.001", "smoothLength": "3"})] + list(extra)
+        if inspector is not None:
+            icp.inspector = inspector
+        return icp
+
+    class Recorder(pm.Inspector):
+        def __init__(self):
+            pm.Inspector.__init__(self)
+            self.calls, self.stats, self.finished, self.inits = [], {}, None, 0
+
+        def init(self):
+            self.inits += 1
+
+        def dumpIteration(self, iterationNumber, parameters, filteredReference, reading, matches, outlierWeights, transformationCheckers):
+            self.calls.append((iterationNumber, np.array(parameters), filteredReference, reading, matches, np.array(outlierWeights), len(transformationCheckers)))
+
+        def addStat(self, name, data):
+            self.stats[name] = data
+
+        def finish(self, iterationCount):
+            self.finished = iterationCount
+
+    reading, reference = pm.DataPoints(rd), pm.DataPoints(rf, {"normals": nrm})
+    plain = chain()
+    T0 = plain(reading, reference)
+    cov0 = np.asarray(plain.errorMinimizer.getCovariance())
+    plain.ctx.close()
+    rec = Recorder()
+    assert rec.needsIterationData() and not pm.NullInspector().needsIterationData() and not pm.PerformanceInspector().needsIterationData()
+    icp = chain(rec)
+    T1 = icp(reading, reference)
+    cov1 = np.asarray(icp.errorMinimizer.getCovariance())
+    icp.ctx.close()
+    assert (T0.view(np.uint32) == T1.view(np.uint32)).all() and plain.iterationCount == icp.iterationCount
+    assert np.allclose(cov0, cov1, rtol=1e-5, atol=1e-12)
+    assert rec.inits == 1 and rec.finished == icp.iterationCount == len(rec.calls) < 12
+    assert rec.stats["IterationsCount"] == icp.iterationCount and abs(rec.stats["OverlapRatio"] - 0.8) < 1e-3
+    assert [c[0] for c in rec.calls] == list(range(len(rec.calls))) and (rec.calls[0][1] == np.eye(4, dtype=np.float32)).all()
+    tree = None
+    for n, T_iter, ref, seen, matches, w, ncheck in rec.calls[:1] + rec.calls[-2:]:
+        assert ncheck == 2 and ref.descriptorExists("normals") and w.shape == matches.ids.shape == (len(rd), 3)
+        if tree is None:
+            tree = oracle.KdTree(ref.features)            # the reference minus its mean: what the matcher was built on
+        io, do = tree.knn(seen.features, 3, nthreads=8)
+        assert (matches.dists.view(np.uint32) == do.view(np.uint32)).all()      # every match, none cut off by a cap
+        ndiff, nties = classify_id_mismatches(io, do, matches.ids, matches.dists)
+        assert ndiff == nties
+        wo, _ = oracle.outlier_weights(do, [(oracle.FILTER_TRIMMEDDIST, 0.8)])
+        assert (w == wo).all()
+    # host-side Bound checker: generous bounds change nothing, tight ones stop the registration with the reference's exception
+    loose = chain(extra=[pm.BoundTransformationChecker({"maxRotationNorm": "1.0", "maxTranslationNorm": "5.0"})])
+    T2 = loose(reading, reference)
+    loose.ctx.close()
+    assert (T0.view(np.uint32) == T2.view(np.uint32)).all()
+    tight = chain(extra=[pm.BoundTransformationChecker({"maxRotationNorm": "0.001", "maxTranslationNorm": "0.001"})])
+    with pytest.raises(pm.ConvergenceError):
+        tight(reading, reference)
+    tight.ctx.close()

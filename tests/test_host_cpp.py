@@ -205,7 +205,7 @@ def test_cpp_runs_reference_yaml_chain_to_golden(host_bin, tmp_path, name):
     fx = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_fixture.npz"))
     ref = np.ascontiguousarray(np.c_[fx["cloud0"], np.ones(len(fx["cloud0"]))].astype(np.float32))
     data = np.ascontiguousarray(np.c_[fx["cloud1"], np.ones(len(fx["cloud1"]))].astype(np.float32))
-    cfg = str(fx["yaml_" + name]).replace("PerformanceInspector", "NullInspector")
+    cfg = str(fx["yaml_" + name])
     res = _run_icp(host_bin, tmp_path, cfg, data, ref, None)
     cur = res["T"].astype(np.float64) @ data.T.astype(np.float64)
     gold = fx["golden_" + name].astype(np.float64) @ data.T.astype(np.float64)

@@ -189,7 +189,7 @@ def test_gpu_runs_reference_yaml_chain_to_golden(fx, name):
     ref, data = homog(fx["cloud0"]), homog(fx["cloud1"])
     capi.lib.pmgpu_host_srand(1)
     icp = pm.ICP()
-    icp.loadFromYaml(str(fx["yaml_" + name]).replace("PerformanceInspector", "NullInspector"))  # inspectors are out of scope
+    icp.loadFromYaml(str(fx["yaml_" + name]))
     T = icp(pm.DataPoints(data), pm.DataPoints(ref))
     icp.ctx.close()
     assert rel_err(T, fx["golden_" + name], data) < 0.03
