@@ -236,6 +236,15 @@ def peaks():
         return {}
 
 
+def reference_install():
+    """the reference itself cannot be built in this image (no Eigen3 / Boost headers / libnabo), so the CPU arm is the
+    oracle port; should a driver-written install ever appear under baseline/_ref, say so on the line instead of hiding it"""
+    for rel in ("baseline/_ref/bin/pmicp", "baseline/_ref/lib/libpointmatcher.so"):
+        if os.path.exists(os.path.join(ROOT, rel)):
+            return "found %s (not used: the arm times the oracle port, kind = port)" % rel
+    return "absent (reference not buildable here; oracle port timed)"
+
+
 # ------------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
     """CPU arm: the oracle port of the reference path on all host threads (rank 0 only), same config: the reference
@@ -271,7 +280,8 @@ def run_reference(args, rank, world):
                                    "(%.2f s) excluded from value, included in e2e" % (tm["iterations"], tm["build_s"], cfg["normals_knn"], t_normals)},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "extra": {"match_share": tm["match_s"] / tm["loop_s"], "build_s": tm["build_s"], "normals_s": t_normals, "loop_s": tm["loop_s"]},
+        "extra": {"match_share": tm["match_s"] / tm["loop_s"], "build_s": tm["build_s"], "normals_s": t_normals, "loop_s": tm["loop_s"],
+                  "reference_install": reference_install()},
     }
 
 
