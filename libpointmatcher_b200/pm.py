@@ -1239,9 +1239,6 @@ class PerformanceInspector(Inspector):
         stream.write(", ".join(sorted(self.stats)))
 
 
-InspectorRegistrar = None  # filled in below, after Registrar
-
-
 # ---- Registrar (Registrar.h:75-218) --------------------------------------------------------------
 class Registrar(dict):
     def create(self, name, params=None):
