@@ -264,8 +264,7 @@ protected:
         p.knn = gpuMatcher->knn;
         p.epsilon = (float)gpuMatcher->epsilon;
         p.max_dist = (float)gpuMatcher->maxDist;
-        p.nfilters = (int)this->outlierFilters.size();
-        this->outlierFilters.spec(p.filter_type, p.filter_param, g);
+        p.nfilters = this->outlierFilters.spec(p.filter_type, p.filter_param, g);
         p.minimizer = gpuMinimizer->kind;
         p.sensor_std_dev = (float)gpuMinimizer->sensorStdDev;
         p.max_iterations = counter ? (int)counter->maxIterationCount : 0x7fffffff;

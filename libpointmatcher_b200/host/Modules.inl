@@ -829,29 +829,33 @@ struct RobustOutlierFilter : public GpuDistOutlierFilter {
 // chain (OutlierFilter.cpp:63-103): product of the filters' weights; empty chain -> dist != inf.
 // A chain made of GPU distance filters is evaluated in one call (one collapsed threshold).
 struct OutlierFilters : public std::vector<std::shared_ptr<OutlierFilter>>, public GpuBound {
+    // a NullOutlierFilter is a factor of one (OutlierFiltersImpl.cpp:45-58): allowed in a GPU chain, never sent to the device
     bool allGpu() const {
         for (const auto& f : *this)
-            if (!dynamic_cast<GpuDistOutlierFilter*>(f.get())) return false;
+            if (!dynamic_cast<GpuDistOutlierFilter*>(f.get()) && !dynamic_cast<NullOutlierFilter*>(f.get())) return false;
         return true;
     }
-    void spec(int* types, float* params, GpuPipeline& pipeline) const {
+    // fills the filter words of the chain, returns how many there are
+    int spec(int* types, float* params, GpuPipeline& pipeline) const {
         int i = 0;
         for (const auto& f : *this) {
             const auto* g = dynamic_cast<const GpuDistOutlierFilter*>(f.get());
+            if (!g) continue;
             g->prepare(pipeline);
             types[i] = g->filterType;
             params[i] = (float)g->value;
             ++i;
         }
+        return i;
     }
     OutlierWeights compute(const DataPoints& filteredReading, const DataPoints& filteredReference, const Matches& input) {
         if (allGpu() && this->size() <= 8) {
             GpuPipeline& g = this->gpu();
             int types[8];
             float params[8];
-            spec(types, params, g);
+            const int n = spec(types, params, g);
             OutlierWeights w(input.ids.rows(), input.ids.cols());
-            g.check(pmgpu_weights(g.ctx, (int)this->size(), types, params, reinterpret_cast<float*>(w.data()), nullptr));
+            g.check(pmgpu_weights(g.ctx, n, types, params, reinterpret_cast<float*>(w.data()), nullptr));
             return w;
         }
         OutlierWeights w = (*this->begin())->compute(filteredReading, filteredReference, input);

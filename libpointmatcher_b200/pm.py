@@ -379,6 +379,20 @@ class _DistFilter(Parametrizable, _Bound):
         return w
 
 
+class NullOutlierFilter(Parametrizable, _Bound):
+    """Does nothing (OutlierFiltersImpl.cpp:45-58: weights of 1): in a chain it is a factor of one, so it never reaches the device"""
+    className = "NullOutlierFilter"
+
+    def spec(self):
+        return None
+
+    def prepare(self, ctx):
+        pass
+
+    def compute(self, filteredReading, filteredReference, matches):
+        return np.ones(np.asarray(matches.ids).shape, np.float32)
+
+
 class MaxDistOutlierFilter(_DistFilter):
     className = "MaxDistOutlierFilter"
     TYPE, PARAM = capi.FILTER_MAXDIST, "maxDist"
@@ -468,9 +482,13 @@ class OutlierFilters(list, _Bound):
     def compute(self, filteredReading, filteredReference, matches):
         for f in self:
             f.prepare(self.ctx)
-        w, limits = _translate(self.ctx.weights, [f.spec() for f in self])
+        w, limits = _translate(self.ctx.weights, self.specs())
         self.limits = limits
         return w
+
+    def specs(self):
+        """the (type, value) words of the chain; a NullOutlierFilter is a factor of one and contributes none"""
+        return [f.spec() for f in self if f.spec() is not None]
 
 
 # ---- ErrorElements, materialised on request (ErrorMinimizer.cpp:58-193) -------------------------------
@@ -1251,7 +1269,7 @@ class Registrar(dict):
 
 
 MatcherRegistrar = Registrar(KDTreeMatcher=KDTreeMatcher, KDTreeVarDistMatcher=KDTreeVarDistMatcher)
-OutlierFilterRegistrar = Registrar(MaxDistOutlierFilter=MaxDistOutlierFilter, MedianDistOutlierFilter=MedianDistOutlierFilter,
+OutlierFilterRegistrar = Registrar(NullOutlierFilter=NullOutlierFilter, MaxDistOutlierFilter=MaxDistOutlierFilter, MedianDistOutlierFilter=MedianDistOutlierFilter,
                                    TrimmedDistOutlierFilter=TrimmedDistOutlierFilter, RobustOutlierFilter=RobustOutlierFilter,
                                    VarTrimmedDistOutlierFilter=VarTrimmedDistOutlierFilter,
                                    SurfaceNormalOutlierFilter=SurfaceNormalOutlierFilter)
@@ -1382,7 +1400,7 @@ class ICP:
         for f in self.outlierFilters:
             f.prepare(self.ctx)
         return capi.make_params(
-            knn=m.knn, epsilon=m.epsilon, max_dist=m.maxDist, filters=[f.spec() for f in self.outlierFilters],
+            knn=m.knn, epsilon=m.epsilon, max_dist=m.maxDist, filters=self.outlierFilters.specs(),
             minimizer=self.errorMinimizer.kind_word(), sensor_std_dev=self.errorMinimizer.sensorStdDev,
             max_iterations=counter[0].maxIterationCount if counter else 0x7FFFFFFF,
             differential=(diff[0].minDiffRotErr, diff[0].minDiffTransErr, diff[0].smoothLength) if diff else None)

@@ -179,6 +179,12 @@ static int run_cpu() {
             CHECK(dynamic_cast<PM::GpuDistOutlierFilter*>(pp.get())->filterType == (PMGPU_ROBUST_WORD(PMGPU_ROBUST_CAUCHY, PMGPU_SCALE_BERG, 0) | PMGPU_ROBUST_P2PLANE));
         }
         CHECK(pm.OutlierFilterRegistrar.create("SurfaceNormalOutlierFilter", {{"maxAngle", "0.42"}})->get<float>("maxAngle") == 0.42f);
+        {   // a NullOutlierFilter is a factor of one: a chain that holds it is still a GPU chain
+            PM::OutlierFilters chain;
+            chain.push_back(pm.OutlierFilterRegistrar.create("NullOutlierFilter"));
+            chain.push_back(pm.OutlierFilterRegistrar.create("TrimmedDistOutlierFilter", {{"ratio", "0.7"}}));
+            CHECK(chain.allGpu());
+        }
         auto var = pm.MatcherRegistrar.create("KDTreeVarDistMatcher", {{"knn", "3"}, {"maxDistField", "radius"}});
         auto* vm = dynamic_cast<PM::KDTreeMatcher*>(var.get());
         CHECK(vm && vm->maxDistField == "radius" && vm->maxDist == -1.f && vm->knn == 3);

@@ -1069,3 +1069,29 @@ def test_python_inspector_is_shown_every_iteration(oracle, synth):
     with pytest.raises(pm.ConvergenceError):
         tight(reading, reference)
     tight.ctx.close()
+
+
+def test_null_outlier_filter_is_a_factor_of_one(synth):
+    """NullOutlierFilter (OutlierFiltersImpl.cpp:45-58) in a chain: the same registration as without it, bit for bit; alone: the
+    empty chain"""
+    from libpointmatcher_b200 import pm
+    rd, rf, _ = synth.scan_pair(30000)
+
+    def run(filters):
+        icp = pm.ICP()
+        icp.matcher = pm.KDTreeMatcher()
+        icp.outlierFilters = pm.OutlierFilters(filters)
+        icp.errorMinimizer = pm.PointToPointErrorMinimizer()
+        icp.transformationCheckers = [pm.CounterTransformationChecker({"maxIterationCount": "8"})]
+        T = icp(pm.DataPoints(rd), pm.DataPoints(rf))
+        ratio = icp.errorMinimizer.getWeightedPointUsedRatio()
+        icp.ctx.close()
+        return T, ratio
+
+    null = pm.OutlierFilterRegistrar.create("NullOutlierFilter")
+    T_a, r_a = run([pm.TrimmedDistOutlierFilter({"ratio": "0.7"})])
+    T_b, r_b = run([null, pm.TrimmedDistOutlierFilter({"ratio": "0.7"}), pm.NullOutlierFilter()])
+    assert (T_a.view(np.uint32) == T_b.view(np.uint32)).all() and r_a == r_b
+    T_c, r_c = run([])
+    T_d, r_d = run([pm.NullOutlierFilter()])
+    assert (T_c.view(np.uint32) == T_d.view(np.uint32)).all() and r_c == r_d == 1.0

@@ -348,3 +348,15 @@ def test_datapoints_concatenate(pm):
     c = pm.DataPoints(np.zeros((1, 4), np.float32), {"normals": np.zeros((1, 3), np.float32)})
     with pytest.raises(pm.InvalidField):
         c.concatenate(pm.DataPoints(np.zeros((1, 4), np.float32), {"normals": np.zeros((1, 2), np.float32)}))
+
+
+def test_null_outlier_filter_contributes_no_filter_word(pm):
+    """NullOutlierFilter (OutlierFiltersImpl.cpp:45-58) is a factor of one: registered, loadable from YAML, absent from the words the
+    device is given"""
+    chain = pm.OutlierFilters([pm.OutlierFilterRegistrar.create("NullOutlierFilter"), pm.TrimmedDistOutlierFilter({"ratio": "0.7"})])
+    assert [t for t, _ in chain.specs()] == [pm.TrimmedDistOutlierFilter.TYPE] and abs(chain.specs()[0][1] - 0.7) < 1e-7
+    icp = pm.ICP()
+    icp.loadFromYaml("outlierFilters:\n  - NullOutlierFilter\nmatcher:\n  KDTreeMatcher\n")
+    assert [type(f).__name__ for f in icp.outlierFilters] == ["NullOutlierFilter"] and icp.outlierFilters.specs() == []
+    with pytest.raises(pm.InvalidParameter):
+        pm.NullOutlierFilter({"ratio": "1"})
