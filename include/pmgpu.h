@@ -68,9 +68,14 @@ enum pmgpu_filter_type {
     PMGPU_FILTER_ROBUST = 3,     /* RobustOutlierFilter      param = tuning                OutlierFiltersImpl.cpp:420-598 */
     PMGPU_FILTER_VARTRIMMEDDIST = 5, /* VarTrimmedDistOutlierFilter param = lambda; minRatio / maxRatio through
                                      pmgpu_set_var_trimmed_ratios       OutlierFiltersImpl.cpp:152-218 */
-    PMGPU_FILTER_SURFACENORMAL = 4 /* SurfaceNormalOutlierFilter param = maxAngle: weight 0 where |n_reading . n_reference| <
+    PMGPU_FILTER_SURFACENORMAL = 4,/* SurfaceNormalOutlierFilter param = maxAngle: weight 0 where |n_reading . n_reference| <
                                       cos(maxAngle), both normalised (OutlierFiltersImpl.cpp:222-285); needs the reference
                                       normals and pmgpu_reading_set_normals, otherwise all ones like the reference */
+    PMGPU_FILTER_MINDIST = 6     /* MinDistOutlierFilter     param = minDist (un-squared): weight 0 below it
+                                                                                            OutlierFiltersImpl.cpp:87-101.
+                                    A match without a neighbour (dist = +inf) always reads weight 0 here; the reference gives it
+                                    1 under a chain of MinDist / Null filters only and drops it in ErrorElements either way
+                                    (ErrorMinimizer.cpp:103-106), so nothing computed from the weights differs */
 };
 /* RobustOutlierFilter: M-estimator weights w(e^2), e^2 = dist / scale^2.  Its discrete
  * parameters travel in the filter word: bits 0-7 PMGPU_FILTER_ROBUST | bits 8-15 robustFct | bits 16-19

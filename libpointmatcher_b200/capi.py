@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # PMGPU_VARIANT selects a tuning build (libpmgpu_<name>.so, see build.py); default: libpmgpu.so
 LIB_PATH = os.path.join(_HERE, "libpmgpu%s.so" % ("_" + os.environ["PMGPU_VARIANT"] if os.environ.get("PMGPU_VARIANT") else ""))
 
-FILTER_MAXDIST, FILTER_MEDIANDIST, FILTER_TRIMMEDDIST, FILTER_ROBUST, FILTER_SURFACENORMAL, FILTER_VARTRIMMEDDIST = 0, 1, 2, 3, 4, 5
+FILTER_MAXDIST, FILTER_MEDIANDIST, FILTER_TRIMMEDDIST, FILTER_ROBUST, FILTER_SURFACENORMAL, FILTER_VARTRIMMEDDIST, FILTER_MINDIST = 0, 1, 2, 3, 4, 5, 6
 ROBUST_P2PLANE = 1 << 28   # RobustOutlierFilter distanceType point2plane, or-ed into its filter word
 MIN_P2POINT, MIN_P2PLANE, MIN_P2POINT_COV, MIN_P2PLANE_COV, MIN_P2POINT_SIM = 0, 1, 2, 3, 4
 MIN_FORCE4DOF = 0x100  # or-ed into a point-to-plane minimiser id

@@ -112,6 +112,7 @@ struct IcpState {
     // select / weights
     float limit[PM_MAX_FILTERS]; // per-filter squared-distance limit
     float limit_all;             // min over filters: weight = dist <= limit_all
+    float limit_lo;              // max over the MinDist filters (0 without one): ... and dist >= limit_lo
     int has_filters;             // 0: empty chain (weight = dist != inf)
     unsigned long long n_valid;  // number of finite distances (all ranks)
     unsigned sel_prefix[PM_MAX_FILTERS];           // radix-select state per quantile filter
@@ -170,7 +171,7 @@ struct IcpState {
 struct SelectSpec {
     int nfilters;
     int type[PM_MAX_FILTERS];
-    float param[PM_MAX_FILTERS];  // MaxDist: squared limit; MedianDist: factor; TrimmedDist: ratio
+    float param[PM_MAX_FILTERS];  // MaxDist / MinDist: squared limit; MedianDist: factor; TrimmedDist: ratio
     __host__ __device__ int kind(int f) const { return type[f] & 0xff; }
     __host__ __device__ bool is_robust(int f) const { return kind(f) == PMGPU_FILTER_ROBUST; }
     __host__ __device__ bool is_quantile(int f) const { return kind(f) == PMGPU_FILTER_MEDIANDIST || kind(f) == PMGPU_FILTER_TRIMMEDDIST; }

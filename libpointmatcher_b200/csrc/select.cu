@@ -348,6 +348,9 @@ int make_select_spec(pmgpu_ctx* ctx, int nfilters, const int* types, const float
         if (types[f] == PMGPU_FILTER_MAXDIST) {
             // maxDist(pow(get<T>("maxDist"), 2)): the square is taken in double (OutlierFiltersImpl.cpp:69)
             spec->param[f] = (float)((double)params[f] * (double)params[f]);
+        } else if (types[f] == PMGPU_FILTER_MINDIST) {
+            // minDist(pow(get<T>("minDist"), 2)), likewise (OutlierFiltersImpl.cpp:90)
+            spec->param[f] = (float)((double)params[f] * (double)params[f]);
         } else if (types[f] == PMGPU_FILTER_TRIMMEDDIST) {
             if (params[f] < 0.f || params[f] > 1.f) {
                 ctx->set_error("quantile must be between 0 and 1");

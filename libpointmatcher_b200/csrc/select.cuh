@@ -16,16 +16,20 @@ namespace pm {
 
 // MaxDist limits are known up front; quantile filters start at +inf and are lowered by pass 2
 __device__ __forceinline__ void select_init_limits(IcpState* st, const SelectSpec& sp) {
-    float all = pm_inf();
+    float all = pm_inf(), lo = 0.f;
     for (int f = 0; f < sp.nfilters; ++f) {
         if (sp.type[f] == PMGPU_FILTER_MAXDIST) {
             st->limit[f] = sp.param[f];
             all = fminf(all, sp.param[f]);
+        } else if (sp.type[f] == PMGPU_FILTER_MINDIST) {
+            st->limit[f] = sp.param[f];
+            lo = fmaxf(lo, sp.param[f]);
         } else {
             st->limit[f] = pm_inf();
         }
     }
     st->limit_all = all;
+    st->limit_lo = lo;
     st->has_filters = sp.nfilters > 0 ? 1 : 0;
     st->cap_need = 0.f;
     const int sn = sp.sn_index();
@@ -110,7 +114,7 @@ __device__ __forceinline__ float pm_sn_weight(const Mat4& T, f4 rn, f4 qn, float
 // (minimize.cu) computes the limits in the same launch that applies them, so its blocks must not read them through a
 // const __restrict__ pointer (non-coherent loads, hoistable above the grid barrier)
 struct PairW {
-    float limit_all;
+    float limit_all, limit_lo;
     int has_filters, robust_on, robust_fct;
     float robust_k, robust_scale, robust_approx2;
     int robust_p2plane;
@@ -119,6 +123,7 @@ struct PairW {
 };
 __device__ __forceinline__ void load_pairw(const IcpState* st, PairW* w) {
     w->limit_all = __ldcg(&st->limit_all);
+    w->limit_lo = __ldcg(&st->limit_lo);
     w->has_filters = __ldcg(&st->has_filters);
     w->robust_on = __ldcg(&st->robust_on);
     w->robust_fct = __ldcg(&st->robust_fct);
@@ -133,7 +138,7 @@ __device__ __forceinline__ void load_pairw(const IcpState* st, PairW* w) {
 template <typename S>
 __device__ __forceinline__ float pm_pair_weight(const S* st, float d) {
     if (d == pm_inf()) return 0.f;  // ErrorMinimizer.cpp:103-106: invalid matches are skipped
-    float w = st->has_filters ? ((d <= st->limit_all) ? 1.f : 0.f) : 1.f;
+    float w = st->has_filters ? ((d <= st->limit_all && d >= st->limit_lo) ? 1.f : 0.f) : 1.f;
     // (distanceType point2plane: the robust factor needs the matched point and its normal — pm_robust_p2plane_weight, applied
     // by the caller once it has gathered them)
     if (st->robust_on && !st->robust_p2plane && w != 0.f) w = __fmul_rn(w, pm_robust_weight(st, d));

@@ -759,6 +759,11 @@ struct MaxDistOutlierFilter : public GpuDistOutlierFilter {
     static const ParametersDoc availableParameters() { return {{"maxDist", "threshold distance (Euclidean norm)", "1", "0.0000001", "inf", &Parametrizable::Comp<T>}}; }
     MaxDistOutlierFilter(const Parameters& params = Parameters()) : GpuDistOutlierFilter("MaxDistOutlierFilter", availableParameters(), params, PMGPU_FILTER_MAXDIST, "maxDist") {}
 };
+struct MinDistOutlierFilter : public GpuDistOutlierFilter {
+    static const std::string description() { return "This filter considers as outlier links whose norms are below a threshold."; }
+    static const ParametersDoc availableParameters() { return {{"minDist", "threshold distance (Euclidean norm)", "1", "0.0000001", "inf", &Parametrizable::Comp<T>}}; }
+    MinDistOutlierFilter(const Parameters& params = Parameters()) : GpuDistOutlierFilter("MinDistOutlierFilter", availableParameters(), params, PMGPU_FILTER_MINDIST, "minDist") {}
+};
 struct MedianDistOutlierFilter : public GpuDistOutlierFilter {
     static const std::string description() { return "This filter considers as outlier links whose norms are above the median link norms times a factor."; }
     static const ParametersDoc availableParameters() { return {{"factor", "points farther away factor * median will be considered outliers.", "3", "0.0000001", "inf", &Parametrizable::Comp<T>}}; }

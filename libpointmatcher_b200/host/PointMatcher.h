@@ -698,6 +698,7 @@ struct PointMatcher {
         ADD_TO_REGISTRAR(Matcher, KDTreeVarDistMatcher, KDTreeVarDistMatcher)
         ADD_TO_REGISTRAR_NO_PARAM(OutlierFilter, NullOutlierFilter, NullOutlierFilter)
         ADD_TO_REGISTRAR(OutlierFilter, MaxDistOutlierFilter, MaxDistOutlierFilter)
+        ADD_TO_REGISTRAR(OutlierFilter, MinDistOutlierFilter, MinDistOutlierFilter)
         ADD_TO_REGISTRAR(OutlierFilter, MedianDistOutlierFilter, MedianDistOutlierFilter)
         ADD_TO_REGISTRAR(OutlierFilter, TrimmedDistOutlierFilter, TrimmedDistOutlierFilter)
         ADD_TO_REGISTRAR(OutlierFilter, VarTrimmedDistOutlierFilter, VarTrimmedDistOutlierFilter)

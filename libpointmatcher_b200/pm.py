@@ -399,6 +399,13 @@ class MaxDistOutlierFilter(_DistFilter):
     PARAMS = (("maxDist", "threshold distance (Euclidean norm)", "1", "0.0000001", "inf", float),)
 
 
+class MinDistOutlierFilter(_DistFilter):
+    """OutlierFiltersImpl.cpp:87-101: links shorter than the threshold are outliers"""
+    className = "MinDistOutlierFilter"
+    TYPE, PARAM = capi.FILTER_MINDIST, "minDist"
+    PARAMS = (("minDist", "threshold distance (Euclidean norm)", "1", "0.0000001", "inf", float),)
+
+
 class MedianDistOutlierFilter(_DistFilter):
     className = "MedianDistOutlierFilter"
     TYPE, PARAM = capi.FILTER_MEDIANDIST, "factor"
@@ -1269,7 +1276,8 @@ class Registrar(dict):
 
 
 MatcherRegistrar = Registrar(KDTreeMatcher=KDTreeMatcher, KDTreeVarDistMatcher=KDTreeVarDistMatcher)
-OutlierFilterRegistrar = Registrar(NullOutlierFilter=NullOutlierFilter, MaxDistOutlierFilter=MaxDistOutlierFilter, MedianDistOutlierFilter=MedianDistOutlierFilter,
+OutlierFilterRegistrar = Registrar(NullOutlierFilter=NullOutlierFilter, MaxDistOutlierFilter=MaxDistOutlierFilter,
+                                   MinDistOutlierFilter=MinDistOutlierFilter, MedianDistOutlierFilter=MedianDistOutlierFilter,
                                    TrimmedDistOutlierFilter=TrimmedDistOutlierFilter, RobustOutlierFilter=RobustOutlierFilter,
                                    VarTrimmedDistOutlierFilter=VarTrimmedDistOutlierFilter,
                                    SurfaceNormalOutlierFilter=SurfaceNormalOutlierFilter)

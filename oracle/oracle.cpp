@@ -712,6 +712,16 @@ int outlier_weights(const float* dists, int knn, int n, int nfilters, const int*
         if (types[f] == ORC_FILTER_MAXDIST) {
             // maxDist(pow(get<T>("maxDist"), 2)): pow(float, int) promotes to double
             limit = float(std::pow(double(params[f]), 2));
+        } else if (types[f] == ORC_FILTER_MINDIST) {
+            // minDist(pow(get<T>("minDist"), 2)); weights = dists >= minDist (OutlierFiltersImpl.cpp:87-101): an infinite
+            // distance passes, and is dropped later by ErrorElements (ErrorMinimizer.cpp:103-106)
+            limit = float(std::pow(double(params[f]), 2));
+            if (limits_out) limits_out[f] = limit;
+            for (long i = 0; i < total; ++i) {
+                const float wf = (dists[i] >= limit) ? 1.f : 0.f;
+                w[i] = (f == 0) ? wf : w[i] * wf;
+            }
+            continue;
         } else if (types[f] == ORC_FILTER_MEDIANDIST) {
             float median;
             const int rc = dists_quantile(dists, total, 0.5f, &median);

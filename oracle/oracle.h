@@ -24,7 +24,8 @@ extern "C" {
 
 /* filter types for the outlier chain (OutlierFiltersImpl.cpp) */
 enum { ORC_FILTER_MAXDIST = 0, ORC_FILTER_MEDIANDIST = 1, ORC_FILTER_TRIMMEDDIST = 2, ORC_FILTER_ROBUST = 3, ORC_FILTER_SURFACENORMAL = 4,
-       ORC_FILTER_VARTRIMMEDDIST = 5 /* param = lambda; minRatio / maxRatio through orc_set_var_trimmed_ratios */ };
+       ORC_FILTER_VARTRIMMEDDIST = 5 /* param = lambda; minRatio / maxRatio through orc_set_var_trimmed_ratios */,
+       ORC_FILTER_MINDIST = 6 /* MinDistOutlierFilter, param = minDist (un-squared), OutlierFiltersImpl.cpp:87-101 */ };
 /* RobustOutlierFilter (OutlierFiltersImpl.cpp:420-598): the filter word carries its discrete parameters:
  *   bits 0-7  ORC_FILTER_ROBUST | bits 8-15 robust function | bits 16-19 scale estimator |
  *   bits 20-27 nbIterationForScale;   filter_param = tuning.  distanceType point2point, approximation inf. */

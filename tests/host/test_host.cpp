@@ -184,6 +184,9 @@ static int run_cpu() {
             chain.push_back(pm.OutlierFilterRegistrar.create("NullOutlierFilter"));
             chain.push_back(pm.OutlierFilterRegistrar.create("TrimmedDistOutlierFilter", {{"ratio", "0.7"}}));
             CHECK(chain.allGpu());
+            auto md = pm.OutlierFilterRegistrar.create("MinDistOutlierFilter", {{"minDist", "0.2"}});
+            CHECK(dynamic_cast<PM::GpuDistOutlierFilter*>(md.get())->filterType == PMGPU_FILTER_MINDIST && md->get<float>("minDist") == 0.2f);
+            CHECK(throws<PM::InvalidParameter>([&] { pm.OutlierFilterRegistrar.create("MinDistOutlierFilter", {{"minDist", "0"}}); }));
         }
         auto var = pm.MatcherRegistrar.create("KDTreeVarDistMatcher", {{"knn", "3"}, {"maxDistField", "radius"}});
         auto* vm = dynamic_cast<PM::KDTreeMatcher*>(var.get());

@@ -354,6 +354,7 @@ def _fused_run(monkeypatch, env, rd, rf, nrm, params_kw, T0=None):
     dict(knn=3, filters=[(1, 2.5)], minimizer=1, max_iterations=8),
     dict(knn=1, filters=[(0, 0.4), (1, 3.0)], minimizer=3, max_iterations=8),
     dict(knn=1, filters=[(0, 0.05)], minimizer=0, max_iterations=6),
+    dict(knn=1, filters=[(6, 0.02), (2, 0.8)], minimizer=1, max_iterations=8),      # MinDist x TrimmedDist
 ])
 def test_capped_loop_is_bit_identical_to_uncapped(monkeypatch, oracle, synth, chain):
     """The adaptive search radius of the fused loop (pmgpu.h "capped matching") must not change a
@@ -1095,3 +1096,33 @@ def test_null_outlier_filter_is_a_factor_of_one(synth):
     T_c, r_c = run([])
     T_d, r_d = run([pm.NullOutlierFilter()])
     assert (T_c.view(np.uint32) == T_d.view(np.uint32)).all() and r_c == r_d == 1.0
+
+
+def test_min_dist_outlier_filter_matches_oracle(gpu_ctx, oracle, synth):
+    """MinDistOutlierFilter (OutlierFiltersImpl.cpp:87-101): weight 0 below minDist^2, alone and in chains; the whole loop with it.
+    A match without a neighbour (dist = +inf) reads 0 on the device and 1 in the reference's matrix — ErrorElements drops it either
+    way (ErrorMinimizer.cpp:103-106)"""
+    from libpointmatcher_b200 import capi
+    rd, rf, _ = synth.scan_pair(60000)
+    gpu_ctx.set_reference(rf)
+    gpu_ctx.set_reading(rd)
+    for k, md in ((1, np.inf), (3, 0.6)):
+        ids, d, _ = gpu_ctx.knn(None, k, 0.0, md)
+        finite = np.isfinite(d)
+        for chain in ([(6, 0.05)], [(6, 0.3), (6, 0.1)], [(6, 0.05), (2, 0.8)], [(0, 0.5), (6, 0.1), (1, 2.0)], [(6, 100.0)]):
+            wo, lo = oracle.outlier_weights(d, chain)
+            wg, lg = gpu_ctx.weights(chain)
+            assert (bits(lo) == bits(lg)).all(), (chain, lo, lg)
+            assert (wo[finite] == wg[finite]).all() and (wg[~finite] == 0).all(), chain
+            assert 0 < wg.sum() < wg.size or chain == [(6, 100.0)]
+    nrm = oracle.surface_normals(rf, knn=10, nthreads=8)["normals"]
+    chain = [(6, 0.03), (2, 0.8)]
+    for minimizer in (0, 1):
+        res_o = oracle.icp(rd, rf, ref_normals=nrm, knn=1, filters=chain, minimizer=minimizer, max_iterations=10, nthreads=8, acc_double=True)
+        with capi.Context(0) as ctx:
+            ctx.set_reference(rf, normals=nrm)
+            ctx.set_reading(rd)
+            res = ctx.icp_run(capi.make_params(knn=1, filters=chain, minimizer=minimizer, max_iterations=10))
+        assert res["iterations"] == res_o["iterations"] == 10
+        assert_transform_close(res["T_iter"], res_o["T"], 1e-5, 1e-5)
+        assert abs(res["stats"]["weightedPointUsedRatio"] - float(res_o["stats"][1])) < 1e-4

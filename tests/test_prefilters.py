@@ -360,3 +360,10 @@ def test_null_outlier_filter_contributes_no_filter_word(pm):
     assert [type(f).__name__ for f in icp.outlierFilters] == ["NullOutlierFilter"] and icp.outlierFilters.specs() == []
     with pytest.raises(pm.InvalidParameter):
         pm.NullOutlierFilter({"ratio": "1"})
+
+
+def test_min_dist_outlier_filter_module(pm):
+    f = pm.OutlierFilterRegistrar.create("MinDistOutlierFilter", {"minDist": "0.2"})
+    assert f.spec()[0] == 6 and abs(f.spec()[1] - 0.2) < 1e-7
+    with pytest.raises(pm.InvalidParameter):
+        pm.MinDistOutlierFilter({"minDist": "0"})
